@@ -1,0 +1,228 @@
+"""BAM / SAM readers for the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline leg may import this module;
+the product (`seeksv_b200/`) never does.
+
+What it restates: the record model of the samtools-0.1.x library the reference links as a prebuilt
+archive (`sam/libbam.a`; only its headers are vendored, so the wire format is taken from them):
+  * BGZF container          sam/bgzf.h:34-60   (gzip members with a BC extra field, <= 64 KiB each)
+  * bam1_core_t / bam1_t    sam/bam.h:169-198  (32-byte core, then qname, cigar, 4-bit seq, qual, aux)
+  * CIGAR encoding          sam/bam.h:128-151  ("MIDNSHP=X", op in the low 4 bits)
+  * 4-bit base table        sam/bam.h:282      ("=ACMGRSVTWYHKDBN")
+  * aux tag access          sam/bam.h:556-566  (bam_aux_get / bam_aux2i)
+"""
+from __future__ import annotations
+
+import gzip
+import struct
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+CIGAR_OPS = "MIDNSHP=X"
+NT16 = "=ACMGRSVTWYHKDBN"
+
+FPAIRED, FPROPER, FUNMAP, FMUNMAP, FREVERSE, FMREVERSE, FREAD1, FREAD2, FSECONDARY, FQCFAIL, FDUP = (
+    1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024)
+
+
+@dataclass
+class Header:
+    names: List[str]
+    lengths: List[int]
+    text: str = ""
+
+
+@dataclass
+class Rec:
+    tid: int
+    pos: int          # 0-based
+    mapq: int
+    bin: int
+    flag: int
+    l_qseq: int
+    mtid: int
+    mpos: int
+    isize: int
+    qname: str
+    cigar: List[Tuple[int, int]]   # (len, op index into CIGAR_OPS)
+    seq4: bytes                    # packed 4-bit bases
+    qual: bytes                    # raw phred, l_qseq bytes
+    aux: bytes
+    size: int = 0                  # 4 + block_size of the packed record
+
+    def seq_str(self, beg: int = 0, end: Optional[int] = None) -> str:
+        end = self.l_qseq if end is None else end
+        s = self.seq4
+        return "".join(NT16[(s[i >> 1] >> 4) & 15] if (i & 1) == 0 else NT16[s[i >> 1] & 15] for i in range(beg, end))
+
+    def qual_str(self, beg: int = 0, end: Optional[int] = None) -> str:
+        end = self.l_qseq if end is None else end
+        return "".join(chr(q + 33) for q in self.qual[beg:end])
+
+
+def read_bgzf(path: str) -> bytes:
+    """Whole uncompressed payload of a BGZF (or plain gzip) file. sam/bgzf.h:34-60."""
+    with gzip.open(path, "rb") as f:
+        return f.read()
+
+
+def parse_bam_stream(data: bytes) -> Tuple[Header, List[Rec], int]:
+    """Parse 'BAM\\1' header + records. Returns (header, records, offset_of_first_record)."""
+    assert data[:4] == b"BAM\1", "not a BAM stream"
+    l_text = struct.unpack_from("<i", data, 4)[0]
+    text = data[8:8 + l_text].decode("latin-1")
+    o = 8 + l_text
+    n_ref = struct.unpack_from("<i", data, o)[0]
+    o += 4
+    names, lengths = [], []
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<i", data, o)[0]
+        o += 4
+        names.append(data[o:o + l_name - 1].decode("latin-1"))
+        o += l_name
+        lengths.append(struct.unpack_from("<i", data, o)[0])
+        o += 4
+    first = o
+    recs = []
+    n = len(data)
+    while o + 4 <= n:
+        block_size = struct.unpack_from("<i", data, o)[0]
+        tid, pos, l_qname, mapq, bin_, n_cigar, flag, l_qseq, mtid, mpos, isize = struct.unpack_from(
+            "<iiBBHHHiiii", data, o + 4)
+        p = o + 36
+        qname = data[p:p + l_qname - 1].decode("latin-1")
+        p += l_qname
+        cig = struct.unpack_from("<%dI" % n_cigar, data, p) if n_cigar else ()
+        cigar = [(c >> 4, c & 15) for c in cig]
+        p += 4 * n_cigar
+        seq4 = data[p:p + (l_qseq + 1) // 2]
+        p += (l_qseq + 1) // 2
+        qual = data[p:p + l_qseq]
+        p += l_qseq
+        aux = data[p:o + 4 + block_size]
+        recs.append(Rec(tid, pos, mapq, bin_, flag, l_qseq, mtid, mpos, isize, qname, cigar, seq4, qual, aux,
+                        4 + block_size))
+        o += 4 + block_size
+    return Header(names, lengths, text), recs, first
+
+
+def read_bam(path: str) -> Tuple[Header, List[Rec]]:
+    h, r, _ = parse_bam_stream(read_bgzf(path))
+    return h, r
+
+
+_BASE2NIB = {c: i for i, c in enumerate(NT16)}
+
+
+def parse_sam(path: str) -> Tuple[Header, List[Rec]]:
+    """SAM text -> the same record model (what samopen(fn, "r") yields; used for clip.sam hand-off and
+    for hand-written known-answer inputs)."""
+    names, lengths, recs = [], [], []
+    opener = gzip.open if path.endswith(".gz") else open
+    with opener(path, "rt", encoding="latin-1") as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if not line:
+                continue
+            if line[0] == "@":
+                if line.startswith("@SQ"):
+                    sn = ln = None
+                    for fld in line.split("\t")[1:]:
+                        if fld.startswith("SN:"):
+                            sn = fld[3:]
+                        elif fld.startswith("LN:"):
+                            ln = int(fld[3:])
+                    names.append(sn)
+                    lengths.append(ln)
+                continue
+            t = line.split("\t")
+            qname, flag, rname, pos, mapq, cigar_s, rnext, pnext, tlen, seq, qual = t[:11]
+            flag = int(flag)
+            tid = names.index(rname) if rname != "*" else -1
+            if rnext == "=":
+                mtid = tid
+            elif rnext == "*":
+                mtid = -1
+            else:
+                mtid = names.index(rnext)
+            cigar = []
+            if cigar_s != "*":
+                num = 0
+                for ch in cigar_s:
+                    if ch.isdigit():
+                        num = num * 10 + ord(ch) - 48
+                    else:
+                        cigar.append((num, CIGAR_OPS.index(ch)))
+                        num = 0
+            if seq == "*":
+                l_qseq, seq4, q = 0, b"", b""
+            else:
+                l_qseq = len(seq)
+                nib = [_BASE2NIB.get(c.upper(), 15) for c in seq]
+                if l_qseq & 1:
+                    nib.append(0)
+                seq4 = bytes((nib[i] << 4) | nib[i + 1] for i in range(0, len(nib), 2))
+                q = bytes([0xFF] * l_qseq) if qual == "*" else bytes(ord(c) - 33 for c in qual)
+            aux = b""
+            for fld in t[11:]:
+                tag, ty, val = fld[:2], fld[3], fld[5:]
+                if ty == "i":
+                    v = int(val)
+                    aux += tag.encode() + (b"i" + struct.pack("<i", v))
+                elif ty == "Z":
+                    aux += tag.encode() + b"Z" + val.encode("latin-1") + b"\0"
+                elif ty == "A":
+                    aux += tag.encode() + b"A" + val.encode("latin-1")[:1]
+                elif ty == "f":
+                    aux += tag.encode() + b"f" + struct.pack("<f", float(val))
+            recs.append(Rec(tid, int(pos) - 1, int(mapq), 0, flag, l_qseq, mtid, int(pnext) - 1, int(tlen), qname,
+                            cigar, seq4, q, aux, 0))
+    return Header(names, lengths), recs
+
+
+def read_alignments(path: str) -> Tuple[Header, List[Rec]]:
+    """The reference opens a file as BAM iff its name ends in ".bam" (clip_reads.h:367-373)."""
+    return read_bam(path) if path.endswith(".bam") else parse_sam(path)
+
+
+def aux_get_int(aux: bytes, tag: bytes) -> int:
+    """bam_aux2i(bam_aux_get(b, tag)): integer value of an aux tag, 0 when absent or not an integer
+    type. Call sites clip_reads.cpp:126-127,158-159; declared sam/bam.h:556-561."""
+    i, n = 0, len(aux)
+    while i + 3 <= n:
+        t, ty = aux[i:i + 2], chr(aux[i + 2])
+        i += 3
+        if t == tag:
+            if ty == "c":
+                return struct.unpack_from("<b", aux, i)[0]
+            if ty == "C":
+                return aux[i]
+            if ty == "s":
+                return struct.unpack_from("<h", aux, i)[0]
+            if ty == "S":
+                return struct.unpack_from("<H", aux, i)[0]
+            if ty == "i":
+                return struct.unpack_from("<i", aux, i)[0]
+            if ty == "I":
+                return struct.unpack_from("<I", aux, i)[0]
+            return 0
+        u = ty.upper()
+        if u in "CA":
+            i += 1
+        elif u == "S":
+            i += 2
+        elif u in "IF":
+            i += 4
+        elif u == "D":
+            i += 8
+        elif u in "ZH":
+            while i < n and aux[i] != 0:
+                i += 1
+            i += 1
+        elif u == "B":
+            sub = chr(aux[i]).upper()
+            cnt = struct.unpack_from("<i", aux, i + 1)[0]
+            i += 5 + cnt * {"C": 1, "S": 2, "I": 4, "F": 4}.get(sub, 1)
+        else:
+            break
+    return 0
