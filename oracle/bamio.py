@@ -226,3 +226,82 @@ def aux_get_int(aux: bytes, tag: bytes) -> int:
         else:
             break
     return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# writers (fixtures only)
+# ------------------------------------------------------------------------------------------------
+def reg2bin(beg: int, end: int) -> int:
+    """bam_reg2bin, sam/bam.h:700-709."""
+    end -= 1
+    if beg >> 14 == end >> 14:
+        return 4681 + (beg >> 14)
+    if beg >> 17 == end >> 17:
+        return 585 + (beg >> 17)
+    if beg >> 20 == end >> 20:
+        return 73 + (beg >> 20)
+    if beg >> 23 == end >> 23:
+        return 9 + (beg >> 23)
+    if beg >> 26 == end >> 26:
+        return 1 + (beg >> 26)
+    return 0
+
+
+def pack_record(r: Rec) -> bytes:
+    qn = r.qname.encode("latin-1") + b"\0"
+    end = r.pos
+    for ln, op in r.cigar:
+        if op in (0, 2, 3):
+            end += ln
+    if end == r.pos:
+        end = r.pos + 1
+    b = reg2bin(r.pos, end) if r.tid >= 0 else 4680
+    body = struct.pack("<iiBBHHHiiii", r.tid, r.pos, len(qn), r.mapq, b, len(r.cigar), r.flag, r.l_qseq, r.mtid,
+                       r.mpos, r.isize)
+    body += qn + b"".join(struct.pack("<I", (ln << 4) | op) for ln, op in r.cigar) + r.seq4 + r.qual + r.aux
+    return struct.pack("<i", len(body)) + body
+
+
+def header_bytes(h: Header) -> bytes:
+    text = h.text.encode("latin-1")
+    out = b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(h.names))
+    for n, l in zip(h.names, h.lengths):
+        nb = n.encode("latin-1") + b"\0"
+        out += struct.pack("<i", len(nb)) + nb + struct.pack("<i", l)
+    return out
+
+
+def bgzf_compress(data: bytes, level: int = 1, block: int = 0xff00) -> bytes:
+    """BGZF container, sam/bgzf.h:34-60: gzip members with the 'BC' extra sub-field + EOF marker."""
+    import zlib
+    out = []
+    for i in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if i is None else data[i:i + block]
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = c.compress(chunk) + c.flush()
+        bsize = len(comp) + 25
+        out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize) + comp +
+                   struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+    return b"".join(out)
+
+
+def write_bam(path: str, h: Header, recs: List[Rec], level: int = 1):
+    with open(path, "wb") as f:
+        f.write(bgzf_compress(header_bytes(h) + b"".join(pack_record(r) for r in recs), level))
+
+
+def make_rec(qname, flag, tid, pos0, mapq, cigar_s, mtid, mpos0, isize, seq, qual, aux=b"") -> Rec:
+    cigar, num = [], 0
+    if cigar_s != "*":
+        for ch in cigar_s:
+            if ch.isdigit():
+                num = num * 10 + ord(ch) - 48
+            else:
+                cigar.append((num, CIGAR_OPS.index(ch)))
+                num = 0
+    nib = [_BASE2NIB.get(c.upper(), 15) for c in seq]
+    if len(nib) & 1:
+        nib.append(0)
+    seq4 = bytes((nib[i] << 4) | nib[i + 1] for i in range(0, len(nib), 2))
+    q = bytes([0xFF] * len(seq)) if qual == "*" else bytes(ord(c) - 33 for c in qual)
+    return Rec(tid, pos0, mapq, 0, flag, len(seq), mtid, mpos0, isize, qname, cigar, seq4, q, aux, 0)

@@ -58,11 +58,13 @@ def change_cigar_type(s: str) -> List[Tuple[int, str]]:
 
 
 def calend(rec: Rec) -> int:
-    """bam_calend of the linked libbam (0-based exclusive end): pos + sum of M, D, N, =, X lengths.
-    (samtools 0.1.18 bam.h `bam_cigar_type(op) & 2`; pinned by tests/golden/calend_probe.)"""
+    """bam_calend of the LINKED libbam (0-based exclusive end): pos + sum of M, D, N lengths only.
+    sam/bam.h:650 declares it; the archive is samtools-0.1.16-era code in which `=` and `X` do not
+    advance the reference (probed: `oracle/_ref/bamtool calend 100 10M5X` -> 110, `10M5=` -> 110,
+    `10M5D` / `10M5N` -> 115; pinned in tests/test_oracle_golden.py)."""
     e = rec.pos
     for ln, op in rec.cigar:
-        if op in (OP_M, OP_D, OP_N, OP_EQ, OP_X):
+        if op in (OP_M, OP_D, OP_N):
             e += ln
     return e
 
@@ -508,21 +510,58 @@ def merge_overlap(ranges) -> Dict[Tuple[str, int], int]:
     return out
 
 
-def depth_arrays(h: Header, recs: List[Rec], min_mapq: int) -> Dict[int, np.ndarray]:
-    """Per-position depth as main_depth sees it (bam2depth.cpp:75-96 with read_bam, bam2depth.h:29-35):
-    reads with tid >= 0 and (flag & 0x704) == 0 after mapQ < min_mapq is turned into UNMAP; a position
-    counts when the read has an M, = or X base there (D and N are in the pileup but subtracted,
-    baseQ = 0 never filters). Returned arrays are 1-based: arr[p]."""
-    out = {}
-    for tid, ln in enumerate(h.lengths):
-        out[tid] = np.zeros(ln + 2, dtype=np.int64)
+PILEUP_MAXCNT = 8000   # bam_plp_init default of the linked libbam
+
+
+def pileup_kept(recs: List[Rec], min_mapq: int, maxcnt: int = PILEUP_MAXCNT) -> List[Rec]:
+    """Which reads enter libbam's pileup (bam_plp_push as driven by bam_mplp_auto, bam2depth.cpp:72-75;
+    behaviour probed with `oracle/_ref/bamtool depth`, see tests/test_oracle_golden.py):
+      * tid >= 0 and (flag & 0x704) == 0 after read_bam turned mapQ < min_mapq into UNMAP
+        (bam2depth.h:29-35);
+      * a read is refused only when it starts at the iterator's current (tid, pos) - i.e. at the same
+        position as the previously accepted read - while more than `maxcnt` buffer nodes are
+        allocated. Allocated nodes = 2 (head sentinel + free tail) + accepted reads on this tid whose
+        end is >= the current position (nodes are released lazily, one position behind).
+    Sequential by nature; coordinate-sorted input assumed (the pileup aborts otherwise)."""
+    import heapq
+    kept = []
+    it_tid, it_pos = 0, 0
+    live: List[int] = []          # min-heap of ends of accepted reads on it_tid
     for b in recs:
         if b.tid < 0 or (b.flag & 0x704) or b.mapq < min_mapq:
             continue
+        end = calend(b)
+        if b.tid == it_tid and b.pos == it_pos:
+            if len(live) + 2 > maxcnt:
+                continue
+            if end > it_pos:
+                heapq.heappush(live, end)
+            # (a zero-reference-length read at the current position is copied but never linked)
+        else:
+            if b.tid != it_tid:
+                live = []
+            it_tid, it_pos = b.tid, b.pos
+            while live and live[0] < it_pos:      # nodes with end <= pos-1 were released
+                heapq.heappop(live)
+            heapq.heappush(live, end)
+        kept.append(b)
+    return kept
+
+
+def depth_arrays(h: Header, recs: List[Rec], min_mapq: int) -> Dict[int, np.ndarray]:
+    """Per-position depth as main_depth sees it (bam2depth.cpp:75-96): reads accepted by the pileup
+    (pileup_kept); a position counts when the read has an M base there. D and N are in the pileup but
+    subtracted (bam2depth.cpp:94); `=` and `X` are IGNORED by this libbam's CIGAR walk - they advance
+    neither reference nor count (probed with `bamtool depth`); baseQ = 0 never filters.
+    Returned arrays are 1-based: arr[p]."""
+    out = {}
+    for tid, ln in enumerate(h.lengths):
+        out[tid] = np.zeros(ln + 2, dtype=np.int64)
+    for b in pileup_kept(recs, min_mapq):
         p = b.pos + 1
         d = out[b.tid]
         for ln, op in b.cigar:
-            if op in (OP_M, OP_EQ, OP_X):
+            if op == OP_M:
                 lo, hi = max(p, 1), min(p + ln, len(d))
                 if lo < hi:
                     d[lo:hi] += 1

@@ -1,0 +1,194 @@
+#!/usr/bin/env python
+"""Regenerate the golden fixtures under tests/golden/ by running the REAL reference (oracle/_ref/seeksv,
+built from /root/reference by oracle/build_ref.sh) plus the reference's bundled bwa 0.7.10.
+
+Run in the build container only (needs /root/reference). The outputs are committed so that the GPU
+box - where /root/reference does not exist - can check parity against them.
+
+    python tests/golden/make_golden.py
+
+Layout:
+  example/   config C1: the reference's own example BAMs (data fixtures), bwa's clip.sam hand-off,
+             and every output of getclip / getsv / somatic (decompressed)
+  micro/     seeded simulator output (tests/golden/simulate.py): tumour + normal SAM/BAM with planted
+             DEL / INV / DUP / CTX / virus integration, same set of outputs
+  kat/       hand-written known-answer BAMs for single quirks; written with
+             oracle.bamio.write_bam because the reference's SAM text parser rejects '=' / 'X'
+"""
+import gzip
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("SEEKSV_REFERENCE", "/root/reference")
+SEEKSV = os.path.join(ROOT, "oracle", "_ref", "seeksv")
+BAMTOOL = os.path.join(ROOT, "oracle", "_ref", "bamtool")
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+import simulate  # noqa: E402
+from oracle import bamio  # noqa: E402
+
+
+def build_kat(kat):
+    """Known-answer records: cluster merge rules, CIGAR op zoo, both-side clips with/without XC,
+    filters (dup, mapQ, hard clip), no-quality read, unmapped-mate pairing, chromosome switch."""
+    import random
+    rng = random.Random(7)
+
+    def rs(n):
+        return "".join(rng.choice("ACGT") for _ in range(n))
+
+    def q(n, c="I"):
+        return c * n
+    ref = rs(1000)
+    L = []
+
+    def add(name, flag, tid, pos1, mapq, cigar, seq, qual, mtid=-1, mpos1=0, tlen=0, aux=b""):
+        L.append(bamio.make_rec(name, flag, tid, pos1 - 1, mapq, cigar, mtid, mpos1 - 1, tlen, seq, qual, aux))
+    clipA = "TTGACCATGA"
+    xc = lambda v: b"XCi" + v.to_bytes(4, "little")
+    # merge rules: same key, suffix-matching clips of different length, strictly-higher quality wins
+    add("m1", 0, 0, 101, 60, "6S30M", clipA[-6:] + ref[100:130], "555555" + q(30))
+    add("m2", 0, 0, 101, 60, "10S25M", clipA + ref[100:125], q(10, "H") + q(25, "G"))
+    add("m3", 16, 0, 101, 60, "8S35M", "GG" + clipA[-6:] + ref[100:135], "I5IIIIII" + q(35, "J"))
+    add("m4", 0, 0, 101, 60, "4S40M", clipA[-4:-1] + "C" + ref[100:140], "IIIK" + q(40))
+    add("m5", 0, 0, 101, 60, "10S25M", clipA[:5] + "A" + clipA[6:] + ref[100:112] + "T" + ref[113:125],
+        q(10, "J") + q(25, "A"))
+    # right clips with I / D / N / = / X (X does not count towards the key position, quirk Q5)
+    add("r1", 0, 0, 201, 60, "10M2I10M3D10=1X9M5S",
+        ref[200:210] + "AA" + ref[210:220] + ref[223:233] + "T" + ref[234:243] + "CCCCC", q(47))
+    add("r2", 0, 0, 206, 60, "20M5N13M6S", ref[205:225] + ref[230:243] + "CCCCCG", q(39))
+    add("r3", 0, 0, 211, 60, "33M5S", ref[210:243] + "CCCCC", q(38, "5"))
+    # both sides clipped: no XC / XC forward / XC reverse (quirk Q4)
+    add("b1", 0, 0, 301, 60, "5S30M7S", "AAAAA" + ref[300:330] + "GGGGGGG", q(42))
+    add("b2", 0, 0, 301, 60, "5S30M7S", "AAAAA" + ref[300:330] + "GGGGGGG", q(42), aux=xc(35))
+    add("b3", 16, 0, 301, 60, "5S30M7S", "AAAAA" + ref[300:330] + "GGGGGGG", q(42), aux=b"NMC\x00" + xc(35))
+    add("x1", 0, 0, 351, 60, "5S30M", "ACGTA" + ref[350:380], q(35), aux=b"XTAU" + xc(30))      # dropped (XC)
+    add("x2", 0, 0, 351, 60, "5S30M", "ACGTA" + ref[350:380], q(35), aux=b"XCZabc\x00")         # XC not an int -> 0
+    add("x3", 0, 0, 351, 60, "5S30M", "ACGTA" + ref[350:380], q(35), aux=b"XCC\x00")            # XC == 0
+    # filters
+    add("d1", 1024, 0, 401, 60, "5S30M", "ACGTA" + ref[400:430], q(35))
+    add("d2", 0, 0, 401, 0, "5S30M", "ACGTA" + ref[400:430], q(35))
+    add("d3", 2048, 0, 401, 60, "5S30M10H", "ACGTA" + ref[400:430], q(35))
+    add("d4", 256, 0, 401, 60, "5S30M", "ACGTA" + ref[400:430], q(35))       # secondary is kept
+    add("d5", 512, 0, 402, 60, "5S30M", "ACGTA" + ref[401:431], "*")          # QC-fail kept; no qualities
+    add("d6", 0, 0, 411, 1, "35M", ref[410:445], q(35))
+    add("d7", 0, 0, 412, 60, "3S30M", "nnn".upper() + ref[411:441], q(33))
+    # unmapped branch (quirk Q2): mapped read with unmapped mate + the mate; same-end repeat; lone read
+    add("u1", 73, 0, 501, 60, "5S30M", "ACGTA" + ref[500:530], q(35), 0, 501)
+    add("u1", 133, 0, 501, 0, "*", rs(35), q(35, "F"), 0, 501)
+    add("u2", 69, 0, 520, 0, "*", rs(20), q(20), 0, 520)
+    add("u2", 69, 0, 521, 0, "*", rs(21), q(21), 0, 520)
+    add("u2", 137, 0, 522, 60, "30M", ref[521:551], q(30), 0, 520)
+    add("u3", 141, 0, 530, 0, "*", rs(10), q(10))
+    add("u4", 77, 0, 531, 0, "*", "", "")
+    # chromosome switch (quirk Q1): the first mapped-branch record of chrB is dropped
+    add("s1", 0, 1, 101, 60, "5S30M", "ACGTA" + rs(30), q(35))
+    add("s2", 0, 1, 101, 60, "5S30M", "ACGTA" + rs(30), q(35))
+    add("s3", 0, 1, 101, 60, "5S30M", "ACGTA" + rs(30), q(35))
+    add("s5", 0, 1, 150, 60, "31M4S", rs(31) + "ACGT", q(35))
+    add("s4", 0, 1, 151, 60, "30M4S", rs(30) + "ACGT", q(34))
+    L.sort(key=lambda r: (r.tid, r.pos))
+    h = bamio.Header(["chrA", "chrB"], [1000, 1000], "@HD\tVN:1.0\tSO:coordinate\n@SQ\tSN:chrA\tLN:1000\n@SQ\tSN:chrB\tLN:1000\n")
+    os.makedirs(kat, exist_ok=True)
+    bamio.write_bam(os.path.join(kat, "quirks.bam"), h, L)
+    # records start on tid 1: the very first record is dropped as well (last_tid starts at 0)
+    bamio.write_bam(os.path.join(kat, "start_tid1.bam"), h, [r for r in L if r.tid == 1])
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, check=True, **kw)
+
+
+def gunzip_to(src, dst):
+    with gzip.open(src, "rb") as f, open(dst, "wb") as o:
+        o.write(f.read())
+
+
+def strip_pg(sam_in, sam_out):
+    with open(sam_in) as f, open(sam_out, "w") as o:
+        for line in f:
+            if not line.startswith("@PG"):
+                o.write(line)
+
+
+def pipeline(work, outdir, bwa, fasta, samples, somatic_pair=None, getsv_args=()):
+    """getclip -> bwa mem -> getsv for each sample, then somatic(normal, tumour)."""
+    for s in samples:
+        bam = os.path.join(outdir, s + ".sort.bam")
+        pre = os.path.join(work, s)
+        run([SEEKSV, "getclip", "-o", pre, bam], stderr=subprocess.DEVNULL)
+        for ext, name in ((".clip.gz", ".clip.txt"), (".clip.fq.gz", ".clip.fq.txt"),
+                          (".unmapped_1.fq.gz", ".unmapped_1.fq.txt"), (".unmapped_2.fq.gz", ".unmapped_2.fq.txt")):
+            gunzip_to(pre + ext, os.path.join(outdir, s + name))
+        with open(pre + ".clip.raw.sam", "w") as o:
+            run([bwa, "mem", fasta, pre + ".clip.fq.gz"], stdout=o, stderr=subprocess.DEVNULL)
+        strip_pg(pre + ".clip.raw.sam", os.path.join(outdir, s + ".clip.sam"))
+        with open(os.path.join(outdir, s + ".getsv.stdout"), "w") as o:
+            run([SEEKSV, "getsv", *getsv_args, os.path.join(outdir, s + ".clip.sam"), bam, pre + ".clip.gz",
+                 os.path.join(outdir, s + ".sv"), pre + ".clipunmap"], stdout=o, stderr=subprocess.DEVNULL)
+        assert os.path.getsize(pre + ".clipunmap") == 0     # quirk Q7
+    if somatic_pair:
+        normal, tumour = somatic_pair
+        run([SEEKSV, "somatic", os.path.join(outdir, normal + ".sort.bam"), os.path.join(work, normal + ".clip.gz"),
+             os.path.join(outdir, tumour + ".sv"), os.path.join(outdir, tumour + ".somatic.temp.sv")],
+            stderr=subprocess.DEVNULL)
+
+
+def main():
+    assert os.path.isdir(REF), "needs the reference checkout"
+    run([os.path.join(ROOT, "oracle", "build_ref.sh")])
+    work = tempfile.mkdtemp(prefix="golden_")
+    bwa = os.path.join(work, "bwa")
+    shutil.copy(os.path.join(REF, "example", "bin", "bwa"), bwa)
+    os.chmod(bwa, 0o755)
+
+    # ---- C1: bundled example ------------------------------------------------------------------
+    ex = os.path.join(HERE, "example")
+    os.makedirs(ex, exist_ok=True)
+    for s in ("cancer", "normal"):
+        for ext in (".sort.bam", ".sort.bam.bai"):
+            shutil.copy(os.path.join(REF, "example", s + ext), os.path.join(ex, s + ext))
+            os.chmod(os.path.join(ex, s + ext), 0o644)
+    refdir = os.path.join(work, "exref")
+    shutil.copytree(os.path.join(REF, "example", "reference"), refdir)
+    pipeline(work, ex, bwa, os.path.join(refdir, "example.fa"), ("normal", "cancer"), ("normal", "cancer"))
+
+    # ---- micro: simulated tumour / normal with every SV class -----------------------------------
+    mi = os.path.join(HERE, "micro")
+    os.makedirs(mi, exist_ok=True)
+    genome = None
+    for kind in ("tumor", "normal"):
+        genome, header, lines = simulate.micro_sample(kind)
+        sam = os.path.join(work, kind + ".sam")
+        with open(sam, "w") as f:
+            f.write("\n".join(header + lines) + "\n")
+        run([BAMTOOL, "sam2bam", sam, os.path.join(mi, kind + ".sort.bam")], stderr=subprocess.DEVNULL)
+        run([BAMTOOL, "index", os.path.join(mi, kind + ".sort.bam")])
+    fa = os.path.join(work, "micro.fa")
+    simulate.write_fasta(genome, fa)
+    run([bwa, "index", fa], stderr=subprocess.DEVNULL)
+    # -n 100000: keep the insert-size / discordant-pair step on although the sample is small
+    pipeline(work, mi, bwa, fa, ("normal", "tumor"), ("normal", "tumor"))
+
+    # ---- known-answer SAMs ------------------------------------------------------------------------
+    kat = os.path.join(HERE, "kat")
+    build_kat(kat)
+    for name in sorted(os.listdir(kat)):
+        if not name.endswith(".bam"):
+            continue
+        pre = os.path.join(work, name[:-4])
+        run([SEEKSV, "getclip", "-o", pre, os.path.join(kat, name)], stderr=subprocess.DEVNULL)
+        for ext, out in ((".clip.gz", ".clip.txt"), (".clip.fq.gz", ".clip.fq.txt"),
+                         (".unmapped_1.fq.gz", ".unmapped_1.fq.txt"), (".unmapped_2.fq.gz", ".unmapped_2.fq.txt")):
+            gunzip_to(pre + ext, os.path.join(kat, name[:-4] + out))
+    shutil.rmtree(work)
+    print("golden fixtures regenerated")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,93 @@
+"""The CPU oracle (oracle/*.py) against the reference's own outputs (tests/golden/, produced by
+oracle/_ref/seeksv == reference v1.2.3, see tests/golden/make_golden.py). CPU only."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT, read_text
+from oracle import bamio, getclip_oracle, getsv_oracle
+
+CASES = [("example", "cancer"), ("example", "normal"), ("micro", "tumor"), ("micro", "normal"),
+         ("kat", "quirks"), ("kat", "start_tid1")]
+
+
+def _bam(d, s):
+    p = os.path.join(GOLDEN, d, s + ".sort.bam")
+    return p if os.path.exists(p) else os.path.join(GOLDEN, d, s + ".bam")
+
+
+@pytest.mark.parametrize("d,s", CASES)
+def test_getclip_matches_reference(d, s):
+    h, recs = bamio.read_bam(_bam(d, s))
+    clip, fq, u1, u2 = getclip_oracle.getclip(h, recs)
+    assert clip == read_text(os.path.join(GOLDEN, d, s + ".clip.txt"))
+    assert fq == read_text(os.path.join(GOLDEN, d, s + ".clip.fq.txt"))
+    assert u1 == read_text(os.path.join(GOLDEN, d, s + ".unmapped_1.fq.txt"))
+    assert u2 == read_text(os.path.join(GOLDEN, d, s + ".unmapped_2.fq.txt"))
+
+
+@pytest.mark.parametrize("d,s", CASES[:4])
+def test_getsv_matches_reference(d, s):
+    h, recs = bamio.read_bam(_bam(d, s))
+    ch, ca = bamio.read_alignments(os.path.join(GOLDEN, d, s + ".clip.sam"))
+    sv, out = getsv_oracle.getsv(h, recs, read_text(os.path.join(GOLDEN, d, s + ".clip.txt")), ch, ca)
+    assert sv == read_text(os.path.join(GOLDEN, d, s + ".sv"))
+    assert out == read_text(os.path.join(GOLDEN, d, s + ".getsv.stdout"))
+
+
+@pytest.mark.parametrize("d,normal,tumour", [("example", "normal", "cancer"), ("micro", "normal", "tumor")])
+def test_somatic_matches_reference(d, normal, tumour):
+    h, recs = bamio.read_bam(_bam(d, normal))
+    got = getsv_oracle.somatic(h, recs, read_text(os.path.join(GOLDEN, d, normal + ".clip.txt")),
+                               read_text(os.path.join(GOLDEN, d, tumour + ".sv")))
+    assert got == read_text(os.path.join(GOLDEN, d, tumour + ".somatic.temp.sv"))
+
+
+def test_insert_size_example():
+    # reference stderr for the example: "Mean insert size : 500 / Mean deviation: 25" 
+    for s in ("cancer", "normal"):
+        h, recs = bamio.read_bam(_bam("example", s))
+        assert getsv_oracle.insert_size_stats(recs, 20, 5000000) == (500, 25)
+
+
+def test_calend_counts_m_d_n_only():
+    # probed on the linked libbam: `oracle/_ref/bamtool calend 100 <cigar>`
+    for cig, want in (("10M", 110), ("10M5D", 115), ("10M5N", 115), ("10M5I", 110), ("5S10M", 110),
+                      ("10M5=", 110), ("10M5X", 110), ("10M5P", 110)):
+        r = bamio.make_rec("q", 0, 0, 100, 60, cig, -1, -1, 0, "", "")
+        assert getsv_oracle.calend(r) == want
+        tool = os.path.join(ROOT, "oracle", "_ref", "bamtool")
+        if os.path.exists(tool):
+            assert int(subprocess.run([tool, "calend", "100", cig], capture_output=True, text=True).stdout) == want
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bamtool")), reason="no oracle/_ref")
+def test_pileup_depth_and_cap_against_libbam(tmp_path):
+    """depth_arrays (incl. the 8000-read cap and the =/X quirk) == the linked libbam's own pileup."""
+    import random
+    rng = random.Random(3)
+    h = bamio.Header(["c1", "c2"], [5000, 5000], "@SQ\tSN:c1\tLN:5000\n@SQ\tSN:c2\tLN:5000\n")
+    recs = []
+    for tid in (0, 1):
+        pos = 10
+        for block in range(40):
+            pos += rng.choice((0, 0, 1, 3, 7, 60))
+            n = rng.choice((1, 5, 200, 3000, 9000)) if tid == 0 else rng.choice((1, 2, 50))
+            for i in range(n):
+                cig = rng.choice(("50M", "20M3D27M", "10S40M", "25M2I23M", "10=5X30M", "30M10N10M", "45M5H"))
+                flag = rng.choice((0, 0, 0, 16, 1024, 256, 4, 512))
+                recs.append(bamio.make_rec("r", flag, tid, pos, rng.choice((0, 30, 60)), cig, -1, -1, 0, "A" * 50,
+                                           "I" * 50))
+    path = str(tmp_path / "cap.bam")
+    bamio.write_bam(path, h, recs)
+    tool = os.path.join(ROOT, "oracle", "_ref", "bamtool")
+    for mq in (0, 20):
+        want = {}
+        for line in subprocess.run([tool, "depth", path, str(mq)], capture_output=True, text=True).stdout.splitlines():
+            t, p, n, m = map(int, line.split("\t"))
+            want[(t, p)] = n - m
+        got = getsv_oracle.depth_arrays(h, recs, mq)
+        for tid in (0, 1):
+            for p in range(1, 5001):
+                assert int(got[tid][p]) == want.get((tid, p), 0), (mq, tid, p)
