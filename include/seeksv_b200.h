@@ -1,0 +1,147 @@
+/* seeksv_b200 - C ABI of the B200-native seeksv hot path.
+ *
+ * The reference (qiukunlong/seeksv v1.2.3) has no plugin / FFI interface: its only stable boundary is
+ * the process CLI plus file formats, and - inside the process - the seams between its I/O loops and
+ * the per-record work. Each entry point below replaces one of those seams;
+ * the citation names the reference function whose work it does (paths relative to
+ * /root/reference/seeksv/). The CLI surface itself (seeksv.cpp:26-457) is kept by the C++ host layer
+ * in seeksv_b200/host/, which is a thin caller of this ABI.
+ *
+ * Conventions: plain C types only; every function returns 0 on success and a negative svb_status on
+ * failure (svb_last_error() gives the message); no exceptions cross the boundary; one svb_ctx per
+ * GPU, used from one host thread at a time. There is NO CPU fallback: without a CUDA device
+ * svb_ctx_create fails with SVB_ERR_NO_DEVICE and nothing else can be called.
+ */
+#ifndef SEEKSV_B200_H
+#define SEEKSV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVB_ABI_VERSION 1
+
+typedef enum svb_status {
+    SVB_OK = 0,
+    SVB_ERR_NO_DEVICE = -1, /* no CUDA device / wrong architecture */
+    SVB_ERR_CUDA = -2,      /* a CUDA runtime call or kernel failed */
+    SVB_ERR_FORMAT = -3,    /* input is not a BAM/BGZF/SAM stream this path understands */
+    SVB_ERR_ARG = -4,       /* bad argument */
+    SVB_ERR_IO = -5,        /* file could not be opened / read / written */
+    SVB_ERR_UNSORTED = -6   /* getsv/somatic need a coordinate-sorted BAM (the reference needs its .bai) */
+} svb_status;
+
+typedef struct svb_ctx svb_ctx; /* one GPU: device, stream, scratch pools, timers   */
+typedef struct svb_bam svb_bam; /* one BAM (or shard of one) resident in HBM        */
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int svb_abi_version(void);
+int svb_ctx_create(int device, svb_ctx **out);
+void svb_ctx_destroy(svb_ctx *ctx);
+const char *svb_last_error(const svb_ctx *ctx); /* ctx may be NULL: error of the last failed create */
+/* The CUDA stream every launch of this ctx goes to (cudaStream_t), so that callers can bracket calls
+ * with their own CUDA events. */
+void *svb_ctx_stream(svb_ctx *ctx);
+
+/* Per-kernel device time accounting (CUDA events on the ctx stream). Enable, run, then read back:
+ * names[i] / ms[i] / launches[i] for up to cap kernels; returns the number of distinct kernels. */
+void svb_prof_enable(svb_ctx *ctx, int on);
+void svb_prof_reset(svb_ctx *ctx);
+int svb_prof_read(svb_ctx *ctx, int cap, const char **names, double *ms, int64_t *launches, double *bytes);
+
+/* ---- BAM residency: replaces samopen/samread -> bam_read1 (clip_reads.h:375,410; cluster.cpp:27,48;
+ *      getsv.cpp:1063-1067; bam2depth.cpp:57-75), i.e. the L0 libbam reader -------------------------- */
+
+/* `stream` = the UNCOMPRESSED BAM byte stream ("BAM\1" header + packed records) or a contiguous shard
+ * of its record section. first_record = byte offset of the first record start inside `stream`
+ * (header length for a whole file). n_ref = number of reference sequences in the header.
+ * _device: `stream` is a device pointer (>= nbytes + 64 readable bytes, 16-byte aligned), borrowed for
+ *          the life of the svb_bam. _host: copied host->device inside the call (pinned or pageable). */
+int svb_bam_from_device(svb_ctx *ctx, const void *d_stream, uint64_t nbytes, uint64_t first_record, int32_t n_ref,
+                        svb_bam **out);
+int svb_bam_from_host(svb_ctx *ctx, const void *h_stream, uint64_t nbytes, uint64_t first_record, int32_t n_ref,
+                      svb_bam **out);
+/* Whole .bam file image (BGZF) in host memory: host threads inflate the blocks into pinned staging
+ * buffers that are streamed to the device with cudaMemcpyAsync; the header is parsed on the host.
+ * n_threads <= 0: use all hardware threads. */
+int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, int n_threads, svb_bam **out);
+int svb_bam_open(svb_ctx *ctx, const char *path, int n_threads, svb_bam **out); /* .bam, else SAM text */
+void svb_bam_free(svb_bam *bam);
+
+uint64_t svb_bam_n_records(const svb_bam *bam);
+uint64_t svb_bam_record_bytes(const svb_bam *bam);  /* sum over records of 4 + block_size */
+int32_t svb_bam_n_ref(const svb_bam *bam);
+const char *svb_bam_ref_name(const svb_bam *bam, int32_t tid); /* NULL when the header was not parsed */
+uint32_t svb_bam_ref_len(const svb_bam *bam, int32_t tid);
+/* Attach header names/lengths to a svb_bam built from a raw stream (needed for text output). */
+int svb_bam_set_refs(svb_bam *bam, int32_t n_ref, const char *const *names, const uint32_t *lengths);
+
+/* ---- getclip: replaces GetSClipReads + GetSeq + GenerateCigar + InsertSeq +
+ *      ReadsInfo::ChangeSeqAndQual (clip_reads.h:120, clip_reads.cpp:57-108,112-192,260-329) and the
+ *      unmapped-mate branch of InputBamOutputReads (clip_reads.h:415-420,172-219) -------------------- */
+typedef struct svb_getclip_params {
+    double match_rate;        /* -t, default 0.9  (seeksv.cpp:131)  */
+    int32_t min_mapq;         /* -q, default 1    (seeksv.cpp:130)  */
+    int32_t save_low_quality; /* -s, default 0    (seeksv.cpp:133)  */
+    /* Sharded runs: tid of the last mapped-branch record BEFORE this shard (quirk Q1); 0 for a whole
+     * file (clip_reads.h:407 starts last_tid at 0). */
+    int32_t prev_tid;
+} svb_getclip_params;
+
+typedef struct svb_clusters svb_clusters; /* host-resident result of svb_getclip */
+
+int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params *p, svb_clusters **out);
+void svb_clusters_free(svb_clusters *c);
+uint64_t svb_clusters_count(const svb_clusters *c);
+uint64_t svb_clusters_candidates(const svb_clusters *c); /* soft-clipped reads that entered clustering */
+/* Decompressed contents of P.clip.gz / P.clip.fq.gz / P.unmapped_1.fq.gz / P.unmapped_2.fq.gz
+ * (DisplaySClipReadsAndClipFq clip_reads.h:300-345, StoreUnmapSeqAndQual clip_reads.h:172-219), as
+ * host buffers owned by the result object. which: 0 clip, 1 clip.fq, 2 unmapped_1, 3 unmapped_2. */
+int svb_clusters_text(const svb_clusters *c, int which, const char **data, uint64_t *len);
+
+/* ---- getsv / somatic device passes ----------------------------------------------------------------- */
+
+/* CalculateInsertsizeDeviation (cluster.h:25, cluster.cpp:15-83): over the first max_pairs records (file
+ * order) with mapQ >= min_mapq, not hard-clipped, PAIRED & PROPER & !DUP, isize > 0.
+ * out[0] = n, out[1] = sum isize, out[2] = mean (= sum / n, 0 if n == 0),
+ * out[3] = sum over those records of (int32)((isize-mean)*(isize-mean)) (the reference's int product). */
+int svb_insert_stats(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64_t max_pairs, int64_t out[4]);
+
+/* FindDiscordantReadPairs (getsv.h:403-404, getsv.cpp:990-1247) for a batch of junctions. */
+typedef struct svb_junction {
+    int32_t up_tid, up_pos;     /* up_pos / down_pos are the 1-based junction coordinates */
+    int32_t down_tid, down_pos; /* tid = -1: name not in the BAM header -> count 0 */
+    char up_strand, down_strand; /* '+' / '-' */
+    char pad_[2];
+} svb_junction;
+typedef struct svb_pair_params {
+    int32_t min_mapq;    /* -q (20)                      */
+    int32_t mean_insert; /* from svb_insert_stats         */
+    int32_t deviation;
+    int32_t times;       /* 4 (seeksv.cpp:161)            */
+} svb_pair_params;
+int svb_discordant_support(svb_ctx *ctx, svb_bam *bam, const svb_junction *junctions, uint64_t n,
+                           const svb_pair_params *p, int32_t *counts /* host, n */);
+
+/* main_depth (bam2depth.h:38, bam2depth.cpp:17-142): depth at every position of a set of disjoint
+ * windows [begin, end] (1-based, inclusive, sorted by (tid, begin)); depth = reads accepted by libbam's
+ * pileup (flag & 0x704 == 0 after mapQ < min_mapq -> UNMAP, 8000-read cap) with an M base at the
+ * position. depth_out holds sum(end - begin + 1) ints, window after window. */
+typedef struct svb_window {
+    int32_t tid, begin, end;
+} svb_window;
+int svb_window_depth(svb_ctx *ctx, svb_bam *bam, const svb_window *windows, uint64_t n_windows, int32_t min_mapq,
+                     int32_t *depth_out /* host */);
+
+/* ---- whole commands (what the CLI calls; same arguments as the reference's Call* functions,
+ *      seeksv.cpp:128-410). They print the reference's progress lines to stderr and return the
+ *      process exit code. ------------------------------------------------------------------------------ */
+int svb_main(int argc, char **argv); /* argv as the seeksv binary gets it */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEEKSV_B200_H */

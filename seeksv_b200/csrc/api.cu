@@ -1,0 +1,270 @@
+// C-ABI glue: contexts, error strings, per-kernel timers, BAM residency.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <thread>
+
+#include "../host/bamfile.h"
+#include "common.cuh"
+
+static thread_local std::string g_create_err;
+
+int svb_fail(svb_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_err = buf;
+    return code;
+}
+
+extern "C" int svb_abi_version(void) { return SVB_ABI_VERSION; }
+
+extern "C" int svb_ctx_create(int device, svb_ctx **out)
+{
+    svb_ctx *ctx = nullptr;  // for CK
+    if (!out) return svb_fail(nullptr, SVB_ERR_ARG, "svb_ctx_create: null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return svb_fail(nullptr, SVB_ERR_NO_DEVICE, "no CUDA device (%s); seeksv_b200 has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return svb_fail(nullptr, SVB_ERR_ARG, "device %d out of range (%d devices)", device, n);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return svb_fail(nullptr, SVB_ERR_NO_DEVICE, "device %d is sm_%d%d; this build is sm_100a only", device, prop.major, prop.minor);
+    CK(cudaSetDevice(device));
+    std::unique_ptr<svb_ctx> c(new svb_ctx());
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // keep freed scratch in the pool: the commands allocate and free the same sizes repeatedly
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = ~0ull;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = c.release();
+    return 0;
+}
+
+extern "C" void svb_ctx_destroy(svb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->prof_flush();
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *svb_last_error(const svb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+extern "C" void *svb_ctx_stream(svb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+void svb_ctx::prof_flush()
+{
+    if (prof_pending.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (auto &p : prof_pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        ProfEntry &e = prof_acc[p.name];
+        e.ms += ms, e.bytes += p.bytes, e.launches += 1;
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    prof_pending.clear();
+}
+extern "C" void svb_prof_enable(svb_ctx *ctx, int on)
+{
+    if (ctx) ctx->prof = on != 0;
+}
+extern "C" void svb_prof_reset(svb_ctx *ctx)
+{
+    if (!ctx) return;
+    ctx->prof_flush();
+    ctx->prof_acc.clear();
+}
+extern "C" int svb_prof_read(svb_ctx *ctx, int cap, const char **names, double *ms, int64_t *launches, double *bytes)
+{
+    if (!ctx) return 0;
+    ctx->prof_flush();
+    int i = 0;
+    for (auto &kv : ctx->prof_acc) {
+        if (i < cap) {
+            if (names) names[i] = kv.first.c_str();
+            if (ms) ms[i] = kv.second.ms;
+            if (launches) launches[i] = kv.second.launches;
+            if (bytes) bytes[i] = kv.second.bytes;
+        }
+        ++i;
+    }
+    return i;
+}
+
+// ---- BAM residency ----------------------------------------------------------------------------------------------
+static int finish_bam(svb_ctx *ctx, std::unique_ptr<svb_bam> &b, svb_bam **out)
+{
+    CKR(index_records(ctx, b.get()));
+    *out = b.release();
+    return 0;
+}
+
+extern "C" int svb_bam_from_device(svb_ctx *ctx, const void *d_stream, uint64_t nbytes, uint64_t first_record, int32_t n_ref,
+                                   svb_bam **out)
+{
+    if (!ctx || !out || (!d_stream && nbytes)) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_device: null argument");
+    if (((uintptr_t)d_stream & 15) != 0) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_device: stream must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    std::unique_ptr<svb_bam> b(new svb_bam());
+    b->ctx = ctx, b->d_data = (const uint8_t *)d_stream, b->nbytes = nbytes, b->first = first_record, b->n_ref = n_ref;
+    return finish_bam(ctx, b, out);
+}
+
+static int upload(svb_ctx *ctx, svb_bam *b, const void *h, uint64_t nbytes)
+{
+    CK(cudaMalloc((void **)&b->d_owned, nbytes + 256));
+    CK(cudaMemsetAsync(b->d_owned + nbytes, 0, 256, ctx->stream));
+    {
+        ProfScope ps(ctx, "h2d_stream", (double)nbytes);
+        CK(cudaMemcpyAsync(b->d_owned, h, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    b->d_data = b->d_owned;
+    b->nbytes = nbytes;
+    return 0;
+}
+
+extern "C" int svb_bam_from_host(svb_ctx *ctx, const void *h_stream, uint64_t nbytes, uint64_t first_record, int32_t n_ref,
+                                 svb_bam **out)
+{
+    if (!ctx || !out || (!h_stream && nbytes)) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_host: null argument");
+    CK(cudaSetDevice(ctx->device));
+    std::unique_ptr<svb_bam> b(new svb_bam());
+    b->ctx = ctx, b->first = first_record, b->n_ref = n_ref;
+    CKR(upload(ctx, b.get(), h_stream, nbytes));
+    return finish_bam(ctx, b, out);
+}
+
+// Host threads inflate BGZF blocks into pinned staging slabs; each finished slab is sent with
+// cudaMemcpyAsync while the next one is being inflated.
+extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, int n_threads, svb_bam **out)
+{
+    if (!ctx || !out || !h_file) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_bgzf: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::vector<BgzfBlock> blocks;
+    uint64_t total = 0;
+    std::string err;
+    if (!bgzf_scan((const uint8_t *)h_file, file_bytes, blocks, total, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
+    std::unique_ptr<svb_bam> b(new svb_bam());
+    b->ctx = ctx;
+    CK(cudaMalloc((void **)&b->d_owned, total + 256));
+    CK(cudaMemsetAsync(b->d_owned + total, 0, 256, ctx->stream));
+    b->d_data = b->d_owned, b->nbytes = total;
+    // slabs of ~32 MiB of uncompressed data, double buffered
+    const uint64_t SLAB = 32ull << 20;
+    uint8_t *pinned[2] = {nullptr, nullptr};
+    cudaEvent_t done[2];
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaHostAlloc((void **)&pinned[i], SLAB + (64 << 10), cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    }
+    std::vector<uint8_t> head;  // first bytes, for the header parse
+    size_t bi = 0;
+    int slab = 0;
+    bool ok = true;
+    auto t0 = std::chrono::steady_clock::now();
+    while (bi < blocks.size() && ok) {
+        size_t bj = bi;
+        uint64_t bytes = 0;
+        while (bj < blocks.size() && bytes + blocks[bj].ulen <= SLAB + (64 << 10) && bytes < SLAB) bytes += blocks[bj++].ulen;
+        CK(cudaEventSynchronize(done[slab]));
+        ok = bgzf_inflate_range((const uint8_t *)h_file, blocks, bi, bj, pinned[slab], n_threads, err);
+        if (!ok) break;
+        if (head.size() < (1u << 20)) head.insert(head.end(), pinned[slab], pinned[slab] + std::min<uint64_t>(bytes, (4u << 20)));
+        CK(cudaMemcpyAsync(b->d_owned + blocks[bi].uoff, pinned[slab], bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(done[slab], ctx->stream));
+        slab ^= 1;
+        bi = bj;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 2; ++i) {
+        cudaFreeHost(pinned[i]);
+        cudaEventDestroy(done[i]);
+    }
+    if (!ok) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
+    if (ctx->prof) {
+        ProfEntry &e = ctx->prof_acc["host_inflate+h2d(wall)"];
+        e.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        e.bytes += (double)total, e.launches += 1;
+    }
+    // header
+    BamHeader hdr;
+    if (!parse_bam_header(head.data(), head.size(), hdr, err)) {
+        // header longer than the captured prefix: fetch what is needed from the device copy
+        std::vector<uint8_t> all(std::min<uint64_t>(total, 256ull << 20));
+        CK(cudaMemcpy(all.data(), b->d_owned, all.size(), cudaMemcpyDeviceToHost));
+        if (!parse_bam_header(all.data(), all.size(), hdr, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
+    }
+    b->first = hdr.first_record, b->n_ref = (int32_t)hdr.names.size();
+    b->names = hdr.names, b->lens = hdr.lengths;
+    CKR(finish_bam(ctx, b, out));
+    if ((*out)->rec_bytes != total - hdr.first_record) {
+        svb_bam_free(*out);
+        *out = nullptr;
+        return svb_fail(ctx, SVB_ERR_FORMAT, "truncated or corrupt BAM: record chain ends %llu bytes early",
+                        (unsigned long long)(total - hdr.first_record - (*out ? 0 : 0)));
+    }
+    return 0;
+}
+
+extern "C" int svb_bam_open(svb_ctx *ctx, const char *path, int n_threads, svb_bam **out)
+{
+    if (!ctx || !path || !out) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_open: null argument");
+    std::string p(path), err;
+    std::vector<uint8_t> file;
+    if (!read_file(p, file, err)) return svb_fail(ctx, SVB_ERR_IO, "%s", err.c_str());
+    // the reference treats a name ending in ".bam" as BAM and anything else as SAM text (clip_reads.h:367-373)
+    if (p.size() >= 4 && p.rfind(".bam") == p.size() - 4) return svb_bam_from_bgzf(ctx, file.data(), file.size(), n_threads, out);
+    BamHeader hdr;
+    std::vector<uint8_t> stream;
+    if (!sam_to_bam_stream(file, hdr, stream, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
+    CKR(svb_bam_from_host(ctx, stream.data(), stream.size(), hdr.first_record, (int32_t)hdr.names.size(), out));
+    (*out)->names = hdr.names, (*out)->lens = hdr.lengths;
+    return 0;
+}
+
+extern "C" void svb_bam_free(svb_bam *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaFree(b->d_owned);
+    cudaFree(b->d_rec_off);
+    LeanRecords &L = b->lean;
+    cudaFree(L.tid), cudaFree(L.pos), cudaFree(L.end), cudaFree(L.flagq);
+    cudaFree(L.lqseq), cudaFree(L.mtid), cudaFree(L.mpos), cudaFree(L.isize);
+    delete b;
+}
+
+extern "C" uint64_t svb_bam_n_records(const svb_bam *b) { return b ? b->n_rec : 0; }
+extern "C" uint64_t svb_bam_record_bytes(const svb_bam *b) { return b ? b->rec_bytes : 0; }
+extern "C" int32_t svb_bam_n_ref(const svb_bam *b) { return b ? b->n_ref : 0; }
+extern "C" const char *svb_bam_ref_name(const svb_bam *b, int32_t tid)
+{
+    return (b && tid >= 0 && (size_t)tid < b->names.size()) ? b->names[tid].c_str() : nullptr;
+}
+extern "C" uint32_t svb_bam_ref_len(const svb_bam *b, int32_t tid)
+{
+    return (b && tid >= 0 && (size_t)tid < b->lens.size()) ? b->lens[tid] : 0;
+}
+extern "C" int svb_bam_set_refs(svb_bam *b, int32_t n_ref, const char *const *names, const uint32_t *lengths)
+{
+    if (!b || n_ref != b->n_ref || !names || !lengths) return SVB_ERR_ARG;
+    b->names.assign(names, names + n_ref);
+    b->lens.assign(lengths, lengths + n_ref);
+    return 0;
+}

@@ -1,0 +1,195 @@
+// Shared declarations of the seeksv_b200 kernel library (sm_100a only, no fallback paths).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <chrono>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/seeksv_b200.h"
+
+#define SVB_SM_COUNT 148  // B200: 148 SMs (grids are sized from the live device attribute, this is the design point)
+
+// ---- BAM wire format (sam/bam.h:128-198 of the reference's vendored headers) -----------------------
+enum : uint32_t {
+    OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8
+};
+enum : uint32_t {
+    F_PAIRED = 1, F_PROPER = 2, F_UNMAP = 4, F_MUNMAP = 8, F_REVERSE = 16, F_MREVERSE = 32, F_READ1 = 64,
+    F_READ2 = 128, F_SECONDARY = 256, F_QCFAIL = 512, F_DUP = 1024
+};
+
+struct ProfEntry {
+    double ms = 0, bytes = 0;
+    int64_t launches = 0;
+};
+
+struct svb_ctx {
+    int device = 0;
+    int sm_count = SVB_SM_COUNT;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool prof = false;
+    std::map<std::string, ProfEntry> prof_acc;
+    struct Pending {
+        std::string name;
+        cudaEvent_t a, b;
+        double bytes;
+    };
+    std::vector<Pending> prof_pending;
+    std::vector<const char *> prof_names;  // storage for svb_prof_read
+    void prof_flush();
+};
+
+// Lean per-record columns produced by decode_records (getsv passes read these, not the raw stream).
+struct LeanRecords {
+    int32_t *tid = nullptr, *pos = nullptr, *end = nullptr;  // end = libbam bam_calend (M,D,N), pos+1 if no CIGAR
+    uint32_t *flagq = nullptr;                                 // flag | mapq << 16 | hardclip << 24
+    int32_t *lqseq = nullptr, *mtid = nullptr, *mpos = nullptr, *isize = nullptr;
+    uint64_t n = 0;
+};
+#define FLAGQ_HARDCLIP (1u << 24)
+
+struct svb_bam {
+    svb_ctx *ctx = nullptr;
+    const uint8_t *d_data = nullptr;
+    uint8_t *d_owned = nullptr;
+    uint64_t nbytes = 0, first = 0;
+    int32_t n_ref = 0;
+    uint64_t n_rec = 0, rec_bytes = 0;
+    uint64_t *d_rec_off = nullptr;  // n_rec + 1 entries
+    std::vector<std::string> names;
+    std::vector<uint32_t> lens;
+    LeanRecords lean;
+    bool lean_ready = false;
+    int32_t max_span = 0;  // max(end - pos) over records, for window queries
+    int sorted = -1;       // -1 unknown, 0 no, 1 coordinate-sorted
+};
+
+// ---- error plumbing ------------------------------------------------------------------------------------
+int svb_fail(svb_ctx *ctx, int code, const char *fmt, ...);
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return svb_fail(ctx, SVB_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define CKR(call)                      \
+    do {                               \
+        int r_ = (call);               \
+        if (r_ != 0) return r_;        \
+    } while (0)
+
+// RAII timer around one kernel launch (CUDA events on the ctx stream, only when profiling is on)
+struct ProfScope {
+    svb_ctx *ctx;
+    cudaEvent_t a = nullptr, b = nullptr;
+    const char *name;
+    double bytes;
+    ProfScope(svb_ctx *c, const char *n, double by) : ctx(c), name(n), bytes(by)
+    {
+        if (ctx->prof) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, ctx->stream);
+        }
+    }
+    ~ProfScope()
+    {
+        if (ctx->prof) {
+            cudaEventRecord(b, ctx->stream);
+            ctx->prof_pending.push_back({name, a, b, bytes});
+        }
+    }
+};
+
+// device scratch that is released on scope exit (stream-ordered pool allocations)
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    cudaStream_t s = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    cudaError_t alloc(size_t count, cudaStream_t st)
+    {
+        release();
+        s = st;
+        n = count;
+        return cudaMallocAsync((void **)&p, (count ? count : 1) * sizeof(T), st);
+    }
+    void release()
+    {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    ~DevBuf() { release(); }
+    T *steal()
+    {
+        T *q = p;
+        p = nullptr;
+        return q;
+    }
+};
+
+// ---- device helpers -------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// 32-bit little-endian load from an arbitrarily aligned address (BAM records are byte-packed). Two aligned
+// word loads + funnel shift; the stream buffer is padded so the second word is always readable.
+__device__ __forceinline__ uint32_t ldu32(const uint8_t *p)
+{
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    uint32_t sh = ((uint32_t)a & 3u) * 8u;
+    uint32_t lo = __ldg(w);
+    if (sh == 0) return lo;
+    uint32_t hi = __ldg(w + 1);
+    return __funnelshift_r(lo, hi, sh);
+}
+__device__ __forceinline__ int32_t ldi32(const uint8_t *p) { return (int32_t)ldu32(p); }
+
+// The 32-byte fixed core of a record (after the 4-byte block_size), decoded.
+struct Core {
+    int32_t block_size, tid, pos, l_qseq, mtid, mpos, isize;
+    uint32_t l_qname, mapq, n_cigar, flag;
+};
+__device__ __forceinline__ Core load_core(const uint8_t *p)
+{
+    Core c;
+    c.block_size = ldi32(p);
+    c.tid = ldi32(p + 4);
+    c.pos = ldi32(p + 8);
+    uint32_t w = ldu32(p + 12);  // l_read_name:8 mapq:8 bin:16
+    c.l_qname = w & 0xff;
+    c.mapq = (w >> 8) & 0xff;
+    uint32_t w2 = ldu32(p + 16);  // n_cigar:16 flag:16
+    c.n_cigar = w2 & 0xffff;
+    c.flag = w2 >> 16;
+    c.l_qseq = ldi32(p + 20);
+    c.mtid = ldi32(p + 24);
+    c.mpos = ldi32(p + 28);
+    c.isize = ldi32(p + 32);
+    return c;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_max(uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#endif
+
+// ---- internal entry points (one per .cu) ------------------------------------------------------------------
+int index_records(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu
+int decode_records(svb_ctx *ctx, svb_bam *bam);                      // bam_decode.cu
+int inclusive_scan_u32(svb_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n);
+int exclusive_scan_u64(svb_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t n);

@@ -1,0 +1,780 @@
+// getclip on the device: soft-clip candidate scan, breakpoint-key sort, per-key greedy clustering and
+// text emission. Replaces the per-record loop of InputBamOutputReads (clip_reads.h:410-440) with its
+// callees GetSClipReads / GetSeq / GenerateCigar / InsertSeq / ReadsInfo::ChangeSeqAndQual
+// (clip_reads.cpp:57-108,112-192,260-329) and the writer DisplaySClipReadsAndClipFq (clip_reads.h:300-345).
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+
+#include "common.cuh"
+
+struct svb_clusters {
+    std::vector<char> text[4];
+    uint64_t n_clusters = 0, n_candidates = 0;
+};
+
+// ---- candidate scan -------------------------------------------------------------------------------------
+struct CandArrays {
+    uint32_t *rec;    // record index
+    int32_t *tid;     // chromosome
+    int32_t *pos;     // key position (1-based breakpoint)
+    uint32_t *begin;  // first base of the "left" part inside the read
+    uint32_t *ll;     // length of the left part (text before the breakpoint)
+    uint32_t *rl;     // length of the right part
+    uint8_t *side;    // 0 = '5' (left clipped), 1 = '3' (right clipped)
+};
+
+// bam_aux2i(bam_aux_get(b, "XC")) - clip_reads.cpp:126-127,158-159; 0 when absent / not an integer type
+__device__ int32_t aux_xc(const uint8_t *s, const uint8_t *end)
+{
+    while (s + 3 <= end) {
+        uint8_t t0 = s[0], t1 = s[1], ty = s[2];
+        s += 3;
+        if (t0 == 'X' && t1 == 'C') {
+            switch (ty) {
+            case 'c': return (int8_t)s[0];
+            case 'C': return s[0];
+            case 's': return (int16_t)(s[0] | (s[1] << 8));
+            case 'S': return s[0] | (s[1] << 8);
+            case 'i':
+            case 'I': return (int32_t)(s[0] | (s[1] << 8) | (s[2] << 16) | ((uint32_t)s[3] << 24));
+            default: return 0;
+            }
+        }
+        uint8_t u = (ty >= 'a' && ty <= 'z') ? ty - 32 : ty;
+        if (u == 'C' || u == 'A') s += 1;
+        else if (u == 'S') s += 2;
+        else if (u == 'I' || u == 'F') s += 4;
+        else if (u == 'D') s += 8;
+        else if (u == 'Z' || u == 'H') {
+            while (s < end && *s) ++s;
+            ++s;
+        } else if (u == 'B') {
+            if (s + 5 > end) return 0;
+            uint8_t sub = s[0];
+            if (sub >= 'a' && sub <= 'z') sub -= 32;
+            uint32_t cnt = s[1] | (s[2] << 8) | (s[3] << 16) | ((uint32_t)s[4] << 24);
+            uint32_t sz = (sub == 'S') ? 2 : (sub == 'I' || sub == 'F') ? 4 : 1;
+            s += 5 + (uint64_t)cnt * sz;
+        } else
+            return 0;
+    }
+    return 0;
+}
+
+// One thread per record. Only the 36-byte fixed part and the CIGAR are touched for the ~98 % of records
+// that are not soft-clipped; sequence and aux bytes are read later, for candidates only.
+__global__ void __launch_bounds__(256)
+    clip_scan(const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, uint64_t n_rec, int32_t min_mapq,
+              int32_t save_low_quality, int32_t prev_tid0, CandArrays c, uint32_t cand_cap, uint32_t *__restrict__ unmapped,
+              uint32_t un_cap, uint32_t *__restrict__ switches, uint32_t sw_cap, uint32_t *__restrict__ counters)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rec) return;
+    const uint8_t *p = d + rec_off[i];
+    Core k = load_core(p);
+    if (k.flag & (F_UNMAP | F_MUNMAP)) {  // clip_reads.h:415 - the unmapped branch wins (quirk Q2)
+        uint32_t s = atomicAdd(&counters[1], 1u);
+        if (s < un_cap) unmapped[s] = (uint32_t)i;
+        return;
+    }
+    // quirk Q1: a record whose tid differs from the previous mapped-branch record's tid triggers the
+    // chromosome flush and is itself dropped (clip_reads.h:423-438)
+    int32_t prev_tid = prev_tid0;
+    for (uint64_t j = i; j > 0;) {
+        --j;
+        const uint8_t *q = d + rec_off[j];
+        uint32_t fl = ldu32(q + 16) >> 16;
+        if (!(fl & (F_UNMAP | F_MUNMAP))) {
+            prev_tid = ldi32(q + 4);
+            break;
+        }
+    }
+    if (k.tid != prev_tid) {
+        uint32_t s = atomicAdd(&counters[2], 1u);
+        if (s < sw_cap) switches[s] = (uint32_t)i;
+        return;
+    }
+    if (k.n_cigar == 0) return;
+    const uint8_t *cig = p + 36 + k.l_qname;
+    uint32_t first = ldu32(cig), last = ldu32(cig + 4 * (k.n_cigar - 1));
+    uint32_t op1 = first & 15, op2 = last & 15;
+    if (op1 == OP_H || op2 == OP_H || (int32_t)k.mapq < min_mapq || (k.flag & F_DUP)) return;  // clip_reads.cpp:118
+    bool s1 = op1 == OP_S, s2 = op2 == OP_S;
+    if (!s1 && !s2) return;
+    // GenerateCigar's l (clip_reads.cpp:322): M, D, =, N - X is not counted (quirk Q5)
+    int32_t reflen = 0;
+    for (uint32_t j = 0; j < k.n_cigar; ++j) {
+        uint32_t w = ldu32(cig + 4 * j), op = w & 15;
+        if (op == OP_M || op == OP_D || op == OP_EQ || op == OP_N) reflen += (int32_t)(w >> 4);
+    }
+    const uint8_t *aux = cig + 4 * k.n_cigar + (k.l_qseq + 1) / 2 + k.l_qseq;
+    int32_t xc = aux_xc(aux, p + 4 + k.block_size);
+    uint32_t len1 = first >> 4, len2 = last >> 4;
+    bool emit5 = false, emit3 = false;
+    uint32_t b5 = 0, l5 = 0, r5 = 0, b3 = 0, l3 = 0, r3 = 0;
+    if (s1 != s2) {
+        if (xc != 0 && !save_low_quality) return;
+        if (s1) {
+            if ((int64_t)len1 > k.l_qseq) return;
+            emit5 = true, l5 = len1, r5 = k.l_qseq - len1;
+        } else {
+            if ((int64_t)len2 > k.l_qseq) return;
+            emit3 = true, l3 = k.l_qseq - len2, r3 = len2;
+        }
+    } else {
+        int64_t mid = (int64_t)k.l_qseq - len1 - len2;
+        if (mid < 0 || k.n_cigar < 2) return;  // (undefined in the reference: a CIGAR that is one S op)
+        if (xc != 0 && !save_low_quality) {
+            if (!(k.flag & F_REVERSE)) emit5 = true;
+            else emit3 = true;
+        } else
+            emit5 = emit3 = true;
+        l5 = len1, r5 = (uint32_t)mid;                  // clip_reads.cpp:152,179
+        b3 = len1, l3 = (uint32_t)mid, r3 = len2;       // clip_reads.cpp:154,185
+    }
+    if (emit5) {
+        uint32_t s = atomicAdd(&counters[0], 1u);
+        if (s < cand_cap) {
+            c.rec[s] = (uint32_t)i, c.tid[s] = k.tid, c.pos[s] = k.pos + 1, c.begin[s] = b5, c.ll[s] = l5, c.rl[s] = r5;
+            c.side[s] = 0;
+        }
+    }
+    if (emit3) {
+        uint32_t s = atomicAdd(&counters[0], 1u);
+        if (s < cand_cap) {
+            c.rec[s] = (uint32_t)i, c.tid[s] = k.tid, c.pos[s] = k.pos + reflen, c.begin[s] = b3, c.ll[s] = l3, c.rl[s] = r3;
+            c.side[s] = 1;
+        }
+    }
+}
+
+// sort key = flush run (number of chromosome switches before the record) | side | position
+__global__ void make_keys(uint32_t n, const uint32_t *__restrict__ order, CandArrays c, const uint32_t *__restrict__ sw,
+                          uint32_t n_sw, uint64_t *__restrict__ key)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = order[i], r = c.rec[s];
+    uint32_t lo = 0, hi = n_sw;  // lower_bound(sw, r): switches with index < r
+    while (lo < hi) {
+        uint32_t m = (lo + hi) >> 1;
+        if (sw[m] < r) lo = m + 1;
+        else hi = m;
+    }
+    key[i] = ((uint64_t)lo << 33) | ((uint64_t)c.side[s] << 32) | (uint32_t)(c.pos[s] ^ 0x80000000);
+}
+
+__global__ void iota_u32(uint32_t n, uint32_t *v)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+
+__global__ void seg_flags(uint32_t n, const uint64_t *__restrict__ key, uint32_t *__restrict__ flag)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
+}
+
+__global__ void seg_starts(uint32_t n, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ segid,
+                           uint32_t *__restrict__ start, uint32_t n_seg)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) start[segid[i] - 1] = i;
+    if (i == 0) start[n_seg] = n;
+}
+
+// per segment: arena bytes = members * (longest left + longest right)
+__global__ void seg_stats(uint32_t n_seg, const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c,
+                          uint32_t *__restrict__ maxl, uint32_t *__restrict__ maxr, uint64_t *__restrict__ bytes)
+{
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    uint32_t ml = 0, mr = 0;
+    for (uint32_t k = start[s]; k < start[s + 1]; ++k) {
+        uint32_t x = order[k];
+        ml = max(ml, c.ll[x]);
+        mr = max(mr, c.rl[x]);
+    }
+    maxl[s] = ml, maxr[s] = mr;
+    bytes[s] = (uint64_t)(start[s + 1] - start[s]) * (ml + mr);
+    if (s == 0) bytes[n_seg] = 0;
+}
+
+struct ClusterOut {
+    uint32_t *len_l, *len_r, *cig_rec, *support;  // indexed by sorted candidate position (seg start + k)
+    uint8_t *noqual;
+    uint32_t *seg_ncl;
+};
+
+// One warp per breakpoint key: the reference's sequential greedy InsertSeq (clip_reads.cpp:260-283) in
+// BAM order, with lane-parallel string compares and consensus updates. Strings live in a per-segment
+// arena: slot k holds [left part right-aligned at column maxl | right part left-aligned at maxl].
+__global__ void __launch_bounds__(128)
+    cluster_build(const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, uint32_t n_seg,
+                  const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c,
+                  const uint32_t *__restrict__ maxl_, const uint32_t *__restrict__ maxr_, const uint64_t *__restrict__ arena_off,
+                  char *__restrict__ arena_seq, char *__restrict__ arena_qual, double limit, ClusterOut out)
+{
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (s >= n_seg) return;
+    const uint32_t a = start[s], b = start[s + 1];
+    const uint32_t maxl = maxl_[s], stride = maxl + maxr_[s];
+    char *S = arena_seq + arena_off[s], *Q = arena_qual + arena_off[s];
+    uint32_t ncl = 0;
+    for (uint32_t k = a; k < b; ++k) {
+        const uint32_t x = order[k];
+        const uint32_t rec = c.rec[x], begin = c.begin[x], ll = c.ll[x], rl = c.rl[x], side = c.side[x];
+        const uint8_t *p = d + rec_off[rec];
+        uint32_t w = ldu32(p + 12), w2 = ldu32(p + 16);
+        int32_t l_qseq = ldi32(p + 20);
+        const uint8_t *seq = p + 36 + (w & 0xff) + 4 * (w2 & 0xffff);
+        const uint8_t *qual = seq + (l_qseq + 1) / 2;
+        const bool noq = l_qseq > 0 && qual[0] == 0xff;
+        char *tS = S + (uint64_t)ncl * stride, *tQ = Q + (uint64_t)ncl * stride;  // tentative new cluster
+        // GetSeq (clip_reads.cpp:286-306): 4-bit codes -> "=ACMGRSVTWYHKDBN", quality + 33
+        for (uint32_t j = lane; j < ll + rl; j += 32) {
+            uint32_t idx = begin + j;
+            uint32_t nib = (seq[idx >> 1] >> ((~idx & 1) << 2)) & 15;
+            uint32_t col = maxl - ll + j;
+            tS[col] = "=ACMGRSVTWYHKDBN"[nib];
+            tQ[col] = noq ? '*' : (char)(qual[idx] + 33);
+        }
+        __syncwarp();
+        int found = -1;
+        for (uint32_t cl = 0; cl < ncl; ++cl) {
+            const char *cS = S + (uint64_t)cl * stride;
+            uint32_t cL = out.len_l[a + cl], cR = out.len_r[a + cl];
+            uint32_t n1 = min(ll, cL), n2 = min(rl, cR);
+            uint32_t m1 = 0, m2 = 0;
+            for (uint32_t j = lane; j < n1; j += 32) m1 += tS[maxl - 1 - j] == cS[maxl - 1 - j];  // CompareStringEndFirst
+            for (uint32_t j = lane; j < n2; j += 32) m2 += tS[maxl + j] == cS[maxl + j];          // CompareStringBeginFirst
+            m1 = warp_sum(m1);
+            m2 = warp_sum(m2);
+            // (double)match/len >= limit; len == 0 gives NaN -> false (clip_reads.cpp:204,216)
+            bool ok = n1 > 0 && n2 > 0 && (double)m1 / (double)n1 >= limit && (double)m2 / (double)n2 >= limit;
+            if (ok) {
+                found = (int)cl;
+                break;
+            }
+        }
+        if (found < 0) {
+            if (lane == 0) {
+                out.len_l[a + ncl] = ll, out.len_r[a + ncl] = rl, out.cig_rec[a + ncl] = rec, out.support[a + ncl] = 1;
+                out.noqual[a + ncl] = noq;
+            }
+            ++ncl;
+        } else {
+            // ReadsInfo::ChangeSeqAndQual (clip_reads.cpp:57-108)
+            char *cS = S + (uint64_t)found * stride, *cQ = Q + (uint64_t)found * stride;
+            uint32_t cL = out.len_l[a + found], cR = out.len_r[a + found];
+            bool cnoq = out.noqual[a + found];
+            uint32_t n1 = min(ll, cL), n2 = min(rl, cR);
+            if (!noq && !cnoq) {  // (with a missing quality string the reference indexes out of bounds)
+                for (uint32_t j = lane; j < n1; j += 32) {
+                    uint32_t col = maxl - 1 - j;
+                    if (cQ[col] < tQ[col]) cQ[col] = tQ[col], cS[col] = tS[col];
+                }
+                for (uint32_t j = lane; j < n2; j += 32) {
+                    uint32_t col = maxl + j;
+                    if (cQ[col] < tQ[col]) cQ[col] = tQ[col], cS[col] = tS[col];
+                }
+            }
+            if (cL <= ll) {  // extend to the longer left part; right-clipped clusters take the new CIGAR
+                for (uint32_t j = lane; j < ll - cL; j += 32) {
+                    uint32_t col = maxl - ll + j;
+                    cS[col] = tS[col], cQ[col] = tQ[col];
+                }
+            }
+            if (cR < rl) {
+                for (uint32_t j = lane; j < rl - cR; j += 32) {
+                    uint32_t col = maxl + cR + j;
+                    cS[col] = tS[col], cQ[col] = tQ[col];
+                }
+            }
+            if (lane == 0) {
+                if (cL <= ll) {
+                    out.len_l[a + found] = ll;
+                    if (side == 1) out.cig_rec[a + found] = rec;
+                }
+                if (cR < rl) {
+                    out.len_r[a + found] = rl;
+                    if (side == 0) out.cig_rec[a + found] = rec;
+                }
+                out.support[a + found] += 1;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) out.seg_ncl[s] = ncl;
+}
+
+// ---- text emission --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dec_len(uint32_t v)
+{
+    uint32_t n = 1;
+    while (v >= 10) v /= 10, ++n;
+    return n;
+}
+__device__ __forceinline__ uint32_t dec_len_i(int32_t v) { return v < 0 ? 1 + dec_len((uint32_t)(-(int64_t)v)) : dec_len((uint32_t)v); }
+__device__ __forceinline__ char *put_dec(char *o, uint32_t v)
+{
+    uint32_t n = dec_len(v);
+    for (uint32_t i = n; i-- > 0;) o[i] = '0' + v % 10, v /= 10;
+    return o + n;
+}
+__device__ __forceinline__ char *put_dec_i(char *o, int32_t v)
+{
+    if (v < 0) {
+        *o++ = '-';
+        return put_dec(o, (uint32_t)(-(int64_t)v));
+    }
+    return put_dec(o, (uint32_t)v);
+}
+
+struct NameTable {
+    const char *blob;
+    const uint32_t *off;  // n_ref + 1
+};
+
+// cigar text of a record without its S/H ops (GenerateCigar + DisplayCigarVector, clip_reads.cpp:309-329,
+// clip_reads.h:489-505)
+__device__ uint32_t cigar_text(const uint8_t *p, char *o)
+{
+    uint32_t w = ldu32(p + 12), n_cigar = ldu32(p + 16) & 0xffff;
+    const uint8_t *cig = p + 36 + (w & 0xff);
+    uint32_t len = 0;
+    for (uint32_t j = 0; j < n_cigar; ++j) {
+        uint32_t x = ldu32(cig + 4 * j), op = x & 15;
+        if (op == OP_H || op == OP_S) continue;
+        if (o) {
+            char *e = put_dec(o + len, x >> 4);
+            *e = "MIDNSHP=X???????"[op];
+            len = (uint32_t)(e - o) + 1;
+        } else
+            len += dec_len(x >> 4) + 1;
+    }
+    return len;
+}
+
+// cluster slot -> flat cluster list; one thread per segment
+__global__ void list_clusters(uint32_t n_seg, const uint32_t *__restrict__ start, const uint32_t *__restrict__ seg_ncl,
+                              const uint32_t *__restrict__ cl_base, uint32_t *__restrict__ cl_seg, uint32_t *__restrict__ cl_slot)
+{
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    uint32_t base = cl_base[s] - seg_ncl[s];  // cl_base is the inclusive scan
+    for (uint32_t k = 0; k < seg_ncl[s]; ++k) cl_seg[base + k] = s, cl_slot[base + k] = k;
+}
+
+__global__ void text_sizes(uint32_t n_cl, const uint32_t *__restrict__ cl_seg, const uint32_t *__restrict__ cl_slot,
+                           const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c, ClusterOut out,
+                           const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, NameTable names,
+                           uint64_t *__restrict__ clip_len, uint64_t *__restrict__ fq_len)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cl) {
+        if (i == n_cl) clip_len[i] = 0, fq_len[i] = 0;
+        return;
+    }
+    uint32_t s = cl_seg[i], a = start[s], k = a + cl_slot[i];
+    uint32_t x = order[a];
+    uint32_t L = out.len_l[k], R = out.len_r[k];
+    uint32_t qL = out.noqual[k] ? 1 : L, qR = out.noqual[k] ? 1 : R;
+    uint32_t name = names.off[c.tid[x] + 1] - names.off[c.tid[x]];
+    uint32_t cg = cigar_text(d + rec_off[out.cig_rec[k]], nullptr);
+    // chr \t pos \t side \t cigar \t aligned \t alignedQ \t clipped \t clippedQ \t support \n
+    clip_len[i] = name + 1 + dec_len_i(c.pos[x]) + 1 + 2 + cg + 1 + L + 1 + qL + 1 + R + 1 + qR + 1 + dec_len(out.support[k]) + 1;
+    uint32_t cl = c.side[x] == 0 ? L : R, cq = c.side[x] == 0 ? qL : qR;
+    fq_len[i] = 1 + cl + 1 + cl + 1 + 2 + cq + 1;  // @seq \n seq \n + \n qual \n
+}
+
+// one warp per cluster writes its clip.gz line and its FASTQ record
+__global__ void __launch_bounds__(128)
+    text_write(uint32_t n_cl, const uint32_t *__restrict__ cl_seg, const uint32_t *__restrict__ cl_slot,
+               const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c, ClusterOut out,
+               const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, NameTable names,
+               const uint32_t *__restrict__ maxl_, const uint32_t *__restrict__ maxr_, const uint64_t *__restrict__ arena_off,
+               const char *__restrict__ arena_seq, const char *__restrict__ arena_qual, const uint64_t *__restrict__ clip_off,
+               const uint64_t *__restrict__ fq_off, char *__restrict__ clip, char *__restrict__ fq)
+{
+    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_cl) return;
+    uint32_t s = cl_seg[i], a = start[s], slot = cl_slot[i], k = a + slot;
+    uint32_t x = order[a];
+    uint32_t maxl = maxl_[s], stride = maxl + maxr_[s];
+    const char *S = arena_seq + arena_off[s] + (uint64_t)slot * stride, *Q = arena_qual + arena_off[s] + (uint64_t)slot * stride;
+    uint32_t L = out.len_l[k], R = out.len_r[k];
+    bool noq = out.noqual[k];
+    uint32_t side = c.side[x];
+    // '5': aligned = right part, clipped = left part; '3': aligned = left, clipped = right (clip_reads.h:308-332)
+    const char *aS = side == 0 ? S + maxl : S + maxl - L, *aQ = side == 0 ? Q + maxl : Q + maxl - L;
+    const char *cS = side == 0 ? S + maxl - L : S + maxl, *cQ = side == 0 ? Q + maxl - L : Q + maxl;
+    uint32_t aN = side == 0 ? R : L, cN = side == 0 ? L : R;
+    uint32_t aQN = noq ? 1 : aN, cQN = noq ? 1 : cN;
+    char *o = clip + clip_off[i];
+    uint32_t head = 0;
+    if (lane == 0) {
+        int32_t tid = c.tid[x];
+        const char *nm = names.blob + names.off[tid];
+        uint32_t nl = names.off[tid + 1] - names.off[tid];
+        char *q = o;
+        for (uint32_t j = 0; j < nl; ++j) *q++ = nm[j];
+        *q++ = '\t';
+        q = put_dec_i(q, c.pos[x]);
+        *q++ = '\t';
+        *q++ = side == 0 ? '5' : '3';
+        *q++ = '\t';
+        q += cigar_text(d + rec_off[out.cig_rec[k]], q);
+        *q++ = '\t';
+        head = (uint32_t)(q - o);
+    }
+    head = __shfl_sync(0xffffffffu, head, 0);
+    char *q = o + head;
+    for (uint32_t j = lane; j < aN; j += 32) q[j] = aS[j];
+    q += aN;
+    if (lane == 0) *q = '\t';
+    ++q;
+    for (uint32_t j = lane; j < aQN; j += 32) q[j] = noq ? '*' : aQ[j];
+    q += aQN;
+    if (lane == 0) *q = '\t';
+    ++q;
+    for (uint32_t j = lane; j < cN; j += 32) q[j] = cS[j];
+    q += cN;
+    if (lane == 0) *q = '\t';
+    ++q;
+    for (uint32_t j = lane; j < cQN; j += 32) q[j] = noq ? '*' : cQ[j];
+    q += cQN;
+    if (lane == 0) {
+        *q++ = '\t';
+        q = put_dec(q, out.support[k]);
+        *q++ = '\n';
+    }
+    // FASTQ record named by its own sequence (clip_reads.h:320,339)
+    char *f = fq + fq_off[i];
+    if (lane == 0) f[0] = '@', f[1 + cN] = '\n', f[2 + 2 * cN] = '\n', f[3 + 2 * cN] = '+', f[4 + 2 * cN] = '\n', f[5 + 2 * cN + cQN] = '\n';
+    for (uint32_t j = lane; j < cN; j += 32) f[1 + j] = cS[j], f[2 + cN + j] = cS[j];
+    for (uint32_t j = lane; j < cQN; j += 32) f[5 + 2 * cN + j] = noq ? '*' : cQ[j];
+}
+
+// ---- unmapped-branch records: pack (flag, qname, seq, qual) for the host-side pairing ---------------------
+__global__ void unmapped_sizes(uint32_t n, const uint32_t *__restrict__ list, const uint8_t *__restrict__ d,
+                               const uint64_t *__restrict__ rec_off, uint64_t *__restrict__ sz)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) {
+        sz[i] = 0;
+        return;
+    }
+    const uint8_t *p = d + rec_off[list[i]];
+    uint32_t lq = ldu32(p + 12) & 0xff;
+    int32_t l = ldi32(p + 20);
+    sz[i] = 12 + lq + 2ull * (uint32_t)l;  // flag, l_qname, l_qseq | qname (with NUL) | seq chars | qual chars
+}
+__global__ void __launch_bounds__(128)
+    unmapped_pack(uint32_t n, const uint32_t *__restrict__ list, const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off,
+                  const uint64_t *__restrict__ off, uint8_t *__restrict__ out)
+{
+    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const uint8_t *p = d + rec_off[list[i]];
+    uint32_t w = ldu32(p + 12), w2 = ldu32(p + 16);
+    uint32_t lq = w & 0xff, flag = w2 >> 16, nc = w2 & 0xffff;
+    int32_t l = ldi32(p + 20);
+    uint8_t *o = out + off[i];
+    if (lane == 0) {
+        uint32_t hdr[3] = {flag, lq, (uint32_t)l};
+        for (int j = 0; j < 12; ++j) o[j] = ((uint8_t *)hdr)[j];
+    }
+    const uint8_t *qn = p + 36, *seq = qn + lq + 4 * nc, *qual = seq + (l + 1) / 2;
+    for (uint32_t j = lane; j < lq; j += 32) o[12 + j] = qn[j];
+    bool noq = l > 0 && qual[0] == 0xff;
+    for (uint32_t j = lane; j < (uint32_t)l; j += 32) {
+        uint32_t nib = (seq[j >> 1] >> ((~j & 1) << 2)) & 15;
+        o[12 + lq + j] = "=ACMGRSVTWYHKDBN"[nib];
+        o[12 + lq + l + j] = noq ? 0xff : qual[j] + 33;
+    }
+}
+
+// ---- host orchestration -----------------------------------------------------------------------------------
+static int sort_u32(svb_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, uint32_t n)
+{
+    size_t tmp = 0;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys_in, keys_out, (int)n, 0, 32, ctx->stream));
+    DevBuf<uint8_t> t;
+    CK(t.alloc(tmp, ctx->stream));
+    CK(cub::DeviceRadixSort::SortKeys(t.p, tmp, keys_in, keys_out, (int)n, 0, 32, ctx->stream));
+    return 0;
+}
+
+static inline unsigned nblk(uint64_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
+
+// StoreUnmapSeqAndQual (clip_reads.h:172-219) over the packed unmapped-branch records, in file order
+static void pair_unmapped(const std::vector<uint8_t> &blob, const std::vector<uint64_t> &off, std::vector<char> &o1,
+                          std::vector<char> &o2)
+{
+    struct Held {
+        const uint8_t *seq, *qual;
+        uint32_t l;
+        char end;
+    };
+    std::unordered_map<std::string, Held> held;
+    auto emit = [](std::vector<char> &o, const std::string &name, char end, const uint8_t *seq, const uint8_t *qual, uint32_t l) {
+        o.push_back('@');
+        o.insert(o.end(), name.begin(), name.end());
+        o.push_back('/');
+        o.push_back(end);
+        o.push_back('\n');
+        o.insert(o.end(), seq, seq + l);
+        o.push_back('\n');
+        o.push_back('+');
+        o.push_back('\n');
+        if (l && qual[0] == 0xff) o.push_back('*');
+        else o.insert(o.end(), qual, qual + l);
+        o.push_back('\n');
+    };
+    for (size_t i = 0; i + 1 < off.size(); ++i) {
+        const uint8_t *p = blob.data() + off[i];
+        uint32_t hdr[3];
+        memcpy(hdr, p, 12);
+        uint32_t flag = hdr[0], lq = hdr[1], l = hdr[2];
+        std::string name((const char *)p + 12, strnlen((const char *)p + 12, lq));
+        const uint8_t *seq = p + 12 + lq, *qual = seq + l;
+        char end = (flag & F_READ1) ? '1' : '2';
+        auto it = held.find(name);
+        if (it == held.end()) {
+            held.emplace(name, Held{seq, qual, l, end});
+        } else if (it->second.end != end) {
+            const Held &h = it->second;
+            if (end == '1') {
+                emit(o1, name, '1', seq, qual, l);
+                emit(o2, name, '2', h.seq, h.qual, h.l);
+            } else {
+                emit(o1, name, '1', h.seq, h.qual, h.l);
+                emit(o2, name, '2', seq, qual, l);
+            }
+            held.erase(it);
+        }  // same end again: neither emitted nor stored
+    }
+}
+
+extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params *prm, svb_clusters **out_)
+{
+    if (!ctx || !bam || !prm || !out_) return svb_fail(ctx, SVB_ERR_ARG, "svb_getclip: null argument");
+    cudaStream_t s = ctx->stream;
+    const uint64_t n_rec = bam->n_rec;
+    if (n_rec >= (1ull << 32)) return svb_fail(ctx, SVB_ERR_ARG, "svb_getclip: more than 2^32 records in one shard");
+    svb_clusters *res = new svb_clusters();
+    std::unique_ptr<svb_clusters> guard(res);
+
+    // ---- 1. scan ------------------------------------------------------------------------------------------
+    DevBuf<uint32_t> counters, un_list, sw_list;
+    DevBuf<uint32_t> c_rec, c_begin, c_ll, c_rl;
+    DevBuf<int32_t> c_tid, c_pos;
+    DevBuf<uint8_t> c_side;
+    CandArrays c;
+    uint32_t hc[3] = {0, 0, 0};
+    uint32_t cand_cap = (uint32_t)std::min<uint64_t>(n_rec / 8 + 4096, 0xffffffffu);
+    uint32_t un_cap = (uint32_t)std::min<uint64_t>(n_rec / 8 + 4096, 0xffffffffu), sw_cap = 1 << 16;
+    CK(counters.alloc(4, s));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CK(c_rec.alloc(cand_cap, s));
+        CK(c_begin.alloc(cand_cap, s));
+        CK(c_ll.alloc(cand_cap, s));
+        CK(c_rl.alloc(cand_cap, s));
+        CK(c_tid.alloc(cand_cap, s));
+        CK(c_pos.alloc(cand_cap, s));
+        CK(c_side.alloc(cand_cap, s));
+        CK(un_list.alloc(un_cap, s));
+        CK(sw_list.alloc(sw_cap, s));
+        c = {c_rec.p, c_tid.p, c_pos.p, c_begin.p, c_ll.p, c_rl.p, c_side.p};
+        CK(cudaMemsetAsync(counters.p, 0, 16, s));
+        if (n_rec) {
+            ProfScope ps(ctx, "clip_scan", (double)bam->rec_bytes);
+            clip_scan<<<nblk(n_rec, 256), 256, 0, s>>>(bam->d_data, bam->d_rec_off, n_rec, prm->min_mapq, prm->save_low_quality,
+                                                        prm->prev_tid, c, cand_cap, un_list.p, un_cap, sw_list.p, sw_cap,
+                                                        counters.p);
+        }
+        CK(cudaMemcpyAsync(hc, counters.p, 12, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (hc[0] <= cand_cap && hc[1] <= un_cap && hc[2] <= sw_cap) break;
+        if (attempt == 1) return svb_fail(ctx, SVB_ERR_CUDA, "svb_getclip: candidate buffers overflowed twice");
+        cand_cap = std::max(cand_cap, hc[0]), un_cap = std::max(un_cap, hc[1]), sw_cap = std::max(sw_cap, hc[2]);
+    }
+    const uint32_t n_cand = hc[0], n_un = hc[1], n_sw = hc[2];
+    res->n_candidates = n_cand;
+
+    // ---- 2. unmapped-branch records -> host pairing ----------------------------------------------------------
+    if (n_un) {
+        DevBuf<uint32_t> un_sorted;
+        DevBuf<uint64_t> sz, off;
+        CK(un_sorted.alloc(n_un, s));
+        CKR(sort_u32(ctx, un_list.p, un_sorted.p, n_un));
+        CK(sz.alloc(n_un + 1, s));
+        CK(off.alloc(n_un + 1, s));
+        unmapped_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_sorted.p, bam->d_data, bam->d_rec_off, sz.p);
+        CKR(exclusive_scan_u64(ctx, sz.p, off.p, n_un + 1));
+        std::vector<uint64_t> hoff(n_un + 1);
+        CK(cudaMemcpyAsync(hoff.data(), off.p, (n_un + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        DevBuf<uint8_t> blob;
+        CK(blob.alloc(hoff[n_un], s));
+        {
+            ProfScope ps(ctx, "unmapped_pack", (double)hoff[n_un]);
+            unmapped_pack<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_sorted.p, bam->d_data, bam->d_rec_off, off.p, blob.p);
+        }
+        std::vector<uint8_t> hblob(hoff[n_un]);
+        CK(cudaMemcpyAsync(hblob.data(), blob.p, hoff[n_un], cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        pair_unmapped(hblob, hoff, res->text[2], res->text[3]);
+    }
+
+    if (n_cand == 0) {
+        *out_ = guard.release();
+        return 0;
+    }
+    if (bam->names.size() != (size_t)bam->n_ref) return svb_fail(ctx, SVB_ERR_ARG, "svb_getclip: reference names not set (svb_bam_set_refs)");
+
+    // ---- 3. order candidates: BAM order first (stable base), then (run, side, pos) -----------------------------
+    DevBuf<uint32_t> sw_sorted, ord0, ord1, ord2, rec_sorted;
+    DevBuf<uint64_t> key0, key1;
+    CK(sw_sorted.alloc(n_sw, s));
+    if (n_sw) CKR(sort_u32(ctx, sw_list.p, sw_sorted.p, n_sw));
+    CK(ord0.alloc(n_cand, s));
+    CK(ord1.alloc(n_cand, s));
+    CK(ord2.alloc(n_cand, s));
+    CK(rec_sorted.alloc(n_cand, s));
+    CK(key0.alloc(n_cand, s));
+    CK(key1.alloc(n_cand, s));
+    iota_u32<<<nblk(n_cand, 256), 256, 0, s>>>(n_cand, ord0.p);
+    {
+        // a both-side-clipped read yields two candidates with the same record index but different sides, so
+        // (key, record) is unique and the two-pass stable sort is deterministic
+        ProfScope ps(ctx, "sort_candidates", (double)n_cand * 24);
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c.rec, rec_sorted.p, ord0.p, ord1.p, (int)n_cand, 0, 32, s));
+        DevBuf<uint8_t> t;
+        CK(t.alloc(tmp, s));
+        CK(cub::DeviceRadixSort::SortPairs(t.p, tmp, c.rec, rec_sorted.p, ord0.p, ord1.p, (int)n_cand, 0, 32, s));
+        make_keys<<<nblk(n_cand, 256), 256, 0, s>>>(n_cand, ord1.p, c, sw_sorted.p, n_sw, key0.p);
+        size_t tmp2 = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, key0.p, key1.p, ord1.p, ord2.p, (int)n_cand, 0, 64, s));
+        DevBuf<uint8_t> t2;
+        CK(t2.alloc(tmp2, s));
+        CK(cub::DeviceRadixSort::SortPairs(t2.p, tmp2, key0.p, key1.p, ord1.p, ord2.p, (int)n_cand, 0, 64, s));
+    }
+    const uint32_t *order = ord2.p;
+
+    // ---- 4. segments (one per breakpoint key) -------------------------------------------------------------------
+    DevBuf<uint32_t> flag, segid;
+    CK(flag.alloc(n_cand, s));
+    CK(segid.alloc(n_cand, s));
+    seg_flags<<<nblk(n_cand, 256), 256, 0, s>>>(n_cand, key1.p, flag.p);
+    CKR(inclusive_scan_u32(ctx, flag.p, segid.p, n_cand));
+    uint32_t n_seg = 0;
+    CK(cudaMemcpyAsync(&n_seg, segid.p + (n_cand - 1), 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    DevBuf<uint32_t> start, maxl, maxr;
+    DevBuf<uint64_t> seg_bytes, arena_off;
+    CK(start.alloc(n_seg + 1, s));
+    CK(maxl.alloc(n_seg, s));
+    CK(maxr.alloc(n_seg, s));
+    CK(seg_bytes.alloc(n_seg + 1, s));
+    CK(arena_off.alloc(n_seg + 1, s));
+    seg_starts<<<nblk(n_cand, 256), 256, 0, s>>>(n_cand, flag.p, segid.p, start.p, n_seg);
+    seg_stats<<<nblk(n_seg, 256), 256, 0, s>>>(n_seg, start.p, order, c, maxl.p, maxr.p, seg_bytes.p);
+    CKR(exclusive_scan_u64(ctx, seg_bytes.p, arena_off.p, n_seg + 1));
+    uint64_t arena_bytes = 0;
+    CK(cudaMemcpyAsync(&arena_bytes, arena_off.p + n_seg, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+
+    // ---- 5. greedy clustering -----------------------------------------------------------------------------------
+    DevBuf<char> arena_seq, arena_qual;
+    DevBuf<uint32_t> len_l, len_r, cig_rec, support, seg_ncl, cl_base;
+    DevBuf<uint8_t> noqual;
+    CK(arena_seq.alloc(arena_bytes, s));
+    CK(arena_qual.alloc(arena_bytes, s));
+    CK(len_l.alloc(n_cand, s));
+    CK(len_r.alloc(n_cand, s));
+    CK(cig_rec.alloc(n_cand, s));
+    CK(support.alloc(n_cand, s));
+    CK(noqual.alloc(n_cand, s));
+    CK(seg_ncl.alloc(n_seg, s));
+    CK(cl_base.alloc(n_seg, s));
+    ClusterOut co{len_l.p, len_r.p, cig_rec.p, support.p, noqual.p, seg_ncl.p};
+    {
+        ProfScope ps(ctx, "cluster_build", (double)arena_bytes * 2);
+        cluster_build<<<nblk((uint64_t)n_seg * 32, 128), 128, 0, s>>>(bam->d_data, bam->d_rec_off, n_seg, start.p, order, c, maxl.p,
+                                                                      maxr.p, arena_off.p, arena_seq.p, arena_qual.p, prm->match_rate, co);
+    }
+    CKR(inclusive_scan_u32(ctx, seg_ncl.p, cl_base.p, n_seg));
+    uint32_t n_cl = 0;
+    CK(cudaMemcpyAsync(&n_cl, cl_base.p + (n_seg - 1), 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    res->n_clusters = n_cl;
+
+    // ---- 6. text ---------------------------------------------------------------------------------------------------
+    std::vector<uint32_t> noff(bam->n_ref + 1, 0);
+    std::string nblob;
+    for (int32_t t = 0; t < bam->n_ref; ++t) {
+        noff[t] = (uint32_t)nblob.size();
+        nblob += bam->names[t];
+    }
+    noff[bam->n_ref] = (uint32_t)nblob.size();
+    DevBuf<char> d_nblob;
+    DevBuf<uint32_t> d_noff, cl_seg, cl_slot;
+    DevBuf<uint64_t> clip_len, fq_len, clip_off, fq_off;
+    CK(d_nblob.alloc(nblob.size() + 1, s));
+    CK(d_noff.alloc(noff.size(), s));
+    CK(cudaMemcpyAsync(d_nblob.p, nblob.data(), nblob.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_noff.p, noff.data(), noff.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(cl_seg.alloc(n_cl, s));
+    CK(cl_slot.alloc(n_cl, s));
+    CK(clip_len.alloc(n_cl + 1, s));
+    CK(fq_len.alloc(n_cl + 1, s));
+    CK(clip_off.alloc(n_cl + 1, s));
+    CK(fq_off.alloc(n_cl + 1, s));
+    NameTable nt{d_nblob.p, d_noff.p};
+    list_clusters<<<nblk(n_seg, 256), 256, 0, s>>>(n_seg, start.p, seg_ncl.p, cl_base.p, cl_seg.p, cl_slot.p);
+    text_sizes<<<nblk(n_cl + 1, 256), 256, 0, s>>>(n_cl, cl_seg.p, cl_slot.p, start.p, order, c, co, bam->d_data, bam->d_rec_off, nt,
+                                                   clip_len.p, fq_len.p);
+    CKR(exclusive_scan_u64(ctx, clip_len.p, clip_off.p, n_cl + 1));
+    CKR(exclusive_scan_u64(ctx, fq_len.p, fq_off.p, n_cl + 1));
+    uint64_t clip_bytes = 0, fq_bytes = 0;
+    CK(cudaMemcpyAsync(&clip_bytes, clip_off.p + n_cl, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&fq_bytes, fq_off.p + n_cl, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    DevBuf<char> d_clip, d_fq;
+    CK(d_clip.alloc(clip_bytes, s));
+    CK(d_fq.alloc(fq_bytes, s));
+    {
+        ProfScope ps(ctx, "text_write", (double)(clip_bytes + fq_bytes));
+        text_write<<<nblk((uint64_t)n_cl * 32, 128), 128, 0, s>>>(n_cl, cl_seg.p, cl_slot.p, start.p, order, c, co, bam->d_data,
+                                                                  bam->d_rec_off, nt, maxl.p, maxr.p, arena_off.p, arena_seq.p,
+                                                                  arena_qual.p, clip_off.p, fq_off.p, d_clip.p, d_fq.p);
+    }
+    res->text[0].resize(clip_bytes);
+    res->text[1].resize(fq_bytes);
+    CK(cudaMemcpyAsync(res->text[0].data(), d_clip.p, clip_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(res->text[1].data(), d_fq.p, fq_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    *out_ = guard.release();
+    return 0;
+}
+
+extern "C" void svb_clusters_free(svb_clusters *c) { delete c; }
+extern "C" uint64_t svb_clusters_count(const svb_clusters *c) { return c ? c->n_clusters : 0; }
+extern "C" uint64_t svb_clusters_candidates(const svb_clusters *c) { return c ? c->n_candidates : 0; }
+extern "C" int svb_clusters_text(const svb_clusters *c, int which, const char **data, uint64_t *len)
+{
+    if (!c || which < 0 || which > 3 || !data || !len) return SVB_ERR_ARG;
+    *data = c->text[which].data();
+    *len = c->text[which].size();
+    return 0;
+}

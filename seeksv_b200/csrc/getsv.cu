@@ -1,0 +1,492 @@
+// getsv / somatic device passes over the lean record columns: insert-size statistics
+// (CalculateInsertsizeDeviation, cluster.cpp:15-83), discordant-pair support per junction
+// (FindDiscordantReadPairs, getsv.cpp:990-1247 with IsConcordant cluster.cpp:136-147) and per-position
+// depth inside merged junction windows (main_depth, bam2depth.cpp:17-142, libbam pileup semantics as
+// probed in tests/test_oracle_golden.py). One decode pass streams the packed records once
+// (decode_records); everything after it reads ~32 B/record of columns instead of ~320 B of record.
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+static inline unsigned nblk(uint64_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
+
+#define FLAGQ_NOCIGAR (1u << 25)
+#define PILEUP_MAXCNT 8000
+
+// ---- decode: packed records -> lean columns -----------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    decode_kernel(const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, uint64_t n_rec, LeanRecords L,
+                  int32_t *__restrict__ max_span, uint32_t *__restrict__ unsorted)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t span = 0;
+    if (i < n_rec) {
+        const uint8_t *p = d + rec_off[i];
+        Core k = load_core(p);
+        const uint8_t *cig = p + 36 + k.l_qname;
+        int32_t end = k.pos;
+        uint32_t fq = k.flag | (k.mapq << 16);
+        if (k.n_cigar == 0) fq |= FLAGQ_NOCIGAR;
+        for (uint32_t j = 0; j < k.n_cigar; ++j) {
+            uint32_t w = ldu32(cig + 4 * j), op = w & 15;
+            // bam_calend of the linked libbam: M, D, N only ('=' and 'X' do not advance; probed)
+            if (op == OP_M || op == OP_D || op == OP_N) end += (int32_t)(w >> 4);
+            if ((j == 0 || j + 1 == k.n_cigar) && op == OP_H) fq |= FLAGQ_HARDCLIP;  // IsHardClip, clip_reads.cpp:247
+        }
+        L.tid[i] = k.tid, L.pos[i] = k.pos, L.end[i] = end, L.flagq[i] = fq;
+        L.lqseq[i] = k.l_qseq, L.mtid[i] = k.mtid, L.mpos[i] = k.mpos, L.isize[i] = k.isize;
+        span = max(end - k.pos, 1);
+        if (i > 0) {  // coordinate order: (tid, pos) ascending, tid -1 last
+            const uint8_t *q = d + rec_off[i - 1];
+            uint32_t t0 = (uint32_t)ldi32(q + 4), t1 = (uint32_t)k.tid;  // -1 -> 0xffffffff sorts last
+            int32_t p0 = ldi32(q + 8);
+            if (t0 > t1 || (t0 == t1 && p0 > k.pos)) atomicOr(unsorted, 1u);
+        }
+    }
+    span = (int32_t)warp_max((uint32_t)span);
+    if ((threadIdx.x & 31) == 0 && span > 0) atomicMax(max_span, span);
+}
+
+int decode_records(svb_ctx *ctx, svb_bam *bam)
+{
+    if (bam->lean_ready) return 0;
+    cudaStream_t s = ctx->stream;
+    uint64_t n = bam->n_rec;
+    LeanRecords &L = bam->lean;
+    size_t cnt = n ? n : 1;
+    CK(cudaMalloc((void **)&L.tid, cnt * 4));
+    CK(cudaMalloc((void **)&L.pos, cnt * 4));
+    CK(cudaMalloc((void **)&L.end, cnt * 4));
+    CK(cudaMalloc((void **)&L.flagq, cnt * 4));
+    CK(cudaMalloc((void **)&L.lqseq, cnt * 4));
+    CK(cudaMalloc((void **)&L.mtid, cnt * 4));
+    CK(cudaMalloc((void **)&L.mpos, cnt * 4));
+    CK(cudaMalloc((void **)&L.isize, cnt * 4));
+    L.n = n;
+    DevBuf<int32_t> scal;
+    CK(scal.alloc(2, s));
+    CK(cudaMemsetAsync(scal.p, 0, 8, s));
+    if (n) {
+        ProfScope ps(ctx, "decode_records", (double)bam->rec_bytes);
+        decode_kernel<<<nblk(n, 256), 256, 0, s>>>(bam->d_data, bam->d_rec_off, n, L, scal.p, (uint32_t *)scal.p + 1);
+    }
+    int32_t h[2];
+    CK(cudaMemcpyAsync(h, scal.p, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    bam->max_span = h[0];
+    bam->sorted = h[1] ? 0 : 1;
+    bam->lean_ready = true;
+    return 0;
+}
+
+// ---- insert size ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool insert_qualifies(uint32_t fq, int32_t isize, int32_t min_mapq)
+{
+    uint32_t flag = fq & 0xffff;
+    if ((int32_t)((fq >> 16) & 0xff) < min_mapq) return false;  // __g_skip_aln in cluster.cpp's TU (quirk Q9)
+    if (fq & FLAGQ_HARDCLIP) return false;
+    return (flag & F_PAIRED) && (flag & F_PROPER) && !(flag & F_DUP) && isize > 0;
+}
+__global__ void insert_flags(uint64_t n, const uint32_t *__restrict__ fq, const int32_t *__restrict__ isize, int32_t min_mapq,
+                             uint32_t *__restrict__ flag)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = insert_qualifies(fq[i], isize[i], min_mapq) ? 1u : 0u;
+}
+// pass 1 (mean == INT_MIN): sum of isize; pass 2: sum of (int32)((isize-mean)*(isize-mean))
+__global__ void __launch_bounds__(256)
+    insert_sums(uint64_t n, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ rank, const int32_t *__restrict__ isize,
+                uint64_t max_pairs, int pass, int32_t mean, unsigned long long *__restrict__ acc)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    long long v = 0;
+    if (i < n && flag[i] && (uint64_t)rank[i] <= max_pairs) {
+        if (pass == 1) v = isize[i];
+        else {
+            uint32_t dlt = (uint32_t)(isize[i] - mean);
+            v = (int32_t)(dlt * dlt);  // the reference multiplies two ints (cluster.cpp:77)
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(acc, (unsigned long long)v);
+}
+
+extern "C" int svb_insert_stats(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64_t max_pairs, int64_t out[4])
+{
+    if (!ctx || !bam || !out) return svb_fail(ctx, SVB_ERR_ARG, "svb_insert_stats: null argument");
+    CKR(decode_records(ctx, bam));
+    cudaStream_t s = ctx->stream;
+    uint64_t n = bam->n_rec;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (n == 0 || max_pairs <= 0) return 0;
+    if (n >= (1ull << 32)) return svb_fail(ctx, SVB_ERR_ARG, "more than 2^32 records in one shard");
+    DevBuf<uint32_t> flag, rank;
+    DevBuf<unsigned long long> acc;
+    CK(flag.alloc(n, s));
+    CK(rank.alloc(n, s));
+    CK(acc.alloc(2, s));
+    CK(cudaMemsetAsync(acc.p, 0, 16, s));
+    {
+        ProfScope ps(ctx, "insert_stats", (double)n * 16);
+        insert_flags<<<nblk(n, 256), 256, 0, s>>>(n, bam->lean.flagq, bam->lean.isize, min_mapq, flag.p);
+        CKR(inclusive_scan_u32(ctx, flag.p, rank.p, n));
+        insert_sums<<<nblk(n, 256), 256, 0, s>>>(n, flag.p, rank.p, bam->lean.isize, (uint64_t)max_pairs, 1, 0, acc.p);
+    }
+    uint32_t total = 0;
+    unsigned long long sum = 0;
+    CK(cudaMemcpyAsync(&total, rank.p + (n - 1), 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&sum, acc.p, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    uint64_t cnt = std::min<uint64_t>(total, (uint64_t)max_pairs);
+    if (cnt == 0) return 0;
+    int32_t mean = (int32_t)(sum / cnt);  // unsigned long / int, stored to int (cluster.cpp:72)
+    {
+        ProfScope ps(ctx, "insert_stats", (double)n * 12);
+        insert_sums<<<nblk(n, 256), 256, 0, s>>>(n, flag.p, rank.p, bam->lean.isize, (uint64_t)max_pairs, 2, mean, acc.p + 1);
+    }
+    long long sq = 0;
+    CK(cudaMemcpyAsync(&sq, acc.p + 1, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    out[0] = (int64_t)cnt, out[1] = (int64_t)sum, out[2] = mean, out[3] = sq;
+    return 0;
+}
+
+// ---- discordant read pairs ------------------------------------------------------------------------------------------
+// first record index with (tid, pos) >= (T, P); tid -1 sorts last
+__device__ __forceinline__ uint64_t lower_bound_tp(const int32_t *__restrict__ tid, const int32_t *__restrict__ pos, uint64_t n,
+                                                   int32_t T, int64_t P)
+{
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t m = (lo + hi) >> 1;
+        uint32_t t = (uint32_t)tid[m];
+        bool less = t < (uint32_t)T || (t == (uint32_t)T && (int64_t)pos[m] < P);
+        if (less) lo = m + 1;
+        else hi = m;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128)
+    discordant_kernel(LeanRecords L, int32_t max_span, const svb_junction *__restrict__ J, uint64_t n_j,
+                      const uint32_t *__restrict__ ref_len, svb_pair_params prm, int32_t *__restrict__ counts)
+{
+    uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (w >= n_j) return;
+    const svb_junction j = J[w];
+    const int kCross = 5;  // kCrossLength, getsv.cpp:15
+    int32_t min_is = prm.mean_insert - prm.deviation * prm.times, max_is = prm.mean_insert + prm.deviation * prm.times;
+    if (min_is < 0) min_is = 0;
+    int32_t tid = j.up_tid, mtid = j.down_tid;
+    uint32_t n = 0;
+    if (tid >= 0 && (j.up_strand == '+' || j.up_strand == '-')) {
+        int32_t beg, end;
+        if (j.up_strand == '+') end = j.up_pos, beg = end - max_is;
+        else beg = j.up_pos - 1 - kCross, end = j.up_pos - 1 + max_is;
+        if (beg <= 0) beg = 1;
+        if ((uint32_t)end > ref_len[tid]) end = (int32_t)ref_len[tid];  // int vs unsigned compare, getsv.cpp:1060
+        // bam_iter_query(idx, tid, beg, end): records on tid with pos < end and calend > beg
+        uint64_t lo = lower_bound_tp(L.tid, L.pos, L.n, tid, (int64_t)beg - max_span);
+        uint64_t hi = lower_bound_tp(L.tid, L.pos, L.n, tid, end);
+        for (uint64_t i = lo + lane; i < hi; i += 32) {
+            uint32_t fq = L.flagq[i], flag = fq & 0xffff;
+            int32_t pos = L.pos[i];
+            int32_t rend = (fq & FLAGQ_NOCIGAR) ? pos + 1 : L.end[i];
+            if (!(rend > beg)) continue;
+            if ((int32_t)((fq >> 16) & 0xff) < prm.min_mapq) continue;  // __g_skip_aln, getsv.cpp:1027,1069
+            if (fq & FLAGQ_HARDCLIP) continue;
+            if (flag & (F_DUP | F_UNMAP | F_MUNMAP)) continue;
+            int32_t isz = L.isize[i];
+            bool rev = flag & F_REVERSE, mrev = flag & F_MREVERSE;
+            {  // IsConcordant, cluster.cpp:136-147 (its own, unclamped minimum)
+                int32_t lo_c = prm.mean_insert - prm.deviation * prm.times;
+                bool conc = false;
+                if (!rev && mrev && lo_c <= isz && isz <= max_is) conc = true;
+                else if (rev && !mrev && isz < 0) {
+                    int32_t a = isz < 0 ? -isz : isz;
+                    conc = lo_c <= a && a <= max_is;
+                }
+                if (conc) continue;
+            }
+            if (mtid == -1 || mtid != L.mtid[i]) continue;
+            int32_t lq = L.lqseq[i], mpos = L.mpos[i];
+            bool hit = false;
+            if (j.up_strand == '+' && j.down_strand == '+' && pos + lq <= j.up_pos + kCross && mpos + 1 >= j.down_pos - kCross) {
+                if (!rev && mrev) {
+                    int32_t isize = j.up_pos - pos + mpos + lq - j.down_pos + 1;
+                    if (tid == mtid && j.up_pos > j.down_pos && j.up_pos - j.down_pos + 1 + 2 * lq <= max_is) {
+                        while (isize <= max_is) {  // tandem duplication: add whole copies (getsv.cpp:1081-1091)
+                            if (isize >= min_is) {
+                                hit = true;
+                                break;
+                            }
+                            isize += j.up_pos - j.down_pos + 1;
+                        }
+                    } else
+                        hit = min_is <= isize && isize <= max_is;
+                }
+            } else if (j.up_strand == '-' && j.down_strand == '+' && rev && mrev && mpos + 1 >= j.down_pos - kCross) {
+                int32_t isize = pos + 1 - j.up_pos + 1 + mpos + lq - j.down_pos + 1;
+                hit = min_is <= isize && isize <= max_is;
+            } else if (j.up_strand == '+' && j.down_strand == '-' && !rev && !mrev && pos + lq <= j.up_pos + kCross &&
+                       mpos + lq <= j.down_pos + kCross) {
+                int32_t isize = j.up_pos - pos + j.down_pos - (mpos + lq) + 1;
+                hit = min_is <= isize && isize <= max_is;
+            }
+            n += hit;
+        }
+    }
+    n = warp_sum(n);
+    if (lane == 0) counts[w] = (int32_t)n;
+}
+
+extern "C" int svb_discordant_support(svb_ctx *ctx, svb_bam *bam, const svb_junction *junctions, uint64_t n,
+                                      const svb_pair_params *p, int32_t *counts)
+{
+    if (!ctx || !bam || !p || (n && (!junctions || !counts))) return svb_fail(ctx, SVB_ERR_ARG, "svb_discordant_support: null argument");
+    CKR(decode_records(ctx, bam));
+    if (n == 0) return 0;
+    if (bam->sorted != 1) return svb_fail(ctx, SVB_ERR_UNSORTED, "the BAM is not coordinate-sorted");
+    if (bam->lens.size() != (size_t)bam->n_ref) return svb_fail(ctx, SVB_ERR_ARG, "reference lengths not set (svb_bam_set_refs)");
+    cudaStream_t s = ctx->stream;
+    DevBuf<svb_junction> dj;
+    DevBuf<int32_t> dc;
+    DevBuf<uint32_t> dl;
+    CK(dj.alloc(n, s));
+    CK(dc.alloc(n, s));
+    CK(dl.alloc(bam->n_ref, s));
+    CK(cudaMemcpyAsync(dj.p, junctions, n * sizeof(svb_junction), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dl.p, bam->lens.data(), (size_t)bam->n_ref * 4, cudaMemcpyHostToDevice, s));
+    {
+        ProfScope ps(ctx, "discordant_support", 0);
+        discordant_kernel<<<nblk(n * 32, 128), 128, 0, s>>>(bam->lean, bam->max_span, dj.p, n, dl.p, *p, dc.p);
+    }
+    CK(cudaMemcpyAsync(counts, dc.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- window depth ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pileup_eligible(int32_t tid, uint32_t fq, int32_t min_mapq)
+{
+    // bam_plp_push: tid >= 0 and (flag & 0x704) == 0, after read_bam (bam2depth.h:29-35) set UNMAP for low mapQ
+    return tid >= 0 && !((fq & 0xffff) & 0x704) && (int32_t)((fq >> 16) & 0xff) >= min_mapq;
+}
+
+__global__ void eligible_flags(LeanRecords L, int32_t min_mapq, uint32_t *__restrict__ flag)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < L.n) flag[i] = pileup_eligible(L.tid[i], L.flagq[i], min_mapq) ? 1u : 0u;
+}
+
+// Upper bound of the pileup buffer occupancy when record i is pushed: eligible records that start within
+// max_span before it. If this never exceeds the cap, libbam's 8000-read limit cannot trigger anywhere.
+__global__ void cap_bound(LeanRecords L, int32_t max_span, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ rank,
+                          uint32_t *__restrict__ hot_tids, uint32_t n_ref)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.n || !flag[i]) return;
+    int32_t tid = L.tid[i];
+    uint64_t lo = lower_bound_tp(L.tid, L.pos, L.n, tid, (int64_t)L.pos[i] - max_span);
+    uint32_t before = lo ? rank[lo - 1] : 0;
+    if (rank[i] - before + 2 > PILEUP_MAXCNT && (uint32_t)tid < n_ref) hot_tids[tid] = 1;
+}
+
+// Exact serial emulation of bam_plp_push's cap for one chromosome (one thread per hot chromosome): a read is
+// refused only if it starts at the same position as the previously accepted read while more than 8000
+// buffer nodes are allocated = 2 + accepted reads whose end >= that position (released lazily).
+__global__ void cap_serial(LeanRecords L, const uint32_t *__restrict__ hot_tids, uint32_t n_ref, const uint32_t *__restrict__ flag,
+                           uint8_t *__restrict__ kept, uint32_t *__restrict__ ring_all, uint32_t ring)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ref || !hot_tids[t]) return;
+    uint32_t *hist = ring_all + (uint64_t)t * ring;  // live accepted reads by end position (mod ring)
+    for (uint32_t k = 0; k < ring; ++k) hist[k] = 0;
+    uint64_t lo = lower_bound_tp(L.tid, L.pos, L.n, (int32_t)t, INT32_MIN);
+    uint64_t hi = lower_bound_tp(L.tid, L.pos, L.n, (int32_t)t + 1, INT32_MIN);
+    int64_t it_pos = -1;  // position of the previously accepted read (iterator position)
+    uint32_t live = 0;
+    bool any = false;
+    for (uint64_t i = lo; i < hi; ++i) {
+        if (!flag[i]) continue;
+        int32_t pos = L.pos[i], end = L.end[i];
+        if (any && pos == it_pos) {
+            if (live + 2 > PILEUP_MAXCNT) {
+                kept[i] = 0;
+                continue;
+            }
+            if (end > pos) hist[(uint32_t)end % ring]++, live++;
+        } else {
+            if (any) {  // release nodes whose end <= pos - 1
+                int64_t from = it_pos, to = pos;  // ends in [from, to) leave; ends < from left earlier
+                if (to - from >= ring) {
+                    for (uint32_t k = 0; k < ring; ++k) hist[k] = 0;
+                    live = 0;
+                } else
+                    for (int64_t e = from; e < to; ++e) {
+                        uint32_t &h = hist[(uint32_t)e % ring];
+                        live -= h, h = 0;
+                    }
+            }
+            it_pos = pos, any = true;
+            hist[(uint32_t)end % ring]++, live++;
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t first_window(const svb_window *__restrict__ W, uint64_t n, int32_t tid, int32_t p)
+{
+    // first window with (tid, end) >= (tid, p); windows are disjoint and sorted, so ends are sorted too
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t m = (lo + hi) >> 1;
+        bool less = W[m].tid < tid || (W[m].tid == tid && W[m].end < p);
+        if (less) lo = m + 1;
+        else hi = m;
+    }
+    return lo;
+}
+
+// One thread per record: +1/-1 marks of its M segments into the difference array of every window it overlaps.
+__global__ void __launch_bounds__(256)
+    depth_marks(const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, LeanRecords L, const uint8_t *__restrict__ kept,
+                const svb_window *__restrict__ W, const uint64_t *__restrict__ woff, uint64_t n_w, int32_t *__restrict__ diff)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.n || !kept[i]) return;
+    int32_t tid = L.tid[i], beg1 = L.pos[i] + 1, end1 = L.end[i];  // 1-based inclusive [beg1, end1]
+    if (end1 < beg1) return;
+    uint64_t w = first_window(W, n_w, tid, beg1);
+    if (w >= n_w || W[w].tid != tid || W[w].begin > end1) return;
+    const uint8_t *p = d + rec_off[i];
+    uint32_t lq = ldu32(p + 12) & 0xff, nc = ldu32(p + 16) & 0xffff;
+    const uint8_t *cig = p + 36 + lq;
+    for (; w < n_w && W[w].tid == tid && W[w].begin <= end1; ++w) {
+        int32_t wb = W[w].begin, we = W[w].end;
+        int32_t *dw = diff + woff[w];
+        int32_t x = beg1;
+        for (uint32_t j = 0; j < nc && x <= we; ++j) {
+            uint32_t c = ldu32(cig + 4 * j), op = c & 15;
+            int32_t len = (int32_t)(c >> 4);
+            if (op == OP_M) {  // '=' / 'X' are ignored by this libbam's CIGAR walk (probed)
+                int32_t lo = max(x, wb), hi = min(x + len - 1, we);
+                if (lo <= hi) {
+                    atomicAdd(&dw[lo - wb], 1);
+                    atomicAdd(&dw[hi + 1 - wb], -1);
+                }
+                x += len;
+            } else if (op == OP_D || op == OP_N)
+                x += len;
+        }
+    }
+}
+
+// prefix sum inside each window (one warp per window), diff -> depth, compacted to the output layout
+__global__ void __launch_bounds__(128)
+    depth_scan(const svb_window *__restrict__ W, const uint64_t *__restrict__ woff, uint64_t n_w, const int32_t *__restrict__ diff,
+               int32_t *__restrict__ depth)
+{
+    uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (w >= n_w) return;
+    uint32_t len = (uint32_t)(W[w].end - W[w].begin + 1);
+    const int32_t *dw = diff + woff[w];
+    int32_t *out = depth + (woff[w] - w);  // diff has one extra slot per window
+    int32_t carry = 0;
+    for (uint32_t base = 0; base < len; base += 32) {
+        uint32_t k = base + lane;
+        int32_t v = k < len ? dw[k] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= (uint32_t)o) v += t;
+        }
+        v += carry;
+        if (k < len) out[k] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+}
+
+__global__ void fill_u8(uint64_t n, const uint32_t *__restrict__ flag, uint8_t *__restrict__ kept)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) kept[i] = (uint8_t)flag[i];
+}
+
+extern "C" int svb_window_depth(svb_ctx *ctx, svb_bam *bam, const svb_window *windows, uint64_t n_w, int32_t min_mapq,
+                                int32_t *depth_out)
+{
+    if (!ctx || !bam || (n_w && (!windows || !depth_out))) return svb_fail(ctx, SVB_ERR_ARG, "svb_window_depth: null argument");
+    CKR(decode_records(ctx, bam));
+    if (n_w == 0) return 0;
+    if (bam->sorted != 1) return svb_fail(ctx, SVB_ERR_UNSORTED, "the BAM is not coordinate-sorted");
+    cudaStream_t s = ctx->stream;
+    uint64_t n = bam->n_rec;
+    std::vector<uint64_t> woff(n_w + 1);
+    uint64_t tot = 0;
+    for (uint64_t w = 0; w < n_w; ++w) {
+        if (windows[w].end < windows[w].begin) return svb_fail(ctx, SVB_ERR_ARG, "svb_window_depth: empty window");
+        if (w && (windows[w].tid < windows[w - 1].tid ||
+                  (windows[w].tid == windows[w - 1].tid && windows[w].begin <= windows[w - 1].end)))
+            return svb_fail(ctx, SVB_ERR_ARG, "svb_window_depth: windows must be sorted and disjoint");
+        woff[w] = tot;
+        tot += (uint64_t)(windows[w].end - windows[w].begin + 1) + 1;
+    }
+    woff[n_w] = tot;
+    uint64_t n_pos = tot - n_w;
+    DevBuf<svb_window> dW;
+    DevBuf<uint64_t> dOff;
+    DevBuf<int32_t> diff, depth;
+    DevBuf<uint32_t> flag, rank, hot, ringbuf;
+    DevBuf<uint8_t> kept;
+    CK(dW.alloc(n_w, s));
+    CK(dOff.alloc(n_w + 1, s));
+    CK(diff.alloc(tot, s));
+    CK(depth.alloc(n_pos, s));
+    CK(cudaMemcpyAsync(dW.p, windows, n_w * sizeof(svb_window), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dOff.p, woff.data(), (n_w + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(diff.p, 0, tot * 4, s));
+    if (n) {
+        uint32_t n_ref = (uint32_t)bam->n_ref;
+        CK(flag.alloc(n, s));
+        CK(rank.alloc(n, s));
+        CK(kept.alloc(n, s));
+        CK(hot.alloc(n_ref + 1, s));
+        CK(cudaMemsetAsync(hot.p, 0, (n_ref + 1) * 4, s));
+        {
+            ProfScope ps(ctx, "depth_eligible", (double)n * 24);
+            eligible_flags<<<nblk(n, 256), 256, 0, s>>>(bam->lean, min_mapq, flag.p);
+            CKR(inclusive_scan_u32(ctx, flag.p, rank.p, n));
+            fill_u8<<<nblk(n, 256), 256, 0, s>>>(n, flag.p, kept.p);
+            cap_bound<<<nblk(n, 256), 256, 0, s>>>(bam->lean, bam->max_span, flag.p, rank.p, hot.p, n_ref);
+        }
+        std::vector<uint32_t> hhot(n_ref);
+        CK(cudaMemcpyAsync(hhot.data(), hot.p, n_ref * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        bool any_hot = false;
+        for (uint32_t t = 0; t < n_ref; ++t) any_hot |= hhot[t] != 0;
+        if (any_hot) {  // rare: coverage beyond libbam's pileup cap (quirk Q12) - serial, exact
+            uint32_t ring = 1;
+            while (ring < (uint32_t)bam->max_span + 2) ring <<= 1;
+            CK(ringbuf.alloc((uint64_t)n_ref * ring, s));
+            ProfScope ps(ctx, "pileup_cap_serial", 0);
+            cap_serial<<<nblk(n_ref, 32), 32, 0, s>>>(bam->lean, hot.p, n_ref, flag.p, kept.p, ringbuf.p, ring);
+        }
+        {
+            ProfScope ps(ctx, "depth_marks", (double)n * 13);
+            depth_marks<<<nblk(n, 256), 256, 0, s>>>(bam->d_data, bam->d_rec_off, bam->lean, kept.p, dW.p, dOff.p, n_w, diff.p);
+        }
+    }
+    {
+        ProfScope ps(ctx, "depth_scan", (double)tot * 8);
+        depth_scan<<<nblk(n_w * 32, 128), 128, 0, s>>>(dW.p, dOff.p, n_w, diff.p, depth.p);
+    }
+    CK(cudaMemcpyAsync(depth_out, depth.p, n_pos * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return 0;
+}

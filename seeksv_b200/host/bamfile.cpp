@@ -1,0 +1,423 @@
+#include "bamfile.h"
+
+#include <zlib.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <thread>
+
+bool read_file(const std::string &path, std::vector<uint8_t> &out, std::string &err)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) {
+        err = "cannot open " + path;
+        return false;
+    }
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize(n > 0 ? (size_t)n : 0);
+    size_t got = n > 0 ? fread(out.data(), 1, (size_t)n, f) : 0;
+    fclose(f);
+    if (got != out.size()) {
+        err = "short read on " + path;
+        return false;
+    }
+    return true;
+}
+
+// BGZF: gzip members with FEXTRA holding the 'BC' sub-field = member size - 1 (sam/bgzf.h:34-60)
+bool bgzf_scan(const uint8_t *f, uint64_t n, std::vector<BgzfBlock> &blocks, uint64_t &total, std::string &err)
+{
+    uint64_t o = 0;
+    total = 0;
+    blocks.clear();
+    while (o < n) {
+        if (o + 18 > n || f[o] != 0x1f || f[o + 1] != 0x8b || f[o + 2] != 8 || !(f[o + 3] & 4)) {
+            err = "not a BGZF block at offset " + std::to_string(o);
+            return false;
+        }
+        uint32_t xlen = f[o + 10] | (f[o + 11] << 8);
+        uint64_t x = o + 12, xe = x + xlen;
+        uint32_t bsize = 0;
+        bool found = false;
+        while (x + 4 <= xe && xe <= n) {
+            uint32_t slen = f[x + 2] | (f[x + 3] << 8);
+            if (f[x] == 'B' && f[x + 1] == 'C' && slen == 2) {
+                bsize = (f[x + 4] | (f[x + 5] << 8)) + 1;
+                found = true;
+            }
+            x += 4 + slen;
+        }
+        if (!found || o + bsize > n || bsize < 12 + xlen + 8) {
+            err = "bad BGZF block at offset " + std::to_string(o);
+            return false;
+        }
+        BgzfBlock b;
+        b.coff = o + 12 + xlen;
+        b.clen = bsize - 12 - xlen - 8;
+        const uint8_t *t = f + o + bsize - 4;
+        b.ulen = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+        b.uoff = total;
+        total += b.ulen;
+        if (b.ulen) blocks.push_back(b);
+        o += bsize;
+    }
+    return true;
+}
+
+static bool inflate_block(const uint8_t *src, uint32_t clen, uint8_t *dst, uint32_t ulen)
+{
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<Bytef *>(src);
+    zs.avail_in = clen;
+    zs.next_out = dst;
+    zs.avail_out = ulen;
+    int r = inflate(&zs, Z_FINISH);
+    bool ok = (r == Z_STREAM_END) && zs.total_out == ulen;
+    inflateEnd(&zs);
+    return ok;
+}
+
+bool bgzf_inflate_range(const uint8_t *file, const std::vector<BgzfBlock> &blocks, size_t b0, size_t b1, uint8_t *dst,
+                        int n_threads, std::string &err)
+{
+    if (b0 >= b1) return true;
+    std::atomic<size_t> next(b0);
+    std::atomic<bool> bad(false);
+    uint64_t base = blocks[b0].uoff;
+    auto work = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(8);
+            if (i >= b1 || bad.load()) return;
+            for (size_t k = i; k < std::min(i + 8, b1); ++k)
+                if (!inflate_block(file + blocks[k].coff, blocks[k].clen, dst + (blocks[k].uoff - base), blocks[k].ulen)) bad = true;
+        }
+    };
+    int nt = (int)std::min<size_t>((size_t)std::max(1, n_threads), (b1 - b0 + 7) / 8);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    if (bad) {
+        err = "BGZF inflate failed";
+        return false;
+    }
+    return true;
+}
+
+bool bgzf_inflate_all(const uint8_t *file, uint64_t n, std::vector<uint8_t> &out, int n_threads, std::string &err)
+{
+    std::vector<BgzfBlock> blocks;
+    uint64_t total;
+    if (!bgzf_scan(file, n, blocks, total, err)) return false;
+    out.resize(total);
+    return bgzf_inflate_range(file, blocks, 0, blocks.size(), out.data(), n_threads, err);
+}
+
+static inline uint32_t rd32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+bool parse_bam_header(const uint8_t *d, uint64_t n, BamHeader &h, std::string &err)
+{
+    if (n < 12 || memcmp(d, "BAM\1", 4) != 0) {
+        err = "[main_samview] fail to read the header.";
+        return false;
+    }
+    uint64_t o = 4;
+    uint32_t l_text = rd32(d + o);
+    o += 4;
+    if (o + l_text + 4 > n) {
+        err = "BAM header truncated";
+        return false;
+    }
+    h.text.assign((const char *)d + o, l_text);
+    o += l_text;
+    uint32_t n_ref = rd32(d + o);
+    o += 4;
+    h.names.clear();
+    h.lengths.clear();
+    for (uint32_t i = 0; i < n_ref; ++i) {
+        if (o + 4 > n) {
+            err = "BAM header truncated";
+            return false;
+        }
+        uint32_t l = rd32(d + o);
+        o += 4;
+        if (o + l + 4 > n) {
+            err = "BAM header truncated";
+            return false;
+        }
+        h.names.emplace_back((const char *)d + o, strnlen((const char *)d + o, l));
+        o += l;
+        h.lengths.push_back(rd32(d + o));
+        o += 4;
+    }
+    h.first_record = o;
+    return true;
+}
+
+static int reg2bin(int beg, int end)
+{
+    --end;
+    if (beg >> 14 == end >> 14) return 4681 + (beg >> 14);
+    if (beg >> 17 == end >> 17) return 585 + (beg >> 17);
+    if (beg >> 20 == end >> 20) return 73 + (beg >> 20);
+    if (beg >> 23 == end >> 23) return 9 + (beg >> 23);
+    if (beg >> 26 == end >> 26) return 1 + (beg >> 26);
+    return 0;
+}
+
+static void put32(std::vector<uint8_t> &v, uint32_t x)
+{
+    v.push_back(x & 0xff), v.push_back((x >> 8) & 0xff), v.push_back((x >> 16) & 0xff), v.push_back(x >> 24);
+}
+
+bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vector<uint8_t> &out, std::string &err)
+{
+    static uint8_t nt16[256];
+    static bool init = false;
+    if (!init) {
+        memset(nt16, 15, sizeof nt16);
+        const char *tab = "=ACMGRSVTWYHKDBN";
+        for (int i = 0; i < 16; ++i) nt16[(uint8_t)tab[i]] = i, nt16[(uint8_t)tolower(tab[i])] = i;
+        init = true;
+    }
+    const char *p = (const char *)text.data(), *e = p + text.size();
+    std::map<std::string, int> name2tid;
+    h = BamHeader();
+    // header lines
+    while (p < e && *p == '@') {
+        const char *nl = (const char *)memchr(p, '\n', e - p);
+        if (!nl) nl = e;
+        std::string line(p, nl);
+        h.text += line + "\n";
+        if (line.compare(0, 3, "@SQ") == 0) {
+            std::string sn;
+            uint32_t ln = 0;
+            size_t a = 0;
+            while (a < line.size()) {
+                size_t b = line.find('\t', a);
+                if (b == std::string::npos) b = line.size();
+                if (line.compare(a, 3, "SN:") == 0) sn = line.substr(a + 3, b - a - 3);
+                if (line.compare(a, 3, "LN:") == 0) ln = (uint32_t)strtoul(line.c_str() + a + 3, nullptr, 10);
+                a = b + 1;
+            }
+            name2tid[sn] = (int)h.names.size();
+            h.names.push_back(sn);
+            h.lengths.push_back(ln);
+        }
+        p = nl < e ? nl + 1 : e;
+    }
+    if (h.names.empty()) {
+        err = "[main_samview] fail to read the header.";
+        return false;
+    }
+    out.clear();
+    out.insert(out.end(), {'B', 'A', 'M', 1});
+    put32(out, (uint32_t)h.text.size());
+    out.insert(out.end(), h.text.begin(), h.text.end());
+    put32(out, (uint32_t)h.names.size());
+    for (size_t i = 0; i < h.names.size(); ++i) {
+        put32(out, (uint32_t)h.names[i].size() + 1);
+        out.insert(out.end(), h.names[i].begin(), h.names[i].end());
+        out.push_back(0);
+        put32(out, h.lengths[i]);
+    }
+    h.first_record = out.size();
+    std::vector<std::pair<const char *, const char *>> f;
+    while (p < e) {
+        const char *nl = (const char *)memchr(p, '\n', e - p);
+        if (!nl) nl = e;
+        const char *le = nl;
+        if (le > p && le[-1] == '\r') --le;
+        if (le == p) {
+            p = nl < e ? nl + 1 : e;
+            continue;
+        }
+        f.clear();
+        for (const char *a = p;;) {
+            const char *b = (const char *)memchr(a, '\t', le - a);
+            if (!b) b = le;
+            f.emplace_back(a, b);
+            if (b == le) break;
+            a = b + 1;
+        }
+        if (f.size() < 11) {
+            err = "SAM line with fewer than 11 fields";
+            return false;
+        }
+        auto str = [&](int i) { return std::string(f[i].first, f[i].second); };
+        std::string qname = str(0), rname = str(2), rnext = str(6);
+        uint32_t flag = (uint32_t)strtoul(f[1].first, nullptr, 10);
+        int32_t pos = (int32_t)strtol(f[3].first, nullptr, 10) - 1, mapq = (int32_t)strtol(f[4].first, nullptr, 10);
+        int32_t mpos = (int32_t)strtol(f[7].first, nullptr, 10) - 1, isize = (int32_t)strtol(f[8].first, nullptr, 10);
+        int32_t tid = -1, mtid = -1;
+        if (rname != "*") {
+            auto it = name2tid.find(rname);
+            if (it != name2tid.end()) tid = it->second;
+        }
+        if (rnext == "=") mtid = tid;
+        else if (rnext != "*") {
+            auto it = name2tid.find(rnext);
+            if (it != name2tid.end()) mtid = it->second;
+        }
+        std::vector<uint32_t> cigar;
+        int32_t end = pos;
+        if (!(f[5].second - f[5].first == 1 && *f[5].first == '*')) {
+            uint32_t num = 0;
+            for (const char *c = f[5].first; c < f[5].second; ++c) {
+                if (*c >= '0' && *c <= '9') num = num * 10 + (*c - '0');
+                else {
+                    const char *ops = "MIDNSHP=X", *o = strchr(ops, *c);
+                    if (!o) {
+                        err = "invalid CIGAR character";
+                        return false;
+                    }
+                    uint32_t op = (uint32_t)(o - ops);
+                    cigar.push_back(num << 4 | op);
+                    if (op == 0 || op == 2 || op == 3) end += num;
+                    num = 0;
+                }
+            }
+        }
+        if (end == pos) end = pos + 1;
+        bool noseq = f[9].second - f[9].first == 1 && *f[9].first == '*';
+        int32_t l_qseq = noseq ? 0 : (int32_t)(f[9].second - f[9].first);
+        std::vector<uint8_t> aux;
+        for (size_t i = 11; i < f.size(); ++i) {
+            const char *a = f[i].first, *b = f[i].second;
+            if (b - a < 5 || a[2] != ':' || a[4] != ':') continue;
+            char ty = a[3];
+            const char *v = a + 5;
+            if (ty == 'i') {
+                long x = strtol(v, nullptr, 10);
+                aux.push_back(a[0]), aux.push_back(a[1]);
+                if (x < 0) {
+                    if (x >= -127) aux.push_back('c'), aux.push_back((uint8_t)(int8_t)x);
+                    else if (x >= -32767) aux.push_back('s'), aux.push_back(x & 0xff), aux.push_back((x >> 8) & 0xff);
+                    else aux.push_back('i'), put32(aux, (uint32_t)x);
+                } else {
+                    if (x <= 255) aux.push_back('C'), aux.push_back((uint8_t)x);
+                    else if (x <= 65535) aux.push_back('S'), aux.push_back(x & 0xff), aux.push_back((x >> 8) & 0xff);
+                    else aux.push_back('I'), put32(aux, (uint32_t)x);
+                }
+            } else if (ty == 'A') {
+                aux.push_back(a[0]), aux.push_back(a[1]), aux.push_back('A'), aux.push_back(*v);
+            } else if (ty == 'Z' || ty == 'H') {
+                aux.push_back(a[0]), aux.push_back(a[1]), aux.push_back(ty);
+                aux.insert(aux.end(), v, b);
+                aux.push_back(0);
+            } else if (ty == 'f') {
+                float x = strtof(v, nullptr);
+                uint32_t u;
+                memcpy(&u, &x, 4);
+                aux.push_back(a[0]), aux.push_back(a[1]), aux.push_back('f');
+                put32(aux, u);
+            }
+        }
+        uint32_t l_qname = (uint32_t)qname.size() + 1;
+        uint32_t bs = 32 + l_qname + 4 * (uint32_t)cigar.size() + (l_qseq + 1) / 2 + l_qseq + (uint32_t)aux.size();
+        put32(out, bs);
+        put32(out, (uint32_t)tid);
+        put32(out, (uint32_t)pos);
+        put32(out, (uint32_t)(tid >= 0 ? reg2bin(pos, end) : 4680) << 16 | ((uint32_t)mapq & 0xff) << 8 | (l_qname & 0xff));
+        put32(out, flag << 16 | ((uint32_t)cigar.size() & 0xffff));
+        put32(out, (uint32_t)l_qseq);
+        put32(out, (uint32_t)mtid);
+        put32(out, (uint32_t)mpos);
+        put32(out, (uint32_t)isize);
+        out.insert(out.end(), qname.begin(), qname.end());
+        out.push_back(0);
+        for (uint32_t c : cigar) put32(out, c);
+        for (int32_t i = 0; i < l_qseq; i += 2) {
+            uint8_t hi = nt16[(uint8_t)f[9].first[i]], lo = i + 1 < l_qseq ? nt16[(uint8_t)f[9].first[i + 1]] : 0;
+            out.push_back(hi << 4 | lo);
+        }
+        bool noqual = f[10].second - f[10].first == 1 && *f[10].first == '*';
+        for (int32_t i = 0; i < l_qseq; ++i) out.push_back(noqual ? 0xff : (uint8_t)(f[10].first[i] - 33));
+        out.insert(out.end(), aux.begin(), aux.end());
+        p = nl < e ? nl + 1 : e;
+    }
+    return true;
+}
+
+bool read_text_maybe_gz(const std::string &path, std::string &out, std::string &err)
+{
+    gzFile g = gzopen(path.c_str(), "rb");  // gzread passes plain text through unchanged
+    if (!g) {
+        err = "Cannot open file " + path;
+        return false;
+    }
+    gzbuffer(g, 1 << 20);
+    out.clear();
+    std::vector<char> buf(1 << 22);
+    int n;
+    while ((n = gzread(g, buf.data(), (unsigned)buf.size())) > 0) out.append(buf.data(), n);
+    gzclose(g);
+    if (n < 0) {
+        err = "read error on " + path;
+        return false;
+    }
+    return true;
+}
+
+static bool gz_member(const char *data, size_t n, std::vector<uint8_t> &out)
+{
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    out.resize(deflateBound(&zs, n) + 32);
+    zs.next_in = (Bytef *)data;
+    zs.avail_in = (uInt)n;
+    zs.next_out = out.data();
+    zs.avail_out = (uInt)out.size();
+    int r = deflate(&zs, Z_FINISH);
+    out.resize(zs.total_out);
+    deflateEnd(&zs);
+    return r == Z_STREAM_END;
+}
+
+// The reference writes through ogzstream (gzstream.C:53-61, default level); parity is on the DECOMPRESSED bytes,
+// so the file is written as independent gzip members compressed in parallel (zcat / gzread concatenate them).
+bool write_gz(const std::string &path, const char *data, uint64_t n, int n_threads, std::string &err)
+{
+    const uint64_t PART = 4ull << 20;
+    size_t parts = (size_t)std::max<uint64_t>(1, (n + PART - 1) / PART);
+    std::vector<std::vector<uint8_t>> comp(parts);
+    std::atomic<size_t> next(0);
+    std::atomic<bool> bad(false);
+    auto work = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= parts) return;
+            uint64_t a = i * PART, b = std::min(n, a + PART);
+            if (!gz_member(data + a, (size_t)(b - a), comp[i])) bad = true;
+        }
+    };
+    int nt = (int)std::min<size_t>((size_t)std::max(1, n_threads), parts);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    if (bad) {
+        err = "gzip compression failed";
+        return false;
+    }
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) {
+        err = "Cannot open file " + path;
+        return false;
+    }
+    for (auto &c : comp)
+        if (fwrite(c.data(), 1, c.size(), f) != c.size()) {
+            fclose(f);
+            err = "write error on " + path;
+            return false;
+        }
+    fclose(f);
+    return true;
+}

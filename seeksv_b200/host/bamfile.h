@@ -1,0 +1,36 @@
+// Host-side container handling: BGZF block scan + threaded inflate, BAM header parse, SAM text -> packed
+// BAM records. Replaces the parts of the reference's prebuilt libbam (sam/libbam.a: bgzf.o, bam.o,
+// bam_import.o, sam.o; headers sam/bgzf.h, sam/bam.h, sam/sam.h) that the hot path sits on.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+struct BgzfBlock {
+    uint64_t coff;  // offset of the deflate payload in the file image
+    uint32_t clen;  // deflate payload length
+    uint64_t uoff;  // offset in the uncompressed stream
+    uint32_t ulen;  // uncompressed length (ISIZE)
+};
+
+struct BamHeader {
+    std::string text;
+    std::vector<std::string> names;
+    std::vector<uint32_t> lengths;
+    uint64_t first_record = 0;  // byte offset of the first record in the uncompressed stream
+};
+
+bool read_file(const std::string &path, std::vector<uint8_t> &out, std::string &err);
+bool bgzf_scan(const uint8_t *file, uint64_t n, std::vector<BgzfBlock> &blocks, uint64_t &total, std::string &err);
+// inflate blocks [b0, b1) into dst (dst[0] corresponds to blocks[b0].uoff) with n_threads host threads
+bool bgzf_inflate_range(const uint8_t *file, const std::vector<BgzfBlock> &blocks, size_t b0, size_t b1, uint8_t *dst,
+                        int n_threads, std::string &err);
+bool bgzf_inflate_all(const uint8_t *file, uint64_t n, std::vector<uint8_t> &out, int n_threads, std::string &err);
+bool parse_bam_header(const uint8_t *data, uint64_t n, BamHeader &h, std::string &err);
+// SAM text (what samopen(fn, "r") reads) -> "BAM\1" header + packed records
+bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vector<uint8_t> &stream, std::string &err);
+// gzip/plain text file -> bytes (igzstream / ifstream of the reference, gzstream.h)
+bool read_text_maybe_gz(const std::string &path, std::string &out, std::string &err);
+// write `data` as a gzip file (ogzstream of the reference; multi-member, compressed by n_threads threads)
+bool write_gz(const std::string &path, const char *data, uint64_t n, int n_threads, std::string &err);

@@ -1,0 +1,481 @@
+// The seeksv command line (seeksv.cpp:26-457 of the reference) over the seeksv_b200 C ABI: same commands,
+// option strings, defaults, positional arguments, file names and exit codes. Everything that walks BAM
+// records happens on the GPU (include/seeksv_b200.h); this file only parses arguments, reads/writes the
+// text files and runs the per-junction bookkeeping (junction.cpp).
+#include <getopt.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <thread>
+
+#include "../../include/seeksv_b200.h"
+#include "bamfile.h"
+#include "junction.h"
+
+using namespace svb;
+
+namespace {
+const char *kVersion = "1.2.3";  // behaviour of the reference version this is a drop-in for (seeksv.cpp:12)
+
+int n_threads()
+{
+    const char *e = getenv("SEEKSV_B200_THREADS");
+    int n = e ? atoi(e) : 0;
+    return n > 0 ? n : (int)std::max(1u, std::thread::hardware_concurrency());
+}
+int device_index()
+{
+    const char *e = getenv("SEEKSV_B200_DEVICE");
+    return e ? atoi(e) : 0;
+}
+
+struct Gpu {  // context + error-to-exit plumbing: every failure is "message on stderr, exit status 1" as in the reference
+    svb_ctx *ctx = nullptr;
+    bool open()
+    {
+        if (svb_ctx_create(device_index(), &ctx) != 0) {
+            std::cerr << "[seeksv_b200] " << svb_last_error(nullptr) << std::endl;
+            return false;
+        }
+        if (getenv("SEEKSV_B200_PROFILE")) svb_prof_enable(ctx, 1);
+        return true;
+    }
+    ~Gpu()
+    {
+        if (ctx && getenv("SEEKSV_B200_PROFILE")) {
+            const char *names[64];
+            double ms[64], bytes[64];
+            int64_t launches[64];
+            int n = svb_prof_read(ctx, 64, names, ms, launches, bytes);
+            for (int i = 0; i < n && i < 64; ++i)
+                fprintf(stderr, "[prof] %-24s %9.3f ms %6lld launches %8.1f GB/s\n", names[i], ms[i], (long long)launches[i],
+                        ms[i] > 0 ? bytes[i] / ms[i] / 1e6 : 0.0);
+        }
+        svb_ctx_destroy(ctx);
+    }
+};
+
+void usage_top()
+{
+    std::cerr << "Program: seeksv (a tool for structural variation detection and virus integration detection)" << '\n'
+              << "Version: " << kVersion << " (seeksv_b200: B200-native hot path)\n"
+              << "Contact: Kunlong Qiu(290832867@qq.com)\n\n"
+              << "Usage: seeksv <command> [options]\n\n"
+              << "Command: getclip\tget soft-clipped reads\n"
+              << "         getsv  \tget final sv\n"
+              << "         somatic\tget somatic sv" << std::endl;
+}
+
+void usage_cmd(const char *prog, const char *command, int i)
+{
+    switch (i) {
+    case 0:
+        std::cerr << "Usage: " << prog << " " << command << " [options] <input.sorted.bam>\n\n"
+                  << "Options: -t <double>           Threshold of match rate while combining two soft-clipped reads [0.9]\n"
+                  << "         -q <int>              Minimum mapping quality of soft-clipped reads [1]\n"
+                  << "         -s                    Save the low quality sequence clipped before alignment by bwa.\n"
+                  << "         -o <string>           Prefix of output files [output]" << std::endl;
+        break;
+    case 1:
+        std::cerr << "Usage: " << prog << " " << command
+                  << " [options] <input clipped sequence bam> <input orignal sorted bam> <soft-clipped reads file(*clip.gz)> <output SVs> "
+                     "<output unmaped clipped sequence fastq>\n"
+                  << "Options: -F <FILE>             Samfile/Bamfile of connected readthrough reads (not supported by seeksv_b200)\n"
+                  << "         -t <double>           Threshold of match rate while combining two soft-clipped reads [0.9]\n"
+                  << "         -l <int>              Maximum search length to find microhomology[50]\n"
+                  << "         -q <int>              Minimum mapping quality of discordant read pair [20]\n"
+                  << "         -Q <int>              Minimum mapping quality of clipped sequences [1]\n"
+                  << "         -w <int>              Minimum mapping quality of connected  readthrough reads [1]\n"
+                  << "         -n <int>              Number of segment(read pairs) used to calculate insert size default [5000000], if you "
+                     "donot want to use abnormal read pairs to call sv, set this parameter to 0.\n"
+                  << "         -b <int>              Minimum number of soft clipping read,it's the sum of left clipped reads and right "
+                     "clipped reads [3]\n"
+                  << "         -d <int>              Minimum distance between the clipped sequence position and the aligned sequence "
+                     "position [50]\n"
+                  << "         -D                    Do not calculate depth of the breakpoints and their ajacency regions\n"
+                  << "         -e <int>              Minimum number of read pairs which support the junction [0]\n"
+                  << "         -f <int>              Minimun mutation frequency(left_pos_clip_percentage >= 0.1 or "
+                     "right_pos_clip_percentage >= 0.1) [0.1].\n"
+                  << "                               If you set -D, this value is invalid and set to [0].\n"
+                  << "         -T <int>              Maximum length of microhomology, SV with microhomology length longer than [50] will "
+                     "be filtered\n"
+                  << "         -m <int>              Minimum length of up_seq or down_seq near the breakpoint when abnormal_read_pair_no "
+                     "== 0 [30]\n"
+                  << "         -i <int>              Maximum indel number of up_seq or down_seq near the breakpoint when "
+                     "abnormal_read_pair_no == 0 [1]\n"
+                  << "         -L <int>              Calculate average depth of default [200] bp upstream or downstream of the breakpoints\n"
+                  << std::endl;
+        break;
+    case 2:
+        std::cerr << "Usage: " << prog << " " << command
+                  << " [options] <input normal original bam> <input normal soft-clipped reads file(*.clip.gz)> <input tumor SV file> <output "
+                     "somatic SV file>\n\n"
+                  << "         -t <int>              Threshold of match rate while comparing two soft-clipped reads [0.9]\n"
+                  << "         -q <int>              Minimum mapping quality of discordant read pair [20]\n"
+                  << "         -l <int>              Maximum search length to find microhomology [30]\n"
+                  << "         -m <int>              Minimum length of the clipped sequence  in normal [10]\n"
+                  << "         -n <int>              Number of segment(read pairs) used to calculate insert size default [5000000], if you "
+                     "donot want to use abnormal read pairs to call sv, set this parameter to 0."
+                  << std::endl;
+        break;
+    }
+}
+
+int fail(const std::string &msg)
+{
+    std::cerr << msg << std::endl;
+    return 1;
+}
+
+// ---- getclip: CallGetclip (seeksv.cpp:128-155) + InputBamOutputReads (clip_reads.h:363-484) ---------------------
+int cmd_getclip(int argc, char **argv)
+{
+    svb_getclip_params prm = {0.9, 1, 0, 0};
+    std::string prefix = "output";
+    int c;
+    optind = 1;
+    while ((c = getopt(argc, argv, "t:q:o:s")) >= 0) {
+        switch (c) {
+        case 't': prm.match_rate = atof(optarg); break;
+        case 'q': prm.min_mapq = atoi(optarg); break;
+        case 's': prm.save_low_quality = 1; break;
+        case 'o': prefix = optarg; break;
+        }
+    }
+    if (argc != optind + 1) {
+        usage_cmd(argv[0], argc > 1 ? argv[1] : "", 0);
+        return 1;
+    }
+    std::string bamfile = argv[optind];
+    Gpu g;
+    if (!g.open()) return 1;
+    svb_bam *bam = nullptr;
+    if (svb_bam_open(g.ctx, bamfile.c_str(), n_threads(), &bam) != 0) {
+        std::cerr << "[main_samview] fail to open file for reading." << std::endl;
+        return fail(std::string("[seeksv_b200] ") + svb_last_error(g.ctx));
+    }
+    svb_clusters *cl = nullptr;
+    int rc = svb_getclip(g.ctx, bam, &prm, &cl);
+    if (rc != 0) {
+        svb_bam_free(bam);
+        return fail(std::string("[seeksv_b200] ") + svb_last_error(g.ctx));
+    }
+    const char *ext[4] = {".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz"};
+    int status = 0;
+    for (int i = 0; i < 4 && status == 0; ++i) {
+        const char *data;
+        uint64_t len;
+        svb_clusters_text(cl, i, &data, &len);
+        std::string err;
+        if (!write_gz(prefix + ext[i], data, len, n_threads(), err)) status = fail(err);
+    }
+    std::cerr << "[GetSClipReads] finished!" << std::endl;
+    svb_clusters_free(cl);
+    svb_bam_free(bam);
+    return status;
+}
+
+// clip.bam (BGZF) or SAM text -> alignment list + reference names
+bool load_alignments(const std::string &path, std::vector<Alignment> &alns, std::vector<std::string> &names, std::string &err)
+{
+    std::vector<uint8_t> file, stream;
+    if (!read_file(path, file, err)) return false;
+    BamHeader h;
+    if (path.size() >= 4 && path.rfind(".bam") == path.size() - 4) {
+        if (!bgzf_inflate_all(file.data(), file.size(), stream, n_threads(), err)) return false;
+        if (!parse_bam_header(stream.data(), stream.size(), h, err)) return false;
+    } else if (!sam_to_bam_stream(file, h, stream, err))
+        return false;
+    names = h.names;
+    if (!parse_alignments(stream, h.first_record, alns)) {
+        err = "corrupt alignment records in " + path;
+        return false;
+    }
+    return true;
+}
+
+bool insert_size(Gpu &g, svb_bam *bam, const std::string &file, int min_mapq, int pairs_used, int &mean, int &dev)
+{
+    // CalculateInsertsizeDeviation, cluster.cpp:15-83: integer mean, (int)sqrt of the double mean square
+    int64_t st[4];
+    if (svb_insert_stats(g.ctx, bam, min_mapq, pairs_used, st) != 0) return false;
+    if (st[0] == 0) return true;  // the reference returns early and leaves both at 0
+    mean = (int)st[2];
+    dev = (int)sqrt((double)st[3] / (double)(int)st[0]);
+    std::cerr << "Bam/sam " << file << "    Mean insert size : " << mean << "\n"
+              << "Mean deviation: " << dev << std::endl;
+    return true;
+}
+
+void to_device_junction(const JunctionKey &k, svb_bam *bam, svb_junction &j)
+{
+    auto tid_of = [&](const std::string &name) {
+        for (int32_t t = 0; t < svb_bam_n_ref(bam); ++t)
+            if (name == svb_bam_ref_name(bam, t)) return t;  // BamGetTid, cluster.cpp:219-229
+        return (int32_t)-1;
+    };
+    j.up_tid = tid_of(k.up_chr), j.down_tid = tid_of(k.down_chr);
+    j.up_pos = k.up_pos, j.down_pos = k.down_pos, j.up_strand = k.up_strand, j.down_strand = k.down_strand;
+    j.pad_[0] = j.pad_[1] = 0;
+}
+
+// ---- getsv: CallGetsv (seeksv.cpp:157-364) -----------------------------------------------------------------------
+int cmd_getsv(int argc, char **argv)
+{
+    std::string connect_bam, seed_file;
+    double frequency = 0.1;
+    int c, flank = 50, min_mapq = 20, pairs_used = 5000000, min_clip_sum = 3, min_distance = 50, max_micro = 50, times = 4, min_pairs = 0,
+           flank_len = 200, min_seq_len = 30, max_indel = 1;
+    bool with_depth = true;
+    optind = 1;
+    while ((c = getopt(argc, argv, "F:B:t:l:q:Q:w:n:a:b:d:e:m:i:R:f:T:L:rD")) >= 0) {
+        switch (c) {
+        case 'F': connect_bam = optarg; break;
+        case 'B': seed_file = optarg; break;
+        case 'l': flank = atoi(optarg); break;
+        case 'q': min_mapq = atoi(optarg); break;
+        case 'n': pairs_used = atoi(optarg); break;
+        case 'b': min_clip_sum = atoi(optarg); break;
+        case 'd': min_distance = atoi(optarg); break;
+        case 'e': min_pairs = atoi(optarg); break;
+        case 'm': min_seq_len = atoi(optarg); break;
+        case 'i': max_indel = atoi(optarg); break;
+        case 'D': with_depth = false; break;
+        case 'f': frequency = atof(optarg); break;
+        case 'T': max_micro = atoi(optarg); break;
+        case 'L': flank_len = atoi(optarg); break;
+        default: break;  // -t -Q -w -a -R -r are parsed and unused, as in the reference
+        }
+    }
+    if (argc != optind + 5 || flank > 90 || flank < 0 || min_seq_len < 0) {
+        usage_cmd(argv[0], argc > 1 ? argv[1] : "", 1);
+        return 1;
+    }
+    if (!connect_bam.empty() || !seed_file.empty())
+        return fail("[seeksv_b200] -F / -B (optional junction seeds, process_bwasw.cpp / getsv.cpp:1292) are outside the hot path and not implemented");
+    std::string clip_aln = argv[optind], original_bam = argv[optind + 1], clipfile = argv[optind + 2], sv_file = argv[optind + 3],
+                unmapped_file = argv[optind + 4];
+    std::string err, clip_text;
+    std::vector<Alignment> alns;
+    std::vector<std::string> aln_names;
+    if (!load_alignments(clip_aln, alns, aln_names, err)) {
+        std::cerr << "[main_samview] fail to open file for reading." << std::endl;
+        return fail(err);
+    }
+    if (!read_text_maybe_gz(clipfile, clip_text, err)) return fail(err);
+    JunctionMap jm;
+    join_clips_with_alignments(parse_clip_text(clip_text), aln_names, alns, jm);
+    std::cerr << "'InputSoftInfoStoreBreakpoint' finished" << std::endl;
+    merge_junctions(jm, flank);
+
+    Gpu g;
+    svb_bam *bam = nullptr;
+    auto need_bam = [&]() -> bool {
+        if (bam) return true;
+        if (!g.ctx && !g.open()) return false;
+        if (svb_bam_open(g.ctx, original_bam.c_str(), n_threads(), &bam) != 0) {
+            std::cerr << "[main_samview] fail to open file for reading." << std::endl;
+            std::cerr << "[seeksv_b200] " << svb_last_error(g.ctx) << std::endl;
+            return false;
+        }
+        return true;
+    };
+    int mean = 0, dev = 0;
+    if (pairs_used >= 100000) {
+        if (!need_bam()) return 1;
+        if (!insert_size(g, bam, original_bam, min_mapq, pairs_used, mean, dev)) return fail(svb_last_error(g.ctx));
+        std::cerr << "'CalculateInsertsizeDeviation' finished" << std::endl;
+        std::vector<svb_junction> dj(jm.size());
+        std::vector<int32_t> counts(jm.size(), 0);
+        size_t i = 0;
+        for (auto &kv : jm) to_device_junction(kv.first, bam, dj[i++]);
+        svb_pair_params pp = {min_mapq, mean, dev, times};
+        if (svb_discordant_support(g.ctx, bam, dj.data(), dj.size(), &pp, counts.data()) != 0) return fail(svb_last_error(g.ctx));
+        i = 0;
+        for (auto &kv : jm) kv.second.pairs = counts[i++];
+        std::cerr << "'FindDiscordantReadPairs' finished" << std::endl;
+    } else
+        min_pairs = 0;
+
+    PosDepth pos2depth;
+    RangeDepth range2depth;
+    WindowMap begin2end;
+    JunctionRanges j2r;
+    if (with_depth) {
+        collect_breaks(jm, flank_len, pos2depth, range2depth, j2r);
+        merge_ranges(range2depth, begin2end);
+        std::cerr << "'MergeOverlap' finished" << std::endl;
+        if (!begin2end.empty()) {
+            if (!need_bam()) return 1;
+            // windows as the device sees them: (tid, begin clamped to >= 1, end); a window whose chromosome is not in
+            // the BAM or that is empty after clamping has no covered position
+            struct Win {
+                const std::string *chr;
+                int begin, end;
+                uint64_t off;
+            };
+            std::vector<svb_window> dw;
+            std::vector<Win> hw;
+            uint64_t total = 0;
+            std::map<std::string, int32_t> tid_of;
+            for (int32_t t = 0; t < svb_bam_n_ref(bam); ++t) tid_of.insert(std::make_pair(std::string(svb_bam_ref_name(bam, t)), t));
+            std::vector<std::pair<svb_window, const std::string *>> tmp;
+            for (auto &kv : begin2end) {
+                auto it = tid_of.find(kv.first.first);
+                if (it == tid_of.end()) continue;
+                int b = std::max(kv.first.second, 1), e = std::min<int64_t>(kv.second, (int64_t)svb_bam_ref_len(bam, it->second) + 1);
+                if (e < b) continue;
+                tmp.push_back(std::make_pair(svb_window{it->second, b, e}, &kv.first.first));
+            }
+            // begin2end is ordered by chromosome NAME; the device wants (tid, begin). Merged windows of one chromosome are
+            // disjoint except for the degenerate wrapped ones, which clamp to [1, end]: merge overlaps defensively.
+            std::sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) {
+                return a.first.tid != b.first.tid ? a.first.tid < b.first.tid : a.first.begin < b.first.begin;
+            });
+            for (auto &w : tmp) {
+                if (!dw.empty() && dw.back().tid == w.first.tid && w.first.begin <= dw.back().end) {
+                    dw.back().end = std::max(dw.back().end, w.first.end);
+                    hw.back().end = dw.back().end;
+                } else {
+                    dw.push_back(w.first);
+                    hw.push_back(Win{w.second, w.first.begin, w.first.end, 0});
+                }
+            }
+            for (size_t i = 0; i < dw.size(); ++i) {
+                hw[i].off = total;
+                total += (uint64_t)(dw[i].end - dw[i].begin + 1);
+            }
+            std::vector<int32_t> depth(total);
+            if (svb_window_depth(g.ctx, bam, dw.data(), dw.size(), min_mapq, depth.data()) != 0) return fail(svb_last_error(g.ctx));
+            // main_depth visits covered positions in BAM order (tid, pos); the range sums are commutative and every
+            // position is written once, so the order of the walk does not matter - but keep it anyway
+            for (size_t i = 0; i < hw.size(); ++i)
+                for (int p = hw[i].begin; p <= hw[i].end; ++p) {
+                    int d = depth[hw[i].off + (uint64_t)(p - hw[i].begin)];
+                    if (d > 0) account_position(*hw[i].chr, p, d, begin2end, pos2depth, range2depth);
+                }
+        }
+        std::cerr << "'main_depth' finished" << std::endl;
+    } else
+        frequency = 0;
+
+    std::string body, filtered, log;
+    OutputFilters f;
+    f.min_clip_sum = min_clip_sum, f.min_pairs = min_pairs, f.frequency = frequency, f.min_distance = min_distance;
+    f.max_micro = max_micro, f.min_seq_len = min_seq_len, f.max_indel = max_indel;
+    write_breakpoints(jm, pos2depth, range2depth, j2r, f, body, filtered, log);
+    std::cerr << log;
+    std::ofstream fout(sv_file.c_str());
+    if (!fout) return fail("Cannot open file " + sv_file);
+    fout << kSvHeader << body;
+    fout.close();
+    std::cout << filtered << std::flush;
+    // OutputOneendUnmapBreakpoint (getsv.cpp:1252-1288) never has anything to write (quirk Q7): the file is created empty
+    std::ofstream fu(unmapped_file.c_str());
+    if (!fu) return fail("Cannot open file " + unmapped_file);
+    fu.close();
+    if (bam) svb_bam_free(bam);
+    return 0;
+}
+
+// ---- somatic: CallSomatic (seeksv.cpp:366-410) ---------------------------------------------------------------------
+int cmd_somatic(int argc, char **argv)
+{
+    int offset = 30, c, min_len = 10, pairs_used = 5000000, min_mapq = 20;
+    double rate = 0.9;
+    optind = 1;
+    while ((c = getopt(argc, argv, "t:q:l:m:n:")) >= 0) {
+        switch (c) {
+        case 't': rate = atof(optarg); break;
+        case 'q': min_mapq = atoi(optarg); break;
+        case 'l': offset = atoi(optarg); break;
+        case 'm': min_len = atoi(optarg); break;
+        case 'n': pairs_used = atoi(optarg); break;
+        }
+    }
+    if (argc != optind + 4) {
+        std::cerr << argc << '\t' << optind << std::endl;
+        usage_cmd(argv[0], argc > 1 ? argv[1] : "", 2);
+        return 1;
+    }
+    if (offset >= 90 || offset < 0) {
+        std::cerr << "Error: value of -l must in range [0, 90) " << std::endl;
+        usage_cmd(argv[0], argc > 1 ? argv[1] : "", 2);
+        return 1;
+    }
+    std::string normal_bam = argv[optind], clipfile = argv[optind + 1], tumor_file = argv[optind + 2], out_file = argv[optind + 3];
+    std::string clip_text, tumor_text, err;
+    if (!read_text_maybe_gz(clipfile, clip_text, err)) return fail(err);
+    Gpu g;
+    if (!g.open()) return 1;
+    svb_bam *bam = nullptr;
+    if (svb_bam_open(g.ctx, normal_bam.c_str(), n_threads(), &bam) != 0) {
+        std::cerr << "[main_samview] fail to open file for reading." << std::endl;
+        return fail(std::string("[seeksv_b200] ") + svb_last_error(g.ctx));
+    }
+    int mean = 0, dev = 0;
+    if (pairs_used >= 100000 && !insert_size(g, bam, normal_bam, min_mapq, pairs_used, mean, dev)) return fail(svb_last_error(g.ctx));
+    std::ofstream fout(out_file.c_str());
+    if (!fout) return fail("Error: Cannot open output file " + out_file);
+    if (!read_text_maybe_gz(tumor_file, tumor_text, err)) return fail("Error: Cannot open output file " + tumor_file);
+    std::vector<SomaticRow> rows;
+    std::string log;
+    somatic_rows(clip_text, tumor_text, rate, offset, min_len, mean, rows, log);
+    std::cerr << log;
+    std::vector<svb_junction> dj;
+    std::vector<size_t> who;
+    for (size_t i = 0; i < rows.size(); ++i)
+        if (!rows[i].is_header && rows[i].query_pairs) {
+            svb_junction j;
+            to_device_junction(rows[i].key, bam, j);
+            dj.push_back(j);
+            who.push_back(i);
+        }
+    std::vector<int32_t> counts(dj.size(), 0), per_row(rows.size(), 0);
+    svb_pair_params pp = {min_mapq, mean, dev, 4};
+    if (!dj.empty() && svb_discordant_support(g.ctx, bam, dj.data(), dj.size(), &pp, counts.data()) != 0) return fail(svb_last_error(g.ctx));
+    for (size_t k = 0; k < who.size(); ++k) per_row[who[k]] = counts[k];
+    for (size_t i = 0; i < rows.size(); ++i) {
+        if (rows[i].is_header) fout << rows[i].prefix;
+        else fout << rows[i].prefix << '\t' << rows[i].normal_left << '\t' << rows[i].normal_right << '\t' << per_row[i] << '\n';
+    }
+    fout.close();
+    svb_bam_free(bam);
+    return 0;
+}
+}  // namespace
+
+extern "C" int svb_main(int argc, char **argv)
+{
+    // main + SelectStep, seeksv.cpp:26-58,444-457
+    if (argc == 1) {
+        usage_top();
+        return 1;
+    }
+    const char *cmds[4] = {"getclip", "getsv", "somatic", "cluster"};
+    int i = 0;
+    for (; i < 4; ++i)
+        if (strcmp(cmds[i], argv[1]) == 0) break;
+    if (i == 4) {
+        std::cerr << "[seeksv] unrecognized command '" << argv[1] << "'" << std::endl;
+        return 1;
+    }
+    if (argc == 2) {
+        usage_cmd("seeksv", argv[1], i);
+        return 1;
+    }
+    switch (i) {
+    case 0: return cmd_getclip(argc - 1, argv + 1);
+    case 1: return cmd_getsv(argc - 1, argv + 1);
+    case 2: return cmd_somatic(argc - 1, argv + 1);
+    default: return 0;  // "cluster" is recognised and does nothing (its dispatch is commented out, seeksv.cpp:454)
+    }
+}

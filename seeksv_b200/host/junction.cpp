@@ -1,0 +1,723 @@
+#include "junction.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+
+namespace svb {
+
+// ---- small helpers ---------------------------------------------------------------------------------------
+bool JunctionKey::operator<(const JunctionKey &o) const
+{
+    // getsv.h:187-225: chromosomes, then strands, then positions
+    if (int c = up_chr.compare(o.up_chr)) return c < 0;
+    if (int c = down_chr.compare(o.down_chr)) return c < 0;
+    if (up_strand != o.up_strand) return up_strand < o.up_strand;
+    if (down_strand != o.down_strand) return down_strand < o.down_strand;
+    if (up_pos != o.up_pos) return up_pos < o.up_pos;
+    return down_pos < o.down_pos;
+}
+
+bool ChrRange::operator<(const ChrRange &o) const
+{
+    if (int c = chr.compare(o.chr)) return c < 0;
+    if (begin != o.begin) return begin < o.begin;
+    return end < o.end;
+}
+
+CigarVec cigar_from_text(const std::string &s)  // ChangeCigarType, getsv.cpp:433-451
+{
+    CigarVec v;
+    int n = 0;
+    for (char ch : s) {
+        if (isdigit((unsigned char)ch)) n = n * 10 + (ch - '0');
+        else {
+            v.emplace_back(n, ch);
+            n = 0;
+        }
+    }
+    return v;
+}
+
+std::string cigar_to_text(const CigarVec &v, int left_clip, int right_clip)  // DisplayCigarVector, clip_reads.h:489-505
+{
+    std::string s;
+    if (left_clip > 0) s += std::to_string(left_clip) + "S";
+    for (auto &p : v) s += std::to_string(p.first) + p.second;
+    if (right_clip > 0) s += std::to_string(right_clip) + "S";
+    return s;
+}
+
+std::string reverse_complement(const std::string &s)  // GetReverseComplementSeq, clip_reads.cpp:414-466
+{
+    std::string r(s.rbegin(), s.rend());
+    for (char &c : r) {
+        switch (c) {
+        case 'A': case 'a': c = 'T'; break;
+        case 'T': case 't': c = 'A'; break;
+        case 'C': case 'c': c = 'G'; break;
+        case 'G': case 'g': c = 'C'; break;
+        case 'n': c = 'N'; break;
+        default: break;
+        }
+    }
+    return r;
+}
+
+double match_rate_from_end(const std::string &a, const std::string &b)  // CompareStringEndFirst, clip_reads.cpp:194-205
+{
+    int la = (int)a.size(), lb = (int)b.size(), n = std::min(la, lb), m = 0;
+    for (int i = 0; i < n; ++i) m += a[la - 1 - i] == b[lb - 1 - i];
+    return (double)m / n;  // n == 0 -> NaN, which fails every >= test
+}
+
+double match_rate_from_begin(const std::string &a, const std::string &b)  // CompareStringBeginFirst, clip_reads.cpp:207-217
+{
+    int n = (int)std::min(a.size(), b.size()), m = 0;
+    for (int i = 0; i < n; ++i) m += a[i] == b[i];
+    return (double)m / n;
+}
+
+std::string format_double(double x)  // ostream << double, precision 6
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%g", x);
+    return buf;
+}
+
+static std::vector<std::string> split_ws(const char *b, const char *e)
+{
+    std::vector<std::string> t;
+    while (b < e) {
+        while (b < e && isspace((unsigned char)*b)) ++b;
+        const char *s = b;
+        while (b < e && !isspace((unsigned char)*b)) ++b;
+        if (b > s) t.emplace_back(s, b);
+    }
+    return t;
+}
+
+std::vector<ClipLine> parse_clip_text(const std::string &text)
+{
+    // `fin >> chr >> pos >> orientation >> cigar >> ... >> support; getline(...)` (getsv.h:453-456)
+    std::vector<ClipLine> out;
+    const char *p = text.data(), *e = p + text.size();
+    while (p < e) {
+        const char *nl = (const char *)memchr(p, '\n', e - p);
+        if (!nl) nl = e;
+        std::vector<std::string> t = split_ws(p, nl);
+        if (t.size() >= 9) {
+            ClipLine c;
+            c.chr = t[0], c.pos = atoi(t[1].c_str()), c.side = t[2][0], c.cigar = t[3];
+            c.aligned_seq = t[4], c.aligned_qual = t[5], c.clipped_seq = t[6], c.clipped_qual = t[7], c.support = atoi(t[8].c_str());
+            out.push_back(std::move(c));
+        }
+        p = nl < e ? nl + 1 : e;
+    }
+    return out;
+}
+
+static inline uint32_t rd32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+bool parse_alignments(const std::vector<uint8_t> &s, uint64_t o, std::vector<Alignment> &out)
+{
+    while (o + 36 <= s.size()) {
+        uint32_t bs = rd32(&s[o]);
+        if (bs < 32 || o + 4 + bs > s.size()) return false;
+        Alignment a;
+        a.tid = (int32_t)rd32(&s[o + 4]), a.pos = (int32_t)rd32(&s[o + 8]);
+        uint32_t w = rd32(&s[o + 12]), w2 = rd32(&s[o + 16]);
+        uint32_t lq = w & 0xff, nc = w2 & 0xffff;
+        a.mapq = (w >> 8) & 0xff, a.flag = w2 >> 16;
+        a.qname.assign((const char *)&s[o + 36], strnlen((const char *)&s[o + 36], lq));
+        a.cigar.resize(nc);
+        for (uint32_t j = 0; j < nc; ++j) a.cigar[j] = rd32(&s[o + 36 + lq + 4 * j]);
+        out.push_back(std::move(a));
+        o += 4 + bs;
+    }
+    return o == s.size();
+}
+
+// ---- join: clip.gz lines x realigned clipped sequences -> junctions -------------------------------------------
+namespace {
+struct AlignInfo {  // getsv.h:24-45
+    std::string chr;
+    int pos = -1, len = -1, lclip = 0, rclip = 0;
+    char strand = '*', type = 'n';
+    CigarVec cigar;
+};
+
+const char *kOps = "MIDNSHP=X";
+
+AlignInfo align_info(const std::vector<std::string> &names, const Alignment &b)  // GetAlignInfo, getsv.cpp:25-71
+{
+    AlignInfo a;
+    if (b.flag & 4) {
+        a.chr = "Exogenous";
+        return a;
+    }
+    a.type = ((b.flag & 256) || b.mapq == 0) ? 'r' : 'u';
+    if (!b.cigar.empty()) {
+        uint32_t f = b.cigar.front(), l = b.cigar.back();
+        if ((f & 15) == 4 || (f & 15) == 5) a.lclip = (int)(f >> 4);
+        if ((l & 15) == 4 || (l & 15) == 5) a.rclip = (int)(l >> 4);
+    }
+    a.len = 0;
+    for (uint32_t c : b.cigar) {  // GenerateCigar, clip_reads.cpp:309-329
+        uint32_t op = c & 15;
+        if (op == 4 || op == 5) continue;
+        if (op == 0 || op == 2 || op == 7 || op == 3) a.len += (int)(c >> 4);
+        a.cigar.emplace_back((int)(c >> 4), kOps[op < 9 ? op : 0]);
+    }
+    a.strand = (b.flag & 16) ? '-' : '+';
+    a.chr = (b.tid >= 0 && (size_t)b.tid < names.size()) ? names[b.tid] : std::string();
+    a.pos = b.pos + 1;
+    return a;
+}
+
+bool hard_clipped(const Alignment &b)  // IsHardClip, clip_reads.cpp:247-257
+{
+    return !b.cigar.empty() && ((b.cigar.front() & 15) == 5 || (b.cigar.back() & 15) == 5);
+}
+
+SeqInfo make_seq(const std::string &s, const CigarVec &c, int lc, int rc, int sup, int uniq)
+{
+    SeqInfo x;
+    x.seq = s, x.cigar = c, x.lclip = lc, x.rclip = rc, x.support = sup, x.uniq = uniq;
+    return x;
+}
+
+JunctionKey make_key(const std::string &uc, int up, char us, const std::string &dc, int dp, char ds)
+{
+    JunctionKey k;
+    k.up_chr = uc, k.up_pos = up, k.up_strand = us, k.down_chr = dc, k.down_pos = dp, k.down_strand = ds;
+    return k;
+}
+
+// GetJunction, getsv.cpp:1705-1845
+void add_junction(const ClipLine &line, AlignInfo &ai, JunctionMap &jm)
+{
+    int uniq;
+    if (ai.type == 'u') uniq = 2;
+    else if (ai.type == 'r') uniq = 1;
+    else return;  // 'n': nothing is stored (quirk Q7)
+    CigarVec cig = cigar_from_text(line.cigar);
+    const std::string &chr = line.chr;
+    const int pos = line.pos, sup = line.support;
+    JunctionKey key;
+    SeqInfo up, down;
+    auto rev = [](CigarVec v) {
+        std::reverse(v.begin(), v.end());
+        return v;
+    };
+    if (ai.strand == '+') {
+        if (line.side == '5') {
+            key = make_key(ai.chr, ai.pos + ai.len - 1, '+', chr, pos, '+');
+            up = make_seq(line.clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
+            down = make_seq(line.aligned_seq, cig, 0, 0, sup, 0);
+        } else if (line.side == '3') {
+            key = make_key(chr, pos, '+', ai.chr, ai.pos, '+');
+            up = make_seq(line.aligned_seq, cig, 0, 0, sup, 0);
+            down = make_seq(line.clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
+        } else
+            return;
+    } else if (ai.strand == '-') {
+        if (line.side == '5') {
+            if (std::make_pair(ai.chr, ai.pos) <= std::make_pair(chr, pos)) {
+                key = make_key(ai.chr, ai.pos, '-', chr, pos, '+');
+                up = make_seq(line.clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
+                down = make_seq(line.aligned_seq, cig, 0, 0, sup, 0);
+            } else {
+                key = make_key(chr, pos, '-', ai.chr, ai.pos, '+');
+                ai.cigar = rev(ai.cigar);  // the reference reverses the stored alignment in place
+                up = make_seq(reverse_complement(line.aligned_seq), rev(cig), 0, 0, sup, 0);
+                down = make_seq(reverse_complement(line.clipped_seq), ai.cigar, ai.rclip, ai.lclip, 0, uniq);
+            }
+        } else if (line.side == '3') {
+            int aend = ai.pos + ai.len - 1;
+            if (std::make_pair(chr, pos) <= std::make_pair(ai.chr, aend)) {
+                key = make_key(chr, pos, '+', ai.chr, aend, '-');
+                up = make_seq(line.aligned_seq, cig, 0, 0, sup, 0);
+                down = make_seq(line.clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
+            } else {
+                key = make_key(ai.chr, aend, '+', chr, pos, '-');
+                ai.cigar = rev(ai.cigar);
+                up = make_seq(reverse_complement(line.clipped_seq), ai.cigar, ai.rclip, ai.lclip, 0, uniq);
+                down = make_seq(reverse_complement(line.aligned_seq), rev(cig), 0, 0, sup, 0);
+            }
+        } else
+            return;
+    } else
+        return;
+    auto range = jm.equal_range(key);
+    bool fresh = true;
+    for (auto it = range.first; it != range.second; ++it) {
+        JunctionInfo &o = it->second;
+        // clip-length signature (getsv.cpp:1817); every matching entry accumulates (quirk Q8)
+        if (o.up.rclip == down.lclip && o.down.lclip == up.rclip) {
+            o.up.uniq = std::max(o.up.uniq, up.uniq);
+            o.down.uniq = std::max(o.down.uniq, down.uniq);
+            o.up.support += up.support;
+            o.down.support += down.support;
+            if (o.micro == -1) o.micro = it->first.up_pos - key.up_pos;
+            fresh = false;
+        }
+    }
+    if (fresh) {
+        JunctionInfo o;
+        o.up = up, o.down = down;
+        jm.insert(std::make_pair(key, o));
+    }
+}
+}  // namespace
+
+// InputSoftInfoStoreBreakpoint<T>, getsv.h:423-541, with its quirks: only the first line of a run of
+// equal clipped sequences is crossed with the alignments, the first alignment of a new run is filed under the
+// previous run's sequence, and the trailing loop does not skip hard-clipped alignments.
+void join_clips_with_alignments(const std::vector<ClipLine> &lines, const std::vector<std::string> &names,
+                                const std::vector<Alignment> &alns, JunctionMap &jm)
+{
+    typedef std::pair<std::string, std::pair<std::string, int>> AlnKey;
+    std::map<AlnKey, AlignInfo> found;
+    const ClipLine *head = nullptr;  // first line of the current run
+    std::string current;
+    size_t ai = 0;
+    auto cross = [&]() {
+        if (head)
+            for (auto &kv : found) add_junction(*head, kv.second, jm);
+    };
+    for (const ClipLine &line : lines) {
+        if (current.empty() || current == line.clipped_seq) {
+            if (!head) head = &line;
+            current = line.clipped_seq;
+            continue;
+        }
+        while (ai < alns.size()) {
+            const Alignment &b = alns[ai++];
+            if (hard_clipped(b)) continue;
+            AlignInfo info = align_info(names, b);
+            AlnKey k(current, std::make_pair(info.chr, info.pos));
+            if (current == b.qname) {
+                found.insert(std::make_pair(k, info));
+            } else {
+                cross();
+                found.clear();
+                found.insert(std::make_pair(k, info));
+                head = &line;
+                current = line.clipped_seq;
+                break;
+            }
+        }
+        // alignment stream exhausted: this line is dropped and the state stays as it is
+    }
+    while (ai < alns.size()) {
+        const Alignment &b = alns[ai++];
+        if (current != b.qname) break;
+        AlignInfo info = align_info(names, b);
+        found.insert(std::make_pair(AlnKey(current, std::make_pair(info.chr, info.pos)), info));
+    }
+    cross();
+}
+
+// MergeJunction, getsv.cpp:1325-1482
+void merge_junctions(JunctionMap &jm, int reach)
+{
+    auto it = jm.begin();
+    while (it != jm.end()) {
+        JunctionInfo &a = it->second;
+        const JunctionKey &ka = it->first;
+        if (a.up.rclip > 0 || a.up.lclip > 0) {
+            ++it;
+            continue;
+        }
+        auto jt = std::next(it);
+        bool absorbed = false;  // `it` was folded into a later entry
+        while (jt != jm.end() && ka.up_chr == jt->first.up_chr && ka.down_chr == jt->first.down_chr &&
+               ka.up_strand == jt->first.up_strand && ka.down_strand == jt->first.down_strand &&
+               jt->first.up_pos - ka.up_pos <= reach) {
+            JunctionInfo &b = jt->second;
+            const JunctionKey &kb = jt->first;
+            if (!(std::abs(kb.down_pos - ka.down_pos) <= reach && b.down.lclip == 0)) {
+                ++jt;
+                continue;
+            }
+            std::string u1, d1, u2, d2;
+            if (a.up.cigar.size() == 1 && b.up.cigar.size() == 1) {
+                int mh = kb.up_pos - ka.up_pos;
+                if ((ka.up_strand == '+' && b.up.seq.size() < (size_t)(mh + 5)) || (ka.up_strand == '-' && a.up.seq.size() < (size_t)(mh + 5))) {
+                    ++jt;
+                    continue;
+                }
+                if (ka.up_strand == '+') {
+                    u1 = a.up.seq, d1 = a.down.seq;
+                    u2 = b.up.seq.substr(0, b.up.seq.size() - mh);
+                    d2 = b.up.seq.substr(b.up.seq.size() - mh) + b.down.seq;
+                } else {
+                    u1 = a.up.seq.substr(0, a.up.seq.size() - mh);
+                    d1 = a.up.seq.substr(a.up.seq.size() - mh) + a.down.seq;
+                    u2 = b.up.seq, d2 = b.down.seq;
+                }
+            } else if (a.down.cigar.size() == 1 && b.down.cigar.size() == 1) {
+                int mh = std::abs(kb.down_pos - ka.down_pos);
+                if ((ka.up_strand == '+' && a.down.seq.size() < (size_t)(mh + 5)) || (ka.up_strand == '-' && b.down.seq.size() < (size_t)(mh + 5))) {
+                    ++jt;
+                    continue;
+                }
+                if (ka.up_strand == '+') {
+                    d1 = a.down.seq.substr(mh), d2 = b.down.seq;
+                    u1 = a.up.seq + a.down.seq.substr(0, mh), u2 = b.up.seq;
+                } else {
+                    d1 = a.down.seq, d2 = b.down.seq.substr(mh);
+                    u1 = a.up.seq, u2 = b.up.seq + b.down.seq.substr(0, mh);
+                }
+            }
+            if (!(match_rate_from_end(u1, u2) >= 0.85 && match_rate_from_begin(d1, d2) >= 0.85)) {
+                ++jt;
+                continue;
+            }
+            a.up.uniq = std::max(a.up.uniq, b.up.uniq);
+            a.down.uniq = std::max(a.down.uniq, b.down.uniq);
+            if (a.micro == -1 && b.micro == -1) {
+                a.up.support += b.up.support;
+                a.down.support += b.down.support;
+                if ((a.up.support != 0 && b.down.support != 0) || (a.down.support != 0 && b.up.support != 0))
+                    a.micro = kb.up_pos - ka.up_pos;
+                jt = jm.erase(jt);
+            } else if (a.micro != -1 && b.micro == -1) {
+                a.up.support += b.up.support;
+                a.down.support += b.down.support;
+                jt = jm.erase(jt);
+            } else if (a.micro == -1 && b.micro != -1) {
+                b.up.support += a.up.support;
+                b.down.support += a.down.support;
+                absorbed = true;
+            } else {
+                if (a.up.support > b.up.support || a.down.support == b.down.support) {
+                    a.up.support += b.up.support;
+                    jt = jm.erase(jt);
+                } else if (a.up.support == b.up.support || a.down.support > b.down.support) {
+                    a.down.support += b.down.support;
+                    jt = jm.erase(jt);
+                } else if (b.up.support > a.up.support && a.down.support == b.down.support) {
+                    b.up.support += a.up.support;
+                    absorbed = true;
+                } else if (b.down.support > a.down.support && b.up.support == a.up.support) {
+                    b.down.support += a.down.support;
+                    absorbed = true;
+                } else
+                    ++jt;
+            }
+            if (absorbed) break;
+        }
+        if (absorbed) it = jm.erase(it);
+        else ++it;
+    }
+}
+
+// ---- depth bookkeeping ---------------------------------------------------------------------------------------------
+void collect_breaks(const JunctionMap &jm, int flank, PosDepth &pos2depth, RangeDepth &range2depth, JunctionRanges &j2r)
+{
+    // GetBreak, getsv.cpp:752-789 (unsigned arithmetic on purpose)
+    for (auto &kv : jm) {
+        const JunctionKey &k = kv.first;
+        pos2depth.insert(std::make_pair(std::make_pair(k.up_chr, k.up_pos), 0));
+        pos2depth.insert(std::make_pair(std::make_pair(k.down_chr, k.down_pos), 0));
+        int l = flank;
+        if (k.up_chr == k.down_chr && k.up_strand == k.down_strand) {
+            int d = std::abs(k.down_pos - 1 - k.up_pos);
+            if (d < flank) l = d;
+        }
+        FlankRanges fr;
+        fr.r[0] = ChrRange{k.up_chr, (unsigned)(k.up_pos - l + 1), (unsigned)k.up_pos};
+        fr.r[1] = ChrRange{k.up_chr, (unsigned)(k.up_pos + 1), (unsigned)(k.up_pos + l)};
+        fr.r[2] = ChrRange{k.down_chr, (unsigned)(k.down_pos - l), (unsigned)(k.down_pos - 1)};
+        fr.r[3] = ChrRange{k.down_chr, (unsigned)k.down_pos, (unsigned)(k.down_pos + l - 1)};
+        for (int i = 0; i < 4; ++i) range2depth.insert(std::make_pair(fr.r[i], 0ul));
+        j2r.insert(std::make_pair(k, fr));
+    }
+}
+
+void merge_ranges(const RangeDepth &range2depth, WindowMap &begin2end)
+{
+    // MergeOverlap, getsv.cpp:804-835
+    if (range2depth.empty()) return;  // (the reference stores one uninitialised window here; it is never matched)
+    std::string chr;
+    unsigned begin = 0, end = 0;
+    bool first = true;
+    for (auto &kv : range2depth) {
+        const ChrRange &r = kv.first;
+        if (first) {
+            chr = r.chr, begin = r.begin, end = r.end, first = false;
+        } else if (chr == r.chr && begin <= r.begin && end + 1 >= r.begin) {
+            if (r.end > end) end = r.end;
+        } else {
+            begin2end.insert(std::make_pair(std::make_pair(chr, (int)begin), (int)end));
+            chr = r.chr, begin = r.begin, end = r.end;
+        }
+    }
+    begin2end.insert(std::make_pair(std::make_pair(chr, (int)begin), (int)end));
+}
+
+void account_position(const std::string &chr, int p, int depth, const WindowMap &begin2end, PosDepth &pos2depth,
+                      RangeDepth &range2depth)
+{
+    // bam2depth.cpp:82-124 for pileup position pos = p - 1
+    auto w = begin2end.upper_bound(std::make_pair(chr, p));
+    if (w == begin2end.begin()) return;
+    --w;
+    if (w->first.first != chr || p > w->second) return;
+    auto r = range2depth.upper_bound(ChrRange{chr, (unsigned)(p + 1), (unsigned)(p + 1)});
+    if (r != range2depth.begin()) {
+        --r;
+        while (r != range2depth.begin()) {
+            if (r->first.chr != w->first.first || r->first.begin < (unsigned)w->first.second) break;
+            if ((unsigned)p <= r->first.end) r->second += depth;
+            --r;
+        }
+        if (r == range2depth.begin()) {
+            if (r->first.chr == w->first.first && r->first.begin >= (unsigned)w->first.second && (unsigned)p <= r->first.end)
+                r->second += depth;
+        }
+    }
+    auto q = pos2depth.find(std::make_pair(chr, p));
+    if (q != pos2depth.end()) q->second = depth;
+}
+
+// ---- output ------------------------------------------------------------------------------------------------------------
+const char *kSvHeader =
+    "@left_chr\tleft_pos\tleft_strand\tleft_clip_read_NO\tright_chr\tright_pos\tright_strand\tright_clip_read_NO\t"
+    "microhomology_length\tabnormal_readpair_NO\tsvtype\tleft_pos_depth\tright_pos_depth\taverage_depth_of_left_pos_5end\t"
+    "average_depth_of_left_pos_3end\taverage_depth_of_right_pos_5end\taverage_depth_of_right_pos_3end\t"
+    "left_pos_clip_percentage\tright_pos_clip_percentage\tleft_seq_cigar\tright_seq_cigar\tleft_seq\tright_seq\n";
+
+static const char *sv_type(const JunctionKey &k)  // GetSVType, clip_reads.cpp:572-581
+{
+    if (k.up_chr != k.down_chr) return "CTX";
+    if (k.up_strand != k.down_strand) return "INV";
+    if (k.up_pos < k.down_pos) return "DEL";
+    if (k.up_pos > k.down_pos) return "INS";
+    return "Unknown";
+}
+
+static double top_base_fraction(const std::string &s)  // CountLargestBaseFrequency, getsv.cpp:1485-1511
+{
+    int n[5] = {0, 0, 0, 0, 0};
+    for (char c : s) {
+        switch (c) {
+        case 'A': case 'a': ++n[0]; break;
+        case 'T': case 't': ++n[1]; break;
+        case 'C': case 'c': ++n[2]; break;
+        case 'G': case 'g': ++n[3]; break;
+        default: ++n[4];
+        }
+    }
+    return *std::max_element(n, n + 5) / (double)(int)s.size();
+}
+
+void write_breakpoints(const JunctionMap &jm, const PosDepth &pos2depth, const RangeDepth &range2depth, const JunctionRanges &j2r,
+                       const OutputFilters &f, std::string &body, std::string &filtered, std::string &log)
+{
+    // OutputBreakpoint, getsv.cpp:838-987
+    for (auto &kv : jm) {
+        const JunctionKey &k = kv.first;
+        const JunctionInfo &o = kv.second;
+        int updepth = 0, downdepth = 0;
+        auto q = pos2depth.find(std::make_pair(k.up_chr, k.up_pos));
+        if (q == pos2depth.end()) log += "Error: There is something wrong in upstream position " + k.up_chr + ":" + std::to_string(k.up_pos) + "\n";
+        else updepth = q->second + o.down.support;
+        q = pos2depth.find(std::make_pair(k.down_chr, k.down_pos));
+        if (q == pos2depth.end()) log += "Error: There is something wrong in downstream position " + k.down_chr + ":" + std::to_string(k.down_pos) + "\n";
+        else downdepth = q->second + o.up.support;
+        int reads = o.up.support + o.down.support;
+        double rate1 = updepth == 0 ? 0 : (double)reads / updepth, rate2 = downdepth == 0 ? 0 : (double)reads / downdepth;
+        std::string head = k.up_chr + "\t" + std::to_string(k.up_pos) + "\t" + k.up_strand + "\t" + std::to_string(o.up.support) + "\t" +
+                           k.down_chr + "\t" + std::to_string(k.down_pos) + "\t" + k.down_strand + "\t" + std::to_string(o.down.support) +
+                           "\t" + std::to_string(o.micro) + "\t" + std::to_string(o.pairs) + "\t" + sv_type(k) + "\t" +
+                           std::to_string(updepth) + "\t" + std::to_string(downdepth) + "\t";
+        std::string tail = format_double(rate1) + "\t" + format_double(rate2) + "\t" + cigar_to_text(o.up.cigar, o.up.lclip, o.up.rclip) + "\t" +
+                           cigar_to_text(o.down.cigar, o.down.lclip, o.down.rclip) + "\t" + o.up.seq + "\t" + o.down.seq + "\n";
+        const char *why = nullptr;
+        if (!(o.up.uniq + o.down.uniq >= 2 || o.pairs > 0)) why = "mappingQ_too_low";
+        else if (k.up_chr == k.down_chr && std::abs(k.up_pos - k.down_pos) < f.min_distance) why = "distance_too_near";
+        else if (o.micro > f.max_micro) why = "microhomology_len_too_long";
+        else if (o.pairs < f.min_pairs) why = "abnormal_read_pair_no_not_pass";
+        else if ((o.up.support > 0 && o.down.support > 0 && rate1 < f.frequency && rate2 < f.frequency) ||
+                 (o.up.support == 0 && rate2 < f.frequency) || (o.down.support == 0 && rate1 < f.frequency))
+            why = "frequency_too_low";
+        else if (o.up.support + o.down.support < f.min_clip_sum) why = "total_clipped_reads_NO_not_pass";
+        else if (o.pairs == 0) {
+            if (o.up.seq.length() < (size_t)(o.up.lclip + o.up.rclip + f.min_seq_len) ||
+                o.down.seq.length() < (size_t)(o.down.lclip + o.down.rclip + f.min_seq_len))
+                why = "seq_length_too_short";
+            else if (o.up.cigar.size() > (size_t)(2 * f.max_indel + 1) || o.down.cigar.size() > (size_t)(2 * f.max_indel + 1))
+                why = "seq_with_too_many_indels";
+            else if (top_base_fraction(o.up.seq) >= 0.8 || top_base_fraction(o.down.seq) >= 0.8)
+                why = "repeat_bases";
+        }
+        if (why) {
+            filtered += std::string(why) + "\t" + head + tail;
+            continue;
+        }
+        unsigned avg[4] = {0, 0, 0, 0};
+        auto jr = j2r.find(k);
+        if (jr != j2r.end()) {
+            for (int i = 0; i < 4; ++i) {
+                auto rd = range2depth.find(jr->second.r[i]);
+                if (rd == range2depth.end()) log += "Error depth in the vicinity of junction " + k.up_chr + "\n";
+                else {
+                    unsigned span = rd->first.end - rd->first.begin + 1;
+                    avg[i] = span ? (unsigned)(rd->second / span) : 0;  // (span 0 would be a division by zero in the reference)
+                }
+            }
+        } else
+            log += "Error depth in the vicinity of junction " + k.up_chr + "\n";
+        body += head;
+        for (int i = 0; i < 4; ++i) body += std::to_string((int)avg[i]) + "\t";
+        body += tail;
+    }
+}
+
+// ---- somatic ------------------------------------------------------------------------------------------------------------------
+namespace {
+struct NormalClip {
+    std::string left, right;  // seq_left / seq_right of ReadsInfo
+    int support;
+};
+typedef std::multimap<std::pair<std::string, int>, NormalClip> ClipTable;
+
+// Compare, clip_reads.cpp:333-372: seq2 = 3'-clipped part, seq4 = 3'-aligned part
+int shifted_compare(const std::string &s1, const std::string &s2, const std::string &s3, const std::string &s4, double rate)
+{
+    if (s2.length() < 10) return -1;
+    size_t pos = s4.find(s2.substr(0, 10));
+    if (pos == std::string::npos) return -1;
+    std::string s5 = s3 + s4.substr(0, pos), s6 = s4.substr(pos);
+    if (match_rate_from_end(s1, s5) >= rate && match_rate_from_begin(s2, s6) >= rate) return (int)pos;
+    return -1;
+}
+
+int first_match(const ClipTable &t, const std::string &chr, int pos, const std::string &begin_seq, const std::string &end_seq, double rate)
+{
+    auto r = t.equal_range(std::make_pair(chr, pos));
+    for (auto it = r.first; it != r.second; ++it)
+        if (match_rate_from_begin(begin_seq, it->second.right) >= rate && match_rate_from_end(end_seq, it->second.left) >= rate)
+            return it->second.support;
+    return 0;
+}
+}  // namespace
+
+void somatic_rows(const std::string &normal_clip_text, const std::string &tumor_sv_text, double rate, int offset, int min_len,
+                  int mean_insert, std::vector<SomaticRow> &rows, std::string &log)
+{
+    // ReadsClipReads<T>, somatic.h:40-70
+    ClipTable t3, t5;
+    for (const ClipLine &c : parse_clip_text(normal_clip_text)) {
+        if (c.clipped_seq.length() < (size_t)min_len) continue;
+        if (c.side == '3') t3.insert(std::make_pair(std::make_pair(c.chr, c.pos), NormalClip{c.aligned_seq, c.clipped_seq, c.support}));
+        else if (c.side == '5') t5.insert(std::make_pair(std::make_pair(c.chr, c.pos), NormalClip{c.clipped_seq, c.aligned_seq, c.support}));
+        else log += "Error:The orientation of soft-clipped reads must be 3 or 5 in position " + c.chr + ":" + std::to_string(c.pos) + "\n";
+    }
+    auto window_first = [&](const ClipTable &t, const std::string &chr, int lo, int hi, auto &&pred) {
+        for (auto it = t.lower_bound(std::make_pair(chr, lo)); it != t.end() && it->first.first == chr && it->first.second <= hi; ++it)
+            if (pred(it->second)) return it->second.support;
+        return 0;
+    };
+    const char *p = tumor_sv_text.data(), *e = p + tumor_sv_text.size();
+    while (p < e) {
+        const char *nl = (const char *)memchr(p, '\n', e - p);
+        if (!nl) nl = e;
+        const char *b = p;
+        while (b < nl && isspace((unsigned char)*b)) ++b;
+        if (b == nl) {
+            p = nl < e ? nl + 1 : e;
+            continue;
+        }
+        SomaticRow row;
+        if (*b == '@') {
+            // `fin >> up_chr; getline(fin, temp); fout << up_chr << temp << ...` (somatic.cpp:59-65)
+            row.is_header = true;
+            row.prefix = std::string(b, nl) + "\tleft_clip_read_NO_of_control\tright_clip_read_NO_of_control\tabnormal_read_pair_no_of_control\n";
+            rows.push_back(row);
+            p = nl < e ? nl + 1 : e;
+            continue;
+        }
+        std::vector<std::string> t = split_ws(b, nl);
+        p = nl < e ? nl + 1 : e;
+        if (t.size() < 23) continue;
+        const std::string &up_chr = t[0], &down_chr = t[4], &up_seq = t[21], &down_seq = t[22];
+        int up_pos = atoi(t[1].c_str()), up_n = atoi(t[3].c_str()), down_pos = atoi(t[5].c_str()), down_n = atoi(t[7].c_str());
+        int micro = atoi(t[8].c_str());
+        char us = t[2][0], ds = t[6][0];
+        row.key = make_key(up_chr, up_pos, us, down_chr, down_pos, ds);
+        int nl_ = 0, nr_ = 0;
+        bool written = true, always = false;
+        std::string rc_up = reverse_complement(up_seq), rc_down = reverse_complement(down_seq);
+        if (us == '+' && ds == '+') {
+            if (micro != -1) {
+                nr_ = first_match(t5, down_chr, down_pos, down_seq, up_seq, rate);
+                if (down_seq.length() >= (size_t)micro)
+                    nl_ = first_match(t3, up_chr, up_pos + micro, down_seq.substr(micro), up_seq + down_seq.substr(0, micro), rate);
+                always = true;  // somatic.cpp:111 runs the pair query unconditionally
+            } else if (up_n == 0) {
+                nr_ = first_match(t5, down_chr, down_pos, down_seq, up_seq, rate);
+                nl_ = window_first(t3, up_chr, up_pos, up_pos + offset,
+                                   [&](const NormalClip &c) { return shifted_compare(c.left, c.right, up_seq, down_seq, rate) != -1; });
+            } else if (down_n == 0) {
+                nl_ = first_match(t3, up_chr, up_pos, down_seq, up_seq, rate);
+                nr_ = window_first(t5, down_chr, down_pos - offset, down_pos,
+                                   [&](const NormalClip &c) { return shifted_compare(up_seq, down_seq, c.left, c.right, rate) != -1; });
+            } else
+                written = false;
+        } else if (us == '+' && ds == '-') {
+            if (micro != -1) {
+                nl_ = first_match(t3, up_chr, up_pos + micro, down_seq.substr(micro), up_seq + down_seq.substr(0, micro), rate);
+                nr_ = first_match(t3, down_chr, down_pos, rc_up, rc_down, rate);
+            } else if (up_n == 0) {
+                nr_ = first_match(t3, down_chr, down_pos, rc_up, rc_down, rate);
+                nl_ = window_first(t3, up_chr, up_pos, up_pos + offset,
+                                   [&](const NormalClip &c) { return shifted_compare(c.left, c.right, up_seq, down_seq, rate) != -1; });
+            } else if (down_n == 0) {
+                nl_ = first_match(t3, up_chr, up_pos, down_seq, up_seq, rate);
+                nr_ = window_first(t3, down_chr, down_pos, down_pos + offset,
+                                   [&](const NormalClip &c) { return shifted_compare(c.left, c.right, rc_down, rc_up, rate) != -1; });
+            } else
+                written = false;
+        } else if (us == '-' && ds == '+') {
+            if (micro != -1) {
+                nl_ = first_match(t5, up_chr, up_pos, rc_up, rc_down, rate);
+                nr_ = first_match(t5, down_chr, down_pos - micro, up_seq.substr(up_seq.length() - micro) + down_seq,
+                                  up_seq.substr(0, up_seq.length() - micro), rate);
+            } else if (up_n == 0) {
+                nr_ = first_match(t5, down_chr, down_pos, down_seq, up_seq, rate);
+                nl_ = window_first(t5, up_chr, up_pos - offset, up_pos,
+                                   [&](const NormalClip &c) { return shifted_compare(rc_up, rc_down, c.left, c.right, rate) != -1; });
+            } else if (down_n == 0) {
+                nl_ = first_match(t5, up_chr, up_pos, rc_up, rc_down, rate);
+                nr_ = window_first(t5, down_chr, down_pos - offset, down_pos,
+                                   [&](const NormalClip &c) { return shifted_compare(up_seq, down_seq, c.left, c.right, rate) != -1; });
+            } else
+                written = false;
+        } else
+            written = false;
+        if (!written) {
+            log += "The tandem repeat length is error in postion: " + up_chr + "\t" + std::to_string(up_pos) + "\n";
+            continue;
+        }
+        row.normal_left = nl_, row.normal_right = nr_;
+        row.query_pairs = always || mean_insert != 0;
+        // the 23 tumour columns, numbers re-parsed and re-printed as the reference's iostreams do (somatic.cpp:66,112)
+        std::string &o = row.prefix;
+        o = up_chr + "\t" + std::to_string(up_pos) + "\t" + us + "\t" + std::to_string(up_n) + "\t" + down_chr + "\t" +
+            std::to_string(down_pos) + "\t" + ds + "\t" + std::to_string(down_n) + "\t" + std::to_string(micro) + "\t" +
+            std::to_string(atoi(t[9].c_str())) + "\t" + t[10];
+        for (int i = 11; i <= 16; ++i) o += "\t" + std::to_string(atoi(t[i].c_str()));
+        o += "\t" + format_double(strtod(t[17].c_str(), nullptr)) + "\t" + format_double(strtod(t[18].c_str(), nullptr));
+        o += "\t" + t[19] + "\t" + t[20] + "\t" + up_seq + "\t" + down_seq;
+        rows.push_back(row);
+    }
+}
+
+}  // namespace svb

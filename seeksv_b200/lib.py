@@ -1,0 +1,292 @@
+"""ctypes bindings of include/seeksv_b200.h (host-side mirror used by tests, bench.py and sharded runs)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def lib_path() -> str:
+    return os.path.join(HERE, "libseeksv_b200.so")
+
+
+def cli_path() -> str:
+    return os.path.join(HERE, "bin", "seeksv")
+
+
+class SvbError(RuntimeError):
+    pass
+
+
+class GetclipParams(C.Structure):
+    _fields_ = [("match_rate", C.c_double), ("min_mapq", C.c_int32), ("save_low_quality", C.c_int32),
+                ("prev_tid", C.c_int32)]
+
+
+class Junction(C.Structure):
+    _fields_ = [("up_tid", C.c_int32), ("up_pos", C.c_int32), ("down_tid", C.c_int32), ("down_pos", C.c_int32),
+                ("up_strand", C.c_char), ("down_strand", C.c_char), ("pad_", C.c_char * 2)]
+
+
+class PairParams(C.Structure):
+    _fields_ = [("min_mapq", C.c_int32), ("mean_insert", C.c_int32), ("deviation", C.c_int32), ("times", C.c_int32)]
+
+
+class Window(C.Structure):
+    _fields_ = [("tid", C.c_int32), ("begin", C.c_int32), ("end", C.c_int32)]
+
+
+EXPORTS = [
+    "svb_abi_version", "svb_ctx_create", "svb_ctx_destroy", "svb_last_error", "svb_ctx_stream", "svb_prof_enable",
+    "svb_prof_reset", "svb_prof_read", "svb_bam_from_device", "svb_bam_from_host", "svb_bam_from_bgzf", "svb_bam_open",
+    "svb_bam_free", "svb_bam_n_records", "svb_bam_record_bytes", "svb_bam_n_ref", "svb_bam_ref_name", "svb_bam_ref_len",
+    "svb_bam_set_refs", "svb_getclip", "svb_clusters_free", "svb_clusters_count", "svb_clusters_candidates",
+    "svb_clusters_text", "svb_insert_stats", "svb_discordant_support", "svb_window_depth", "svb_main",
+]
+
+
+def load():
+    """dlopen the CUDA library. Raises if it has not been built: there is no fallback implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise SvbError("%s is missing - run `python -m seeksv_b200.build` (no CPU fallback exists)" % p)
+    L = C.CDLL(p)
+    vp, u64, i32, i64 = C.c_void_p, C.c_uint64, C.c_int32, C.c_int64
+    L.svb_abi_version.restype = C.c_int
+    L.svb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.svb_ctx_destroy.argtypes = [vp]
+    L.svb_ctx_destroy.restype = None
+    L.svb_last_error.argtypes = [vp]
+    L.svb_last_error.restype = C.c_char_p
+    L.svb_ctx_stream.argtypes = [vp]
+    L.svb_ctx_stream.restype = vp
+    L.svb_prof_enable.argtypes = [vp, C.c_int]
+    L.svb_prof_enable.restype = None
+    L.svb_prof_reset.argtypes = [vp]
+    L.svb_prof_reset.restype = None
+    L.svb_prof_read.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(i64),
+                                C.POINTER(C.c_double)]
+    L.svb_bam_from_device.argtypes = [vp, vp, u64, u64, i32, C.POINTER(vp)]
+    L.svb_bam_from_host.argtypes = [vp, vp, u64, u64, i32, C.POINTER(vp)]
+    L.svb_bam_from_bgzf.argtypes = [vp, vp, u64, C.c_int, C.POINTER(vp)]
+    L.svb_bam_open.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.svb_bam_free.argtypes = [vp]
+    L.svb_bam_free.restype = None
+    for f in ("svb_bam_n_records", "svb_bam_record_bytes"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = u64
+    L.svb_bam_n_ref.argtypes = [vp]
+    L.svb_bam_n_ref.restype = i32
+    L.svb_bam_ref_name.argtypes = [vp, i32]
+    L.svb_bam_ref_name.restype = C.c_char_p
+    L.svb_bam_ref_len.argtypes = [vp, i32]
+    L.svb_bam_ref_len.restype = C.c_uint32
+    L.svb_bam_set_refs.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
+    L.svb_getclip.argtypes = [vp, vp, C.POINTER(GetclipParams), C.POINTER(vp)]
+    L.svb_clusters_free.argtypes = [vp]
+    L.svb_clusters_free.restype = None
+    L.svb_clusters_count.argtypes = [vp]
+    L.svb_clusters_count.restype = u64
+    L.svb_clusters_candidates.argtypes = [vp]
+    L.svb_clusters_candidates.restype = u64
+    L.svb_clusters_text.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(u64)]
+    L.svb_insert_stats.argtypes = [vp, vp, i32, i64, C.POINTER(i64)]
+    L.svb_discordant_support.argtypes = [vp, vp, C.POINTER(Junction), u64, C.POINTER(PairParams), C.POINTER(i32)]
+    L.svb_window_depth.argtypes = [vp, vp, C.POINTER(Window), u64, i32, C.POINTER(i32)]
+    L.svb_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    _lib = L
+    return L
+
+
+class Context:
+    """One GPU (svb_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load()
+        self.h = C.c_void_p()
+        rc = self.L.svb_ctx_create(device, C.byref(self.h))
+        if rc != 0:
+            raise SvbError("svb_ctx_create(%d) = %d: %s" % (device, rc, self.L.svb_last_error(None).decode()))
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            raise SvbError("%s = %d: %s" % (what, rc, self.L.svb_last_error(self.h).decode()))
+
+    @property
+    def stream(self) -> int:
+        return self.L.svb_ctx_stream(self.h) or 0
+
+    def prof(self, on: bool = True):
+        self.L.svb_prof_enable(self.h, 1 if on else 0)
+
+    def prof_reset(self):
+        self.L.svb_prof_reset(self.h)
+
+    def prof_read(self):
+        cap = 64
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        n_l = (C.c_int64 * cap)()
+        by = (C.c_double * cap)()
+        n = self.L.svb_prof_read(self.h, cap, names, ms, n_l, by)
+        return {names[i].decode(): dict(ms=ms[i], launches=n_l[i], bytes=by[i]) for i in range(min(n, cap))}
+
+    def close(self):
+        if self.h:
+            self.L.svb_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Bam:
+    """A BAM (or shard) resident in HBM (svb_bam)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.h = ctx, handle
+        self._keep = None
+
+    @classmethod
+    def open(cls, ctx: Context, path: str, threads: int = 0) -> "Bam":
+        h = C.c_void_p()
+        ctx.check(ctx.L.svb_bam_open(ctx.h, path.encode(), threads, C.byref(h)), "svb_bam_open(%s)" % path)
+        return cls(ctx, h)
+
+    @classmethod
+    def from_bgzf(cls, ctx: Context, file_bytes, threads: int = 0) -> "Bam":
+        """file image of a .bam in host memory (bytes / numpy uint8 / pinned torch tensor pointer+len tuple)"""
+        ptr, n, keep = _host_ptr(file_bytes)
+        h = C.c_void_p()
+        ctx.check(ctx.L.svb_bam_from_bgzf(ctx.h, ptr, n, threads, C.byref(h)), "svb_bam_from_bgzf")
+        b = cls(ctx, h)
+        return b
+
+    @classmethod
+    def from_host(cls, ctx: Context, stream, first_record: int, n_ref: int) -> "Bam":
+        ptr, n, keep = _host_ptr(stream)
+        h = C.c_void_p()
+        ctx.check(ctx.L.svb_bam_from_host(ctx.h, ptr, n, first_record, n_ref, C.byref(h)), "svb_bam_from_host")
+        return cls(ctx, h)
+
+    @classmethod
+    def from_device(cls, ctx: Context, dptr: int, nbytes: int, first_record: int, n_ref: int, keep=None) -> "Bam":
+        h = C.c_void_p()
+        ctx.check(ctx.L.svb_bam_from_device(ctx.h, C.c_void_p(dptr), nbytes, first_record, n_ref, C.byref(h)),
+                  "svb_bam_from_device")
+        b = cls(ctx, h)
+        b._keep = keep
+        return b
+
+    def set_refs(self, names: Sequence[str], lengths: Sequence[int]):
+        n = len(names)
+        arr = (C.c_char_p * n)(*[s.encode() for s in names])
+        ln = (C.c_uint32 * n)(*lengths)
+        self.ctx.check(self.ctx.L.svb_bam_set_refs(self.h, n, arr, ln), "svb_bam_set_refs")
+
+    @property
+    def n_records(self) -> int:
+        return self.ctx.L.svb_bam_n_records(self.h)
+
+    @property
+    def record_bytes(self) -> int:
+        return self.ctx.L.svb_bam_record_bytes(self.h)
+
+    @property
+    def ref_names(self) -> List[str]:
+        L = self.ctx.L
+        return [L.svb_bam_ref_name(self.h, t).decode() for t in range(L.svb_bam_n_ref(self.h))]
+
+    @property
+    def ref_lens(self) -> List[int]:
+        L = self.ctx.L
+        return [L.svb_bam_ref_len(self.h, t) for t in range(L.svb_bam_n_ref(self.h))]
+
+    def getclip(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0) -> Tuple[bytes, bytes, bytes, bytes]:
+        """(clip, clip.fq, unmapped_1, unmapped_2) decompressed file contents."""
+        p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid)
+        out = C.c_void_p()
+        self.ctx.check(self.ctx.L.svb_getclip(self.ctx.h, self.h, C.byref(p), C.byref(out)), "svb_getclip")
+        try:
+            res = []
+            for which in range(4):
+                d = C.c_char_p()
+                n = C.c_uint64()
+                self.ctx.L.svb_clusters_text(out, which, C.byref(d), C.byref(n))
+                res.append(C.string_at(d, n.value) if n.value else b"")
+            self.last_clusters = self.ctx.L.svb_clusters_count(out)
+            self.last_candidates = self.ctx.L.svb_clusters_candidates(out)
+            return tuple(res)
+        finally:
+            self.ctx.L.svb_clusters_free(out)
+
+    def insert_stats(self, min_mapq=20, max_pairs=5000000):
+        out = (C.c_int64 * 4)()
+        self.ctx.check(self.ctx.L.svb_insert_stats(self.ctx.h, self.h, min_mapq, max_pairs, out), "svb_insert_stats")
+        return tuple(out)
+
+    def discordant_support(self, junctions, min_mapq, mean, dev, times=4) -> List[int]:
+        """junctions: (up_tid, up_pos, up_strand, down_tid, down_pos, down_strand)"""
+        n = len(junctions)
+        arr = (Junction * max(n, 1))()
+        for i, (ut, up, us, dt, dp, ds) in enumerate(junctions):
+            arr[i] = Junction(ut, up, dt, dp, us.encode(), ds.encode(), b"")
+        cnt = (C.c_int32 * max(n, 1))()
+        pp = PairParams(min_mapq, mean, dev, times)
+        self.ctx.check(self.ctx.L.svb_discordant_support(self.ctx.h, self.h, arr, n, C.byref(pp), cnt),
+                       "svb_discordant_support")
+        return list(cnt[:n])
+
+    def window_depth(self, windows, min_mapq) -> List[List[int]]:
+        """windows: sorted disjoint (tid, begin1, end1); returns per-window depth lists"""
+        n = len(windows)
+        arr = (Window * max(n, 1))(*[Window(*w) for w in windows])
+        tot = sum(w[2] - w[1] + 1 for w in windows)
+        out = (C.c_int32 * max(tot, 1))()
+        self.ctx.check(self.ctx.L.svb_window_depth(self.ctx.h, self.h, arr, n, min_mapq, out), "svb_window_depth")
+        res, o = [], 0
+        for w in windows:
+            k = w[2] - w[1] + 1
+            res.append(list(out[o:o + k]))
+            o += k
+        return res
+
+    def close(self):
+        if self.h:
+            self.ctx.L.svb_bam_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _host_ptr(obj):
+    """(void*, nbytes, keepalive) for bytes / bytearray / numpy arrays / torch CPU tensors"""
+    if isinstance(obj, (bytes, bytearray)):
+        buf = (C.c_char * len(obj)).from_buffer_copy(obj) if isinstance(obj, bytes) else (C.c_char * len(obj)).from_buffer(obj)
+        return C.cast(buf, C.c_void_p), len(obj), buf
+    if hasattr(obj, "data_ptr"):     # torch tensor
+        return C.c_void_p(obj.data_ptr()), obj.numel() * obj.element_size(), obj
+    if hasattr(obj, "ctypes"):       # numpy
+        return C.c_void_p(obj.ctypes.data), obj.nbytes, obj
+    raise TypeError("unsupported host buffer")
+
+
+def run_cli(args: Sequence[str]) -> int:
+    """svb_main in-process (same as executing bin/seeksv)."""
+    L = load()
+    argv = [b"seeksv"] + [a.encode() for a in args]
+    arr = (C.c_char_p * (len(argv) + 1))(*argv, None)
+    return L.svb_main(len(argv), arr)

@@ -132,6 +132,10 @@ def pipeline(work, outdir, bwa, fasta, samples, somatic_pair=None, getsv_args=()
             run([SEEKSV, "getsv", *getsv_args, os.path.join(outdir, s + ".clip.sam"), bam, pre + ".clip.gz",
                  os.path.join(outdir, s + ".sv"), pre + ".clipunmap"], stdout=o, stderr=subprocess.DEVNULL)
         assert os.path.getsize(pre + ".clipunmap") == 0     # quirk Q7
+        # host-only mode (no insert size, no discordant pairs, no depth): exercises join / merge / filters alone
+        with open(os.path.join(outdir, s + ".n0D.stdout"), "w") as o:
+            run([SEEKSV, "getsv", "-n", "0", "-D", os.path.join(outdir, s + ".clip.sam"), bam, pre + ".clip.gz",
+                 os.path.join(outdir, s + ".n0D.sv"), pre + ".clipunmap"], stdout=o, stderr=subprocess.DEVNULL)
     if somatic_pair:
         normal, tumour = somatic_pair
         run([SEEKSV, "somatic", os.path.join(outdir, normal + ".sort.bam"), os.path.join(work, normal + ".clip.gz"),

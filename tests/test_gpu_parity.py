@@ -1,0 +1,181 @@
+"""Parity of the CUDA path (through the C ABI / the CLI that sits on it) against the reference's own outputs
+(tests/golden/, made by oracle/_ref/seeksv) and against the CPU oracle on seeded inputs. Needs a B200."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT, read_text
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("example", "cancer"), ("example", "normal"), ("micro", "tumor"), ("micro", "normal"),
+         ("kat", "quirks"), ("kat", "start_tid1")]
+
+
+def _bam(d, s):
+    p = os.path.join(GOLDEN, d, s + ".sort.bam")
+    return p if os.path.exists(p) else os.path.join(GOLDEN, d, s + ".bam")
+
+
+def _cli():
+    from seeksv_b200 import cli_path
+    assert os.path.exists(cli_path()), "build the CLI first (python -m seeksv_b200.build)"
+    return cli_path()
+
+
+def _zcat(path):
+    with gzip.open(path, "rb") as f:
+        return f.read().decode("latin-1")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import seeksv_b200
+    c = seeksv_b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("d,s", CASES)
+def test_getclip_cli_bit_exact(d, s, tmp_path):
+    pre = str(tmp_path / s)
+    r = subprocess.run([_cli(), "getclip", "-o", pre, _bam(d, s)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for ext, name in ((".clip.gz", ".clip.txt"), (".clip.fq.gz", ".clip.fq.txt"),
+                      (".unmapped_1.fq.gz", ".unmapped_1.fq.txt"), (".unmapped_2.fq.gz", ".unmapped_2.fq.txt")):
+        assert _zcat(pre + ext) == read_text(os.path.join(GOLDEN, d, s + name)), ext
+
+
+@pytest.mark.parametrize("d,s", CASES)
+def test_getclip_c_abi_matches_oracle(ctx, d, s):
+    import seeksv_b200
+    from oracle import bamio, getclip_oracle
+    h, recs = bamio.read_bam(_bam(d, s))
+    want = getclip_oracle.getclip(h, recs)
+    bam = seeksv_b200.Bam.open(ctx, _bam(d, s))
+    assert bam.n_records == len(recs)
+    got = bam.getclip()
+    for g, w in zip(got, want):
+        assert g.decode("latin-1") == w
+    # non-default parameters
+    want = getclip_oracle.getclip(h, recs, limit=0.8, min_mapq=30, save_low_quality=True)
+    got = bam.getclip(match_rate=0.8, min_mapq=30, save_low_quality=True)
+    for g, w in zip(got, want):
+        assert g.decode("latin-1") == w
+    bam.close()
+
+
+@pytest.mark.parametrize("d,s", CASES[:4])
+def test_getsv_cli_bit_exact(d, s, tmp_path):
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, s + ".clip.txt")).encode("latin-1"))
+    out, unm = str(tmp_path / "out.sv"), str(tmp_path / "unm")
+    r = subprocess.run([_cli(), "getsv", os.path.join(GOLDEN, d, s + ".clip.sam"), _bam(d, s), clip, out, unm],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".sv"))
+    assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".getsv.stdout"))
+    assert os.path.getsize(unm) == 0
+
+
+@pytest.mark.parametrize("d,normal,tumour", [("example", "normal", "cancer"), ("micro", "normal", "tumor")])
+def test_somatic_cli_bit_exact(d, normal, tumour, tmp_path):
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, normal + ".clip.txt")).encode("latin-1"))
+    out = str(tmp_path / "somatic.sv")
+    r = subprocess.run([_cli(), "somatic", _bam(d, normal), clip, os.path.join(GOLDEN, d, tumour + ".sv"), out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, tumour + ".somatic.temp.sv"))
+
+
+@pytest.mark.parametrize("d,s", CASES[:4])
+def test_device_passes_match_oracle(ctx, d, s):
+    """insert-size sums, discordant-pair counts and window depth through the C ABI vs the CPU oracle"""
+    import random
+    import seeksv_b200
+    from oracle import bamio, getsv_oracle as G
+    h, recs = bamio.read_bam(_bam(d, s))
+    bam = seeksv_b200.Bam.open(ctx, _bam(d, s))
+    for mq, cap in ((20, 5000000), (0, 1000), (30, 7)):
+        n, tot, mean, sq = bam.insert_stats(mq, cap)
+        want = G.insert_size_stats(recs, mq, cap)
+        if want is None:
+            assert n == 0
+        else:
+            import math
+            assert (mean, int(math.sqrt(sq / n))) == want
+    mean, dev = G.insert_size_stats(recs, 20, 5000000)
+    rng = random.Random(5)
+    juncs = []
+    for _ in range(300):
+        ut, dt = rng.randrange(len(h.names)), rng.randrange(len(h.names))
+        if rng.random() < 0.6:
+            dt = ut
+        up = rng.randrange(1, h.lengths[ut])
+        dp = max(1, min(h.lengths[dt], up + rng.randrange(-600, 600))) if dt == ut and rng.random() < 0.7 else rng.randrange(1, h.lengths[dt])
+        juncs.append((ut, up, rng.choice("+-"), dt, dp, rng.choice("+-")))
+    juncs.append((-1, 5, "+", 0, 5, "+"))
+    juncs.append((0, 5, "+", -1, 5, "+"))
+    got = bam.discordant_support(juncs, 20, mean, dev, 4)
+    for j, g in zip(juncs, got):
+        ut, up, us, dt, dp, ds = j
+        key = (h.names[ut] if ut >= 0 else "nope", h.names[dt] if dt >= 0 else "nope", us, ds, up, dp)
+        assert g == G.discordant_pairs(h, recs, key, 20, mean, dev, 4), j
+    # depth over random disjoint windows
+    for mq in (20, 0):
+        dep = G.depth_arrays(h, recs, mq)
+        wins = []
+        for tid, ln in enumerate(h.lengths):
+            p = 1
+            while True:
+                p += rng.randrange(1, 700)
+                e = p + rng.randrange(0, 500)
+                if e > ln:
+                    break
+                wins.append((tid, p, e))
+                p = e + 1
+        got = bam.window_depth(wins, mq)
+        for (tid, b, e), g in zip(wins, got):
+            assert g == [int(x) for x in dep[tid][b:e + 1]], (tid, b, e)
+    bam.close()
+
+
+def test_pileup_cap_matches_oracle(ctx, tmp_path):
+    """coverage beyond libbam's 8000-read pileup cap (quirk Q12) and the =/X CIGAR quirk"""
+    import random
+    import seeksv_b200
+    from oracle import bamio, getsv_oracle as G
+    rng = random.Random(3)
+    h = bamio.Header(["c1", "c2"], [5000, 5000], "@SQ\tSN:c1\tLN:5000\n@SQ\tSN:c2\tLN:5000\n")
+    recs = []
+    for tid in (0, 1):
+        pos = 10
+        for block in range(40):
+            pos += rng.choice((0, 0, 1, 3, 7, 60))
+            n = rng.choice((1, 5, 200, 3000, 9000)) if tid == 0 else rng.choice((1, 2, 50))
+            for i in range(n):
+                cig = rng.choice(("50M", "20M3D27M", "10S40M", "25M2I23M", "10=5X30M", "30M10N10M", "45M5H"))
+                flag = rng.choice((0, 0, 0, 16, 1024, 256, 4, 512))
+                recs.append(bamio.make_rec("r", flag, tid, pos, rng.choice((0, 30, 60)), cig, -1, -1, 0, "A" * 50, "I" * 50))
+    path = str(tmp_path / "cap.bam")
+    bamio.write_bam(path, h, recs)
+    bam = seeksv_b200.Bam.open(ctx, path)
+    for mq in (0, 20):
+        dep = G.depth_arrays(h, recs, mq)
+        wins = [(0, 1, 2500), (0, 2600, 5000), (1, 1, 5000)]
+        got = bam.window_depth(wins, mq)
+        for (tid, b, e), g in zip(wins, got):
+            assert g == [int(x) for x in dep[tid][b:e + 1]], (mq, tid)
+    bam.close()
+
+
+def test_no_cpu_fallback():
+    """the product never imports the oracle, and the library refuses to run without its CUDA device"""
+    import seeksv_b200.lib as lib
+    src = open(lib.__file__).read()
+    assert "oracle" not in src
