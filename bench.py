@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py - BAM records/sec through getclip + getsv (BASELINE.json metric) on synthetic BAMs.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3            # our arm (CUDA path through the C ABI)
+    python bench.py --impl reference --steps 2 --warmup 1    # the reference's own CPU implementation (oracle/_ref)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     # one chromosome-sized shard per GPU, weak scaling
+
+Workload (config.workload = "C2"): BASELINE.json configs[1] - synthetic 30x chr21-size (46,709,983 bp) paired-end
+150 bp BAM with 500 planted deletions / inversions / moved segments (tools/svsim.cpp, seed 20261017). The external
+`bwa mem` realign step between the two commands is replaced by tools/minialign.cpp and is NOT timed, exactly as the
+reference pipeline keeps it outside seeksv.
+
+One step = one getclip pass + one getsv pass over the BAM:
+  value : inputs (uncompressed BAM stream) already resident in HBM; record index + soft-clip scan + sort + clustering
+          + text emission, then record index + decode + insert-size statistics + discordant-pair support + window depth.
+  e2e   : the same two commands end to end through the C-ABI entry point the CLI is (svb_main: file image in host
+          memory -> host-thread BGZF inflate -> pinned staging -> cudaMemcpyAsync -> kernels -> results back to host
+          -> output files written), i.e. what `seeksv getclip ...; seeksv getsv ...` costs a user.
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+WORK = os.environ.get("SEEKSV_B200_BENCH_DIR", "/tmp/seeksv_b200_bench")
+BIN = os.path.join(ROOT, "seeksv_b200", "bin")
+REF_SEEKSV = os.path.join(ROOT, "oracle", "_ref", "seeksv")
+C2_LEN = 46709983
+SAMPLE_LEN = 5000000      # bounded sample for the CPU arm: ~1.0 M records, ~10 s of single-core reference work
+SEED = 20261017
+
+
+def ensure_tools():
+    from seeksv_b200 import build as b
+    b.build()
+    for tool in ("svsim", "minialign"):
+        out = os.path.join(BIN, tool)
+        src = os.path.join(ROOT, "tools", tool + ".cpp")
+        if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", src, "-o", out, "-lz"], check=True)
+
+
+def make_bam(prefix, contig, length, seed, nsv):
+    if not os.path.exists(prefix + ".bam"):
+        subprocess.run([os.path.join(BIN, "svsim"), "--out", prefix, "--genome", "%s:%d" % (contig, length), "--cov", "30",
+                        "--nsv", str(nsv), "--seed", str(seed)], check=True, stderr=subprocess.DEVNULL)
+    return prefix + ".bam"
+
+
+def realign(prefix, clip_fq_gz):
+    """the external realign step (untimed): clip.fq.gz -> clip.sam"""
+    sam = prefix + ".clip.sam"
+    with open(sam, "w") as o:
+        subprocess.run([os.path.join(BIN, "minialign"), prefix + ".fa", clip_fq_gz], check=True, stdout=o)
+    return sam
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+        self.q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([x.strip() for x in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def time_reference(bam, sam_and_clip, work, tag):
+    """wall-clock of the reference CLI: getclip, then getsv (its own inflate, index queries and pileup included)"""
+    pre = os.path.join(work, tag)
+    t0 = time.perf_counter()
+    subprocess.run([REF_SEEKSV, "getclip", "-o", pre, bam], check=True, stderr=subprocess.DEVNULL)
+    t1 = time.perf_counter()
+    sam = sam_and_clip(pre)
+    t2 = time.perf_counter()
+    with open(pre + ".stdout", "w") as o:
+        subprocess.run([REF_SEEKSV, "getsv", sam, bam, pre + ".clip.gz", pre + ".sv", pre + ".unm"], check=True, stdout=o,
+                       stderr=subprocess.DEVNULL)
+    t3 = time.perf_counter()
+    return (t1 - t0) + (t3 - t2)
+
+
+def count_records(bam):
+    import gzip
+    import struct
+    n = 0
+    with gzip.open(bam, "rb") as f:
+        data = f.read()
+    o = 8 + struct.unpack_from("<i", data, 4)[0]
+    nref = struct.unpack_from("<i", data, o)[0]
+    o += 4
+    for _ in range(nref):
+        o += 8 + struct.unpack_from("<i", data, o)[0]
+    while o + 4 <= len(data):
+        o += 4 + struct.unpack_from("<i", data, o)[0]
+        n += 1
+    return n
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation on a bounded sample of the workload (rank 0 only)"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.makedirs(WORK, exist_ok=True)
+    if not os.path.exists(REF_SEEKSV):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/seeksv not built (needs /root/reference at build time)"}))
+        return
+    ensure_tools()
+    pre = os.path.join(WORK, "sample")
+    bam = make_bam(pre, "chr21", SAMPLE_LEN, SEED, max(1, int(500 * SAMPLE_LEN / C2_LEN)))
+    n_rec = count_records(bam)
+    sam_cache = {}
+
+    def sam_for(p):
+        if "sam" not in sam_cache:
+            shutil.copy(pre + ".fa", p + ".fa")
+            sam_cache["sam"] = realign(p, p + ".clip.fq.gz")
+        return sam_cache["sam"]
+    for _ in range(args.warmup):
+        time_reference(bam, sam_for, WORK, "refarm")
+    ts = [time_reference(bam, sam_for, WORK, "refarm") for _ in range(args.steps)]
+    t = sum(ts)
+    v = n_rec * args.steps / t
+    sample = "svsim chr21:%d 30x 150bp PE (%d records; first %.1f%% of the C2 genome length), getclip+getsv CLI wall-clock" % (
+        SAMPLE_LEN, n_rec, 100.0 * SAMPLE_LEN / C2_LEN)
+    print(json.dumps({
+        "impl": "reference", "metric": "BAM records/sec getclip+getsv", "value": v, "unit": "records/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "C2", "sample": sample, "threads": 1},
+        "cpu_baseline": {"value": v, "unit": "records/s", "cores": 1, "kind": "reference", "sample": sample,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--genome-len", type=int, default=C2_LEN, help="chromosome length of the synthetic BAM (C2: chr21 size)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    os.makedirs(WORK, exist_ok=True)
+    if rank == 0:
+        ensure_tools()
+    if world > 1:
+        dist.barrier()
+    import seeksv_b200 as S
+
+    # ---- inputs (untimed): one chromosome-sized BAM per rank - the genome is partitioned by chromosome ----------
+    contig = "chr21" if world == 1 else "chr%d" % (rank + 1)
+    pre = os.path.join(WORK, "c2_%s_%d" % (contig, args.genome_len))
+    nsv = max(1, int(500 * args.genome_len / C2_LEN))
+    bam_path = make_bam(pre, contig, args.genome_len, SEED + rank, nsv)
+    ctx = S.Context(local)
+    file_img = torch.from_file(bam_path, shared=False, size=os.path.getsize(bam_path), dtype=torch.uint8).pin_memory()
+    resident = S.Bam.from_bgzf(ctx, file_img)          # uncompressed stream in HBM (kept for the whole run)
+    dptr, nbytes, first = resident.device_stream()
+    names, lens = resident.ref_names, resident.ref_lens
+    n_rec, rec_bytes = resident.n_records, resident.record_bytes
+    # realign hand-off and getsv plan from our own getclip output (parity with the reference is tested elsewhere)
+    clip = resident.getclip()
+    import gzip
+    with gzip.open(pre + ".clip.gz", "wb", compresslevel=1) as f:
+        f.write(clip[0])
+    with gzip.open(pre + ".clip.fq.gz", "wb", compresslevel=1) as f:
+        f.write(clip[1])
+    sam = realign(pre, pre + ".clip.fq.gz")
+    juncs, wins = S.plan_getsv(sam, pre + ".clip.gz", names, lens, 50, 200)
+    n_clusters = clip[0].count(b"\n")
+    counts_dev = torch.zeros(max(1, len(juncs)), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.ExternalStream(ctx.stream)
+
+    def device_step():
+        """getclip + getsv on the HBM-resident stream"""
+        b = S.Bam.from_device(ctx, dptr, nbytes, first, len(names))
+        b.set_refs(names, lens)
+        out = b.getclip()
+        b.close()
+        b = S.Bam.from_device(ctx, dptr, nbytes, first, len(names))
+        b.set_refs(names, lens)
+        n, tot, mean, sq = b.insert_stats(20, 5000000)
+        dev = int((sq / n) ** 0.5) if n else 0
+        cnt = b.discordant_support(juncs, 20, mean, dev, 4)
+        dep = b.window_depth(wins, 20)
+        b.close()
+        if world > 1:   # final candidate merge: every rank learns every shard's support counts (small NCCL allgather)
+            counts_dev[:len(cnt)] = torch.tensor(cnt, dtype=torch.int32)
+            gathered = [torch.empty_like(counts_dev) for _ in range(world)]
+            dist.all_gather(gathered, counts_dev)
+        return len(out[0]) + len(out[1]) + 4 * len(cnt) + 4 * sum(len(d) for d in dep)
+
+    out_dir = os.path.join(WORK, "out_%d" % rank)
+    os.makedirs(out_dir, exist_ok=True)
+
+    def e2e_step():
+        """the two commands through svb_main (what the CLI runs), files in the page cache"""
+        rc = S.run_cli(["getclip", "-o", os.path.join(out_dir, "x"), bam_path])
+        assert rc == 0
+        rc = S.run_cli(["getsv", sam, bam_path, os.path.join(out_dir, "x.clip.gz"), os.path.join(out_dir, "x.sv"),
+                        os.path.join(out_dir, "x.unm")])
+        assert rc == 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                last = fn()
+            ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max(ev0.elapsed_time(ev1), 0.0)
+        t = torch.tensor([ms, wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item(), t[1].item(), last
+
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(2)
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.prof(True)
+    ctx.prof_reset()
+    ms_dev, wall_dev, d2h = timed(device_step, args.steps)
+    prof = ctx.prof_read()
+    ctx.prof(False)
+    os.dup2(devnull, 2)          # the commands print the reference's progress lines on stderr
+    sys.stdout.flush()
+    saved_out = os.dup(1)
+    os.dup2(devnull, 1)          # ... and getsv lists filtered junctions on stdout
+    try:
+        for _ in range(max(1, args.warmup // 3)):
+            e2e_step()
+        ms_e2e, wall_e2e, _ = timed(e2e_step, args.steps)
+    finally:
+        os.dup2(saved, 2)
+        os.dup2(saved_out, 1)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    total_rec = torch.tensor([n_rec], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_rec)
+    total_rec = total_rec.item()
+    value = total_rec * args.steps / (ms_dev / 1e3)
+    e2e = total_rec * args.steps / wall_e2e    # svb_main runs on its own context/stream: host clock, max over ranks
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        full_pass = {"guess_starts", "walk_count", "walk_write", "clip_scan", "decode_records"}
+        kern = {k: v for k, v in prof.items() if v["launches"] > 0 and "wall" not in k}
+        dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
+        roofline = None
+        if dom:
+            v = kern[dom]
+            per_launch = (v["bytes"] / v["launches"]) if v["bytes"] else (rec_bytes if dom in full_pass else 0)
+            avg_ms = v["ms"] / v["launches"]
+            ach = per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                        "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
+                        "kernels_ms_per_step": {k: round(x["ms"] / args.steps, 4) for k, x in sorted(kern.items())}}
+        line = {
+            "metric": "BAM records/sec getclip+getsv", "value": value, "unit": "records/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "C2" if args.genome_len == C2_LEN else "C2-shape-%dbp" % args.genome_len,
+                       "records_per_gpu": n_rec, "record_bytes_per_gpu": rec_bytes, "clusters": n_clusters,
+                       "junction_candidates": len(juncs), "depth_windows": len(wins),
+                       "sharding": "one chromosome-sized BAM per GPU" if world > 1 else "single GPU",
+                       "l2_note": "inputs (%.2f GB per pass) are far larger than the 126 MB L2; no flush needed" % (rec_bytes / 1e9)},
+            "e2e": {"value": e2e, "unit": "records/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * wall_e2e / args.steps, "path": "svb_main getclip + svb_main getsv, BGZF file image -> outputs"},
+            "gpu_launches": int(sum(v["launches"] for v in kern.values())),
+            "clocks": sampler.summary(), "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_SEEKSV):
+            spre = os.path.join(WORK, "sample")
+            sbam = make_bam(spre, "chr21", SAMPLE_LEN, SEED, max(1, int(500 * SAMPLE_LEN / C2_LEN)))
+            sn = count_records(sbam)
+
+            def sam_for(p):
+                shutil.copy(spre + ".fa", p + ".fa")
+                return realign(p, p + ".clip.fq.gz")
+            t = time_reference(sbam, sam_for, WORK, "cpu_baseline")
+            line["cpu_baseline"] = {"value": sn / t, "unit": "records/s", "cores": 1, "kind": "reference", "host_cores": os.cpu_count(),
+                                    "sample": "svsim chr21:%d 30x (%d records), reference seeksv getclip+getsv CLI wall-clock, 1 thread "
+                                              "(the reference has no parallelism)" % (SAMPLE_LEN, sn)}
+        elif world == 1:
+            line["cpu_baseline"] = {"value": None, "unit": "records/s", "cores": 1, "kind": "reference",
+                                    "sample": "unavailable: oracle/_ref/seeksv not built"}
+        print(json.dumps(line))
+    resident.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -71,6 +71,10 @@ int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, int
 int svb_bam_open(svb_ctx *ctx, const char *path, int n_threads, svb_bam **out); /* .bam, else SAM text */
 void svb_bam_free(svb_bam *bam);
 
+/* The resident uncompressed stream of a svb_bam (device pointer, byte count, offset of the first record), e.g. to
+ * build further svb_bam views over it with svb_bam_from_device. Valid until svb_bam_free(bam). */
+int svb_bam_device_stream(const svb_bam *bam, const void **d_stream, uint64_t *nbytes, uint64_t *first_record);
+
 uint64_t svb_bam_n_records(const svb_bam *bam);
 uint64_t svb_bam_record_bytes(const svb_bam *bam);  /* sum over records of 4 + block_size */
 int32_t svb_bam_n_ref(const svb_bam *bam);
@@ -135,6 +139,17 @@ typedef struct svb_window {
 } svb_window;
 int svb_window_depth(svb_ctx *ctx, svb_bam *bam, const svb_window *windows, uint64_t n_windows, int32_t min_mapq,
                      int32_t *depth_out /* host */);
+
+/* Host-side planning step of getsv, exposed so that callers which keep the BAM resident (bench.py, sharded
+ * runs) can drive the device passes themselves: joins P.clip.gz with the realigned clip.bam/clip.sam
+ * (InputSoftInfoStoreBreakpoint getsv.h:423-541 + GetJunction getsv.cpp:1705), merges junctions (MergeJunction
+ * getsv.cpp:1325, reach = -l), and returns the junction list in Junction::operator< order plus the merged
+ * depth windows (GetBreak getsv.cpp:752 + MergeOverlap getsv.cpp:804, flank = -L) clamped to the
+ * chromosomes and sorted by (tid, begin). Arrays are malloc'ed; release them with svb_free. No GPU work. */
+int svb_plan_getsv(const char *clip_alignments_path, const char *clip_file_path, int32_t n_ref, const char *const *ref_names,
+                   const uint32_t *ref_lens, int32_t merge_reach, int32_t flank_len, svb_junction **junctions,
+                   uint64_t *n_junctions, svb_window **windows, uint64_t *n_windows);
+void svb_free(void *p);
 
 /* ---- whole commands (what the CLI calls; same arguments as the reference's Call* functions,
  *      seeksv.cpp:128-410). They print the reference's progress lines to stderr and return the

@@ -213,10 +213,10 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
     b->names = hdr.names, b->lens = hdr.lengths;
     CKR(finish_bam(ctx, b, out));
     if ((*out)->rec_bytes != total - hdr.first_record) {
+        unsigned long long missing = (unsigned long long)(total - hdr.first_record - (*out)->rec_bytes);
         svb_bam_free(*out);
         *out = nullptr;
-        return svb_fail(ctx, SVB_ERR_FORMAT, "truncated or corrupt BAM: record chain ends %llu bytes early",
-                        (unsigned long long)(total - hdr.first_record - (*out ? 0 : 0)));
+        return svb_fail(ctx, SVB_ERR_FORMAT, "truncated or corrupt BAM: record chain ends %llu bytes early", missing);
     }
     return 0;
 }
@@ -250,6 +250,12 @@ extern "C" void svb_bam_free(svb_bam *b)
     delete b;
 }
 
+extern "C" int svb_bam_device_stream(const svb_bam *b, const void **d, uint64_t *n, uint64_t *first)
+{
+    if (!b || !d || !n || !first) return SVB_ERR_ARG;
+    *d = b->d_data, *n = b->nbytes, *first = b->first;
+    return 0;
+}
 extern "C" uint64_t svb_bam_n_records(const svb_bam *b) { return b ? b->n_rec : 0; }
 extern "C" uint64_t svb_bam_record_bytes(const svb_bam *b) { return b ? b->rec_bytes : 0; }
 extern "C" int32_t svb_bam_n_ref(const svb_bam *b) { return b ? b->n_ref : 0; }

@@ -202,6 +202,46 @@ bool load_alignments(const std::string &path, std::vector<Alignment> &alns, std:
     return true;
 }
 
+struct Win {  // a device window with the chromosome name the host maps are keyed by
+    const std::string *chr;
+    int begin, end;
+    uint64_t off;
+};
+
+// begin2end (ordered by chromosome NAME, int begin/end possibly wrapped, quirk Q11) -> windows as the device wants
+// them: (tid, begin clamped to >= 1, end clamped to the chromosome), sorted by (tid, begin), disjoint. A window
+// whose chromosome is not in the BAM or that is empty after clamping has no covered position.
+uint64_t device_windows(const WindowMap &begin2end, const std::map<std::string, int32_t> &tid_of, const std::vector<uint32_t> &lens,
+                        std::vector<svb_window> &dw, std::vector<Win> &hw)
+{
+    std::vector<std::pair<svb_window, const std::string *>> tmp;
+    for (auto &kv : begin2end) {
+        auto it = tid_of.find(kv.first.first);
+        if (it == tid_of.end()) continue;
+        int b = std::max(kv.first.second, 1), e = (int)std::min<int64_t>(kv.second, (int64_t)lens[it->second] + 1);
+        if (e < b) continue;
+        tmp.push_back(std::make_pair(svb_window{it->second, b, e}, &kv.first.first));
+    }
+    std::sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) {
+        return a.first.tid != b.first.tid ? a.first.tid < b.first.tid : a.first.begin < b.first.begin;
+    });
+    for (auto &w : tmp) {
+        if (!dw.empty() && dw.back().tid == w.first.tid && w.first.begin <= dw.back().end) {
+            dw.back().end = std::max(dw.back().end, w.first.end);
+            hw.back().end = dw.back().end;
+        } else {
+            dw.push_back(w.first);
+            hw.push_back(Win{w.second, w.first.begin, w.first.end, 0});
+        }
+    }
+    uint64_t total = 0;
+    for (size_t i = 0; i < dw.size(); ++i) {
+        hw[i].off = total;
+        total += (uint64_t)(dw[i].end - dw[i].begin + 1);
+    }
+    return total;
+}
+
 bool insert_size(Gpu &g, svb_bam *bam, const std::string &file, int min_mapq, int pairs_used, int &mean, int &dev)
 {
     // CalculateInsertsizeDeviation, cluster.cpp:15-83: integer mean, (int)sqrt of the double mean square
@@ -315,44 +355,15 @@ int cmd_getsv(int argc, char **argv)
         std::cerr << "'MergeOverlap' finished" << std::endl;
         if (!begin2end.empty()) {
             if (!need_bam()) return 1;
-            // windows as the device sees them: (tid, begin clamped to >= 1, end); a window whose chromosome is not in
-            // the BAM or that is empty after clamping has no covered position
-            struct Win {
-                const std::string *chr;
-                int begin, end;
-                uint64_t off;
-            };
             std::vector<svb_window> dw;
             std::vector<Win> hw;
-            uint64_t total = 0;
             std::map<std::string, int32_t> tid_of;
-            for (int32_t t = 0; t < svb_bam_n_ref(bam); ++t) tid_of.insert(std::make_pair(std::string(svb_bam_ref_name(bam, t)), t));
-            std::vector<std::pair<svb_window, const std::string *>> tmp;
-            for (auto &kv : begin2end) {
-                auto it = tid_of.find(kv.first.first);
-                if (it == tid_of.end()) continue;
-                int b = std::max(kv.first.second, 1), e = std::min<int64_t>(kv.second, (int64_t)svb_bam_ref_len(bam, it->second) + 1);
-                if (e < b) continue;
-                tmp.push_back(std::make_pair(svb_window{it->second, b, e}, &kv.first.first));
+            std::vector<uint32_t> lens;
+            for (int32_t t = 0; t < svb_bam_n_ref(bam); ++t) {
+                tid_of.insert(std::make_pair(std::string(svb_bam_ref_name(bam, t)), t));
+                lens.push_back(svb_bam_ref_len(bam, t));
             }
-            // begin2end is ordered by chromosome NAME; the device wants (tid, begin). Merged windows of one chromosome are
-            // disjoint except for the degenerate wrapped ones, which clamp to [1, end]: merge overlaps defensively.
-            std::sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) {
-                return a.first.tid != b.first.tid ? a.first.tid < b.first.tid : a.first.begin < b.first.begin;
-            });
-            for (auto &w : tmp) {
-                if (!dw.empty() && dw.back().tid == w.first.tid && w.first.begin <= dw.back().end) {
-                    dw.back().end = std::max(dw.back().end, w.first.end);
-                    hw.back().end = dw.back().end;
-                } else {
-                    dw.push_back(w.first);
-                    hw.push_back(Win{w.second, w.first.begin, w.first.end, 0});
-                }
-            }
-            for (size_t i = 0; i < dw.size(); ++i) {
-                hw[i].off = total;
-                total += (uint64_t)(dw[i].end - dw[i].begin + 1);
-            }
+            uint64_t total = device_windows(begin2end, tid_of, lens, dw, hw);
             std::vector<int32_t> depth(total);
             if (svb_window_depth(g.ctx, bam, dw.data(), dw.size(), min_mapq, depth.data()) != 0) return fail(svb_last_error(g.ctx));
             // main_depth visits covered positions in BAM order (tid, pos); the range sums are commutative and every
@@ -452,6 +463,48 @@ int cmd_somatic(int argc, char **argv)
     return 0;
 }
 }  // namespace
+
+extern "C" void svb_free(void *p) { free(p); }
+
+extern "C" int svb_plan_getsv(const char *clip_aln, const char *clip_file, int32_t n_ref, const char *const *ref_names,
+                              const uint32_t *ref_lens, int32_t reach, int32_t flank_len, svb_junction **junctions, uint64_t *n_j,
+                              svb_window **windows, uint64_t *n_w)
+{
+    if (!clip_aln || !clip_file || !junctions || !n_j || !windows || !n_w || (n_ref && (!ref_names || !ref_lens))) return SVB_ERR_ARG;
+    std::string err, clip_text;
+    std::vector<Alignment> alns;
+    std::vector<std::string> aln_names;
+    if (!load_alignments(clip_aln, alns, aln_names, err) || !read_text_maybe_gz(clip_file, clip_text, err)) return SVB_ERR_IO;
+    JunctionMap jm;
+    join_clips_with_alignments(parse_clip_text(clip_text), aln_names, alns, jm);
+    merge_junctions(jm, reach);
+    std::map<std::string, int32_t> tid_of;
+    std::vector<uint32_t> lens(ref_lens, ref_lens + n_ref);
+    for (int32_t t = 0; t < n_ref; ++t) tid_of.insert(std::make_pair(std::string(ref_names[t]), t));
+    *n_j = jm.size();
+    *junctions = (svb_junction *)malloc(std::max<size_t>(1, jm.size()) * sizeof(svb_junction));
+    size_t i = 0;
+    for (auto &kv : jm) {
+        svb_junction &j = (*junctions)[i++];
+        auto a = tid_of.find(kv.first.up_chr), b = tid_of.find(kv.first.down_chr);
+        j.up_tid = a == tid_of.end() ? -1 : a->second, j.down_tid = b == tid_of.end() ? -1 : b->second;
+        j.up_pos = kv.first.up_pos, j.down_pos = kv.first.down_pos;
+        j.up_strand = kv.first.up_strand, j.down_strand = kv.first.down_strand, j.pad_[0] = j.pad_[1] = 0;
+    }
+    PosDepth pos2depth;
+    RangeDepth range2depth;
+    WindowMap begin2end;
+    JunctionRanges j2r;
+    collect_breaks(jm, flank_len, pos2depth, range2depth, j2r);
+    merge_ranges(range2depth, begin2end);
+    std::vector<svb_window> dw;
+    std::vector<Win> hw;
+    device_windows(begin2end, tid_of, lens, dw, hw);
+    *n_w = dw.size();
+    *windows = (svb_window *)malloc(std::max<size_t>(1, dw.size()) * sizeof(svb_window));
+    if (!dw.empty()) memcpy(*windows, dw.data(), dw.size() * sizeof(svb_window));
+    return 0;
+}
 
 extern "C" int svb_main(int argc, char **argv)
 {

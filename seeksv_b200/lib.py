@@ -42,9 +42,10 @@ class Window(C.Structure):
 EXPORTS = [
     "svb_abi_version", "svb_ctx_create", "svb_ctx_destroy", "svb_last_error", "svb_ctx_stream", "svb_prof_enable",
     "svb_prof_reset", "svb_prof_read", "svb_bam_from_device", "svb_bam_from_host", "svb_bam_from_bgzf", "svb_bam_open",
-    "svb_bam_free", "svb_bam_n_records", "svb_bam_record_bytes", "svb_bam_n_ref", "svb_bam_ref_name", "svb_bam_ref_len",
+    "svb_bam_free", "svb_bam_device_stream", "svb_bam_n_records", "svb_bam_record_bytes", "svb_bam_n_ref", "svb_bam_ref_name", "svb_bam_ref_len",
     "svb_bam_set_refs", "svb_getclip", "svb_clusters_free", "svb_clusters_count", "svb_clusters_candidates",
-    "svb_clusters_text", "svb_insert_stats", "svb_discordant_support", "svb_window_depth", "svb_main",
+    "svb_clusters_text", "svb_insert_stats", "svb_discordant_support", "svb_window_depth", "svb_plan_getsv", "svb_free",
+    "svb_main",
 ]
 
 
@@ -78,6 +79,7 @@ def load():
     L.svb_bam_open.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(vp)]
     L.svb_bam_free.argtypes = [vp]
     L.svb_bam_free.restype = None
+    L.svb_bam_device_stream.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
     for f in ("svb_bam_n_records", "svb_bam_record_bytes"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = u64
@@ -100,6 +102,11 @@ def load():
     L.svb_discordant_support.argtypes = [vp, vp, C.POINTER(Junction), u64, C.POINTER(PairParams), C.POINTER(i32)]
     L.svb_window_depth.argtypes = [vp, vp, C.POINTER(Window), u64, i32, C.POINTER(i32)]
     L.svb_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    L.svb_plan_getsv.argtypes = [C.c_char_p, C.c_char_p, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), i32, i32,
+                                 C.POINTER(C.POINTER(Junction)), C.POINTER(u64), C.POINTER(C.POINTER(Window)),
+                                 C.POINTER(u64)]
+    L.svb_free.argtypes = [vp]
+    L.svb_free.restype = None
     _lib = L
     return L
 
@@ -193,6 +200,12 @@ class Bam:
         ln = (C.c_uint32 * n)(*lengths)
         self.ctx.check(self.ctx.L.svb_bam_set_refs(self.h, n, arr, ln), "svb_bam_set_refs")
 
+    def device_stream(self) -> Tuple[int, int, int]:
+        """(device pointer, nbytes, first_record) of the resident uncompressed stream"""
+        d, n, f = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.ctx.L.svb_bam_device_stream(self.h, C.byref(d), C.byref(n), C.byref(f)), "svb_bam_device_stream")
+        return d.value or 0, n.value, f.value
+
     @property
     def n_records(self) -> int:
         return self.ctx.L.svb_bam_n_records(self.h)
@@ -282,6 +295,29 @@ def _host_ptr(obj):
     if hasattr(obj, "ctypes"):       # numpy
         return C.c_void_p(obj.ctypes.data), obj.nbytes, obj
     raise TypeError("unsupported host buffer")
+
+
+def plan_getsv(clip_alignments: str, clip_file: str, ref_names: Sequence[str], ref_lens: Sequence[int], reach: int = 50,
+               flank_len: int = 200):
+    """Host-side planning of getsv (svb_plan_getsv): junction tuples in output order and merged depth windows."""
+    L = load()
+    n = len(ref_names)
+    names = (C.c_char_p * n)(*[s.encode() for s in ref_names])
+    lens = (C.c_uint32 * n)(*ref_lens)
+    pj, pw = C.POINTER(Junction)(), C.POINTER(Window)()
+    nj, nw = C.c_uint64(), C.c_uint64()
+    rc = L.svb_plan_getsv(clip_alignments.encode(), clip_file.encode(), n, names, lens, reach, flank_len, C.byref(pj),
+                          C.byref(nj), C.byref(pw), C.byref(nw))
+    if rc != 0:
+        raise SvbError("svb_plan_getsv = %d" % rc)
+    try:
+        juncs = [(pj[i].up_tid, pj[i].up_pos, pj[i].up_strand.decode(), pj[i].down_tid, pj[i].down_pos,
+                  pj[i].down_strand.decode()) for i in range(nj.value)]
+        wins = [(pw[i].tid, pw[i].begin, pw[i].end) for i in range(nw.value)]
+    finally:
+        L.svb_free(pj)
+        L.svb_free(pw)
+    return juncs, wins
 
 
 def run_cli(args: Sequence[str]) -> int:

@@ -179,3 +179,45 @@ def test_no_cpu_fallback():
     import seeksv_b200.lib as lib
     src = open(lib.__file__).read()
     assert "oracle" not in src
+
+
+@pytest.mark.parametrize("genome,extra", [("chr21:3000000", []), ("chr7:1500000,chr12:1000000,chr3:800000", ["--virus"])])
+def test_synthetic_cli_vs_reference_binary(genome, extra, tmp_path):
+    """svsim BAM (30x, planted DEL/INV/moved segments[, virus contigs at >5000x]) through both CLIs: every output of
+    getclip, getsv and somatic must be byte-identical to the real reference binary (oracle/_ref/seeksv)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "seeksv")
+    svsim = os.path.join(ROOT, "seeksv_b200", "bin", "svsim")
+    mini = os.path.join(ROOT, "seeksv_b200", "bin", "minialign")
+    if not (os.path.exists(ref) and os.path.exists(svsim) and os.path.exists(mini)):
+        pytest.skip("needs oracle/_ref/seeksv and the svsim / minialign tools (python bench.py builds them)")
+    t = str(tmp_path)
+    outs = {}
+    for sample in ("tumor", "normal"):
+        subprocess.run([svsim, "--out", f"{t}/{sample}", "--genome", genome, "--nsv", "40", "--sample", sample] + extra,
+                       check=True, capture_output=True)
+    for tag, exe in (("ref", ref), ("b200", _cli())):
+        for sample in ("tumor", "normal"):
+            pre = f"{t}/{tag}.{sample}"
+            bam = f"{t}/{sample}.bam"
+            r = subprocess.run([exe, "getclip", "-o", pre, bam], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            if tag == "ref":
+                with open(f"{t}/{sample}.clip.sam", "w") as o:
+                    subprocess.run([mini, f"{t}/{sample}.fa", pre + ".clip.fq.gz"], check=True, stdout=o)
+            r = subprocess.run([exe, "getsv", f"{t}/{sample}.clip.sam", bam, pre + ".clip.gz", pre + ".sv", pre + ".unm"],
+                               capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            outs[(tag, sample, "stdout")] = r.stdout
+            for ext in (".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz"):
+                outs[(tag, sample, ext)] = _zcat(pre + ext)
+            outs[(tag, sample, ".sv")] = read_text(pre + ".sv")
+        pre = f"{t}/{tag}"
+        r = subprocess.run([exe, "somatic", f"{t}/normal.bam", f"{pre}.normal.clip.gz", f"{pre}.tumor.sv", f"{pre}.somatic.sv"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs[(tag, "tumor", "somatic")] = read_text(f"{pre}.somatic.sv")
+    n_sv = outs[("ref", "tumor", ".sv")].count("\n")
+    assert n_sv > 20, "the planted SVs must be found by the reference itself"
+    for (tag, sample, what), v in outs.items():
+        if tag == "ref":
+            assert outs[("b200", sample, what)] == v, (sample, what)
