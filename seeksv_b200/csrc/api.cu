@@ -64,6 +64,40 @@ extern "C" void svb_ctx_destroy(svb_ctx *ctx)
 extern "C" const char *svb_last_error(const svb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 extern "C" void *svb_ctx_stream(svb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
+char *svb_ctx::pinned_get(uint64_t bytes, uint64_t *cap)
+{
+    if (bytes == 0) {
+        *cap = 0;
+        return nullptr;
+    }
+    int best = -1;
+    for (size_t i = 0; i < pinned_free.size(); ++i)
+        if (pinned_free[i].second >= bytes && (best < 0 || pinned_free[i].second < pinned_free[best].second)) best = (int)i;
+    if (best >= 0) {
+        char *p = pinned_free[best].first;
+        *cap = pinned_free[best].second;
+        pinned_free.erase(pinned_free.begin() + best);
+        return p;
+    }
+    uint64_t want = bytes + bytes / 4 + 4096;
+    char *p = nullptr;
+    if (cudaHostAlloc((void **)&p, want, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    *cap = want;
+    return p;
+}
+void svb_ctx::pinned_put(char *p, uint64_t cap)
+{
+    if (pinned_free.size() >= 16) {
+        cudaFreeHost(p);
+        return;
+    }
+    pinned_free.emplace_back(p, cap);
+}
+svb_ctx::~svb_ctx()
+{
+    for (auto &b : pinned_free) cudaFreeHost(b.first);
+}
+
 void svb_ctx::prof_flush()
 {
     if (prof_pending.empty()) return;
@@ -242,11 +276,13 @@ extern "C" void svb_bam_free(svb_bam *b)
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    cudaFree(b->d_owned);
-    cudaFree(b->d_rec_off);
+    cudaStream_t s = b->ctx->stream;
+    if (b->d_rec_off) cudaFreeAsync(b->d_rec_off, s);
     LeanRecords &L = b->lean;
-    cudaFree(L.tid), cudaFree(L.pos), cudaFree(L.end), cudaFree(L.flagq);
-    cudaFree(L.lqseq), cudaFree(L.mtid), cudaFree(L.mpos), cudaFree(L.isize);
+    void *cols[8] = {L.tid, L.pos, L.end, L.flagq, L.lqseq, L.mtid, L.mpos, L.isize};
+    for (void *c : cols)
+        if (c) cudaFreeAsync(c, s);
+    if (b->d_owned) cudaFree(b->d_owned);
     delete b;
 }
 

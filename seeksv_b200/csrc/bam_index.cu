@@ -7,7 +7,7 @@
 // its own part of the chain, and a verification pass checks that every chunk's exit offset equals the
 // next chunk's guess. By induction from chunk 0 (whose entry is exact: the header length) a verified
 // chain is the true chain - the heuristic only affects speed, never the result. Chunks that fail are
-// re-walked from their true entry by a serial fix-up kernel (never needed for well-formed BAMs).
+// re-walked from their predecessor's exit in repair rounds until the whole chain verifies.
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -24,19 +24,25 @@ __device__ __forceinline__ bool plausible_one(const uint8_t *d, uint64_t n, uint
     int32_t tid = ldi32(d + o + 4);
     if (tid < -1 || tid >= n_ref) return false;
     int32_t pos = ldi32(d + o + 8);
-    if (pos < -1) return false;
+    if (pos < -1 || pos >= (1 << 29)) return false;  // BAM coordinates are below 2^29
     uint32_t w = ldu32(d + o + 12);
     uint32_t l_qname = w & 0xff;
-    if (l_qname == 0) return false;
-    uint32_t n_cigar = ldu32(d + o + 16) & 0xffff;
+    if (l_qname < 2) return false;
+    uint32_t w2 = ldu32(d + o + 16);
+    uint32_t n_cigar = w2 & 0xffff;
+    if ((w2 >> 16) & 0xf000) return false;  // flag bits above 0x800 are not defined
     int32_t l_qseq = ldi32(d + o + 20);
     if (l_qseq < 0) return false;
     int32_t mtid = ldi32(d + o + 24);
     if (mtid < -1 || mtid >= n_ref) return false;
-    if (ldi32(d + o + 28) < -1) return false;
+    int32_t mpos = ldi32(d + o + 28);
+    if (mpos < -1 || mpos >= (1 << 29)) return false;
     uint64_t need = 32ull + l_qname + 4ull * n_cigar + ((uint64_t)l_qseq + 1) / 2 + (uint64_t)l_qseq;
     if (need > (uint64_t)bs) return false;
-    if (d[o + 36 + l_qname - 1] != 0) return false;  // qname is NUL terminated
+    if ((uint64_t)bs - need > 4ull * (uint64_t)l_qseq + 8192) return false;  // aux block of a sane size
+    uint8_t c0 = d[o + 36];
+    if (c0 < 33 || c0 > 126) return false;           // qname starts with a printable character ...
+    if (d[o + 36 + l_qname - 1] != 0) return false;  // ... and is NUL terminated
     *next = o + 4 + (uint64_t)bs;
     return true;
 }
@@ -110,23 +116,19 @@ __global__ void verify_chain(uint64_t n_chunks, const uint64_t *__restrict__ gue
     if (!ok) atomicOr(bad, 1u);
 }
 
-// serial repair of the chain (one thread): only launched when verify_chain found a mismatch
-__global__ void fix_chain(const uint8_t *__restrict__ d, uint64_t n, uint64_t first, uint64_t n_chunks, uint64_t *guess,
-                          uint32_t *count, uint64_t *exit_, uint32_t *corrupt)
+// Repair round: every chunk whose guess differs from its predecessor's exit re-walks from that exit. The first
+// mismatching chunk always gets its true entry (its predecessor is correct by induction), so repeating
+// verify + repair converges; the number of rounds is the longest run of consecutive wrong chunks (1 in practice).
+__global__ void __launch_bounds__(128) repair_chain(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks, uint64_t *guess,
+                                                    uint32_t *count, uint64_t *exit_, const uint64_t *__restrict__ exit_prev)
 {
-    uint64_t entry = first;
-    for (uint64_t c = 0; c < n_chunks; ++c) {
-        if (guess[c] != entry || exit_[c] == BAD) {
-            guess[c] = entry;
-            uint64_t end = min(n, (c + 1) << CHUNK_LOG2);
-            walk_chunk(d, n, entry, end, &count[c], &exit_[c], nullptr);
-            if (exit_[c] == BAD) {
-                *corrupt = 1;
-                return;
-            }
-        }
-        entry = exit_[c];
-    }
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 || c >= n_chunks) return;
+    uint64_t entry = exit_prev[c - 1];
+    if (entry == BAD || guess[c] == entry) return;
+    guess[c] = entry;
+    uint64_t end = min(n, (c + 1) << CHUNK_LOG2);
+    walk_chunk(d, n, entry, end, &count[c], &exit_[c], nullptr);
 }
 
 __global__ void __launch_bounds__(128) walk_write(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks,
@@ -195,12 +197,18 @@ int index_records(svb_ctx *ctx, svb_bam *bam)
     uint32_t hflags[2];
     CK(cudaMemcpyAsync(hflags, flags.p, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (hflags[0]) {
-        ProfScope ps(ctx, "fix_chain", 0);
-        fix_chain<<<1, 1, 0, s>>>(d, n, first, n_chunks, guess.p, count.p, exit_.p, flags.p + 1);
+    for (uint64_t round = 0; hflags[0]; ++round) {
+        // a wrong guess (never seen on well-formed BAMs with the two-record test, but possible in principle)
+        if (round >= 256) return svb_fail(ctx, SVB_ERR_FORMAT, "corrupt BAM record chain (block_size < 32)");
+        ProfScope ps(ctx, "repair_chain", 0);
+        DevBuf<uint64_t> snap;
+        CK(snap.alloc(n_chunks, s));
+        CK(cudaMemcpyAsync(snap.p, exit_.p, n_chunks * 8, cudaMemcpyDeviceToDevice, s));
+        repair_chain<<<(unsigned)((n_chunks + 127) / 128), 128, 0, s>>>(d, n, n_chunks, guess.p, count.p, exit_.p, snap.p);
+        CK(cudaMemsetAsync(flags.p, 0, 8, s));
+        verify_chain<<<(unsigned)((n_chunks + 255) / 256), 256, 0, s>>>(n_chunks, guess.p, exit_.p, flags.p);
         CK(cudaMemcpyAsync(hflags, flags.p, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        if (hflags[1]) return svb_fail(ctx, SVB_ERR_FORMAT, "corrupt BAM record chain (block_size < 32)");
     }
     CK(cudaMemsetAsync(cnt64.p + n_chunks, 0, 8, s));
     count_to_u64<<<(unsigned)((n_chunks + 255) / 256), 256, 0, s>>>(n_chunks, count.p, cnt64.p);
@@ -211,7 +219,7 @@ int index_records(svb_ctx *ctx, svb_bam *bam)
     CK(cudaStreamSynchronize(s));
     bam->n_rec = n_rec;
     bam->rec_bytes = (last_exit >= first && last_exit <= n) ? last_exit - first : 0;
-    CK(cudaMalloc((void **)&bam->d_rec_off, (n_rec + 1) * sizeof(uint64_t)));
+    CK(cudaMallocAsync((void **)&bam->d_rec_off, (n_rec + 1) * sizeof(uint64_t), s));
     {
         ProfScope ps(ctx, "walk_write", 0);
         walk_write<<<(unsigned)((n_chunks + 127) / 128), 128, 0, s>>>(d, n, n_chunks, guess.p, base.p, bam->d_rec_off);

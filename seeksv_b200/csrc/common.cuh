@@ -41,6 +41,28 @@ struct svb_ctx {
     std::vector<Pending> prof_pending;
     std::vector<const char *> prof_names;  // storage for svb_prof_read
     void prof_flush();
+    // recycled pinned host buffers (cudaHostAlloc is slow; results are produced over and over)
+    std::vector<std::pair<char *, uint64_t>> pinned_free;
+    char *pinned_get(uint64_t bytes, uint64_t *cap);
+    void pinned_put(char *p, uint64_t cap);
+    ~svb_ctx();
+};
+
+struct PinnedBuf {
+    char *p = nullptr;
+    uint64_t n = 0, cap = 0;
+    int reserve(svb_ctx *ctx, uint64_t bytes)
+    {
+        release(ctx);
+        p = ctx->pinned_get(bytes, &cap);
+        n = p ? bytes : 0;
+        return (p || bytes == 0) ? 0 : SVB_ERR_CUDA;
+    }
+    void release(svb_ctx *ctx)
+    {
+        if (p && ctx) ctx->pinned_put(p, cap);
+        p = nullptr, n = cap = 0;
+    }
 };
 
 // Lean per-record columns produced by decode_records (getsv passes read these, not the raw stream).

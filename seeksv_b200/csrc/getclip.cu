@@ -6,13 +6,18 @@
 
 #include <algorithm>
 #include <cstring>
-#include <unordered_map>
+#include <memory>
 
 #include "common.cuh"
 
 struct svb_clusters {
-    std::vector<char> text[4];
+    svb_ctx *ctx = nullptr;
+    PinnedBuf text[4];  // pinned host memory: D2H at full PCIe rate, recycled through the ctx pool
     uint64_t n_clusters = 0, n_candidates = 0;
+    ~svb_clusters()
+    {
+        for (auto &t : text) t.release(ctx);
+    }
 };
 
 // ---- candidate scan -------------------------------------------------------------------------------------
@@ -461,44 +466,130 @@ __global__ void __launch_bounds__(128)
     for (uint32_t j = lane; j < cQN; j += 32) f[5 + 2 * cN + j] = noq ? '*' : cQ[j];
 }
 
-// ---- unmapped-branch records: pack (flag, qname, seq, qual) for the host-side pairing ---------------------
-__global__ void unmapped_sizes(uint32_t n, const uint32_t *__restrict__ list, const uint8_t *__restrict__ d,
-                               const uint64_t *__restrict__ rec_off, uint64_t *__restrict__ sz)
+// ---- unmapped-branch records: StoreUnmapSeqAndQual (clip_reads.h:172-219) on the device --------------------------
+// The reference keeps a std::map<qname, held mate> over the whole file: the first record of a name is held; a later
+// record of the same name and the OTHER end emits the pair (read1 to file 1, read2 to file 2) and erases the entry; a
+// later record of the same end is ignored. Output order = file order of the completing record. Here: hash the
+// names, stable-sort entries by hash (entries stay in file order inside a group), run the tiny per-name automaton
+// with one thread per hash group (real name compares, so hash collisions cannot change the result), then emit text.
+__device__ __forceinline__ uint32_t qname_len(const uint8_t *p) { return ldu32(p + 12) & 0xff; }
+
+__global__ void unmapped_hash(uint32_t n, const uint32_t *__restrict__ list, const uint8_t *__restrict__ d,
+                              const uint64_t *__restrict__ rec_off, uint64_t *__restrict__ key, uint32_t *__restrict__ val)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    if (i == n) {
-        sz[i] = 0;
-        return;
-    }
-    const uint8_t *p = d + rec_off[list[i]];
-    uint32_t lq = ldu32(p + 12) & 0xff;
-    int32_t l = ldi32(p + 20);
-    sz[i] = 12 + lq + 2ull * (uint32_t)l;  // flag, l_qname, l_qseq | qname (with NUL) | seq chars | qual chars
-}
-__global__ void __launch_bounds__(128)
-    unmapped_pack(uint32_t n, const uint32_t *__restrict__ list, const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off,
-                  const uint64_t *__restrict__ off, uint8_t *__restrict__ out)
-{
-    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n) return;
     const uint8_t *p = d + rec_off[list[i]];
-    uint32_t w = ldu32(p + 12), w2 = ldu32(p + 16);
-    uint32_t lq = w & 0xff, flag = w2 >> 16, nc = w2 & 0xffff;
-    int32_t l = ldi32(p + 20);
-    uint8_t *o = out + off[i];
-    if (lane == 0) {
-        uint32_t hdr[3] = {flag, lq, (uint32_t)l};
-        for (int j = 0; j < 12; ++j) o[j] = ((uint8_t *)hdr)[j];
+    uint32_t lq = qname_len(p);
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint32_t j = 0; j < lq && p[36 + j]; ++j) h = (h ^ p[36 + j]) * 0x100000001b3ull;
+    key[i] = h, val[i] = i;
+}
+
+__device__ bool same_name(const uint8_t *a, const uint8_t *b)
+{
+    uint32_t la = qname_len(a), lb = qname_len(b);
+    for (uint32_t j = 0;; ++j) {
+        uint8_t x = j < la ? a[36 + j] : 0, y = j < lb ? b[36 + j] : 0;
+        if (x != y) return false;
+        if (x == 0) return true;
     }
-    const uint8_t *qn = p + 36, *seq = qn + lq + 4 * nc, *qual = seq + (l + 1) / 2;
-    for (uint32_t j = lane; j < lq; j += 32) o[12 + j] = qn[j];
+}
+
+// one thread per hash group; mate_of[e] = entry that was held when e completed a pair, else 0xffffffff
+__global__ void unmapped_pair(uint32_t n, const uint64_t *__restrict__ key, const uint32_t *__restrict__ ent,
+                              const uint32_t *__restrict__ list, const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off,
+                              uint32_t *__restrict__ mate_of, uint32_t *__restrict__ overflow)
+{
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || (j > 0 && key[j] == key[j - 1])) return;
+    const int H = 8;
+    uint32_t held[H];
+    int nh = 0;
+    for (uint32_t k = j; k < n && key[k] == key[j]; ++k) {
+        uint32_t e = ent[k];
+        const uint8_t *p = d + rec_off[list[e]];
+        bool r1 = (ldu32(p + 16) >> 16) & F_READ1;
+        int hit = -1;
+        for (int h = 0; h < nh; ++h)
+            if (same_name(p, d + rec_off[list[held[h]]])) {
+                hit = h;
+                break;
+            }
+        if (hit < 0) {
+            if (nh < H) held[nh++] = e;
+            else atomicOr(overflow, 1u);
+        } else {
+            const uint8_t *q = d + rec_off[list[held[hit]]];
+            bool q1 = (ldu32(q + 16) >> 16) & F_READ1;
+            if (q1 != r1) {
+                mate_of[e] = held[hit];
+                held[hit] = held[--nh];
+            }  // same end again: neither emitted nor stored
+        }
+    }
+}
+
+// FASTQ record length of one mate: "@name/1\nSEQ\n+\nQUAL\n" (qual "*" when the BAM stores 0xff, empty when l_qseq == 0)
+__device__ __forceinline__ uint32_t unmapped_fq_len(const uint8_t *p)
+{
+    uint32_t lq = qname_len(p), nl = 0;
+    while (nl < lq && p[36 + nl]) ++nl;
+    int32_t l = ldi32(p + 20);
+    uint32_t nc = ldu32(p + 16) & 0xffff;
+    const uint8_t *qual = p + 36 + lq + 4 * nc + (l + 1) / 2;
+    uint32_t ql = l > 0 ? (qual[0] == 0xff ? 1u : (uint32_t)l) : 0u;
+    return 1 + nl + 2 + 1 + (uint32_t)l + 1 + 2 + ql + 1;
+}
+
+__global__ void unmapped_sizes(uint32_t n, const uint32_t *__restrict__ list, const uint32_t *__restrict__ mate_of,
+                               const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, uint64_t *__restrict__ sz1,
+                               uint64_t *__restrict__ sz2)
+{
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > n) return;
+    uint64_t a = 0, b = 0;
+    if (e < n && mate_of[e] != 0xffffffffu) {
+        const uint8_t *p = d + rec_off[list[e]], *q = d + rec_off[list[mate_of[e]]];
+        bool p1 = (ldu32(p + 16) >> 16) & F_READ1;
+        a = unmapped_fq_len(p1 ? p : q), b = unmapped_fq_len(p1 ? q : p);
+    }
+    sz1[e] = a, sz2[e] = b;
+}
+
+__device__ void write_unmapped_fq(const uint8_t *p, char end, char *o, uint32_t lane)
+{
+    uint32_t lq = qname_len(p), nl = 0;
+    while (nl < lq && p[36 + nl]) ++nl;
+    int32_t l = ldi32(p + 20);
+    uint32_t nc = ldu32(p + 16) & 0xffff;
+    const uint8_t *seq = p + 36 + lq + 4 * nc, *qual = seq + (l + 1) / 2;
     bool noq = l > 0 && qual[0] == 0xff;
+    uint32_t ql = l > 0 ? (noq ? 1u : (uint32_t)l) : 0u;
+    if (lane == 0) {
+        o[0] = '@', o[1 + nl] = '/', o[2 + nl] = end, o[3 + nl] = '\n';
+        o[4 + nl + l] = '\n', o[5 + nl + l] = '+', o[6 + nl + l] = '\n', o[7 + nl + l + ql] = '\n';
+        if (noq) o[7 + nl + l] = '*';
+    }
+    for (uint32_t j = lane; j < nl; j += 32) o[1 + j] = (char)p[36 + j];
     for (uint32_t j = lane; j < (uint32_t)l; j += 32) {
         uint32_t nib = (seq[j >> 1] >> ((~j & 1) << 2)) & 15;
-        o[12 + lq + j] = "=ACMGRSVTWYHKDBN"[nib];
-        o[12 + lq + l + j] = noq ? 0xff : qual[j] + 33;
+        o[4 + nl + j] = "=ACMGRSVTWYHKDBN"[nib];  // GetSeqAndQual, clip_reads.cpp:375-388 (no toupper needed)
+        if (!noq) o[7 + nl + l + j] = (char)(qual[j] + 33);
     }
+}
+
+__global__ void __launch_bounds__(128)
+    unmapped_write(uint32_t n, const uint32_t *__restrict__ list, const uint32_t *__restrict__ mate_of, const uint8_t *__restrict__ d,
+                   const uint64_t *__restrict__ rec_off, const uint64_t *__restrict__ off1, const uint64_t *__restrict__ off2,
+                   char *__restrict__ out1, char *__restrict__ out2)
+{
+    uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= n || mate_of[e] == 0xffffffffu) return;
+    const uint8_t *p = d + rec_off[list[e]], *q = d + rec_off[list[mate_of[e]]];
+    bool p1 = (ldu32(p + 16) >> 16) & F_READ1;
+    write_unmapped_fq(p1 ? p : q, '1', out1 + off1[e], lane);
+    write_unmapped_fq(p1 ? q : p, '2', out2 + off2[e], lane);
 }
 
 // ---- host orchestration -----------------------------------------------------------------------------------
@@ -514,55 +605,6 @@ static int sort_u32(svb_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, uint32_
 
 static inline unsigned nblk(uint64_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
 
-// StoreUnmapSeqAndQual (clip_reads.h:172-219) over the packed unmapped-branch records, in file order
-static void pair_unmapped(const std::vector<uint8_t> &blob, const std::vector<uint64_t> &off, std::vector<char> &o1,
-                          std::vector<char> &o2)
-{
-    struct Held {
-        const uint8_t *seq, *qual;
-        uint32_t l;
-        char end;
-    };
-    std::unordered_map<std::string, Held> held;
-    auto emit = [](std::vector<char> &o, const std::string &name, char end, const uint8_t *seq, const uint8_t *qual, uint32_t l) {
-        o.push_back('@');
-        o.insert(o.end(), name.begin(), name.end());
-        o.push_back('/');
-        o.push_back(end);
-        o.push_back('\n');
-        o.insert(o.end(), seq, seq + l);
-        o.push_back('\n');
-        o.push_back('+');
-        o.push_back('\n');
-        if (l && qual[0] == 0xff) o.push_back('*');
-        else o.insert(o.end(), qual, qual + l);
-        o.push_back('\n');
-    };
-    for (size_t i = 0; i + 1 < off.size(); ++i) {
-        const uint8_t *p = blob.data() + off[i];
-        uint32_t hdr[3];
-        memcpy(hdr, p, 12);
-        uint32_t flag = hdr[0], lq = hdr[1], l = hdr[2];
-        std::string name((const char *)p + 12, strnlen((const char *)p + 12, lq));
-        const uint8_t *seq = p + 12 + lq, *qual = seq + l;
-        char end = (flag & F_READ1) ? '1' : '2';
-        auto it = held.find(name);
-        if (it == held.end()) {
-            held.emplace(name, Held{seq, qual, l, end});
-        } else if (it->second.end != end) {
-            const Held &h = it->second;
-            if (end == '1') {
-                emit(o1, name, '1', seq, qual, l);
-                emit(o2, name, '2', h.seq, h.qual, h.l);
-            } else {
-                emit(o1, name, '1', h.seq, h.qual, h.l);
-                emit(o2, name, '2', seq, qual, l);
-            }
-            held.erase(it);
-        }  // same end again: neither emitted nor stored
-    }
-}
-
 extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params *prm, svb_clusters **out_)
 {
     if (!ctx || !bam || !prm || !out_) return svb_fail(ctx, SVB_ERR_ARG, "svb_getclip: null argument");
@@ -570,6 +612,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
     const uint64_t n_rec = bam->n_rec;
     if (n_rec >= (1ull << 32)) return svb_fail(ctx, SVB_ERR_ARG, "svb_getclip: more than 2^32 records in one shard");
     svb_clusters *res = new svb_clusters();
+    res->ctx = ctx;
     std::unique_ptr<svb_clusters> guard(res);
 
     // ---- 1. scan ------------------------------------------------------------------------------------------
@@ -609,29 +652,57 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
     const uint32_t n_cand = hc[0], n_un = hc[1], n_sw = hc[2];
     res->n_candidates = n_cand;
 
-    // ---- 2. unmapped-branch records -> host pairing ----------------------------------------------------------
+    // ---- 2. unmapped-branch records: pair mates by name on the device, emit the two FASTQ files ---------------------
     if (n_un) {
-        DevBuf<uint32_t> un_sorted;
-        DevBuf<uint64_t> sz, off;
+        DevBuf<uint32_t> un_sorted, val0, val1, mate_of, ovf;
+        DevBuf<uint64_t> key0, key1, sz1, sz2, off1, off2;
         CK(un_sorted.alloc(n_un, s));
         CKR(sort_u32(ctx, un_list.p, un_sorted.p, n_un));
-        CK(sz.alloc(n_un + 1, s));
-        CK(off.alloc(n_un + 1, s));
-        unmapped_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_sorted.p, bam->d_data, bam->d_rec_off, sz.p);
-        CKR(exclusive_scan_u64(ctx, sz.p, off.p, n_un + 1));
-        std::vector<uint64_t> hoff(n_un + 1);
-        CK(cudaMemcpyAsync(hoff.data(), off.p, (n_un + 1) * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        DevBuf<uint8_t> blob;
-        CK(blob.alloc(hoff[n_un], s));
+        CK(val0.alloc(n_un, s));
+        CK(val1.alloc(n_un, s));
+        CK(key0.alloc(n_un, s));
+        CK(key1.alloc(n_un, s));
+        CK(mate_of.alloc(n_un, s));
+        CK(ovf.alloc(1, s));
+        CK(sz1.alloc(n_un + 1, s));
+        CK(sz2.alloc(n_un + 1, s));
+        CK(off1.alloc(n_un + 1, s));
+        CK(off2.alloc(n_un + 1, s));
+        CK(cudaMemsetAsync(mate_of.p, 0xff, (size_t)n_un * 4, s));
+        CK(cudaMemsetAsync(ovf.p, 0, 4, s));
+        uint64_t tot[2] = {0, 0};
         {
-            ProfScope ps(ctx, "unmapped_pack", (double)hoff[n_un]);
-            unmapped_pack<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_sorted.p, bam->d_data, bam->d_rec_off, off.p, blob.p);
+            ProfScope ps(ctx, "unmapped_pair", 0);
+            unmapped_hash<<<nblk(n_un, 256), 256, 0, s>>>(n_un, un_sorted.p, bam->d_data, bam->d_rec_off, key0.p, val0.p);
+            size_t tmp = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, key0.p, key1.p, val0.p, val1.p, (int)n_un, 0, 64, s));
+            DevBuf<uint8_t> t;
+            CK(t.alloc(tmp, s));
+            CK(cub::DeviceRadixSort::SortPairs(t.p, tmp, key0.p, key1.p, val0.p, val1.p, (int)n_un, 0, 64, s));
+            unmapped_pair<<<nblk(n_un, 128), 128, 0, s>>>(n_un, key1.p, val1.p, un_sorted.p, bam->d_data, bam->d_rec_off, mate_of.p, ovf.p);
+            unmapped_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_sorted.p, mate_of.p, bam->d_data, bam->d_rec_off, sz1.p, sz2.p);
+            CKR(exclusive_scan_u64(ctx, sz1.p, off1.p, n_un + 1));
+            CKR(exclusive_scan_u64(ctx, sz2.p, off2.p, n_un + 1));
         }
-        std::vector<uint8_t> hblob(hoff[n_un]);
-        CK(cudaMemcpyAsync(hblob.data(), blob.p, hoff[n_un], cudaMemcpyDeviceToHost, s));
+        uint32_t hovf = 0;
+        CK(cudaMemcpyAsync(&tot[0], off1.p + n_un, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&tot[1], off2.p + n_un, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&hovf, ovf.p, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        pair_unmapped(hblob, hoff, res->text[2], res->text[3]);
+        if (hovf) return svb_fail(ctx, SVB_ERR_FORMAT, "more than 8 distinct read names share one 64-bit name hash");
+        DevBuf<char> o1, o2;
+        CK(o1.alloc(tot[0], s));
+        CK(o2.alloc(tot[1], s));
+        {
+            ProfScope ps(ctx, "unmapped_write", (double)(tot[0] + tot[1]));
+            unmapped_write<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_sorted.p, mate_of.p, bam->d_data, bam->d_rec_off, off1.p,
+                                                                          off2.p, o1.p, o2.p);
+        }
+        CKR(res->text[2].reserve(ctx, tot[0]));
+        CKR(res->text[3].reserve(ctx, tot[1]));
+        CK(cudaMemcpyAsync(res->text[2].p, o1.p, tot[0], cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(res->text[3].p, o2.p, tot[1], cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
     }
 
     if (n_cand == 0) {
@@ -758,10 +829,10 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
                                                                   bam->d_rec_off, nt, maxl.p, maxr.p, arena_off.p, arena_seq.p,
                                                                   arena_qual.p, clip_off.p, fq_off.p, d_clip.p, d_fq.p);
     }
-    res->text[0].resize(clip_bytes);
-    res->text[1].resize(fq_bytes);
-    CK(cudaMemcpyAsync(res->text[0].data(), d_clip.p, clip_bytes, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(res->text[1].data(), d_fq.p, fq_bytes, cudaMemcpyDeviceToHost, s));
+    CKR(res->text[0].reserve(ctx, clip_bytes));
+    CKR(res->text[1].reserve(ctx, fq_bytes));
+    CK(cudaMemcpyAsync(res->text[0].p, d_clip.p, clip_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(res->text[1].p, d_fq.p, fq_bytes, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     *out_ = guard.release();
@@ -774,7 +845,7 @@ extern "C" uint64_t svb_clusters_candidates(const svb_clusters *c) { return c ? 
 extern "C" int svb_clusters_text(const svb_clusters *c, int which, const char **data, uint64_t *len)
 {
     if (!c || which < 0 || which > 3 || !data || !len) return SVB_ERR_ARG;
-    *data = c->text[which].data();
-    *len = c->text[which].size();
+    *data = c->text[which].p ? c->text[which].p : "";
+    *len = c->text[which].n;
     return 0;
 }

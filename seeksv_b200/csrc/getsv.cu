@@ -54,14 +54,14 @@ int decode_records(svb_ctx *ctx, svb_bam *bam)
     uint64_t n = bam->n_rec;
     LeanRecords &L = bam->lean;
     size_t cnt = n ? n : 1;
-    CK(cudaMalloc((void **)&L.tid, cnt * 4));
-    CK(cudaMalloc((void **)&L.pos, cnt * 4));
-    CK(cudaMalloc((void **)&L.end, cnt * 4));
-    CK(cudaMalloc((void **)&L.flagq, cnt * 4));
-    CK(cudaMalloc((void **)&L.lqseq, cnt * 4));
-    CK(cudaMalloc((void **)&L.mtid, cnt * 4));
-    CK(cudaMalloc((void **)&L.mpos, cnt * 4));
-    CK(cudaMalloc((void **)&L.isize, cnt * 4));
+    CK(cudaMallocAsync((void **)&L.tid, cnt * 4, s));
+    CK(cudaMallocAsync((void **)&L.pos, cnt * 4, s));
+    CK(cudaMallocAsync((void **)&L.end, cnt * 4, s));
+    CK(cudaMallocAsync((void **)&L.flagq, cnt * 4, s));
+    CK(cudaMallocAsync((void **)&L.lqseq, cnt * 4, s));
+    CK(cudaMallocAsync((void **)&L.mtid, cnt * 4, s));
+    CK(cudaMallocAsync((void **)&L.mpos, cnt * 4, s));
+    CK(cudaMallocAsync((void **)&L.isize, cnt * 4, s));
     L.n = n;
     DevBuf<int32_t> scal;
     CK(scal.alloc(2, s));

@@ -6,6 +6,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <map>
 #include <cstdio>
@@ -129,6 +130,18 @@ void usage_cmd(const char *prog, const char *command, int i)
     }
 }
 
+// wall-clock phase log on stderr when SEEKSV_B200_TIMING is set (for profiling the end-to-end path)
+struct Phase {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    bool on = getenv("SEEKSV_B200_TIMING") != nullptr;
+    void mark(const char *what)
+    {
+        auto t1 = std::chrono::steady_clock::now();
+        if (on) fprintf(stderr, "[time] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 int fail(const std::string &msg)
 {
     std::cerr << msg << std::endl;
@@ -155,15 +168,19 @@ int cmd_getclip(int argc, char **argv)
         return 1;
     }
     std::string bamfile = argv[optind];
+    Phase ph;
     Gpu g;
     if (!g.open()) return 1;
+    ph.mark("getclip: context");
     svb_bam *bam = nullptr;
     if (svb_bam_open(g.ctx, bamfile.c_str(), n_threads(), &bam) != 0) {
         std::cerr << "[main_samview] fail to open file for reading." << std::endl;
         return fail(std::string("[seeksv_b200] ") + svb_last_error(g.ctx));
     }
+    ph.mark("getclip: load BAM to HBM");
     svb_clusters *cl = nullptr;
     int rc = svb_getclip(g.ctx, bam, &prm, &cl);
+    ph.mark("getclip: device passes");
     if (rc != 0) {
         svb_bam_free(bam);
         return fail(std::string("[seeksv_b200] ") + svb_last_error(g.ctx));
@@ -177,6 +194,7 @@ int cmd_getclip(int argc, char **argv)
         std::string err;
         if (!write_gz(prefix + ext[i], data, len, n_threads(), err)) status = fail(err);
     }
+    ph.mark("getclip: gzip + write outputs");
     std::cerr << "[GetSClipReads] finished!" << std::endl;
     svb_clusters_free(cl);
     svb_bam_free(bam);
@@ -306,15 +324,19 @@ int cmd_getsv(int argc, char **argv)
     std::string err, clip_text;
     std::vector<Alignment> alns;
     std::vector<std::string> aln_names;
+    Phase ph;
     if (!load_alignments(clip_aln, alns, aln_names, err)) {
         std::cerr << "[main_samview] fail to open file for reading." << std::endl;
         return fail(err);
     }
+    ph.mark("getsv: read clip alignments");
     if (!read_text_maybe_gz(clipfile, clip_text, err)) return fail(err);
+    ph.mark("getsv: read clip.gz");
     JunctionMap jm;
     join_clips_with_alignments(parse_clip_text(clip_text), aln_names, alns, jm);
     std::cerr << "'InputSoftInfoStoreBreakpoint' finished" << std::endl;
     merge_junctions(jm, flank);
+    ph.mark("getsv: join + merge junctions");
 
     Gpu g;
     svb_bam *bam = nullptr;
@@ -331,6 +353,7 @@ int cmd_getsv(int argc, char **argv)
     int mean = 0, dev = 0;
     if (pairs_used >= 100000) {
         if (!need_bam()) return 1;
+        ph.mark("getsv: load BAM to HBM");
         if (!insert_size(g, bam, original_bam, min_mapq, pairs_used, mean, dev)) return fail(svb_last_error(g.ctx));
         std::cerr << "'CalculateInsertsizeDeviation' finished" << std::endl;
         std::vector<svb_junction> dj(jm.size());
@@ -377,6 +400,7 @@ int cmd_getsv(int argc, char **argv)
         std::cerr << "'main_depth' finished" << std::endl;
     } else
         frequency = 0;
+    ph.mark("getsv: device passes + depth");
 
     std::string body, filtered, log;
     OutputFilters f;
