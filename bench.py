@@ -213,24 +213,36 @@ def main():
     counts_dev = torch.zeros(max(1, len(juncs)), dtype=torch.int32, device="cuda")
     stream = torch.cuda.ExternalStream(ctx.stream)
 
+    # C arrays for the getsv passes are built once; results land in preallocated host arrays (no per-step marshalling)
+    import ctypes as C
+    from seeksv_b200 import lib as SL
+    nj, nw = len(juncs), len(wins)
+    j_arr = (SL.Junction * max(nj, 1))(*[SL.Junction(ut, up, dt, dp, us.encode(), ds.encode(), b"") for ut, up, us, dt, dp, ds in juncs])
+    w_arr = (SL.Window * max(nw, 1))(*[SL.Window(*w) for w in wins])
+    n_pos = sum(w[2] - w[1] + 1 for w in wins)
+    cnt_host = torch.zeros(max(nj, 1), dtype=torch.int32).pin_memory()
+    dep_host = torch.zeros(max(n_pos, 1), dtype=torch.int32).pin_memory()
+    cnt_arr = C.cast(cnt_host.data_ptr(), C.POINTER(C.c_int32))
+    dep_arr = C.cast(dep_host.data_ptr(), C.POINTER(C.c_int32))
+
     def device_step():
         """getclip + getsv on the HBM-resident stream"""
         b = S.Bam.from_device(ctx, dptr, nbytes, first, len(names))
         b.set_refs(names, lens)
-        out = b.getclip()
+        sizes = b.getclip_sizes()
         b.close()
         b = S.Bam.from_device(ctx, dptr, nbytes, first, len(names))
         b.set_refs(names, lens)
         n, tot, mean, sq = b.insert_stats(20, 5000000)
         dev = int((sq / n) ** 0.5) if n else 0
-        cnt = b.discordant_support(juncs, 20, mean, dev, 4)
-        dep = b.window_depth(wins, 20)
+        b.discordant_support_raw(j_arr, nj, SL.PairParams(20, mean, dev, 4), cnt_arr)
+        b.window_depth_raw(w_arr, nw, 20, dep_arr)
         b.close()
         if world > 1:   # final candidate merge: every rank learns every shard's support counts (small NCCL allgather)
-            counts_dev[:len(cnt)] = torch.tensor(cnt, dtype=torch.int32)
+            counts_dev.copy_(cnt_host, non_blocking=True)
             gathered = [torch.empty_like(counts_dev) for _ in range(world)]
             dist.all_gather(gathered, counts_dev)
-        return len(out[0]) + len(out[1]) + 4 * len(cnt) + 4 * sum(len(d) for d in dep)
+        return sum(sizes) + 4 * nj + 4 * n_pos
 
     out_dir = os.path.join(WORK, "out_%d" % rank)
     os.makedirs(out_dir, exist_ok=True)

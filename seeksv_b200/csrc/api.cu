@@ -139,9 +139,25 @@ extern "C" int svb_prof_read(svb_ctx *ctx, int cap, const char **names, double *
     return i;
 }
 
+struct WallScope {  // host wall-clock accounting next to the kernel timers (only when profiling is on)
+    svb_ctx *ctx;
+    const char *name;
+    double bytes;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    WallScope(svb_ctx *c, const char *n, double b = 0) : ctx(c), name(n), bytes(b) {}
+    ~WallScope()
+    {
+        if (!ctx->prof) return;
+        ProfEntry &e = ctx->prof_acc[name];
+        e.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        e.bytes += bytes, e.launches += 1;
+    }
+};
+
 // ---- BAM residency ----------------------------------------------------------------------------------------------
 static int finish_bam(svb_ctx *ctx, std::unique_ptr<svb_bam> &b, svb_bam **out)
 {
+    WallScope ws(ctx, "index_records(wall)");
     CKR(index_records(ctx, b.get()));
     *out = b.release();
     return 0;
@@ -192,20 +208,28 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
     std::vector<BgzfBlock> blocks;
     uint64_t total = 0;
     std::string err;
-    if (!bgzf_scan((const uint8_t *)h_file, file_bytes, blocks, total, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
+    {
+        WallScope ws(ctx, "bgzf_scan(wall)");
+        if (!bgzf_scan((const uint8_t *)h_file, file_bytes, blocks, total, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
+    }
     std::unique_ptr<svb_bam> b(new svb_bam());
     b->ctx = ctx;
-    CK(cudaMalloc((void **)&b->d_owned, total + 256));
-    CK(cudaMemsetAsync(b->d_owned + total, 0, 256, ctx->stream));
-    b->d_data = b->d_owned, b->nbytes = total;
-    // slabs of ~32 MiB of uncompressed data, double buffered
+    // slabs of ~32 MiB of uncompressed data, double buffered, from the recycled pinned pool
     const uint64_t SLAB = 32ull << 20;
     uint8_t *pinned[2] = {nullptr, nullptr};
+    uint64_t pcap[2] = {0, 0};
     cudaEvent_t done[2];
-    for (int i = 0; i < 2; ++i) {
-        CK(cudaHostAlloc((void **)&pinned[i], SLAB + (64 << 10), cudaHostAllocDefault));
-        CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    {
+        WallScope ws(ctx, "stream_alloc(wall)");
+        CK(cudaMalloc((void **)&b->d_owned, total + 256));
+        CK(cudaMemsetAsync(b->d_owned + total, 0, 256, ctx->stream));
+        for (int i = 0; i < 2; ++i) {
+            pinned[i] = (uint8_t *)ctx->pinned_get(SLAB + (64 << 10), &pcap[i]);
+            if (!pinned[i]) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate pinned staging");
+            CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        }
     }
+    b->d_data = b->d_owned, b->nbytes = total;
     std::vector<uint8_t> head;  // first bytes, for the header parse
     size_t bi = 0;
     int slab = 0;
@@ -226,7 +250,7 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
     }
     CK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 2; ++i) {
-        cudaFreeHost(pinned[i]);
+        ctx->pinned_put((char *)pinned[i], pcap[i]);
         cudaEventDestroy(done[i]);
     }
     if (!ok) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
@@ -259,10 +283,18 @@ extern "C" int svb_bam_open(svb_ctx *ctx, const char *path, int n_threads, svb_b
 {
     if (!ctx || !path || !out) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_open: null argument");
     std::string p(path), err;
+    // the reference treats a name ending in ".bam" as BAM and anything else as SAM text (clip_reads.h:367-373)
+    if (p.size() >= 4 && p.rfind(".bam") == p.size() - 4) {
+        // map the file: the inflate threads read the compressed blocks straight from the page cache
+        MappedFile mf;
+        {
+            WallScope ws(ctx, "file_map(wall)");
+            if (!mf.open(p, err)) return svb_fail(ctx, SVB_ERR_IO, "%s", err.c_str());
+        }
+        return svb_bam_from_bgzf(ctx, mf.data, mf.size, n_threads, out);
+    }
     std::vector<uint8_t> file;
     if (!read_file(p, file, err)) return svb_fail(ctx, SVB_ERR_IO, "%s", err.c_str());
-    // the reference treats a name ending in ".bam" as BAM and anything else as SAM text (clip_reads.h:367-373)
-    if (p.size() >= 4 && p.rfind(".bam") == p.size() - 4) return svb_bam_from_bgzf(ctx, file.data(), file.size(), n_threads, out);
     BamHeader hdr;
     std::vector<uint8_t> stream;
     if (!sam_to_bam_stream(file, hdr, stream, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());

@@ -1,5 +1,9 @@
 #include "bamfile.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <atomic>
@@ -7,6 +11,38 @@
 #include <cstring>
 #include <map>
 #include <thread>
+
+bool MappedFile::open(const std::string &path, std::string &err)
+{
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) {
+        err = "cannot open " + path;
+        return false;
+    }
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        ::close(fd);
+        err = "cannot stat " + path;
+        return false;
+    }
+    size = (uint64_t)st.st_size;
+    if (size) {
+        void *p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (p == MAP_FAILED) {
+            ::close(fd);
+            err = "cannot map " + path;
+            return false;
+        }
+        madvise(p, size, MADV_SEQUENTIAL | MADV_WILLNEED);
+        data = (const uint8_t *)p;
+    }
+    ::close(fd);
+    return true;
+}
+MappedFile::~MappedFile()
+{
+    if (data) munmap((void *)data, size);
+}
 
 bool read_file(const std::string &path, std::vector<uint8_t> &out, std::string &err)
 {
@@ -365,11 +401,20 @@ bool read_text_maybe_gz(const std::string &path, std::string &out, std::string &
     return true;
 }
 
+static int gz_level()
+{
+    // the reference's ogzstream uses zlib's default level; parity is defined on the DECOMPRESSED bytes, and the files are
+    // read back exactly once (by bwa and by getsv), so the writer trades a little size for a lot of speed by default
+    const char *e = getenv("SEEKSV_B200_GZ_LEVEL");
+    int l = e ? atoi(e) : 1;
+    return l < 0 || l > 9 ? 1 : l;
+}
+
 static bool gz_member(const char *data, size_t n, std::vector<uint8_t> &out)
 {
     z_stream zs;
     memset(&zs, 0, sizeof zs);
-    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    if (deflateInit2(&zs, gz_level(), Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
     out.resize(deflateBound(&zs, n) + 32);
     zs.next_in = (Bytef *)data;
     zs.avail_in = (uInt)n;
@@ -381,24 +426,32 @@ static bool gz_member(const char *data, size_t n, std::vector<uint8_t> &out)
     return r == Z_STREAM_END;
 }
 
-// The reference writes through ogzstream (gzstream.C:53-61, default level); parity is on the DECOMPRESSED bytes,
-// so the file is written as independent gzip members compressed in parallel (zcat / gzread concatenate them).
-bool write_gz(const std::string &path, const char *data, uint64_t n, int n_threads, std::string &err)
+// The reference writes through ogzstream (gzstream.C:53-61); here every file is cut into 1 MiB parts that are compressed as
+// independent gzip members by one thread pool over ALL files (zcat / gzread concatenate members transparently).
+bool write_gz_many(const std::vector<GzJob> &jobs, int n_threads, std::string &err)
 {
-    const uint64_t PART = 4ull << 20;
-    size_t parts = (size_t)std::max<uint64_t>(1, (n + PART - 1) / PART);
-    std::vector<std::vector<uint8_t>> comp(parts);
+    const uint64_t PART = 1ull << 20;
+    struct Part {
+        size_t job;
+        uint64_t a, b;
+    };
+    std::vector<Part> parts;
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        uint64_t n = jobs[j].n;
+        if (n == 0) parts.push_back(Part{j, 0, 0});
+        for (uint64_t a = 0; a < n; a += PART) parts.push_back(Part{j, a, std::min(n, a + PART)});
+    }
+    std::vector<std::vector<uint8_t>> comp(parts.size());
     std::atomic<size_t> next(0);
     std::atomic<bool> bad(false);
     auto work = [&]() {
         for (;;) {
             size_t i = next.fetch_add(1);
-            if (i >= parts) return;
-            uint64_t a = i * PART, b = std::min(n, a + PART);
-            if (!gz_member(data + a, (size_t)(b - a), comp[i])) bad = true;
+            if (i >= parts.size()) return;
+            if (!gz_member(jobs[parts[i].job].data + parts[i].a, (size_t)(parts[i].b - parts[i].a), comp[i])) bad = true;
         }
     };
-    int nt = (int)std::min<size_t>((size_t)std::max(1, n_threads), parts);
+    int nt = (int)std::min<size_t>((size_t)std::max(1, n_threads), parts.size());
     std::vector<std::thread> th;
     for (int t = 1; t < nt; ++t) th.emplace_back(work);
     work();
@@ -407,17 +460,25 @@ bool write_gz(const std::string &path, const char *data, uint64_t n, int n_threa
         err = "gzip compression failed";
         return false;
     }
-    FILE *f = fopen(path.c_str(), "wb");
-    if (!f) {
-        err = "Cannot open file " + path;
-        return false;
-    }
-    for (auto &c : comp)
-        if (fwrite(c.data(), 1, c.size(), f) != c.size()) {
-            fclose(f);
-            err = "write error on " + path;
+    size_t i = 0;
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        FILE *f = fopen(jobs[j].path.c_str(), "wb");
+        if (!f) {
+            err = "Cannot open file " + jobs[j].path;
             return false;
         }
-    fclose(f);
+        for (; i < parts.size() && parts[i].job == j; ++i)
+            if (fwrite(comp[i].data(), 1, comp[i].size(), f) != comp[i].size()) {
+                fclose(f);
+                err = "write error on " + jobs[j].path;
+                return false;
+            }
+        fclose(f);
+    }
     return true;
+}
+
+bool write_gz(const std::string &path, const char *data, uint64_t n, int n_threads, std::string &err)
+{
+    return write_gz_many({GzJob{path, data, n}}, n_threads, err);
 }

@@ -21,6 +21,12 @@ struct BamHeader {
     uint64_t first_record = 0;  // byte offset of the first record in the uncompressed stream
 };
 
+struct MappedFile {  // read-only mmap of a whole file
+    const uint8_t *data = nullptr;
+    uint64_t size = 0;
+    bool open(const std::string &path, std::string &err);
+    ~MappedFile();
+};
 bool read_file(const std::string &path, std::vector<uint8_t> &out, std::string &err);
 bool bgzf_scan(const uint8_t *file, uint64_t n, std::vector<BgzfBlock> &blocks, uint64_t &total, std::string &err);
 // inflate blocks [b0, b1) into dst (dst[0] corresponds to blocks[b0].uoff) with n_threads host threads
@@ -34,3 +40,9 @@ bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vect
 bool read_text_maybe_gz(const std::string &path, std::string &out, std::string &err);
 // write `data` as a gzip file (ogzstream of the reference; multi-member, compressed by n_threads threads)
 bool write_gz(const std::string &path, const char *data, uint64_t n, int n_threads, std::string &err);
+struct GzJob {
+    std::string path;
+    const char *data;
+    uint64_t n;
+};
+bool write_gz_many(const std::vector<GzJob> &jobs, int n_threads, std::string &err);

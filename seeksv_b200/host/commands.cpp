@@ -187,13 +187,15 @@ int cmd_getclip(int argc, char **argv)
     }
     const char *ext[4] = {".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz"};
     int status = 0;
-    for (int i = 0; i < 4 && status == 0; ++i) {
+    std::vector<GzJob> jobs;
+    for (int i = 0; i < 4; ++i) {
         const char *data;
         uint64_t len;
         svb_clusters_text(cl, i, &data, &len);
-        std::string err;
-        if (!write_gz(prefix + ext[i], data, len, n_threads(), err)) status = fail(err);
+        jobs.push_back(GzJob{prefix + ext[i], data, len});
     }
+    std::string werr;
+    if (!write_gz_many(jobs, n_threads(), werr)) status = fail(werr);
     ph.mark("getclip: gzip + write outputs");
     std::cerr << "[GetSClipReads] finished!" << std::endl;
     svb_clusters_free(cl);

@@ -242,6 +242,29 @@ class Bam:
         finally:
             self.ctx.L.svb_clusters_free(out)
 
+    def getclip_sizes(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0) -> Tuple[int, int, int, int]:
+        """svb_getclip without copying the four host buffers into Python objects: returns their lengths"""
+        p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid)
+        out = C.c_void_p()
+        self.ctx.check(self.ctx.L.svb_getclip(self.ctx.h, self.h, C.byref(p), C.byref(out)), "svb_getclip")
+        try:
+            res = []
+            for which in range(4):
+                d = C.c_char_p()
+                n = C.c_uint64()
+                self.ctx.L.svb_clusters_text(out, which, C.byref(d), C.byref(n))
+                res.append(n.value)
+            return tuple(res)
+        finally:
+            self.ctx.L.svb_clusters_free(out)
+
+    def discordant_support_raw(self, junction_array, n, pair_params, counts_array):
+        self.ctx.check(self.ctx.L.svb_discordant_support(self.ctx.h, self.h, junction_array, n, C.byref(pair_params), counts_array),
+                       "svb_discordant_support")
+
+    def window_depth_raw(self, window_array, n, min_mapq, depth_array):
+        self.ctx.check(self.ctx.L.svb_window_depth(self.ctx.h, self.h, window_array, n, min_mapq, depth_array), "svb_window_depth")
+
     def insert_stats(self, min_mapq=20, max_pairs=5000000):
         out = (C.c_int64 * 4)()
         self.ctx.check(self.ctx.L.svb_insert_stats(self.ctx.h, self.h, min_mapq, max_pairs, out), "svb_insert_stats")
