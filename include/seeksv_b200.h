@@ -64,9 +64,10 @@ int svb_bam_from_device(svb_ctx *ctx, const void *d_stream, uint64_t nbytes, uin
                         svb_bam **out);
 int svb_bam_from_host(svb_ctx *ctx, const void *h_stream, uint64_t nbytes, uint64_t first_record, int32_t n_ref,
                       svb_bam **out);
-/* Whole .bam file image (BGZF) in host memory: host threads inflate the blocks into pinned staging
- * buffers that are streamed to the device with cudaMemcpyAsync; the header is parsed on the host.
- * n_threads <= 0: use all hardware threads. */
+/* Whole .bam file image (BGZF) in host memory. Default: the compressed image goes through pinned staging slabs
+ * (cudaMemcpyAsync) and every BGZF block is inflated on the device (one warp per block). With
+ * SEEKSV_B200_HOST_INFLATE=1 host threads inflate into the pinned slabs instead and the uncompressed bytes are
+ * streamed. The two paths produce identical bytes. n_threads <= 0: use all hardware threads. */
 int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, int n_threads, svb_bam **out);
 int svb_bam_open(svb_ctx *ctx, const char *path, int n_threads, svb_bam **out); /* .bam, else SAM text */
 void svb_bam_free(svb_bam *bam);
@@ -74,6 +75,12 @@ void svb_bam_free(svb_bam *bam);
 /* The resident uncompressed stream of a svb_bam (device pointer, byte count, offset of the first record), e.g. to
  * build further svb_bam views over it with svb_bam_from_device. Valid until svb_bam_free(bam). */
 int svb_bam_device_stream(const svb_bam *bam, const void **d_stream, uint64_t *nbytes, uint64_t *first_record);
+
+/* Inflate any BGZF image on the device (inflate.cu alone) and copy the result to h_out; *out_len is always set to
+ * the uncompressed size, so a first call with h_out = NULL sizes the buffer (diagnostics / tests). */
+int svb_inflate_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, void *h_out, uint64_t out_cap, uint64_t *out_len);
+/* Copy a range of the resident uncompressed stream back to the host (diagnostics / tests). */
+int svb_bam_copy_stream(const svb_bam *bam, void *h_dst, uint64_t offset, uint64_t nbytes);
 
 uint64_t svb_bam_n_records(const svb_bam *bam);
 uint64_t svb_bam_record_bytes(const svb_bam *bam);  /* sum over records of 4 + block_size */

@@ -271,13 +271,14 @@ def header_bytes(h: Header) -> bytes:
     return out
 
 
-def bgzf_compress(data: bytes, level: int = 1, block: int = 0xff00) -> bytes:
-    """BGZF container, sam/bgzf.h:34-60: gzip members with the 'BC' extra sub-field + EOF marker."""
+def bgzf_compress(data: bytes, level: int = 1, block: int = 0xff00, strategy: int = 0) -> bytes:
+    """BGZF container, sam/bgzf.h:34-60: gzip members with the 'BC' extra sub-field + EOF marker.
+    strategy: zlib strategy (0 default, 4 = Z_FIXED forces fixed-Huffman blocks)."""
     import zlib
     out = []
     for i in list(range(0, len(data), block)) + [None]:
         chunk = b"" if i is None else data[i:i + block]
-        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
         comp = c.compress(chunk) + c.flush()
         bsize = len(comp) + 25
         out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize) + comp +

@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <memory>
 #include <thread>
 
@@ -198,8 +199,42 @@ extern "C" int svb_bam_from_host(svb_ctx *ctx, const void *h_stream, uint64_t nb
     return finish_bam(ctx, b, out);
 }
 
-// Host threads inflate BGZF blocks into pinned staging slabs; each finished slab is sent with
-// cudaMemcpyAsync while the next one is being inflated.
+// Parallel memcpy into a pinned slab (the source is the page cache behind an mmap, or any pageable buffer)
+static void parallel_copy(uint8_t *dst, const uint8_t *src, uint64_t n, int n_threads)
+{
+    const uint64_t PART = 1ull << 20;
+    uint64_t parts = (n + PART - 1) / PART;
+    int nt = (int)std::min<uint64_t>((uint64_t)std::max(1, n_threads), parts);
+    if (nt <= 1) {
+        memcpy(dst, src, n);
+        return;
+    }
+    std::atomic<uint64_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            uint64_t i = next.fetch_add(1);
+            if (i >= parts) return;
+            uint64_t a = i * PART, b = std::min(n, a + PART);
+            memcpy(dst + a, src + a, b - a);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+}
+
+static bool use_host_inflate()
+{
+    const char *e = getenv("SEEKSV_B200_HOST_INFLATE");
+    return e && *e && *e != '0';
+}
+
+// BGZF file image (host) -> uncompressed stream in HBM.
+//  default : the COMPRESSED image is staged through pinned slabs (parallel memcpy + cudaMemcpyAsync) and inflated on
+//            the device, one warp per BGZF block (inflate.cu) - about a third of the PCIe bytes and no host zlib;
+//  SEEKSV_B200_HOST_INFLATE=1 : host threads inflate the blocks into the pinned slabs (zlib) and the uncompressed
+//            bytes are streamed with cudaMemcpyAsync, each slab overlapping the inflation of the next.
 extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, int n_threads, svb_bam **out)
 {
     if (!ctx || !out || !h_file) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_bgzf: null argument");
@@ -214,15 +249,17 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
     }
     std::unique_ptr<svb_bam> b(new svb_bam());
     b->ctx = ctx;
-    // slabs of ~32 MiB of uncompressed data, double buffered, from the recycled pinned pool
+    const bool host_inflate = use_host_inflate();
     const uint64_t SLAB = 32ull << 20;
     uint8_t *pinned[2] = {nullptr, nullptr};
     uint64_t pcap[2] = {0, 0};
     cudaEvent_t done[2];
+    DevBuf<uint8_t> d_file;
     {
         WallScope ws(ctx, "stream_alloc(wall)");
         CK(cudaMalloc((void **)&b->d_owned, total + 256));
         CK(cudaMemsetAsync(b->d_owned + total, 0, 256, ctx->stream));
+        if (!host_inflate) CK(d_file.alloc(file_bytes + 256, ctx->stream));
         for (int i = 0; i < 2; ++i) {
             pinned[i] = (uint8_t *)ctx->pinned_get(SLAB + (64 << 10), &pcap[i]);
             if (!pinned[i]) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate pinned staging");
@@ -230,35 +267,56 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
         }
     }
     b->d_data = b->d_owned, b->nbytes = total;
-    std::vector<uint8_t> head;  // first bytes, for the header parse
-    size_t bi = 0;
-    int slab = 0;
+    std::vector<uint8_t> head;  // first uncompressed bytes, for the header parse
     bool ok = true;
-    auto t0 = std::chrono::steady_clock::now();
-    while (bi < blocks.size() && ok) {
-        size_t bj = bi;
-        uint64_t bytes = 0;
-        while (bj < blocks.size() && bytes + blocks[bj].ulen <= SLAB + (64 << 10) && bytes < SLAB) bytes += blocks[bj++].ulen;
-        CK(cudaEventSynchronize(done[slab]));
-        ok = bgzf_inflate_range((const uint8_t *)h_file, blocks, bi, bj, pinned[slab], n_threads, err);
-        if (!ok) break;
-        if (head.size() < (1u << 20)) head.insert(head.end(), pinned[slab], pinned[slab] + std::min<uint64_t>(bytes, (4u << 20)));
-        CK(cudaMemcpyAsync(b->d_owned + blocks[bi].uoff, pinned[slab], bytes, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaEventRecord(done[slab], ctx->stream));
-        slab ^= 1;
-        bi = bj;
+    int slab = 0;
+    if (host_inflate) {
+        WallScope ws(ctx, "host_inflate+h2d(wall)", (double)total);
+        size_t bi = 0;
+        while (bi < blocks.size() && ok) {
+            size_t bj = bi;
+            uint64_t bytes = 0;
+            while (bj < blocks.size() && bytes + blocks[bj].ulen <= SLAB + (64 << 10) && bytes < SLAB) bytes += blocks[bj++].ulen;
+            CK(cudaEventSynchronize(done[slab]));
+            ok = bgzf_inflate_range((const uint8_t *)h_file, blocks, bi, bj, pinned[slab], n_threads, err);
+            if (!ok) break;
+            if (head.size() < (1u << 20)) head.insert(head.end(), pinned[slab], pinned[slab] + std::min<uint64_t>(bytes, (4u << 20)));
+            CK(cudaMemcpyAsync(b->d_owned + blocks[bi].uoff, pinned[slab], bytes, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaEventRecord(done[slab], ctx->stream));
+            slab ^= 1;
+            bi = bj;
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        {
+            WallScope ws(ctx, "h2d_compressed(wall)", (double)file_bytes);
+            CK(cudaMemsetAsync(d_file.p + file_bytes, 0, 256, ctx->stream));
+            for (uint64_t o = 0; o < file_bytes; o += SLAB) {
+                uint64_t n = std::min(SLAB, file_bytes - o);
+                CK(cudaEventSynchronize(done[slab]));
+                parallel_copy(pinned[slab], (const uint8_t *)h_file + o, n, n_threads);
+                CK(cudaMemcpyAsync(d_file.p + o, pinned[slab], n, cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaEventRecord(done[slab], ctx->stream));
+                slab ^= 1;
+            }
+        }
+        static_assert(sizeof(BgzfBlock) == 24, "BgzfBlock must match the device-side block descriptor");
+        DevBuf<BgzfBlock> d_blocks;
+        CK(d_blocks.alloc(blocks.size(), ctx->stream));
+        CK(cudaMemcpyAsync(d_blocks.p, blocks.data(), blocks.size() * sizeof(BgzfBlock), cudaMemcpyHostToDevice, ctx->stream));
+        int rc = inflate_on_device(ctx, d_file.p, d_blocks.p, (uint32_t)blocks.size(), b->d_owned, (double)total);
+        if (rc != 0) {
+            for (int i = 0; i < 2; ++i) ctx->pinned_put((char *)pinned[i], pcap[i]), cudaEventDestroy(done[i]);
+            return rc;
+        }
+        head.resize(std::min<uint64_t>(total, 1u << 20));
+        CK(cudaMemcpy(head.data(), b->d_owned, head.size(), cudaMemcpyDeviceToHost));
     }
-    CK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 2; ++i) {
         ctx->pinned_put((char *)pinned[i], pcap[i]);
         cudaEventDestroy(done[i]);
     }
     if (!ok) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
-    if (ctx->prof) {
-        ProfEntry &e = ctx->prof_acc["host_inflate+h2d(wall)"];
-        e.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        e.bytes += (double)total, e.launches += 1;
-    }
     // header
     BamHeader hdr;
     if (!parse_bam_header(head.data(), head.size(), hdr, err)) {
@@ -277,6 +335,39 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
         return svb_fail(ctx, SVB_ERR_FORMAT, "truncated or corrupt BAM: record chain ends %llu bytes early", missing);
     }
     return 0;
+}
+
+// Inflate an arbitrary BGZF image on the device and return the bytes (diagnostics / tests of the inflate kernel alone).
+extern "C" int svb_inflate_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, void *h_out, uint64_t out_cap, uint64_t *out_len)
+{
+    if (!ctx || !h_file || !out_len) return svb_fail(ctx, SVB_ERR_ARG, "svb_inflate_bgzf: null argument");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<BgzfBlock> blocks;
+    uint64_t total = 0;
+    std::string err;
+    if (!bgzf_scan((const uint8_t *)h_file, file_bytes, blocks, total, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
+    *out_len = total;
+    if (!h_out || out_cap < total) return total ? svb_fail(ctx, SVB_ERR_ARG, "svb_inflate_bgzf: output buffer too small") : 0;
+    DevBuf<uint8_t> d_file, d_out;
+    DevBuf<BgzfBlock> d_blocks;
+    CK(d_file.alloc(file_bytes + 256, ctx->stream));
+    CK(d_out.alloc(total + 256, ctx->stream));
+    CK(d_blocks.alloc(blocks.size(), ctx->stream));
+    CK(cudaMemsetAsync(d_file.p + file_bytes, 0, 256, ctx->stream));
+    CK(cudaMemcpyAsync(d_file.p, h_file, file_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_blocks.p, blocks.data(), blocks.size() * sizeof(BgzfBlock), cudaMemcpyHostToDevice, ctx->stream));
+    CKR(inflate_on_device(ctx, d_file.p, d_blocks.p, (uint32_t)blocks.size(), d_out.p, (double)total));
+    CK(cudaMemcpyAsync(h_out, d_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int svb_bam_copy_stream(const svb_bam *b, void *h_dst, uint64_t offset, uint64_t nbytes)
+{
+    if (!b || !h_dst || offset + nbytes > b->nbytes) return SVB_ERR_ARG;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    return cudaMemcpy(h_dst, b->d_data + offset, nbytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : SVB_ERR_CUDA;
 }
 
 extern "C" int svb_bam_open(svb_ctx *ctx, const char *path, int n_threads, svb_bam **out)

@@ -212,6 +212,8 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t v)
 
 // ---- internal entry points (one per .cu) ------------------------------------------------------------------
 int index_records(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu
-int decode_records(svb_ctx *ctx, svb_bam *bam);                      // bam_decode.cu
+int decode_records(svb_ctx *ctx, svb_bam *bam);                      // getsv.cu
+int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out,
+                      double out_bytes);                             // inflate.cu
 int inclusive_scan_u32(svb_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n);
 int exclusive_scan_u64(svb_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t n);

@@ -1,0 +1,337 @@
+// BGZF inflate on the device: one warp per BGZF block (RFC 1951 DEFLATE: stored, fixed and dynamic Huffman blocks).
+//
+// Replaces the bgzf.o / zlib inflate of the reference's libbam (sam/bgzf.h:34-134; `bam_read1` -> `bgzf_read` ->
+// `inflate_block`), which SURVEY.md section 0 measures at ~75 % of getclip's run time on the host. BGZF blocks are
+// independent deflate streams of at most 64 KiB of output, so a whole BAM offers tens of thousands of blocks to
+// decode concurrently. Inside a warp lane 0 owns the bit reader and the Huffman decode (serial by nature); all 32
+// lanes build the decode tables and perform the LZ77 match copies. Decode tables live in shared memory
+// (4.3 KB per warp): a 10-bit single-lookup table for literal/length codes, an 8-bit one for distance codes, and a
+// canonical (count / sorted-symbol) fallback for the rare longer codes.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LIT_FAST = 10, DIST_FAST = 8, WARPS_PER_CTA = 8;
+
+struct WarpTables {
+    uint16_t lit_fast[1 << LIT_FAST];    // (len << 9) | symbol, 0 = not a short code
+    uint16_t dist_fast[1 << DIST_FAST];  // (len << 9) | symbol
+    uint16_t lit_sym[288], dist_sym[32];  // symbols sorted by (code length, symbol) for the canonical slow path
+    uint16_t lit_count[16], dist_count[16];
+    uint16_t code[288];  // canonical code of each symbol while a table is being built
+    uint8_t lens[320];   // code lengths: literal/length alphabet followed by the distance alphabet
+    uint8_t cl_fast[128];  // code-length alphabet: (len << 5) | symbol, 7-bit lookup
+};
+
+__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct BitReader {  // lives in lane 0's registers
+    const uint8_t *in, *end;
+    uint64_t buf;
+    int cnt;
+    __device__ void init(const uint8_t *p, const uint8_t *e)
+    {
+        in = p, end = e, buf = 0, cnt = 0;
+        while (((uintptr_t)in & 3) && cnt <= 56) {  // byte loads until the pointer is word aligned
+            buf |= (uint64_t)(*in++) << cnt;
+            cnt += 8;
+        }
+    }
+    __device__ __forceinline__ void refill()  // keeps at least 32 valid bits (the file image is padded past its end)
+    {
+        if (cnt < 32) {
+            buf |= (uint64_t)__ldg((const uint32_t *)in) << cnt;
+            in += 4;
+            cnt += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1); }
+    __device__ __forceinline__ void skip(int n) { buf >>= n, cnt -= n; }
+    __device__ __forceinline__ uint32_t bits(int n)
+    {
+        uint32_t v = peek(n);
+        skip(n);
+        return v;
+    }
+    __device__ void align_byte() { skip(cnt & 7); }
+};
+
+// Build the decode tables of one alphabet from its code lengths (canonical Huffman, RFC 1951 3.2.2).
+// Lane 0 assigns codes serially (<= 288 symbols); all lanes fill the single-lookup table.
+__device__ void build_table(const uint8_t *lens, int n, uint16_t *fast, int fast_bits, uint16_t *sym_sorted, uint16_t *count,
+                            uint16_t *code, uint32_t lane)
+{
+    for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
+    if (lane < 16) count[lane] = 0;
+    __syncwarp();
+    if (lane == 0) {
+        for (int s = 0; s < n; ++s) count[lens[s]]++;
+        count[0] = 0;
+        uint16_t next_code[16], offs[16];
+        uint32_t c = 0;
+        offs[1] = 0;
+        next_code[0] = 0;
+        for (int b = 1; b <= 15; ++b) {
+            c = (c + count[b - 1]) << 1;
+            next_code[b] = (uint16_t)c;
+            if (b < 15) offs[b + 1] = offs[b] + count[b];
+        }
+        for (int s = 0; s < n; ++s) {
+            int l = lens[s];
+            if (l) {
+                code[s] = next_code[l]++;
+                sym_sorted[offs[l]++] = (uint16_t)s;
+            }
+        }
+    }
+    __syncwarp();
+    for (int s = lane; s < n; s += 32) {
+        int l = lens[s];
+        if (l && l <= fast_bits) {
+            uint32_t rev = __brev((uint32_t)code[s]) >> (32 - l);  // codes are sent MSB first, bits are read LSB first
+            uint16_t e = (uint16_t)(l << 9 | s);
+            for (uint32_t k = rev; k < (1u << fast_bits); k += 1u << l) fast[k] = e;
+        }
+    }
+    __syncwarp();
+}
+
+// canonical bit-by-bit decode for codes longer than the lookup width
+__device__ int slow_decode(BitReader &br, const uint16_t *count, const uint16_t *sym_sorted)
+{
+    int code = 0, first = 0, index = 0;
+    for (int len = 1; len <= 15; ++len) {
+        code |= (int)br.bits(1);
+        int c = count[len];
+        if (code - c < first) return sym_sorted[index + (code - first)];
+        index += c, first += c;
+        first <<= 1, code <<= 1;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ int decode_sym(BitReader &br, const uint16_t *fast, int fast_bits, const uint16_t *count,
+                                          const uint16_t *sym_sorted)
+{
+    uint16_t e = fast[br.peek(fast_bits)];
+    if (e) {
+        br.skip(e >> 9);
+        return e & 511;
+    }
+    return slow_decode(br, count, sym_sorted);
+}
+
+}  // namespace
+
+struct InflateBlock {
+    uint64_t coff, uoff;
+    uint32_t clen, ulen;
+};
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+    inflate_bgzf(const uint8_t *__restrict__ file, const InflateBlock *__restrict__ blocks, uint32_t n_blocks, uint8_t *__restrict__ out,
+                 uint32_t *__restrict__ error)
+{
+    __shared__ WarpTables tables[WARPS_PER_CTA];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x * WARPS_PER_CTA + wid;
+    if (b >= n_blocks) return;
+    WarpTables &T = tables[wid];
+    const InflateBlock blk = blocks[b];
+    uint8_t *dst = out + blk.uoff;
+    BitReader br;
+    if (lane == 0) br.init(file + blk.coff, file + blk.coff + blk.clen);
+    uint32_t pos = 0;
+    bool bad = false;
+    for (;;) {
+        uint32_t hdr = 0;
+        if (lane == 0) {
+            br.refill();
+            hdr = br.bits(3);
+        }
+        hdr = __shfl_sync(0xffffffffu, hdr, 0);
+        const uint32_t final_block = hdr & 1, type = hdr >> 1;
+        if (type == 0) {  // stored
+            uint32_t len = 0;
+            const uint8_t *src = nullptr;
+            if (lane == 0) {
+                br.align_byte();
+                br.refill();
+                len = br.bits(16);
+                br.refill();
+                br.skip(16);  // NLEN
+                // rewind the word-wise reader to the byte position of the payload
+                src = br.in - (br.cnt >> 3);
+                br.init(src + len, br.end);
+            }
+            len = __shfl_sync(0xffffffffu, len, 0);
+            src = (const uint8_t *)__shfl_sync(0xffffffffu, (unsigned long long)src, 0);
+            if (pos + len > blk.ulen) {
+                bad = true;
+                break;
+            }
+            for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i];
+            pos += len;
+        } else if (type == 1 || type == 2) {
+            int n_lit = 288, n_dist = 30;
+            if (type == 1) {  // fixed Huffman codes (RFC 1951 3.2.6)
+                for (int i = lane; i < 288; i += 32) T.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+                for (int i = lane; i < 30; i += 32) T.lens[288 + i] = 5;
+            } else {  // dynamic: code lengths are themselves Huffman coded (3.2.7), decoded serially by lane 0
+                int ok = 1;
+                if (lane == 0) {
+                    br.refill();
+                    n_lit = (int)br.bits(5) + 257;
+                    n_dist = (int)br.bits(5) + 1;
+                    int n_cl = (int)br.bits(4) + 4;
+                    uint8_t cl[19];
+                    for (int i = 0; i < 19; ++i) cl[i] = 0;
+                    for (int i = 0; i < n_cl; ++i) {
+                        br.refill();
+                        cl[c_cl_order[i]] = (uint8_t)br.bits(3);
+                    }
+                    // 7-bit lookup for the code-length alphabet
+                    for (int i = 0; i < 128; ++i) T.cl_fast[i] = 0;
+                    uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, next[8];
+                    for (int i = 0; i < 19; ++i) cnt[cl[i]]++;
+                    cnt[0] = 0;
+                    uint32_t c = 0;
+                    next[0] = 0;
+                    for (int l = 1; l < 8; ++l) {
+                        c = (c + cnt[l - 1]) << 1;
+                        next[l] = c;
+                    }
+                    for (int s = 0; s < 19; ++s) {
+                        int l = cl[s];
+                        if (!l) continue;
+                        uint32_t rev = __brev(next[l]++) >> (32 - l);
+                        for (uint32_t k = rev; k < 128; k += 1u << l) T.cl_fast[k] = (uint8_t)(l << 5 | s);
+                    }
+                    int i = 0, total = n_lit + n_dist;
+                    if (n_lit > 286 || n_dist > 30) ok = 0;
+                    while (ok && i < total) {
+                        br.refill();
+                        uint8_t e = T.cl_fast[br.peek(7)];
+                        if (!e) {
+                            ok = 0;
+                            break;
+                        }
+                        br.skip(e >> 5);
+                        int s = e & 31;
+                        if (s < 16) T.lens[i++] = (uint8_t)s;
+                        else {
+                            int rep, v = 0;
+                            if (s == 16) {
+                                if (i == 0) {
+                                    ok = 0;
+                                    break;
+                                }
+                                v = T.lens[i - 1];
+                                rep = 3 + (int)br.bits(2);
+                            } else if (s == 17) rep = 3 + (int)br.bits(3);
+                            else rep = 11 + (int)br.bits(7);
+                            if (i + rep > total) {
+                                ok = 0;
+                                break;
+                            }
+                            while (rep--) T.lens[i++] = (uint8_t)v;
+                        }
+                    }
+                }
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                n_lit = __shfl_sync(0xffffffffu, n_lit, 0);
+                n_dist = __shfl_sync(0xffffffffu, n_dist, 0);
+                if (!ok) {
+                    bad = true;
+                    break;
+                }
+                __syncwarp();
+                // the distance lengths follow the literal/length lengths directly: move them to their own slot
+                if (n_lit < 288) {
+                    uint8_t v = lane < (uint32_t)n_dist ? T.lens[n_lit + lane] : 0;
+                    __syncwarp();
+                    if (lane < (uint32_t)n_dist) T.lens[288 + lane] = v;
+                    for (int i = n_lit + lane; i < 288; i += 32) T.lens[i] = 0;
+                    __syncwarp();
+                    for (int i = n_lit + lane; i < 288; i += 32) T.lens[i] = 0;
+                }
+            }
+            __syncwarp();
+            build_table(T.lens, type == 1 ? 288 : n_lit, T.lit_fast, LIT_FAST, T.lit_sym, T.lit_count, T.code, lane);
+            build_table(T.lens + 288, n_dist, T.dist_fast, DIST_FAST, T.dist_sym, T.dist_count, T.code, lane);
+            // symbol loop: lane 0 decodes, the warp copies matches
+            for (;;) {
+                int sym = 0;
+                uint32_t len = 0, dist = 0;
+                if (lane == 0) {
+                    br.refill();
+                    sym = decode_sym(br, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
+                    // runs of literals stay on lane 0: no warp-wide exchange until a match or the end of the block
+                    while (sym >= 0 && sym < 256 && pos < blk.ulen) {
+                        dst[pos++] = (uint8_t)sym;
+                        br.refill();
+                        sym = decode_sym(br, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
+                    }
+                    if (sym > 256 && sym < 286) {
+                        int li = sym - 257;
+                        len = c_len_base[li] + br.bits(c_len_extra[li]);
+                        br.refill();
+                        int ds = decode_sym(br, T.dist_fast, DIST_FAST, T.dist_count, T.dist_sym);
+                        if (ds < 0 || ds >= 30) sym = -1;
+                        else dist = c_dist_base[ds] + br.bits(c_dist_extra[ds]);
+                    } else if (sym != 256)
+                        sym = -1;
+                }
+                sym = __shfl_sync(0xffffffffu, sym, 0);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (sym == 256) break;
+                len = __shfl_sync(0xffffffffu, len, 0);
+                dist = __shfl_sync(0xffffffffu, dist, 0);
+                if (sym < 0 || dist > pos || pos + len > blk.ulen) {
+                    bad = true;
+                    break;
+                }
+                // LZ77 copy; an overlapping match (dist < len) repeats the last `dist` bytes, which are all written already
+                const uint8_t *src = dst + pos - dist;
+                __syncwarp();  // lane 0's literal stores must be visible to the lanes that copy
+                if (dist >= len) {
+                    for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i];
+                } else {
+                    for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i % dist];
+                }
+                pos += len;
+                __syncwarp();
+            }
+            if (bad) break;
+        } else {
+            bad = true;
+            break;
+        }
+        if (final_block) break;
+    }
+    if ((bad || pos != blk.ulen) && lane == 0) atomicOr(error, 1u);
+}
+
+// host wrapper: file image + block table already on the device
+int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, double out_bytes)
+{
+    cudaStream_t s = ctx->stream;
+    DevBuf<uint32_t> err;
+    CK(err.alloc(1, s));
+    CK(cudaMemsetAsync(err.p, 0, 4, s));
+    if (n_blocks) {
+        ProfScope ps(ctx, "inflate_bgzf", out_bytes);
+        inflate_bgzf<<<(n_blocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, s>>>(d_file, (const InflateBlock *)d_blocks,
+                                                                                                 n_blocks, d_out, err.p);
+    }
+    uint32_t h = 0;
+    CK(cudaMemcpyAsync(&h, err.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (h) return svb_fail(ctx, SVB_ERR_FORMAT, "BGZF inflate failed (corrupt deflate stream)");
+    return 0;
+}

@@ -7,10 +7,10 @@
 #include <string>
 #include <vector>
 
-struct BgzfBlock {
+struct BgzfBlock {  // (layout shared with the device inflate kernel: 24 bytes)
     uint64_t coff;  // offset of the deflate payload in the file image
-    uint32_t clen;  // deflate payload length
     uint64_t uoff;  // offset in the uncompressed stream
+    uint32_t clen;  // deflate payload length
     uint32_t ulen;  // uncompressed length (ISIZE)
 };
 

@@ -42,7 +42,7 @@ class Window(C.Structure):
 EXPORTS = [
     "svb_abi_version", "svb_ctx_create", "svb_ctx_destroy", "svb_last_error", "svb_ctx_stream", "svb_prof_enable",
     "svb_prof_reset", "svb_prof_read", "svb_bam_from_device", "svb_bam_from_host", "svb_bam_from_bgzf", "svb_bam_open",
-    "svb_bam_free", "svb_bam_device_stream", "svb_bam_n_records", "svb_bam_record_bytes", "svb_bam_n_ref", "svb_bam_ref_name", "svb_bam_ref_len",
+    "svb_bam_free", "svb_bam_device_stream", "svb_bam_copy_stream", "svb_inflate_bgzf", "svb_bam_n_records", "svb_bam_record_bytes", "svb_bam_n_ref", "svb_bam_ref_name", "svb_bam_ref_len",
     "svb_bam_set_refs", "svb_getclip", "svb_clusters_free", "svb_clusters_count", "svb_clusters_candidates",
     "svb_clusters_text", "svb_insert_stats", "svb_discordant_support", "svb_window_depth", "svb_plan_getsv", "svb_free",
     "svb_main",
@@ -80,6 +80,8 @@ def load():
     L.svb_bam_free.argtypes = [vp]
     L.svb_bam_free.restype = None
     L.svb_bam_device_stream.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+    L.svb_bam_copy_stream.argtypes = [vp, vp, u64, u64]
+    L.svb_inflate_bgzf.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64)]
     for f in ("svb_bam_n_records", "svb_bam_record_bytes"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = u64
@@ -156,6 +158,16 @@ class Context:
             pass
 
 
+def inflate_bgzf(ctx: "Context", image: bytes) -> bytes:
+    """device-side BGZF inflate of an arbitrary image (tests of inflate.cu)"""
+    n = C.c_uint64()
+    src = (C.c_char * len(image)).from_buffer_copy(image)
+    ctx.check(ctx.L.svb_inflate_bgzf(ctx.h, src, len(image), None, 0, C.byref(n)), "svb_inflate_bgzf(size)")
+    out = (C.c_char * max(1, n.value))()
+    ctx.check(ctx.L.svb_inflate_bgzf(ctx.h, src, len(image), out, n.value, C.byref(n)), "svb_inflate_bgzf")
+    return bytes(out[:n.value])
+
+
 class Bam:
     """A BAM (or shard) resident in HBM (svb_bam)."""
 
@@ -205,6 +217,13 @@ class Bam:
         d, n, f = C.c_void_p(), C.c_uint64(), C.c_uint64()
         self.ctx.check(self.ctx.L.svb_bam_device_stream(self.h, C.byref(d), C.byref(n), C.byref(f)), "svb_bam_device_stream")
         return d.value or 0, n.value, f.value
+
+    def copy_stream(self) -> bytes:
+        """the whole resident uncompressed stream, copied back to the host (tests)"""
+        _, n, _ = self.device_stream()
+        buf = (C.c_char * n)()
+        self.ctx.check(self.ctx.L.svb_bam_copy_stream(self.h, buf, 0, n), "svb_bam_copy_stream")
+        return bytes(buf)
 
     @property
     def n_records(self) -> int:

@@ -221,3 +221,35 @@ def test_synthetic_cli_vs_reference_binary(genome, extra, tmp_path):
     for (tag, sample, what), v in outs.items():
         if tag == "ref":
             assert outs[("b200", sample, what)] == v, (sample, what)
+
+
+def test_device_inflate_matches_zlib(ctx, tmp_path, monkeypatch):
+    """BGZF inflate on the device (one warp per block) == zlib, for dynamic / fixed / stored deflate blocks and
+    for the host-thread inflate path (SEEKSV_B200_HOST_INFLATE=1)."""
+    import random
+    import seeksv_b200
+    from oracle import bamio
+    rng = random.Random(11)
+    raw = bamio.read_bgzf(_bam("micro", "tumor"))
+    cases = {"fixture": open(_bam("example", "cancer"), "rb").read()}
+    for name, level, strategy, block in (("level0_stored", 0, 0, 0xff00), ("level1", 1, 0, 0xff00), ("level9", 9, 0, 0xff00),
+                                         ("fixed", 6, 4, 0xff00), ("tiny_blocks", 6, 0, 777), ("huffman_only", 6, 2, 0x8000),
+                                         ("rle", 6, 3, 0xfff0)):
+        cases[name] = bamio.bgzf_compress(raw, level, block, strategy)
+    # incompressible + highly repetitive payload after a valid BAM (long matches, dist < len copies, long codes)
+    noise = bytes(rng.randrange(256) for _ in range(70000)) + b"A" * 100000 + bytes(range(256)) * 300
+    cases["mixed"] = bamio.bgzf_compress(raw + noise, 6)
+    for name, img in cases.items():
+        want = __import__("gzip").decompress(img)
+        for host in ("0", "1"):
+            monkeypatch.setenv("SEEKSV_B200_HOST_INFLATE", host)
+            if name == "mixed":
+                # not a well-formed record chain: the BAM load must fail cleanly; the inflate kernel alone must not
+                with pytest.raises(seeksv_b200.SvbError):
+                    seeksv_b200.Bam.from_bgzf(ctx, img)
+                from seeksv_b200.lib import inflate_bgzf
+                assert inflate_bgzf(ctx, img) == want
+                continue
+            bam = seeksv_b200.Bam.from_bgzf(ctx, img)
+            assert bam.copy_stream() == want, (name, host)
+            bam.close()
