@@ -177,7 +177,7 @@ extern "C" int svb_bam_from_device(svb_ctx *ctx, const void *d_stream, uint64_t 
 
 static int upload(svb_ctx *ctx, svb_bam *b, const void *h, uint64_t nbytes)
 {
-    CK(cudaMalloc((void **)&b->d_owned, nbytes + 256));
+    CK(cudaMallocAsync((void **)&b->d_owned, nbytes + 256, ctx->stream));
     CK(cudaMemsetAsync(b->d_owned + nbytes, 0, 256, ctx->stream));
     {
         ProfScope ps(ctx, "h2d_stream", (double)nbytes);
@@ -257,7 +257,7 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
     DevBuf<uint8_t> d_file;
     {
         WallScope ws(ctx, "stream_alloc(wall)");
-        CK(cudaMalloc((void **)&b->d_owned, total + 256));
+        CK(cudaMallocAsync((void **)&b->d_owned, total + 256, ctx->stream));  // pool: reused by the next load in this process
         CK(cudaMemsetAsync(b->d_owned + total, 0, 256, ctx->stream));
         if (!host_inflate) CK(d_file.alloc(file_bytes + 256, ctx->stream));
         for (int i = 0; i < 2; ++i) {
@@ -347,7 +347,8 @@ extern "C" int svb_inflate_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_
     std::string err;
     if (!bgzf_scan((const uint8_t *)h_file, file_bytes, blocks, total, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
     *out_len = total;
-    if (!h_out || out_cap < total) return total ? svb_fail(ctx, SVB_ERR_ARG, "svb_inflate_bgzf: output buffer too small") : 0;
+    if (!h_out) return 0;  // size query
+    if (out_cap < total) return svb_fail(ctx, SVB_ERR_ARG, "svb_inflate_bgzf: output buffer too small");
     DevBuf<uint8_t> d_file, d_out;
     DevBuf<BgzfBlock> d_blocks;
     CK(d_file.alloc(file_bytes + 256, ctx->stream));
@@ -405,7 +406,7 @@ extern "C" void svb_bam_free(svb_bam *b)
     void *cols[8] = {L.tid, L.pos, L.end, L.flagq, L.lqseq, L.mtid, L.mpos, L.isize};
     for (void *c : cols)
         if (c) cudaFreeAsync(c, s);
-    if (b->d_owned) cudaFree(b->d_owned);
+    if (b->d_owned) cudaFreeAsync(b->d_owned, s);
     delete b;
 }
 

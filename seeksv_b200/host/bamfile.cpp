@@ -65,42 +65,96 @@ bool read_file(const std::string &path, std::vector<uint8_t> &out, std::string &
 }
 
 // BGZF: gzip members with FEXTRA holding the 'BC' sub-field = member size - 1 (sam/bgzf.h:34-60)
-bool bgzf_scan(const uint8_t *f, uint64_t n, std::vector<BgzfBlock> &blocks, uint64_t &total, std::string &err)
+// header at f[o]: returns the member size, 0 if this is not a BGZF member header
+static uint32_t bgzf_member(const uint8_t *f, uint64_t n, uint64_t o, uint32_t *xlen_out)
 {
-    uint64_t o = 0;
-    total = 0;
-    blocks.clear();
-    while (o < n) {
-        if (o + 18 > n || f[o] != 0x1f || f[o + 1] != 0x8b || f[o + 2] != 8 || !(f[o + 3] & 4)) {
-            err = "not a BGZF block at offset " + std::to_string(o);
-            return false;
-        }
-        uint32_t xlen = f[o + 10] | (f[o + 11] << 8);
-        uint64_t x = o + 12, xe = x + xlen;
-        uint32_t bsize = 0;
-        bool found = false;
-        while (x + 4 <= xe && xe <= n) {
-            uint32_t slen = f[x + 2] | (f[x + 3] << 8);
-            if (f[x] == 'B' && f[x + 1] == 'C' && slen == 2) {
-                bsize = (f[x + 4] | (f[x + 5] << 8)) + 1;
-                found = true;
-            }
-            x += 4 + slen;
-        }
-        if (!found || o + bsize > n || bsize < 12 + xlen + 8) {
-            err = "bad BGZF block at offset " + std::to_string(o);
-            return false;
-        }
+    if (o + 18 > n || f[o] != 0x1f || f[o + 1] != 0x8b || f[o + 2] != 8 || !(f[o + 3] & 4)) return 0;
+    uint32_t xlen = f[o + 10] | (f[o + 11] << 8);
+    uint64_t x = o + 12, xe = x + xlen;
+    if (xe > n) return 0;
+    uint32_t bsize = 0;
+    while (x + 4 <= xe) {
+        uint32_t slen = f[x + 2] | (f[x + 3] << 8);
+        if (f[x] == 'B' && f[x + 1] == 'C' && slen == 2 && x + 6 <= xe) bsize = (f[x + 4] | (f[x + 5] << 8)) + 1;
+        x += 4 + slen;
+    }
+    if (!bsize || o + bsize > n || bsize < 12 + xlen + 8) return 0;
+    *xlen_out = xlen;
+    return bsize;
+}
+
+// The member chain is serial (each header gives the next offset). Like the record chain on the device it is cut into
+// segments whose first header is GUESSED (magic + BC + a valid successor), walked in parallel, and stitched only where
+// each segment's exit equals the next segment's guess; anything else falls back to the serial walk.
+static bool walk_members(const uint8_t *f, uint64_t n, uint64_t from, uint64_t until, std::vector<BgzfBlock> &out, uint64_t &exit_)
+{
+    uint64_t o = from;
+    while (o < until) {
+        uint32_t xlen, bsize = bgzf_member(f, n, o, &xlen);
+        if (!bsize) return false;
         BgzfBlock b;
         b.coff = o + 12 + xlen;
         b.clen = bsize - 12 - xlen - 8;
         const uint8_t *t = f + o + bsize - 4;
         b.ulen = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
-        b.uoff = total;
-        total += b.ulen;
-        if (b.ulen) blocks.push_back(b);
+        b.uoff = 0;
+        out.push_back(b);
         o += bsize;
     }
+    exit_ = o;
+    return true;
+}
+
+bool bgzf_scan(const uint8_t *f, uint64_t n, std::vector<BgzfBlock> &blocks, uint64_t &total, std::string &err)
+{
+    total = 0;
+    blocks.clear();
+    int nseg = (int)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), n >> 22);  // >= 4 MiB per segment
+    bool stitched = false;
+    if (nseg > 1) {
+        std::vector<uint64_t> guess(nseg, 0), exit_(nseg, 0);
+        std::vector<std::vector<BgzfBlock>> part(nseg);
+        std::vector<char> ok(nseg, 0);
+        std::vector<std::thread> th;
+        for (int s = 0; s < nseg; ++s)
+            th.emplace_back([&, s]() {
+                uint64_t lo = n / nseg * s, hi = s + 1 == nseg ? n : n / nseg * (s + 1);
+                uint64_t g = lo;
+                if (s > 0) {
+                    g = n;
+                    for (uint64_t o = lo; o < std::min(n, lo + (1u << 17)); ++o) {
+                        uint32_t xl, bs = bgzf_member(f, n, o, &xl), xl2;
+                        if (bs && (o + bs == n || bgzf_member(f, n, o + bs, &xl2))) {
+                            g = o;
+                            break;
+                        }
+                    }
+                }
+                guess[s] = g;
+                ok[s] = g <= hi && walk_members(f, n, g, hi, part[s], exit_[s]);
+            });
+        for (auto &t : th) t.join();
+        stitched = true;
+        for (int s = 0; s < nseg && stitched; ++s) stitched = ok[s] && (s == 0 || exit_[s - 1] == guess[s]);
+        if (stitched && exit_[nseg - 1] != n) stitched = false;
+        if (stitched)
+            for (auto &p : part) blocks.insert(blocks.end(), p.begin(), p.end());
+    }
+    if (!stitched) {
+        blocks.clear();
+        uint64_t e = 0;
+        if (!walk_members(f, n, 0, n, blocks, e) || e != n) {
+            err = "not a BGZF file (bad block header)";
+            return false;
+        }
+    }
+    size_t w = 0;
+    for (size_t i = 0; i < blocks.size(); ++i) {
+        blocks[i].uoff = total;
+        total += blocks[i].ulen;
+        if (blocks[i].ulen) blocks[w++] = blocks[i];
+    }
+    blocks.resize(w);
     return true;
 }
 
@@ -381,8 +435,62 @@ bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vect
     return true;
 }
 
+// gzip file written by write_gz_many: every member announces its size in an 'SV' extra sub-field
+static bool read_indexed_gz(const uint8_t *f, uint64_t n, std::string &out)
+{
+    struct Member {
+        uint64_t off, size, uoff;
+        uint32_t ulen;
+    };
+    std::vector<Member> ms;
+    uint64_t o = 0, total = 0;
+    while (o < n) {
+        if (o + 28 > n || f[o] != 0x1f || f[o + 1] != 0x8b || f[o + 2] != 8 || f[o + 3] != 4) return false;
+        if (f[o + 10] != 8 || f[o + 11] != 0 || f[o + 12] != 'S' || f[o + 13] != 'V' || f[o + 14] != 4 || f[o + 15] != 0) return false;
+        uint64_t sz = f[o + 16] | (f[o + 17] << 8) | (f[o + 18] << 16) | ((uint64_t)f[o + 19] << 24);
+        if (sz < 28 || o + sz > n) return false;
+        const uint8_t *t = f + o + sz - 4;
+        uint32_t ulen = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+        ms.push_back(Member{o, sz, total, ulen});
+        total += ulen;
+        o += sz;
+    }
+    out.resize(total);
+    std::atomic<size_t> next(0);
+    std::atomic<bool> bad(false);
+    auto work = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= ms.size()) return;
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, 15 + 16) != Z_OK) {
+                bad = true;
+                return;
+            }
+            zs.next_in = const_cast<Bytef *>(f + ms[i].off), zs.avail_in = (uInt)ms[i].size;
+            zs.next_out = (Bytef *)&out[ms[i].uoff], zs.avail_out = ms[i].ulen;
+            int r = ms[i].ulen ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+            if (r != Z_STREAM_END || (ms[i].ulen && zs.total_out != ms[i].ulen)) bad = true;
+            inflateEnd(&zs);
+        }
+    };
+    int nt = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), ms.size());
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    return !bad;
+}
+
 bool read_text_maybe_gz(const std::string &path, std::string &out, std::string &err)
 {
+    {
+        MappedFile mf;
+        std::string e2;
+        if (mf.open(path, e2) && mf.size >= 28 && read_indexed_gz(mf.data, mf.size, out)) return true;
+        out.clear();
+    }
     gzFile g = gzopen(path.c_str(), "rb");  // gzread passes plain text through unchanged
     if (!g) {
         err = "Cannot open file " + path;
@@ -415,7 +523,16 @@ static bool gz_member(const char *data, size_t n, std::vector<uint8_t> &out)
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     if (deflateInit2(&zs, gz_level(), Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
-    out.resize(deflateBound(&zs, n) + 32);
+    // extra sub-field 'SV' (ignored by every gzip reader): total size of this member, so that our own reader can find the
+    // member boundaries and inflate the members in parallel - the idea of BGZF's 'BC' field with a 32-bit size
+    gz_header head;
+    memset(&head, 0, sizeof head);
+    static const Bytef extra_proto[8] = {'S', 'V', 4, 0, 0, 0, 0, 0};
+    Bytef extra[8];
+    memcpy(extra, extra_proto, 8);
+    head.extra = extra, head.extra_len = 8, head.os = 3;
+    deflateSetHeader(&zs, &head);
+    out.resize(deflateBound(&zs, n) + 64);
     zs.next_in = (Bytef *)data;
     zs.avail_in = (uInt)n;
     zs.next_out = out.data();
@@ -423,7 +540,10 @@ static bool gz_member(const char *data, size_t n, std::vector<uint8_t> &out)
     int r = deflate(&zs, Z_FINISH);
     out.resize(zs.total_out);
     deflateEnd(&zs);
-    return r == Z_STREAM_END;
+    if (r != Z_STREAM_END || out.size() < 20) return false;
+    uint32_t sz = (uint32_t)out.size();
+    for (int i = 0; i < 4; ++i) out[16 + i] = (sz >> (8 * i)) & 0xff;  // header(10) XLEN(2) 'S' 'V' LEN(2) | size
+    return true;
 }
 
 // The reference writes through ogzstream (gzstream.C:53-61); here every file is cut into 1 MiB parts that are compressed as

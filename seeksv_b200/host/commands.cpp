@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cmath>
 #include <map>
 #include <cstdio>
@@ -262,6 +263,79 @@ uint64_t device_windows(const WindowMap &begin2end, const std::map<std::string, 
     return total;
 }
 
+// Closed form of main_depth's two map walks (bam2depth.cpp:82-124, literal version: svb::account_position). For a
+// covered position P the reference (1) finds the LAST merged window whose begin is <= P and requires P <= its end,
+// (2) adds depth(P) to every range r on the chromosome with (r.begin, r.end) <= (P+1, P+1), P <= r.end and
+// r.begin >= window.begin (unsigned compare), (3) stores depth(P) if P is a junction position. Turned around per range:
+// r collects depth over [r.begin, r.end] plus - only for the degenerate 0/1-length ranges of quirk Q11 - the position
+// r.begin - 1, restricted to positions whose window satisfies the unsigned compare. Sums come from prefix sums.
+void account_depth(const std::vector<Win> &hw, const std::vector<int32_t> &depth, const WindowMap &begin2end, PosDepth &pos2depth,
+                   RangeDepth &range2depth)
+{
+    struct DevWin {
+        int begin, end;
+        uint64_t off;
+    };
+    struct MapWin {
+        int begin, end;
+        int64_t lo, hi;  // positions for which this entry is "the last window with begin <= P" and P <= end
+    };
+    std::map<std::string, std::vector<DevWin>> dev;
+    for (auto &w : hw) dev[*w.chr].push_back(DevWin{w.begin, w.end, w.off});
+    std::vector<uint64_t> prefix(depth.size() + 1, 0);
+    for (size_t i = 0; i < depth.size(); ++i) prefix[i + 1] = prefix[i] + (uint64_t)depth[i];
+    auto sum = [&](const std::vector<DevWin> &v, int64_t a, int64_t b) -> uint64_t {  // sum of depth over [a, b]
+        uint64_t s = 0;
+        auto it = std::lower_bound(v.begin(), v.end(), a, [](const DevWin &w, int64_t x) { return (int64_t)w.end < x; });
+        for (; it != v.end() && it->begin <= b; ++it) {
+            int64_t lo = std::max<int64_t>(a, it->begin), hi = std::min<int64_t>(b, it->end);
+            if (lo <= hi) s += prefix[it->off + (uint64_t)(hi - it->begin) + 1] - prefix[it->off + (uint64_t)(lo - it->begin)];
+        }
+        return s;
+    };
+    std::map<std::string, std::vector<MapWin>> mw;
+    for (auto &kv : begin2end) mw[kv.first.first].push_back(MapWin{kv.first.second, kv.second, 0, -1});
+    for (auto &kv : mw) {
+        auto &v = kv.second;  // map order: ascending (int) begin
+        for (size_t i = 0; i < v.size(); ++i) {
+            v[i].lo = std::max<int64_t>(1, v[i].begin);
+            v[i].hi = v[i].end;
+            if (i + 1 < v.size()) v[i].hi = std::min<int64_t>(v[i].hi, (int64_t)v[i + 1].begin - 1);
+        }
+    }
+    for (auto &kv : range2depth) {
+        const ChrRange &r = kv.first;
+        auto m = mw.find(r.chr);
+        auto d = dev.find(r.chr);
+        if (m == mw.end() || d == dev.end()) continue;
+        int64_t b = r.begin, e = r.end;  // unsigned values
+        uint64_t total = 0;
+        auto add = [&](int64_t lo, int64_t hi) {
+            if (lo > hi) return;
+            for (const MapWin &w : m->second) {
+                if (w.hi < lo || w.lo > hi) continue;
+                if (!(r.begin >= (unsigned)w.begin)) continue;  // bam2depth.cpp:107, unsigned vs int
+                total += sum(d->second, std::max(lo, w.lo), std::min(hi, w.hi));
+            }
+        };
+        if (b <= e && b <= INT32_MAX) add(std::max<int64_t>(b, 1), std::min<int64_t>(e, INT32_MAX));
+        if ((e == b - 1 || e == b) && b - 1 >= 1 && b - 1 <= INT32_MAX) add(b - 1, b - 1);
+        kv.second += total;
+    }
+    for (auto &kv : pos2depth) {
+        auto m = mw.find(kv.first.first);
+        auto d = dev.find(kv.first.first);
+        if (m == mw.end() || d == dev.end()) continue;
+        int64_t p = kv.first.second;
+        for (const MapWin &w : m->second)
+            if (w.lo <= p && p <= w.hi) {
+                uint64_t v = sum(d->second, p, p);
+                if (v > 0) kv.second = (int)v;  // only covered positions are visited by the pileup
+                break;
+            }
+    }
+}
+
 bool insert_size(Gpu &g, svb_bam *bam, const std::string &file, int min_mapq, int pairs_used, int &mean, int &dev)
 {
     // CalculateInsertsizeDeviation, cluster.cpp:15-83: integer mean, (int)sqrt of the double mean square
@@ -393,11 +467,14 @@ int cmd_getsv(int argc, char **argv)
             if (svb_window_depth(g.ctx, bam, dw.data(), dw.size(), min_mapq, depth.data()) != 0) return fail(svb_last_error(g.ctx));
             // main_depth visits covered positions in BAM order (tid, pos); the range sums are commutative and every
             // position is written once, so the order of the walk does not matter - but keep it anyway
-            for (size_t i = 0; i < hw.size(); ++i)
-                for (int p = hw[i].begin; p <= hw[i].end; ++p) {
-                    int d = depth[hw[i].off + (uint64_t)(p - hw[i].begin)];
-                    if (d > 0) account_position(*hw[i].chr, p, d, begin2end, pos2depth, range2depth);
-                }
+            if (getenv("SEEKSV_B200_LITERAL_DEPTH_WALK")) {  // the reference's own per-position map walks (cross-check)
+                for (size_t i = 0; i < hw.size(); ++i)
+                    for (int p = hw[i].begin; p <= hw[i].end; ++p) {
+                        int d = depth[hw[i].off + (uint64_t)(p - hw[i].begin)];
+                        if (d > 0) account_position(*hw[i].chr, p, d, begin2end, pos2depth, range2depth);
+                    }
+            } else
+                account_depth(hw, depth, begin2end, pos2depth, range2depth);
         }
         std::cerr << "'main_depth' finished" << std::endl;
     } else

@@ -253,3 +253,25 @@ def test_device_inflate_matches_zlib(ctx, tmp_path, monkeypatch):
             bam = seeksv_b200.Bam.from_bgzf(ctx, img)
             assert bam.copy_stream() == want, (name, host)
             bam.close()
+
+
+def test_depth_accounting_closed_form_equals_literal_walk(tmp_path, monkeypatch):
+    """getsv with the closed-form range sums vs the literal per-position map walks of bam2depth.cpp:82-124, with flank
+    lengths and distances that produce degenerate 0/1-length and wrapped (unsigned) ranges (quirk Q11)."""
+    d, s = "micro", "tumor"
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, s + ".clip.txt")).encode("latin-1"))
+    outs = {}
+    for flank in ("200", "1", "0", "30000"):
+        for mode in ("closed", "literal"):
+            if mode == "literal":
+                monkeypatch.setenv("SEEKSV_B200_LITERAL_DEPTH_WALK", "1")
+            else:
+                monkeypatch.delenv("SEEKSV_B200_LITERAL_DEPTH_WALK", raising=False)
+            out = str(tmp_path / ("%s_%s.sv" % (mode, flank)))
+            r = subprocess.run([_cli(), "getsv", "-d", "0", "-L", flank, os.path.join(GOLDEN, d, s + ".clip.sam"), _bam(d, s), clip, out,
+                                str(tmp_path / "unm")], capture_output=True, text=True, env=dict(os.environ))
+            assert r.returncode == 0, r.stderr
+            outs[(mode, flank)] = read_text(out) + r.stdout
+        assert outs[("closed", flank)] == outs[("literal", flank)], flank
