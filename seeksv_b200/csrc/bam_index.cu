@@ -19,23 +19,23 @@ static constexpr uint64_t BAD = ~0ull;
 __device__ __forceinline__ bool plausible_one(const uint8_t *d, uint64_t n, uint64_t o, int32_t n_ref, uint64_t *next)
 {
     if (o + 36 > n) return false;
-    int32_t bs = ldi32(d + o);
+    int32_t bs = ldi32s(d + o);
     if (bs < 33 || o + 4 + (uint64_t)bs > n) return false;
-    int32_t tid = ldi32(d + o + 4);
+    int32_t tid = ldi32s(d + o + 4);
     if (tid < -1 || tid >= n_ref) return false;
-    int32_t pos = ldi32(d + o + 8);
+    int32_t pos = ldi32s(d + o + 8);
     if (pos < -1 || pos >= (1 << 29)) return false;  // BAM coordinates are below 2^29
-    uint32_t w = ldu32(d + o + 12);
+    uint32_t w = ldu32s(d + o + 12);
     uint32_t l_qname = w & 0xff;
     if (l_qname < 2) return false;
-    uint32_t w2 = ldu32(d + o + 16);
+    uint32_t w2 = ldu32s(d + o + 16);
     uint32_t n_cigar = w2 & 0xffff;
     if ((w2 >> 16) & 0xf000) return false;  // flag bits above 0x800 are not defined
-    int32_t l_qseq = ldi32(d + o + 20);
+    int32_t l_qseq = ldi32s(d + o + 20);
     if (l_qseq < 0) return false;
-    int32_t mtid = ldi32(d + o + 24);
+    int32_t mtid = ldi32s(d + o + 24);
     if (mtid < -1 || mtid >= n_ref) return false;
-    int32_t mpos = ldi32(d + o + 28);
+    int32_t mpos = ldi32s(d + o + 28);
     if (mpos < -1 || mpos >= (1 << 29)) return false;
     uint64_t need = 32ull + l_qname + 4ull * n_cigar + ((uint64_t)l_qseq + 1) / 2 + (uint64_t)l_qseq;
     if (need > (uint64_t)bs) return false;
@@ -81,7 +81,7 @@ __device__ __forceinline__ void walk_chunk(const uint8_t *d, uint64_t n, uint64_
     uint32_t k = 0;
     while (o < chunk_end) {
         if (o + 4 > n) break;  // partial tail (shard cut mid-record)
-        int32_t bs = ldi32(d + o);
+        int32_t bs = ldi32s(d + o);
         if (bs < 32) {  // cannot be a record: corrupt chain (or a wrong guess)
             o = BAD;
             break;

@@ -173,6 +173,21 @@ __device__ __forceinline__ uint32_t ldu32(const uint8_t *p)
 }
 __device__ __forceinline__ int32_t ldi32(const uint8_t *p) { return (int32_t)ldu32(p); }
 
+// Same, for the sparse one-touch accesses of the full-pass kernels (record heads ~300 B apart): ld.global.cg caches in
+// L2 only. With the read-only (LDG.CONSTANT) path L1 pulls the whole 128-byte line for every touched sector - ncu showed
+// 4.1 sectors/record for a 4-byte read - which made these kernels DRAM-bound on bytes nobody uses.
+__device__ __forceinline__ uint32_t ldu32s(const uint8_t *p)
+{
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    uint32_t sh = ((uint32_t)a & 3u) * 8u;
+    uint32_t lo = __ldcg(w);
+    if (sh == 0) return lo;
+    uint32_t hi = __ldcg(w + 1);
+    return __funnelshift_r(lo, hi, sh);
+}
+__device__ __forceinline__ int32_t ldi32s(const uint8_t *p) { return (int32_t)ldu32s(p); }
+
 // The 32-byte fixed core of a record (after the 4-byte block_size), decoded.
 struct Core {
     int32_t block_size, tid, pos, l_qseq, mtid, mpos, isize;
@@ -180,20 +195,28 @@ struct Core {
 };
 __device__ __forceinline__ Core load_core(const uint8_t *p)
 {
+    // ten consecutive aligned words cover the 36 bytes at any alignment; one funnel shift per field
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    uint32_t sh = ((uint32_t)a & 3u) * 8u;
+    uint32_t r[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) r[i] = __ldcg(w + i);
+    uint32_t f[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f[i] = sh ? __funnelshift_r(r[i], r[i + 1], sh) : r[i];
     Core c;
-    c.block_size = ldi32(p);
-    c.tid = ldi32(p + 4);
-    c.pos = ldi32(p + 8);
-    uint32_t w = ldu32(p + 12);  // l_read_name:8 mapq:8 bin:16
-    c.l_qname = w & 0xff;
-    c.mapq = (w >> 8) & 0xff;
-    uint32_t w2 = ldu32(p + 16);  // n_cigar:16 flag:16
-    c.n_cigar = w2 & 0xffff;
-    c.flag = w2 >> 16;
-    c.l_qseq = ldi32(p + 20);
-    c.mtid = ldi32(p + 24);
-    c.mpos = ldi32(p + 28);
-    c.isize = ldi32(p + 32);
+    c.block_size = (int32_t)f[0];
+    c.tid = (int32_t)f[1];
+    c.pos = (int32_t)f[2];
+    c.l_qname = f[3] & 0xff;  // l_read_name:8 mapq:8 bin:16
+    c.mapq = (f[3] >> 8) & 0xff;
+    c.n_cigar = f[4] & 0xffff;  // n_cigar:16 flag:16
+    c.flag = f[4] >> 16;
+    c.l_qseq = (int32_t)f[5];
+    c.mtid = (int32_t)f[6];
+    c.mpos = (int32_t)f[7];
+    c.isize = (int32_t)f[8];
     return c;
 }
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v)

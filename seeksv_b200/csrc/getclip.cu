@@ -91,9 +91,9 @@ __global__ void __launch_bounds__(256)
     for (uint64_t j = i; j > 0;) {
         --j;
         const uint8_t *q = d + rec_off[j];
-        uint32_t fl = ldu32(q + 16) >> 16;
+        uint32_t fl = ldu32s(q + 16) >> 16;
         if (!(fl & (F_UNMAP | F_MUNMAP))) {
-            prev_tid = ldi32(q + 4);
+            prev_tid = ldi32s(q + 4);
             break;
         }
     }
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256)
     }
     if (k.n_cigar == 0) return;
     const uint8_t *cig = p + 36 + k.l_qname;
-    uint32_t first = ldu32(cig), last = ldu32(cig + 4 * (k.n_cigar - 1));
+    uint32_t first = ldu32s(cig), last = ldu32s(cig + 4 * (k.n_cigar - 1));
     uint32_t op1 = first & 15, op2 = last & 15;
     if (op1 == OP_H || op2 == OP_H || (int32_t)k.mapq < min_mapq || (k.flag & F_DUP)) return;  // clip_reads.cpp:118
     bool s1 = op1 == OP_S, s2 = op2 == OP_S;

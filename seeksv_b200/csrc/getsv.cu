@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256)
         uint32_t fq = k.flag | (k.mapq << 16);
         if (k.n_cigar == 0) fq |= FLAGQ_NOCIGAR;
         for (uint32_t j = 0; j < k.n_cigar; ++j) {
-            uint32_t w = ldu32(cig + 4 * j), op = w & 15;
+            uint32_t w = ldu32s(cig + 4 * j), op = w & 15;
             // bam_calend of the linked libbam: M, D, N only ('=' and 'X' do not advance; probed)
             if (op == OP_M || op == OP_D || op == OP_N) end += (int32_t)(w >> 4);
             if ((j == 0 || j + 1 == k.n_cigar) && op == OP_H) fq |= FLAGQ_HARDCLIP;  // IsHardClip, clip_reads.cpp:247
@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(256)
         span = max(end - k.pos, 1);
         if (i > 0) {  // coordinate order: (tid, pos) ascending, tid -1 last
             const uint8_t *q = d + rec_off[i - 1];
-            uint32_t t0 = (uint32_t)ldi32(q + 4), t1 = (uint32_t)k.tid;  // -1 -> 0xffffffff sorts last
-            int32_t p0 = ldi32(q + 8);
+            uint32_t t0 = (uint32_t)ldi32s(q + 4), t1 = (uint32_t)k.tid;  // -1 -> 0xffffffff sorts last
+            int32_t p0 = ldi32s(q + 8);
             if (t0 > t1 || (t0 == t1 && p0 > k.pos)) atomicOr(unsorted, 1u);
         }
     }
