@@ -43,6 +43,13 @@ extern "C" int svb_ctx_create(int device, svb_ctx **out)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        // The full-pass kernels read ~40-100 bytes out of every ~300-byte record: with the default L2 fetch granularity a
+        // touched 32-byte sector drags its whole 128-byte line out of HBM. 32 B keeps DRAM traffic at what is used.
+        const char *e = getenv("SEEKSV_B200_L2_FETCH");
+        size_t g = e ? (size_t)atoi(e) : 32;
+        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+    }
     // keep freed scratch in the pool: the commands allocate and free the same sizes repeatedly
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, device));

@@ -173,19 +173,11 @@ __device__ __forceinline__ uint32_t ldu32(const uint8_t *p)
 }
 __device__ __forceinline__ int32_t ldi32(const uint8_t *p) { return (int32_t)ldu32(p); }
 
-// Same, for the sparse one-touch accesses of the full-pass kernels (record heads ~300 B apart): ld.global.cg caches in
-// L2 only. With the read-only (LDG.CONSTANT) path L1 pulls the whole 128-byte line for every touched sector - ncu showed
-// 4.1 sectors/record for a 4-byte read - which made these kernels DRAM-bound on bytes nobody uses.
-__device__ __forceinline__ uint32_t ldu32s(const uint8_t *p)
-{
-    uintptr_t a = (uintptr_t)p;
-    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
-    uint32_t sh = ((uint32_t)a & 3u) * 8u;
-    uint32_t lo = __ldcg(w);
-    if (sh == 0) return lo;
-    uint32_t hi = __ldcg(w + 1);
-    return __funnelshift_r(lo, hi, sh);
-}
+// Alias used by the sparse one-touch accesses of the full-pass kernels (record heads ~300 B apart). ncu (profiles/)
+// showed that what over-fetches there is the L2 -> DRAM fetch granularity (a 4-byte read pulled a whole 128-byte line,
+// 4.1 sectors/record), not L1: bypassing L1 with ld.global.cg only added L2 requests for the multi-word reads and was
+// slower, so these stay on the read-only path and the context lowers cudaLimitMaxL2FetchGranularity instead.
+__device__ __forceinline__ uint32_t ldu32s(const uint8_t *p) { return ldu32(p); }
 __device__ __forceinline__ int32_t ldi32s(const uint8_t *p) { return (int32_t)ldu32s(p); }
 
 // The 32-byte fixed core of a record (after the 4-byte block_size), decoded.
@@ -201,7 +193,7 @@ __device__ __forceinline__ Core load_core(const uint8_t *p)
     uint32_t sh = ((uint32_t)a & 3u) * 8u;
     uint32_t r[10];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) r[i] = __ldcg(w + i);
+    for (int i = 0; i < 10; ++i) r[i] = __ldg(w + i);
     uint32_t f[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) f[i] = sh ? __funnelshift_r(r[i], r[i + 1], sh) : r[i];

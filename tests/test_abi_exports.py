@@ -1,0 +1,89 @@
+"""CPU-only checks of the C-ABI boundary: the library builds for sm_100a without a GPU, loads, exports every symbol that
+include/seeksv_b200.h declares (and the ctypes mirror binds them all), refuses to run without a device (no CPU fallback),
+and the CLI keeps the reference's argument handling (seeksv.cpp:26-58,128-155,366-410)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT, read_text
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from seeksv_b200 import build, lib_path
+    build.build()
+    return ctypes.CDLL(lib_path())
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "seeksv_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(svb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), n
+    from seeksv_b200 import lib as pylib
+    assert sorted(pylib.EXPORTS) == names, "seeksv_b200/lib.py must bind exactly the header's entry points"
+
+
+def test_abi_version_and_no_cpu_fallback(lib):
+    assert lib.svb_abi_version() == 1
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ctx = ctypes.c_void_p()
+    rc = lib.svb_ctx_create(0, ctypes.byref(ctx))
+    assert rc == -1 and not ctx.value          # SVB_ERR_NO_DEVICE: nothing can run without the CUDA device
+    lib.svb_last_error.restype = ctypes.c_char_p
+    assert b"no CPU fallback" in lib.svb_last_error(None)
+
+
+def test_product_never_touches_the_oracle():
+    """no import / include / exec of anything under oracle/ in the product tree (comments may mention the tests)"""
+    pat = re.compile(r"(^\s*(from|import)\s+oracle)|(#include\s*[\"<][^\n]*oracle)|(oracle/_ref)|(oracle\.)", re.M)
+    for d, _, files in os.walk(os.path.join(ROOT, "seeksv_b200")):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(d, f), errors="ignore").read()
+                assert not pat.search(src), (d, f)
+
+
+def _cli(args):
+    from seeksv_b200 import cli_path
+    return subprocess.run([cli_path()] + args, capture_output=True, text=True)
+
+
+def test_cli_argument_surface(lib):
+    r = _cli([])
+    assert r.returncode == 1 and "Usage: seeksv <command> [options]" in r.stderr
+    r = _cli(["frobnicate"])
+    assert r.returncode == 1 and "[seeksv] unrecognized command 'frobnicate'" in r.stderr
+    for cmd, frag in (("getclip", "<input.sorted.bam>"), ("getsv", "<output SVs>"), ("somatic", "<input tumor SV file>")):
+        r = _cli([cmd])
+        assert r.returncode == 1 and frag in r.stderr
+    assert _cli(["getsv", "-l", "91", "a", "b", "c", "d", "e"]).returncode == 1      # -l must be 0..90 (seeksv.cpp:191)
+    assert _cli(["somatic", "-l", "90", "a", "b", "c", "d"]).returncode == 1         # -l must be 0..89 (seeksv.cpp:386)
+    assert _cli(["cluster", "x"]).returncode == 0                                    # recognised, dispatch disabled
+
+
+@pytest.mark.parametrize("d,s", [("example", "cancer"), ("example", "normal"), ("micro", "tumor"), ("micro", "normal")])
+def test_getsv_host_only_mode_matches_reference(lib, d, s, tmp_path):
+    """`getsv -n 0 -D` needs no BAM pass (no insert size, no pairs, no depth): join + merge + filters + formatting of the
+    host layer against the reference binary's output - runs without a GPU."""
+    import gzip
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, s + ".clip.txt")).encode("latin-1"))
+    out = str(tmp_path / "out.sv")
+    r = _cli(["getsv", "-n", "0", "-D", os.path.join(GOLDEN, d, s + ".clip.sam"), os.path.join(GOLDEN, d, s + ".sort.bam"), clip, out,
+              str(tmp_path / "unm")])
+    assert r.returncode == 0, r.stderr
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".n0D.sv"))
+    assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".n0D.stdout"))
