@@ -182,6 +182,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    os.environ["SEEKSV_B200_DEVICE"] = str(local)     # the CLI entry point (svb_main) picks its GPU from the environment
     os.makedirs(WORK, exist_ok=True)
     if rank == 0:
         ensure_tools()
@@ -210,7 +211,11 @@ def main():
     sam = realign(pre, pre + ".clip.fq.gz")
     juncs, wins = S.plan_getsv(sam, pre + ".clip.gz", names, lens, 50, 200)
     n_clusters = clip[0].count(b"\n")
-    counts_dev = torch.zeros(max(1, len(juncs)), dtype=torch.int32, device="cuda")
+    # the merge buffer has the same length on every rank (shards find different numbers of junction candidates)
+    n_merge = torch.tensor([max(1, len(juncs))], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(n_merge, op=dist.ReduceOp.MAX)
+    counts_dev = torch.zeros(int(n_merge.item()), dtype=torch.int32, device="cuda")
     stream = torch.cuda.ExternalStream(ctx.stream)
 
     # C arrays for the getsv passes are built once; results land in preallocated host arrays (no per-step marshalling)
@@ -239,7 +244,7 @@ def main():
         b.window_depth_raw(w_arr, nw, 20, dep_arr)
         b.close()
         if world > 1:   # final candidate merge: every rank learns every shard's support counts (small NCCL allgather)
-            counts_dev.copy_(cnt_host, non_blocking=True)
+            counts_dev[:cnt_host.numel()].copy_(cnt_host, non_blocking=True)
             gathered = [torch.empty_like(counts_dev) for _ in range(world)]
             dist.all_gather(gathered, counts_dev)
         return sum(sizes) + 4 * nj + 4 * n_pos
@@ -362,7 +367,11 @@ def main():
     resident.close()
     ctx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+        # skip interpreter teardown: freeing pinned tensors after NCCL has torn its context down aborts the process
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
