@@ -321,7 +321,7 @@ def main():
         except Exception:
             pass
         peak = peaks.get("hbm_gbs", 6650.0)
-        full_pass = {"guess_starts", "walk_count", "walk_write", "clip_scan", "decode_records"}
+        full_pass = {"guess_starts", "walk_count", "clip_walk", "decode_walk"}
         kern = {k: v for k, v in prof.items() if v["launches"] > 0 and "wall" not in k}
         dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
         roofline = None

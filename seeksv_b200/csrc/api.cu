@@ -334,14 +334,8 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
     }
     b->first = hdr.first_record, b->n_ref = (int32_t)hdr.names.size();
     b->names = hdr.names, b->lens = hdr.lengths;
-    CKR(finish_bam(ctx, b, out));
-    if ((*out)->rec_bytes != total - hdr.first_record) {
-        unsigned long long missing = (unsigned long long)(total - hdr.first_record - (*out)->rec_bytes);
-        svb_bam_free(*out);
-        *out = nullptr;
-        return svb_fail(ctx, SVB_ERR_FORMAT, "truncated or corrupt BAM: record chain ends %llu bytes early", missing);
-    }
-    return 0;
+    b->whole_file = true;  // the record chain has to end exactly at the end of the stream (checked when it is walked)
+    return finish_bam(ctx, b, out);
 }
 
 // Inflate an arbitrary BGZF image on the device and return the bytes (diagnostics / tests of the inflate kernel alone).
@@ -408,9 +402,9 @@ extern "C" void svb_bam_free(svb_bam *b)
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     cudaStream_t s = b->ctx->stream;
-    if (b->d_rec_off) cudaFreeAsync(b->d_rec_off, s);
     LeanRecords &L = b->lean;
-    void *cols[8] = {L.tid, L.pos, L.end, L.flagq, L.lqseq, L.mtid, L.mpos, L.isize};
+    void *cols[15] = {L.tid, L.pos, L.end, L.flagq, L.lqseq, L.mtid, L.mpos, L.isize, L.off, b->d_guess, b->d_count, b->d_base,
+                      b->d_q_cnt, b->d_q_sum, b->d_q_sq};
     for (void *c : cols)
         if (c) cudaFreeAsync(c, s);
     if (b->d_owned) cudaFreeAsync(b->d_owned, s);
@@ -423,8 +417,19 @@ extern "C" int svb_bam_device_stream(const svb_bam *b, const void **d, uint64_t 
     *d = b->d_data, *n = b->nbytes, *first = b->first;
     return 0;
 }
-extern "C" uint64_t svb_bam_n_records(const svb_bam *b) { return b ? b->n_rec : 0; }
-extern "C" uint64_t svb_bam_record_bytes(const svb_bam *b) { return b ? b->rec_bytes : 0; }
+// counts are produced by the first pass that walks the chain (lazily here when nobody has walked it yet)
+extern "C" uint64_t svb_bam_n_records(const svb_bam *b)
+{
+    if (!b) return 0;
+    if (!b->counted) ensure_counts(b->ctx, const_cast<svb_bam *>(b));
+    return b->n_rec;
+}
+extern "C" uint64_t svb_bam_record_bytes(const svb_bam *b)
+{
+    if (!b) return 0;
+    if (!b->counted) ensure_counts(b->ctx, const_cast<svb_bam *>(b));
+    return b->rec_bytes;
+}
 extern "C" int32_t svb_bam_n_ref(const svb_bam *b) { return b ? b->n_ref : 0; }
 extern "C" const char *svb_bam_ref_name(const svb_bam *b, int32_t tid)
 {

@@ -70,6 +70,7 @@ struct LeanRecords {
     int32_t *tid = nullptr, *pos = nullptr, *end = nullptr;  // end = libbam bam_calend (M,D,N), pos+1 if no CIGAR
     uint32_t *flagq = nullptr;                                 // flag | mapq << 16 | hardclip << 24
     int32_t *lqseq = nullptr, *mtid = nullptr, *mpos = nullptr, *isize = nullptr;
+    uint64_t *off = nullptr;  // byte offset of the record in the stream (CIGARs are re-read from there)
     uint64_t n = 0;
 };
 #define FLAGQ_HARDCLIP (1u << 24)
@@ -81,7 +82,18 @@ struct svb_bam {
     uint64_t nbytes = 0, first = 0;
     int32_t n_ref = 0;
     uint64_t n_rec = 0, rec_bytes = 0;
-    uint64_t *d_rec_off = nullptr;  // n_rec + 1 entries
+    // record chain (bam_index.cu): the stream is cut into 16 KiB chunks; guess[c] = offset of the first record that
+    // starts at or after the chunk, count[c] = records starting inside it, base[c] = exclusive prefix of count
+    uint64_t n_chunks = 0;
+    uint64_t *d_guess = nullptr, *d_base = nullptr;
+    uint32_t *d_count = nullptr;
+    bool counted = false;  // count / base / n_rec / rec_bytes are valid (ensure_counts)
+    bool whole_file = false;  // built from a complete BAM: the chain must end exactly at the end of the stream
+    // per-chunk insert-size partial sums gathered by the decode walker for one mapQ threshold (getsv.cu)
+    int32_t stats_mapq = -1;
+    uint32_t *d_q_cnt = nullptr;
+    uint64_t *d_q_sum = nullptr, *d_q_sq = nullptr;
+    int32_t q_max = 0;
     std::vector<std::string> names;
     std::vector<uint32_t> lens;
     LeanRecords lean;
@@ -226,8 +238,16 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t v)
 #endif
 
 // ---- internal entry points (one per .cu) ------------------------------------------------------------------
-int index_records(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu
-int decode_records(svb_ctx *ctx, svb_bam *bam);                      // getsv.cu
+static constexpr uint32_t CHUNK_LOG2 = 14;  // 16 KiB chunks: ~50 records of 300 B per walker thread
+static constexpr uint64_t CHUNK = 1ull << CHUNK_LOG2;
+static constexpr uint64_t BAD_OFFSET = ~0ull;
+int index_records(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu: guesses only
+int ensure_counts(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu: verified chain + counts + prefix
+int finish_counts(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit);  // prefix + totals from valid per-chunk counts
+// after a fused walker filled exit_[]: verify against the guesses; *ok = 0 means the guesses were repaired
+// (bam->d_guess updated, counts valid) and the walker has to run again
+int verify_or_repair(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit, int *ok);
+int decode_records(svb_ctx *ctx, svb_bam *bam, int32_t stats_mapq = -1);  // getsv.cu
 int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out,
                       double out_bytes);                             // inflate.cu
 int inclusive_scan_u32(svb_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n);

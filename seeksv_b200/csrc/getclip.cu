@@ -22,7 +22,7 @@ struct svb_clusters {
 
 // ---- candidate scan -------------------------------------------------------------------------------------
 struct CandArrays {
-    uint32_t *rec;    // record index
+    uint64_t *off;    // byte offset of the record in the stream (= its rank in file order)
     int32_t *tid;     // chromosome
     int32_t *pos;     // key position (1-based breakpoint)
     uint32_t *begin;  // first base of the "left" part inside the read
@@ -69,42 +69,25 @@ __device__ int32_t aux_xc(const uint8_t *s, const uint8_t *end)
     return 0;
 }
 
-// One thread per record. Only the 36-byte fixed part and the CIGAR are touched for the ~98 % of records
-// that are not soft-clipped; sequence and aux bytes are read later, for candidates only.
-__global__ void __launch_bounds__(256)
-    clip_scan(const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, uint64_t n_rec, int32_t min_mapq,
-              int32_t save_low_quality, int32_t prev_tid0, CandArrays c, uint32_t cand_cap, uint32_t *__restrict__ unmapped,
-              uint32_t un_cap, uint32_t *__restrict__ switches, uint32_t sw_cap, uint32_t *__restrict__ counters)
+struct ScanOut {
+    CandArrays c;
+    uint32_t cand_cap;
+    uint64_t *unmapped;
+    uint32_t un_cap;
+    uint64_t *switches;
+    uint32_t sw_cap;
+    uint32_t *counters;  // [0] candidates, [1] unmapped-branch records, [2] chromosome switches
+};
+
+// GetSClipReads (clip_reads.cpp:112-192) for one mapped-branch record that survived the chromosome-switch test.
+// Sequence and aux bytes are only touched for soft-clipped reads (~2 % of the records).
+__device__ void eval_clip(const uint8_t *__restrict__ d, uint64_t o, const Core &k, int32_t min_mapq, int32_t save_low_quality,
+                          const ScanOut &out)
 {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_rec) return;
-    const uint8_t *p = d + rec_off[i];
-    Core k = load_core(p);
-    if (k.flag & (F_UNMAP | F_MUNMAP)) {  // clip_reads.h:415 - the unmapped branch wins (quirk Q2)
-        uint32_t s = atomicAdd(&counters[1], 1u);
-        if (s < un_cap) unmapped[s] = (uint32_t)i;
-        return;
-    }
-    // quirk Q1: a record whose tid differs from the previous mapped-branch record's tid triggers the
-    // chromosome flush and is itself dropped (clip_reads.h:423-438)
-    int32_t prev_tid = prev_tid0;
-    for (uint64_t j = i; j > 0;) {
-        --j;
-        const uint8_t *q = d + rec_off[j];
-        uint32_t fl = ldu32s(q + 16) >> 16;
-        if (!(fl & (F_UNMAP | F_MUNMAP))) {
-            prev_tid = ldi32s(q + 4);
-            break;
-        }
-    }
-    if (k.tid != prev_tid) {
-        uint32_t s = atomicAdd(&counters[2], 1u);
-        if (s < sw_cap) switches[s] = (uint32_t)i;
-        return;
-    }
     if (k.n_cigar == 0) return;
+    const uint8_t *p = d + o;
     const uint8_t *cig = p + 36 + k.l_qname;
-    uint32_t first = ldu32s(cig), last = ldu32s(cig + 4 * (k.n_cigar - 1));
+    uint32_t first = ldu32(cig), last = ldu32(cig + 4 * (k.n_cigar - 1));
     uint32_t op1 = first & 15, op2 = last & 15;
     if (op1 == OP_H || op2 == OP_H || (int32_t)k.mapq < min_mapq || (k.flag & F_DUP)) return;  // clip_reads.cpp:118
     bool s1 = op1 == OP_S, s2 = op2 == OP_S;
@@ -137,32 +120,100 @@ __global__ void __launch_bounds__(256)
             else emit3 = true;
         } else
             emit5 = emit3 = true;
-        l5 = len1, r5 = (uint32_t)mid;                  // clip_reads.cpp:152,179
-        b3 = len1, l3 = (uint32_t)mid, r3 = len2;       // clip_reads.cpp:154,185
+        l5 = len1, r5 = (uint32_t)mid;             // clip_reads.cpp:152,179
+        b3 = len1, l3 = (uint32_t)mid, r3 = len2;  // clip_reads.cpp:154,185
     }
+    const CandArrays &c = out.c;
     if (emit5) {
-        uint32_t s = atomicAdd(&counters[0], 1u);
-        if (s < cand_cap) {
-            c.rec[s] = (uint32_t)i, c.tid[s] = k.tid, c.pos[s] = k.pos + 1, c.begin[s] = b5, c.ll[s] = l5, c.rl[s] = r5;
+        uint32_t s = atomicAdd(&out.counters[0], 1u);
+        if (s < out.cand_cap) {
+            c.off[s] = o, c.tid[s] = k.tid, c.pos[s] = k.pos + 1, c.begin[s] = b5, c.ll[s] = l5, c.rl[s] = r5;
             c.side[s] = 0;
         }
     }
     if (emit3) {
-        uint32_t s = atomicAdd(&counters[0], 1u);
-        if (s < cand_cap) {
-            c.rec[s] = (uint32_t)i, c.tid[s] = k.tid, c.pos[s] = k.pos + reflen, c.begin[s] = b3, c.ll[s] = l3, c.rl[s] = r3;
+        uint32_t s = atomicAdd(&out.counters[0], 1u);
+        if (s < out.cand_cap) {
+            c.off[s] = o, c.tid[s] = k.tid, c.pos[s] = k.pos + reflen, c.begin[s] = b3, c.ll[s] = l3, c.rl[s] = r3;
             c.side[s] = 1;
         }
     }
 }
 
+#define NO_TID INT32_MIN
+
+// The getclip walker: one thread per 16 KiB chunk follows the record chain from the chunk's guessed first record and does
+// the whole per-record work of InputBamOutputReads' loop (clip_reads.h:410-440) on the way - unmapped branch (quirk
+// Q2), chromosome-switch drop (quirk Q1, against the previous mapped-branch record it has just walked over), soft-clip
+// predicate. Each record head is fetched from HBM exactly once. The first mapped-branch record of a chunk needs the
+// last one of an earlier chunk and is left to clip_first.
+__global__ void __launch_bounds__(128)
+    clip_walk(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks, const uint64_t *__restrict__ guess,
+              uint32_t *__restrict__ count, uint64_t *__restrict__ exit_, uint64_t *__restrict__ first_mb,
+              int32_t *__restrict__ last_mb_tid, int32_t min_mapq, int32_t save_low_quality, ScanOut out)
+{
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    uint64_t o = guess[c], end = min(n, (c + 1) << CHUNK_LOG2), first = BAD_OFFSET;
+    uint32_t cnt = 0;
+    int32_t prev_tid = NO_TID;
+    while (o < end) {
+        if (o + 36 > n) break;  // partial tail
+        Core k = load_core(d + o);
+        if (k.block_size < 32) {
+            o = BAD_OFFSET;
+            break;
+        }
+        if (o + 4 + (uint64_t)k.block_size > n) break;
+        ++cnt;
+        if (k.flag & (F_UNMAP | F_MUNMAP)) {  // clip_reads.h:415 - the unmapped branch wins (quirk Q2)
+            uint32_t s = atomicAdd(&out.counters[1], 1u);
+            if (s < out.un_cap) out.unmapped[s] = o;
+        } else {
+            if (prev_tid == NO_TID) first = o;
+            else if (k.tid != prev_tid) {  // flush + drop (clip_reads.h:423-438)
+                uint32_t s = atomicAdd(&out.counters[2], 1u);
+                if (s < out.sw_cap) out.switches[s] = o;
+            } else
+                eval_clip(d, o, k, min_mapq, save_low_quality, out);
+            prev_tid = k.tid;
+        }
+        o += 4 + (uint64_t)k.block_size;
+    }
+    count[c] = cnt, exit_[c] = o, first_mb[c] = first, last_mb_tid[c] = prev_tid;
+}
+
+__global__ void __launch_bounds__(128)
+    clip_first(const uint8_t *__restrict__ d, uint64_t n_chunks, const uint64_t *__restrict__ first_mb,
+               const int32_t *__restrict__ last_mb_tid, int32_t prev_tid0, int32_t min_mapq, int32_t save_low_quality, ScanOut out)
+{
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks || first_mb[c] == BAD_OFFSET) return;
+    int32_t prev = prev_tid0;  // clip_reads.h:407: last_tid starts at 0 (or the previous shard's last tid)
+    for (uint64_t j = c; j > 0;) {
+        --j;
+        if (last_mb_tid[j] != NO_TID) {
+            prev = last_mb_tid[j];
+            break;
+        }
+    }
+    uint64_t o = first_mb[c];
+    Core k = load_core(d + o);
+    if (k.tid != prev) {
+        uint32_t s = atomicAdd(&out.counters[2], 1u);
+        if (s < out.sw_cap) out.switches[s] = o;
+    } else
+        eval_clip(d, o, k, min_mapq, save_low_quality, out);
+}
+
 // sort key = flush run (number of chromosome switches before the record) | side | position
-__global__ void make_keys(uint32_t n, const uint32_t *__restrict__ order, CandArrays c, const uint32_t *__restrict__ sw,
+__global__ void make_keys(uint32_t n, const uint32_t *__restrict__ order, CandArrays c, const uint64_t *__restrict__ sw,
                           uint32_t n_sw, uint64_t *__restrict__ key)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t s = order[i], r = c.rec[s];
+    uint32_t s = order[i];
+    uint64_t r = c.off[s];
     uint32_t lo = 0, hi = n_sw;  // lower_bound(sw, r): switches with index < r
     while (lo < hi) {
         uint32_t m = (lo + hi) >> 1;
@@ -210,7 +261,8 @@ __global__ void seg_stats(uint32_t n_seg, const uint32_t *__restrict__ start, co
 }
 
 struct ClusterOut {
-    uint32_t *len_l, *len_r, *cig_rec, *support;  // indexed by sorted candidate position (seg start + k)
+    uint32_t *len_l, *len_r, *support;  // indexed by sorted candidate position (seg start + k)
+    uint64_t *cig_off;                  // record whose CIGAR the cluster carries
     uint8_t *noqual;
     uint32_t *seg_ncl;
 };
@@ -219,7 +271,7 @@ struct ClusterOut {
 // BAM order, with lane-parallel string compares and consensus updates. Strings live in a per-segment
 // arena: slot k holds [left part right-aligned at column maxl | right part left-aligned at maxl].
 __global__ void __launch_bounds__(128)
-    cluster_build(const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, uint32_t n_seg,
+    cluster_build(const uint8_t *__restrict__ d, uint32_t n_seg,
                   const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c,
                   const uint32_t *__restrict__ maxl_, const uint32_t *__restrict__ maxr_, const uint64_t *__restrict__ arena_off,
                   char *__restrict__ arena_seq, char *__restrict__ arena_qual, double limit, ClusterOut out)
@@ -233,8 +285,9 @@ __global__ void __launch_bounds__(128)
     uint32_t ncl = 0;
     for (uint32_t k = a; k < b; ++k) {
         const uint32_t x = order[k];
-        const uint32_t rec = c.rec[x], begin = c.begin[x], ll = c.ll[x], rl = c.rl[x], side = c.side[x];
-        const uint8_t *p = d + rec_off[rec];
+        const uint64_t rec = c.off[x];
+        const uint32_t begin = c.begin[x], ll = c.ll[x], rl = c.rl[x], side = c.side[x];
+        const uint8_t *p = d + rec;
         uint32_t w = ldu32(p + 12), w2 = ldu32(p + 16);
         int32_t l_qseq = ldi32(p + 20);
         const uint8_t *seq = p + 36 + (w & 0xff) + 4 * (w2 & 0xffff);
@@ -269,7 +322,7 @@ __global__ void __launch_bounds__(128)
         }
         if (found < 0) {
             if (lane == 0) {
-                out.len_l[a + ncl] = ll, out.len_r[a + ncl] = rl, out.cig_rec[a + ncl] = rec, out.support[a + ncl] = 1;
+                out.len_l[a + ncl] = ll, out.len_r[a + ncl] = rl, out.cig_off[a + ncl] = rec, out.support[a + ncl] = 1;
                 out.noqual[a + ncl] = noq;
             }
             ++ncl;
@@ -304,11 +357,11 @@ __global__ void __launch_bounds__(128)
             if (lane == 0) {
                 if (cL <= ll) {
                     out.len_l[a + found] = ll;
-                    if (side == 1) out.cig_rec[a + found] = rec;
+                    if (side == 1) out.cig_off[a + found] = rec;
                 }
                 if (cR < rl) {
                     out.len_r[a + found] = rl;
-                    if (side == 0) out.cig_rec[a + found] = rec;
+                    if (side == 0) out.cig_off[a + found] = rec;
                 }
                 out.support[a + found] += 1;
             }
@@ -378,8 +431,8 @@ __global__ void list_clusters(uint32_t n_seg, const uint32_t *__restrict__ start
 
 __global__ void text_sizes(uint32_t n_cl, const uint32_t *__restrict__ cl_seg, const uint32_t *__restrict__ cl_slot,
                            const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c, ClusterOut out,
-                           const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, NameTable names,
-                           uint64_t *__restrict__ clip_len, uint64_t *__restrict__ fq_len)
+                           const uint8_t *__restrict__ d, NameTable names, uint64_t *__restrict__ clip_len,
+                           uint64_t *__restrict__ fq_len)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cl) {
@@ -391,7 +444,7 @@ __global__ void text_sizes(uint32_t n_cl, const uint32_t *__restrict__ cl_seg, c
     uint32_t L = out.len_l[k], R = out.len_r[k];
     uint32_t qL = out.noqual[k] ? 1 : L, qR = out.noqual[k] ? 1 : R;
     uint32_t name = names.off[c.tid[x] + 1] - names.off[c.tid[x]];
-    uint32_t cg = cigar_text(d + rec_off[out.cig_rec[k]], nullptr);
+    uint32_t cg = cigar_text(d + out.cig_off[k], nullptr);
     // chr \t pos \t side \t cigar \t aligned \t alignedQ \t clipped \t clippedQ \t support \n
     clip_len[i] = name + 1 + dec_len_i(c.pos[x]) + 1 + 2 + cg + 1 + L + 1 + qL + 1 + R + 1 + qR + 1 + dec_len(out.support[k]) + 1;
     uint32_t cl = c.side[x] == 0 ? L : R, cq = c.side[x] == 0 ? qL : qR;
@@ -402,8 +455,7 @@ __global__ void text_sizes(uint32_t n_cl, const uint32_t *__restrict__ cl_seg, c
 __global__ void __launch_bounds__(128)
     text_write(uint32_t n_cl, const uint32_t *__restrict__ cl_seg, const uint32_t *__restrict__ cl_slot,
                const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c, ClusterOut out,
-               const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, NameTable names,
-               const uint32_t *__restrict__ maxl_, const uint32_t *__restrict__ maxr_, const uint64_t *__restrict__ arena_off,
+               const uint8_t *__restrict__ d, NameTable names, const uint32_t *__restrict__ maxl_, const uint32_t *__restrict__ maxr_, const uint64_t *__restrict__ arena_off,
                const char *__restrict__ arena_seq, const char *__restrict__ arena_qual, const uint64_t *__restrict__ clip_off,
                const uint64_t *__restrict__ fq_off, char *__restrict__ clip, char *__restrict__ fq)
 {
@@ -434,7 +486,7 @@ __global__ void __launch_bounds__(128)
         *q++ = '\t';
         *q++ = side == 0 ? '5' : '3';
         *q++ = '\t';
-        q += cigar_text(d + rec_off[out.cig_rec[k]], q);
+        q += cigar_text(d + out.cig_off[k], q);
         *q++ = '\t';
         head = (uint32_t)(q - o);
     }
@@ -474,12 +526,12 @@ __global__ void __launch_bounds__(128)
 // with one thread per hash group (real name compares, so hash collisions cannot change the result), then emit text.
 __device__ __forceinline__ uint32_t qname_len(const uint8_t *p) { return ldu32(p + 12) & 0xff; }
 
-__global__ void unmapped_hash(uint32_t n, const uint32_t *__restrict__ list, const uint8_t *__restrict__ d,
-                              const uint64_t *__restrict__ rec_off, uint64_t *__restrict__ key, uint32_t *__restrict__ val)
+__global__ void unmapped_hash(uint32_t n, const uint64_t *__restrict__ list, const uint8_t *__restrict__ d,
+                              uint64_t *__restrict__ key, uint32_t *__restrict__ val)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint8_t *p = d + rec_off[list[i]];
+    const uint8_t *p = d + list[i];
     uint32_t lq = qname_len(p);
     uint64_t h = 0xcbf29ce484222325ull;
     for (uint32_t j = 0; j < lq && p[36 + j]; ++j) h = (h ^ p[36 + j]) * 0x100000001b3ull;
@@ -498,8 +550,8 @@ __device__ bool same_name(const uint8_t *a, const uint8_t *b)
 
 // one thread per hash group; mate_of[e] = entry that was held when e completed a pair, else 0xffffffff
 __global__ void unmapped_pair(uint32_t n, const uint64_t *__restrict__ key, const uint32_t *__restrict__ ent,
-                              const uint32_t *__restrict__ list, const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off,
-                              uint32_t *__restrict__ mate_of, uint32_t *__restrict__ overflow)
+                              const uint64_t *__restrict__ list, const uint8_t *__restrict__ d, uint32_t *__restrict__ mate_of,
+                              uint32_t *__restrict__ overflow)
 {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n || (j > 0 && key[j] == key[j - 1])) return;
@@ -508,11 +560,11 @@ __global__ void unmapped_pair(uint32_t n, const uint64_t *__restrict__ key, cons
     int nh = 0;
     for (uint32_t k = j; k < n && key[k] == key[j]; ++k) {
         uint32_t e = ent[k];
-        const uint8_t *p = d + rec_off[list[e]];
+        const uint8_t *p = d + list[e];
         bool r1 = (ldu32(p + 16) >> 16) & F_READ1;
         int hit = -1;
         for (int h = 0; h < nh; ++h)
-            if (same_name(p, d + rec_off[list[held[h]]])) {
+            if (same_name(p, d + list[held[h]])) {
                 hit = h;
                 break;
             }
@@ -520,7 +572,7 @@ __global__ void unmapped_pair(uint32_t n, const uint64_t *__restrict__ key, cons
             if (nh < H) held[nh++] = e;
             else atomicOr(overflow, 1u);
         } else {
-            const uint8_t *q = d + rec_off[list[held[hit]]];
+            const uint8_t *q = d + list[held[hit]];
             bool q1 = (ldu32(q + 16) >> 16) & F_READ1;
             if (q1 != r1) {
                 mate_of[e] = held[hit];
@@ -542,15 +594,14 @@ __device__ __forceinline__ uint32_t unmapped_fq_len(const uint8_t *p)
     return 1 + nl + 2 + 1 + (uint32_t)l + 1 + 2 + ql + 1;
 }
 
-__global__ void unmapped_sizes(uint32_t n, const uint32_t *__restrict__ list, const uint32_t *__restrict__ mate_of,
-                               const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, uint64_t *__restrict__ sz1,
-                               uint64_t *__restrict__ sz2)
+__global__ void unmapped_sizes(uint32_t n, const uint64_t *__restrict__ list, const uint32_t *__restrict__ mate_of,
+                               const uint8_t *__restrict__ d, uint64_t *__restrict__ sz1, uint64_t *__restrict__ sz2)
 {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e > n) return;
     uint64_t a = 0, b = 0;
     if (e < n && mate_of[e] != 0xffffffffu) {
-        const uint8_t *p = d + rec_off[list[e]], *q = d + rec_off[list[mate_of[e]]];
+        const uint8_t *p = d + list[e], *q = d + list[mate_of[e]];
         bool p1 = (ldu32(p + 16) >> 16) & F_READ1;
         a = unmapped_fq_len(p1 ? p : q), b = unmapped_fq_len(p1 ? q : p);
     }
@@ -580,26 +631,26 @@ __device__ void write_unmapped_fq(const uint8_t *p, char end, char *o, uint32_t 
 }
 
 __global__ void __launch_bounds__(128)
-    unmapped_write(uint32_t n, const uint32_t *__restrict__ list, const uint32_t *__restrict__ mate_of, const uint8_t *__restrict__ d,
-                   const uint64_t *__restrict__ rec_off, const uint64_t *__restrict__ off1, const uint64_t *__restrict__ off2,
-                   char *__restrict__ out1, char *__restrict__ out2)
+    unmapped_write(uint32_t n, const uint64_t *__restrict__ list, const uint32_t *__restrict__ mate_of, const uint8_t *__restrict__ d,
+                   const uint64_t *__restrict__ off1, const uint64_t *__restrict__ off2, char *__restrict__ out1,
+                   char *__restrict__ out2)
 {
     uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= n || mate_of[e] == 0xffffffffu) return;
-    const uint8_t *p = d + rec_off[list[e]], *q = d + rec_off[list[mate_of[e]]];
+    const uint8_t *p = d + list[e], *q = d + list[mate_of[e]];
     bool p1 = (ldu32(p + 16) >> 16) & F_READ1;
     write_unmapped_fq(p1 ? p : q, '1', out1 + off1[e], lane);
     write_unmapped_fq(p1 ? q : p, '2', out2 + off2[e], lane);
 }
 
 // ---- host orchestration -----------------------------------------------------------------------------------
-static int sort_u32(svb_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, uint32_t n)
+static int sort_u64(svb_ctx *ctx, uint64_t *keys_in, uint64_t *keys_out, uint32_t n, int bits)
 {
     size_t tmp = 0;
-    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys_in, keys_out, (int)n, 0, 32, ctx->stream));
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys_in, keys_out, (int)n, 0, bits, ctx->stream));
     DevBuf<uint8_t> t;
     CK(t.alloc(tmp, ctx->stream));
-    CK(cub::DeviceRadixSort::SortKeys(t.p, tmp, keys_in, keys_out, (int)n, 0, 32, ctx->stream));
+    CK(cub::DeviceRadixSort::SortKeys(t.p, tmp, keys_in, keys_out, (int)n, 0, bits, ctx->stream));
     return 0;
 }
 
@@ -609,24 +660,31 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
 {
     if (!ctx || !bam || !prm || !out_) return svb_fail(ctx, SVB_ERR_ARG, "svb_getclip: null argument");
     cudaStream_t s = ctx->stream;
-    const uint64_t n_rec = bam->n_rec;
-    if (n_rec >= (1ull << 32)) return svb_fail(ctx, SVB_ERR_ARG, "svb_getclip: more than 2^32 records in one shard");
     svb_clusters *res = new svb_clusters();
     res->ctx = ctx;
     std::unique_ptr<svb_clusters> guard(res);
+    const uint64_t n_chunks = bam->n_chunks, stream_bytes = bam->nbytes - bam->first;
+    int off_bits = 1;
+    while (off_bits < 64 && (bam->nbytes >> off_bits)) ++off_bits;  // offsets sort on just the bits they use
 
-    // ---- 1. scan ------------------------------------------------------------------------------------------
-    DevBuf<uint32_t> counters, un_list, sw_list;
-    DevBuf<uint32_t> c_rec, c_begin, c_ll, c_rl;
-    DevBuf<int32_t> c_tid, c_pos;
+    // ---- 1. the walker: every record head once ------------------------------------------------------------------
+    DevBuf<uint32_t> counters;
+    DevBuf<uint64_t> un_list, sw_list, c_off, exit_, first_mb;
+    DevBuf<uint32_t> c_begin, c_ll, c_rl;
+    DevBuf<int32_t> c_tid, c_pos, last_mb_tid;
     DevBuf<uint8_t> c_side;
     CandArrays c;
     uint32_t hc[3] = {0, 0, 0};
-    uint32_t cand_cap = (uint32_t)std::min<uint64_t>(n_rec / 8 + 4096, 0xffffffffu);
-    uint32_t un_cap = (uint32_t)std::min<uint64_t>(n_rec / 8 + 4096, 0xffffffffu), sw_cap = 1 << 16;
+    // sized from the stream (a record is at least ~40 bytes; ~2 % of them are soft-clipped), grown once on overflow
+    uint64_t est = stream_bytes / 200;
+    uint32_t cand_cap = (uint32_t)std::min<uint64_t>(est / 8 + 4096, 0xffffffffu);
+    uint32_t un_cap = (uint32_t)std::min<uint64_t>(est / 8 + 4096, 0xffffffffu), sw_cap = 1 << 16;
     CK(counters.alloc(4, s));
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        CK(c_rec.alloc(cand_cap, s));
+    CK(exit_.alloc(n_chunks, s));
+    CK(first_mb.alloc(n_chunks, s));
+    CK(last_mb_tid.alloc(n_chunks, s));
+    for (int attempt = 0;; ++attempt) {
+        CK(c_off.alloc(cand_cap, s));
         CK(c_begin.alloc(cand_cap, s));
         CK(c_ll.alloc(cand_cap, s));
         CK(c_rl.alloc(cand_cap, s));
@@ -635,29 +693,35 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         CK(c_side.alloc(cand_cap, s));
         CK(un_list.alloc(un_cap, s));
         CK(sw_list.alloc(sw_cap, s));
-        c = {c_rec.p, c_tid.p, c_pos.p, c_begin.p, c_ll.p, c_rl.p, c_side.p};
+        c = {c_off.p, c_tid.p, c_pos.p, c_begin.p, c_ll.p, c_rl.p, c_side.p};
+        ScanOut so{c, cand_cap, un_list.p, un_cap, sw_list.p, sw_cap, counters.p};
         CK(cudaMemsetAsync(counters.p, 0, 16, s));
-        if (n_rec) {
-            ProfScope ps(ctx, "clip_scan", (double)bam->rec_bytes);
-            clip_scan<<<nblk(n_rec, 256), 256, 0, s>>>(bam->d_data, bam->d_rec_off, n_rec, prm->min_mapq, prm->save_low_quality,
-                                                        prm->prev_tid, c, cand_cap, un_list.p, un_cap, sw_list.p, sw_cap,
-                                                        counters.p);
+        {
+            ProfScope ps(ctx, "clip_walk", (double)stream_bytes);
+            clip_walk<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->d_guess, bam->d_count, exit_.p,
+                                                        first_mb.p, last_mb_tid.p, prm->min_mapq, prm->save_low_quality, so);
+            clip_first<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, n_chunks, first_mb.p, last_mb_tid.p, prm->prev_tid, prm->min_mapq,
+                                                         prm->save_low_quality, so);
         }
+        int ok = 0;
+        CKR(verify_or_repair(ctx, bam, exit_.p, &ok));  // (synchronises)
         CK(cudaMemcpyAsync(hc, counters.p, 12, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        if (hc[0] <= cand_cap && hc[1] <= un_cap && hc[2] <= sw_cap) break;
-        if (attempt == 1) return svb_fail(ctx, SVB_ERR_CUDA, "svb_getclip: candidate buffers overflowed twice");
-        cand_cap = std::max(cand_cap, hc[0]), un_cap = std::max(un_cap, hc[1]), sw_cap = std::max(sw_cap, hc[2]);
+        bool fits = hc[0] <= cand_cap && hc[1] <= un_cap && hc[2] <= sw_cap;
+        if (ok && fits) break;
+        if (attempt >= 3) return svb_fail(ctx, SVB_ERR_CUDA, "svb_getclip: the record walk did not settle");
+        if (ok) cand_cap = std::max(cand_cap, hc[0]), un_cap = std::max(un_cap, hc[1]), sw_cap = std::max(sw_cap, hc[2]);
     }
+    if (!bam->counted) CKR(finish_counts(ctx, bam, exit_.p));  // the walker counted the records of every chunk on its way
     const uint32_t n_cand = hc[0], n_un = hc[1], n_sw = hc[2];
     res->n_candidates = n_cand;
 
     // ---- 2. unmapped-branch records: pair mates by name on the device, emit the two FASTQ files ---------------------
     if (n_un) {
-        DevBuf<uint32_t> un_sorted, val0, val1, mate_of, ovf;
-        DevBuf<uint64_t> key0, key1, sz1, sz2, off1, off2;
+        DevBuf<uint32_t> val0, val1, mate_of, ovf;
+        DevBuf<uint64_t> un_sorted, key0, key1, sz1, sz2, off1, off2;
         CK(un_sorted.alloc(n_un, s));
-        CKR(sort_u32(ctx, un_list.p, un_sorted.p, n_un));
+        CKR(sort_u64(ctx, un_list.p, un_sorted.p, n_un, off_bits));
         CK(val0.alloc(n_un, s));
         CK(val1.alloc(n_un, s));
         CK(key0.alloc(n_un, s));
@@ -673,14 +737,14 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         uint64_t tot[2] = {0, 0};
         {
             ProfScope ps(ctx, "unmapped_pair", 0);
-            unmapped_hash<<<nblk(n_un, 256), 256, 0, s>>>(n_un, un_sorted.p, bam->d_data, bam->d_rec_off, key0.p, val0.p);
+            unmapped_hash<<<nblk(n_un, 256), 256, 0, s>>>(n_un, un_sorted.p, bam->d_data, key0.p, val0.p);
             size_t tmp = 0;
             CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, key0.p, key1.p, val0.p, val1.p, (int)n_un, 0, 64, s));
             DevBuf<uint8_t> t;
             CK(t.alloc(tmp, s));
             CK(cub::DeviceRadixSort::SortPairs(t.p, tmp, key0.p, key1.p, val0.p, val1.p, (int)n_un, 0, 64, s));
-            unmapped_pair<<<nblk(n_un, 128), 128, 0, s>>>(n_un, key1.p, val1.p, un_sorted.p, bam->d_data, bam->d_rec_off, mate_of.p, ovf.p);
-            unmapped_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_sorted.p, mate_of.p, bam->d_data, bam->d_rec_off, sz1.p, sz2.p);
+            unmapped_pair<<<nblk(n_un, 128), 128, 0, s>>>(n_un, key1.p, val1.p, un_sorted.p, bam->d_data, mate_of.p, ovf.p);
+            unmapped_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_sorted.p, mate_of.p, bam->d_data, sz1.p, sz2.p);
             CKR(exclusive_scan_u64(ctx, sz1.p, off1.p, n_un + 1));
             CKR(exclusive_scan_u64(ctx, sz2.p, off2.p, n_un + 1));
         }
@@ -695,8 +759,8 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         CK(o2.alloc(tot[1], s));
         {
             ProfScope ps(ctx, "unmapped_write", (double)(tot[0] + tot[1]));
-            unmapped_write<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_sorted.p, mate_of.p, bam->d_data, bam->d_rec_off, off1.p,
-                                                                          off2.p, o1.p, o2.p);
+            unmapped_write<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_sorted.p, mate_of.p, bam->d_data, off1.p, off2.p, o1.p,
+                                                                          o2.p);
         }
         CKR(res->text[2].reserve(ctx, tot[0]));
         CKR(res->text[3].reserve(ctx, tot[1]));
@@ -712,10 +776,10 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
     if (bam->names.size() != (size_t)bam->n_ref) return svb_fail(ctx, SVB_ERR_ARG, "svb_getclip: reference names not set (svb_bam_set_refs)");
 
     // ---- 3. order candidates: BAM order first (stable base), then (run, side, pos) -----------------------------
-    DevBuf<uint32_t> sw_sorted, ord0, ord1, ord2, rec_sorted;
-    DevBuf<uint64_t> key0, key1;
+    DevBuf<uint32_t> ord0, ord1, ord2;
+    DevBuf<uint64_t> sw_sorted, rec_sorted, key0, key1;
     CK(sw_sorted.alloc(n_sw, s));
-    if (n_sw) CKR(sort_u32(ctx, sw_list.p, sw_sorted.p, n_sw));
+    if (n_sw) CKR(sort_u64(ctx, sw_list.p, sw_sorted.p, n_sw, off_bits));
     CK(ord0.alloc(n_cand, s));
     CK(ord1.alloc(n_cand, s));
     CK(ord2.alloc(n_cand, s));
@@ -728,10 +792,10 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         // (key, record) is unique and the two-pass stable sort is deterministic
         ProfScope ps(ctx, "sort_candidates", (double)n_cand * 24);
         size_t tmp = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c.rec, rec_sorted.p, ord0.p, ord1.p, (int)n_cand, 0, 32, s));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c.off, rec_sorted.p, ord0.p, ord1.p, (int)n_cand, 0, off_bits, s));
         DevBuf<uint8_t> t;
         CK(t.alloc(tmp, s));
-        CK(cub::DeviceRadixSort::SortPairs(t.p, tmp, c.rec, rec_sorted.p, ord0.p, ord1.p, (int)n_cand, 0, 32, s));
+        CK(cub::DeviceRadixSort::SortPairs(t.p, tmp, c.off, rec_sorted.p, ord0.p, ord1.p, (int)n_cand, 0, off_bits, s));
         make_keys<<<nblk(n_cand, 256), 256, 0, s>>>(n_cand, ord1.p, c, sw_sorted.p, n_sw, key0.p);
         size_t tmp2 = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, key0.p, key1.p, ord1.p, ord2.p, (int)n_cand, 0, 64, s));
@@ -766,21 +830,22 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
 
     // ---- 5. greedy clustering -----------------------------------------------------------------------------------
     DevBuf<char> arena_seq, arena_qual;
-    DevBuf<uint32_t> len_l, len_r, cig_rec, support, seg_ncl, cl_base;
+    DevBuf<uint32_t> len_l, len_r, support, seg_ncl, cl_base;
+    DevBuf<uint64_t> cig_off;
     DevBuf<uint8_t> noqual;
     CK(arena_seq.alloc(arena_bytes, s));
     CK(arena_qual.alloc(arena_bytes, s));
     CK(len_l.alloc(n_cand, s));
     CK(len_r.alloc(n_cand, s));
-    CK(cig_rec.alloc(n_cand, s));
+    CK(cig_off.alloc(n_cand, s));
     CK(support.alloc(n_cand, s));
     CK(noqual.alloc(n_cand, s));
     CK(seg_ncl.alloc(n_seg, s));
     CK(cl_base.alloc(n_seg, s));
-    ClusterOut co{len_l.p, len_r.p, cig_rec.p, support.p, noqual.p, seg_ncl.p};
+    ClusterOut co{len_l.p, len_r.p, support.p, cig_off.p, noqual.p, seg_ncl.p};
     {
         ProfScope ps(ctx, "cluster_build", (double)arena_bytes * 2);
-        cluster_build<<<nblk((uint64_t)n_seg * 32, 128), 128, 0, s>>>(bam->d_data, bam->d_rec_off, n_seg, start.p, order, c, maxl.p,
+        cluster_build<<<nblk((uint64_t)n_seg * 32, 128), 128, 0, s>>>(bam->d_data, n_seg, start.p, order, c, maxl.p,
                                                                       maxr.p, arena_off.p, arena_seq.p, arena_qual.p, prm->match_rate, co);
     }
     CKR(inclusive_scan_u32(ctx, seg_ncl.p, cl_base.p, n_seg));
@@ -812,7 +877,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
     CK(fq_off.alloc(n_cl + 1, s));
     NameTable nt{d_nblob.p, d_noff.p};
     list_clusters<<<nblk(n_seg, 256), 256, 0, s>>>(n_seg, start.p, seg_ncl.p, cl_base.p, cl_seg.p, cl_slot.p);
-    text_sizes<<<nblk(n_cl + 1, 256), 256, 0, s>>>(n_cl, cl_seg.p, cl_slot.p, start.p, order, c, co, bam->d_data, bam->d_rec_off, nt,
+    text_sizes<<<nblk(n_cl + 1, 256), 256, 0, s>>>(n_cl, cl_seg.p, cl_slot.p, start.p, order, c, co, bam->d_data, nt,
                                                    clip_len.p, fq_len.p);
     CKR(exclusive_scan_u64(ctx, clip_len.p, clip_off.p, n_cl + 1));
     CKR(exclusive_scan_u64(ctx, fq_len.p, fq_off.p, n_cl + 1));
@@ -825,9 +890,9 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
     CK(d_fq.alloc(fq_bytes, s));
     {
         ProfScope ps(ctx, "text_write", (double)(clip_bytes + fq_bytes));
-        text_write<<<nblk((uint64_t)n_cl * 32, 128), 128, 0, s>>>(n_cl, cl_seg.p, cl_slot.p, start.p, order, c, co, bam->d_data,
-                                                                  bam->d_rec_off, nt, maxl.p, maxr.p, arena_off.p, arena_seq.p,
-                                                                  arena_qual.p, clip_off.p, fq_off.p, d_clip.p, d_fq.p);
+        text_write<<<nblk((uint64_t)n_cl * 32, 128), 128, 0, s>>>(n_cl, cl_seg.p, cl_slot.p, start.p, order, c, co, bam->d_data, nt,
+                                                                  maxl.p, maxr.p, arena_off.p, arena_seq.p, arena_qual.p, clip_off.p,
+                                                                  fq_off.p, d_clip.p, d_fq.p);
     }
     CKR(res->text[0].reserve(ctx, clip_bytes));
     CKR(res->text[1].reserve(ctx, fq_bytes));

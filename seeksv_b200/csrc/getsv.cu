@@ -14,44 +14,88 @@ static inline unsigned nblk(uint64_t n, unsigned b) { return (unsigned)((n + b -
 #define PILEUP_MAXCNT 8000
 
 // ---- decode: packed records -> lean columns -----------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    decode_kernel(const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, uint64_t n_rec, LeanRecords L,
-                  int32_t *__restrict__ max_span, uint32_t *__restrict__ unsorted)
+__device__ __forceinline__ bool insert_qualifies(uint32_t fq, int32_t isize, int32_t min_mapq)
 {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int32_t span = 0;
-    if (i < n_rec) {
-        const uint8_t *p = d + rec_off[i];
-        Core k = load_core(p);
-        const uint8_t *cig = p + 36 + k.l_qname;
-        int32_t end = k.pos;
-        uint32_t fq = k.flag | (k.mapq << 16);
-        if (k.n_cigar == 0) fq |= FLAGQ_NOCIGAR;
-        for (uint32_t j = 0; j < k.n_cigar; ++j) {
-            uint32_t w = ldu32s(cig + 4 * j), op = w & 15;
-            // bam_calend of the linked libbam: M, D, N only ('=' and 'X' do not advance; probed)
-            if (op == OP_M || op == OP_D || op == OP_N) end += (int32_t)(w >> 4);
-            if ((j == 0 || j + 1 == k.n_cigar) && op == OP_H) fq |= FLAGQ_HARDCLIP;  // IsHardClip, clip_reads.cpp:247
-        }
-        L.tid[i] = k.tid, L.pos[i] = k.pos, L.end[i] = end, L.flagq[i] = fq;
-        L.lqseq[i] = k.l_qseq, L.mtid[i] = k.mtid, L.mpos[i] = k.mpos, L.isize[i] = k.isize;
-        span = max(end - k.pos, 1);
-        if (i > 0) {  // coordinate order: (tid, pos) ascending, tid -1 last
-            const uint8_t *q = d + rec_off[i - 1];
-            uint32_t t0 = (uint32_t)ldi32s(q + 4), t1 = (uint32_t)k.tid;  // -1 -> 0xffffffff sorts last
-            int32_t p0 = ldi32s(q + 8);
-            if (t0 > t1 || (t0 == t1 && p0 > k.pos)) atomicOr(unsorted, 1u);
-        }
-    }
-    span = (int32_t)warp_max((uint32_t)span);
-    if ((threadIdx.x & 31) == 0 && span > 0) atomicMax(max_span, span);
+    uint32_t flag = fq & 0xffff;
+    if ((int32_t)((fq >> 16) & 0xff) < min_mapq) return false;  // __g_skip_aln in cluster.cpp's TU (quirk Q9)
+    if (fq & FLAGQ_HARDCLIP) return false;
+    return (flag & F_PAIRED) && (flag & F_PROPER) && !(flag & F_DUP) && isize > 0;
 }
 
-int decode_records(svb_ctx *ctx, svb_bam *bam)
+// The getsv walker: one thread per 16 KiB chunk follows the verified record chain (guess + per-chunk record base from
+// ensure_counts) and writes the lean columns of its records; every record head is fetched once. On the way it gathers
+// the chunk's partial sums for CalculateInsertsizeDeviation (cluster.cpp:48-70) at one mapQ threshold.
+__global__ void __launch_bounds__(128)
+    decode_walk(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks, const uint64_t *__restrict__ guess,
+                const uint64_t *__restrict__ base, LeanRecords L, int32_t stats_mapq, uint32_t *__restrict__ q_cnt,
+                uint64_t *__restrict__ q_sum, uint64_t *__restrict__ q_sq, int32_t *__restrict__ scal /* max_span, unsorted, q_max */)
+{
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t span = 0, qmax = 0;
+    uint32_t unsorted = 0;
+    if (c < n_chunks) {
+        uint64_t o = guess[c], end = min(n, (c + 1) << CHUNK_LOG2), i = base[c];
+        uint32_t qc = 0, pt = 0;
+        uint64_t qs = 0, qq = 0;
+        int32_t pp = 0;
+        bool have_prev = false;
+        while (o < end) {
+            if (o + 36 > n) break;
+            Core k = load_core(d + o);
+            if (k.block_size < 32 || o + 4 + (uint64_t)k.block_size > n) break;  // (the chain is verified: tail only)
+            const uint8_t *cig = d + o + 36 + k.l_qname;
+            int32_t rend = k.pos;
+            uint32_t fq = k.flag | (k.mapq << 16);
+            if (k.n_cigar == 0) fq |= FLAGQ_NOCIGAR;
+            for (uint32_t j = 0; j < k.n_cigar; ++j) {
+                uint32_t w = ldu32(cig + 4 * j), op = w & 15;
+                // bam_calend of the linked libbam: M, D, N only ('=' and 'X' do not advance; probed)
+                if (op == OP_M || op == OP_D || op == OP_N) rend += (int32_t)(w >> 4);
+                if ((j == 0 || j + 1 == k.n_cigar) && op == OP_H) fq |= FLAGQ_HARDCLIP;  // IsHardClip, clip_reads.cpp:247
+            }
+            L.tid[i] = k.tid, L.pos[i] = k.pos, L.end[i] = rend, L.flagq[i] = fq;
+            L.lqseq[i] = k.l_qseq, L.mtid[i] = k.mtid, L.mpos[i] = k.mpos, L.isize[i] = k.isize;
+            L.off[i] = o;
+            span = max(span, max(rend - k.pos, 1));
+            if (have_prev && (pt > (uint32_t)k.tid || (pt == (uint32_t)k.tid && pp > k.pos))) unsorted = 1;  // tid -1 sorts last
+            pt = (uint32_t)k.tid, pp = k.pos, have_prev = true;
+            if (stats_mapq >= 0 && insert_qualifies(fq, k.isize, stats_mapq)) {
+                ++qc, qs += (uint64_t)k.isize, qq += (uint64_t)k.isize * (uint64_t)k.isize;
+                qmax = max(qmax, k.isize);
+            }
+            ++i;
+            o += 4 + (uint64_t)k.block_size;
+        }
+        q_cnt[c] = qc, q_sum[c] = qs, q_sq[c] = qq;
+    }
+    span = (int32_t)warp_max((uint32_t)span);
+    qmax = (int32_t)warp_max((uint32_t)qmax);
+    unsorted = warp_max(unsorted);
+    if ((threadIdx.x & 31) == 0) {
+        if (span > 0) atomicMax(&scal[0], span);
+        if (unsorted) atomicOr((uint32_t *)&scal[1], 1u);
+        if (qmax > 0) atomicMax(&scal[2], qmax);
+    }
+}
+
+// coordinate order across chunk boundaries: the last record of a chunk against the first of the next
+__global__ void boundary_order(uint64_t n_chunks, const uint64_t *__restrict__ base, LeanRecords L, uint32_t *__restrict__ unsorted)
+{
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 || c >= n_chunks) return;
+    uint64_t i = base[c];
+    if (i == 0 || i >= L.n || base[c + 1] == i) return;
+    uint32_t t0 = (uint32_t)L.tid[i - 1], t1 = (uint32_t)L.tid[i];
+    if (t0 > t1 || (t0 == t1 && L.pos[i - 1] > L.pos[i])) atomicOr(unsorted, 1u);
+}
+
+int decode_records(svb_ctx *ctx, svb_bam *bam, int32_t stats_mapq)
 {
     if (bam->lean_ready) return 0;
+    CKR(ensure_counts(ctx, bam));
     cudaStream_t s = ctx->stream;
-    uint64_t n = bam->n_rec;
+    uint64_t n = bam->n_rec, n_chunks = bam->n_chunks;
+    if (n >= (1ull << 32)) return svb_fail(ctx, SVB_ERR_ARG, "more than 2^32 records in one shard");
     LeanRecords &L = bam->lean;
     size_t cnt = n ? n : 1;
     CK(cudaMallocAsync((void **)&L.tid, cnt * 4, s));
@@ -62,32 +106,33 @@ int decode_records(svb_ctx *ctx, svb_bam *bam)
     CK(cudaMallocAsync((void **)&L.mtid, cnt * 4, s));
     CK(cudaMallocAsync((void **)&L.mpos, cnt * 4, s));
     CK(cudaMallocAsync((void **)&L.isize, cnt * 4, s));
+    CK(cudaMallocAsync((void **)&L.off, cnt * 8, s));
+    CK(cudaMallocAsync((void **)&bam->d_q_cnt, n_chunks * 4, s));
+    CK(cudaMallocAsync((void **)&bam->d_q_sum, n_chunks * 8, s));
+    CK(cudaMallocAsync((void **)&bam->d_q_sq, n_chunks * 8, s));
     L.n = n;
     DevBuf<int32_t> scal;
-    CK(scal.alloc(2, s));
-    CK(cudaMemsetAsync(scal.p, 0, 8, s));
-    if (n) {
-        ProfScope ps(ctx, "decode_records", (double)bam->rec_bytes);
-        decode_kernel<<<nblk(n, 256), 256, 0, s>>>(bam->d_data, bam->d_rec_off, n, L, scal.p, (uint32_t *)scal.p + 1);
+    CK(scal.alloc(4, s));
+    CK(cudaMemsetAsync(scal.p, 0, 16, s));
+    {
+        ProfScope ps(ctx, "decode_walk", (double)bam->rec_bytes);
+        decode_walk<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->d_guess, bam->d_base, L, stats_mapq,
+                                                      bam->d_q_cnt, bam->d_q_sum, bam->d_q_sq, scal.p);
+        boundary_order<<<nblk(n_chunks, 256), 256, 0, s>>>(n_chunks, bam->d_base, L, (uint32_t *)scal.p + 1);
     }
-    int32_t h[2];
-    CK(cudaMemcpyAsync(h, scal.p, 8, cudaMemcpyDeviceToHost, s));
+    int32_t h[4];
+    CK(cudaMemcpyAsync(h, scal.p, 16, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     bam->max_span = h[0];
     bam->sorted = h[1] ? 0 : 1;
+    bam->q_max = h[2];
+    bam->stats_mapq = stats_mapq;
     bam->lean_ready = true;
     return 0;
 }
 
 // ---- insert size ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool insert_qualifies(uint32_t fq, int32_t isize, int32_t min_mapq)
-{
-    uint32_t flag = fq & 0xffff;
-    if ((int32_t)((fq >> 16) & 0xff) < min_mapq) return false;  // __g_skip_aln in cluster.cpp's TU (quirk Q9)
-    if (fq & FLAGQ_HARDCLIP) return false;
-    return (flag & F_PAIRED) && (flag & F_PROPER) && !(flag & F_DUP) && isize > 0;
-}
 __global__ void insert_flags(uint64_t n, const uint32_t *__restrict__ fq, const int32_t *__restrict__ isize, int32_t min_mapq,
                              uint32_t *__restrict__ flag)
 {
@@ -113,15 +158,56 @@ __global__ void __launch_bounds__(256)
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(acc, (unsigned long long)v);
 }
 
+__global__ void chunk_totals(uint64_t n_chunks, const uint32_t *__restrict__ q_cnt, const uint64_t *__restrict__ q_sum,
+                             const uint64_t *__restrict__ q_sq, unsigned long long *__restrict__ tot)
+{
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long a = 0, b = 0, q = 0;
+    if (c < n_chunks) a = q_cnt[c], b = q_sum[c], q = q_sq[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if ((threadIdx.x & 31) == 0 && a) {
+        atomicAdd(&tot[0], a);
+        atomicAdd(&tot[1], b);
+        atomicAdd(&tot[2], q);
+    }
+}
+
 extern "C" int svb_insert_stats(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64_t max_pairs, int64_t out[4])
 {
     if (!ctx || !bam || !out) return svb_fail(ctx, SVB_ERR_ARG, "svb_insert_stats: null argument");
-    CKR(decode_records(ctx, bam));
+    CKR(decode_records(ctx, bam, min_mapq));  // the decode walker gathers per-chunk partial sums for this mapQ on its way
     cudaStream_t s = ctx->stream;
     uint64_t n = bam->n_rec;
     out[0] = out[1] = out[2] = out[3] = 0;
     if (n == 0 || max_pairs <= 0) return 0;
     if (n >= (1ull << 32)) return svb_fail(ctx, SVB_ERR_ARG, "more than 2^32 records in one shard");
+    if (bam->stats_mapq == min_mapq && bam->q_max <= 46340) {
+        // Fast path: every |isize - mean| stays below sqrt(2^31), so the reference's int products cannot wrap and
+        // sum (x - m)^2 = sum x^2 - 2 m sum x + n m^2 holds exactly in 64-bit integers. Valid when all qualifying records
+        // are used (total <= -n); otherwise the ordered cut-off needs the per-record path below.
+        DevBuf<unsigned long long> tot;
+        CK(tot.alloc(3, s));
+        CK(cudaMemsetAsync(tot.p, 0, 24, s));
+        {
+            ProfScope ps(ctx, "insert_stats", (double)bam->n_chunks * 20);
+            chunk_totals<<<nblk(bam->n_chunks, 256), 256, 0, s>>>(bam->n_chunks, bam->d_q_cnt, bam->d_q_sum, bam->d_q_sq, tot.p);
+        }
+        unsigned long long h[3];
+        CK(cudaMemcpyAsync(h, tot.p, 24, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h[0] <= (unsigned long long)max_pairs) {
+            if (h[0] == 0) return 0;
+            long long mean = (long long)(h[1] / h[0]);
+            out[0] = (int64_t)h[0], out[1] = (int64_t)h[1], out[2] = mean;
+            out[3] = (int64_t)h[2] - 2 * mean * (int64_t)h[1] + (int64_t)h[0] * mean * mean;
+            return 0;
+        }
+    }
     DevBuf<uint32_t> flag, rank;
     DevBuf<unsigned long long> acc;
     CK(flag.alloc(n, s));
@@ -283,19 +369,6 @@ __global__ void eligible_flags(LeanRecords L, int32_t min_mapq, uint32_t *__rest
     if (i < L.n) flag[i] = pileup_eligible(L.tid[i], L.flagq[i], min_mapq) ? 1u : 0u;
 }
 
-// Upper bound of the pileup buffer occupancy when record i is pushed: eligible records that start within
-// max_span before it. If this never exceeds the cap, libbam's 8000-read limit cannot trigger anywhere.
-__global__ void cap_bound(LeanRecords L, int32_t max_span, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ rank,
-                          uint32_t *__restrict__ hot_tids, uint32_t n_ref)
-{
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L.n || !flag[i]) return;
-    int32_t tid = L.tid[i];
-    uint64_t lo = lower_bound_tp(L.tid, L.pos, L.n, tid, (int64_t)L.pos[i] - max_span);
-    uint32_t before = lo ? rank[lo - 1] : 0;
-    if (rank[i] - before + 2 > PILEUP_MAXCNT && (uint32_t)tid < n_ref) hot_tids[tid] = 1;
-}
-
 // Exact serial emulation of bam_plp_push's cap for one chromosome (one thread per hot chromosome): a read is
 // refused only if it starts at the same position as the previously accepted read while more than 8000
 // buffer nodes are allocated = 2 + accepted reads whose end >= that position (released lazily).
@@ -352,17 +425,29 @@ __device__ __forceinline__ uint64_t first_window(const svb_window *__restrict__ 
 }
 
 // One thread per record: +1/-1 marks of its M segments into the difference array of every window it overlaps.
+// kept == nullptr: every pileup-eligible read is kept and the kernel also tests libbam's 8000-read cap bound: if the record
+// 7998 places earlier on the same chromosome starts within max_span of this one, more than 8000 buffer nodes are
+// possible and the chromosome is flagged for the exact serial emulation (cap_serial), after which the marks are redone.
 __global__ void __launch_bounds__(256)
-    depth_marks(const uint8_t *__restrict__ d, const uint64_t *__restrict__ rec_off, LeanRecords L, const uint8_t *__restrict__ kept,
-                const svb_window *__restrict__ W, const uint64_t *__restrict__ woff, uint64_t n_w, int32_t *__restrict__ diff)
+    depth_marks(const uint8_t *__restrict__ d, LeanRecords L, int32_t min_mapq, int32_t max_span, const uint8_t *__restrict__ kept,
+                uint32_t *__restrict__ hot_tids, const svb_window *__restrict__ W, const uint64_t *__restrict__ woff, uint64_t n_w,
+                int32_t *__restrict__ diff)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L.n || !kept[i]) return;
-    int32_t tid = L.tid[i], beg1 = L.pos[i] + 1, end1 = L.end[i];  // 1-based inclusive [beg1, end1]
+    if (i >= L.n) return;
+    int32_t tid = L.tid[i];
+    if (!pileup_eligible(tid, L.flagq[i], min_mapq)) return;
+    if (kept) {
+        if (!kept[i]) return;
+    } else if (i >= PILEUP_MAXCNT - 2) {
+        uint64_t j = i - (PILEUP_MAXCNT - 2);
+        if (L.tid[j] == tid && L.pos[j] >= L.pos[i] - max_span) hot_tids[tid] = 1;
+    }
+    int32_t beg1 = L.pos[i] + 1, end1 = L.end[i];  // 1-based inclusive [beg1, end1]
     if (end1 < beg1) return;
     uint64_t w = first_window(W, n_w, tid, beg1);
     if (w >= n_w || W[w].tid != tid || W[w].begin > end1) return;
-    const uint8_t *p = d + rec_off[i];
+    const uint8_t *p = d + L.off[i];
     uint32_t lq = ldu32(p + 12) & 0xff, nc = ldu32(p + 16) & 0xffff;
     const uint8_t *cig = p + 36 + lq;
     for (; w < n_w && W[w].tid == tid && W[w].begin <= end1; ++w) {
@@ -441,7 +526,7 @@ extern "C" int svb_window_depth(svb_ctx *ctx, svb_bam *bam, const svb_window *wi
     DevBuf<svb_window> dW;
     DevBuf<uint64_t> dOff;
     DevBuf<int32_t> diff, depth;
-    DevBuf<uint32_t> flag, rank, hot, ringbuf;
+    DevBuf<uint32_t> flag, hot, ringbuf;
     DevBuf<uint8_t> kept;
     CK(dW.alloc(n_w, s));
     CK(dOff.alloc(n_w + 1, s));
@@ -452,33 +537,34 @@ extern "C" int svb_window_depth(svb_ctx *ctx, svb_bam *bam, const svb_window *wi
     CK(cudaMemsetAsync(diff.p, 0, tot * 4, s));
     if (n) {
         uint32_t n_ref = (uint32_t)bam->n_ref;
-        CK(flag.alloc(n, s));
-        CK(rank.alloc(n, s));
-        CK(kept.alloc(n, s));
         CK(hot.alloc(n_ref + 1, s));
         CK(cudaMemsetAsync(hot.p, 0, (n_ref + 1) * 4, s));
         {
-            ProfScope ps(ctx, "depth_eligible", (double)n * 24);
-            eligible_flags<<<nblk(n, 256), 256, 0, s>>>(bam->lean, min_mapq, flag.p);
-            CKR(inclusive_scan_u32(ctx, flag.p, rank.p, n));
-            fill_u8<<<nblk(n, 256), 256, 0, s>>>(n, flag.p, kept.p);
-            cap_bound<<<nblk(n, 256), 256, 0, s>>>(bam->lean, bam->max_span, flag.p, rank.p, hot.p, n_ref);
+            ProfScope ps(ctx, "depth_marks", (double)n * 13);
+            depth_marks<<<nblk(n, 256), 256, 0, s>>>(bam->d_data, bam->lean, min_mapq, bam->max_span, nullptr, hot.p, dW.p, dOff.p, n_w,
+                                                     diff.p);
         }
         std::vector<uint32_t> hhot(n_ref);
         CK(cudaMemcpyAsync(hhot.data(), hot.p, n_ref * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         bool any_hot = false;
         for (uint32_t t = 0; t < n_ref; ++t) any_hot |= hhot[t] != 0;
-        if (any_hot) {  // rare: coverage beyond libbam's pileup cap (quirk Q12) - serial, exact
+        if (any_hot) {  // rare: coverage beyond libbam's pileup cap (quirk Q12) - serial, exact; then the marks are redone
+            CK(flag.alloc(n, s));
+            CK(kept.alloc(n, s));
+            eligible_flags<<<nblk(n, 256), 256, 0, s>>>(bam->lean, min_mapq, flag.p);
+            fill_u8<<<nblk(n, 256), 256, 0, s>>>(n, flag.p, kept.p);
             uint32_t ring = 1;
             while (ring < (uint32_t)bam->max_span + 2) ring <<= 1;
             CK(ringbuf.alloc((uint64_t)n_ref * ring, s));
-            ProfScope ps(ctx, "pileup_cap_serial", 0);
-            cap_serial<<<nblk(n_ref, 32), 32, 0, s>>>(bam->lean, hot.p, n_ref, flag.p, kept.p, ringbuf.p, ring);
-        }
-        {
+            {
+                ProfScope ps(ctx, "pileup_cap_serial", 0);
+                cap_serial<<<nblk(n_ref, 32), 32, 0, s>>>(bam->lean, hot.p, n_ref, flag.p, kept.p, ringbuf.p, ring);
+            }
+            CK(cudaMemsetAsync(diff.p, 0, tot * 4, s));
             ProfScope ps(ctx, "depth_marks", (double)n * 13);
-            depth_marks<<<nblk(n, 256), 256, 0, s>>>(bam->d_data, bam->d_rec_off, bam->lean, kept.p, dW.p, dOff.p, n_w, diff.p);
+            depth_marks<<<nblk(n, 256), 256, 0, s>>>(bam->d_data, bam->lean, min_mapq, bam->max_span, kept.p, nullptr, dW.p, dOff.p, n_w,
+                                                     diff.p);
         }
     }
     {
