@@ -403,8 +403,7 @@ extern "C" void svb_bam_free(svb_bam *b)
     cudaStreamSynchronize(b->ctx->stream);
     cudaStream_t s = b->ctx->stream;
     LeanRecords &L = b->lean;
-    void *cols[15] = {L.tid, L.pos, L.end, L.flagq, L.lqseq, L.mtid, L.mpos, L.isize, L.off, b->d_guess, b->d_count, b->d_base,
-                      b->d_q_cnt, b->d_q_sum, b->d_q_sq};
+    void *cols[7] = {L.rec, b->d_guess, b->d_count, b->d_base, b->d_q_cnt, b->d_q_sum, b->d_q_sq};
     for (void *c : cols)
         if (c) cudaFreeAsync(c, s);
     if (b->d_owned) cudaFreeAsync(b->d_owned, s);

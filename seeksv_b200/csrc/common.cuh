@@ -65,12 +65,17 @@ struct PinnedBuf {
     }
 };
 
-// Lean per-record columns produced by decode_records (getsv passes read these, not the raw stream).
+// Lean per-record rows produced by the decode walker (getsv passes read these, not the raw stream). Rows, not columns:
+// a walker thread writes the ~50 records of its chunk one after the other, so its output is one contiguous 2 KB run
+// (column arrays made every 4-byte store its own DRAM sector: 2.9 ms instead of 0.3 ms for C2, profiles/r1_summary.md).
+struct __align__(8) LeanRec {
+    int32_t tid, pos, end;  // end = bam_calend of the linked libbam (M, D, N)
+    uint32_t flagq;         // flag | mapq << 16 | hardclip << 24 | no-cigar << 25
+    int32_t lqseq, mtid, mpos, isize;
+    uint64_t off;           // byte offset of the record in the stream (CIGARs are re-read from there)
+};
 struct LeanRecords {
-    int32_t *tid = nullptr, *pos = nullptr, *end = nullptr;  // end = libbam bam_calend (M,D,N), pos+1 if no CIGAR
-    uint32_t *flagq = nullptr;                                 // flag | mapq << 16 | hardclip << 24
-    int32_t *lqseq = nullptr, *mtid = nullptr, *mpos = nullptr, *isize = nullptr;
-    uint64_t *off = nullptr;  // byte offset of the record in the stream (CIGARs are re-read from there)
+    LeanRec *rec = nullptr;
     uint64_t n = 0;
 };
 #define FLAGQ_HARDCLIP (1u << 24)

@@ -157,14 +157,20 @@ __global__ void __launch_bounds__(128)
     uint64_t o = guess[c], end = min(n, (c + 1) << CHUNK_LOG2), first = BAD_OFFSET;
     uint32_t cnt = 0;
     int32_t prev_tid = NO_TID;
-    while (o < end) {
-        if (o + 36 > n) break;  // partial tail
-        Core k = load_core(d + o);
+    bool live = o < end && o + 36 <= n;  // (a partial tail shorter than a fixed part ends the walk)
+    Core k;
+    if (live) k = load_core(d + o);
+    while (live) {
         if (k.block_size < 32) {
             o = BAD_OFFSET;
             break;
         }
         if (o + 4 + (uint64_t)k.block_size > n) break;
+        // software pipeline: request the next record's fixed part before this record's CIGAR / aux bytes are waited for
+        uint64_t on = o + 4 + (uint64_t)k.block_size;
+        bool next_live = on < end && on + 36 <= n;
+        Core kn;
+        if (next_live) kn = load_core(d + on);
         ++cnt;
         if (k.flag & (F_UNMAP | F_MUNMAP)) {  // clip_reads.h:415 - the unmapped branch wins (quirk Q2)
             uint32_t s = atomicAdd(&out.counters[1], 1u);
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(128)
                 eval_clip(d, o, k, min_mapq, save_low_quality, out);
             prev_tid = k.tid;
         }
-        o += 4 + (uint64_t)k.block_size;
+        o = on, k = kn, live = next_live;
     }
     count[c] = cnt, exit_[c] = o, first_mb[c] = first, last_mb_tid[c] = prev_tid;
 }

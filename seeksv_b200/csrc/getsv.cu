@@ -39,10 +39,16 @@ __global__ void __launch_bounds__(128)
         uint64_t qs = 0, qq = 0;
         int32_t pp = 0;
         bool have_prev = false;
-        while (o < end) {
-            if (o + 36 > n) break;
-            Core k = load_core(d + o);
+        bool live = o < end && o + 36 <= n;
+        Core k;
+        if (live) k = load_core(d + o);
+        while (live) {
             if (k.block_size < 32 || o + 4 + (uint64_t)k.block_size > n) break;  // (the chain is verified: tail only)
+            // software pipeline: the next record's fixed part is requested before this record's CIGAR is waited for
+            uint64_t on = o + 4 + (uint64_t)k.block_size;
+            bool next_live = on < end && on + 36 <= n;
+            Core kn;
+            if (next_live) kn = load_core(d + on);
             const uint8_t *cig = d + o + 36 + k.l_qname;
             int32_t rend = k.pos;
             uint32_t fq = k.flag | (k.mapq << 16);
@@ -53,9 +59,10 @@ __global__ void __launch_bounds__(128)
                 if (op == OP_M || op == OP_D || op == OP_N) rend += (int32_t)(w >> 4);
                 if ((j == 0 || j + 1 == k.n_cigar) && op == OP_H) fq |= FLAGQ_HARDCLIP;  // IsHardClip, clip_reads.cpp:247
             }
-            L.tid[i] = k.tid, L.pos[i] = k.pos, L.end[i] = rend, L.flagq[i] = fq;
-            L.lqseq[i] = k.l_qseq, L.mtid[i] = k.mtid, L.mpos[i] = k.mpos, L.isize[i] = k.isize;
-            L.off[i] = o;
+            LeanRec r;
+            r.tid = k.tid, r.pos = k.pos, r.end = rend, r.flagq = fq;
+            r.lqseq = k.l_qseq, r.mtid = k.mtid, r.mpos = k.mpos, r.isize = k.isize, r.off = o;
+            L.rec[i] = r;
             span = max(span, max(rend - k.pos, 1));
             if (have_prev && (pt > (uint32_t)k.tid || (pt == (uint32_t)k.tid && pp > k.pos))) unsorted = 1;  // tid -1 sorts last
             pt = (uint32_t)k.tid, pp = k.pos, have_prev = true;
@@ -64,7 +71,7 @@ __global__ void __launch_bounds__(128)
                 qmax = max(qmax, k.isize);
             }
             ++i;
-            o += 4 + (uint64_t)k.block_size;
+            o = on, k = kn, live = next_live;
         }
         q_cnt[c] = qc, q_sum[c] = qs, q_sq[c] = qq;
     }
@@ -85,8 +92,8 @@ __global__ void boundary_order(uint64_t n_chunks, const uint64_t *__restrict__ b
     if (c == 0 || c >= n_chunks) return;
     uint64_t i = base[c];
     if (i == 0 || i >= L.n || base[c + 1] == i) return;
-    uint32_t t0 = (uint32_t)L.tid[i - 1], t1 = (uint32_t)L.tid[i];
-    if (t0 > t1 || (t0 == t1 && L.pos[i - 1] > L.pos[i])) atomicOr(unsorted, 1u);
+    uint32_t t0 = (uint32_t)L.rec[i - 1].tid, t1 = (uint32_t)L.rec[i].tid;
+    if (t0 > t1 || (t0 == t1 && L.rec[i - 1].pos > L.rec[i].pos)) atomicOr(unsorted, 1u);
 }
 
 int decode_records(svb_ctx *ctx, svb_bam *bam, int32_t stats_mapq)
@@ -98,15 +105,7 @@ int decode_records(svb_ctx *ctx, svb_bam *bam, int32_t stats_mapq)
     if (n >= (1ull << 32)) return svb_fail(ctx, SVB_ERR_ARG, "more than 2^32 records in one shard");
     LeanRecords &L = bam->lean;
     size_t cnt = n ? n : 1;
-    CK(cudaMallocAsync((void **)&L.tid, cnt * 4, s));
-    CK(cudaMallocAsync((void **)&L.pos, cnt * 4, s));
-    CK(cudaMallocAsync((void **)&L.end, cnt * 4, s));
-    CK(cudaMallocAsync((void **)&L.flagq, cnt * 4, s));
-    CK(cudaMallocAsync((void **)&L.lqseq, cnt * 4, s));
-    CK(cudaMallocAsync((void **)&L.mtid, cnt * 4, s));
-    CK(cudaMallocAsync((void **)&L.mpos, cnt * 4, s));
-    CK(cudaMallocAsync((void **)&L.isize, cnt * 4, s));
-    CK(cudaMallocAsync((void **)&L.off, cnt * 8, s));
+    CK(cudaMallocAsync((void **)&L.rec, cnt * sizeof(LeanRec), s));
     CK(cudaMallocAsync((void **)&bam->d_q_cnt, n_chunks * 4, s));
     CK(cudaMallocAsync((void **)&bam->d_q_sum, n_chunks * 8, s));
     CK(cudaMallocAsync((void **)&bam->d_q_sq, n_chunks * 8, s));
@@ -133,23 +132,22 @@ int decode_records(svb_ctx *ctx, svb_bam *bam, int32_t stats_mapq)
 }
 
 // ---- insert size ------------------------------------------------------------------------------------------------
-__global__ void insert_flags(uint64_t n, const uint32_t *__restrict__ fq, const int32_t *__restrict__ isize, int32_t min_mapq,
-                             uint32_t *__restrict__ flag)
+__global__ void insert_flags(uint64_t n, const LeanRec *__restrict__ rec, int32_t min_mapq, uint32_t *__restrict__ flag)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flag[i] = insert_qualifies(fq[i], isize[i], min_mapq) ? 1u : 0u;
+    if (i < n) flag[i] = insert_qualifies(rec[i].flagq, rec[i].isize, min_mapq) ? 1u : 0u;
 }
 // pass 1 (mean == INT_MIN): sum of isize; pass 2: sum of (int32)((isize-mean)*(isize-mean))
 __global__ void __launch_bounds__(256)
-    insert_sums(uint64_t n, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ rank, const int32_t *__restrict__ isize,
+    insert_sums(uint64_t n, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ rank, const LeanRec *__restrict__ rec,
                 uint64_t max_pairs, int pass, int32_t mean, unsigned long long *__restrict__ acc)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     long long v = 0;
     if (i < n && flag[i] && (uint64_t)rank[i] <= max_pairs) {
-        if (pass == 1) v = isize[i];
+        if (pass == 1) v = rec[i].isize;
         else {
-            uint32_t dlt = (uint32_t)(isize[i] - mean);
+            uint32_t dlt = (uint32_t)(rec[i].isize - mean);
             v = (int32_t)(dlt * dlt);  // the reference multiplies two ints (cluster.cpp:77)
         }
     }
@@ -216,9 +214,9 @@ extern "C" int svb_insert_stats(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, in
     CK(cudaMemsetAsync(acc.p, 0, 16, s));
     {
         ProfScope ps(ctx, "insert_stats", (double)n * 16);
-        insert_flags<<<nblk(n, 256), 256, 0, s>>>(n, bam->lean.flagq, bam->lean.isize, min_mapq, flag.p);
+        insert_flags<<<nblk(n, 256), 256, 0, s>>>(n, bam->lean.rec, min_mapq, flag.p);
         CKR(inclusive_scan_u32(ctx, flag.p, rank.p, n));
-        insert_sums<<<nblk(n, 256), 256, 0, s>>>(n, flag.p, rank.p, bam->lean.isize, (uint64_t)max_pairs, 1, 0, acc.p);
+        insert_sums<<<nblk(n, 256), 256, 0, s>>>(n, flag.p, rank.p, bam->lean.rec, (uint64_t)max_pairs, 1, 0, acc.p);
     }
     uint32_t total = 0;
     unsigned long long sum = 0;
@@ -230,7 +228,7 @@ extern "C" int svb_insert_stats(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, in
     int32_t mean = (int32_t)(sum / cnt);  // unsigned long / int, stored to int (cluster.cpp:72)
     {
         ProfScope ps(ctx, "insert_stats", (double)n * 12);
-        insert_sums<<<nblk(n, 256), 256, 0, s>>>(n, flag.p, rank.p, bam->lean.isize, (uint64_t)max_pairs, 2, mean, acc.p + 1);
+        insert_sums<<<nblk(n, 256), 256, 0, s>>>(n, flag.p, rank.p, bam->lean.rec, (uint64_t)max_pairs, 2, mean, acc.p + 1);
     }
     long long sq = 0;
     CK(cudaMemcpyAsync(&sq, acc.p + 1, 8, cudaMemcpyDeviceToHost, s));
@@ -241,14 +239,13 @@ extern "C" int svb_insert_stats(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, in
 
 // ---- discordant read pairs ------------------------------------------------------------------------------------------
 // first record index with (tid, pos) >= (T, P); tid -1 sorts last
-__device__ __forceinline__ uint64_t lower_bound_tp(const int32_t *__restrict__ tid, const int32_t *__restrict__ pos, uint64_t n,
-                                                   int32_t T, int64_t P)
+__device__ __forceinline__ uint64_t lower_bound_tp(const LeanRec *__restrict__ rec, uint64_t n, int32_t T, int64_t P)
 {
     uint64_t lo = 0, hi = n;
     while (lo < hi) {
         uint64_t m = (lo + hi) >> 1;
-        uint32_t t = (uint32_t)tid[m];
-        bool less = t < (uint32_t)T || (t == (uint32_t)T && (int64_t)pos[m] < P);
+        uint32_t t = (uint32_t)rec[m].tid;
+        bool less = t < (uint32_t)T || (t == (uint32_t)T && (int64_t)rec[m].pos < P);
         if (less) lo = m + 1;
         else hi = m;
     }
@@ -275,17 +272,18 @@ __global__ void __launch_bounds__(128)
         if (beg <= 0) beg = 1;
         if ((uint32_t)end > ref_len[tid]) end = (int32_t)ref_len[tid];  // int vs unsigned compare, getsv.cpp:1060
         // bam_iter_query(idx, tid, beg, end): records on tid with pos < end and calend > beg
-        uint64_t lo = lower_bound_tp(L.tid, L.pos, L.n, tid, (int64_t)beg - max_span);
-        uint64_t hi = lower_bound_tp(L.tid, L.pos, L.n, tid, end);
+        uint64_t lo = lower_bound_tp(L.rec, L.n, tid, (int64_t)beg - max_span);
+        uint64_t hi = lower_bound_tp(L.rec, L.n, tid, end);
         for (uint64_t i = lo + lane; i < hi; i += 32) {
-            uint32_t fq = L.flagq[i], flag = fq & 0xffff;
-            int32_t pos = L.pos[i];
-            int32_t rend = (fq & FLAGQ_NOCIGAR) ? pos + 1 : L.end[i];
+            const LeanRec r = L.rec[i];
+            uint32_t fq = r.flagq, flag = fq & 0xffff;
+            int32_t pos = r.pos;
+            int32_t rend = (fq & FLAGQ_NOCIGAR) ? pos + 1 : r.end;
             if (!(rend > beg)) continue;
             if ((int32_t)((fq >> 16) & 0xff) < prm.min_mapq) continue;  // __g_skip_aln, getsv.cpp:1027,1069
             if (fq & FLAGQ_HARDCLIP) continue;
             if (flag & (F_DUP | F_UNMAP | F_MUNMAP)) continue;
-            int32_t isz = L.isize[i];
+            int32_t isz = r.isize;
             bool rev = flag & F_REVERSE, mrev = flag & F_MREVERSE;
             {  // IsConcordant, cluster.cpp:136-147 (its own, unclamped minimum)
                 int32_t lo_c = prm.mean_insert - prm.deviation * prm.times;
@@ -297,8 +295,8 @@ __global__ void __launch_bounds__(128)
                 }
                 if (conc) continue;
             }
-            if (mtid == -1 || mtid != L.mtid[i]) continue;
-            int32_t lq = L.lqseq[i], mpos = L.mpos[i];
+            if (mtid == -1 || mtid != r.mtid) continue;
+            int32_t lq = r.lqseq, mpos = r.mpos;
             bool hit = false;
             if (j.up_strand == '+' && j.down_strand == '+' && pos + lq <= j.up_pos + kCross && mpos + 1 >= j.down_pos - kCross) {
                 if (!rev && mrev) {
@@ -366,7 +364,7 @@ __device__ __forceinline__ bool pileup_eligible(int32_t tid, uint32_t fq, int32_
 __global__ void eligible_flags(LeanRecords L, int32_t min_mapq, uint32_t *__restrict__ flag)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < L.n) flag[i] = pileup_eligible(L.tid[i], L.flagq[i], min_mapq) ? 1u : 0u;
+    if (i < L.n) flag[i] = pileup_eligible(L.rec[i].tid, L.rec[i].flagq, min_mapq) ? 1u : 0u;
 }
 
 // Exact serial emulation of bam_plp_push's cap for one chromosome (one thread per hot chromosome): a read is
@@ -379,14 +377,14 @@ __global__ void cap_serial(LeanRecords L, const uint32_t *__restrict__ hot_tids,
     if (t >= n_ref || !hot_tids[t]) return;
     uint32_t *hist = ring_all + (uint64_t)t * ring;  // live accepted reads by end position (mod ring)
     for (uint32_t k = 0; k < ring; ++k) hist[k] = 0;
-    uint64_t lo = lower_bound_tp(L.tid, L.pos, L.n, (int32_t)t, INT32_MIN);
-    uint64_t hi = lower_bound_tp(L.tid, L.pos, L.n, (int32_t)t + 1, INT32_MIN);
+    uint64_t lo = lower_bound_tp(L.rec, L.n, (int32_t)t, INT32_MIN);
+    uint64_t hi = lower_bound_tp(L.rec, L.n, (int32_t)t + 1, INT32_MIN);
     int64_t it_pos = -1;  // position of the previously accepted read (iterator position)
     uint32_t live = 0;
     bool any = false;
     for (uint64_t i = lo; i < hi; ++i) {
         if (!flag[i]) continue;
-        int32_t pos = L.pos[i], end = L.end[i];
+        int32_t pos = L.rec[i].pos, end = L.rec[i].end;
         if (any && pos == it_pos) {
             if (live + 2 > PILEUP_MAXCNT) {
                 kept[i] = 0;
@@ -435,19 +433,20 @@ __global__ void __launch_bounds__(256)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L.n) return;
-    int32_t tid = L.tid[i];
-    if (!pileup_eligible(tid, L.flagq[i], min_mapq)) return;
+    const LeanRec r = L.rec[i];
+    int32_t tid = r.tid;
+    if (!pileup_eligible(tid, r.flagq, min_mapq)) return;
     if (kept) {
         if (!kept[i]) return;
     } else if (i >= PILEUP_MAXCNT - 2) {
         uint64_t j = i - (PILEUP_MAXCNT - 2);
-        if (L.tid[j] == tid && L.pos[j] >= L.pos[i] - max_span) hot_tids[tid] = 1;
+        if (L.rec[j].tid == tid && L.rec[j].pos >= r.pos - max_span) hot_tids[tid] = 1;
     }
-    int32_t beg1 = L.pos[i] + 1, end1 = L.end[i];  // 1-based inclusive [beg1, end1]
+    int32_t beg1 = r.pos + 1, end1 = r.end;  // 1-based inclusive [beg1, end1]
     if (end1 < beg1) return;
     uint64_t w = first_window(W, n_w, tid, beg1);
     if (w >= n_w || W[w].tid != tid || W[w].begin > end1) return;
-    const uint8_t *p = d + L.off[i];
+    const uint8_t *p = d + r.off;
     uint32_t lq = ldu32(p + 12) & 0xff, nc = ldu32(p + 16) & 0xffff;
     const uint8_t *cig = p + 36 + lq;
     for (; w < n_w && W[w].tid == tid && W[w].begin <= end1; ++w) {
