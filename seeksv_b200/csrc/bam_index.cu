@@ -11,6 +11,8 @@
 // only. Wrong guesses are repaired from the predecessor's exit in parallel rounds and the walker is run again.
 #include <cub/device/device_scan.cuh>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 __device__ __forceinline__ bool plausible_one(const uint8_t *d, uint64_t n, uint64_t o, int32_t n_ref, uint64_t *next)
@@ -45,8 +47,8 @@ __device__ __forceinline__ bool plausible_one(const uint8_t *d, uint64_t n, uint
 }
 
 // one warp per chunk: lanes test 32 consecutive byte offsets at a time
-__global__ void __launch_bounds__(256) guess_starts(const uint8_t *__restrict__ d, uint64_t n, uint64_t first,
-                                                    int32_t n_ref, uint64_t n_chunks, uint64_t *__restrict__ guess)
+__global__ void __launch_bounds__(256) guess_starts(const uint8_t *__restrict__ d, uint64_t n, uint64_t first, int32_t n_ref,
+                                                    uint64_t n_chunks, uint32_t CHUNK_LOG2, uint64_t *__restrict__ guess)
 {
     uint64_t c = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint32_t lane = threadIdx.x & 31;
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(256) guess_starts(const uint8_t *__restrict__ 
         if (lane == 0) guess[c] = first;
         return;
     }
-    uint64_t limit = min(n, start + 8 * CHUNK);
+    uint64_t limit = min(n, start + ((uint64_t)8 << CHUNK_LOG2));
     uint64_t found = BAD_OFFSET;
     for (uint64_t base = start; base < limit; base += 32) {
         uint64_t o = base + lane, nx = 0, nx2 = 0;
@@ -93,7 +95,7 @@ __device__ __forceinline__ void walk_chunk(const uint8_t *d, uint64_t n, uint64_
 }
 
 // one thread per chunk: latency-bound pointer chase, hidden by having every chunk in flight at once
-__global__ void __launch_bounds__(128) walk_count(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks,
+__global__ void __launch_bounds__(128) walk_count(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks, uint32_t CHUNK_LOG2,
                                                   const uint64_t *__restrict__ guess, uint32_t *__restrict__ count,
                                                   uint64_t *__restrict__ exit_)
 {
@@ -116,8 +118,9 @@ __global__ void verify_chain(uint64_t n_chunks, const uint64_t *__restrict__ gue
 // Repair round: every chunk whose guess differs from its predecessor's exit re-walks from that exit. The first
 // mismatching chunk always gets its true entry (its predecessor is correct by induction), so repeating
 // verify + repair converges; the number of rounds is the longest run of consecutive wrong chunks (1 in practice).
-__global__ void __launch_bounds__(128) repair_chain(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks, uint64_t *guess,
-                                                    uint32_t *count, uint64_t *exit_, const uint64_t *__restrict__ exit_prev)
+__global__ void __launch_bounds__(128) repair_chain(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks, uint32_t CHUNK_LOG2,
+                                                    uint64_t *guess, uint32_t *count, uint64_t *exit_,
+                                                    const uint64_t *__restrict__ exit_prev)
 {
     uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 || c >= n_chunks) return;
@@ -162,7 +165,13 @@ int index_records(svb_ctx *ctx, svb_bam *bam)
 {
     uint64_t n = bam->nbytes, first = bam->first;
     if (first > n) return svb_fail(ctx, SVB_ERR_ARG, "first_record beyond the stream");
-    uint64_t n_chunks = (n + CHUNK - 1) >> CHUNK_LOG2;
+    {
+        const char *e = getenv("SEEKSV_B200_CHUNK_LOG2");
+        int v = e ? atoi(e) : 0;
+        if (v >= 10 && v <= 20) bam->chunk_log2 = (uint32_t)v;
+    }
+    const uint32_t CHUNK_LOG2 = bam->chunk_log2;
+    uint64_t n_chunks = (n + (1ull << CHUNK_LOG2) - 1) >> CHUNK_LOG2;
     if (n_chunks == 0) n_chunks = 1;
     bam->n_chunks = n_chunks;
     cudaStream_t s = ctx->stream;
@@ -171,7 +180,7 @@ int index_records(svb_ctx *ctx, svb_bam *bam)
     CK(cudaMallocAsync((void **)&bam->d_base, (n_chunks + 1) * 8, s));
     {
         ProfScope ps(ctx, "guess_starts", (double)(n - first));
-        guess_starts<<<nblk(n_chunks * 32, 256), 256, 0, s>>>(bam->d_data, n, first, bam->n_ref, n_chunks, bam->d_guess);
+        guess_starts<<<nblk(n_chunks * 32, 256), 256, 0, s>>>(bam->d_data, n, first, bam->n_ref, n_chunks, CHUNK_LOG2, bam->d_guess);
     }
     CK(cudaGetLastError());
     return 0;
@@ -196,7 +205,7 @@ int verify_or_repair(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit, int *ok
     DevBuf<uint64_t> ex, snap;
     CK(ex.alloc(n_chunks, s));
     CK(snap.alloc(n_chunks, s));
-    walk_count<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->d_guess, bam->d_count, ex.p);
+    walk_count<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->chunk_log2, bam->d_guess, bam->d_count, ex.p);
     for (int round = 0;; ++round) {
         CK(cudaMemsetAsync(flags.p, 0, 4, s));
         verify_chain<<<nblk(n_chunks, 256), 256, 0, s>>>(n_chunks, bam->d_guess, ex.p, flags.p);
@@ -206,7 +215,8 @@ int verify_or_repair(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit, int *ok
         if (round >= 256) return svb_fail(ctx, SVB_ERR_FORMAT, "corrupt BAM record chain (block_size < 32)");
         ProfScope ps(ctx, "repair_chain", 0);
         CK(cudaMemcpyAsync(snap.p, ex.p, n_chunks * 8, cudaMemcpyDeviceToDevice, s));
-        repair_chain<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->d_guess, bam->d_count, ex.p, snap.p);
+        repair_chain<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->chunk_log2, bam->d_guess, bam->d_count, ex.p,
+                                                         snap.p);
     }
     bam->counted = false;
     return 0;
@@ -224,7 +234,7 @@ int ensure_counts(svb_ctx *ctx, svb_bam *bam)
     for (int attempt = 0;; ++attempt) {
         {
             ProfScope ps(ctx, "walk_count", (double)(bam->nbytes - bam->first));
-            walk_count<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->d_guess, bam->d_count, ex.p);
+            walk_count<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->chunk_log2, bam->d_guess, bam->d_count, ex.p);
         }
         int ok = 0;
         CKR(verify_or_repair(ctx, bam, ex.p, &ok));

@@ -90,6 +90,7 @@ struct svb_bam {
     // record chain (bam_index.cu): the stream is cut into 16 KiB chunks; guess[c] = offset of the first record that
     // starts at or after the chunk, count[c] = records starting inside it, base[c] = exclusive prefix of count
     uint64_t n_chunks = 0;
+    uint32_t chunk_log2 = 13;  // 8 KiB chunks: ~25 records of 300 B per walker thread (SEEKSV_B200_CHUNK_LOG2)
     uint64_t *d_guess = nullptr, *d_base = nullptr;
     uint32_t *d_count = nullptr;
     bool counted = false;  // count / base / n_rec / rec_bytes are valid (ensure_counts)
@@ -243,8 +244,6 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t v)
 #endif
 
 // ---- internal entry points (one per .cu) ------------------------------------------------------------------
-static constexpr uint32_t CHUNK_LOG2 = 14;  // 16 KiB chunks: ~50 records of 300 B per walker thread
-static constexpr uint64_t CHUNK = 1ull << CHUNK_LOG2;
 static constexpr uint64_t BAD_OFFSET = ~0ull;
 int index_records(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu: guesses only
 int ensure_counts(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu: verified chain + counts + prefix

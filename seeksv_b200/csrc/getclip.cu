@@ -76,8 +76,24 @@ struct ScanOut {
     uint32_t un_cap;
     uint64_t *switches;
     uint32_t sw_cap;
-    uint32_t *counters;  // [0] candidates, [1] unmapped-branch records, [2] chromosome switches
+    uint32_t *counters;  // [0] candidates, [1] unmapped-branch records, [2] chromosome switches, [3] soft-clipped records
+    uint64_t *clipped;   // records whose first or last CIGAR op is S and that pass the cheap filters: evaluated by clip_eval
+    uint32_t clipped_cap;
 };
+
+// The cheap part of GetSClipReads (clip_reads.cpp:116-118,122): first / last CIGAR op and the H / mapQ / DUP filters.
+// Only records that pass (about 2 %) are queued for the expensive part (reference length, XC aux scan, emission), so the
+// walker's warps do not stall 31 lanes while one lane scans an aux block.
+__device__ __forceinline__ void queue_if_clipped(const uint8_t *__restrict__ d, uint64_t o, const Core &k, int32_t min_mapq,
+                                                 const ScanOut &out)
+{
+    if (k.n_cigar == 0 || (int32_t)k.mapq < min_mapq || (k.flag & F_DUP)) return;
+    const uint8_t *cig = d + o + 36 + k.l_qname;
+    uint32_t op1 = ldu32(cig) & 15, op2 = ldu32(cig + 4 * (k.n_cigar - 1)) & 15;
+    if (op1 == OP_H || op2 == OP_H || (op1 != OP_S && op2 != OP_S)) return;
+    uint32_t s = atomicAdd(&out.counters[3], 1u);
+    if (s < out.clipped_cap) out.clipped[s] = o;
+}
 
 // GetSClipReads (clip_reads.cpp:112-192) for one mapped-branch record that survived the chromosome-switch test.
 // Sequence and aux bytes are only touched for soft-clipped reads (~2 % of the records).
@@ -148,7 +164,7 @@ __device__ void eval_clip(const uint8_t *__restrict__ d, uint64_t o, const Core 
 // predicate. Each record head is fetched from HBM exactly once. The first mapped-branch record of a chunk needs the
 // last one of an earlier chunk and is left to clip_first.
 __global__ void __launch_bounds__(128)
-    clip_walk(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks, const uint64_t *__restrict__ guess,
+    clip_walk(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks, uint32_t CHUNK_LOG2, const uint64_t *__restrict__ guess,
               uint32_t *__restrict__ count, uint64_t *__restrict__ exit_, uint64_t *__restrict__ first_mb,
               int32_t *__restrict__ last_mb_tid, int32_t min_mapq, int32_t save_low_quality, ScanOut out)
 {
@@ -181,7 +197,7 @@ __global__ void __launch_bounds__(128)
                 uint32_t s = atomicAdd(&out.counters[2], 1u);
                 if (s < out.sw_cap) out.switches[s] = o;
             } else
-                eval_clip(d, o, k, min_mapq, save_low_quality, out);
+                queue_if_clipped(d, o, k, min_mapq, out);
             prev_tid = k.tid;
         }
         o = on, k = kn, live = next_live;
@@ -209,7 +225,19 @@ __global__ void __launch_bounds__(128)
         uint32_t s = atomicAdd(&out.counters[2], 1u);
         if (s < out.sw_cap) out.switches[s] = o;
     } else
-        eval_clip(d, o, k, min_mapq, save_low_quality, out);
+        queue_if_clipped(d, o, k, min_mapq, out);
+}
+
+// the expensive part of GetSClipReads for the queued soft-clipped records (one thread each)
+__global__ void __launch_bounds__(128)
+    clip_eval(const uint8_t *__restrict__ d, int32_t min_mapq, int32_t save_low_quality, ScanOut out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = min(out.counters[3], out.clipped_cap);
+    if (i >= n) return;
+    uint64_t o = out.clipped[i];
+    Core k = load_core(d + o);
+    eval_clip(d, o, k, min_mapq, save_low_quality, out);
 }
 
 // sort key = flush run (number of chromosome switches before the record) | side | position
@@ -675,12 +703,12 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
 
     // ---- 1. the walker: every record head once ------------------------------------------------------------------
     DevBuf<uint32_t> counters;
-    DevBuf<uint64_t> un_list, sw_list, c_off, exit_, first_mb;
+    DevBuf<uint64_t> un_list, sw_list, c_off, exit_, first_mb, clipped;
     DevBuf<uint32_t> c_begin, c_ll, c_rl;
     DevBuf<int32_t> c_tid, c_pos, last_mb_tid;
     DevBuf<uint8_t> c_side;
     CandArrays c;
-    uint32_t hc[3] = {0, 0, 0};
+    uint32_t hc[4] = {0, 0, 0, 0};
     // sized from the stream (a record is at least ~40 bytes; ~2 % of them are soft-clipped), grown once on overflow
     uint64_t est = stream_bytes / 200;
     uint32_t cand_cap = (uint32_t)std::min<uint64_t>(est / 8 + 4096, 0xffffffffu);
@@ -699,24 +727,33 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         CK(c_side.alloc(cand_cap, s));
         CK(un_list.alloc(un_cap, s));
         CK(sw_list.alloc(sw_cap, s));
+        CK(clipped.alloc(cand_cap, s));
         c = {c_off.p, c_tid.p, c_pos.p, c_begin.p, c_ll.p, c_rl.p, c_side.p};
-        ScanOut so{c, cand_cap, un_list.p, un_cap, sw_list.p, sw_cap, counters.p};
+        ScanOut so{c, cand_cap, un_list.p, un_cap, sw_list.p, sw_cap, counters.p, clipped.p, cand_cap};
         CK(cudaMemsetAsync(counters.p, 0, 16, s));
         {
             ProfScope ps(ctx, "clip_walk", (double)stream_bytes);
-            clip_walk<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->d_guess, bam->d_count, exit_.p,
-                                                        first_mb.p, last_mb_tid.p, prm->min_mapq, prm->save_low_quality, so);
+            clip_walk<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->chunk_log2, bam->d_guess, bam->d_count,
+                                                        exit_.p, first_mb.p, last_mb_tid.p, prm->min_mapq, prm->save_low_quality, so);
             clip_first<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, n_chunks, first_mb.p, last_mb_tid.p, prm->prev_tid, prm->min_mapq,
                                                          prm->save_low_quality, so);
         }
+        {
+            // at most cand_cap queued records are evaluated; an overflow of the queue is caught below and the pass repeated
+            ProfScope ps(ctx, "clip_eval", 0);
+            clip_eval<<<nblk(cand_cap, 128), 128, 0, s>>>(bam->d_data, prm->min_mapq, prm->save_low_quality, so);
+        }
         int ok = 0;
         CKR(verify_or_repair(ctx, bam, exit_.p, &ok));  // (synchronises)
-        CK(cudaMemcpyAsync(hc, counters.p, 12, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hc, counters.p, 16, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        bool fits = hc[0] <= cand_cap && hc[1] <= un_cap && hc[2] <= sw_cap;
+        bool fits = hc[0] <= cand_cap && hc[3] <= cand_cap && hc[1] <= un_cap && hc[2] <= sw_cap;
         if (ok && fits) break;
         if (attempt >= 3) return svb_fail(ctx, SVB_ERR_CUDA, "svb_getclip: the record walk did not settle");
-        if (ok) cand_cap = std::max(cand_cap, hc[0]), un_cap = std::max(un_cap, hc[1]), sw_cap = std::max(sw_cap, hc[2]);
+        if (ok) {
+            cand_cap = std::max(cand_cap, std::max(hc[0], 2 * hc[3]));  // a record yields at most two candidates
+            un_cap = std::max(un_cap, hc[1]), sw_cap = std::max(sw_cap, hc[2]);
+        }
     }
     if (!bam->counted) CKR(finish_counts(ctx, bam, exit_.p));  // the walker counted the records of every chunk on its way
     const uint32_t n_cand = hc[0], n_un = hc[1], n_sw = hc[2];

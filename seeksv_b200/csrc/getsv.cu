@@ -26,7 +26,7 @@ __device__ __forceinline__ bool insert_qualifies(uint32_t fq, int32_t isize, int
 // ensure_counts) and writes the lean columns of its records; every record head is fetched once. On the way it gathers
 // the chunk's partial sums for CalculateInsertsizeDeviation (cluster.cpp:48-70) at one mapQ threshold.
 __global__ void __launch_bounds__(128)
-    decode_walk(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks, const uint64_t *__restrict__ guess,
+    decode_walk(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks, uint32_t CHUNK_LOG2, const uint64_t *__restrict__ guess,
                 const uint64_t *__restrict__ base, LeanRecords L, int32_t stats_mapq, uint32_t *__restrict__ q_cnt,
                 uint64_t *__restrict__ q_sum, uint64_t *__restrict__ q_sq, int32_t *__restrict__ scal /* max_span, unsorted, q_max */)
 {
@@ -115,7 +115,8 @@ int decode_records(svb_ctx *ctx, svb_bam *bam, int32_t stats_mapq)
     CK(cudaMemsetAsync(scal.p, 0, 16, s));
     {
         ProfScope ps(ctx, "decode_walk", (double)bam->rec_bytes);
-        decode_walk<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->d_guess, bam->d_base, L, stats_mapq,
+        decode_walk<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->chunk_log2, bam->d_guess, bam->d_base, L,
+                                                      stats_mapq,
                                                       bam->d_q_cnt, bam->d_q_sum, bam->d_q_sq, scal.p);
         boundary_order<<<nblk(n_chunks, 256), 256, 0, s>>>(n_chunks, bam->d_base, L, (uint32_t *)scal.p + 1);
     }
