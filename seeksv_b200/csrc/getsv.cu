@@ -59,10 +59,12 @@ __global__ void __launch_bounds__(128)
                 if (op == OP_M || op == OP_D || op == OP_N) rend += (int32_t)(w >> 4);
                 if ((j == 0 || j + 1 == k.n_cigar) && op == OP_H) fq |= FLAGQ_HARDCLIP;  // IsHardClip, clip_reads.cpp:247
             }
-            LeanRec r;
-            r.tid = k.tid, r.pos = k.pos, r.end = rend, r.flagq = fq;
-            r.lqseq = k.l_qseq, r.mtid = k.mtid, r.mpos = k.mpos, r.isize = k.isize, r.off = o;
-            L.rec[i] = r;
+            {
+                uint4 *row = (uint4 *)&L.rec[i];
+                row[0] = make_uint4((uint32_t)k.tid, (uint32_t)k.pos, (uint32_t)rend, fq);
+                row[1] = make_uint4((uint32_t)k.l_qseq, (uint32_t)k.mtid, (uint32_t)k.mpos, (uint32_t)k.isize);
+                row[2] = make_uint4((uint32_t)o, (uint32_t)(o >> 32), 0u, 0u);
+            }
             span = max(span, max(rend - k.pos, 1));
             if (have_prev && (pt > (uint32_t)k.tid || (pt == (uint32_t)k.tid && pp > k.pos))) unsorted = 1;  // tid -1 sorts last
             pt = (uint32_t)k.tid, pp = k.pos, have_prev = true;
