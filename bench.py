@@ -63,35 +63,43 @@ def realign(prefix, clip_fq_gz):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md), sampled in-process through NVML - spawning
+    nvidia-smi five times a second takes driver locks and measurably slows the host side of the end-to-end path."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
-        self.q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
 
     def run(self):
-        while not self.stop_flag:
+        nv = self.nv
+        while not self.stop_flag and nv is not None:
             try:
-                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                self.rows.append([x.strip() for x in r.stdout.strip().split(",")])
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, mx, r))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
-        sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 6:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        reasons = sorted(name for name, bit in bits.items() if any(r[2] & bit for r in self.rows))
         return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml"}
 
 
 def time_reference(bam, sam_and_clip, work, tag):

@@ -43,11 +43,22 @@ struct Gpu {  // context + error-to-exit plumbing: every failure is "message on 
     svb_ctx *ctx = nullptr;
     bool open()
     {
-        if (svb_ctx_create(device_index(), &ctx) != 0) {
-            std::cerr << "[seeksv_b200] " << svb_last_error(nullptr) << std::endl;
-            return false;
+        // One context per device for the life of the process: a program that calls svb_main repeatedly (bench.py, a
+        // pipeline driver) keeps the pinned staging pool and the stream-ordered device pool warm between commands. The
+        // CLI binary runs one command per process, so for it this is simply "create".
+        static std::map<int, svb_ctx *> cached;
+        int dev = device_index();
+        auto it = cached.find(dev);
+        if (it != cached.end()) ctx = it->second;
+        else {
+            if (svb_ctx_create(dev, &ctx) != 0) {
+                std::cerr << "[seeksv_b200] " << svb_last_error(nullptr) << std::endl;
+                return false;
+            }
+            cached[dev] = ctx;
         }
-        if (getenv("SEEKSV_B200_PROFILE")) svb_prof_enable(ctx, 1);
+        svb_prof_enable(ctx, getenv("SEEKSV_B200_PROFILE") ? 1 : 0);
+        svb_prof_reset(ctx);
         return true;
     }
     ~Gpu()
@@ -61,7 +72,6 @@ struct Gpu {  // context + error-to-exit plumbing: every failure is "message on 
                 fprintf(stderr, "[prof] %-24s %9.3f ms %6lld launches %8.1f GB/s\n", names[i], ms[i], (long long)launches[i],
                         ms[i] > 0 ? bytes[i] / ms[i] / 1e6 : 0.0);
         }
-        svb_ctx_destroy(ctx);
     }
 };
 
@@ -205,22 +215,23 @@ int cmd_getclip(int argc, char **argv)
 }
 
 // clip.bam (BGZF) or SAM text -> alignment list + reference names
-bool load_alignments(const std::string &path, std::vector<Alignment> &alns, std::vector<std::string> &names, std::string &err)
+bool load_alignments(const std::string &path, AlignmentSet &set, std::string &err)
 {
-    std::vector<uint8_t> file, stream;
+    std::vector<uint8_t> file;
     if (!read_file(path, file, err)) return false;
-    BamHeader h;
     if (path.size() >= 4 && path.rfind(".bam") == path.size() - 4) {
-        if (!bgzf_inflate_all(file.data(), file.size(), stream, n_threads(), err)) return false;
-        if (!parse_bam_header(stream.data(), stream.size(), h, err)) return false;
-    } else if (!sam_to_bam_stream(file, h, stream, err))
-        return false;
-    names = h.names;
-    if (!parse_alignments(stream, h.first_record, alns)) {
-        err = "corrupt alignment records in " + path;
-        return false;
+        BamHeader h;
+        if (!bgzf_inflate_all(file.data(), file.size(), set.storage, n_threads(), err)) return false;
+        if (!parse_bam_header(set.storage.data(), set.storage.size(), h, err)) return false;
+        set.ref_names = h.names;
+        if (!parse_bam_alignments(set, h.first_record)) {
+            err = "corrupt alignment records in " + path;
+            return false;
+        }
+        return true;
     }
-    return true;
+    set.storage.swap(file);
+    return parse_sam_alignments(set, n_threads(), err);
 }
 
 struct Win {  // a device window with the chromosome name the host maps are keyed by
@@ -398,10 +409,9 @@ int cmd_getsv(int argc, char **argv)
     std::string clip_aln = argv[optind], original_bam = argv[optind + 1], clipfile = argv[optind + 2], sv_file = argv[optind + 3],
                 unmapped_file = argv[optind + 4];
     std::string err, clip_text;
-    std::vector<Alignment> alns;
-    std::vector<std::string> aln_names;
+    AlignmentSet alns;
     Phase ph;
-    if (!load_alignments(clip_aln, alns, aln_names, err)) {
+    if (!load_alignments(clip_aln, alns, err)) {
         std::cerr << "[main_samview] fail to open file for reading." << std::endl;
         return fail(err);
     }
@@ -409,7 +419,7 @@ int cmd_getsv(int argc, char **argv)
     if (!read_text_maybe_gz(clipfile, clip_text, err)) return fail(err);
     ph.mark("getsv: read clip.gz");
     JunctionMap jm;
-    join_clips_with_alignments(parse_clip_text(clip_text), aln_names, alns, jm);
+    join_clips_with_alignments(parse_clip_text(clip_text, n_threads()), alns, jm);
     std::cerr << "'InputSoftInfoStoreBreakpoint' finished" << std::endl;
     merge_junctions(jm, flank);
     ph.mark("getsv: join + merge junctions");
@@ -575,11 +585,10 @@ extern "C" int svb_plan_getsv(const char *clip_aln, const char *clip_file, int32
 {
     if (!clip_aln || !clip_file || !junctions || !n_j || !windows || !n_w || (n_ref && (!ref_names || !ref_lens))) return SVB_ERR_ARG;
     std::string err, clip_text;
-    std::vector<Alignment> alns;
-    std::vector<std::string> aln_names;
-    if (!load_alignments(clip_aln, alns, aln_names, err) || !read_text_maybe_gz(clip_file, clip_text, err)) return SVB_ERR_IO;
+    AlignmentSet alns;
+    if (!load_alignments(clip_aln, alns, err) || !read_text_maybe_gz(clip_file, clip_text, err)) return SVB_ERR_IO;
     JunctionMap jm;
-    join_clips_with_alignments(parse_clip_text(clip_text), aln_names, alns, jm);
+    join_clips_with_alignments(parse_clip_text(clip_text, n_threads()), alns, jm);
     merge_junctions(jm, reach);
     std::map<std::string, int32_t> tid_of;
     std::vector<uint32_t> lens(ref_lens, ref_lens + n_ref);

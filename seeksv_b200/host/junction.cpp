@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <sstream>
+#include <thread>
 
 namespace svb {
 
@@ -100,30 +102,88 @@ static std::vector<std::string> split_ws(const char *b, const char *e)
     return t;
 }
 
-std::vector<ClipLine> parse_clip_text(const std::string &text)
+// cut [b, e) at line boundaries into roughly equal parts
+static std::vector<std::pair<const char *, const char *>> line_chunks(const char *b, const char *e, int parts)
 {
-    // `fin >> chr >> pos >> orientation >> cigar >> ... >> support; getline(...)` (getsv.h:453-456)
-    std::vector<ClipLine> out;
-    const char *p = text.data(), *e = p + text.size();
-    while (p < e) {
-        const char *nl = (const char *)memchr(p, '\n', e - p);
-        if (!nl) nl = e;
-        std::vector<std::string> t = split_ws(p, nl);
-        if (t.size() >= 9) {
-            ClipLine c;
-            c.chr = t[0], c.pos = atoi(t[1].c_str()), c.side = t[2][0], c.cigar = t[3];
-            c.aligned_seq = t[4], c.aligned_qual = t[5], c.clipped_seq = t[6], c.clipped_qual = t[7], c.support = atoi(t[8].c_str());
-            out.push_back(std::move(c));
+    std::vector<std::pair<const char *, const char *>> out;
+    const char *p = b;
+    for (int i = 1; i <= parts && p < e; ++i) {
+        const char *q = i == parts ? e : b + (e - b) / parts * i;
+        if (q < p) q = p;
+        if (q < e) {
+            const char *nl = (const char *)memchr(q, '\n', e - q);
+            q = nl ? nl + 1 : e;
         }
-        p = nl < e ? nl + 1 : e;
+        out.emplace_back(p, q);
+        p = q;
     }
+    return out;
+}
+
+template <typename F>
+static void run_parallel(size_t n, int n_threads, F f)
+{
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n) return;
+            f(i);
+        }
+    };
+    int nt = (int)std::min<size_t>((size_t)std::max(1, n_threads), n);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+}
+
+static int hw_threads(int n) { return n > 0 ? n : (int)std::max(1u, std::thread::hardware_concurrency()); }
+
+std::vector<ClipLine> parse_clip_text(const std::string &text, int n_threads)
+{
+    // `fin >> chr >> pos >> orientation >> cigar >> ... >> support; getline(...)` (getsv.h:453-456): whitespace-separated
+    // tokens, the rest of the line is dropped. Fields are views into `text`; line chunks are parsed in parallel.
+    const char *b = text.data(), *e = b + text.size();
+    auto chunks = line_chunks(b, e, text.size() > (1u << 20) ? hw_threads(n_threads) : 1);
+    std::vector<std::vector<ClipLine>> part(chunks.size());
+    run_parallel(chunks.size(), hw_threads(n_threads), [&](size_t ci) {
+        const char *p = chunks[ci].first, *ce = chunks[ci].second;
+        while (p < ce) {
+            const char *nl = (const char *)memchr(p, '\n', ce - p);
+            if (!nl) nl = ce;
+            std::string_view t[9];
+            int nt = 0;
+            const char *q = p;
+            while (q < nl && nt < 9) {
+                while (q < nl && isspace((unsigned char)*q)) ++q;
+                const char *s0 = q;
+                while (q < nl && !isspace((unsigned char)*q)) ++q;
+                if (q > s0) t[nt++] = std::string_view(s0, (size_t)(q - s0));
+            }
+            if (nt == 9) {
+                ClipLine c;
+                c.chr = t[0], c.pos = atoi(std::string(t[1]).c_str()), c.side = t[2][0], c.cigar = t[3];
+                c.aligned_seq = t[4], c.aligned_qual = t[5], c.clipped_seq = t[6], c.clipped_qual = t[7];
+                c.support = atoi(std::string(t[8]).c_str());
+                part[ci].push_back(c);
+            }
+            p = nl < ce ? nl + 1 : ce;
+        }
+    });
+    std::vector<ClipLine> out;
+    size_t total = 0;
+    for (auto &v : part) total += v.size();
+    out.reserve(total);
+    for (auto &v : part) out.insert(out.end(), v.begin(), v.end());
     return out;
 }
 
 static inline uint32_t rd32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
 
-bool parse_alignments(const std::vector<uint8_t> &s, uint64_t o, std::vector<Alignment> &out)
+bool parse_bam_alignments(AlignmentSet &set, uint64_t o)
 {
+    const std::vector<uint8_t> &s = set.storage;
     while (o + 36 <= s.size()) {
         uint32_t bs = rd32(&s[o]);
         if (bs < 32 || o + 4 + bs > s.size()) return false;
@@ -132,13 +192,114 @@ bool parse_alignments(const std::vector<uint8_t> &s, uint64_t o, std::vector<Ali
         uint32_t w = rd32(&s[o + 12]), w2 = rd32(&s[o + 16]);
         uint32_t lq = w & 0xff, nc = w2 & 0xffff;
         a.mapq = (w >> 8) & 0xff, a.flag = w2 >> 16;
-        a.qname.assign((const char *)&s[o + 36], strnlen((const char *)&s[o + 36], lq));
-        a.cigar.resize(nc);
-        for (uint32_t j = 0; j < nc; ++j) a.cigar[j] = rd32(&s[o + 36 + lq + 4 * j]);
-        out.push_back(std::move(a));
+        a.qname = std::string_view((const char *)&s[o + 36], strnlen((const char *)&s[o + 36], lq));
+        a.cigar_begin = (uint32_t)set.cigar_words.size(), a.cigar_n = nc;
+        for (uint32_t j = 0; j < nc; ++j) set.cigar_words.push_back(rd32(&s[o + 36 + lq + 4 * j]));
+        set.recs.push_back(a);
         o += 4 + bs;
     }
     return o == s.size();
+}
+
+bool parse_sam_alignments(AlignmentSet &set, int n_threads, std::string &err)
+{
+    const char *b = (const char *)set.storage.data(), *e = b + set.storage.size();
+    // header: @SQ lines give the reference names (samopen(fn, "r") needs them: "fail to read the header" otherwise)
+    const char *p = b;
+    std::map<std::string, int> name2tid;
+    while (p < e && *p == '@') {
+        const char *nl = (const char *)memchr(p, '\n', e - p);
+        if (!nl) nl = e;
+        if (nl - p > 3 && p[1] == 'S' && p[2] == 'Q') {
+            std::string line(p, nl);
+            size_t a = line.find("\tSN:");
+            if (a != std::string::npos) {
+                size_t z = line.find('\t', a + 4);
+                std::string sn = line.substr(a + 4, (z == std::string::npos ? line.size() : z) - a - 4);
+                name2tid[sn] = (int)set.ref_names.size();
+                set.ref_names.push_back(sn);
+            }
+        }
+        p = nl < e ? nl + 1 : e;
+    }
+    if (set.ref_names.empty()) {
+        err = "[main_samview] fail to read the header.";
+        return false;
+    }
+    auto chunks = line_chunks(p, e, (e - p) > (1 << 20) ? hw_threads(n_threads) : 1);
+    struct Part {
+        std::vector<Alignment> recs;
+        std::vector<uint32_t> cig;
+        bool bad = false;
+    };
+    std::vector<Part> part(chunks.size());
+    run_parallel(chunks.size(), hw_threads(n_threads), [&](size_t ci) {
+        const char *q = chunks[ci].first, *ce = chunks[ci].second;
+        Part &P = part[ci];
+        while (q < ce) {
+            const char *nl = (const char *)memchr(q, '\n', ce - q);
+            if (!nl) nl = ce;
+            const char *le = nl;
+            if (le > q && le[-1] == '\r') --le;
+            if (le > q) {
+                std::string_view f[6];
+                int nf = 0;
+                for (const char *a = q; nf < 6;) {
+                    const char *t = (const char *)memchr(a, '\t', le - a);
+                    if (!t) t = le;
+                    f[nf++] = std::string_view(a, (size_t)(t - a));
+                    if (t == le) break;
+                    a = t + 1;
+                }
+                if (nf < 6) {
+                    P.bad = true;
+                    return;
+                }
+                Alignment al;
+                al.qname = f[0];
+                al.flag = (uint32_t)strtoul(f[1].data(), nullptr, 10);
+                al.tid = -1;
+                if (!(f[2].size() == 1 && f[2][0] == '*')) {
+                    auto it = name2tid.find(std::string(f[2]));
+                    if (it != name2tid.end()) al.tid = it->second;
+                }
+                al.pos = (int32_t)strtol(f[3].data(), nullptr, 10) - 1;
+                al.mapq = (int32_t)strtol(f[4].data(), nullptr, 10);
+                al.cigar_begin = (uint32_t)P.cig.size();
+                if (!(f[5].size() == 1 && f[5][0] == '*')) {
+                    uint32_t num = 0;
+                    for (char ch : f[5]) {
+                        if (ch >= '0' && ch <= '9') num = num * 10 + (uint32_t)(ch - '0');
+                        else {
+                            const char *ops = "MIDNSHP=X", *o = strchr(ops, ch);
+                            if (!o) {
+                                P.bad = true;
+                                return;
+                            }
+                            P.cig.push_back(num << 4 | (uint32_t)(o - ops));
+                            num = 0;
+                        }
+                    }
+                }
+                al.cigar_n = (uint32_t)P.cig.size() - al.cigar_begin;
+                P.recs.push_back(al);
+            }
+            q = nl < ce ? nl + 1 : ce;
+        }
+    });
+    for (auto &P : part) {
+        if (P.bad) {
+            err = "malformed SAM line";
+            return false;
+        }
+        uint32_t shift = (uint32_t)set.cigar_words.size();
+        set.cigar_words.insert(set.cigar_words.end(), P.cig.begin(), P.cig.end());
+        for (Alignment a : P.recs) {
+            a.cigar_begin += shift;
+            set.recs.push_back(a);
+        }
+    }
+    return true;
 }
 
 // ---- join: clip.gz lines x realigned clipped sequences -> junctions -------------------------------------------
@@ -152,21 +313,24 @@ struct AlignInfo {  // getsv.h:24-45
 
 const char *kOps = "MIDNSHP=X";
 
-AlignInfo align_info(const std::vector<std::string> &names, const Alignment &b)  // GetAlignInfo, getsv.cpp:25-71
+AlignInfo align_info(const AlignmentSet &set, const Alignment &b)  // GetAlignInfo, getsv.cpp:25-71
 {
+    const std::vector<std::string> &names = set.ref_names;
+    const uint32_t *cg = set.cigar_words.data() + b.cigar_begin;
     AlignInfo a;
     if (b.flag & 4) {
         a.chr = "Exogenous";
         return a;
     }
     a.type = ((b.flag & 256) || b.mapq == 0) ? 'r' : 'u';
-    if (!b.cigar.empty()) {
-        uint32_t f = b.cigar.front(), l = b.cigar.back();
+    if (b.cigar_n) {
+        uint32_t f = cg[0], l = cg[b.cigar_n - 1];
         if ((f & 15) == 4 || (f & 15) == 5) a.lclip = (int)(f >> 4);
         if ((l & 15) == 4 || (l & 15) == 5) a.rclip = (int)(l >> 4);
     }
     a.len = 0;
-    for (uint32_t c : b.cigar) {  // GenerateCigar, clip_reads.cpp:309-329
+    for (uint32_t ci = 0; ci < b.cigar_n; ++ci) {  // GenerateCigar, clip_reads.cpp:309-329
+        uint32_t c = cg[ci];
         uint32_t op = c & 15;
         if (op == 4 || op == 5) continue;
         if (op == 0 || op == 2 || op == 7 || op == 3) a.len += (int)(c >> 4);
@@ -178,9 +342,10 @@ AlignInfo align_info(const std::vector<std::string> &names, const Alignment &b) 
     return a;
 }
 
-bool hard_clipped(const Alignment &b)  // IsHardClip, clip_reads.cpp:247-257
+bool hard_clipped(const AlignmentSet &set, const Alignment &b)  // IsHardClip, clip_reads.cpp:247-257
 {
-    return !b.cigar.empty() && ((b.cigar.front() & 15) == 5 || (b.cigar.back() & 15) == 5);
+    const uint32_t *cg = set.cigar_words.data() + b.cigar_begin;
+    return b.cigar_n && ((cg[0] & 15) == 5 || (cg[b.cigar_n - 1] & 15) == 5);
 }
 
 SeqInfo make_seq(const std::string &s, const CigarVec &c, int lc, int rc, int sup, int uniq)
@@ -204,8 +369,8 @@ void add_junction(const ClipLine &line, AlignInfo &ai, JunctionMap &jm)
     if (ai.type == 'u') uniq = 2;
     else if (ai.type == 'r') uniq = 1;
     else return;  // 'n': nothing is stored (quirk Q7)
-    CigarVec cig = cigar_from_text(line.cigar);
-    const std::string &chr = line.chr;
+    CigarVec cig = cigar_from_text(std::string(line.cigar));
+    const std::string chr(line.chr), clipped_seq(line.clipped_seq), aligned_seq(line.aligned_seq);
     const int pos = line.pos, sup = line.support;
     JunctionKey key;
     SeqInfo up, down;
@@ -216,37 +381,37 @@ void add_junction(const ClipLine &line, AlignInfo &ai, JunctionMap &jm)
     if (ai.strand == '+') {
         if (line.side == '5') {
             key = make_key(ai.chr, ai.pos + ai.len - 1, '+', chr, pos, '+');
-            up = make_seq(line.clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
-            down = make_seq(line.aligned_seq, cig, 0, 0, sup, 0);
+            up = make_seq(clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
+            down = make_seq(aligned_seq, cig, 0, 0, sup, 0);
         } else if (line.side == '3') {
             key = make_key(chr, pos, '+', ai.chr, ai.pos, '+');
-            up = make_seq(line.aligned_seq, cig, 0, 0, sup, 0);
-            down = make_seq(line.clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
+            up = make_seq(aligned_seq, cig, 0, 0, sup, 0);
+            down = make_seq(clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
         } else
             return;
     } else if (ai.strand == '-') {
         if (line.side == '5') {
             if (std::make_pair(ai.chr, ai.pos) <= std::make_pair(chr, pos)) {
                 key = make_key(ai.chr, ai.pos, '-', chr, pos, '+');
-                up = make_seq(line.clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
-                down = make_seq(line.aligned_seq, cig, 0, 0, sup, 0);
+                up = make_seq(clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
+                down = make_seq(aligned_seq, cig, 0, 0, sup, 0);
             } else {
                 key = make_key(chr, pos, '-', ai.chr, ai.pos, '+');
                 ai.cigar = rev(ai.cigar);  // the reference reverses the stored alignment in place
-                up = make_seq(reverse_complement(line.aligned_seq), rev(cig), 0, 0, sup, 0);
-                down = make_seq(reverse_complement(line.clipped_seq), ai.cigar, ai.rclip, ai.lclip, 0, uniq);
+                up = make_seq(reverse_complement(aligned_seq), rev(cig), 0, 0, sup, 0);
+                down = make_seq(reverse_complement(clipped_seq), ai.cigar, ai.rclip, ai.lclip, 0, uniq);
             }
         } else if (line.side == '3') {
             int aend = ai.pos + ai.len - 1;
             if (std::make_pair(chr, pos) <= std::make_pair(ai.chr, aend)) {
                 key = make_key(chr, pos, '+', ai.chr, aend, '-');
-                up = make_seq(line.aligned_seq, cig, 0, 0, sup, 0);
-                down = make_seq(line.clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
+                up = make_seq(aligned_seq, cig, 0, 0, sup, 0);
+                down = make_seq(clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
             } else {
                 key = make_key(ai.chr, aend, '+', chr, pos, '-');
                 ai.cigar = rev(ai.cigar);
-                up = make_seq(reverse_complement(line.clipped_seq), ai.cigar, ai.rclip, ai.lclip, 0, uniq);
-                down = make_seq(reverse_complement(line.aligned_seq), rev(cig), 0, 0, sup, 0);
+                up = make_seq(reverse_complement(clipped_seq), ai.cigar, ai.rclip, ai.lclip, 0, uniq);
+                down = make_seq(reverse_complement(aligned_seq), rev(cig), 0, 0, sup, 0);
             }
         } else
             return;
@@ -277,13 +442,14 @@ void add_junction(const ClipLine &line, AlignInfo &ai, JunctionMap &jm)
 // InputSoftInfoStoreBreakpoint<T>, getsv.h:423-541, with its quirks: only the first line of a run of
 // equal clipped sequences is crossed with the alignments, the first alignment of a new run is filed under the
 // previous run's sequence, and the trailing loop does not skip hard-clipped alignments.
-void join_clips_with_alignments(const std::vector<ClipLine> &lines, const std::vector<std::string> &names,
-                                const std::vector<Alignment> &alns, JunctionMap &jm)
+void join_clips_with_alignments(const std::vector<ClipLine> &lines, const AlignmentSet &set, JunctionMap &jm)
 {
-    typedef std::pair<std::string, std::pair<std::string, int>> AlnKey;
+    // keys are (sequence the alignment was filed under, (chromosome, position)); views into the clip text, no copies
+    typedef std::pair<std::string_view, std::pair<std::string, int>> AlnKey;
+    const std::vector<Alignment> &alns = set.recs;
     std::map<AlnKey, AlignInfo> found;
     const ClipLine *head = nullptr;  // first line of the current run
-    std::string current;
+    std::string_view current;
     size_t ai = 0;
     auto cross = [&]() {
         if (head)
@@ -297,12 +463,13 @@ void join_clips_with_alignments(const std::vector<ClipLine> &lines, const std::v
         }
         while (ai < alns.size()) {
             const Alignment &b = alns[ai++];
-            if (hard_clipped(b)) continue;
-            AlignInfo info = align_info(names, b);
-            AlnKey k(current, std::make_pair(info.chr, info.pos));
+            if (hard_clipped(set, b)) continue;
             if (current == b.qname) {
-                found.insert(std::make_pair(k, info));
+                AlignInfo info = align_info(set, b);
+                found.insert(std::make_pair(AlnKey(current, std::make_pair(info.chr, info.pos)), info));
             } else {
+                AlignInfo info = align_info(set, b);
+                AlnKey k(current, std::make_pair(info.chr, info.pos));
                 cross();
                 found.clear();
                 found.insert(std::make_pair(k, info));
@@ -316,7 +483,7 @@ void join_clips_with_alignments(const std::vector<ClipLine> &lines, const std::v
     while (ai < alns.size()) {
         const Alignment &b = alns[ai++];
         if (current != b.qname) break;
-        AlignInfo info = align_info(names, b);
+        AlignInfo info = align_info(set, b);
         found.insert(std::make_pair(AlnKey(current, std::make_pair(info.chr, info.pos)), info));
     }
     cross();
@@ -616,9 +783,10 @@ void somatic_rows(const std::string &normal_clip_text, const std::string &tumor_
     ClipTable t3, t5;
     for (const ClipLine &c : parse_clip_text(normal_clip_text)) {
         if (c.clipped_seq.length() < (size_t)min_len) continue;
-        if (c.side == '3') t3.insert(std::make_pair(std::make_pair(c.chr, c.pos), NormalClip{c.aligned_seq, c.clipped_seq, c.support}));
-        else if (c.side == '5') t5.insert(std::make_pair(std::make_pair(c.chr, c.pos), NormalClip{c.clipped_seq, c.aligned_seq, c.support}));
-        else log += "Error:The orientation of soft-clipped reads must be 3 or 5 in position " + c.chr + ":" + std::to_string(c.pos) + "\n";
+        std::string chr(c.chr), aseq(c.aligned_seq), cseq(c.clipped_seq);
+        if (c.side == '3') t3.insert(std::make_pair(std::make_pair(chr, c.pos), NormalClip{aseq, cseq, c.support}));
+        else if (c.side == '5') t5.insert(std::make_pair(std::make_pair(chr, c.pos), NormalClip{cseq, aseq, c.support}));
+        else log += "Error:The orientation of soft-clipped reads must be 3 or 5 in position " + chr + ":" + std::to_string(c.pos) + "\n";
     }
     auto window_first = [&](const ClipTable &t, const std::string &chr, int lo, int hi, auto &&pred) {
         for (auto it = t.lower_bound(std::make_pair(chr, lo)); it != t.end() && it->first.first == chr && it->first.second <= hi; ++it)

@@ -8,6 +8,7 @@
 
 #include <map>
 #include <string>
+#include <string_view>
 #include <utility>
 #include <vector>
 
@@ -35,17 +36,24 @@ struct JunctionInfo {  // OtherInfo, getsv.h:88-107
 
 typedef std::multimap<JunctionKey, JunctionInfo> JunctionMap;
 
-struct ClipLine {  // one line of P.clip.gz (clip_reads.h:308-332)
-    std::string chr, cigar, aligned_seq, aligned_qual, clipped_seq, clipped_qual;
+struct ClipLine {  // one line of P.clip.gz (clip_reads.h:308-332); views into the decompressed file text
+    std::string_view chr, cigar, aligned_seq, aligned_qual, clipped_seq, clipped_qual;
     int pos = 0, support = 0;
     char side = '5';
 };
 
 struct Alignment {  // the fields of a clip.bam / clip.sam record that GetAlignInfo reads (getsv.cpp:25-71)
-    std::string qname;
+    std::string_view qname;  // view into the alignment file image / converted stream
     uint32_t flag = 0;
     int32_t tid = -1, pos = 0, mapq = 0;
-    std::vector<uint32_t> cigar;
+    uint32_t cigar_begin = 0, cigar_n = 0;  // slice of the shared CIGAR word array
+};
+
+struct AlignmentSet {
+    std::vector<Alignment> recs;
+    std::vector<uint32_t> cigar_words;
+    std::vector<std::string> ref_names;
+    std::vector<uint8_t> storage;  // what the qname views point into
 };
 
 struct ChrRange {  // getsv.h:231-258 - unsigned on purpose (quirk Q11)
@@ -58,8 +66,11 @@ struct FlankRanges {
     ChrRange r[4];
 };
 
-std::vector<ClipLine> parse_clip_text(const std::string &text);
-bool parse_alignments(const std::vector<uint8_t> &stream, uint64_t first_record, std::vector<Alignment> &out);
+std::vector<ClipLine> parse_clip_text(const std::string &text, int n_threads = 0);
+// packed BAM records (after the header) -> alignment list; qname views point into `set.storage`
+bool parse_bam_alignments(AlignmentSet &set, uint64_t first_record);
+// SAM text (in set.storage) -> alignment list, parsed by n_threads threads
+bool parse_sam_alignments(AlignmentSet &set, int n_threads, std::string &err);
 CigarVec cigar_from_text(const std::string &s);
 std::string cigar_to_text(const CigarVec &v, int left_clip, int right_clip);
 std::string reverse_complement(const std::string &s);
@@ -67,8 +78,7 @@ double match_rate_from_end(const std::string &a, const std::string &b);
 double match_rate_from_begin(const std::string &a, const std::string &b);
 std::string format_double(double x);
 
-void join_clips_with_alignments(const std::vector<ClipLine> &lines, const std::vector<std::string> &ref_names,
-                                const std::vector<Alignment> &alns, JunctionMap &jm);
+void join_clips_with_alignments(const std::vector<ClipLine> &lines, const AlignmentSet &alns, JunctionMap &jm);
 void merge_junctions(JunctionMap &jm, int search_length);
 
 typedef std::map<std::pair<std::string, int>, int> PosDepth;        // pos2depth
