@@ -3,15 +3,16 @@
 // Replaces the bgzf.o / zlib inflate of the reference's libbam (sam/bgzf.h:34-134; `bam_read1` -> `bgzf_read` ->
 // `inflate_block`), which SURVEY.md section 0 measures at ~75 % of getclip's run time on the host. BGZF blocks are
 // independent deflate streams of at most 64 KiB of output, so a whole BAM offers tens of thousands of blocks to
-// decode concurrently. Inside a warp lane 0 owns the bit reader and the Huffman decode (serial by nature); all 32
-// lanes build the decode tables and perform the LZ77 match copies. Decode tables live in shared memory
-// (4.3 KB per warp): a 10-bit single-lookup table for literal/length codes, an 8-bit one for distance codes, and a
-// canonical (count / sorted-symbol) fallback for the rare longer codes.
+// decode concurrently. One CTA of two warps handles a block: in the decoder warp lane 0 owns the bit reader and the
+// Huffman decode (serial by nature) and all 32 lanes build the decode tables; the copier warp performs the LZ77 match
+// copies, many matches at a time. Decode tables live in shared memory (4.3 KB): a 10-bit single-lookup table for
+// literal/length codes, an 8-bit one for distance codes, and a canonical (count / sorted-symbol) fallback for the rare
+// longer codes.
 #include "common.cuh"
 
 namespace {
 
-constexpr int LIT_FAST = 10, DIST_FAST = 8, WARPS_PER_CTA = 8;
+constexpr int LIT_FAST = 10, DIST_FAST = 8;
 
 struct WarpTables {
     uint16_t lit_fast[1 << LIT_FAST];    // (len << 9) | symbol, 0 = not a short code
@@ -132,20 +133,115 @@ struct InflateBlock {
     uint32_t clen, ulen;
 };
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+// ---- decoder warp -> copier warp hand-over --------------------------------------------------------------------------
+// One CTA (two warps) per BGZF block. Warp 0 decodes Huffman symbols and writes literals straight to the output; every
+// LZ77 match is pushed into a small shared-memory ring. Warp 1 drains the ring: up to 32 matches at a time, one per lane,
+// as long as their source bytes lie below the first match of the batch (everything there is final), so the ~L2 latency
+// of reading back recently written output is paid once per batch instead of once per match. In the one-warp version
+// (profiles/r1_summary.md: 52 ms for C2, SM-bound at 1.7 % of DRAM bandwidth) that latency stalled the decoder itself.
+constexpr int QCAP = 128;
+struct MatchQ {
+    uint32_t pos[QCAP];
+    uint32_t len_dist[QCAP];  // len << 16 | dist
+    volatile uint32_t tail;   // written by the decoder
+    volatile uint32_t head;   // written by the copier
+    volatile uint32_t done;   // decoder finished (value 1) or failed (value 2)
+};
+
+__device__ __forceinline__ uint8_t ld_out(const uint8_t *p)
+{
+    // output bytes are read back through L2 (ld.global.cg): they were written by another warp of this CTA
+    return __ldcg(p);
+}
+
+__device__ void copier_warp(MatchQ &q, uint8_t *__restrict__ dst, uint32_t lane)
+{
+    uint32_t head = 0;
+    for (;;) {
+        uint32_t tail = q.tail;
+        if (head == tail) {
+            if (q.done) {
+                tail = q.tail;
+                if (head == tail) break;
+            } else
+                __nanosleep(64);
+            continue;
+        }
+        __threadfence_block();  // acquire: the decoder's literal stores before its push are visible
+        uint32_t n = min(tail - head, 32u);
+        uint32_t pos = 0, len = 0, dist = 0;
+        if (lane < n) {
+            uint32_t i = (head + lane) % QCAP;
+            pos = q.pos[i];
+            len = q.len_dist[i] >> 16, dist = q.len_dist[i] & 0xffff;
+        }
+        uint32_t batch_start = __shfl_sync(0xffffffffu, pos, 0);
+        // simple = short, and its source lies entirely below the batch (no byte of this batch is read)
+        bool simple = lane < n && len <= 40 && pos - dist + len <= batch_start;
+        uint32_t not_simple = __ballot_sync(0xffffffffu, !(simple)) ;
+        uint32_t k = not_simple ? (uint32_t)(__ffs(not_simple) - 1) : 32u;
+        if (k > n) k = n;
+        if (k == 0) {
+            // the first match overlaps itself / is long: the whole warp copies it (dist < len repeats the last dist bytes)
+            uint32_t l0 = __shfl_sync(0xffffffffu, len, 0), d0 = __shfl_sync(0xffffffffu, dist, 0);
+            const uint8_t *src = dst + batch_start - d0;
+            if (d0 >= l0) {
+                for (uint32_t i = lane; i < l0; i += 32) dst[batch_start + i] = ld_out(src + i);
+            } else if (d0 >= 32) {
+                // chunks of 32 bytes never read what they write in the same step
+                for (uint32_t base = 0; base < l0; base += 32) {
+                    uint32_t i = base + lane;
+                    uint8_t v = 0;
+                    if (i < l0) v = ld_out(src + i);
+                    __syncwarp();
+                    if (i < l0) dst[batch_start + i] = v;
+                    __threadfence_block();
+                    __syncwarp();
+                }
+            } else {
+                // short period: every output byte is one of the last d0 bytes before the match (all final already)
+                for (uint32_t i = lane; i < l0; i += 32) dst[batch_start + i] = ld_out(src + i % d0);
+            }
+            k = 1;
+        } else if (lane < k) {
+            const uint8_t *src = dst + pos - dist;
+            uint8_t *o = dst + pos;
+            uint32_t i = 0;
+            for (; i + 8 <= len; i += 8) {  // loads first, stores after: eight bytes in flight per lane
+                uint8_t v0 = ld_out(src + i), v1 = ld_out(src + i + 1), v2 = ld_out(src + i + 2), v3 = ld_out(src + i + 3);
+                uint8_t v4 = ld_out(src + i + 4), v5 = ld_out(src + i + 5), v6 = ld_out(src + i + 6), v7 = ld_out(src + i + 7);
+                o[i] = v0, o[i + 1] = v1, o[i + 2] = v2, o[i + 3] = v3, o[i + 4] = v4, o[i + 5] = v5, o[i + 6] = v6, o[i + 7] = v7;
+            }
+            for (; i < len; ++i) o[i] = ld_out(src + i);
+        }
+        __threadfence_block();
+        __syncwarp();
+        head += k;
+        if (lane == 0) q.head = head;
+    }
+}
+
+__global__ void __launch_bounds__(64)
     inflate_bgzf(const uint8_t *__restrict__ file, const InflateBlock *__restrict__ blocks, uint32_t n_blocks, uint8_t *__restrict__ out,
                  uint32_t *__restrict__ error)
 {
-    __shared__ WarpTables tables[WARPS_PER_CTA];
+    __shared__ WarpTables T;
+    __shared__ MatchQ q;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t b = blockIdx.x * WARPS_PER_CTA + wid;
+    const uint32_t b = blockIdx.x;
     if (b >= n_blocks) return;
-    WarpTables &T = tables[wid];
     const InflateBlock blk = blocks[b];
     uint8_t *dst = out + blk.uoff;
+    if (threadIdx.x == 0) q.tail = 0, q.head = 0, q.done = 0;
+    __syncthreads();
+    if (wid == 1) {
+        copier_warp(q, dst, lane);
+        return;
+    }
+    // ---- warp 0: the decoder ------------------------------------------------------------------------------------
     BitReader br;
     if (lane == 0) br.init(file + blk.coff, file + blk.coff + blk.clen);
-    uint32_t pos = 0;
+    uint32_t pos = 0, tail = 0;
     bool bad = false;
     for (;;) {
         uint32_t hdr = 0;
@@ -175,6 +271,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
                 break;
             }
             for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i];
+            __threadfence_block();  // later matches may read these bytes from the other warp
+            __syncwarp();
             pos += len;
         } else if (type == 1 || type == 2) {
             int n_lit = 288, n_dist = 30;
@@ -251,69 +349,77 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
                 }
                 __syncwarp();
                 // the distance lengths follow the literal/length lengths directly: move them to their own slot
-                if (n_lit < 288) {
-                    uint8_t v = lane < (uint32_t)n_dist ? T.lens[n_lit + lane] : 0;
-                    __syncwarp();
-                    if (lane < (uint32_t)n_dist) T.lens[288 + lane] = v;
-                    for (int i = n_lit + lane; i < 288; i += 32) T.lens[i] = 0;
-                    __syncwarp();
-                    for (int i = n_lit + lane; i < 288; i += 32) T.lens[i] = 0;
-                }
+                uint8_t v = lane < (uint32_t)n_dist ? T.lens[n_lit + lane] : 0;
+                __syncwarp();
+                if (lane < (uint32_t)n_dist) T.lens[288 + lane] = v;
+                __syncwarp();
+                for (int i = n_lit + lane; i < 288; i += 32) T.lens[i] = 0;
             }
             __syncwarp();
             build_table(T.lens, type == 1 ? 288 : n_lit, T.lit_fast, LIT_FAST, T.lit_sym, T.lit_count, T.code, lane);
             build_table(T.lens + 288, n_dist, T.dist_fast, DIST_FAST, T.dist_sym, T.dist_count, T.code, lane);
-            // symbol loop: lane 0 decodes, the warp copies matches
-            for (;;) {
-                int sym = 0;
-                uint32_t len = 0, dist = 0;
-                if (lane == 0) {
+            // symbol loop: lane 0 alone; literals go straight out, matches go to the copier warp
+            int status = 0;  // 0 = end of block, 1 = error
+            if (lane == 0) {
+                for (;;) {
                     br.refill();
-                    sym = decode_sym(br, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
-                    // runs of literals stay on lane 0: no warp-wide exchange until a match or the end of the block
-                    while (sym >= 0 && sym < 256 && pos < blk.ulen) {
-                        dst[pos++] = (uint8_t)sym;
-                        br.refill();
-                        sym = decode_sym(br, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
+                    int sym = decode_sym(br, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
+                    if (sym < 0) {
+                        status = 1;
+                        break;
                     }
-                    if (sym > 256 && sym < 286) {
-                        int li = sym - 257;
-                        len = c_len_base[li] + br.bits(c_len_extra[li]);
-                        br.refill();
-                        int ds = decode_sym(br, T.dist_fast, DIST_FAST, T.dist_count, T.dist_sym);
-                        if (ds < 0 || ds >= 30) sym = -1;
-                        else dist = c_dist_base[ds] + br.bits(c_dist_extra[ds]);
-                    } else if (sym != 256)
-                        sym = -1;
+                    if (sym < 256) {
+                        if (pos >= blk.ulen) {
+                            status = 1;
+                            break;
+                        }
+                        dst[pos++] = (uint8_t)sym;
+                        continue;
+                    }
+                    if (sym == 256) break;
+                    if (sym >= 286) {
+                        status = 1;
+                        break;
+                    }
+                    int li = sym - 257;
+                    uint32_t len = c_len_base[li] + br.bits(c_len_extra[li]);
+                    br.refill();
+                    int ds = decode_sym(br, T.dist_fast, DIST_FAST, T.dist_count, T.dist_sym);
+                    if (ds < 0 || ds >= 30) {
+                        status = 1;
+                        break;
+                    }
+                    uint32_t dist = c_dist_base[ds] + br.bits(c_dist_extra[ds]);
+                    if (dist > pos || pos + len > blk.ulen) {
+                        status = 1;
+                        break;
+                    }
+                    while (tail - q.head >= QCAP) __nanosleep(32);  // ring full: wait for the copier
+                    uint32_t slot = tail % QCAP;
+                    q.pos[slot] = pos;
+                    q.len_dist[slot] = len << 16 | dist;
+                    __threadfence_block();  // release: literals written so far + the entry, then the new tail
+                    q.tail = ++tail;
+                    pos += len;
                 }
-                sym = __shfl_sync(0xffffffffu, sym, 0);
-                pos = __shfl_sync(0xffffffffu, pos, 0);
-                if (sym == 256) break;
-                len = __shfl_sync(0xffffffffu, len, 0);
-                dist = __shfl_sync(0xffffffffu, dist, 0);
-                if (sym < 0 || dist > pos || pos + len > blk.ulen) {
-                    bad = true;
-                    break;
-                }
-                // LZ77 copy; an overlapping match (dist < len) repeats the last `dist` bytes, which are all written already
-                const uint8_t *src = dst + pos - dist;
-                __syncwarp();  // lane 0's literal stores must be visible to the lanes that copy
-                if (dist >= len) {
-                    for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i];
-                } else {
-                    for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i % dist];
-                }
-                pos += len;
-                __syncwarp();
             }
-            if (bad) break;
+            status = __shfl_sync(0xffffffffu, status, 0);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (status) {
+                bad = true;
+                break;
+            }
         } else {
             bad = true;
             break;
         }
         if (final_block) break;
     }
-    if ((bad || pos != blk.ulen) && lane == 0) atomicOr(error, 1u);
+    if (lane == 0) {
+        __threadfence_block();
+        q.done = 1;
+        if (bad || pos != blk.ulen) atomicOr(error, 1u);
+    }
 }
 
 // host wrapper: file image + block table already on the device
@@ -325,8 +431,7 @@ int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks,
     CK(cudaMemsetAsync(err.p, 0, 4, s));
     if (n_blocks) {
         ProfScope ps(ctx, "inflate_bgzf", out_bytes);
-        inflate_bgzf<<<(n_blocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, s>>>(d_file, (const InflateBlock *)d_blocks,
-                                                                                                 n_blocks, d_out, err.p);
+        inflate_bgzf<<<n_blocks, 64, 0, s>>>(d_file, (const InflateBlock *)d_blocks, n_blocks, d_out, err.p);
     }
     uint32_t h = 0;
     CK(cudaMemcpyAsync(&h, err.p, 4, cudaMemcpyDeviceToHost, s));
