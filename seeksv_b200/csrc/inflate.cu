@@ -3,16 +3,19 @@
 // Replaces the bgzf.o / zlib inflate of the reference's libbam (sam/bgzf.h:34-134; `bam_read1` -> `bgzf_read` ->
 // `inflate_block`), which SURVEY.md section 0 measures at ~75 % of getclip's run time on the host. BGZF blocks are
 // independent deflate streams of at most 64 KiB of output, so a whole BAM offers tens of thousands of blocks to
-// decode concurrently. One CTA of two warps handles a block: in the decoder warp lane 0 owns the bit reader and the
-// Huffman decode (serial by nature) and all 32 lanes build the decode tables; the copier warp performs the LZ77 match
-// copies, many matches at a time. Decode tables live in shared memory (4.3 KB): a 10-bit single-lookup table for
-// literal/length codes, an 8-bit one for distance codes, and a canonical (count / sorted-symbol) fallback for the rare
-// longer codes.
+// decode concurrently. Inside a warp lane 0 owns the bit reader and the Huffman decode (serial by nature); all 32
+// lanes build the decode tables and perform the LZ77 match copies. Decode tables live in shared memory
+// (4.3 KB per warp): a 10-bit single-lookup table for literal/length codes, an 8-bit one for distance codes, and a
+// canonical (count / sorted-symbol) fallback for the rare longer codes.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int LIT_FAST = 10, DIST_FAST = 8;
+constexpr int LIT_FAST = 10, DIST_FAST = 8, WARPS_PER_CTA = 8;
 
 struct WarpTables {
     uint16_t lit_fast[1 << LIT_FAST];    // (len << 9) | symbol, 0 = not a short code
@@ -133,115 +136,20 @@ struct InflateBlock {
     uint32_t clen, ulen;
 };
 
-// ---- decoder warp -> copier warp hand-over --------------------------------------------------------------------------
-// One CTA (two warps) per BGZF block. Warp 0 decodes Huffman symbols and writes literals straight to the output; every
-// LZ77 match is pushed into a small shared-memory ring. Warp 1 drains the ring: up to 32 matches at a time, one per lane,
-// as long as their source bytes lie below the first match of the batch (everything there is final), so the ~L2 latency
-// of reading back recently written output is paid once per batch instead of once per match. In the one-warp version
-// (profiles/r1_summary.md: 52 ms for C2, SM-bound at 1.7 % of DRAM bandwidth) that latency stalled the decoder itself.
-constexpr int QCAP = 128;
-struct MatchQ {
-    uint32_t pos[QCAP];
-    uint32_t len_dist[QCAP];  // len << 16 | dist
-    volatile uint32_t tail;   // written by the decoder
-    volatile uint32_t head;   // written by the copier
-    volatile uint32_t done;   // decoder finished (value 1) or failed (value 2)
-};
-
-__device__ __forceinline__ uint8_t ld_out(const uint8_t *p)
-{
-    // output bytes are read back through L2 (ld.global.cg): they were written by another warp of this CTA
-    return __ldcg(p);
-}
-
-__device__ void copier_warp(MatchQ &q, uint8_t *__restrict__ dst, uint32_t lane)
-{
-    uint32_t head = 0;
-    for (;;) {
-        uint32_t tail = q.tail;
-        if (head == tail) {
-            if (q.done) {
-                tail = q.tail;
-                if (head == tail) break;
-            } else
-                __nanosleep(64);
-            continue;
-        }
-        __threadfence_block();  // acquire: the decoder's literal stores before its push are visible
-        uint32_t n = min(tail - head, 32u);
-        uint32_t pos = 0, len = 0, dist = 0;
-        if (lane < n) {
-            uint32_t i = (head + lane) % QCAP;
-            pos = q.pos[i];
-            len = q.len_dist[i] >> 16, dist = q.len_dist[i] & 0xffff;
-        }
-        uint32_t batch_start = __shfl_sync(0xffffffffu, pos, 0);
-        // simple = short, and its source lies entirely below the batch (no byte of this batch is read)
-        bool simple = lane < n && len <= 40 && pos - dist + len <= batch_start;
-        uint32_t not_simple = __ballot_sync(0xffffffffu, !(simple)) ;
-        uint32_t k = not_simple ? (uint32_t)(__ffs(not_simple) - 1) : 32u;
-        if (k > n) k = n;
-        if (k == 0) {
-            // the first match overlaps itself / is long: the whole warp copies it (dist < len repeats the last dist bytes)
-            uint32_t l0 = __shfl_sync(0xffffffffu, len, 0), d0 = __shfl_sync(0xffffffffu, dist, 0);
-            const uint8_t *src = dst + batch_start - d0;
-            if (d0 >= l0) {
-                for (uint32_t i = lane; i < l0; i += 32) dst[batch_start + i] = ld_out(src + i);
-            } else if (d0 >= 32) {
-                // chunks of 32 bytes never read what they write in the same step
-                for (uint32_t base = 0; base < l0; base += 32) {
-                    uint32_t i = base + lane;
-                    uint8_t v = 0;
-                    if (i < l0) v = ld_out(src + i);
-                    __syncwarp();
-                    if (i < l0) dst[batch_start + i] = v;
-                    __threadfence_block();
-                    __syncwarp();
-                }
-            } else {
-                // short period: every output byte is one of the last d0 bytes before the match (all final already)
-                for (uint32_t i = lane; i < l0; i += 32) dst[batch_start + i] = ld_out(src + i % d0);
-            }
-            k = 1;
-        } else if (lane < k) {
-            const uint8_t *src = dst + pos - dist;
-            uint8_t *o = dst + pos;
-            uint32_t i = 0;
-            for (; i + 8 <= len; i += 8) {  // loads first, stores after: eight bytes in flight per lane
-                uint8_t v0 = ld_out(src + i), v1 = ld_out(src + i + 1), v2 = ld_out(src + i + 2), v3 = ld_out(src + i + 3);
-                uint8_t v4 = ld_out(src + i + 4), v5 = ld_out(src + i + 5), v6 = ld_out(src + i + 6), v7 = ld_out(src + i + 7);
-                o[i] = v0, o[i + 1] = v1, o[i + 2] = v2, o[i + 3] = v3, o[i + 4] = v4, o[i + 5] = v5, o[i + 6] = v6, o[i + 7] = v7;
-            }
-            for (; i < len; ++i) o[i] = ld_out(src + i);
-        }
-        __threadfence_block();
-        __syncwarp();
-        head += k;
-        if (lane == 0) q.head = head;
-    }
-}
-
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     inflate_bgzf(const uint8_t *__restrict__ file, const InflateBlock *__restrict__ blocks, uint32_t n_blocks, uint8_t *__restrict__ out,
                  uint32_t *__restrict__ error)
 {
-    __shared__ WarpTables T;
-    __shared__ MatchQ q;
+    __shared__ WarpTables tables[WARPS_PER_CTA];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t b = blockIdx.x;
+    const uint32_t b = blockIdx.x * WARPS_PER_CTA + wid;
     if (b >= n_blocks) return;
+    WarpTables &T = tables[wid];
     const InflateBlock blk = blocks[b];
     uint8_t *dst = out + blk.uoff;
-    if (threadIdx.x == 0) q.tail = 0, q.head = 0, q.done = 0;
-    __syncthreads();
-    if (wid == 1) {
-        copier_warp(q, dst, lane);
-        return;
-    }
-    // ---- warp 0: the decoder ------------------------------------------------------------------------------------
     BitReader br;
     if (lane == 0) br.init(file + blk.coff, file + blk.coff + blk.clen);
-    uint32_t pos = 0, tail = 0;
+    uint32_t pos = 0;
     bool bad = false;
     for (;;) {
         uint32_t hdr = 0;
@@ -271,8 +179,6 @@ __global__ void __launch_bounds__(64)
                 break;
             }
             for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i];
-            __threadfence_block();  // later matches may read these bytes from the other warp
-            __syncwarp();
             pos += len;
         } else if (type == 1 || type == 2) {
             int n_lit = 288, n_dist = 30;
@@ -349,28 +255,225 @@ __global__ void __launch_bounds__(64)
                 }
                 __syncwarp();
                 // the distance lengths follow the literal/length lengths directly: move them to their own slot
-                uint8_t v = lane < (uint32_t)n_dist ? T.lens[n_lit + lane] : 0;
-                __syncwarp();
-                if (lane < (uint32_t)n_dist) T.lens[288 + lane] = v;
-                __syncwarp();
-                for (int i = n_lit + lane; i < 288; i += 32) T.lens[i] = 0;
+                if (n_lit < 288) {
+                    uint8_t v = lane < (uint32_t)n_dist ? T.lens[n_lit + lane] : 0;
+                    __syncwarp();
+                    if (lane < (uint32_t)n_dist) T.lens[288 + lane] = v;
+                    for (int i = n_lit + lane; i < 288; i += 32) T.lens[i] = 0;
+                    __syncwarp();
+                    for (int i = n_lit + lane; i < 288; i += 32) T.lens[i] = 0;
+                }
             }
             __syncwarp();
             build_table(T.lens, type == 1 ? 288 : n_lit, T.lit_fast, LIT_FAST, T.lit_sym, T.lit_count, T.code, lane);
             build_table(T.lens + 288, n_dist, T.dist_fast, DIST_FAST, T.dist_sym, T.dist_count, T.code, lane);
-            // symbol loop: lane 0 alone; literals go straight out, matches go to the copier warp
-            int status = 0;  // 0 = end of block, 1 = error
-            if (lane == 0) {
+            // symbol loop: lane 0 decodes, the warp copies matches
+            for (;;) {
+                int sym = 0;
+                uint32_t len = 0, dist = 0;
+                if (lane == 0) {
+                    br.refill();
+                    sym = decode_sym(br, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
+                    // runs of literals stay on lane 0: no warp-wide exchange until a match or the end of the block
+                    while (sym >= 0 && sym < 256 && pos < blk.ulen) {
+                        dst[pos++] = (uint8_t)sym;
+                        br.refill();
+                        sym = decode_sym(br, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
+                    }
+                    if (sym > 256 && sym < 286) {
+                        int li = sym - 257;
+                        len = c_len_base[li] + br.bits(c_len_extra[li]);
+                        br.refill();
+                        int ds = decode_sym(br, T.dist_fast, DIST_FAST, T.dist_count, T.dist_sym);
+                        if (ds < 0 || ds >= 30) sym = -1;
+                        else dist = c_dist_base[ds] + br.bits(c_dist_extra[ds]);
+                    } else if (sym != 256)
+                        sym = -1;
+                }
+                sym = __shfl_sync(0xffffffffu, sym, 0);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (sym == 256) break;
+                len = __shfl_sync(0xffffffffu, len, 0);
+                dist = __shfl_sync(0xffffffffu, dist, 0);
+                if (sym < 0 || dist > pos || pos + len > blk.ulen) {
+                    bad = true;
+                    break;
+                }
+                // LZ77 copy; an overlapping match (dist < len) repeats the last `dist` bytes, which are all written already
+                const uint8_t *src = dst + pos - dist;
+                __syncwarp();  // lane 0's literal stores must be visible to the lanes that copy
+                if (dist >= len) {
+                    for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i];
+                } else {
+                    for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i % dist];
+                }
+                pos += len;
+                __syncwarp();
+            }
+            if (bad) break;
+        } else {
+            bad = true;
+            break;
+        }
+        if (final_block) break;
+    }
+    if ((bad || pos != blk.ulen) && lane == 0) atomicOr(error, 1u);
+}
+
+// ---- thread-per-block variant ------------------------------------------------------------------------------------------
+// ncu on the warp-per-block kernel (profiles/r1_summary.md): SM throughput 85 %, DRAM 1.7 % - it is bound by instruction
+// issue, with one active lane per warp doing the serial Huffman decode and 31 lanes idle most of the time. A BAM offers
+// tens of thousands of independent BGZF blocks, so the other classic mapping fits better: ONE THREAD per block, every
+// lane of a warp decoding its own stream. Decode tables move from shared memory to a per-thread slice of a global
+// scratch buffer (1.9 KB per thread, L1/L2 resident); the same instructions now serve up to 32 streams at once.
+namespace {
+constexpr int T_LIT_FAST = 9, T_DIST_FAST = 7;
+struct ThreadTables {
+    uint16_t lit_fast[1 << T_LIT_FAST];
+    uint16_t dist_fast[1 << T_DIST_FAST];
+    uint16_t lit_sym[288], dist_sym[32];
+    uint16_t lit_count[16], dist_count[16];
+    uint8_t lens[320];
+};
+
+__device__ void build_table_serial(const uint8_t *lens, int n, uint16_t *fast, int fast_bits, uint16_t *sym_sorted, uint16_t *count)
+{
+    for (int i = 0; i < (1 << fast_bits); ++i) fast[i] = 0;
+    for (int i = 0; i < 16; ++i) count[i] = 0;
+    for (int s = 0; s < n; ++s) count[lens[s]]++;
+    count[0] = 0;
+    uint16_t next_code[16], offs[16];
+    uint32_t c = 0;
+    offs[1] = 0;
+    next_code[0] = 0;
+    for (int b = 1; b <= 15; ++b) {
+        c = (c + count[b - 1]) << 1;
+        next_code[b] = (uint16_t)c;
+        if (b < 15) offs[b + 1] = offs[b] + count[b];
+    }
+    for (int s = 0; s < n; ++s) {
+        int l = lens[s];
+        if (!l) continue;
+        uint32_t code = next_code[l]++;
+        sym_sorted[offs[l]++] = (uint16_t)s;
+        if (l <= fast_bits) {
+            uint32_t rev = __brev(code) >> (32 - l);
+            uint16_t e = (uint16_t)(l << 9 | s);
+            for (uint32_t k = rev; k < (1u << fast_bits); k += 1u << l) fast[k] = e;
+        }
+    }
+}
+}  // namespace
+
+__global__ void __launch_bounds__(128)
+    inflate_bgzf_tpb(const uint8_t *__restrict__ file, const InflateBlock *__restrict__ blocks, uint32_t n_blocks, uint8_t *__restrict__ out,
+                     ThreadTables *__restrict__ scratch, uint32_t *__restrict__ error)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    ThreadTables &T = scratch[tid];
+    for (uint32_t b = tid; b < n_blocks; b += stride) {
+        const InflateBlock blk = blocks[b];
+        uint8_t *dst = out + blk.uoff;
+        BitReader br;
+        br.init(file + blk.coff, file + blk.coff + blk.clen);
+        uint32_t pos = 0;
+        bool bad = false;
+        for (;;) {
+            br.refill();
+            uint32_t hdr = br.bits(3);
+            const uint32_t final_block = hdr & 1, type = hdr >> 1;
+            if (type == 0) {  // stored
+                br.align_byte();
+                br.refill();
+                uint32_t len = br.bits(16);
+                br.refill();
+                br.skip(16);  // NLEN
+                const uint8_t *src = br.in - (br.cnt >> 3);
+                if (pos + len > blk.ulen) {
+                    bad = true;
+                    break;
+                }
+                for (uint32_t i = 0; i < len; ++i) dst[pos + i] = src[i];
+                pos += len;
+                br.init(src + len, br.end);
+            } else if (type == 1 || type == 2) {
+                int n_lit = 288, n_dist = 30;
+                if (type == 1) {
+                    for (int i = 0; i < 288; ++i) T.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+                    for (int i = 0; i < 30; ++i) T.lens[288 + i] = 5;
+                } else {
+                    br.refill();
+                    n_lit = (int)br.bits(5) + 257;
+                    n_dist = (int)br.bits(5) + 1;
+                    int n_cl = (int)br.bits(4) + 4;
+                    uint8_t cl[19];
+                    for (int i = 0; i < 19; ++i) cl[i] = 0;
+                    for (int i = 0; i < n_cl; ++i) {
+                        br.refill();
+                        cl[c_cl_order[i]] = (uint8_t)br.bits(3);
+                    }
+                    // code-length alphabet: canonical codes, decoded bit by bit (at most 7 bits, ~300 symbols per block)
+                    uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    uint8_t sorted[19];
+                    for (int i = 0; i < 19; ++i) cnt[cl[i]]++;
+                    cnt[0] = 0;
+                    {
+                        uint32_t offs[8];
+                        offs[1] = 0;
+                        for (int l = 1; l < 7; ++l) offs[l + 1] = offs[l] + cnt[l];
+                        for (int sdx = 0; sdx < 19; ++sdx)
+                            if (cl[sdx]) sorted[offs[cl[sdx]]++] = (uint8_t)sdx;
+                    }
+                    int i = 0, total = n_lit + n_dist;
+                    if (n_lit > 286 || n_dist > 30) bad = true;
+                    while (!bad && i < total) {
+                        br.refill();
+                        int code = 0, first = 0, index = 0, sym = -1;
+                        for (int len = 1; len <= 7; ++len) {
+                            code |= (int)br.bits(1);
+                            int c = (int)cnt[len];
+                            if (code - c < first) {
+                                sym = sorted[index + (code - first)];
+                                break;
+                            }
+                            index += c, first += c;
+                            first <<= 1, code <<= 1;
+                        }
+                        if (sym < 0) {
+                            bad = true;
+                            break;
+                        }
+                        if (sym < 16) T.lens[i++] = (uint8_t)sym;
+                        else {
+                            int rep, v = 0;
+                            if (sym == 16) {
+                                if (i == 0) {
+                                    bad = true;
+                                    break;
+                                }
+                                v = T.lens[i - 1];
+                                rep = 3 + (int)br.bits(2);
+                            } else if (sym == 17) rep = 3 + (int)br.bits(3);
+                            else rep = 11 + (int)br.bits(7);
+                            if (i + rep > total) {
+                                bad = true;
+                                break;
+                            }
+                            while (rep--) T.lens[i++] = (uint8_t)v;
+                        }
+                    }
+                    if (bad) break;
+                    for (int k = n_dist - 1; k >= 0; --k) T.lens[288 + k] = T.lens[n_lit + k];  // (n_lit + k <= 288 + k: no overlap problem going down)
+                    for (int k = n_lit; k < 288; ++k) T.lens[k] = 0;
+                }
+                build_table_serial(T.lens, type == 1 ? 288 : n_lit, T.lit_fast, T_LIT_FAST, T.lit_sym, T.lit_count);
+                build_table_serial(T.lens + 288, n_dist, T.dist_fast, T_DIST_FAST, T.dist_sym, T.dist_count);
                 for (;;) {
                     br.refill();
-                    int sym = decode_sym(br, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
-                    if (sym < 0) {
-                        status = 1;
-                        break;
-                    }
+                    int sym = decode_sym(br, T.lit_fast, T_LIT_FAST, T.lit_count, T.lit_sym);
                     if (sym < 256) {
-                        if (pos >= blk.ulen) {
-                            status = 1;
+                        if (sym < 0 || pos >= blk.ulen) {
+                            bad = true;
                             break;
                         }
                         dst[pos++] = (uint8_t)sym;
@@ -378,46 +481,34 @@ __global__ void __launch_bounds__(64)
                     }
                     if (sym == 256) break;
                     if (sym >= 286) {
-                        status = 1;
+                        bad = true;
                         break;
                     }
                     int li = sym - 257;
                     uint32_t len = c_len_base[li] + br.bits(c_len_extra[li]);
                     br.refill();
-                    int ds = decode_sym(br, T.dist_fast, DIST_FAST, T.dist_count, T.dist_sym);
+                    int ds = decode_sym(br, T.dist_fast, T_DIST_FAST, T.dist_count, T.dist_sym);
                     if (ds < 0 || ds >= 30) {
-                        status = 1;
+                        bad = true;
                         break;
                     }
                     uint32_t dist = c_dist_base[ds] + br.bits(c_dist_extra[ds]);
                     if (dist > pos || pos + len > blk.ulen) {
-                        status = 1;
+                        bad = true;
                         break;
                     }
-                    while (tail - q.head >= QCAP) __nanosleep(32);  // ring full: wait for the copier
-                    uint32_t slot = tail % QCAP;
-                    q.pos[slot] = pos;
-                    q.len_dist[slot] = len << 16 | dist;
-                    __threadfence_block();  // release: literals written so far + the entry, then the new tail
-                    q.tail = ++tail;
+                    const uint8_t *src = dst + pos - dist;
+                    uint8_t *o = dst + pos;
+                    for (uint32_t i = 0; i < len; ++i) o[i] = src[i];  // byte order makes overlapping matches (dist < len) right
                     pos += len;
                 }
-            }
-            status = __shfl_sync(0xffffffffu, status, 0);
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (status) {
+                if (bad) break;
+            } else {
                 bad = true;
                 break;
             }
-        } else {
-            bad = true;
-            break;
+            if (final_block) break;
         }
-        if (final_block) break;
-    }
-    if (lane == 0) {
-        __threadfence_block();
-        q.done = 1;
         if (bad || pos != blk.ulen) atomicOr(error, 1u);
     }
 }
@@ -429,9 +520,18 @@ int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks,
     DevBuf<uint32_t> err;
     CK(err.alloc(1, s));
     CK(cudaMemsetAsync(err.p, 0, 4, s));
-    if (n_blocks) {
+    const char *mode = getenv("SEEKSV_B200_INFLATE");  // "warp": the warp-per-block kernel (kept for comparison)
+    if (n_blocks && mode && !strcmp(mode, "warp")) {
         ProfScope ps(ctx, "inflate_bgzf", out_bytes);
-        inflate_bgzf<<<n_blocks, 64, 0, s>>>(d_file, (const InflateBlock *)d_blocks, n_blocks, d_out, err.p);
+        inflate_bgzf<<<(n_blocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, s>>>(d_file, (const InflateBlock *)d_blocks,
+                                                                                                 n_blocks, d_out, err.p);
+    } else if (n_blocks) {
+        // one thread per BGZF block; at most ~4 resident CTAs of 128 threads per SM are launched and loop over the blocks
+        uint32_t threads = 128, ctas = std::min<uint32_t>((n_blocks + threads - 1) / threads, (uint32_t)ctx->sm_count * 4);
+        DevBuf<ThreadTables> scratch;
+        CK(scratch.alloc((size_t)ctas * threads, s));
+        ProfScope ps(ctx, "inflate_bgzf_tpb", out_bytes);
+        inflate_bgzf_tpb<<<ctas, threads, 0, s>>>(d_file, (const InflateBlock *)d_blocks, n_blocks, d_out, scratch.p, err.p);
     }
     uint32_t h = 0;
     CK(cudaMemcpyAsync(&h, err.p, 4, cudaMemcpyDeviceToHost, s));
