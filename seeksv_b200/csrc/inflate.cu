@@ -7,10 +7,6 @@
 // lanes build the decode tables and perform the LZ77 match copies. Decode tables live in shared memory
 // (4.3 KB per warp): a 10-bit single-lookup table for literal/length codes, an 8-bit one for distance codes, and a
 // canonical (count / sorted-symbol) fallback for the rare longer codes.
-#include <algorithm>
-#include <cstdlib>
-#include <cstring>
-
 #include "common.cuh"
 
 namespace {
@@ -320,199 +316,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     if ((bad || pos != blk.ulen) && lane == 0) atomicOr(error, 1u);
 }
 
-// ---- thread-per-block variant ------------------------------------------------------------------------------------------
-// ncu on the warp-per-block kernel (profiles/r1_summary.md): SM throughput 85 %, DRAM 1.7 % - it is bound by instruction
-// issue, with one active lane per warp doing the serial Huffman decode and 31 lanes idle most of the time. A BAM offers
-// tens of thousands of independent BGZF blocks, so the other classic mapping fits better: ONE THREAD per block, every
-// lane of a warp decoding its own stream. Decode tables move from shared memory to a per-thread slice of a global
-// scratch buffer (1.9 KB per thread, L1/L2 resident); the same instructions now serve up to 32 streams at once.
-namespace {
-constexpr int T_LIT_FAST = 9, T_DIST_FAST = 7;
-struct ThreadTables {
-    uint16_t lit_fast[1 << T_LIT_FAST];
-    uint16_t dist_fast[1 << T_DIST_FAST];
-    uint16_t lit_sym[288], dist_sym[32];
-    uint16_t lit_count[16], dist_count[16];
-    uint8_t lens[320];
-};
-
-__device__ void build_table_serial(const uint8_t *lens, int n, uint16_t *fast, int fast_bits, uint16_t *sym_sorted, uint16_t *count)
-{
-    for (int i = 0; i < (1 << fast_bits); ++i) fast[i] = 0;
-    for (int i = 0; i < 16; ++i) count[i] = 0;
-    for (int s = 0; s < n; ++s) count[lens[s]]++;
-    count[0] = 0;
-    uint16_t next_code[16], offs[16];
-    uint32_t c = 0;
-    offs[1] = 0;
-    next_code[0] = 0;
-    for (int b = 1; b <= 15; ++b) {
-        c = (c + count[b - 1]) << 1;
-        next_code[b] = (uint16_t)c;
-        if (b < 15) offs[b + 1] = offs[b] + count[b];
-    }
-    for (int s = 0; s < n; ++s) {
-        int l = lens[s];
-        if (!l) continue;
-        uint32_t code = next_code[l]++;
-        sym_sorted[offs[l]++] = (uint16_t)s;
-        if (l <= fast_bits) {
-            uint32_t rev = __brev(code) >> (32 - l);
-            uint16_t e = (uint16_t)(l << 9 | s);
-            for (uint32_t k = rev; k < (1u << fast_bits); k += 1u << l) fast[k] = e;
-        }
-    }
-}
-}  // namespace
-
-__global__ void __launch_bounds__(128)
-    inflate_bgzf_tpb(const uint8_t *__restrict__ file, const InflateBlock *__restrict__ blocks, uint32_t n_blocks, uint8_t *__restrict__ out,
-                     ThreadTables *__restrict__ scratch, uint32_t *__restrict__ error)
-{
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    ThreadTables &T = scratch[tid];
-    for (uint32_t b = tid; b < n_blocks; b += stride) {
-        const InflateBlock blk = blocks[b];
-        uint8_t *dst = out + blk.uoff;
-        BitReader br;
-        br.init(file + blk.coff, file + blk.coff + blk.clen);
-        uint32_t pos = 0;
-        bool bad = false;
-        for (;;) {
-            br.refill();
-            uint32_t hdr = br.bits(3);
-            const uint32_t final_block = hdr & 1, type = hdr >> 1;
-            if (type == 0) {  // stored
-                br.align_byte();
-                br.refill();
-                uint32_t len = br.bits(16);
-                br.refill();
-                br.skip(16);  // NLEN
-                const uint8_t *src = br.in - (br.cnt >> 3);
-                if (pos + len > blk.ulen) {
-                    bad = true;
-                    break;
-                }
-                for (uint32_t i = 0; i < len; ++i) dst[pos + i] = src[i];
-                pos += len;
-                br.init(src + len, br.end);
-            } else if (type == 1 || type == 2) {
-                int n_lit = 288, n_dist = 30;
-                if (type == 1) {
-                    for (int i = 0; i < 288; ++i) T.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
-                    for (int i = 0; i < 30; ++i) T.lens[288 + i] = 5;
-                } else {
-                    br.refill();
-                    n_lit = (int)br.bits(5) + 257;
-                    n_dist = (int)br.bits(5) + 1;
-                    int n_cl = (int)br.bits(4) + 4;
-                    uint8_t cl[19];
-                    for (int i = 0; i < 19; ++i) cl[i] = 0;
-                    for (int i = 0; i < n_cl; ++i) {
-                        br.refill();
-                        cl[c_cl_order[i]] = (uint8_t)br.bits(3);
-                    }
-                    // code-length alphabet: canonical codes, decoded bit by bit (at most 7 bits, ~300 symbols per block)
-                    uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    uint8_t sorted[19];
-                    for (int i = 0; i < 19; ++i) cnt[cl[i]]++;
-                    cnt[0] = 0;
-                    {
-                        uint32_t offs[8];
-                        offs[1] = 0;
-                        for (int l = 1; l < 7; ++l) offs[l + 1] = offs[l] + cnt[l];
-                        for (int sdx = 0; sdx < 19; ++sdx)
-                            if (cl[sdx]) sorted[offs[cl[sdx]]++] = (uint8_t)sdx;
-                    }
-                    int i = 0, total = n_lit + n_dist;
-                    if (n_lit > 286 || n_dist > 30) bad = true;
-                    while (!bad && i < total) {
-                        br.refill();
-                        int code = 0, first = 0, index = 0, sym = -1;
-                        for (int len = 1; len <= 7; ++len) {
-                            code |= (int)br.bits(1);
-                            int c = (int)cnt[len];
-                            if (code - c < first) {
-                                sym = sorted[index + (code - first)];
-                                break;
-                            }
-                            index += c, first += c;
-                            first <<= 1, code <<= 1;
-                        }
-                        if (sym < 0) {
-                            bad = true;
-                            break;
-                        }
-                        if (sym < 16) T.lens[i++] = (uint8_t)sym;
-                        else {
-                            int rep, v = 0;
-                            if (sym == 16) {
-                                if (i == 0) {
-                                    bad = true;
-                                    break;
-                                }
-                                v = T.lens[i - 1];
-                                rep = 3 + (int)br.bits(2);
-                            } else if (sym == 17) rep = 3 + (int)br.bits(3);
-                            else rep = 11 + (int)br.bits(7);
-                            if (i + rep > total) {
-                                bad = true;
-                                break;
-                            }
-                            while (rep--) T.lens[i++] = (uint8_t)v;
-                        }
-                    }
-                    if (bad) break;
-                    for (int k = n_dist - 1; k >= 0; --k) T.lens[288 + k] = T.lens[n_lit + k];  // (n_lit + k <= 288 + k: no overlap problem going down)
-                    for (int k = n_lit; k < 288; ++k) T.lens[k] = 0;
-                }
-                build_table_serial(T.lens, type == 1 ? 288 : n_lit, T.lit_fast, T_LIT_FAST, T.lit_sym, T.lit_count);
-                build_table_serial(T.lens + 288, n_dist, T.dist_fast, T_DIST_FAST, T.dist_sym, T.dist_count);
-                for (;;) {
-                    br.refill();
-                    int sym = decode_sym(br, T.lit_fast, T_LIT_FAST, T.lit_count, T.lit_sym);
-                    if (sym < 256) {
-                        if (sym < 0 || pos >= blk.ulen) {
-                            bad = true;
-                            break;
-                        }
-                        dst[pos++] = (uint8_t)sym;
-                        continue;
-                    }
-                    if (sym == 256) break;
-                    if (sym >= 286) {
-                        bad = true;
-                        break;
-                    }
-                    int li = sym - 257;
-                    uint32_t len = c_len_base[li] + br.bits(c_len_extra[li]);
-                    br.refill();
-                    int ds = decode_sym(br, T.dist_fast, T_DIST_FAST, T.dist_count, T.dist_sym);
-                    if (ds < 0 || ds >= 30) {
-                        bad = true;
-                        break;
-                    }
-                    uint32_t dist = c_dist_base[ds] + br.bits(c_dist_extra[ds]);
-                    if (dist > pos || pos + len > blk.ulen) {
-                        bad = true;
-                        break;
-                    }
-                    const uint8_t *src = dst + pos - dist;
-                    uint8_t *o = dst + pos;
-                    for (uint32_t i = 0; i < len; ++i) o[i] = src[i];  // byte order makes overlapping matches (dist < len) right
-                    pos += len;
-                }
-                if (bad) break;
-            } else {
-                bad = true;
-                break;
-            }
-            if (final_block) break;
-        }
-        if (bad || pos != blk.ulen) atomicOr(error, 1u);
-    }
-}
-
 // host wrapper: file image + block table already on the device
 int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, double out_bytes)
 {
@@ -520,18 +323,10 @@ int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks,
     DevBuf<uint32_t> err;
     CK(err.alloc(1, s));
     CK(cudaMemsetAsync(err.p, 0, 4, s));
-    const char *mode = getenv("SEEKSV_B200_INFLATE");  // "warp": the warp-per-block kernel (kept for comparison)
-    if (n_blocks && mode && !strcmp(mode, "warp")) {
+    if (n_blocks) {
         ProfScope ps(ctx, "inflate_bgzf", out_bytes);
         inflate_bgzf<<<(n_blocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, s>>>(d_file, (const InflateBlock *)d_blocks,
                                                                                                  n_blocks, d_out, err.p);
-    } else if (n_blocks) {
-        // one thread per BGZF block; at most ~4 resident CTAs of 128 threads per SM are launched and loop over the blocks
-        uint32_t threads = 128, ctas = std::min<uint32_t>((n_blocks + threads - 1) / threads, (uint32_t)ctx->sm_count * 4);
-        DevBuf<ThreadTables> scratch;
-        CK(scratch.alloc((size_t)ctas * threads, s));
-        ProfScope ps(ctx, "inflate_bgzf_tpb", out_bytes);
-        inflate_bgzf_tpb<<<ctas, threads, 0, s>>>(d_file, (const InflateBlock *)d_blocks, n_blocks, d_out, scratch.p, err.p);
     }
     uint32_t h = 0;
     CK(cudaMemcpyAsync(&h, err.p, 4, cudaMemcpyDeviceToHost, s));
