@@ -91,10 +91,11 @@ struct svb_bam {
     // record chain (bam_index.cu): the stream is cut into 16 KiB chunks; guess[c] = offset of the first record that
     // starts at or after the chunk, count[c] = records starting inside it, base[c] = exclusive prefix of count
     uint64_t n_chunks = 0;
-    uint32_t chunk_log2 = 13;  // 8 KiB chunks: ~25 records of 300 B per walker thread (SEEKSV_B200_CHUNK_LOG2)
+    uint32_t chunk_log2 = 14;  // 16 KiB chunks = streaming tiles (SEEKSV_B200_CHUNK_LOG2 changes it for the walkers)
     uint64_t *d_guess = nullptr, *d_base = nullptr;
     uint32_t *d_count = nullptr;
     bool counted = false;  // count / base / n_rec / rec_bytes are valid (ensure_counts)
+    bool guessed = false;  // d_guess holds first-record guesses (guess_starts or a streaming pass)
     bool whole_file = false;  // built from a complete BAM: the chain must end exactly at the end of the stream
     // per-chunk insert-size partial sums gathered by the decode walker for one mapQ threshold (getsv.cu)
     int32_t stats_mapq = -1;
@@ -258,7 +259,11 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t v)
 
 // ---- internal entry points (one per .cu) ------------------------------------------------------------------
 static constexpr uint64_t BAD_OFFSET = ~0ull;
-int index_records(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu: guesses only
+int index_records(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu: chunk arrays (+ guesses for the walkers)
+int ensure_guess(svb_ctx *ctx, svb_bam *bam);                        // bam_index.cu: guess_starts once
+// The full passes run as TMA-staged streaming kernels (stream.cuh) when the chunk size equals the tile size; the chunk
+// walkers are the fallback after a failed verification and can be forced with SEEKSV_B200_PASS=walk.
+bool stream_mode(const svb_bam *bam);
 int ensure_counts(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu: verified chain + counts + prefix
 int finish_counts(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit);  // prefix + totals from valid per-chunk counts
 // after a fused walker filled exit_[]: verify against the guesses; *ok = 0 means the guesses were repaired

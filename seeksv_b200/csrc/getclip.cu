@@ -9,6 +9,7 @@
 #include <memory>
 
 #include "common.cuh"
+#include "stream.cuh"
 
 struct svb_clusters {
     svb_ctx *ctx = nullptr;
@@ -226,6 +227,87 @@ __global__ void __launch_bounds__(128)
         if (s < out.sw_cap) out.switches[s] = o;
     } else
         queue_if_clipped(d, o, k, min_mapq, out);
+}
+
+// The getclip full pass, streaming form (stream.cuh): TMA-staged 16 KiB tiles, one record per thread from shared memory.
+// Same outputs as clip_walk (per-tile count / exit / first mapped-branch record / last mapped-branch tid, the unmapped
+// list, the chromosome switches and the queue of soft-clipped records), so clip_first / clip_eval / verification follow
+// unchanged.
+__global__ void __launch_bounds__(STREAM_THREADS)
+    clip_stream(const uint8_t *__restrict__ d, uint64_t n, uint64_t padded, uint64_t first, int32_t n_ref, uint64_t n_tiles,
+                uint64_t *__restrict__ guess, uint32_t *__restrict__ count, uint64_t *__restrict__ exit_,
+                uint64_t *__restrict__ first_mb, int32_t *__restrict__ last_mb_tid, int32_t min_mapq, ScanOut out)
+{
+    __shared__ StreamShared S;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&S.full[s], 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < STAGES; ++s) {
+            uint64_t t = blockIdx.x + (uint64_t)s * gridDim.x;
+            if (t < n_tiles) issue_tile(S, s, d, padded, t);
+        }
+    uint32_t it = 0;
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&S.full[s], (it / STAGES) & 1);
+        const uint64_t tile_abs = t << TILE_LOG2;
+        TileWin w{S.stage[s], d + tile_abs, (uint32_t)min((uint64_t)(TILE + HALO), padded - tile_abs)};
+        index_tile(S, w, t, n, first, n_ref, d);
+        const uint32_t n_rec = S.n_rec;
+        for (uint32_t k = tid; k < n_rec; k += STREAM_THREADS) {
+            const uint32_t off = S.rec_off[k];
+            const Core c = w.core(off);
+            const uint64_t o = tile_abs + off;
+            if (c.flag & (F_UNMAP | F_MUNMAP)) {  // clip_reads.h:415 - the unmapped branch wins (quirk Q2)
+                uint32_t slot = atomicAdd(&out.counters[1], 1u);
+                if (slot < out.un_cap) out.unmapped[slot] = o;
+                continue;
+            }
+            unsigned long long key = (unsigned long long)k << 32 | (uint32_t)c.tid;
+            atomicMin(&S.first_mb, key);
+            atomicMax(&S.last_mb, key);
+            // quirk Q1: tid of the previous mapped-branch record (normally the record just before this one)
+            int32_t prev_tid = NO_TID;
+            for (uint32_t j = k; j > 0;) {
+                --j;
+                uint32_t oj = S.rec_off[j];
+                if (!((w.u32(oj + 16) >> 16) & (F_UNMAP | F_MUNMAP))) {
+                    prev_tid = (int32_t)w.u32(oj + 4);
+                    break;
+                }
+            }
+            if (prev_tid == NO_TID) continue;  // first mapped-branch record of the tile: clip_first looks into earlier tiles
+            if (c.tid != prev_tid) {  // flush + drop (clip_reads.h:423-438)
+                uint32_t slot = atomicAdd(&out.counters[2], 1u);
+                if (slot < out.sw_cap) out.switches[slot] = o;
+                continue;
+            }
+            // cheap part of GetSClipReads (clip_reads.cpp:116-118,122) from the staged bytes
+            if (c.n_cigar == 0 || (int32_t)c.mapq < min_mapq || (c.flag & F_DUP)) continue;
+            uint32_t cg = off + 36 + c.l_qname;
+            uint32_t op1 = w.u32(cg) & 15, op2 = w.u32(cg + 4 * (c.n_cigar - 1)) & 15;
+            if (op1 == OP_H || op2 == OP_H || (op1 != OP_S && op2 != OP_S)) continue;
+            uint32_t slot = atomicAdd(&out.counters[3], 1u);
+            if (slot < out.clipped_cap) out.clipped[slot] = o;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            count[t] = n_rec, exit_[t] = S.exit_, guess[t] = S.entry;
+            bool have = S.first_mb != ~0ull;
+            first_mb[t] = have ? tile_abs + S.rec_off[(uint32_t)(S.first_mb >> 32)] : BAD_OFFSET;
+            last_mb_tid[t] = have ? (int32_t)(uint32_t)S.last_mb : NO_TID;
+            uint64_t tn = t + (uint64_t)STAGES * gridDim.x;
+            if (tn < n_tiles) {
+                fence_proxy_async();  // the stage was read through the generic proxy; the bulk copy writes it through the async proxy
+                issue_tile(S, s, d, padded, tn);
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // the expensive part of GetSClipReads for the queued soft-clipped records (one thread each)
@@ -717,6 +799,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
     CK(exit_.alloc(n_chunks, s));
     CK(first_mb.alloc(n_chunks, s));
     CK(last_mb_tid.alloc(n_chunks, s));
+    int attempt_walk = 0;
     for (int attempt = 0;; ++attempt) {
         CK(c_off.alloc(cand_cap, s));
         CK(c_begin.alloc(cand_cap, s));
@@ -731,7 +814,20 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         c = {c_off.p, c_tid.p, c_pos.p, c_begin.p, c_ll.p, c_rl.p, c_side.p};
         ScanOut so{c, cand_cap, un_list.p, un_cap, sw_list.p, sw_cap, counters.p, clipped.p, cand_cap};
         CK(cudaMemsetAsync(counters.p, 0, 16, s));
-        {
+        if (stream_mode(bam) && attempt_walk == 0) {
+            // streaming pass: its own first-record guesses go to bam->d_guess and are verified below like the walker's
+            int per_sm = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, clip_stream, STREAM_THREADS, 0));
+            unsigned grid = (unsigned)std::min<uint64_t>(n_chunks, (uint64_t)std::max(1, per_sm) * ctx->sm_count);
+            ProfScope ps(ctx, "clip_stream", (double)stream_bytes);
+            clip_stream<<<grid, STREAM_THREADS, 0, s>>>(bam->d_data, bam->nbytes, (bam->nbytes + 15) & ~15ull, bam->first, bam->n_ref,
+                                                        n_chunks, bam->d_guess, bam->d_count, exit_.p, first_mb.p, last_mb_tid.p,
+                                                        prm->min_mapq, so);
+            clip_first<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, n_chunks, first_mb.p, last_mb_tid.p, prm->prev_tid, prm->min_mapq,
+                                                         prm->save_low_quality, so);
+            bam->guessed = true;  // d_guess now holds this pass's guesses (verified or repaired below)
+        } else {
+            CKR(ensure_guess(ctx, bam));
             ProfScope ps(ctx, "clip_walk", (double)stream_bytes);
             clip_walk<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->chunk_log2, bam->d_guess, bam->d_count,
                                                         exit_.p, first_mb.p, last_mb_tid.p, prm->min_mapq, prm->save_low_quality, so);
@@ -744,7 +840,8 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
             clip_eval<<<nblk(cand_cap, 128), 128, 0, s>>>(bam->d_data, prm->min_mapq, prm->save_low_quality, so);
         }
         int ok = 0;
-        CKR(verify_or_repair(ctx, bam, exit_.p, &ok));  // (synchronises)
+        CKR(verify_or_repair(ctx, bam, exit_.p, &ok));  // (synchronises); a failed verification repairs the guesses
+        if (!ok) attempt_walk = 1;                      // ... and the pass is repeated by the walker, which starts from them
         CK(cudaMemcpyAsync(hc, counters.p, 16, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         bool fits = hc[0] <= cand_cap && hc[3] <= cand_cap && hc[1] <= un_cap && hc[2] <= sw_cap;
