@@ -329,7 +329,7 @@ def main():
         except Exception:
             pass
         peak = peaks.get("hbm_gbs", 6650.0)
-        full_pass = {"guess_starts", "walk_count", "clip_walk", "decode_walk"}
+        full_pass = {"guess_starts", "walk_count", "clip_walk", "decode_walk", "clip_stream", "decode_stream"}
         kern = {k: v for k, v in prof.items() if v["launches"] > 0 and "wall" not in k}
         dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
         roofline = None

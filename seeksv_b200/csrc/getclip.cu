@@ -258,41 +258,58 @@ __global__ void __launch_bounds__(STREAM_THREADS)
         TileWin w{S.stage[s], d + tile_abs, (uint32_t)min((uint64_t)(TILE + HALO), padded - tile_abs)};
         index_tile(S, w, t, n, first, n_ref, d);
         const uint32_t n_rec = S.n_rec;
-        for (uint32_t k = tid; k < n_rec; k += STREAM_THREADS) {
-            const uint32_t off = S.rec_off[k];
-            const Core c = w.core(off);
-            const uint64_t o = tile_abs + off;
-            if (c.flag & (F_UNMAP | F_MUNMAP)) {  // clip_reads.h:415 - the unmapped branch wins (quirk Q2)
-                uint32_t slot = atomicAdd(&out.counters[1], 1u);
-                if (slot < out.un_cap) out.unmapped[slot] = o;
-                continue;
-            }
-            unsigned long long key = (unsigned long long)k << 32 | (uint32_t)c.tid;
-            atomicMin(&S.first_mb, key);
-            atomicMax(&S.last_mb, key);
-            // quirk Q1: tid of the previous mapped-branch record (normally the record just before this one)
-            int32_t prev_tid = NO_TID;
-            for (uint32_t j = k; j > 0;) {
-                --j;
-                uint32_t oj = S.rec_off[j];
-                if (!((w.u32(oj + 16) >> 16) & (F_UNMAP | F_MUNMAP))) {
-                    prev_tid = (int32_t)w.u32(oj + 4);
-                    break;
+        for (uint32_t kb = 0; kb < n_rec; kb += STREAM_THREADS) {
+            const uint32_t k = kb + tid;
+            unsigned long long kmin = ~0ull, kmax = 0ull;  // (k << 32 | tid) of this lane's record if it is mapped-branch
+            bool have = false;
+            if (k < n_rec) {
+                const uint32_t off = S.rec_off[k];
+                const Core c = w.core(off);
+                const uint64_t o = tile_abs + off;
+                if (c.flag & (F_UNMAP | F_MUNMAP)) {  // clip_reads.h:415 - the unmapped branch wins (quirk Q2)
+                    uint32_t slot = atomicAdd(&out.counters[1], 1u);
+                    if (slot < out.un_cap) out.unmapped[slot] = o;
+                } else {
+                    have = true;
+                    kmin = kmax = (unsigned long long)k << 32 | (uint32_t)c.tid;
+                    // quirk Q1: tid of the previous mapped-branch record (normally the record just before this one)
+                    int32_t prev_tid = NO_TID;
+                    for (uint32_t j = k; j > 0;) {
+                        --j;
+                        uint32_t oj = S.rec_off[j];
+                        if (!((w.u32(oj + 16) >> 16) & (F_UNMAP | F_MUNMAP))) {
+                            prev_tid = (int32_t)w.u32(oj + 4);
+                            break;
+                        }
+                    }
+                    if (prev_tid == NO_TID) {
+                        // first mapped-branch record of the tile: clip_first looks into earlier tiles
+                    } else if (c.tid != prev_tid) {  // flush + drop (clip_reads.h:423-438)
+                        uint32_t slot = atomicAdd(&out.counters[2], 1u);
+                        if (slot < out.sw_cap) out.switches[slot] = o;
+                    } else if (c.n_cigar != 0 && (int32_t)c.mapq >= min_mapq && !(c.flag & F_DUP)) {
+                        // cheap part of GetSClipReads (clip_reads.cpp:116-118,122) from the staged bytes
+                        uint32_t cg = off + 36 + c.l_qname;
+                        uint32_t op1 = w.u32(cg) & 15, op2 = w.u32(cg + 4 * (c.n_cigar - 1)) & 15;
+                        if (op1 != OP_H && op2 != OP_H && (op1 == OP_S || op2 == OP_S)) {
+                            uint32_t slot = atomicAdd(&out.counters[3], 1u);
+                            if (slot < out.clipped_cap) out.clipped[slot] = o;
+                        }
+                    }
                 }
             }
-            if (prev_tid == NO_TID) continue;  // first mapped-branch record of the tile: clip_first looks into earlier tiles
-            if (c.tid != prev_tid) {  // flush + drop (clip_reads.h:423-438)
-                uint32_t slot = atomicAdd(&out.counters[2], 1u);
-                if (slot < out.sw_cap) out.switches[slot] = o;
-                continue;
+            // first / last mapped-branch record of the tile: warp reduction, one shared-memory atomic per warp
+            if (__any_sync(0xffffffffu, have)) {
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, sft));
+                    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, sft));
+                }
+                if ((tid & 31) == 0) {
+                    atomicMin(&S.first_mb, kmin);
+                    atomicMax(&S.last_mb, kmax);
+                }
             }
-            // cheap part of GetSClipReads (clip_reads.cpp:116-118,122) from the staged bytes
-            if (c.n_cigar == 0 || (int32_t)c.mapq < min_mapq || (c.flag & F_DUP)) continue;
-            uint32_t cg = off + 36 + c.l_qname;
-            uint32_t op1 = w.u32(cg) & 15, op2 = w.u32(cg + 4 * (c.n_cigar - 1)) & 15;
-            if (op1 == OP_H || op2 == OP_H || (op1 != OP_S && op2 != OP_S)) continue;
-            uint32_t slot = atomicAdd(&out.counters[3], 1u);
-            if (slot < out.clipped_cap) out.clipped[slot] = o;
         }
         __syncthreads();
         if (tid == 0) {

@@ -7,6 +7,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
+#include "stream.cuh"
 
 static inline unsigned nblk(uint64_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
 
@@ -87,6 +88,134 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// The getsv full pass, streaming form (stream.cuh). Each CTA stages a tile with TMA, indexes it in shared memory, gets the
+// global index of the tile's first record from a single-pass chained prefix over the tile record counts (decoupled
+// look-back: a tile publishes its count, then sums its predecessors' counts until it meets a published running total), and
+// writes one 48-byte row per thread - consecutive threads, consecutive rows: fully coalesced stores.
+static constexpr uint64_t ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+
+__global__ void __launch_bounds__(STREAM_THREADS)
+    decode_stream(const uint8_t *__restrict__ d, uint64_t n, uint64_t padded, uint64_t first, int32_t n_ref, uint64_t n_tiles,
+                  uint64_t *__restrict__ guess, uint32_t *__restrict__ count, uint64_t *__restrict__ exit_, uint64_t *__restrict__ base_out,
+                  unsigned long long *__restrict__ state, LeanRecords L, uint64_t row_cap, int32_t stats_mapq,
+                  uint32_t *__restrict__ q_cnt, uint64_t *__restrict__ q_sum, uint64_t *__restrict__ q_sq,
+                  int32_t *__restrict__ scal /* max_span, unsorted, q_max, overflow */)
+{
+    __shared__ StreamShared S;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&S.full[s], 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < STAGES; ++s) {
+            uint64_t t = blockIdx.x + (uint64_t)s * gridDim.x;
+            if (t < n_tiles) issue_tile(S, s, d, padded, t);
+        }
+    uint32_t it = 0;
+    int32_t span = 0, qmax = 0;
+    uint32_t unsorted = 0;
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&S.full[s], (it / STAGES) & 1);
+        const uint64_t tile_abs = t << TILE_LOG2;
+        TileWin w{S.stage[s], d + tile_abs, (uint32_t)min((uint64_t)(TILE + HALO), padded - tile_abs)};
+        index_tile(S, w, t, n, first, n_ref, d);
+        const uint32_t n_rec = S.n_rec;
+        if (tid == 0) {
+            uint64_t base = 0;
+            if (t > 0) {
+                atomicExch(&state[t], ST_AGG | n_rec);
+                uint64_t p = t - 1, sum = 0;
+                for (;;) {
+                    unsigned long long v = *(volatile unsigned long long *)&state[p];
+                    if ((v >> 62) == 0) continue;  // predecessor not there yet
+                    sum += v & ST_MASK;
+                    if ((v >> 62) == 2) break;
+                    --p;
+                }
+                base = sum;
+            }
+            atomicExch(&state[t], ST_INC | (base + n_rec));
+            S.base = base;
+            S.red[0] = S.red[1] = S.red[2] = 0;
+        }
+        __syncthreads();
+        const uint64_t base = S.base;
+        for (uint32_t kb = 0; kb < n_rec; kb += STREAM_THREADS) {
+            const uint32_t k = kb + tid;
+            uint32_t qc = 0;
+            uint64_t qs = 0, qq = 0;
+            if (k < n_rec) {
+                const uint32_t off = S.rec_off[k];
+                const Core c = w.core(off);
+                const uint32_t cg = off + 36 + c.l_qname;
+                int32_t rend = c.pos;
+                uint32_t fq = c.flag | (c.mapq << 16);
+                if (c.n_cigar == 0) fq |= FLAGQ_NOCIGAR;
+                for (uint32_t j = 0; j < c.n_cigar; ++j) {
+                    uint32_t x = w.u32(cg + 4 * j), op = x & 15;
+                    // bam_calend of the linked libbam: M, D, N only ('=' and 'X' do not advance; probed)
+                    if (op == OP_M || op == OP_D || op == OP_N) rend += (int32_t)(x >> 4);
+                    if ((j == 0 || j + 1 == c.n_cigar) && op == OP_H) fq |= FLAGQ_HARDCLIP;  // IsHardClip, clip_reads.cpp:247
+                }
+                const uint64_t o = tile_abs + off, row = base + k;
+                if (row < row_cap) {
+                    uint4 *r = (uint4 *)&L.rec[row];
+                    r[0] = make_uint4((uint32_t)c.tid, (uint32_t)c.pos, (uint32_t)rend, fq);
+                    r[1] = make_uint4((uint32_t)c.l_qseq, (uint32_t)c.mtid, (uint32_t)c.mpos, (uint32_t)c.isize);
+                    r[2] = make_uint4((uint32_t)o, (uint32_t)(o >> 32), 0u, 0u);
+                } else
+                    scal[3] = 1;
+                span = max(span, max(rend - c.pos, 1));
+                if (k > 0) {  // coordinate order inside the tile (tile boundaries: boundary_order)
+                    uint32_t op_ = S.rec_off[k - 1];
+                    uint32_t pt = w.u32(op_ + 4);
+                    int32_t pp = (int32_t)w.u32(op_ + 8);
+                    if (pt > (uint32_t)c.tid || (pt == (uint32_t)c.tid && pp > c.pos)) unsorted = 1;  // tid -1 sorts last
+                }
+                if (stats_mapq >= 0 && insert_qualifies(fq, c.isize, stats_mapq)) {
+                    qc = 1, qs = (uint64_t)c.isize, qq = (uint64_t)c.isize * (uint64_t)c.isize;
+                    qmax = max(qmax, c.isize);
+                }
+            }
+            if (stats_mapq >= 0 && __any_sync(0xffffffffu, qc != 0)) {
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    qc += __shfl_xor_sync(0xffffffffu, qc, sft);
+                    qs += __shfl_xor_sync(0xffffffffu, qs, sft);
+                    qq += __shfl_xor_sync(0xffffffffu, qq, sft);
+                }
+                if ((tid & 31) == 0) {
+                    atomicAdd(&S.red[0], (unsigned long long)qc);
+                    atomicAdd(&S.red[1], (unsigned long long)qs);
+                    atomicAdd(&S.red[2], (unsigned long long)qq);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            count[t] = n_rec, exit_[t] = S.exit_, guess[t] = S.entry, base_out[t] = base;
+            q_cnt[t] = (uint32_t)S.red[0], q_sum[t] = S.red[1], q_sq[t] = S.red[2];
+            uint64_t tn = t + (uint64_t)STAGES * gridDim.x;
+            if (tn < n_tiles) {
+                fence_proxy_async();
+                issue_tile(S, s, d, padded, tn);
+            }
+        }
+        __syncthreads();
+    }
+    span = (int32_t)warp_max((uint32_t)span);
+    qmax = (int32_t)warp_max((uint32_t)qmax);
+    unsorted = warp_max(unsorted);
+    if ((tid & 31) == 0) {
+        if (span > 0) atomicMax(&scal[0], span);
+        if (unsorted) atomicOr((uint32_t *)&scal[1], 1u);
+        if (qmax > 0) atomicMax(&scal[2], qmax);
+    }
+}
+
 // coordinate order across chunk boundaries: the last record of a chunk against the first of the next
 __global__ void boundary_order(uint64_t n_chunks, const uint64_t *__restrict__ base, LeanRecords L, uint32_t *__restrict__ unsorted)
 {
@@ -98,33 +227,91 @@ __global__ void boundary_order(uint64_t n_chunks, const uint64_t *__restrict__ b
     if (t0 > t1 || (t0 == t1 && L.rec[i - 1].pos > L.rec[i].pos)) atomicOr(unsorted, 1u);
 }
 
+static int free_lean(svb_ctx *ctx, svb_bam *bam)
+{
+    cudaStream_t s = ctx->stream;
+    void *p[4] = {bam->lean.rec, bam->d_q_cnt, bam->d_q_sum, bam->d_q_sq};
+    for (void *x : p)
+        if (x) cudaFreeAsync(x, s);
+    bam->lean.rec = nullptr, bam->d_q_cnt = nullptr, bam->d_q_sum = nullptr, bam->d_q_sq = nullptr;
+    return 0;
+}
+
 int decode_records(svb_ctx *ctx, svb_bam *bam, int32_t stats_mapq)
 {
     if (bam->lean_ready) return 0;
-    CKR(ensure_counts(ctx, bam));
     cudaStream_t s = ctx->stream;
-    uint64_t n = bam->n_rec, n_chunks = bam->n_chunks;
-    if (n >= (1ull << 32)) return svb_fail(ctx, SVB_ERR_ARG, "more than 2^32 records in one shard");
+    const uint64_t n_chunks = bam->n_chunks, stream_bytes = bam->nbytes - bam->first;
     LeanRecords &L = bam->lean;
-    size_t cnt = n ? n : 1;
-    CK(cudaMallocAsync((void **)&L.rec, cnt * sizeof(LeanRec), s));
-    CK(cudaMallocAsync((void **)&bam->d_q_cnt, n_chunks * 4, s));
-    CK(cudaMallocAsync((void **)&bam->d_q_sum, n_chunks * 8, s));
-    CK(cudaMallocAsync((void **)&bam->d_q_sq, n_chunks * 8, s));
-    L.n = n;
     DevBuf<int32_t> scal;
     CK(scal.alloc(4, s));
-    CK(cudaMemsetAsync(scal.p, 0, 16, s));
-    {
-        ProfScope ps(ctx, "decode_walk", (double)bam->rec_bytes);
-        decode_walk<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->chunk_log2, bam->d_guess, bam->d_base, L,
-                                                      stats_mapq,
-                                                      bam->d_q_cnt, bam->d_q_sum, bam->d_q_sq, scal.p);
-        boundary_order<<<nblk(n_chunks, 256), 256, 0, s>>>(n_chunks, bam->d_base, L, (uint32_t *)scal.p + 1);
+    int32_t h[4] = {0, 0, 0, 0};
+    bool done = false;
+    if (stream_mode(bam)) {
+        // one streaming pass: rows are allocated for "a record is at least 96 bytes" (a 50-base read is ~120), the exact
+        // count comes out of the pass; shorter records overflow the estimate and the walker path below redoes the pass
+        uint64_t cap = stream_bytes / 96 + 1024;
+        CK(cudaMallocAsync((void **)&L.rec, cap * sizeof(LeanRec), s));
+        CK(cudaMallocAsync((void **)&bam->d_q_cnt, n_chunks * 4, s));
+        CK(cudaMallocAsync((void **)&bam->d_q_sum, n_chunks * 8, s));
+        CK(cudaMallocAsync((void **)&bam->d_q_sq, n_chunks * 8, s));
+        DevBuf<unsigned long long> state;
+        DevBuf<uint64_t> exit_;
+        CK(state.alloc(n_chunks, s));
+        CK(exit_.alloc(n_chunks, s));
+        CK(cudaMemsetAsync(state.p, 0, n_chunks * 8, s));
+        CK(cudaMemsetAsync(scal.p, 0, 16, s));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_stream, STREAM_THREADS, 0));
+        unsigned grid = (unsigned)std::min<uint64_t>(n_chunks, (uint64_t)std::max(1, per_sm) * ctx->sm_count);
+        {
+            ProfScope ps(ctx, "decode_stream", (double)stream_bytes);
+            decode_stream<<<grid, STREAM_THREADS, 0, s>>>(bam->d_data, bam->nbytes, (bam->nbytes + 15) & ~15ull, bam->first, bam->n_ref,
+                                                          n_chunks, bam->d_guess, bam->d_count, exit_.p, bam->d_base, state.p, L, cap,
+                                                          stats_mapq, bam->d_q_cnt, bam->d_q_sum, bam->d_q_sq, scal.p);
+        }
+        bam->guessed = true;
+        int ok = 0;
+        CKR(verify_or_repair(ctx, bam, exit_.p, &ok));
+        CK(cudaMemcpyAsync(h, scal.p, 16, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (ok && !h[3]) {
+            CKR(finish_counts(ctx, bam, exit_.p));  // prefix of the per-tile counts, totals, end-of-stream check
+            L.n = bam->n_rec;
+            if (L.n >= (1ull << 32)) return svb_fail(ctx, SVB_ERR_ARG, "more than 2^32 records in one shard");
+            done = true;
+        } else
+            free_lean(ctx, bam);
     }
-    int32_t h[4];
-    CK(cudaMemcpyAsync(h, scal.p, 16, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    if (!done) {
+        CKR(ensure_counts(ctx, bam));
+        uint64_t n = bam->n_rec;
+        if (n >= (1ull << 32)) return svb_fail(ctx, SVB_ERR_ARG, "more than 2^32 records in one shard");
+        size_t cnt = n ? n : 1;
+        CK(cudaMallocAsync((void **)&L.rec, cnt * sizeof(LeanRec), s));
+        CK(cudaMallocAsync((void **)&bam->d_q_cnt, n_chunks * 4, s));
+        CK(cudaMallocAsync((void **)&bam->d_q_sum, n_chunks * 8, s));
+        CK(cudaMallocAsync((void **)&bam->d_q_sq, n_chunks * 8, s));
+        L.n = n;
+        CK(cudaMemsetAsync(scal.p, 0, 16, s));
+        {
+            ProfScope ps(ctx, "decode_walk", (double)bam->rec_bytes);
+            decode_walk<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->chunk_log2, bam->d_guess, bam->d_base, L,
+                                                          stats_mapq, bam->d_q_cnt, bam->d_q_sum, bam->d_q_sq, scal.p);
+        }
+        CK(cudaMemcpyAsync(h, scal.p, 16, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    {
+        DevBuf<uint32_t> uns;
+        CK(uns.alloc(1, s));
+        CK(cudaMemsetAsync(uns.p, 0, 4, s));
+        boundary_order<<<nblk(n_chunks, 256), 256, 0, s>>>(n_chunks, bam->d_base, L, uns.p);
+        uint32_t hu = 0;
+        CK(cudaMemcpyAsync(&hu, uns.p, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (hu) h[1] = 1;
+    }
     CK(cudaGetLastError());
     bam->max_span = h[0];
     bam->sorted = h[1] ? 0 : 1;
