@@ -185,9 +185,12 @@ int index_records(svb_ctx *ctx, svb_bam *bam)
 
 bool stream_mode(const svb_bam *bam)
 {
+    // Measured on C2 (profiles/r1_summary.md): the TMA-staged streaming passes are correct but 4-5x slower than the chunk
+    // walkers (clip_stream 1.85 ms vs clip_walk 0.50 ms) - per tile, finding the first record and walking the chain is
+    // serial work for one lane while the CTA's other 127 threads wait, and only ~6 tiles fit in an SM's shared memory at a
+    // time; the walkers keep ~1000 chains in flight per SM. The walkers are therefore the default.
     const char *e = getenv("SEEKSV_B200_PASS");
-    if (e && !strcmp(e, "walk")) return false;
-    return bam->chunk_log2 == 14;
+    return e && !strcmp(e, "stream") && bam->chunk_log2 == 14;
 }
 
 int ensure_guess(svb_ctx *ctx, svb_bam *bam)

@@ -261,8 +261,8 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t v)
 static constexpr uint64_t BAD_OFFSET = ~0ull;
 int index_records(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu: chunk arrays (+ guesses for the walkers)
 int ensure_guess(svb_ctx *ctx, svb_bam *bam);                        // bam_index.cu: guess_starts once
-// The full passes run as TMA-staged streaming kernels (stream.cuh) when the chunk size equals the tile size; the chunk
-// walkers are the fallback after a failed verification and can be forced with SEEKSV_B200_PASS=walk.
+// The full passes have two forms: chunk walkers (default) and TMA-staged streaming kernels (stream.cuh,
+// SEEKSV_B200_PASS=stream; same results, slower on this workload - see stream_mode()).
 bool stream_mode(const svb_bam *bam);
 int ensure_counts(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu: verified chain + counts + prefix
 int finish_counts(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit);  // prefix + totals from valid per-chunk counts

@@ -278,3 +278,25 @@ def test_depth_accounting_closed_form_equals_literal_walk(tmp_path, monkeypatch)
             assert r.returncode == 0, r.stderr
             outs[(mode, flank)] = read_text(out) + r.stdout
         assert outs[("closed", flank)] == outs[("literal", flank)], flank
+
+
+@pytest.mark.parametrize("mode", ["stream", "walk12"])
+def test_alternative_full_pass_forms_give_identical_results(mode, tmp_path, monkeypatch):
+    """the TMA-staged streaming passes (SEEKSV_B200_PASS=stream) and a different walker chunk size produce the same bytes"""
+    if mode == "stream":
+        monkeypatch.setenv("SEEKSV_B200_PASS", "stream")
+    else:
+        monkeypatch.setenv("SEEKSV_B200_CHUNK_LOG2", "12")
+    for d, s in (("micro", "tumor"), ("example", "cancer"), ("kat", "quirks")):
+        pre = str(tmp_path / (mode + s))
+        r = subprocess.run([_cli(), "getclip", "-o", pre, _bam(d, s)], capture_output=True, text=True, env=dict(os.environ))
+        assert r.returncode == 0, r.stderr
+        assert _zcat(pre + ".clip.gz") == read_text(os.path.join(GOLDEN, d, s + ".clip.txt"))
+        assert _zcat(pre + ".unmapped_1.fq.gz") == read_text(os.path.join(GOLDEN, d, s + ".unmapped_1.fq.txt"))
+        if d == "kat":
+            continue
+        out = str(tmp_path / (mode + s + ".sv"))
+        r = subprocess.run([_cli(), "getsv", os.path.join(GOLDEN, d, s + ".clip.sam"), _bam(d, s), pre + ".clip.gz", out, str(tmp_path / "unm")],
+                           capture_output=True, text=True, env=dict(os.environ))
+        assert r.returncode == 0, r.stderr
+        assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".sv"))
