@@ -171,6 +171,11 @@ def reference_arm(args):
         "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch on the C2 stream, from the committed ncu --set full capture
+# (profiles/r1_ncu_full_walkers_raw.csv); the workload is seeded, so the byte counts are those of this run's input.
+NCU_TRAFFIC = {"decode_walk": 2.034737e9 + 487.891968e6, "clip_walk": 1.901033e9 + 11.937792e6, "walk_count": 1.207181e9 + 7.521792e6}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -339,7 +344,9 @@ def main():
             avg_ms = v["ms"] / v["launches"]
             ach = per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
             roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                        "traffic": NCU_TRAFFIC.get(dom) if args.genome_len == C2_LEN else None,
+                        "traffic_source": "profiles/r1_ncu_full_walkers_raw.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
+                        "peak_source": "measured" if peaks else "fallback",
                         "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
                         "kernels_ms_per_step": {k: round(x["ms"] / args.steps, 4) for k, x in sorted(kern.items())}}
         line = {

@@ -43,6 +43,8 @@ extern "C" int svb_ctx_create(int device, svb_ctx **out)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < svb_ctx::N_AUX; ++i) CK(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
     {
         // The full-pass kernels read ~40-100 bytes out of every ~300-byte record: with the default L2 fetch granularity a
         // touched 32-byte sector drags its whole 128-byte line out of HBM. 32 B keeps DRAM traffic at what is used.
@@ -66,6 +68,9 @@ extern "C" void svb_ctx_destroy(svb_ctx *ctx)
     ctx->prof_flush();
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (cudaStream_t a : ctx->aux)
+        if (a) cudaStreamDestroy(a);
     delete ctx;
 }
 
@@ -295,23 +300,53 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
         }
         CK(cudaStreamSynchronize(ctx->stream));
     } else {
-        {
-            WallScope ws(ctx, "h2d_compressed(wall)", (double)file_bytes);
-            CK(cudaMemsetAsync(d_file.p + file_bytes, 0, 256, ctx->stream));
-            for (uint64_t o = 0; o < file_bytes; o += SLAB) {
-                uint64_t n = std::min(SLAB, file_bytes - o);
-                CK(cudaEventSynchronize(done[slab]));
-                parallel_copy(pinned[slab], (const uint8_t *)h_file + o, n, n_threads);
-                CK(cudaMemcpyAsync(d_file.p + o, pinned[slab], n, cudaMemcpyHostToDevice, ctx->stream));
-                CK(cudaEventRecord(done[slab], ctx->stream));
-                slab ^= 1;
-            }
-        }
+        // Pipelined: the compressed image goes up slab by slab on the copy stream; as soon as a slab has landed, the
+        // BGZF blocks it completes are inflated on one of the side streams, so the upload (page cache -> pinned -> HBM)
+        // and the inflate kernel overlap and the load costs max(upload, inflate) instead of their sum.
+        WallScope ws(ctx, "h2d_compressed+inflate(wall)", (double)total);
         static_assert(sizeof(BgzfBlock) == 24, "BgzfBlock must match the device-side block descriptor");
         DevBuf<BgzfBlock> d_blocks;
+        DevBuf<uint32_t> d_err;
         CK(d_blocks.alloc(blocks.size(), ctx->stream));
+        CK(d_err.alloc(1, ctx->stream));
         CK(cudaMemcpyAsync(d_blocks.p, blocks.data(), blocks.size() * sizeof(BgzfBlock), cudaMemcpyHostToDevice, ctx->stream));
-        int rc = inflate_on_device(ctx, d_file.p, d_blocks.p, (uint32_t)blocks.size(), b->d_owned, (double)total);
+        CK(cudaMemsetAsync(d_err.p, 0, 4, ctx->stream));
+        CK(cudaMemsetAsync(d_file.p + file_bytes, 0, 256, ctx->stream));
+        cudaEvent_t ready;
+        CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        CK(cudaEventRecord(ready, ctx->stream));  // allocations and the block table are ordered before the side streams
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+        for (cudaStream_t a : ctx->aux) CK(cudaStreamWaitEvent(a, ready, 0));
+        size_t next_block = 0;
+        int lane = 0, rc = 0;
+        for (uint64_t o = 0; o < file_bytes && rc == 0; o += SLAB) {
+            uint64_t n = std::min(SLAB, file_bytes - o);
+            CK(cudaEventSynchronize(done[slab]));
+            parallel_copy(pinned[slab], (const uint8_t *)h_file + o, n, n_threads);
+            CK(cudaMemcpyAsync(d_file.p + o, pinned[slab], n, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(done[slab], ctx->copy_stream));
+            size_t b1 = next_block;
+            if (o + n >= file_bytes) b1 = blocks.size();
+            else
+                while (b1 < blocks.size() && blocks[b1].coff + blocks[b1].clen <= o + n) ++b1;
+            if (b1 > next_block) {
+                cudaStream_t a = ctx->aux[lane];
+                lane = (lane + 1) % svb_ctx::N_AUX;
+                CK(cudaStreamWaitEvent(a, done[slab], 0));
+                rc = inflate_launch(a, d_file.p, d_blocks.p + next_block, (uint32_t)(b1 - next_block), b->d_owned, d_err.p);
+                next_block = b1;
+            }
+            slab ^= 1;
+        }
+        for (cudaStream_t a : ctx->aux) {  // join the side streams
+            CK(cudaEventRecord(ready, a));
+            CK(cudaStreamWaitEvent(ctx->stream, ready, 0));
+        }
+        uint32_t h_err = 0;
+        CK(cudaMemcpyAsync(&h_err, d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaEventDestroy(ready);
+        if (rc == 0 && h_err) rc = svb_fail(ctx, SVB_ERR_FORMAT, "BGZF inflate failed (corrupt deflate stream)");
         if (rc != 0) {
             for (int i = 0; i < 2; ++i) ctx->pinned_put((char *)pinned[i], pcap[i]), cudaEventDestroy(done[i]);
             return rc;

@@ -30,6 +30,10 @@ struct svb_ctx {
     int device = 0;
     int sm_count = SVB_SM_COUNT;
     cudaStream_t stream = nullptr;
+    // side streams of the pipelined load (svb_bam_from_bgzf): one for the host->device copies, a few for the inflate
+    // launches that follow each uploaded slab
+    static constexpr int N_AUX = 8;
+    cudaStream_t copy_stream = nullptr, aux[N_AUX] = {};
     std::string err;
     bool prof = false;
     std::map<std::string, ProfEntry> prof_acc;
@@ -270,6 +274,7 @@ int finish_counts(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit);  // prefi
 // (bam->d_guess updated, counts valid) and the walker has to run again
 int verify_or_repair(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit, int *ok);
 int decode_records(svb_ctx *ctx, svb_bam *bam, int32_t stats_mapq = -1);  // getsv.cu
+int inflate_launch(cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err);
 int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out,
                       double out_bytes);                             // inflate.cu
 int inclusive_scan_u32(svb_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n);

@@ -29,35 +29,39 @@ __constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49
 __constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-struct BitReader {  // lives in lane 0's registers
-    const uint8_t *in, *end;
-    uint64_t buf;
-    int cnt;
-    __device__ void init(const uint8_t *p, const uint8_t *e)
+// Bit reader in lane 0's registers: three consecutive 32-bit words of the input and a bit position inside the first;
+// the 32 bits that follow the position are one funnel shift away, consuming bits is one add and - every 32 bits - a
+// register rotation whose load is not needed before another 32 bits have been consumed (latency off the critical path).
+// The file image is padded past its end, so reading ahead is safe.
+struct BitReader {
+    const uint32_t *wp;  // address of `lo`
+    uint32_t lo, hi, nx, bp;
+    __device__ void init(const uint8_t *p)
     {
-        in = p, end = e, buf = 0, cnt = 0;
-        while (((uintptr_t)in & 3) && cnt <= 56) {  // byte loads until the pointer is word aligned
-            buf |= (uint64_t)(*in++) << cnt;
-            cnt += 8;
+        wp = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
+        bp = (uint32_t)((uintptr_t)p & 3) * 8;
+        lo = __ldg(wp), hi = __ldg(wp + 1), nx = __ldg(wp + 2);
+    }
+    __device__ __forceinline__ uint32_t window() const { return __funnelshift_r(lo, hi, bp); }  // next 32 bits
+    __device__ __forceinline__ void consume(uint32_t n)  // n <= 32
+    {
+        bp += n;
+        if (bp >= 32) {
+            bp -= 32;
+            lo = hi, hi = nx;
+            ++wp;
+            nx = __ldg(wp + 2);
         }
     }
-    __device__ __forceinline__ void refill()  // keeps at least 32 valid bits (the file image is padded past its end)
-    {
-        if (cnt < 32) {
-            buf |= (uint64_t)__ldg((const uint32_t *)in) << cnt;
-            in += 4;
-            cnt += 32;
-        }
-    }
-    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1); }
-    __device__ __forceinline__ void skip(int n) { buf >>= n, cnt -= n; }
-    __device__ __forceinline__ uint32_t bits(int n)
+    __device__ __forceinline__ uint32_t peek(uint32_t n) const { return window() & ((1u << n) - 1); }  // n < 32
+    __device__ __forceinline__ uint32_t bits(uint32_t n)
     {
         uint32_t v = peek(n);
-        skip(n);
+        consume(n);
         return v;
     }
-    __device__ void align_byte() { skip(cnt & 7); }
+    __device__ void align_byte() { consume((8 - (bp & 7)) & 7); }
+    __device__ const uint8_t *byte_ptr() const { return (const uint8_t *)wp + (bp >> 3); }  // after align_byte()
 };
 
 // Build the decode tables of one alphabet from its code lengths (canonical Huffman, RFC 1951 3.2.2).
@@ -100,14 +104,19 @@ __device__ void build_table(const uint8_t *lens, int n, uint16_t *fast, int fast
     __syncwarp();
 }
 
-// canonical bit-by-bit decode for codes longer than the lookup width
+// canonical decode for codes longer than the lookup width: walks the 15 possible lengths on the 32-bit window
 __device__ int slow_decode(BitReader &br, const uint16_t *count, const uint16_t *sym_sorted)
 {
+    uint32_t w = br.window();
     int code = 0, first = 0, index = 0;
     for (int len = 1; len <= 15; ++len) {
-        code |= (int)br.bits(1);
+        code |= (int)(w & 1);
+        w >>= 1;
         int c = count[len];
-        if (code - c < first) return sym_sorted[index + (code - first)];
+        if (code - c < first) {
+            br.consume(len);
+            return sym_sorted[index + (code - first)];
+        }
         index += c, first += c;
         first <<= 1, code <<= 1;
     }
@@ -117,10 +126,10 @@ __device__ int slow_decode(BitReader &br, const uint16_t *count, const uint16_t 
 __device__ __forceinline__ int decode_sym(BitReader &br, const uint16_t *fast, int fast_bits, const uint16_t *count,
                                           const uint16_t *sym_sorted)
 {
-    uint16_t e = fast[br.peek(fast_bits)];
+    uint32_t e = fast[br.window() & ((1u << fast_bits) - 1)];
     if (e) {
-        br.skip(e >> 9);
-        return e & 511;
+        br.consume(e >> 9);
+        return (int)(e & 511);
     }
     return slow_decode(br, count, sym_sorted);
 }
@@ -144,15 +153,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     const InflateBlock blk = blocks[b];
     uint8_t *dst = out + blk.uoff;
     BitReader br;
-    if (lane == 0) br.init(file + blk.coff, file + blk.coff + blk.clen);
+    if (lane == 0) br.init(file + blk.coff);
     uint32_t pos = 0;
     bool bad = false;
     for (;;) {
         uint32_t hdr = 0;
-        if (lane == 0) {
-            br.refill();
-            hdr = br.bits(3);
-        }
+        if (lane == 0) hdr = br.bits(3);
         hdr = __shfl_sync(0xffffffffu, hdr, 0);
         const uint32_t final_block = hdr & 1, type = hdr >> 1;
         if (type == 0) {  // stored
@@ -160,13 +166,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
             const uint8_t *src = nullptr;
             if (lane == 0) {
                 br.align_byte();
-                br.refill();
                 len = br.bits(16);
-                br.refill();
-                br.skip(16);  // NLEN
-                // rewind the word-wise reader to the byte position of the payload
-                src = br.in - (br.cnt >> 3);
-                br.init(src + len, br.end);
+                br.consume(16);  // NLEN
+                src = br.byte_ptr();
+                br.init(src + len);
             }
             len = __shfl_sync(0xffffffffu, len, 0);
             src = (const uint8_t *)__shfl_sync(0xffffffffu, (unsigned long long)src, 0);
@@ -184,16 +187,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
             } else {  // dynamic: code lengths are themselves Huffman coded (3.2.7), decoded serially by lane 0
                 int ok = 1;
                 if (lane == 0) {
-                    br.refill();
                     n_lit = (int)br.bits(5) + 257;
                     n_dist = (int)br.bits(5) + 1;
                     int n_cl = (int)br.bits(4) + 4;
                     uint8_t cl[19];
                     for (int i = 0; i < 19; ++i) cl[i] = 0;
-                    for (int i = 0; i < n_cl; ++i) {
-                        br.refill();
-                        cl[c_cl_order[i]] = (uint8_t)br.bits(3);
-                    }
+                    for (int i = 0; i < n_cl; ++i) cl[c_cl_order[i]] = (uint8_t)br.bits(3);
                     // 7-bit lookup for the code-length alphabet
                     for (int i = 0; i < 128; ++i) T.cl_fast[i] = 0;
                     uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, next[8];
@@ -214,13 +213,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
                     int i = 0, total = n_lit + n_dist;
                     if (n_lit > 286 || n_dist > 30) ok = 0;
                     while (ok && i < total) {
-                        br.refill();
                         uint8_t e = T.cl_fast[br.peek(7)];
                         if (!e) {
                             ok = 0;
                             break;
                         }
-                        br.skip(e >> 5);
+                        br.consume(e >> 5);
                         int s = e & 31;
                         if (s < 16) T.lens[i++] = (uint8_t)s;
                         else {
@@ -268,18 +266,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
                 int sym = 0;
                 uint32_t len = 0, dist = 0;
                 if (lane == 0) {
-                    br.refill();
                     sym = decode_sym(br, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
                     // runs of literals stay on lane 0: no warp-wide exchange until a match or the end of the block
-                    while (sym >= 0 && sym < 256 && pos < blk.ulen) {
+                    while ((uint32_t)sym < 256u && pos < blk.ulen) {
                         dst[pos++] = (uint8_t)sym;
-                        br.refill();
                         sym = decode_sym(br, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
                     }
                     if (sym > 256 && sym < 286) {
                         int li = sym - 257;
                         len = c_len_base[li] + br.bits(c_len_extra[li]);
-                        br.refill();
                         int ds = decode_sym(br, T.dist_fast, DIST_FAST, T.dist_count, T.dist_sym);
                         if (ds < 0 || ds >= 30) sym = -1;
                         else dist = c_dist_base[ds] + br.bits(c_dist_extra[ds]);
@@ -316,7 +311,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     if ((bad || pos != blk.ulen) && lane == 0) atomicOr(error, 1u);
 }
 
-// host wrapper: file image + block table already on the device
+// asynchronous launch over a range of blocks; *d_err is OR-ed with 1 when a block is corrupt
+int inflate_launch(cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err)
+{
+    if (!n_blocks) return 0;
+    inflate_bgzf<<<(n_blocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, s>>>(d_file, (const InflateBlock *)d_blocks, n_blocks,
+                                                                                             d_out, d_err);
+    return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
+}
+
+// synchronous wrapper: file image + block table already on the device
 int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, double out_bytes)
 {
     cudaStream_t s = ctx->stream;
