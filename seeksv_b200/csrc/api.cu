@@ -271,7 +271,7 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
         WallScope ws(ctx, "stream_alloc(wall)");
         CK(cudaMallocAsync((void **)&b->d_owned, total + 256, ctx->stream));  // pool: reused by the next load in this process
         CK(cudaMemsetAsync(b->d_owned + total, 0, 256, ctx->stream));
-        if (!host_inflate) CK(d_file.alloc(file_bytes + 256, ctx->stream));
+        if (!host_inflate) CK(d_file.alloc(file_bytes + SVB_INFLATE_PAD, ctx->stream));
         for (int i = 0; i < 2; ++i) {
             pinned[i] = (uint8_t *)ctx->pinned_get(SLAB + (64 << 10), &pcap[i]);
             if (!pinned[i]) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate pinned staging");
@@ -311,7 +311,7 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
         CK(d_err.alloc(1, ctx->stream));
         CK(cudaMemcpyAsync(d_blocks.p, blocks.data(), blocks.size() * sizeof(BgzfBlock), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(d_err.p, 0, 4, ctx->stream));
-        CK(cudaMemsetAsync(d_file.p + file_bytes, 0, 256, ctx->stream));
+        CK(cudaMemsetAsync(d_file.p + file_bytes, 0, SVB_INFLATE_PAD, ctx->stream));
         cudaEvent_t ready;
         CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
         CK(cudaEventRecord(ready, ctx->stream));  // allocations and the block table are ordered before the side streams
@@ -322,7 +322,10 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
         for (uint64_t o = 0; o < file_bytes && rc == 0; o += SLAB) {
             uint64_t n = std::min(SLAB, file_bytes - o);
             CK(cudaEventSynchronize(done[slab]));
-            parallel_copy(pinned[slab], (const uint8_t *)h_file + o, n, n_threads);
+            {
+                WallScope wc(ctx, "stage_copy(wall)", (double)n);
+                parallel_copy(pinned[slab], (const uint8_t *)h_file + o, n, n_threads);
+            }
             CK(cudaMemcpyAsync(d_file.p + o, pinned[slab], n, cudaMemcpyHostToDevice, ctx->copy_stream));
             CK(cudaEventRecord(done[slab], ctx->copy_stream));
             size_t b1 = next_block;
@@ -387,10 +390,10 @@ extern "C" int svb_inflate_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_
     if (out_cap < total) return svb_fail(ctx, SVB_ERR_ARG, "svb_inflate_bgzf: output buffer too small");
     DevBuf<uint8_t> d_file, d_out;
     DevBuf<BgzfBlock> d_blocks;
-    CK(d_file.alloc(file_bytes + 256, ctx->stream));
+    CK(d_file.alloc(file_bytes + SVB_INFLATE_PAD, ctx->stream));
     CK(d_out.alloc(total + 256, ctx->stream));
     CK(d_blocks.alloc(blocks.size(), ctx->stream));
-    CK(cudaMemsetAsync(d_file.p + file_bytes, 0, 256, ctx->stream));
+    CK(cudaMemsetAsync(d_file.p + file_bytes, 0, SVB_INFLATE_PAD, ctx->stream));
     CK(cudaMemcpyAsync(d_file.p, h_file, file_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_blocks.p, blocks.data(), blocks.size() * sizeof(BgzfBlock), cudaMemcpyHostToDevice, ctx->stream));
     CKR(inflate_on_device(ctx, d_file.p, d_blocks.p, (uint32_t)blocks.size(), d_out.p, (double)total));

@@ -274,6 +274,8 @@ int finish_counts(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit);  // prefi
 // (bam->d_guess updated, counts valid) and the walker has to run again
 int verify_or_repair(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit, int *ok);
 int decode_records(svb_ctx *ctx, svb_bam *bam, int32_t stats_mapq = -1);  // getsv.cu
+// the inflate kernel reads ahead of the current bit position: the device copy of the file image is padded by this much
+static constexpr uint64_t SVB_INFLATE_PAD = 1024;
 int inflate_launch(cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err);
 int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out,
                       double out_bytes);                             // inflate.cu

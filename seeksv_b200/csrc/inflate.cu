@@ -3,22 +3,31 @@
 // Replaces the bgzf.o / zlib inflate of the reference's libbam (sam/bgzf.h:34-134; `bam_read1` -> `bgzf_read` ->
 // `inflate_block`), which SURVEY.md section 0 measures at ~75 % of getclip's run time on the host. BGZF blocks are
 // independent deflate streams of at most 64 KiB of output, so a whole BAM offers tens of thousands of blocks to
-// decode concurrently. Inside a warp lane 0 owns the bit reader and the Huffman decode (serial by nature); all 32
-// lanes build the decode tables and perform the LZ77 match copies. Decode tables live in shared memory
-// (4.3 KB per warp): a 10-bit single-lookup table for literal/length codes, an 8-bit one for distance codes, and a
-// canonical (count / sorted-symbol) fallback for the rare longer codes.
+// decode concurrently. Inside a warp lane 0 owns the bit reader and the Huffman decode (serial by nature) and turns the
+// bit stream into batches of up to 32 tokens (a literal byte or a (length, distance) match); the 32 lanes then place
+// the batch with one prefix sum and copy in parallel: one token per lane for literals and short matches whose source
+// lies before the batch, the whole warp per token for long or batch-dependent matches (in stream order). BAM data is
+// match-dominated (overlapping reads: ~96 % of the bytes of the C2 workload come from matches of mean length 8), so
+// the per-token warp-wide work is what had to be amortised. Decode tables live in shared memory (7 KB per warp):
+// a 10-bit single-lookup table for literal/length codes and an 8-bit one for distance codes whose entries already
+// carry the base value and the number of extra bits, and a canonical (count / sorted-symbol) fallback for the rare
+// longer codes.
 #include "common.cuh"
 
 namespace {
 
-constexpr int LIT_FAST = 10, DIST_FAST = 8, WARPS_PER_CTA = 8;
+constexpr int LIT_FAST = 10, DIST_FAST = 8, WARPS_PER_CTA = 4, BATCH = 32, COOP_LEN = 16, RING = 128;
 
 struct WarpTables {
-    uint16_t lit_fast[1 << LIT_FAST];    // (len << 9) | symbol, 0 = not a short code
-    uint16_t dist_fast[1 << DIST_FAST];  // (len << 9) | symbol
+    // entries: bits 0-3 code length, 4-7 number of extra bits, bit 8 literal, bit 9 end of block, bit 10 invalid symbol,
+    // bits 16-31 value (literal byte, length base or distance base); 0 = not a short code
+    uint32_t lit_fast[1 << LIT_FAST];
+    uint32_t dist_fast[1 << DIST_FAST];
+    // (ring and tok double as the 288 x u16 scratch for canonical codes while a table is being built)
+    uint32_t ring[RING + 1];  // the next RING words of the compressed stream (refilled by all lanes before each batch)
+    uint32_t tok[BATCH];  // token batch: bit 31 literal (byte in bits 0-7), else length in bits 0-8 and distance in bits 9-24
     uint16_t lit_sym[288], dist_sym[32];  // symbols sorted by (code length, symbol) for the canonical slow path
     uint16_t lit_count[16], dist_count[16];
-    uint16_t code[288];  // canonical code of each symbol while a table is being built
     uint8_t lens[320];   // code lengths: literal/length alphabet followed by the distance alphabet
     uint8_t cl_fast[128];  // code-length alphabet: (len << 5) | symbol, 7-bit lookup
 };
@@ -42,6 +51,12 @@ struct BitReader {
         bp = (uint32_t)((uintptr_t)p & 3) * 8;
         lo = __ldg(wp), hi = __ldg(wp + 1), nx = __ldg(wp + 2);
     }
+    __device__ void init_at(const uint32_t *base, uint32_t bitpos)
+    {
+        wp = base + (bitpos >> 5), bp = bitpos & 31;
+        lo = __ldg(wp), hi = __ldg(wp + 1), nx = __ldg(wp + 2);
+    }
+    __device__ uint32_t bit_offset(const uint32_t *base) const { return (uint32_t)(wp - base) * 32 + bp; }
     __device__ __forceinline__ uint32_t window() const { return __funnelshift_r(lo, hi, bp); }  // next 32 bits
     __device__ __forceinline__ void consume(uint32_t n)  // n <= 32
     {
@@ -64,9 +79,26 @@ struct BitReader {
     __device__ const uint8_t *byte_ptr() const { return (const uint8_t *)wp + (bp >> 3); }  // after align_byte()
 };
 
+constexpr uint32_t E_LITERAL = 1u << 8, E_END = 1u << 9, E_INVALID = 1u << 10;
+
+// table entry of a symbol (without its code length, which the caller ORs into bits 0-3)
+__device__ __forceinline__ uint32_t lit_entry(int s)
+{
+    if (s < 256) return E_LITERAL | (uint32_t)s << 16;
+    if (s == 256) return E_END;
+    if (s > 285) return E_INVALID;
+    return (uint32_t)c_len_extra[s - 257] << 4 | (uint32_t)c_len_base[s - 257] << 16;
+}
+__device__ __forceinline__ uint32_t dist_entry(int s)
+{
+    if (s > 29) return E_INVALID;
+    return (uint32_t)c_dist_extra[s] << 4 | (uint32_t)c_dist_base[s] << 16;
+}
+
 // Build the decode tables of one alphabet from its code lengths (canonical Huffman, RFC 1951 3.2.2).
 // Lane 0 assigns codes serially (<= 288 symbols); all lanes fill the single-lookup table.
-__device__ void build_table(const uint8_t *lens, int n, uint16_t *fast, int fast_bits, uint16_t *sym_sorted, uint16_t *count,
+template <bool IS_LIT>
+__device__ void build_table(const uint8_t *lens, int n, uint32_t *fast, int fast_bits, uint16_t *sym_sorted, uint16_t *count,
                             uint16_t *code, uint32_t lane)
 {
     for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
@@ -97,24 +129,23 @@ __device__ void build_table(const uint8_t *lens, int n, uint16_t *fast, int fast
         int l = lens[s];
         if (l && l <= fast_bits) {
             uint32_t rev = __brev((uint32_t)code[s]) >> (32 - l);  // codes are sent MSB first, bits are read LSB first
-            uint16_t e = (uint16_t)(l << 9 | s);
+            uint32_t e = (uint32_t)l | (IS_LIT ? lit_entry(s) : dist_entry(s));
             for (uint32_t k = rev; k < (1u << fast_bits); k += 1u << l) fast[k] = e;
         }
     }
     __syncwarp();
 }
 
-// canonical decode for codes longer than the lookup width: walks the 15 possible lengths on the 32-bit window
-__device__ int slow_decode(BitReader &br, const uint16_t *count, const uint16_t *sym_sorted)
+// canonical decode for codes longer than the lookup width, on a 32-bit window; returns the symbol and its code length
+__device__ int slow_decode(uint32_t w, const uint16_t *count, const uint16_t *sym_sorted, uint32_t *code_len)
 {
-    uint32_t w = br.window();
     int code = 0, first = 0, index = 0;
     for (int len = 1; len <= 15; ++len) {
         code |= (int)(w & 1);
         w >>= 1;
         int c = count[len];
         if (code - c < first) {
-            br.consume(len);
+            *code_len = (uint32_t)len;
             return sym_sorted[index + (code - first)];
         }
         index += c, first += c;
@@ -123,15 +154,24 @@ __device__ int slow_decode(BitReader &br, const uint16_t *count, const uint16_t 
     return -1;
 }
 
-__device__ __forceinline__ int decode_sym(BitReader &br, const uint16_t *fast, int fast_bits, const uint16_t *count,
-                                          const uint16_t *sym_sorted)
+// one symbol as a table entry (bits 0-3 = its code length); E_INVALID for an undecodable code
+template <bool IS_LIT>
+__device__ __forceinline__ uint32_t decode_entry(uint32_t w, const uint32_t *fast, int fast_bits, const uint16_t *count,
+                                                 const uint16_t *sym_sorted)
 {
-    uint32_t e = fast[br.window() & ((1u << fast_bits) - 1)];
-    if (e) {
-        br.consume(e >> 9);
-        return (int)(e & 511);
-    }
-    return slow_decode(br, count, sym_sorted);
+    uint32_t e = fast[w & ((1u << fast_bits) - 1)];
+    if (e) return e;
+    uint32_t l = 0;
+    int s = slow_decode(w, count, sym_sorted, &l);
+    if (s < 0) return E_INVALID;
+    return l | (IS_LIT ? lit_entry(s) : dist_entry(s));
+}
+
+// 32 bits of the compressed stream at bit position bp, from the shared-memory ring (ring[RING] mirrors ring[0])
+__device__ __forceinline__ uint32_t ring_window(const uint32_t *ring, uint32_t bp)
+{
+    const uint32_t *p = ring + ((bp >> 5) & (RING - 1));
+    return __funnelshift_r(p[0], p[1], bp);
 }
 
 }  // namespace
@@ -152,6 +192,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     WarpTables &T = tables[wid];
     const InflateBlock blk = blocks[b];
     uint8_t *dst = out + blk.uoff;
+    const uint32_t *wbase = (const uint32_t *)((uintptr_t)(file + blk.coff) & ~(uintptr_t)3);  // bit positions count from here
     BitReader br;
     if (lane == 0) br.init(file + blk.coff);
     uint32_t pos = 0;
@@ -259,48 +300,103 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
                 }
             }
             __syncwarp();
-            build_table(T.lens, type == 1 ? 288 : n_lit, T.lit_fast, LIT_FAST, T.lit_sym, T.lit_count, T.code, lane);
-            build_table(T.lens + 288, n_dist, T.dist_fast, DIST_FAST, T.dist_sym, T.dist_count, T.code, lane);
-            // symbol loop: lane 0 decodes, the warp copies matches
+            build_table<true>(T.lens, type == 1 ? 288 : n_lit, T.lit_fast, LIT_FAST, T.lit_sym, T.lit_count, (uint16_t *)T.ring, lane);
+            build_table<false>(T.lens + 288, n_dist, T.dist_fast, DIST_FAST, T.dist_sym, T.dist_count, (uint16_t *)T.ring, lane);
+            // token loop: lane 0 decodes a batch, the warp places and copies it. Inside the loop the bit reader is just a bit
+            // position: the words come from a shared-memory ring that all lanes refill (coalesced) before each batch.
+            uint32_t bitpos = 0;
+            if (lane == 0) bitpos = br.bit_offset(wbase);
             for (;;) {
-                int sym = 0;
-                uint32_t len = 0, dist = 0;
-                if (lane == 0) {
-                    sym = decode_sym(br, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
-                    // runs of literals stay on lane 0: no warp-wide exchange until a match or the end of the block
-                    while ((uint32_t)sym < 256u && pos < blk.ulen) {
-                        dst[pos++] = (uint8_t)sym;
-                        sym = decode_sym(br, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
+                bitpos = __shfl_sync(0xffffffffu, bitpos, 0);
+                {   // a batch consumes at most 32 * 48 bits = 48 words; 96 words are fetched
+                    const uint32_t cw = bitpos >> 5;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        uint32_t idx = cw + lane + 32 * j, v = __ldg(wbase + idx);
+                        T.ring[idx & (RING - 1)] = v;
+                        if ((idx & (RING - 1)) == 0) T.ring[RING] = v;
                     }
-                    if (sym > 256 && sym < 286) {
-                        int li = sym - 257;
-                        len = c_len_base[li] + br.bits(c_len_extra[li]);
-                        int ds = decode_sym(br, T.dist_fast, DIST_FAST, T.dist_count, T.dist_sym);
-                        if (ds < 0 || ds >= 30) sym = -1;
-                        else dist = c_dist_base[ds] + br.bits(c_dist_extra[ds]);
-                    } else if (sym != 256)
-                        sym = -1;
                 }
-                sym = __shfl_sync(0xffffffffu, sym, 0);
-                pos = __shfl_sync(0xffffffffu, pos, 0);
-                if (sym == 256) break;
-                len = __shfl_sync(0xffffffffu, len, 0);
-                dist = __shfl_sync(0xffffffffu, dist, 0);
-                if (sym < 0 || dist > pos || pos + len > blk.ulen) {
+                __syncwarp();
+                uint32_t ntok = 0;
+                int status = 0;  // 0 = more to come, 1 = end of block, -1 = corrupt
+                if (lane == 0) {
+                    uint32_t bp = bitpos;
+                    while (ntok < BATCH) {
+                        const uint32_t w = ring_window(T.ring, bp);
+                        const uint32_t e = decode_entry<true>(w, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
+                        const uint32_t l = e & 15;
+                        uint32_t tok;
+                        if (e & E_LITERAL) {
+                            tok = 0x80000000u | (e >> 16);
+                            bp += l;
+                        } else if (e & (E_END | E_INVALID)) {
+                            bp += l;
+                            status = (e & E_END) ? 1 : -1;
+                            break;
+                        } else {
+                            const uint32_t x = (e >> 4) & 15;
+                            const uint32_t len = (e >> 16) + ((w >> l) & ((1u << x) - 1));  // l + x <= 20 bits of the window
+                            bp += l + x;
+                            const uint32_t w2 = ring_window(T.ring, bp);
+                            const uint32_t d = decode_entry<false>(w2, T.dist_fast, DIST_FAST, T.dist_count, T.dist_sym);
+                            if (d & E_INVALID) {
+                                status = -1;
+                                break;
+                            }
+                            const uint32_t l2 = d & 15, x2 = (d >> 4) & 15;
+                            const uint32_t dist = (d >> 16) + ((w2 >> l2) & ((1u << x2) - 1));  // l2 + x2 <= 28
+                            bp += l2 + x2;
+                            tok = len | dist << 9;
+                        }
+                        T.tok[ntok++] = tok;
+                    }
+                    bitpos = bp;
+                }
+                ntok = __shfl_sync(0xffffffffu, ntok, 0);
+                status = __shfl_sync(0xffffffffu, status, 0);
+                __syncwarp();
+                const uint32_t tok = lane < ntok ? T.tok[lane] : 0u;
+                const bool is_lit = tok >> 31;
+                const uint32_t n = is_lit ? 1u : (tok & 511u), dist = (tok >> 9) & 0xffffu;
+                uint32_t incl = n;  // inclusive prefix sum of the output sizes
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (uint32_t)d) incl += v;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), off = incl - n, o = pos + off;
+                const bool is_match = !is_lit && n != 0;
+                if (status < 0 || pos + total > blk.ulen || __any_sync(0xffffffffu, is_match && dist > o)) {
                     bad = true;
                     break;
                 }
-                // LZ77 copy; an overlapping match (dist < len) repeats the last `dist` bytes, which are all written already
-                const uint8_t *src = dst + pos - dist;
-                __syncwarp();  // lane 0's literal stores must be visible to the lanes that copy
-                if (dist >= len) {
-                    for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i];
-                } else {
-                    for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i % dist];
+                // matches whose source ends before this batch's output are independent of the other tokens
+                const bool coop = is_match && (n > COOP_LEN || dist < off + n);
+                if (is_lit) dst[o] = (uint8_t)tok;
+                else if (is_match && !coop) {
+                    const uint8_t *src = dst + o - dist;
+                    for (uint32_t k = 0; k < n; ++k) dst[o + k] = src[k];
                 }
-                pos += len;
-                __syncwarp();
+                uint32_t pending = __ballot_sync(0xffffffffu, coop);
+                __syncwarp();  // the stores above are visible to the lanes that copy below
+                while (pending) {  // long or batch-dependent matches: whole warp per token, in stream order
+                    const int t = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    const uint32_t o_t = __shfl_sync(0xffffffffu, o, t), n_t = __shfl_sync(0xffffffffu, n, t),
+                                   d_t = __shfl_sync(0xffffffffu, dist, t);
+                    const uint8_t *src = dst + o_t - d_t;
+                    if (d_t >= n_t) {
+                        for (uint32_t i = lane; i < n_t; i += 32) dst[o_t + i] = src[i];
+                    } else {  // overlapping match: the last d_t bytes repeat
+                        for (uint32_t i = lane; i < n_t; i += 32) dst[o_t + i] = src[i % d_t];
+                    }
+                    __syncwarp();
+                }
+                pos += total;
+                if (status == 1) break;
             }
+            if (!bad && lane == 0) br.init_at(wbase, bitpos);  // back to the register reader for the next block header
             if (bad) break;
         } else {
             bad = true;
