@@ -158,6 +158,15 @@ int svb_plan_getsv(const char *clip_alignments_path, const char *clip_file_path,
                    uint64_t *n_junctions, svb_window **windows, uint64_t *n_windows);
 void svb_free(void *p);
 
+/* ---- gzip text files (host only) ----
+ * Replaces the reference's ogzstream / igzstream (gzstream.h:86-117, gzstream.C:53-114; call sites clip_reads.h:392-395,
+ * getsv.h:433, somatic.h:45). svb_write_gz writes `n` bytes as a multi-member gzip file (1 MiB members compressed by a
+ * thread pool; every member carries its size in an 'SV' extra sub-field, which ordinary gzip readers skip).
+ * svb_read_gz returns the decompressed content of any gzip or plain text file in a malloc'ed buffer (svb_free);
+ * files written by svb_write_gz are inflated member-parallel. n_threads <= 0: all host cores. */
+int svb_write_gz(const char *path, const void *data, uint64_t n, int n_threads);
+int svb_read_gz(const char *path, char **data, uint64_t *n);
+
 /* ---- whole commands (what the CLI calls; same arguments as the reference's Call* functions,
  *      seeksv.cpp:128-410). They print the reference's progress lines to stderr and return the
  *      process exit code. ------------------------------------------------------------------------------ */

@@ -6,6 +6,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -511,15 +512,196 @@ bool read_text_maybe_gz(const std::string &path, std::string &out, std::string &
 
 static int gz_level()
 {
-    // the reference's ogzstream uses zlib's default level; parity is defined on the DECOMPRESSED bytes, and the files are
-    // read back exactly once (by bwa and by getsv), so the writer trades a little size for a lot of speed by default
+    // The reference's ogzstream uses zlib's default level; parity is defined on the DECOMPRESSED bytes, and the files are
+    // read back exactly once (by bwa and by getsv). Default (-1): the Huffman-only writer below, ~8x faster than zlib
+    // level 1 for ~20 % larger files (reads and qualities have few LZ77 matches to offer anyway).
+    // SEEKSV_B200_GZ_LEVEL=0..9 selects zlib at that level.
     const char *e = getenv("SEEKSV_B200_GZ_LEVEL");
-    int l = e ? atoi(e) : 1;
-    return l < 0 || l > 9 ? 1 : l;
+    if (!e) return -1;
+    int l = atoi(e);
+    return l < 0 || l > 9 ? -1 : l;
 }
+
+// ---- Huffman-only DEFLATE writer (RFC 1951 dynamic blocks with literals only) ------------------------------------------
+namespace {
+
+// code lengths (<= limit) of an optimal prefix code; frequencies are flattened until the longest code fits
+void huffman_lengths(const uint32_t *freq_in, int n, int limit, uint8_t *len)
+{
+    std::vector<uint32_t> freq(freq_in, freq_in + n);
+    for (;;) {
+        struct Node {
+            uint64_t w;
+            int parent;
+        };
+        std::vector<int> leaves;
+        for (int i = 0; i < n; ++i) {
+            len[i] = 0;
+            if (freq[i]) leaves.push_back(i);
+        }
+        if (leaves.empty()) return;
+        if (leaves.size() == 1) {
+            len[leaves[0]] = 1;
+            return;
+        }
+        std::sort(leaves.begin(), leaves.end(), [&](int a, int b) { return freq[a] != freq[b] ? freq[a] < freq[b] : a < b; });
+        const int m = (int)leaves.size();
+        std::vector<Node> node(2 * m - 1);
+        for (int i = 0; i < m; ++i) node[i] = Node{freq[leaves[i]], -1};
+        int qa = 0, qb = m, end = m;  // two-queue merge: leaves [qa, m), internal nodes [qb, end)
+        auto take = [&]() {
+            if (qa < m && (qb >= end || node[qa].w <= node[qb].w)) return qa++;
+            return qb++;
+        };
+        while (end < 2 * m - 1) {
+            int a = take(), b = take();
+            node[end] = Node{node[a].w + node[b].w, -1};
+            node[a].parent = node[b].parent = end;
+            ++end;
+        }
+        int longest = 0;
+        std::vector<int> depth(2 * m - 1, 0);
+        for (int i = 2 * m - 3; i >= 0; --i) depth[i] = depth[node[i].parent] + 1;
+        for (int i = 0; i < m; ++i) {
+            len[leaves[i]] = (uint8_t)std::min(depth[i], 255);
+            longest = std::max(longest, depth[i]);
+        }
+        if (longest <= limit) return;
+        for (int i = 0; i < n; ++i)
+            if (freq[i]) freq[i] = (freq[i] + 1) / 2;
+    }
+}
+
+// canonical codes, bit-reversed for LSB-first output
+void canonical_codes(const uint8_t *len, int n, uint16_t *code)
+{
+    uint32_t count[16] = {0}, next[16] = {0};
+    for (int i = 0; i < n; ++i) count[len[i]]++;
+    count[0] = 0;
+    uint32_t c = 0;
+    for (int b = 1; b <= 15; ++b) {
+        c = (c + count[b - 1]) << 1;
+        next[b] = c;
+    }
+    for (int i = 0; i < n; ++i) {
+        uint32_t l = len[i], v = l ? next[l]++ : 0, r = 0;
+        for (uint32_t k = 0; k < l; ++k) r |= ((v >> k) & 1u) << (l - 1 - k);
+        code[i] = (uint16_t)r;
+    }
+}
+
+struct BitWriter {
+    uint8_t *p;
+    uint64_t acc = 0;
+    int nb = 0;
+    inline void put(uint32_t v, int n)  // n <= 32
+    {
+        acc |= (uint64_t)v << nb;
+        nb += n;
+        if (nb >= 32) {
+            uint32_t w = (uint32_t)acc;
+            memcpy(p, &w, 4);
+            p += 4;
+            acc >>= 32;
+            nb -= 32;
+        }
+    }
+    uint8_t *finish()
+    {
+        while (nb > 0) {
+            *p++ = (uint8_t)acc;
+            acc >>= 8;
+            nb -= 8;
+        }
+        nb = 0;
+        return p;
+    }
+};
+
+// fixed, complete code for the code-length alphabet: 13 symbols of 4 bits, 6 of 5 bits (Kraft sum 1)
+const uint8_t kClLen[19] = {4, 5, 5, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 4, 4};
+const uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// one deflate block per 64 KiB piece of the input; returns the end of the output
+uint8_t *huffman_deflate(const uint8_t *in, size_t n, uint8_t *out)
+{
+    const size_t PIECE = 64 << 10;
+    BitWriter bw{out};
+    uint16_t cl_code[19];
+    canonical_codes(kClLen, 19, cl_code);
+    size_t a = 0;
+    do {
+        const size_t b = std::min(n, a + PIECE);
+        uint32_t freq[257] = {0};
+        for (size_t i = a; i < b; ++i) freq[in[i]]++;
+        freq[256] = 1;
+        uint8_t len[258];
+        huffman_lengths(freq, 257, 15, len);
+        if (b == a) len[0] = 1;  // empty piece: end-of-block alone would be a one-symbol code; add an unused partner
+        len[257] = 1;            // the single (unused) distance code
+        uint16_t code[257];
+        canonical_codes(len, 257, code);
+        bw.put(b == n ? 1 : 0, 1);
+        bw.put(2, 2);    // dynamic Huffman
+        bw.put(0, 5);    // HLIT: 257 literal/length codes
+        bw.put(0, 5);    // HDIST: 1 distance code
+        bw.put(15, 4);   // HCLEN: 19 code-length codes
+        for (int i = 0; i < 19; ++i) bw.put(kClLen[kClOrder[i]], 3);
+        for (int i = 0; i < 258;) {
+            if (len[i] == 0) {
+                int r = 1;
+                while (i + r < 258 && len[i + r] == 0 && r < 138) ++r;
+                if (r >= 11) {
+                    bw.put(cl_code[18], kClLen[18]);
+                    bw.put(r - 11, 7);
+                } else if (r >= 3) {
+                    bw.put(cl_code[17], kClLen[17]);
+                    bw.put(r - 3, 3);
+                } else {
+                    r = 1;
+                    bw.put(cl_code[0], kClLen[0]);
+                }
+                i += r;
+            } else {
+                bw.put(cl_code[len[i]], kClLen[len[i]]);
+                ++i;
+            }
+        }
+        uint32_t packed[256];  // code | length << 16
+        for (int i = 0; i < 256; ++i) packed[i] = code[i] | (uint32_t)len[i] << 16;
+        size_t i = a;
+        for (; i + 2 <= b; i += 2) {  // two symbols per flush check: <= 30 bits
+            uint32_t e0 = packed[in[i]], e1 = packed[in[i + 1]];
+            uint32_t l0 = e0 >> 16;
+            bw.put((e0 & 0xffff) | (e1 & 0xffff) << l0, (int)(l0 + (e1 >> 16)));
+        }
+        if (i < b) bw.put(packed[in[i]] & 0xffff, (int)(packed[in[i]] >> 16));
+        bw.put(code[256], len[256]);
+        a = b;
+    } while (a < n);
+    return bw.finish();
+}
+
+bool huffman_gz_member(const char *data, size_t n, std::vector<uint8_t> &out)
+{
+    out.resize(n * 2 + (n / (64 << 10) + 1) * 512 + 64);
+    static const uint8_t head[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 3, 8, 0, 'S', 'V', 4, 0, 0, 0};
+    memcpy(out.data(), head, 18);
+    uint8_t *e = huffman_deflate((const uint8_t *)data, n, out.data() + 20);
+    uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)data, (uInt)n), isz = (uint32_t)n;
+    for (int i = 0; i < 4; ++i) *e++ = (crc >> (8 * i)) & 0xff;
+    for (int i = 0; i < 4; ++i) *e++ = (isz >> (8 * i)) & 0xff;
+    out.resize((size_t)(e - out.data()));
+    uint32_t sz = (uint32_t)out.size();
+    for (int i = 0; i < 4; ++i) out[16 + i] = (sz >> (8 * i)) & 0xff;
+    return true;
+}
+
+}  // namespace
 
 static bool gz_member(const char *data, size_t n, std::vector<uint8_t> &out)
 {
+    if (gz_level() < 0) return huffman_gz_member(data, n, out);
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     if (deflateInit2(&zs, gz_level(), Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;

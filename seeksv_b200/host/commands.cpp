@@ -577,6 +577,27 @@ int cmd_somatic(int argc, char **argv)
 }
 }  // namespace
 
+extern "C" int svb_write_gz(const char *path, const void *data, uint64_t n, int n_threads)
+{
+    if (!path || (!data && n)) return SVB_ERR_ARG;
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::string err;
+    return write_gz(path, (const char *)data, n, n_threads, err) ? 0 : SVB_ERR_IO;
+}
+
+extern "C" int svb_read_gz(const char *path, char **data, uint64_t *n)
+{
+    if (!path || !data || !n) return SVB_ERR_ARG;
+    std::string text, err;
+    if (!read_text_maybe_gz(path, text, err)) return SVB_ERR_IO;
+    *data = (char *)malloc(text.size() + 1);
+    if (!*data) return SVB_ERR_IO;
+    memcpy(*data, text.data(), text.size());
+    (*data)[text.size()] = 0;
+    *n = text.size();
+    return 0;
+}
+
 extern "C" void svb_free(void *p) { free(p); }
 
 extern "C" int svb_plan_getsv(const char *clip_aln, const char *clip_file, int32_t n_ref, const char *const *ref_names,

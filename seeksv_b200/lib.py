@@ -45,6 +45,7 @@ EXPORTS = [
     "svb_bam_free", "svb_bam_device_stream", "svb_bam_copy_stream", "svb_inflate_bgzf", "svb_bam_n_records", "svb_bam_record_bytes", "svb_bam_n_ref", "svb_bam_ref_name", "svb_bam_ref_len",
     "svb_bam_set_refs", "svb_getclip", "svb_clusters_free", "svb_clusters_count", "svb_clusters_candidates",
     "svb_clusters_text", "svb_insert_stats", "svb_discordant_support", "svb_window_depth", "svb_plan_getsv", "svb_free",
+    "svb_write_gz", "svb_read_gz",
     "svb_main",
 ]
 
@@ -107,6 +108,8 @@ def load():
     L.svb_plan_getsv.argtypes = [C.c_char_p, C.c_char_p, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), i32, i32,
                                  C.POINTER(C.POINTER(Junction)), C.POINTER(u64), C.POINTER(C.POINTER(Window)),
                                  C.POINTER(u64)]
+    L.svb_write_gz.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_int]
+    L.svb_read_gz.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.svb_free.argtypes = [vp]
     L.svb_free.restype = None
     _lib = L
@@ -360,6 +363,26 @@ def plan_getsv(clip_alignments: str, clip_file: str, ref_names: Sequence[str], r
         L.svb_free(pj)
         L.svb_free(pw)
     return juncs, wins
+
+
+def write_gz(path: str, data: bytes, threads: int = 0) -> None:
+    """multi-member gzip writer of the CLI outputs (svb_write_gz); no GPU involved"""
+    rc = load().svb_write_gz(path.encode(), data, len(data), threads)
+    if rc != 0:
+        raise SvbError("svb_write_gz(%s) = %d" % (path, rc))
+
+
+def read_gz(path: str) -> bytes:
+    """reader of gzip / plain text inputs (svb_read_gz); member-parallel for files written by write_gz"""
+    L = load()
+    p, n = C.c_void_p(), C.c_uint64()
+    rc = L.svb_read_gz(path.encode(), C.byref(p), C.byref(n))
+    if rc != 0:
+        raise SvbError("svb_read_gz(%s) = %d" % (path, rc))
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        L.svb_free(p)
 
 
 def run_cli(args: Sequence[str]) -> int:

@@ -1,0 +1,53 @@
+"""The CLI's gzip writer / reader (host only: svb_write_gz, svb_read_gz) against Python's gzip, which is zlib - the library
+the reference's gzstream (gzstream.C:53-114) and bwa read these files with."""
+import gzip
+import os
+import random
+
+import pytest
+
+import seeksv_b200.lib as L
+from conftest import GOLDEN
+
+
+def _cases():
+    rnd = random.Random(7)
+    text = open(os.path.join(GOLDEN, "example", "cancer.clip.txt"), "rb").read()
+    return {
+        "empty": b"",
+        "one_byte": b"A",
+        "one_symbol": b"I" * 300000,
+        "clip_text": text * 6,                                    # several 1 MiB members
+        "incompressible": rnd.randbytes(2_200_000),
+        "skewed": bytes(rnd.choices(range(256), weights=[2 ** (-i / 8) for i in range(256)], k=1_500_000)),
+        "needs_length_limit": b"".join(bytes([i]) * (2 ** min(i, 21)) for i in range(23)),  # Fibonacci-like: codes > 15 bits
+        "piece_edges": b"ACGT" * (16384 * 3) + b"N",              # exact multiples of the 64 KiB deflate piece, odd tail
+    }
+
+
+@pytest.mark.parametrize("level", [None, "1", "6"])
+def test_writer_output_is_plain_gzip_and_reader_round_trips(tmp_path, monkeypatch, level):
+    if level is None:
+        monkeypatch.delenv("SEEKSV_B200_GZ_LEVEL", raising=False)   # Huffman-only dynamic blocks
+    else:
+        monkeypatch.setenv("SEEKSV_B200_GZ_LEVEL", level)           # zlib at that level
+    for name, data in _cases().items():
+        p = str(tmp_path / (name + ".gz"))
+        L.write_gz(p, data, threads=3)
+        raw = open(p, "rb").read()
+        assert raw[:4] == b"\x1f\x8b\x08\x04" and raw[12:14] == b"SV", name
+        assert gzip.decompress(raw) == data, name
+        assert L.read_gz(p) == data, name
+
+
+def test_reader_accepts_foreign_gzip_and_plain_text(tmp_path):
+    data = open(os.path.join(GOLDEN, "example", "cancer.clip.txt"), "rb").read()
+    p = str(tmp_path / "foreign.gz")
+    with gzip.open(p, "wb") as f:       # single member, no 'SV' field: the gzread path (what the reference's igzstream does)
+        f.write(data)
+    assert L.read_gz(p) == data
+    q = str(tmp_path / "plain.txt")
+    open(q, "wb").write(data)
+    assert L.read_gz(q) == data
+    with pytest.raises(L.SvbError):
+        L.read_gz(str(tmp_path / "missing.gz"))
