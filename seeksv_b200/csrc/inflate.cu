@@ -13,10 +13,11 @@
 // carry the base value and the number of extra bits, and a canonical (count / sorted-symbol) fallback for the rare
 // longer codes.
 #include "common.cuh"
+#include <cstddef>
 
 namespace {
 
-constexpr int LIT_FAST = 10, DIST_FAST = 8, WARPS_PER_CTA = 4, BATCH = 32, COOP_LEN = 16, RING = 128;
+constexpr int LIT_FAST = 10, DIST_FAST = 8, BLOCKS_PER_CTA = 4, MAX_BATCH = 32, COOP_LEN = 16, RING = 128;
 
 struct WarpTables {
     // entries: bits 0-3 code length, 4-7 number of extra bits, bit 8 literal, bit 9 end of block, bit 10 invalid symbol,
@@ -25,12 +26,15 @@ struct WarpTables {
     uint32_t dist_fast[1 << DIST_FAST];
     // (ring and tok double as the 288 x u16 scratch for canonical codes while a table is being built)
     uint32_t ring[RING + 1];  // the next RING words of the compressed stream (refilled by all lanes before each batch)
-    uint32_t tok[BATCH];  // token batch: bit 31 literal (byte in bits 0-7), else length in bits 0-8 and distance in bits 9-24
+    uint32_t tok[MAX_BATCH];  // token batch: bit 31 literal (byte in bits 0-7), else length in bits 0-8 and distance in bits 9-24
     uint16_t lit_sym[288], dist_sym[32];  // symbols sorted by (code length, symbol) for the canonical slow path
     uint16_t lit_count[16], dist_count[16];
     uint8_t lens[320];   // code lengths: literal/length alphabet followed by the distance alphabet
     uint8_t cl_fast[128];  // code-length alphabet: (len << 5) | symbol, 7-bit lookup
 };
+static_assert(offsetof(WarpTables, tok) + sizeof(uint32_t) * MAX_BATCH - offsetof(WarpTables, ring) >= 288 * sizeof(uint16_t),
+              "ring + tok double as the canonical-code scratch of build_table");
+
 
 __constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 __constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -96,14 +100,14 @@ __device__ __forceinline__ uint32_t dist_entry(int s)
 }
 
 // Build the decode tables of one alphabet from its code lengths (canonical Huffman, RFC 1951 3.2.2).
-// Lane 0 assigns codes serially (<= 288 symbols); all lanes fill the single-lookup table.
-template <bool IS_LIT>
+// The group leader assigns codes serially (<= 288 symbols); all lanes of the group fill the single-lookup table.
+template <bool IS_LIT, int GROUP>
 __device__ void build_table(const uint8_t *lens, int n, uint32_t *fast, int fast_bits, uint16_t *sym_sorted, uint16_t *count,
-                            uint16_t *code, uint32_t lane)
+                            uint16_t *code, uint32_t lane, uint32_t gm)
 {
-    for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
+    for (int i = lane; i < (1 << fast_bits); i += GROUP) fast[i] = 0;
     if (lane < 16) count[lane] = 0;
-    __syncwarp();
+    __syncwarp(gm);
     if (lane == 0) {
         for (int s = 0; s < n; ++s) count[lens[s]]++;
         count[0] = 0;
@@ -124,8 +128,8 @@ __device__ void build_table(const uint8_t *lens, int n, uint32_t *fast, int fast
             }
         }
     }
-    __syncwarp();
-    for (int s = lane; s < n; s += 32) {
+    __syncwarp(gm);
+    for (int s = lane; s < n; s += GROUP) {
         int l = lens[s];
         if (l && l <= fast_bits) {
             uint32_t rev = __brev((uint32_t)code[s]) >> (32 - l);  // codes are sent MSB first, bits are read LSB first
@@ -133,7 +137,7 @@ __device__ void build_table(const uint8_t *lens, int n, uint32_t *fast, int fast
             for (uint32_t k = rev; k < (1u << fast_bits); k += 1u << l) fast[k] = e;
         }
     }
-    __syncwarp();
+    __syncwarp(gm);
 }
 
 // canonical decode for codes longer than the lookup width, on a 32-bit window; returns the symbol and its code length
@@ -181,238 +185,280 @@ struct InflateBlock {
     uint32_t clen, ulen;
 };
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+// Two BGZF blocks per warp, 16 lanes each ("group"): the serial Huffman decode is one lane's work, so with one block per
+// warp ~80 % of the issued instructions had a single active lane. Two decoder lanes that execute the same instruction
+// stream halve that. Each group runs a small state machine (block header / token batches / done); the warp meets at the
+// top of every round so that groups in the same state execute their section converged.
+template <int GROUP>
+__global__ void __launch_bounds__(BLOCKS_PER_CTA * GROUP, 8)
     inflate_bgzf(const uint8_t *__restrict__ file, const InflateBlock *__restrict__ blocks, uint32_t n_blocks, uint8_t *__restrict__ out,
                  uint32_t *__restrict__ error)
 {
-    __shared__ WarpTables tables[WARPS_PER_CTA];
+    constexpr int GROUPS = 32 / GROUP, BATCH = GROUP;
+    __shared__ WarpTables tables[BLOCKS_PER_CTA];
+    enum { S_HEADER, S_TOKENS, S_DONE };
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t b = blockIdx.x * WARPS_PER_CTA + wid;
-    if (b >= n_blocks) return;
-    WarpTables &T = tables[wid];
-    const InflateBlock blk = blocks[b];
+    const uint32_t glane = lane & (GROUP - 1), grp = lane / GROUP, leader = grp * GROUP;
+    const uint32_t gm = (uint32_t)((1ull << GROUP) - 1ull) << leader;  // this group's lanes
+    const uint32_t b = blockIdx.x * BLOCKS_PER_CTA + wid * GROUPS + grp;
+    WarpTables &T = tables[wid * GROUPS + grp];
+    int state = b < n_blocks ? S_HEADER : S_DONE;
+    InflateBlock blk = {0, 0, 0, 0};
+    if (state != S_DONE) blk = blocks[b];
     uint8_t *dst = out + blk.uoff;
     const uint32_t *wbase = (const uint32_t *)((uintptr_t)(file + blk.coff) & ~(uintptr_t)3);  // bit positions count from here
     BitReader br;
-    if (lane == 0) br.init(file + blk.coff);
-    uint32_t pos = 0;
+    br.init(file + blk.coff);  // (only the group leader's copy is used)
+    uint32_t pos = 0, final_block = 0, bitpos = 0;
     bool bad = false;
     for (;;) {
-        uint32_t hdr = 0;
-        if (lane == 0) hdr = br.bits(3);
-        hdr = __shfl_sync(0xffffffffu, hdr, 0);
-        const uint32_t final_block = hdr & 1, type = hdr >> 1;
-        if (type == 0) {  // stored
-            uint32_t len = 0;
-            const uint8_t *src = nullptr;
-            if (lane == 0) {
-                br.align_byte();
-                len = br.bits(16);
-                br.consume(16);  // NLEN
-                src = br.byte_ptr();
-                br.init(src + len);
-            }
-            len = __shfl_sync(0xffffffffu, len, 0);
-            src = (const uint8_t *)__shfl_sync(0xffffffffu, (unsigned long long)src, 0);
-            if (pos + len > blk.ulen) {
-                bad = true;
-                break;
-            }
-            for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i];
-            pos += len;
-        } else if (type == 1 || type == 2) {
-            int n_lit = 288, n_dist = 30;
-            if (type == 1) {  // fixed Huffman codes (RFC 1951 3.2.6)
-                for (int i = lane; i < 288; i += 32) T.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
-                for (int i = lane; i < 30; i += 32) T.lens[288 + i] = 5;
-            } else {  // dynamic: code lengths are themselves Huffman coded (3.2.7), decoded serially by lane 0
-                int ok = 1;
-                if (lane == 0) {
-                    n_lit = (int)br.bits(5) + 257;
-                    n_dist = (int)br.bits(5) + 1;
-                    int n_cl = (int)br.bits(4) + 4;
-                    uint8_t cl[19];
-                    for (int i = 0; i < 19; ++i) cl[i] = 0;
-                    for (int i = 0; i < n_cl; ++i) cl[c_cl_order[i]] = (uint8_t)br.bits(3);
-                    // 7-bit lookup for the code-length alphabet
-                    for (int i = 0; i < 128; ++i) T.cl_fast[i] = 0;
-                    uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, next[8];
-                    for (int i = 0; i < 19; ++i) cnt[cl[i]]++;
-                    cnt[0] = 0;
-                    uint32_t c = 0;
-                    next[0] = 0;
-                    for (int l = 1; l < 8; ++l) {
-                        c = (c + cnt[l - 1]) << 1;
-                        next[l] = c;
-                    }
-                    for (int s = 0; s < 19; ++s) {
-                        int l = cl[s];
-                        if (!l) continue;
-                        uint32_t rev = __brev(next[l]++) >> (32 - l);
-                        for (uint32_t k = rev; k < 128; k += 1u << l) T.cl_fast[k] = (uint8_t)(l << 5 | s);
-                    }
-                    int i = 0, total = n_lit + n_dist;
-                    if (n_lit > 286 || n_dist > 30) ok = 0;
-                    while (ok && i < total) {
-                        uint8_t e = T.cl_fast[br.peek(7)];
-                        if (!e) {
-                            ok = 0;
-                            break;
+        __syncwarp();
+        if (state == S_HEADER) {
+            uint32_t hdr = 0;
+            if (glane == 0) hdr = br.bits(3);
+            hdr = __shfl_sync(gm, hdr, leader);
+            final_block = hdr & 1;
+            const uint32_t type = hdr >> 1;
+            if (type == 0) {  // stored
+                uint32_t len = 0;
+                const uint8_t *src = nullptr;
+                if (glane == 0) {
+                    br.align_byte();
+                    len = br.bits(16);
+                    br.consume(16);  // NLEN
+                    src = br.byte_ptr();
+                    br.init(src + len);
+                }
+                len = __shfl_sync(gm, len, leader);
+                src = (const uint8_t *)__shfl_sync(gm, (unsigned long long)src, leader);
+                if (pos + len > blk.ulen) bad = true;
+                else {
+                    for (uint32_t i = glane; i < len; i += GROUP) dst[pos + i] = src[i];
+                    pos += len;
+                }
+                state = (bad || final_block) ? S_DONE : S_HEADER;
+            } else if (type == 1 || type == 2) {
+                int n_lit = 288, n_dist = 30, ok = 1;
+                if (type == 1) {  // fixed Huffman codes (RFC 1951 3.2.6)
+                    for (int i = glane; i < 288; i += GROUP) T.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+                    for (int i = glane; i < 32; i += GROUP) T.lens[288 + i] = i < 30 ? 5 : 0;
+                } else {  // dynamic: code lengths are themselves Huffman coded (3.2.7), decoded serially by the leader
+                    if (glane == 0) {
+                        n_lit = (int)br.bits(5) + 257;
+                        n_dist = (int)br.bits(5) + 1;
+                        int n_cl = (int)br.bits(4) + 4;
+                        uint8_t cl[19];
+                        for (int i = 0; i < 19; ++i) cl[i] = 0;
+                        for (int i = 0; i < n_cl; ++i) cl[c_cl_order[i]] = (uint8_t)br.bits(3);
+                        // 7-bit lookup for the code-length alphabet
+                        for (int i = 0; i < 128; ++i) T.cl_fast[i] = 0;
+                        uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, next[8];
+                        for (int i = 0; i < 19; ++i) cnt[cl[i]]++;
+                        cnt[0] = 0;
+                        uint32_t c = 0;
+                        next[0] = 0;
+                        for (int l = 1; l < 8; ++l) {
+                            c = (c + cnt[l - 1]) << 1;
+                            next[l] = c;
                         }
-                        br.consume(e >> 5);
-                        int s = e & 31;
-                        if (s < 16) T.lens[i++] = (uint8_t)s;
-                        else {
-                            int rep, v = 0;
-                            if (s == 16) {
-                                if (i == 0) {
-                                    ok = 0;
-                                    break;
-                                }
-                                v = T.lens[i - 1];
-                                rep = 3 + (int)br.bits(2);
-                            } else if (s == 17) rep = 3 + (int)br.bits(3);
-                            else rep = 11 + (int)br.bits(7);
-                            if (i + rep > total) {
+                        for (int sy = 0; sy < 19; ++sy) {
+                            int l = cl[sy];
+                            if (!l) continue;
+                            uint32_t rev = __brev(next[l]++) >> (32 - l);
+                            for (uint32_t k = rev; k < 128; k += 1u << l) T.cl_fast[k] = (uint8_t)(l << 5 | sy);
+                        }
+                        int i = 0, total = n_lit + n_dist;
+                        if (n_lit > 286 || n_dist > 30) ok = 0;
+                        while (ok && i < total) {
+                            uint8_t e = T.cl_fast[br.peek(7)];
+                            if (!e) {
                                 ok = 0;
                                 break;
                             }
-                            while (rep--) T.lens[i++] = (uint8_t)v;
-                        }
-                    }
-                }
-                ok = __shfl_sync(0xffffffffu, ok, 0);
-                n_lit = __shfl_sync(0xffffffffu, n_lit, 0);
-                n_dist = __shfl_sync(0xffffffffu, n_dist, 0);
-                if (!ok) {
-                    bad = true;
-                    break;
-                }
-                __syncwarp();
-                // the distance lengths follow the literal/length lengths directly: move them to their own slot
-                if (n_lit < 288) {
-                    uint8_t v = lane < (uint32_t)n_dist ? T.lens[n_lit + lane] : 0;
-                    __syncwarp();
-                    if (lane < (uint32_t)n_dist) T.lens[288 + lane] = v;
-                    for (int i = n_lit + lane; i < 288; i += 32) T.lens[i] = 0;
-                    __syncwarp();
-                    for (int i = n_lit + lane; i < 288; i += 32) T.lens[i] = 0;
-                }
-            }
-            __syncwarp();
-            build_table<true>(T.lens, type == 1 ? 288 : n_lit, T.lit_fast, LIT_FAST, T.lit_sym, T.lit_count, (uint16_t *)T.ring, lane);
-            build_table<false>(T.lens + 288, n_dist, T.dist_fast, DIST_FAST, T.dist_sym, T.dist_count, (uint16_t *)T.ring, lane);
-            // token loop: lane 0 decodes a batch, the warp places and copies it. Inside the loop the bit reader is just a bit
-            // position: the words come from a shared-memory ring that all lanes refill (coalesced) before each batch.
-            uint32_t bitpos = 0;
-            if (lane == 0) bitpos = br.bit_offset(wbase);
-            for (;;) {
-                bitpos = __shfl_sync(0xffffffffu, bitpos, 0);
-                {   // a batch consumes at most 32 * 48 bits = 48 words; 96 words are fetched
-                    const uint32_t cw = bitpos >> 5;
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        uint32_t idx = cw + lane + 32 * j, v = __ldg(wbase + idx);
-                        T.ring[idx & (RING - 1)] = v;
-                        if ((idx & (RING - 1)) == 0) T.ring[RING] = v;
-                    }
-                }
-                __syncwarp();
-                uint32_t ntok = 0;
-                int status = 0;  // 0 = more to come, 1 = end of block, -1 = corrupt
-                if (lane == 0) {
-                    uint32_t bp = bitpos;
-                    while (ntok < BATCH) {
-                        const uint32_t w = ring_window(T.ring, bp);
-                        const uint32_t e = decode_entry<true>(w, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
-                        const uint32_t l = e & 15;
-                        uint32_t tok;
-                        if (e & E_LITERAL) {
-                            tok = 0x80000000u | (e >> 16);
-                            bp += l;
-                        } else if (e & (E_END | E_INVALID)) {
-                            bp += l;
-                            status = (e & E_END) ? 1 : -1;
-                            break;
-                        } else {
-                            const uint32_t x = (e >> 4) & 15;
-                            const uint32_t len = (e >> 16) + ((w >> l) & ((1u << x) - 1));  // l + x <= 20 bits of the window
-                            bp += l + x;
-                            const uint32_t w2 = ring_window(T.ring, bp);
-                            const uint32_t d = decode_entry<false>(w2, T.dist_fast, DIST_FAST, T.dist_count, T.dist_sym);
-                            if (d & E_INVALID) {
-                                status = -1;
-                                break;
+                            br.consume(e >> 5);
+                            int sy = e & 31;
+                            if (sy < 16) T.lens[i++] = (uint8_t)sy;
+                            else {
+                                int rep, v = 0;
+                                if (sy == 16) {
+                                    if (i == 0) {
+                                        ok = 0;
+                                        break;
+                                    }
+                                    v = T.lens[i - 1];
+                                    rep = 3 + (int)br.bits(2);
+                                } else if (sy == 17) rep = 3 + (int)br.bits(3);
+                                else rep = 11 + (int)br.bits(7);
+                                if (i + rep > total) {
+                                    ok = 0;
+                                    break;
+                                }
+                                while (rep--) T.lens[i++] = (uint8_t)v;
                             }
-                            const uint32_t l2 = d & 15, x2 = (d >> 4) & 15;
-                            const uint32_t dist = (d >> 16) + ((w2 >> l2) & ((1u << x2) - 1));  // l2 + x2 <= 28
-                            bp += l2 + x2;
-                            tok = len | dist << 9;
                         }
-                        T.tok[ntok++] = tok;
                     }
-                    bitpos = bp;
-                }
-                ntok = __shfl_sync(0xffffffffu, ntok, 0);
-                status = __shfl_sync(0xffffffffu, status, 0);
-                __syncwarp();
-                const uint32_t tok = lane < ntok ? T.tok[lane] : 0u;
-                const bool is_lit = tok >> 31;
-                const uint32_t n = is_lit ? 1u : (tok & 511u), dist = (tok >> 9) & 0xffffu;
-                uint32_t incl = n;  // inclusive prefix sum of the output sizes
+                    ok = __shfl_sync(gm, ok, leader);
+                    n_lit = __shfl_sync(gm, n_lit, leader);
+                    n_dist = __shfl_sync(gm, n_dist, leader);
+                    __syncwarp(gm);
+                    if (ok) {
+                        // the distance lengths follow the literal/length lengths directly: move them to their own slot
+                        uint8_t v[32 / GROUP];
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= (uint32_t)d) incl += v;
-                }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), off = incl - n, o = pos + off;
-                const bool is_match = !is_lit && n != 0;
-                if (status < 0 || pos + total > blk.ulen || __any_sync(0xffffffffu, is_match && dist > o)) {
-                    bad = true;
-                    break;
-                }
-                // matches whose source ends before this batch's output are independent of the other tokens
-                const bool coop = is_match && (n > COOP_LEN || dist < off + n);
-                if (is_lit) dst[o] = (uint8_t)tok;
-                else if (is_match && !coop) {
-                    const uint8_t *src = dst + o - dist;
-                    for (uint32_t k = 0; k < n; ++k) dst[o + k] = src[k];
-                }
-                uint32_t pending = __ballot_sync(0xffffffffu, coop);
-                __syncwarp();  // the stores above are visible to the lanes that copy below
-                while (pending) {  // long or batch-dependent matches: whole warp per token, in stream order
-                    const int t = __ffs(pending) - 1;
-                    pending &= pending - 1;
-                    const uint32_t o_t = __shfl_sync(0xffffffffu, o, t), n_t = __shfl_sync(0xffffffffu, n, t),
-                                   d_t = __shfl_sync(0xffffffffu, dist, t);
-                    const uint8_t *src = dst + o_t - d_t;
-                    if (d_t >= n_t) {
-                        for (uint32_t i = lane; i < n_t; i += 32) dst[o_t + i] = src[i];
-                    } else {  // overlapping match: the last d_t bytes repeat
-                        for (uint32_t i = lane; i < n_t; i += 32) dst[o_t + i] = src[i % d_t];
+                        for (int j = 0; j < 32 / GROUP; ++j) {
+                            int i = (int)glane + j * GROUP;
+                            v[j] = i < n_dist ? T.lens[n_lit + i] : 0;
+                        }
+                        __syncwarp(gm);
+#pragma unroll
+                        for (int j = 0; j < 32 / GROUP; ++j) T.lens[288 + glane + j * GROUP] = v[j];
+                        for (int i = n_lit + (int)glane; i < 288; i += GROUP) T.lens[i] = 0;
                     }
-                    __syncwarp();
                 }
-                pos += total;
-                if (status == 1) break;
-            }
-            if (!bad && lane == 0) br.init_at(wbase, bitpos);  // back to the register reader for the next block header
-            if (bad) break;
-        } else {
-            bad = true;
-            break;
+                if (!ok) bad = true, state = S_DONE;
+                else {
+                    __syncwarp(gm);
+                    build_table<true, GROUP>(T.lens, type == 1 ? 288 : n_lit, T.lit_fast, LIT_FAST, T.lit_sym, T.lit_count, (uint16_t *)T.ring, glane,
+                                      gm);
+                    build_table<false, GROUP>(T.lens + 288, n_dist, T.dist_fast, DIST_FAST, T.dist_sym, T.dist_count, (uint16_t *)T.ring, glane, gm);
+                    if (glane == 0) bitpos = br.bit_offset(wbase);
+                    bitpos = __shfl_sync(gm, bitpos, leader);
+                    state = S_TOKENS;
+                }
+            } else
+                bad = true, state = S_DONE;
         }
-        if (final_block) break;
+        // Groups in the token state run the batch converged: every warp-level primitive below names all of their lanes
+        // (mt), so the two decoding leaders execute the same instructions side by side. (The header section above uses
+        // per-group masks and may run the groups one after the other; it is rare.)
+        const uint32_t mt = __ballot_sync(0xffffffffu, state == S_TOKENS);
+        if (state == S_TOKENS) {
+            // One batch: the leader turns bits into up to GROUP tokens, the group places and copies them. The bit reader is
+            // just a bit position here: the words come from a shared-memory ring that the group refills (coalesced) first.
+            {   // a batch consumes at most GROUP * 48 bits; 3 * GROUP words are fetched
+                const uint32_t cw = bitpos >> 5;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    uint32_t idx = cw + glane + GROUP * j, v = __ldg(wbase + idx);
+                    T.ring[idx & (RING - 1)] = v;
+                    if ((idx & (RING - 1)) == 0) T.ring[RING] = v;
+                }
+            }
+            __syncwarp(mt);
+            uint32_t ntok = 0;
+            int status = 0;  // 0 = more to come, 1 = end of block, -1 = corrupt
+            if (glane == 0) {
+                uint32_t bp = bitpos;
+                while (ntok < BATCH) {
+                    const uint32_t w = ring_window(T.ring, bp);
+                    const uint32_t e = decode_entry<true>(w, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
+                    const uint32_t l = e & 15;
+                    uint32_t tok;
+                    if (e & E_LITERAL) {
+                        tok = 0x80000000u | (e >> 16);
+                        bp += l;
+                    } else if (e & (E_END | E_INVALID)) {
+                        bp += l;
+                        status = (e & E_END) ? 1 : -1;
+                        break;
+                    } else {
+                        const uint32_t x = (e >> 4) & 15;
+                        const uint32_t len = (e >> 16) + ((w >> l) & ((1u << x) - 1));  // l + x <= 20 bits of the window
+                        bp += l + x;
+                        const uint32_t w2 = ring_window(T.ring, bp);
+                        const uint32_t d = decode_entry<false>(w2, T.dist_fast, DIST_FAST, T.dist_count, T.dist_sym);
+                        if (d & E_INVALID) {
+                            status = -1;
+                            break;
+                        }
+                        const uint32_t l2 = d & 15, x2 = (d >> 4) & 15;
+                        const uint32_t dist = (d >> 16) + ((w2 >> l2) & ((1u << x2) - 1));  // l2 + x2 <= 28
+                        bp += l2 + x2;
+                        tok = len | dist << 9;
+                    }
+                    T.tok[ntok++] = tok;
+                }
+                bitpos = bp;
+            }
+            ntok = __shfl_sync(mt, ntok, leader);
+            status = __shfl_sync(mt, status, leader);
+            bitpos = __shfl_sync(mt, bitpos, leader);
+            __syncwarp(mt);
+            const uint32_t tok = glane < ntok ? T.tok[glane] : 0u;
+            const bool is_lit = tok >> 31;
+            const uint32_t n = is_lit ? 1u : (tok & 511u), dist = (tok >> 9) & 0xffffu;
+            uint32_t incl = n;  // inclusive prefix sum of the output sizes
+#pragma unroll
+            for (int d = 1; d < GROUP; d <<= 1) {
+                uint32_t v = __shfl_up_sync(mt, incl, d, GROUP);
+                if (glane >= (uint32_t)d) incl += v;
+            }
+            const uint32_t total = __shfl_sync(mt, incl, leader + GROUP - 1), off = incl - n, o = pos + off;
+            const bool is_match = !is_lit && n != 0;
+            const bool fail = status < 0 || pos + total > blk.ulen || (__ballot_sync(mt, is_match && dist > o) & gm) != 0;
+            // matches whose source ends before this batch's output are independent of the other tokens
+            const bool coop = !fail && is_match && (n > COOP_LEN || dist < off + n);
+            if (!fail) {
+                if (is_lit) dst[o] = (uint8_t)tok;
+                else if (is_match && !coop) {  // n <= COOP_LEN: all loads are issued before the first store waits for one
+                    const uint8_t *src = dst + o - dist;
+                    uint8_t v[COOP_LEN];
+#pragma unroll
+                    for (uint32_t k = 0; k < COOP_LEN; ++k)
+                        if (k < n) v[k] = src[k];
+#pragma unroll
+                    for (uint32_t k = 0; k < COOP_LEN; ++k)
+                        if (k < n) dst[o + k] = v[k];
+                }
+            }
+            uint32_t pending = __ballot_sync(mt, coop) & gm;
+            __syncwarp(mt);  // the stores above are visible to the lanes that copy below
+            while (__any_sync(mt, pending != 0)) {  // long or batch-dependent matches: whole group per token, in stream order
+                const bool act = pending != 0;
+                const int t = act ? __ffs(pending) - 1 : (int)leader;
+                pending &= pending - 1;
+                const uint32_t o_t = __shfl_sync(mt, o, t), n_s = __shfl_sync(mt, n, t), d_t = __shfl_sync(mt, dist, t);
+                const uint32_t n_t = act ? n_s : 0u;
+                const uint8_t *src = dst + o_t - d_t;
+                if (d_t >= n_t) {
+                    for (uint32_t i = glane; i < n_t; i += GROUP) dst[o_t + i] = src[i];
+                } else {  // overlapping match: the last d_t bytes repeat
+                    for (uint32_t i = glane; i < n_t; i += GROUP) dst[o_t + i] = src[i % d_t];
+                }
+                __syncwarp(mt);
+            }
+            if (fail) bad = true, state = S_DONE;
+            else {
+                pos += total;
+                if (status == 1) {
+                    if (glane == 0) br.init_at(wbase, bitpos);  // back to the register reader for the next block header
+                    state = final_block ? S_DONE : S_HEADER;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, state == S_DONE)) break;
     }
-    if ((bad || pos != blk.ulen) && lane == 0) atomicOr(error, 1u);
+    if (b < n_blocks && (bad || pos != blk.ulen) && glane == 0) atomicOr(error, 1u);
+}
+
+// BGZF blocks per warp: 1 (default) or 2 (SEEKSV_B200_INFLATE_GROUP=16, two 16-lane groups per warp; measured slower on
+// C2: fewer warps per SM leave the dependent shared-memory lookups of the decode loop exposed)
+static void launch_inflate(cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err)
+{
+    static const int group = [] {
+        const char *e = getenv("SEEKSV_B200_INFLATE_GROUP");
+        return e && atoi(e) == 16 ? 16 : 32;
+    }();
+    const uint32_t grid = (n_blocks + BLOCKS_PER_CTA - 1) / BLOCKS_PER_CTA;
+    if (group == 16) inflate_bgzf<16><<<grid, BLOCKS_PER_CTA * 16, 0, s>>>(d_file, (const InflateBlock *)d_blocks, n_blocks, d_out, d_err);
+    else inflate_bgzf<32><<<grid, BLOCKS_PER_CTA * 32, 0, s>>>(d_file, (const InflateBlock *)d_blocks, n_blocks, d_out, d_err);
 }
 
 // asynchronous launch over a range of blocks; *d_err is OR-ed with 1 when a block is corrupt
 int inflate_launch(cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err)
 {
     if (!n_blocks) return 0;
-    inflate_bgzf<<<(n_blocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, s>>>(d_file, (const InflateBlock *)d_blocks, n_blocks,
-                                                                                             d_out, d_err);
+    launch_inflate(s, d_file, d_blocks, n_blocks, d_out, d_err);
     return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
 }
 
@@ -425,8 +471,7 @@ int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks,
     CK(cudaMemsetAsync(err.p, 0, 4, s));
     if (n_blocks) {
         ProfScope ps(ctx, "inflate_bgzf", out_bytes);
-        inflate_bgzf<<<(n_blocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, s>>>(d_file, (const InflateBlock *)d_blocks,
-                                                                                                 n_blocks, d_out, err.p);
+        launch_inflate(s, d_file, d_blocks, n_blocks, d_out, err.p);
     }
     uint32_t h = 0;
     CK(cudaMemcpyAsync(&h, err.p, 4, cudaMemcpyDeviceToHost, s));

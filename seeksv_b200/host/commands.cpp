@@ -16,6 +16,7 @@
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <future>
 #include <thread>
 
 #include "../../include/seeksv_b200.h"
@@ -411,6 +412,26 @@ int cmd_getsv(int argc, char **argv)
     std::string err, clip_text;
     AlignmentSet alns;
     Phase ph;
+    // The insert-size pass always needs the original BAM: its load (file -> HBM, inflate on the device) runs on a helper
+    // thread while this thread reads and joins the clip files. Errors are still reported in the reference's order.
+    Gpu g;
+    svb_bam *bam = nullptr;
+    struct Prefetch {
+        std::future<int> f;
+        svb_bam **bam;
+        int wait() { return f.valid() ? f.get() : 0; }
+        ~Prefetch()
+        {
+            wait();
+            if (*bam) svb_bam_free(*bam), *bam = nullptr;
+        }
+    } prefetch{{}, &bam};
+    bool load_failed = false;
+    if (pairs_used >= 100000)
+        prefetch.f = std::async(std::launch::async, [&]() -> int {
+            if (!g.open()) return 1;
+            return svb_bam_open(g.ctx, original_bam.c_str(), n_threads(), &bam) != 0 ? 2 : 0;
+        });
     if (!load_alignments(clip_aln, alns, err)) {
         std::cerr << "[main_samview] fail to open file for reading." << std::endl;
         return fail(err);
@@ -424,12 +445,16 @@ int cmd_getsv(int argc, char **argv)
     merge_junctions(jm, flank);
     ph.mark("getsv: join + merge junctions");
 
-    Gpu g;
-    svb_bam *bam = nullptr;
     auto need_bam = [&]() -> bool {
-        if (bam) return true;
-        if (!g.ctx && !g.open()) return false;
-        if (svb_bam_open(g.ctx, original_bam.c_str(), n_threads(), &bam) != 0) {
+        int rc = prefetch.wait();
+        if (rc == 1 || load_failed) return false;
+        if (rc == 0 && bam) return true;
+        if (rc == 0) {
+            if (!g.ctx && !g.open()) return false;
+            rc = svb_bam_open(g.ctx, original_bam.c_str(), n_threads(), &bam) != 0 ? 2 : 0;
+        }
+        if (rc != 0) {
+            load_failed = true;
             std::cerr << "[main_samview] fail to open file for reading." << std::endl;
             std::cerr << "[seeksv_b200] " << svb_last_error(g.ctx) << std::endl;
             return false;
@@ -506,8 +531,7 @@ int cmd_getsv(int argc, char **argv)
     std::ofstream fu(unmapped_file.c_str());
     if (!fu) return fail("Cannot open file " + unmapped_file);
     fu.close();
-    if (bam) svb_bam_free(bam);
-    return 0;
+    return 0;  // (the BAM is released by `prefetch`)
 }
 
 // ---- somatic: CallSomatic (seeksv.cpp:366-410) ---------------------------------------------------------------------
