@@ -311,7 +311,7 @@ def main():
     saved_out = os.dup(1)
     os.dup2(devnull, 1)          # ... and getsv lists filtered junctions on stdout
     try:
-        for _ in range(max(1, args.warmup // 3)):
+        for _ in range(max(1, args.warmup)):
             e2e_step()
         ms_e2e, wall_e2e, _ = timed(e2e_step, args.steps)
     finally:

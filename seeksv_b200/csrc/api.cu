@@ -68,6 +68,8 @@ extern "C" void svb_ctx_destroy(svb_ctx *ctx)
     ctx->prof_flush();
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
+    for (auto &e : ctx->big_free) cudaFree(e.first);
+    ctx->big_free.clear();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (cudaStream_t a : ctx->aux)
         if (a) cudaStreamDestroy(a);
@@ -76,6 +78,42 @@ extern "C" void svb_ctx_destroy(svb_ctx *ctx)
 
 extern "C" const char *svb_last_error(const svb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 extern "C" void *svb_ctx_stream(svb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+uint8_t *svb_ctx::big_get(uint64_t bytes, uint64_t *cap)
+{
+    int best = -1;
+    for (size_t i = 0; i < big_free.size(); ++i)
+        if (big_free[i].second >= bytes && big_free[i].second <= 2 * bytes + (64ull << 20) &&
+            (best < 0 || big_free[i].second < big_free[best].second))
+            best = (int)i;
+    if (best >= 0) {
+        uint8_t *p = big_free[best].first;
+        *cap = big_free[best].second;
+        big_free.erase(big_free.begin() + best);
+        return p;
+    }
+    uint8_t *p = nullptr;
+    uint64_t want = bytes + bytes / 16;  // a little head room: the next file of the same kind usually fits
+    if (cudaMallocAsync((void **)&p, want, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    *cap = want;
+    return p;
+}
+
+void svb_ctx::big_put(uint8_t *p, uint64_t cap)
+{
+    if (!p) return;
+    big_free.emplace_back(p, cap);
+    while (big_free.size() > 2) {  // keep the two largest
+        size_t smallest = 0;
+        for (size_t i = 1; i < big_free.size(); ++i)
+            if (big_free[i].second < big_free[smallest].second) smallest = i;
+        cudaFreeAsync(big_free[smallest].first, stream);
+        big_free.erase(big_free.begin() + smallest);
+    }
+}
 
 char *svb_ctx::pinned_get(uint64_t bytes, uint64_t *cap)
 {
@@ -189,7 +227,8 @@ extern "C" int svb_bam_from_device(svb_ctx *ctx, const void *d_stream, uint64_t 
 
 static int upload(svb_ctx *ctx, svb_bam *b, const void *h, uint64_t nbytes)
 {
-    CK(cudaMallocAsync((void **)&b->d_owned, nbytes + 256, ctx->stream));
+    b->d_owned = ctx->big_get(nbytes + 256, &b->owned_cap);
+    if (!b->d_owned) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate %llu bytes of device memory", (unsigned long long)nbytes);
     CK(cudaMemsetAsync(b->d_owned + nbytes, 0, 256, ctx->stream));
     {
         ProfScope ps(ctx, "h2d_stream", (double)nbytes);
@@ -266,12 +305,28 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
     uint8_t *pinned[2] = {nullptr, nullptr};
     uint64_t pcap[2] = {0, 0};
     cudaEvent_t done[2];
-    DevBuf<uint8_t> d_file;
+    struct BigBuf {  // the compressed image: back to the context's cache on every way out
+        svb_ctx *ctx;
+        uint8_t *p = nullptr;
+        uint64_t cap = 0;
+        ~BigBuf()
+        {
+            if (!p) return;
+            cudaStreamSynchronize(ctx->copy_stream);
+            for (cudaStream_t a : ctx->aux) cudaStreamSynchronize(a);
+            cudaStreamSynchronize(ctx->stream);
+            ctx->big_put(p, cap);
+        }
+    } d_file{ctx};
     {
         WallScope ws(ctx, "stream_alloc(wall)");
-        CK(cudaMallocAsync((void **)&b->d_owned, total + 256, ctx->stream));  // pool: reused by the next load in this process
+        b->d_owned = ctx->big_get(total + 256, &b->owned_cap);
+        if (!b->d_owned) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate %llu bytes of device memory", (unsigned long long)total);
         CK(cudaMemsetAsync(b->d_owned + total, 0, 256, ctx->stream));
-        if (!host_inflate) CK(d_file.alloc(file_bytes + SVB_INFLATE_PAD, ctx->stream));
+        if (!host_inflate) {
+            d_file.p = ctx->big_get(file_bytes + SVB_INFLATE_PAD, &d_file.cap);
+            if (!d_file.p) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate %llu bytes of device memory", (unsigned long long)file_bytes);
+        }
         for (int i = 0; i < 2; ++i) {
             pinned[i] = (uint8_t *)ctx->pinned_get(SLAB + (64 << 10), &pcap[i]);
             if (!pinned[i]) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate pinned staging");
@@ -444,7 +499,7 @@ extern "C" void svb_bam_free(svb_bam *b)
     void *cols[7] = {L.rec, b->d_guess, b->d_count, b->d_base, b->d_q_cnt, b->d_q_sum, b->d_q_sq};
     for (void *c : cols)
         if (c) cudaFreeAsync(c, s);
-    if (b->d_owned) cudaFreeAsync(b->d_owned, s);
+    if (b->d_owned) b->ctx->big_put(b->d_owned, b->owned_cap);  // (the stream was synchronised above)
     delete b;
 }
 

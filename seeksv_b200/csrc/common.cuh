@@ -49,6 +49,12 @@ struct svb_ctx {
     std::vector<std::pair<char *, uint64_t>> pinned_free;
     char *pinned_get(uint64_t bytes, uint64_t *cap);
     void pinned_put(char *p, uint64_t cap);
+    // The two large device buffers of a load (the uncompressed stream and the compressed file image) are kept for the next
+    // load of this context instead of going back to the pool: the pool may have split them for smaller requests in the
+    // meantime, and growing it again by gigabytes stalls a load for hundreds of milliseconds.
+    std::vector<std::pair<uint8_t *, uint64_t>> big_free;
+    uint8_t *big_get(uint64_t bytes, uint64_t *cap);  // contents undefined; usable on `stream` (and after its events)
+    void big_put(uint8_t *p, uint64_t cap);           // caller has synchronised every stream that used p
     ~svb_ctx();
 };
 
@@ -89,6 +95,7 @@ struct svb_bam {
     svb_ctx *ctx = nullptr;
     const uint8_t *d_data = nullptr;
     uint8_t *d_owned = nullptr;
+    uint64_t owned_cap = 0;
     uint64_t nbytes = 0, first = 0;
     int32_t n_ref = 0;
     uint64_t n_rec = 0, rec_bytes = 0;
