@@ -358,7 +358,8 @@ def main():
                        "junction_candidates": len(juncs), "depth_windows": len(wins),
                        "sharding": "one chromosome-sized BAM per GPU" if world > 1 else "single GPU",
                        "l2_note": "inputs (%.2f GB per pass) are far larger than the 126 MB L2; no flush needed" % (rec_bytes / 1e9)},
-            "e2e": {"value": e2e, "unit": "records/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e, "unit": "records/s", "h2d_bytes_per_step": 2 * os.path.getsize(bam_path), "d2h_bytes_per_step": int(d2h),
+                    "h2d_note": "each command uploads the BGZF file image (inflated on the device to %d bytes)" % nbytes,
                     "ms_per_step": 1e3 * wall_e2e / args.steps, "path": "svb_main getclip + svb_main getsv, BGZF file image -> outputs"},
             "gpu_launches": int(sum(v["launches"] for v in kern.values())),
             "clocks": sampler.summary(), "roofline": roofline,
