@@ -186,46 +186,72 @@ def read_alignments(path: str) -> Tuple[Header, List[Rec]]:
 
 
 def aux_get_int(aux: bytes, tag: bytes) -> int:
-    """bam_aux2i(bam_aux_get(b, tag)): integer value of an aux tag, 0 when absent or not an integer
-    type. Call sites clip_reads.cpp:126-127,158-159; declared sam/bam.h:556-561."""
-    i, n = 0, len(aux)
-    while i + 3 <= n:
-        t, ty = aux[i:i + 2], chr(aux[i + 2])
-        i += 3
-        if t == tag:
+    """bam_aux2i(bam_aux_get(b, tag)) of the libbam the reference links (call sites clip_reads.cpp:126-127,158-159;
+    declared sam/bam.h:556-561), pinned by probing the archive (`oracle/_ref/bamtool auxi`, tests/test_oracle_golden.py):
+
+      * the walk upper-cases the type before asking for its size, and the size table only knows 'C'/'A' (1), 'S' (2) and
+        'I' (4) in upper case: a float ('f') or double ('d') field is NOT skipped - its value bytes are read as the next
+        tag - so an XC behind one is normally not found; inside a 'B' array the raw sub-type is used, where 'f' is known;
+      * the value comes back as int32 ('I' above 2^31 wraps); non-integer types give 0.
+
+    Bytes past the end of the record (only reachable after such a mis-step) are taken as 0 here; the library would read
+    whatever the previous record left in its buffer."""
+    return aux_walk(aux, tag)[0]
+
+
+def aux_walk(aux: bytes, tag: bytes) -> Tuple[int, bool]:
+    """(value, overrun): the walk of aux_get_int; `overrun` says that it read past the end of the record, where the library
+    sees stale bytes of earlier records (the fixtures avoid such records: the reference's result is then undefined)."""
+    n = len(aux)
+    over = [False]
+
+    def at(i):
+        if 0 <= i < n:
+            return aux[i]
+        over[0] = True
+        return 0
+
+    s = 0
+    while s < n:
+        hit = at(s) == tag[0] and at(s + 1) == tag[1]
+        s += 2
+        if hit:
+            ty = chr(at(s))
+            s += 1
             if ty == "c":
-                return struct.unpack_from("<b", aux, i)[0]
+                v = at(s)
+                return (v - 256 if v > 127 else v), over[0]
             if ty == "C":
-                return aux[i]
+                return at(s), over[0]
             if ty == "s":
-                return struct.unpack_from("<h", aux, i)[0]
+                v = at(s) | at(s + 1) << 8
+                return (v - 65536 if v > 32767 else v), over[0]
             if ty == "S":
-                return struct.unpack_from("<H", aux, i)[0]
-            if ty == "i":
-                return struct.unpack_from("<i", aux, i)[0]
-            if ty == "I":
-                return struct.unpack_from("<I", aux, i)[0]
-            return 0
-        u = ty.upper()
-        if u in "CA":
-            i += 1
-        elif u == "S":
-            i += 2
-        elif u in "IF":
-            i += 4
-        elif u == "D":
-            i += 8
-        elif u in "ZH":
-            while i < n and aux[i] != 0:
-                i += 1
-            i += 1
+                return at(s) | at(s + 1) << 8, over[0]
+            if ty in "iI":
+                v = at(s) | at(s + 1) << 8 | at(s + 2) << 16 | at(s + 3) << 24
+                return (v - (1 << 32) if v >= (1 << 31) else v), over[0]
+            return 0, over[0]
+        u = chr(at(s)).upper()
+        s += 1
+        if u in "ZH":
+            while s < n and aux[s] != 0:
+                s += 1
+            if s >= n:
+                over[0] = True
+            s += 1
         elif u == "B":
-            sub = chr(aux[i]).upper()
-            cnt = struct.unpack_from("<i", aux, i + 1)[0]
-            i += 5 + cnt * {"C": 1, "S": 2, "I": 4, "F": 4}.get(sub, 1)
+            sub = chr(at(s))
+            cnt = at(s + 1) | at(s + 2) << 8 | at(s + 3) << 16 | at(s + 4) << 24
+            if cnt >= (1 << 31):
+                cnt -= 1 << 32
+            step = (5 + cnt * (1 if sub in "cCA" else 2 if sub in "sS" else 4 if sub in "iIf" else 0)) & 0xFFFFFFFF
+            if step >= (1 << 31):  # 32-bit int arithmetic in the library: a wrapped product walks backwards, off the record
+                return 0, True
+            s += step
         else:
-            break
-    return 0
+            s += 1 if u in "CA" else 2 if u == "S" else 4 if u == "I" else 0
+    return 0, over[0]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -6,6 +6,8 @@
  *                                        "tid pos1 n_plp n_del_or_skip" per covered position (probe for
  *                                        the pileup semantics of the linked libbam: flag mask, =/X ops,
  *                                        the 8000-read cap)
+ *   bamtool auxi    in.bam TAG        -- bam_aux2i(bam_aux_get(b, TAG)) per record (probe: how the linked libbam walks
+ *                                        the aux block, i.e. which types it knows how to skip)
  *   bamtool calend  pos 10M2D5X...    -- bam_calend() of the linked libbam for a CIGAR (probe: which ops
  *                                        advance the reference end in this build of the library)
  * Test infrastructure only (oracle/): never linked or executed by the product. */
@@ -61,6 +63,19 @@ int main(int argc, char **argv)
         samclose(out);
         samclose(in);
         fprintf(stderr, "bamtool: %ld records\n", n);
+        return 0;
+    }
+    if (argc >= 4 && strcmp(argv[1], "auxi") == 0) {  /* bam_aux2i(bam_aux_get(b, TAG)) for every record (probe of the aux walk) */
+        samfile_t *in = samopen(argv[2], "rb", 0);
+        if (!in || !in->header) { fprintf(stderr, "bamtool: cannot open %s\n", argv[2]); return 1; }
+        bam1_t *b = bam_init1();
+        while (samread(in, b) >= 0) {
+            uint8_t *s = bam_aux_get(b, argv[3]);
+            printf("%s\t%d\t%d\n", bam1_qname(b), s ? 1 : 0, (int)bam_aux2i(s));
+            fflush(stdout);  /* the walk can run off the record on malformed input: keep what was printed */
+        }
+        bam_destroy1(b);
+        samclose(in);
         return 0;
     }
     if (argc >= 4 && strcmp(argv[1], "calend") == 0) {

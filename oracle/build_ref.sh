@@ -19,7 +19,7 @@ if [ ! -d "$REF/seeksv" ]; then
   exit 0
 fi
 mkdir -p "$OUT"
-if [ -x "$OUT/seeksv" ] && [ "$OUT/seeksv" -nt "$HERE/build_ref.sh" ] && [ -x "$OUT/bamtool" ]; then
+if [ -x "$OUT/seeksv" ] && [ "$OUT/seeksv" -nt "$HERE/build_ref.sh" ] && [ -x "$OUT/bamtool" ] && [ "$OUT/bamtool" -nt "$HERE/bamtool.c" ]; then
   exit 0
 fi
 T=$(mktemp -d)

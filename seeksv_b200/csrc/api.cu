@@ -44,6 +44,7 @@ extern "C" int svb_ctx_create(int device, svb_ctx **out)
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming));
     for (int i = 0; i < svb_ctx::N_AUX; ++i) CK(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
     {
         // The full-pass kernels read ~40-100 bytes out of every ~300-byte record: with the default L2 fetch granularity a
@@ -70,6 +71,7 @@ extern "C" void svb_ctx_destroy(svb_ctx *ctx)
     cudaStreamDestroy(ctx->stream);
     for (auto &e : ctx->big_free) cudaFree(e.first);
     ctx->big_free.clear();
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (cudaStream_t a : ctx->aux)
         if (a) cudaStreamDestroy(a);

@@ -34,6 +34,7 @@ struct svb_ctx {
     // launches that follow each uploaded slab
     static constexpr int N_AUX = 8;
     cudaStream_t copy_stream = nullptr, aux[N_AUX] = {};
+    cudaEvent_t fork_event = nullptr;  // orders work handed from `stream` to `copy_stream`
     std::string err;
     bool prof = false;
     std::map<std::string, ProfEntry> prof_acc;

@@ -32,40 +32,46 @@ struct CandArrays {
     uint8_t *side;    // 0 = '5' (left clipped), 1 = '3' (right clipped)
 };
 
-// bam_aux2i(bam_aux_get(b, "XC")) - clip_reads.cpp:126-127,158-159; 0 when absent / not an integer type
-__device__ int32_t aux_xc(const uint8_t *s, const uint8_t *end)
+// bam_aux2i(bam_aux_get(b, "XC")) - clip_reads.cpp:126-127,158-159 - as the libbam the reference links behaves (probed with
+// oracle/bamtool.c `auxi`, restated in oracle/bamio.py:aux_walk): the walk upper-cases a field's type before looking up its
+// size and the size table knows only 'C'/'A' (1), 'S' (2), 'I' (4) in upper case, so a float or double field is NOT skipped -
+// its value bytes are parsed as the next tag and an XC behind it is normally missed. Inside a 'B' array the raw sub-type is
+// used ('f' known there) and the step is 32-bit int arithmetic. Bytes past the record read as 0 (the library would see stale
+// buffer contents: undefined in the reference). Value: int32; non-integer types give 0.
+__device__ int32_t aux_xc(const uint8_t *a, uint32_t n)
 {
-    while (s + 3 <= end) {
-        uint8_t t0 = s[0], t1 = s[1], ty = s[2];
-        s += 3;
-        if (t0 == 'X' && t1 == 'C') {
+    auto at = [&](uint32_t i) -> uint32_t { return i < n ? a[i] : 0u; };
+    uint32_t s = 0;
+    while (s < n) {
+        const bool hit = at(s) == 'X' && at(s + 1) == 'C';
+        s += 2;
+        if (hit) {
+            const uint32_t ty = at(s);
+            ++s;
             switch (ty) {
-            case 'c': return (int8_t)s[0];
-            case 'C': return s[0];
-            case 's': return (int16_t)(s[0] | (s[1] << 8));
-            case 'S': return s[0] | (s[1] << 8);
+            case 'c': return (int8_t)at(s);
+            case 'C': return (int32_t)at(s);
+            case 's': return (int16_t)(at(s) | at(s + 1) << 8);
+            case 'S': return (int32_t)(at(s) | at(s + 1) << 8);
             case 'i':
-            case 'I': return (int32_t)(s[0] | (s[1] << 8) | (s[2] << 16) | ((uint32_t)s[3] << 24));
+            case 'I': return (int32_t)(at(s) | at(s + 1) << 8 | at(s + 2) << 16 | at(s + 3) << 24);
             default: return 0;
             }
         }
-        uint8_t u = (ty >= 'a' && ty <= 'z') ? ty - 32 : ty;
-        if (u == 'C' || u == 'A') s += 1;
-        else if (u == 'S') s += 2;
-        else if (u == 'I' || u == 'F') s += 4;
-        else if (u == 'D') s += 8;
-        else if (u == 'Z' || u == 'H') {
-            while (s < end && *s) ++s;
+        uint32_t u = at(s);
+        if (u >= 'a' && u <= 'z') u -= 32;
+        ++s;
+        if (u == 'Z' || u == 'H') {
+            while (s < n && a[s]) ++s;
             ++s;
         } else if (u == 'B') {
-            if (s + 5 > end) return 0;
-            uint8_t sub = s[0];
-            if (sub >= 'a' && sub <= 'z') sub -= 32;
-            uint32_t cnt = s[1] | (s[2] << 8) | (s[3] << 16) | ((uint32_t)s[4] << 24);
-            uint32_t sz = (sub == 'S') ? 2 : (sub == 'I' || sub == 'F') ? 4 : 1;
-            s += 5 + (uint64_t)cnt * sz;
+            const uint32_t sub = at(s), cnt = at(s + 1) | at(s + 2) << 8 | at(s + 3) << 16 | at(s + 4) << 24;
+            const uint32_t sz = (sub == 'c' || sub == 'C' || sub == 'A') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+            const uint32_t step = 5u + cnt * sz;  // wraps like the library's int product
+            if (step >= 0x80000000u) return 0;    // a backwards step leaves the record: undefined in the reference
+            s += step;
         } else
-            return 0;
+            s += (u == 'C' || u == 'A') ? 1 : u == 'S' ? 2 : u == 'I' ? 4 : 0;
     }
     return 0;
 }
@@ -116,7 +122,7 @@ __device__ void eval_clip(const uint8_t *__restrict__ d, uint64_t o, const Core 
         if (op == OP_M || op == OP_D || op == OP_EQ || op == OP_N) reflen += (int32_t)(w >> 4);
     }
     const uint8_t *aux = cig + 4 * k.n_cigar + (k.l_qseq + 1) / 2 + k.l_qseq;
-    int32_t xc = aux_xc(aux, p + 4 + k.block_size);
+    int32_t xc = aux_xc(aux, (uint32_t)max((int64_t)0, (int64_t)(p + 4 + k.block_size - aux)));
     uint32_t len1 = first >> 4, len2 = last >> 4;
     bool emit5 = false, emit3 = false;
     uint32_t b5 = 0, l5 = 0, r5 = 0, b3 = 0, l3 = 0, r3 = 0;
@@ -874,6 +880,11 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
     res->n_candidates = n_cand;
 
     // ---- 2. unmapped-branch records: pair mates by name on the device, emit the two FASTQ files ---------------------
+    DevBuf<char> un_o1, un_o2;
+    struct CopyJoin {  // declared after the buffers the copy stream reads: joined before they are released, on every way out
+        cudaStream_t c;
+        ~CopyJoin() { cudaStreamSynchronize(c); }
+    } copy_join{ctx->copy_stream};
     if (n_un) {
         DevBuf<uint32_t> val0, val1, mate_of, ovf;
         DevBuf<uint64_t> un_sorted, key0, key1, sz1, sz2, off1, off2;
@@ -911,19 +922,20 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         CK(cudaMemcpyAsync(&hovf, ovf.p, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         if (hovf) return svb_fail(ctx, SVB_ERR_FORMAT, "more than 8 distinct read names share one 64-bit name hash");
-        DevBuf<char> o1, o2;
-        CK(o1.alloc(tot[0], s));
-        CK(o2.alloc(tot[1], s));
+        CK(un_o1.alloc(tot[0], s));
+        CK(un_o2.alloc(tot[1], s));
         {
             ProfScope ps(ctx, "unmapped_write", (double)(tot[0] + tot[1]));
-            unmapped_write<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_sorted.p, mate_of.p, bam->d_data, off1.p, off2.p, o1.p,
-                                                                          o2.p);
+            unmapped_write<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_sorted.p, mate_of.p, bam->d_data, off1.p, off2.p,
+                                                                          un_o1.p, un_o2.p);
         }
         CKR(res->text[2].reserve(ctx, tot[0]));
         CKR(res->text[3].reserve(ctx, tot[1]));
-        CK(cudaMemcpyAsync(res->text[2].p, o1.p, tot[0], cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(res->text[3].p, o2.p, tot[1], cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        // the two FASTQ texts travel to the host on the copy stream while the candidate pipeline below runs
+        CK(cudaEventRecord(ctx->fork_event, s));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_event, 0));
+        CK(cudaMemcpyAsync(res->text[2].p, un_o1.p, tot[0], cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaMemcpyAsync(res->text[3].p, un_o2.p, tot[1], cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
 
     if (n_cand == 0) {

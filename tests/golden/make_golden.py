@@ -100,6 +100,9 @@ def build_kat(kat):
     bamio.write_bam(os.path.join(kat, "start_tid1.bam"), h, [r for r in L if r.tid == 1])
 
 
+FUZZ_SEEDS, FUZZ_RECORDS = (11, 12), 1800
+
+
 def run(cmd, **kw):
     return subprocess.run(cmd, check=True, **kw)
 
@@ -190,6 +193,19 @@ def main():
         for ext, out in ((".clip.gz", ".clip.txt"), (".clip.fq.gz", ".clip.fq.txt"),
                          (".unmapped_1.fq.gz", ".unmapped_1.fq.txt"), (".unmapped_2.fq.gz", ".unmapped_2.fq.txt")):
             gunzip_to(pre + ext, os.path.join(kat, name[:-4] + out))
+    # ---- fuzz: awkward records (tests/fuzzgen.py), the full pipeline of the reference on them -------------------
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fuzzgen
+    fz = os.path.join(HERE, "fuzz")
+    os.makedirs(fz, exist_ok=True)
+    for seed in FUZZ_SEEDS:
+        name = "f%d" % seed
+        _, _, genome = fuzzgen.write(os.path.join(fz, name + ".sort.bam"), seed, FUZZ_RECORDS)
+        run([BAMTOOL, "index", os.path.join(fz, name + ".sort.bam")])
+        fa = os.path.join(work, name + ".fa")
+        fuzzgen.write_fasta(genome, fa)
+        run([bwa, "index", fa], stderr=subprocess.DEVNULL)
+        pipeline(work, fz, bwa, fa, (name,))
     shutil.rmtree(work)
     print("golden fixtures regenerated")
 

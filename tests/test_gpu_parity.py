@@ -10,8 +10,9 @@ from conftest import GOLDEN, ROOT, read_text
 
 pytestmark = pytest.mark.gpu
 
-CASES = [("example", "cancer"), ("example", "normal"), ("micro", "tumor"), ("micro", "normal"),
-         ("kat", "quirks"), ("kat", "start_tid1")]
+GETSV_CASES = [("example", "cancer"), ("example", "normal"), ("micro", "tumor"), ("micro", "normal"),
+               ("fuzz", "f11"), ("fuzz", "f12")]   # fuzz: tests/fuzzgen.py through the reference binary (make_golden.py)
+CASES = GETSV_CASES + [("kat", "quirks"), ("kat", "start_tid1")]
 
 
 def _bam(d, s):
@@ -67,7 +68,7 @@ def test_getclip_c_abi_matches_oracle(ctx, d, s):
     bam.close()
 
 
-@pytest.mark.parametrize("d,s", CASES[:4])
+@pytest.mark.parametrize("d,s", GETSV_CASES)
 def test_getsv_cli_bit_exact(d, s, tmp_path):
     clip = str(tmp_path / "clip.gz")
     with gzip.open(clip, "wb") as f:
@@ -93,7 +94,7 @@ def test_somatic_cli_bit_exact(d, normal, tumour, tmp_path):
     assert read_text(out) == read_text(os.path.join(GOLDEN, d, tumour + ".somatic.temp.sv"))
 
 
-@pytest.mark.parametrize("d,s", CASES[:4])
+@pytest.mark.parametrize("d,s", GETSV_CASES)
 def test_device_passes_match_oracle(ctx, d, s):
     """insert-size sums, discordant-pair counts and window depth through the C ABI vs the CPU oracle"""
     import random

@@ -8,8 +8,9 @@ import pytest
 from conftest import GOLDEN, ROOT, read_text
 from oracle import bamio, getclip_oracle, getsv_oracle
 
-CASES = [("example", "cancer"), ("example", "normal"), ("micro", "tumor"), ("micro", "normal"),
-         ("kat", "quirks"), ("kat", "start_tid1")]
+GETSV_CASES = [("example", "cancer"), ("example", "normal"), ("micro", "tumor"), ("micro", "normal"),
+               ("fuzz", "f11"), ("fuzz", "f12")]   # fuzz: tests/fuzzgen.py through the reference binary (make_golden.py)
+CASES = GETSV_CASES + [("kat", "quirks"), ("kat", "start_tid1")]
 
 
 def _bam(d, s):
@@ -27,7 +28,7 @@ def test_getclip_matches_reference(d, s):
     assert u2 == read_text(os.path.join(GOLDEN, d, s + ".unmapped_2.fq.txt"))
 
 
-@pytest.mark.parametrize("d,s", CASES[:4])
+@pytest.mark.parametrize("d,s", GETSV_CASES)
 def test_getsv_matches_reference(d, s):
     h, recs = bamio.read_bam(_bam(d, s))
     ch, ca = bamio.read_alignments(os.path.join(GOLDEN, d, s + ".clip.sam"))
@@ -49,6 +50,45 @@ def test_insert_size_example():
     for s in ("cancer", "normal"):
         h, recs = bamio.read_bam(_bam("example", s))
         assert getsv_oracle.insert_size_stats(recs, 20, 5000000) == (500, 25)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bamtool")), reason="no oracle/_ref")
+def test_aux_walk_against_libbam(tmp_path):
+    """bamio.aux_get_int == bam_aux2i(bam_aux_get()) of the linked libbam on random aux blocks, including the float / double
+    fields that library cannot step over (an XC behind one is normally lost - the reference then treats the read as XC=0)."""
+    import random
+    import struct
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fuzzgen
+    rng = random.Random(3)
+    h = bamio.Header(["c"], [1000], "")
+    recs = []
+    for i in range(3000):
+        while True:
+            parts = [fuzzgen._aux(rng, None)]
+            if rng.random() < 0.7:
+                parts.insert(rng.randrange(2), b"FLf" + struct.pack("<f", rng.random() * 1000))
+            if rng.random() < 0.3:
+                parts.insert(rng.randrange(len(parts) + 1), b"DBd" + struct.pack("<d", rng.random()))
+            kind = rng.choice("cCsSiIAZ")
+            val = {"c": struct.pack("<b", -7), "C": b"\xc8", "s": struct.pack("<h", -300), "S": struct.pack("<H", 60000),
+                   "i": struct.pack("<i", rng.randrange(1, 300)), "I": struct.pack("<I", 4000000000), "A": b"7", "Z": b"12\0"}[kind]
+            parts.insert(rng.randrange(len(parts) + 1), b"XC" + kind.encode() + val)
+            aux = b"".join(parts)
+            if not bamio.aux_walk(aux, b"XC")[1]:   # a walk that leaves the record reads stale buffer bytes in the library
+                break
+        recs.append(bamio.make_rec("r%d" % i, 0, 0, 10, 30, "10M", -1, -1, 0, "ACGTACGTAC", "IIIIIIIIII", aux))
+    path = str(tmp_path / "aux.bam")
+    bamio.write_bam(path, h, recs)
+    out = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "bamtool"), "auxi", path, "XC"], capture_output=True).stdout.split(b"\n")
+    assert len(out) == len(recs) + 1
+    lost = 0
+    for line, r in zip(out, recs):
+        want = int(line.rsplit(b"\t", 2)[2])
+        assert bamio.aux_get_int(r.aux, b"XC") == want, (line, r.aux)
+        lost += want == 0
+    assert 0 < lost < len(recs)   # both outcomes are exercised
 
 
 def test_calend_counts_m_d_n_only():
