@@ -192,9 +192,22 @@ def main():
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    if world > 1:
+        # NCCL announces its version on stdout at the first collective: keep stdout for the one JSON line
+        sys.stdout.flush()
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.all_reduce(torch.zeros(1, device="cuda"))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(keep, 1)
+            os.close(keep)
+        # the ranks share the host: split the cores for the host side of the commands (staging copies, parsing, gzip)
+        os.environ.setdefault("SEEKSV_B200_THREADS", str(max(2, (os.cpu_count() or 2) // world)))
     os.environ["SEEKSV_B200_DEVICE"] = str(local)     # the CLI entry point (svb_main) picks its GPU from the environment
     os.makedirs(WORK, exist_ok=True)
     if rank == 0:

@@ -1,9 +1,11 @@
 // C-ABI glue: contexts, error strings, per-kernel timers, BAM residency.
+#include <sys/mman.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <atomic>
 #include <memory>
+#include <future>
 #include <thread>
 
 #include "../host/bamfile.h"
@@ -283,143 +285,188 @@ static bool use_host_inflate()
     return e && *e && *e != '0';
 }
 
-// BGZF file image (host) -> uncompressed stream in HBM.
-//  default : the COMPRESSED image is staged through pinned slabs (parallel memcpy + cudaMemcpyAsync) and inflated on
-//            the device, one warp per BGZF block (inflate.cu) - about a third of the PCIe bytes and no host zlib;
-//  SEEKSV_B200_HOST_INFLATE=1 : host threads inflate the blocks into the pinned slabs (zlib) and the uncompressed
-//            bytes are streamed with cudaMemcpyAsync, each slab overlapping the inflation of the next.
-extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, int n_threads, svb_bam **out)
+namespace {
+struct BigBuf {  // a large device buffer that goes back to the context's cache on every way out
+    svb_ctx *ctx;
+    uint8_t *p = nullptr;
+    uint64_t cap = 0;
+    ~BigBuf()
+    {
+        if (!p) return;
+        cudaStreamSynchronize(ctx->copy_stream);
+        for (cudaStream_t a : ctx->aux) cudaStreamSynchronize(a);
+        cudaStreamSynchronize(ctx->stream);
+        ctx->big_put(p, cap);
+    }
+};
+struct Slabs {  // two recycled pinned staging buffers, each with the event that says "the device has taken it"
+    static constexpr uint64_t SLAB = 32ull << 20;
+    svb_ctx *ctx;
+    uint8_t *p[2] = {nullptr, nullptr};
+    uint64_t cap[2] = {0, 0};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    bool init()
+    {
+        for (int i = 0; i < 2; ++i) {
+            p[i] = (uint8_t *)ctx->pinned_get(SLAB + (64 << 10), &cap[i]);
+            if (!p[i] || cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        return true;
+    }
+    ~Slabs()
+    {
+        for (int i = 0; i < 2; ++i) {
+            if (done[i]) cudaEventSynchronize(done[i]), cudaEventDestroy(done[i]);
+            if (p[i]) ctx->pinned_put((char *)p[i], cap[i]);
+        }
+    }
+};
+
+// north-star variant: host threads inflate the blocks into the pinned slabs (zlib), the uncompressed bytes are streamed
+int load_bgzf_host_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, uint64_t file_bytes, int n_threads, std::vector<uint8_t> &head)
 {
-    if (!ctx || !out || !h_file) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_bgzf: null argument");
-    CK(cudaSetDevice(ctx->device));
-    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
     std::vector<BgzfBlock> blocks;
     uint64_t total = 0;
     std::string err;
     {
         WallScope ws(ctx, "bgzf_scan(wall)");
-        if (!bgzf_scan((const uint8_t *)h_file, file_bytes, blocks, total, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
+        if (!bgzf_scan(h_file, file_bytes, blocks, total, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
     }
-    std::unique_ptr<svb_bam> b(new svb_bam());
-    b->ctx = ctx;
-    const bool host_inflate = use_host_inflate();
-    const uint64_t SLAB = 32ull << 20;
-    uint8_t *pinned[2] = {nullptr, nullptr};
-    uint64_t pcap[2] = {0, 0};
-    cudaEvent_t done[2];
-    struct BigBuf {  // the compressed image: back to the context's cache on every way out
-        svb_ctx *ctx;
-        uint8_t *p = nullptr;
-        uint64_t cap = 0;
-        ~BigBuf()
+    WallScope ws(ctx, "host_inflate+h2d(wall)", (double)total);
+    b->d_owned = ctx->big_get(total + 256, &b->owned_cap);
+    if (!b->d_owned) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate %llu bytes of device memory", (unsigned long long)total);
+    b->d_data = b->d_owned, b->nbytes = total;
+    CK(cudaMemsetAsync(b->d_owned + total, 0, 256, ctx->stream));
+    Slabs sl{ctx};
+    if (!sl.init()) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate pinned staging");
+    int slab = 0;
+    size_t bi = 0;
+    while (bi < blocks.size()) {
+        size_t bj = bi;
+        uint64_t bytes = 0;
+        while (bj < blocks.size() && bytes + blocks[bj].ulen <= Slabs::SLAB + (64 << 10) && bytes < Slabs::SLAB) bytes += blocks[bj++].ulen;
+        CK(cudaEventSynchronize(sl.done[slab]));
+        if (!bgzf_inflate_range(h_file, blocks, bi, bj, sl.p[slab], n_threads, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
+        if (head.size() < (1u << 20)) head.insert(head.end(), sl.p[slab], sl.p[slab] + std::min<uint64_t>(bytes, (4u << 20)));
+        CK(cudaMemcpyAsync(b->d_owned + blocks[bi].uoff, sl.p[slab], bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(sl.done[slab], ctx->stream));
+        slab ^= 1;
+        bi = bj;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Default: the COMPRESSED image goes up slab by slab on the copy stream (page cache -> pinned -> HBM) while a helper thread
+// finds the BGZF block boundaries; from the moment the block table is known, the blocks that every landed slab completes
+// are inflated on the side streams (inflate.cu). Upload, scan and inflate overlap: the load costs about max of the three.
+int load_bgzf_device_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, uint64_t file_bytes, int n_threads,
+                             std::vector<uint8_t> &head)
+{
+    WallScope ws(ctx, "h2d_compressed+inflate(wall)", (double)file_bytes);
+    static_assert(sizeof(BgzfBlock) == 24, "BgzfBlock must match the device-side block descriptor");
+    std::vector<BgzfBlock> blocks;
+    uint64_t total = 0;
+    std::string scan_err;
+    std::future<bool> scan = std::async(std::launch::async, [&]() { return bgzf_scan(h_file, file_bytes, blocks, total, scan_err); });
+    struct Join {  // the helper thread writes into this frame: never leave while it runs
+        std::future<bool> &f;
+        ~Join()
         {
-            if (!p) return;
-            cudaStreamSynchronize(ctx->copy_stream);
-            for (cudaStream_t a : ctx->aux) cudaStreamSynchronize(a);
-            cudaStreamSynchronize(ctx->stream);
-            ctx->big_put(p, cap);
+            if (f.valid()) f.wait();
         }
-    } d_file{ctx};
-    {
-        WallScope ws(ctx, "stream_alloc(wall)");
+    } join{scan};
+    BigBuf d_file{ctx};
+    d_file.p = ctx->big_get(file_bytes + SVB_INFLATE_PAD, &d_file.cap);
+    if (!d_file.p) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate %llu bytes of device memory", (unsigned long long)file_bytes);
+    Slabs sl{ctx};
+    if (!sl.init()) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate pinned staging");
+    DevBuf<BgzfBlock> d_blocks;
+    DevBuf<uint32_t> d_err;
+    cudaEvent_t ready;
+    CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    struct EventGuard {
+        cudaEvent_t e;
+        ~EventGuard() { cudaEventDestroy(e); }
+    } ready_guard{ready};
+    CK(cudaMemsetAsync(d_file.p + file_bytes, 0, SVB_INFLATE_PAD, ctx->stream));
+    CK(cudaEventRecord(ready, ctx->stream));  // the image buffer is ordered before the copy stream
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+    bool have_blocks = false;
+    auto start_inflate = [&]() -> int {  // the scan is in: allocate the output, ship the block table
+        if (!scan.get()) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", scan_err.c_str());
         b->d_owned = ctx->big_get(total + 256, &b->owned_cap);
         if (!b->d_owned) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate %llu bytes of device memory", (unsigned long long)total);
+        b->d_data = b->d_owned, b->nbytes = total;
         CK(cudaMemsetAsync(b->d_owned + total, 0, 256, ctx->stream));
-        if (!host_inflate) {
-            d_file.p = ctx->big_get(file_bytes + SVB_INFLATE_PAD, &d_file.cap);
-            if (!d_file.p) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate %llu bytes of device memory", (unsigned long long)file_bytes);
-        }
-        for (int i = 0; i < 2; ++i) {
-            pinned[i] = (uint8_t *)ctx->pinned_get(SLAB + (64 << 10), &pcap[i]);
-            if (!pinned[i]) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate pinned staging");
-            CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-        }
-    }
-    b->d_data = b->d_owned, b->nbytes = total;
-    std::vector<uint8_t> head;  // first uncompressed bytes, for the header parse
-    bool ok = true;
-    int slab = 0;
-    if (host_inflate) {
-        WallScope ws(ctx, "host_inflate+h2d(wall)", (double)total);
-        size_t bi = 0;
-        while (bi < blocks.size() && ok) {
-            size_t bj = bi;
-            uint64_t bytes = 0;
-            while (bj < blocks.size() && bytes + blocks[bj].ulen <= SLAB + (64 << 10) && bytes < SLAB) bytes += blocks[bj++].ulen;
-            CK(cudaEventSynchronize(done[slab]));
-            ok = bgzf_inflate_range((const uint8_t *)h_file, blocks, bi, bj, pinned[slab], n_threads, err);
-            if (!ok) break;
-            if (head.size() < (1u << 20)) head.insert(head.end(), pinned[slab], pinned[slab] + std::min<uint64_t>(bytes, (4u << 20)));
-            CK(cudaMemcpyAsync(b->d_owned + blocks[bi].uoff, pinned[slab], bytes, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaEventRecord(done[slab], ctx->stream));
-            slab ^= 1;
-            bi = bj;
-        }
-        CK(cudaStreamSynchronize(ctx->stream));
-    } else {
-        // Pipelined: the compressed image goes up slab by slab on the copy stream; as soon as a slab has landed, the
-        // BGZF blocks it completes are inflated on one of the side streams, so the upload (page cache -> pinned -> HBM)
-        // and the inflate kernel overlap and the load costs max(upload, inflate) instead of their sum.
-        WallScope ws(ctx, "h2d_compressed+inflate(wall)", (double)total);
-        static_assert(sizeof(BgzfBlock) == 24, "BgzfBlock must match the device-side block descriptor");
-        DevBuf<BgzfBlock> d_blocks;
-        DevBuf<uint32_t> d_err;
         CK(d_blocks.alloc(blocks.size(), ctx->stream));
         CK(d_err.alloc(1, ctx->stream));
         CK(cudaMemcpyAsync(d_blocks.p, blocks.data(), blocks.size() * sizeof(BgzfBlock), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(d_err.p, 0, 4, ctx->stream));
-        CK(cudaMemsetAsync(d_file.p + file_bytes, 0, SVB_INFLATE_PAD, ctx->stream));
-        cudaEvent_t ready;
-        CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-        CK(cudaEventRecord(ready, ctx->stream));  // allocations and the block table are ordered before the side streams
-        CK(cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+        CK(cudaEventRecord(ready, ctx->stream));  // output buffer and block table are ordered before the side streams
         for (cudaStream_t a : ctx->aux) CK(cudaStreamWaitEvent(a, ready, 0));
-        size_t next_block = 0;
-        int lane = 0, rc = 0;
-        for (uint64_t o = 0; o < file_bytes && rc == 0; o += SLAB) {
-            uint64_t n = std::min(SLAB, file_bytes - o);
-            CK(cudaEventSynchronize(done[slab]));
-            {
-                WallScope wc(ctx, "stage_copy(wall)", (double)n);
-                parallel_copy(pinned[slab], (const uint8_t *)h_file + o, n, n_threads);
-            }
-            CK(cudaMemcpyAsync(d_file.p + o, pinned[slab], n, cudaMemcpyHostToDevice, ctx->copy_stream));
-            CK(cudaEventRecord(done[slab], ctx->copy_stream));
+        have_blocks = true;
+        return 0;
+    };
+    size_t next_block = 0;
+    int lane = 0, slab = 0;
+    for (uint64_t o = 0; o < file_bytes; o += Slabs::SLAB) {
+        const uint64_t n = std::min(Slabs::SLAB, file_bytes - o);
+        const bool last = o + n >= file_bytes;
+        CK(cudaEventSynchronize(sl.done[slab]));
+        {
+            WallScope wc(ctx, "stage_copy(wall)", (double)n);
+            parallel_copy(sl.p[slab], h_file + o, n, n_threads);
+        }
+        CK(cudaMemcpyAsync(d_file.p + o, sl.p[slab], n, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(sl.done[slab], ctx->copy_stream));
+        if (!have_blocks && (last || scan.wait_for(std::chrono::seconds(0)) == std::future_status::ready)) CKR(start_inflate());
+        if (have_blocks) {
             size_t b1 = next_block;
-            if (o + n >= file_bytes) b1 = blocks.size();
+            if (last) b1 = blocks.size();
             else
                 while (b1 < blocks.size() && blocks[b1].coff + blocks[b1].clen <= o + n) ++b1;
             if (b1 > next_block) {
                 cudaStream_t a = ctx->aux[lane];
                 lane = (lane + 1) % svb_ctx::N_AUX;
-                CK(cudaStreamWaitEvent(a, done[slab], 0));
-                rc = inflate_launch(a, d_file.p, d_blocks.p + next_block, (uint32_t)(b1 - next_block), b->d_owned, d_err.p);
+                CK(cudaStreamWaitEvent(a, sl.done[slab], 0));  // (the copy stream is in order: this slab implies the earlier ones)
+                CKR(inflate_launch(a, d_file.p, d_blocks.p + next_block, (uint32_t)(b1 - next_block), b->d_owned, d_err.p));
                 next_block = b1;
             }
-            slab ^= 1;
         }
-        for (cudaStream_t a : ctx->aux) {  // join the side streams
-            CK(cudaEventRecord(ready, a));
-            CK(cudaStreamWaitEvent(ctx->stream, ready, 0));
-        }
-        uint32_t h_err = 0;
-        CK(cudaMemcpyAsync(&h_err, d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        cudaEventDestroy(ready);
-        if (rc == 0 && h_err) rc = svb_fail(ctx, SVB_ERR_FORMAT, "BGZF inflate failed (corrupt deflate stream)");
-        if (rc != 0) {
-            for (int i = 0; i < 2; ++i) ctx->pinned_put((char *)pinned[i], pcap[i]), cudaEventDestroy(done[i]);
-            return rc;
-        }
-        head.resize(std::min<uint64_t>(total, 1u << 20));
-        CK(cudaMemcpy(head.data(), b->d_owned, head.size(), cudaMemcpyDeviceToHost));
+        slab ^= 1;
     }
-    for (int i = 0; i < 2; ++i) {
-        ctx->pinned_put((char *)pinned[i], pcap[i]);
-        cudaEventDestroy(done[i]);
+    if (!have_blocks) CKR(start_inflate());  // (empty file)
+    for (cudaStream_t a : ctx->aux) {  // join the side streams
+        CK(cudaEventRecord(ready, a));
+        CK(cudaStreamWaitEvent(ctx->stream, ready, 0));
     }
-    if (!ok) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
-    // header
+    uint32_t h_err = 0;
+    CK(cudaMemcpyAsync(&h_err, d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    head.resize(std::min<uint64_t>(total, 1u << 20));
+    CK(cudaMemcpyAsync(head.data(), b->d_owned, head.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (h_err) return svb_fail(ctx, SVB_ERR_FORMAT, "BGZF inflate failed (corrupt deflate stream)");
+    return 0;
+}
+}  // namespace
+
+// BGZF file image (host) -> uncompressed stream in HBM.
+//  default : the COMPRESSED image is uploaded and inflated on the device, one warp per BGZF block (inflate.cu) - about a
+//            third of the PCIe bytes and no host zlib;
+//  SEEKSV_B200_HOST_INFLATE=1 : host threads inflate the blocks (zlib) and the uncompressed bytes are uploaded.
+extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, int n_threads, svb_bam **out)
+{
+    if (!ctx || !out || !h_file) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_bgzf: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::unique_ptr<svb_bam, void (*)(svb_bam *)> b(new svb_bam(), [](svb_bam *x) { svb_bam_free(x); });
+    b->ctx = ctx;
+    std::vector<uint8_t> head;  // first uncompressed bytes, for the header parse
+    std::string err;
+    if (use_host_inflate()) CKR(load_bgzf_host_inflate(ctx, b.get(), (const uint8_t *)h_file, file_bytes, n_threads, head));
+    else CKR(load_bgzf_device_inflate(ctx, b.get(), (const uint8_t *)h_file, file_bytes, n_threads, head));
+    const uint64_t total = b->nbytes;
     BamHeader hdr;
     if (!parse_bam_header(head.data(), head.size(), hdr, err)) {
         // header longer than the captured prefix: fetch what is needed from the device copy
@@ -430,7 +477,9 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
     b->first = hdr.first_record, b->n_ref = (int32_t)hdr.names.size();
     b->names = hdr.names, b->lens = hdr.lengths;
     b->whole_file = true;  // the record chain has to end exactly at the end of the stream (checked when it is walked)
-    return finish_bam(ctx, b, out);
+    svb_bam *raw = b.release();
+    std::unique_ptr<svb_bam> plain(raw);
+    return finish_bam(ctx, plain, out);
 }
 
 // Inflate an arbitrary BGZF image on the device and return the bytes (diagnostics / tests of the inflate kernel alone).
@@ -479,7 +528,12 @@ extern "C" int svb_bam_open(svb_ctx *ctx, const char *path, int n_threads, svb_b
             WallScope ws(ctx, "file_map(wall)");
             if (!mf.open(p, err)) return svb_fail(ctx, SVB_ERR_IO, "%s", err.c_str());
         }
-        return svb_bam_from_bgzf(ctx, mf.data, mf.size, n_threads, out);
+        int rc = svb_bam_from_bgzf(ctx, mf.data, mf.size, n_threads, out);
+        if (mf.data) {  // tearing down a mapping of this size takes milliseconds: not on the caller's time
+            std::thread([d = mf.data, n = mf.size]() { munmap((void *)d, n); }).detach();
+            mf.data = nullptr;
+        }
+        return rc;
     }
     std::vector<uint8_t> file;
     if (!read_file(p, file, err)) return svb_fail(ctx, SVB_ERR_IO, "%s", err.c_str());

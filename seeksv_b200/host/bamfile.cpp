@@ -8,9 +8,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <thread>
 
 bool MappedFile::open(const std::string &path, std::string &err)
@@ -632,8 +634,13 @@ uint8_t *huffman_deflate(const uint8_t *in, size_t n, uint8_t *out)
     size_t a = 0;
     do {
         const size_t b = std::min(n, a + PIECE);
-        uint32_t freq[257] = {0};
-        for (size_t i = a; i < b; ++i) freq[in[i]]++;
+        uint32_t freq[257] = {0}, f1[256] = {0}, f2[256] = {0}, f3[256] = {0};
+        {   // four interleaved histograms: runs of one symbol do not serialise on a single counter
+            size_t i = a;
+            for (; i + 4 <= b; i += 4) freq[in[i]]++, f1[in[i + 1]]++, f2[in[i + 2]]++, f3[in[i + 3]]++;
+            for (; i < b; ++i) freq[in[i]]++;
+            for (int k = 0; k < 256; ++k) freq[k] += f1[k] + f2[k] + f3[k];
+        }
         freq[256] = 1;
         uint8_t len[258];
         huffman_lengths(freq, 257, 15, len);
@@ -684,16 +691,22 @@ uint8_t *huffman_deflate(const uint8_t *in, size_t n, uint8_t *out)
 
 bool huffman_gz_member(const char *data, size_t n, std::vector<uint8_t> &out)
 {
-    out.resize(n * 2 + (n / (64 << 10) + 1) * 512 + 64);
+    // worst case of a 15-bit-limited code on a 64 KiB piece stays below 2 bytes per input byte; the scratch is per thread and
+    // only the used part is copied out (a vector resize would zero two megabytes per member)
+    static thread_local std::unique_ptr<uint8_t[]> scratch;
+    static thread_local size_t scratch_cap = 0;
+    const size_t need = n * 2 + (n / (64 << 10) + 1) * 512 + 64;
+    if (scratch_cap < need) scratch.reset(new uint8_t[need]), scratch_cap = need;
+    uint8_t *buf = scratch.get();
     static const uint8_t head[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 3, 8, 0, 'S', 'V', 4, 0, 0, 0};
-    memcpy(out.data(), head, 18);
-    uint8_t *e = huffman_deflate((const uint8_t *)data, n, out.data() + 20);
+    memcpy(buf, head, 18);
+    uint8_t *e = huffman_deflate((const uint8_t *)data, n, buf + 20);
     uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)data, (uInt)n), isz = (uint32_t)n;
     for (int i = 0; i < 4; ++i) *e++ = (crc >> (8 * i)) & 0xff;
     for (int i = 0; i < 4; ++i) *e++ = (isz >> (8 * i)) & 0xff;
-    out.resize((size_t)(e - out.data()));
-    uint32_t sz = (uint32_t)out.size();
-    for (int i = 0; i < 4; ++i) out[16 + i] = (sz >> (8 * i)) & 0xff;
+    const uint32_t sz = (uint32_t)(e - buf);
+    for (int i = 0; i < 4; ++i) buf[16 + i] = (sz >> (8 * i)) & 0xff;
+    out.assign(buf, e);
     return true;
 }
 
@@ -744,39 +757,47 @@ bool write_gz_many(const std::vector<GzJob> &jobs, int n_threads, std::string &e
         for (uint64_t a = 0; a < n; a += PART) parts.push_back(Part{j, a, std::min(n, a + PART)});
     }
     std::vector<std::vector<uint8_t>> comp(parts.size());
+    std::unique_ptr<std::atomic<int>[]> ready(new std::atomic<int>[parts.size()]);  // 0 pending, 1 compressed, -1 failed
+    for (size_t i = 0; i < parts.size(); ++i) ready[i].store(0, std::memory_order_relaxed);
     std::atomic<size_t> next(0);
-    std::atomic<bool> bad(false);
     auto work = [&]() {
         for (;;) {
             size_t i = next.fetch_add(1);
             if (i >= parts.size()) return;
-            if (!gz_member(jobs[parts[i].job].data + parts[i].a, (size_t)(parts[i].b - parts[i].a), comp[i])) bad = true;
+            bool ok = gz_member(jobs[parts[i].job].data + parts[i].a, (size_t)(parts[i].b - parts[i].a), comp[i]);
+            ready[i].store(ok ? 1 : -1, std::memory_order_release);
         }
     };
+    // one writer per file, appending each member as soon as it is compressed (parts are handed out in file order)
+    std::vector<std::string> errs(jobs.size());
+    std::vector<size_t> first(jobs.size() + 1, parts.size());
+    for (size_t i = parts.size(); i-- > 0;) first[parts[i].job] = i;
+    for (size_t j = jobs.size(); j-- > 0;)
+        if (first[j] == parts.size()) first[j] = first[j + 1];
+    auto write_one = [&](size_t j) {
+        FILE *f = fopen(jobs[j].path.c_str(), "wb");
+        if (!f) errs[j] = "Cannot open file " + jobs[j].path;
+        for (size_t i = first[j]; i < parts.size() && parts[i].job == j; ++i) {
+            int r;
+            while ((r = ready[i].load(std::memory_order_acquire)) == 0) std::this_thread::sleep_for(std::chrono::microseconds(50));
+            if (r < 0 && errs[j].empty()) errs[j] = "gzip compression failed";
+            if (f && errs[j].empty() && fwrite(comp[i].data(), 1, comp[i].size(), f) != comp[i].size()) errs[j] = "write error on " + jobs[j].path;
+            std::vector<uint8_t>().swap(comp[i]);
+        }
+        if (f) fclose(f);
+    };
+    std::vector<std::thread> writers, th;
+    for (size_t j = 0; j < jobs.size(); ++j) writers.emplace_back(write_one, j);
     int nt = (int)std::min<size_t>((size_t)std::max(1, n_threads), parts.size());
-    std::vector<std::thread> th;
     for (int t = 1; t < nt; ++t) th.emplace_back(work);
     work();
     for (auto &t : th) t.join();
-    if (bad) {
-        err = "gzip compression failed";
-        return false;
-    }
-    size_t i = 0;
-    for (size_t j = 0; j < jobs.size(); ++j) {
-        FILE *f = fopen(jobs[j].path.c_str(), "wb");
-        if (!f) {
-            err = "Cannot open file " + jobs[j].path;
+    for (auto &t : writers) t.join();
+    for (auto &e : errs)
+        if (!e.empty()) {
+            err = e;
             return false;
         }
-        for (; i < parts.size() && parts[i].job == j; ++i)
-            if (fwrite(comp[i].data(), 1, comp[i].size(), f) != comp[i].size()) {
-                fclose(f);
-                err = "write error on " + jobs[j].path;
-                return false;
-            }
-        fclose(f);
-    }
     return true;
 }
 
