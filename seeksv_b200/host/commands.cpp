@@ -17,6 +17,11 @@
 #include <iostream>
 #include <string>
 #include <future>
+#include <mutex>
+#include <spawn.h>
+#include <sys/wait.h>
+#include <sys/stat.h>
+#include <cerrno>
 #include <thread>
 
 #include "../../include/seeksv_b200.h"
@@ -24,6 +29,8 @@
 #include "junction.h"
 
 using namespace svb;
+
+extern char **environ;
 
 namespace {
 const char *kVersion = "1.2.3";  // behaviour of the reference version this is a drop-in for (seeksv.cpp:12)
@@ -76,6 +83,67 @@ struct Gpu {  // context + error-to-exit plumbing: every failure is "message on 
     }
 };
 
+// ---- BAM residency across commands -----------------------------------------------------
+// getclip and getsv of one sample read the same BAM with an external aligner run in between. Inside `seeksv run`
+// (several commands in ONE process) a BAM that a command has loaded stays in HBM - uncompressed stream, chunk table and
+// all - and the next command that names the same file (same path, size and mtime) takes it over instead of reading,
+// uploading and inflating it again. Outside `run` nothing is kept.
+struct Resident {
+    std::string key;
+    svb_bam *bam;
+};
+bool g_keep_resident = false;
+std::vector<Resident> g_resident;  // most recently released last; at most two (tumour + normal)
+std::mutex g_resident_mutex;       // (getsv opens its BAM from a helper thread)
+
+std::string bam_key(const std::string &path)
+{
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0) return std::string();
+    char *rp = realpath(path.c_str(), nullptr);
+    std::string key = std::string(rp ? rp : path.c_str()) + "|" + std::to_string((long long)st.st_size) + "|" +
+                      std::to_string((long long)st.st_mtim.tv_sec) + "." + std::to_string((long long)st.st_mtim.tv_nsec);
+    free(rp);
+    return key;
+}
+
+int open_bam(svb_ctx *ctx, const std::string &path, svb_bam **out)
+{
+    if (g_keep_resident) {
+        std::string key = bam_key(path);
+        std::lock_guard<std::mutex> lock(g_resident_mutex);
+        for (size_t i = 0; i < g_resident.size(); ++i)
+            if (!key.empty() && g_resident[i].key == key) {
+                *out = g_resident[i].bam;
+                g_resident.erase(g_resident.begin() + i);
+                return 0;
+            }
+    }
+    return svb_bam_open(ctx, path.c_str(), n_threads(), out);
+}
+
+void release_bam(const std::string &path, svb_bam *bam)
+{
+    if (!bam) return;
+    std::string key = g_keep_resident ? bam_key(path) : std::string();
+    if (key.empty()) {
+        svb_bam_free(bam);
+        return;
+    }
+    std::lock_guard<std::mutex> lock(g_resident_mutex);
+    g_resident.push_back(Resident{key, bam});
+    while (g_resident.size() > 2) {
+        svb_bam_free(g_resident.front().bam);
+        g_resident.erase(g_resident.begin());
+    }
+}
+
+void drop_resident()
+{
+    for (auto &r : g_resident) svb_bam_free(r.bam);
+    g_resident.clear();
+}
+
 void usage_top()
 {
     std::cerr << "Program: seeksv (a tool for structural variation detection and virus integration detection)" << '\n'
@@ -84,7 +152,9 @@ void usage_top()
               << "Usage: seeksv <command> [options]\n\n"
               << "Command: getclip\tget soft-clipped reads\n"
               << "         getsv  \tget final sv\n"
-              << "         somatic\tget somatic sv" << std::endl;
+              << "         somatic\tget somatic sv\n"
+              << "         run    \tseveral commands in one process, BAMs stay on the GPU in between:\n"
+              << "                \tseeksv run -- getclip ... -- <any shell command, e.g. the aligner> -- getsv ..." << std::endl;
 }
 
 void usage_cmd(const char *prog, const char *command, int i)
@@ -185,7 +255,7 @@ int cmd_getclip(int argc, char **argv)
     if (!g.open()) return 1;
     ph.mark("getclip: context");
     svb_bam *bam = nullptr;
-    if (svb_bam_open(g.ctx, bamfile.c_str(), n_threads(), &bam) != 0) {
+    if (open_bam(g.ctx, bamfile, &bam) != 0) {
         std::cerr << "[main_samview] fail to open file for reading." << std::endl;
         return fail(std::string("[seeksv_b200] ") + svb_last_error(g.ctx));
     }
@@ -197,6 +267,8 @@ int cmd_getclip(int argc, char **argv)
         svb_bam_free(bam);
         return fail(std::string("[seeksv_b200] ") + svb_last_error(g.ctx));
     }
+    release_bam(bamfile, bam);  // (kept on the GPU for the next command inside `seeksv run`, freed otherwise)
+    bam = nullptr;
     const char *ext[4] = {".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz"};
     int status = 0;
     std::vector<GzJob> jobs;
@@ -211,7 +283,6 @@ int cmd_getclip(int argc, char **argv)
     ph.mark("getclip: gzip + write outputs");
     std::cerr << "[GetSClipReads] finished!" << std::endl;
     svb_clusters_free(cl);
-    svb_bam_free(bam);
     return status;
 }
 
@@ -419,18 +490,19 @@ int cmd_getsv(int argc, char **argv)
     struct Prefetch {
         std::future<int> f;
         svb_bam **bam;
+        const std::string *path;
         int wait() { return f.valid() ? f.get() : 0; }
         ~Prefetch()
         {
             wait();
-            if (*bam) svb_bam_free(*bam), *bam = nullptr;
+            if (*bam) release_bam(*path, *bam), *bam = nullptr;
         }
-    } prefetch{{}, &bam};
+    } prefetch{{}, &bam, &original_bam};
     bool load_failed = false;
     if (pairs_used >= 100000)
         prefetch.f = std::async(std::launch::async, [&]() -> int {
             if (!g.open()) return 1;
-            return svb_bam_open(g.ctx, original_bam.c_str(), n_threads(), &bam) != 0 ? 2 : 0;
+            return open_bam(g.ctx, original_bam, &bam) != 0 ? 2 : 0;
         });
     if (!load_alignments(clip_aln, alns, err)) {
         std::cerr << "[main_samview] fail to open file for reading." << std::endl;
@@ -451,7 +523,7 @@ int cmd_getsv(int argc, char **argv)
         if (rc == 0 && bam) return true;
         if (rc == 0) {
             if (!g.ctx && !g.open()) return false;
-            rc = svb_bam_open(g.ctx, original_bam.c_str(), n_threads(), &bam) != 0 ? 2 : 0;
+            rc = open_bam(g.ctx, original_bam, &bam) != 0 ? 2 : 0;
         }
         if (rc != 0) {
             load_failed = true;
@@ -565,7 +637,7 @@ int cmd_somatic(int argc, char **argv)
     Gpu g;
     if (!g.open()) return 1;
     svb_bam *bam = nullptr;
-    if (svb_bam_open(g.ctx, normal_bam.c_str(), n_threads(), &bam) != 0) {
+    if (open_bam(g.ctx, normal_bam, &bam) != 0) {
         std::cerr << "[main_samview] fail to open file for reading." << std::endl;
         return fail(std::string("[seeksv_b200] ") + svb_last_error(g.ctx));
     }
@@ -596,7 +668,7 @@ int cmd_somatic(int argc, char **argv)
         else fout << rows[i].prefix << '\t' << rows[i].normal_left << '\t' << rows[i].normal_right << '\t' << per_row[i] << '\n';
     }
     fout.close();
-    svb_bam_free(bam);
+    release_bam(normal_bam, bam);
     return 0;
 }
 }  // namespace
@@ -663,6 +735,60 @@ extern "C" int svb_plan_getsv(const char *clip_aln, const char *clip_file, int32
     return 0;
 }
 
+// `seeksv run -- <command> [-- <command> ...]`: getclip / getsv / somatic segments run in this process (BAMs stay resident
+// between them), every other segment is executed as an external command (one word: through `sh -c`) and waited for.
+static int cmd_run(int argc, char **argv)
+{
+    std::vector<std::vector<std::string>> segs;
+    for (int i = 1; i < argc; ++i) {
+        if (strcmp(argv[i], "--") == 0) {
+            segs.emplace_back();
+            continue;
+        }
+        if (segs.empty()) segs.emplace_back();
+        segs.back().push_back(argv[i]);
+    }
+    segs.erase(std::remove_if(segs.begin(), segs.end(), [](const std::vector<std::string> &v) { return v.empty(); }), segs.end());
+    if (segs.empty()) {
+        usage_top();
+        return 1;
+    }
+    g_keep_resident = true;
+    int rc = 0;
+    for (auto &seg : segs) {
+        const std::string &c = seg[0];
+        if (c == "getclip" || c == "getsv" || c == "somatic") {
+            std::vector<char *> av;
+            std::string prog = "seeksv";
+            av.push_back(&prog[0]);
+            for (auto &a : seg) av.push_back(&a[0]);
+            rc = svb_main((int)av.size(), av.data());
+        } else {
+            std::cout << std::flush;
+            std::cerr << std::flush;
+            std::vector<std::string> cmd = seg;
+            if (cmd.size() == 1) cmd = {"sh", "-c", seg[0]};
+            std::vector<char *> av;
+            for (auto &a : cmd) av.push_back(&a[0]);
+            av.push_back(nullptr);
+            pid_t pid = 0;
+            if (posix_spawnp(&pid, av[0], nullptr, nullptr, av.data(), environ) != 0) {
+                std::cerr << "[seeksv run] cannot execute " << cmd[0] << std::endl;
+                rc = 1;
+            } else {
+                int st = 0;
+                while (waitpid(pid, &st, 0) < 0 && errno == EINTR) {}
+                rc = WIFEXITED(st) ? WEXITSTATUS(st) : 1;
+                if (rc != 0) std::cerr << "[seeksv run] '" << c << "' ended with status " << rc << std::endl;
+            }
+        }
+        if (rc != 0) break;
+    }
+    drop_resident();
+    g_keep_resident = false;
+    return rc;
+}
+
 extern "C" int svb_main(int argc, char **argv)
 {
     // main + SelectStep, seeksv.cpp:26-58,444-457
@@ -670,6 +796,7 @@ extern "C" int svb_main(int argc, char **argv)
         usage_top();
         return 1;
     }
+    if (strcmp(argv[1], "run") == 0) return cmd_run(argc - 1, argv + 1);
     const char *cmds[4] = {"getclip", "getsv", "somatic", "cluster"};
     int i = 0;
     for (; i < 4; ++i)

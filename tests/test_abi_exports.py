@@ -88,3 +88,25 @@ def test_getsv_host_only_mode_matches_reference(lib, d, s, tmp_path):
     assert r.returncode == 0, r.stderr
     assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".n0D.sv"))
     assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".n0D.stdout"))
+
+
+def test_run_command_chains_segments_and_stops_on_failure(lib, tmp_path):
+    """`seeksv run -- a -- b -- c`: seeksv commands run in-process, other segments are executed and waited for; the chain
+    stops at the first non-zero status. (Host-only getsv mode, so no GPU is needed here.)"""
+    import gzip
+    d, s = "micro", "tumor"
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, s + ".clip.txt")).encode("latin-1"))
+    out, marker = str(tmp_path / "out.sv"), str(tmp_path / "marker")
+    getsv = ["getsv", "-n", "0", "-D", os.path.join(GOLDEN, d, s + ".clip.sam"), os.path.join(GOLDEN, d, s + ".sort.bam"), clip, out,
+             str(tmp_path / "unm")]
+    r = _cli(["run", "--", "sh", "-c", "echo one > " + marker, "--", "echo two >> " + marker, "--"] + getsv)
+    assert r.returncode == 0, r.stderr
+    assert open(marker).read() == "one\ntwo\n"
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".n0D.sv"))
+    os.remove(out)
+    r = _cli(["run", "--", "exit 3", "--"] + getsv)
+    assert r.returncode == 3 and not os.path.exists(out)
+    r = _cli(["run"])
+    assert r.returncode == 1

@@ -301,3 +301,19 @@ def test_alternative_full_pass_forms_give_identical_results(mode, tmp_path, monk
                            capture_output=True, text=True, env=dict(os.environ))
         assert r.returncode == 0, r.stderr
         assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".sv"))
+
+
+@pytest.mark.parametrize("d,s", [("micro", "tumor"), ("fuzz", "f11")])
+def test_run_keeps_the_bam_resident_and_gives_the_same_outputs(d, s, tmp_path):
+    """`seeksv run -- getclip ... -- <aligner stand-in> -- getsv ...`: one process, the BAM is loaded once (the second command
+    takes the resident copy over), outputs identical to the separate commands / the reference"""
+    pre = str(tmp_path / s)
+    out = str(tmp_path / (s + ".sv"))
+    env = dict(os.environ, SEEKSV_B200_TIMING="1")
+    r = subprocess.run([_cli(), "run", "--", "getclip", "-o", pre, _bam(d, s), "--", "test -s %s.clip.fq.gz" % pre, "--",
+                        "getsv", os.path.join(GOLDEN, d, s + ".clip.sam"), _bam(d, s), pre + ".clip.gz", out, str(tmp_path / "unm")],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert _zcat(pre + ".clip.gz") == read_text(os.path.join(GOLDEN, d, s + ".clip.txt"))
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".sv"))
+    assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".getsv.stdout"))
