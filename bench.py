@@ -334,7 +334,8 @@ def main():
         for _ in range(max(1, args.warmup)):
             e2e_step()
         ms_e2e, wall_e2e, _ = timed(e2e_step, args.steps)
-        fused_step()
+        for _ in range(max(1, args.warmup)):
+            fused_step()
         _, wall_fused, _ = timed(fused_step, args.steps)
     finally:
         os.dup2(saved, 2)
