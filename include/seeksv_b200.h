@@ -70,6 +70,21 @@ int svb_bam_from_host(svb_ctx *ctx, const void *h_stream, uint64_t nbytes, uint6
  * streamed. The two paths produce identical bytes. n_threads <= 0: use all hardware threads. */
 int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, int n_threads, svb_bam **out);
 int svb_bam_open(svb_ctx *ctx, const char *path, int n_threads, svb_bam **out); /* .bam, else SAM text */
+
+/* Chromosome shard of an indexed, coordinate-sorted BAM: the records of references [tid_begin, tid_end), cut at exact
+ * record boundaries with the .bai (bai_path NULL: bam_path + ".bai"; the index the reference requires for getsv and
+ * somatic, seeksv.cpp:272-279, somatic.cpp:47-54, read with bam_index_load there). Only the BGZF blocks of the range are
+ * read and inflated. The range that reaches the last reference with records also holds the unplaced reads at the end of
+ * the file. The handle carries the full reference dictionary, so tids mean the same in every shard. */
+int svb_bam_open_refs(svb_ctx *ctx, const char *bam_path, const char *bai_path, int32_t tid_begin, int32_t tid_end, int n_threads,
+                      svb_bam **out);
+/* tid of the last record of the stream that takes getclip's mapped branch (neither FUNMAP nor FMUNMAP set,
+ * clip_reads.h:415-438): what the next shard passes as svb_getclip_params.prev_tid. *has_one = 0 if there is none. */
+int svb_bam_last_mapped_tid(svb_ctx *ctx, svb_bam *bam, int32_t *has_one, int32_t *tid);
+/* Host only: BGZF virtual offset (compressed offset << 16 | offset inside the block) of the first record of every reference
+ * according to the .bai, ~0 for references without records. Returns the number of references in the index (writes at most
+ * `cap` entries), negative on error. */
+int64_t svb_bai_first_offsets(const char *bai_path, uint64_t *first_voff, int64_t cap);
 void svb_bam_free(svb_bam *bam);
 
 /* The resident uncompressed stream of a svb_bam (device pointer, byte count, offset of the first record), e.g. to
@@ -100,6 +115,11 @@ typedef struct svb_getclip_params {
     /* Sharded runs: tid of the last mapped-branch record BEFORE this shard (quirk Q1); 0 for a whole
      * file (clip_reads.h:407 starts last_tid at 0). */
     int32_t prev_tid;
+    /* Sharded runs: mates of the unmapped branch are paired by name across the WHOLE file (clip_reads.h:172-219), so a
+     * shard cannot pair on its own. With this flag set the shard skips the pairing (texts 2 and 3 stay empty) and hands
+     * back its unmapped-branch records instead (svb_clusters_unmapped_records); the merging rank concatenates the shards'
+     * records in file order into one small stream and runs svb_getclip on it for the two FASTQ texts. */
+    int32_t export_unmapped_records;
 } svb_getclip_params;
 
 typedef struct svb_clusters svb_clusters; /* host-resident result of svb_getclip */
@@ -112,6 +132,8 @@ uint64_t svb_clusters_candidates(const svb_clusters *c); /* soft-clipped reads t
  * (DisplaySClipReadsAndClipFq clip_reads.h:300-345, StoreUnmapSeqAndQual clip_reads.h:172-219), as
  * host buffers owned by the result object. which: 0 clip, 1 clip.fq, 2 unmapped_1, 3 unmapped_2. */
 int svb_clusters_text(const svb_clusters *c, int which, const char **data, uint64_t *len);
+/* The packed BAM records (block_size + body, file order) of the unmapped branch; only with export_unmapped_records. */
+int svb_clusters_unmapped_records(const svb_clusters *c, const char **data, uint64_t *len);
 
 /* ---- getsv / somatic device passes ----------------------------------------------------------------- */
 

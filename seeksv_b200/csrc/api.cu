@@ -361,7 +361,7 @@ int load_bgzf_host_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, uint
 // finds the BGZF block boundaries; from the moment the block table is known, the blocks that every landed slab completes
 // are inflated on the side streams (inflate.cu). Upload, scan and inflate overlap: the load costs about max of the three.
 int load_bgzf_device_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, uint64_t file_bytes, int n_threads,
-                             std::vector<uint8_t> &head)
+                             std::vector<uint8_t> &head, uint32_t lead = 0)  // lead: bytes left free in front of the output
 {
     WallScope ws(ctx, "h2d_compressed+inflate(wall)", (double)file_bytes);
     static_assert(sizeof(BgzfBlock) == 24, "BgzfBlock must match the device-side block descriptor");
@@ -395,10 +395,10 @@ int load_bgzf_device_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, ui
     bool have_blocks = false;
     auto start_inflate = [&]() -> int {  // the scan is in: allocate the output, ship the block table
         if (!scan.get()) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", scan_err.c_str());
-        b->d_owned = ctx->big_get(total + 256, &b->owned_cap);
+        b->d_owned = ctx->big_get(lead + total + 256, &b->owned_cap);
         if (!b->d_owned) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate %llu bytes of device memory", (unsigned long long)total);
-        b->d_data = b->d_owned, b->nbytes = total;
-        CK(cudaMemsetAsync(b->d_owned + total, 0, 256, ctx->stream));
+        b->d_data = b->d_owned + lead, b->nbytes = total;
+        CK(cudaMemsetAsync(b->d_owned + lead + total, 0, 256, ctx->stream));
         CK(d_blocks.alloc(blocks.size(), ctx->stream));
         CK(d_err.alloc(1, ctx->stream));
         CK(cudaMemcpyAsync(d_blocks.p, blocks.data(), blocks.size() * sizeof(BgzfBlock), cudaMemcpyHostToDevice, ctx->stream));
@@ -430,7 +430,7 @@ int load_bgzf_device_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, ui
                 cudaStream_t a = ctx->aux[lane];
                 lane = (lane + 1) % svb_ctx::N_AUX;
                 CK(cudaStreamWaitEvent(a, sl.done[slab], 0));  // (the copy stream is in order: this slab implies the earlier ones)
-                CKR(inflate_launch(a, d_file.p, d_blocks.p + next_block, (uint32_t)(b1 - next_block), b->d_owned, d_err.p));
+                CKR(inflate_launch(a, d_file.p, d_blocks.p + next_block, (uint32_t)(b1 - next_block), b->d_owned + lead, d_err.p));
                 next_block = b1;
             }
         }
@@ -444,7 +444,7 @@ int load_bgzf_device_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, ui
     uint32_t h_err = 0;
     CK(cudaMemcpyAsync(&h_err, d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     head.resize(std::min<uint64_t>(total, 1u << 20));
-    CK(cudaMemcpyAsync(head.data(), b->d_owned, head.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(head.data(), b->d_data, head.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (h_err) return svb_fail(ctx, SVB_ERR_FORMAT, "BGZF inflate failed (corrupt deflate stream)");
     return 0;
@@ -543,6 +543,72 @@ extern "C" int svb_bam_open(svb_ctx *ctx, const char *path, int n_threads, svb_b
     CKR(svb_bam_from_host(ctx, stream.data(), stream.size(), hdr.first_record, (int32_t)hdr.names.size(), out));
     (*out)->names = hdr.names, (*out)->lens = hdr.lengths;
     return 0;
+}
+
+// Records of references [tid_begin, tid_end) of a coordinate-sorted, indexed BAM (the chromosome shard of one rank). The
+// .bai gives the BGZF virtual offset of the first record of every reference (bam_index_build, sam/bam.h:498-536), so the
+// shard is cut at exact record boundaries: only the BGZF blocks between the two offsets are read, uploaded and inflated.
+// The range that reaches the last reference with records also takes the unplaced reads at the end of the file.
+extern "C" int svb_bam_open_refs(svb_ctx *ctx, const char *bam_path, const char *bai_path, int32_t tid_begin, int32_t tid_end,
+                                 int n_threads, svb_bam **out)
+{
+    if (!ctx || !bam_path || !out) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_open_refs: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::string err, bai = bai_path ? bai_path : std::string(bam_path) + ".bai";
+    MappedFile mf;
+    if (!mf.open(bam_path, err)) return svb_fail(ctx, SVB_ERR_IO, "%s", err.c_str());
+    BamHeader hdr;
+    if (!read_bam_header(mf.data, mf.size, hdr, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
+    std::vector<uint64_t> first;
+    if (!bai_first_offsets(bai, first, err)) return svb_fail(ctx, SVB_ERR_IO, "%s", err.c_str());
+    const int32_t n_ref = (int32_t)hdr.names.size();
+    if (first.size() != (size_t)n_ref) return svb_fail(ctx, SVB_ERR_FORMAT, "%s does not belong to %s (reference count)", bai.c_str(), bam_path);
+    tid_begin = std::max(tid_begin, 0), tid_end = std::min(tid_end, n_ref);
+    const uint64_t NONE = ~0ull;
+    uint64_t v0 = NONE, v1 = NONE;  // virtual offsets: first record of the range, first record after it (NONE: end of file)
+    for (int32_t t = tid_begin; t < tid_end && v0 == NONE; ++t) v0 = first[t];
+    for (int32_t t = tid_end; t < n_ref && v1 == NONE; ++t) v1 = first[t];
+    std::unique_ptr<svb_bam, void (*)(svb_bam *)> b(new svb_bam(), [](svb_bam *x) { svb_bam_free(x); });
+    b->ctx = ctx;
+    b->first = 0, b->n_ref = n_ref, b->names = hdr.names, b->lens = hdr.lengths;
+    b->whole_file = true;  // the shard ends on a record boundary: the chain has to end exactly there
+    if (v0 != NONE) {
+        const uint64_t c0 = v0 >> 16, u0 = v0 & 0xffff;
+        uint64_t c_end = mf.size, u1 = 0;
+        bool cut_last = false;
+        if (v1 != NONE) {
+            c_end = v1 >> 16, u1 = v1 & 0xffff;
+            if (u1) {  // the block that holds the boundary is needed too
+                uint32_t bs = bgzf_block_size(mf.data, mf.size, c_end);
+                if (!bs) return svb_fail(ctx, SVB_ERR_FORMAT, "index offset does not point at a BGZF block");
+                c_end += bs;
+                cut_last = true;
+            }
+        }
+        if (c0 >= c_end || c_end > mf.size) return svb_fail(ctx, SVB_ERR_FORMAT, "index offsets out of range");
+        std::vector<uint8_t> head;
+        const uint32_t lead = (uint32_t)((16 - (u0 & 15)) & 15);  // the shard's first byte lands on a 16-byte boundary
+        CKR(load_bgzf_device_inflate(ctx, b.get(), mf.data + c0, c_end - c0, n_threads, head, lead));
+        uint64_t total = b->nbytes, tail_cut = 0;
+        if (cut_last) {
+            // uncompressed size of the last block = its ISIZE field
+            const uint8_t *t = mf.data + c_end - 4;
+            uint64_t last_ulen = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint64_t)t[3] << 24);
+            if (u1 > last_ulen) return svb_fail(ctx, SVB_ERR_FORMAT, "index offset beyond its block");
+            tail_cut = last_ulen - u1;
+        }
+        if (u0 + tail_cut > total) return svb_fail(ctx, SVB_ERR_FORMAT, "index offsets out of range");
+        b->d_data += u0, b->nbytes = total - u0 - tail_cut;
+    } else {  // no records in the range: an empty stream (on a real allocation, so that every kernel has a valid pointer)
+        b->d_owned = ctx->big_get(4096, &b->owned_cap);
+        if (!b->d_owned) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate device memory");
+        CK(cudaMemsetAsync(b->d_owned, 0, 4096, ctx->stream));
+        b->d_data = b->d_owned, b->nbytes = 0;
+    }
+    svb_bam *raw = b.release();
+    std::unique_ptr<svb_bam> plain(raw);
+    return finish_bam(ctx, plain, out);
 }
 
 extern "C" void svb_bam_free(svb_bam *b)

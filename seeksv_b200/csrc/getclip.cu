@@ -14,10 +14,12 @@
 struct svb_clusters {
     svb_ctx *ctx = nullptr;
     PinnedBuf text[4];  // pinned host memory: D2H at full PCIe rate, recycled through the ctx pool
+    PinnedBuf unmapped_records;  // sharded runs: the raw unmapped-branch records (svb_getclip_params.export_unmapped_records)
     uint64_t n_clusters = 0, n_candidates = 0;
     ~svb_clusters()
     {
         for (auto &t : text) t.release(ctx);
+        unmapped_records.release(ctx);
     }
 };
 
@@ -795,6 +797,62 @@ static int sort_u64(svb_ctx *ctx, uint64_t *keys_in, uint64_t *keys_out, uint32_
 
 static inline unsigned nblk(uint64_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
 
+// ---- shard plumbing: raw records of the unmapped branch, packed in file order ------------------------------------
+__global__ void record_sizes(uint32_t n, const uint64_t *__restrict__ off, const uint8_t *__restrict__ d, uint64_t *__restrict__ size)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    size[i] = i < n ? 4ull + ldu32(d + off[i]) : 0ull;
+}
+__global__ void record_copy(uint32_t n, const uint64_t *__restrict__ off, const uint8_t *__restrict__ d, const uint64_t *__restrict__ dst_off,
+                            uint8_t *__restrict__ dst)
+{
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const uint8_t *src = d + off[w];
+    uint8_t *out = dst + dst_off[w];
+    const uint64_t bytes = dst_off[w + 1] - dst_off[w];
+    for (uint64_t i = lane; i < bytes; i += 32) out[i] = src[i];
+}
+
+// ---- shard plumbing: tid of the last mapped-branch record (what the next shard needs as prev_tid, quirk Q1) -----------
+__global__ void last_mapped_walk(const uint8_t *__restrict__ d, uint64_t n_chunks, const uint64_t *__restrict__ guess,
+                                 const uint32_t *__restrict__ count, int32_t *__restrict__ chunk_tid, unsigned long long *__restrict__ last_chunk)
+{
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    uint64_t o = guess[c];
+    int32_t tid = 0;
+    bool any = false;
+    for (uint32_t i = 0, k = count[c]; i < k; ++i) {
+        const Core core = load_core(d + o);
+        if (!(core.flag & (F_UNMAP | F_MUNMAP))) tid = core.tid, any = true;  // clip_reads.h:415,423-438: only these move last_tid
+        o += 4 + (uint64_t)(uint32_t)core.block_size;
+    }
+    chunk_tid[c] = tid;
+    if (any) atomicMax(last_chunk, (unsigned long long)c + 1);
+}
+
+extern "C" int svb_bam_last_mapped_tid(svb_ctx *ctx, svb_bam *bam, int32_t *has_one, int32_t *tid)
+{
+    if (!ctx || !bam || !has_one || !tid) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_last_mapped_tid: null argument");
+    CK(cudaSetDevice(ctx->device));
+    CKR(ensure_counts(ctx, bam));  // verified chunk table
+    cudaStream_t s = ctx->stream;
+    DevBuf<int32_t> chunk_tid;
+    DevBuf<unsigned long long> last_chunk;
+    CK(chunk_tid.alloc(bam->n_chunks, s));
+    CK(last_chunk.alloc(1, s));
+    CK(cudaMemsetAsync(last_chunk.p, 0, 8, s));
+    last_mapped_walk<<<nblk(bam->n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->n_chunks, bam->d_guess, bam->d_count, chunk_tid.p, last_chunk.p);
+    unsigned long long lc = 0;
+    CK(cudaMemcpyAsync(&lc, last_chunk.p, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *has_one = lc != 0, *tid = 0;
+    if (lc) CK(cudaMemcpy(tid, chunk_tid.p + (lc - 1), 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params *prm, svb_clusters **out_)
 {
     if (!ctx || !bam || !prm || !out_) return svb_fail(ctx, SVB_ERR_ARG, "svb_getclip: null argument");
@@ -885,15 +943,31 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         cudaStream_t c;
         ~CopyJoin() { cudaStreamSynchronize(c); }
     } copy_join{ctx->copy_stream};
+    DevBuf<uint32_t> val0, val1, mate_of, ovf;
+    DevBuf<uint64_t> un_sorted, ukey0, ukey1, sz1, sz2, off1, off2;
     if (n_un) {
-        DevBuf<uint32_t> val0, val1, mate_of, ovf;
-        DevBuf<uint64_t> un_sorted, key0, key1, sz1, sz2, off1, off2;
         CK(un_sorted.alloc(n_un, s));
         CKR(sort_u64(ctx, un_list.p, un_sorted.p, n_un, off_bits));
+    }
+    if (n_un && prm->export_unmapped_records) {  // a shard: hand the records to the merging rank instead of pairing here
+        DevBuf<uint64_t> sz, ro;
+        CK(sz.alloc(n_un + 1, s));
+        CK(ro.alloc(n_un + 1, s));
+        record_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_sorted.p, bam->d_data, sz.p);
+        CKR(exclusive_scan_u64(ctx, sz.p, ro.p, n_un + 1));
+        uint64_t total = 0;
+        CK(cudaMemcpyAsync(&total, ro.p + n_un, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(un_o1.alloc(total, s));
+        record_copy<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_sorted.p, bam->d_data, ro.p, (uint8_t *)un_o1.p);
+        CKR(res->unmapped_records.reserve(ctx, total));
+        CK(cudaMemcpyAsync(res->unmapped_records.p, un_o1.p, total, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    } else if (n_un) {
         CK(val0.alloc(n_un, s));
         CK(val1.alloc(n_un, s));
-        CK(key0.alloc(n_un, s));
-        CK(key1.alloc(n_un, s));
+        CK(ukey0.alloc(n_un, s));
+        CK(ukey1.alloc(n_un, s));
         CK(mate_of.alloc(n_un, s));
         CK(ovf.alloc(1, s));
         CK(sz1.alloc(n_un + 1, s));
@@ -905,13 +979,13 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         uint64_t tot[2] = {0, 0};
         {
             ProfScope ps(ctx, "unmapped_pair", 0);
-            unmapped_hash<<<nblk(n_un, 256), 256, 0, s>>>(n_un, un_sorted.p, bam->d_data, key0.p, val0.p);
+            unmapped_hash<<<nblk(n_un, 256), 256, 0, s>>>(n_un, un_sorted.p, bam->d_data, ukey0.p, val0.p);
             size_t tmp = 0;
-            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, key0.p, key1.p, val0.p, val1.p, (int)n_un, 0, 64, s));
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ukey0.p, ukey1.p, val0.p, val1.p, (int)n_un, 0, 64, s));
             DevBuf<uint8_t> t;
             CK(t.alloc(tmp, s));
-            CK(cub::DeviceRadixSort::SortPairs(t.p, tmp, key0.p, key1.p, val0.p, val1.p, (int)n_un, 0, 64, s));
-            unmapped_pair<<<nblk(n_un, 128), 128, 0, s>>>(n_un, key1.p, val1.p, un_sorted.p, bam->d_data, mate_of.p, ovf.p);
+            CK(cub::DeviceRadixSort::SortPairs(t.p, tmp, ukey0.p, ukey1.p, val0.p, val1.p, (int)n_un, 0, 64, s));
+            unmapped_pair<<<nblk(n_un, 128), 128, 0, s>>>(n_un, ukey1.p, val1.p, un_sorted.p, bam->d_data, mate_of.p, ovf.p);
             unmapped_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_sorted.p, mate_of.p, bam->d_data, sz1.p, sz2.p);
             CKR(exclusive_scan_u64(ctx, sz1.p, off1.p, n_un + 1));
             CKR(exclusive_scan_u64(ctx, sz2.p, off2.p, n_un + 1));
@@ -1076,6 +1150,14 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
 extern "C" void svb_clusters_free(svb_clusters *c) { delete c; }
 extern "C" uint64_t svb_clusters_count(const svb_clusters *c) { return c ? c->n_clusters : 0; }
 extern "C" uint64_t svb_clusters_candidates(const svb_clusters *c) { return c ? c->n_candidates : 0; }
+extern "C" int svb_clusters_unmapped_records(const svb_clusters *c, const char **data, uint64_t *len)
+{
+    if (!c || !data || !len) return SVB_ERR_ARG;
+    *data = c->unmapped_records.p ? c->unmapped_records.p : "";
+    *len = c->unmapped_records.n;
+    return 0;
+}
+
 extern "C" int svb_clusters_text(const svb_clusters *c, int which, const char **data, uint64_t *len)
 {
     if (!c || which < 0 || which > 3 || !data || !len) return SVB_ERR_ARG;

@@ -86,6 +86,12 @@ static uint32_t bgzf_member(const uint8_t *f, uint64_t n, uint64_t o, uint32_t *
     return bsize;
 }
 
+uint32_t bgzf_block_size(const uint8_t *file, uint64_t n, uint64_t offset)
+{
+    uint32_t xl;
+    return bgzf_member(file, n, offset, &xl);
+}
+
 // The member chain is serial (each header gives the next offset). Like the record chain on the device it is cut into
 // segments whose first header is GUESSED (magic + BC + a valid successor), walked in parallel, and stitched only where
 // each segment's exit equals the next segment's guess; anything else falls back to the serial walk.
@@ -159,6 +165,79 @@ bool bgzf_scan(const uint8_t *f, uint64_t n, std::vector<BgzfBlock> &blocks, uin
     }
     blocks.resize(w);
     return true;
+}
+
+static bool inflate_block(const uint8_t *src, uint32_t clen, uint8_t *dst, uint32_t ulen);
+
+bool bai_first_offsets(const std::string &bai_path, std::vector<uint64_t> &first_voff, std::string &err)
+{
+    std::vector<uint8_t> d;
+    if (!read_file(bai_path, d, err)) return false;
+    auto bad = [&]() {
+        err = "malformed index " + bai_path;
+        return false;
+    };
+    if (d.size() < 8 || memcmp(d.data(), "BAI\1", 4) != 0) return bad();
+    size_t o = 4;
+    auto i32 = [&](int32_t &v) {
+        if (o + 4 > d.size()) return false;
+        memcpy(&v, &d[o], 4);
+        o += 4;
+        return true;
+    };
+    int32_t n_ref = 0;
+    if (!i32(n_ref) || n_ref < 0) return bad();
+    first_voff.assign((size_t)n_ref, ~0ull);
+    for (int32_t t = 0; t < n_ref; ++t) {
+        int32_t n_bin = 0;
+        if (!i32(n_bin) || n_bin < 0) return bad();
+        for (int32_t b = 0; b < n_bin; ++b) {
+            int32_t bin_raw = 0, n_chunk = 0;
+            if (!i32(bin_raw) || !i32(n_chunk) || n_chunk < 0 || o + 16ull * (uint64_t)n_chunk > d.size()) return bad();
+            const uint32_t bin = (uint32_t)bin_raw;
+            for (int32_t c = 0; c < n_chunk; ++c) {
+                uint64_t beg;
+                memcpy(&beg, &d[o + 16 * (size_t)c], 8);
+                if (bin != 37450u) first_voff[t] = std::min(first_voff[t], beg);  // 37450: samtools' metadata pseudo-bin
+            }
+            o += 16 * (size_t)n_chunk;
+        }
+        int32_t n_intv = 0;
+        if (!i32(n_intv) || n_intv < 0 || o + 8ull * (uint64_t)n_intv > d.size()) return bad();
+        o += 8 * (size_t)n_intv;
+    }
+    return true;
+}
+
+bool read_bam_header(const uint8_t *f, uint64_t n, BamHeader &h, std::string &err)
+{
+    std::vector<uint8_t> text;
+    std::vector<BgzfBlock> blocks;
+    uint64_t o = 0, want = 1u << 20;
+    for (;;) {
+        while (o < n && text.size() < want) {
+            uint32_t xl, bs = bgzf_member(f, n, o, &xl);
+            if (!bs || o + bs > n) {
+                err = "not a BGZF file (bad block header)";
+                return false;
+            }
+            uint32_t ulen = f[o + bs - 4] | (f[o + bs - 3] << 8) | (f[o + bs - 2] << 16) | ((uint32_t)f[o + bs - 1] << 24);
+            size_t at = text.size();
+            text.resize(at + ulen);
+            if (ulen && !inflate_block(f + o + 12 + xl, bs - xl - 20, text.data() + at, ulen)) {
+                err = "BGZF inflate failed";
+                return false;
+            }
+            o += bs;
+        }
+        std::string e2;
+        if (parse_bam_header(text.data(), text.size(), h, e2)) return true;
+        if (o >= n) {
+            err = e2;
+            return false;
+        }
+        want *= 4;
+    }
 }
 
 static bool inflate_block(const uint8_t *src, uint32_t clen, uint8_t *dst, uint32_t ulen)

@@ -28,12 +28,18 @@ struct MappedFile {  // read-only mmap of a whole file
     ~MappedFile();
 };
 bool read_file(const std::string &path, std::vector<uint8_t> &out, std::string &err);
+uint32_t bgzf_block_size(const uint8_t *file, uint64_t n, uint64_t offset);  // whole member at `offset`, 0 if it is not one
 bool bgzf_scan(const uint8_t *file, uint64_t n, std::vector<BgzfBlock> &blocks, uint64_t &total, std::string &err);
 // inflate blocks [b0, b1) into dst (dst[0] corresponds to blocks[b0].uoff) with n_threads host threads
 bool bgzf_inflate_range(const uint8_t *file, const std::vector<BgzfBlock> &blocks, size_t b0, size_t b1, uint8_t *dst,
                         int n_threads, std::string &err);
 bool bgzf_inflate_all(const uint8_t *file, uint64_t n, std::vector<uint8_t> &out, int n_threads, std::string &err);
 bool parse_bam_header(const uint8_t *data, uint64_t n, BamHeader &h, std::string &err);
+// BAM header of a BGZF file image: inflates leading blocks on the host until the header parses
+bool read_bam_header(const uint8_t *file, uint64_t n, BamHeader &h, std::string &err);
+// .bai (sam/bam.h:498-536 bam_index_*; written by bam_index_build): BGZF virtual offset (coffset << 16 | uoffset) of the
+// first record of every reference, ~0 for a reference without records
+bool bai_first_offsets(const std::string &bai_path, std::vector<uint64_t> &first_voff, std::string &err);
 // SAM text (what samopen(fn, "r") reads) -> "BAM\1" header + packed records
 bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vector<uint8_t> &stream, std::string &err);
 // gzip/plain text file -> bytes (igzstream / ifstream of the reference, gzstream.h)

@@ -233,7 +233,7 @@ int fail(const std::string &msg)
 // ---- getclip: CallGetclip (seeksv.cpp:128-155) + InputBamOutputReads (clip_reads.h:363-484) ---------------------
 int cmd_getclip(int argc, char **argv)
 {
-    svb_getclip_params prm = {0.9, 1, 0, 0};
+    svb_getclip_params prm = {0.9, 1, 0, 0, 0};
     std::string prefix = "output";
     int c;
     optind = 1;
@@ -679,6 +679,16 @@ extern "C" int svb_write_gz(const char *path, const void *data, uint64_t n, int 
     if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
     std::string err;
     return write_gz(path, (const char *)data, n, n_threads, err) ? 0 : SVB_ERR_IO;
+}
+
+extern "C" int64_t svb_bai_first_offsets(const char *bai_path, uint64_t *first_voff, int64_t cap)
+{
+    if (!bai_path) return SVB_ERR_ARG;
+    std::vector<uint64_t> v;
+    std::string err;
+    if (!bai_first_offsets(bai_path, v, err)) return SVB_ERR_IO;
+    for (size_t i = 0; i < v.size() && (int64_t)i < cap && first_voff; ++i) first_voff[i] = v[i];
+    return (int64_t)v.size();
 }
 
 extern "C" int svb_read_gz(const char *path, char **data, uint64_t *n)

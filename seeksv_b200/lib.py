@@ -23,7 +23,7 @@ class SvbError(RuntimeError):
 
 class GetclipParams(C.Structure):
     _fields_ = [("match_rate", C.c_double), ("min_mapq", C.c_int32), ("save_low_quality", C.c_int32),
-                ("prev_tid", C.c_int32)]
+                ("prev_tid", C.c_int32), ("export_unmapped_records", C.c_int32)]
 
 
 class Junction(C.Structure):
@@ -45,7 +45,7 @@ EXPORTS = [
     "svb_bam_free", "svb_bam_device_stream", "svb_bam_copy_stream", "svb_inflate_bgzf", "svb_bam_n_records", "svb_bam_record_bytes", "svb_bam_n_ref", "svb_bam_ref_name", "svb_bam_ref_len",
     "svb_bam_set_refs", "svb_getclip", "svb_clusters_free", "svb_clusters_count", "svb_clusters_candidates",
     "svb_clusters_text", "svb_insert_stats", "svb_discordant_support", "svb_window_depth", "svb_plan_getsv", "svb_free",
-    "svb_write_gz", "svb_read_gz",
+    "svb_write_gz", "svb_read_gz", "svb_bam_open_refs", "svb_bai_first_offsets", "svb_bam_last_mapped_tid", "svb_clusters_unmapped_records",
     "svb_main",
 ]
 
@@ -101,6 +101,7 @@ def load():
     L.svb_clusters_candidates.argtypes = [vp]
     L.svb_clusters_candidates.restype = u64
     L.svb_clusters_text.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(u64)]
+    L.svb_clusters_unmapped_records.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(u64)]
     L.svb_insert_stats.argtypes = [vp, vp, i32, i64, C.POINTER(i64)]
     L.svb_discordant_support.argtypes = [vp, vp, C.POINTER(Junction), u64, C.POINTER(PairParams), C.POINTER(i32)]
     L.svb_window_depth.argtypes = [vp, vp, C.POINTER(Window), u64, i32, C.POINTER(i32)]
@@ -108,6 +109,10 @@ def load():
     L.svb_plan_getsv.argtypes = [C.c_char_p, C.c_char_p, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), i32, i32,
                                  C.POINTER(C.POINTER(Junction)), C.POINTER(u64), C.POINTER(C.POINTER(Window)),
                                  C.POINTER(u64)]
+    L.svb_bam_open_refs.argtypes = [vp, C.c_char_p, C.c_char_p, i32, i32, C.c_int, C.POINTER(vp)]
+    L.svb_bam_last_mapped_tid.argtypes = [vp, vp, C.POINTER(i32), C.POINTER(i32)]
+    L.svb_bai_first_offsets.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.c_int64]
+    L.svb_bai_first_offsets.restype = C.c_int64
     L.svb_write_gz.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_int]
     L.svb_read_gz.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.svb_free.argtypes = [vp]
@@ -185,6 +190,20 @@ class Bam:
         return cls(ctx, h)
 
     @classmethod
+    def open_refs(cls, ctx: Context, path: str, tid_begin: int, tid_end: int, bai: str = None, threads: int = 0) -> "Bam":
+        """records of references [tid_begin, tid_end) of an indexed BAM (one rank's chromosome shard)"""
+        h = C.c_void_p()
+        ctx.check(ctx.L.svb_bam_open_refs(ctx.h, path.encode(), bai.encode() if bai else None, tid_begin, tid_end, threads, C.byref(h)),
+                  "svb_bam_open_refs(%s, %d, %d)" % (path, tid_begin, tid_end))
+        return cls(ctx, h)
+
+    def last_mapped_tid(self):
+        """tid of the last mapped-branch record (None if the shard has none): the next shard's prev_tid"""
+        has, tid = C.c_int32(), C.c_int32()
+        self.ctx.check(self.ctx.L.svb_bam_last_mapped_tid(self.ctx.h, self.h, C.byref(has), C.byref(tid)), "svb_bam_last_mapped_tid")
+        return tid.value if has.value else None
+
+    @classmethod
     def from_bgzf(cls, ctx: Context, file_bytes, threads: int = 0) -> "Bam":
         """file image of a .bam in host memory (bytes / numpy uint8 / pinned torch tensor pointer+len tuple)"""
         ptr, n, keep = _host_ptr(file_bytes)
@@ -246,9 +265,10 @@ class Bam:
         L = self.ctx.L
         return [L.svb_bam_ref_len(self.h, t) for t in range(L.svb_bam_n_ref(self.h))]
 
-    def getclip(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0) -> Tuple[bytes, bytes, bytes, bytes]:
-        """(clip, clip.fq, unmapped_1, unmapped_2) decompressed file contents."""
-        p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid)
+    def getclip(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0, export_unmapped=False):
+        """(clip, clip.fq, unmapped_1, unmapped_2) decompressed file contents. export_unmapped (shards): the unmapped branch is
+        not paired here; its packed records are left in self.last_unmapped_records for the merging rank."""
+        p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid, 1 if export_unmapped else 0)
         out = C.c_void_p()
         self.ctx.check(self.ctx.L.svb_getclip(self.ctx.h, self.h, C.byref(p), C.byref(out)), "svb_getclip")
         try:
@@ -258,6 +278,9 @@ class Bam:
                 n = C.c_uint64()
                 self.ctx.L.svb_clusters_text(out, which, C.byref(d), C.byref(n))
                 res.append(C.string_at(d, n.value) if n.value else b"")
+            d, n = C.c_char_p(), C.c_uint64()
+            self.ctx.L.svb_clusters_unmapped_records(out, C.byref(d), C.byref(n))
+            self.last_unmapped_records = C.string_at(d, n.value) if n.value else b""
             self.last_clusters = self.ctx.L.svb_clusters_count(out)
             self.last_candidates = self.ctx.L.svb_clusters_candidates(out)
             return tuple(res)
@@ -266,7 +289,7 @@ class Bam:
 
     def getclip_sizes(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0) -> Tuple[int, int, int, int]:
         """svb_getclip without copying the four host buffers into Python objects: returns their lengths"""
-        p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid)
+        p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid, 0)
         out = C.c_void_p()
         self.ctx.check(self.ctx.L.svb_getclip(self.ctx.h, self.h, C.byref(p), C.byref(out)), "svb_getclip")
         try:
@@ -363,6 +386,17 @@ def plan_getsv(clip_alignments: str, clip_file: str, ref_names: Sequence[str], r
         L.svb_free(pj)
         L.svb_free(pw)
     return juncs, wins
+
+
+def bai_first_offsets(bai_path: str):
+    """BGZF virtual offset of the first record of every reference (None where the reference has no records); host only"""
+    L = load()
+    n = L.svb_bai_first_offsets(bai_path.encode(), None, 0)
+    if n < 0:
+        raise SvbError("svb_bai_first_offsets(%s) = %d" % (bai_path, n))
+    arr = (C.c_uint64 * max(1, n))()
+    L.svb_bai_first_offsets(bai_path.encode(), arr, n)
+    return [None if arr[i] == 2 ** 64 - 1 else int(arr[i]) for i in range(n)]
 
 
 def write_gz(path: str, data: bytes, threads: int = 0) -> None:

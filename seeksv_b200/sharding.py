@@ -56,14 +56,21 @@ def all_gather_objects(obj, dist=None):
 
 
 def sharded_getclip(worker, dist=None) -> Optional[Tuple[str, str, str, str]]:
-    """worker.last_mapped_tid() -> Optional[int]; worker.getclip(prev_tid) -> 4 texts. Rank 0 returns the merged texts."""
+    """worker.last_mapped_tid() -> Optional[int]; worker.getclip(prev_tid) -> 4 texts. Rank 0 returns the merged texts.
+
+    Mates of the unmapped branch are paired by name across the whole file (clip_reads.h:172-219), so a worker may return
+    its unmapped-branch RECORDS instead of the two FASTQ texts (a 5th element: packed BAM records in file order, texts 2
+    and 3 empty); rank 0 then pairs the concatenation with worker.pair_unmapped(records) -> (unmapped_1, unmapped_2)."""
     rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
     lasts = all_gather_objects(worker.last_mapped_tid(), dist)
     mine = worker.getclip(prev_tids(lasts)[rank])
     parts = all_gather_objects(mine, dist)
     if rank != 0:
         return None
-    return tuple("".join(p[i] for p in parts) for i in range(4))
+    texts = ["".join(p[i] for p in parts) for i in range(4)]
+    if any(len(p) > 4 for p in parts):
+        texts[2], texts[3] = worker.pair_unmapped(b"".join(p[4] for p in parts if len(p) > 4))
+    return tuple(texts)
 
 
 def prefix_cutoffs(counts: Sequence[int], max_pairs: int) -> List[int]:
@@ -74,3 +81,46 @@ def prefix_cutoffs(counts: Sequence[int], max_pairs: int) -> List[int]:
         out.append(take)
         left -= take
     return out
+
+
+class RefShardWorker:
+    """The `worker` of sharded_getclip on a GPU: one rank's chromosome shard of ONE indexed BAM, cut with the .bai at exact
+    record boundaries (svb_bam_open_refs) - only the shard's BGZF blocks are read, uploaded and inflated."""
+
+    def __init__(self, ctx, bam_path: str, tid_begin: int, tid_end: int, bai: Optional[str] = None, **getclip_kw):
+        from . import lib
+        self.bam = lib.Bam.open_refs(ctx, bam_path, tid_begin, tid_end, bai)
+        self.kw = getclip_kw
+
+    def last_mapped_tid(self) -> Optional[int]:
+        return self.bam.last_mapped_tid()
+
+    def getclip(self, prev_tid: int):
+        texts = self.bam.getclip(prev_tid=prev_tid, export_unmapped=True, **self.kw)
+        return tuple(t.decode("latin-1") for t in texts) + (self.bam.last_unmapped_records,)
+
+    def pair_unmapped(self, records: bytes) -> Tuple[str, str]:
+        """the merging rank: the shards' unmapped-branch records, concatenated in file order, as one small stream"""
+        if not records:
+            return "", ""
+        from . import lib
+        mini = lib.Bam.from_host(self.bam.ctx, records, 0, len(self.bam.ref_names))
+        mini.set_refs(self.bam.ref_names, self.bam.ref_lens)
+        try:
+            texts = mini.getclip(**self.kw)
+        finally:
+            mini.close()
+        return texts[2].decode("latin-1"), texts[3].decode("latin-1")
+
+    def close(self):
+        self.bam.close()
+
+
+def open_ref_shard(ctx, bam_path: str, rank: int, world: int, bai: Optional[str] = None, **getclip_kw) -> RefShardWorker:
+    """rank's share of the references of bam_path, balanced by reference length (assign_chromosomes)"""
+    from . import lib
+    probe = lib.Bam.open_refs(ctx, bam_path, 0, 0, bai)   # header only: no records are loaded for an empty range
+    lens = probe.ref_lens
+    probe.close()
+    lo, hi = assign_chromosomes(lens, world)[rank]
+    return RefShardWorker(ctx, bam_path, lo, hi, bai, **getclip_kw)

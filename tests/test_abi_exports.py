@@ -110,3 +110,36 @@ def test_run_command_chains_segments_and_stops_on_failure(lib, tmp_path):
     assert r.returncode == 3 and not os.path.exists(out)
     r = _cli(["run"])
     assert r.returncode == 1
+
+
+@pytest.mark.parametrize("d,s", [("example", "cancer"), ("micro", "tumor"), ("fuzz", "f11"), ("fuzz", "f12")])
+def test_bai_first_offsets_point_at_the_first_record_of_each_reference(lib, d, s):
+    """the .bai reader behind svb_bam_open_refs (chromosome shards): its virtual offsets against a walk of the BAM itself"""
+    import struct
+    import zlib
+    import seeksv_b200.lib as L
+    path = os.path.join(GOLDEN, d, s + ".sort.bam")
+    raw = open(path, "rb").read()
+    blocks, o, u = [], 0, 0          # (compressed offset, uncompressed offset, uncompressed length)
+    stream = bytearray()
+    while o < len(raw):
+        bsize = struct.unpack_from("<H", raw, o + 16)[0] + 1
+        data = zlib.decompress(raw[o + 18:o + bsize - 8], -15)
+        blocks.append((o, u, len(data)))
+        stream += data
+        u += len(data)
+        o += bsize
+    l_text = struct.unpack_from("<i", stream, 4)[0]
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<i", stream, p)[0]
+    p += 4
+    for _ in range(n_ref):
+        p += 8 + struct.unpack_from("<i", stream, p)[0]
+    want = [None] * n_ref
+    while p + 4 <= len(stream):
+        bs, tid = struct.unpack_from("<ii", stream, p)
+        if 0 <= tid < n_ref and want[tid] is None:
+            co, uo, _ = [b for b in blocks if b[1] <= p < b[1] + b[2]][0]
+            want[tid] = co << 16 | (p - uo)
+        p += 4 + bs
+    assert L.bai_first_offsets(path + ".bai") == want

@@ -317,3 +317,41 @@ def test_run_keeps_the_bam_resident_and_gives_the_same_outputs(d, s, tmp_path):
     assert _zcat(pre + ".clip.gz") == read_text(os.path.join(GOLDEN, d, s + ".clip.txt"))
     assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".sv"))
     assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".getsv.stdout"))
+
+
+@pytest.mark.parametrize("d,s", [("fuzz", "f11"), ("fuzz", "f12"), ("micro", "tumor"), ("example", "cancer")])
+def test_chromosome_shards_of_one_bam_reproduce_the_whole_file(ctx, d, s):
+    """svb_bam_open_refs cuts an indexed BAM at reference boundaries (.bai virtual offsets); the shards, run one after the
+    other as ranks would (prev_tid chain, seeksv_b200/sharding.py), give the whole-file outputs; the getsv passes add up"""
+    import seeksv_b200
+    from seeksv_b200 import sharding
+    from oracle import bamio
+    path = _bam(d, s)
+    h, recs = bamio.read_bam(path)
+    whole = seeksv_b200.Bam.open(ctx, path)
+    n_ref = len(h.names)
+    golden = [read_text(os.path.join(GOLDEN, d, s + e)) for e in (".clip.txt", ".clip.fq.txt", ".unmapped_1.fq.txt", ".unmapped_2.fq.txt")]
+    for world in sorted({1, 2, 3, n_ref, n_ref + 2}):
+        workers = [sharding.open_ref_shard(ctx, path, r, world) for r in range(world)]
+        assert sum(w.bam.n_records for w in workers) == len(recs)
+        for w, (lo, hi) in zip(workers, sharding.assign_chromosomes(h.lengths, world)):
+            want_last = [r.tid for r in recs if lo <= r.tid < hi and not r.flag & 12]
+            assert w.last_mapped_tid() == (want_last[-1] if want_last else None)
+        prev = sharding.prev_tids([w.last_mapped_tid() for w in workers])
+        parts = [w.getclip(p) for w, p in zip(workers, prev)]   # (clip, clip.fq, "", "", unmapped-branch records)
+        for i in range(2):
+            assert "".join(p[i] for p in parts) == golden[i], (world, i)
+        # mates are paired by name across the whole file: the merging rank pairs the shards' records
+        u1, u2 = workers[0].pair_unmapped(b"".join(p[4] for p in parts))
+        assert (u1, u2) == (golden[2], golden[3]), world
+        # getsv side: qualifying-pair sums and per-junction counts are additive over shards
+        n_w, tot_w, mean_w, _ = whole.insert_stats(20, 5000000)
+        stats = [w.bam.insert_stats(20, 5000000) for w in workers]
+        assert sum(x[0] for x in stats) == n_w and sum(x[1] for x in stats) == tot_w
+        juncs = [(t, p, "+", t, p + 300, "-") for t in range(n_ref) for p in range(100, min(h.lengths[t] - 400, 20000), 1500)]
+        want = whole.discordant_support(juncs, 20, mean_w, 25, 4)
+        got = [w.bam.discordant_support(juncs, 20, mean_w, 25, 4) for w in workers]
+        assert [sum(col) for col in zip(*got)] == list(want)
+        for w in workers:
+            w.close()
+    whole.close()

@@ -46,7 +46,15 @@ def _worker(rank, world, port, case, q):
 
             def getclip(self, prev_tid):
                 # the oracle starts last_tid at 0: emulate prev_tid by a phantom state (clip_reads.h:407)
-                return _getclip_with_prev(getclip_oracle, h, mine, prev_tid)
+                clip, fq, _, _ = _getclip_with_prev(getclip_oracle, h, mine, prev_tid)
+                # mates are paired by name across the whole file: export the unmapped-branch records, rank 0 pairs them
+                return clip, fq, "", "", b"".join(bamio.pack_record(r) for r in mine if r.flag & 12)
+
+            def pair_unmapped(self, records):
+                _, urecs, _ = bamio.parse_bam_stream(bamio.header_bytes(h) + records)
+                out = getclip_oracle.getclip(h, urecs)
+                assert out[0] == "" and out[1] == ""
+                return out[2], out[3]
         merged = sharding.sharded_getclip(OracleWorker(), dist)
         # getsv side: counts and depth are owned by one rank each -> all_reduce(sum) reproduces the whole-file values
         clip_text = read_text(os.path.join(GOLDEN, d, s + ".clip.txt"))
@@ -106,7 +114,7 @@ def _getclip_with_prev(getclip_oracle, h, recs, prev_tid):
     return getclip_oracle.getclip(h, [phantom] + list(recs))
 
 
-@pytest.mark.parametrize("case", [("micro", "tumor"), ("example", "cancer")])
+@pytest.mark.parametrize("case", [("micro", "tumor"), ("example", "cancer"), ("fuzz", "f11")])   # fuzz: mates in different shards
 def test_chromosome_sharding_world2(case):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
