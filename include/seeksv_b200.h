@@ -78,6 +78,16 @@ int svb_bam_open(svb_ctx *ctx, const char *path, int n_threads, svb_bam **out); 
  * the file. The handle carries the full reference dictionary, so tids mean the same in every shard. */
 int svb_bam_open_refs(svb_ctx *ctx, const char *bam_path, const char *bai_path, int32_t tid_begin, int32_t tid_end, int n_threads,
                       svb_bam **out);
+/* Coordinate-range shard of an indexed BAM: the records between two BGZF virtual offsets that are record boundaries
+ * (entries of the .bai's linear index, svb_bai_linear_offsets). v_begin = 0: from the first record; v_end = ~0: to the end
+ * of the file. seeksv_b200/sharding.py:plan_range_shards picks the offsets, the halo and the key bounds. */
+int svb_bam_open_voffsets(svb_ctx *ctx, const char *bam_path, uint64_t v_begin, uint64_t v_end, int n_threads, svb_bam **out);
+/* Host only, for planning range shards: the linear index of one reference (virtual offset of the first record that overlaps
+ * each 16 kb window, 0 = none; returns the number of windows), (tid, 0-based pos) of the record at a virtual offset, and
+ * the number of uncompressed bytes between two virtual offsets. */
+int64_t svb_bai_linear_offsets(const char *bai_path, int32_t tid, uint64_t *voff, int64_t cap);
+int svb_bam_peek_record(const char *bam_path, uint64_t voffset, int32_t *tid, int32_t *pos);
+int svb_voffset_distance(const char *bam_path, uint64_t v_a, uint64_t v_b, uint64_t *bytes);
 /* tid of the last record of the stream that takes getclip's mapped branch (neither FUNMAP nor FMUNMAP set,
  * clip_reads.h:415-438): what the next shard passes as svb_getclip_params.prev_tid. *has_one = 0 if there is none. */
 int svb_bam_last_mapped_tid(svb_ctx *ctx, svb_bam *bam, int32_t *has_one, int32_t *tid);
@@ -120,6 +130,14 @@ typedef struct svb_getclip_params {
      * back its unmapped-branch records instead (svb_clusters_unmapped_records); the merging rank concatenates the shards'
      * records in file order into one small stream and runs svb_getclip on it for the two FASTQ texts. */
     int32_t export_unmapped_records;
+    /* Coordinate-range shards (inside a chromosome): the stream is [context + halo][own records]. Records that start
+     * before halo_bytes (stream offset of the first own record) only lend their soft clips: they are not part of the
+     * unmapped branch's output. With key_filter set, only breakpoint keys (tid, 1-based pos) in [lo, hi) are clustered
+     * here - a key belongs to the shard whose own records start at or before it - so every key is clustered on exactly
+     * one shard, with all of its reads, in file order (seeksv_b200/sharding.py plans halo and bounds from the .bai). */
+    int32_t key_filter;
+    int32_t key_lo_tid, key_lo_pos, key_hi_tid, key_hi_pos;
+    uint64_t halo_bytes;
 } svb_getclip_params;
 
 typedef struct svb_clusters svb_clusters; /* host-resident result of svb_getclip */

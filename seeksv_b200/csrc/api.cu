@@ -545,10 +545,57 @@ extern "C" int svb_bam_open(svb_ctx *ctx, const char *path, int n_threads, svb_b
     return 0;
 }
 
+// The records between two BGZF virtual offsets (both record boundaries, e.g. from the .bai): only the blocks in between are
+// read, uploaded and inflated; the view starts on a 16-byte boundary. v0 == NONE: an empty view.
+static int open_between(svb_ctx *ctx, const MappedFile &mf, const BamHeader &hdr, uint64_t v0, uint64_t v1, int n_threads, svb_bam **out)
+{
+    const uint64_t NONE = ~0ull;
+    std::string err;
+    std::unique_ptr<svb_bam, void (*)(svb_bam *)> b(new svb_bam(), [](svb_bam *x) { svb_bam_free(x); });
+    b->ctx = ctx;
+    b->first = 0, b->n_ref = (int32_t)hdr.names.size(), b->names = hdr.names, b->lens = hdr.lengths;
+    b->whole_file = true;  // the view ends on a record boundary: the chain has to end exactly there
+    if (v0 != NONE && v0 != v1) {
+        const uint64_t c0 = v0 >> 16, u0 = v0 & 0xffff;
+        uint64_t c_end = mf.size, u1 = 0;
+        bool cut_last = false;
+        if (v1 != NONE) {
+            c_end = v1 >> 16, u1 = v1 & 0xffff;
+            if (u1) {  // the block that holds the boundary is needed too
+                uint32_t bs = c_end < mf.size ? bgzf_block_size(mf.data, mf.size, c_end) : 0;
+                if (!bs) return svb_fail(ctx, SVB_ERR_FORMAT, "virtual offset does not point at a BGZF block");
+                c_end += bs;
+                cut_last = true;
+            }
+        }
+        if (c0 >= c_end || c_end > mf.size) return svb_fail(ctx, SVB_ERR_FORMAT, "virtual offsets out of range");
+        std::vector<uint8_t> head;
+        const uint32_t lead = (uint32_t)((16 - (u0 & 15)) & 15);  // the view's first byte lands on a 16-byte boundary
+        CKR(load_bgzf_device_inflate(ctx, b.get(), mf.data + c0, c_end - c0, n_threads, head, lead));
+        uint64_t total = b->nbytes, tail_cut = 0;
+        if (cut_last) {
+            const uint8_t *t = mf.data + c_end - 4;  // uncompressed size of the last block = its ISIZE field
+            uint64_t last_ulen = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint64_t)t[3] << 24);
+            if (u1 > last_ulen) return svb_fail(ctx, SVB_ERR_FORMAT, "virtual offset beyond its block");
+            tail_cut = last_ulen - u1;
+        }
+        if (u0 + tail_cut > total) return svb_fail(ctx, SVB_ERR_FORMAT, "virtual offsets out of range");
+        b->d_data += u0, b->nbytes = total - u0 - tail_cut;
+    } else {  // no records in the range: an empty stream (on a real allocation, so that every kernel has a valid pointer)
+        b->d_owned = ctx->big_get(4096, &b->owned_cap);
+        if (!b->d_owned) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate device memory");
+        CK(cudaMemsetAsync(b->d_owned, 0, 4096, ctx->stream));
+        b->d_data = b->d_owned, b->nbytes = 0;
+    }
+    svb_bam *raw = b.release();
+    std::unique_ptr<svb_bam> plain(raw);
+    return finish_bam(ctx, plain, out);
+}
+
 // Records of references [tid_begin, tid_end) of a coordinate-sorted, indexed BAM (the chromosome shard of one rank). The
 // .bai gives the BGZF virtual offset of the first record of every reference (bam_index_build, sam/bam.h:498-536), so the
-// shard is cut at exact record boundaries: only the BGZF blocks between the two offsets are read, uploaded and inflated.
-// The range that reaches the last reference with records also takes the unplaced reads at the end of the file.
+// shard is cut at exact record boundaries. The range that reaches the last reference with records also takes the
+// unplaced reads at the end of the file.
 extern "C" int svb_bam_open_refs(svb_ctx *ctx, const char *bam_path, const char *bai_path, int32_t tid_begin, int32_t tid_end,
                                  int n_threads, svb_bam **out)
 {
@@ -569,46 +616,35 @@ extern "C" int svb_bam_open_refs(svb_ctx *ctx, const char *bam_path, const char 
     uint64_t v0 = NONE, v1 = NONE;  // virtual offsets: first record of the range, first record after it (NONE: end of file)
     for (int32_t t = tid_begin; t < tid_end && v0 == NONE; ++t) v0 = first[t];
     for (int32_t t = tid_end; t < n_ref && v1 == NONE; ++t) v1 = first[t];
-    std::unique_ptr<svb_bam, void (*)(svb_bam *)> b(new svb_bam(), [](svb_bam *x) { svb_bam_free(x); });
-    b->ctx = ctx;
-    b->first = 0, b->n_ref = n_ref, b->names = hdr.names, b->lens = hdr.lengths;
-    b->whole_file = true;  // the shard ends on a record boundary: the chain has to end exactly there
-    if (v0 != NONE) {
-        const uint64_t c0 = v0 >> 16, u0 = v0 & 0xffff;
-        uint64_t c_end = mf.size, u1 = 0;
-        bool cut_last = false;
-        if (v1 != NONE) {
-            c_end = v1 >> 16, u1 = v1 & 0xffff;
-            if (u1) {  // the block that holds the boundary is needed too
-                uint32_t bs = bgzf_block_size(mf.data, mf.size, c_end);
-                if (!bs) return svb_fail(ctx, SVB_ERR_FORMAT, "index offset does not point at a BGZF block");
-                c_end += bs;
-                cut_last = true;
-            }
+    return open_between(ctx, mf, hdr, v0, v1, n_threads, out);
+}
+
+// Coordinate-range shard: the records between two virtual offsets taken from the .bai's linear index (record boundaries).
+// v_begin == 0: from the first record of the file; v_end == ~0: to the end of the file.
+extern "C" int svb_bam_open_voffsets(svb_ctx *ctx, const char *bam_path, uint64_t v_begin, uint64_t v_end, int n_threads, svb_bam **out)
+{
+    if (!ctx || !bam_path || !out) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_open_voffsets: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::string err;
+    MappedFile mf;
+    if (!mf.open(bam_path, err)) return svb_fail(ctx, SVB_ERR_IO, "%s", err.c_str());
+    BamHeader hdr;
+    if (!read_bam_header(mf.data, mf.size, hdr, err)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s", err.c_str());
+    if (v_begin == 0) {  // virtual offset of the byte after the header
+        uint64_t c = 0, left = hdr.first_record;
+        for (;;) {
+            uint32_t bs = c < mf.size ? bgzf_block_size(mf.data, mf.size, c) : 0;
+            if (!bs) return svb_fail(ctx, SVB_ERR_FORMAT, "not a BGZF file (bad block header)");
+            const uint8_t *t = mf.data + c + bs - 4;
+            uint64_t ulen = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint64_t)t[3] << 24);
+            if (left < ulen) break;
+            left -= ulen, c += bs;
+            if (c >= mf.size) break;
         }
-        if (c0 >= c_end || c_end > mf.size) return svb_fail(ctx, SVB_ERR_FORMAT, "index offsets out of range");
-        std::vector<uint8_t> head;
-        const uint32_t lead = (uint32_t)((16 - (u0 & 15)) & 15);  // the shard's first byte lands on a 16-byte boundary
-        CKR(load_bgzf_device_inflate(ctx, b.get(), mf.data + c0, c_end - c0, n_threads, head, lead));
-        uint64_t total = b->nbytes, tail_cut = 0;
-        if (cut_last) {
-            // uncompressed size of the last block = its ISIZE field
-            const uint8_t *t = mf.data + c_end - 4;
-            uint64_t last_ulen = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint64_t)t[3] << 24);
-            if (u1 > last_ulen) return svb_fail(ctx, SVB_ERR_FORMAT, "index offset beyond its block");
-            tail_cut = last_ulen - u1;
-        }
-        if (u0 + tail_cut > total) return svb_fail(ctx, SVB_ERR_FORMAT, "index offsets out of range");
-        b->d_data += u0, b->nbytes = total - u0 - tail_cut;
-    } else {  // no records in the range: an empty stream (on a real allocation, so that every kernel has a valid pointer)
-        b->d_owned = ctx->big_get(4096, &b->owned_cap);
-        if (!b->d_owned) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate device memory");
-        CK(cudaMemsetAsync(b->d_owned, 0, 4096, ctx->stream));
-        b->d_data = b->d_owned, b->nbytes = 0;
+        v_begin = c >= mf.size ? ~0ull : (c << 16 | left);
     }
-    svb_bam *raw = b.release();
-    std::unique_ptr<svb_bam> plain(raw);
-    return finish_bam(ctx, plain, out);
+    return open_between(ctx, mf, hdr, v_begin, v_end, n_threads, out);
 }
 
 extern "C" void svb_bam_free(svb_bam *b)

@@ -88,6 +88,14 @@ struct ScanOut {
     uint32_t *counters;  // [0] candidates, [1] unmapped-branch records, [2] chromosome switches, [3] soft-clipped records
     uint64_t *clipped;   // records whose first or last CIGAR op is S and that pass the cheap filters: evaluated by clip_eval
     uint32_t clipped_cap;
+    // range shards: only breakpoint keys (tid, pos) in [lo, hi) belong to this shard (whole file: everything)
+    int32_t lo_tid, lo_pos, hi_tid, hi_pos;
+    __device__ __forceinline__ bool owns(int32_t tid, int32_t pos) const
+    {
+        const bool ge_lo = tid > lo_tid || (tid == lo_tid && pos >= lo_pos);
+        const bool lt_hi = tid < hi_tid || (tid == hi_tid && pos < hi_pos);
+        return ge_lo && lt_hi;
+    }
 };
 
 // The cheap part of GetSClipReads (clip_reads.cpp:116-118,122): first / last CIGAR op and the H / mapQ / DUP filters.
@@ -149,6 +157,8 @@ __device__ void eval_clip(const uint8_t *__restrict__ d, uint64_t o, const Core 
         b3 = len1, l3 = (uint32_t)mid, r3 = len2;  // clip_reads.cpp:154,185
     }
     const CandArrays &c = out.c;
+    emit5 = emit5 && out.owns(k.tid, k.pos + 1);
+    emit3 = emit3 && out.owns(k.tid, k.pos + reflen);
     if (emit5) {
         uint32_t s = atomicAdd(&out.counters[0], 1u);
         if (s < out.cand_cap) {
@@ -797,6 +807,12 @@ static int sort_u64(svb_ctx *ctx, uint64_t *keys_in, uint64_t *keys_out, uint32_
 
 static inline unsigned nblk(uint64_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
 
+__global__ void count_below(uint32_t n, const uint64_t *__restrict__ off, uint64_t limit, uint32_t *__restrict__ count)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && off[i] < limit) atomicAdd(count, 1u);
+}
+
 // ---- shard plumbing: raw records of the unmapped branch, packed in file order ------------------------------------
 __global__ void record_sizes(uint32_t n, const uint64_t *__restrict__ off, const uint8_t *__restrict__ d, uint64_t *__restrict__ size)
 {
@@ -893,7 +909,8 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         CK(sw_list.alloc(sw_cap, s));
         CK(clipped.alloc(cand_cap, s));
         c = {c_off.p, c_tid.p, c_pos.p, c_begin.p, c_ll.p, c_rl.p, c_side.p};
-        ScanOut so{c, cand_cap, un_list.p, un_cap, sw_list.p, sw_cap, counters.p, clipped.p, cand_cap};
+        ScanOut so{c, cand_cap, un_list.p, un_cap, sw_list.p, sw_cap, counters.p, clipped.p, cand_cap, INT32_MIN, INT32_MIN, INT32_MAX, INT32_MAX};
+        if (prm->key_filter) so.lo_tid = prm->key_lo_tid, so.lo_pos = prm->key_lo_pos, so.hi_tid = prm->key_hi_tid, so.hi_pos = prm->key_hi_pos;
         CK(cudaMemsetAsync(counters.p, 0, 16, s));
         if (stream_mode(bam) && attempt_walk == 0) {
             // streaming pass: its own first-record guesses go to bam->d_guess and are verified below like the walker's
@@ -934,7 +951,8 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         }
     }
     if (!bam->counted) CKR(finish_counts(ctx, bam, exit_.p));  // the walker counted the records of every chunk on its way
-    const uint32_t n_cand = hc[0], n_un = hc[1], n_sw = hc[2];
+    const uint32_t n_cand = hc[0], n_sw = hc[2];
+    uint32_t n_un = hc[1];
     res->n_candidates = n_cand;
 
     // ---- 2. unmapped-branch records: pair mates by name on the device, emit the two FASTQ files ---------------------
@@ -949,17 +967,29 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         CK(un_sorted.alloc(n_un, s));
         CKR(sort_u64(ctx, un_list.p, un_sorted.p, n_un, off_bits));
     }
+    const uint64_t *un_first = un_sorted.p;  // (the kernels below read un_sorted through this pointer)
+    if (n_un && prm->halo_bytes) {
+        // range shards: records in front of the shard's own region only lend their soft clips; the list is sorted by offset
+        DevBuf<uint32_t> skip;
+        CK(skip.alloc(1, s));
+        CK(cudaMemsetAsync(skip.p, 0, 4, s));
+        count_below<<<nblk(n_un, 256), 256, 0, s>>>(n_un, un_sorted.p, prm->halo_bytes, skip.p);
+        uint32_t h_skip = 0;
+        CK(cudaMemcpyAsync(&h_skip, skip.p, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        un_first += h_skip, n_un -= h_skip;
+    }
     if (n_un && prm->export_unmapped_records) {  // a shard: hand the records to the merging rank instead of pairing here
         DevBuf<uint64_t> sz, ro;
         CK(sz.alloc(n_un + 1, s));
         CK(ro.alloc(n_un + 1, s));
-        record_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_sorted.p, bam->d_data, sz.p);
+        record_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_first, bam->d_data, sz.p);
         CKR(exclusive_scan_u64(ctx, sz.p, ro.p, n_un + 1));
         uint64_t total = 0;
         CK(cudaMemcpyAsync(&total, ro.p + n_un, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         CK(un_o1.alloc(total, s));
-        record_copy<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_sorted.p, bam->d_data, ro.p, (uint8_t *)un_o1.p);
+        record_copy<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_first, bam->d_data, ro.p, (uint8_t *)un_o1.p);
         CKR(res->unmapped_records.reserve(ctx, total));
         CK(cudaMemcpyAsync(res->unmapped_records.p, un_o1.p, total, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -979,14 +1009,14 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         uint64_t tot[2] = {0, 0};
         {
             ProfScope ps(ctx, "unmapped_pair", 0);
-            unmapped_hash<<<nblk(n_un, 256), 256, 0, s>>>(n_un, un_sorted.p, bam->d_data, ukey0.p, val0.p);
+            unmapped_hash<<<nblk(n_un, 256), 256, 0, s>>>(n_un, un_first, bam->d_data, ukey0.p, val0.p);
             size_t tmp = 0;
             CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ukey0.p, ukey1.p, val0.p, val1.p, (int)n_un, 0, 64, s));
             DevBuf<uint8_t> t;
             CK(t.alloc(tmp, s));
             CK(cub::DeviceRadixSort::SortPairs(t.p, tmp, ukey0.p, ukey1.p, val0.p, val1.p, (int)n_un, 0, 64, s));
-            unmapped_pair<<<nblk(n_un, 128), 128, 0, s>>>(n_un, ukey1.p, val1.p, un_sorted.p, bam->d_data, mate_of.p, ovf.p);
-            unmapped_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_sorted.p, mate_of.p, bam->d_data, sz1.p, sz2.p);
+            unmapped_pair<<<nblk(n_un, 128), 128, 0, s>>>(n_un, ukey1.p, val1.p, un_first, bam->d_data, mate_of.p, ovf.p);
+            unmapped_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_first, mate_of.p, bam->d_data, sz1.p, sz2.p);
             CKR(exclusive_scan_u64(ctx, sz1.p, off1.p, n_un + 1));
             CKR(exclusive_scan_u64(ctx, sz2.p, off2.p, n_un + 1));
         }
@@ -1000,7 +1030,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         CK(un_o2.alloc(tot[1], s));
         {
             ProfScope ps(ctx, "unmapped_write", (double)(tot[0] + tot[1]));
-            unmapped_write<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_sorted.p, mate_of.p, bam->d_data, off1.p, off2.p,
+            unmapped_write<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_first, mate_of.p, bam->d_data, off1.p, off2.p,
                                                                           un_o1.p, un_o2.p);
         }
         CKR(res->text[2].reserve(ctx, tot[0]));

@@ -209,6 +209,92 @@ bool bai_first_offsets(const std::string &bai_path, std::vector<uint64_t> &first
     return true;
 }
 
+bool bai_linear_offsets(const std::string &bai_path, std::vector<std::vector<uint64_t>> &linear, std::string &err)
+{
+    std::vector<uint8_t> d;
+    if (!read_file(bai_path, d, err)) return false;
+    auto bad = [&]() {
+        err = "malformed index " + bai_path;
+        return false;
+    };
+    if (d.size() < 8 || memcmp(d.data(), "BAI\1", 4) != 0) return bad();
+    size_t o = 4;
+    auto i32 = [&](int32_t &v) {
+        if (o + 4 > d.size()) return false;
+        memcpy(&v, &d[o], 4);
+        o += 4;
+        return true;
+    };
+    int32_t n_ref = 0;
+    if (!i32(n_ref) || n_ref < 0) return bad();
+    linear.assign((size_t)n_ref, {});
+    for (int32_t t = 0; t < n_ref; ++t) {
+        int32_t n_bin = 0;
+        if (!i32(n_bin) || n_bin < 0) return bad();
+        for (int32_t b = 0; b < n_bin; ++b) {
+            int32_t bin_raw = 0, n_chunk = 0;
+            if (!i32(bin_raw) || !i32(n_chunk) || n_chunk < 0 || o + 16ull * (uint64_t)n_chunk > d.size()) return bad();
+            o += 16 * (size_t)n_chunk;
+        }
+        int32_t n_intv = 0;
+        if (!i32(n_intv) || n_intv < 0 || o + 8ull * (uint64_t)n_intv > d.size()) return bad();
+        linear[t].resize((size_t)n_intv);
+        if (n_intv) memcpy(linear[t].data(), &d[o], 8 * (size_t)n_intv);
+        o += 8 * (size_t)n_intv;
+    }
+    return true;
+}
+
+bool bgzf_voffset_distance(const uint8_t *f, uint64_t n, uint64_t v_a, uint64_t v_b, uint64_t &bytes, std::string &err)
+{
+    uint64_t c = v_a >> 16, cb = v_b >> 16, acc = 0;
+    if (v_a > v_b || cb > n) {
+        err = "virtual offsets out of order";
+        return false;
+    }
+    while (c < cb) {
+        uint32_t xl, bs = bgzf_member(f, n, c, &xl);
+        if (!bs) {
+            err = "virtual offset does not point at a BGZF block";
+            return false;
+        }
+        const uint8_t *t = f + c + bs - 4;
+        acc += t[0] | (t[1] << 8) | (t[2] << 16) | ((uint64_t)t[3] << 24);
+        c += bs;
+    }
+    if (c != cb) {
+        err = "virtual offset does not point at a BGZF block";
+        return false;
+    }
+    bytes = acc + (v_b & 0xffff) - (v_a & 0xffff);
+    return true;
+}
+
+bool bgzf_read_at(const uint8_t *f, uint64_t n, uint64_t voff, uint8_t *dst, uint32_t want, std::string &err)
+{
+    uint64_t c = voff >> 16, skip = voff & 0xffff;
+    uint32_t got = 0;
+    std::vector<uint8_t> buf;
+    while (got < want) {
+        uint32_t xl, bs = c < n ? bgzf_member(f, n, c, &xl) : 0;
+        if (!bs) {
+            err = "virtual offset does not point at a BGZF block";
+            return false;
+        }
+        const uint8_t *t = f + c + bs - 4;
+        uint32_t ulen = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+        buf.resize(ulen);
+        if (ulen && !inflate_block(f + c + 12 + xl, bs - xl - 20, buf.data(), ulen)) {
+            err = "BGZF inflate failed";
+            return false;
+        }
+        for (uint64_t i = skip; i < ulen && got < want; ++i) dst[got++] = buf[i];
+        skip = skip > ulen ? skip - ulen : 0;
+        c += bs;
+    }
+    return true;
+}
+
 bool read_bam_header(const uint8_t *f, uint64_t n, BamHeader &h, std::string &err)
 {
     std::vector<uint8_t> text;

@@ -40,6 +40,12 @@ bool read_bam_header(const uint8_t *file, uint64_t n, BamHeader &h, std::string 
 // .bai (sam/bam.h:498-536 bam_index_*; written by bam_index_build): BGZF virtual offset (coffset << 16 | uoffset) of the
 // first record of every reference, ~0 for a reference without records
 bool bai_first_offsets(const std::string &bai_path, std::vector<uint64_t> &first_voff, std::string &err);
+// the linear index of every reference: virtual offset of the first record that overlaps each 16 kb window (0: none recorded)
+bool bai_linear_offsets(const std::string &bai_path, std::vector<std::vector<uint64_t>> &linear, std::string &err);
+// uncompressed bytes between two virtual offsets of a BGZF file image (walks the block headers from a to b; a <= b)
+bool bgzf_voffset_distance(const uint8_t *file, uint64_t n, uint64_t v_a, uint64_t v_b, uint64_t &bytes, std::string &err);
+// `want` uncompressed bytes starting at a virtual offset (host zlib; for peeking at single records)
+bool bgzf_read_at(const uint8_t *file, uint64_t n, uint64_t voff, uint8_t *dst, uint32_t want, std::string &err);
 // SAM text (what samopen(fn, "r") reads) -> "BAM\1" header + packed records
 bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vector<uint8_t> &stream, std::string &err);
 // gzip/plain text file -> bytes (igzstream / ifstream of the reference, gzstream.h)

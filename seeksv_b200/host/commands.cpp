@@ -233,7 +233,7 @@ int fail(const std::string &msg)
 // ---- getclip: CallGetclip (seeksv.cpp:128-155) + InputBamOutputReads (clip_reads.h:363-484) ---------------------
 int cmd_getclip(int argc, char **argv)
 {
-    svb_getclip_params prm = {0.9, 1, 0, 0, 0};
+    svb_getclip_params prm = {0.9, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     std::string prefix = "output";
     int c;
     optind = 1;
@@ -689,6 +689,39 @@ extern "C" int64_t svb_bai_first_offsets(const char *bai_path, uint64_t *first_v
     if (!bai_first_offsets(bai_path, v, err)) return SVB_ERR_IO;
     for (size_t i = 0; i < v.size() && (int64_t)i < cap && first_voff; ++i) first_voff[i] = v[i];
     return (int64_t)v.size();
+}
+
+extern "C" int64_t svb_bai_linear_offsets(const char *bai_path, int32_t tid, uint64_t *voff, int64_t cap)
+{
+    if (!bai_path) return SVB_ERR_ARG;
+    std::vector<std::vector<uint64_t>> lin;
+    std::string err;
+    if (!bai_linear_offsets(bai_path, lin, err)) return SVB_ERR_IO;
+    if (tid < 0 || (size_t)tid >= lin.size()) return SVB_ERR_ARG;
+    for (size_t i = 0; i < lin[tid].size() && (int64_t)i < cap && voff; ++i) voff[i] = lin[tid][i];
+    return (int64_t)lin[tid].size();
+}
+
+extern "C" int svb_bam_peek_record(const char *bam_path, uint64_t voffset, int32_t *tid, int32_t *pos)
+{
+    if (!bam_path || !tid || !pos) return SVB_ERR_ARG;
+    MappedFile mf;
+    std::string err;
+    if (!mf.open(bam_path, err)) return SVB_ERR_IO;
+    uint8_t head[12];
+    if (!bgzf_read_at(mf.data, mf.size, voffset, head, 12, err)) return SVB_ERR_FORMAT;
+    memcpy(tid, head + 4, 4);
+    memcpy(pos, head + 8, 4);
+    return 0;
+}
+
+extern "C" int svb_voffset_distance(const char *bam_path, uint64_t v_a, uint64_t v_b, uint64_t *bytes)
+{
+    if (!bam_path || !bytes) return SVB_ERR_ARG;
+    MappedFile mf;
+    std::string err;
+    if (!mf.open(bam_path, err)) return SVB_ERR_IO;
+    return bgzf_voffset_distance(mf.data, mf.size, v_a, v_b, *bytes, err) ? 0 : SVB_ERR_FORMAT;
 }
 
 extern "C" int svb_read_gz(const char *path, char **data, uint64_t *n)

@@ -23,7 +23,9 @@ class SvbError(RuntimeError):
 
 class GetclipParams(C.Structure):
     _fields_ = [("match_rate", C.c_double), ("min_mapq", C.c_int32), ("save_low_quality", C.c_int32),
-                ("prev_tid", C.c_int32), ("export_unmapped_records", C.c_int32)]
+                ("prev_tid", C.c_int32), ("export_unmapped_records", C.c_int32), ("key_filter", C.c_int32),
+                ("key_lo_tid", C.c_int32), ("key_lo_pos", C.c_int32), ("key_hi_tid", C.c_int32), ("key_hi_pos", C.c_int32),
+                ("halo_bytes", C.c_uint64)]
 
 
 class Junction(C.Structure):
@@ -46,6 +48,7 @@ EXPORTS = [
     "svb_bam_set_refs", "svb_getclip", "svb_clusters_free", "svb_clusters_count", "svb_clusters_candidates",
     "svb_clusters_text", "svb_insert_stats", "svb_discordant_support", "svb_window_depth", "svb_plan_getsv", "svb_free",
     "svb_write_gz", "svb_read_gz", "svb_bam_open_refs", "svb_bai_first_offsets", "svb_bam_last_mapped_tid", "svb_clusters_unmapped_records",
+    "svb_bam_open_voffsets", "svb_bai_linear_offsets", "svb_bam_peek_record", "svb_voffset_distance",
     "svb_main",
 ]
 
@@ -110,6 +113,11 @@ def load():
                                  C.POINTER(C.POINTER(Junction)), C.POINTER(u64), C.POINTER(C.POINTER(Window)),
                                  C.POINTER(u64)]
     L.svb_bam_open_refs.argtypes = [vp, C.c_char_p, C.c_char_p, i32, i32, C.c_int, C.POINTER(vp)]
+    L.svb_bam_open_voffsets.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(vp)]
+    L.svb_bai_linear_offsets.argtypes = [C.c_char_p, i32, C.POINTER(C.c_uint64), C.c_int64]
+    L.svb_bai_linear_offsets.restype = C.c_int64
+    L.svb_bam_peek_record.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(i32), C.POINTER(i32)]
+    L.svb_voffset_distance.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
     L.svb_bam_last_mapped_tid.argtypes = [vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.svb_bai_first_offsets.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.c_int64]
     L.svb_bai_first_offsets.restype = C.c_int64
@@ -197,6 +205,14 @@ class Bam:
                   "svb_bam_open_refs(%s, %d, %d)" % (path, tid_begin, tid_end))
         return cls(ctx, h)
 
+    @classmethod
+    def open_voffsets(cls, ctx: Context, path: str, v_begin: int, v_end: Optional[int], threads: int = 0) -> "Bam":
+        """records between two BGZF virtual offsets (record boundaries from the .bai); v_begin 0 = first record, v_end None = EOF"""
+        h = C.c_void_p()
+        ctx.check(ctx.L.svb_bam_open_voffsets(ctx.h, path.encode(), v_begin, 2 ** 64 - 1 if v_end is None else v_end, threads, C.byref(h)),
+                  "svb_bam_open_voffsets(%s)" % path)
+        return cls(ctx, h)
+
     def last_mapped_tid(self):
         """tid of the last mapped-branch record (None if the shard has none): the next shard's prev_tid"""
         has, tid = C.c_int32(), C.c_int32()
@@ -265,10 +281,15 @@ class Bam:
         L = self.ctx.L
         return [L.svb_bam_ref_len(self.h, t) for t in range(L.svb_bam_n_ref(self.h))]
 
-    def getclip(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0, export_unmapped=False):
+    def getclip(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0, export_unmapped=False, key_range=None,
+                halo_bytes=0):
         """(clip, clip.fq, unmapped_1, unmapped_2) decompressed file contents. export_unmapped (shards): the unmapped branch is
         not paired here; its packed records are left in self.last_unmapped_records for the merging rank."""
         p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid, 1 if export_unmapped else 0)
+        if key_range is not None:   # ((lo_tid, lo_pos), (hi_tid, hi_pos)): breakpoint keys owned by this range shard
+            (p.key_lo_tid, p.key_lo_pos), (p.key_hi_tid, p.key_hi_pos) = key_range
+            p.key_filter = 1
+        p.halo_bytes = halo_bytes
         out = C.c_void_p()
         self.ctx.check(self.ctx.L.svb_getclip(self.ctx.h, self.h, C.byref(p), C.byref(out)), "svb_getclip")
         try:
@@ -289,7 +310,7 @@ class Bam:
 
     def getclip_sizes(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0) -> Tuple[int, int, int, int]:
         """svb_getclip without copying the four host buffers into Python objects: returns their lengths"""
-        p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid, 0)
+        p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid)
         out = C.c_void_p()
         self.ctx.check(self.ctx.L.svb_getclip(self.ctx.h, self.h, C.byref(p), C.byref(out)), "svb_getclip")
         try:
@@ -397,6 +418,35 @@ def bai_first_offsets(bai_path: str):
     arr = (C.c_uint64 * max(1, n))()
     L.svb_bai_first_offsets(bai_path.encode(), arr, n)
     return [None if arr[i] == 2 ** 64 - 1 else int(arr[i]) for i in range(n)]
+
+
+def bai_linear_offsets(bai_path: str, tid: int):
+    """linear index of one reference: virtual offset of the first record overlapping each 16 kb window (0 = none); host only"""
+    L = load()
+    n = L.svb_bai_linear_offsets(bai_path.encode(), tid, None, 0)
+    if n < 0:
+        raise SvbError("svb_bai_linear_offsets(%s, %d) = %d" % (bai_path, tid, n))
+    arr = (C.c_uint64 * max(1, n))()
+    L.svb_bai_linear_offsets(bai_path.encode(), tid, arr, n)
+    return [int(arr[i]) for i in range(n)]
+
+
+def peek_record(bam_path: str, voffset: int):
+    """(tid, 0-based pos) of the record at a virtual offset; host only"""
+    tid, pos = C.c_int32(), C.c_int32()
+    rc = load().svb_bam_peek_record(bam_path.encode(), voffset, C.byref(tid), C.byref(pos))
+    if rc != 0:
+        raise SvbError("svb_bam_peek_record(%s, %d) = %d" % (bam_path, voffset, rc))
+    return tid.value, pos.value
+
+
+def voffset_distance(bam_path: str, v_a: int, v_b: int) -> int:
+    """uncompressed bytes between two virtual offsets; host only"""
+    n = C.c_uint64()
+    rc = load().svb_voffset_distance(bam_path.encode(), v_a, v_b, C.byref(n))
+    if rc != 0:
+        raise SvbError("svb_voffset_distance = %d" % rc)
+    return n.value
 
 
 def write_gz(path: str, data: bytes, threads: int = 0) -> None:

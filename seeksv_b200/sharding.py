@@ -124,3 +124,152 @@ def open_ref_shard(ctx, bam_path: str, rank: int, world: int, bai: Optional[str]
     probe.close()
     lo, hi = assign_chromosomes(lens, world)[rank]
     return RefShardWorker(ctx, bam_path, lo, hi, bai, **getclip_kw)
+
+
+# ---- coordinate-range shards inside chromosomes ---------------------------------------------------------
+# The .bai's linear index holds, for every 16 kb window of every reference, the virtual offset of the first record that
+# overlaps the window. These offsets are record boundaries, so a BAM can be cut there without looking at the data, and they
+# bound the reach of earlier records exactly: every record whose alignment ends beyond the start of window w lies at or
+# after linear[w]. A shard that owns the records from cut c on therefore loads
+#     [context][halo][own records ...)      context: from the previous index offset (gives the walk a predecessor record)
+#                                           halo:    from linear[window(pos of the record at c) - 1] up to c
+# and clusters only the breakpoint keys (tid, pos) >= (tid_c, pos_c + 1) and below the next shard's bound: every key is
+# clustered on exactly one shard, with all of its reads, in file order. No data is exchanged between ranks; all ranks
+# compute the same plan from the index. Outputs merge per chromosome: the '5' lines of all shards, then the '3' lines.
+class RangePlan:
+    def __init__(self, v_view, v_halo, v_own, v_end, key_lo, key_hi, prev_tid, halo_bytes, context_bytes):
+        self.v_view, self.v_halo, self.v_own, self.v_end = v_view, v_halo, v_own, v_end
+        self.key_lo, self.key_hi, self.prev_tid = key_lo, key_hi, prev_tid
+        self.halo_bytes, self.context_bytes = halo_bytes, context_bytes
+
+    @property
+    def empty(self):
+        return self.v_own is not None and self.v_own == self.v_end
+
+
+KEY_MIN, KEY_MAX = (-(2 ** 31), -(2 ** 31)), (2 ** 31 - 1, 2 ** 31 - 1)
+
+
+def plan_range_shards(bam_path: str, bai_path: Optional[str], n_ref: int, world: int, context_steps: int = 1) -> List[RangePlan]:
+    import bisect
+    import os
+    from . import lib
+    bai_path = bai_path or bam_path + ".bai"
+    lin = [lib.bai_linear_offsets(bai_path, t) for t in range(n_ref)]
+    vset = sorted({v for L in lin for v in L if v})
+    size = os.path.getsize(bam_path)
+    cuts = []
+    for r in range(1, world):
+        if not vset:
+            break
+        target = size * r // world
+        j = bisect.bisect_left(vset, target << 16)
+        cand = [vset[k] for k in (j - 1, j) if 0 <= k < len(vset)]
+        v = min(cand, key=lambda x: abs((x >> 16) - target))
+        if v > vset[0]:
+            cuts.append(v)
+    cuts = sorted(set(cuts))
+    bounds = [lib.peek_record(bam_path, c) for c in cuts]
+    plans = []
+    for k in range(len(cuts) + 1):
+        v_own = cuts[k - 1] if k else 0
+        v_end = cuts[k] if k < len(cuts) else None
+        key_lo = (bounds[k - 1][0], bounds[k - 1][1] + 1) if k else KEY_MIN
+        key_hi = (bounds[k][0], bounds[k][1] + 1) if k < len(cuts) else KEY_MAX
+        if k == 0:
+            plans.append(RangePlan(0, 0, 0, v_end, key_lo, key_hi, 0, 0, 0))
+            continue
+        tid, pos = bounds[k - 1]
+        w = max((pos >> 14) - 1, 0)
+        L = lin[tid]
+        hv = 0
+        for i in range(min(w, len(L) - 1), -1, -1):   # (a window nobody overlaps has no entry: the previous one bounds it)
+            if L[i]:
+                hv = L[i]
+                break
+        if not hv:
+            hv = min(v for v in L if v)
+        hv = min(hv, v_own)
+        j = bisect.bisect_left(vset, hv)
+        j_view = j - context_steps
+        v_view = vset[j_view] if j_view >= 0 else 0
+        prev_tid = lib.peek_record(bam_path, v_view)[0] if v_view else 0
+        start = v_view or vset[0]
+        plans.append(RangePlan(v_view, hv, v_own, v_end, key_lo, key_hi, prev_tid,
+                               lib.voffset_distance(bam_path, start, v_own), lib.voffset_distance(bam_path, start, hv)))
+    while len(plans) < world:   # more ranks than cut points: the rest get nothing
+        plans.append(RangePlan(0, 0, 0, 0, KEY_MAX, KEY_MAX, 0, 0, 0))
+        plans[-1].v_own = plans[-1].v_end = 1
+    return plans
+
+
+def merge_range_texts(parts: Sequence[Tuple[str, str]]) -> Tuple[str, str]:
+    """parts: (clip text, clip.fq text) of the range shards in file order -> the whole-file texts: per chromosome (file order)
+    the '5' lines of all shards, then the '3' lines (DisplaySClipReadsAndClipFq, clip_reads.h:300-345); 4 FASTQ lines per line"""
+    order, groups = [], {}
+    for clip, fq in parts:
+        lines, fql = clip.split("\n")[:-1], fq.split("\n")[:-1]
+        assert len(fql) == 4 * len(lines)
+        for i, line in enumerate(lines):
+            f = line.split("\t", 3)
+            key = (f[0], f[2])
+            if f[0] not in order:
+                order.append(f[0])
+            g = groups.setdefault(key, ([], []))
+            g[0].append(line)
+            g[1].extend(fql[4 * i:4 * i + 4])
+    out, outfq = [], []
+    for chrom in order:
+        for side in ("5", "3"):
+            g = groups.get((chrom, side))
+            if g:
+                out.extend(g[0])
+                outfq.extend(g[1])
+    return "".join(x + "\n" for x in out), "".join(x + "\n" for x in outfq)
+
+
+class RangeShardWorker:
+    """One rank's coordinate-range shard of an indexed BAM on the GPU (plan_range_shards)."""
+
+    def __init__(self, ctx, bam_path: str, plan: RangePlan, **getclip_kw):
+        from . import lib
+        self.ctx, self.path, self.plan, self.kw = ctx, bam_path, plan, getclip_kw
+        self.bam = lib.Bam.open_voffsets(ctx, bam_path, plan.v_view, plan.v_end) if not plan.empty else None
+
+    def context_has_mapped_record(self) -> bool:
+        """the walk needs a mapped-branch record in front of the halo (else plan again with a larger context_steps)"""
+        if self.bam is None or not self.plan.v_view:
+            return True
+        from . import lib
+        dptr, _, _ = self.bam.device_stream()
+        ctx_view = lib.Bam.from_device(self.ctx, dptr, self.plan.context_bytes, 0, len(self.bam.ref_names))
+        try:
+            return ctx_view.last_mapped_tid() is not None
+        finally:
+            ctx_view.close()
+
+    def getclip(self):
+        if self.bam is None:
+            return "", "", "", "", b""
+        p = self.plan
+        texts = self.bam.getclip(prev_tid=p.prev_tid, export_unmapped=True, key_range=(p.key_lo, p.key_hi), halo_bytes=p.halo_bytes,
+                                 **self.kw)
+        return tuple(t.decode("latin-1") for t in texts) + (self.bam.last_unmapped_records,)
+
+    def pair_unmapped(self, records: bytes) -> Tuple[str, str]:
+        return RefShardWorker.pair_unmapped(self, records)
+
+    def close(self):
+        if self.bam is not None:
+            self.bam.close()
+
+
+def sharded_getclip_ranges(worker, dist=None) -> Optional[Tuple[str, str, str, str]]:
+    """worker.getclip() -> (clip, clip.fq, "", "", unmapped-branch records) of its range shard; rank 0 merges"""
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    parts = all_gather_objects(worker.getclip(), dist)
+    if rank != 0:
+        return None
+    clip, fq = merge_range_texts([(p[0], p[1]) for p in parts])
+    u1, u2 = worker.pair_unmapped(b"".join(p[4] for p in parts))
+    return clip, fq, u1, u2

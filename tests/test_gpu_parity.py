@@ -355,3 +355,29 @@ def test_chromosome_shards_of_one_bam_reproduce_the_whole_file(ctx, d, s):
         for w in workers:
             w.close()
     whole.close()
+
+
+@pytest.mark.parametrize("d,s", [("fuzz", "f11"), ("fuzz", "f12"), ("micro", "tumor"), ("example", "cancer")])
+def test_coordinate_range_shards_of_one_bam_reproduce_the_whole_file(ctx, d, s):
+    """range shards inside chromosomes (plan from the .bai's linear index, halo + key ownership on the device, merge per
+    chromosome and side, mates paired on the merging rank), run one after the other as ranks would"""
+    from seeksv_b200 import sharding
+    path = _bam(d, s)
+    n_ref = len(seeksv_b200_header(path))
+    golden = tuple(read_text(os.path.join(GOLDEN, d, s + e)) for e in (".clip.txt", ".clip.fq.txt", ".unmapped_1.fq.txt", ".unmapped_2.fq.txt"))
+    for world in (1, 2, 3, 5, 8):
+        plans = sharding.plan_range_shards(path, None, n_ref, world)
+        workers = [sharding.RangeShardWorker(ctx, path, p) for p in plans]
+        assert all(w.context_has_mapped_record() for w in workers)
+        parts = [w.getclip() for w in workers]
+        clip, fq = sharding.merge_range_texts([(p[0], p[1]) for p in parts])
+        live = [w for w in workers if w.bam is not None]
+        u1, u2 = live[0].pair_unmapped(b"".join(p[4] for p in parts))
+        assert (clip, fq, u1, u2) == golden, world
+        for w in workers:
+            w.close()
+
+
+def seeksv_b200_header(path):
+    from oracle import bamio
+    return bamio.read_bam(path)[0].names
