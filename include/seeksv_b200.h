@@ -58,7 +58,8 @@ int svb_prof_read(svb_ctx *ctx, int cap, const char **names, double *ms, int64_t
 /* `stream` = the UNCOMPRESSED BAM byte stream ("BAM\1" header + packed records) or a contiguous shard
  * of its record section. first_record = byte offset of the first record start inside `stream`
  * (header length for a whole file). n_ref = number of reference sequences in the header.
- * _device: `stream` is a device pointer (>= nbytes + 64 readable bytes, 16-byte aligned), borrowed for
+ * _device: `stream` is a device pointer (>= nbytes + 64 readable bytes, and 16 readable bytes in front of it unless it
+ *          is 16-byte aligned), borrowed for
  *          the life of the svb_bam. _host: copied host->device inside the call (pinned or pageable). */
 int svb_bam_from_device(svb_ctx *ctx, const void *d_stream, uint64_t nbytes, uint64_t first_record, int32_t n_ref,
                         svb_bam **out);

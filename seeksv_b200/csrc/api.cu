@@ -222,7 +222,11 @@ extern "C" int svb_bam_from_device(svb_ctx *ctx, const void *d_stream, uint64_t 
                                    svb_bam **out)
 {
     if (!ctx || !out || (!d_stream && nbytes)) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_device: null argument");
-    if (((uintptr_t)d_stream & 15) != 0) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_device: stream must be 16-byte aligned");
+    {   // only the TMA-staged streaming passes need an aligned base (bulk copies); the walkers read with aligned-down loads
+        const char *e = getenv("SEEKSV_B200_PASS");
+        if (e && !strcmp(e, "stream") && ((uintptr_t)d_stream & 15) != 0)
+            return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_device: stream must be 16-byte aligned for the streaming passes");
+    }
     CK(cudaSetDevice(ctx->device));
     std::unique_ptr<svb_bam> b(new svb_bam());
     b->ctx = ctx, b->d_data = (const uint8_t *)d_stream, b->nbytes = nbytes, b->first = first_record, b->n_ref = n_ref;

@@ -259,6 +259,17 @@ class RangeShardWorker:
     def pair_unmapped(self, records: bytes) -> Tuple[str, str]:
         return RefShardWorker.pair_unmapped(self, records)
 
+    def own_view(self):
+        """the shard's own records only (no context, no halo): what the additive getsv passes run on"""
+        if self.bam is None:
+            return None
+        from . import lib
+        dptr, nbytes, _ = self.bam.device_stream()
+        v = lib.Bam.from_device(self.ctx, dptr + self.plan.halo_bytes, nbytes - self.plan.halo_bytes, 0, len(self.bam.ref_names),
+                                keep=self.bam)
+        v.set_refs(self.bam.ref_names, self.bam.ref_lens)
+        return v
+
     def close(self):
         if self.bam is not None:
             self.bam.close()

@@ -374,6 +374,22 @@ def test_coordinate_range_shards_of_one_bam_reproduce_the_whole_file(ctx, d, s):
         live = [w for w in workers if w.bam is not None]
         u1, u2 = live[0].pair_unmapped(b"".join(p[4] for p in parts))
         assert (clip, fq, u1, u2) == golden, world
+        # getsv side on the own regions: record counts, qualifying-pair sums and per-junction counts add up to the whole file's
+        import seeksv_b200
+        whole = seeksv_b200.Bam.open(ctx, path)
+        own = [w.own_view() for w in live]
+        assert sum(v.n_records for v in own) == whole.n_records
+        n_w, tot_w, mean_w, _ = whole.insert_stats(20, 5000000)
+        stats = [v.insert_stats(20, 5000000) for v in own]
+        assert sum(x[0] for x in stats) == n_w and sum(x[1] for x in stats) == tot_w
+        lens = whole.ref_lens
+        juncs = [(t, p, "+", t, p + 300, "-") for t in range(n_ref) for p in range(100, min(lens[t] - 400, 20000), 1500)]
+        want = whole.discordant_support(juncs, 20, mean_w, 25, 4)
+        got = [v.discordant_support(juncs, 20, mean_w, 25, 4) for v in own]
+        assert [sum(col) for col in zip(*got)] == list(want)
+        for v in own:
+            v.close()
+        whole.close()
         for w in workers:
             w.close()
 
