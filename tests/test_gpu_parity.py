@@ -397,3 +397,39 @@ def test_coordinate_range_shards_of_one_bam_reproduce_the_whole_file(ctx, d, s):
 def seeksv_b200_header(path):
     from oracle import bamio
     return bamio.read_bam(path)[0].names
+
+
+def test_cli_fails_cleanly_on_damaged_inputs(tmp_path):
+    """message on stderr + exit status 1 (the reference's convention), never a crash or a hang"""
+    good = open(_bam("micro", "tumor"), "rb").read()
+    cases = {
+        "truncated.bam": good[:len(good) // 2 + 123],                       # cut in the middle of a BGZF block
+        "cut_at_block.bam": good[:_block_boundary(good, len(good) // 2)],    # whole blocks, but the record chain is cut
+        "text.bam": b"this is not a BAM file\n" * 100,
+        "empty.bam": b"",
+        "payload.bam": good[:5000] + bytes(b ^ 0x5A for b in good[5000:5400]) + good[5400:],   # damaged deflate payload
+    }
+    for name, data in cases.items():
+        p = str(tmp_path / name)
+        open(p, "wb").write(data)
+        r = subprocess.run([_cli(), "getclip", "-o", str(tmp_path / "o"), p], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 1, (name, r.returncode, r.stderr[-300:])
+        assert r.stderr.strip(), name
+    r = subprocess.run([_cli(), "getclip", "-o", str(tmp_path / "o"), str(tmp_path / "missing.bam")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "fail to open" in r.stderr
+    # header only: a valid BAM without records gives four empty outputs
+    from oracle import bamio
+    h, _ = bamio.read_bam(_bam("micro", "tumor"))
+    p = str(tmp_path / "header_only.bam")
+    bamio.write_bam(p, h, [])
+    r = subprocess.run([_cli(), "getclip", "-o", str(tmp_path / "h"), p], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert _zcat(str(tmp_path / "h.clip.gz")) == "" and _zcat(str(tmp_path / "h.unmapped_1.fq.gz")) == ""
+
+
+def _block_boundary(raw, near):
+    import struct
+    o = 0
+    while o < near:
+        o += struct.unpack_from("<H", raw, o + 16)[0] + 1
+    return o
