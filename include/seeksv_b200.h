@@ -139,6 +139,10 @@ typedef struct svb_getclip_params {
     int32_t key_filter;
     int32_t key_lo_tid, key_lo_pos, key_hi_tid, key_hi_pos;
     uint64_t halo_bytes;
+    /* 1: the four outputs are compressed on the device and handed back as gzip file images (svb_clusters_gz) instead of
+     * text (svb_clusters_text then returns empty buffers): smaller device->host copy, no deflate work on the host. The
+     * images are what svb_write_gz would write for the same text (multi-member, Huffman-only). */
+    int32_t gz_outputs;
 } svb_getclip_params;
 
 typedef struct svb_clusters svb_clusters; /* host-resident result of svb_getclip */
@@ -151,6 +155,8 @@ uint64_t svb_clusters_candidates(const svb_clusters *c); /* soft-clipped reads t
  * (DisplaySClipReadsAndClipFq clip_reads.h:300-345, StoreUnmapSeqAndQual clip_reads.h:172-219), as
  * host buffers owned by the result object. which: 0 clip, 1 clip.fq, 2 unmapped_1, 3 unmapped_2. */
 int svb_clusters_text(const svb_clusters *c, int which, const char **data, uint64_t *len);
+/* gz_outputs: the gzip file image of output `which` (write it to P.clip.gz etc. as is). */
+int svb_clusters_gz(const svb_clusters *c, int which, const char **data, uint64_t *len);
 /* The packed BAM records (block_size + body, file order) of the unmapped branch; only with export_unmapped_records. */
 int svb_clusters_unmapped_records(const svb_clusters *c, const char **data, uint64_t *len);
 
@@ -206,6 +212,8 @@ void svb_free(void *p);
  * svb_read_gz returns the decompressed content of any gzip or plain text file in a malloc'ed buffer (svb_free);
  * files written by svb_write_gz are inflated member-parallel. n_threads <= 0: all host cores. */
 int svb_write_gz(const char *path, const void *data, uint64_t n, int n_threads);
+/* The same file image made on the device (gzip.cu): text in host memory -> malloc'ed gzip image (svb_free). */
+int svb_gzip_text(svb_ctx *ctx, const void *text, uint64_t n, char **gz, uint64_t *gz_len);
 int svb_read_gz(const char *path, char **data, uint64_t *n);
 
 /* ---- whole commands (what the CLI calls; same arguments as the reference's Call* functions,

@@ -34,7 +34,8 @@ struct svb_ctx {
     // launches that follow each uploaded slab
     static constexpr int N_AUX = 8;
     cudaStream_t copy_stream = nullptr, aux[N_AUX] = {};
-    cudaEvent_t fork_event = nullptr;  // orders work handed from `stream` to `copy_stream`
+    cudaEvent_t fork_event = nullptr;
+    bool gz_tables_ready = false;  // gzip.cu's constant tables are on this device  // orders work handed from `stream` to `copy_stream`
     std::string err;
     bool prof = false;
     std::map<std::string, ProfEntry> prof_acc;
@@ -284,6 +285,8 @@ int verify_or_repair(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit, int *ok
 int decode_records(svb_ctx *ctx, svb_bam *bam, int32_t stats_mapq = -1);  // getsv.cu
 // the inflate kernel reads ahead of the current bit position: the device copy of the file image is padded by this much
 static constexpr uint64_t SVB_INFLATE_PAD = 1024;
+struct PinnedBuf;
+int gzip_on_device(svb_ctx *ctx, const char *d_text, uint64_t n, PinnedBuf *out);  // gzip.cu
 int inflate_launch(cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err);
 int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out,
                       double out_bytes);                             // inflate.cu

@@ -14,11 +14,14 @@
 struct svb_clusters {
     svb_ctx *ctx = nullptr;
     PinnedBuf text[4];  // pinned host memory: D2H at full PCIe rate, recycled through the ctx pool
+    PinnedBuf gz[4];             // the same four files as gzip images, compressed on the device (svb_getclip_params.gz_outputs)
+    bool gz_mode = false;
     PinnedBuf unmapped_records;  // sharded runs: the raw unmapped-branch records (svb_getclip_params.export_unmapped_records)
     uint64_t n_clusters = 0, n_candidates = 0;
     ~svb_clusters()
     {
         for (auto &t : text) t.release(ctx);
+        for (auto &t : gz) t.release(ctx);
         unmapped_records.release(ctx);
     }
 };
@@ -957,6 +960,8 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
 
     // ---- 2. unmapped-branch records: pair mates by name on the device, emit the two FASTQ files ---------------------
     DevBuf<char> un_o1, un_o2;
+    bool have_unmapped_gz = false;
+    res->gz_mode = prm->gz_outputs != 0 && !prm->export_unmapped_records;
     struct CopyJoin {  // declared after the buffers the copy stream reads: joined before they are released, on every way out
         cudaStream_t c;
         ~CopyJoin() { cudaStreamSynchronize(c); }
@@ -1033,6 +1038,11 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
             unmapped_write<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_first, mate_of.p, bam->d_data, off1.p, off2.p,
                                                                           un_o1.p, un_o2.p);
         }
+        if (res->gz_mode) {
+            CKR(gzip_on_device(ctx, un_o1.p, tot[0], &res->gz[2]));
+            CKR(gzip_on_device(ctx, un_o2.p, tot[1], &res->gz[3]));
+            have_unmapped_gz = true;
+        } else {
         CKR(res->text[2].reserve(ctx, tot[0]));
         CKR(res->text[3].reserve(ctx, tot[1]));
         // the two FASTQ texts travel to the host on the copy stream while the candidate pipeline below runs
@@ -1040,9 +1050,20 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_event, 0));
         CK(cudaMemcpyAsync(res->text[2].p, un_o1.p, tot[0], cudaMemcpyDeviceToHost, ctx->copy_stream));
         CK(cudaMemcpyAsync(res->text[3].p, un_o2.p, tot[1], cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+    }
+    // gzip mode: every file exists, if only as one empty member (what the reference's ogzstream leaves behind as well)
+    auto empty_gz = [&](int which) -> int { return res->gz[which].p ? 0 : gzip_on_device(ctx, nullptr, 0, &res->gz[which]); };
+    if (res->gz_mode && !have_unmapped_gz) {
+        CKR(empty_gz(2));
+        CKR(empty_gz(3));
     }
 
     if (n_cand == 0) {
+        if (res->gz_mode) {
+            CKR(empty_gz(0));
+            CKR(empty_gz(1));
+        }
         *out_ = guard.release();
         return 0;
     }
@@ -1167,10 +1188,15 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
                                                                   maxl.p, maxr.p, arena_off.p, arena_seq.p, arena_qual.p, clip_off.p,
                                                                   fq_off.p, d_clip.p, d_fq.p);
     }
-    CKR(res->text[0].reserve(ctx, clip_bytes));
-    CKR(res->text[1].reserve(ctx, fq_bytes));
-    CK(cudaMemcpyAsync(res->text[0].p, d_clip.p, clip_bytes, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(res->text[1].p, d_fq.p, fq_bytes, cudaMemcpyDeviceToHost, s));
+    if (res->gz_mode) {
+        CKR(gzip_on_device(ctx, d_clip.p, clip_bytes, &res->gz[0]));
+        CKR(gzip_on_device(ctx, d_fq.p, fq_bytes, &res->gz[1]));
+    } else {
+        CKR(res->text[0].reserve(ctx, clip_bytes));
+        CKR(res->text[1].reserve(ctx, fq_bytes));
+        CK(cudaMemcpyAsync(res->text[0].p, d_clip.p, clip_bytes, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(res->text[1].p, d_fq.p, fq_bytes, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     *out_ = guard.release();
@@ -1180,6 +1206,33 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
 extern "C" void svb_clusters_free(svb_clusters *c) { delete c; }
 extern "C" uint64_t svb_clusters_count(const svb_clusters *c) { return c ? c->n_clusters : 0; }
 extern "C" uint64_t svb_clusters_candidates(const svb_clusters *c) { return c ? c->n_candidates : 0; }
+// gzip.cu alone (tests / other text outputs): host text -> device -> gzip image in a malloc'ed host buffer (svb_free)
+extern "C" int svb_gzip_text(svb_ctx *ctx, const void *text, uint64_t n, char **gz, uint64_t *gz_len)
+{
+    if (!ctx || (!text && n) || !gz || !gz_len) return svb_fail(ctx, SVB_ERR_ARG, "svb_gzip_text: null argument");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<char> d;
+    CK(d.alloc(n, ctx->stream));
+    if (n) CK(cudaMemcpyAsync(d.p, text, n, cudaMemcpyHostToDevice, ctx->stream));
+    PinnedBuf out;
+    int rc = gzip_on_device(ctx, d.p, n, &out);
+    if (rc == 0) {
+        *gz = (char *)malloc(out.n ? out.n : 1);
+        if (!*gz) rc = svb_fail(ctx, SVB_ERR_IO, "out of memory");
+        else memcpy(*gz, out.p, out.n), *gz_len = out.n;
+    }
+    out.release(ctx);
+    return rc;
+}
+
+extern "C" int svb_clusters_gz(const svb_clusters *c, int which, const char **data, uint64_t *len)
+{
+    if (!c || which < 0 || which > 3 || !data || !len) return SVB_ERR_ARG;
+    *data = c->gz[which].p ? c->gz[which].p : "";
+    *len = c->gz[which].n;
+    return 0;
+}
+
 extern "C" int svb_clusters_unmapped_records(const svb_clusters *c, const char **data, uint64_t *len)
 {
     if (!c || !data || !len) return SVB_ERR_ARG;

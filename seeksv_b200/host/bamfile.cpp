@@ -966,6 +966,36 @@ bool write_gz_many(const std::vector<GzJob> &jobs, int n_threads, std::string &e
     return true;
 }
 
+bool gz_on_host()
+{
+    const char *m = getenv("SEEKSV_B200_GZ");
+    return gz_level() >= 0 || (m && !strcmp(m, "host"));
+}
+
+bool write_files(const std::vector<GzJob> &jobs, std::string &err)
+{
+    std::vector<std::string> errs(jobs.size());
+    auto write_one = [&](size_t j) {
+        FILE *f = fopen(jobs[j].path.c_str(), "wb");
+        if (!f) {
+            errs[j] = "Cannot open file " + jobs[j].path;
+            return;
+        }
+        if (jobs[j].n && fwrite(jobs[j].data, 1, jobs[j].n, f) != jobs[j].n) errs[j] = "write error on " + jobs[j].path;
+        fclose(f);
+    };
+    std::vector<std::thread> th;
+    for (size_t j = 1; j < jobs.size(); ++j) th.emplace_back(write_one, j);
+    if (!jobs.empty()) write_one(0);
+    for (auto &t : th) t.join();
+    for (auto &e : errs)
+        if (!e.empty()) {
+            err = e;
+            return false;
+        }
+    return true;
+}
+
 bool write_gz(const std::string &path, const char *data, uint64_t n, int n_threads, std::string &err)
 {
     return write_gz_many({GzJob{path, data, n}}, n_threads, err);

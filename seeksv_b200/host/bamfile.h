@@ -58,3 +58,6 @@ struct GzJob {
     uint64_t n;
 };
 bool write_gz_many(const std::vector<GzJob> &jobs, int n_threads, std::string &err);
+bool gz_on_host();  // SEEKSV_B200_GZ_LEVEL / SEEKSV_B200_GZ=host: the outputs are compressed by host threads, not on the device
+// ready-made file images (compressed on the device): one writer thread per file
+bool write_files(const std::vector<GzJob> &jobs, std::string &err);

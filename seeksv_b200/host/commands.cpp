@@ -233,7 +233,8 @@ int fail(const std::string &msg)
 // ---- getclip: CallGetclip (seeksv.cpp:128-155) + InputBamOutputReads (clip_reads.h:363-484) ---------------------
 int cmd_getclip(int argc, char **argv)
 {
-    svb_getclip_params prm = {0.9, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    svb_getclip_params prm = {0.9, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    prm.gz_outputs = gz_on_host() ? 0 : 1;  // default: the four files are compressed on the device
     std::string prefix = "output";
     int c;
     optind = 1;
@@ -275,11 +276,12 @@ int cmd_getclip(int argc, char **argv)
     for (int i = 0; i < 4; ++i) {
         const char *data;
         uint64_t len;
-        svb_clusters_text(cl, i, &data, &len);
+        if (prm.gz_outputs) svb_clusters_gz(cl, i, &data, &len);
+        else svb_clusters_text(cl, i, &data, &len);
         jobs.push_back(GzJob{prefix + ext[i], data, len});
     }
     std::string werr;
-    if (!write_gz_many(jobs, n_threads(), werr)) status = fail(werr);
+    if (!(prm.gz_outputs ? write_files(jobs, werr) : write_gz_many(jobs, n_threads(), werr))) status = fail(werr);
     ph.mark("getclip: gzip + write outputs");
     std::cerr << "[GetSClipReads] finished!" << std::endl;
     svb_clusters_free(cl);

@@ -25,7 +25,7 @@ class GetclipParams(C.Structure):
     _fields_ = [("match_rate", C.c_double), ("min_mapq", C.c_int32), ("save_low_quality", C.c_int32),
                 ("prev_tid", C.c_int32), ("export_unmapped_records", C.c_int32), ("key_filter", C.c_int32),
                 ("key_lo_tid", C.c_int32), ("key_lo_pos", C.c_int32), ("key_hi_tid", C.c_int32), ("key_hi_pos", C.c_int32),
-                ("halo_bytes", C.c_uint64)]
+                ("halo_bytes", C.c_uint64), ("gz_outputs", C.c_int32)]
 
 
 class Junction(C.Structure):
@@ -48,7 +48,7 @@ EXPORTS = [
     "svb_bam_set_refs", "svb_getclip", "svb_clusters_free", "svb_clusters_count", "svb_clusters_candidates",
     "svb_clusters_text", "svb_insert_stats", "svb_discordant_support", "svb_window_depth", "svb_plan_getsv", "svb_free",
     "svb_write_gz", "svb_read_gz", "svb_bam_open_refs", "svb_bai_first_offsets", "svb_bam_last_mapped_tid", "svb_clusters_unmapped_records",
-    "svb_bam_open_voffsets", "svb_bai_linear_offsets", "svb_bam_peek_record", "svb_voffset_distance",
+    "svb_clusters_gz", "svb_gzip_text", "svb_bam_open_voffsets", "svb_bai_linear_offsets", "svb_bam_peek_record", "svb_voffset_distance",
     "svb_main",
 ]
 
@@ -104,6 +104,8 @@ def load():
     L.svb_clusters_candidates.argtypes = [vp]
     L.svb_clusters_candidates.restype = u64
     L.svb_clusters_text.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(u64)]
+    L.svb_gzip_text.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(vp), C.POINTER(u64)]
+    L.svb_clusters_gz.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(u64)]
     L.svb_clusters_unmapped_records.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(u64)]
     L.svb_insert_stats.argtypes = [vp, vp, i32, i64, C.POINTER(i64)]
     L.svb_discordant_support.argtypes = [vp, vp, C.POINTER(Junction), u64, C.POINTER(PairParams), C.POINTER(i32)]
@@ -308,9 +310,26 @@ class Bam:
         finally:
             self.ctx.L.svb_clusters_free(out)
 
-    def getclip_sizes(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0) -> Tuple[int, int, int, int]:
+    def getclip_gz(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0):
+        """the four outputs as gzip file images, compressed on the device (what the CLI writes)"""
+        p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid)
+        p.gz_outputs = 1
+        out = C.c_void_p()
+        self.ctx.check(self.ctx.L.svb_getclip(self.ctx.h, self.h, C.byref(p), C.byref(out)), "svb_getclip")
+        try:
+            res = []
+            for which in range(4):
+                d, n = C.c_char_p(), C.c_uint64()
+                self.ctx.L.svb_clusters_gz(out, which, C.byref(d), C.byref(n))
+                res.append(C.string_at(d, n.value) if n.value else b"")
+            return tuple(res)
+        finally:
+            self.ctx.L.svb_clusters_free(out)
+
+    def getclip_sizes(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0, gz=False) -> Tuple[int, int, int, int]:
         """svb_getclip without copying the four host buffers into Python objects: returns their lengths"""
         p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid)
+        p.gz_outputs = 1 if gz else 0
         out = C.c_void_p()
         self.ctx.check(self.ctx.L.svb_getclip(self.ctx.h, self.h, C.byref(p), C.byref(out)), "svb_getclip")
         try:
@@ -318,7 +337,7 @@ class Bam:
             for which in range(4):
                 d = C.c_char_p()
                 n = C.c_uint64()
-                self.ctx.L.svb_clusters_text(out, which, C.byref(d), C.byref(n))
+                (self.ctx.L.svb_clusters_gz if gz else self.ctx.L.svb_clusters_text)(out, which, C.byref(d), C.byref(n))
                 res.append(n.value)
             return tuple(res)
         finally:
@@ -407,6 +426,16 @@ def plan_getsv(clip_alignments: str, clip_file: str, ref_names: Sequence[str], r
         L.svb_free(pj)
         L.svb_free(pw)
     return juncs, wins
+
+
+def gzip_text(ctx: "Context", data: bytes) -> bytes:
+    """gzip file image of `data`, compressed on the device (gzip.cu)"""
+    p, n = C.c_void_p(), C.c_uint64()
+    ctx.check(ctx.L.svb_gzip_text(ctx.h, data, len(data), C.byref(p), C.byref(n)), "svb_gzip_text")
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        ctx.L.svb_free(p)
 
 
 def bai_first_offsets(bai_path: str):

@@ -442,3 +442,45 @@ def _block_boundary(raw, near):
     while o < near:
         o += struct.unpack_from("<H", raw, o + 16)[0] + 1
     return o
+
+
+@pytest.mark.parametrize("d,s", CASES)
+def test_device_gzip_images_decompress_to_the_texts(ctx, d, s, tmp_path):
+    """svb_getclip with gz_outputs: the four gzip images made on the device (gzip.cu) are valid gzip - Python's zlib checks every
+    member's CRC32 and ISIZE - and decompress to exactly the texts of the plain mode; the product's own reader agrees"""
+    import seeksv_b200
+    import seeksv_b200.lib as L
+    bam = seeksv_b200.Bam.open(ctx, _bam(d, s))
+    texts = bam.getclip()
+    images = bam.getclip_gz()
+    bam.close()
+    for i, (t, g) in enumerate(zip(texts, images)):
+        assert g[:4] == b"\x1f\x8b\x08\x04" and g[12:14] == b"SV", i
+        assert gzip.decompress(g) == t, i
+        p = str(tmp_path / ("o%d.gz" % i))
+        open(p, "wb").write(g)
+        assert L.read_gz(p) == t, i
+
+
+def test_device_gzip_on_awkward_texts(ctx):
+    """the gzip kernels alone, through svb_gzip_text: empty input, one byte, one symbol, piece and member edges, skewed and
+    incompressible bytes (codes longer than 15 bits must be limited)"""
+    import random
+    import seeksv_b200.lib as L
+    rnd = random.Random(11)
+    cases = [b"", b"A", b"I" * 300000, b"ACGT" * (16384 * 3) + b"N", rnd.randbytes((1 << 20) + 17), rnd.randbytes(65536),
+             bytes(rnd.choices(range(256), weights=[2 ** (-i / 8) for i in range(256)], k=1_500_000)),
+             b"".join(bytes([i]) * (2 ** min(i, 21)) for i in range(23))]
+    for data in cases:
+        g = L.gzip_text(ctx, data)
+        assert gzip.decompress(g) == data, len(data)
+
+
+def test_cli_host_gzip_modes_give_the_same_files(tmp_path):
+    d, s = "micro", "tumor"
+    want = read_text(os.path.join(GOLDEN, d, s + ".clip.txt"))
+    for name, env in (("huff", {"SEEKSV_B200_GZ": "host"}), ("zlib", {"SEEKSV_B200_GZ_LEVEL": "6"})):
+        pre = str(tmp_path / name)
+        r = subprocess.run([_cli(), "getclip", "-o", pre, _bam(d, s)], capture_output=True, text=True, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr
+        assert _zcat(pre + ".clip.gz") == want
