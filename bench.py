@@ -260,7 +260,7 @@ def main():
         """getclip + getsv on the HBM-resident stream"""
         b = S.Bam.from_device(ctx, dptr, nbytes, first, len(names))
         b.set_refs(names, lens)
-        sizes = b.getclip_sizes(gz=True)      # the four outputs as gzip images, compressed on the device (what the CLI writes)
+        sizes = b.getclip_sizes()             # the operator's plain results: four texts in (pinned) host memory
         b.close()
         b = S.Bam.from_device(ctx, dptr, nbytes, first, len(names))
         b.set_refs(names, lens)

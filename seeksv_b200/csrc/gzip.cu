@@ -382,18 +382,29 @@ int gzip_on_device(svb_ctx *ctx, const char *d_text, uint64_t n, PinnedBuf *out)
     CK(piece_bit_off.alloc(n_pieces, s));
     CK(member_off.alloc(n_members + 1, s));
     CK(member_crc.alloc(n_members, s));
-    ProfScope ps(ctx, "gzip_text", (double)n);
-    gz_hist_crc<<<n_pieces, GZ_THREADS, 0, s>>>((const uint8_t *)d_text, n, hist.p, crc_raw.p);
-    gz_codes<<<(n_pieces + 63) / 64, 64, 0, s>>>(n_pieces, n, hist.p, codes.p, hdr.p, hdr_bits.p, piece_bits.p);
-    gz_layout<<<1, 1024, 0, s>>>(n_pieces, n_members, n, piece_bits.p, crc_raw.p, piece_bit_off.p, member_off.p, member_crc.p);
+    {
+        ProfScope ps(ctx, "gz_hist_crc", (double)n);
+        gz_hist_crc<<<n_pieces, GZ_THREADS, 0, s>>>((const uint8_t *)d_text, n, hist.p, crc_raw.p);
+    }
+    {
+        ProfScope ps(ctx, "gz_codes", 0);
+        gz_codes<<<(n_pieces + 63) / 64, 64, 0, s>>>(n_pieces, n, hist.p, codes.p, hdr.p, hdr_bits.p, piece_bits.p);
+    }
+    {
+        ProfScope ps(ctx, "gz_layout", 0);
+        gz_layout<<<1, 1024, 0, s>>>(n_pieces, n_members, n, piece_bits.p, crc_raw.p, piece_bit_off.p, member_off.p, member_crc.p);
+    }
     uint64_t total = 0;
     CK(cudaMemcpyAsync(&total, member_off.p + n_members, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     DevBuf<uint32_t> gz;
     CK(gz.alloc(total / 4 + 2, s));
     CK(cudaMemsetAsync(gz.p, 0, (total / 4 + 2) * 4, s));
-    gz_encode<<<n_pieces, GZ_THREADS, 0, s>>>((const uint8_t *)d_text, n, n_pieces, codes.p, hdr.p, hdr_bits.p, piece_bits.p, piece_bit_off.p,
-                                              member_off.p, member_crc.p, gz.p);
+    {
+        ProfScope ps(ctx, "gz_encode", (double)n);
+        gz_encode<<<n_pieces, GZ_THREADS, 0, s>>>((const uint8_t *)d_text, n, n_pieces, codes.p, hdr.p, hdr_bits.p, piece_bits.p,
+                                                  piece_bit_off.p, member_off.p, member_crc.p, gz.p);
+    }
     CK(cudaGetLastError());
     CKR(out->reserve(ctx, total));
     CK(cudaMemcpyAsync(out->p, gz.p, total, cudaMemcpyDeviceToHost, s));
