@@ -960,7 +960,16 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
 
     // ---- 2. unmapped-branch records: pair mates by name on the device, emit the two FASTQ files ---------------------
     DevBuf<char> un_o1, un_o2;
-    bool have_unmapped_gz = false;
+    bool have_unmapped_gz = false, unmapped_copy_pending = false;
+    uint64_t un_bytes[2] = {0, 0};
+    auto start_unmapped_copy = [&]() -> int {
+        if (!unmapped_copy_pending) return 0;
+        unmapped_copy_pending = false;
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_event, 0));
+        CK(cudaMemcpyAsync(res->text[2].p, un_o1.p, un_bytes[0], cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaMemcpyAsync(res->text[3].p, un_o2.p, un_bytes[1], cudaMemcpyDeviceToHost, ctx->copy_stream));
+        return 0;
+    };
     res->gz_mode = prm->gz_outputs != 0 && !prm->export_unmapped_records;
     struct CopyJoin {  // declared after the buffers the copy stream reads: joined before they are released, on every way out
         cudaStream_t c;
@@ -1045,11 +1054,10 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         } else {
         CKR(res->text[2].reserve(ctx, tot[0]));
         CKR(res->text[3].reserve(ctx, tot[1]));
-        // the two FASTQ texts travel to the host on the copy stream while the candidate pipeline below runs
+        // the two FASTQ texts travel to the host on the copy stream while the candidate pipeline below runs; the copies are
+        // queued after the sorts (start_unmapped_copy): queued here they slowed the sort's many small launches down by 2x
         CK(cudaEventRecord(ctx->fork_event, s));
-        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_event, 0));
-        CK(cudaMemcpyAsync(res->text[2].p, un_o1.p, tot[0], cudaMemcpyDeviceToHost, ctx->copy_stream));
-        CK(cudaMemcpyAsync(res->text[3].p, un_o2.p, tot[1], cudaMemcpyDeviceToHost, ctx->copy_stream));
+        unmapped_copy_pending = true, un_bytes[0] = tot[0], un_bytes[1] = tot[1];
         }
     }
     // gzip mode: every file exists, if only as one empty member (what the reference's ogzstream leaves behind as well)
@@ -1060,6 +1068,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
     }
 
     if (n_cand == 0) {
+        CKR(start_unmapped_copy());
         if (res->gz_mode) {
             CKR(empty_gz(0));
             CKR(empty_gz(1));
@@ -1098,6 +1107,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         CK(cub::DeviceRadixSort::SortPairs(t2.p, tmp2, key0.p, key1.p, ord1.p, ord2.p, (int)n_cand, 0, 64, s));
     }
     const uint32_t *order = ord2.p;
+    CKR(start_unmapped_copy());
 
     // ---- 4. segments (one per breakpoint key) -------------------------------------------------------------------
     DevBuf<uint32_t> flag, segid;

@@ -25,7 +25,7 @@ struct WarpTables {
     uint32_t lit_fast[1 << LIT_FAST];
     uint32_t dist_fast[1 << DIST_FAST];
     // (ring and tok double as the 288 x u16 scratch for canonical codes while a table is being built)
-    uint32_t ring[RING + 1];  // the next RING words of the compressed stream (refilled by all lanes before each batch)
+    uint32_t ring[RING + 2];  // the next RING words of the compressed stream (refilled by all lanes before each batch)
     uint32_t tok[MAX_BATCH];  // token batch: bit 31 literal (byte in bits 0-7), else length in bits 0-8 and distance in bits 9-24
     uint16_t lit_sym[288], dist_sym[32];  // symbols sorted by (code length, symbol) for the canonical slow path
     uint16_t lit_count[16], dist_count[16];
@@ -169,13 +169,6 @@ __device__ __forceinline__ uint32_t decode_entry(uint32_t w, const uint32_t *fas
     int s = slow_decode(w, count, sym_sorted, &l);
     if (s < 0) return E_INVALID;
     return l | (IS_LIT ? lit_entry(s) : dist_entry(s));
-}
-
-// 32 bits of the compressed stream at bit position bp, from the shared-memory ring (ring[RING] mirrors ring[0])
-__device__ __forceinline__ uint32_t ring_window(const uint32_t *ring, uint32_t bp)
-{
-    const uint32_t *p = ring + ((bp >> 5) & (RING - 1));
-    return __funnelshift_r(p[0], p[1], bp);
 }
 
 }  // namespace
@@ -341,7 +334,7 @@ __global__ void __launch_bounds__(BLOCKS_PER_CTA * GROUP, 8)
                 for (int j = 0; j < 3; ++j) {
                     uint32_t idx = cw + glane + GROUP * j, v = __ldg(wbase + idx);
                     T.ring[idx & (RING - 1)] = v;
-                    if ((idx & (RING - 1)) == 0) T.ring[RING] = v;
+                    if ((idx & (RING - 1)) < 2) T.ring[RING + (idx & (RING - 1))] = v;  // mirror: three consecutive words never wrap
                 }
             }
             __syncwarp(mt);
@@ -350,7 +343,11 @@ __global__ void __launch_bounds__(BLOCKS_PER_CTA * GROUP, 8)
             if (glane == 0) {
                 uint32_t bp = bitpos;
                 while (ntok < BATCH) {
-                    const uint32_t w = ring_window(T.ring, bp);
+                    // 64 bits of the stream at bp: a literal/length code with its extra bits (<= 20) and a distance code with
+                    // its extra bits (<= 28) both fit, so one look at the ring serves the whole token
+                    const uint32_t *rp = T.ring + ((bp >> 5) & (RING - 1));
+                    const uint32_t r0 = rp[0], r1 = rp[1], r2 = rp[2];
+                    const uint32_t w = __funnelshift_r(r0, r1, bp), whi = __funnelshift_r(r1, r2, bp);
                     const uint32_t e = decode_entry<true>(w, T.lit_fast, LIT_FAST, T.lit_count, T.lit_sym);
                     const uint32_t l = e & 15;
                     uint32_t tok;
@@ -362,10 +359,9 @@ __global__ void __launch_bounds__(BLOCKS_PER_CTA * GROUP, 8)
                         status = (e & E_END) ? 1 : -1;
                         break;
                     } else {
-                        const uint32_t x = (e >> 4) & 15;
+                        const uint32_t x = (e >> 4) & 15, used = l + x;
                         const uint32_t len = (e >> 16) + ((w >> l) & ((1u << x) - 1));  // l + x <= 20 bits of the window
-                        bp += l + x;
-                        const uint32_t w2 = ring_window(T.ring, bp);
+                        const uint32_t w2 = __funnelshift_r(w, whi, used);
                         const uint32_t d = decode_entry<false>(w2, T.dist_fast, DIST_FAST, T.dist_count, T.dist_sym);
                         if (d & E_INVALID) {
                             status = -1;
@@ -373,7 +369,7 @@ __global__ void __launch_bounds__(BLOCKS_PER_CTA * GROUP, 8)
                         }
                         const uint32_t l2 = d & 15, x2 = (d >> 4) & 15;
                         const uint32_t dist = (d >> 16) + ((w2 >> l2) & ((1u << x2) - 1));  // l2 + x2 <= 28
-                        bp += l2 + x2;
+                        bp += used + l2 + x2;
                         tok = len | dist << 9;
                     }
                     T.tok[ntok++] = tok;
