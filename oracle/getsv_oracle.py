@@ -698,11 +698,63 @@ def output_breakpoints(jmap: JunctionMap, pos2depth, range2depth, j2r, min_clip_
     return "".join(out), "".join(filt)
 
 
+def read_breakpoint(text: str, jmap: "JunctionMap"):
+    """ReadBreakpoint, getsv.cpp:1291-1323 (getsv -B): junctions of an earlier output file are put into the map before the
+    join. The reference reads with `fin >> token`, i.e. by whitespace-separated tokens, not by lines; a line that starts
+    with '@' is skipped to its end; after the 23rd token the rest of the line is dropped. A token that does not convert
+    ends the loop (the stream fails)."""
+    i, n = 0, len(text)
+
+    def skip_ws(i):
+        while i < n and text[i] in " \t\n\r\v\f":
+            i += 1
+        return i
+
+    def token(i):
+        i = skip_ws(i)
+        j = i
+        while j < n and text[j] not in " \t\n\r\v\f":
+            j += 1
+        return text[i:j], j
+
+    def rest_of_line(i):
+        j = text.find("\n", i)
+        return n if j < 0 else j + 1
+    while True:
+        up_chr, i = token(i)
+        if not up_chr:
+            return
+        if up_chr[0] == "@":
+            i = rest_of_line(i)
+            continue
+        tok = []
+        for _ in range(22):
+            t, i = token(i)
+            tok.append(t)
+        i = rest_of_line(i)
+        try:
+            up_pos, up_strand, up_n = int(tok[0]), tok[1], int(tok[2])
+            down_chr, down_pos, down_strand, down_n = tok[3], int(tok[4]), tok[5], int(tok[6])
+            micro, pairs = int(tok[7]), int(tok[8])
+            for k in range(10, 16):
+                int(tok[k])
+            float(tok[16]), float(tok[17])
+        except ValueError:
+            return
+        if len(up_strand) != 1 or len(down_strand) != 1:
+            return  # (`fin >> char` takes one character: longer tokens desynchronise the reference - not modelled)
+        up = SeqInfo(tok[20], change_cigar_type(tok[18]), 0, 0, up_n, 0)
+        down = SeqInfo(tok[21], change_cigar_type(tok[19]), 0, 0, down_n, 0)
+        jmap.insert(jkey(up_chr, up_pos, up_strand, down_chr, down_pos, down_strand), Other(up, down, micro, pairs))
+
+
 def getsv(h: Header, recs: List[Rec], clip_text: str, clip_h: Header, clip_alns: List[Rec], *, flank=50,
           min_mapq=20, pairs_used=5000000, min_clip_sum=3, min_dist=50, max_micro=50, times=4, min_pairs=0,
-          flank_len=200, min_seq_len=30, max_indel=1, freq=0.1, output_depth=True) -> Tuple[str, str]:
-    """CallGetsv, seeksv.cpp:157-364 (without -F / -B). Returns (out.sv.txt contents, stdout)."""
+          flank_len=200, min_seq_len=30, max_indel=1, freq=0.1, output_depth=True, seed_text=None) -> Tuple[str, str]:
+    """CallGetsv, seeksv.cpp:157-364 (without -F). seed_text: contents of the -B file. Returns (out.sv.txt contents, stdout)."""
     jmap = JunctionMap()
+    if seed_text is not None:
+        read_breakpoint(seed_text, jmap)
     join_clip_alignments(parse_clip_text(clip_text), clip_h, clip_alns, jmap)
     merge_junction(jmap, flank)
     if pairs_used >= 100000:

@@ -478,8 +478,8 @@ int cmd_getsv(int argc, char **argv)
         usage_cmd(argv[0], argc > 1 ? argv[1] : "", 1);
         return 1;
     }
-    if (!connect_bam.empty() || !seed_file.empty())
-        return fail("[seeksv_b200] -F / -B (optional junction seeds, process_bwasw.cpp / getsv.cpp:1292) are outside the hot path and not implemented");
+    if (!connect_bam.empty())
+        return fail("[seeksv_b200] -F (junctions from a bwasw split-read BAM, process_bwasw.cpp) is outside the hot path and not implemented");
     std::string clip_aln = argv[optind], original_bam = argv[optind + 1], clipfile = argv[optind + 2], sv_file = argv[optind + 3],
                 unmapped_file = argv[optind + 4];
     std::string err, clip_text;
@@ -514,6 +514,16 @@ int cmd_getsv(int argc, char **argv)
     if (!read_text_maybe_gz(clipfile, clip_text, err)) return fail(err);
     ph.mark("getsv: read clip.gz");
     JunctionMap jm;
+    if (!seed_file.empty()) {  // ReadBreakpoint, seeksv.cpp:215-219
+        std::string seed_text;
+        std::ifstream sf(seed_file.c_str());
+        if (!sf) std::cerr << "Cannot open file " << seed_file << std::endl;  // (the reference goes on without the seeds)
+        else {
+            seed_text.assign(std::istreambuf_iterator<char>(sf), std::istreambuf_iterator<char>());
+            read_breakpoints(seed_text, jm);
+        }
+        std::cerr << "[ReadBreakpoint] finish" << std::endl;
+    }
     join_clips_with_alignments(parse_clip_text(clip_text, n_threads()), alns, jm);
     std::cerr << "'InputSoftInfoStoreBreakpoint' finished" << std::endl;
     merge_junctions(jm, flank);

@@ -490,6 +490,36 @@ void join_clips_with_alignments(const std::vector<ClipLine> &lines, const Alignm
 }
 
 // MergeJunction, getsv.cpp:1325-1482
+// ReadBreakpoint (getsv.cpp:1291-1323) reads with `fin >> token`: by whitespace-separated tokens, not by lines. A line that
+// starts with '@' is dropped; after the 23rd token the rest of the line is dropped; a token that does not convert puts the
+// stream into its fail state and ends the loop. The same stream operators on the same types reproduce all of that.
+void read_breakpoints(const std::string &sv_text, JunctionMap &jm)
+{
+    std::istringstream fin(sv_text);
+    std::string up_chr, down_chr, sv_type, up_cigar, down_cigar, up_seq, down_seq, rest;
+    int up_pos = 0, up_reads = 0, down_pos = 0, down_reads = 0, micro = 0, pairs = 0, d1, d2, d3, d4, d5, d6;
+    char up_strand = '+', down_strand = '+';
+    double r1, r2;
+    while (fin >> up_chr) {
+        if (up_chr[0] == '@') {
+            std::getline(fin, rest);
+            continue;
+        }
+        fin >> up_pos >> up_strand >> up_reads >> down_chr >> down_pos >> down_strand >> down_reads >> micro >> pairs >> sv_type >> d1 >>
+            d2 >> d3 >> d4 >> d5 >> d6 >> r1 >> r2 >> up_cigar >> down_cigar >> up_seq >> down_seq;
+        std::getline(fin, rest);
+        // (after a failed conversion the reference still inserts what the variables hold, then its loop ends: same here)
+        JunctionKey key;
+        key.up_chr = up_chr, key.down_chr = down_chr, key.up_pos = up_pos, key.down_pos = down_pos;
+        key.up_strand = up_strand, key.down_strand = down_strand;
+        JunctionInfo info;
+        info.up.seq = up_seq, info.up.cigar = cigar_from_text(up_cigar), info.up.support = up_reads;
+        info.down.seq = down_seq, info.down.cigar = cigar_from_text(down_cigar), info.down.support = down_reads;
+        info.micro = micro, info.pairs = pairs;
+        jm.insert(std::make_pair(key, info));
+    }
+}
+
 void merge_junctions(JunctionMap &jm, int reach)
 {
     auto it = jm.begin();

@@ -78,6 +78,8 @@ double match_rate_from_end(const std::string &a, const std::string &b);
 double match_rate_from_begin(const std::string &a, const std::string &b);
 std::string format_double(double x);
 
+// getsv -B: the junctions of an earlier output file enter the map before the join (ReadBreakpoint, getsv.cpp:1291-1323)
+void read_breakpoints(const std::string &sv_text, JunctionMap &jm);
 void join_clips_with_alignments(const std::vector<ClipLine> &lines, const AlignmentSet &alns, JunctionMap &jm);
 void merge_junctions(JunctionMap &jm, int search_length);
 

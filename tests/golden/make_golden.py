@@ -101,6 +101,7 @@ def build_kat(kat):
 
 
 FUZZ_SEEDS, FUZZ_RECORDS = (11, 12), 1800
+SEEDED = ("tumor", "f11", "cancer")   # samples that also get `getsv -B <their own output>` goldens
 
 
 def run(cmd, **kw):
@@ -139,6 +140,12 @@ def pipeline(work, outdir, bwa, fasta, samples, somatic_pair=None, getsv_args=()
         with open(os.path.join(outdir, s + ".n0D.stdout"), "w") as o:
             run([SEEKSV, "getsv", "-n", "0", "-D", os.path.join(outdir, s + ".clip.sam"), bam, pre + ".clip.gz",
                  os.path.join(outdir, s + ".n0D.sv"), pre + ".clipunmap"], stdout=o, stderr=subprocess.DEVNULL)
+        # -B: the junctions of an earlier output seed the map (ReadBreakpoint, getsv.cpp:1291-1323); with and without the BAM passes
+        if s in SEEDED:
+            for tag, extra in ((".B", ()), (".B.n0D", ("-n", "0", "-D"))):
+                with open(os.path.join(outdir, s + tag + ".stdout"), "w") as o:
+                    run([SEEKSV, "getsv", "-B", os.path.join(outdir, s + ".sv"), *extra, os.path.join(outdir, s + ".clip.sam"), bam,
+                         pre + ".clip.gz", os.path.join(outdir, s + tag + ".sv"), pre + ".clipunmap"], stdout=o, stderr=subprocess.DEVNULL)
     if somatic_pair:
         normal, tumour = somatic_pair
         run([SEEKSV, "somatic", os.path.join(outdir, normal + ".sort.bam"), os.path.join(work, normal + ".clip.gz"),

@@ -143,3 +143,18 @@ def test_bai_first_offsets_point_at_the_first_record_of_each_reference(lib, d, s
             want[tid] = co << 16 | (p - uo)
         p += 4 + bs
     assert L.bai_first_offsets(path + ".bai") == want
+
+
+@pytest.mark.parametrize("d,s", [("micro", "tumor"), ("fuzz", "f11"), ("example", "cancer")])
+def test_getsv_seed_file_host_only_matches_reference(lib, d, s, tmp_path):
+    """`getsv -B <earlier output> -n 0 -D`: ReadBreakpoint of the host layer against the reference binary's output (no GPU)"""
+    import gzip
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, s + ".clip.txt")).encode("latin-1"))
+    out = str(tmp_path / "out.sv")
+    r = _cli(["getsv", "-B", os.path.join(GOLDEN, d, s + ".sv"), "-n", "0", "-D", os.path.join(GOLDEN, d, s + ".clip.sam"),
+              os.path.join(GOLDEN, d, s + ".sort.bam"), clip, out, str(tmp_path / "unm")])
+    assert r.returncode == 0, r.stderr
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".B.n0D.sv"))
+    assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".B.n0D.stdout"))

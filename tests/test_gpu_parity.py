@@ -484,3 +484,17 @@ def test_cli_host_gzip_modes_give_the_same_files(tmp_path):
         r = subprocess.run([_cli(), "getclip", "-o", pre, _bam(d, s)], capture_output=True, text=True, env=dict(os.environ, **env))
         assert r.returncode == 0, r.stderr
         assert _zcat(pre + ".clip.gz") == want
+
+
+@pytest.mark.parametrize("d,s", [("micro", "tumor"), ("fuzz", "f11"), ("example", "cancer")])
+def test_getsv_seed_file_cli_bit_exact(d, s, tmp_path):
+    """getsv -B with the BAM passes on (insert size, discordant pairs, depth of the seeded junctions too)"""
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, s + ".clip.txt")).encode("latin-1"))
+    out = str(tmp_path / "out.sv")
+    r = subprocess.run([_cli(), "getsv", "-B", os.path.join(GOLDEN, d, s + ".sv"), os.path.join(GOLDEN, d, s + ".clip.sam"), _bam(d, s), clip, out,
+                        str(tmp_path / "unm")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".B.sv"))
+    assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".B.stdout"))

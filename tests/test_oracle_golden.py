@@ -131,3 +131,18 @@ def test_pileup_depth_and_cap_against_libbam(tmp_path):
         for tid in (0, 1):
             for p in range(1, 5001):
                 assert int(got[tid][p]) == want.get((tid, p), 0), (mq, tid, p)
+
+
+@pytest.mark.parametrize("d,s", [("micro", "tumor"), ("fuzz", "f11"), ("example", "cancer")])
+def test_getsv_with_seed_file_matches_reference(d, s):
+    """getsv -B <an earlier output>: ReadBreakpoint (getsv.cpp:1291-1323) seeds the junction map before the join"""
+    h, recs = bamio.read_bam(_bam(d, s))
+    ch, ca = bamio.read_alignments(os.path.join(GOLDEN, d, s + ".clip.sam"))
+    clip = read_text(os.path.join(GOLDEN, d, s + ".clip.txt"))
+    seed = read_text(os.path.join(GOLDEN, d, s + ".sv"))
+    sv, out = getsv_oracle.getsv(h, recs, clip, ch, ca, seed_text=seed)
+    assert sv == read_text(os.path.join(GOLDEN, d, s + ".B.sv"))
+    assert out == read_text(os.path.join(GOLDEN, d, s + ".B.stdout"))
+    sv, out = getsv_oracle.getsv(h, recs, clip, ch, ca, seed_text=seed, pairs_used=0, output_depth=False)
+    assert sv == read_text(os.path.join(GOLDEN, d, s + ".B.n0D.sv"))
+    assert out == read_text(os.path.join(GOLDEN, d, s + ".B.n0D.stdout"))
