@@ -498,3 +498,15 @@ def test_getsv_seed_file_cli_bit_exact(d, s, tmp_path):
     assert r.returncode == 0, r.stderr
     assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".B.sv"))
     assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".B.stdout"))
+
+
+@pytest.mark.parametrize("by", ["range", "chromosome"])
+def test_mgpu_entry_point_single_rank(by, tmp_path):
+    """seeksv_b200.mgpu (the torchrun entry point for one BAM on several GPUs) as a single rank: same four files"""
+    from seeksv_b200 import mgpu
+    d, s = "fuzz", "f12"
+    pre = str(tmp_path / by)
+    assert mgpu.main(["getclip", "--by", by, "-o", pre, _bam(d, s)]) == 0
+    for ext, name in ((".clip.gz", ".clip.txt"), (".clip.fq.gz", ".clip.fq.txt"), (".unmapped_1.fq.gz", ".unmapped_1.fq.txt"),
+                      (".unmapped_2.fq.gz", ".unmapped_2.fq.txt")):
+        assert _zcat(pre + ext) == read_text(os.path.join(GOLDEN, d, s + name)), ext
