@@ -748,13 +748,122 @@ def read_breakpoint(text: str, jmap: "JunctionMap"):
         jmap.insert(jkey(up_chr, up_pos, up_strand, down_chr, down_pos, down_strand), Other(up, down, micro, pairs))
 
 
+def minus_cigar_right(vec: List[Tuple[int, str]], length: int) -> List[Tuple[int, str]]:
+    """MinusCigarRight, clip_reads.cpp:507-546: cut `length` read bases (M / I) off the right end of the op list."""
+    total = sum(ln for ln, op in vec if op in "MI")
+    if total <= length:
+        return list(vec)
+    left = total - length
+    out = []
+    for ln, op in vec:
+        if op in "MI":
+            if ln >= left:
+                out.append((left, op))
+                return out
+            left -= ln
+        out.append((ln, op))
+    return out
+
+
+def add_cigar_left(vec: List[Tuple[int, str]], length: int) -> List[Tuple[int, str]]:
+    """AddCigarLeft, clip_reads.cpp:548-558."""
+    vec = list(vec)
+    if vec[0][1] == "M":
+        vec[0] = (vec[0][0] + length, "M")
+    else:
+        vec.insert(0, (length, "M"))
+    return vec
+
+
+def find_junction(h: Header, recs: List[Rec], min_mapq: int, jmap: "JunctionMap"):
+    """FindJunction, process_bwasw.cpp:5-227 (getsv -F): junctions from "connected read-through reads" - a read that the
+    aligner reports as two records with the same name, each soft-clipped on one side. The first record of a name is kept
+    (std::map), the second one that fits it (same strand + opposite sides, or opposite strands + same side) makes a junction
+    and removes the name; records that do not fit change nothing."""
+    from .getclip_oracle import generate_cigar, get_seq
+    from .bamio import FDUP, FREVERSE, FUNMAP
+    pending = {}
+    for r in recs:
+        if r.mapq < min_mapq or (r.flag & FUNMAP) or not r.cigar:      # __g_skip_aln (sam/sam_view.h:26-39) with g_min_mapQ = -w
+            continue
+        op1, op2 = "MIDNSHP=X"[r.cigar[0][1]], "MIDNSHP=X"[r.cigar[-1][1]]
+        if op1 == "H" or op2 == "H" or (op1 == "S" and op2 == "S") or (op1 == "M" and op2 == "M") or (r.flag & FDUP):
+            continue
+        vec, maplen = generate_cigar(r)
+        if op1 == "S":
+            side, left_len = "5", r.cigar[0][0]
+            right_len, pos = r.l_qseq - left_len, r.pos + 1
+        else:   # (the reference takes every other shape as clipped on the right)
+            side, right_len = "3", r.cigar[-1][0]
+            left_len, pos = r.l_qseq - right_len, r.pos + maplen
+        strand = "-" if r.flag & FREVERSE else "+"
+        left, _, right, _ = get_seq(r, 0, left_len, right_len)
+        cur = dict(chr=h.names[r.tid], pos=pos, left=left, right=right, cigar=vec, side=side, strand=strand)
+        prev = pending.get(r.qname)
+        if prev is None:
+            pending[r.qname] = cur
+            continue
+        same_strand_other_side = prev["strand"] == strand and prev["side"] != side
+        other_strand_same_side = prev["strand"] != strand and prev["side"] == side
+        if not (same_strand_other_side or other_strand_same_side):
+            continue
+        if same_strand_other_side:
+            up, down = (cur, prev) if prev["side"] == "5" else (prev, cur)
+            if len(up["left"]) >= len(down["left"]):
+                micro = len(up["left"]) - len(down["left"])
+                key = jkey(up["chr"], up["pos"] - micro, "+", down["chr"], down["pos"], "+")
+                up_i = SeqInfo(down["left"], minus_cigar_right(up["cigar"], micro), 0, 0, 0, 2)
+                down_i = SeqInfo(down["right"], down["cigar"], 0, 0, 1, 2)
+            else:
+                micro = 0
+                key = jkey(up["chr"], up["pos"], "+", down["chr"], down["pos"], "+")
+                up_i = SeqInfo(down["left"], up["cigar"], 0, len(down["left"]) - len(up["left"]), 0, 2)
+                down_i = SeqInfo(down["right"], down["cigar"], 0, 0, 1, 2)
+        else:
+            up, down = (prev, cur) if (prev["chr"], prev["pos"]) < (cur["chr"], cur["pos"]) else (cur, prev)
+            if side == "5":
+                if len(up["right"]) >= len(down["left"]):
+                    micro = len(up["right"]) - len(down["left"])
+                    key = jkey(up["chr"], up["pos"], "-", down["chr"], down["pos"] + micro, "+")
+                    up_i = SeqInfo(revcomp(up["right"]), up["cigar"], 0, 0, 0, 2)
+                    down_i = SeqInfo(revcomp(up["left"]), add_cigar_left(down["cigar"], micro), 0, 0, 1, 2)
+                else:
+                    micro = 0
+                    key = jkey(up["chr"], up["pos"], "-", down["chr"], down["pos"], "+")
+                    up_i = SeqInfo(down["left"], up["cigar"], 0, len(down["left"]) - len(up["right"]), 0, 2)
+                    down_i = SeqInfo(down["right"], down["cigar"], 0, 0, 1, 2)
+            else:
+                if len(up["left"]) >= len(down["right"]):
+                    micro = len(up["left"]) - len(down["right"])
+                    key = jkey(up["chr"], up["pos"] - micro, "+", down["chr"], down["pos"], "-")
+                    up_i = SeqInfo(revcomp(down["right"]), minus_cigar_right(up["cigar"], micro), 0, 0, 0, 2)
+                    down_i = SeqInfo(revcomp(down["left"]), down["cigar"], 0, 0, 1, 2)
+                else:
+                    micro = 0
+                    key = jkey(up["chr"], up["pos"], "+", down["chr"], down["pos"], "-")
+                    up_i = SeqInfo(up["left"], up["cigar"], 0, 0, 0, 2)
+                    down_i = SeqInfo(up["right"], down["cigar"], len(down["right"]) - len(up["left"]), 0, 1, 2)
+        lo, hi = jmap.equal_range(key)
+        if lo == hi:
+            jmap.insert(key, Other(up_i, down_i, micro, 0))
+        else:
+            o = jmap.vals[lo]
+            if len(o.up.seq) != len(up_i.seq) or len(o.down.seq) != len(down_i.seq):
+                o.down.support += 1
+        del pending[r.qname]
+
+
 def getsv(h: Header, recs: List[Rec], clip_text: str, clip_h: Header, clip_alns: List[Rec], *, flank=50,
           min_mapq=20, pairs_used=5000000, min_clip_sum=3, min_dist=50, max_micro=50, times=4, min_pairs=0,
-          flank_len=200, min_seq_len=30, max_indel=1, freq=0.1, output_depth=True, seed_text=None) -> Tuple[str, str]:
-    """CallGetsv, seeksv.cpp:157-364 (without -F). seed_text: contents of the -B file. Returns (out.sv.txt contents, stdout)."""
+          flank_len=200, min_seq_len=30, max_indel=1, freq=0.1, output_depth=True, seed_text=None, connect=None,
+          connect_min_mapq=1) -> Tuple[str, str]:
+    """CallGetsv, seeksv.cpp:157-364. seed_text: contents of the -B file; connect: (header, records) of the -F file
+    (connect_min_mapq = -w). Returns (out.sv.txt contents, stdout)."""
     jmap = JunctionMap()
     if seed_text is not None:
         read_breakpoint(seed_text, jmap)
+    if connect is not None:
+        find_junction(connect[0], connect[1], connect_min_mapq, jmap)
     join_clip_alignments(parse_clip_text(clip_text), clip_h, clip_alns, jmap)
     merge_junction(jmap, flank)
     if pairs_used >= 100000:

@@ -452,12 +452,13 @@ int cmd_getsv(int argc, char **argv)
     std::string connect_bam, seed_file;
     double frequency = 0.1;
     int c, flank = 50, min_mapq = 20, pairs_used = 5000000, min_clip_sum = 3, min_distance = 50, max_micro = 50, times = 4, min_pairs = 0,
-           flank_len = 200, min_seq_len = 30, max_indel = 1;
+           flank_len = 200, min_seq_len = 30, max_indel = 1, connect_min_mapq = 1;
     bool with_depth = true;
     optind = 1;
     while ((c = getopt(argc, argv, "F:B:t:l:q:Q:w:n:a:b:d:e:m:i:R:f:T:L:rD")) >= 0) {
         switch (c) {
         case 'F': connect_bam = optarg; break;
+        case 'w': connect_min_mapq = atoi(optarg); break;
         case 'B': seed_file = optarg; break;
         case 'l': flank = atoi(optarg); break;
         case 'q': min_mapq = atoi(optarg); break;
@@ -471,15 +472,14 @@ int cmd_getsv(int argc, char **argv)
         case 'f': frequency = atof(optarg); break;
         case 'T': max_micro = atoi(optarg); break;
         case 'L': flank_len = atoi(optarg); break;
-        default: break;  // -t -Q -w -a -R -r are parsed and unused, as in the reference
+        default: break;  // -t -Q -a -R -r are parsed and unused, as in the reference
         }
     }
     if (argc != optind + 5 || flank > 90 || flank < 0 || min_seq_len < 0) {
         usage_cmd(argv[0], argc > 1 ? argv[1] : "", 1);
         return 1;
     }
-    if (!connect_bam.empty())
-        return fail("[seeksv_b200] -F (junctions from a bwasw split-read BAM, process_bwasw.cpp) is outside the hot path and not implemented");
+
     std::string clip_aln = argv[optind], original_bam = argv[optind + 1], clipfile = argv[optind + 2], sv_file = argv[optind + 3],
                 unmapped_file = argv[optind + 4];
     std::string err, clip_text;
@@ -523,6 +523,22 @@ int cmd_getsv(int argc, char **argv)
             read_breakpoints(seed_text, jm);
         }
         std::cerr << "[ReadBreakpoint] finish" << std::endl;
+    }
+    if (!connect_bam.empty()) {  // FindJunction, seeksv.cpp:221-225
+        std::vector<uint8_t> file, stream;
+        BamHeader ch;
+        std::string cerr_text;
+        bool ok = read_file(connect_bam, file, cerr_text);
+        if (ok && connect_bam.size() >= 4 && connect_bam.rfind(".bam") == connect_bam.size() - 4)
+            ok = bgzf_inflate_all(file.data(), file.size(), stream, n_threads(), cerr_text) && parse_bam_header(stream.data(), stream.size(), ch, cerr_text);
+        else if (ok)
+            ok = sam_to_bam_stream(file, ch, stream, cerr_text);
+        if (!ok) {
+            std::cerr << "[main_samview] fail to open file for reading." << std::endl;
+            return fail(cerr_text);
+        }
+        find_junctions(stream.data(), stream.size(), ch.first_record, ch.names, connect_min_mapq, jm);
+        std::cerr << "'FindJunction' finished" << std::endl;
     }
     join_clips_with_alignments(parse_clip_text(clip_text, n_threads()), alns, jm);
     std::cerr << "'InputSoftInfoStoreBreakpoint' finished" << std::endl;

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <map>
 #include <sstream>
 #include <thread>
 
@@ -490,6 +491,168 @@ void join_clips_with_alignments(const std::vector<ClipLine> &lines, const Alignm
 }
 
 // MergeJunction, getsv.cpp:1325-1482
+// ---- getsv -F (FindJunction, process_bwasw.cpp:5-227) -----------------------------------------------------------------------
+namespace {
+struct HalfRead {  // Alignment, process_bwasw.h:27-80 (the quality strings are never used)
+    std::string chr, left, right;
+    int pos = 0;
+    CigarVec cigar;
+    char side = '5', strand = '+';
+};
+
+void minus_cigar_right(CigarVec &v, int length)  // MinusCigarRight, clip_reads.cpp:507-546
+{
+    int total = 0;
+    for (auto &e : v)
+        if (e.second == 'M' || e.second == 'I') total += e.first;
+    if (total <= length) return;
+    int left = total - length;
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (v[i].second != 'M' && v[i].second != 'I') continue;
+        if (v[i].first >= left) {
+            v[i].first = left;
+            v.resize(i + 1);
+            return;
+        }
+        left -= v[i].first;
+    }
+}
+
+void add_cigar_left(CigarVec &v, int length)  // AddCigarLeft, clip_reads.cpp:548-558
+{
+    if (!v.empty() && v[0].second == 'M') v[0].first += length;
+    else v.insert(v.begin(), std::make_pair(length, 'M'));
+}
+
+SeqInfo seq_info(const std::string &seq, const CigarVec &cigar, int lclip, int rclip, int support, int uniq)
+{
+    SeqInfo s;
+    s.seq = seq, s.cigar = cigar, s.lclip = lclip, s.rclip = rclip, s.support = support, s.uniq = uniq;
+    return s;
+}
+
+JunctionKey junction_key(const std::string &uc, int up, char us, const std::string &dc, int dp, char ds)
+{
+    JunctionKey k;
+    k.up_chr = uc, k.up_pos = up, k.up_strand = us, k.down_chr = dc, k.down_pos = dp, k.down_strand = ds;
+    return k;
+}
+}  // namespace
+
+void find_junctions(const uint8_t *stream, uint64_t n, uint64_t first, const std::vector<std::string> &ref_names, int min_mapq,
+                    JunctionMap &jm)
+{
+    static const char kBases[] = "=ACMGRSVTWYHKDBN", kOps[] = "MIDNSHP=X";
+    std::map<std::string, HalfRead> pending;  // the first record of a read name waits for one that fits it
+    auto i32 = [&](uint64_t o) {
+        int32_t v;
+        memcpy(&v, stream + o, 4);
+        return v;
+    };
+    for (uint64_t o = first; o + 36 <= n;) {
+        const int32_t block = i32(o);
+        if (block < 32 || o + 4 + (uint64_t)block > n) break;
+        const uint64_t rec = o + 4;
+        o = rec + (uint64_t)block;
+        const int32_t tid = i32(rec), pos0 = i32(rec + 4), l_qseq = i32(rec + 16);
+        const uint32_t bmq = (uint32_t)i32(rec + 8), fnc = (uint32_t)i32(rec + 12);
+        const uint32_t l_qname = bmq & 0xff, mapq = (bmq >> 8) & 0xff, n_cigar = fnc & 0xffff, flag = fnc >> 16;
+        if ((int)mapq < min_mapq || (flag & 4) || n_cigar == 0) continue;  // __g_skip_aln with g_min_mapQ = -w, then FUNMAP
+        const uint64_t cig = rec + 32 + l_qname, seq = cig + 4ull * n_cigar;
+        if (seq + ((uint64_t)l_qseq + 1) / 2 > o || tid < 0 || (size_t)tid >= ref_names.size()) continue;
+        const uint32_t c1 = (uint32_t)i32(cig), c2 = (uint32_t)i32(cig + 4ull * (n_cigar - 1));
+        const char op1 = kOps[std::min<uint32_t>(c1 & 15, 8)], op2 = kOps[std::min<uint32_t>(c2 & 15, 8)];
+        if (op1 == 'H' || op2 == 'H' || (op1 == 'S' && op2 == 'S') || (op1 == 'M' && op2 == 'M') || (flag & 1024)) continue;
+        HalfRead cur;
+        int maplen = 0;  // GenerateCigar, clip_reads.cpp:309-329
+        for (uint32_t k = 0; k < n_cigar; ++k) {
+            const uint32_t c = (uint32_t)i32(cig + 4ull * k), op = c & 15, len = c >> 4;
+            if (op == 4 || op == 5) continue;
+            if (op == 0 || op == 2 || op == 7 || op == 3) maplen += (int)len;
+            cur.cigar.push_back(std::make_pair((int)len, kOps[std::min<uint32_t>(op, 8)]));
+        }
+        int left_len, right_len;
+        if (op1 == 'S') {
+            cur.side = '5', left_len = (int)(c1 >> 4), right_len = l_qseq - left_len, cur.pos = pos0 + 1;
+        } else {  // (every other shape counts as clipped on the right)
+            cur.side = '3', right_len = (int)(c2 >> 4), left_len = l_qseq - right_len, cur.pos = pos0 + maplen;
+        }
+        cur.strand = (flag & 16) ? '-' : '+';
+        cur.chr = ref_names[tid];
+        auto base = [&](int i) { return (char)toupper(kBases[(stream[seq + (i >> 1)] >> ((~i & 1) << 2)) & 15]); };
+        for (int i = 0; i < left_len && i < l_qseq; ++i) cur.left.push_back(base(i));                      // GetSeq, clip_reads.cpp:286-306
+        for (int i = std::max(left_len, 0); i < left_len + right_len && i < l_qseq; ++i) cur.right.push_back(base(i));
+        const std::string name((const char *)stream + rec + 32);
+        auto it = pending.find(name);
+        if (it == pending.end()) {
+            pending.insert(std::make_pair(name, cur));
+            continue;
+        }
+        const HalfRead &prev = it->second;
+        const bool same_strand_other_side = prev.strand == cur.strand && prev.side != cur.side;
+        const bool other_strand_same_side = prev.strand != cur.strand && prev.side == cur.side;
+        if (!same_strand_other_side && !other_strand_same_side) continue;  // does not fit: nothing changes
+        JunctionKey key;
+        SeqInfo up_i, down_i;
+        int micro;
+        if (same_strand_other_side) {
+            const HalfRead &up = prev.side == '5' ? cur : prev, &down = prev.side == '5' ? prev : cur;
+            if (up.left.size() >= down.left.size()) {
+                micro = (int)(up.left.size() - down.left.size());
+                key = junction_key(up.chr, up.pos - micro, '+', down.chr, down.pos, '+');
+                CigarVec c = up.cigar;
+                minus_cigar_right(c, micro);
+                up_i = seq_info(down.left, c, 0, 0, 0, 2), down_i = seq_info(down.right, down.cigar, 0, 0, 1, 2);
+            } else {
+                micro = 0;
+                key = junction_key(up.chr, up.pos, '+', down.chr, down.pos, '+');
+                up_i = seq_info(down.left, up.cigar, 0, (int)down.left.size() - (int)up.left.size(), 0, 2);
+                down_i = seq_info(down.right, down.cigar, 0, 0, 1, 2);
+            }
+        } else {
+            const bool prev_first = std::make_pair(prev.chr, prev.pos) < std::make_pair(cur.chr, cur.pos);
+            const HalfRead &up = prev_first ? prev : cur, &down = prev_first ? cur : prev;
+            if (cur.side == '5') {
+                if (up.right.size() >= down.left.size()) {
+                    micro = (int)(up.right.size() - down.left.size());
+                    key = junction_key(up.chr, up.pos, '-', down.chr, down.pos + micro, '+');
+                    CigarVec c = down.cigar;
+                    add_cigar_left(c, micro);
+                    up_i = seq_info(reverse_complement(up.right), up.cigar, 0, 0, 0, 2);
+                    down_i = seq_info(reverse_complement(up.left), c, 0, 0, 1, 2);
+                } else {
+                    micro = 0;
+                    key = junction_key(up.chr, up.pos, '-', down.chr, down.pos, '+');
+                    up_i = seq_info(down.left, up.cigar, 0, (int)down.left.size() - (int)up.right.size(), 0, 2);
+                    down_i = seq_info(down.right, down.cigar, 0, 0, 1, 2);
+                }
+            } else {
+                if (up.left.size() >= down.right.size()) {
+                    micro = (int)(up.left.size() - down.right.size());
+                    key = junction_key(up.chr, up.pos - micro, '+', down.chr, down.pos, '-');
+                    CigarVec c = up.cigar;
+                    minus_cigar_right(c, micro);
+                    up_i = seq_info(reverse_complement(down.right), c, 0, 0, 0, 2);
+                    down_i = seq_info(reverse_complement(down.left), down.cigar, 0, 0, 1, 2);
+                } else {
+                    micro = 0;
+                    key = junction_key(up.chr, up.pos, '+', down.chr, down.pos, '-');
+                    up_i = seq_info(up.left, up.cigar, 0, 0, 0, 2);
+                    down_i = seq_info(up.right, down.cigar, (int)down.right.size() - (int)up.left.size(), 0, 1, 2);
+                }
+            }
+        }
+        auto jit = jm.find(key);
+        if (jit == jm.end()) {
+            JunctionInfo info;
+            info.up = up_i, info.down = down_i, info.micro = micro, info.pairs = 0;
+            jm.insert(std::make_pair(key, info));
+        } else if (jit->second.up.seq.size() != up_i.seq.size() || jit->second.down.seq.size() != down_i.seq.size())
+            jit->second.down.support++;
+        pending.erase(it);
+    }
+}
+
 // ReadBreakpoint (getsv.cpp:1291-1323) reads with `fin >> token`: by whitespace-separated tokens, not by lines. A line that
 // starts with '@' is dropped; after the 23rd token the rest of the line is dropped; a token that does not convert puts the
 // stream into its fail state and ends the loop. The same stream operators on the same types reproduce all of that.

@@ -80,6 +80,10 @@ std::string format_double(double x);
 
 // getsv -B: the junctions of an earlier output file enter the map before the join (ReadBreakpoint, getsv.cpp:1291-1323)
 void read_breakpoints(const std::string &sv_text, JunctionMap &jm);
+// getsv -F: junctions from "connected read-through reads" (FindJunction, process_bwasw.cpp:5-227). `stream` holds packed BAM
+// records from `first` on (a BAM's uncompressed stream, or SAM text converted by sam_to_bam_stream).
+void find_junctions(const uint8_t *stream, uint64_t n, uint64_t first, const std::vector<std::string> &ref_names, int min_mapq,
+                    JunctionMap &jm);
 void join_clips_with_alignments(const std::vector<ClipLine> &lines, const AlignmentSet &alns, JunctionMap &jm);
 void merge_junctions(JunctionMap &jm, int search_length);
 

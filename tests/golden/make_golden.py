@@ -101,7 +101,60 @@ def build_kat(kat):
 
 
 FUZZ_SEEDS, FUZZ_RECORDS = (11, 12), 1800
+CONNECTED = ("tumor", "f11")          # samples that also get `getsv -F <connected reads>` goldens
 SEEDED = ("tumor", "f11", "cancer")   # samples that also get `getsv -B <their own output>` goldens
+
+
+def build_connect_sam(bam_path, out_path, seed=5, n_reads=160):
+    """getsv -F input: "connected read-through reads" - each read is reported as two records with the same name, each soft-clipped
+    on one side (process_bwasw.cpp:5-227). Seeded; covers both orientations, both length orders (micro-homology or not),
+    repeats of one junction with other lengths, and the records FindJunction skips or leaves pending."""
+    import random
+    rng = random.Random(seed)
+    h, _ = bamio.read_bam(bam_path)
+    lines = ["@HD\tVN:1.0\tSO:unsorted"] + ["@SQ\tSN:%s\tLN:%d" % (n, l) for n, l in zip(h.names, h.lengths)]
+
+    def seq(n):
+        return "".join(rng.choice("ACGT") for _ in range(n))
+
+    def rec(name, flag, tid, pos1, mapq, cigar, s):
+        return "\t".join([name, str(flag), h.names[tid], str(pos1), str(mapq), cigar, "*", "0", "0", s, "I" * len(s)])
+    loci = []
+    for i in range(n_reads):
+        name = "cr%d" % i
+        kind = rng.choice(["same", "same", "opp5", "opp3", "bad", "single", "repeat"])
+        if kind == "repeat" and loci:
+            ta, pa, tb, pb = rng.choice(loci)
+            kind = "same"
+        else:
+            ta, tb = rng.randrange(len(h.names)), rng.randrange(len(h.names))
+            pa, pb = rng.randrange(200, h.lengths[ta] - 400), rng.randrange(200, h.lengths[tb] - 400)
+            loci.append((ta, pa, tb, pb))
+        a_len, b_len = rng.randrange(30, 90), rng.randrange(30, 90)
+        total = a_len + b_len - rng.choice([0, 0, 0, 3, 7])           # overlap of the two aligned parts = micro-homology
+        s = seq(total)
+        mid = "%dM" % a_len if rng.random() < 0.7 else "%dM2I%dM" % (a_len // 2, a_len - a_len // 2 - 2)
+        three = rec(name, 0, ta, pa - a_len + 1, rng.choice([0, 1, 30, 60, 60]), mid + "%dS" % (total - a_len), s)       # aligned left part, 3' clipped
+        five = rec(name, 0, tb, pb, rng.choice([1, 30, 60, 60]), "%dS%dM" % (total - b_len, b_len), s)                    # aligned right part, 5' clipped
+        if kind == "same":
+            pair = [three, five] if rng.random() < 0.5 else [five, three]
+        elif kind == "opp5":   # both 5' clipped, opposite strands
+            pair = [rec(name, 0, ta, pa, 60, "%dS%dM" % (total - a_len, a_len), s), rec(name, 16, tb, pb, 60, "%dS%dM" % (total - b_len, b_len), s)]
+        elif kind == "opp3":   # both 3' clipped, opposite strands
+            pair = [rec(name, 16, ta, pa, 60, "%dM%dS" % (a_len, total - a_len), s), rec(name, 0, tb, pb, 60, "%dM%dS" % (b_len, total - b_len), s)]
+        elif kind == "bad":    # same strand, same side: the second record is ignored and the first stays pending; a third one may fit
+            pair = [three, rec(name, 0, tb, pb, 60, "%dM%dS" % (b_len, total - b_len), s), five]
+        else:
+            pair = [rng.choice([three, five])]
+        lines.extend(pair)
+        if rng.random() < 0.1:   # records FindJunction skips: duplicate, hard clip, clipped on both sides, not clipped, unmapped
+            lines.append(rec("skip%d" % i, 1024, ta, pa, 60, "%dM%dS" % (a_len, total - a_len), s))
+            lines.append(rec("skip%d" % i, 0, ta, pa, 60, "5H%dM%dS" % (a_len, total - a_len - 5), s[5:]))
+            lines.append(rec("skip%d" % i, 0, ta, pa, 60, "5S%dM%dS" % (a_len - 5, total - a_len), s))
+            lines.append(rec("skip%d" % i, 0, ta, pa, 60, "%dM" % total, s))
+            lines.append(rec("skip%d" % i, 4, ta, pa, 60, "%dM%dS" % (a_len, total - a_len), s))
+    with open(out_path, "w") as f:
+        f.write("\n".join(lines) + "\n")
 
 
 def run(cmd, **kw):
@@ -140,6 +193,15 @@ def pipeline(work, outdir, bwa, fasta, samples, somatic_pair=None, getsv_args=()
         with open(os.path.join(outdir, s + ".n0D.stdout"), "w") as o:
             run([SEEKSV, "getsv", "-n", "0", "-D", os.path.join(outdir, s + ".clip.sam"), bam, pre + ".clip.gz",
                  os.path.join(outdir, s + ".n0D.sv"), pre + ".clipunmap"], stdout=o, stderr=subprocess.DEVNULL)
+        # -F: junctions from connected read-through reads (FindJunction, process_bwasw.cpp:5-227), alone and together with -B
+        if s in CONNECTED:
+            connect = os.path.join(outdir, s + ".connect.sam")
+            build_connect_sam(bam, connect)
+            for tag, extra in ((".F", ("-F", connect)), (".F.n0D", ("-F", connect, "-n", "0", "-D")),
+                               (".FB.n0D", ("-F", connect, "-B", os.path.join(outdir, s + ".sv"), "-w", "30", "-n", "0", "-D"))):
+                with open(os.path.join(outdir, s + tag + ".stdout"), "w") as o:
+                    run([SEEKSV, "getsv", *extra, os.path.join(outdir, s + ".clip.sam"), bam, pre + ".clip.gz",
+                         os.path.join(outdir, s + tag + ".sv"), pre + ".clipunmap"], stdout=o, stderr=subprocess.DEVNULL)
         # -B: the junctions of an earlier output seed the map (ReadBreakpoint, getsv.cpp:1291-1323); with and without the BAM passes
         if s in SEEDED:
             for tag, extra in ((".B", ()), (".B.n0D", ("-n", "0", "-D"))):

@@ -158,3 +158,22 @@ def test_getsv_seed_file_host_only_matches_reference(lib, d, s, tmp_path):
     assert r.returncode == 0, r.stderr
     assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".B.n0D.sv"))
     assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".B.n0D.stdout"))
+
+
+@pytest.mark.parametrize("d,s", [("micro", "tumor"), ("fuzz", "f11")])
+def test_getsv_connected_reads_host_only_matches_reference(lib, d, s, tmp_path):
+    """`getsv -F <connected reads> [-B ... -w 30] -n 0 -D`: FindJunction of the host layer against the reference binary (no GPU)"""
+    import gzip
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, s + ".clip.txt")).encode("latin-1"))
+    connect = os.path.join(GOLDEN, d, s + ".connect.sam")
+    tail = [os.path.join(GOLDEN, d, s + ".clip.sam"), os.path.join(GOLDEN, d, s + ".sort.bam"), clip]
+    for tag, extra in ((".F.n0D", ["-F", connect]), (".FB.n0D", ["-F", connect, "-B", os.path.join(GOLDEN, d, s + ".sv"), "-w", "30"])):
+        out = str(tmp_path / (tag + ".sv"))
+        r = _cli(["getsv"] + extra + ["-n", "0", "-D"] + tail + [out, str(tmp_path / "unm")])
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == read_text(os.path.join(GOLDEN, d, s + tag + ".stdout")), tag
+        assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + tag + ".sv")), tag
+    r = _cli(["getsv", "-F", str(tmp_path / "missing.sam"), "-n", "0", "-D"] + tail + [str(tmp_path / "x.sv"), str(tmp_path / "unm")])
+    assert r.returncode == 1 and "fail to open" in r.stderr

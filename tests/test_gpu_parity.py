@@ -510,3 +510,17 @@ def test_mgpu_entry_point_single_rank(by, tmp_path):
     for ext, name in ((".clip.gz", ".clip.txt"), (".clip.fq.gz", ".clip.fq.txt"), (".unmapped_1.fq.gz", ".unmapped_1.fq.txt"),
                       (".unmapped_2.fq.gz", ".unmapped_2.fq.txt")):
         assert _zcat(pre + ext) == read_text(os.path.join(GOLDEN, d, s + name)), ext
+
+
+@pytest.mark.parametrize("d,s", [("micro", "tumor"), ("fuzz", "f11")])
+def test_getsv_connected_reads_cli_bit_exact(d, s, tmp_path):
+    """getsv -F with the BAM passes on: discordant pairs and depth of the connected-read junctions as well"""
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, s + ".clip.txt")).encode("latin-1"))
+    out = str(tmp_path / "out.sv")
+    r = subprocess.run([_cli(), "getsv", "-F", os.path.join(GOLDEN, d, s + ".connect.sam"), os.path.join(GOLDEN, d, s + ".clip.sam"), _bam(d, s),
+                        clip, out, str(tmp_path / "unm")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".F.stdout"))
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".F.sv"))

@@ -146,3 +146,22 @@ def test_getsv_with_seed_file_matches_reference(d, s):
     sv, out = getsv_oracle.getsv(h, recs, clip, ch, ca, seed_text=seed, pairs_used=0, output_depth=False)
     assert sv == read_text(os.path.join(GOLDEN, d, s + ".B.n0D.sv"))
     assert out == read_text(os.path.join(GOLDEN, d, s + ".B.n0D.stdout"))
+
+
+@pytest.mark.parametrize("d,s", [("micro", "tumor"), ("fuzz", "f11")])
+def test_getsv_with_connected_reads_matches_reference(d, s):
+    """getsv -F <connected read-through reads>: FindJunction (process_bwasw.cpp:5-227), alone and together with -B / -w"""
+    h, recs = bamio.read_bam(_bam(d, s))
+    ch, ca = bamio.read_alignments(os.path.join(GOLDEN, d, s + ".clip.sam"))
+    clip = read_text(os.path.join(GOLDEN, d, s + ".clip.txt"))
+    connect = bamio.read_alignments(os.path.join(GOLDEN, d, s + ".connect.sam"))
+    sv, out = getsv_oracle.getsv(h, recs, clip, ch, ca, connect=connect)
+    assert out == read_text(os.path.join(GOLDEN, d, s + ".F.stdout"))
+    assert sv == read_text(os.path.join(GOLDEN, d, s + ".F.sv"))
+    sv, out = getsv_oracle.getsv(h, recs, clip, ch, ca, connect=connect, pairs_used=0, output_depth=False)
+    assert out == read_text(os.path.join(GOLDEN, d, s + ".F.n0D.stdout"))
+    assert sv == read_text(os.path.join(GOLDEN, d, s + ".F.n0D.sv"))
+    seed = read_text(os.path.join(GOLDEN, d, s + ".sv"))
+    sv, out = getsv_oracle.getsv(h, recs, clip, ch, ca, connect=connect, connect_min_mapq=30, seed_text=seed, pairs_used=0, output_depth=False)
+    assert out == read_text(os.path.join(GOLDEN, d, s + ".FB.n0D.stdout"))
+    assert sv == read_text(os.path.join(GOLDEN, d, s + ".FB.n0D.sv"))
