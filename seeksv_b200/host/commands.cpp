@@ -171,7 +171,7 @@ void usage_cmd(const char *prog, const char *command, int i)
         std::cerr << "Usage: " << prog << " " << command
                   << " [options] <input clipped sequence bam> <input orignal sorted bam> <soft-clipped reads file(*clip.gz)> <output SVs> "
                      "<output unmaped clipped sequence fastq>\n"
-                  << "Options: -F <FILE>             Samfile/Bamfile of connected readthrough reads (not supported by seeksv_b200)\n"
+                  << "Options: -F <FILE>             Samfile/Bamfile of connected readthrough reads\n"
                   << "         -t <double>           Threshold of match rate while combining two soft-clipped reads [0.9]\n"
                   << "         -l <int>              Maximum search length to find microhomology[50]\n"
                   << "         -q <int>              Minimum mapping quality of discordant read pair [20]\n"
