@@ -1,5 +1,6 @@
 // C-ABI glue: contexts, error strings, per-kernel timers, BAM residency.
 #include <sys/mman.h>
+#include <unistd.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -258,7 +259,39 @@ extern "C" int svb_bam_from_host(svb_ctx *ctx, const void *h_stream, uint64_t nb
     return finish_bam(ctx, b, out);
 }
 
-// Parallel memcpy into a pinned slab (the source is the page cache behind an mmap, or any pageable buffer)
+// Fill a pinned slab from a file with parallel pread()s: the kernel copies straight out of the page cache, without the
+// page faults that touching a fresh mapping of the file costs (one per 4 KiB, ~200 k per GB - CPU time the ranks of a
+// multi-GPU run do not have). Returns false on a short read.
+static bool parallel_pread(uint8_t *dst, int fd, uint64_t file_off, uint64_t n, int n_threads)
+{
+    const uint64_t PART = 1ull << 20;
+    uint64_t parts = (n + PART - 1) / PART;
+    int nt = (int)std::min<uint64_t>((uint64_t)std::max(1, n_threads), parts);
+    std::atomic<uint64_t> next(0);
+    std::atomic<bool> ok(true);
+    auto work = [&]() {
+        for (;;) {
+            uint64_t i = next.fetch_add(1);
+            if (i >= parts) return;
+            uint64_t a = i * PART, b = std::min(n, a + PART);
+            while (a < b) {
+                ssize_t r = pread(fd, dst + a, b - a, (off_t)(file_off + a));
+                if (r <= 0) {
+                    ok = false;
+                    return;
+                }
+                a += (uint64_t)r;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    return ok;
+}
+
+// Parallel memcpy into a pinned slab (the source is any pageable buffer)
 static void parallel_copy(uint8_t *dst, const uint8_t *src, uint64_t n, int n_threads)
 {
     const uint64_t PART = 1ull << 20;
@@ -365,7 +398,8 @@ int load_bgzf_host_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, uint
 // finds the BGZF block boundaries; from the moment the block table is known, the blocks that every landed slab completes
 // are inflated on the side streams (inflate.cu). Upload, scan and inflate overlap: the load costs about max of the three.
 int load_bgzf_device_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, uint64_t file_bytes, int n_threads,
-                             std::vector<uint8_t> &head, uint32_t lead = 0)  // lead: bytes left free in front of the output
+                             std::vector<uint8_t> &head, uint32_t lead = 0,  // lead: bytes left free in front of the output
+                             int fd = -1, uint64_t fd_base = 0)              // fd >= 0: h_file is the file at offset fd_base
 {
     WallScope ws(ctx, "h2d_compressed+inflate(wall)", (double)file_bytes);
     static_assert(sizeof(BgzfBlock) == 24, "BgzfBlock must match the device-side block descriptor");
@@ -420,7 +454,7 @@ int load_bgzf_device_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, ui
         CK(cudaEventSynchronize(sl.done[slab]));
         {
             WallScope wc(ctx, "stage_copy(wall)", (double)n);
-            parallel_copy(sl.p[slab], h_file + o, n, n_threads);
+            if (fd < 0 || !parallel_pread(sl.p[slab], fd, fd_base + o, n, n_threads)) parallel_copy(sl.p[slab], h_file + o, n, n_threads);
         }
         CK(cudaMemcpyAsync(d_file.p + o, sl.p[slab], n, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaEventRecord(sl.done[slab], ctx->copy_stream));
@@ -459,7 +493,13 @@ int load_bgzf_device_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, ui
 //  default : the COMPRESSED image is uploaded and inflated on the device, one warp per BGZF block (inflate.cu) - about a
 //            third of the PCIe bytes and no host zlib;
 //  SEEKSV_B200_HOST_INFLATE=1 : host threads inflate the blocks (zlib) and the uncompressed bytes are uploaded.
+static int bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, int n_threads, svb_bam **out, int fd);
 extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, int n_threads, svb_bam **out)
+{
+    return bam_from_bgzf(ctx, h_file, file_bytes, n_threads, out, -1);
+}
+// fd >= 0: h_file is a mapping of that file (the slabs are then filled with pread instead of touching the mapping)
+static int bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_bytes, int n_threads, svb_bam **out, int fd)
 {
     if (!ctx || !out || !h_file) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_bgzf: null argument");
     CK(cudaSetDevice(ctx->device));
@@ -469,7 +509,7 @@ extern "C" int svb_bam_from_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file
     std::vector<uint8_t> head;  // first uncompressed bytes, for the header parse
     std::string err;
     if (use_host_inflate()) CKR(load_bgzf_host_inflate(ctx, b.get(), (const uint8_t *)h_file, file_bytes, n_threads, head));
-    else CKR(load_bgzf_device_inflate(ctx, b.get(), (const uint8_t *)h_file, file_bytes, n_threads, head));
+    else CKR(load_bgzf_device_inflate(ctx, b.get(), (const uint8_t *)h_file, file_bytes, n_threads, head, 0, fd, 0));
     const uint64_t total = b->nbytes;
     BamHeader hdr;
     if (!parse_bam_header(head.data(), head.size(), hdr, err)) {
@@ -532,7 +572,7 @@ extern "C" int svb_bam_open(svb_ctx *ctx, const char *path, int n_threads, svb_b
             WallScope ws(ctx, "file_map(wall)");
             if (!mf.open(p, err)) return svb_fail(ctx, SVB_ERR_IO, "%s", err.c_str());
         }
-        int rc = svb_bam_from_bgzf(ctx, mf.data, mf.size, n_threads, out);
+        int rc = bam_from_bgzf(ctx, mf.data, mf.size, n_threads, out, mf.fd);
         if (mf.data) {  // tearing down a mapping of this size takes milliseconds: not on the caller's time
             std::thread([d = mf.data, n = mf.size]() { munmap((void *)d, n); }).detach();
             mf.data = nullptr;
@@ -575,7 +615,7 @@ static int open_between(svb_ctx *ctx, const MappedFile &mf, const BamHeader &hdr
         if (c0 >= c_end || c_end > mf.size) return svb_fail(ctx, SVB_ERR_FORMAT, "virtual offsets out of range");
         std::vector<uint8_t> head;
         const uint32_t lead = (uint32_t)((16 - (u0 & 15)) & 15);  // the view's first byte lands on a 16-byte boundary
-        CKR(load_bgzf_device_inflate(ctx, b.get(), mf.data + c0, c_end - c0, n_threads, head, lead));
+        CKR(load_bgzf_device_inflate(ctx, b.get(), mf.data + c0, c_end - c0, n_threads, head, lead, mf.fd, c0));
         uint64_t total = b->nbytes, tail_cut = 0;
         if (cut_last) {
             const uint8_t *t = mf.data + c_end - 4;  // uncompressed size of the last block = its ISIZE field

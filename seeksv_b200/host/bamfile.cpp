@@ -22,6 +22,7 @@ bool MappedFile::open(const std::string &path, std::string &err)
         err = "cannot open " + path;
         return false;
     }
+    this->fd = -1;
     struct stat st;
     if (fstat(fd, &st) != 0) {
         ::close(fd);
@@ -36,15 +37,15 @@ bool MappedFile::open(const std::string &path, std::string &err)
             err = "cannot map " + path;
             return false;
         }
-        madvise(p, size, MADV_SEQUENTIAL | MADV_WILLNEED);
         data = (const uint8_t *)p;
     }
-    ::close(fd);
+    this->fd = fd;
     return true;
 }
 MappedFile::~MappedFile()
 {
     if (data) munmap((void *)data, size);
+    if (fd >= 0) ::close(fd);
 }
 
 bool read_file(const std::string &path, std::vector<uint8_t> &out, std::string &err)

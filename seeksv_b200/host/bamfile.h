@@ -21,9 +21,10 @@ struct BamHeader {
     uint64_t first_record = 0;  // byte offset of the first record in the uncompressed stream
 };
 
-struct MappedFile {  // read-only mmap of a whole file
+struct MappedFile {  // read-only mmap of a whole file (the descriptor stays open for pread)
     const uint8_t *data = nullptr;
     uint64_t size = 0;
+    int fd = -1;
     bool open(const std::string &path, std::string &err);
     ~MappedFile();
 };
