@@ -524,3 +524,60 @@ def test_getsv_connected_reads_cli_bit_exact(d, s, tmp_path):
     assert r.returncode == 0, r.stderr
     assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".F.stdout"))
     assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".F.sv"))
+
+
+def test_c2_scale_properties(tmp_path):
+    """BASELINE.json's C2 size (chr21-sized chromosome, 30x, ~9.2 M records, 2.7 GB uncompressed), where the Python oracle is out of
+    reach: size-independent properties instead - determinism (two runs, identical bytes), shard invariance (8 coordinate-range shards
+    and the whole file give the same four outputs), structure of the outputs (positions ascending per chromosome and side, both mate
+    files pair up), and the simulator's known insert-size distribution and depth."""
+    import hashlib
+    import seeksv_b200
+    from seeksv_b200 import sharding
+    svsim = os.path.join(ROOT, "seeksv_b200", "bin", "svsim")
+    pre = str(tmp_path / "c2")
+    subprocess.run([svsim, "--out", pre, "--genome", "chr21:46709983", "--cov", "30", "--nsv", "500", "--seed", "20261017"], check=True,
+                   stderr=subprocess.DEVNULL)
+    bam = pre + ".bam"
+    ctx = seeksv_b200.Context(0)
+    whole = seeksv_b200.Bam.open(ctx, bam)
+    n_rec = whole.n_records
+    assert 9_000_000 < n_rec < 9_500_000
+    first = whole.getclip()
+    again = whole.getclip()
+    assert [hashlib.md5(t).hexdigest() for t in first] == [hashlib.md5(t).hexdigest() for t in again]
+    # shard invariance
+    plans = sharding.plan_range_shards(bam, None, 1, 8)
+    assert sum(not p.empty for p in plans) == 8
+    parts, own_records = [], 0
+    for p in plans:
+        w = sharding.RangeShardWorker(ctx, bam, p)
+        assert w.context_has_mapped_record()
+        parts.append(w.getclip())
+        v = w.own_view()
+        own_records += v.n_records
+        v.close()
+        if p is plans[-1]:
+            u1, u2 = w.pair_unmapped(b"".join(x[4] for x in parts))
+        w.close()
+    assert own_records == n_rec
+    clip, fq = sharding.merge_range_texts([(x[0], x[1]) for x in parts])
+    assert (clip.encode("latin-1"), fq.encode("latin-1"), u1.encode("latin-1"), u2.encode("latin-1")) == first
+    # structure
+    last = {}
+    n_lines = 0
+    for line in first[0].decode("latin-1").split("\n")[:-1]:
+        f = line.split("\t", 3)
+        key, pos = (f[0], f[2]), int(f[1])
+        assert pos >= last.get(key, 0), line[:80]
+        last[key] = pos
+        n_lines += 1
+    assert first[1].count(b"\n") == 4 * n_lines                      # one FASTQ record per cluster
+    assert first[2].count(b"\n") == first[3].count(b"\n") > 0       # the mate files pair up
+    # the simulator draws insert sizes from N(500, 25^2) and covers the chromosome 30x with 150 bp reads
+    n, tot, mean, sq = whole.insert_stats(20, 5000000)
+    assert n > 1_000_000 and 495 <= mean <= 505 and 20 <= int((sq / n) ** 0.5) <= 30
+    depth = whole.window_depth([(0, 10_000_000, 10_100_000)], 20)[0]
+    assert 24 <= sum(depth) / len(depth) <= 36
+    whole.close()
+    ctx.close()
