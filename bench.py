@@ -241,7 +241,13 @@ def main():
     n_merge = torch.tensor([max(1, len(juncs))], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(n_merge, op=dist.ReduceOp.MAX)
-    counts_dev = torch.zeros(int(n_merge.item()), dtype=torch.int32, device="cuda")
+    # final candidate merge: two buffer sets, so that the merge of step i overlaps the kernels of step i + 1
+    n_slots = int(n_merge.item())
+    counts_dev = [torch.zeros(n_slots, dtype=torch.int32, device="cuda") for _ in range(2)]
+    merged_dev = [torch.empty(n_slots * max(world, 1), dtype=torch.int32, device="cuda") for _ in range(2)]
+    pending_merge = [None, None]
+    step_no = [0]
+    stage_host = None
     stream = torch.cuda.ExternalStream(ctx.stream)
 
     # C arrays for the getsv passes are built once; results land in preallocated host arrays (no per-step marshalling)
@@ -253,6 +259,7 @@ def main():
     n_pos = sum(w[2] - w[1] + 1 for w in wins)
     cnt_host = torch.zeros(max(nj, 1), dtype=torch.int32).pin_memory()
     dep_host = torch.zeros(max(n_pos, 1), dtype=torch.int32).pin_memory()
+    stage_host = [torch.zeros_like(cnt_host).pin_memory() for _ in range(2)]
     cnt_arr = C.cast(cnt_host.data_ptr(), C.POINTER(C.c_int32))
     dep_arr = C.cast(dep_host.data_ptr(), C.POINTER(C.c_int32))
 
@@ -270,9 +277,13 @@ def main():
         b.window_depth_raw(w_arr, nw, 20, dep_arr)
         b.close()
         if world > 1:   # final candidate merge: every rank learns every shard's support counts (small NCCL allgather)
-            counts_dev[:cnt_host.numel()].copy_(cnt_host, non_blocking=True)
-            gathered = [torch.empty_like(counts_dev) for _ in range(world)]
-            dist.all_gather(gathered, counts_dev)
+            k = step_no[0] & 1
+            step_no[0] += 1
+            if pending_merge[k] is not None:
+                pending_merge[k].wait()      # the buffers of two steps ago are free again
+            stage_host[k].copy_(cnt_host)     # (the next step overwrites cnt_host while this copy may still be queued)
+            counts_dev[k][:cnt_host.numel()].copy_(stage_host[k], non_blocking=True)
+            pending_merge[k] = dist.all_gather_into_tensor(merged_dev[k], counts_dev[k], async_op=True)
         return sum(sizes) + 4 * nj + 4 * n_pos
 
     out_dir = os.path.join(WORK, "out_%d" % rank)
@@ -294,6 +305,10 @@ def main():
         assert rc == 0
 
     def barrier():
+        for k in range(2):               # every merge that is still in flight belongs to the region that ends here
+            if pending_merge[k] is not None:
+                pending_merge[k].wait()
+                pending_merge[k] = None
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
