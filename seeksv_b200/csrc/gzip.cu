@@ -7,7 +7,7 @@
 // literals only (one per 64 KiB piece; RFC 1951 3.2.7), CRC32 and ISIZE. Any gzip reader concatenates the members.
 //
 //   gz_hist_crc   one CTA per piece: byte histogram (per-warp shared-memory counters) and the piece's raw CRC-32
-//   gz_codes      one thread per piece: length-limited Huffman code (<= 15 bits), canonical codes, the block header bits
+//   gz_codes      one warp per piece: length-limited Huffman code (<= 15 bits), canonical codes, the block header bits
 //   gz_layout     bit offset of every piece inside its member, member sizes and offsets, member CRCs (GF(2) shifts)
 //   gz_encode     one CTA per piece: per-thread slices -> bit lengths -> block scan -> bits OR-ed / stored into the output
 #include "common.cuh"
@@ -44,11 +44,12 @@ __device__ uint32_t crc_shift(uint32_t r, uint64_t nbytes)  // r after nbytes ze
 __global__ void __launch_bounds__(GZ_THREADS) gz_hist_crc(const uint8_t *__restrict__ text, uint64_t n, uint32_t *__restrict__ hist,
                                                           uint32_t *__restrict__ crc_raw)
 {
-    __shared__ uint32_t h[GZ_THREADS / 32][256];
+    // four counter sets per warp (by lane & 3): the lanes of a warp mostly see the same few symbols at the same time
+    __shared__ uint32_t h[GZ_THREADS / 32][4][256];
     __shared__ uint32_t tab[256];
     __shared__ uint32_t part[GZ_THREADS];
-    const uint32_t t = threadIdx.x, w = t >> 5;
-    for (uint32_t i = t; i < (GZ_THREADS / 32) * 256; i += GZ_THREADS) (&h[0][0])[i] = 0;
+    const uint32_t t = threadIdx.x, w = t >> 5, sub = t & 3;
+    for (uint32_t i = t; i < (GZ_THREADS / 32) * 4 * 256; i += GZ_THREADS) (&h[0][0][0])[i] = 0;
     tab[t] = c_crc_table[t];
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * PIECE;
@@ -57,18 +58,29 @@ __global__ void __launch_bounds__(GZ_THREADS) gz_hist_crc(const uint8_t *__restr
     uint32_t crc = 0;  // raw: register starts at 0, no final inversion
     for (uint64_t i = a; i < b; ++i) {
         const uint32_t c = text[base + i];
-        atomicAdd(&h[w][c], 1u);
+        atomicAdd(&h[w][sub][c], 1u);
         crc = tab[(crc ^ c) & 0xff] ^ (crc >> 8);
     }
     part[t] = crc;
     __syncthreads();
     uint32_t s = 0;
-    for (uint32_t k = 0; k < GZ_THREADS / 32; ++k) s += h[k][t];
+    for (uint32_t k = 0; k < GZ_THREADS / 32; ++k) s += h[k][0][t] + h[k][1][t] + h[k][2][t] + h[k][3][t];
     hist[(uint64_t)blockIdx.x * 257 + t] = s;
-    if (t == 0) {
-        hist[(uint64_t)blockIdx.x * 257 + 256] = 1;  // end of block
+    if (t == 0) hist[(uint64_t)blockIdx.x * 257 + 256] = 1;  // end of block
+    // raw(A || B) = shift(raw(A), |B|) ^ raw(B)
+    if (piece_len == PIECE) {  // all slices full: pairwise tree, level j joins neighbours 2^j slices apart (2^(8+j) bytes each)
+        for (int j = 0; (1u << j) < GZ_THREADS; ++j) {
+            uint32_t r = 0;
+            const bool active = (t & ((2u << j) - 1)) == 0;
+            if (active) r = crc_shift_pow2(part[t], 8 + j) ^ part[t + (1u << j)];
+            __syncthreads();
+            if (active) part[t] = r;
+            __syncthreads();
+        }
+        if (t == 0) crc_raw[blockIdx.x] = part[0];
+    } else if (t == 0) {  // the last piece of a text: slice lengths differ
         uint32_t r = 0;
-        for (uint32_t k = 0; k < GZ_THREADS; ++k) {  // raw(A || B) = shift(raw(A), |B|) ^ raw(B)
+        for (uint32_t k = 0; k < GZ_THREADS; ++k) {
             const uint64_t lo = min(piece_len, (uint64_t)k * SLICE), hi = min(piece_len, (uint64_t)(k + 1) * SLICE);
             if (hi == lo) break;
             r = (hi - lo == SLICE ? crc_shift_pow2(r, 8) : crc_shift(r, hi - lo)) ^ part[k];
@@ -100,78 +112,116 @@ struct PieceBits {  // LSB-first bit writer into 32-bit words (header constructi
     }
 };
 
-__global__ void gz_codes(uint32_t n_pieces, uint64_t n, const uint32_t *__restrict__ hist, uint32_t *__restrict__ codes,
-                         uint32_t *__restrict__ hdr, uint32_t *__restrict__ hdr_bits, uint64_t *__restrict__ piece_bits)
+constexpr int CODES_WARPS = 4;
+struct CodeScratch {  // per warp
+    uint32_t freq[260];
+    uint32_t wgt[520];     // node weights, then node depths
+    int16_t parent[520];
+    uint16_t sym[260];     // used symbols, ascending
+    uint16_t order[260];   // used symbols by (frequency, symbol)
+};
+
+// One warp per piece: the O(alphabet) loops and the sort are spread over the lanes, the inherently serial parts (two-queue
+// merge, canonical code assignment, header bits) run on lane 0 out of shared memory.
+__global__ void __launch_bounds__(CODES_WARPS * 32)
+    gz_codes(uint32_t n_pieces, uint64_t n, const uint32_t *__restrict__ hist, uint32_t *__restrict__ codes, uint32_t *__restrict__ hdr,
+             uint32_t *__restrict__ hdr_bits, uint64_t *__restrict__ piece_bits)
 {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pieces) return;
+    __shared__ CodeScratch scratch[CODES_WARPS];
+    __shared__ uint8_t len_s[CODES_WARPS][260];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t p = blockIdx.x * CODES_WARPS + wid;
+    if (p >= n_pieces) return;  // (whole warps leave together)
+    CodeScratch &C = scratch[wid];
+    uint8_t *len = len_s[wid];
     const uint32_t *f = hist + (uint64_t)p * 257;
-    uint32_t freq[257];
-    uint8_t len[258];
-    int n_used = 0;
-    for (int i = 0; i < 257; ++i) freq[i] = f[i], n_used += freq[i] != 0;
+    for (int i = lane; i < 257; i += 32) C.freq[i] = f[i];
+    __syncwarp();
     // length-limited prefix code: Huffman by sorted two-queue merge; frequencies are flattened until the longest code fits
     for (;;) {
-        uint16_t order[257];
-        uint64_t wgt[513];
-        int16_t parent[513];
         int m = 0;
-        for (int i = 0; i < 257; ++i) {
-            len[i] = 0;
-            if (freq[i]) order[m++] = (uint16_t)i;
+        for (int base = 0; base < 288; base += 32) {  // used symbols, compacted in ascending order
+            const int sy = base + (int)lane;
+            const bool used = sy < 257 && C.freq[sy] != 0;
+            const uint32_t bal = __ballot_sync(0xffffffffu, used);
+            if (used) C.sym[m + __popc(bal & ((1u << lane) - 1))] = (uint16_t)sy;
+            m += __popc(bal);
         }
+        for (int i = lane; i < 258; i += 32) len[i] = 0;
+        __syncwarp();
         if (m == 1) {
-            len[order[0]] = 1;
+            if (lane == 0) len[C.sym[0]] = 1;
+            __syncwarp();
             break;
         }
-        for (int i = 1; i < m; ++i) {  // insertion sort by (frequency, symbol)
-            uint16_t s = order[i];
-            int j = i - 1;
-            while (j >= 0 && (freq[order[j]] > freq[s] || (freq[order[j]] == freq[s] && order[j] > s))) order[j + 1] = order[j], --j;
-            order[j + 1] = s;
+        for (int a = lane; a < m; a += 32) {  // rank sort by (frequency, symbol)
+            const uint32_t fa = C.freq[C.sym[a]];
+            int r = 0;
+            for (int b = 0; b < m; ++b) {
+                const uint32_t fb = C.freq[C.sym[b]];
+                r += (fb < fa) || (fb == fa && b < a);
+            }
+            C.order[r] = C.sym[a];
         }
-        for (int i = 0; i < m; ++i) wgt[i] = freq[order[i]], parent[i] = -1;
-        int qa = 0, qb = m, end = m;
-        while (end < 2 * m - 1) {
-            int pick[2];
-            for (int k = 0; k < 2; ++k) pick[k] = (qa < m && (qb >= end || wgt[qa] <= wgt[qb])) ? qa++ : qb++;
-            wgt[end] = wgt[pick[0]] + wgt[pick[1]];
-            parent[end] = -1;
-            parent[pick[0]] = parent[pick[1]] = (int16_t)end;
-            ++end;
-        }
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) C.wgt[i] = C.freq[C.order[i]], C.parent[i] = -1;
+        __syncwarp();
         int longest = 0;
-        // depth of a node = depth of its parent + 1; parents have larger indices: walk down from the root
-        for (int i = 2 * m - 2; i >= 0; --i) wgt[i] = parent[i] < 0 ? 0 : wgt[parent[i]] + 1;
-        for (int i = 0; i < m; ++i) {
-            len[order[i]] = (uint8_t)min((uint64_t)255, wgt[i]);
-            longest = max(longest, (int)wgt[i]);
+        if (lane == 0) {
+            int qa = 0, qb = m, end = m;
+            while (end < 2 * m - 1) {
+                int pick[2];
+                for (int k = 0; k < 2; ++k) pick[k] = (qa < m && (qb >= end || C.wgt[qa] <= C.wgt[qb])) ? qa++ : qb++;
+                C.wgt[end] = C.wgt[pick[0]] + C.wgt[pick[1]];
+                C.parent[end] = -1;
+                C.parent[pick[0]] = C.parent[pick[1]] = (int16_t)end;
+                ++end;
+            }
+            // depth of a node = depth of its parent + 1; parents have larger indices: walk down from the root
+            for (int i = 2 * m - 2; i >= 0; --i) C.wgt[i] = C.parent[i] < 0 ? 0 : C.wgt[C.parent[i]] + 1;
+            for (int i = 0; i < m; ++i) {
+                len[C.order[i]] = (uint8_t)min(255u, C.wgt[i]);
+                longest = max(longest, (int)C.wgt[i]);
+            }
         }
+        longest = __shfl_sync(0xffffffffu, longest, 0);
+        __syncwarp();
         if (longest <= 15) break;
-        for (int i = 0; i < 257; ++i)
-            if (freq[i]) freq[i] = (freq[i] + 1) / 2;
+        for (int i = lane; i < 257; i += 32)
+            if (C.freq[i]) C.freq[i] = (C.freq[i] + 1) / 2;
+        __syncwarp();
     }
     const uint64_t base = (uint64_t)p * PIECE;
     const bool empty_piece = base >= n;
-    if (empty_piece) len[0] = 1;  // end-of-block alone would be a one-symbol code: give it an unused partner
-    len[257] = 1;                 // the single (unused) distance code
-    // canonical codes, bit-reversed for LSB-first output
-    uint32_t count[16], next[16];
-    for (int i = 0; i < 16; ++i) count[i] = 0;
-    for (int i = 0; i < 257; ++i) count[len[i]]++;
-    count[0] = 0;
-    uint32_t c = 0;
-    next[0] = 0;
-    for (int b = 1; b <= 15; ++b) {
-        c = (c + count[b - 1]) << 1;
-        next[b] = c;
+    if (lane == 0) {
+        if (empty_piece) len[0] = 1;  // end-of-block alone would be a one-symbol code: give it an unused partner
+        len[257] = 1;                 // the single (unused) distance code
+        // canonical codes, bit-reversed for LSB-first output (into C.wgt: code | length << 16)
+        uint32_t count[16], next[16];
+        for (int i = 0; i < 16; ++i) count[i] = 0;
+        for (int i = 0; i < 257; ++i) count[len[i]]++;
+        count[0] = 0;
+        uint32_t c = 0;
+        next[0] = 0;
+        for (int b = 1; b <= 15; ++b) {
+            c = (c + count[b - 1]) << 1;
+            next[b] = c;
+        }
+        for (int i = 0; i < 257; ++i) {
+            const uint32_t l = len[i], v = l ? next[l]++ : 0;
+            C.wgt[i] = (l ? __brev(v) >> (32 - l) : 0) | l << 16;
+        }
     }
+    __syncwarp();
     uint64_t data_bits = 0;
-    for (int i = 0; i < 257; ++i) {
-        const uint32_t l = len[i], v = l ? next[l]++ : 0;
-        codes[(uint64_t)p * 257 + i] = (l ? __brev(v) >> (32 - l) : 0) | l << 16;
-        data_bits += (uint64_t)f[i] * l;  // (true frequencies, not the flattened ones)
+    for (int i = lane; i < 257; i += 32) {
+        const uint32_t cl = C.wgt[i];
+        codes[(uint64_t)p * 257 + i] = cl;
+        data_bits += (uint64_t)f[i] * (cl >> 16);  // (true frequencies, not the flattened ones)
     }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) data_bits += __shfl_xor_sync(0xffffffffu, data_bits, d);
+    if (lane != 0) return;
     // the block header (RFC 1951 3.2.7) with the fixed code-length code
     uint32_t cl_code[19];
     {
@@ -388,7 +438,7 @@ int gzip_on_device(svb_ctx *ctx, const char *d_text, uint64_t n, PinnedBuf *out)
     }
     {
         ProfScope ps(ctx, "gz_codes", 0);
-        gz_codes<<<(n_pieces + 63) / 64, 64, 0, s>>>(n_pieces, n, hist.p, codes.p, hdr.p, hdr_bits.p, piece_bits.p);
+        gz_codes<<<(n_pieces + CODES_WARPS - 1) / CODES_WARPS, CODES_WARPS * 32, 0, s>>>(n_pieces, n, hist.p, codes.p, hdr.p, hdr_bits.p, piece_bits.p);
     }
     {
         ProfScope ps(ctx, "gz_layout", 0);
