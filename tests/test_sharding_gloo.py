@@ -139,3 +139,42 @@ def test_assign_and_prefix_helpers():
     assert sh[0][0] == 0 and sh[-1][1] == 24 and all(a[1] == b[0] for a, b in zip(sh, sh[1:])) and all(hi > lo for lo, hi in sh)
     assert sharding.prev_tids([0, None, 3, 4]) == [0, 0, 0, 3]
     assert sharding.prefix_cutoffs([10, 10, 10], 15) == [10, 5, 0]
+
+
+def _range_worker(rank, world, port, case, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from seeksv_b200 import sharding
+        from test_range_sharding import OracleRangeWorker, records_with_voffsets
+        d, s = case
+        path = os.path.join(GOLDEN, d, s + ".sort.bam")
+        h, recs, voffs = records_with_voffsets(path)
+        plan = sharding.plan_range_shards(path, None, len(h.names), world)[rank]     # every rank computes the same plan
+        merged = sharding.sharded_getclip_ranges(OracleRangeWorker(h, recs, voffs, plan), dist)
+        if rank == 0:
+            q.put(merged)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", [("fuzz", "f12"), ("example", "normal")])
+def test_range_sharding_world2(case):
+    """sharded_getclip_ranges over a real process group (gloo, 2 ranks): plan from the .bai on every rank, oracle workers, rank 0 merges"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_range_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    d, s = case
+    for got, name in zip(merged, (".clip.txt", ".clip.fq.txt", ".unmapped_1.fq.txt", ".unmapped_2.fq.txt")):
+        assert got == read_text(os.path.join(GOLDEN, d, s + name)), name
