@@ -39,12 +39,7 @@ SEED = 20261017
 
 def ensure_tools():
     from seeksv_b200 import build as b
-    b.build()
-    for tool in ("svsim", "minialign"):
-        out = os.path.join(BIN, tool)
-        src = os.path.join(ROOT, "tools", tool + ".cpp")
-        if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", src, "-o", out, "-lz"], check=True)
+    b.build()      # library, CLI, and the svsim / minialign helpers
 
 
 def make_bam(prefix, contig, length, seed, nsv):

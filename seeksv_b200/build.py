@@ -65,9 +65,20 @@ def build(verbose=False):
         _run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lz", "-lpthread", "-Xlinker", "-rpath,$ORIGIN"])
     if _stale(CLI, [LIB, os.path.join(HERE, "host/main.cpp")]):
         _run(["g++"] + CXXFLAGS + ["host/main.cpp", "-o", CLI, "-L" + HERE, "-lseeksv_b200", "-Wl,-rpath,$ORIGIN/.."])
+    build_tools()
     if verbose:
         print("built", LIB, "and", CLI)
     return LIB
+
+
+def build_tools():
+    """The test/bench helpers (workload simulator, stand-in aligner for the external bwa step): plain host C++."""
+    tools = os.path.join(HERE, "..", "tools")
+    for tool in ("svsim", "minialign"):
+        out = os.path.join(os.path.dirname(CLI), tool)
+        src = os.path.join(tools, tool + ".cpp")
+        if _stale(out, [src]):
+            _run(["g++", "-O2", "-std=c++17", "-pthread", src, "-o", out, "-lz"])
 
 
 if __name__ == "__main__":

@@ -1,0 +1,173 @@
+"""Seeded fuzz campaign on the CPU (build container only: needs /root/reference for bwa and oracle/_ref for the reference).
+
+    python tools/fuzz_campaign.py [--seeds 100:140] [--records 1800] [--gpu]
+
+For every seed: tests/fuzzgen.py writes an awkward BAM, the REAL reference (oracle/_ref/seeksv) runs getclip -> bwa mem ->
+getsv (plain, `-n 0 -D`, `-B`) -> somatic(self), and then
+  * the Python oracle (oracle/getclip_oracle.py, getsv_oracle.py) must reproduce every output byte for byte - this pins the
+    checker on inputs beyond the committed fixtures;
+  * the host layer of the product (`seeksv getsv -n 0 -D`, no BAM pass -> runs without a GPU) must reproduce the `-n 0 -D`
+    outputs;
+  * with --gpu (on a B200 box with oracle/_ref present; bwa's SAM is then replaced by tools/minialign) the product CLI runs the
+    whole pipeline too.
+Prints one line per seed and a summary; exit status 1 if anything differed. Test infrastructure, not product code.
+"""
+import argparse
+import gzip
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import fuzzgen  # noqa: E402
+from oracle import bamio, getclip_oracle, getsv_oracle  # noqa: E402
+
+REF = os.environ.get("SEEKSV_REFERENCE", "/root/reference")
+SEEKSV = os.path.join(ROOT, "oracle", "_ref", "seeksv")
+BAMTOOL = os.path.join(ROOT, "oracle", "_ref", "bamtool")
+CLI = os.path.join(ROOT, "seeksv_b200", "bin", "seeksv")
+MINI = os.path.join(ROOT, "seeksv_b200", "bin", "minialign")
+
+
+def text(p):
+    with open(p, "rb") as f:
+        return f.read().decode("latin-1")
+
+
+def zcat(p):
+    with gzip.open(p, "rb") as f:
+        return f.read().decode("latin-1")
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, capture_output=True, text=True, **kw)
+
+
+def one_seed(seed, records, work, bwa, gpu):
+    bad = []
+    bam = os.path.join(work, "f.sort.bam")
+    _, _, genome = fuzzgen.write(bam, seed, records)
+    subprocess.run([BAMTOOL, "index", bam], check=True)
+    fa = os.path.join(work, "f.fa")
+    fuzzgen.write_fasta(genome, fa)
+    pre = os.path.join(work, "ref")
+    r = run([SEEKSV, "getclip", "-o", pre, bam])
+    if r.returncode != 0:
+        return ["reference getclip failed (%d)" % r.returncode]
+    ref = {e: zcat(pre + e) for e in (".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz")}
+    sam = os.path.join(work, "clip.sam")
+    if bwa:
+        subprocess.run([bwa, "index", fa], check=True, capture_output=True)
+        with open(sam, "w") as o:
+            subprocess.run([bwa, "mem", fa, pre + ".clip.fq.gz"], check=True, stdout=o, stderr=subprocess.DEVNULL)
+    else:
+        with open(sam, "w") as o:
+            subprocess.run([MINI, fa, pre + ".clip.fq.gz"], check=True, stdout=o)
+    variants = {"": [], ".n0D": ["-n", "0", "-D"]}
+    for tag, extra in list(variants.items()):
+        r = run([SEEKSV, "getsv", *extra, sam, bam, pre + ".clip.gz", pre + tag + ".sv", pre + ".unm"])
+        if r.returncode != 0:
+            return ["reference getsv%s failed (%d)" % (tag, r.returncode)]
+        ref["sv" + tag], ref["out" + tag] = text(pre + tag + ".sv"), r.stdout
+    r = run([SEEKSV, "getsv", "-B", pre + ".sv", sam, bam, pre + ".clip.gz", pre + ".B.sv", pre + ".unm"])
+    ref["sv.B"], ref["out.B"] = (text(pre + ".B.sv"), r.stdout) if r.returncode == 0 else (None, None)
+    r = run([SEEKSV, "somatic", bam, pre + ".clip.gz", pre + ".sv", pre + ".somatic"])
+    ref["somatic"] = text(pre + ".somatic") if r.returncode == 0 else None
+
+    # --- the oracle against the reference
+    h, recs = bamio.read_bam(bam)
+    got = getclip_oracle.getclip(h, recs)
+    for g, e in zip(got, (".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz")):
+        if g != ref[e]:
+            bad.append("oracle getclip " + e)
+    ch, ca = bamio.read_alignments(sam)
+    sv, out = getsv_oracle.getsv(h, recs, ref[".clip.gz"], ch, ca)
+    if sv != ref["sv"]:
+        bad.append("oracle getsv .sv")
+    if out != ref["out"]:
+        bad.append("oracle getsv stdout")
+    if ref["somatic"] is not None:
+        if getsv_oracle.somatic(h, recs, ref[".clip.gz"], ref["sv"]) != ref["somatic"]:
+            bad.append("oracle somatic")
+
+    # --- the product's host layer (no BAM pass, no GPU) against the reference
+    if os.path.exists(CLI):
+        r = run([CLI, "getsv", "-n", "0", "-D", sam, bam, pre + ".clip.gz", os.path.join(work, "host.sv"), os.path.join(work, "host.unm")])
+        if r.returncode != 0:
+            bad.append("host getsv -n0 -D exit %d" % r.returncode)
+        else:
+            if text(os.path.join(work, "host.sv")) != ref["sv.n0D"]:
+                bad.append("host -n0 -D .sv")
+            if r.stdout != ref["out.n0D"]:
+                bad.append("host -n0 -D stdout")
+
+    # --- the whole product pipeline (B200 only)
+    if gpu:
+        p = os.path.join(work, "b200")
+        r = run([CLI, "getclip", "-o", p, bam])
+        if r.returncode != 0:
+            bad.append("b200 getclip exit %d: %s" % (r.returncode, r.stderr[-200:]))
+        else:
+            for e in (".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz"):
+                if zcat(p + e) != ref[e]:
+                    bad.append("b200 getclip " + e)
+            r = run([CLI, "getsv", sam, bam, p + ".clip.gz", p + ".sv", p + ".unm"])
+            if r.returncode != 0 or text(p + ".sv") != ref["sv"] or r.stdout != ref["out"]:
+                bad.append("b200 getsv")
+            if ref["sv.B"] is not None:
+                r = run([CLI, "getsv", "-B", pre + ".sv", sam, bam, p + ".clip.gz", p + ".B.sv", p + ".unm"])
+                if r.returncode != 0 or text(p + ".B.sv") != ref["sv.B"] or r.stdout != ref["out.B"]:
+                    bad.append("b200 getsv -B")
+            if ref["somatic"] is not None:
+                r = run([CLI, "somatic", bam, pre + ".clip.gz", pre + ".sv", p + ".somatic"])
+                if r.returncode != 0 or text(p + ".somatic") != ref["somatic"]:
+                    bad.append("b200 somatic")
+    n_sv = ref["sv"].count("\n")
+    return bad, n_sv, len(recs)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", default="100:120")
+    ap.add_argument("--records", type=int, default=1800)
+    ap.add_argument("--gpu", action="store_true")
+    ap.add_argument("--keep", action="store_true", help="keep the work directory of failing seeds")
+    a = ap.parse_args()
+    lo, hi = (int(x) for x in a.seeds.split(":"))
+    assert os.path.exists(SEEKSV) and os.path.exists(BAMTOOL), "oracle/build_ref.sh first"
+    top = tempfile.mkdtemp(prefix="fuzzcamp_")
+    bwa = None
+    if os.path.exists(os.path.join(REF, "example", "bin", "bwa")):
+        bwa = os.path.join(top, "bwa")
+        shutil.copy(os.path.join(REF, "example", "bin", "bwa"), bwa)
+        os.chmod(bwa, 0o755)
+    failed = 0
+    for seed in range(lo, hi):
+        work = os.path.join(top, "s%d" % seed)
+        os.makedirs(work)
+        res = one_seed(seed, a.records, work, bwa, a.gpu)
+        if isinstance(res, list):
+            print("seed %d: SKIP %s" % (seed, res[0]), flush=True)
+            shutil.rmtree(work)
+            continue
+        bad, n_sv, n_rec = res
+        print("seed %d: %d records, %d sv lines: %s" % (seed, n_rec, n_sv, "ok" if not bad else "DIFF " + "; ".join(bad)), flush=True)
+        if bad:
+            failed += 1
+            if a.keep:
+                continue
+        shutil.rmtree(work)
+    if not (failed and a.keep):
+        shutil.rmtree(top, ignore_errors=True)
+    else:
+        print("kept:", top)
+    print("%d of %d seeds differed" % (failed, hi - lo))
+    return 1 if failed else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
