@@ -590,19 +590,20 @@ def main_depth(h: Header, recs: List[Rec], positions, ranges, begin2end, min_map
                 continue
             wbeg = u32(wk[1])
             j = bisect.bisect_right(ranges, (name, u32(P + 1), u32(P + 1)))
-            if j > 0:
+            if j == 0:
+                continue      # bam2depth.cpp:102: the `continue` also skips the point depth at :123-124
+            j -= 1
+            while j != 0:
+                r = ranges[j]
+                if r[0] != name or r[1] < wbeg:
+                    break
+                if P <= r[2]:
+                    range2depth[r] += int(d[P])
                 j -= 1
-                while j != 0:
-                    r = ranges[j]
-                    if r[0] != name or r[1] < wbeg:
-                        break
-                    if P <= r[2]:
-                        range2depth[r] += int(d[P])
-                    j -= 1
-                if j == 0:
-                    r = ranges[0]
-                    if r[0] == name and r[1] >= wbeg and P <= r[2]:
-                        range2depth[r] += int(d[P])
+            if j == 0:
+                r = ranges[0]
+                if r[0] == name and r[1] >= wbeg and P <= r[2]:
+                    range2depth[r] += int(d[P])
             if (name, P) in pos2depth:
                 pos2depth[(name, P)] = int(d[P])
     return pos2depth, range2depth

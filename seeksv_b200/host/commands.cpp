@@ -351,7 +351,8 @@ uint64_t device_windows(const WindowMap &begin2end, const std::map<std::string, 
 // Closed form of main_depth's two map walks (bam2depth.cpp:82-124, literal version: svb::account_position). For a
 // covered position P the reference (1) finds the LAST merged window whose begin is <= P and requires P <= its end,
 // (2) adds depth(P) to every range r on the chromosome with (r.begin, r.end) <= (P+1, P+1), P <= r.end and
-// r.begin >= window.begin (unsigned compare), (3) stores depth(P) if P is a junction position. Turned around per range:
+// r.begin >= window.begin (unsigned compare), (3) stores depth(P) if P is a junction position - steps (2) and (3) only
+// when the range map holds any key <= (chr, P+1, P+1) at all (the `continue` of bam2depth.cpp:102). Turned around per range:
 // r collects depth over [r.begin, r.end] plus - only for the degenerate 0/1-length ranges of quirk Q11 - the position
 // r.begin - 1, restricted to positions whose window satisfies the unsigned compare. Sums come from prefix sums.
 void account_depth(const std::vector<Win> &hw, const std::vector<int32_t> &depth, const WindowMap &begin2end, PosDepth &pos2depth,
@@ -412,6 +413,9 @@ void account_depth(const std::vector<Win> &hw, const std::vector<int32_t> &depth
         auto d = dev.find(kv.first.first);
         if (m == mw.end() || d == dev.end()) continue;
         int64_t p = kv.first.second;
+        // bam2depth.cpp:101-102: no range at or below (chr, P+1, P+1) in the WHOLE map -> `continue` before the point depth
+        // is stored (only the first positions of the lexicographically smallest chromosome can be hit)
+        if (range2depth.upper_bound(ChrRange{kv.first.first, (unsigned)(p + 1), (unsigned)(p + 1)}) == range2depth.begin()) continue;
         for (const MapWin &w : m->second)
             if (w.lo <= p && p <= w.hi) {
                 uint64_t v = sum(d->second, p, p);

@@ -830,17 +830,16 @@ void account_position(const std::string &chr, int p, int depth, const WindowMap 
     --w;
     if (w->first.first != chr || p > w->second) return;
     auto r = range2depth.upper_bound(ChrRange{chr, (unsigned)(p + 1), (unsigned)(p + 1)});
-    if (r != range2depth.begin()) {
+    if (r == range2depth.begin()) return;  // bam2depth.cpp:102: this `continue` also skips the point depth below
+    --r;
+    while (r != range2depth.begin()) {
+        if (r->first.chr != w->first.first || r->first.begin < (unsigned)w->first.second) break;
+        if ((unsigned)p <= r->first.end) r->second += depth;
         --r;
-        while (r != range2depth.begin()) {
-            if (r->first.chr != w->first.first || r->first.begin < (unsigned)w->first.second) break;
-            if ((unsigned)p <= r->first.end) r->second += depth;
-            --r;
-        }
-        if (r == range2depth.begin()) {
-            if (r->first.chr == w->first.first && r->first.begin >= (unsigned)w->first.second && (unsigned)p <= r->first.end)
-                r->second += depth;
-        }
+    }
+    if (r == range2depth.begin()) {
+        if (r->first.chr == w->first.first && r->first.begin >= (unsigned)w->first.second && (unsigned)p <= r->first.end)
+            r->second += depth;
     }
     auto q = pos2depth.find(std::make_pair(chr, p));
     if (q != pos2depth.end()) q->second = depth;

@@ -581,3 +581,23 @@ def test_c2_scale_properties(tmp_path):
     assert 24 <= sum(depth) / len(depth) <= 36
     whole.close()
     ctx.close()
+
+
+def test_fuzz_seed_106_point_depth_quirk_cli_bit_exact(tmp_path):
+    """Regression fixture from tools/fuzz_campaign.py: a junction at chrA:97 lies in front of the first flank range of the
+    smallest-named chromosome, so main_depth's `continue` (bam2depth.cpp:102) leaves its point depth at 0. getclip and
+    getsv through the CLI against the reference's outputs, closed-form and literal depth accounting."""
+    d, s = "fuzz", "f106"
+    pre = str(tmp_path / s)
+    r = subprocess.run([_cli(), "getclip", "-o", pre, _bam(d, s)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for ext, name in ((".clip.gz", ".clip.txt"), (".clip.fq.gz", ".clip.fq.txt"), (".unmapped_1.fq.gz", ".unmapped_1.fq.txt"),
+                      (".unmapped_2.fq.gz", ".unmapped_2.fq.txt")):
+        assert _zcat(pre + ext) == read_text(os.path.join(GOLDEN, d, s + name)), ext
+    for env in ({}, {"SEEKSV_B200_LITERAL_DEPTH_WALK": "1"}):
+        out = str(tmp_path / "out.sv")
+        r = subprocess.run([_cli(), "getsv", os.path.join(GOLDEN, d, s + ".clip.sam"), _bam(d, s), pre + ".clip.gz", out,
+                            str(tmp_path / "unm")], capture_output=True, text=True, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr
+        assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".sv")), env
+        assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".getsv.stdout")), env
