@@ -274,7 +274,7 @@ def main():
         fa = os.path.join(work, name + ".fa")
         fuzzgen.write_fasta(genome, fa)
         run([bwa, "index", fa], stderr=subprocess.DEVNULL)
-        pipeline(work, fz, bwa, fa, (name,))
+        pipeline(work, fz, bwa, fa, (name,), (name, name))     # somatic against itself: every call has control support
     shutil.rmtree(work)
     print("golden fixtures regenerated")
 

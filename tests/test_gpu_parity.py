@@ -601,3 +601,17 @@ def test_fuzz_seed_106_point_depth_quirk_cli_bit_exact(tmp_path):
         assert r.returncode == 0, r.stderr
         assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".sv")), env
         assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".getsv.stdout")), env
+
+
+@pytest.mark.parametrize("s", ["f11", "f12", "f106"])
+def test_somatic_on_fuzz_fixtures_cli_bit_exact(s, tmp_path):
+    """somatic of a fuzzed sample against itself (every tumour call finds control support): the host string matching and the
+    discordant-pair queries on the 'normal' BAM against the reference's output."""
+    d = "fuzz"
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, s + ".clip.txt")).encode("latin-1"))
+    out = str(tmp_path / "somatic.sv")
+    r = subprocess.run([_cli(), "somatic", _bam(d, s), clip, os.path.join(GOLDEN, d, s + ".sv"), out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".somatic.temp.sv"))

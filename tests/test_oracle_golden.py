@@ -39,7 +39,8 @@ def test_getsv_matches_reference(d, s):
     assert out == read_text(os.path.join(GOLDEN, d, s + ".getsv.stdout"))
 
 
-@pytest.mark.parametrize("d,normal,tumour", [("example", "normal", "cancer"), ("micro", "normal", "tumor")])
+@pytest.mark.parametrize("d,normal,tumour", [("example", "normal", "cancer"), ("micro", "normal", "tumor"),
+                                             ("fuzz", "f11", "f11"), ("fuzz", "f12", "f12"), ("fuzz", "f106", "f106")])
 def test_somatic_matches_reference(d, normal, tumour):
     h, recs = bamio.read_bam(_bam(d, normal))
     got = getsv_oracle.somatic(h, recs, read_text(os.path.join(GOLDEN, d, normal + ".clip.txt")),

@@ -1,6 +1,6 @@
 """Seeded fuzz campaign on the CPU (build container only: needs /root/reference for bwa and oracle/_ref for the reference).
 
-    python tools/fuzz_campaign.py [--seeds 100:140] [--records 1800] [--gpu]
+    python tools/fuzz_campaign.py [--seeds 100:140] [--records 1800] [--options 3] [--gpu]
 
 For every seed: tests/fuzzgen.py writes an awkward BAM, the REAL reference (oracle/_ref/seeksv) runs getclip -> bwa mem ->
 getsv (plain, `-n 0 -D`, `-B`) -> somatic(self), and then
@@ -15,6 +15,7 @@ Prints one line per seed and a summary; exit status 1 if anything differed. Test
 import argparse
 import gzip
 import os
+import random
 import shutil
 import subprocess
 import sys
@@ -47,7 +48,7 @@ def run(cmd, **kw):
     return subprocess.run(cmd, capture_output=True, text=True, **kw)
 
 
-def one_seed(seed, records, work, bwa, gpu):
+def one_seed(seed, records, work, bwa, gpu, n_opts=0):
     bad = []
     bam = os.path.join(work, "f.sort.bam")
     _, _, genome = fuzzgen.write(bam, seed, records)
@@ -126,6 +127,43 @@ def one_seed(seed, records, work, bwa, gpu):
                 r = run([CLI, "somatic", bam, pre + ".clip.gz", pre + ".sv", p + ".somatic"])
                 if r.returncode != 0 or text(p + ".somatic") != ref["somatic"]:
                     bad.append("b200 somatic")
+    # --- random option vectors (Appendix E of SURVEY.md): reference vs oracle (full getsv, getclip) and vs the host layer
+    rng = random.Random(seed * 7919 + 1)
+    for k in range(n_opts):
+        # getclip -t / -q / -s
+        t, q, sl = rng.choice([0.5, 0.8, 0.85, 0.9, 0.95, 1.0]), rng.choice([0, 1, 10, 20, 30, 60]), rng.random() < 0.5
+        po = os.path.join(work, "opt%d" % k)
+        r = run([SEEKSV, "getclip", "-t", str(t), "-q", str(q)] + (["-s"] if sl else []) + ["-o", po, bam])
+        if r.returncode == 0:
+            want = [zcat(po + e) for e in (".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz")]
+            if list(getclip_oracle.getclip(h, recs, limit=t, min_mapq=q, save_low_quality=sl)) != want:
+                bad.append("oracle getclip -t %s -q %d%s" % (t, q, " -s" if sl else ""))
+        # getsv: every numeric option that has an effect
+        o = dict(l=rng.choice([0, 5, 20, 50, 90]), q=rng.choice([0, 1, 20, 30]), b=rng.choice([1, 2, 3, 5]), d=rng.choice([0, 10, 50, 500]),
+                 T=rng.choice([0, 5, 50]), m=rng.choice([0, 30, 60]), i=rng.choice([0, 1, 3]), L=rng.choice([1, 20, 200, 1000]),
+                 e=rng.choice([0, 0, 1, 2]), f=rng.choice([0, 0.05, 0.1, 0.5]))
+        argv = []
+        for name, v in o.items():
+            argv += ["-" + name, str(v)]
+        r = run([SEEKSV, "getsv", *argv, sam, bam, pre + ".clip.gz", po + ".sv", po + ".unm"])
+        if r.returncode == 0:
+            sv, out = getsv_oracle.getsv(h, recs, ref[".clip.gz"], ch, ca, flank=o["l"], min_mapq=o["q"], min_clip_sum=o["b"],
+                                         min_dist=o["d"], max_micro=o["T"], min_seq_len=o["m"], max_indel=o["i"], flank_len=o["L"],
+                                         min_pairs=o["e"], freq=o["f"])
+            if sv != text(po + ".sv") or out != r.stdout:
+                bad.append("oracle getsv " + " ".join(argv))
+        # the host layer with the same options, BAM passes off
+        hargv = [a for a in argv] + ["-n", "0", "-D"]
+        r = run([SEEKSV, "getsv", *hargv, sam, bam, pre + ".clip.gz", po + ".h.sv", po + ".unm"])
+        if r.returncode == 0 and os.path.exists(CLI):
+            r2 = run([CLI, "getsv", *hargv, sam, bam, pre + ".clip.gz", po + ".h2.sv", po + ".unm2"])
+            if r2.returncode != 0 or text(po + ".h2.sv") != text(po + ".h.sv") or r2.stdout != r.stdout:
+                bad.append("host getsv " + " ".join(hargv))
+        if gpu and os.path.exists(CLI):
+            r = run([SEEKSV, "getsv", *argv, sam, bam, pre + ".clip.gz", po + ".sv", po + ".unm"])
+            r2 = run([CLI, "getsv", *argv, sam, bam, pre + ".clip.gz", po + ".g.sv", po + ".unm2"])
+            if r.returncode == 0 and (r2.returncode != 0 or text(po + ".g.sv") != text(po + ".sv") or r2.stdout != r.stdout):
+                bad.append("b200 getsv " + " ".join(argv))
     n_sv = ref["sv"].count("\n")
     return bad, n_sv, len(recs)
 
@@ -135,6 +173,7 @@ def main():
     ap.add_argument("--seeds", default="100:120")
     ap.add_argument("--records", type=int, default=1800)
     ap.add_argument("--gpu", action="store_true")
+    ap.add_argument("--options", type=int, default=0, help="random option vectors per seed (getclip -t/-q/-s, getsv -l..-f)")
     ap.add_argument("--keep", action="store_true", help="keep the work directory of failing seeds")
     a = ap.parse_args()
     lo, hi = (int(x) for x in a.seeds.split(":"))
@@ -149,7 +188,7 @@ def main():
     for seed in range(lo, hi):
         work = os.path.join(top, "s%d" % seed)
         os.makedirs(work)
-        res = one_seed(seed, a.records, work, bwa, a.gpu)
+        res = one_seed(seed, a.records, work, bwa, a.gpu, a.options)
         if isinstance(res, list):
             print("seed %d: SKIP %s" % (seed, res[0]), flush=True)
             shutil.rmtree(work)
