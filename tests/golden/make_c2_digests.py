@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Digests of the REAL reference's outputs on BASELINE.json's C2 workload (build container only: needs oracle/_ref/seeksv).
+
+    python tests/golden/make_c2_digests.py      # ~2 minutes of single-core reference work
+
+C2 = tools/svsim.cpp with the arguments bench.py uses (chr21-sized chromosome, 30x, 150 bp pairs, 500 planted events, seed
+20261017): 9.2 M records, 2.7 GB uncompressed. The reference's outputs are 65 MB, so only their MD5s and sizes are committed
+(tests/golden/c2/digests.json); the GPU test regenerates the same BAM with svsim on the box and compares digests. The realign
+step is tools/minialign.cpp in both arms (deterministic; bwa is not on the GPU box).
+"""
+import gzip
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SEEKSV = os.path.join(ROOT, "oracle", "_ref", "seeksv")
+BIN = os.path.join(ROOT, "seeksv_b200", "bin")
+SVSIM_ARGS = ["--genome", "chr21:46709983", "--cov", "30", "--nsv", "500", "--seed", "20261017"]
+
+
+def digest(data):
+    return {"md5": hashlib.md5(data).hexdigest(), "bytes": len(data)}
+
+
+def main():
+    assert os.path.exists(SEEKSV), "oracle/build_ref.sh first"
+    work = sys.argv[1] if len(sys.argv) > 1 else tempfile.mkdtemp(prefix="c2_")
+    pre = os.path.join(work, "c2")
+    if not os.path.exists(pre + ".bam"):
+        subprocess.run([os.path.join(BIN, "svsim"), "--out", pre] + SVSIM_ARGS, check=True)
+    ref = os.path.join(work, "ref")
+    subprocess.run([SEEKSV, "getclip", "-o", ref, pre + ".bam"], check=True, stderr=subprocess.DEVNULL)
+    out = {"svsim_args": SVSIM_ARGS, "reference": "oracle/_ref/seeksv (v1.2.3 built from the unmodified sources)"}
+    for ext in (".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz"):
+        with gzip.open(ref + ext, "rb") as f:
+            out[ext] = digest(f.read())
+    with open(ref + ".clip.sam", "wb") as o:
+        subprocess.run([os.path.join(BIN, "minialign"), pre + ".fa", ref + ".clip.fq.gz"], check=True, stdout=o)
+    out["clip.sam"] = digest(open(ref + ".clip.sam", "rb").read())
+    for tag, extra in (("getsv", []), ("getsv -n 0 -D", ["-n", "0", "-D"])):
+        r = subprocess.run([SEEKSV, "getsv", *extra, ref + ".clip.sam", pre + ".bam", ref + ".clip.gz", ref + ".sv", ref + ".unm"],
+                           check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        out[tag] = {"sv": digest(open(ref + ".sv", "rb").read()), "stdout": digest(r.stdout)}
+    # somatic of the sample against itself
+    subprocess.run([SEEKSV, "getsv", ref + ".clip.sam", pre + ".bam", ref + ".clip.gz", ref + ".sv", ref + ".unm"], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([SEEKSV, "somatic", pre + ".bam", ref + ".clip.gz", ref + ".sv", ref + ".somatic"], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out["somatic (self)"] = digest(open(ref + ".somatic", "rb").read())
+    with open(os.path.join(HERE, "c2", "digests.json"), "w") as f:
+        json.dump(out, f, indent=1)
+        f.write("\n")
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

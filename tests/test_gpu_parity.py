@@ -615,3 +615,44 @@ def test_somatic_on_fuzz_fixtures_cli_bit_exact(s, tmp_path):
     r = subprocess.run([_cli(), "somatic", _bam(d, s), clip, os.path.join(GOLDEN, d, s + ".sv"), out], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".somatic.temp.sv"))
+
+
+def test_c2_full_size_outputs_equal_the_reference_digests(tmp_path):
+    """BASELINE.json's C2 workload at full size (9.2 M records) through the CLI: MD5 and size of every output of getclip, getsv
+    (with and without the BAM passes) and somatic against the digests of the reference's own outputs on the same BAM
+    (tests/golden/c2/digests.json, made in the build container by tests/golden/make_c2_digests.py - ~2 minutes of single-core
+    reference work that the GPU box does not repeat). svsim is deterministic (any thread count), minialign stands in for bwa in
+    both arms."""
+    import hashlib
+    import json
+    with open(os.path.join(GOLDEN, "c2", "digests.json")) as f:
+        want = json.load(f)
+    svsim = os.path.join(ROOT, "seeksv_b200", "bin", "svsim")
+    mini = os.path.join(ROOT, "seeksv_b200", "bin", "minialign")
+    if not (os.path.exists(svsim) and os.path.exists(mini)):
+        pytest.skip("needs the svsim / minialign tools (python -m seeksv_b200.build)")
+
+    def dig(data):
+        return {"md5": hashlib.md5(data).hexdigest(), "bytes": len(data)}
+
+    pre = str(tmp_path / "c2")
+    subprocess.run([svsim, "--out", pre] + want["svsim_args"], check=True, stderr=subprocess.DEVNULL)
+    out = str(tmp_path / "b200")
+    r = subprocess.run([_cli(), "getclip", "-o", out, pre + ".bam"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for ext in (".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz"):
+        with gzip.open(out + ext, "rb") as f:
+            assert dig(f.read()) == want[ext], ext
+    with open(out + ".clip.sam", "wb") as o:
+        subprocess.run([mini, pre + ".fa", out + ".clip.fq.gz"], check=True, stdout=o)
+    assert dig(open(out + ".clip.sam", "rb").read()) == want["clip.sam"]
+    for tag, extra in (("getsv", []), ("getsv -n 0 -D", ["-n", "0", "-D"])):
+        sv = out + (".n0D.sv" if extra else ".sv")
+        r = subprocess.run([_cli(), "getsv", *extra, out + ".clip.sam", pre + ".bam", out + ".clip.gz", sv, out + ".unm"],
+                           capture_output=True)
+        assert r.returncode == 0, r.stderr
+        assert dig(open(sv, "rb").read()) == want[tag]["sv"], tag
+        assert dig(r.stdout) == want[tag]["stdout"], tag
+    r = subprocess.run([_cli(), "somatic", pre + ".bam", out + ".clip.gz", out + ".sv", out + ".somatic"], capture_output=True)
+    assert r.returncode == 0, r.stderr
+    assert dig(open(out + ".somatic", "rb").read()) == want["somatic (self)"]
