@@ -215,6 +215,10 @@ int svb_write_gz(const char *path, const void *data, uint64_t n, int n_threads);
 /* The same file image made on the device (gzip.cu): text in host memory -> malloc'ed gzip image (svb_free). */
 int svb_gzip_text(svb_ctx *ctx, const void *text, uint64_t n, char **gz, uint64_t *gz_len);
 int svb_read_gz(const char *path, char **data, uint64_t *n);
+/* SAM text -> the uncompressed BAM byte stream svb_bam_from_host takes ("BAM\1" header + packed records; host only, malloc'ed,
+ * svb_free). This is the conversion svb_bam_open / getsv apply to an input whose name does not end in ".bam"; it replaces
+ * samopen(fn, "r") + sam_read1 of the linked libbam (bam_import.o; call sites clip_reads.h:375, getsv.h:445). */
+int svb_sam_to_stream(const char *sam_path, char **stream, uint64_t *nbytes, uint64_t *first_record);
 
 /* ---- whole commands (what the CLI calls; same arguments as the reference's Call* functions,
  *      seeksv.cpp:128-410). They print the reference's progress lines to stderr and return the

@@ -14,6 +14,7 @@ archive (`sam/libbam.a`; only its headers are vendored, so the wire format is ta
 from __future__ import annotations
 
 import gzip
+import re
 import struct
 from dataclasses import dataclass, field
 from typing import List, Optional, Tuple
@@ -90,7 +91,10 @@ def parse_bam_stream(data: bytes) -> Tuple[Header, List[Rec], int]:
         tid, pos, l_qname, mapq, bin_, n_cigar, flag, l_qseq, mtid, mpos, isize = struct.unpack_from(
             "<iiBBHHHiiii", data, o + 4)
         p = o + 36
-        qname = data[p:p + l_qname - 1].decode("latin-1")
+        # bam1_qname is a C string: it ends at the first NUL (normally at l_qname - 1; the records libbam's SAM reader makes
+        # from names of 255+ characters carry no NUL there and the name runs on into the CIGAR words)
+        nul = data.find(b"\0", p, o + 4 + block_size)
+        qname = data[p:nul if nul >= 0 else o + 4 + block_size].decode("latin-1")
         p += l_qname
         cig = struct.unpack_from("<%dI" % n_cigar, data, p) if n_cigar else ()
         cigar = [(c >> 4, c & 15) for c in cig]
@@ -114,70 +118,142 @@ def read_bam(path: str) -> Tuple[Header, List[Rec]]:
 _BASE2NIB = {c: i for i, c in enumerate(NT16)}
 
 
-def parse_sam(path: str) -> Tuple[Header, List[Rec]]:
-    """SAM text -> the same record model (what samopen(fn, "r") yields; used for clip.sam hand-off and
-    for hand-written known-answer inputs)."""
-    names, lengths, recs = [], [], []
+def sam_flag(text: str) -> int:
+    """FLAG column as the linked libbam's sam_read1 takes it (probed with `bamtool sam2bam`): a number in any C base
+    (strtol base 0), else a string of flag letters."""
+    if text[:1].isdigit():
+        m = re.match(r"0[xX][0-9a-fA-F]+|0[0-7]*|[0-9]+", text)
+        t = m.group(0)
+        return int(t, 16) if t[:2] in ("0x", "0X") else int(t, 8) if len(t) > 1 and t[0] == "0" else int(t)
+    f = 0
+    for c in text:
+        k = "pPuUrR12sfd".find(c)
+        if k >= 0:
+            f |= 1 << k
+    return f
+
+
+def _c_int(text: str) -> int:
+    m = re.match(r"\s*[+-]?\d+", text)
+    return int(m.group(0)) if m else 0
+
+
+def _c_float(text: str) -> float:
+    m = re.match(r"\s*[+-]?(\d+\.?\d*([eE][+-]?\d+)?|\.\d+([eE][+-]?\d+)?)", text)
+    return float(m.group(0)) if m else 0.0
+
+
+def sam_line_to_record(line: str, names: List[str]) -> bytes:
+    """One SAM line -> the packed BAM record libbam's sam_read1 builds (bam_import.o of sam/libbam.a; call sites
+    clip_reads.h:375, getsv.h:445), byte for byte - pinned against `bamtool sam2bam` in tests/test_sam_text.py:
+    CIGAR "*" sets the unmapped flag; the bin is computed from pos / end even without a reference; aux integers narrow
+    to the smallest type (c for -127..-1, s, i / C, S, I); l_qname is 8 bits wide, so a name of 255+ characters is cut
+    to (length + 1) & 0xff bytes WITHOUT its NUL."""
+    t = line.split("\t")
+    qname, flag_s, rname, pos, mapq, cigar_s, rnext, pnext, tlen, seq, qual = t[:11]
+    flag = sam_flag(flag_s)
+    tid = names.index(rname) if rname in names and rname != "*" else -1
+    if rnext == "=":
+        mtid = tid
+    else:
+        mtid = names.index(rnext) if rnext in names and rnext != "*" else -1
+    pos0 = _c_int(pos) - 1
+    cigar = []
+    end = pos0
+    if cigar_s != "*":
+        num = 0
+        for ch in cigar_s:
+            if ch.isdigit():
+                num = num * 10 + ord(ch) - 48
+            else:
+                op = CIGAR_OPS.index(ch)
+                cigar.append((num << 4) | op)
+                if op in (0, 2, 3):
+                    end += num
+                num = 0
+    else:
+        flag |= FUNMAP
+    if end == pos0:
+        end = pos0 + 1
+    if seq == "*":
+        l_qseq, seq4, q = 0, b"", b""
+    else:
+        l_qseq = len(seq)
+        nib = [_BASE2NIB.get(c.upper(), 15) for c in seq]
+        if l_qseq & 1:
+            nib.append(0)
+        seq4 = bytes((nib[i] << 4) | nib[i + 1] for i in range(0, len(nib), 2))
+        q = bytes([0xFF] * l_qseq) if qual == "*" else bytes((ord(c) - 33) & 0xFF for c in qual)
+    aux = b""
+    for fld in t[11:]:
+        if len(fld) < 5 or fld[2] != ":" or fld[4] != ":":
+            continue
+        tag, ty, val = fld[:2].encode("latin-1"), fld[3], fld[5:]
+        if ty in "iI":
+            v = _c_int(val)
+            if v < 0:
+                aux += tag + (b"c" + struct.pack("<b", v) if v >= -127 else b"s" + struct.pack("<h", v) if v >= -32767
+                              else b"i" + struct.pack("<I", v & 0xFFFFFFFF))
+            else:
+                aux += tag + (b"C" + struct.pack("<B", v) if v <= 255 else b"S" + struct.pack("<H", v) if v <= 65535
+                              else b"I" + struct.pack("<I", v & 0xFFFFFFFF))
+        elif ty in "ZH":
+            aux += tag + ty.encode() + val.encode("latin-1") + b"\0"
+        elif ty in "AacC":
+            aux += tag + b"A" + val.encode("latin-1")[:1]
+        elif ty == "f":
+            aux += tag + b"f" + struct.pack("<f", _c_float(val))
+        elif ty == "d":
+            aux += tag + b"d" + struct.pack("<d", _c_float(val))
+        elif ty == "B" and val:
+            sub, items = val[0], val.split(",")[1:]
+            aux += tag + b"B" + sub.encode() + struct.pack("<i", len(items))
+            for it in items:
+                if sub == "f":
+                    aux += struct.pack("<f", _c_float(it))
+                else:
+                    v = int(it, 0)
+                    aux += struct.pack({"c": "<B", "C": "<B", "s": "<H", "S": "<H"}.get(sub, "<I"),
+                                       v & {"c": 0xFF, "C": 0xFF, "s": 0xFFFF, "S": 0xFFFF}.get(sub, 0xFFFFFFFF))
+    qn = qname.encode("latin-1")
+    l_qname = (len(qn) + 1) & 0xFF
+    name_bytes = qn + b"\0" if l_qname == len(qn) + 1 else qn[:l_qname]
+    body = struct.pack("<iiBBHHHiiii", tid, pos0, l_qname, _c_int(mapq) & 0xFF, reg2bin(pos0, end), len(cigar), flag & 0xFFFF,
+                       l_qseq, mtid, _c_int(pnext) - 1, _c_int(tlen))
+    body += name_bytes + b"".join(struct.pack("<I", c) for c in cigar) + seq4 + q + aux
+    return struct.pack("<i", len(body)) + body
+
+
+def sam_to_stream(path: str) -> bytes:
+    """SAM text file -> the uncompressed BAM stream samopen(fn, "r") + samwrite of the linked libbam produce."""
     opener = gzip.open if path.endswith(".gz") else open
-    with opener(path, "rt", encoding="latin-1") as f:
-        for line in f:
-            line = line.rstrip("\n")
+    names, lengths, text, recs = [], [], [], []
+    with opener(path, "rt", encoding="latin-1", newline="") as f:
+        for line in f.read().split("\n"):
+            line = line.rstrip("\r")
             if not line:
                 continue
-            if line[0] == "@":
+            if line[0] == "@" and not recs:
+                text.append(line + "\n")
                 if line.startswith("@SQ"):
-                    sn = ln = None
+                    sn, ln = None, 0
                     for fld in line.split("\t")[1:]:
                         if fld.startswith("SN:"):
                             sn = fld[3:]
                         elif fld.startswith("LN:"):
-                            ln = int(fld[3:])
+                            ln = _c_int(fld[3:])
                     names.append(sn)
                     lengths.append(ln)
                 continue
-            t = line.split("\t")
-            qname, flag, rname, pos, mapq, cigar_s, rnext, pnext, tlen, seq, qual = t[:11]
-            flag = int(flag)
-            tid = names.index(rname) if rname != "*" else -1
-            if rnext == "=":
-                mtid = tid
-            elif rnext == "*":
-                mtid = -1
-            else:
-                mtid = names.index(rnext)
-            cigar = []
-            if cigar_s != "*":
-                num = 0
-                for ch in cigar_s:
-                    if ch.isdigit():
-                        num = num * 10 + ord(ch) - 48
-                    else:
-                        cigar.append((num, CIGAR_OPS.index(ch)))
-                        num = 0
-            if seq == "*":
-                l_qseq, seq4, q = 0, b"", b""
-            else:
-                l_qseq = len(seq)
-                nib = [_BASE2NIB.get(c.upper(), 15) for c in seq]
-                if l_qseq & 1:
-                    nib.append(0)
-                seq4 = bytes((nib[i] << 4) | nib[i + 1] for i in range(0, len(nib), 2))
-                q = bytes([0xFF] * l_qseq) if qual == "*" else bytes(ord(c) - 33 for c in qual)
-            aux = b""
-            for fld in t[11:]:
-                tag, ty, val = fld[:2], fld[3], fld[5:]
-                if ty == "i":
-                    v = int(val)
-                    aux += tag.encode() + (b"i" + struct.pack("<i", v))
-                elif ty == "Z":
-                    aux += tag.encode() + b"Z" + val.encode("latin-1") + b"\0"
-                elif ty == "A":
-                    aux += tag.encode() + b"A" + val.encode("latin-1")[:1]
-                elif ty == "f":
-                    aux += tag.encode() + b"f" + struct.pack("<f", float(val))
-            recs.append(Rec(tid, int(pos) - 1, int(mapq), 0, flag, l_qseq, mtid, int(pnext) - 1, int(tlen), qname,
-                            cigar, seq4, q, aux, 0))
-    return Header(names, lengths), recs
+            recs.append(sam_line_to_record(line, names))
+    return header_bytes(Header(names, lengths, "".join(text))) + b"".join(recs)
+
+
+def parse_sam(path: str) -> Tuple[Header, List[Rec]]:
+    """SAM text -> the same record model, through the exact bytes samopen(fn, "r") yields (used for the clip.sam hand-off
+    and for hand-written known-answer inputs)."""
+    h, r, _ = parse_bam_stream(sam_to_stream(path))
+    return h, r
 
 
 def read_alignments(path: str) -> Tuple[Header, List[Rec]]:

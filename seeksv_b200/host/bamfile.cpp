@@ -435,6 +435,18 @@ static void put32(std::vector<uint8_t> &v, uint32_t x)
     v.push_back(x & 0xff), v.push_back((x >> 8) & 0xff), v.push_back((x >> 16) & 0xff), v.push_back(x >> 24);
 }
 
+// FLAG column as the linked libbam's sam_read1 takes it: a number in any C base (strtol base 0), else flag letters
+uint32_t sam_flag(const char *a, const char *b)
+{
+    if (a < b && *a >= '0' && *a <= '9') return (uint32_t)strtol(a, nullptr, 0);
+    uint32_t f = 0;
+    for (; a < b; ++a) {
+        const char *tab = "pPuUrR12sfd", *o = strchr(tab, *a);
+        if (o && *a) f |= 1u << (o - tab);
+    }
+    return f;
+}
+
 bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vector<uint8_t> &out, std::string &err)
 {
     static uint8_t nt16[256];
@@ -511,7 +523,7 @@ bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vect
         }
         auto str = [&](int i) { return std::string(f[i].first, f[i].second); };
         std::string qname = str(0), rname = str(2), rnext = str(6);
-        uint32_t flag = (uint32_t)strtoul(f[1].first, nullptr, 10);
+        uint32_t flag = sam_flag(f[1].first, f[1].second);
         int32_t pos = (int32_t)strtol(f[3].first, nullptr, 10) - 1, mapq = (int32_t)strtol(f[4].first, nullptr, 10);
         int32_t mpos = (int32_t)strtol(f[7].first, nullptr, 10) - 1, isize = (int32_t)strtol(f[8].first, nullptr, 10);
         int32_t tid = -1, mtid = -1;
@@ -543,6 +555,8 @@ bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vect
                 }
             }
         }
+        else
+            flag |= 4;  // libbam's sam_read1 ("mapped sequence without CIGAR"): a record with CIGAR "*" leaves as unmapped
         if (end == pos) end = pos + 1;
         bool noseq = f[9].second - f[9].first == 1 && *f[9].first == '*';
         int32_t l_qseq = noseq ? 0 : (int32_t)(f[9].second - f[9].first);
@@ -552,8 +566,8 @@ bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vect
             if (b - a < 5 || a[2] != ':' || a[4] != ':') continue;
             char ty = a[3];
             const char *v = a + 5;
-            if (ty == 'i') {
-                long x = strtol(v, nullptr, 10);
+            if (ty == 'i' || ty == 'I') {
+                long long x = strtoll(v, nullptr, 10);
                 aux.push_back(a[0]), aux.push_back(a[1]);
                 if (x < 0) {
                     if (x >= -127) aux.push_back('c'), aux.push_back((uint8_t)(int8_t)x);
@@ -564,7 +578,7 @@ bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vect
                     else if (x <= 65535) aux.push_back('S'), aux.push_back(x & 0xff), aux.push_back((x >> 8) & 0xff);
                     else aux.push_back('I'), put32(aux, (uint32_t)x);
                 }
-            } else if (ty == 'A') {
+            } else if (ty == 'A' || ty == 'a' || ty == 'c' || ty == 'C') {
                 aux.push_back(a[0]), aux.push_back(a[1]), aux.push_back('A'), aux.push_back(*v);
             } else if (ty == 'Z' || ty == 'H') {
                 aux.push_back(a[0]), aux.push_back(a[1]), aux.push_back(ty);
@@ -576,21 +590,54 @@ bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vect
                 memcpy(&u, &x, 4);
                 aux.push_back(a[0]), aux.push_back(a[1]), aux.push_back('f');
                 put32(aux, u);
+            } else if (ty == 'd') {
+                double x = strtod(v, nullptr);
+                uint64_t u;
+                memcpy(&u, &x, 8);
+                aux.push_back(a[0]), aux.push_back(a[1]), aux.push_back('d');
+                put32(aux, (uint32_t)u), put32(aux, (uint32_t)(u >> 32));
+            } else if (ty == 'B' && v < b) {  // typed array: XB:B:i,1,2,3
+                char sub = *v;
+                uint32_t n = 0;
+                for (const char *c = v; c < b; ++c) n += *c == ',';
+                aux.push_back(a[0]), aux.push_back(a[1]), aux.push_back('B'), aux.push_back((uint8_t)sub);
+                put32(aux, n);
+                const char *c = v + 1;
+                for (uint32_t k = 0; k < n && c < b; ++k) {
+                    ++c;  // the comma
+                    char *next = nullptr;
+                    if (sub == 'f') {
+                        float x = strtof(c, &next);
+                        uint32_t u;
+                        memcpy(&u, &x, 4);
+                        put32(aux, u);
+                    } else {
+                        long long x = strtoll(c, &next, 0);
+                        if (sub == 'c' || sub == 'C') aux.push_back((uint8_t)x);
+                        else if (sub == 's' || sub == 'S') aux.push_back(x & 0xff), aux.push_back((x >> 8) & 0xff);
+                        else put32(aux, (uint32_t)x);
+                    }
+                    c = next && next > c ? next : b;
+                }
             }
         }
-        uint32_t l_qname = (uint32_t)qname.size() + 1;
+        // libbam keeps l_qname in 8 bits and copies that many bytes: a name of 255+ characters leaves truncated and without its NUL
+        uint32_t l_qname = ((uint32_t)qname.size() + 1) & 0xff;
         uint32_t bs = 32 + l_qname + 4 * (uint32_t)cigar.size() + (l_qseq + 1) / 2 + l_qseq + (uint32_t)aux.size();
         put32(out, bs);
         put32(out, (uint32_t)tid);
         put32(out, (uint32_t)pos);
-        put32(out, (uint32_t)(tid >= 0 ? reg2bin(pos, end) : 4680) << 16 | ((uint32_t)mapq & 0xff) << 8 | (l_qname & 0xff));
+        put32(out, (uint32_t)reg2bin(pos, end) << 16 | ((uint32_t)mapq & 0xff) << 8 | l_qname);  // (pos -1 gives bin 4680)
         put32(out, flag << 16 | ((uint32_t)cigar.size() & 0xffff));
         put32(out, (uint32_t)l_qseq);
         put32(out, (uint32_t)mtid);
         put32(out, (uint32_t)mpos);
         put32(out, (uint32_t)isize);
-        out.insert(out.end(), qname.begin(), qname.end());
-        out.push_back(0);
+        if (l_qname == qname.size() + 1) {
+            out.insert(out.end(), qname.begin(), qname.end());
+            out.push_back(0);
+        } else
+            out.insert(out.end(), qname.begin(), qname.begin() + l_qname);
         for (uint32_t c : cigar) put32(out, c);
         for (int32_t i = 0; i < l_qseq; i += 2) {
             uint8_t hi = nt16[(uint8_t)f[9].first[i]], lo = i + 1 < l_qseq ? nt16[(uint8_t)f[9].first[i + 1]] : 0;

@@ -47,7 +47,11 @@ bool bai_linear_offsets(const std::string &bai_path, std::vector<std::vector<uin
 bool bgzf_voffset_distance(const uint8_t *file, uint64_t n, uint64_t v_a, uint64_t v_b, uint64_t &bytes, std::string &err);
 // `want` uncompressed bytes starting at a virtual offset (host zlib; for peeking at single records)
 bool bgzf_read_at(const uint8_t *file, uint64_t n, uint64_t voff, uint8_t *dst, uint32_t want, std::string &err);
-// SAM text (what samopen(fn, "r") reads) -> "BAM\1" header + packed records
+// FLAG column of a SAM line the way the linked libbam reads it (decimal / hex / octal number, or flag letters "pPuUrR12sfd")
+uint32_t sam_flag(const char *begin, const char *end);
+// SAM text (what samopen(fn, "r") reads) -> "BAM\1" header + packed records, byte for byte what libbam's sam_read1 builds
+// (tests/test_sam_text.py): CIGAR "*" sets the unmapped flag, integers narrow to the smallest aux type, names of 255+
+// characters are cut to (length + 1) & 0xff bytes
 bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vector<uint8_t> &stream, std::string &err);
 // gzip/plain text file -> bytes (igzstream / ifstream of the reference, gzstream.h)
 bool read_text_maybe_gz(const std::string &path, std::string &out, std::string &err);

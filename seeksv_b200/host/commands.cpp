@@ -769,6 +769,21 @@ extern "C" int svb_read_gz(const char *path, char **data, uint64_t *n)
     return 0;
 }
 
+extern "C" int svb_sam_to_stream(const char *sam_path, char **stream, uint64_t *nbytes, uint64_t *first_record)
+{
+    if (!sam_path || !stream || !nbytes || !first_record) return SVB_ERR_ARG;
+    std::vector<uint8_t> file, out;
+    std::string err;
+    if (!read_file(sam_path, file, err)) return SVB_ERR_IO;
+    BamHeader h;
+    if (!sam_to_bam_stream(file, h, out, err)) return SVB_ERR_FORMAT;
+    *stream = (char *)malloc(out.size() + 1);
+    if (!*stream) return SVB_ERR_IO;
+    memcpy(*stream, out.data(), out.size());
+    *nbytes = out.size(), *first_record = h.first_record;
+    return 0;
+}
+
 extern "C" void svb_free(void *p) { free(p); }
 
 extern "C" int svb_plan_getsv(const char *clip_aln, const char *clip_file, int32_t n_ref, const char *const *ref_names,

@@ -1,4 +1,5 @@
 #include "junction.h"
+#include "bamfile.h"
 
 #include <algorithm>
 #include <cmath>
@@ -6,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <list>
 #include <map>
 #include <sstream>
 #include <thread>
@@ -193,7 +195,9 @@ bool parse_bam_alignments(AlignmentSet &set, uint64_t o)
         uint32_t w = rd32(&s[o + 12]), w2 = rd32(&s[o + 16]);
         uint32_t lq = w & 0xff, nc = w2 & 0xffff;
         a.mapq = (w >> 8) & 0xff, a.flag = w2 >> 16;
-        a.qname = std::string_view((const char *)&s[o + 36], strnlen((const char *)&s[o + 36], lq));
+        // bam1_qname is a C string (getsv.h:479 compares it as one): it ends at the first NUL, not at l_qname - the records
+        // libbam's SAM reader builds from names of 255+ characters have no NUL inside l_qname (bounded by the record here)
+        a.qname = std::string_view((const char *)&s[o + 36], strnlen((const char *)&s[o + 36], bs - 32));
         a.cigar_begin = (uint32_t)set.cigar_words.size(), a.cigar_n = nc;
         for (uint32_t j = 0; j < nc; ++j) set.cigar_words.push_back(rd32(&s[o + 36 + lq + 4 * j]));
         set.recs.push_back(a);
@@ -231,6 +235,7 @@ bool parse_sam_alignments(AlignmentSet &set, int n_threads, std::string &err)
     struct Part {
         std::vector<Alignment> recs;
         std::vector<uint32_t> cig;
+        std::list<std::string> names;  // rebuilt names of 255+ characters (node addresses survive the splice below)
         bool bad = false;
     };
     std::vector<Part> part(chunks.size());
@@ -258,7 +263,7 @@ bool parse_sam_alignments(AlignmentSet &set, int n_threads, std::string &err)
                 }
                 Alignment al;
                 al.qname = f[0];
-                al.flag = (uint32_t)strtoul(f[1].data(), nullptr, 10);
+                al.flag = sam_flag(f[1].data(), f[1].data() + f[1].size());
                 al.tid = -1;
                 if (!(f[2].size() == 1 && f[2][0] == '*')) {
                     auto it = name2tid.find(std::string(f[2]));
@@ -282,7 +287,25 @@ bool parse_sam_alignments(AlignmentSet &set, int n_threads, std::string &err)
                         }
                     }
                 }
+                else
+                    al.flag |= 4;  // libbam's sam_read1: CIGAR "*" makes the record unmapped
                 al.cigar_n = (uint32_t)P.cig.size() - al.cigar_begin;
+                if (f[0].size() >= 255) {
+                    // libbam keeps l_qname in 8 bits: the record holds the first (length + 1) & 0xff characters, no NUL, and
+                    // bam1_qname() runs on into the CIGAR words (then sequence, ...) up to the first zero byte. Such a name
+                    // never equals a clipped sequence again, which shifts the lock-step join of getsv.h:467-505 by one line.
+                    std::string name(f[0].substr(0, (f[0].size() + 1) & 0xff));
+                    bool ended = false;
+                    for (uint32_t j = al.cigar_begin; j < P.cig.size() && !ended; ++j)
+                        for (int k = 0; k < 4 && !ended; ++k) {
+                            char c = (char)(P.cig[j] >> (8 * k));
+                            if (c) name.push_back(c);
+                            else ended = true;
+                        }
+                    if (!ended) name.push_back('\x01');  // (packed bases / qualities follow: no letter sequence either)
+                    P.names.push_back(std::move(name));
+                    al.qname = P.names.back();
+                }
                 P.recs.push_back(al);
             }
             q = nl < ce ? nl + 1 : ce;
@@ -295,6 +318,7 @@ bool parse_sam_alignments(AlignmentSet &set, int n_threads, std::string &err)
         }
         uint32_t shift = (uint32_t)set.cigar_words.size();
         set.cigar_words.insert(set.cigar_words.end(), P.cig.begin(), P.cig.end());
+        set.rebuilt_names.splice(set.rebuilt_names.end(), P.names);
         for (Alignment a : P.recs) {
             a.cigar_begin += shift;
             set.recs.push_back(a);
@@ -922,17 +946,19 @@ void write_breakpoints(const JunctionMap &jm, const PosDepth &pos2depth, const R
         }
         unsigned avg[4] = {0, 0, 0, 0};
         auto jr = j2r.find(k);
+        const std::string where = k.up_chr + "\t" + std::to_string(k.up_pos) + "\t" + k.up_strand + "\t" + k.down_chr + "\t" +
+                                  std::to_string(k.down_pos) + "\t" + k.down_strand + "\n";  // getsv.cpp:942
         if (jr != j2r.end()) {
             for (int i = 0; i < 4; ++i) {
                 auto rd = range2depth.find(jr->second.r[i]);
-                if (rd == range2depth.end()) log += "Error depth in the vicinity of junction " + k.up_chr + "\n";
+                if (rd == range2depth.end()) log += "Error depth in the vicinity of junction " + where;
                 else {
                     unsigned span = rd->first.end - rd->first.begin + 1;
                     avg[i] = span ? (unsigned)(rd->second / span) : 0;  // (span 0 would be a division by zero in the reference)
                 }
             }
         } else
-            log += "Error depth in the vicinity of junction " + k.up_chr + "\n";
+            log += "Error depth in the vicinity of junction " + where;
         body += head;
         for (int i = 0; i < 4; ++i) body += std::to_string((int)avg[i]) + "\t";
         body += tail;

@@ -6,6 +6,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <list>
 #include <map>
 #include <string>
 #include <string_view>
@@ -54,6 +55,7 @@ struct AlignmentSet {
     std::vector<uint32_t> cigar_words;
     std::vector<std::string> ref_names;
     std::vector<uint8_t> storage;  // what the qname views point into
+    std::list<std::string> rebuilt_names;  // ... except the names libbam would have cut (SAM names of 255+ characters)
 };
 
 struct ChrRange {  // getsv.h:231-258 - unsigned on purpose (quirk Q11)

@@ -49,7 +49,7 @@ EXPORTS = [
     "svb_clusters_text", "svb_insert_stats", "svb_discordant_support", "svb_window_depth", "svb_plan_getsv", "svb_free",
     "svb_write_gz", "svb_read_gz", "svb_bam_open_refs", "svb_bai_first_offsets", "svb_bam_last_mapped_tid", "svb_clusters_unmapped_records",
     "svb_clusters_gz", "svb_gzip_text", "svb_bam_open_voffsets", "svb_bai_linear_offsets", "svb_bam_peek_record", "svb_voffset_distance",
-    "svb_main",
+    "svb_sam_to_stream", "svb_main",
 ]
 
 
@@ -125,6 +125,7 @@ def load():
     L.svb_bai_first_offsets.restype = C.c_int64
     L.svb_write_gz.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_int]
     L.svb_read_gz.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.svb_sam_to_stream.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.svb_free.argtypes = [vp]
     L.svb_free.restype = None
     _lib = L
@@ -483,6 +484,20 @@ def write_gz(path: str, data: bytes, threads: int = 0) -> None:
     rc = load().svb_write_gz(path.encode(), data, len(data), threads)
     if rc != 0:
         raise SvbError("svb_write_gz(%s) = %d" % (path, rc))
+
+
+def sam_to_stream(path: str):
+    """SAM text file -> (uncompressed BAM byte stream, offset of the first record): the host-side conversion behind Bam.open / getsv
+    for inputs that are not .bam (svb_sam_to_stream)"""
+    L = load()
+    p, n, first = C.c_void_p(), C.c_uint64(), C.c_uint64()
+    rc = L.svb_sam_to_stream(path.encode(), C.byref(p), C.byref(n), C.byref(first))
+    if rc != 0:
+        raise SvbError("svb_sam_to_stream(%s) = %d" % (path, rc))
+    try:
+        return C.string_at(p, n.value), first.value
+    finally:
+        L.svb_free(p)
 
 
 def read_gz(path: str) -> bytes:

@@ -656,3 +656,26 @@ def test_c2_full_size_outputs_equal_the_reference_digests(tmp_path):
     r = subprocess.run([_cli(), "somatic", pre + ".bam", out + ".clip.gz", out + ".sv", out + ".somatic"], capture_output=True)
     assert r.returncode == 0, r.stderr
     assert dig(open(out + ".somatic", "rb").read()) == want["somatic (self)"]
+
+
+def test_long_clips_cli_bit_exact(tmp_path):
+    """tests/golden/long: clipped sequences of 254 / 255 / 256 / 300 / 600 bases. getclip writes them as FASTQ read names, the
+    realigner's SAM carries them as QNAME, and libbam's 8-bit l_qname makes every name of 255+ characters unmatchable, which
+    shifts the lock-step join (getsv.h:467-505) by one line - getclip, getsv and somatic against the reference's outputs."""
+    d, s = "long", "lq"
+    pre = str(tmp_path / s)
+    r = subprocess.run([_cli(), "getclip", "-o", pre, _bam(d, s)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for ext, name in ((".clip.gz", ".clip.txt"), (".clip.fq.gz", ".clip.fq.txt"), (".unmapped_1.fq.gz", ".unmapped_1.fq.txt"),
+                      (".unmapped_2.fq.gz", ".unmapped_2.fq.txt")):
+        assert _zcat(pre + ext) == read_text(os.path.join(GOLDEN, d, s + name)), ext
+    out = str(tmp_path / "out.sv")
+    r = subprocess.run([_cli(), "getsv", os.path.join(GOLDEN, d, s + ".clip.sam"), _bam(d, s), pre + ".clip.gz", out, str(tmp_path / "unm")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".sv"))
+    assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".getsv.stdout"))
+    som = str(tmp_path / "somatic.sv")
+    r = subprocess.run([_cli(), "somatic", _bam(d, s), pre + ".clip.gz", os.path.join(GOLDEN, d, s + ".sv"), som], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert read_text(som) == read_text(os.path.join(GOLDEN, d, s + ".somatic.temp.sv"))
