@@ -177,3 +177,23 @@ def test_getsv_connected_reads_host_only_matches_reference(lib, d, s, tmp_path):
         assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + tag + ".sv")), tag
     r = _cli(["getsv", "-F", str(tmp_path / "missing.sam"), "-n", "0", "-D"] + tail + [str(tmp_path / "x.sv"), str(tmp_path / "unm")])
     assert r.returncode == 1 and "fail to open" in r.stderr
+
+
+@pytest.mark.parametrize("d,s", [("example", "cancer"), ("micro", "tumor"), ("fuzz", "f11"), ("long", "lq")])
+def test_getsv_reads_the_realigned_clips_as_bam_too(lib, d, s, tmp_path):
+    """The reference's usual hand-off is `samtools view -Sb clip.sam > clip.bam` (README.md:30-31): a file name ending in .bam is
+    read as BGZF BAM (getsv.h:437-441). Same host-only run as above with the alignments converted to BAM (the bytes libbam's own
+    SAM reader produces, pinned in tests/test_sam_text.py)."""
+    import gzip
+    from oracle import bamio
+    clip_bam = str(tmp_path / "clip.bam")
+    with open(clip_bam, "wb") as f:
+        f.write(bamio.bgzf_compress(bamio.sam_to_stream(os.path.join(GOLDEN, d, s + ".clip.sam"))))
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, s + ".clip.txt")).encode("latin-1"))
+    out = str(tmp_path / "out.sv")
+    r = _cli(["getsv", "-n", "0", "-D", clip_bam, os.path.join(GOLDEN, d, s + ".sort.bam"), clip, out, str(tmp_path / "unm")])
+    assert r.returncode == 0, r.stderr
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".n0D.sv"))
+    assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".n0D.stdout"))
