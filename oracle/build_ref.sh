@@ -19,9 +19,12 @@ if [ ! -d "$REF/seeksv" ]; then
   exit 0
 fi
 mkdir -p "$OUT"
-if [ -x "$OUT/seeksv" ] && [ "$OUT/seeksv" -nt "$HERE/build_ref.sh" ] && [ -x "$OUT/bamtool" ] && [ "$OUT/bamtool" -nt "$HERE/bamtool.c" ]; then
+if [ -x "$OUT/seeksv" ] && [ "$OUT/seeksv" -nt "$HERE/build_ref.sh" ] && [ -x "$OUT/bamtool" ] && [ "$OUT/bamtool" -nt "$HERE/bamtool.c" ] \
+   && [ -x "$OUT/svcompare" ] && [ "$OUT/svcompare" -nt "$HERE/build_ref.sh" ]; then
   exit 0
 fi
+# the stand-alone evaluator (one source file + junction.h; its Makefile is `g++ svcompare.cpp -o svcompare`)
+(cd "$REF/svcompare" && g++ -O2 -w svcompare.cpp -o "$OUT/svcompare")
 T=$(mktemp -d)
 trap 'rm -rf "$T"' EXIT
 mkdir "$T/seeksv"
@@ -46,4 +49,4 @@ g++ -O2 -w -no-pie bam2depth.cpp cluster.cpp gzstream.C seeksv.cpp clip_reads.cp
 # helper linked against the same libbam: sam->bam conversion and .bai building (the bundled samtools
 # binary needs libncurses.so.5 and does not run in this image)
 g++ -O2 -w -no-pie -I"$REF/sam" "$HERE/bamtool.c" -x none -o "$OUT/bamtool" -L"$REF/sam" -lbam -lz -lpthread -lm
-echo "[build_ref] built $OUT/seeksv and $OUT/bamtool" >&2
+echo "[build_ref] built $OUT/seeksv, $OUT/bamtool and $OUT/svcompare" >&2

@@ -72,9 +72,10 @@ def build(verbose=False):
 
 
 def build_tools():
-    """The test/bench helpers (workload simulator, stand-in aligner for the external bwa step): plain host C++."""
+    """The test/bench helpers (workload simulator, stand-in aligner for the external bwa step) and the stand-alone call
+    evaluator svcompare: plain host C++."""
     tools = os.path.join(HERE, "..", "tools")
-    for tool in ("svsim", "minialign"):
+    for tool in ("svsim", "minialign", "svcompare"):
         out = os.path.join(os.path.dirname(CLI), tool)
         src = os.path.join(tools, tool + ".cpp")
         if _stale(out, [src]):
