@@ -385,6 +385,12 @@ def main():
                         "peak_source": "measured" if peaks else "fallback",
                         "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
                         "kernels_ms_per_step": {k: round(x["ms"] / args.steps, 4) for k, x in sorted(kern.items())}}
+            # the whole step against the same roofline: getclip and getsv each stream every record once
+            step_s = ms_dev / args.steps * 1e-3
+            step_gbs = 2.0 * rec_bytes / step_s / 1e9 if step_s > 0 else 0.0
+            roofline["step"] = {"algorithmic_bytes": 2.0 * rec_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
+                                "kernel_ms": round(sum(x["ms"] for x in kern.values()) / args.steps, 4),
+                                "note": "per GPU (rank 0): 2 x record bytes / device time of one getclip + getsv step, results copied to host memory"}
         line = {
             "metric": "BAM records/sec getclip+getsv", "value": value, "unit": "records/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -679,3 +679,21 @@ def test_long_clips_cli_bit_exact(tmp_path):
     r = subprocess.run([_cli(), "somatic", _bam(d, s), pre + ".clip.gz", os.path.join(GOLDEN, d, s + ".sv"), som], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert read_text(som) == read_text(os.path.join(GOLDEN, d, s + ".somatic.temp.sv"))
+
+
+@pytest.mark.parametrize("d,s", [("micro", "tumor"), ("example", "cancer")])
+def test_getclip_reads_sam_text_input(d, s, tmp_path):
+    """getclip opens any file whose name does not end in .bam as SAM text (clip_reads.h:367-375). The SAM is libbam's own rendering of
+    the fixture BAM (`bamtool bam2sam`); the host converts it back (byte-identical stream, tests/test_sam_text.py) and the device
+    passes must give the fixture's outputs."""
+    bamtool = os.path.join(ROOT, "oracle", "_ref", "bamtool")
+    if not os.path.exists(bamtool):
+        pytest.skip("needs oracle/_ref/bamtool")
+    sam = str(tmp_path / (s + ".sam"))
+    subprocess.run([bamtool, "bam2sam", _bam(d, s), sam], check=True, capture_output=True)
+    pre = str(tmp_path / s)
+    r = subprocess.run([_cli(), "getclip", "-o", pre, sam], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for ext, name in ((".clip.gz", ".clip.txt"), (".clip.fq.gz", ".clip.fq.txt"), (".unmapped_1.fq.gz", ".unmapped_1.fq.txt"),
+                      (".unmapped_2.fq.gz", ".unmapped_2.fq.txt")):
+        assert _zcat(pre + ext) == read_text(os.path.join(GOLDEN, d, s + name)), ext
