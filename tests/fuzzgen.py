@@ -58,22 +58,35 @@ def _aux(rng, xc=None):
     return out
 
 
-def generate(seed, n_records=2500):
+def generate(seed, n_records=2500, edge=False):
+    """edge=True (tools/fuzz_campaign.py --edge; the committed fixtures use edge=False and its random stream is untouched):
+    breakpoints and the places the clipped parts come from crowd at the first and last 250 bases of every contig (window clamps,
+    unsigned flank ranges, the first keys of the range maps), and one clipped part in ten is 320 bases long (read names of
+    255+ characters in the realigner's SAM)."""
     rng = random.Random(seed)
     genome = ["".join(rng.choice("ACGT") for _ in range(ln)) for _, ln in CONTIGS]
     foreign = {}   # breakpoint -> clipped-away sequence shared by the reads of that breakpoint
 
     def far_segment():   # 60 bases of the genome elsewhere (either strand), so that the realigner can place the clipped parts
         t = rng.randrange(len(CONTIGS))
-        q = rng.randrange(0, CONTIGS[t][1] - 60)
-        seg = genome[t][q:q + 60]
+        n = 60
+        if edge:
+            n = 320 if rng.random() < 0.1 else 60
+            q = rng.choice([rng.randrange(0, 200), rng.randrange(CONTIGS[t][1] - n - 200, CONTIGS[t][1] - n), rng.randrange(0, CONTIGS[t][1] - n)])
+        else:
+            q = rng.randrange(0, CONTIGS[t][1] - 60)
+        seg = genome[t][q:q + n]
         if rng.random() < 0.5:
             seg = seg[::-1].translate(str.maketrans("ACGT", "TGCA"))
         return seg
     recs = []
     for tid, (_, ln) in enumerate(CONTIGS):
         n_here = n_records * ln // sum(l for _, l in CONTIGS)
-        breakpoints = sorted(rng.randrange(200, ln - 200) for _ in range(max(3, n_here // 40)))
+        if edge:
+            breakpoints = sorted(rng.choice([rng.randrange(1, 250), rng.randrange(ln - 250, ln - 1), rng.randrange(200, ln - 200)])
+                                 for _ in range(max(3, n_here // 40)))
+        else:
+            breakpoints = sorted(rng.randrange(200, ln - 200) for _ in range(max(3, n_here // 40)))
         for i in range(n_here):
             long_read = rng.random() < 0.01
             aligned = rng.randrange(8000, 40000) if long_read else rng.randrange(30, 151)
@@ -129,14 +142,14 @@ def generate(seed, n_records=2500):
                 if key not in foreign:
                     foreign[key] = far_segment()
                 f = foreign[key]
-                k = rng.randrange(1, 61)
-                lclip = f[60 - k:]
+                k = rng.randrange(1, len(f) + 1)
+                lclip = f[len(f) - k:]
             if side in "RB":
                 key = (tid, pos0 + aligned, "R")
                 if key not in foreign:
                     foreign[key] = far_segment()
                 f = foreign[key]
-                k = rng.randrange(1, 61)
+                k = rng.randrange(1, len(f) + 1)
                 rclip = f[:k]
             if rng.random() < 0.04:
                 hl = rng.randrange(1, 50)
@@ -202,8 +215,8 @@ def generate(seed, n_records=2500):
     return header, recs, genome
 
 
-def write(path, seed, n_records=2500):
-    h, recs, genome = generate(seed, n_records)
+def write(path, seed, n_records=2500, edge=False):
+    h, recs, genome = generate(seed, n_records, edge)
     bamio.write_bam(path, h, recs)
     return h, recs, genome
 

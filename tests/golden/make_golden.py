@@ -101,6 +101,7 @@ def build_kat(kat):
 
 
 FUZZ_SEEDS, FUZZ_RECORDS = (11, 12, 106), 1800   # 106: found by tools/fuzz_campaign.py (point depth skipped by bam2depth.cpp:102)
+FUZZ_EDGE_SEEDS = (3,)   # fuzzgen's edge mode: breakpoints at the contig ends, clipped parts of up to 320 bases
 CONNECTED = ("tumor", "f11")          # samples that also get `getsv -F <connected reads>` goldens
 SEEDED = ("tumor", "f11", "cancer")   # samples that also get `getsv -B <their own output>` goldens
 
@@ -288,9 +289,9 @@ def main():
     import fuzzgen
     fz = os.path.join(HERE, "fuzz")
     os.makedirs(fz, exist_ok=True)
-    for seed in FUZZ_SEEDS:
-        name = "f%d" % seed
-        _, _, genome = fuzzgen.write(os.path.join(fz, name + ".sort.bam"), seed, FUZZ_RECORDS)
+    for seed, edge in [(x, False) for x in FUZZ_SEEDS] + [(x, True) for x in FUZZ_EDGE_SEEDS]:
+        name = ("e%d" if edge else "f%d") % seed
+        _, _, genome = fuzzgen.write(os.path.join(fz, name + ".sort.bam"), seed, FUZZ_RECORDS, edge)
         run([BAMTOOL, "index", os.path.join(fz, name + ".sort.bam")])
         fa = os.path.join(work, name + ".fa")
         fuzzgen.write_fasta(genome, fa)

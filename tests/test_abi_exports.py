@@ -74,7 +74,7 @@ def test_cli_argument_surface(lib):
 
 
 @pytest.mark.parametrize("d,s", [("example", "cancer"), ("example", "normal"), ("micro", "tumor"), ("micro", "normal"),
-                                 ("fuzz", "f11"), ("fuzz", "f12"), ("fuzz", "f106"), ("long", "lq")])
+                                 ("fuzz", "f11"), ("fuzz", "f12"), ("fuzz", "f106"), ("fuzz", "e3"), ("long", "lq")])
 def test_getsv_host_only_mode_matches_reference(lib, d, s, tmp_path):
     """`getsv -n 0 -D` needs no BAM pass (no insert size, no pairs, no depth): join + merge + filters + formatting of the
     host layer against the reference binary's output - runs without a GPU."""

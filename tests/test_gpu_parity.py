@@ -583,11 +583,14 @@ def test_c2_scale_properties(tmp_path):
     ctx.close()
 
 
-def test_fuzz_seed_106_point_depth_quirk_cli_bit_exact(tmp_path):
-    """Regression fixture from tools/fuzz_campaign.py: a junction at chrA:97 lies in front of the first flank range of the
-    smallest-named chromosome, so main_depth's `continue` (bam2depth.cpp:102) leaves its point depth at 0. getclip and
-    getsv through the CLI against the reference's outputs, closed-form and literal depth accounting."""
-    d, s = "fuzz", "f106"
+@pytest.mark.parametrize("s", ["f106", "e3"])
+def test_campaign_fixtures_cli_bit_exact(s, tmp_path):
+    """Fixtures from tools/fuzz_campaign.py. f106: a junction at chrA:97 lies in front of the first flank range of the
+    smallest-named chromosome, so main_depth's `continue` (bam2depth.cpp:102) leaves its point depth at 0. e3: fuzzgen's edge
+    mode - breakpoints and realigned clips inside the first and last 250 bases of every contig (window clamps of the
+    discordant-pair and depth passes, wrapped flank ranges) and clipped parts of up to 320 bases. getclip and getsv through the
+    CLI against the reference's outputs, closed-form and literal depth accounting."""
+    d = "fuzz"
     pre = str(tmp_path / s)
     r = subprocess.run([_cli(), "getclip", "-o", pre, _bam(d, s)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -603,7 +606,7 @@ def test_fuzz_seed_106_point_depth_quirk_cli_bit_exact(tmp_path):
         assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".getsv.stdout")), env
 
 
-@pytest.mark.parametrize("s", ["f11", "f12", "f106"])
+@pytest.mark.parametrize("s", ["f11", "f12", "f106", "e3"])
 def test_somatic_on_fuzz_fixtures_cli_bit_exact(s, tmp_path):
     """somatic of a fuzzed sample against itself (every tumour call finds control support): the host string matching and the
     discordant-pair queries on the 'normal' BAM against the reference's output."""

@@ -9,7 +9,7 @@ from conftest import GOLDEN, ROOT, read_text
 from oracle import bamio, getclip_oracle, getsv_oracle
 
 GETSV_CASES = [("example", "cancer"), ("example", "normal"), ("micro", "tumor"), ("micro", "normal"),
-               ("fuzz", "f11"), ("fuzz", "f12"), ("fuzz", "f106"), ("long", "lq")]   # fuzz: tests/fuzzgen.py through the reference binary
+               ("fuzz", "f11"), ("fuzz", "f12"), ("fuzz", "f106"), ("fuzz", "e3"), ("long", "lq")]   # fuzz: tests/fuzzgen.py through the reference binary
 # (make_golden.py); f106 was found by tools/fuzz_campaign.py: a junction position in front of the first flank range of the
 # smallest-named chromosome keeps point depth 0 (the `continue` at bam2depth.cpp:102 skips the store at :123-124);
 # long/lq: clipped sequences of 254-600 bases as clip.sam read names (libbam's 8-bit l_qname shifts the join, make_golden.py)
@@ -42,7 +42,7 @@ def test_getsv_matches_reference(d, s):
 
 @pytest.mark.parametrize("d,normal,tumour", [("example", "normal", "cancer"), ("micro", "normal", "tumor"),
                                              ("fuzz", "f11", "f11"), ("fuzz", "f12", "f12"), ("fuzz", "f106", "f106"),
-                                             ("long", "lq", "lq")])
+                                             ("fuzz", "e3", "e3"), ("long", "lq", "lq")])
 def test_somatic_matches_reference(d, normal, tumour):
     h, recs = bamio.read_bam(_bam(d, normal))
     got = getsv_oracle.somatic(h, recs, read_text(os.path.join(GOLDEN, d, normal + ".clip.txt")),

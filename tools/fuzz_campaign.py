@@ -48,10 +48,10 @@ def run(cmd, **kw):
     return subprocess.run(cmd, capture_output=True, text=True, **kw)
 
 
-def one_seed(seed, records, work, bwa, gpu, n_opts=0):
+def one_seed(seed, records, work, bwa, gpu, n_opts=0, edge=False):
     bad = []
     bam = os.path.join(work, "f.sort.bam")
-    _, _, genome = fuzzgen.write(bam, seed, records)
+    _, _, genome = fuzzgen.write(bam, seed, records, edge)
     subprocess.run([BAMTOOL, "index", bam], check=True)
     fa = os.path.join(work, "f.fa")
     fuzzgen.write_fasta(genome, fa)
@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--records", type=int, default=1800)
     ap.add_argument("--gpu", action="store_true")
     ap.add_argument("--options", type=int, default=0, help="random option vectors per seed (getclip -t/-q/-s, getsv -l..-f)")
+    ap.add_argument("--edge", action="store_true", help="fuzzgen edge mode: breakpoints at the contig ends, clipped parts of 320 bases")
     ap.add_argument("--keep", action="store_true", help="keep the work directory of failing seeds")
     a = ap.parse_args()
     lo, hi = (int(x) for x in a.seeds.split(":"))
@@ -188,7 +189,7 @@ def main():
     for seed in range(lo, hi):
         work = os.path.join(top, "s%d" % seed)
         os.makedirs(work)
-        res = one_seed(seed, a.records, work, bwa, a.gpu, a.options)
+        res = one_seed(seed, a.records, work, bwa, a.gpu, a.options, a.edge)
         if isinstance(res, list):
             print("seed %d: SKIP %s" % (seed, res[0]), flush=True)
             shutil.rmtree(work)
