@@ -14,7 +14,7 @@ from conftest import GOLDEN, read_text
 from oracle import bamio, getclip_oracle
 from seeksv_b200 import sharding
 
-CASES = [("fuzz", "f11"), ("fuzz", "f12"), ("micro", "tumor"), ("example", "cancer"), ("example", "normal")]
+CASES = [("fuzz", "f11"), ("fuzz", "f12"), ("micro", "tumor"), ("example", "cancer"), ("example", "normal"), ("fuzz", "f106"), ("fuzz", "e3")]
 
 
 def records_with_voffsets(path):
