@@ -526,7 +526,19 @@ def test_getsv_connected_reads_cli_bit_exact(d, s, tmp_path):
     assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".F.sv"))
 
 
-def test_c2_scale_properties(tmp_path):
+@pytest.fixture(scope="module")
+def c2_prefix(tmp_path_factory):
+    """BASELINE.json's C2 workload, generated once per test run: <prefix>.bam / .bam.bai / .fa / .truth.tsv"""
+    svsim = os.path.join(ROOT, "seeksv_b200", "bin", "svsim")
+    if not os.path.exists(svsim):
+        pytest.skip("needs the svsim tool (python -m seeksv_b200.build)")
+    pre = str(tmp_path_factory.mktemp("c2") / "c2")
+    subprocess.run([svsim, "--out", pre, "--genome", "chr21:46709983", "--cov", "30", "--nsv", "500", "--seed", "20261017"], check=True,
+                   stderr=subprocess.DEVNULL)
+    return pre
+
+
+def test_c2_scale_properties(c2_prefix):
     """BASELINE.json's C2 size (chr21-sized chromosome, 30x, ~9.2 M records, 2.7 GB uncompressed), where the Python oracle is out of
     reach: size-independent properties instead - determinism (two runs, identical bytes), shard invariance (8 coordinate-range shards
     and the whole file give the same four outputs), structure of the outputs (positions ascending per chromosome and side, both mate
@@ -534,11 +546,7 @@ def test_c2_scale_properties(tmp_path):
     import hashlib
     import seeksv_b200
     from seeksv_b200 import sharding
-    svsim = os.path.join(ROOT, "seeksv_b200", "bin", "svsim")
-    pre = str(tmp_path / "c2")
-    subprocess.run([svsim, "--out", pre, "--genome", "chr21:46709983", "--cov", "30", "--nsv", "500", "--seed", "20261017"], check=True,
-                   stderr=subprocess.DEVNULL)
-    bam = pre + ".bam"
+    bam = c2_prefix + ".bam"
     ctx = seeksv_b200.Context(0)
     whole = seeksv_b200.Bam.open(ctx, bam)
     n_rec = whole.n_records
@@ -620,7 +628,7 @@ def test_somatic_on_fuzz_fixtures_cli_bit_exact(s, tmp_path):
     assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".somatic.temp.sv"))
 
 
-def test_c2_full_size_outputs_equal_the_reference_digests(tmp_path):
+def test_c2_full_size_outputs_equal_the_reference_digests(c2_prefix, tmp_path):
     """BASELINE.json's C2 workload at full size (9.2 M records) through the CLI: MD5 and size of every output of getclip, getsv
     (with and without the BAM passes) and somatic against the digests of the reference's own outputs on the same BAM
     (tests/golden/c2/digests.json, made in the build container by tests/golden/make_c2_digests.py - ~2 minutes of single-core
@@ -630,16 +638,15 @@ def test_c2_full_size_outputs_equal_the_reference_digests(tmp_path):
     import json
     with open(os.path.join(GOLDEN, "c2", "digests.json")) as f:
         want = json.load(f)
-    svsim = os.path.join(ROOT, "seeksv_b200", "bin", "svsim")
     mini = os.path.join(ROOT, "seeksv_b200", "bin", "minialign")
-    if not (os.path.exists(svsim) and os.path.exists(mini)):
-        pytest.skip("needs the svsim / minialign tools (python -m seeksv_b200.build)")
+    if not os.path.exists(mini):
+        pytest.skip("needs the minialign tool (python -m seeksv_b200.build)")
+    assert want["svsim_args"] == ["--genome", "chr21:46709983", "--cov", "30", "--nsv", "500", "--seed", "20261017"]   # = c2_prefix
 
     def dig(data):
         return {"md5": hashlib.md5(data).hexdigest(), "bytes": len(data)}
 
-    pre = str(tmp_path / "c2")
-    subprocess.run([svsim, "--out", pre] + want["svsim_args"], check=True, stderr=subprocess.DEVNULL)
+    pre = c2_prefix
     out = str(tmp_path / "b200")
     r = subprocess.run([_cli(), "getclip", "-o", out, pre + ".bam"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
