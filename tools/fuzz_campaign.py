@@ -24,6 +24,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import fuzzgen  # noqa: E402
 from oracle import bamio, getclip_oracle, getsv_oracle  # noqa: E402
 
@@ -48,7 +49,7 @@ def run(cmd, **kw):
     return subprocess.run(cmd, capture_output=True, text=True, **kw)
 
 
-def one_seed(seed, records, work, bwa, gpu, n_opts=0, edge=False):
+def one_seed(seed, records, work, bwa, gpu, n_opts=0, edge=False, connect_n=0):
     bad = []
     bam = os.path.join(work, "f.sort.bam")
     _, _, genome = fuzzgen.write(bam, seed, records, edge)
@@ -127,6 +128,30 @@ def one_seed(seed, records, work, bwa, gpu, n_opts=0, edge=False):
                 r = run([CLI, "somatic", bam, pre + ".clip.gz", pre + ".sv", p + ".somatic"])
                 if r.returncode != 0 or text(p + ".somatic") != ref["somatic"]:
                     bad.append("b200 somatic")
+    # --- the optional junction sources: -F <connected read-through reads> (FindJunction, process_bwasw.cpp:5-227), -w, -B
+    if connect_n:
+        import make_golden
+        connect = os.path.join(work, "connect.sam")
+        make_golden.build_connect_sam(bam, connect, seed=seed, n_reads=connect_n)
+        cset = bamio.read_alignments(connect)
+        w = random.Random(seed).choice([1, 1, 30, 60])
+        for tag, argv, kw in (("-F", ["-F", connect, "-w", str(w), "-n", "0", "-D"], dict(connect=cset, connect_min_mapq=w, pairs_used=0, output_depth=False)),
+                              ("-F full", ["-F", connect], dict(connect=cset)),
+                              ("-F -B", ["-F", connect, "-B", pre + ".sv", "-n", "0", "-D"],
+                               dict(connect=cset, seed_text=ref["sv"], pairs_used=0, output_depth=False))):
+            out_sv = os.path.join(work, "cF.sv")
+            r = run([SEEKSV, "getsv", *argv, sam, bam, pre + ".clip.gz", out_sv, pre + ".unm"])
+            if r.returncode != 0:
+                continue
+            want_sv, want_out = text(out_sv), r.stdout
+            sv, out = getsv_oracle.getsv(h, recs, ref[".clip.gz"], ch, ca, **kw)
+            if sv != want_sv or out != want_out:
+                bad.append("oracle getsv " + tag)
+            if os.path.exists(CLI) and (gpu or "-D" in argv):
+                r2 = run([CLI, "getsv", *argv, sam, bam, pre + ".clip.gz", os.path.join(work, "cF2.sv"), os.path.join(work, "cF2.unm")])
+                if r2.returncode != 0 or text(os.path.join(work, "cF2.sv")) != want_sv or r2.stdout != want_out:
+                    bad.append(("b200 getsv " if "-D" not in argv else "host getsv ") + tag)
+
     # --- random option vectors (Appendix E of SURVEY.md): reference vs oracle (full getsv, getclip) and vs the host layer
     rng = random.Random(seed * 7919 + 1)
     for k in range(n_opts):
@@ -174,6 +199,7 @@ def main():
     ap.add_argument("--records", type=int, default=1800)
     ap.add_argument("--gpu", action="store_true")
     ap.add_argument("--options", type=int, default=0, help="random option vectors per seed (getclip -t/-q/-s, getsv -l..-f)")
+    ap.add_argument("--connect", type=int, default=0, help="also run getsv -F / -w / -B with this many connected read-through reads")
     ap.add_argument("--edge", action="store_true", help="fuzzgen edge mode: breakpoints at the contig ends, clipped parts of 320 bases")
     ap.add_argument("--keep", action="store_true", help="keep the work directory of failing seeds")
     a = ap.parse_args()
@@ -189,7 +215,7 @@ def main():
     for seed in range(lo, hi):
         work = os.path.join(top, "s%d" % seed)
         os.makedirs(work)
-        res = one_seed(seed, a.records, work, bwa, a.gpu, a.options, a.edge)
+        res = one_seed(seed, a.records, work, bwa, a.gpu, a.options, a.edge, a.connect)
         if isinstance(res, list):
             print("seed %d: SKIP %s" % (seed, res[0]), flush=True)
             shutil.rmtree(work)
