@@ -53,7 +53,7 @@ def _aux(rng, xc=None):
             n = rng.randrange(0, 6)
             out += tag + b"B" + sub.encode() + struct.pack("<i", n) + bytes(rng.randrange(256) for _ in range(n * {"c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4}[sub]))
     if xc is not None:
-        kind = rng.choice("cCsSiI" if xc < 128 else "sSiI")
+        kind = rng.choice("cCsSiI" if xc < 128 else "sSiI" if xc < 32768 else "SiI")
         out += b"XC" + kind.encode() + struct.pack({"c": "<b", "C": "<B", "s": "<h", "S": "<H", "i": "<i", "I": "<I"}[kind], xc)
     return out
 
