@@ -9,6 +9,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee gpurun_out/gpu_tests.log
 # reference vs oracle vs CUDA path on fresh fuzz seeds (oracle/_ref travels with the snapshot; bwa does not: minialign)
 timeout 600 python tools/fuzz_campaign.py --gpu --seeds 1000:1040 --options 2 2>&1 | grep -v ": ok" | tee gpurun_out/fuzz_gpu.log
+timeout 400 python tools/fuzz_campaign.py --gpu --edge --seeds 1040:1070 --connect 160 2>&1 | grep -v ": ok" | tee -a gpurun_out/fuzz_gpu.log
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 tail -c 3000 gpurun_out/bench_n1.json
 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json 2>/dev/null
