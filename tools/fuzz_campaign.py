@@ -200,10 +200,13 @@ def main():
     ap.add_argument("--gpu", action="store_true")
     ap.add_argument("--options", type=int, default=0, help="random option vectors per seed (getclip -t/-q/-s, getsv -l..-f)")
     ap.add_argument("--connect", type=int, default=0, help="also run getsv -F / -w / -B with this many connected read-through reads")
+    ap.add_argument("--contigs", default="", help="name:length,... instead of fuzzgen's chrB / chrA / virus (map orders by NAME matter)")
     ap.add_argument("--edge", action="store_true", help="fuzzgen edge mode: breakpoints at the contig ends, clipped parts of 320 bases")
     ap.add_argument("--keep", action="store_true", help="keep the work directory of failing seeds")
     a = ap.parse_args()
     lo, hi = (int(x) for x in a.seeds.split(":"))
+    if a.contigs:
+        fuzzgen.CONTIGS = [(c.split(":")[0], int(c.split(":")[1])) for c in a.contigs.split(",")]
     assert os.path.exists(SEEKSV) and os.path.exists(BAMTOOL), "oracle/build_ref.sh first"
     top = tempfile.mkdtemp(prefix="fuzzcamp_")
     bwa = None
