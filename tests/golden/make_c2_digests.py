@@ -21,6 +21,15 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SEEKSV = os.path.join(ROOT, "oracle", "_ref", "seeksv")
 BIN = os.path.join(ROOT, "seeksv_b200", "bin")
 SVSIM_ARGS = ["--genome", "chr21:46709983", "--cov", "30", "--nsv", "500", "--seed", "20261017"]
+# smaller stand-ins for the shapes of BASELINE.json's other configs (python tests/golden/make_c2_digests.py <workdir> c3mini ...):
+#   c3mini: 24 contigs chr1..chr22, chrX, chrY (the name order chr1 < chr10 < chr11 ... < chr2 matters, quirk Q10), 30x
+#   c5mini: human contig + HBV / HPV16 contigs at several thousand x (pileup cap, quirk Q12), virus-integration junctions
+CONFIGS = {
+    "c2": SVSIM_ARGS,
+    "c3mini": ["--genome", ",".join("chr%s:%d" % (n, 300000 + 20000 * i) for i, n in enumerate(list(range(1, 23)) + ["X", "Y"])),
+               "--cov", "30", "--nsv", "240", "--seed", "20261018"],
+    "c5mini": ["--genome", "chr21:6000000", "--virus", "--cov", "30", "--nsv", "80", "--seed", "20261019"],
+}
 
 
 def digest(data):
@@ -30,12 +39,17 @@ def digest(data):
 def main():
     assert os.path.exists(SEEKSV), "oracle/build_ref.sh first"
     work = sys.argv[1] if len(sys.argv) > 1 else tempfile.mkdtemp(prefix="c2_")
-    pre = os.path.join(work, "c2")
+    for name in (sys.argv[2:] or ["c2"]):
+        one(work, name, CONFIGS[name])
+
+
+def one(work, name, svsim_args):
+    pre = os.path.join(work, name)
     if not os.path.exists(pre + ".bam"):
-        subprocess.run([os.path.join(BIN, "svsim"), "--out", pre] + SVSIM_ARGS, check=True)
-    ref = os.path.join(work, "ref")
+        subprocess.run([os.path.join(BIN, "svsim"), "--out", pre] + svsim_args, check=True)
+    ref = os.path.join(work, name + ".ref")
     subprocess.run([SEEKSV, "getclip", "-o", ref, pre + ".bam"], check=True, stderr=subprocess.DEVNULL)
-    out = {"svsim_args": SVSIM_ARGS, "reference": "oracle/_ref/seeksv (v1.2.3 built from the unmodified sources)"}
+    out = {"svsim_args": svsim_args, "reference": "oracle/_ref/seeksv (v1.2.3 built from the unmodified sources)"}
     for ext in (".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz"):
         with gzip.open(ref + ext, "rb") as f:
             out[ext] = digest(f.read())
@@ -52,7 +66,7 @@ def main():
     subprocess.run([SEEKSV, "somatic", pre + ".bam", ref + ".clip.gz", ref + ".sv", ref + ".somatic"], check=True,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     out["somatic (self)"] = digest(open(ref + ".somatic", "rb").read())
-    with open(os.path.join(HERE, "c2", "digests.json"), "w") as f:
+    with open(os.path.join(HERE, "c2", "digests.json" if name == "c2" else name + ".digests.json"), "w") as f:
         json.dump(out, f, indent=1)
         f.write("\n")
     print(json.dumps(out, indent=1))

@@ -628,25 +628,17 @@ def test_somatic_on_fuzz_fixtures_cli_bit_exact(s, tmp_path):
     assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".somatic.temp.sv"))
 
 
-def test_c2_full_size_outputs_equal_the_reference_digests(c2_prefix, tmp_path):
-    """BASELINE.json's C2 workload at full size (9.2 M records) through the CLI: MD5 and size of every output of getclip, getsv
-    (with and without the BAM passes) and somatic against the digests of the reference's own outputs on the same BAM
-    (tests/golden/c2/digests.json, made in the build container by tests/golden/make_c2_digests.py - ~2 minutes of single-core
-    reference work that the GPU box does not repeat). svsim is deterministic (any thread count), minialign stands in for bwa in
-    both arms."""
+def _check_digests(pre, want, tmp_path):
+    """getclip -> minialign -> getsv (with and without the BAM passes) -> somatic(self) through the CLI on <pre>.bam / <pre>.fa;
+    MD5 and size of every output against `want` (a digests.json made by tests/golden/make_c2_digests.py from the reference's run)."""
     import hashlib
-    import json
-    with open(os.path.join(GOLDEN, "c2", "digests.json")) as f:
-        want = json.load(f)
     mini = os.path.join(ROOT, "seeksv_b200", "bin", "minialign")
     if not os.path.exists(mini):
         pytest.skip("needs the minialign tool (python -m seeksv_b200.build)")
-    assert want["svsim_args"] == ["--genome", "chr21:46709983", "--cov", "30", "--nsv", "500", "--seed", "20261017"]   # = c2_prefix
 
     def dig(data):
         return {"md5": hashlib.md5(data).hexdigest(), "bytes": len(data)}
 
-    pre = c2_prefix
     out = str(tmp_path / "b200")
     r = subprocess.run([_cli(), "getclip", "-o", out, pre + ".bam"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -666,6 +658,19 @@ def test_c2_full_size_outputs_equal_the_reference_digests(c2_prefix, tmp_path):
     r = subprocess.run([_cli(), "somatic", pre + ".bam", out + ".clip.gz", out + ".sv", out + ".somatic"], capture_output=True)
     assert r.returncode == 0, r.stderr
     assert dig(open(out + ".somatic", "rb").read()) == want["somatic (self)"]
+
+
+def test_c2_full_size_outputs_equal_the_reference_digests(c2_prefix, tmp_path):
+    """BASELINE.json's C2 workload at full size (9.2 M records) through the CLI: MD5 and size of every output of getclip, getsv
+    (with and without the BAM passes) and somatic against the digests of the reference's own outputs on the same BAM
+    (tests/golden/c2/digests.json, made in the build container by tests/golden/make_c2_digests.py - ~2 minutes of single-core
+    reference work that the GPU box does not repeat). svsim is deterministic (any thread count), minialign stands in for bwa in
+    both arms. Verified on the B200 in round 1 (profiles/r1_late_c2.log)."""
+    import json
+    with open(os.path.join(GOLDEN, "c2", "digests.json")) as f:
+        want = json.load(f)
+    assert want["svsim_args"] == ["--genome", "chr21:46709983", "--cov", "30", "--nsv", "500", "--seed", "20261017"]   # = c2_prefix
+    _check_digests(c2_prefix, want, tmp_path)
 
 
 def test_long_clips_cli_bit_exact(tmp_path):
@@ -707,3 +712,19 @@ def test_getclip_reads_sam_text_input(d, s, tmp_path):
     for ext, name in ((".clip.gz", ".clip.txt"), (".clip.fq.gz", ".clip.fq.txt"), (".unmapped_1.fq.gz", ".unmapped_1.fq.txt"),
                       (".unmapped_2.fq.gz", ".unmapped_2.fq.txt")):
         assert _zcat(pre + ext) == read_text(os.path.join(GOLDEN, d, s + name)), ext
+
+
+@pytest.mark.parametrize("name", ["c3mini", "c5mini"])
+def test_other_config_shapes_equal_the_reference_digests(name, tmp_path):
+    """Stand-ins for the shapes of BASELINE.json's configs 3 and 5 (24 contigs chr1..chrY whose names sort chr1 < chr10 < ... < chr2;
+    a human contig plus HBV / HPV16 contigs at several thousand x), 2.5 M / 1.6 M records: digests of the reference's outputs
+    (tests/golden/c2/<name>.digests.json) against the CLI's."""
+    import json
+    svsim = os.path.join(ROOT, "seeksv_b200", "bin", "svsim")
+    if not os.path.exists(svsim):
+        pytest.skip("needs the svsim tool (python -m seeksv_b200.build)")
+    with open(os.path.join(GOLDEN, "c2", name + ".digests.json")) as f:
+        want = json.load(f)
+    pre = str(tmp_path / name)
+    subprocess.run([svsim, "--out", pre] + want["svsim_args"], check=True, stderr=subprocess.DEVNULL)
+    _check_digests(pre, want, tmp_path)
