@@ -114,7 +114,7 @@ def _getclip_with_prev(getclip_oracle, h, recs, prev_tid):
     return getclip_oracle.getclip(h, [phantom] + list(recs))
 
 
-@pytest.mark.parametrize("case", [("micro", "tumor"), ("example", "cancer"), ("fuzz", "f11")])   # fuzz: mates in different shards
+@pytest.mark.parametrize("case", [("micro", "tumor"), ("example", "cancer"), ("fuzz", "f11"), ("fuzz", "e3")])   # fuzz: mates in different shards
 def test_chromosome_sharding_world2(case):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -162,7 +162,7 @@ def _range_worker(rank, world, port, case, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", [("fuzz", "f12"), ("example", "normal")])
+@pytest.mark.parametrize("case", [("fuzz", "f12"), ("example", "normal"), ("fuzz", "e3")])
 def test_range_sharding_world2(case):
     """sharded_getclip_ranges over a real process group (gloo, 2 ranks): plan from the .bai on every rank, oracle workers, rank 0 merges"""
     ctx = mp.get_context("spawn")
