@@ -90,7 +90,9 @@ def main():
         o.write("# SASS listings (sm_100a) of the hand-written kernels\n\n"
                 "Made by `python tools/dump_sass.py` from the objects `python -m seeksv_b200.build` leaves in `seeksv_b200/build/`\n"
                 "(`cuobjdump -sass -fun <kernel>`; CUB's sort/scan instantiations are library code and left out). No tensor-core\n"
-                "or TMA instruction appears on purpose: the path is integer/byte work on packed, unaligned records, bound by HBM.\n"
+                "instruction appears on purpose: the path is integer/byte work on packed, unaligned records, bound by HBM. The two\n"
+                "`*_stream` kernels (the TMA-staged alternative form of the full passes, off by default) show the bulk-copy path:\n"
+                "`UBLKCP.S.G` (cp.async.bulk global -> shared) with `SYNCS.ARRIVE.TRANS64` / `SYNCS.PHASECHK.TRANS64.TRYWAIT` (mbarrier).\n"
                 "Columns: registers per thread, static shared bytes, stack bytes (`cuobjdump -res-usage`), SASS instruction count,\n"
                 "global loads (of which 128-bit / read-only `.CONSTANT`), global stores (of which 128-bit), shared-memory accesses,\n"
                 "warp shuffles/votes/matches, funnel shifts (`SHF`, the unaligned-word assembly), atomics, local-memory accesses\n"
