@@ -143,6 +143,9 @@ static void run_parallel(size_t n, int n_threads, F f)
 
 static int hw_threads(int n) { return n > 0 ? n : (int)std::max(1u, std::thread::hardware_concurrency()); }
 
+// isspace() of the "C" locale (what `fin >> token` skips) without the call per byte: 30 MB of clip text went through it
+static inline bool is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
 std::vector<ClipLine> parse_clip_text(const std::string &text, int n_threads)
 {
     // `fin >> chr >> pos >> orientation >> cigar >> ... >> support; getline(...)` (getsv.h:453-456): whitespace-separated
@@ -159,9 +162,9 @@ std::vector<ClipLine> parse_clip_text(const std::string &text, int n_threads)
             int nt = 0;
             const char *q = p;
             while (q < nl && nt < 9) {
-                while (q < nl && isspace((unsigned char)*q)) ++q;
+                while (q < nl && is_space(*q)) ++q;
                 const char *s0 = q;
-                while (q < nl && !isspace((unsigned char)*q)) ++q;
+                while (q < nl && !is_space(*q)) ++q;
                 if (q > s0) t[nt++] = std::string_view(s0, (size_t)(q - s0));
             }
             if (nt == 9) {
