@@ -15,4 +15,6 @@ tail -c 3000 gpurun_out/bench_n1.json
 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+# ceilings for the walkers: streaming read vs scattered / dependent 128-byte line reads
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/scatter_bw tools/scatter_bw.cu && /tmp/scatter_bw 2.7 | tee gpurun_out/scatter_bw.jsonl
 echo done
