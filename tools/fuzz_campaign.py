@@ -185,14 +185,15 @@ def one_seed(seed, records, work, bwa, gpu, n_opts=0, edge=False, connect_n=0):
             if r2.returncode != 0 or text(po + ".h2.sv") != text(po + ".h.sv") or r2.stdout != r.stdout:
                 bad.append("host getsv " + " ".join(hargv))
         # somatic -t / -q / -l / -m (the sample against itself)
-        so = dict(t=rng.choice([0.5, 0.8, 0.9, 1.0]), q=rng.choice([0, 20, 30]), l=rng.choice([0, 10, 30, 89]), m=rng.choice([1, 10, 40]))
+        so = dict(t=rng.choice([0.5, 0.8, 0.9, 1.0]), q=rng.choice([0, 20, 30]), l=rng.choice([0, 10, 30, 89]), m=rng.choice([1, 10, 40]),
+                  n=rng.choice([5000000, 5000000, 0, 99999]))
         sargv = []
         for name, v in so.items():
             sargv += ["-" + name, str(v)]
         r = run([SEEKSV, "somatic", *sargv, bam, pre + ".clip.gz", pre + ".sv", po + ".somatic"])
         if r.returncode == 0:
             if getsv_oracle.somatic(h, recs, ref[".clip.gz"], ref["sv"], rate=so["t"], min_mapq=so["q"], offset=so["l"],
-                                    min_len=so["m"]) != text(po + ".somatic"):
+                                    min_len=so["m"], pairs_used=so["n"]) != text(po + ".somatic"):
                 bad.append("oracle somatic " + " ".join(sargv))
             if gpu and os.path.exists(CLI):
                 r2 = run([CLI, "somatic", *sargv, bam, pre + ".clip.gz", pre + ".sv", po + ".g.somatic"])
