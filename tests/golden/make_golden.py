@@ -14,6 +14,12 @@ Layout:
              DEL / INV / DUP / CTX / virus integration, same set of outputs
   kat/       hand-written known-answer BAMs for single quirks; written with
              oracle.bamio.write_bam because the reference's SAM text parser rejects '=' / 'X'
+  fuzz/      tests/fuzzgen.py through the whole reference pipeline: f11, f12 (first fixtures), f106 (found by
+             tools/fuzz_campaign.py: point depth skipped by bam2depth.cpp:102), e3 (the generator's edge mode: breakpoints at
+             the contig ends, clipped parts of up to 320 bases); every sample also as `somatic` against itself
+  long/      clipped sequences of 254 - 600 bases (read names of 255+ characters in the realigner's SAM, libbam's 8-bit l_qname)
+  c2/        (made by make_c2_digests.py, not by this script) MD5 + size of the reference's outputs on the full-size C2 workload
+             and on two smaller stand-ins for the shapes of configs 3 and 5
 """
 import gzip
 import os
