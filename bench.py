@@ -166,9 +166,29 @@ def reference_arm(args):
         "e2e": {"value": v, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch on the C2 stream, from the committed ncu --set full capture
-# (profiles/r1_ncu_full_walkers_raw.csv); the workload is seeded, so the byte counts are those of this run's input.
-NCU_TRAFFIC = {"decode_walk": 2.034737e9 + 487.891968e6, "clip_walk": 1.901033e9 + 11.937792e6, "walk_count": 1.207181e9 + 7.521792e6}
+def ncu_traffic(kernel_scope):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind a timer scope, from the NEWEST committed
+    `ncu --set full` raw CSV under profiles/ that holds the kernel (page raw; the workload is seeded, so the byte counts are
+    those of this run's input). Returns (bytes or None, source string)."""
+    import csv
+    import glob
+    kernel = {"rec_walk_fused": "rec_walk<(bool)1, (bool)1>", "rec_walk_clip": "rec_walk<(bool)1, (bool)0>",
+              "rec_walk_rows": "rec_walk<(bool)0, (bool)1>", "rec_walk_count": "rec_walk<(bool)0, (bool)0>"}.get(kernel_scope, kernel_scope)
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_*raw.csv")), key=os.path.getmtime, reverse=True)
+    files.sort(key=lambda f: os.path.basename(f)[:3], reverse=True)     # newest round first
+    for f in files:
+        try:
+            rows = list(csv.reader(open(f)))
+            hdr, units = rows[0], rows[1]
+            ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            for r in rows[2:]:
+                if kernel.replace(" ", "") in r[ki].replace(" ", ""):
+                    tot = float(r[ri]) * unit.get(units[ri], 1.0) + float(r[wi]) * unit.get(units[wi], 1.0)
+                    return tot, "profiles/%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch on C2)" % os.path.basename(f)
+        except Exception:
+            continue
+    return None, "no committed ncu --set full capture holds this kernel"
 
 
 def main():
@@ -179,6 +199,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--genome-len", type=int, default=C2_LEN, help="chromosome length of the synthetic BAM (C2: chr21 size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--value-only", action="store_true", help="only the HBM-resident step (for ncu launch lists): no e2e legs, no CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -258,18 +279,19 @@ def main():
     cnt_arr = C.cast(cnt_host.data_ptr(), C.POINTER(C.c_int32))
     dep_arr = C.cast(dep_host.data_ptr(), C.POINTER(C.c_int32))
 
+    gp = SL.GetsvParams(20, 4, 5000000)
+    st_arr = (C.c_int64 * 4)()
+    fused_walk = [True]
+
     def device_step():
-        """getclip + getsv on the HBM-resident stream"""
+        """getclip + getsv on the HBM-resident stream, as `seeksv run` does them: ONE handle over the stream (chunk guesses made
+        once), getclip's pass over the records also leaves getsv's rows (with_rows), the getsv passes are one fused call. The
+        four texts stay in HBM (svb_clusters_text would copy them on request); counts and depth come back to pinned memory.
+        fused_walk off: the getsv passes stream the records themselves (two passes per step, as two separate commands)."""
         b = S.Bam.from_device(ctx, dptr, nbytes, first, len(names))
         b.set_refs(names, lens)
-        sizes = b.getclip_sizes()             # the operator's plain results: four texts in (pinned) host memory
-        b.close()
-        b = S.Bam.from_device(ctx, dptr, nbytes, first, len(names))
-        b.set_refs(names, lens)
-        n, tot, mean, sq = b.insert_stats(20, 5000000)
-        dev = int((sq / n) ** 0.5) if n else 0
-        b.discordant_support_raw(j_arr, nj, SL.PairParams(20, mean, dev, 4), cnt_arr)
-        b.window_depth_raw(w_arr, nw, 20, dep_arr)
+        sizes = b.getclip_sizes(with_rows=fused_walk[0])
+        b.getsv_passes_raw(gp, j_arr, nj, w_arr, nw, st_arr, cnt_arr, dep_arr)
         b.close()
         if world > 1:   # final candidate merge: every rank learns every shard's support counts (small NCCL allgather)
             k = step_no[0] & 1
@@ -279,7 +301,7 @@ def main():
             stage_host[k].copy_(cnt_host)     # (the next step overwrites cnt_host while this copy may still be queued)
             counts_dev[k][:cnt_host.numel()].copy_(stage_host[k], non_blocking=True)
             pending_merge[k] = dist.all_gather_into_tensor(merged_dev[k], counts_dev[k], async_op=True)
-        return sum(sizes) + 4 * nj + 4 * n_pos
+        return 4 * nj + 4 * n_pos + 32
 
     out_dir = os.path.join(WORK, "out_%d" % rank)
     os.makedirs(out_dir, exist_ok=True)
@@ -331,22 +353,30 @@ def main():
         device_step()
     sampler = ClockSampler(local)
     sampler.start()
-    ctx.prof(True)
+    ms_dev, wall_dev, d2h = timed(device_step, args.steps)      # the headline: no timers inside
+    ctx.prof(True)                                              # the same steps again with the per-kernel CUDA-event timers on
     ctx.prof_reset()
-    ms_dev, wall_dev, d2h = timed(device_step, args.steps)
+    ms_prof, _, _ = timed(device_step, args.steps)
     prof = ctx.prof_read()
     ctx.prof(False)
+    fused_walk[0] = False          # for comparison: the same step with two passes over the records (not the headline)
+    for _ in range(2):
+        device_step()
+    ms_two, _, _ = timed(device_step, args.steps)
+    fused_walk[0] = True
     os.dup2(devnull, 2)          # the commands print the reference's progress lines on stderr
     sys.stdout.flush()
     saved_out = os.dup(1)
     os.dup2(devnull, 1)          # ... and getsv lists filtered junctions on stdout
+    wall_e2e = wall_fused = float("nan")
     try:
-        for _ in range(max(1, args.warmup)):
-            e2e_step()
-        ms_e2e, wall_e2e, _ = timed(e2e_step, args.steps)
-        for _ in range(max(1, args.warmup)):
-            fused_step()
-        _, wall_fused, _ = timed(fused_step, args.steps)
+        if not args.value_only:
+            for _ in range(max(1, args.warmup)):
+                e2e_step()
+            ms_e2e, wall_e2e, _ = timed(e2e_step, args.steps)
+            for _ in range(max(1, args.warmup)):
+                fused_step()
+            _, wall_fused, _ = timed(fused_step, args.steps)
     finally:
         os.dup2(saved, 2)
         os.dup2(saved_out, 1)
@@ -367,7 +397,7 @@ def main():
         except Exception:
             pass
         peak = peaks.get("hbm_gbs", 6650.0)
-        full_pass = {"guess_starts", "walk_count", "clip_walk", "decode_walk", "clip_stream", "decode_stream"}
+        full_pass = {"guess_starts", "rec_walk_fused", "rec_walk_clip", "rec_walk_rows", "rec_walk_count"}
         kern = {k: v for k, v in prof.items() if v["launches"] > 0 and "wall" not in k}
         # the roofline is quoted for the dominant FULL-PASS kernel (the ones that stream the records); the candidate-side scopes
         # (sorts, clustering: ~2 % of the data, many tiny launches) are listed in kernels_ms_per_step but have no HBM roofline
@@ -379,18 +409,28 @@ def main():
             per_launch = (v["bytes"] / v["launches"]) if v["bytes"] else (rec_bytes if dom in full_pass else 0)
             avg_ms = v["ms"] / v["launches"]
             ach = per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+            traffic, traffic_src = ncu_traffic(dom) if args.genome_len == C2_LEN else (None, "not the C2 workload")
             roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": NCU_TRAFFIC.get(dom) if args.genome_len == C2_LEN else None,
-                        "traffic_source": "profiles/r1_ncu_full_walkers_raw.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
+                        "traffic": traffic, "traffic_source": traffic_src,
+                        "dram_frac": (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic and avg_ms > 0 else None,
                         "peak_source": "measured" if peaks else "fallback",
                         "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
                         "kernels_ms_per_step": {k: round(x["ms"] / args.steps, 4) for k, x in sorted(kern.items())}}
             # the whole step against the same roofline: getclip and getsv each stream every record once
             step_s = ms_dev / args.steps * 1e-3
             step_gbs = 2.0 * rec_bytes / step_s / 1e9 if step_s > 0 else 0.0
+            two_s = ms_two / args.steps * 1e-3
             roofline["step"] = {"algorithmic_bytes": 2.0 * rec_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
                                 "kernel_ms": round(sum(x["ms"] for x in kern.values()) / args.steps, 4),
-                                "note": "per GPU (rank 0): 2 x record bytes / device time of one getclip + getsv step, results copied to host memory"}
+                                "ms_per_step_with_timers": ms_prof / args.steps,
+                                "passes_over_records": 1,
+                                "frac_one_pass_basis": (rec_bytes / step_s / 1e9 / peak) if step_s > 0 else None,
+                                "two_pass_step": {"ms_per_step": ms_two / args.steps, "frac": (2.0 * rec_bytes / two_s / 1e9 / peak) if two_s > 0 else None,
+                                                  "note": "the same step with with_rows off: the getsv passes stream the records themselves, as two separate commands do"},
+                                "note": "per GPU (rank 0). algorithmic_bytes = 2 x record bytes: getclip and getsv each have to stream every record "
+                                        "(SURVEY.md section 8d); the resident pipeline timed here (`seeksv run`) serves both from ONE pass of the record "
+                                        "walker (passes_over_records), frac_one_pass_basis divides by that. Kernel scopes on the side stream overlap "
+                                        "the main stream, so kernel_ms can exceed the step"}
         line = {
             "metric": "BAM records/sec getclip+getsv", "value": value, "unit": "records/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -400,16 +440,19 @@ def main():
                        "junction_candidates": len(juncs), "depth_windows": len(wins),
                        "sharding": "one chromosome-sized BAM per GPU" if world > 1 else "single GPU",
                        "l2_note": "inputs (%.2f GB per pass) are far larger than the 126 MB L2; no flush needed" % (rec_bytes / 1e9)},
-            "e2e": {"value": e2e, "unit": "records/s", "h2d_bytes_per_step": 2 * os.path.getsize(bam_path), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e, "unit": "records/s", "h2d_bytes_per_step": 2 * os.path.getsize(bam_path), "d2h_bytes_per_step": int(sum(os.path.getsize(os.path.join(out_dir, f)) for f in os.listdir(out_dir) if f.startswith("x.") and f.endswith(".gz")) + 4 * nj + 4 * n_pos),
                     "h2d_note": "each command uploads the BGZF file image (inflated on the device to %d bytes)" % nbytes,
                     "ms_per_step": 1e3 * wall_e2e / args.steps, "path": "svb_main getclip + svb_main getsv, BGZF file image -> outputs"},
             "e2e_fused": {"value": total_rec * args.steps / wall_fused, "unit": "records/s", "ms_per_step": 1e3 * wall_fused / args.steps,
                           "h2d_bytes_per_step": os.path.getsize(bam_path),
                           "path": "svb_main run -- getclip -- getsv (one process, BAM loaded once and kept in HBM; not the headline)"},
+            "value_d2h_bytes_per_step": int(d2h),
             "gpu_launches": int(sum(v["launches"] for v in kern.values())),
             "clocks": sampler.summary(), "roofline": roofline,
         }
-        if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_SEEKSV):
+        if args.value_only:
+            pass
+        elif world == 1 and not args.no_cpu_baseline and os.path.exists(REF_SEEKSV):
             spre = os.path.join(WORK, "sample")
             sbam = make_bam(spre, "chr21", SAMPLE_LEN, SEED, max(1, int(500 * SAMPLE_LEN / C2_LEN)))
             sn = count_records(sbam)

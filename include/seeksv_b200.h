@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SVB_ABI_VERSION 1
+#define SVB_ABI_VERSION 2
 
 typedef enum svb_status {
     SVB_OK = 0,
@@ -143,6 +143,10 @@ typedef struct svb_getclip_params {
      * text (svb_clusters_text then returns empty buffers): smaller device->host copy, no deflate work on the host. The
      * images are what svb_write_gz would write for the same text (multi-member, Huffman-only). */
     int32_t gz_outputs;
+    /* 1: the walk over the records also leaves getsv's per-record rows in HBM (same pass, +32 bytes written per record), so
+     * that svb_insert_stats / svb_discordant_support / svb_window_depth / svb_getsv_passes on the SAME handle do not stream
+     * the records a second time (`seeksv run`: getclip and getsv of one BAM in one process). */
+    int32_t with_rows;
 } svb_getclip_params;
 
 typedef struct svb_clusters svb_clusters; /* host-resident result of svb_getclip */
@@ -153,8 +157,11 @@ uint64_t svb_clusters_count(const svb_clusters *c);
 uint64_t svb_clusters_candidates(const svb_clusters *c); /* soft-clipped reads that entered clustering */
 /* Decompressed contents of P.clip.gz / P.clip.fq.gz / P.unmapped_1.fq.gz / P.unmapped_2.fq.gz
  * (DisplaySClipReadsAndClipFq clip_reads.h:300-345, StoreUnmapSeqAndQual clip_reads.h:172-219), as
- * host buffers owned by the result object. which: 0 clip, 1 clip.fq, 2 unmapped_1, 3 unmapped_2. */
+ * host buffers owned by the result object. which: 0 clip, 1 clip.fq, 2 unmapped_1, 3 unmapped_2.
+ * svb_getclip leaves the texts in HBM; the first svb_clusters_text of a text copies it to (pinned) host memory.
+ * svb_clusters_text_len gives a text's length without copying it. */
 int svb_clusters_text(const svb_clusters *c, int which, const char **data, uint64_t *len);
+int svb_clusters_text_len(const svb_clusters *c, int which, uint64_t *len);
 /* gz_outputs: the gzip file image of output `which` (write it to P.clip.gz etc. as is). */
 int svb_clusters_gz(const svb_clusters *c, int which, const char **data, uint64_t *len);
 /* The packed BAM records (block_size + body, file order) of the unmapped branch; only with export_unmapped_records. */
@@ -192,6 +199,19 @@ typedef struct svb_window {
     int32_t tid, begin, end;
 } svb_window;
 int svb_window_depth(svb_ctx *ctx, svb_bam *bam, const svb_window *windows, uint64_t n_windows, int32_t min_mapq,
+                     int32_t *depth_out /* host */);
+
+/* The three passes above as ONE stream-ordered sequence with one read-back (what getsv does to the original BAM after
+ * the junction list is known, seeksv.cpp:272-300): insert-size statistics with -q / -n, the pair test of every junction with
+ * the mean and deviation that never leave the device, depth of every window position. stats_out as svb_insert_stats
+ * (deviation = (int)sqrt((double)out[3] / (int)out[0]) as the reference computes it). */
+typedef struct svb_getsv_params {
+    int32_t min_mapq;   /* -q (20): insert-size records, discordant pairs and pileup */
+    int32_t times;      /* 4 (seeksv.cpp:161) */
+    int64_t max_pairs;  /* -n (5000000) */
+} svb_getsv_params;
+int svb_getsv_passes(svb_ctx *ctx, svb_bam *bam, const svb_getsv_params *p, const svb_junction *junctions, uint64_t n_junctions,
+                     const svb_window *windows, uint64_t n_windows, int64_t stats_out[4], int32_t *counts /* host */,
                      int32_t *depth_out /* host */);
 
 /* Host-side planning step of getsv, exposed so that callers which keep the BAM resident (bench.py, sharded

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libseeksv_b200.so")
 CLI = os.path.join(HERE, "bin", "seeksv")
 OBJ = os.path.join(HERE, "build")
-CU = ["csrc/bam_index.cu", "csrc/getclip.cu", "csrc/getsv.cu", "csrc/inflate.cu", "csrc/gzip.cu", "csrc/api.cu"]
+CU = ["csrc/walk.cu", "csrc/getclip.cu", "csrc/getsv.cu", "csrc/inflate.cu", "csrc/gzip.cu", "csrc/api.cu"]
 CPP = ["host/bamfile.cpp", "host/junction.cpp", "host/commands.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -48,6 +48,8 @@ extern "C" int svb_ctx_create(int device, svb_ctx **out)
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->join_event, cudaEventDisableTiming));
+    CK(cudaHostAlloc((void **)&c->ctl_host, 4096, cudaHostAllocDefault));
     for (int i = 0; i < svb_ctx::N_AUX; ++i) CK(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
     {
         // The full-pass kernels read ~40-100 bytes out of every ~300-byte record: with the default L2 fetch granularity a
@@ -74,6 +76,10 @@ extern "C" void svb_ctx_destroy(svb_ctx *ctx)
     cudaStreamDestroy(ctx->stream);
     for (auto &e : ctx->big_free) cudaFree(e.first);
     ctx->big_free.clear();
+    for (int w = 0; w < 2; ++w)
+        if (ctx->ws[w]) cudaFree(ctx->ws[w]);
+    if (ctx->ctl_host) cudaFreeHost(ctx->ctl_host);
+    if (ctx->join_event) cudaEventDestroy(ctx->join_event);
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (cudaStream_t a : ctx->aux)
@@ -120,6 +126,21 @@ void svb_ctx::big_put(uint8_t *p, uint64_t cap)
     }
 }
 
+// the workspace of a sync-free pipeline: grows, never shrinks (a command owns it from its first launch to its read-back)
+int svb_ctx::ws_reserve(int which, uint64_t bytes)
+{
+    svb_ctx *ctx = this;
+    if (ws_cap[which] >= bytes) return 0;
+    CK(cudaStreamSynchronize(stream));
+    for (cudaStream_t a : aux) CK(cudaStreamSynchronize(a));
+    if (ws[which]) CK(cudaFree(ws[which]));
+    ws[which] = nullptr, ws_cap[which] = 0;
+    const uint64_t want = bytes + bytes / 8 + (1u << 20);
+    CK(cudaMalloc((void **)&ws[which], want));
+    ws_cap[which] = want;
+    return 0;
+}
+
 char *svb_ctx::pinned_get(uint64_t bytes, uint64_t *cap)
 {
     if (bytes == 0) {
@@ -151,6 +172,7 @@ void svb_ctx::pinned_put(char *p, uint64_t cap)
 }
 svb_ctx::~svb_ctx()
 {
+    for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
     for (auto &b : pinned_free) cudaFreeHost(b.first);
 }
 
@@ -158,13 +180,14 @@ void svb_ctx::prof_flush()
 {
     if (prof_pending.empty()) return;
     cudaStreamSynchronize(stream);
+    for (cudaStream_t a : aux) cudaStreamSynchronize(a);
     for (auto &p : prof_pending) {
         float ms = 0;
         cudaEventElapsedTime(&ms, p.a, p.b);
         ProfEntry &e = prof_acc[p.name];
         e.ms += ms, e.bytes += p.bytes, e.launches += 1;
-        cudaEventDestroy(p.a);
-        cudaEventDestroy(p.b);
+        prof_events.push_back(p.a);
+        prof_events.push_back(p.b);
     }
     prof_pending.clear();
 }
@@ -223,11 +246,6 @@ extern "C" int svb_bam_from_device(svb_ctx *ctx, const void *d_stream, uint64_t 
                                    svb_bam **out)
 {
     if (!ctx || !out || (!d_stream && nbytes)) return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_device: null argument");
-    {   // only the TMA-staged streaming passes need an aligned base (bulk copies); the walkers read with aligned-down loads
-        const char *e = getenv("SEEKSV_B200_PASS");
-        if (e && !strcmp(e, "stream") && ((uintptr_t)d_stream & 15) != 0)
-            return svb_fail(ctx, SVB_ERR_ARG, "svb_bam_from_device: stream must be 16-byte aligned for the streaming passes");
-    }
     CK(cudaSetDevice(ctx->device));
     std::unique_ptr<svb_bam> b(new svb_bam());
     b->ctx = ctx, b->d_data = (const uint8_t *)d_stream, b->nbytes = nbytes, b->first = first_record, b->n_ref = n_ref;
@@ -697,8 +715,7 @@ extern "C" void svb_bam_free(svb_bam *b)
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     cudaStream_t s = b->ctx->stream;
-    LeanRecords &L = b->lean;
-    void *cols[7] = {L.rec, b->d_guess, b->d_count, b->d_base, b->d_q_cnt, b->d_q_sum, b->d_q_sq};
+    void *cols[5] = {b->rows.row, b->d_guess /* + base, exit, count: one allocation */, b->d_fkey, b->d_scal, b->d_ref_len};
     for (void *c : cols)
         if (c) cudaFreeAsync(c, s);
     if (b->d_owned) b->ctx->big_put(b->d_owned, b->owned_cap);  // (the stream was synchronised above)
@@ -715,13 +732,13 @@ extern "C" int svb_bam_device_stream(const svb_bam *b, const void **d, uint64_t 
 extern "C" uint64_t svb_bam_n_records(const svb_bam *b)
 {
     if (!b) return 0;
-    if (!b->counted) ensure_counts(b->ctx, const_cast<svb_bam *>(b));
+    if (!b->counted && ensure_counts(b->ctx, const_cast<svb_bam *>(b)) != 0) return 0;
     return b->n_rec;
 }
 extern "C" uint64_t svb_bam_record_bytes(const svb_bam *b)
 {
     if (!b) return 0;
-    if (!b->counted) ensure_counts(b->ctx, const_cast<svb_bam *>(b));
+    if (!b->counted && ensure_counts(b->ctx, const_cast<svb_bam *>(b)) != 0) return 0;
     return b->rec_bytes;
 }
 extern "C" int32_t svb_bam_n_ref(const svb_bam *b) { return b ? b->n_ref : 0; }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <chrono>
 #include <map>
 #include <string>
@@ -45,6 +46,14 @@ struct svb_ctx {
         double bytes;
     };
     std::vector<Pending> prof_pending;
+    std::vector<cudaEvent_t> prof_events;  // recycled timing events (cudaEventCreate per scope cost more than the kernels it timed)
+    cudaEvent_t prof_event()
+    {
+        cudaEvent_t e = nullptr;
+        if (!prof_events.empty()) e = prof_events.back(), prof_events.pop_back();
+        else cudaEventCreate(&e);
+        return e;
+    }
     std::vector<const char *> prof_names;  // storage for svb_prof_read
     void prof_flush();
     // recycled pinned host buffers (cudaHostAlloc is slow; results are produced over and over)
@@ -57,6 +66,18 @@ struct svb_ctx {
     std::vector<std::pair<uint8_t *, uint64_t>> big_free;
     uint8_t *big_get(uint64_t bytes, uint64_t *cap);  // contents undefined; usable on `stream` (and after its events)
     void big_put(uint8_t *p, uint64_t cap);           // caller has synchronised every stream that used p
+    // One grow-only scratch buffer per command family: the sync-free pipelines carve all their temporaries out of it (Bump,
+    // prim.cuh) instead of allocating array by array. A command owns it from its first launch to its final read-back.
+    uint8_t *ws[2] = {nullptr, nullptr};
+    uint64_t ws_cap[2] = {0, 0};
+    int ws_reserve(int which, uint64_t bytes);        // (re)allocates when too small; contents undefined
+    // small pinned block for the control-block read-backs
+    char *ctl_host = nullptr;
+    // capacity hints: what the last svb_getclip of this context needed (texts, arenas, queues), so that a repeated call
+    // on similar data never overflows its first estimate
+    uint64_t hint[16] = {};
+    bool walk_attr = false;                           // the walker's shared-memory opt-in is set on this device
+    cudaEvent_t join_event = nullptr;                 // side stream -> main stream
     ~svb_ctx();
 };
 
@@ -77,21 +98,23 @@ struct PinnedBuf {
     }
 };
 
-// Lean per-record rows produced by the decode walker (getsv passes read these, not the raw stream). Rows, not columns:
-// a walker thread writes the ~50 records of its chunk one after the other, so its output is one contiguous 2 KB run
-// (column arrays made every 4-byte store its own DRAM sector: 2.9 ms instead of 0.3 ms for C2, profiles/r1_summary.md).
-struct __align__(16) LeanRec {  // 48 bytes: three 16-byte stores per record
+// Lean per-record rows produced by the record walker (the getsv passes read these, not the raw stream): 32 bytes, written with
+// ONE 256-bit store per record. Rows live in per-chunk slots - record k of chunk c is rows[c * R + k] - so the walker needs no
+// per-chunk row base (which would cost a counting pass over the stream first) and the same pass can serve getclip and getsv.
+// Measured on the B200 with tools/walk_lab.cu: 32-byte rows 0.39 ms, 48-byte rows (three 16-byte stores) 0.47 ms, dense or slotted alike.
+struct __align__(32) Row {
     int32_t tid, pos, end;  // end = bam_calend of the linked libbam (M, D, N)
     uint32_t flagq;         // flag | mapq << 16 | hardclip << 24 | no-cigar << 25
     int32_t lqseq, mtid, mpos, isize;
-    uint64_t off;           // byte offset of the record in the stream (CIGARs are re-read from there)
-    uint64_t pad_;
 };
-struct LeanRecords {
-    LeanRec *rec = nullptr;
-    uint64_t n = 0;
+struct RowTable {
+    Row *row = nullptr;
+    uint32_t R = 0;  // slots per chunk
 };
 #define FLAGQ_HARDCLIP (1u << 24)
+#define FLAGQ_NOCIGAR (1u << 25)
+#define ROWS_R_FIRST 256u  // first try: fits chunks whose records average >= 64 bytes
+#define ROWS_R_MAX 448u    // a 16 KiB chunk cannot hold more records than this (a record is at least 38 bytes)
 
 struct svb_bam {
     svb_ctx *ctx = nullptr;
@@ -105,22 +128,22 @@ struct svb_bam {
     // starts at or after the chunk, count[c] = records starting inside it, base[c] = exclusive prefix of count
     uint64_t n_chunks = 0;
     uint32_t chunk_log2 = 14;  // 16 KiB chunks = streaming tiles (SEEKSV_B200_CHUNK_LOG2 changes it for the walkers)
-    uint64_t *d_guess = nullptr, *d_base = nullptr;
+    uint64_t *d_guess = nullptr, *d_base = nullptr, *d_exit = nullptr;
     uint32_t *d_count = nullptr;
-    bool counted = false;  // count / base / n_rec / rec_bytes are valid (ensure_counts)
-    bool guessed = false;  // d_guess holds first-record guesses (guess_starts or a streaming pass)
+    bool counted = false;  // count / base / n_rec / rec_bytes are valid (a verified walk has run)
+    bool guessed = false;  // d_guess holds first-record guesses (guess_starts)
     bool whole_file = false;  // built from a complete BAM: the chain must end exactly at the end of the stream
-    // per-chunk insert-size partial sums gathered by the decode walker for one mapQ threshold (getsv.cu)
-    int32_t stats_mapq = -1;
-    uint32_t *d_q_cnt = nullptr;
-    uint64_t *d_q_sum = nullptr, *d_q_sq = nullptr;
-    int32_t q_max = 0;
     std::vector<std::string> names;
     std::vector<uint32_t> lens;
-    LeanRecords lean;
-    bool lean_ready = false;
+    // rows of the records (walk.cu), valid when rows_ready; the getsv passes keep their per-BAM scalars on the device (getsv.cu)
+    RowTable rows;
+    bool rows_ready = false;
+    uint64_t *d_fkey = nullptr;   // per chunk: (tid, pos) of the first record at or after the chunk, tid -1 last (rows_index)
+    int32_t *d_scal = nullptr;    // [0] max span, [1] unsorted flag, [2] indexed flag
+    bool rows_indexed = false;
     int32_t max_span = 0;  // max(end - pos) over records, for window queries
     int sorted = -1;       // -1 unknown, 0 no, 1 coordinate-sorted
+    uint32_t *d_ref_len = nullptr;  // reference lengths on the device (uploaded once per handle)
 };
 
 // ---- error plumbing ------------------------------------------------------------------------------------
@@ -143,18 +166,18 @@ struct ProfScope {
     cudaEvent_t a = nullptr, b = nullptr;
     const char *name;
     double bytes;
-    ProfScope(svb_ctx *c, const char *n, double by) : ctx(c), name(n), bytes(by)
+    cudaStream_t st;
+    ProfScope(svb_ctx *c, const char *n, double by, cudaStream_t on = nullptr) : ctx(c), name(n), bytes(by), st(on ? on : c->stream)
     {
         if (ctx->prof) {
-            cudaEventCreate(&a);
-            cudaEventCreate(&b);
-            cudaEventRecord(a, ctx->stream);
+            a = ctx->prof_event(), b = ctx->prof_event();
+            cudaEventRecord(a, st);
         }
     }
     ~ProfScope()
     {
         if (ctx->prof) {
-            cudaEventRecord(b, ctx->stream);
+            cudaEventRecord(b, st);
             ctx->prof_pending.push_back({name, a, b, bytes});
         }
     }
@@ -205,13 +228,6 @@ __device__ __forceinline__ uint32_t ldu32(const uint8_t *p)
     return __funnelshift_r(lo, hi, sh);
 }
 __device__ __forceinline__ int32_t ldi32(const uint8_t *p) { return (int32_t)ldu32(p); }
-
-// Alias used by the sparse one-touch accesses of the full-pass kernels (record heads ~300 B apart). ncu (profiles/)
-// showed that what over-fetches there is the L2 -> DRAM fetch granularity (a 4-byte read pulled a whole 128-byte line,
-// 4.1 sectors/record), not L1: bypassing L1 with ld.global.cg only added L2 requests for the multi-word reads and was
-// slower, so these stay on the read-only path and the context lowers cudaLimitMaxL2FetchGranularity instead.
-__device__ __forceinline__ uint32_t ldu32s(const uint8_t *p) { return ldu32(p); }
-__device__ __forceinline__ int32_t ldi32s(const uint8_t *p) { return (int32_t)ldu32s(p); }
 
 // The 32-byte fixed core of a record (after the 4-byte block_size), decoded.
 struct Core {
@@ -272,17 +288,14 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t v)
 
 // ---- internal entry points (one per .cu) ------------------------------------------------------------------
 static constexpr uint64_t BAD_OFFSET = ~0ull;
-int index_records(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu: chunk arrays (+ guesses for the walkers)
-int ensure_guess(svb_ctx *ctx, svb_bam *bam);                        // bam_index.cu: guess_starts once
-// The full passes have two forms: chunk walkers (default) and TMA-staged streaming kernels (stream.cuh,
-// SEEKSV_B200_PASS=stream; same results, slower on this workload - see stream_mode()).
-bool stream_mode(const svb_bam *bam);
-int ensure_counts(svb_ctx *ctx, svb_bam *bam);                       // bam_index.cu: verified chain + counts + prefix
-int finish_counts(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit);  // prefix + totals from valid per-chunk counts
-// after a fused walker filled exit_[]: verify against the guesses; *ok = 0 means the guesses were repaired
-// (bam->d_guess updated, counts valid) and the walker has to run again
-int verify_or_repair(svb_ctx *ctx, svb_bam *bam, const uint64_t *d_exit, int *ok);
-int decode_records(svb_ctx *ctx, svb_bam *bam, int32_t stats_mapq = -1);  // getsv.cu
+#define NO_TID INT32_MIN
+int index_records(svb_ctx *ctx, svb_bam *bam);  // walk.cu: chunk arrays (guesses are made by the first pass that needs them)
+int ensure_guess(svb_ctx *ctx, svb_bam *bam);   // walk.cu: guess_starts once
+// walk.cu: verified chain + per-chunk counts + their prefix + rows (one pass of the record walker without the getclip work)
+int ensure_counts(svb_ctx *ctx, svb_bam *bam);
+int ensure_rows(svb_ctx *ctx, svb_bam *bam);
+// a walk left exit[] without matching the guesses: repair guesses with plain walks (synchronises); the walk has to run again
+int repair_guesses(svb_ctx *ctx, svb_bam *bam);
 // the inflate kernel reads ahead of the current bit position: the device copy of the file image is padded by this much
 static constexpr uint64_t SVB_INFLATE_PAD = 1024;
 struct PinnedBuf;
@@ -290,5 +303,3 @@ int gzip_on_device(svb_ctx *ctx, const char *d_text, uint64_t n, PinnedBuf *out)
 int inflate_launch(cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err);
 int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out,
                       double out_bytes);                             // inflate.cu
-int inclusive_scan_u32(svb_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n);
-int exclusive_scan_u64(svb_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t n);

@@ -2,24 +2,50 @@
 // text emission. Replaces the per-record loop of InputBamOutputReads (clip_reads.h:410-440) with its
 // callees GetSClipReads / GetSeq / GenerateCigar / InsertSeq / ReadsInfo::ChangeSeqAndQual
 // (clip_reads.cpp:57-108,112-192,260-329) and the writer DisplaySClipReadsAndClipFq (clip_reads.h:300-345).
-#include <cub/device/device_radix_sort.cuh>
-
+//
+// Round 2: the whole command is ONE stream-ordered sequence of launches. Every element count (candidates, segments, clusters,
+// text bytes) stays in a device control block; buffers are capacity-bounded and carved from one workspace; kernels loop over
+// device-side counts; the host reads the control block once at the end (overflow = run again with the sizes it reports).
+// Round 1 synchronised nine times per call and the GPU sat idle between the pieces (profiles/r1_summary.md). Results stay in
+// HBM until svb_clusters_text / svb_clusters_gz asks for them.
 #include <algorithm>
 #include <cstring>
 #include <memory>
 
-#include "common.cuh"
-#include "stream.cuh"
+#include "walk.cuh"
+
+// ---- device control block ------------------------------------------------------------------------------------------------------
+struct ClipCtl {
+    uint32_t counters[4];  // [0] clipped records [1] unmapped-branch records [2] chromosome switches [3] candidates
+    uint32_t flags[4];     // [0] row slots overflowed [1] chain does not verify [2] spare [3] spare
+    uint64_t c64[2];       // records, end of the chain
+    uint32_t n_seg, n_cl, un_skip, un_own;
+    uint32_t abort_main, abort_side, pad0, pad1;
+    uint64_t arena_bytes, clip_bytes, fq_bytes, un1_bytes, un2_bytes, export_bytes;
+};
 
 struct svb_clusters {
     svb_ctx *ctx = nullptr;
-    PinnedBuf text[4];  // pinned host memory: D2H at full PCIe rate, recycled through the ctx pool
+    char *d_text[4] = {nullptr, nullptr, nullptr, nullptr};  // device: the four texts (or nothing in gz mode once compressed)
+    uint64_t text_len[4] = {0, 0, 0, 0};
+    mutable PinnedBuf text[4];  // pinned host copies, made on first request
+    mutable bool text_here[4] = {false, false, false, false};
     PinnedBuf gz[4];             // the same four files as gzip images, compressed on the device (svb_getclip_params.gz_outputs)
     bool gz_mode = false;
-    PinnedBuf unmapped_records;  // sharded runs: the raw unmapped-branch records (svb_getclip_params.export_unmapped_records)
+    uint8_t *d_export = nullptr;  // sharded runs: the raw unmapped-branch records (svb_getclip_params.export_unmapped_records)
+    uint64_t export_len = 0;
+    mutable PinnedBuf unmapped_records;
+    mutable bool export_here = false;
     uint64_t n_clusters = 0, n_candidates = 0;
+    void drop_device()
+    {
+        for (auto &t : d_text)
+            if (t) cudaFreeAsync(t, ctx->stream), t = nullptr;
+        if (d_export) cudaFreeAsync(d_export, ctx->stream), d_export = nullptr;
+    }
     ~svb_clusters()
     {
+        drop_device();
         for (auto &t : text) t.release(ctx);
         for (auto &t : gz) t.release(ctx);
         unmapped_records.release(ctx);
@@ -81,16 +107,8 @@ __device__ int32_t aux_xc(const uint8_t *a, uint32_t n)
     return 0;
 }
 
-struct ScanOut {
-    CandArrays c;
-    uint32_t cand_cap;
-    uint64_t *unmapped;
-    uint32_t un_cap;
-    uint64_t *switches;
-    uint32_t sw_cap;
-    uint32_t *counters;  // [0] candidates, [1] unmapped-branch records, [2] chromosome switches, [3] soft-clipped records
-    uint64_t *clipped;   // records whose first or last CIGAR op is S and that pass the cheap filters: evaluated by clip_eval
-    uint32_t clipped_cap;
+struct ClipParams {
+    int32_t min_mapq, save_low_quality;
     // range shards: only breakpoint keys (tid, pos) in [lo, hi) belong to this shard (whole file: everything)
     int32_t lo_tid, lo_pos, hi_tid, hi_pos;
     __device__ __forceinline__ bool owns(int32_t tid, int32_t pos) const
@@ -101,33 +119,25 @@ struct ScanOut {
     }
 };
 
-// The cheap part of GetSClipReads (clip_reads.cpp:116-118,122): first / last CIGAR op and the H / mapQ / DUP filters.
-// Only records that pass (about 2 %) are queued for the expensive part (reference length, XC aux scan, emission), so the
-// walker's warps do not stall 31 lanes while one lane scans an aux block.
-__device__ __forceinline__ void queue_if_clipped(const uint8_t *__restrict__ d, uint64_t o, const Core &k, int32_t min_mapq,
-                                                 const ScanOut &out)
-{
-    if (k.n_cigar == 0 || (int32_t)k.mapq < min_mapq || (k.flag & F_DUP)) return;
-    const uint8_t *cig = d + o + 36 + k.l_qname;
-    uint32_t op1 = ldu32(cig) & 15, op2 = ldu32(cig + 4 * (k.n_cigar - 1)) & 15;
-    if (op1 == OP_H || op2 == OP_H || (op1 != OP_S && op2 != OP_S)) return;
-    uint32_t s = atomicAdd(&out.counters[3], 1u);
-    if (s < out.clipped_cap) out.clipped[s] = o;
-}
+struct Emit {
+    bool e5 = false, e3 = false;
+    int32_t pos5 = 0, pos3 = 0;
+    uint32_t b5 = 0, l5 = 0, r5 = 0, b3 = 0, l3 = 0, r3 = 0;
+};
 
 // GetSClipReads (clip_reads.cpp:112-192) for one mapped-branch record that survived the chromosome-switch test.
 // Sequence and aux bytes are only touched for soft-clipped reads (~2 % of the records).
-__device__ void eval_clip(const uint8_t *__restrict__ d, uint64_t o, const Core &k, int32_t min_mapq, int32_t save_low_quality,
-                          const ScanOut &out)
+__device__ Emit eval_clip(const uint8_t *__restrict__ d, uint64_t o, const Core &k, const ClipParams &P)
 {
-    if (k.n_cigar == 0) return;
+    Emit E;
+    if (k.n_cigar == 0) return E;
     const uint8_t *p = d + o;
     const uint8_t *cig = p + 36 + k.l_qname;
     uint32_t first = ldu32(cig), last = ldu32(cig + 4 * (k.n_cigar - 1));
     uint32_t op1 = first & 15, op2 = last & 15;
-    if (op1 == OP_H || op2 == OP_H || (int32_t)k.mapq < min_mapq || (k.flag & F_DUP)) return;  // clip_reads.cpp:118
+    if (op1 == OP_H || op2 == OP_H || (int32_t)k.mapq < P.min_mapq || (k.flag & F_DUP)) return E;  // clip_reads.cpp:118
     bool s1 = op1 == OP_S, s2 = op2 == OP_S;
-    if (!s1 && !s2) return;
+    if (!s1 && !s2) return E;
     // GenerateCigar's l (clip_reads.cpp:322): M, D, =, N - X is not counted (quirk Q5)
     int32_t reflen = 0;
     for (uint32_t j = 0; j < k.n_cigar; ++j) {
@@ -137,282 +147,194 @@ __device__ void eval_clip(const uint8_t *__restrict__ d, uint64_t o, const Core 
     const uint8_t *aux = cig + 4 * k.n_cigar + (k.l_qseq + 1) / 2 + k.l_qseq;
     int32_t xc = aux_xc(aux, (uint32_t)max((int64_t)0, (int64_t)(p + 4 + k.block_size - aux)));
     uint32_t len1 = first >> 4, len2 = last >> 4;
-    bool emit5 = false, emit3 = false;
-    uint32_t b5 = 0, l5 = 0, r5 = 0, b3 = 0, l3 = 0, r3 = 0;
     if (s1 != s2) {
-        if (xc != 0 && !save_low_quality) return;
+        if (xc != 0 && !P.save_low_quality) return E;
         if (s1) {
-            if ((int64_t)len1 > k.l_qseq) return;
-            emit5 = true, l5 = len1, r5 = k.l_qseq - len1;
+            if ((int64_t)len1 > k.l_qseq) return E;
+            E.e5 = true, E.l5 = len1, E.r5 = k.l_qseq - len1;
         } else {
-            if ((int64_t)len2 > k.l_qseq) return;
-            emit3 = true, l3 = k.l_qseq - len2, r3 = len2;
+            if ((int64_t)len2 > k.l_qseq) return E;
+            E.e3 = true, E.l3 = k.l_qseq - len2, E.r3 = len2;
         }
     } else {
         int64_t mid = (int64_t)k.l_qseq - len1 - len2;
-        if (mid < 0 || k.n_cigar < 2) return;  // (undefined in the reference: a CIGAR that is one S op)
-        if (xc != 0 && !save_low_quality) {
-            if (!(k.flag & F_REVERSE)) emit5 = true;
-            else emit3 = true;
+        if (mid < 0 || k.n_cigar < 2) return E;  // (undefined in the reference: a CIGAR that is one S op)
+        if (xc != 0 && !P.save_low_quality) {
+            if (!(k.flag & F_REVERSE)) E.e5 = true;
+            else E.e3 = true;
         } else
-            emit5 = emit3 = true;
-        l5 = len1, r5 = (uint32_t)mid;             // clip_reads.cpp:152,179
-        b3 = len1, l3 = (uint32_t)mid, r3 = len2;  // clip_reads.cpp:154,185
+            E.e5 = E.e3 = true;
+        E.l5 = len1, E.r5 = (uint32_t)mid;               // clip_reads.cpp:152,179
+        E.b3 = len1, E.l3 = (uint32_t)mid, E.r3 = len2;  // clip_reads.cpp:154,185
     }
-    const CandArrays &c = out.c;
-    emit5 = emit5 && out.owns(k.tid, k.pos + 1);
-    emit3 = emit3 && out.owns(k.tid, k.pos + reflen);
-    if (emit5) {
-        uint32_t s = atomicAdd(&out.counters[0], 1u);
-        if (s < out.cand_cap) {
-            c.off[s] = o, c.tid[s] = k.tid, c.pos[s] = k.pos + 1, c.begin[s] = b5, c.ll[s] = l5, c.rl[s] = r5;
-            c.side[s] = 0;
-        }
-    }
-    if (emit3) {
-        uint32_t s = atomicAdd(&out.counters[0], 1u);
-        if (s < out.cand_cap) {
-            c.off[s] = o, c.tid[s] = k.tid, c.pos[s] = k.pos + reflen, c.begin[s] = b3, c.ll[s] = l3, c.rl[s] = r3;
-            c.side[s] = 1;
-        }
-    }
+    E.pos5 = k.pos + 1, E.pos3 = k.pos + reflen;
+    E.e5 = E.e5 && P.owns(k.tid, E.pos5);
+    E.e3 = E.e3 && P.owns(k.tid, E.pos3);
+    return E;
 }
 
-#define NO_TID INT32_MIN
-
-// The getclip walker: one thread per 16 KiB chunk follows the record chain from the chunk's guessed first record and does
-// the whole per-record work of InputBamOutputReads' loop (clip_reads.h:410-440) on the way - unmapped branch (quirk
-// Q2), chromosome-switch drop (quirk Q1, against the previous mapped-branch record it has just walked over), soft-clip
-// predicate. Each record head is fetched from HBM exactly once. The first mapped-branch record of a chunk needs the
-// last one of an earlier chunk and is left to clip_first.
+// The first mapped-branch record of a chunk needs the last one of an earlier chunk (quirk Q1): one thread per chunk
 __global__ void __launch_bounds__(128)
-    clip_walk(const uint8_t *__restrict__ d, uint64_t n, uint64_t n_chunks, uint32_t CHUNK_LOG2, const uint64_t *__restrict__ guess,
-              uint32_t *__restrict__ count, uint64_t *__restrict__ exit_, uint64_t *__restrict__ first_mb,
-              int32_t *__restrict__ last_mb_tid, int32_t min_mapq, int32_t save_low_quality, ScanOut out)
+    clip_first(const uint8_t *__restrict__ d, uint64_t n_chunks, int32_t prev_tid0, ClipQueues q)
 {
     uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_chunks) return;
-    uint64_t o = guess[c], end = min(n, (c + 1) << CHUNK_LOG2), first = BAD_OFFSET;
-    uint32_t cnt = 0;
-    int32_t prev_tid = NO_TID;
-    bool live = o < end && o + 36 <= n;  // (a partial tail shorter than a fixed part ends the walk)
-    Core k;
-    if (live) k = load_core(d + o);
-    while (live) {
-        if (k.block_size < 32) {
-            o = BAD_OFFSET;
-            break;
-        }
-        if (o + 4 + (uint64_t)k.block_size > n) break;
-        // software pipeline: request the next record's fixed part before this record's CIGAR / aux bytes are waited for
-        uint64_t on = o + 4 + (uint64_t)k.block_size;
-        bool next_live = on < end && on + 36 <= n;
-        Core kn;
-        if (next_live) kn = load_core(d + on);
-        ++cnt;
-        if (k.flag & (F_UNMAP | F_MUNMAP)) {  // clip_reads.h:415 - the unmapped branch wins (quirk Q2)
-            uint32_t s = atomicAdd(&out.counters[1], 1u);
-            if (s < out.un_cap) out.unmapped[s] = o;
-        } else {
-            if (prev_tid == NO_TID) first = o;
-            else if (k.tid != prev_tid) {  // flush + drop (clip_reads.h:423-438)
-                uint32_t s = atomicAdd(&out.counters[2], 1u);
-                if (s < out.sw_cap) out.switches[s] = o;
-            } else
-                queue_if_clipped(d, o, k, min_mapq, out);
-            prev_tid = k.tid;
-        }
-        o = on, k = kn, live = next_live;
-    }
-    count[c] = cnt, exit_[c] = o, first_mb[c] = first, last_mb_tid[c] = prev_tid;
-}
-
-__global__ void __launch_bounds__(128)
-    clip_first(const uint8_t *__restrict__ d, uint64_t n_chunks, const uint64_t *__restrict__ first_mb,
-               const int32_t *__restrict__ last_mb_tid, int32_t prev_tid0, int32_t min_mapq, int32_t save_low_quality, ScanOut out)
-{
-    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_chunks || first_mb[c] == BAD_OFFSET) return;
+    if (c >= n_chunks || q.first_mb[c] == BAD_OFFSET) return;
     int32_t prev = prev_tid0;  // clip_reads.h:407: last_tid starts at 0 (or the previous shard's last tid)
     for (uint64_t j = c; j > 0;) {
         --j;
-        if (last_mb_tid[j] != NO_TID) {
-            prev = last_mb_tid[j];
+        if (q.last_mb_tid[j] != NO_TID) {
+            prev = q.last_mb_tid[j];
             break;
         }
     }
-    uint64_t o = first_mb[c];
+    uint64_t o = q.first_mb[c];
     Core k = load_core(d + o);
     if (k.tid != prev) {
-        uint32_t s = atomicAdd(&out.counters[2], 1u);
-        if (s < out.sw_cap) out.switches[s] = o;
-    } else
-        queue_if_clipped(d, o, k, min_mapq, out);
-}
-
-// The getclip full pass, streaming form (stream.cuh): TMA-staged 16 KiB tiles, one record per thread from shared memory.
-// Same outputs as clip_walk (per-tile count / exit / first mapped-branch record / last mapped-branch tid, the unmapped
-// list, the chromosome switches and the queue of soft-clipped records), so clip_first / clip_eval / verification follow
-// unchanged.
-__global__ void __launch_bounds__(STREAM_THREADS)
-    clip_stream(const uint8_t *__restrict__ d, uint64_t n, uint64_t padded, uint64_t first, int32_t n_ref, uint64_t n_tiles,
-                uint64_t *__restrict__ guess, uint32_t *__restrict__ count, uint64_t *__restrict__ exit_,
-                uint64_t *__restrict__ first_mb, int32_t *__restrict__ last_mb_tid, int32_t min_mapq, ScanOut out)
-{
-    __shared__ StreamShared S;
-    const uint32_t tid = threadIdx.x;
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&S.full[s], 1);
-        fence_proxy_async();
-    }
-    __syncthreads();
-    if (tid == 0)
-        for (int s = 0; s < STAGES; ++s) {
-            uint64_t t = blockIdx.x + (uint64_t)s * gridDim.x;
-            if (t < n_tiles) issue_tile(S, s, d, padded, t);
+        uint32_t s = atomicAdd(&q.counters[2], 1u);
+        if (s < q.sw_cap) q.switches[s] = o;
+    } else if (k.n_cigar != 0 && (int32_t)k.mapq >= q.min_mapq && !(k.flag & F_DUP)) {
+        const uint8_t *cig = d + o + 36 + k.l_qname;
+        uint32_t op1 = ldu32(cig) & 15, op2 = ldu32(cig + 4 * (k.n_cigar - 1)) & 15;
+        if (op1 != OP_H && op2 != OP_H && (op1 == OP_S || op2 == OP_S)) {
+            uint32_t s = atomicAdd(&q.counters[0], 1u);
+            if (s < q.clipped_cap) q.clipped[s] = o;
         }
-    uint32_t it = 0;
-    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const int s = it % STAGES;
-        mbar_wait(&S.full[s], (it / STAGES) & 1);
-        const uint64_t tile_abs = t << TILE_LOG2;
-        TileWin w{S.stage[s], d + tile_abs, (uint32_t)min((uint64_t)(TILE + HALO), padded - tile_abs)};
-        index_tile(S, w, t, n, first, n_ref, d);
-        const uint32_t n_rec = S.n_rec;
-        for (uint32_t kb = 0; kb < n_rec; kb += STREAM_THREADS) {
-            const uint32_t k = kb + tid;
-            unsigned long long kmin = ~0ull, kmax = 0ull;  // (k << 32 | tid) of this lane's record if it is mapped-branch
-            bool have = false;
-            if (k < n_rec) {
-                const uint32_t off = S.rec_off[k];
-                const Core c = w.core(off);
-                const uint64_t o = tile_abs + off;
-                if (c.flag & (F_UNMAP | F_MUNMAP)) {  // clip_reads.h:415 - the unmapped branch wins (quirk Q2)
-                    uint32_t slot = atomicAdd(&out.counters[1], 1u);
-                    if (slot < out.un_cap) out.unmapped[slot] = o;
-                } else {
-                    have = true;
-                    kmin = kmax = (unsigned long long)k << 32 | (uint32_t)c.tid;
-                    // quirk Q1: tid of the previous mapped-branch record (normally the record just before this one)
-                    int32_t prev_tid = NO_TID;
-                    for (uint32_t j = k; j > 0;) {
-                        --j;
-                        uint32_t oj = S.rec_off[j];
-                        if (!((w.u32(oj + 16) >> 16) & (F_UNMAP | F_MUNMAP))) {
-                            prev_tid = (int32_t)w.u32(oj + 4);
-                            break;
-                        }
-                    }
-                    if (prev_tid == NO_TID) {
-                        // first mapped-branch record of the tile: clip_first looks into earlier tiles
-                    } else if (c.tid != prev_tid) {  // flush + drop (clip_reads.h:423-438)
-                        uint32_t slot = atomicAdd(&out.counters[2], 1u);
-                        if (slot < out.sw_cap) out.switches[slot] = o;
-                    } else if (c.n_cigar != 0 && (int32_t)c.mapq >= min_mapq && !(c.flag & F_DUP)) {
-                        // cheap part of GetSClipReads (clip_reads.cpp:116-118,122) from the staged bytes
-                        uint32_t cg = off + 36 + c.l_qname;
-                        uint32_t op1 = w.u32(cg) & 15, op2 = w.u32(cg + 4 * (c.n_cigar - 1)) & 15;
-                        if (op1 != OP_H && op2 != OP_H && (op1 == OP_S || op2 == OP_S)) {
-                            uint32_t slot = atomicAdd(&out.counters[3], 1u);
-                            if (slot < out.clipped_cap) out.clipped[slot] = o;
-                        }
-                    }
-                }
-            }
-            // first / last mapped-branch record of the tile: warp reduction, one shared-memory atomic per warp
-            if (__any_sync(0xffffffffu, have)) {
-#pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) {
-                    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, sft));
-                    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, sft));
-                }
-                if ((tid & 31) == 0) {
-                    atomicMin(&S.first_mb, kmin);
-                    atomicMax(&S.last_mb, kmax);
-                }
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            count[t] = n_rec, exit_[t] = S.exit_, guess[t] = S.entry;
-            bool have = S.first_mb != ~0ull;
-            first_mb[t] = have ? tile_abs + S.rec_off[(uint32_t)(S.first_mb >> 32)] : BAD_OFFSET;
-            last_mb_tid[t] = have ? (int32_t)(uint32_t)S.last_mb : NO_TID;
-            uint64_t tn = t + (uint64_t)STAGES * gridDim.x;
-            if (tn < n_tiles) {
-                fence_proxy_async();  // the stage was read through the generic proxy; the bulk copy writes it through the async proxy
-                issue_tile(S, s, d, padded, tn);
-            }
-        }
-        __syncthreads();
     }
 }
 
-// the expensive part of GetSClipReads for the queued soft-clipped records (one thread each)
+// the expensive part of GetSClipReads for the queued soft-clipped records: one thread each, one candidate append per warp
 __global__ void __launch_bounds__(128)
-    clip_eval(const uint8_t *__restrict__ d, int32_t min_mapq, int32_t save_low_quality, ScanOut out)
+    clip_eval(const uint8_t *__restrict__ d, ClipQueues q, ClipParams P, CandArrays c, uint32_t cand_cap, ClipCtl *ctl)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n = min(out.counters[3], out.clipped_cap);
-    if (i >= n) return;
-    uint64_t o = out.clipped[i];
-    Core k = load_core(d + o);
-    eval_clip(d, o, k, min_mapq, save_low_quality, out);
-}
-
-// sort key = flush run (number of chromosome switches before the record) | side | position
-__global__ void make_keys(uint32_t n, const uint32_t *__restrict__ order, CandArrays c, const uint64_t *__restrict__ sw,
-                          uint32_t n_sw, uint64_t *__restrict__ key)
-{
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t s = order[i];
-    uint64_t r = c.off[s];
-    uint32_t lo = 0, hi = n_sw;  // lower_bound(sw, r): switches with index < r
-    while (lo < hi) {
-        uint32_t m = (lo + hi) >> 1;
-        if (sw[m] < r) lo = m + 1;
-        else hi = m;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n = min(q.counters[0], q.clipped_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0 &&
+        (q.counters[0] > q.clipped_cap || q.counters[1] > q.un_cap || q.counters[2] > q.sw_cap))
+        ctl->abort_main = 1;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
+        const uint32_t i = base + lane;
+        Emit E;
+        uint64_t o = 0;
+        int32_t tid = 0;
+        if (i < n) {
+            o = q.clipped[i];
+            Core k = load_core(d + o);
+            tid = k.tid;
+            E = eval_clip(d, o, k, P);
+        }
+        const uint32_t mine = (uint32_t)E.e5 + (uint32_t)E.e3;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= (uint32_t)s) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (!total) continue;
+        uint32_t b0 = 0;
+        if (lane == 0) b0 = atomicAdd(&q.counters[3], total);
+        b0 = __shfl_sync(0xffffffffu, b0, 0);
+        uint32_t s = b0 + incl - mine;
+        if (E.e5 && s < cand_cap) {
+            c.off[s] = o, c.tid[s] = tid, c.pos[s] = E.pos5, c.begin[s] = E.b5, c.ll[s] = E.l5, c.rl[s] = E.r5, c.side[s] = 0;
+        }
+        s += E.e5;
+        if (E.e3 && s < cand_cap) {
+            c.off[s] = o, c.tid[s] = tid, c.pos[s] = E.pos3, c.begin[s] = E.b3, c.ll[s] = E.l3, c.rl[s] = E.r3, c.side[s] = 1;
+        }
     }
-    key[i] = ((uint64_t)lo << 33) | ((uint64_t)c.side[s] << 32) | (uint32_t)(c.pos[s] ^ 0x80000000);
 }
 
-__global__ void iota_u32(uint32_t n, uint32_t *v)
+// first sort: (record offset, candidate index)
+__global__ void cand_sort_input(const uint32_t *__restrict__ n_ptr, uint32_t cap, const uint64_t *__restrict__ off, uint64_t *__restrict__ key,
+                                uint32_t *__restrict__ val, ClipCtl *ctl)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = i;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && *n_ptr > cap) ctl->abort_main = 1;
+    const uint32_t n = min(*n_ptr, cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) key[i] = off[i], val[i] = i;
 }
 
-__global__ void seg_flags(uint32_t n, const uint64_t *__restrict__ key, uint32_t *__restrict__ flag)
+// second sort key = flush run (number of chromosome switches before the record) | side | position
+static constexpr uint32_t SW_LINEAR = 1024;
+__global__ void __launch_bounds__(256)
+    make_keys(const uint32_t *__restrict__ counters, uint32_t cand_cap, uint32_t sw_cap, const uint32_t *__restrict__ order, CandArrays c,
+              const uint64_t *__restrict__ sw_sorted, uint64_t *__restrict__ key, uint32_t *__restrict__ val)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
+    __shared__ uint64_t ssw[SW_LINEAR];
+    const uint32_t n = min(counters[3], cand_cap), n_sw = min(counters[2], sw_cap);
+    const bool linear = n_sw <= SW_LINEAR;  // few switches (a coordinate-sorted BAM has one per chromosome): count them directly
+    if (linear) {
+        for (uint32_t j = threadIdx.x; j < n_sw; j += blockDim.x) ssw[j] = sw_sorted[j];
+        __syncthreads();
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t s = order[i];
+        const uint64_t r = c.off[s];
+        uint32_t run = 0;
+        if (linear) {
+            for (uint32_t j = 0; j < n_sw; ++j) run += ssw[j] < r;
+        } else {
+            uint32_t lo = 0, hi = n_sw;  // lower_bound(sw, r): switches with offset < r
+            while (lo < hi) {
+                uint32_t m = (lo + hi) >> 1;
+                if (sw_sorted[m] < r) lo = m + 1;
+                else hi = m;
+            }
+            run = lo;
+        }
+        key[i] = ((uint64_t)run << 33) | ((uint64_t)c.side[s] << 32) | (uint32_t)(c.pos[s] ^ 0x80000000);
+        val[i] = s;
+    }
 }
 
-__global__ void seg_starts(uint32_t n, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ segid,
-                           uint32_t *__restrict__ start, uint32_t n_seg)
-{
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && flag[i]) start[segid[i] - 1] = i;
-    if (i == 0) start[n_seg] = n;
-}
+// ---- segments (one per breakpoint key) ---------------------------------------------------------------------------------------
+struct SegScanOp {
+    const uint32_t *counters;
+    uint32_t cand_cap;
+    const uint64_t *key;
+    uint32_t *start;
+    ClipCtl *ctl;
+    __device__ uint64_t n() const { return ctl->abort_main ? 0 : min(counters[3], cand_cap); }
+    __device__ void load(uint64_t i, uint64_t (&v)[1]) const { v[0] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0; }
+    __device__ void store(uint64_t i, const uint64_t (&excl)[1], const uint64_t (&v)[1]) const
+    {
+        if (v[0]) start[excl[0]] = (uint32_t)i;
+    }
+    __device__ void total(const uint64_t (&t)[1]) const
+    {
+        ctl->n_seg = (uint32_t)t[0];
+        start[t[0]] = (uint32_t)n();
+    }
+};
 
 // per segment: arena bytes = members * (longest left + longest right)
-__global__ void seg_stats(uint32_t n_seg, const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c,
-                          uint32_t *__restrict__ maxl, uint32_t *__restrict__ maxr, uint64_t *__restrict__ bytes)
-{
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_seg) return;
-    uint32_t ml = 0, mr = 0;
-    for (uint32_t k = start[s]; k < start[s + 1]; ++k) {
-        uint32_t x = order[k];
-        ml = max(ml, c.ll[x]);
-        mr = max(mr, c.rl[x]);
+struct SegStatsOp {
+    const uint32_t *start, *order;
+    CandArrays c;
+    uint32_t *maxl, *maxr;
+    uint64_t *arena_off;
+    uint64_t arena_cap;
+    ClipCtl *ctl;
+    __device__ uint64_t n() const { return ctl->abort_main ? 0 : ctl->n_seg; }
+    __device__ void load(uint64_t s, uint64_t (&v)[1]) const
+    {
+        uint32_t ml = 0, mr = 0;
+        for (uint32_t k = start[s]; k < start[s + 1]; ++k) {
+            uint32_t x = order[k];
+            ml = max(ml, c.ll[x]);
+            mr = max(mr, c.rl[x]);
+        }
+        maxl[s] = ml, maxr[s] = mr;
+        v[0] = (uint64_t)(start[s + 1] - start[s]) * (ml + mr);
     }
-    maxl[s] = ml, maxr[s] = mr;
-    bytes[s] = (uint64_t)(start[s + 1] - start[s]) * (ml + mr);
-    if (s == 0) bytes[n_seg] = 0;
-}
+    __device__ void store(uint64_t s, const uint64_t (&excl)[1], const uint64_t (&)[1]) const { arena_off[s] = excl[0]; }
+    __device__ void total(const uint64_t (&t)[1]) const
+    {
+        ctl->arena_bytes = t[0];
+        if (t[0] > arena_cap) ctl->abort_main = 1;
+    }
+};
 
 struct ClusterOut {
     uint32_t *len_l, *len_r, *support;  // indexed by sorted candidate position (seg start + k)
@@ -425,105 +347,121 @@ struct ClusterOut {
 // BAM order, with lane-parallel string compares and consensus updates. Strings live in a per-segment
 // arena: slot k holds [left part right-aligned at column maxl | right part left-aligned at maxl].
 __global__ void __launch_bounds__(128)
-    cluster_build(const uint8_t *__restrict__ d, uint32_t n_seg,
+    cluster_build(const uint8_t *__restrict__ d, const ClipCtl *__restrict__ ctl,
                   const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c,
                   const uint32_t *__restrict__ maxl_, const uint32_t *__restrict__ maxr_, const uint64_t *__restrict__ arena_off,
                   char *__restrict__ arena_seq, char *__restrict__ arena_qual, double limit, ClusterOut out)
 {
-    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    if (s >= n_seg) return;
-    const uint32_t a = start[s], b = start[s + 1];
-    const uint32_t maxl = maxl_[s], stride = maxl + maxr_[s];
-    char *S = arena_seq + arena_off[s], *Q = arena_qual + arena_off[s];
-    uint32_t ncl = 0;
-    for (uint32_t k = a; k < b; ++k) {
-        const uint32_t x = order[k];
-        const uint64_t rec = c.off[x];
-        const uint32_t begin = c.begin[x], ll = c.ll[x], rl = c.rl[x], side = c.side[x];
-        const uint8_t *p = d + rec;
-        uint32_t w = ldu32(p + 12), w2 = ldu32(p + 16);
-        int32_t l_qseq = ldi32(p + 20);
-        const uint8_t *seq = p + 36 + (w & 0xff) + 4 * (w2 & 0xffff);
-        const uint8_t *qual = seq + (l_qseq + 1) / 2;
-        const bool noq = l_qseq > 0 && qual[0] == 0xff;
-        char *tS = S + (uint64_t)ncl * stride, *tQ = Q + (uint64_t)ncl * stride;  // tentative new cluster
-        // GetSeq (clip_reads.cpp:286-306): 4-bit codes -> "=ACMGRSVTWYHKDBN", quality + 33
-        for (uint32_t j = lane; j < ll + rl; j += 32) {
-            uint32_t idx = begin + j;
-            uint32_t nib = (seq[idx >> 1] >> ((~idx & 1) << 2)) & 15;
-            uint32_t col = maxl - ll + j;
-            tS[col] = "=ACMGRSVTWYHKDBN"[nib];
-            tQ[col] = noq ? '*' : (char)(qual[idx] + 33);
-        }
-        __syncwarp();
-        int found = -1;
-        for (uint32_t cl = 0; cl < ncl; ++cl) {
-            const char *cS = S + (uint64_t)cl * stride;
-            uint32_t cL = out.len_l[a + cl], cR = out.len_r[a + cl];
-            uint32_t n1 = min(ll, cL), n2 = min(rl, cR);
-            uint32_t m1 = 0, m2 = 0;
-            for (uint32_t j = lane; j < n1; j += 32) m1 += tS[maxl - 1 - j] == cS[maxl - 1 - j];  // CompareStringEndFirst
-            for (uint32_t j = lane; j < n2; j += 32) m2 += tS[maxl + j] == cS[maxl + j];          // CompareStringBeginFirst
-            m1 = warp_sum(m1);
-            m2 = warp_sum(m2);
-            // (double)match/len >= limit; len == 0 gives NaN -> false (clip_reads.cpp:204,216)
-            bool ok = n1 > 0 && n2 > 0 && (double)m1 / (double)n1 >= limit && (double)m2 / (double)n2 >= limit;
-            if (ok) {
-                found = (int)cl;
-                break;
+    if (ctl->abort_main) return;
+    const uint32_t n_seg = ctl->n_seg, lane = threadIdx.x & 31;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_seg; s += n_warps) {
+        const uint32_t a = start[s], b = start[s + 1];
+        const uint32_t maxl = maxl_[s], stride = maxl + maxr_[s];
+        char *S = arena_seq + arena_off[s], *Q = arena_qual + arena_off[s];
+        uint32_t ncl = 0;
+        for (uint32_t k = a; k < b; ++k) {
+            const uint32_t x = order[k];
+            const uint64_t rec = c.off[x];
+            const uint32_t begin = c.begin[x], ll = c.ll[x], rl = c.rl[x], side = c.side[x];
+            const uint8_t *p = d + rec;
+            uint32_t w = ldu32(p + 12), w2 = ldu32(p + 16);
+            int32_t l_qseq = ldi32(p + 20);
+            const uint8_t *seq = p + 36 + (w & 0xff) + 4 * (w2 & 0xffff);
+            const uint8_t *qual = seq + (l_qseq + 1) / 2;
+            const bool noq = l_qseq > 0 && qual[0] == 0xff;
+            char *tS = S + (uint64_t)ncl * stride, *tQ = Q + (uint64_t)ncl * stride;  // tentative new cluster
+            // GetSeq (clip_reads.cpp:286-306): 4-bit codes -> "=ACMGRSVTWYHKDBN", quality + 33
+            for (uint32_t j = lane; j < ll + rl; j += 32) {
+                uint32_t idx = begin + j;
+                uint32_t nib = (seq[idx >> 1] >> ((~idx & 1) << 2)) & 15;
+                uint32_t col = maxl - ll + j;
+                tS[col] = "=ACMGRSVTWYHKDBN"[nib];
+                tQ[col] = noq ? '*' : (char)(qual[idx] + 33);
             }
-        }
-        if (found < 0) {
-            if (lane == 0) {
-                out.len_l[a + ncl] = ll, out.len_r[a + ncl] = rl, out.cig_off[a + ncl] = rec, out.support[a + ncl] = 1;
-                out.noqual[a + ncl] = noq;
-            }
-            ++ncl;
-        } else {
-            // ReadsInfo::ChangeSeqAndQual (clip_reads.cpp:57-108)
-            char *cS = S + (uint64_t)found * stride, *cQ = Q + (uint64_t)found * stride;
-            uint32_t cL = out.len_l[a + found], cR = out.len_r[a + found];
-            bool cnoq = out.noqual[a + found];
-            uint32_t n1 = min(ll, cL), n2 = min(rl, cR);
-            if (!noq && !cnoq) {  // (with a missing quality string the reference indexes out of bounds)
-                for (uint32_t j = lane; j < n1; j += 32) {
-                    uint32_t col = maxl - 1 - j;
-                    if (cQ[col] < tQ[col]) cQ[col] = tQ[col], cS[col] = tS[col];
-                }
-                for (uint32_t j = lane; j < n2; j += 32) {
-                    uint32_t col = maxl + j;
-                    if (cQ[col] < tQ[col]) cQ[col] = tQ[col], cS[col] = tS[col];
+            __syncwarp();
+            int found = -1;
+            for (uint32_t cl = 0; cl < ncl; ++cl) {
+                const char *cS = S + (uint64_t)cl * stride;
+                uint32_t cL = out.len_l[a + cl], cR = out.len_r[a + cl];
+                uint32_t n1 = min(ll, cL), n2 = min(rl, cR);
+                uint32_t m1 = 0, m2 = 0;
+                for (uint32_t j = lane; j < n1; j += 32) m1 += tS[maxl - 1 - j] == cS[maxl - 1 - j];  // CompareStringEndFirst
+                for (uint32_t j = lane; j < n2; j += 32) m2 += tS[maxl + j] == cS[maxl + j];          // CompareStringBeginFirst
+                m1 = warp_sum(m1);
+                m2 = warp_sum(m2);
+                // (double)match/len >= limit; len == 0 gives NaN -> false (clip_reads.cpp:204,216)
+                bool ok = n1 > 0 && n2 > 0 && (double)m1 / (double)n1 >= limit && (double)m2 / (double)n2 >= limit;
+                if (ok) {
+                    found = (int)cl;
+                    break;
                 }
             }
-            if (cL <= ll) {  // extend to the longer left part; right-clipped clusters take the new CIGAR
-                for (uint32_t j = lane; j < ll - cL; j += 32) {
-                    uint32_t col = maxl - ll + j;
-                    cS[col] = tS[col], cQ[col] = tQ[col];
+            if (found < 0) {
+                if (lane == 0) {
+                    out.len_l[a + ncl] = ll, out.len_r[a + ncl] = rl, out.cig_off[a + ncl] = rec, out.support[a + ncl] = 1;
+                    out.noqual[a + ncl] = noq;
                 }
-            }
-            if (cR < rl) {
-                for (uint32_t j = lane; j < rl - cR; j += 32) {
-                    uint32_t col = maxl + cR + j;
-                    cS[col] = tS[col], cQ[col] = tQ[col];
+                ++ncl;
+            } else {
+                // ReadsInfo::ChangeSeqAndQual (clip_reads.cpp:57-108)
+                char *cS = S + (uint64_t)found * stride, *cQ = Q + (uint64_t)found * stride;
+                uint32_t cL = out.len_l[a + found], cR = out.len_r[a + found];
+                bool cnoq = out.noqual[a + found];
+                uint32_t n1 = min(ll, cL), n2 = min(rl, cR);
+                if (!noq && !cnoq) {  // (with a missing quality string the reference indexes out of bounds)
+                    for (uint32_t j = lane; j < n1; j += 32) {
+                        uint32_t col = maxl - 1 - j;
+                        if (cQ[col] < tQ[col]) cQ[col] = tQ[col], cS[col] = tS[col];
+                    }
+                    for (uint32_t j = lane; j < n2; j += 32) {
+                        uint32_t col = maxl + j;
+                        if (cQ[col] < tQ[col]) cQ[col] = tQ[col], cS[col] = tS[col];
+                    }
                 }
-            }
-            if (lane == 0) {
-                if (cL <= ll) {
-                    out.len_l[a + found] = ll;
-                    if (side == 1) out.cig_off[a + found] = rec;
+                if (cL <= ll) {  // extend to the longer left part; right-clipped clusters take the new CIGAR
+                    for (uint32_t j = lane; j < ll - cL; j += 32) {
+                        uint32_t col = maxl - ll + j;
+                        cS[col] = tS[col], cQ[col] = tQ[col];
+                    }
                 }
                 if (cR < rl) {
-                    out.len_r[a + found] = rl;
-                    if (side == 0) out.cig_off[a + found] = rec;
+                    for (uint32_t j = lane; j < rl - cR; j += 32) {
+                        uint32_t col = maxl + cR + j;
+                        cS[col] = tS[col], cQ[col] = tQ[col];
+                    }
                 }
-                out.support[a + found] += 1;
+                if (lane == 0) {
+                    if (cL <= ll) {
+                        out.len_l[a + found] = ll;
+                        if (side == 1) out.cig_off[a + found] = rec;
+                    }
+                    if (cR < rl) {
+                        out.len_r[a + found] = rl;
+                        if (side == 0) out.cig_off[a + found] = rec;
+                    }
+                    out.support[a + found] += 1;
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
+        if (lane == 0) out.seg_ncl[s] = ncl;
     }
-    if (lane == 0) out.seg_ncl[s] = ncl;
 }
+
+// cluster slot -> flat cluster list
+struct ClusterScanOp {
+    const uint32_t *seg_ncl;
+    uint32_t *cl_seg, *cl_slot;
+    ClipCtl *ctl;
+    __device__ uint64_t n() const { return ctl->abort_main ? 0 : ctl->n_seg; }
+    __device__ void load(uint64_t s, uint64_t (&v)[1]) const { v[0] = seg_ncl[s]; }
+    __device__ void store(uint64_t s, const uint64_t (&excl)[1], const uint64_t (&v)[1]) const
+    {
+        for (uint32_t k = 0; k < (uint32_t)v[0]; ++k) cl_seg[excl[0] + k] = (uint32_t)s, cl_slot[excl[0] + k] = k;
+    }
+    __device__ void total(const uint64_t (&t)[1]) const { ctl->n_cl = (uint32_t)t[0]; }
+};
 
 // ---- text emission --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t dec_len(uint32_t v)
@@ -573,123 +511,143 @@ __device__ uint32_t cigar_text(const uint8_t *p, char *o)
     return len;
 }
 
-// cluster slot -> flat cluster list; one thread per segment
-__global__ void list_clusters(uint32_t n_seg, const uint32_t *__restrict__ start, const uint32_t *__restrict__ seg_ncl,
-                              const uint32_t *__restrict__ cl_base, uint32_t *__restrict__ cl_seg, uint32_t *__restrict__ cl_slot)
-{
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_seg) return;
-    uint32_t base = cl_base[s] - seg_ncl[s];  // cl_base is the inclusive scan
-    for (uint32_t k = 0; k < seg_ncl[s]; ++k) cl_seg[base + k] = s, cl_slot[base + k] = k;
-}
-
-__global__ void text_sizes(uint32_t n_cl, const uint32_t *__restrict__ cl_seg, const uint32_t *__restrict__ cl_slot,
-                           const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c, ClusterOut out,
-                           const uint8_t *__restrict__ d, NameTable names, uint64_t *__restrict__ clip_len,
-                           uint64_t *__restrict__ fq_len)
-{
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cl) {
-        if (i == n_cl) clip_len[i] = 0, fq_len[i] = 0;
-        return;
+struct TextScanOp {
+    const uint32_t *cl_seg, *cl_slot, *start, *order;
+    CandArrays c;
+    ClusterOut out;
+    const uint8_t *d;
+    NameTable names;
+    uint64_t *clip_off, *fq_off;
+    uint64_t clip_cap, fq_cap;
+    ClipCtl *ctl;
+    __device__ uint64_t n() const { return ctl->abort_main ? 0 : ctl->n_cl; }
+    __device__ void load(uint64_t i, uint64_t (&v)[2]) const
+    {
+        uint32_t s = cl_seg[i], a = start[s], k = a + cl_slot[i];
+        uint32_t x = order[a];
+        uint32_t L = out.len_l[k], R = out.len_r[k];
+        uint32_t qL = out.noqual[k] ? 1 : L, qR = out.noqual[k] ? 1 : R;
+        uint32_t name = names.off[c.tid[x] + 1] - names.off[c.tid[x]];
+        uint32_t cg = cigar_text(d + out.cig_off[k], nullptr);
+        // chr \t pos \t side \t cigar \t aligned \t alignedQ \t clipped \t clippedQ \t support \n
+        v[0] = name + 1 + dec_len_i(c.pos[x]) + 1 + 2 + cg + 1 + L + 1 + qL + 1 + R + 1 + qR + 1 + dec_len(out.support[k]) + 1;
+        uint32_t cl = c.side[x] == 0 ? L : R, cq = c.side[x] == 0 ? qL : qR;
+        v[1] = 1 + cl + 1 + cl + 1 + 2 + cq + 1;  // @seq \n seq \n + \n qual \n
     }
-    uint32_t s = cl_seg[i], a = start[s], k = a + cl_slot[i];
-    uint32_t x = order[a];
-    uint32_t L = out.len_l[k], R = out.len_r[k];
-    uint32_t qL = out.noqual[k] ? 1 : L, qR = out.noqual[k] ? 1 : R;
-    uint32_t name = names.off[c.tid[x] + 1] - names.off[c.tid[x]];
-    uint32_t cg = cigar_text(d + out.cig_off[k], nullptr);
-    // chr \t pos \t side \t cigar \t aligned \t alignedQ \t clipped \t clippedQ \t support \n
-    clip_len[i] = name + 1 + dec_len_i(c.pos[x]) + 1 + 2 + cg + 1 + L + 1 + qL + 1 + R + 1 + qR + 1 + dec_len(out.support[k]) + 1;
-    uint32_t cl = c.side[x] == 0 ? L : R, cq = c.side[x] == 0 ? qL : qR;
-    fq_len[i] = 1 + cl + 1 + cl + 1 + 2 + cq + 1;  // @seq \n seq \n + \n qual \n
-}
+    __device__ void store(uint64_t i, const uint64_t (&excl)[2], const uint64_t (&)[2]) const { clip_off[i] = excl[0], fq_off[i] = excl[1]; }
+    __device__ void total(const uint64_t (&t)[2]) const
+    {
+        ctl->clip_bytes = t[0], ctl->fq_bytes = t[1];
+        if (t[0] > clip_cap || t[1] > fq_cap) ctl->abort_main = 1;
+    }
+};
 
 // one warp per cluster writes its clip.gz line and its FASTQ record
 __global__ void __launch_bounds__(128)
-    text_write(uint32_t n_cl, const uint32_t *__restrict__ cl_seg, const uint32_t *__restrict__ cl_slot,
+    text_write(const ClipCtl *__restrict__ ctl, const uint32_t *__restrict__ cl_seg, const uint32_t *__restrict__ cl_slot,
                const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c, ClusterOut out,
                const uint8_t *__restrict__ d, NameTable names, const uint32_t *__restrict__ maxl_, const uint32_t *__restrict__ maxr_, const uint64_t *__restrict__ arena_off,
                const char *__restrict__ arena_seq, const char *__restrict__ arena_qual, const uint64_t *__restrict__ clip_off,
                const uint64_t *__restrict__ fq_off, char *__restrict__ clip, char *__restrict__ fq)
 {
-    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (i >= n_cl) return;
-    uint32_t s = cl_seg[i], a = start[s], slot = cl_slot[i], k = a + slot;
-    uint32_t x = order[a];
-    uint32_t maxl = maxl_[s], stride = maxl + maxr_[s];
-    const char *S = arena_seq + arena_off[s] + (uint64_t)slot * stride, *Q = arena_qual + arena_off[s] + (uint64_t)slot * stride;
-    uint32_t L = out.len_l[k], R = out.len_r[k];
-    bool noq = out.noqual[k];
-    uint32_t side = c.side[x];
-    // '5': aligned = right part, clipped = left part; '3': aligned = left, clipped = right (clip_reads.h:308-332)
-    const char *aS = side == 0 ? S + maxl : S + maxl - L, *aQ = side == 0 ? Q + maxl : Q + maxl - L;
-    const char *cS = side == 0 ? S + maxl - L : S + maxl, *cQ = side == 0 ? Q + maxl - L : Q + maxl;
-    uint32_t aN = side == 0 ? R : L, cN = side == 0 ? L : R;
-    uint32_t aQN = noq ? 1 : aN, cQN = noq ? 1 : cN;
-    char *o = clip + clip_off[i];
-    uint32_t head = 0;
-    if (lane == 0) {
-        int32_t tid = c.tid[x];
-        const char *nm = names.blob + names.off[tid];
-        uint32_t nl = names.off[tid + 1] - names.off[tid];
-        char *q = o;
-        for (uint32_t j = 0; j < nl; ++j) *q++ = nm[j];
-        *q++ = '\t';
-        q = put_dec_i(q, c.pos[x]);
-        *q++ = '\t';
-        *q++ = side == 0 ? '5' : '3';
-        *q++ = '\t';
-        q += cigar_text(d + out.cig_off[k], q);
-        *q++ = '\t';
-        head = (uint32_t)(q - o);
+    if (ctl->abort_main) return;
+    const uint32_t n_cl = ctl->n_cl, lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_cl; i += n_warps) {
+        uint32_t s = cl_seg[i], a = start[s], slot = cl_slot[i], k = a + slot;
+        uint32_t x = order[a];
+        uint32_t maxl = maxl_[s], stride = maxl + maxr_[s];
+        const char *S = arena_seq + arena_off[s] + (uint64_t)slot * stride, *Q = arena_qual + arena_off[s] + (uint64_t)slot * stride;
+        uint32_t L = out.len_l[k], R = out.len_r[k];
+        bool noq = out.noqual[k];
+        uint32_t side = c.side[x];
+        // '5': aligned = right part, clipped = left part; '3': aligned = left, clipped = right (clip_reads.h:308-332)
+        const char *aS = side == 0 ? S + maxl : S + maxl - L, *aQ = side == 0 ? Q + maxl : Q + maxl - L;
+        const char *cS = side == 0 ? S + maxl - L : S + maxl, *cQ = side == 0 ? Q + maxl - L : Q + maxl;
+        uint32_t aN = side == 0 ? R : L, cN = side == 0 ? L : R;
+        uint32_t aQN = noq ? 1 : aN, cQN = noq ? 1 : cN;
+        char *o = clip + clip_off[i];
+        uint32_t head = 0;
+        if (lane == 0) {
+            int32_t tid = c.tid[x];
+            const char *nm = names.blob + names.off[tid];
+            uint32_t nl = names.off[tid + 1] - names.off[tid];
+            char *q = o;
+            for (uint32_t j = 0; j < nl; ++j) *q++ = nm[j];
+            *q++ = '\t';
+            q = put_dec_i(q, c.pos[x]);
+            *q++ = '\t';
+            *q++ = side == 0 ? '5' : '3';
+            *q++ = '\t';
+            q += cigar_text(d + out.cig_off[k], q);
+            *q++ = '\t';
+            head = (uint32_t)(q - o);
+        }
+        head = __shfl_sync(0xffffffffu, head, 0);
+        char *q = o + head;
+        for (uint32_t j = lane; j < aN; j += 32) q[j] = aS[j];
+        q += aN;
+        if (lane == 0) *q = '\t';
+        ++q;
+        for (uint32_t j = lane; j < aQN; j += 32) q[j] = noq ? '*' : aQ[j];
+        q += aQN;
+        if (lane == 0) *q = '\t';
+        ++q;
+        for (uint32_t j = lane; j < cN; j += 32) q[j] = cS[j];
+        q += cN;
+        if (lane == 0) *q = '\t';
+        ++q;
+        for (uint32_t j = lane; j < cQN; j += 32) q[j] = noq ? '*' : cQ[j];
+        q += cQN;
+        if (lane == 0) {
+            *q++ = '\t';
+            q = put_dec(q, out.support[k]);
+            *q++ = '\n';
+        }
+        // FASTQ record named by its own sequence (clip_reads.h:320,339)
+        char *f = fq + fq_off[i];
+        if (lane == 0) f[0] = '@', f[1 + cN] = '\n', f[2 + 2 * cN] = '\n', f[3 + 2 * cN] = '+', f[4 + 2 * cN] = '\n', f[5 + 2 * cN + cQN] = '\n';
+        for (uint32_t j = lane; j < cN; j += 32) f[1 + j] = cS[j], f[2 + cN + j] = cS[j];
+        for (uint32_t j = lane; j < cQN; j += 32) f[5 + 2 * cN + j] = noq ? '*' : cQ[j];
     }
-    head = __shfl_sync(0xffffffffu, head, 0);
-    char *q = o + head;
-    for (uint32_t j = lane; j < aN; j += 32) q[j] = aS[j];
-    q += aN;
-    if (lane == 0) *q = '\t';
-    ++q;
-    for (uint32_t j = lane; j < aQN; j += 32) q[j] = noq ? '*' : aQ[j];
-    q += aQN;
-    if (lane == 0) *q = '\t';
-    ++q;
-    for (uint32_t j = lane; j < cN; j += 32) q[j] = cS[j];
-    q += cN;
-    if (lane == 0) *q = '\t';
-    ++q;
-    for (uint32_t j = lane; j < cQN; j += 32) q[j] = noq ? '*' : cQ[j];
-    q += cQN;
-    if (lane == 0) {
-        *q++ = '\t';
-        q = put_dec(q, out.support[k]);
-        *q++ = '\n';
-    }
-    // FASTQ record named by its own sequence (clip_reads.h:320,339)
-    char *f = fq + fq_off[i];
-    if (lane == 0) f[0] = '@', f[1 + cN] = '\n', f[2 + 2 * cN] = '\n', f[3 + 2 * cN] = '+', f[4 + 2 * cN] = '\n', f[5 + 2 * cN + cQN] = '\n';
-    for (uint32_t j = lane; j < cN; j += 32) f[1 + j] = cS[j], f[2 + cN + j] = cS[j];
-    for (uint32_t j = lane; j < cQN; j += 32) f[5 + 2 * cN + j] = noq ? '*' : cQ[j];
 }
 
 // ---- unmapped-branch records: StoreUnmapSeqAndQual (clip_reads.h:172-219) on the device --------------------------
 // The reference keeps a std::map<qname, held mate> over the whole file: the first record of a name is held; a later
 // record of the same name and the OTHER end emits the pair (read1 to file 1, read2 to file 2) and erases the entry; a
-// later record of the same end is ignored. Output order = file order of the completing record. Here: hash the
-// names, stable-sort entries by hash (entries stay in file order inside a group), run the tiny per-name automaton
-// with one thread per hash group (real name compares, so hash collisions cannot change the result), then emit text.
+// later record of the same end is ignored. Output order = file order of the completing record. Here: sort the queued
+// records by offset, hash the names, stable-sort entries by hash (entries stay in file order inside a group), run the tiny
+// per-name automaton with one thread per hash group (real name compares, so hash collisions cannot change the result), then
+// emit text. The whole branch runs on a side stream next to the candidate pipeline.
 __device__ __forceinline__ uint32_t qname_len(const uint8_t *p) { return ldu32(p + 12) & 0xff; }
 
-__global__ void unmapped_hash(uint32_t n, const uint64_t *__restrict__ list, const uint8_t *__restrict__ d,
+// the unmapped list is sorted by offset: records in front of the shard's own region (range shards) only lend their soft clips
+__global__ void unmapped_own(const uint32_t *__restrict__ counters, uint32_t un_cap, const uint64_t *__restrict__ sorted, uint64_t halo_bytes,
+                             ClipCtl *ctl)
+{
+    if (counters[1] > un_cap) ctl->abort_side = 1;
+    const uint32_t n = min(counters[1], un_cap);
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t m = (lo + hi) >> 1;
+        if (sorted[m] < halo_bytes) lo = m + 1;
+        else hi = m;
+    }
+    ctl->un_skip = lo, ctl->un_own = n - lo;
+}
+
+__global__ void unmapped_hash(const ClipCtl *__restrict__ ctl, const uint64_t *__restrict__ sorted, const uint8_t *__restrict__ d,
                               uint64_t *__restrict__ key, uint32_t *__restrict__ val)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t *p = d + list[i];
-    uint32_t lq = qname_len(p);
-    uint64_t h = 0xcbf29ce484222325ull;
-    for (uint32_t j = 0; j < lq && p[36 + j]; ++j) h = (h ^ p[36 + j]) * 0x100000001b3ull;
-    key[i] = h, val[i] = i;
+    if (ctl->abort_side) return;
+    const uint32_t n = ctl->un_own;
+    const uint64_t *list = sorted + ctl->un_skip;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint8_t *p = d + list[i];
+        uint32_t lq = qname_len(p);
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (uint32_t j = 0; j < lq && p[36 + j]; ++j) h = (h ^ p[36 + j]) * 0x100000001b3ull;
+        key[i] = h & 0xffffffffu, val[i] = i;  // 32 bits order the groups; the names themselves decide inside a group
+    }
 }
 
 __device__ bool same_name(const uint8_t *a, const uint8_t *b)
@@ -702,36 +660,58 @@ __device__ bool same_name(const uint8_t *a, const uint8_t *b)
     }
 }
 
-// one thread per hash group; mate_of[e] = entry that was held when e completed a pair, else 0xffffffff
-__global__ void unmapped_pair(uint32_t n, const uint64_t *__restrict__ key, const uint32_t *__restrict__ ent,
-                              const uint64_t *__restrict__ list, const uint8_t *__restrict__ d, uint32_t *__restrict__ mate_of,
-                              uint32_t *__restrict__ overflow)
+// one thread per hash group; mate_of[e] = entry that was held when e completed a pair, else 0xffffffff. Up to H names of a
+// group are tracked in registers; a group with more distinct names at once (a 64-bit hash collision of more than eight names)
+// switches to replaying the group's history for every further entry - exact, only slower.
+__global__ void unmapped_pair(const ClipCtl *__restrict__ ctl, const uint64_t *__restrict__ key, const uint32_t *__restrict__ ent,
+                               const uint64_t *__restrict__ sorted, const uint8_t *__restrict__ d, uint32_t *__restrict__ mate_of)
 {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n || (j > 0 && key[j] == key[j - 1])) return;
-    const int H = 8;
-    uint32_t held[H];
-    int nh = 0;
-    for (uint32_t k = j; k < n && key[k] == key[j]; ++k) {
-        uint32_t e = ent[k];
-        const uint8_t *p = d + list[e];
-        bool r1 = (ldu32(p + 16) >> 16) & F_READ1;
-        int hit = -1;
-        for (int h = 0; h < nh; ++h)
-            if (same_name(p, d + list[held[h]])) {
-                hit = h;
-                break;
+    if (ctl->abort_side) return;
+    const uint32_t n = ctl->un_own;
+    const uint64_t *list = sorted + ctl->un_skip;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        if (j > 0 && key[j] == key[j - 1]) continue;  // (keys are the low 32 bits of the name hash)
+        const int H = 8;
+        uint32_t held[H];
+        int nh = 0;
+        bool replay = false;
+        for (uint32_t k = j; k < n && key[k] == key[j]; ++k) {
+            uint32_t e = ent[k];
+            const uint8_t *p = d + list[e];
+            bool r1 = (ldu32(p + 16) >> 16) & F_READ1;
+            if (replay) {  // state of this name from the group's history: held entry or none
+                uint32_t h = 0xffffffffu;
+                bool h1 = false;
+                for (uint32_t k2 = j; k2 < k; ++k2) {
+                    const uint8_t *q = d + list[ent[k2]];
+                    if (!same_name(p, q)) continue;
+                    bool q1 = (ldu32(q + 16) >> 16) & F_READ1;
+                    if (h == 0xffffffffu) h = ent[k2], h1 = q1;
+                    else if (q1 != h1) h = 0xffffffffu;
+                }
+                if (h != 0xffffffffu && h1 != r1) mate_of[e] = h;
+                continue;
             }
-        if (hit < 0) {
-            if (nh < H) held[nh++] = e;
-            else atomicOr(overflow, 1u);
-        } else {
-            const uint8_t *q = d + list[held[hit]];
-            bool q1 = (ldu32(q + 16) >> 16) & F_READ1;
-            if (q1 != r1) {
-                mate_of[e] = held[hit];
-                held[hit] = held[--nh];
-            }  // same end again: neither emitted nor stored
+            int hit = -1;
+            for (int h = 0; h < nh; ++h)
+                if (same_name(p, d + list[held[h]])) {
+                    hit = h;
+                    break;
+                }
+            if (hit < 0) {
+                if (nh < H) held[nh++] = e;
+                else {
+                    replay = true;
+                    --k;  // this entry again, by replay
+                }
+            } else {
+                const uint8_t *q = d + list[held[hit]];
+                bool q1 = (ldu32(q + 16) >> 16) & F_READ1;
+                if (q1 != r1) {
+                    mate_of[e] = held[hit];
+                    held[hit] = held[--nh];
+                }  // same end again: neither emitted nor stored
+            }
         }
     }
 }
@@ -748,19 +728,31 @@ __device__ __forceinline__ uint32_t unmapped_fq_len(const uint8_t *p)
     return 1 + nl + 2 + 1 + (uint32_t)l + 1 + 2 + ql + 1;
 }
 
-__global__ void unmapped_sizes(uint32_t n, const uint64_t *__restrict__ list, const uint32_t *__restrict__ mate_of,
-                               const uint8_t *__restrict__ d, uint64_t *__restrict__ sz1, uint64_t *__restrict__ sz2)
-{
-    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e > n) return;
-    uint64_t a = 0, b = 0;
-    if (e < n && mate_of[e] != 0xffffffffu) {
-        const uint8_t *p = d + list[e], *q = d + list[mate_of[e]];
-        bool p1 = (ldu32(p + 16) >> 16) & F_READ1;
-        a = unmapped_fq_len(p1 ? p : q), b = unmapped_fq_len(p1 ? q : p);
+struct UnSizesOp {
+    const uint64_t *sorted;
+    const uint32_t *mate_of;
+    const uint8_t *d;
+    uint64_t *off1, *off2;
+    uint64_t cap1, cap2;
+    ClipCtl *ctl;
+    __device__ uint64_t n() const { return ctl->abort_side ? 0 : ctl->un_own; }
+    __device__ void load(uint64_t e, uint64_t (&v)[2]) const
+    {
+        v[0] = v[1] = 0;
+        if (mate_of[e] != 0xffffffffu) {
+            const uint64_t *list = sorted + ctl->un_skip;
+            const uint8_t *p = d + list[e], *q = d + list[mate_of[e]];
+            bool p1 = (ldu32(p + 16) >> 16) & F_READ1;
+            v[0] = unmapped_fq_len(p1 ? p : q), v[1] = unmapped_fq_len(p1 ? q : p);
+        }
     }
-    sz1[e] = a, sz2[e] = b;
-}
+    __device__ void store(uint64_t e, const uint64_t (&excl)[2], const uint64_t (&)[2]) const { off1[e] = excl[0], off2[e] = excl[1]; }
+    __device__ void total(const uint64_t (&t)[2]) const
+    {
+        ctl->un1_bytes = t[0], ctl->un2_bytes = t[1];
+        if (t[0] > cap1 || t[1] > cap2) ctl->abort_side = 1;
+    }
+};
 
 __device__ void write_unmapped_fq(const uint8_t *p, char end, char *o, uint32_t lane)
 {
@@ -785,53 +777,50 @@ __device__ void write_unmapped_fq(const uint8_t *p, char end, char *o, uint32_t 
 }
 
 __global__ void __launch_bounds__(128)
-    unmapped_write(uint32_t n, const uint64_t *__restrict__ list, const uint32_t *__restrict__ mate_of, const uint8_t *__restrict__ d,
+    unmapped_write(const ClipCtl *__restrict__ ctl, const uint64_t *__restrict__ sorted, const uint32_t *__restrict__ mate_of, const uint8_t *__restrict__ d,
                    const uint64_t *__restrict__ off1, const uint64_t *__restrict__ off2, char *__restrict__ out1,
                    char *__restrict__ out2)
 {
-    uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (e >= n || mate_of[e] == 0xffffffffu) return;
-    const uint8_t *p = d + list[e], *q = d + list[mate_of[e]];
-    bool p1 = (ldu32(p + 16) >> 16) & F_READ1;
-    write_unmapped_fq(p1 ? p : q, '1', out1 + off1[e], lane);
-    write_unmapped_fq(p1 ? q : p, '2', out2 + off2[e], lane);
-}
-
-// ---- host orchestration -----------------------------------------------------------------------------------
-static int sort_u64(svb_ctx *ctx, uint64_t *keys_in, uint64_t *keys_out, uint32_t n, int bits)
-{
-    size_t tmp = 0;
-    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys_in, keys_out, (int)n, 0, bits, ctx->stream));
-    DevBuf<uint8_t> t;
-    CK(t.alloc(tmp, ctx->stream));
-    CK(cub::DeviceRadixSort::SortKeys(t.p, tmp, keys_in, keys_out, (int)n, 0, bits, ctx->stream));
-    return 0;
-}
-
-static inline unsigned nblk(uint64_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
-
-__global__ void count_below(uint32_t n, const uint64_t *__restrict__ off, uint64_t limit, uint32_t *__restrict__ count)
-{
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && off[i] < limit) atomicAdd(count, 1u);
+    if (ctl->abort_side) return;
+    const uint32_t n = ctl->un_own, lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint64_t *list = sorted + ctl->un_skip;
+    for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += n_warps) {
+        if (mate_of[e] == 0xffffffffu) continue;
+        const uint8_t *p = d + list[e], *q = d + list[mate_of[e]];
+        bool p1 = (ldu32(p + 16) >> 16) & F_READ1;
+        write_unmapped_fq(p1 ? p : q, '1', out1 + off1[e], lane);
+        write_unmapped_fq(p1 ? q : p, '2', out2 + off2[e], lane);
+    }
 }
 
 // ---- shard plumbing: raw records of the unmapped branch, packed in file order ------------------------------------
-__global__ void record_sizes(uint32_t n, const uint64_t *__restrict__ off, const uint8_t *__restrict__ d, uint64_t *__restrict__ size)
+struct ExportScanOp {
+    const uint64_t *sorted;
+    const uint8_t *d;
+    uint64_t *dst_off;
+    uint64_t cap;
+    ClipCtl *ctl;
+    __device__ uint64_t n() const { return ctl->abort_side ? 0 : ctl->un_own; }
+    __device__ void load(uint64_t i, uint64_t (&v)[1]) const { v[0] = 4ull + ldu32(d + sorted[ctl->un_skip + i]); }
+    __device__ void store(uint64_t i, const uint64_t (&excl)[1], const uint64_t (&)[1]) const { dst_off[i] = excl[0]; }
+    __device__ void total(const uint64_t (&t)[1]) const
+    {
+        ctl->export_bytes = t[0];
+        if (t[0] > cap) ctl->abort_side = 1;
+    }
+};
+__global__ void record_copy(const ClipCtl *__restrict__ ctl, const uint64_t *__restrict__ sorted, const uint8_t *__restrict__ d,
+                            const uint64_t *__restrict__ dst_off, uint8_t *__restrict__ dst)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    size[i] = i < n ? 4ull + ldu32(d + off[i]) : 0ull;
-}
-__global__ void record_copy(uint32_t n, const uint64_t *__restrict__ off, const uint8_t *__restrict__ d, const uint64_t *__restrict__ dst_off,
-                            uint8_t *__restrict__ dst)
-{
-    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= n) return;
-    const uint8_t *src = d + off[w];
-    uint8_t *out = dst + dst_off[w];
-    const uint64_t bytes = dst_off[w + 1] - dst_off[w];
-    for (uint64_t i = lane; i < bytes; i += 32) out[i] = src[i];
+    if (ctl->abort_side) return;
+    const uint32_t n = ctl->un_own, lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint64_t *list = sorted + ctl->un_skip;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += n_warps) {
+        const uint8_t *src = d + list[w];
+        uint8_t *out = dst + dst_off[w];
+        const uint64_t bytes = 4ull + ldu32(src);
+        for (uint64_t i = lane; i < bytes; i += 32) out[i] = src[i];
+    }
 }
 
 // ---- shard plumbing: tid of the last mapped-branch record (what the next shard needs as prev_tid, quirk Q1) -----------
@@ -851,6 +840,8 @@ __global__ void last_mapped_walk(const uint8_t *__restrict__ d, uint64_t n_chunk
     chunk_tid[c] = tid;
     if (any) atomicMax(last_chunk, (unsigned long long)c + 1);
 }
+
+static inline unsigned nblk(uint64_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
 
 extern "C" int svb_bam_last_mapped_tid(svb_ctx *ctx, svb_bam *bam, int32_t *has_one, int32_t *tid)
 {
@@ -872,348 +863,291 @@ extern "C" int svb_bam_last_mapped_tid(svb_ctx *ctx, svb_bam *bam, int32_t *has_
     return 0;
 }
 
+// ---- host orchestration -----------------------------------------------------------------------------------
+namespace {
+enum Hint { H_CLIPPED, H_UNMAPPED, H_SWITCH, H_CAND, H_ARENA, H_CLIP, H_FQ, H_UN1, H_UN2, H_EXPORT };
+
+struct Caps {
+    uint32_t clipped, un, sw, cand;
+    uint64_t arena, clip, fq, un1, un2, exp;
+};
+
+// everything the pipeline keeps in the workspace
+struct ClipBuffers {
+    ClipCtl *ctl;
+    unsigned long long *ticket;
+    ClipQueues q;
+    CandArrays c;
+    uint64_t *key[2];
+    uint32_t *val[2];
+    uint64_t *sw_sorted, *un_sorted, *ukey[2];
+    uint32_t *uval[2], *mate_of;
+    uint32_t *start, *maxl, *maxr;
+    uint64_t *arena_off;
+    char *arena_seq, *arena_qual;
+    ClusterOut co;
+    uint32_t *cl_seg, *cl_slot;
+    uint64_t *clip_off, *fq_off, *off1, *off2;
+    char *nblob;
+    uint32_t *noff;
+    RadixScratch rs_off, rs_key, rs_sw, rs_un, rs_hash;
+    ScanScratch sc_chunk, sc_seg, sc_stats, sc_cl, sc_text, sc_un;
+    size_t zero_end;  // [0, zero_end) is cleared before the first launch
+};
+
+void carve(Bump &b, ClipBuffers &B, const Caps &cap, uint64_t n_chunks, int off_passes, int key_passes, size_t name_bytes, int32_t n_ref, bool pair_mode,
+           bool export_mode)
+{
+    // --- cleared region: control block, tickets, look-back states
+    B.ctl = b.get<ClipCtl>(1);
+    B.ticket = b.get<unsigned long long>(1);
+    B.rs_off = radix_scratch(b, cap.cand, off_passes);
+    B.rs_key = radix_scratch(b, cap.cand, key_passes);
+    B.rs_sw = radix_scratch(b, cap.sw, off_passes);
+    B.rs_un = radix_scratch(b, cap.un, off_passes);
+    B.rs_hash = radix_scratch(b, pair_mode ? cap.un : 1, 4);
+    B.sc_chunk = scan_scratch(b, n_chunks, 1);
+    B.sc_seg = scan_scratch(b, cap.cand, 1);
+    B.sc_stats = scan_scratch(b, cap.cand, 1);
+    B.sc_cl = scan_scratch(b, cap.cand, 1);
+    B.sc_text = scan_scratch(b, cap.cand, 2);
+    B.sc_un = scan_scratch(b, cap.un, 2);
+    B.zero_end = (b.used + 255) & ~(size_t)255;
+    // --- queues and per-chunk side arrays
+    B.q.clipped = b.get<uint64_t>(cap.clipped), B.q.clipped_cap = cap.clipped;
+    B.q.unmapped = b.get<uint64_t>(cap.un), B.q.un_cap = cap.un;
+    B.q.switches = b.get<uint64_t>(cap.sw), B.q.sw_cap = cap.sw;
+    B.q.counters = B.ctl ? B.ctl->counters : nullptr;
+    B.q.first_mb = b.get<uint64_t>(n_chunks);
+    B.q.last_mb_tid = b.get<int32_t>(n_chunks);
+    // --- candidates
+    B.c.off = b.get<uint64_t>(cap.cand), B.c.tid = b.get<int32_t>(cap.cand), B.c.pos = b.get<int32_t>(cap.cand);
+    B.c.begin = b.get<uint32_t>(cap.cand), B.c.ll = b.get<uint32_t>(cap.cand), B.c.rl = b.get<uint32_t>(cap.cand);
+    B.c.side = b.get<uint8_t>(cap.cand);
+    for (int i = 0; i < 2; ++i) B.key[i] = b.get<uint64_t>(cap.cand), B.val[i] = b.get<uint32_t>(cap.cand);
+    B.sw_sorted = b.get<uint64_t>(cap.sw);
+    B.un_sorted = b.get<uint64_t>(cap.un);
+    for (int i = 0; i < 2; ++i) B.ukey[i] = b.get<uint64_t>(pair_mode ? cap.un : 1), B.uval[i] = b.get<uint32_t>(pair_mode ? cap.un : 1);
+    B.mate_of = b.get<uint32_t>(pair_mode ? cap.un : 1);
+    B.start = b.get<uint32_t>((size_t)cap.cand + 1), B.maxl = b.get<uint32_t>(cap.cand), B.maxr = b.get<uint32_t>(cap.cand);
+    B.arena_off = b.get<uint64_t>(cap.cand);
+    B.arena_seq = b.get<char>(cap.arena), B.arena_qual = b.get<char>(cap.arena);
+    B.co.len_l = b.get<uint32_t>(cap.cand), B.co.len_r = b.get<uint32_t>(cap.cand), B.co.support = b.get<uint32_t>(cap.cand);
+    B.co.cig_off = b.get<uint64_t>(cap.cand), B.co.noqual = b.get<uint8_t>(cap.cand), B.co.seg_ncl = b.get<uint32_t>(cap.cand);
+    B.cl_seg = b.get<uint32_t>(cap.cand), B.cl_slot = b.get<uint32_t>(cap.cand);
+    B.clip_off = b.get<uint64_t>(cap.cand), B.fq_off = b.get<uint64_t>(cap.cand);
+    B.off1 = b.get<uint64_t>((pair_mode || export_mode) ? cap.un : 1), B.off2 = b.get<uint64_t>(pair_mode ? cap.un : 1);
+    B.nblob = b.get<char>(name_bytes + 1);
+    B.noff = b.get<uint32_t>((size_t)n_ref + 1);
+}
+
+int bits_of(uint64_t v)
+{
+    int b = 1;
+    while (b < 64 && (v >> b)) ++b;
+    return b;
+}
+}  // namespace
+
 extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params *prm, svb_clusters **out_)
 {
     if (!ctx || !bam || !prm || !out_) return svb_fail(ctx, SVB_ERR_ARG, "svb_getclip: null argument");
-    cudaStream_t s = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    if (bam->names.size() != (size_t)bam->n_ref) return svb_fail(ctx, SVB_ERR_ARG, "svb_getclip: reference names not set (svb_bam_set_refs)");
+    cudaStream_t s = ctx->stream, side = ctx->aux[0];
     svb_clusters *res = new svb_clusters();
     res->ctx = ctx;
     std::unique_ptr<svb_clusters> guard(res);
     const uint64_t n_chunks = bam->n_chunks, stream_bytes = bam->nbytes - bam->first;
-    int off_bits = 1;
-    while (off_bits < 64 && (bam->nbytes >> off_bits)) ++off_bits;  // offsets sort on just the bits they use
-
-    // ---- 1. the walker: every record head once ------------------------------------------------------------------
-    DevBuf<uint32_t> counters;
-    DevBuf<uint64_t> un_list, sw_list, c_off, exit_, first_mb, clipped;
-    DevBuf<uint32_t> c_begin, c_ll, c_rl;
-    DevBuf<int32_t> c_tid, c_pos, last_mb_tid;
-    DevBuf<uint8_t> c_side;
-    CandArrays c;
-    uint32_t hc[4] = {0, 0, 0, 0};
-    // sized from the stream (a record is at least ~40 bytes; ~2 % of them are soft-clipped), grown once on overflow
-    uint64_t est = stream_bytes / 200;
-    uint32_t cand_cap = (uint32_t)std::min<uint64_t>(est / 8 + 4096, 0xffffffffu);
-    uint32_t un_cap = (uint32_t)std::min<uint64_t>(est / 8 + 4096, 0xffffffffu), sw_cap = 1 << 16;
-    CK(counters.alloc(4, s));
-    CK(exit_.alloc(n_chunks, s));
-    CK(first_mb.alloc(n_chunks, s));
-    CK(last_mb_tid.alloc(n_chunks, s));
-    int attempt_walk = 0;
-    for (int attempt = 0;; ++attempt) {
-        CK(c_off.alloc(cand_cap, s));
-        CK(c_begin.alloc(cand_cap, s));
-        CK(c_ll.alloc(cand_cap, s));
-        CK(c_rl.alloc(cand_cap, s));
-        CK(c_tid.alloc(cand_cap, s));
-        CK(c_pos.alloc(cand_cap, s));
-        CK(c_side.alloc(cand_cap, s));
-        CK(un_list.alloc(un_cap, s));
-        CK(sw_list.alloc(sw_cap, s));
-        CK(clipped.alloc(cand_cap, s));
-        c = {c_off.p, c_tid.p, c_pos.p, c_begin.p, c_ll.p, c_rl.p, c_side.p};
-        ScanOut so{c, cand_cap, un_list.p, un_cap, sw_list.p, sw_cap, counters.p, clipped.p, cand_cap, INT32_MIN, INT32_MIN, INT32_MAX, INT32_MAX};
-        if (prm->key_filter) so.lo_tid = prm->key_lo_tid, so.lo_pos = prm->key_lo_pos, so.hi_tid = prm->key_hi_tid, so.hi_pos = prm->key_hi_pos;
-        CK(cudaMemsetAsync(counters.p, 0, 16, s));
-        if (stream_mode(bam) && attempt_walk == 0) {
-            // streaming pass: its own first-record guesses go to bam->d_guess and are verified below like the walker's
-            int per_sm = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, clip_stream, STREAM_THREADS, 0));
-            unsigned grid = (unsigned)std::min<uint64_t>(n_chunks, (uint64_t)std::max(1, per_sm) * ctx->sm_count);
-            ProfScope ps(ctx, "clip_stream", (double)stream_bytes);
-            clip_stream<<<grid, STREAM_THREADS, 0, s>>>(bam->d_data, bam->nbytes, (bam->nbytes + 15) & ~15ull, bam->first, bam->n_ref,
-                                                        n_chunks, bam->d_guess, bam->d_count, exit_.p, first_mb.p, last_mb_tid.p,
-                                                        prm->min_mapq, so);
-            clip_first<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, n_chunks, first_mb.p, last_mb_tid.p, prm->prev_tid, prm->min_mapq,
-                                                         prm->save_low_quality, so);
-            bam->guessed = true;  // d_guess now holds this pass's guesses (verified or repaired below)
-        } else {
-            CKR(ensure_guess(ctx, bam));
-            ProfScope ps(ctx, "clip_walk", (double)stream_bytes);
-            clip_walk<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->chunk_log2, bam->d_guess, bam->d_count,
-                                                        exit_.p, first_mb.p, last_mb_tid.p, prm->min_mapq, prm->save_low_quality, so);
-            clip_first<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, n_chunks, first_mb.p, last_mb_tid.p, prm->prev_tid, prm->min_mapq,
-                                                         prm->save_low_quality, so);
-        }
-        {
-            // at most cand_cap queued records are evaluated; an overflow of the queue is caught below and the pass repeated
-            ProfScope ps(ctx, "clip_eval", 0);
-            clip_eval<<<nblk(cand_cap, 128), 128, 0, s>>>(bam->d_data, prm->min_mapq, prm->save_low_quality, so);
-        }
-        int ok = 0;
-        CKR(verify_or_repair(ctx, bam, exit_.p, &ok));  // (synchronises); a failed verification repairs the guesses
-        if (!ok) attempt_walk = 1;                      // ... and the pass is repeated by the walker, which starts from them
-        CK(cudaMemcpyAsync(hc, counters.p, 16, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        bool fits = hc[0] <= cand_cap && hc[3] <= cand_cap && hc[1] <= un_cap && hc[2] <= sw_cap;
-        if (ok && fits) break;
-        if (attempt >= 3) return svb_fail(ctx, SVB_ERR_CUDA, "svb_getclip: the record walk did not settle");
-        if (ok) {
-            cand_cap = std::max(cand_cap, std::max(hc[0], 2 * hc[3]));  // a record yields at most two candidates
-            un_cap = std::max(un_cap, hc[1]), sw_cap = std::max(sw_cap, hc[2]);
-        }
-    }
-    if (!bam->counted) CKR(finish_counts(ctx, bam, exit_.p));  // the walker counted the records of every chunk on its way
-    const uint32_t n_cand = hc[0], n_sw = hc[2];
-    uint32_t n_un = hc[1];
-    res->n_candidates = n_cand;
-
-    // ---- 2. unmapped-branch records: pair mates by name on the device, emit the two FASTQ files ---------------------
-    DevBuf<char> un_o1, un_o2;
-    bool have_unmapped_gz = false, unmapped_copy_pending = false;
-    uint64_t un_bytes[2] = {0, 0};
-    auto start_unmapped_copy = [&]() -> int {
-        if (!unmapped_copy_pending) return 0;
-        unmapped_copy_pending = false;
-        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_event, 0));
-        CK(cudaMemcpyAsync(res->text[2].p, un_o1.p, un_bytes[0], cudaMemcpyDeviceToHost, ctx->copy_stream));
-        CK(cudaMemcpyAsync(res->text[3].p, un_o2.p, un_bytes[1], cudaMemcpyDeviceToHost, ctx->copy_stream));
-        return 0;
-    };
-    res->gz_mode = prm->gz_outputs != 0 && !prm->export_unmapped_records;
-    struct CopyJoin {  // declared after the buffers the copy stream reads: joined before they are released, on every way out
-        cudaStream_t c;
-        ~CopyJoin() { cudaStreamSynchronize(c); }
-    } copy_join{ctx->copy_stream};
-    DevBuf<uint32_t> val0, val1, mate_of, ovf;
-    DevBuf<uint64_t> un_sorted, ukey0, ukey1, sz1, sz2, off1, off2;
-    if (n_un) {
-        CK(un_sorted.alloc(n_un, s));
-        CKR(sort_u64(ctx, un_list.p, un_sorted.p, n_un, off_bits));
-    }
-    const uint64_t *un_first = un_sorted.p;  // (the kernels below read un_sorted through this pointer)
-    if (n_un && prm->halo_bytes) {
-        // range shards: records in front of the shard's own region only lend their soft clips; the list is sorted by offset
-        DevBuf<uint32_t> skip;
-        CK(skip.alloc(1, s));
-        CK(cudaMemsetAsync(skip.p, 0, 4, s));
-        count_below<<<nblk(n_un, 256), 256, 0, s>>>(n_un, un_sorted.p, prm->halo_bytes, skip.p);
-        uint32_t h_skip = 0;
-        CK(cudaMemcpyAsync(&h_skip, skip.p, 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        un_first += h_skip, n_un -= h_skip;
-    }
-    if (n_un && prm->export_unmapped_records) {  // a shard: hand the records to the merging rank instead of pairing here
-        DevBuf<uint64_t> sz, ro;
-        CK(sz.alloc(n_un + 1, s));
-        CK(ro.alloc(n_un + 1, s));
-        record_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_first, bam->d_data, sz.p);
-        CKR(exclusive_scan_u64(ctx, sz.p, ro.p, n_un + 1));
-        uint64_t total = 0;
-        CK(cudaMemcpyAsync(&total, ro.p + n_un, 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        CK(un_o1.alloc(total, s));
-        record_copy<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_first, bam->d_data, ro.p, (uint8_t *)un_o1.p);
-        CKR(res->unmapped_records.reserve(ctx, total));
-        CK(cudaMemcpyAsync(res->unmapped_records.p, un_o1.p, total, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-    } else if (n_un) {
-        CK(val0.alloc(n_un, s));
-        CK(val1.alloc(n_un, s));
-        CK(ukey0.alloc(n_un, s));
-        CK(ukey1.alloc(n_un, s));
-        CK(mate_of.alloc(n_un, s));
-        CK(ovf.alloc(1, s));
-        CK(sz1.alloc(n_un + 1, s));
-        CK(sz2.alloc(n_un + 1, s));
-        CK(off1.alloc(n_un + 1, s));
-        CK(off2.alloc(n_un + 1, s));
-        CK(cudaMemsetAsync(mate_of.p, 0xff, (size_t)n_un * 4, s));
-        CK(cudaMemsetAsync(ovf.p, 0, 4, s));
-        uint64_t tot[2] = {0, 0};
-        {
-            ProfScope ps(ctx, "unmapped_pair", 0);
-            unmapped_hash<<<nblk(n_un, 256), 256, 0, s>>>(n_un, un_first, bam->d_data, ukey0.p, val0.p);
-            size_t tmp = 0;
-            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ukey0.p, ukey1.p, val0.p, val1.p, (int)n_un, 0, 64, s));
-            DevBuf<uint8_t> t;
-            CK(t.alloc(tmp, s));
-            CK(cub::DeviceRadixSort::SortPairs(t.p, tmp, ukey0.p, ukey1.p, val0.p, val1.p, (int)n_un, 0, 64, s));
-            unmapped_pair<<<nblk(n_un, 128), 128, 0, s>>>(n_un, ukey1.p, val1.p, un_first, bam->d_data, mate_of.p, ovf.p);
-            unmapped_sizes<<<nblk(n_un + 1, 256), 256, 0, s>>>(n_un, un_first, mate_of.p, bam->d_data, sz1.p, sz2.p);
-            CKR(exclusive_scan_u64(ctx, sz1.p, off1.p, n_un + 1));
-            CKR(exclusive_scan_u64(ctx, sz2.p, off2.p, n_un + 1));
-        }
-        uint32_t hovf = 0;
-        CK(cudaMemcpyAsync(&tot[0], off1.p + n_un, 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(&tot[1], off2.p + n_un, 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(&hovf, ovf.p, 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        if (hovf) return svb_fail(ctx, SVB_ERR_FORMAT, "more than 8 distinct read names share one 64-bit name hash");
-        CK(un_o1.alloc(tot[0], s));
-        CK(un_o2.alloc(tot[1], s));
-        {
-            ProfScope ps(ctx, "unmapped_write", (double)(tot[0] + tot[1]));
-            unmapped_write<<<nblk((uint64_t)n_un * 32, 128), 128, 0, s>>>(n_un, un_first, mate_of.p, bam->d_data, off1.p, off2.p,
-                                                                          un_o1.p, un_o2.p);
-        }
-        if (res->gz_mode) {
-            CKR(gzip_on_device(ctx, un_o1.p, tot[0], &res->gz[2]));
-            CKR(gzip_on_device(ctx, un_o2.p, tot[1], &res->gz[3]));
-            have_unmapped_gz = true;
-        } else {
-        CKR(res->text[2].reserve(ctx, tot[0]));
-        CKR(res->text[3].reserve(ctx, tot[1]));
-        // the two FASTQ texts travel to the host on the copy stream while the candidate pipeline below runs; the copies are
-        // queued after the sorts (start_unmapped_copy): queued here they slowed the sort's many small launches down by 2x
-        CK(cudaEventRecord(ctx->fork_event, s));
-        unmapped_copy_pending = true, un_bytes[0] = tot[0], un_bytes[1] = tot[1];
-        }
-    }
-    // gzip mode: every file exists, if only as one empty member (what the reference's ogzstream leaves behind as well)
-    auto empty_gz = [&](int which) -> int { return res->gz[which].p ? 0 : gzip_on_device(ctx, nullptr, 0, &res->gz[which]); };
-    if (res->gz_mode && !have_unmapped_gz) {
-        CKR(empty_gz(2));
-        CKR(empty_gz(3));
-    }
-
-    if (n_cand == 0) {
-        CKR(start_unmapped_copy());
-        if (res->gz_mode) {
-            CKR(empty_gz(0));
-            CKR(empty_gz(1));
-        }
-        *out_ = guard.release();
-        return 0;
-    }
-    if (bam->names.size() != (size_t)bam->n_ref) return svb_fail(ctx, SVB_ERR_ARG, "svb_getclip: reference names not set (svb_bam_set_refs)");
-
-    // ---- 3. order candidates: BAM order first (stable base), then (run, side, pos) -----------------------------
-    DevBuf<uint32_t> ord0, ord1, ord2;
-    DevBuf<uint64_t> sw_sorted, rec_sorted, key0, key1;
-    CK(sw_sorted.alloc(n_sw, s));
-    if (n_sw) CKR(sort_u64(ctx, sw_list.p, sw_sorted.p, n_sw, off_bits));
-    CK(ord0.alloc(n_cand, s));
-    CK(ord1.alloc(n_cand, s));
-    CK(ord2.alloc(n_cand, s));
-    CK(rec_sorted.alloc(n_cand, s));
-    CK(key0.alloc(n_cand, s));
-    CK(key1.alloc(n_cand, s));
-    iota_u32<<<nblk(n_cand, 256), 256, 0, s>>>(n_cand, ord0.p);
-    {
-        // a both-side-clipped read yields two candidates with the same record index but different sides, so
-        // (key, record) is unique and the two-pass stable sort is deterministic
-        ProfScope ps(ctx, "sort_candidates", (double)n_cand * 24);
-        size_t tmp = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c.off, rec_sorted.p, ord0.p, ord1.p, (int)n_cand, 0, off_bits, s));
-        DevBuf<uint8_t> t;
-        CK(t.alloc(tmp, s));
-        CK(cub::DeviceRadixSort::SortPairs(t.p, tmp, c.off, rec_sorted.p, ord0.p, ord1.p, (int)n_cand, 0, off_bits, s));
-        make_keys<<<nblk(n_cand, 256), 256, 0, s>>>(n_cand, ord1.p, c, sw_sorted.p, n_sw, key0.p);
-        size_t tmp2 = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, key0.p, key1.p, ord1.p, ord2.p, (int)n_cand, 0, 64, s));
-        DevBuf<uint8_t> t2;
-        CK(t2.alloc(tmp2, s));
-        CK(cub::DeviceRadixSort::SortPairs(t2.p, tmp2, key0.p, key1.p, ord1.p, ord2.p, (int)n_cand, 0, 64, s));
-    }
-    const uint32_t *order = ord2.p;
-    CKR(start_unmapped_copy());
-
-    // ---- 4. segments (one per breakpoint key) -------------------------------------------------------------------
-    DevBuf<uint32_t> flag, segid;
-    CK(flag.alloc(n_cand, s));
-    CK(segid.alloc(n_cand, s));
-    seg_flags<<<nblk(n_cand, 256), 256, 0, s>>>(n_cand, key1.p, flag.p);
-    CKR(inclusive_scan_u32(ctx, flag.p, segid.p, n_cand));
-    uint32_t n_seg = 0;
-    CK(cudaMemcpyAsync(&n_seg, segid.p + (n_cand - 1), 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    DevBuf<uint32_t> start, maxl, maxr;
-    DevBuf<uint64_t> seg_bytes, arena_off;
-    CK(start.alloc(n_seg + 1, s));
-    CK(maxl.alloc(n_seg, s));
-    CK(maxr.alloc(n_seg, s));
-    CK(seg_bytes.alloc(n_seg + 1, s));
-    CK(arena_off.alloc(n_seg + 1, s));
-    seg_starts<<<nblk(n_cand, 256), 256, 0, s>>>(n_cand, flag.p, segid.p, start.p, n_seg);
-    seg_stats<<<nblk(n_seg, 256), 256, 0, s>>>(n_seg, start.p, order, c, maxl.p, maxr.p, seg_bytes.p);
-    CKR(exclusive_scan_u64(ctx, seg_bytes.p, arena_off.p, n_seg + 1));
-    uint64_t arena_bytes = 0;
-    CK(cudaMemcpyAsync(&arena_bytes, arena_off.p + n_seg, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-
-    // ---- 5. greedy clustering -----------------------------------------------------------------------------------
-    DevBuf<char> arena_seq, arena_qual;
-    DevBuf<uint32_t> len_l, len_r, support, seg_ncl, cl_base;
-    DevBuf<uint64_t> cig_off;
-    DevBuf<uint8_t> noqual;
-    CK(arena_seq.alloc(arena_bytes, s));
-    CK(arena_qual.alloc(arena_bytes, s));
-    CK(len_l.alloc(n_cand, s));
-    CK(len_r.alloc(n_cand, s));
-    CK(cig_off.alloc(n_cand, s));
-    CK(support.alloc(n_cand, s));
-    CK(noqual.alloc(n_cand, s));
-    CK(seg_ncl.alloc(n_seg, s));
-    CK(cl_base.alloc(n_seg, s));
-    ClusterOut co{len_l.p, len_r.p, support.p, cig_off.p, noqual.p, seg_ncl.p};
-    {
-        ProfScope ps(ctx, "cluster_build", (double)arena_bytes * 2);
-        cluster_build<<<nblk((uint64_t)n_seg * 32, 128), 128, 0, s>>>(bam->d_data, n_seg, start.p, order, c, maxl.p,
-                                                                      maxr.p, arena_off.p, arena_seq.p, arena_qual.p, prm->match_rate, co);
-    }
-    CKR(inclusive_scan_u32(ctx, seg_ncl.p, cl_base.p, n_seg));
-    uint32_t n_cl = 0;
-    CK(cudaMemcpyAsync(&n_cl, cl_base.p + (n_seg - 1), 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    res->n_clusters = n_cl;
-
-    // ---- 6. text ---------------------------------------------------------------------------------------------------
-    std::vector<uint32_t> noff(bam->n_ref + 1, 0);
+    const bool export_mode = prm->export_unmapped_records != 0, pair_mode = !export_mode;
+    res->gz_mode = prm->gz_outputs != 0 && !export_mode;
+    const bool want_rows = prm->with_rows != 0;
+    const int off_passes = (bits_of(bam->nbytes) + 7) / 8;  // offsets sort on just the bytes they use
+    // key = run << 33 | side << 32 | pos: runs are numbered by chromosome switches (at most sw_cap of them)
     std::string nblob;
+    std::vector<uint32_t> noff(bam->n_ref + 1, 0);
     for (int32_t t = 0; t < bam->n_ref; ++t) {
         noff[t] = (uint32_t)nblob.size();
         nblob += bam->names[t];
     }
     noff[bam->n_ref] = (uint32_t)nblob.size();
-    DevBuf<char> d_nblob;
-    DevBuf<uint32_t> d_noff, cl_seg, cl_slot;
-    DevBuf<uint64_t> clip_len, fq_len, clip_off, fq_off;
-    CK(d_nblob.alloc(nblob.size() + 1, s));
-    CK(d_noff.alloc(noff.size(), s));
-    CK(cudaMemcpyAsync(d_nblob.p, nblob.data(), nblob.size(), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(d_noff.p, noff.data(), noff.size() * 4, cudaMemcpyHostToDevice, s));
-    CK(cl_seg.alloc(n_cl, s));
-    CK(cl_slot.alloc(n_cl, s));
-    CK(clip_len.alloc(n_cl + 1, s));
-    CK(fq_len.alloc(n_cl + 1, s));
-    CK(clip_off.alloc(n_cl + 1, s));
-    CK(fq_off.alloc(n_cl + 1, s));
-    NameTable nt{d_nblob.p, d_noff.p};
-    list_clusters<<<nblk(n_seg, 256), 256, 0, s>>>(n_seg, start.p, seg_ncl.p, cl_base.p, cl_seg.p, cl_slot.p);
-    text_sizes<<<nblk(n_cl + 1, 256), 256, 0, s>>>(n_cl, cl_seg.p, cl_slot.p, start.p, order, c, co, bam->d_data, nt,
-                                                   clip_len.p, fq_len.p);
-    CKR(exclusive_scan_u64(ctx, clip_len.p, clip_off.p, n_cl + 1));
-    CKR(exclusive_scan_u64(ctx, fq_len.p, fq_off.p, n_cl + 1));
-    uint64_t clip_bytes = 0, fq_bytes = 0;
-    CK(cudaMemcpyAsync(&clip_bytes, clip_off.p + n_cl, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&fq_bytes, fq_off.p + n_cl, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    DevBuf<char> d_clip, d_fq;
-    CK(d_clip.alloc(clip_bytes, s));
-    CK(d_fq.alloc(fq_bytes, s));
+
+    // capacities: sized from the stream (a record is at least ~40 bytes; ~2 % of them are soft-clipped) and from what the last
+    // call on this context needed; an overflow reports the exact need and the pass is run again
+    Caps cap;
     {
-        ProfScope ps(ctx, "text_write", (double)(clip_bytes + fq_bytes));
-        text_write<<<nblk((uint64_t)n_cl * 32, 128), 128, 0, s>>>(n_cl, cl_seg.p, cl_slot.p, start.p, order, c, co, bam->d_data, nt,
-                                                                  maxl.p, maxr.p, arena_off.p, arena_seq.p, arena_qual.p, clip_off.p,
-                                                                  fq_off.p, d_clip.p, d_fq.p);
+        const uint64_t est = stream_bytes / 1600 + 4096;
+        auto want32 = [&](Hint h, uint64_t base) { return (uint32_t)std::min<uint64_t>(std::max(base, ctx->hint[h] + ctx->hint[h] / 8 + 1024), 0xfffffff0u); };
+        auto want64 = [&](Hint h, uint64_t base) { return std::max(base, ctx->hint[h] + ctx->hint[h] / 8 + 4096); };
+        cap.clipped = want32(H_CLIPPED, est), cap.un = want32(H_UNMAPPED, est), cap.sw = want32(H_SWITCH, 1 << 16);
+        cap.cand = want32(H_CAND, est);
+        cap.arena = want64(H_ARENA, stream_bytes / 48 + (1 << 20));
+        cap.clip = want64(H_CLIP, stream_bytes / 40 + (1 << 20)), cap.fq = want64(H_FQ, stream_bytes / 96 + (1 << 20));
+        cap.un1 = pair_mode ? want64(H_UN1, stream_bytes / 64 + (1 << 20)) : 1, cap.un2 = pair_mode ? want64(H_UN2, stream_bytes / 64 + (1 << 20)) : 1;
+        cap.exp = export_mode ? want64(H_EXPORT, stream_bytes / 32 + (1 << 20)) : 1;
     }
-    if (res->gz_mode) {
-        CKR(gzip_on_device(ctx, d_clip.p, clip_bytes, &res->gz[0]));
-        CKR(gzip_on_device(ctx, d_fq.p, fq_bytes, &res->gz[1]));
-    } else {
-        CKR(res->text[0].reserve(ctx, clip_bytes));
-        CKR(res->text[1].reserve(ctx, fq_bytes));
-        CK(cudaMemcpyAsync(res->text[0].p, d_clip.p, clip_bytes, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(res->text[1].p, d_fq.p, fq_bytes, cudaMemcpyDeviceToHost, s));
+    ClipCtl h{};
+    for (int attempt = 0;; ++attempt) {
+        if (attempt > 6) return svb_fail(ctx, SVB_ERR_CUDA, "svb_getclip: the pass did not settle");
+        const int key_passes = (33 + bits_of(cap.sw) + 7) / 8;
+        // ---- buffers
+        ClipBuffers B{};
+        {
+            Bump measure(nullptr);
+            carve(measure, B, cap, n_chunks, off_passes, key_passes, nblob.size(), bam->n_ref, pair_mode, export_mode);
+            CKR(ctx->ws_reserve(0, measure.used));
+            Bump real(ctx->ws[0]);
+            carve(real, B, cap, n_chunks, off_passes, key_passes, nblob.size(), bam->n_ref, pair_mode, export_mode);
+        }
+        B.q.min_mapq = prm->min_mapq;
+        res->drop_device();
+        CK(cudaMallocAsync((void **)&res->d_text[0], cap.clip, s));
+        CK(cudaMallocAsync((void **)&res->d_text[1], cap.fq, s));
+        CK(cudaMallocAsync((void **)&res->d_text[2], cap.un1, s));
+        CK(cudaMallocAsync((void **)&res->d_text[3], cap.un2, s));
+        if (export_mode) CK(cudaMallocAsync((void **)&res->d_export, cap.exp, s));
+        if (want_rows && !bam->rows_ready) CKR(alloc_rows(ctx, bam, bam->rows.R == ROWS_R_MAX ? ROWS_R_MAX : ROWS_R_FIRST));
+        const bool do_rows = want_rows && !bam->rows_ready;
+        CK(cudaMemsetAsync(ctx->ws[0], 0, B.zero_end, s));
+        CK(cudaMemcpyAsync(B.nblob, nblob.data(), nblob.size(), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(B.noff, noff.data(), noff.size() * 4, cudaMemcpyHostToDevice, s));
+        ClipCtl *ctl = B.ctl;
+        ClipParams P{prm->min_mapq, prm->save_low_quality, INT32_MIN, INT32_MIN, INT32_MAX, INT32_MAX};
+        if (prm->key_filter) P.lo_tid = prm->key_lo_tid, P.lo_pos = prm->key_lo_pos, P.hi_tid = prm->key_hi_tid, P.hi_pos = prm->key_hi_pos;
+
+        // ---- 1. the walker: every record head once (getclip's scan and, when asked, getsv's rows)
+        CKR(launch_walk(ctx, s, bam, true, do_rows, B.q, ctl->flags, B.ticket));
+        clip_first<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, n_chunks, prm->prev_tid, B.q);
+        launch_chunk_scan(ctx, s, bam, B.sc_chunk, &ctl->flags[1], ctl->c64);
+        CK(cudaEventRecord(ctx->fork_event, s));
+
+        // ---- 2. side stream: unmapped-branch records - pair mates by name, emit the two FASTQ files (or export the records)
+        CK(cudaStreamWaitEvent(side, ctx->fork_event, 0));
+        {
+            ProfScope ps(ctx, "unmapped_pair", 0, side);
+            RadixJob ju{{B.q.unmapped, B.un_sorted}, {nullptr, nullptr}, &ctl->counters[1], cap.un, 0, off_passes, B.rs_un};
+            radix_sort(ctx, side, ju);
+            unmapped_own<<<1, 1, 0, side>>>(ctl->counters, cap.un, B.un_sorted, prm->halo_bytes, ctl);
+            if (export_mode) {
+                ExportScanOp op{B.un_sorted, bam->d_data, B.off1, cap.exp, ctl};
+                launch_scan<1>(ctx, side, op, B.sc_un, cap.un);
+                record_copy<<<grid_for(ctx, (uint64_t)cap.un * 32, 128, 8), 128, 0, side>>>(ctl, B.un_sorted, bam->d_data, B.off1, res->d_export);
+            } else {
+                const unsigned g = grid_for(ctx, cap.un, 256, 4);
+                unmapped_hash<<<g, 256, 0, side>>>(ctl, B.un_sorted, bam->d_data, B.ukey[0], B.uval[0]);
+                RadixJob jh{{B.ukey[0], B.ukey[1]}, {B.uval[0], B.uval[1]}, &ctl->un_own, cap.un, 0, 4, B.rs_hash};
+                radix_sort(ctx, side, jh);
+                CK(cudaMemsetAsync(B.mate_of, 0xff, (size_t)cap.un * 4, side));
+                unmapped_pair<<<g, 256, 0, side>>>(ctl, B.ukey[1], B.uval[1], B.un_sorted, bam->d_data, B.mate_of);
+                UnSizesOp op{B.un_sorted, B.mate_of, bam->d_data, B.off1, B.off2, cap.un1, cap.un2, ctl};
+                launch_scan<2>(ctx, side, op, B.sc_un, cap.un);
+            }
+        }
+        if (pair_mode) {
+            ProfScope ps(ctx, "unmapped_write", 0, side);
+            unmapped_write<<<grid_for(ctx, (uint64_t)cap.un * 32, 128, 8), 128, 0, side>>>(ctl, B.un_sorted, B.mate_of, bam->d_data, B.off1, B.off2,
+                                                                                         res->d_text[2], res->d_text[3]);
+        }
+        {   // the switch list, sorted (make_keys numbers the flush runs with it)
+            RadixJob js{{B.q.switches, B.sw_sorted}, {nullptr, nullptr}, &ctl->counters[2], cap.sw, 0, off_passes, B.rs_sw};
+            radix_sort(ctx, side, js);
+        }
+        CK(cudaEventRecord(ctx->join_event, side));
+
+        // ---- 3. main stream: evaluate the queued soft-clipped records, order candidates: BAM order first (stable base), then (run, side, pos)
+        {
+            ProfScope ps(ctx, "clip_eval", 0);
+            clip_eval<<<grid_for(ctx, cap.clipped, 128, 8), 128, 0, s>>>(bam->d_data, B.q, P, B.c, cap.cand, ctl);
+        }
+        {
+            // a both-side-clipped read yields two candidates with the same record offset but different sides, so
+            // (key, record) is unique and the two-pass stable sort is deterministic
+            ProfScope ps(ctx, "sort_candidates", 0);
+            const unsigned g = grid_for(ctx, cap.cand, 256, 4);
+            cand_sort_input<<<g, 256, 0, s>>>(&ctl->counters[3], cap.cand, B.c.off, B.key[0], B.val[0], ctl);
+            RadixJob j1{{B.key[0], B.key[1]}, {B.val[0], B.val[1]}, &ctl->counters[3], cap.cand, 0, off_passes, B.rs_off};
+            radix_sort(ctx, s, j1);
+            CK(cudaStreamWaitEvent(s, ctx->join_event, 0));  // (the sorted switch list comes from the side stream)
+            make_keys<<<g, 256, 0, s>>>(ctl->counters, cap.cand, cap.sw, B.val[1], B.c, B.sw_sorted, B.key[0], B.val[0]);
+            RadixJob j2{{B.key[0], B.key[1]}, {B.val[0], B.val[1]}, &ctl->counters[3], cap.cand, 0, key_passes, B.rs_key};
+            radix_sort(ctx, s, j2);
+        }
+        const uint32_t *order = B.val[1];
+        // ---- 4. segments, 5. greedy clustering, 6. text
+        {
+            ProfScope ps(ctx, "segments", 0);
+            SegScanOp op1{ctl->counters, cap.cand, B.key[1], B.start, ctl};
+            launch_scan<1>(ctx, s, op1, B.sc_seg, cap.cand);
+            SegStatsOp op2{B.start, order, B.c, B.maxl, B.maxr, B.arena_off, cap.arena, ctl};
+            launch_scan<1>(ctx, s, op2, B.sc_stats, cap.cand);
+        }
+        {
+            ProfScope ps(ctx, "cluster_build", 0);
+            cluster_build<<<grid_for(ctx, (uint64_t)cap.cand * 32, 128, 16), 128, 0, s>>>(bam->d_data, ctl, B.start, order, B.c, B.maxl, B.maxr, B.arena_off,
+                                                                                        B.arena_seq, B.arena_qual, prm->match_rate, B.co);
+        }
+        NameTable nt{B.nblob, B.noff};
+        {
+            ProfScope ps(ctx, "text_write", 0);
+            ClusterScanOp op3{B.co.seg_ncl, B.cl_seg, B.cl_slot, ctl};
+            launch_scan<1>(ctx, s, op3, B.sc_cl, cap.cand);
+            TextScanOp op4{B.cl_seg, B.cl_slot, B.start, order, B.c, B.co, bam->d_data, nt, B.clip_off, B.fq_off, cap.clip, cap.fq, ctl};
+            launch_scan<2>(ctx, s, op4, B.sc_text, cap.cand);
+            text_write<<<grid_for(ctx, (uint64_t)cap.cand * 32, 128, 16), 128, 0, s>>>(ctl, B.cl_seg, B.cl_slot, B.start, order, B.c, B.co, bam->d_data, nt,
+                                                                                     B.maxl, B.maxr, B.arena_off, B.arena_seq, B.arena_qual, B.clip_off,
+                                                                                     B.fq_off, res->d_text[0], res->d_text[1]);
+        }
+        // ---- the one read-back
+        CK(cudaMemcpyAsync(ctx->ctl_host, ctl, sizeof(ClipCtl), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        memcpy(&h, ctx->ctl_host, sizeof h);
+        if (h.flags[1]) {  // a guess was wrong: repair them and walk again
+            if (attempt >= 3) return svb_fail(ctx, SVB_ERR_FORMAT, "record chain does not verify");
+            CKR(repair_guesses(ctx, bam));
+            continue;
+        }
+        bool again = false;
+        auto grow32 = [&](uint32_t &c, uint32_t need) {
+            if (need > c) c = need + need / 16 + 64, again = true;
+        };
+        auto grow64 = [&](uint64_t &c, uint64_t need) {
+            if (need > c) c = need + need / 16 + 4096, again = true;
+        };
+        grow32(cap.clipped, h.counters[0]), grow32(cap.un, h.counters[1]), grow32(cap.sw, h.counters[2]), grow32(cap.cand, h.counters[3]);
+        // (byte counts are exact when the stage that computes them ran, 0 when an earlier overflow cut the pipeline short)
+        grow64(cap.arena, h.arena_bytes), grow64(cap.clip, h.clip_bytes), grow64(cap.fq, h.fq_bytes);
+        grow64(cap.un1, h.un1_bytes), grow64(cap.un2, h.un2_bytes), grow64(cap.exp, h.export_bytes);
+        if (do_rows) {
+            if (h.flags[0]) free_rows(bam);  // more records in a chunk than row slots: the getsv passes make their own rows
+            else if (!again) bam->rows_ready = true, bam->rows_indexed = false;
+        }
+        if (again) continue;
+        if (h.abort_main || h.abort_side) return svb_fail(ctx, SVB_ERR_CUDA, "svb_getclip: inconsistent overflow state");
+        break;
     }
-    CK(cudaStreamSynchronize(s));
-    CK(cudaGetLastError());
+    if (!bam->counted) CKR(accept_counts(ctx, bam, h.c64[0], h.c64[1]));
+    ctx->hint[H_CLIPPED] = h.counters[0], ctx->hint[H_UNMAPPED] = h.counters[1], ctx->hint[H_SWITCH] = h.counters[2], ctx->hint[H_CAND] = h.counters[3];
+    ctx->hint[H_ARENA] = h.arena_bytes, ctx->hint[H_CLIP] = h.clip_bytes, ctx->hint[H_FQ] = h.fq_bytes;
+    ctx->hint[H_UN1] = h.un1_bytes, ctx->hint[H_UN2] = h.un2_bytes, ctx->hint[H_EXPORT] = h.export_bytes;
+    res->n_candidates = h.counters[3], res->n_clusters = h.n_cl;
+    res->text_len[0] = h.clip_bytes, res->text_len[1] = h.fq_bytes, res->text_len[2] = h.un1_bytes, res->text_len[3] = h.un2_bytes;
+    res->export_len = h.export_bytes;
+    if (res->gz_mode) {  // the four files leave the device as gzip images (gzip.cu); an empty file is one empty member
+        for (int w = 0; w < 4; ++w) CKR(gzip_on_device(ctx, res->d_text[w], res->text_len[w], &res->gz[w]));
+        res->drop_device();
+        for (int w = 0; w < 4; ++w) res->text_len[w] = 0;
+    }
     *out_ = guard.release();
     return 0;
 }
 
-extern "C" void svb_clusters_free(svb_clusters *c) { delete c; }
+extern "C" void svb_clusters_free(svb_clusters *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    delete c;
+}
 extern "C" uint64_t svb_clusters_count(const svb_clusters *c) { return c ? c->n_clusters : 0; }
 extern "C" uint64_t svb_clusters_candidates(const svb_clusters *c) { return c ? c->n_candidates : 0; }
 // gzip.cu alone (tests / other text outputs): host text -> device -> gzip image in a malloc'ed host buffer (svb_free)
@@ -1243,9 +1177,18 @@ extern "C" int svb_clusters_gz(const svb_clusters *c, int which, const char **da
     return 0;
 }
 
+// Results stay in HBM until they are asked for: the first request of a text copies it into pinned host memory.
 extern "C" int svb_clusters_unmapped_records(const svb_clusters *c, const char **data, uint64_t *len)
 {
     if (!c || !data || !len) return SVB_ERR_ARG;
+    svb_ctx *ctx = c->ctx;
+    if (!c->export_here && c->d_export && c->export_len) {
+        CK(cudaSetDevice(ctx->device));
+        CKR(c->unmapped_records.reserve(ctx, c->export_len));
+        CK(cudaMemcpyAsync(c->unmapped_records.p, c->d_export, c->export_len, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        c->export_here = true;
+    }
     *data = c->unmapped_records.p ? c->unmapped_records.p : "";
     *len = c->unmapped_records.n;
     return 0;
@@ -1254,7 +1197,22 @@ extern "C" int svb_clusters_unmapped_records(const svb_clusters *c, const char *
 extern "C" int svb_clusters_text(const svb_clusters *c, int which, const char **data, uint64_t *len)
 {
     if (!c || which < 0 || which > 3 || !data || !len) return SVB_ERR_ARG;
+    svb_ctx *ctx = c->ctx;
+    if (!c->text_here[which] && c->d_text[which] && c->text_len[which]) {
+        CK(cudaSetDevice(ctx->device));
+        CKR(c->text[which].reserve(ctx, c->text_len[which]));
+        CK(cudaMemcpyAsync(c->text[which].p, c->d_text[which], c->text_len[which], cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        c->text_here[which] = true;
+    }
     *data = c->text[which].p ? c->text[which].p : "";
     *len = c->text[which].n;
+    return 0;
+}
+// sizes of the four texts without copying them (the results stay in HBM)
+extern "C" int svb_clusters_text_len(const svb_clusters *c, int which, uint64_t *len)
+{
+    if (!c || which < 0 || which > 3 || !len) return SVB_ERR_ARG;
+    *len = c->gz_mode ? 0 : c->text_len[which];
     return 0;
 }

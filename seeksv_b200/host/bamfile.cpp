@@ -107,6 +107,7 @@ static bool walk_members(const uint8_t *f, uint64_t n, uint64_t from, uint64_t u
         b.clen = bsize - 12 - xlen - 8;
         const uint8_t *t = f + o + bsize - 4;
         b.ulen = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+        if (b.ulen > 65536) return false;  // BGZF: at most 64 KiB per block (libbam inflates into a fixed 64 KiB buffer)
         b.uoff = 0;
         out.push_back(b);
         o += bsize;

@@ -147,16 +147,25 @@ void drop_resident()
 void usage_top()
 {
     std::cerr << "Program: seeksv (a tool for structural variation detection and virus integration detection)" << '\n'
-              << "Version: " << kVersion << " (seeksv_b200: B200-native hot path)\n"
+              << "Version: " << kVersion << '\n'
               << "Contact: Kunlong Qiu(290832867@qq.com)\n\n"
               << "Usage: seeksv <command> [options]\n\n"
               << "Command: getclip\tget soft-clipped reads\n"
               << "         getsv  \tget final sv\n"
-              << "         somatic\tget somatic sv\n"
-              << "         run    \tseveral commands in one process, BAMs stay on the GPU in between:\n"
-              << "                \tseeksv run -- getclip ... -- <any shell command, e.g. the aligner> -- getsv ..." << std::endl;
+              << "         somatic\tget somatic sv" << std::endl;
 }
 
+// not part of the reference's surface (seeksv.cpp:60-72 is reproduced byte for byte above): shown by `seeksv run` / `seeksv run --help`
+void usage_run()
+{
+    std::cerr << "Usage: seeksv run -- <command> [-- <command> ...]\n\n"
+              << "Several commands in one process; BAMs stay resident on the GPU in between. getclip / getsv / somatic segments\n"
+              << "take the arguments of the commands of the same name, any other segment is executed as an external command\n"
+              << "(e.g. the aligner): seeksv run -- getclip -o P in.bam -- 'bwa mem ref.fa P.clip.fq.gz > P.clip.sam' -- getsv ..." << std::endl;
+}
+
+// Usage(argv[0], argv[1], i) of the reference's Call* functions (seeksv.cpp:146,188,193,384,389,432) runs on the argument vector
+// SelectStep has already shifted by one (seeksv.cpp:448-452), so a wrong arity prints "Usage: getclip -o [options] ...": kept.
 void usage_cmd(const char *prog, const char *command, int i)
 {
     switch (i) {
@@ -175,7 +184,8 @@ void usage_cmd(const char *prog, const char *command, int i)
                   << "         -t <double>           Threshold of match rate while combining two soft-clipped reads [0.9]\n"
                   << "         -l <int>              Maximum search length to find microhomology[50]\n"
                   << "         -q <int>              Minimum mapping quality of discordant read pair [20]\n"
-                  << "         -Q <int>              Minimum mapping quality of clipped sequences [1]\n"
+                  << "         -Q <int>              Minimum mapping quality of clipped sequences [1], if you use bwa samse to align the reads, please set\n"
+                  << "                               this flag to 20\n"
                   << "         -w <int>              Minimum mapping quality of connected  readthrough reads [1]\n"
                   << "         -n <int>              Number of segment(read pairs) used to calculate insert size default [5000000], if you "
                      "donot want to use abnormal read pairs to call sv, set this parameter to 0.\n"
@@ -233,8 +243,9 @@ int fail(const std::string &msg)
 // ---- getclip: CallGetclip (seeksv.cpp:128-155) + InputBamOutputReads (clip_reads.h:363-484) ---------------------
 int cmd_getclip(int argc, char **argv)
 {
-    svb_getclip_params prm = {0.9, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    svb_getclip_params prm = {0.9, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     prm.gz_outputs = gz_on_host() ? 0 : 1;  // default: the four files are compressed on the device
+    prm.with_rows = g_keep_resident ? 1 : 0;  // `seeksv run`: a getsv of the same BAM follows - one pass over the records serves both
     std::string prefix = "output";
     int c;
     optind = 1;
@@ -839,8 +850,8 @@ static int cmd_run(int argc, char **argv)
         segs.back().push_back(argv[i]);
     }
     segs.erase(std::remove_if(segs.begin(), segs.end(), [](const std::vector<std::string> &v) { return v.empty(); }), segs.end());
-    if (segs.empty()) {
-        usage_top();
+    if (segs.empty() || segs[0][0] == "--help" || segs[0][0] == "-h") {
+        usage_run();
         return 1;
     }
     g_keep_resident = true;

@@ -197,6 +197,7 @@ bool parse_bam_alignments(AlignmentSet &set, uint64_t o)
         a.tid = (int32_t)rd32(&s[o + 4]), a.pos = (int32_t)rd32(&s[o + 8]);
         uint32_t w = rd32(&s[o + 12]), w2 = rd32(&s[o + 16]);
         uint32_t lq = w & 0xff, nc = w2 & 0xffff;
+        if (32ull + lq + 4ull * nc > bs) return false;  // the CIGAR has to lie inside the record (same test as the device walker)
         a.mapq = (w >> 8) & 0xff, a.flag = w2 >> 16;
         // bam1_qname is a C string (getsv.h:479 compares it as one): it ends at the first NUL, not at l_qname - the records
         // libbam's SAM reader builds from names of 255+ characters have no NUL inside l_qname (bounded by the record here)

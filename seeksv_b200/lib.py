@@ -25,7 +25,11 @@ class GetclipParams(C.Structure):
     _fields_ = [("match_rate", C.c_double), ("min_mapq", C.c_int32), ("save_low_quality", C.c_int32),
                 ("prev_tid", C.c_int32), ("export_unmapped_records", C.c_int32), ("key_filter", C.c_int32),
                 ("key_lo_tid", C.c_int32), ("key_lo_pos", C.c_int32), ("key_hi_tid", C.c_int32), ("key_hi_pos", C.c_int32),
-                ("halo_bytes", C.c_uint64), ("gz_outputs", C.c_int32)]
+                ("halo_bytes", C.c_uint64), ("gz_outputs", C.c_int32), ("with_rows", C.c_int32)]
+
+
+class GetsvParams(C.Structure):
+    _fields_ = [("min_mapq", C.c_int32), ("times", C.c_int32), ("max_pairs", C.c_int64)]
 
 
 class Junction(C.Structure):
@@ -49,7 +53,7 @@ EXPORTS = [
     "svb_clusters_text", "svb_insert_stats", "svb_discordant_support", "svb_window_depth", "svb_plan_getsv", "svb_free",
     "svb_write_gz", "svb_read_gz", "svb_bam_open_refs", "svb_bai_first_offsets", "svb_bam_last_mapped_tid", "svb_clusters_unmapped_records",
     "svb_clusters_gz", "svb_gzip_text", "svb_bam_open_voffsets", "svb_bai_linear_offsets", "svb_bam_peek_record", "svb_voffset_distance",
-    "svb_sam_to_stream", "svb_main",
+    "svb_sam_to_stream", "svb_main", "svb_getsv_passes", "svb_clusters_text_len",
 ]
 
 
@@ -104,6 +108,9 @@ def load():
     L.svb_clusters_candidates.argtypes = [vp]
     L.svb_clusters_candidates.restype = u64
     L.svb_clusters_text.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(u64)]
+    L.svb_clusters_text_len.argtypes = [vp, C.c_int, C.POINTER(u64)]
+    L.svb_getsv_passes.argtypes = [vp, vp, C.POINTER(GetsvParams), C.POINTER(Junction), u64, C.POINTER(Window), u64, C.POINTER(i64),
+                                   C.POINTER(i32), C.POINTER(i32)]
     L.svb_gzip_text.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(vp), C.POINTER(u64)]
     L.svb_clusters_gz.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(u64)]
     L.svb_clusters_unmapped_records.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(u64)]
@@ -285,7 +292,7 @@ class Bam:
         return [L.svb_bam_ref_len(self.h, t) for t in range(L.svb_bam_n_ref(self.h))]
 
     def getclip(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0, export_unmapped=False, key_range=None,
-                halo_bytes=0):
+                halo_bytes=0, with_rows=False):
         """(clip, clip.fq, unmapped_1, unmapped_2) decompressed file contents. export_unmapped (shards): the unmapped branch is
         not paired here; its packed records are left in self.last_unmapped_records for the merging rank."""
         p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid, 1 if export_unmapped else 0)
@@ -293,6 +300,7 @@ class Bam:
             (p.key_lo_tid, p.key_lo_pos), (p.key_hi_tid, p.key_hi_pos) = key_range
             p.key_filter = 1
         p.halo_bytes = halo_bytes
+        p.with_rows = 1 if with_rows else 0
         out = C.c_void_p()
         self.ctx.check(self.ctx.L.svb_getclip(self.ctx.h, self.h, C.byref(p), C.byref(out)), "svb_getclip")
         try:
@@ -327,10 +335,13 @@ class Bam:
         finally:
             self.ctx.L.svb_clusters_free(out)
 
-    def getclip_sizes(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0, gz=False) -> Tuple[int, int, int, int]:
-        """svb_getclip without copying the four host buffers into Python objects: returns their lengths"""
+    def getclip_sizes(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0, gz=False, with_rows=False,
+                      fetch=False) -> Tuple[int, int, int, int]:
+        """svb_getclip without turning the four texts into Python objects: returns their lengths. The texts stay in HBM unless
+        fetch is set (then they are copied to pinned host memory, as svb_clusters_text does on request)."""
         p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid)
         p.gz_outputs = 1 if gz else 0
+        p.with_rows = 1 if with_rows else 0
         out = C.c_void_p()
         self.ctx.check(self.ctx.L.svb_getclip(self.ctx.h, self.h, C.byref(p), C.byref(out)), "svb_getclip")
         try:
@@ -338,11 +349,37 @@ class Bam:
             for which in range(4):
                 d = C.c_char_p()
                 n = C.c_uint64()
-                (self.ctx.L.svb_clusters_gz if gz else self.ctx.L.svb_clusters_text)(out, which, C.byref(d), C.byref(n))
+                if gz:
+                    self.ctx.L.svb_clusters_gz(out, which, C.byref(d), C.byref(n))
+                elif fetch:
+                    self.ctx.L.svb_clusters_text(out, which, C.byref(d), C.byref(n))
+                else:
+                    self.ctx.L.svb_clusters_text_len(out, which, C.byref(n))
                 res.append(n.value)
+            self.last_clusters = self.ctx.L.svb_clusters_count(out)
             return tuple(res)
         finally:
             self.ctx.L.svb_clusters_free(out)
+
+    def getsv_passes_raw(self, params, junction_array, n_j, window_array, n_w, stats_array, counts_array, depth_array):
+        """svb_getsv_passes on prebuilt C arrays (bench.py): insert-size statistics, pair support and window depth, one read-back"""
+        self.ctx.check(self.ctx.L.svb_getsv_passes(self.ctx.h, self.h, C.byref(params), junction_array, n_j, window_array, n_w, stats_array,
+                                                   counts_array, depth_array), "svb_getsv_passes")
+
+    def getsv_passes(self, junctions, windows, min_mapq=20, max_pairs=5000000, times=4):
+        """(stats[4], counts per junction, depth lists per window) from one fused call"""
+        nj, nw = len(junctions), len(windows)
+        j_arr = (Junction * max(nj, 1))(*[Junction(ut, up, dt, dp, us.encode(), ds.encode(), b"") for ut, up, us, dt, dp, ds in junctions])
+        w_arr = (Window * max(nw, 1))(*[Window(*w) for w in windows])
+        tot = sum(w[2] - w[1] + 1 for w in windows)
+        st, cnt, dep = (C.c_int64 * 4)(), (C.c_int32 * max(nj, 1))(), (C.c_int32 * max(tot, 1))()
+        self.getsv_passes_raw(GetsvParams(min_mapq, times, max_pairs), j_arr, nj, w_arr, nw, st, cnt, dep)
+        res, o = [], 0
+        for w in windows:
+            k = w[2] - w[1] + 1
+            res.append(list(dep[o:o + k]))
+            o += k
+        return tuple(st), list(cnt[:nj]), res
 
     def discordant_support_raw(self, junction_array, n, pair_params, counts_array):
         self.ctx.check(self.ctx.L.svb_discordant_support(self.ctx.h, self.h, junction_array, n, C.byref(pair_params), counts_array),

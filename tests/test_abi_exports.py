@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_no_cpu_fallback(lib):
-    assert lib.svb_abi_version() == 1
+    assert lib.svb_abi_version() == 2
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")

@@ -143,6 +143,27 @@ def test_device_passes_match_oracle(ctx, d, s):
         got = bam.window_depth(wins, mq)
         for (tid, b, e), g in zip(wins, got):
             assert g == [int(x) for x in dep[tid][b:e + 1]], (tid, b, e)
+        if mq == 20:
+            # the fused call (one stream-ordered sequence, statistics stay on the device) and the rows written by getclip's own pass
+            # (with_rows) give the same answers as the three single passes
+            want_counts = bam.discordant_support(juncs, 20, mean, dev, 4)
+            for fresh in (False, True):
+                b2 = bam
+                if fresh:
+                    b2 = seeksv_b200.Bam.open(ctx, _bam(d, s))
+                    b2.getclip_sizes(with_rows=True)
+                for cap in (5000000, 1000):
+                    st, cnts, deps = b2.getsv_passes(juncs, wins, 20, cap, 4)
+                    w2 = G.insert_size_stats(recs, 20, cap)
+                    import math
+                    assert (st[2], int(math.sqrt(st[3] / st[0]))) == w2
+                    assert deps == got
+                    if cap == 5000000:
+                        assert cnts == want_counts
+                    else:
+                        assert cnts == b2.discordant_support(juncs, 20, w2[0], w2[1], 4)
+                if fresh:
+                    b2.close()
     bam.close()
 
 
@@ -281,13 +302,10 @@ def test_depth_accounting_closed_form_equals_literal_walk(tmp_path, monkeypatch)
         assert outs[("closed", flank)] == outs[("literal", flank)], flank
 
 
-@pytest.mark.parametrize("mode", ["stream", "walk12"])
+@pytest.mark.parametrize("mode", ["walk10", "walk12"])
 def test_alternative_full_pass_forms_give_identical_results(mode, tmp_path, monkeypatch):
-    """the TMA-staged streaming passes (SEEKSV_B200_PASS=stream) and a different walker chunk size produce the same bytes"""
-    if mode == "stream":
-        monkeypatch.setenv("SEEKSV_B200_PASS", "stream")
-    else:
-        monkeypatch.setenv("SEEKSV_B200_CHUNK_LOG2", "12")
+    """other walker chunk sizes (more chains, more guesses, other chunk boundaries) produce the same bytes"""
+    monkeypatch.setenv("SEEKSV_B200_CHUNK_LOG2", mode[4:])
     for d, s in (("micro", "tumor"), ("example", "cancer"), ("kat", "quirks")):
         pre = str(tmp_path / (mode + s))
         r = subprocess.run([_cli(), "getclip", "-o", pre, _bam(d, s)], capture_output=True, text=True, env=dict(os.environ))
