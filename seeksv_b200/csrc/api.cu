@@ -76,6 +76,8 @@ extern "C" void svb_ctx_destroy(svb_ctx *ctx)
     cudaStreamDestroy(ctx->stream);
     for (auto &e : ctx->big_free) cudaFree(e.first);
     ctx->big_free.clear();
+    for (auto &e : ctx->dev_free) cudaFree(e.first);
+    ctx->dev_free.clear();
     for (int w = 0; w < 2; ++w)
         if (ctx->ws[w]) cudaFree(ctx->ws[w]);
     if (ctx->ctl_host) cudaFreeHost(ctx->ctl_host);
@@ -139,6 +141,41 @@ int svb_ctx::ws_reserve(int which, uint64_t bytes)
     CK(cudaMalloc((void **)&ws[which], want));
     ws_cap[which] = want;
     return 0;
+}
+
+uint8_t *svb_ctx::dev_get(uint64_t bytes, uint64_t *cap)
+{
+    int best = -1;
+    for (size_t i = 0; i < dev_free.size(); ++i)
+        if (dev_free[i].second >= bytes && dev_free[i].second <= 3 * bytes + (32ull << 20) &&
+            (best < 0 || dev_free[i].second < dev_free[best].second))
+            best = (int)i;
+    if (best >= 0) {
+        uint8_t *p = dev_free[best].first;
+        *cap = dev_free[best].second;
+        dev_free.erase(dev_free.begin() + best);
+        return p;
+    }
+    uint8_t *p = nullptr;
+    const uint64_t want = bytes + bytes / 8 + 4096;
+    if (cudaMallocAsync((void **)&p, want, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    *cap = want;
+    return p;
+}
+void svb_ctx::dev_put(uint8_t *p, uint64_t cap)
+{
+    if (!p) return;
+    dev_free.emplace_back(p, cap);
+    while (dev_free.size() > 16) {  // drop the smallest
+        size_t smallest = 0;
+        for (size_t i = 1; i < dev_free.size(); ++i)
+            if (dev_free[i].second < dev_free[smallest].second) smallest = i;
+        cudaFreeAsync(dev_free[smallest].first, stream);
+        dev_free.erase(dev_free.begin() + smallest);
+    }
 }
 
 char *svb_ctx::pinned_get(uint64_t bytes, uint64_t *cap)
@@ -715,7 +752,8 @@ extern "C" void svb_bam_free(svb_bam *b)
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     cudaStream_t s = b->ctx->stream;
-    void *cols[5] = {b->rows.row, b->d_guess /* + base, exit, count: one allocation */, b->d_fkey, b->d_scal, b->d_ref_len};
+    free_rows(b);
+    void *cols[4] = {b->d_guess /* + base, exit, count: one allocation */, b->d_fkey, b->d_scal, b->d_ref_len};
     for (void *c : cols)
         if (c) cudaFreeAsync(c, s);
     if (b->d_owned) b->ctx->big_put(b->d_owned, b->owned_cap);  // (the stream was synchronised above)

@@ -66,6 +66,12 @@ struct svb_ctx {
     std::vector<std::pair<uint8_t *, uint64_t>> big_free;
     uint8_t *big_get(uint64_t bytes, uint64_t *cap);  // contents undefined; usable on `stream` (and after its events)
     void big_put(uint8_t *p, uint64_t cap);           // caller has synchronised every stream that used p
+    // Mid-size device buffers that a command needs again and again with about the same size (record rows, result texts): kept
+    // in the context instead of going back to the stream-ordered pool - the pool splits a big freed block for the next small
+    // request and then has to map fresh memory for the big one again (milliseconds per step, measured).
+    std::vector<std::pair<uint8_t *, uint64_t>> dev_free;
+    uint8_t *dev_get(uint64_t bytes, uint64_t *cap);  // usable on `stream` (and after its events)
+    void dev_put(uint8_t *p, uint64_t cap);           // p's last use is ordered before later work on `stream`
     // One grow-only scratch buffer per command family: the sync-free pipelines carve all their temporaries out of it (Bump,
     // prim.cuh) instead of allocating array by array. A command owns it from its first launch to its final read-back.
     uint8_t *ws[2] = {nullptr, nullptr};
@@ -109,7 +115,9 @@ struct __align__(32) Row {
 };
 struct RowTable {
     Row *row = nullptr;
-    uint32_t R = 0;  // slots per chunk
+    uint16_t *roff = nullptr;  // offset of the record inside its chunk (behind the rows, same allocation): CIGARs are re-read from there
+    uint32_t R = 0;            // slots per chunk
+    uint64_t cap = 0;          // bytes of the allocation (dev_get)
 };
 #define FLAGQ_HARDCLIP (1u << 24)
 #define FLAGQ_NOCIGAR (1u << 25)
@@ -296,6 +304,8 @@ int ensure_counts(svb_ctx *ctx, svb_bam *bam);
 int ensure_rows(svb_ctx *ctx, svb_bam *bam);
 // a walk left exit[] without matching the guesses: repair guesses with plain walks (synchronises); the walk has to run again
 int repair_guesses(svb_ctx *ctx, svb_bam *bam);
+int alloc_rows(svb_ctx *ctx, svb_bam *bam, uint32_t R);  // walk.cu
+void free_rows(svb_bam *bam);
 // the inflate kernel reads ahead of the current bit position: the device copy of the file image is padded by this much
 static constexpr uint64_t SVB_INFLATE_PAD = 1024;
 struct PinnedBuf;

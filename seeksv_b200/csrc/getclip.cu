@@ -20,14 +20,14 @@ struct ClipCtl {
     uint32_t flags[4];     // [0] row slots overflowed [1] chain does not verify [2] spare [3] spare
     uint64_t c64[2];       // records, end of the chain
     uint32_t n_seg, n_cl, un_skip, un_own;
-    uint32_t abort_main, abort_side, pad0, pad1;
+    uint32_t abort_main, abort_side, tk_cluster, tk_text;  // tickets of the persistent warps of cluster_build / text_write
     uint64_t arena_bytes, clip_bytes, fq_bytes, un1_bytes, un2_bytes, export_bytes;
 };
 
 struct svb_clusters {
     svb_ctx *ctx = nullptr;
     char *d_text[4] = {nullptr, nullptr, nullptr, nullptr};  // device: the four texts (or nothing in gz mode once compressed)
-    uint64_t text_len[4] = {0, 0, 0, 0};
+    uint64_t text_len[4] = {0, 0, 0, 0}, d_cap[5] = {0, 0, 0, 0, 0};
     mutable PinnedBuf text[4];  // pinned host copies, made on first request
     mutable bool text_here[4] = {false, false, false, false};
     PinnedBuf gz[4];             // the same four files as gzip images, compressed on the device (svb_getclip_params.gz_outputs)
@@ -39,9 +39,17 @@ struct svb_clusters {
     uint64_t n_clusters = 0, n_candidates = 0;
     void drop_device()
     {
-        for (auto &t : d_text)
-            if (t) cudaFreeAsync(t, ctx->stream), t = nullptr;
-        if (d_export) cudaFreeAsync(d_export, ctx->stream), d_export = nullptr;
+        for (int w = 0; w < 4; ++w)
+            if (d_text[w]) ctx->dev_put((uint8_t *)d_text[w], d_cap[w]), d_text[w] = nullptr;
+        if (d_export) ctx->dev_put(d_export, d_cap[4]), d_export = nullptr;
+    }
+    int take(int w, uint64_t bytes)
+    {
+        uint8_t *p = ctx->dev_get(bytes, &d_cap[w]);
+        if (!p) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate %llu bytes of device memory for the results", (unsigned long long)bytes);
+        if (w < 4) d_text[w] = (char *)p;
+        else d_export = p;
+        return 0;
     }
     ~svb_clusters()
     {
@@ -224,6 +232,15 @@ __global__ void __launch_bounds__(128)
             E = eval_clip(d, o, k, P);
         }
         const uint32_t mine = (uint32_t)E.e5 + (uint32_t)E.e3;
+        if (mine) {
+            // cluster_build reads this record's bases and qualities next: ask L2 for those lines now (the head and the aux block
+            // at the record's end have just been read; the middle of the record has not)
+            const uint8_t *p = d + o;
+            const uint32_t lq = ldu32(p + 12) & 0xff, nc = ldu32(p + 16) & 0xffff;
+            const int32_t l = ldi32(p + 20);
+            const uintptr_t a0 = (uintptr_t)(p + 36 + lq + 4 * nc) & ~(uintptr_t)127, a1 = (uintptr_t)(p + 36 + lq + 4 * nc + (l + 1) / 2 + l);
+            for (uintptr_t a = a0; a < a1; a += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
         uint32_t incl = mine;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
@@ -347,15 +364,22 @@ struct ClusterOut {
 // BAM order, with lane-parallel string compares and consensus updates. Strings live in a per-segment
 // arena: slot k holds [left part right-aligned at column maxl | right part left-aligned at maxl].
 __global__ void __launch_bounds__(128)
-    cluster_build(const uint8_t *__restrict__ d, const ClipCtl *__restrict__ ctl,
+    cluster_build(const uint8_t *__restrict__ d, ClipCtl *__restrict__ ctl,
                   const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c,
                   const uint32_t *__restrict__ maxl_, const uint32_t *__restrict__ maxr_, const uint64_t *__restrict__ arena_off,
                   char *__restrict__ arena_seq, char *__restrict__ arena_qual, double limit, ClusterOut out)
 {
     if (ctl->abort_main) return;
     const uint32_t n_seg = ctl->n_seg, lane = threadIdx.x & 31;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_seg; s += n_warps) {
+    // warps take four keys at a time from a ticket counter: a key with many reads (a real breakpoint) keeps its warp busy for a
+    // while, and a fixed assignment left the last warps running alone
+    for (;;) {
+        uint32_t s0 = 0;
+        if (lane == 0) s0 = atomicAdd(&ctl->tk_cluster, 4u);
+        s0 = __shfl_sync(0xffffffffu, s0, 0);
+        if (s0 >= n_seg) break;
+        const uint32_t s1 = min(s0 + 4u, n_seg);
+      for (uint32_t s = s0; s < s1; ++s) {
         const uint32_t a = start[s], b = start[s + 1];
         const uint32_t maxl = maxl_[s], stride = maxl + maxr_[s];
         char *S = arena_seq + arena_off[s], *Q = arena_qual + arena_off[s];
@@ -446,6 +470,7 @@ __global__ void __launch_bounds__(128)
             __syncwarp();
         }
         if (lane == 0) out.seg_ncl[s] = ncl;
+      }
     }
 }
 
@@ -544,15 +569,21 @@ struct TextScanOp {
 
 // one warp per cluster writes its clip.gz line and its FASTQ record
 __global__ void __launch_bounds__(128)
-    text_write(const ClipCtl *__restrict__ ctl, const uint32_t *__restrict__ cl_seg, const uint32_t *__restrict__ cl_slot,
+    text_write(ClipCtl *__restrict__ ctl, const uint32_t *__restrict__ cl_seg, const uint32_t *__restrict__ cl_slot,
                const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c, ClusterOut out,
                const uint8_t *__restrict__ d, NameTable names, const uint32_t *__restrict__ maxl_, const uint32_t *__restrict__ maxr_, const uint64_t *__restrict__ arena_off,
                const char *__restrict__ arena_seq, const char *__restrict__ arena_qual, const uint64_t *__restrict__ clip_off,
                const uint64_t *__restrict__ fq_off, char *__restrict__ clip, char *__restrict__ fq)
 {
     if (ctl->abort_main) return;
-    const uint32_t n_cl = ctl->n_cl, lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_cl; i += n_warps) {
+    const uint32_t n_cl = ctl->n_cl, lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t i0 = 0;
+        if (lane == 0) i0 = atomicAdd(&ctl->tk_text, 8u);
+        i0 = __shfl_sync(0xffffffffu, i0, 0);
+        if (i0 >= n_cl) break;
+        const uint32_t i1 = min(i0 + 8u, n_cl);
+      for (uint32_t i = i0; i < i1; ++i) {
         uint32_t s = cl_seg[i], a = start[s], slot = cl_slot[i], k = a + slot;
         uint32_t x = order[a];
         uint32_t maxl = maxl_[s], stride = maxl + maxr_[s];
@@ -608,6 +639,7 @@ __global__ void __launch_bounds__(128)
         if (lane == 0) f[0] = '@', f[1 + cN] = '\n', f[2 + 2 * cN] = '\n', f[3 + 2 * cN] = '+', f[4 + 2 * cN] = '\n', f[5 + 2 * cN + cQN] = '\n';
         for (uint32_t j = lane; j < cN; j += 32) f[1 + j] = cS[j], f[2 + cN + j] = cS[j];
         for (uint32_t j = lane; j < cQN; j += 32) f[5 + 2 * cN + j] = noq ? '*' : cQ[j];
+      }
     }
 }
 
@@ -906,12 +938,12 @@ void carve(Bump &b, ClipBuffers &B, const Caps &cap, uint64_t n_chunks, int off_
     B.rs_sw = radix_scratch(b, cap.sw, off_passes);
     B.rs_un = radix_scratch(b, cap.un, off_passes);
     B.rs_hash = radix_scratch(b, pair_mode ? cap.un : 1, 4);
-    B.sc_chunk = scan_scratch(b, n_chunks, 1);
-    B.sc_seg = scan_scratch(b, cap.cand, 1);
-    B.sc_stats = scan_scratch(b, cap.cand, 1);
-    B.sc_cl = scan_scratch(b, cap.cand, 1);
-    B.sc_text = scan_scratch(b, cap.cand, 2);
-    B.sc_un = scan_scratch(b, cap.un, 2);
+    B.sc_chunk = scan_scratch(b, n_chunks, 1, 8);
+    B.sc_seg = scan_scratch(b, cap.cand, 1, 8);
+    B.sc_stats = scan_scratch(b, cap.cand, 1, 2);
+    B.sc_cl = scan_scratch(b, cap.cand, 1, 4);
+    B.sc_text = scan_scratch(b, cap.cand, 2, 2);
+    B.sc_un = scan_scratch(b, cap.un, 2, 2);
     B.zero_end = (b.used + 255) & ~(size_t)255;
     // --- queues and per-chunk side arrays
     B.q.clipped = b.get<uint64_t>(cap.clipped), B.q.clipped_cap = cap.clipped;
@@ -1001,11 +1033,11 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         }
         B.q.min_mapq = prm->min_mapq;
         res->drop_device();
-        CK(cudaMallocAsync((void **)&res->d_text[0], cap.clip, s));
-        CK(cudaMallocAsync((void **)&res->d_text[1], cap.fq, s));
-        CK(cudaMallocAsync((void **)&res->d_text[2], cap.un1, s));
-        CK(cudaMallocAsync((void **)&res->d_text[3], cap.un2, s));
-        if (export_mode) CK(cudaMallocAsync((void **)&res->d_export, cap.exp, s));
+        CKR(res->take(0, cap.clip));
+        CKR(res->take(1, cap.fq));
+        CKR(res->take(2, cap.un1));
+        CKR(res->take(3, cap.un2));
+        if (export_mode) CKR(res->take(4, cap.exp));
         if (want_rows && !bam->rows_ready) CKR(alloc_rows(ctx, bam, bam->rows.R == ROWS_R_MAX ? ROWS_R_MAX : ROWS_R_FIRST));
         const bool do_rows = want_rows && !bam->rows_ready;
         CK(cudaMemsetAsync(ctx->ws[0], 0, B.zero_end, s));
@@ -1030,7 +1062,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
             unmapped_own<<<1, 1, 0, side>>>(ctl->counters, cap.un, B.un_sorted, prm->halo_bytes, ctl);
             if (export_mode) {
                 ExportScanOp op{B.un_sorted, bam->d_data, B.off1, cap.exp, ctl};
-                launch_scan<1>(ctx, side, op, B.sc_un, cap.un);
+                launch_scan<1, 2>(ctx, side, op, B.sc_un, cap.un);
                 record_copy<<<grid_for(ctx, (uint64_t)cap.un * 32, 128, 8), 128, 0, side>>>(ctl, B.un_sorted, bam->d_data, B.off1, res->d_export);
             } else {
                 const unsigned g = grid_for(ctx, cap.un, 256, 4);
@@ -1040,7 +1072,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
                 CK(cudaMemsetAsync(B.mate_of, 0xff, (size_t)cap.un * 4, side));
                 unmapped_pair<<<g, 256, 0, side>>>(ctl, B.ukey[1], B.uval[1], B.un_sorted, bam->d_data, B.mate_of);
                 UnSizesOp op{B.un_sorted, B.mate_of, bam->d_data, B.off1, B.off2, cap.un1, cap.un2, ctl};
-                launch_scan<2>(ctx, side, op, B.sc_un, cap.un);
+                launch_scan<2, 2>(ctx, side, op, B.sc_un, cap.un);
             }
         }
         if (pair_mode) {
@@ -1077,9 +1109,9 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         {
             ProfScope ps(ctx, "segments", 0);
             SegScanOp op1{ctl->counters, cap.cand, B.key[1], B.start, ctl};
-            launch_scan<1>(ctx, s, op1, B.sc_seg, cap.cand);
+            launch_scan<1, 8>(ctx, s, op1, B.sc_seg, cap.cand);
             SegStatsOp op2{B.start, order, B.c, B.maxl, B.maxr, B.arena_off, cap.arena, ctl};
-            launch_scan<1>(ctx, s, op2, B.sc_stats, cap.cand);
+            launch_scan<1, 2>(ctx, s, op2, B.sc_stats, cap.cand);
         }
         {
             ProfScope ps(ctx, "cluster_build", 0);
@@ -1090,9 +1122,9 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         {
             ProfScope ps(ctx, "text_write", 0);
             ClusterScanOp op3{B.co.seg_ncl, B.cl_seg, B.cl_slot, ctl};
-            launch_scan<1>(ctx, s, op3, B.sc_cl, cap.cand);
+            launch_scan<1, 4>(ctx, s, op3, B.sc_cl, cap.cand);
             TextScanOp op4{B.cl_seg, B.cl_slot, B.start, order, B.c, B.co, bam->d_data, nt, B.clip_off, B.fq_off, cap.clip, cap.fq, ctl};
-            launch_scan<2>(ctx, s, op4, B.sc_text, cap.cand);
+            launch_scan<2, 2>(ctx, s, op4, B.sc_text, cap.cand);
             text_write<<<grid_for(ctx, (uint64_t)cap.cand * 32, 128, 16), 128, 0, s>>>(ctl, B.cl_seg, B.cl_slot, B.start, order, B.c, B.co, bam->d_data, nt,
                                                                                      B.maxl, B.maxr, B.arena_off, B.arena_seq, B.arena_qual, B.clip_off,
                                                                                      B.fq_off, res->d_text[0], res->d_text[1]);

@@ -33,7 +33,8 @@ __device__ __forceinline__ bool insert_qualifies(uint32_t fq, int32_t isize, int
 
 struct RowsView {
     const Row *row;
-    uint32_t R;
+    const uint16_t *roff;  // offset of a record inside its chunk
+    uint32_t R, chunk_log2;
     const uint32_t *count;
     const uint64_t *base;  // dense index of a chunk's first row (n_chunks + 1 entries)
     const uint64_t *fkey;  // key of the first row at or after the chunk (rows_index)
@@ -115,13 +116,13 @@ __global__ void __launch_bounds__(256)
 // mean and deviation on the device (cluster.cpp:72-80) when the closed form is exact: every qualifying record is used
 // (total <= -n) and every |isize - mean| stays below sqrt(2^31), so that the reference's int products cannot wrap and
 // sum (x - m)^2 = sum x^2 - 2 m sum x + n m^2 holds in 64-bit integers. Otherwise need_slow asks the host for the ordered path.
-__global__ void __launch_bounds__(1024)
-    insert_finish(SvCtl *ctl, long long max_pairs, uint64_t n_chunks, const uint32_t *__restrict__ q_cnt, const uint64_t *__restrict__ q_sum,
-                  const uint64_t *__restrict__ q_sq)
+__global__ void __launch_bounds__(256)
+    insert_totals(SvCtl *ctl, uint64_t n_chunks, const uint32_t *__restrict__ q_cnt, const uint64_t *__restrict__ q_sum, const uint64_t *__restrict__ q_sq)
 {
-    __shared__ unsigned long long red[3][32];
+    __shared__ unsigned long long red[3][8];
     unsigned long long a = 0, b = 0, q = 0;
-    for (uint64_t c = threadIdx.x; c < n_chunks; c += blockDim.x) a += q_cnt[c], b += q_sum[c], q += q_sq[c];
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += (uint64_t)gridDim.x * blockDim.x)
+        a += q_cnt[c], b += q_sum[c], q += q_sq[c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -133,8 +134,11 @@ __global__ void __launch_bounds__(1024)
     if (threadIdx.x != 0) return;
     a = b = q = 0;
     for (uint32_t w = 0; w < blockDim.x / 32; ++w) a += red[0][w], b += red[1][w], q += red[2][w];
-    ctl->tot[0] = a, ctl->tot[1] = b, ctl->tot[2] = q;
-    const unsigned long long n = a;
+    if (a) atomicAdd(&ctl->tot[0], a), atomicAdd(&ctl->tot[1], b), atomicAdd(&ctl->tot[2], q);
+}
+__global__ void insert_finish(SvCtl *ctl, long long max_pairs)
+{
+    const unsigned long long n = ctl->tot[0];
     ctl->mean = 0, ctl->dev = 0, ctl->sq = 0, ctl->need_slow = 0;
     if (n == 0 || max_pairs <= 0) return;
     if (n > (unsigned long long)max_pairs || ctl->q_max > 46340) {
@@ -311,8 +315,9 @@ __device__ __forceinline__ uint64_t first_window(const svb_window *__restrict__ 
     return lo;
 }
 
-// chunks that hold records which can reach a window: one thread per window
-__global__ void depth_select(RowsView V, const int32_t *__restrict__ scal, const svb_window *__restrict__ W, uint64_t n_w, uint8_t *__restrict__ pick)
+// chunks that hold records which can reach a window: one thread per window, each chunk listed once
+__global__ void depth_select(RowsView V, const int32_t *__restrict__ scal, const svb_window *__restrict__ W, uint64_t n_w, uint32_t *__restrict__ pick,
+                             uint32_t *__restrict__ list, uint32_t *__restrict__ n_list)
 {
     const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_w) return;
@@ -321,51 +326,51 @@ __global__ void depth_select(RowsView V, const int32_t *__restrict__ scal, const
     const uint64_t Klo = row_key(W[w].tid, (int32_t)max(plo, (int64_t)INT32_MIN)), Khi = row_key(W[w].tid, W[w].end);  // pos < end (1-based end = pos + 1 <= end)
     uint64_t c0 = chunk_lower_bound(V.fkey, V.n_chunks, Klo), c1 = chunk_lower_bound(V.fkey, V.n_chunks, Khi);
     if (c0 > 0) --c0;
-    for (uint64_t c = c0; c < c1; ++c) pick[c] = 1;
+    for (uint64_t c = c0; c < c1; ++c)
+        if (atomicExch(&pick[c], 1u) == 0) list[atomicAdd(n_list, 1u)] = (uint32_t)c;
 }
 
-// One thread per picked chunk: follow the chunk's record chain (the rows give tid / pos / end / flags, the chain gives the
-// offsets) and put +1/-1 marks of the M segments of every eligible record into the difference array of each window it overlaps.
+// One warp per listed chunk, one lane per record: +1/-1 marks of the M segments of every eligible record into the difference
+// array of each window it overlaps (the rows give tid / pos / end / flags, roff the place of the record for its CIGAR).
 // kept == nullptr: every pileup-eligible read is kept. kept != nullptr: the survivors of libbam's 8000-read cap (cap_serial).
 __global__ void __launch_bounds__(128)
-    depth_marks(const uint8_t *__restrict__ d, RowsView V, const uint64_t *__restrict__ guess, const uint8_t *__restrict__ pick, int32_t min_mapq,
+    depth_marks(const uint8_t *__restrict__ d, RowsView V, const uint32_t *__restrict__ list, const uint32_t *__restrict__ n_list, int32_t min_mapq,
                 const uint8_t *__restrict__ kept, const svb_window *__restrict__ W, const uint64_t *__restrict__ woff, uint64_t n_w,
                 int32_t *__restrict__ diff)
 {
-    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= V.n_chunks || !pick[c]) return;
-    const uint32_t cnt = min(V.count[c], V.R);
-    uint64_t o = guess[c];
-    for (uint32_t k = 0; k < cnt; ++k) {
-        const uint8_t *p = d + o;
-        const uint32_t bs = ldu32(p);
-        o += 4 + (uint64_t)bs;
-        const Row r = V.row[c * V.R + k];
-        const int32_t tid = r.tid;
-        if (!pileup_eligible(tid, r.flagq, min_mapq)) continue;
-        if (kept && !kept[c * V.R + k]) continue;
-        const int32_t beg1 = r.pos + 1, end1 = r.end;  // 1-based inclusive [beg1, end1]
-        if (end1 < beg1) continue;
-        uint64_t w = first_window(W, n_w, tid, beg1);
-        if (w >= n_w || W[w].tid != tid || W[w].begin > end1) continue;
-        const uint32_t lq = ldu32(p + 12) & 0xff, nc = ldu32(p + 16) & 0xffff;
-        const uint8_t *cig = p + 36 + lq;
-        for (; w < n_w && W[w].tid == tid && W[w].begin <= end1; ++w) {
-            int32_t wb = W[w].begin, we = W[w].end;
-            int32_t *dw = diff + woff[w];
-            int32_t x = beg1;
-            for (uint32_t j = 0; j < nc && x <= we; ++j) {
-                uint32_t cw = ldu32(cig + 4 * j), op = cw & 15;
-                int32_t len = (int32_t)(cw >> 4);
-                if (op == OP_M) {  // '=' / 'X' are ignored by this libbam's CIGAR walk (probed)
-                    int32_t lo = max(x, wb), hi = min(x + len - 1, we);
-                    if (lo <= hi) {
-                        atomicAdd(&dw[lo - wb], 1);
-                        atomicAdd(&dw[hi + 1 - wb], -1);
-                    }
-                    x += len;
-                } else if (op == OP_D || op == OP_N)
-                    x += len;
+    const uint32_t lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5, n = *n_list;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
+        const uint64_t c = list[i];
+        const uint32_t cnt = min(V.count[c], V.R);
+        for (uint32_t k = lane; k < cnt; k += 32) {
+            const Row r = V.row[c * V.R + k];
+            const int32_t tid = r.tid;
+            if (!pileup_eligible(tid, r.flagq, min_mapq)) continue;
+            if (kept && !kept[c * V.R + k]) continue;
+            const int32_t beg1 = r.pos + 1, end1 = r.end;  // 1-based inclusive [beg1, end1]
+            if (end1 < beg1) continue;
+            uint64_t w = first_window(W, n_w, tid, beg1);
+            if (w >= n_w || W[w].tid != tid || W[w].begin > end1) continue;
+            const uint8_t *p = d + (c << V.chunk_log2) + V.roff[c * V.R + k];
+            const uint32_t lq = ldu32(p + 12) & 0xff, nc = ldu32(p + 16) & 0xffff;
+            const uint8_t *cig = p + 36 + lq;
+            for (; w < n_w && W[w].tid == tid && W[w].begin <= end1; ++w) {
+                int32_t wb = W[w].begin, we = W[w].end;
+                int32_t *dw = diff + woff[w];
+                int32_t x = beg1;
+                for (uint32_t j = 0; j < nc && x <= we; ++j) {
+                    uint32_t cw = ldu32(cig + 4 * j), op = cw & 15;
+                    int32_t len = (int32_t)(cw >> 4);
+                    if (op == OP_M) {  // '=' / 'X' are ignored by this libbam's CIGAR walk (probed)
+                        int32_t lo = max(x, wb), hi = min(x + len - 1, we);
+                        if (lo <= hi) {
+                            atomicAdd(&dw[lo - wb], 1);
+                            atomicAdd(&dw[hi + 1 - wb], -1);
+                        }
+                        x += len;
+                    } else if (op == OP_D || op == OP_N)
+                        x += len;
+                }
             }
         }
     }
@@ -477,7 +482,10 @@ __global__ void __launch_bounds__(128)
 
 // ---- host orchestration ---------------------------------------------------------------------------------------------------
 namespace {
-RowsView view_of(const svb_bam *bam) { return RowsView{bam->rows.row, bam->rows.R, bam->d_count, bam->d_base, bam->d_fkey, bam->n_chunks}; }
+RowsView view_of(const svb_bam *bam)
+{
+    return RowsView{bam->rows.row, bam->rows.roff, bam->rows.R, bam->chunk_log2, bam->d_count, bam->d_base, bam->d_fkey, bam->n_chunks};
+}
 
 struct SvBuffers {
     SvCtl *ctl;
@@ -490,7 +498,7 @@ struct SvBuffers {
     svb_window *W;
     uint64_t *woff;
     int32_t *diff, *depth;
-    uint8_t *pick;
+    uint32_t *pick, *list, *n_list;
     uint32_t *hot;
     size_t zero_end;
 };
@@ -498,8 +506,9 @@ void carve(Bump &b, SvBuffers &B, uint64_t n_chunks, uint64_t n_j, uint64_t n_w,
 {
     B.ctl = b.get<SvCtl>(1);
     B.acc = b.get<unsigned long long>(2);
-    B.sc_q = scan_scratch(b, n_chunks, 1);
-    B.pick = b.get<uint8_t>(n_w ? n_chunks : 1);
+    B.sc_q = scan_scratch(b, n_chunks, 1, 8);
+    B.pick = b.get<uint32_t>(n_w ? n_chunks : 1);
+    B.n_list = b.get<uint32_t>(1);
     B.hot = b.get<uint32_t>((size_t)n_ref + 1);
     B.diff = b.get<int32_t>(diff_len);
     B.zero_end = (b.used + 255) & ~(size_t)255;
@@ -507,6 +516,7 @@ void carve(Bump &b, SvBuffers &B, uint64_t n_chunks, uint64_t n_j, uint64_t n_w,
     B.J = b.get<svb_junction>(n_j), B.counts = b.get<int32_t>(n_j);
     B.W = b.get<svb_window>(n_w), B.woff = b.get<uint64_t>(n_w + 1);
     B.depth = b.get<int32_t>(n_pos);
+    B.list = b.get<uint32_t>(n_w ? n_chunks : 1);
 }
 
 // rows of the records + their index (first keys, span, order): made once per handle
@@ -582,7 +592,10 @@ int run_passes(svb_ctx *ctx, svb_bam *bam, const Request &rq)
         if (need_index && rq.stats) rows_pass<true, true><<<g_chunks, 256, 0, s>>>(V, bam->d_fkey, bam->d_scal, rq.stats_mapq, B.q_cnt, B.q_sum, B.q_sq, B.ctl);
         else if (need_index) rows_pass<true, false><<<g_chunks, 256, 0, s>>>(V, bam->d_fkey, bam->d_scal, 0, B.q_cnt, B.q_sum, B.q_sq, B.ctl);
         else rows_pass<false, true><<<g_chunks, 256, 0, s>>>(V, bam->d_fkey, bam->d_scal, rq.stats_mapq, B.q_cnt, B.q_sum, B.q_sq, B.ctl);
-        if (rq.stats) insert_finish<<<1, 1024, 0, s>>>(B.ctl, (long long)rq.max_pairs, n_chunks, B.q_cnt, B.q_sum, B.q_sq);
+        if (rq.stats) {
+            insert_totals<<<(unsigned)std::min<uint64_t>(nblk(n_chunks, 256), (uint64_t)ctx->sm_count), 256, 0, s>>>(B.ctl, n_chunks, B.q_cnt, B.q_sum, B.q_sq);
+            insert_finish<<<1, 1, 0, s>>>(B.ctl, (long long)rq.max_pairs);
+        }
     }
     const bool fused_pairs = rq.n_j && rq.pp_from_stats;
     auto launch_pairs = [&](const SvCtl *from_ctl) -> int {
@@ -598,8 +611,8 @@ int run_passes(svb_ctx *ctx, svb_bam *bam, const Request &rq)
         CK(cudaMemcpyAsync(B.woff, woff.data(), (rq.n_w + 1) * 8, cudaMemcpyHostToDevice, s));
         {
             ProfScope ps(ctx, "depth_marks", 0);
-            depth_select<<<nblk(rq.n_w, 128), 128, 0, s>>>(V, bam->d_scal, B.W, rq.n_w, B.pick);
-            depth_marks<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, V, bam->d_guess, B.pick, rq.depth_mapq, nullptr, B.W, B.woff, rq.n_w, B.diff);
+            depth_select<<<nblk(rq.n_w, 128), 128, 0, s>>>(V, bam->d_scal, B.W, rq.n_w, B.pick, B.list, B.n_list);
+            depth_marks<<<grid_for(ctx, n_chunks * 32, 128, 8), 128, 0, s>>>(bam->d_data, V, B.list, B.n_list, rq.depth_mapq, nullptr, B.W, B.woff, rq.n_w, B.diff);
             hot_check<<<nblk(n_chunks, 128), 128, 0, s>>>(V, bam->d_scal, rq.depth_mapq, B.hot, B.ctl);
         }
         {
@@ -633,7 +646,7 @@ int run_passes(svb_ctx *ctx, svb_bam *bam, const Request &rq)
             CK(cudaMemsetAsync(B.acc, 0, 16, s));
             {
                 ProfScope ps(ctx, "insert_stats", 0);
-                launch_scan<1>(ctx, s, op, B.sc_q, n_chunks);
+                launch_scan<1, 8>(ctx, s, op, B.sc_q, n_chunks);
                 insert_ordered<<<g_chunks, 256, 0, s>>>(V, rq.stats_mapq, B.q_base, (uint64_t)rq.max_pairs, 1, 0, B.acc);
             }
             unsigned long long sum = 0;
@@ -682,7 +695,7 @@ int run_passes(svb_ctx *ctx, svb_bam *bam, const Request &rq)
         CK(cudaMemsetAsync(B.diff, 0, tot * 4, s));
         {
             ProfScope ps(ctx, "depth_marks", 0);
-            depth_marks<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, V, bam->d_guess, B.pick, rq.depth_mapq, kept.p, B.W, B.woff, rq.n_w, B.diff);
+            depth_marks<<<grid_for(ctx, n_chunks * 32, 128, 8), 128, 0, s>>>(bam->d_data, V, B.list, B.n_list, rq.depth_mapq, kept.p, B.W, B.woff, rq.n_w, B.diff);
         }
         depth_scan<<<nblk(rq.n_w * 32, 128), 128, 0, s>>>(B.W, B.woff, rq.n_w, B.diff, B.depth);
         CK(cudaMemcpyAsync(rq.depth_out, B.depth, n_pos * 4, cudaMemcpyDeviceToHost, s));

@@ -28,8 +28,6 @@ void launch_chunk_scan(svb_ctx *ctx, cudaStream_t s, svb_bam *bam, const ScanScr
 
 // host side of the above once the control words are back: fills n_rec / rec_bytes / counted, checks the end of a whole file
 int accept_counts(svb_ctx *ctx, svb_bam *bam, uint64_t n_rec, uint64_t chain_end);
-int alloc_rows(svb_ctx *ctx, svb_bam *bam, uint32_t R);
-void free_rows(svb_bam *bam);
 
 #ifdef __CUDACC__
 // Warp-buffered append to a global queue: the walker's lanes meet a queued record every ~50 records, and one global atomic per
