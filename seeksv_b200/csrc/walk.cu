@@ -112,14 +112,29 @@ __global__ void __launch_bounds__(256) guess_starts(const uint8_t *__restrict__ 
     GuessWin g{win[wib], d, astart, avail};
     uint64_t limit = min(n, start + ((uint64_t)8 << CHUNK_LOG2));
     uint64_t found = BAD_OFFSET;
-    for (uint64_t base = start; base < limit; base += 32) {
-        uint64_t o = base + lane, nx = 0, nx2 = 0;
-        bool ok = plausible_one(g, n, o, n_ref, &nx);
-        if (ok && nx < n) ok = plausible_one(g, n, nx, n_ref, &nx2);  // two records deep
-        uint32_t m = __ballot_sync(0xffffffffu, ok);
-        if (m) {
-            found = base + (__ffs(m) - 1);
-            break;
+    for (uint64_t base = start; base < limit && found == BAD_OFFSET; base += 32) {
+        // cheap first look at every offset (the kernel was bound by instruction issue, not by memory: ~850 warp instructions per
+        // chunk when every lane ran the whole test): block_size and tid have to be sane before anything else is read
+        const uint64_t o = base + lane;
+        bool maybe = false;
+        if (o + 36 <= n) {
+            const uint32_t bs = g.u32(o), tid1 = g.u32(o + 4) + 1u;  // tid in [-1, n_ref)
+            maybe = bs >= 33u && bs < (1u << 28) && tid1 <= (uint32_t)n_ref;
+        }
+        uint32_t cand = __ballot_sync(0xffffffffu, maybe);
+        while (cand) {  // candidates in offset order, the whole test by one lane each (the others wait: there are few)
+            const int l = __ffs(cand) - 1;
+            cand &= cand - 1;
+            bool ok = false;
+            if ((int)lane == l) {
+                uint64_t nx = 0, nx2 = 0;
+                ok = plausible_one(g, n, o, n_ref, &nx);
+                if (ok && nx < n) ok = plausible_one(g, n, nx, n_ref, &nx2);  // two records deep
+            }
+            if (__shfl_sync(0xffffffffu, (int)ok, l)) {
+                found = base + l;
+                break;
+            }
         }
     }
     if (lane == 0) guess[c] = found == BAD_OFFSET ? n : found;
