@@ -209,6 +209,239 @@ def ncu_traffic(kernel_scope):
     return None, "no committed ncu --set full capture holds this kernel"
 
 
+def partitioned_main(args, torch, dist, rank, world, local):
+    """--gpus N > 1: ONE coordinate-sorted multi-chromosome BAM (3 contigs per GPU, N x the C2 genome: weak scaling), partitioned by
+    coordinate range across the ranks (seeksv_b200/sharding.py: cuts at .bai linear-index offsets, halo + breakpoint-key ownership),
+    every rank's shard resident in HBM. One step per rank = getclip on its shard (keys it owns; its pass over the records also
+    leaves getsv's rows) -> all-to-all of the unmapped-branch records by read-name group over NVLink (device buffers) and pairing
+    of the received group -> getsv's statistics, pair support and depth on its own records, combined with NCCL collectives on
+    device tensors (all_gather of 4 integers, all_reduce of the counts / depths). The untimed prologue checks the sharded results
+    against the same commands on the whole file on one GPU."""
+    import ctypes as C
+    import gzip
+    import hashlib
+    import seeksv_b200 as S
+    from seeksv_b200 import lib as SL, mgpu, sharding
+    device = "cuda:%d" % local
+    n_contigs = 3 * world
+    clen = args.genome_len // 3
+    pre = os.path.join(WORK, "part_%dx%d" % (n_contigs, clen))
+    bam_path = pre + ".bam"
+    if rank == 0 and not os.path.exists(bam_path):
+        genome = ",".join("chr%d:%d" % (i + 1, clen) for i in range(n_contigs))
+        subprocess.run([os.path.join(BIN, "svsim"), "--out", pre, "--genome", genome, "--cov", "30", "--nsv", str(max(1, int(500 * world * args.genome_len / C2_LEN))),
+                        "--seed", str(SEED)], check=True, stderr=subprocess.DEVNULL)
+    dist.barrier()
+    ctx = S.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    worker = mgpu.open_range_worker(ctx, dist, bam_path, None, rank, world)
+    plan = worker.plan
+    assert worker.bam is not None, "a rank without records: the BAM is too small for this many ranks"
+    names, lens = worker.bam.ref_names, worker.bam.ref_lens
+    dptr, nbytes, first = worker.bam.device_stream()
+
+    # ---- whole file on rank 0 (untimed): realign hand-off, getsv plan, and the results the shards have to reproduce -------------
+    ref = None
+    if rank == 0:
+        whole = S.Bam.open(ctx, bam_path)
+        clip = whole.getclip()
+        with gzip.open(pre + ".clip.gz", "wb", compresslevel=1) as f:
+            f.write(clip[0])
+        with gzip.open(pre + ".clip.fq.gz", "wb", compresslevel=1) as f:
+            f.write(clip[1])
+        sam = realign(pre, pre + ".clip.fq.gz")
+        juncs, wins = S.plan_getsv(sam, pre + ".clip.gz", names, lens, 50, 200)
+        st, cnts, deps = whole.getsv_passes(juncs, wins, 20, 5000000, 4)
+        n_total, whole_bytes = whole.n_records, whole.record_bytes
+        whole.close()
+        ref = dict(clip=clip, st=st, cnts=cnts, deps=[x for d in deps for x in d], n_clusters=clip[0].count(b"\n"))
+        plan_obj = [juncs, wins, n_total, whole_bytes, sam]
+    else:
+        plan_obj = [None] * 5
+    dist.broadcast_object_list(plan_obj, src=0)
+    juncs, wins, n_total, whole_bytes, sam = plan_obj
+    nj, n_pos = len(juncs), sum(w[2] - w[1] + 1 for w in wins)
+
+    class Step:
+        keep = None
+
+    def shard_step(keep=False):
+        b = S.Bam.from_device(ctx, dptr, nbytes, first, len(names))
+        b.set_refs(names, lens)
+        b.set_own_offset(plan.halo_bytes)
+        cl = b.getclip_handle(prev_tid=plan.prev_tid, export_unmapped=True, key_range=(plan.key_lo, plan.key_hi), halo_bytes=plan.halo_bytes,
+                              with_rows=True, export_partitions=world)
+        recv, n_recv = sharding.exchange_unmapped(cl, dist, world, device)
+        mini = S.Bam.from_device(ctx, recv.data_ptr(), n_recv, 0, len(names))
+        mini.set_refs(names, lens)
+        cu = mini.getclip_handle(unmapped_only=True)
+        gw = sharding.GpuShardWorker(b, device)
+        gw._arrays = prepared
+        n, mean, dev = sharding.sharded_insert_stats(gw, dist, device, 20, 5000000)
+        t = sharding.sharded_pairs_depth(gw, dist, 20, mean, dev, 4, juncs, wins)
+        if keep:
+            Step.keep = (cl.text(0), cl.text(1), cu.text(2), cu.text(3), (n, mean, dev), t.cpu().numpy().copy())
+        cu.close()
+        mini.close()
+        cl.close()
+        b.close()
+        return 4 * (nj + n_pos)
+
+    probe = sharding.GpuShardWorker(None, device)
+    probe.prepare(juncs, wins)
+    prepared = probe._arrays
+
+    # ---- the check (untimed): merged shard results == whole-file results ----------------------------------------------------------
+    with torch.cuda.stream(stream):
+        shard_step(keep=True)
+    torch.cuda.synchronize()
+    mine = Step.keep
+    every = sharding.all_gather_objects((mine[0], mine[1], mine[2], mine[3]), dist)
+    if rank == 0:
+        clip_m, fq_m = sharding.merge_range_texts_fast([(e[0], e[1]) for e in every])
+        assert clip_m == ref["clip"][0] and fq_m == ref["clip"][1], "sharded getclip differs from the whole-file run"
+
+        def records(text):
+            lines = text.split(b"\n")[:-1]
+            return [b"\n".join(lines[i:i + 4]) for i in range(0, len(lines), 4)]
+        for which in (2, 3):          # every name group's FASTQ == the whole-file FASTQ restricted to the names of the group, in order
+            groups = [[] for _ in range(world)]
+            for r in records(ref["clip"][which]):
+                name = r[1:r.index(b"\n")].rsplit(b"/", 1)[0]
+                groups[sharding.fnv1a64(name) % world].append(r)
+            for g in range(world):
+                assert records(every[g][which]) == groups[g], "sharded unmapped-mate pairing differs from the whole-file run (group %d)" % g
+        n, mean, dev = mine[4]
+        import math
+        assert (mean, dev) == (ref["st"][2], int(math.sqrt(ref["st"][3] / ref["st"][0]))), "sharded insert-size statistics differ"
+        assert mine[5][:nj].tolist() == ref["cnts"] and mine[5][nj:nj + n_pos].tolist() == ref["deps"], "sharded pair support / depth differ"
+    dist.barrier()
+    Step.keep = None
+
+    # ---- timing ---------------------------------------------------------------------------------------------------------------------
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                last = fn()
+            ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([max(ev0.elapsed_time(ev1), 0.0), wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item(), t[1].item(), last
+
+    for _ in range(args.warmup):
+        with torch.cuda.stream(stream):
+            shard_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, wall_dev, d2h = timed(shard_step, args.steps)
+    ctx.prof(True)
+    ctx.prof_reset()
+    ms_prof, _, _ = timed(shard_step, args.steps)
+    prof = ctx.prof_read()
+    ctx.prof(False)
+
+    # ---- end to end: the two commands on N GPUs through the multi-GPU entry points, BGZF file -> output files --------------------
+    out_dir = os.path.join(WORK, "pout")
+    if rank == 0:
+        os.makedirs(out_dir, exist_ok=True)
+    dist.barrier()
+
+    class A:
+        pass
+
+    def e2e_step():
+        a = A()
+        a.match_rate, a.min_mapq, a.save_low_quality, a.by, a.bai = 0.9, 1, False, "range", None
+        a.bam, a.prefix = bam_path, os.path.join(out_dir, "x")
+        mgpu.run_getclip(ctx, dist, device, a)
+        dist.barrier()
+        a.rest = [sam, bam_path, os.path.join(out_dir, "x.clip.gz"), os.path.join(out_dir, "x.sv"), os.path.join(out_dir, "x.unm")]
+        rc = mgpu.run_getsv(ctx, dist, device, a)
+        assert rc == 0
+        return 0
+
+    wall_e2e = float("nan")
+    if not args.value_only:
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved, saved_out = os.dup(2), os.dup(1)
+        os.dup2(devnull, 2)
+        sys.stdout.flush()
+        os.dup2(devnull, 1)
+        try:
+            e2e_step()
+            _, wall_e2e, _ = timed(e2e_step, max(1, min(args.steps, 3)))
+            wall_e2e /= max(1, min(args.steps, 3))
+        finally:
+            os.dup2(saved, 2)
+            os.dup2(saved_out, 1)
+        if rank == 0:     # the files of the multi-GPU commands against the whole-file run
+            with gzip.open(os.path.join(out_dir, "x.clip.gz"), "rb") as f:
+                assert f.read() == ref["clip"][0], "multi-GPU getclip file differs from the whole-file run"
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        kern = {k: v for k, v in prof.items() if v["launches"] > 0 and "wall" not in k}
+        dom = "rec_walk_fused"
+        value = n_total * args.steps / (ms_dev / 1e3)
+        roofline = None
+        if dom in kern:
+            v = kern[dom]
+            avg_ms = v["ms"] / v["launches"]
+            per_launch = v["bytes"] / v["launches"]
+            ach = per_launch / (avg_ms * 1e-3) / 1e9
+            step_s = ms_dev / args.steps * 1e-3
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                        "peak_source": "measured" if peaks else "fallback", "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
+                        "kernels_ms_per_step": {k: round(x["ms"] / args.steps, 4) for k, x in sorted(kern.items())},
+                        "step": {"algorithmic_bytes_all_gpus": 2.0 * whole_bytes, "achieved_all_gpus": 2.0 * whole_bytes / step_s / 1e9,
+                                 "frac_per_gpu": 2.0 * whole_bytes / step_s / 1e9 / peak / world, "ms_per_step_with_timers": ms_prof / args.steps,
+                                 "note": "rank 0's kernels; 2 x record bytes of the whole BAM / step time, per GPU"}}
+        line = {
+            "metric": "BAM records/sec getclip+getsv", "value": value, "unit": "records/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "C2 x %d: one BAM of %d contigs x %d bp (C3's shape at N x the C2 size)" % (world, n_contigs, clen),
+                       "records": n_total, "record_bytes": whole_bytes, "records_per_gpu": n_total // world, "clusters": ref["n_clusters"],
+                       "junction_candidates": nj, "depth_windows": len(wins),
+                       "sharding": "coordinate ranges of one coordinate-sorted BAM (cuts at .bai linear-index offsets, equal compressed bytes; halo + "
+                                   "breakpoint-key ownership), one shard per GPU resident in HBM",
+                       "collectives": "NCCL on device tensors: all_gather(4 x int64) + all_reduce for the insert-size statistics, all_to_all_single of the "
+                                      "unmapped-branch records by read-name group, all_reduce(int32 x %d) of pair counts and depths" % (nj + n_pos),
+                       "checked": "sharded clip / clip.fq / unmapped FASTQ / statistics / pair counts / depths == the whole-file run (untimed prologue)",
+                       "l2_note": "each shard (%.2f GB) is far larger than the 126 MB L2; no flush needed" % (nbytes / 1e9)},
+            "e2e": {"value": n_total / wall_e2e if wall_e2e == wall_e2e else None, "unit": "records/s", "ms_per_step": 1e3 * wall_e2e,
+                    "h2d_bytes_per_step": 2 * os.path.getsize(bam_path), "d2h_bytes_per_step": None,
+                    "path": "seeksv_b200.mgpu getclip + getsv on N ranks: BGZF file (page cache) -> each rank loads its shard twice -> device passes -> "
+                            "NCCL merges -> rank 0 writes the reference's files"},
+            "gpu_launches": int(sum(v["launches"] for v in kern.values())),
+            "clocks": sampler.summary(), "roofline": roofline,
+        }
+        print(json.dumps(line))
+    worker.close()
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -249,6 +482,8 @@ def main():
     if world > 1:
         dist.barrier()
     import seeksv_b200 as S
+    if world > 1:
+        return partitioned_main(args, torch, dist, rank, world, local)
 
     # ---- inputs (untimed): one chromosome-sized BAM per rank - the genome is partitioned by chromosome ----------
     contig = "chr21" if world == 1 else "chr%d" % (rank + 1)

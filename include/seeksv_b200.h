@@ -147,6 +147,14 @@ typedef struct svb_getclip_params {
      * that svb_insert_stats / svb_discordant_support / svb_window_depth / svb_getsv_passes on the SAME handle do not stream
      * the records a second time (`seeksv run`: getclip and getsv of one BAM in one process). */
     int32_t with_rows;
+    /* 1: only the unmapped branch is evaluated (texts 2 and 3); the stream is the concatenation of unmapped-branch records that
+     * the shards of one BAM handed over (svb_clusters_export_device), in file order. */
+    int32_t unmapped_only;
+    /* with export_unmapped_records: the exported records are grouped by FNV-1a-64(read name) % export_partitions (file order
+     * inside a group; 0 or 1: one group; at most 64), so that N ranks can exchange them all-to-all and each pair the names of
+     * one group - mates share a name, so every pair is decided on exactly one rank. svb_clusters_export_parts gives the byte
+     * offsets of the groups. */
+    int32_t export_partitions;
 } svb_getclip_params;
 
 typedef struct svb_clusters svb_clusters; /* host-resident result of svb_getclip */
@@ -166,6 +174,10 @@ int svb_clusters_text_len(const svb_clusters *c, int which, uint64_t *len);
 int svb_clusters_gz(const svb_clusters *c, int which, const char **data, uint64_t *len);
 /* The packed BAM records (block_size + body, file order) of the unmapped branch; only with export_unmapped_records. */
 int svb_clusters_unmapped_records(const svb_clusters *c, const char **data, uint64_t *len);
+/* The same records where svb_getclip left them: in HBM (device pointer, valid until svb_clusters_free), for device-to-device
+ * exchange between ranks; offsets[0 .. n_parts] = byte offsets of the export_partitions groups (offsets[n_parts] = len). */
+int svb_clusters_export_device(const svb_clusters *c, const void **d_records, uint64_t *len);
+int svb_clusters_export_parts(const svb_clusters *c, uint64_t *offsets, int32_t n_parts);
 
 /* ---- getsv / somatic device passes ----------------------------------------------------------------- */
 
@@ -214,6 +226,20 @@ int svb_getsv_passes(svb_ctx *ctx, svb_bam *bam, const svb_getsv_params *p, cons
                      const svb_window *windows, uint64_t n_windows, int64_t stats_out[4], int32_t *counts /* host */,
                      int32_t *depth_out /* host */);
 
+/* Shards of one BAM on several GPUs: the insert-size statistics in additive pieces, so that the ranks can add
+ * them up (NCCL all-reduce / all-gather of a few integers) and derive mean and deviation exactly as one process would.
+ * svb_bam_set_own_offset: coordinate-range shards load [context][halo][own records); the getsv passes count own records only.
+ * svb_insert_partial: out = {records taken, sum isize, sum isize^2, records with isize > 46340} over the first `take`
+ *   qualifying own records in file order (take < 0: all). A non-zero out[3] anywhere means the reference's int products may
+ *   wrap: then the exact sum of (int32)((isize - mean)^2) comes from svb_insert_sq with the global mean.
+ * svb_pairs_depth: pair support and window depth of the own records with given statistics; counts / depth_out may be DEVICE
+ *   pointers (one NCCL all-reduce adds the shards up). */
+int svb_bam_set_own_offset(svb_bam *bam, uint64_t own_offset);
+int svb_insert_partial(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64_t take, int64_t out[4]);
+int svb_insert_sq(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64_t take, int32_t mean, int64_t *sq);
+int svb_pairs_depth(svb_ctx *ctx, svb_bam *bam, const svb_pair_params *p, const svb_junction *junctions, uint64_t n_junctions,
+                    const svb_window *windows, uint64_t n_windows, int32_t *counts, int32_t *depth_out);
+
 /* Host-side planning step of getsv, exposed so that callers which keep the BAM resident (bench.py, sharded
  * runs) can drive the device passes themselves: joins P.clip.gz with the realigned clip.bam/clip.sam
  * (InputSoftInfoStoreBreakpoint getsv.h:423-541 + GetJunction getsv.cpp:1705), merges junctions (MergeJunction
@@ -223,6 +249,10 @@ int svb_getsv_passes(svb_ctx *ctx, svb_bam *bam, const svb_getsv_params *p, cons
 int svb_plan_getsv(const char *clip_alignments_path, const char *clip_file_path, int32_t n_ref, const char *const *ref_names,
                    const uint32_t *ref_lens, int32_t merge_reach, int32_t flank_len, svb_junction **junctions,
                    uint64_t *n_junctions, svb_window **windows, uint64_t *n_windows);
+/* The junctions `somatic` asks the NORMAL BAM about (somatic.cpp:111-409), in the order in which the command batches them, for
+ * callers that run the pair test themselves (sharded runs). No GPU work; release with svb_free. */
+int svb_plan_somatic(const char *normal_clip_path, const char *tumor_sv_path, double match_rate, int32_t offset, int32_t min_len,
+                     int32_t mean_insert, int32_t n_ref, const char *const *ref_names, svb_junction **junctions, uint64_t *n_junctions);
 void svb_free(void *p);
 
 /* ---- gzip text files (host only) ----

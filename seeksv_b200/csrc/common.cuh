@@ -152,6 +152,7 @@ struct svb_bam {
     int32_t max_span = 0;  // max(end - pos) over records, for window queries
     int sorted = -1;       // -1 unknown, 0 no, 1 coordinate-sorted
     uint32_t *d_ref_len = nullptr;  // reference lengths on the device (uploaded once per handle)
+    uint64_t own_offset = 0;        // range shards: the getsv passes ignore records that start before this offset (halo)
 };
 
 // ---- error plumbing ------------------------------------------------------------------------------------

@@ -22,6 +22,7 @@ struct ClipCtl {
     uint32_t n_seg, n_cl, un_skip, un_own;
     uint32_t abort_main, abort_side, tk_cluster, tk_text;  // tickets of the persistent warps of cluster_build / text_write
     uint64_t arena_bytes, clip_bytes, fq_bytes, un1_bytes, un2_bytes, export_bytes;
+    uint64_t part_off[65];  // export_partitions: byte offset + 1 of every group that has records (0: none)
 };
 
 struct svb_clusters {
@@ -34,6 +35,8 @@ struct svb_clusters {
     bool gz_mode = false;
     uint8_t *d_export = nullptr;  // sharded runs: the raw unmapped-branch records (svb_getclip_params.export_unmapped_records)
     uint64_t export_len = 0;
+    uint64_t part_off[65] = {};
+    int32_t n_parts = 1;
     mutable PinnedBuf unmapped_records;
     mutable bool export_here = false;
     uint64_t n_clusters = 0, n_candidates = 0;
@@ -826,29 +829,50 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---- shard plumbing: raw records of the unmapped branch, packed in file order ------------------------------------
+// group of a record: FNV-1a-64 of its name modulo the number of groups; key = group, value = file-order index
+__global__ void export_group(const ClipCtl *__restrict__ ctl, const uint64_t *__restrict__ sorted, const uint8_t *__restrict__ d, uint32_t parts,
+                             uint64_t *__restrict__ key, uint32_t *__restrict__ val)
+{
+    if (ctl->abort_side) return;
+    const uint32_t n = ctl->un_own;
+    const uint64_t *list = sorted + ctl->un_skip;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint8_t *p = d + list[i];
+        uint32_t lq = qname_len(p);
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (uint32_t j = 0; j < lq && p[36 + j]; ++j) h = (h ^ p[36 + j]) * 0x100000001b3ull;
+        key[i] = parts > 1 ? h % parts : 0, val[i] = i;
+    }
+}
 struct ExportScanOp {
     const uint64_t *sorted;
+    const uint64_t *gkey;   // group of the i-th exported record
+    const uint32_t *order;  // its file-order index
     const uint8_t *d;
     uint64_t *dst_off;
     uint64_t cap;
     ClipCtl *ctl;
     __device__ uint64_t n() const { return ctl->abort_side ? 0 : ctl->un_own; }
-    __device__ void load(uint64_t i, uint64_t (&v)[1]) const { v[0] = 4ull + ldu32(d + sorted[ctl->un_skip + i]); }
-    __device__ void store(uint64_t i, const uint64_t (&excl)[1], const uint64_t (&)[1]) const { dst_off[i] = excl[0]; }
+    __device__ void load(uint64_t i, uint64_t (&v)[1]) const { v[0] = 4ull + ldu32(d + sorted[ctl->un_skip + order[i]]); }
+    __device__ void store(uint64_t i, const uint64_t (&excl)[1], const uint64_t (&)[1]) const
+    {
+        dst_off[i] = excl[0];
+        if (i == 0 || gkey[i] != gkey[i - 1]) ctl->part_off[gkey[i] & 63] = excl[0] + 1;
+    }
     __device__ void total(const uint64_t (&t)[1]) const
     {
         ctl->export_bytes = t[0];
         if (t[0] > cap) ctl->abort_side = 1;
     }
 };
-__global__ void record_copy(const ClipCtl *__restrict__ ctl, const uint64_t *__restrict__ sorted, const uint8_t *__restrict__ d,
-                            const uint64_t *__restrict__ dst_off, uint8_t *__restrict__ dst)
+__global__ void record_copy(const ClipCtl *__restrict__ ctl, const uint64_t *__restrict__ sorted, const uint32_t *__restrict__ order,
+                            const uint8_t *__restrict__ d, const uint64_t *__restrict__ dst_off, uint8_t *__restrict__ dst)
 {
     if (ctl->abort_side) return;
     const uint32_t n = ctl->un_own, lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint64_t *list = sorted + ctl->un_skip;
     for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += n_warps) {
-        const uint8_t *src = d + list[w];
+        const uint8_t *src = d + list[order[w]];
         uint8_t *out = dst + dst_off[w];
         const uint64_t bytes = 4ull + ldu32(src);
         for (uint64_t i = lane; i < bytes; i += 32) out[i] = src[i];
@@ -937,7 +961,7 @@ void carve(Bump &b, ClipBuffers &B, const Caps &cap, uint64_t n_chunks, int off_
     B.rs_key = radix_scratch(b, cap.cand, key_passes);
     B.rs_sw = radix_scratch(b, cap.sw, off_passes);
     B.rs_un = radix_scratch(b, cap.un, off_passes);
-    B.rs_hash = radix_scratch(b, pair_mode ? cap.un : 1, 4);
+    B.rs_hash = radix_scratch(b, cap.un, 4);
     B.sc_chunk = scan_scratch(b, n_chunks, 1, 8);
     B.sc_seg = scan_scratch(b, cap.cand, 1, 8);
     B.sc_stats = scan_scratch(b, cap.cand, 1, 2);
@@ -959,7 +983,7 @@ void carve(Bump &b, ClipBuffers &B, const Caps &cap, uint64_t n_chunks, int off_
     for (int i = 0; i < 2; ++i) B.key[i] = b.get<uint64_t>(cap.cand), B.val[i] = b.get<uint32_t>(cap.cand);
     B.sw_sorted = b.get<uint64_t>(cap.sw);
     B.un_sorted = b.get<uint64_t>(cap.un);
-    for (int i = 0; i < 2; ++i) B.ukey[i] = b.get<uint64_t>(pair_mode ? cap.un : 1), B.uval[i] = b.get<uint32_t>(pair_mode ? cap.un : 1);
+    for (int i = 0; i < 2; ++i) B.ukey[i] = b.get<uint64_t>(cap.un), B.uval[i] = b.get<uint32_t>(cap.un);
     B.mate_of = b.get<uint32_t>(pair_mode ? cap.un : 1);
     B.start = b.get<uint32_t>((size_t)cap.cand + 1), B.maxl = b.get<uint32_t>(cap.cand), B.maxr = b.get<uint32_t>(cap.cand);
     B.arena_off = b.get<uint64_t>(cap.cand);
@@ -993,7 +1017,8 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
     const uint64_t n_chunks = bam->n_chunks, stream_bytes = bam->nbytes - bam->first;
     const bool export_mode = prm->export_unmapped_records != 0, pair_mode = !export_mode;
     res->gz_mode = prm->gz_outputs != 0 && !export_mode;
-    const bool want_rows = prm->with_rows != 0;
+    const bool want_rows = prm->with_rows != 0, unmapped_only = prm->unmapped_only != 0;
+    const int n_parts = std::max(1, std::min(64, prm->export_partitions));
     const int off_passes = (bits_of(bam->nbytes) + 7) / 8;  // offsets sort on just the bytes they use
     // key = run << 33 | side << 32 | pos: runs are numbered by chromosome switches (at most sw_cap of them)
     std::string nblob;
@@ -1061,9 +1086,13 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
             radix_sort(ctx, side, ju);
             unmapped_own<<<1, 1, 0, side>>>(ctl->counters, cap.un, B.un_sorted, prm->halo_bytes, ctl);
             if (export_mode) {
-                ExportScanOp op{B.un_sorted, bam->d_data, B.off1, cap.exp, ctl};
+                const unsigned g = grid_for(ctx, cap.un, 256, 4);
+                export_group<<<g, 256, 0, side>>>(ctl, B.un_sorted, bam->d_data, (uint32_t)n_parts, B.ukey[0], B.uval[0]);
+                RadixJob jg{{B.ukey[0], B.ukey[1]}, {B.uval[0], B.uval[1]}, &ctl->un_own, cap.un, 0, 1, B.rs_hash};
+                radix_sort(ctx, side, jg);  // stable: file order inside a group
+                ExportScanOp op{B.un_sorted, B.ukey[1], B.uval[1], bam->d_data, B.off1, cap.exp, ctl};
                 launch_scan<1, 2>(ctx, side, op, B.sc_un, cap.un);
-                record_copy<<<grid_for(ctx, (uint64_t)cap.un * 32, 128, 8), 128, 0, side>>>(ctl, B.un_sorted, bam->d_data, B.off1, res->d_export);
+                record_copy<<<grid_for(ctx, (uint64_t)cap.un * 32, 128, 8), 128, 0, side>>>(ctl, B.un_sorted, B.uval[1], bam->d_data, B.off1, res->d_export);
             } else {
                 const unsigned g = grid_for(ctx, cap.un, 256, 4);
                 unmapped_hash<<<g, 256, 0, side>>>(ctl, B.un_sorted, bam->d_data, B.ukey[0], B.uval[0]);
@@ -1086,7 +1115,9 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         }
         CK(cudaEventRecord(ctx->join_event, side));
 
+        if (unmapped_only) CK(cudaStreamWaitEvent(s, ctx->join_event, 0));
         // ---- 3. main stream: evaluate the queued soft-clipped records, order candidates: BAM order first (stable base), then (run, side, pos)
+        if (!unmapped_only) {
         {
             ProfScope ps(ctx, "clip_eval", 0);
             clip_eval<<<grid_for(ctx, cap.clipped, 128, 8), 128, 0, s>>>(bam->d_data, B.q, P, B.c, cap.cand, ctl);
@@ -1129,6 +1160,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
                                                                                      B.maxl, B.maxr, B.arena_off, B.arena_seq, B.arena_qual, B.clip_off,
                                                                                      B.fq_off, res->d_text[0], res->d_text[1]);
         }
+        }
         // ---- the one read-back
         CK(cudaMemcpyAsync(ctx->ctl_host, ctl, sizeof(ClipCtl), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -1164,7 +1196,15 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
     ctx->hint[H_UN1] = h.un1_bytes, ctx->hint[H_UN2] = h.un2_bytes, ctx->hint[H_EXPORT] = h.export_bytes;
     res->n_candidates = h.counters[3], res->n_clusters = h.n_cl;
     res->text_len[0] = h.clip_bytes, res->text_len[1] = h.fq_bytes, res->text_len[2] = h.un1_bytes, res->text_len[3] = h.un2_bytes;
-    res->export_len = h.export_bytes;
+    res->export_len = h.export_bytes, res->n_parts = n_parts;
+    {   // group offsets: a group without records starts where the next one does
+        uint64_t next = h.export_bytes;
+        res->part_off[n_parts] = next;
+        for (int p = n_parts - 1; p >= 0; --p) {
+            if (h.part_off[p]) next = h.part_off[p] - 1;
+            res->part_off[p] = next;
+        }
+    }
     if (res->gz_mode) {  // the four files leave the device as gzip images (gzip.cu); an empty file is one empty member
         for (int w = 0; w < 4; ++w) CKR(gzip_on_device(ctx, res->d_text[w], res->text_len[w], &res->gz[w]));
         res->drop_device();
@@ -1246,5 +1286,18 @@ extern "C" int svb_clusters_text_len(const svb_clusters *c, int which, uint64_t 
 {
     if (!c || which < 0 || which > 3 || !len) return SVB_ERR_ARG;
     *len = c->gz_mode ? 0 : c->text_len[which];
+    return 0;
+}
+
+extern "C" int svb_clusters_export_device(const svb_clusters *c, const void **d_records, uint64_t *len)
+{
+    if (!c || !d_records || !len) return SVB_ERR_ARG;
+    *d_records = c->d_export, *len = c->export_len;
+    return 0;
+}
+extern "C" int svb_clusters_export_parts(const svb_clusters *c, uint64_t *offsets, int32_t n_parts)
+{
+    if (!c || !offsets || n_parts != c->n_parts) return SVB_ERR_ARG;
+    for (int p = 0; p <= n_parts; ++p) offsets[p] = c->part_off[p];
     return 0;
 }

@@ -39,6 +39,13 @@ struct RowsView {
     const uint64_t *base;  // dense index of a chunk's first row (n_chunks + 1 entries)
     const uint64_t *fkey;  // key of the first row at or after the chunk (rows_index)
     uint64_t n_chunks;
+    uint64_t own_off;      // range shards: records that start before this stream offset belong to the previous shard (halo)
+    __device__ __forceinline__ bool owned(uint64_t c, uint32_t k) const
+    {
+        if (own_off == 0) return true;
+        const uint64_t oc = own_off >> chunk_log2;
+        return c > oc || (c == oc && ((c << chunk_log2) + roff[c * R + k]) >= own_off);
+    }
 };
 
 // ---- one pass over the rows: index (first keys, longest reference span, coordinate order) and insert-size partial sums -------
@@ -76,7 +83,7 @@ __global__ void __launch_bounds__(256)
             }
             if (have && prev > row_key(r.tid, r.pos)) unsorted = 1;
         }
-        if (STATS && insert_qualifies(r.flagq, r.isize, stats_mapq)) {
+        if (STATS && insert_qualifies(r.flagq, r.isize, stats_mapq) && V.owned(c, k)) {
             ++qc, qs += (uint64_t)r.isize, qq += (uint64_t)r.isize * (uint64_t)r.isize;
             qmax = max(qmax, r.isize);
         }
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(256)
     uint64_t run = q_base[c];
     if (run >= max_pairs) return;
     const Row *rows = V.row + c * V.R;
-    long long v = 0;
+    long long v = 0, n3 = 0, sq3 = 0, big3 = 0;
     for (uint32_t k0 = 0; k0 < cnt; k0 += 32) {
         const uint32_t k = k0 + lane;
         bool q = false;
@@ -181,12 +188,15 @@ __global__ void __launch_bounds__(256)
         if (k < cnt) {
             const Row r = rows[k];
             isize = r.isize;
-            q = insert_qualifies(r.flagq, isize, min_mapq);
+            q = insert_qualifies(r.flagq, isize, min_mapq) && V.owned(c, k);
         }
         const uint32_t m = __ballot_sync(0xffffffffu, q);
         if (q && run + __popc(m & ((1u << lane) - 1u)) < max_pairs) {
             if (pass == 1) v += isize;
-            else {
+            else if (pass == 3) {  // shard partials: count, sum of squares and "large" count next to the sum
+                v += isize;
+                n3 += 1, sq3 += (long long)isize * isize, big3 += isize > 46340;
+            } else {
                 uint32_t dlt = (uint32_t)(isize - mean);
                 v += (int32_t)(dlt * dlt);  // the reference multiplies two ints (cluster.cpp:77)
             }
@@ -194,8 +204,20 @@ __global__ void __launch_bounds__(256)
         run += __popc(m);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (pass == 3) {
+            n3 += __shfl_xor_sync(0xffffffffu, n3, o);
+            sq3 += __shfl_xor_sync(0xffffffffu, sq3, o);
+            big3 += __shfl_xor_sync(0xffffffffu, big3, o);
+        }
+    }
     if (lane == 0 && v) atomicAdd(acc, (unsigned long long)v);
+    if (lane == 0 && pass == 3 && n3) {
+        atomicAdd(acc + 1, (unsigned long long)n3);
+        atomicAdd(acc + 2, (unsigned long long)sq3);
+        if (big3) atomicAdd(acc + 3, (unsigned long long)big3);
+    }
 }
 
 // ---- discordant read pairs ------------------------------------------------------------------------------------------
@@ -242,7 +264,7 @@ __global__ void __launch_bounds__(128)
             for (uint32_t k = lane; k < cnt; k += 32) {
                 const Row r = V.row[c * V.R + k];
                 const uint64_t key = row_key(r.tid, r.pos);
-                if (key < Klo || key >= Khi) continue;
+                if (key < Klo || key >= Khi || !V.owned(c, k)) continue;
                 uint32_t fq = r.flagq, flag = fq & 0xffff;
                 int32_t pos = r.pos;
                 int32_t rend = (fq & FLAGQ_NOCIGAR) ? pos + 1 : r.end;
@@ -345,7 +367,7 @@ __global__ void __launch_bounds__(128)
         for (uint32_t k = lane; k < cnt; k += 32) {
             const Row r = V.row[c * V.R + k];
             const int32_t tid = r.tid;
-            if (!pileup_eligible(tid, r.flagq, min_mapq)) continue;
+            if (!pileup_eligible(tid, r.flagq, min_mapq) || !V.owned(c, k)) continue;
             if (kept && !kept[c * V.R + k]) continue;
             const int32_t beg1 = r.pos + 1, end1 = r.end;  // 1-based inclusive [beg1, end1]
             if (end1 < beg1) continue;
@@ -484,7 +506,7 @@ __global__ void __launch_bounds__(128)
 namespace {
 RowsView view_of(const svb_bam *bam)
 {
-    return RowsView{bam->rows.row, bam->rows.roff, bam->rows.R, bam->chunk_log2, bam->d_count, bam->d_base, bam->d_fkey, bam->n_chunks};
+    return RowsView{bam->rows.row, bam->rows.roff, bam->rows.R, bam->chunk_log2, bam->d_count, bam->d_base, bam->d_fkey, bam->n_chunks, bam->own_offset};
 }
 
 struct SvBuffers {
@@ -505,7 +527,7 @@ struct SvBuffers {
 void carve(Bump &b, SvBuffers &B, uint64_t n_chunks, uint64_t n_j, uint64_t n_w, uint64_t diff_len, uint64_t n_pos, int32_t n_ref)
 {
     B.ctl = b.get<SvCtl>(1);
-    B.acc = b.get<unsigned long long>(2);
+    B.acc = b.get<unsigned long long>(4);
     B.sc_q = scan_scratch(b, n_chunks, 1, 8);
     B.pick = b.get<uint32_t>(n_w ? n_chunks : 1);
     B.n_list = b.get<uint32_t>(1);
@@ -602,7 +624,7 @@ int run_passes(svb_ctx *ctx, svb_bam *bam, const Request &rq)
         CK(cudaMemcpyAsync(B.J, rq.junctions, rq.n_j * sizeof(svb_junction), cudaMemcpyHostToDevice, s));
         ProfScope ps(ctx, "discordant_support", 0);
         discordant_kernel<<<nblk(rq.n_j * 32, 128), 128, 0, s>>>(V, bam->d_scal, B.J, rq.n_j, bam->d_ref_len, rq.pp, from_ctl, B.counts);
-        CK(cudaMemcpyAsync(rq.counts, B.counts, rq.n_j * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(rq.counts, B.counts, rq.n_j * 4, cudaMemcpyDefault, s));  // (the caller's array may live on the device)
         return 0;
     };
     if (rq.n_j) CKR(launch_pairs(fused_pairs ? B.ctl : nullptr));
@@ -619,7 +641,7 @@ int run_passes(svb_ctx *ctx, svb_bam *bam, const Request &rq)
             ProfScope ps(ctx, "depth_scan", (double)tot * 8);
             depth_scan<<<nblk(rq.n_w * 32, 128), 128, 0, s>>>(B.W, B.woff, rq.n_w, B.diff, B.depth);
         }
-        CK(cudaMemcpyAsync(rq.depth_out, B.depth, n_pos * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(rq.depth_out, B.depth, n_pos * 4, cudaMemcpyDefault, s));
     }
     // ---- the one read-back
     struct {
@@ -643,7 +665,7 @@ int run_passes(svb_ctx *ctx, svb_bam *bam, const Request &rq)
             QBaseOp op{n_chunks, B.q_cnt, B.q_base};
             CK(cudaMemsetAsync(B.sc_q.ticket, 0, 4, s));
             CK(cudaMemsetAsync(B.sc_q.state, 0, (size_t)B.sc_q.tiles_cap * 8, s));
-            CK(cudaMemsetAsync(B.acc, 0, 16, s));
+            CK(cudaMemsetAsync(B.acc, 0, 32, s));
             {
                 ProfScope ps(ctx, "insert_stats", 0);
                 launch_scan<1, 8>(ctx, s, op, B.sc_q, n_chunks);
@@ -674,7 +696,7 @@ int run_passes(svb_ctx *ctx, svb_bam *bam, const Request &rq)
             r2.pp.deviation = out[0] ? (int32_t)sqrt((double)out[3] / (double)(int32_t)out[0]) : 0;
             CK(cudaMemcpyAsync(B.J, rq.junctions, rq.n_j * sizeof(svb_junction), cudaMemcpyHostToDevice, s));
             discordant_kernel<<<nblk(rq.n_j * 32, 128), 128, 0, s>>>(V, bam->d_scal, B.J, rq.n_j, bam->d_ref_len, r2.pp, nullptr, B.counts);
-            CK(cudaMemcpyAsync(rq.counts, B.counts, rq.n_j * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(rq.counts, B.counts, rq.n_j * 4, cudaMemcpyDefault, s));  // (the caller's array may live on the device)
             CK(cudaStreamSynchronize(s));
         }
     }
@@ -698,7 +720,7 @@ int run_passes(svb_ctx *ctx, svb_bam *bam, const Request &rq)
             depth_marks<<<grid_for(ctx, n_chunks * 32, 128, 8), 128, 0, s>>>(bam->d_data, V, B.list, B.n_list, rq.depth_mapq, kept.p, B.W, B.woff, rq.n_w, B.diff);
         }
         depth_scan<<<nblk(rq.n_w * 32, 128), 128, 0, s>>>(B.W, B.woff, rq.n_w, B.diff, B.depth);
-        CK(cudaMemcpyAsync(rq.depth_out, B.depth, n_pos * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(rq.depth_out, B.depth, n_pos * 4, cudaMemcpyDefault, s));
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
     }
@@ -743,4 +765,114 @@ extern "C" int svb_getsv_passes(svb_ctx *ctx, svb_bam *bam, const svb_getsv_para
     rq.pp.min_mapq = p->min_mapq, rq.pp.times = p->times;
     rq.windows = windows, rq.n_w = n_w, rq.depth_mapq = p->min_mapq, rq.depth_out = depth_out;
     return run_passes(ctx, bam, rq);
+}
+
+// ---- shards of one BAM on several GPUs: the statistics in additive pieces ---------------------------------
+// out = {records taken, sum of isize, sum of isize^2, records with isize > 46340} over the first `take` qualifying OWN records of
+// this shard in file order (take < 0: all of them). The ranks add these up (NCCL) and derive mean and deviation as
+// insert_finish does; a non-zero fourth value means the reference's int products could wrap and the exact second pass
+// (svb_insert_sq) is needed.
+extern "C" int svb_insert_partial(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64_t take, int64_t out[4])
+{
+    if (!ctx || !bam || !out) return svb_fail(ctx, SVB_ERR_ARG, "svb_insert_partial: null argument");
+    CK(cudaSetDevice(ctx->device));
+    CKR(prepare_rows(ctx, bam));
+    cudaStream_t s = ctx->stream;
+    const uint64_t n_chunks = bam->n_chunks;
+    SvBuffers B{};
+    {
+        Bump measure(nullptr);
+        carve(measure, B, n_chunks, 0, 0, 1, 1, bam->n_ref);
+        CKR(ctx->ws_reserve(1, measure.used));
+        Bump real(ctx->ws[1]);
+        carve(real, B, n_chunks, 0, 0, 1, 1, bam->n_ref);
+    }
+    CK(cudaMemsetAsync(ctx->ws[1], 0, B.zero_end, s));
+    const bool need_index = !bam->rows_indexed;
+    if (need_index) CK(cudaMemsetAsync(bam->d_scal, 0, 16, s));
+    RowsView V = view_of(bam);
+    const unsigned g_chunks = nblk(n_chunks * 32, 256);
+    {
+        ProfScope ps(ctx, "rows_pass", (double)bam->n_rec * sizeof(Row));
+        if (need_index) rows_pass<true, true><<<g_chunks, 256, 0, s>>>(V, bam->d_fkey, bam->d_scal, min_mapq, B.q_cnt, B.q_sum, B.q_sq, B.ctl);
+        else rows_pass<false, true><<<g_chunks, 256, 0, s>>>(V, bam->d_fkey, bam->d_scal, min_mapq, B.q_cnt, B.q_sum, B.q_sq, B.ctl);
+        insert_totals<<<(unsigned)std::min<uint64_t>(nblk(n_chunks, 256), (uint64_t)ctx->sm_count), 256, 0, s>>>(B.ctl, n_chunks, B.q_cnt, B.q_sum, B.q_sq);
+    }
+    struct {
+        SvCtl ctl;
+        int32_t scal[4];
+    } *h = (decltype(h))ctx->ctl_host;
+    CK(cudaMemcpyAsync(&h->ctl, B.ctl, sizeof(SvCtl), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->scal, bam->d_scal, 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    const SvCtl hc = h->ctl;
+    bam->max_span = h->scal[0], bam->sorted = h->scal[1] ? 0 : 1, bam->rows_indexed = true;
+    if (take < 0 || (uint64_t)take >= hc.tot[0]) {
+        out[0] = (int64_t)hc.tot[0], out[1] = (int64_t)hc.tot[1], out[2] = (int64_t)hc.tot[2], out[3] = hc.q_max > 46340 ? 1 : 0;
+        return 0;
+    }
+    QBaseOp op{n_chunks, B.q_cnt, B.q_base};
+    launch_scan<1, 8>(ctx, s, op, B.sc_q, n_chunks);
+    insert_ordered<<<g_chunks, 256, 0, s>>>(V, min_mapq, B.q_base, (uint64_t)take, 3, 0, B.acc);
+    unsigned long long a[4];
+    CK(cudaMemcpyAsync(a, B.acc, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    out[0] = (int64_t)a[1], out[1] = (int64_t)a[0], out[2] = (int64_t)a[2], out[3] = (int64_t)a[3];
+    return 0;
+}
+
+// second pass of the wrap-exact path: sum over the same records of (int32)((isize - mean) * (isize - mean)) (cluster.cpp:77)
+extern "C" int svb_insert_sq(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64_t take, int32_t mean, int64_t *sq)
+{
+    if (!ctx || !bam || !sq) return svb_fail(ctx, SVB_ERR_ARG, "svb_insert_sq: null argument");
+    CK(cudaSetDevice(ctx->device));
+    CKR(prepare_rows(ctx, bam));
+    cudaStream_t s = ctx->stream;
+    const uint64_t n_chunks = bam->n_chunks;
+    SvBuffers B{};
+    {
+        Bump measure(nullptr);
+        carve(measure, B, n_chunks, 0, 0, 1, 1, bam->n_ref);
+        CKR(ctx->ws_reserve(1, measure.used));
+        Bump real(ctx->ws[1]);
+        carve(real, B, n_chunks, 0, 0, 1, 1, bam->n_ref);
+    }
+    CK(cudaMemsetAsync(ctx->ws[1], 0, B.zero_end, s));
+    const bool need_index = !bam->rows_indexed;
+    if (need_index) CK(cudaMemsetAsync(bam->d_scal, 0, 16, s));
+    RowsView V = view_of(bam);
+    const unsigned g_chunks = nblk(n_chunks * 32, 256);
+    if (need_index) rows_pass<true, true><<<g_chunks, 256, 0, s>>>(V, bam->d_fkey, bam->d_scal, min_mapq, B.q_cnt, B.q_sum, B.q_sq, B.ctl);
+    else rows_pass<false, true><<<g_chunks, 256, 0, s>>>(V, bam->d_fkey, bam->d_scal, min_mapq, B.q_cnt, B.q_sum, B.q_sq, B.ctl);
+    bam->rows_indexed = true;
+    QBaseOp op{n_chunks, B.q_cnt, B.q_base};
+    launch_scan<1, 8>(ctx, s, op, B.sc_q, n_chunks);
+    insert_ordered<<<g_chunks, 256, 0, s>>>(V, min_mapq, B.q_base, take < 0 ? ~0ull : (uint64_t)take, 2, mean, B.acc);
+    long long v = 0;
+    CK(cudaMemcpyAsync(&v, B.acc, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    *sq = v;
+    return 0;
+}
+
+// pair support and window depth of this shard's own records with given statistics, one read-back; counts / depth_out may be
+// device pointers (the ranks add them up with one NCCL all-reduce)
+extern "C" int svb_pairs_depth(svb_ctx *ctx, svb_bam *bam, const svb_pair_params *p, const svb_junction *junctions, uint64_t n_j,
+                               const svb_window *windows, uint64_t n_w, int32_t *counts, int32_t *depth_out)
+{
+    if (!ctx || !bam || !p || (n_j && (!junctions || !counts)) || (n_w && (!windows || !depth_out)))
+        return svb_fail(ctx, SVB_ERR_ARG, "svb_pairs_depth: null argument");
+    Request rq;
+    rq.junctions = junctions, rq.n_j = n_j, rq.pp = *p, rq.counts = counts;
+    rq.windows = windows, rq.n_w = n_w, rq.depth_mapq = p->min_mapq, rq.depth_out = depth_out;
+    return run_passes(ctx, bam, rq);
+}
+
+extern "C" int svb_bam_set_own_offset(svb_bam *bam, uint64_t own_offset)
+{
+    if (!bam || own_offset > bam->nbytes) return SVB_ERR_ARG;
+    bam->own_offset = own_offset;
+    return 0;
 }

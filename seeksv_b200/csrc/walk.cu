@@ -24,117 +24,62 @@
 
 #include "walk.cuh"
 
-// Byte window of a chunk's beginning, staged in shared memory by the warp that guesses the chunk's first record; reads beyond it
-// fall back to global memory.
-struct GuessWin {
-    const uint8_t *sm;   // staged bytes [start, start + avail) of the stream
-    const uint8_t *d;    // the stream
-    uint64_t start;
-    uint32_t avail;
-    __device__ __forceinline__ uint32_t u32(uint64_t o) const
-    {
-        const uint64_t r = o - start;
-        if (r + 8 <= avail) {  // (o >= start always)
-            const uint32_t *w = (const uint32_t *)(sm + (r & ~3ull));
-            const uint32_t sh = ((uint32_t)r & 3u) * 8u;
-            return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
-        }
-        return ldu32(d + o);
-    }
-    __device__ __forceinline__ uint8_t u8(uint64_t o) const
-    {
-        const uint64_t r = o - start;
-        return r < avail ? sm[r] : d[o];
-    }
-};
-
-__device__ __forceinline__ bool plausible_one(const GuessWin &g, uint64_t n, uint64_t o, int32_t n_ref, uint64_t *next)
+__device__ __forceinline__ bool plausible_one(const uint8_t *d, uint64_t n, uint64_t o, int32_t n_ref, uint64_t *next)
 {
     if (o + 36 > n) return false;
-    int32_t bs = (int32_t)g.u32(o);
+    int32_t bs = ldi32(d + o);
     if (bs < 33 || o + 4 + (uint64_t)bs > n) return false;
-    int32_t tid = (int32_t)g.u32(o + 4);
+    int32_t tid = ldi32(d + o + 4);
     if (tid < -1 || tid >= n_ref) return false;
-    int32_t pos = (int32_t)g.u32(o + 8);
+    int32_t pos = ldi32(d + o + 8);
     if (pos < -1 || pos >= (1 << 29)) return false;  // BAM coordinates are below 2^29
-    uint32_t w = g.u32(o + 12);
+    uint32_t w = ldu32(d + o + 12);
     uint32_t l_qname = w & 0xff;
     if (l_qname < 2) return false;
-    uint32_t w2 = g.u32(o + 16);
+    uint32_t w2 = ldu32(d + o + 16);
     uint32_t n_cigar = w2 & 0xffff;
     if ((w2 >> 16) & 0xf000) return false;  // flag bits above 0x800 are not defined
-    int32_t l_qseq = (int32_t)g.u32(o + 20);
+    int32_t l_qseq = ldi32(d + o + 20);
     if (l_qseq < 0) return false;
-    int32_t mtid = (int32_t)g.u32(o + 24);
+    int32_t mtid = ldi32(d + o + 24);
     if (mtid < -1 || mtid >= n_ref) return false;
-    int32_t mpos = (int32_t)g.u32(o + 28);
+    int32_t mpos = ldi32(d + o + 28);
     if (mpos < -1 || mpos >= (1 << 29)) return false;
     uint64_t need = 32ull + l_qname + 4ull * n_cigar + ((uint64_t)l_qseq + 1) / 2 + (uint64_t)l_qseq;
     if (need > (uint64_t)bs) return false;
     if ((uint64_t)bs - need > 4ull * (uint64_t)l_qseq + 8192) return false;  // aux block of a sane size
-    uint8_t c0 = g.u8(o + 36);
-    if (c0 < 33 || c0 > 126) return false;                // qname starts with a printable character ...
-    if (g.u8(o + 36 + l_qname - 1) != 0) return false;    // ... and is NUL terminated
+    uint8_t c0 = d[o + 36];
+    if (c0 < 33 || c0 > 126) return false;           // qname starts with a printable character ...
+    if (d[o + 36 + l_qname - 1] != 0) return false;  // ... and is NUL terminated
     *next = o + 4 + (uint64_t)bs;
     return true;
 }
 
-// One warp per chunk. The warp stages the first kilobyte of its chunk in shared memory with one coalesced load (two 16-byte
-// pieces per lane), then the lanes test 32 consecutive byte offsets at a time against it: the first record of a chunk starts
-// ~150 bytes in on average and the record after it (second half of the test) ~300 bytes later, so most chunks are settled by
-// that one DRAM round trip (the first form read every tested field from global memory: 0.12 ms for C2, now measured in
-// profiles/r2_summary.md).
-constexpr uint32_t GUESS_WIN = 1024;
+// One warp per chunk: lanes test 32 consecutive byte offsets at a time (global loads; the lines are in L1 after the first touch).
+// Two other forms were measured on the B200 and were slower than this 0.12 ms (profiles/r2_summary.md): staging the chunk's first
+// kilobyte in shared memory (0.15 ms: the kernel is bound by instruction issue - ~850 warp instructions per chunk - not by memory)
+// and a cheap per-offset prefilter followed by one-lane full tests (0.32 ms: the serialised tests cost more than they save).
 __global__ void __launch_bounds__(256) guess_starts(const uint8_t *__restrict__ d, uint64_t n, uint64_t first, int32_t n_ref,
                                                     uint64_t n_chunks, uint32_t CHUNK_LOG2, uint64_t *__restrict__ guess)
 {
-    __shared__ __align__(16) uint8_t win[8][GUESS_WIN + 16];
     uint64_t c = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t lane = threadIdx.x & 31;
     if (c >= n_chunks) return;
     uint64_t start = c << CHUNK_LOG2;
     if (start <= first) {
         if (lane == 0) guess[c] = first;
         return;
     }
-    // stage [astart, astart + GUESS_WIN) where astart = start rounded down to 16 bytes of the ADDRESS (the stream may be unaligned)
-    const uintptr_t addr = (uintptr_t)(d + start);
-    const uint32_t lead = (uint32_t)(addr & 15);
-    const uint64_t astart = start - lead;
-    // readable: up to n + 64 (the buffer's padding), and the 16 bytes in front of an unaligned stream
-    const uint32_t avail = (uint32_t)min((uint64_t)GUESS_WIN, ((n + 64 - astart) >> 4) << 4);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const uint32_t off = (h * 32 + lane) * 16;
-        if (off + 16 <= avail) *(uint4 *)&win[wib][off] = __ldg((const uint4 *)(d + astart + off));
-    }
-    __syncwarp();
-    GuessWin g{win[wib], d, astart, avail};
     uint64_t limit = min(n, start + ((uint64_t)8 << CHUNK_LOG2));
     uint64_t found = BAD_OFFSET;
-    for (uint64_t base = start; base < limit && found == BAD_OFFSET; base += 32) {
-        // cheap first look at every offset (the kernel was bound by instruction issue, not by memory: ~850 warp instructions per
-        // chunk when every lane ran the whole test): block_size and tid have to be sane before anything else is read
-        const uint64_t o = base + lane;
-        bool maybe = false;
-        if (o + 36 <= n) {
-            const uint32_t bs = g.u32(o), tid1 = g.u32(o + 4) + 1u;  // tid in [-1, n_ref)
-            maybe = bs >= 33u && bs < (1u << 28) && tid1 <= (uint32_t)n_ref;
-        }
-        uint32_t cand = __ballot_sync(0xffffffffu, maybe);
-        while (cand) {  // candidates in offset order, the whole test by one lane each (the others wait: there are few)
-            const int l = __ffs(cand) - 1;
-            cand &= cand - 1;
-            bool ok = false;
-            if ((int)lane == l) {
-                uint64_t nx = 0, nx2 = 0;
-                ok = plausible_one(g, n, o, n_ref, &nx);
-                if (ok && nx < n) ok = plausible_one(g, n, nx, n_ref, &nx2);  // two records deep
-            }
-            if (__shfl_sync(0xffffffffu, (int)ok, l)) {
-                found = base + l;
-                break;
-            }
+    for (uint64_t base = start; base < limit; base += 32) {
+        uint64_t o = base + lane, nx = 0, nx2 = 0;
+        bool ok = plausible_one(d, n, o, n_ref, &nx);
+        if (ok && nx < n) ok = plausible_one(d, n, nx, n_ref, &nx2);  // two records deep
+        uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (m) {
+            found = base + (__ffs(m) - 1);
+            break;
         }
     }
     if (lane == 0) guess[c] = found == BAD_OFFSET ? n : found;

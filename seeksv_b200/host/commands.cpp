@@ -436,8 +436,54 @@ void account_depth(const std::vector<Win> &hw, const std::vector<int32_t> &depth
     }
 }
 
+// Multi-GPU runs (python -m seeksv_b200.mgpu getsv / somatic): the ranks run the device passes on their shards of the BAM and
+// add the results up (NCCL); rank 0 then runs this command for the host bookkeeping and the output files with
+// SEEKSV_B200_SHARD_RESULTS naming a file that holds those results - int32 little endian: 'SVBR', n (records behind the
+// statistics), mean, deviation, number of junction counts, the counts, number of depth values, the depth values - in the
+// order in which this command asks for them. The BAM is then opened for its header only.
+struct ShardResults {
+    bool on = false;
+    int32_t n = 0, mean = 0, dev = 0;
+    std::vector<int32_t> counts, depth;
+    bool load()
+    {
+        const char *path = getenv("SEEKSV_B200_SHARD_RESULTS");
+        if (!path || !*path) return true;
+        std::ifstream f(path, std::ios::binary);
+        std::vector<char> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        if (raw.size() < 24 || memcmp(raw.data(), "SVBR", 4) != 0) return false;
+        const int32_t *w = (const int32_t *)raw.data();
+        const size_t nw = raw.size() / 4;
+        n = w[1], mean = w[2], dev = w[3];
+        size_t o = 4;
+        const int32_t nc = w[o++];
+        if (nc < 0 || o + (size_t)nc + 1 > nw) return false;
+        counts.assign(w + o, w + o + nc);
+        o += nc;
+        const int32_t nd = w[o++];
+        if (nd < 0 || o + (size_t)nd > nw) return false;
+        depth.assign(w + o, w + o + nd);
+        on = true;
+        return true;
+    }
+};
+ShardResults g_shard;
+
+int open_original(svb_ctx *ctx, const std::string &path, svb_bam **out)
+{
+    if (g_shard.on) return svb_bam_open_refs(ctx, path.c_str(), nullptr, 0, 0, n_threads(), out);  // header only: no records are loaded
+    return open_bam(ctx, path, out);
+}
+
 bool insert_size(Gpu &g, svb_bam *bam, const std::string &file, int min_mapq, int pairs_used, int &mean, int &dev)
 {
+    if (g_shard.on) {
+        if (g_shard.n == 0) return true;
+        mean = g_shard.mean, dev = g_shard.dev;
+        std::cerr << "Bam/sam " << file << "    Mean insert size : " << mean << "\n"
+                  << "Mean deviation: " << dev << std::endl;
+        return true;
+    }
     // CalculateInsertsizeDeviation, cluster.cpp:15-83: integer mean, (int)sqrt of the double mean square
     int64_t st[4];
     if (svb_insert_stats(g.ctx, bam, min_mapq, pairs_used, st) != 0) return false;
@@ -519,7 +565,7 @@ int cmd_getsv(int argc, char **argv)
     if (pairs_used >= 100000)
         prefetch.f = std::async(std::launch::async, [&]() -> int {
             if (!g.open()) return 1;
-            return open_bam(g.ctx, original_bam, &bam) != 0 ? 2 : 0;
+            return open_original(g.ctx, original_bam, &bam) != 0 ? 2 : 0;
         });
     if (!load_alignments(clip_aln, alns, err)) {
         std::cerr << "[main_samview] fail to open file for reading." << std::endl;
@@ -566,7 +612,7 @@ int cmd_getsv(int argc, char **argv)
         if (rc == 0 && bam) return true;
         if (rc == 0) {
             if (!g.ctx && !g.open()) return false;
-            rc = open_bam(g.ctx, original_bam, &bam) != 0 ? 2 : 0;
+            rc = open_original(g.ctx, original_bam, &bam) != 0 ? 2 : 0;
         }
         if (rc != 0) {
             load_failed = true;
@@ -587,7 +633,11 @@ int cmd_getsv(int argc, char **argv)
         size_t i = 0;
         for (auto &kv : jm) to_device_junction(kv.first, bam, dj[i++]);
         svb_pair_params pp = {min_mapq, mean, dev, times};
-        if (svb_discordant_support(g.ctx, bam, dj.data(), dj.size(), &pp, counts.data()) != 0) return fail(svb_last_error(g.ctx));
+        if (g_shard.on) {
+            if (g_shard.counts.size() != counts.size()) return fail("[seeksv_b200] SEEKSV_B200_SHARD_RESULTS: junction count mismatch");
+            counts = g_shard.counts;
+        } else if (svb_discordant_support(g.ctx, bam, dj.data(), dj.size(), &pp, counts.data()) != 0)
+            return fail(svb_last_error(g.ctx));
         i = 0;
         for (auto &kv : jm) kv.second.pairs = counts[i++];
         std::cerr << "'FindDiscordantReadPairs' finished" << std::endl;
@@ -614,7 +664,11 @@ int cmd_getsv(int argc, char **argv)
             }
             uint64_t total = device_windows(begin2end, tid_of, lens, dw, hw);
             std::vector<int32_t> depth(total);
-            if (svb_window_depth(g.ctx, bam, dw.data(), dw.size(), min_mapq, depth.data()) != 0) return fail(svb_last_error(g.ctx));
+            if (g_shard.on) {
+                if (g_shard.depth.size() != depth.size()) return fail("[seeksv_b200] SEEKSV_B200_SHARD_RESULTS: depth length mismatch");
+                depth = g_shard.depth;
+            } else if (svb_window_depth(g.ctx, bam, dw.data(), dw.size(), min_mapq, depth.data()) != 0)
+                return fail(svb_last_error(g.ctx));
             // main_depth visits covered positions in BAM order (tid, pos); the range sums are commutative and every
             // position is written once, so the order of the walk does not matter - but keep it anyway
             if (getenv("SEEKSV_B200_LITERAL_DEPTH_WALK")) {  // the reference's own per-position map walks (cross-check)
@@ -680,7 +734,7 @@ int cmd_somatic(int argc, char **argv)
     Gpu g;
     if (!g.open()) return 1;
     svb_bam *bam = nullptr;
-    if (open_bam(g.ctx, normal_bam, &bam) != 0) {
+    if (open_original(g.ctx, normal_bam, &bam) != 0) {
         std::cerr << "[main_samview] fail to open file for reading." << std::endl;
         return fail(std::string("[seeksv_b200] ") + svb_last_error(g.ctx));
     }
@@ -704,7 +758,11 @@ int cmd_somatic(int argc, char **argv)
         }
     std::vector<int32_t> counts(dj.size(), 0), per_row(rows.size(), 0);
     svb_pair_params pp = {min_mapq, mean, dev, 4};
-    if (!dj.empty() && svb_discordant_support(g.ctx, bam, dj.data(), dj.size(), &pp, counts.data()) != 0) return fail(svb_last_error(g.ctx));
+    if (g_shard.on) {
+        if (g_shard.counts.size() != counts.size()) return fail("[seeksv_b200] SEEKSV_B200_SHARD_RESULTS: junction count mismatch");
+        counts = g_shard.counts;
+    } else if (!dj.empty() && svb_discordant_support(g.ctx, bam, dj.data(), dj.size(), &pp, counts.data()) != 0)
+        return fail(svb_last_error(g.ctx));
     for (size_t k = 0; k < who.size(); ++k) per_row[who[k]] = counts[k];
     for (size_t i = 0; i < rows.size(); ++i) {
         if (rows[i].is_header) fout << rows[i].prefix;
@@ -836,6 +894,37 @@ extern "C" int svb_plan_getsv(const char *clip_aln, const char *clip_file, int32
     return 0;
 }
 
+// The junctions `somatic` asks the normal BAM about (the rows of ReadTumorFileAndOutputSomaticInfo that run
+// FindDiscordantReadPairs, somatic.cpp:111-409), in the order in which cmd_somatic batches them: for callers that run the
+// pair test themselves (sharded runs). mean_insert is the normal BAM's mean insert size (0 when -n < 100000).
+extern "C" int svb_plan_somatic(const char *normal_clip_path, const char *tumor_sv_path, double match_rate, int32_t offset, int32_t min_len,
+                                int32_t mean_insert, int32_t n_ref, const char *const *ref_names, svb_junction **junctions, uint64_t *n_junctions)
+{
+    if (!normal_clip_path || !tumor_sv_path || !junctions || !n_junctions || (n_ref && !ref_names)) return SVB_ERR_ARG;
+    std::string clip_text, tumor_text, err, log;
+    if (!read_text_maybe_gz(normal_clip_path, clip_text, err) || !read_text_maybe_gz(tumor_sv_path, tumor_text, err)) return SVB_ERR_IO;
+    std::vector<SomaticRow> rows;
+    somatic_rows(clip_text, tumor_text, match_rate, offset, min_len, mean_insert, rows, log);
+    auto tid_of = [&](const std::string &name) {
+        for (int32_t t = 0; t < n_ref; ++t)
+            if (name == ref_names[t]) return t;
+        return (int32_t)-1;
+    };
+    std::vector<svb_junction> dj;
+    for (const SomaticRow &r : rows)
+        if (!r.is_header && r.query_pairs) {
+            svb_junction j;
+            j.up_tid = tid_of(r.key.up_chr), j.down_tid = tid_of(r.key.down_chr);
+            j.up_pos = r.key.up_pos, j.down_pos = r.key.down_pos, j.up_strand = r.key.up_strand, j.down_strand = r.key.down_strand;
+            j.pad_[0] = j.pad_[1] = 0;
+            dj.push_back(j);
+        }
+    *n_junctions = dj.size();
+    *junctions = (svb_junction *)malloc(std::max<size_t>(1, dj.size()) * sizeof(svb_junction));
+    if (!dj.empty()) memcpy(*junctions, dj.data(), dj.size() * sizeof(svb_junction));
+    return 0;
+}
+
 // `seeksv run -- <command> [-- <command> ...]`: getclip / getsv / somatic segments run in this process (BAMs stay resident
 // between them), every other segment is executed as an external command (one word: through `sh -c`) and waited for.
 static int cmd_run(int argc, char **argv)
@@ -895,6 +984,11 @@ extern "C" int svb_main(int argc, char **argv)
     // main + SelectStep, seeksv.cpp:26-58,444-457
     if (argc == 1) {
         usage_top();
+        return 1;
+    }
+    g_shard = ShardResults();
+    if (!g_shard.load()) {
+        std::cerr << "[seeksv_b200] cannot read SEEKSV_B200_SHARD_RESULTS" << std::endl;
         return 1;
     }
     if (strcmp(argv[1], "run") == 0) return cmd_run(argc - 1, argv + 1);

@@ -25,7 +25,8 @@ class GetclipParams(C.Structure):
     _fields_ = [("match_rate", C.c_double), ("min_mapq", C.c_int32), ("save_low_quality", C.c_int32),
                 ("prev_tid", C.c_int32), ("export_unmapped_records", C.c_int32), ("key_filter", C.c_int32),
                 ("key_lo_tid", C.c_int32), ("key_lo_pos", C.c_int32), ("key_hi_tid", C.c_int32), ("key_hi_pos", C.c_int32),
-                ("halo_bytes", C.c_uint64), ("gz_outputs", C.c_int32), ("with_rows", C.c_int32)]
+                ("halo_bytes", C.c_uint64), ("gz_outputs", C.c_int32), ("with_rows", C.c_int32),
+                ("unmapped_only", C.c_int32), ("export_partitions", C.c_int32)]
 
 
 class GetsvParams(C.Structure):
@@ -53,7 +54,8 @@ EXPORTS = [
     "svb_clusters_text", "svb_insert_stats", "svb_discordant_support", "svb_window_depth", "svb_plan_getsv", "svb_free",
     "svb_write_gz", "svb_read_gz", "svb_bam_open_refs", "svb_bai_first_offsets", "svb_bam_last_mapped_tid", "svb_clusters_unmapped_records",
     "svb_clusters_gz", "svb_gzip_text", "svb_bam_open_voffsets", "svb_bai_linear_offsets", "svb_bam_peek_record", "svb_voffset_distance",
-    "svb_sam_to_stream", "svb_main", "svb_getsv_passes", "svb_clusters_text_len",
+    "svb_sam_to_stream", "svb_main", "svb_getsv_passes", "svb_clusters_text_len", "svb_clusters_export_device",
+    "svb_clusters_export_parts", "svb_bam_set_own_offset", "svb_insert_partial", "svb_insert_sq", "svb_pairs_depth", "svb_plan_somatic",
 ]
 
 
@@ -111,6 +113,12 @@ def load():
     L.svb_clusters_text_len.argtypes = [vp, C.c_int, C.POINTER(u64)]
     L.svb_getsv_passes.argtypes = [vp, vp, C.POINTER(GetsvParams), C.POINTER(Junction), u64, C.POINTER(Window), u64, C.POINTER(i64),
                                    C.POINTER(i32), C.POINTER(i32)]
+    L.svb_clusters_export_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.svb_clusters_export_parts.argtypes = [vp, C.POINTER(u64), i32]
+    L.svb_bam_set_own_offset.argtypes = [vp, u64]
+    L.svb_insert_partial.argtypes = [vp, vp, i32, i64, C.POINTER(i64)]
+    L.svb_insert_sq.argtypes = [vp, vp, i32, i64, i32, C.POINTER(i64)]
+    L.svb_pairs_depth.argtypes = [vp, vp, C.POINTER(PairParams), C.POINTER(Junction), u64, C.POINTER(Window), u64, vp, vp]
     L.svb_gzip_text.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(vp), C.POINTER(u64)]
     L.svb_clusters_gz.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(u64)]
     L.svb_clusters_unmapped_records.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(u64)]
@@ -121,6 +129,8 @@ def load():
     L.svb_plan_getsv.argtypes = [C.c_char_p, C.c_char_p, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), i32, i32,
                                  C.POINTER(C.POINTER(Junction)), C.POINTER(u64), C.POINTER(C.POINTER(Window)),
                                  C.POINTER(u64)]
+    L.svb_plan_somatic.argtypes = [C.c_char_p, C.c_char_p, C.c_double, i32, i32, i32, i32, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(Junction)),
+                                   C.POINTER(u64)]
     L.svb_bam_open_refs.argtypes = [vp, C.c_char_p, C.c_char_p, i32, i32, C.c_int, C.POINTER(vp)]
     L.svb_bam_open_voffsets.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(vp)]
     L.svb_bai_linear_offsets.argtypes = [C.c_char_p, i32, C.POINTER(C.c_uint64), C.c_int64]
@@ -192,6 +202,55 @@ def inflate_bgzf(ctx: "Context", image: bytes) -> bytes:
     out = (C.c_char * max(1, n.value))()
     ctx.check(ctx.L.svb_inflate_bgzf(ctx.h, src, len(image), out, n.value, C.byref(n)), "svb_inflate_bgzf")
     return bytes(out[:n.value])
+
+
+class Clusters:
+    """Result of svb_getclip, kept as a handle: the four texts (and, for shards, the exported unmapped-branch records) stay in HBM
+    until they are asked for."""
+
+    def __init__(self, ctx: "Context", handle):
+        self.ctx, self.h = ctx, handle
+
+    @property
+    def n_clusters(self) -> int:
+        return self.ctx.L.svb_clusters_count(self.h)
+
+    def text_len(self, which: int) -> int:
+        n = C.c_uint64()
+        self.ctx.L.svb_clusters_text_len(self.h, which, C.byref(n))
+        return n.value
+
+    def text(self, which: int) -> bytes:
+        d, n = C.c_char_p(), C.c_uint64()
+        self.ctx.check(self.ctx.L.svb_clusters_text(self.h, which, C.byref(d), C.byref(n)), "svb_clusters_text")
+        return C.string_at(d, n.value) if n.value else b""
+
+    def export_device(self) -> Tuple[int, int]:
+        """(device pointer, bytes) of the exported unmapped-branch records"""
+        d, n = C.c_void_p(), C.c_uint64()
+        self.ctx.check(self.ctx.L.svb_clusters_export_device(self.h, C.byref(d), C.byref(n)), "svb_clusters_export_device")
+        return d.value or 0, n.value
+
+    def export_parts(self, n_parts: int) -> List[int]:
+        arr = (C.c_uint64 * (n_parts + 1))()
+        self.ctx.check(self.ctx.L.svb_clusters_export_parts(self.h, arr, n_parts), "svb_clusters_export_parts")
+        return list(arr)
+
+    def unmapped_records(self) -> bytes:
+        d, n = C.c_char_p(), C.c_uint64()
+        self.ctx.L.svb_clusters_unmapped_records(self.h, C.byref(d), C.byref(n))
+        return C.string_at(d, n.value) if n.value else b""
+
+    def close(self):
+        if self.h:
+            self.ctx.L.svb_clusters_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Bam:
@@ -361,6 +420,38 @@ class Bam:
         finally:
             self.ctx.L.svb_clusters_free(out)
 
+    def getclip_handle(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0, export_unmapped=False, key_range=None,
+                       halo_bytes=0, with_rows=False, unmapped_only=False, export_partitions=0) -> Clusters:
+        """svb_getclip, results left in HBM behind a Clusters handle"""
+        p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid, 1 if export_unmapped else 0)
+        if key_range is not None:
+            (p.key_lo_tid, p.key_lo_pos), (p.key_hi_tid, p.key_hi_pos) = key_range
+            p.key_filter = 1
+        p.halo_bytes, p.with_rows = halo_bytes, 1 if with_rows else 0
+        p.unmapped_only, p.export_partitions = 1 if unmapped_only else 0, export_partitions
+        out = C.c_void_p()
+        self.ctx.check(self.ctx.L.svb_getclip(self.ctx.h, self.h, C.byref(p), C.byref(out)), "svb_getclip")
+        return Clusters(self.ctx, out)
+
+    def set_own_offset(self, own_offset: int):
+        self.ctx.check(self.ctx.L.svb_bam_set_own_offset(self.h, own_offset), "svb_bam_set_own_offset")
+
+    def insert_partial(self, min_mapq=20, take=-1):
+        """{taken, sum, sum of squares, records above 46340} over the first `take` qualifying own records (additive over shards)"""
+        out = (C.c_int64 * 4)()
+        self.ctx.check(self.ctx.L.svb_insert_partial(self.ctx.h, self.h, min_mapq, take, out), "svb_insert_partial")
+        return tuple(out)
+
+    def insert_sq(self, min_mapq, take, mean) -> int:
+        out = C.c_int64()
+        self.ctx.check(self.ctx.L.svb_insert_sq(self.ctx.h, self.h, min_mapq, take, mean, C.byref(out)), "svb_insert_sq")
+        return out.value
+
+    def pairs_depth_raw(self, pair_params, junction_array, n_j, window_array, n_w, counts_ptr, depth_ptr):
+        """svb_pairs_depth; counts_ptr / depth_ptr are integers (host or DEVICE addresses)"""
+        self.ctx.check(self.ctx.L.svb_pairs_depth(self.ctx.h, self.h, C.byref(pair_params), junction_array, n_j, window_array, n_w,
+                                                  C.c_void_p(counts_ptr), C.c_void_p(depth_ptr)), "svb_pairs_depth")
+
     def getsv_passes_raw(self, params, junction_array, n_j, window_array, n_w, stats_array, counts_array, depth_array):
         """svb_getsv_passes on prebuilt C arrays (bench.py): insert-size statistics, pair support and window depth, one read-back"""
         self.ctx.check(self.ctx.L.svb_getsv_passes(self.ctx.h, self.h, C.byref(params), junction_array, n_j, window_array, n_w, stats_array,
@@ -464,6 +555,22 @@ def plan_getsv(clip_alignments: str, clip_file: str, ref_names: Sequence[str], r
         L.svb_free(pj)
         L.svb_free(pw)
     return juncs, wins
+
+
+def plan_somatic(normal_clip: str, tumor_sv: str, ref_names: Sequence[str], match_rate=0.9, offset=30, min_len=10, mean_insert=0):
+    """junction tuples `somatic` asks the normal BAM about (svb_plan_somatic), in the command's order"""
+    L = load()
+    n = len(ref_names)
+    names = (C.c_char_p * n)(*[s.encode() for s in ref_names])
+    pj, nj = C.POINTER(Junction)(), C.c_uint64()
+    rc = L.svb_plan_somatic(normal_clip.encode(), tumor_sv.encode(), match_rate, offset, min_len, mean_insert, n, names, C.byref(pj), C.byref(nj))
+    if rc != 0:
+        raise SvbError("svb_plan_somatic = %d" % rc)
+    try:
+        return [(pj[i].up_tid, pj[i].up_pos, pj[i].up_strand.decode(), pj[i].down_tid, pj[i].down_pos, pj[i].down_strand.decode())
+                for i in range(nj.value)]
+    finally:
+        L.svb_free(pj)
 
 
 def gzip_text(ctx: "Context", data: bytes) -> bytes:

@@ -284,3 +284,199 @@ def sharded_getclip_ranges(worker, dist=None) -> Optional[Tuple[str, str, str, s
     clip, fq = merge_range_texts([(p[0], p[1]) for p in parts])
     u1, u2 = worker.pair_unmapped(b"".join(p[4] for p in parts))
     return clip, fq, u1, u2
+
+
+# ---- getsv / somatic on shards: additive device passes, combined with collectives on (device) tensors ------------------------------
+# Every rank holds a `worker` over its own records (lib.Bam with set_own_offset for range shards; the CPU oracle in the gloo tests):
+#   worker.insert_partial(min_mapq, take) -> (taken, sum, sum of squares, records above 46340)     additive
+#   worker.insert_sq(min_mapq, take, mean) -> sum of (int32)((isize - mean)^2)                     additive (wrap-exact second pass)
+#   worker.pairs_depth(min_mapq, mean, dev, times, junctions, windows) -> tensor int32 [n_j + n_pos] additive
+# Collectives run on tensors of `device` (cuda with NCCL over NVLink, cpu with gloo); nothing is pickled.
+def _all_gather_i64(values, dist, device):
+    import torch
+    t = torch.tensor(list(values), dtype=torch.int64, device=device)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return [t.tolist()]
+    out = torch.empty(dist.get_world_size() * t.numel(), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, t) if device != "cpu" else dist.all_gather(list(out.view(dist.get_world_size(), -1).unbind(0)), t)
+    return out.view(dist.get_world_size(), -1).tolist()
+
+
+def _all_reduce_i64(values, dist, device):
+    import torch
+    t = torch.tensor(list(values), dtype=torch.int64, device=device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t)
+    return t.tolist()
+
+
+def mean_dev(n: int, sx: int, sq: int) -> Tuple[int, int]:
+    """cluster.cpp:72-80: integer mean, (int)sqrt of the double quotient; sq = sum of squared differences from that mean"""
+    import math
+    if n == 0:
+        return 0, 0
+    return sx // n, int(math.sqrt(float(sq) / float(n)))
+
+
+def sharded_insert_stats(worker, dist, device, min_mapq: int, max_pairs: int):
+    """CalculateInsertsizeDeviation over the shards of one BAM: (n, mean, dev) of the first max_pairs qualifying records of the WHOLE
+    file. One all_gather of four integers per rank; a second small all_reduce only when the -n cut falls inside a shard; a third
+    only when an insert size is large enough for the reference's int products to wrap."""
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    full = worker.insert_partial(min_mapq, -1)
+    every = _all_gather_i64(full, dist, device)
+    counts = [e[0] for e in every]
+    takes = prefix_cutoffs(counts, max_pairs) if max_pairs > 0 else [0] * len(counts)
+    if takes == counts:
+        n, sx, sxx, big = (sum(e[k] for e in every) for k in range(4))
+    else:
+        take = takes[rank]
+        mine = full if take == counts[rank] else ((0, 0, 0, 0) if take == 0 else worker.insert_partial(min_mapq, take))
+        n, sx, sxx, big = _all_reduce_i64(mine, dist, device)
+    if n == 0:
+        return 0, 0, 0
+    mean = sx // n
+    mean = ((mean + 2 ** 31) % 2 ** 32) - 2 ** 31          # stored to an int (cluster.cpp:72)
+    if big == 0:
+        sq = sxx - 2 * mean * sx + n * mean * mean
+    else:       # the reference multiplies two ints (cluster.cpp:77): redo the squares with its truncation
+        own_take = -1 if takes == counts else takes[rank]
+        mine = worker.insert_sq(min_mapq, own_take, mean) if own_take != 0 else 0
+        sq = _all_reduce_i64([mine], dist, device)[0]
+    return n, mean, mean_dev(n, mean * n, sq)[1]
+
+
+def sharded_pairs_depth(worker, dist, min_mapq, mean, dev, times, junctions, windows):
+    """per-junction discordant-pair counts and per-position window depth, summed over the shards with ONE all_reduce of the
+    tensor the workers filled (device memory under NCCL)"""
+    t = worker.pairs_depth(min_mapq, mean, dev, times, junctions, windows)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t)
+    return t
+
+
+class GpuShardWorker:
+    """the getsv-side `worker` on a GPU: a lib.Bam over this rank's records (range shards: own_offset = halo bytes)"""
+
+    def __init__(self, bam, device):
+        self.bam, self.device = bam, device
+        self._arrays = None
+
+    def insert_partial(self, min_mapq, take):
+        return self.bam.insert_partial(min_mapq, take)
+
+    def insert_sq(self, min_mapq, take, mean):
+        return self.bam.insert_sq(min_mapq, take, mean)
+
+    def prepare(self, junctions, windows):
+        """C arrays and the result tensor, built once for a junction / window list"""
+        import ctypes as C
+        import torch
+        from . import lib
+        nj, nw = len(junctions), len(windows)
+        j_arr = (lib.Junction * max(nj, 1))(*[lib.Junction(ut, up, dt, dp, us.encode(), ds.encode(), b"") for ut, up, us, dt, dp, ds in junctions])
+        w_arr = (lib.Window * max(nw, 1))(*[lib.Window(*w) for w in windows])
+        n_pos = sum(w[2] - w[1] + 1 for w in windows)
+        out = torch.zeros(max(nj + n_pos, 1), dtype=torch.int32, device=self.device)
+        self._arrays = (j_arr, nj, w_arr, nw, n_pos, out)
+        return out
+
+    def pairs_depth(self, min_mapq, mean, dev, times, junctions, windows):
+        from . import lib
+        if self._arrays is None:
+            self.prepare(junctions, windows)
+        j_arr, nj, w_arr, nw, n_pos, out = self._arrays
+        self.bam.pairs_depth_raw(lib.PairParams(min_mapq, mean, dev, times), j_arr, nj, w_arr, nw, out.data_ptr(), out.data_ptr() + 4 * nj)
+        return out
+
+
+def fnv1a64(name: bytes) -> int:
+    """the name hash that groups exported unmapped-branch records (export_partitions; getclip.cu:export_group)"""
+    h = 0xcbf29ce484222325
+    for b in name:
+        h = ((h ^ b) * 0x100000001b3) & 0xffffffffffffffff
+    return h
+
+
+def exchange_unmapped(clusters, dist, world: int, device):
+    """All-to-all of the exported unmapped-branch records over device memory: rank r receives, from every shard in file order,
+    the records whose name hashes to group r (mates share a name: every pair is decided on exactly one rank). Returns a uint8
+    device tensor holding the received records in file order (plus readable padding)."""
+    import torch
+    dptr, n = clusters.export_device()
+    parts = clusters.export_parts(world)
+    send_sizes = [parts[r + 1] - parts[r] for r in range(world)]
+    sizes = _all_gather_i64(send_sizes, dist, device)                     # sizes[src][dst]
+    rank = dist.get_rank()
+    recv_sizes = [sizes[src][rank] for src in range(world)]
+    send = _as_tensor(dptr, max(n, 1), device)[:n]
+    recv = torch.zeros(sum(recv_sizes) + 256, dtype=torch.uint8, device=device)
+    dist.all_to_all_single(recv[:sum(recv_sizes)], send, recv_sizes, send_sizes)
+    return recv, sum(recv_sizes)
+
+
+class _DevMem:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _as_tensor(ptr: int, n: int, device):
+    """a uint8 tensor over device memory owned by the library (no copy)"""
+    import torch
+    if not ptr:
+        return torch.zeros(n, dtype=torch.uint8, device=device)
+    return torch.as_tensor(_DevMem(ptr, n), device=device)
+
+
+def merge_range_texts_fast(parts: Sequence[Tuple[bytes, bytes]]) -> Tuple[bytes, bytes]:
+    """merge_range_texts on bytes with numpy: a shard's clip text is ordered by (chromosome, side, position), so the lines of one
+    (chromosome, side) block are contiguous and the whole-file text is a concatenation of blocks - no line is parsed twice."""
+    import numpy as np
+    order, blocks = [], {}
+    for clip, fq in parts:
+        if not clip:
+            continue
+        buf = np.frombuffer(clip, dtype=np.uint8)
+        nl = np.flatnonzero(buf == 10)
+        starts = np.concatenate(([0], nl[:-1] + 1))
+        tabs = np.flatnonzero(buf == 9)
+        first_tab = tabs[np.searchsorted(tabs, starts)]                  # end of the chromosome name
+        third = tabs[np.searchsorted(tabs, starts) + 1] + 1              # the side character follows the second tab
+        side = buf[third]
+        # a block changes where the name or the side changes: compare (name length, side) cheaply, confirm names at the boundaries
+        name_len = first_tab - starts
+        change = np.flatnonzero((side[1:] != side[:-1]) | (name_len[1:] != name_len[:-1])) + 1
+        cand = np.concatenate(([0], change, [len(starts)]))
+        # same length and side but another name: split further by comparing the name bytes of neighbouring lines inside a block
+        bounds = [0]
+        for a, b in zip(cand[:-1], cand[1:]):
+            L = int(name_len[a])
+            if b - a > 1 and L:
+                names = buf[(starts[a:b, None] + np.arange(L)[None, :])]
+                diff = np.flatnonzero((names[1:] != names[:-1]).any(axis=1)) + 1 + a
+                bounds.extend(int(x) for x in diff)
+            bounds.append(int(b))
+        bounds = sorted(set(bounds))
+        fbuf = np.frombuffer(fq, dtype=np.uint8)
+        fnl = np.flatnonzero(fbuf == 10)
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            if a == b:
+                continue
+            chrom = clip[int(starts[a]):int(first_tab[a])]
+            sd = bytes([int(side[a])])
+            c0, c1 = int(starts[a]), int(nl[b - 1]) + 1
+            f0 = 0 if a == 0 else int(fnl[4 * a - 1]) + 1
+            f1 = int(fnl[4 * b - 1]) + 1
+            if chrom not in order:
+                order.append(chrom)
+            g = blocks.setdefault((chrom, sd), ([], []))
+            g[0].append(clip[c0:c1])
+            g[1].append(fq[f0:f1])
+    out, outfq = [], []
+    for chrom in order:
+        for sd in (b"5", b"3"):
+            g = blocks.get((chrom, sd))
+            if g:
+                out.extend(g[0])
+                outfq.extend(g[1])
+    return b"".join(out), b"".join(outfq)

@@ -530,6 +530,30 @@ def test_mgpu_entry_point_single_rank(by, tmp_path):
         assert _zcat(pre + ext) == read_text(os.path.join(GOLDEN, d, s + name)), ext
 
 
+@pytest.mark.parametrize("d,s", [("micro", "tumor"), ("fuzz", "f11"), ("example", "cancer")])
+def test_mgpu_getsv_single_rank(d, s, tmp_path):
+    """seeksv_b200.mgpu getsv as a single rank: the additive shard passes (svb_insert_partial, svb_pairs_depth on a range shard with
+    its own-record offset), handed to the host command through SEEKSV_B200_SHARD_RESULTS - same .sv as the single-process command"""
+    from seeksv_b200 import mgpu
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, s + ".clip.txt")).encode("latin-1"))
+    out, unm = str(tmp_path / "out.sv"), str(tmp_path / "unm")
+    assert mgpu.main(["getsv", "--", os.path.join(GOLDEN, d, s + ".clip.sam"), _bam(d, s), clip, out, unm]) == 0
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".sv"))
+
+
+@pytest.mark.parametrize("d,normal,tumour", [("example", "normal", "cancer"), ("micro", "normal", "tumor")])
+def test_mgpu_somatic_single_rank(d, normal, tumour, tmp_path):
+    from seeksv_b200 import mgpu
+    clip = str(tmp_path / "clip.gz")
+    with gzip.open(clip, "wb") as f:
+        f.write(read_text(os.path.join(GOLDEN, d, normal + ".clip.txt")).encode("latin-1"))
+    out = str(tmp_path / "somatic.sv")
+    assert mgpu.main(["somatic", "--", _bam(d, normal), clip, os.path.join(GOLDEN, d, tumour + ".sv"), out]) == 0
+    assert read_text(out) == read_text(os.path.join(GOLDEN, d, tumour + ".somatic.temp.sv"))
+
+
 @pytest.mark.parametrize("d,s", [("micro", "tumor"), ("fuzz", "f11")])
 def test_getsv_connected_reads_cli_bit_exact(d, s, tmp_path):
     """getsv -F with the BAM passes on: discordant pairs and depth of the connected-read junctions as well"""

@@ -178,3 +178,92 @@ def test_range_sharding_world2(case):
     d, s = case
     for got, name in zip(merged, (".clip.txt", ".clip.fq.txt", ".unmapped_1.fq.txt", ".unmapped_2.fq.txt")):
         assert got == read_text(os.path.join(GOLDEN, d, s + name)), name
+
+
+def _stats_worker(rank, world, port, q):
+    """sharded_insert_stats / sharded_pairs_depth over gloo with synthetic per-shard insert sizes (no BAM involved): the whole-file
+    rule - first max_pairs qualifying records in file order, integer mean, int products that may wrap - must come out"""
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import math
+        import random
+        import torch
+        from seeksv_b200 import sharding
+        results = []
+        for case, (sizes, big, cap) in enumerate([((700, 900, 400), False, 5000000), ((700, 900, 400), False, 1000), ((5, 0, 9), False, 7),
+                                                  ((300, 300, 300), True, 5000000), ((300, 300, 300), True, 450), ((0, 0, 0), False, 10)]):
+            rng = random.Random(100 + case)
+            shards = [[rng.randrange(200, 900) for _ in range(n)] for n in sizes]
+            if big:
+                shards[1][5] = 70000          # (isize - mean)^2 wraps an int
+                shards[2][7] = 71000
+            shards = (shards + [[]] * world)[:world] if world <= 3 else shards + [[]] * (world - 3)
+            mine = shards[rank] if rank < len(shards) else []
+
+            class W:
+                def insert_partial(self, mq, take):
+                    xs = mine if take < 0 else mine[:take]
+                    return (len(xs), sum(xs), sum(x * x for x in xs), sum(1 for x in xs if x > 46340))
+
+                def insert_sq(self, mq, take, mean):
+                    xs = mine if take < 0 else mine[:take]
+                    tot = 0
+                    for x in xs:
+                        p = ((x - mean) * (x - mean)) & 0xffffffff
+                        tot += p - (1 << 32) if p & 0x80000000 else p
+                    return tot
+
+                def pairs_depth(self, mq, mean, dev, times, juncs, wins):
+                    return torch.tensor([rank + 1, 10 * (rank + 1), mean], dtype=torch.int32)
+            n, mean, dev = sharding.sharded_insert_stats(W(), dist, "cpu", 20, cap)
+            flat = [x for s_ in shards for x in s_][:cap]
+            if not flat:
+                want = (0, 0, 0)
+            else:
+                m = sum(flat) // len(flat)
+                sq = 0
+                for x in flat:
+                    p = ((x - m) * (x - m)) & 0xffffffff
+                    sq += p - (1 << 32) if p & 0x80000000 else p
+                want = (len(flat), m, int(math.sqrt(float(sq) / float(len(flat)))))
+            results.append(((n, mean, dev), want))
+            t = sharding.sharded_pairs_depth(W(), dist, 20, mean, dev, 4, [], [])
+            results.append((t.tolist()[:2], [sum(r + 1 for r in range(world)), sum(10 * (r + 1) for r in range(world))]))
+        q.put((rank, results))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_statistics_and_sums_over_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stats_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, results in got:
+        for have, want in results:
+            assert tuple(have) == tuple(want), (rank, have, want)
+
+
+def test_text_merge_fast_equals_reference_merge():
+    from seeksv_b200 import sharding
+    for d, s in (("micro", "tumor"), ("example", "cancer"), ("fuzz", "f11"), ("fuzz", "f12")):
+        clip = read_text(os.path.join(GOLDEN, d, s + ".clip.txt"))
+        fq = read_text(os.path.join(GOLDEN, d, s + ".clip.fq.txt"))
+        lines, fl = clip.split("\n")[:-1], fq.split("\n")[:-1]
+        for cuts in ((), (len(lines) // 3,), (len(lines) // 4, len(lines) // 2, len(lines) // 2 + 1)):
+            b = [0] + list(cuts) + [len(lines)]
+            parts = [("".join(x + "\n" for x in lines[i:j]), "".join(x + "\n" for x in fl[4 * i:4 * j])) for i, j in zip(b[:-1], b[1:])]
+            want = sharding.merge_range_texts(parts)
+            got = sharding.merge_range_texts_fast([(p[0].encode("latin-1"), p[1].encode("latin-1")) for p in parts])
+            assert got[0] == want[0].encode("latin-1") and got[1] == want[1].encode("latin-1"), (d, s, cuts)

@@ -15,3 +15,20 @@ for case in fuzz/f11 fuzz/f12 micro/tumor example/cancer; do
     echo "ok $case --by $by (N=$N)"
   done
 done
+# getsv and somatic on N ranks: additive passes on the shards' own records + collectives on device tensors
+for case in fuzz/f11 micro/tumor example/cancer; do
+  zcat -f tests/golden/$case.clip.txt | gzip -1 > "$out/clip.gz"
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29517 \
+    -m seeksv_b200.mgpu getsv -- tests/golden/$case.clip.sam tests/golden/$case.sort.bam "$out/clip.gz" "$out/o.sv" "$out/o.unm" > "$out/o.stdout" 2>/dev/null
+  cmp "$out/o.sv" tests/golden/$case.sv || { echo "MISMATCH getsv $case"; exit 1; }
+  cmp "$out/o.stdout" tests/golden/$case.getsv.stdout || { echo "MISMATCH getsv stdout $case"; exit 1; }
+  echo "ok getsv $case (N=$N)"
+done
+for trio in example:normal:cancer micro:normal:tumor; do
+  d=${trio%%:*}; rest=${trio#*:}; normal=${rest%%:*}; tumour=${rest##*:}
+  zcat -f tests/golden/$d/$normal.clip.txt | gzip -1 > "$out/nclip.gz"
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29517 \
+    -m seeksv_b200.mgpu somatic -- tests/golden/$d/$normal.sort.bam "$out/nclip.gz" tests/golden/$d/$tumour.sv "$out/o.somatic" 2>/dev/null
+  cmp "$out/o.somatic" tests/golden/$d/$tumour.somatic.temp.sv || { echo "MISMATCH somatic $d"; exit 1; }
+  echo "ok somatic $d (N=$N)"
+done
