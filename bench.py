@@ -265,26 +265,95 @@ def partitioned_main(args, torch, dist, rank, world, local):
     class Step:
         keep = None
 
+    # the pairing of the received name group runs on a second context (own stream, own workspace) in a helper thread, next to the
+    # getsv passes of the main thread: the two do not depend on each other
+    import queue
+    import threading
+    ctx2 = S.Context(local)
+    jobs, done = queue.Queue(), queue.Queue()
+
+    def pair_thread():
+        torch.cuda.set_device(local)
+        while True:
+            job = jobs.get()
+            if job is None:
+                return
+            exchange, recv, n_recv = job
+            try:
+                exchange.wait()
+                torch.cuda.current_stream().synchronize()
+                mini = S.Bam.from_device(ctx2, recv.data_ptr(), n_recv, 0, len(names))
+                mini.set_refs(names, lens)
+                done.put((mini, mini.getclip_handle(unmapped_only=True)))
+            except Exception as e:      # noqa: BLE001
+                done.put(e)
+    pairer = threading.Thread(target=pair_thread, daemon=True)
+    pairer.start()
+    vec = torch.zeros(world + 4, dtype=torch.int64, device=device)           # [bytes for every name group | n, sum x, sum x^2, large]
+    vec_all = torch.zeros(world * (world + 4), dtype=torch.int64, device=device)
+    part = torch.zeros(4, dtype=torch.int64, device=device)
+    sizes_host = torch.zeros(world, dtype=torch.int64).pin_memory()
+    phases = {}
+
     def shard_step(keep=False):
+        t0 = time.perf_counter()
         b = S.Bam.from_device(ctx, dptr, nbytes, first, len(names))
         b.set_refs(names, lens)
         b.set_own_offset(plan.halo_bytes)
         cl = b.getclip_handle(prev_tid=plan.prev_tid, export_unmapped=True, key_range=(plan.key_lo, plan.key_hi), halo_bytes=plan.halo_bytes,
                               with_rows=True, export_partitions=world)
-        recv, n_recv = sharding.exchange_unmapped(cl, dist, world, device)
-        mini = S.Bam.from_device(ctx, recv.data_ptr(), n_recv, 0, len(names))
-        mini.set_refs(names, lens)
-        cu = mini.getclip_handle(unmapped_only=True)
+        t1 = time.perf_counter()
+        # one all_gather carries the exchange's byte counts and the shard's insert-size sums (device tensors, no read-back before it)
+        parts = cl.export_parts(world)
+        for r in range(world):
+            sizes_host[r] = parts[r + 1] - parts[r]
+        vec[:world].copy_(sizes_host, non_blocking=True)
+        b.insert_partial_async(20, -1, vec.data_ptr() + 8 * world)
+        dist.all_gather_into_tensor(vec_all, vec)
+        every = vec_all.view(world, world + 4).tolist()
+        t2 = time.perf_counter()
+        # the unmapped-branch records travel all-to-all by read-name group (NVLink, device buffers) while the statistics are settled
+        send_sizes = [int(x) for x in every[rank][:world]]
+        recv_sizes = [int(every[src][rank]) for src in range(world)]
+        dptr_e, n_e = cl.export_device()
+        send = sharding._as_tensor(dptr_e, max(n_e, 1), device)[:n_e]
+        recv = torch.zeros(sum(recv_sizes) + 256, dtype=torch.uint8, device=device)
+        exchange = dist.all_to_all_single(recv[:sum(recv_sizes)], send, recv_sizes, send_sizes, async_op=True)
+        jobs.put((exchange, recv, sum(recv_sizes)))
+        counts = [e[world] for e in every]
+        takes = sharding.prefix_cutoffs(counts, 5000000)
+        if takes == counts:
+            n, sx, sxx, big = (sum(e[world + k] for e in every) for k in range(4))
+        else:       # the -n cut falls inside a shard: that shard sums its prefix again, one small all_reduce
+            if takes[rank] == counts[rank]:
+                part.copy_(vec[world:])
+            elif takes[rank] == 0:
+                part.zero_()
+            else:
+                b.insert_partial_async(20, takes[rank], part.data_ptr())
+            dist.all_reduce(part)
+            n, sx, sxx, big = part.tolist()
+        assert big == 0, "insert sizes above 46340: the wrap-exact path is sharding.sharded_insert_stats"
+        mean = sx // n if n else 0
+        dev = sharding.mean_dev(n, sx, sxx - 2 * mean * sx + n * mean * mean)[1] if n else 0
+        t3 = time.perf_counter()
         gw = sharding.GpuShardWorker(b, device)
         gw._arrays = prepared
-        n, mean, dev = sharding.sharded_insert_stats(gw, dist, device, 20, 5000000)
         t = sharding.sharded_pairs_depth(gw, dist, 20, mean, dev, 4, juncs, wins)
+        t4 = time.perf_counter()
+        got = done.get()
+        if isinstance(got, Exception):
+            raise got
+        mini, cu = got
+        t5 = time.perf_counter()
         if keep:
             Step.keep = (cl.text(0), cl.text(1), cu.text(2), cu.text(3), (n, mean, dev), t.cpu().numpy().copy())
         cu.close()
         mini.close()
         cl.close()
         b.close()
+        for k, v in (("getclip", t1 - t0), ("gather", t2 - t1), ("stats", t3 - t2), ("pairs_depth", t4 - t3), ("unmapped", t5 - t4)):
+            phases[k] = phases.get(k, 0.0) + v
         return 4 * (nj + n_pos)
 
     probe = sharding.GpuShardWorker(None, device)
@@ -343,7 +412,9 @@ def partitioned_main(args, torch, dist, rank, world, local):
             shard_step()
     sampler = ClockSampler(local)
     sampler.start()
+    phases.clear()
     ms_dev, wall_dev, d2h = timed(shard_step, args.steps)
+    host_phases = {k: round(1e3 * v / args.steps, 4) for k, v in phases.items()}
     ctx.prof(True)
     ctx.prof_reset()
     ms_prof, _, _ = timed(shard_step, args.steps)
@@ -412,6 +483,7 @@ def partitioned_main(args, torch, dist, rank, world, local):
                         "kernels_ms_per_step": {k: round(x["ms"] / args.steps, 4) for k, x in sorted(kern.items())},
                         "step": {"algorithmic_bytes_all_gpus": 2.0 * whole_bytes, "achieved_all_gpus": 2.0 * whole_bytes / step_s / 1e9,
                                  "frac_per_gpu": 2.0 * whole_bytes / step_s / 1e9 / peak / world, "ms_per_step_with_timers": ms_prof / args.steps,
+                                 "host_ms_per_phase_rank0": host_phases,
                                  "note": "rank 0's kernels; 2 x record bytes of the whole BAM / step time, per GPU"}}
         line = {
             "metric": "BAM records/sec getclip+getsv", "value": value, "unit": "records/s", "n_gpus": world, "steps": args.steps,
@@ -434,6 +506,7 @@ def partitioned_main(args, torch, dist, rank, world, local):
             "clocks": sampler.summary(), "roofline": roofline,
         }
         print(json.dumps(line))
+    jobs.put(None)
     worker.close()
     ctx.close()
     dist.barrier()

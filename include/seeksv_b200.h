@@ -237,6 +237,8 @@ int svb_getsv_passes(svb_ctx *ctx, svb_bam *bam, const svb_getsv_params *p, cons
 int svb_bam_set_own_offset(svb_bam *bam, uint64_t own_offset);
 int svb_insert_partial(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64_t take, int64_t out[4]);
 int svb_insert_sq(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64_t take, int32_t mean, int64_t *sq);
+/* svb_insert_partial without the read-back: the four values land in d_out (DEVICE memory) in stream order. */
+int svb_insert_partial_async(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64_t take, int64_t *d_out);
 int svb_pairs_depth(svb_ctx *ctx, svb_bam *bam, const svb_pair_params *p, const svb_junction *junctions, uint64_t n_junctions,
                     const svb_window *windows, uint64_t n_windows, int32_t *counts, int32_t *depth_out);
 

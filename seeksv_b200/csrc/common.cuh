@@ -121,8 +121,10 @@ struct RowTable {
 };
 #define FLAGQ_HARDCLIP (1u << 24)
 #define FLAGQ_NOCIGAR (1u << 25)
-#define ROWS_R_FIRST 256u  // first try: fits chunks whose records average >= 64 bytes
-#define ROWS_R_MAX 448u    // a 16 KiB chunk cannot hold more records than this (a record is at least 38 bytes)
+// row slots per chunk: first try fits chunks whose records average >= 64 bytes; a chunk cannot hold more records than the
+// second (a record is at least 38 bytes)
+#define ROWS_R_FIRST 256u
+#define ROWS_R_MAX 448u
 
 struct svb_bam {
     svb_ctx *ctx = nullptr;
@@ -305,6 +307,8 @@ int ensure_counts(svb_ctx *ctx, svb_bam *bam);
 int ensure_rows(svb_ctx *ctx, svb_bam *bam);
 // a walk left exit[] without matching the guesses: repair guesses with plain walks (synchronises); the walk has to run again
 int repair_guesses(svb_ctx *ctx, svb_bam *bam);
+static inline uint32_t rows_first(const svb_bam *b) { return std::max(16u, ROWS_R_FIRST >> (14 - b->chunk_log2)); }
+static inline uint32_t rows_max(const svb_bam *b) { return (ROWS_R_MAX >> (14 - b->chunk_log2)) + 4; }
 int alloc_rows(svb_ctx *ctx, svb_bam *bam, uint32_t R);  // walk.cu
 void free_rows(svb_bam *bam);
 // the inflate kernel reads ahead of the current bit position: the device copy of the file image is padded by this much

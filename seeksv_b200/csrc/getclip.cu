@@ -1063,7 +1063,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         CKR(res->take(2, cap.un1));
         CKR(res->take(3, cap.un2));
         if (export_mode) CKR(res->take(4, cap.exp));
-        if (want_rows && !bam->rows_ready) CKR(alloc_rows(ctx, bam, bam->rows.R == ROWS_R_MAX ? ROWS_R_MAX : ROWS_R_FIRST));
+        if (want_rows && !bam->rows_ready) CKR(alloc_rows(ctx, bam, rows_first(bam)));
         const bool do_rows = want_rows && !bam->rows_ready;
         CK(cudaMemsetAsync(ctx->ws[0], 0, B.zero_end, s));
         CK(cudaMemcpyAsync(B.nblob, nblob.data(), nblob.size(), cudaMemcpyHostToDevice, s));

@@ -822,6 +822,53 @@ extern "C" int svb_insert_partial(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, 
     return 0;
 }
 
+// {taken, sum, sum of squares, large} for the async form below: from the totals (take < 0) or from the ordered kernel's accumulators
+__global__ void partial_out(const SvCtl *__restrict__ ctl, const unsigned long long *__restrict__ acc, int from_acc, long long *__restrict__ out)
+{
+    if (from_acc) out[0] = (long long)acc[1], out[1] = (long long)acc[0], out[2] = (long long)acc[2], out[3] = (long long)acc[3];
+    else out[0] = (long long)ctl->tot[0], out[1] = (long long)ctl->tot[1], out[2] = (long long)ctl->tot[2], out[3] = ctl->q_max > 46340 ? 1 : 0;
+}
+
+// svb_insert_partial without the read-back: the four values are written to d_out (DEVICE memory, int64[4]) in stream order, so
+// that the ranks can feed them to a collective directly. take >= 0 must not exceed the shard's qualifying count by the caller's
+// own bookkeeping (it is clamped by the kernels either way).
+extern "C" int svb_insert_partial_async(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64_t take, int64_t *d_out)
+{
+    if (!ctx || !bam || !d_out) return svb_fail(ctx, SVB_ERR_ARG, "svb_insert_partial_async: null argument");
+    CK(cudaSetDevice(ctx->device));
+    CKR(prepare_rows(ctx, bam));
+    cudaStream_t s = ctx->stream;
+    const uint64_t n_chunks = bam->n_chunks;
+    SvBuffers B{};
+    {
+        Bump measure(nullptr);
+        carve(measure, B, n_chunks, 0, 0, 1, 1, bam->n_ref);
+        CKR(ctx->ws_reserve(1, measure.used));
+        Bump real(ctx->ws[1]);
+        carve(real, B, n_chunks, 0, 0, 1, 1, bam->n_ref);
+    }
+    CK(cudaMemsetAsync(ctx->ws[1], 0, B.zero_end, s));
+    const bool need_index = !bam->rows_indexed;
+    if (need_index) CK(cudaMemsetAsync(bam->d_scal, 0, 16, s));
+    RowsView V = view_of(bam);
+    const unsigned g_chunks = nblk(n_chunks * 32, 256);
+    {
+        ProfScope ps(ctx, "rows_pass", (double)bam->n_rec * sizeof(Row));
+        if (need_index) rows_pass<true, true><<<g_chunks, 256, 0, s>>>(V, bam->d_fkey, bam->d_scal, min_mapq, B.q_cnt, B.q_sum, B.q_sq, B.ctl);
+        else rows_pass<false, true><<<g_chunks, 256, 0, s>>>(V, bam->d_fkey, bam->d_scal, min_mapq, B.q_cnt, B.q_sum, B.q_sq, B.ctl);
+        if (take < 0) insert_totals<<<(unsigned)std::min<uint64_t>(nblk(n_chunks, 256), (uint64_t)ctx->sm_count), 256, 0, s>>>(B.ctl, n_chunks, B.q_cnt, B.q_sum, B.q_sq);
+        else {
+            QBaseOp op{n_chunks, B.q_cnt, B.q_base};
+            launch_scan<1, 8>(ctx, s, op, B.sc_q, n_chunks);
+            insert_ordered<<<g_chunks, 256, 0, s>>>(V, min_mapq, B.q_base, (uint64_t)take, 3, 0, B.acc);
+        }
+        partial_out<<<1, 1, 0, s>>>(B.ctl, B.acc, take >= 0, (long long *)d_out);
+    }
+    bam->rows_indexed = true;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // second pass of the wrap-exact path: sum over the same records of (int32)((isize - mean) * (isize - mean)) (cluster.cpp:77)
 extern "C" int svb_insert_sq(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64_t take, int32_t mean, int64_t *sq)
 {

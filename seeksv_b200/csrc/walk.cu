@@ -429,6 +429,11 @@ int index_records(svb_ctx *ctx, svb_bam *bam)
     uint64_t n = bam->nbytes, first = bam->first;
     if (first > n) return svb_fail(ctx, SVB_ERR_ARG, "first_record beyond the stream");
     {
+        // 16 KiB chunks for anything large; a small stream (the unmapped-branch records the shards of a BAM exchange, a test
+        // fixture) gets smaller chunks, so that the walk still has tens of thousands of chains to hide its latency behind
+        uint32_t l2 = 14;
+        while (l2 > 10 && (n >> l2) < 150000) --l2;
+        bam->chunk_log2 = l2;
         const char *e = getenv("SEEKSV_B200_CHUNK_LOG2");
         int v = e ? atoi(e) : 0;
         if (v >= 10 && v <= 14) bam->chunk_log2 = (uint32_t)v;
@@ -482,7 +487,7 @@ static int walk_alone(svb_ctx *ctx, svb_bam *bam, bool rows)
 {
     cudaStream_t s = ctx->stream;
     CK(cudaSetDevice(ctx->device));
-    const uint32_t R_try[2] = {ROWS_R_FIRST, ROWS_R_MAX};
+    const uint32_t R_try[2] = {rows_first(bam), rows_max(bam)};
     int r_i = 0;
     for (int attempt = 0;; ++attempt) {
         if (rows) CKR(alloc_rows(ctx, bam, R_try[r_i]));
@@ -519,7 +524,7 @@ static int walk_alone(svb_ctx *ctx, svb_bam *bam, bool rows)
             continue;
         }
         if (rows && h.flags[0]) {  // more records in a chunk than row slots: once more with the largest possible slot count
-            if (r_i == 1) return svb_fail(ctx, SVB_ERR_FORMAT, "a 16 KiB chunk holds more than %u records", ROWS_R_MAX);
+            if (r_i == 1) return svb_fail(ctx, SVB_ERR_FORMAT, "a chunk holds more than %u records", R_try[1]);
             r_i = 1;
             continue;
         }

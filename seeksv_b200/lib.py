@@ -55,7 +55,7 @@ EXPORTS = [
     "svb_write_gz", "svb_read_gz", "svb_bam_open_refs", "svb_bai_first_offsets", "svb_bam_last_mapped_tid", "svb_clusters_unmapped_records",
     "svb_clusters_gz", "svb_gzip_text", "svb_bam_open_voffsets", "svb_bai_linear_offsets", "svb_bam_peek_record", "svb_voffset_distance",
     "svb_sam_to_stream", "svb_main", "svb_getsv_passes", "svb_clusters_text_len", "svb_clusters_export_device",
-    "svb_clusters_export_parts", "svb_bam_set_own_offset", "svb_insert_partial", "svb_insert_sq", "svb_pairs_depth", "svb_plan_somatic",
+    "svb_clusters_export_parts", "svb_bam_set_own_offset", "svb_insert_partial", "svb_insert_sq", "svb_pairs_depth", "svb_plan_somatic", "svb_insert_partial_async",
 ]
 
 
@@ -117,6 +117,7 @@ def load():
     L.svb_clusters_export_parts.argtypes = [vp, C.POINTER(u64), i32]
     L.svb_bam_set_own_offset.argtypes = [vp, u64]
     L.svb_insert_partial.argtypes = [vp, vp, i32, i64, C.POINTER(i64)]
+    L.svb_insert_partial_async.argtypes = [vp, vp, i32, i64, vp]
     L.svb_insert_sq.argtypes = [vp, vp, i32, i64, i32, C.POINTER(i64)]
     L.svb_pairs_depth.argtypes = [vp, vp, C.POINTER(PairParams), C.POINTER(Junction), u64, C.POINTER(Window), u64, vp, vp]
     L.svb_gzip_text.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(vp), C.POINTER(u64)]
@@ -441,6 +442,10 @@ class Bam:
         out = (C.c_int64 * 4)()
         self.ctx.check(self.ctx.L.svb_insert_partial(self.ctx.h, self.h, min_mapq, take, out), "svb_insert_partial")
         return tuple(out)
+
+    def insert_partial_async(self, min_mapq, take, device_ptr: int):
+        """svb_insert_partial_async: the four values go to device memory at device_ptr, in stream order (no read-back)"""
+        self.ctx.check(self.ctx.L.svb_insert_partial_async(self.ctx.h, self.h, min_mapq, take, C.c_void_p(device_ptr)), "svb_insert_partial_async")
 
     def insert_sq(self, min_mapq, take, mean) -> int:
         out = C.c_int64()
