@@ -80,6 +80,7 @@ extern "C" void svb_ctx_destroy(svb_ctx *ctx)
     ctx->dev_free.clear();
     for (int w = 0; w < 2; ++w)
         if (ctx->ws[w]) cudaFree(ctx->ws[w]);
+    if (ctx->inflate_scratch) cudaFree(ctx->inflate_scratch);
     if (ctx->ctl_host) cudaFreeHost(ctx->ctl_host);
     if (ctx->join_event) cudaEventDestroy(ctx->join_event);
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
@@ -523,7 +524,7 @@ int load_bgzf_device_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, ui
                 cudaStream_t a = ctx->aux[lane];
                 lane = (lane + 1) % svb_ctx::N_AUX;
                 CK(cudaStreamWaitEvent(a, sl.done[slab], 0));  // (the copy stream is in order: this slab implies the earlier ones)
-                CKR(inflate_launch(a, d_file.p, d_blocks.p + next_block, (uint32_t)(b1 - next_block), b->d_owned + lead, d_err.p));
+                CKR(inflate_launch(ctx, a, d_file.p, d_blocks.p + next_block, (uint32_t)(b1 - next_block), b->d_owned + lead, d_err.p));
                 next_block = b1;
             }
         }

@@ -84,6 +84,9 @@ struct svb_ctx {
     uint64_t hint[16] = {};
     bool walk_attr = false;                           // the walker's shared-memory opt-in is set on this device
     cudaEvent_t join_event = nullptr;                 // side stream -> main stream
+    // inflate.cu: slot bitmap + per-resident-warp match lists of the speculative inflate kernel (allocated on first use)
+    uint8_t *inflate_scratch = nullptr;
+    uint32_t inflate_slot_words = 0, inflate_slots_per_sm = 0, inflate_scratch_head = 0;
     ~svb_ctx();
 };
 
@@ -315,6 +318,6 @@ void free_rows(svb_bam *bam);
 static constexpr uint64_t SVB_INFLATE_PAD = 1024;
 struct PinnedBuf;
 int gzip_on_device(svb_ctx *ctx, const char *d_text, uint64_t n, PinnedBuf *out);  // gzip.cu
-int inflate_launch(cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err);
+int inflate_launch(svb_ctx *ctx, cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err);
 int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out,
                       double out_bytes);                             // inflate.cu

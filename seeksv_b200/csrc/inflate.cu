@@ -14,6 +14,8 @@
 // longer codes.
 #include "common.cuh"
 #include <cstddef>
+#include <cstring>
+#include <mutex>
 
 namespace {
 
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(BLOCKS_PER_CTA * GROUP, 8)
     if (state != S_DONE) blk = blocks[b];
     uint8_t *dst = out + blk.uoff;
     const uint32_t *wbase = (const uint32_t *)((uintptr_t)(file + blk.coff) & ~(uintptr_t)3);  // bit positions count from here
+    const uint32_t end = (uint32_t)((uintptr_t)(file + blk.coff) & 3) * 8 + blk.clen * 8;      // end of the deflate payload
     BitReader br;
     br.init(file + blk.coff);  // (only the group leader's copy is used)
     uint32_t pos = 0, final_block = 0, bitpos = 0;
@@ -213,18 +216,19 @@ __global__ void __launch_bounds__(BLOCKS_PER_CTA * GROUP, 8)
             final_block = hdr & 1;
             const uint32_t type = hdr >> 1;
             if (type == 0) {  // stored
-                uint32_t len = 0;
+                uint32_t len = 0, ok = 0;
                 const uint8_t *src = nullptr;
                 if (glane == 0) {
                     br.align_byte();
                     len = br.bits(16);
-                    br.consume(16);  // NLEN
+                    const uint32_t nlen = br.bits(16);
                     src = br.byte_ptr();
-                    br.init(src + len);
+                    ok = (len ^ nlen) == 0xffffu && br.bit_offset(wbase) + len * 8 <= end;  // inside the payload
+                    if (ok) br.init(src + len);
                 }
-                len = __shfl_sync(gm, len, leader);
+                len = __shfl_sync(gm, len, leader), ok = __shfl_sync(gm, ok, leader);
                 src = (const uint8_t *)__shfl_sync(gm, (unsigned long long)src, leader);
-                if (pos + len > blk.ulen) bad = true;
+                if (!ok || pos + len > blk.ulen) bad = true;
                 else {
                     for (uint32_t i = glane; i < len; i += GROUP) dst[pos + i] = src[i];
                     pos += len;
@@ -317,6 +321,7 @@ __global__ void __launch_bounds__(BLOCKS_PER_CTA * GROUP, 8)
                     if (glane == 0) bitpos = br.bit_offset(wbase);
                     bitpos = __shfl_sync(gm, bitpos, leader);
                     state = S_TOKENS;
+                    if (bitpos >= end) bad = true, state = S_DONE;  // the header ran out of the payload
                 }
             } else
                 bad = true, state = S_DONE;
@@ -391,7 +396,7 @@ __global__ void __launch_bounds__(BLOCKS_PER_CTA * GROUP, 8)
             }
             const uint32_t total = __shfl_sync(mt, incl, leader + GROUP - 1), off = incl - n, o = pos + off;
             const bool is_match = !is_lit && n != 0;
-            const bool fail = status < 0 || pos + total > blk.ulen || (__ballot_sync(mt, is_match && dist > o) & gm) != 0;
+            const bool fail = status < 0 || bitpos > end || pos + total > blk.ulen || (__ballot_sync(mt, is_match && dist > o) & gm) != 0;
             // matches whose source ends before this batch's output are independent of the other tokens
             const bool coop = !fail && is_match && (n > COOP_LEN || dist < off + n);
             if (!fail) {
@@ -437,24 +442,566 @@ __global__ void __launch_bounds__(BLOCKS_PER_CTA * GROUP, 8)
     if (b < n_blocks && (bad || pos != blk.ulen) && glane == 0) atomicOr(error, 1u);
 }
 
-// BGZF blocks per warp: 1 (default) or 2 (SEEKSV_B200_INFLATE_GROUP=16, two 16-lane groups per warp; measured slower on
-// C2: fewer warps per SM leave the dependent shared-memory lookups of the decode loop exposed)
-static void launch_inflate(cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err)
+// =====================================================================================================================
+// Default kernel (round 2): SPECULATIVE decode - all 32 lanes of the warp decode Huffman codes of the same deflate block.
+//
+// The serial form above keeps 31 lanes idle while lane 0 decodes (80 % of its issued instructions had one active thread).
+// Huffman streams resynchronise: a decoder started at a wrong bit position falls onto true code boundaries after a few
+// tokens. So the bit range of a deflate block is cut into 32 equal sub-ranges and every lane decodes its own, lane 0 from the
+// true start, the others from a guess. Then rounds: lane i+1 restarts at the bit position where lane i LEFT its sub-range;
+// a lane whose entry did not change keeps its result. Lane 0 is exact, so after round r lanes 0..r are exact (induction) and
+// the fixed point is the serial decode whatever the guesses did - they only decide how many rounds it takes (on the C2
+// workload 97 % of the blocks are final after ONE repeat; lock-step work 0.14 of the serial token count,
+// tools/spec_decode_sim.cpp). The passes only count (bytes, matches per lane); a prefix sum over the lanes then gives
+// every lane its place in a per-warp token list (global scratch, one slot per resident warp) and the last pass emits the tokens
+// (a literal byte or a (length, distance) match, 4 bytes each). The copy phase takes the list in stream order, up to 32 tokens
+// / 1 KiB of output at a time, and assembles that piece of output in SHARED memory: literals and the matches whose source lies
+// in front of the piece go in parallel (one per lane, whole warp for long ones), the matches that read this piece's own output
+// follow one at a time through shared memory (a ~30-cycle round trip instead of a trip to L2 - that loop was 60 % of the first
+// version's time, profiles/r2_inflate.md); the piece is then written out coalesced.
+//
+// Tables: single lookup for codes up to 10 (literal/length) / 8 (distance) bits, SECOND-LEVEL tables behind the root for the
+// longer ones (replaces the 15-step canonical loop; tools/huff2_proto.cpp), built warp-parallel: symbol ranks by
+// __match_any_sync, sub-table widths from the cumulative code space. Sizes follow zlib's `enough`: 288 symbols / root 10 / 15
+// bits need <= 1334 entries, 32 / 8 / 15 <= 402 (complete codes; incomplete ones are refused exactly where zlib refuses them).
+namespace {
+constexpr int LIT_ROOT = 10, DIST_ROOT = 8, LIT_CAP = 1344, DIST_CAP = 416, SPEC_WARPS = 4, MIN_SPAN_BITS = 64;
+constexpr uint32_t TOK_CAP = 20480;  // tokens per emission segment (a lane's sub-range holds <= 2^19 / 32 = 16384 tokens)
+constexpr uint32_t SPAN = 1024;      // output bytes assembled in shared memory per token batch
+constexpr uint32_t T_SUB = 1u << 5, T_LIT = 1u << 6, T_END = 1u << 7, T_BAD = 1u << 14;
+// table entry: bits 0-4 bits to consume, bit 5 pointer to a sub-table (bits 8-11 its index width, bits 16-31 its offset),
+// bit 6 literal, bit 7 end of block, bits 8-11 number of extra bits, bit 14 invalid symbol, bits 16-31 value; 0 = no such code
+
+struct SpecMem {
+    uint32_t lit[LIT_CAP];
+    uint32_t dist[DIST_CAP];
+    union {
+        struct {                   // table building
+            uint8_t lens[320];     // literal/length code lengths, the distance alphabet from [288]
+            uint8_t cl_fast[128];  // code-length alphabet: (len << 5) | symbol, 7-bit lookup
+            uint16_t rank[288];    // rank of a symbol among the symbols of its code length
+        };
+        uint8_t span[SPAN];        // copy phase: the output bytes of the current token batch
+    };
+    uint32_t cnt[16], first[16], cum[16];
+};
+
+__device__ __forceinline__ uint32_t spec_lit_entry(int s)
 {
-    static const int group = [] {
-        const char *e = getenv("SEEKSV_B200_INFLATE_GROUP");
-        return e && atoi(e) == 16 ? 16 : 32;
-    }();
+    if (s < 256) return T_LIT | (uint32_t)s << 16;
+    if (s == 256) return T_END;
+    if (s > 285) return T_BAD;
+    return (uint32_t)c_len_extra[s - 257] << 8 | (uint32_t)c_len_base[s - 257] << 16;
+}
+__device__ __forceinline__ uint32_t spec_dist_entry(int s)
+{
+    if (s > 29) return T_BAD;
+    return (uint32_t)c_dist_extra[s] << 8 | (uint32_t)c_dist_base[s] << 16;
+}
+
+// Canonical Huffman tables (RFC 1951 3.2.2) of one alphabet, built by the whole warp. false = over-subscribed, incomplete
+// (zlib inftrees.c: an incomplete code is accepted only when its longest code has one bit) or too large for the table.
+template <bool IS_LIT>
+__device__ bool spec_build(SpecMem &M, const uint8_t *lens, int n, uint32_t *T, uint32_t lane)
+{
+    constexpr int R = IS_LIT ? LIT_ROOT : DIST_ROOT;
+    constexpr uint32_t CAP = IS_LIT ? LIT_CAP : DIST_CAP;
+    for (uint32_t i = lane; i < (1u << R); i += 32) T[i] = 0;
+    if (lane < 16) M.cnt[lane] = 0;
+    __syncwarp();
+    for (int s0 = 0; s0 < n; s0 += 32) {  // counts per length + rank of every symbol inside its length
+        const int s = s0 + (int)lane;
+        const uint32_t l = s < n ? lens[s] : 0u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, l);
+        const uint32_t r = __popc(peers & ((1u << lane) - 1u)), base = M.cnt[l];
+        if (s < n) M.rank[s] = (uint16_t)(base + r);
+        __syncwarp();
+        if (r == 0) M.cnt[l] = base + __popc(peers);
+        __syncwarp();
+    }
+    if (lane == 0) {  // first code per length and cumulative code space in units of 2^-15
+        uint32_t cum = 0, maxl = 0;
+        for (int l = 1; l <= 15; ++l) {
+            M.first[l] = cum >> (15 - l);
+            const uint32_t c = M.cnt[l];
+            if (c) maxl = l;
+            cum += c << (15 - l);
+            M.cum[l] = cum;
+        }
+        M.first[0] = cum, M.cum[0] = maxl;
+    }
+    __syncwarp();
+    const uint32_t space = M.first[0], maxl = M.cum[0];
+    if (space > 32768u || (space < 32768u && maxl > 1)) return false;
+    if (maxl > (uint32_t)R) {
+        // every R-bit prefix from the first long code on heads a sub-table as wide as its longest code - the code that ends
+        // where the prefix ends (codes ascend with their length)
+        uint32_t off = 1u << R;
+        for (uint32_t p0 = M.cum[R] >> (15 - R); p0 < (1u << R); p0 += 32) {
+            const uint32_t p = p0 + lane;
+            const bool have = p < (1u << R);
+            uint32_t w = 0;
+            if (have) {
+                const uint32_t lim = (p + 1) << (15 - R);
+                int l = R + 1;
+                while (l < 15 && M.cum[l] < lim) ++l;
+                w = (uint32_t)(l - R);
+            }
+            const uint32_t sz = have ? 1u << w : 0u;
+            uint32_t incl = sz;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += v;
+            }
+            const uint32_t my = off + incl - sz;
+            off += __shfl_sync(0xffffffffu, incl, 31);
+            if (have && my + sz <= CAP) T[__brev(p) >> (32 - R)] = (uint32_t)R | T_SUB | w << 8 | my << 16;
+        }
+        if (off > CAP) return false;
+    }
+    __syncwarp();
+    for (int s = (int)lane; s < n; s += 32) {
+        const uint32_t l = lens[s];
+        if (!l) continue;
+        const uint32_t rev = __brev(M.first[l] + M.rank[s]) >> (32 - l);  // codes are sent MSB first, bits are read LSB first
+        const uint32_t e = IS_LIT ? spec_lit_entry(s) : spec_dist_entry(s);
+        if (l <= (uint32_t)R) {
+            for (uint32_t k = rev; k < (1u << R); k += 1u << l) T[k] = e | l;
+        } else {
+            const uint32_t root = T[rev & ((1u << R) - 1u)], w = (root >> 8) & 15u, off = root >> 16;
+            for (uint32_t k = rev >> R; k < (1u << w); k += 1u << (l - R)) T[off + k] = e | (l - R);
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+enum { SP_OK = 0, SP_END = 1, SP_BAD = 2 };
+struct Span {
+    uint32_t exit, nbytes, ntok;
+    int status;  // SP_OK: left the range at `exit`; SP_END: end-of-block code consumed, `exit` behind it; SP_BAD: invalid code
+};
+
+// One lane decodes tokens from bit `bp` until its position reaches `bound` (tested between tokens). EMIT: the tokens are appended
+// to tk[] (bit 31 literal, byte in bits 0-7; else length in bits 0-8, distance in bits 9-24); otherwise only counted. Bit
+// positions count from the word wbase.
+template <bool EMIT>
+__device__ __forceinline__ void spec_decode(const uint32_t *__restrict__ wbase, const uint32_t *lit, const uint32_t *dtab, uint32_t bp,
+                                            const uint32_t bound, Span &r, uint32_t *tk)
+{
+    uint32_t wi = bp >> 5, sh = bp & 31u;
+    uint32_t w0 = __ldg(wbase + wi), w1 = __ldg(wbase + wi + 1), w2 = __ldg(wbase + wi + 2), w3 = __ldg(wbase + wi + 3);
+    uint32_t nb = 0, nt = 0;
+    int status = SP_OK;
+    // (no break / early exit: the loop has ONE way out, behind which the compiler reconverges the warp - with early exits the
+    // lanes stayed split into groups for the rest of the block and every later shuffle took the divergent slow path)
+    while (bp < bound && status == SP_OK) {
+        // 64 bits of the stream: a literal/length code with its extra bits (<= 20) and a distance code with its extra bits
+        // (<= 28) both fit
+        const uint32_t w = __funnelshift_r(w0, w1, sh), whi = __funnelshift_r(w1, w2, sh);
+        uint32_t e = lit[w & ((1u << LIT_ROOT) - 1u)];
+        uint32_t used = e & 31u;
+        if (e & T_SUB) {
+            e = lit[(e >> 16) + ((w >> LIT_ROOT) & ((1u << ((e >> 8) & 15u)) - 1u))];
+            used = LIT_ROOT + (e & 31u);
+        }
+        if (e & T_LIT) {
+            if (EMIT) tk[nt] = 0x80000000u | (e >> 16);
+            nb += 1, nt += 1;
+        } else if (e == 0 || (e & (T_END | T_BAD))) {
+            status = (e & T_END) ? SP_END : SP_BAD;
+            if (!(e & T_END)) used = 0;
+        } else {
+            const uint32_t x = (e >> 8) & 15u, len = (e >> 16) + ((w >> used) & ((1u << x) - 1u));
+            used += x;
+            const uint32_t v = __funnelshift_r(w, whi, used);
+            uint32_t d = dtab[v & ((1u << DIST_ROOT) - 1u)];
+            uint32_t used2 = d & 31u;
+            if (d & T_SUB) {
+                d = dtab[(d >> 16) + ((v >> DIST_ROOT) & ((1u << ((d >> 8) & 15u)) - 1u))];
+                used2 = DIST_ROOT + (d & 31u);
+            }
+            if (d == 0 || (d & T_BAD)) {
+                status = SP_BAD, used = 0;
+            } else {
+                const uint32_t x2 = (d >> 8) & 15u, dist = (d >> 16) + ((v >> used2) & ((1u << x2) - 1u));
+                used += used2 + x2;
+                if (EMIT) tk[nt] = len | dist << 9;
+                nb += len, nt += 1;
+            }
+        }
+        bp += used, sh += used;
+        if (sh >= 32) {
+            sh -= 32, ++wi;
+            w0 = w1, w1 = w2, w2 = w3, w3 = __ldg(wbase + wi + 3);
+        }
+        if (sh >= 32) {
+            sh -= 32, ++wi;
+            w0 = w1, w1 = w2, w2 = w3, w3 = __ldg(wbase + wi + 3);
+        }
+    }
+    r.exit = bp, r.nbytes = nb, r.ntok = nt, r.status = status;
+}
+
+// Scratch slots for the token lists: one per RESIDENT warp of this kernel, whatever launch or stream it belongs to. A warp
+// claims a free bit (starting at its SM's word, where one is free by construction) and gives it back at the end.
+// (Warp-uniform control flow: lane 0 does the atomics, every lane runs the loop. With the loop inside `if (lane == 0)` the warp
+// came out of it split into {lane 0} and {the others} and stayed split for the whole block - every shuffle took the divergent
+// slow path and every instruction issued twice; profiles/r2_inflate.md.)
+__device__ uint32_t slot_claim(uint32_t *bitmap, uint32_t n_words, uint32_t lane)
+{
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    uint32_t w = smid % n_words;
+    for (;;) {
+        uint32_t got = 0xffffffffu;
+        if (lane == 0) {
+            const uint32_t cur = atomicOr(bitmap + w, 0u);
+            if (~cur) {
+                const uint32_t bit = 1u << (__ffs(~cur) - 1);
+                if (!(atomicOr(bitmap + w, bit) & bit)) got = w * 32 + (__ffs(bit) - 1);
+            } else
+                w = (w + 1) % n_words;  // (a lost race retries the same word)
+        }
+        got = __shfl_sync(0xffffffffu, got, 0);
+        if (got != 0xffffffffu) return got;
+    }
+}
+}  // namespace
+
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(SPEC_WARPS * 32, MIN_CTAS)
+    inflate_bgzf_spec(const uint8_t *__restrict__ file, const InflateBlock *__restrict__ blocks, uint32_t n_blocks, uint8_t *__restrict__ out,
+                      uint32_t *__restrict__ error, uint32_t *slot_bitmap, uint32_t slot_words, uint32_t slots_per_sm, uint32_t *slot_mem)
+{
+    __shared__ SpecMem mem[SPEC_WARPS];
+    const uint32_t lane = threadIdx.x & 31, full = 0xffffffffu;
+    const uint32_t b = blockIdx.x * SPEC_WARPS + (threadIdx.x >> 5);
+    if (b >= n_blocks) return;
+    SpecMem &M = mem[threadIdx.x >> 5];
+    const InflateBlock blk = blocks[b];
+    uint8_t *dst = out + blk.uoff;
+    const uint32_t *wbase = (const uint32_t *)((uintptr_t)(file + blk.coff) & ~(uintptr_t)3);  // bit positions count from here
+    const uint32_t end = (uint32_t)((uintptr_t)(file + blk.coff) & 3) * 8 + blk.clen * 8;      // end of the deflate payload
+    const uint32_t slot = slot_claim(slot_bitmap, slot_words, lane);
+    uint32_t *list = slot_mem + ((size_t)(slot >> 5) * slots_per_sm + (slot & 31)) * TOK_CAP;
+    BitReader br;
+    br.init(file + blk.coff);  // (lane 0's copy reads the block headers)
+    uint32_t pos = 0, bitpos = 0;
+    bool bad = blk.ulen > 65536u;
+    while (!bad) {
+        uint32_t hdr = 0;
+        if (lane == 0) hdr = br.bits(3);
+        hdr = __shfl_sync(full, hdr, 0);
+        const uint32_t final_block = hdr & 1, type = hdr >> 1;
+        if (type == 0) {  // stored
+            uint32_t len = 0, nlen = 0, at = 0;
+            if (lane == 0) {
+                br.align_byte();
+                len = br.bits(16), nlen = br.bits(16);
+                at = br.bit_offset(wbase);
+            }
+            len = __shfl_sync(full, len, 0), nlen = __shfl_sync(full, nlen, 0), at = __shfl_sync(full, at, 0);
+            if ((len ^ nlen) != 0xffffu || at + len * 8 > end || pos + len > blk.ulen) {
+                bad = true;
+                break;
+            }
+            const uint8_t *src = (const uint8_t *)wbase + (at >> 3);
+            for (uint32_t i = lane; i < len; i += 32) dst[pos + i] = src[i];
+            pos += len;
+            if (lane == 0) br.init(src + len);
+            if (final_block) break;
+            continue;
+        }
+        if (type == 3) {
+            bad = true;
+            break;
+        }
+        int n_lit = 288, n_dist = 32, ok = 1;
+        if (type == 1) {  // fixed Huffman codes (RFC 1951 3.2.6); 286, 287 and 30, 31 take part in the code but are invalid
+            for (int i = lane; i < 288; i += 32) M.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+            M.lens[288 + lane] = 5;
+        } else {  // dynamic: code lengths are themselves Huffman coded (3.2.7), decoded serially by lane 0
+            if (lane == 0) {
+                n_lit = (int)br.bits(5) + 257;
+                n_dist = (int)br.bits(5) + 1;
+                const int n_cl = (int)br.bits(4) + 4;
+                uint8_t cl[19];
+                for (int i = 0; i < 19; ++i) cl[i] = 0;
+                for (int i = 0; i < n_cl; ++i) cl[c_cl_order[i]] = (uint8_t)br.bits(3);
+                for (int i = 0; i < 128; ++i) M.cl_fast[i] = 0;
+                uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, next[8];
+                for (int i = 0; i < 19; ++i) cnt[cl[i]]++;
+                cnt[0] = 0;
+                uint32_t c = 0;
+                next[0] = 0;
+                for (int l = 1; l < 8; ++l) {
+                    c = (c + cnt[l - 1]) << 1;
+                    next[l] = c;
+                }
+                for (int sy = 0; sy < 19; ++sy) {
+                    const int l = cl[sy];
+                    if (!l) continue;
+                    const uint32_t rev = __brev(next[l]++) >> (32 - l);
+                    for (uint32_t k = rev; k < 128; k += 1u << l) M.cl_fast[k] = (uint8_t)(l << 5 | sy);
+                }
+                int i = 0;
+                const int total = n_lit + n_dist;
+                if (n_lit > 286 || n_dist > 30) ok = 0;
+                while (ok && i < total) {
+                    const uint8_t e = M.cl_fast[br.peek(7)];
+                    if (!e) {
+                        ok = 0;
+                        break;
+                    }
+                    br.consume(e >> 5);
+                    const int sy = e & 31;
+                    if (sy < 16) M.lens[i++] = (uint8_t)sy;
+                    else {
+                        int rep, v = 0;
+                        if (sy == 16) {
+                            if (i == 0) {
+                                ok = 0;
+                                break;
+                            }
+                            v = M.lens[i - 1];
+                            rep = 3 + (int)br.bits(2);
+                        } else if (sy == 17) rep = 3 + (int)br.bits(3);
+                        else rep = 11 + (int)br.bits(7);
+                        if (i + rep > total) {
+                            ok = 0;
+                            break;
+                        }
+                        while (rep--) M.lens[i++] = (uint8_t)v;
+                    }
+                }
+                if (ok && M.lens[256] == 0) ok = 0;  // no end-of-block code
+            }
+            ok = __shfl_sync(full, ok, 0);
+            n_lit = __shfl_sync(full, n_lit, 0), n_dist = __shfl_sync(full, n_dist, 0);
+            if (!ok) {
+                bad = true;
+                break;
+            }
+            __syncwarp();
+            const uint8_t dl = (int)lane < n_dist ? M.lens[n_lit + lane] : (uint8_t)0;  // the distance lengths follow directly
+            __syncwarp();
+            M.lens[288 + lane] = dl;
+            for (int i = n_lit + (int)lane; i < 288; i += 32) M.lens[i] = 0;
+        }
+        __syncwarp();
+        if (!spec_build<true>(M, M.lens, n_lit, M.lit, lane) || !spec_build<false>(M, M.lens + 288, n_dist, M.dist, lane)) {
+            bad = true;
+            break;
+        }
+        if (lane == 0) bitpos = br.bit_offset(wbase);
+        bitpos = __shfl_sync(full, bitpos, 0);
+        if (bitpos >= end) {
+            bad = true;
+            break;
+        }
+        // ---- speculative passes ----
+        const uint32_t start = bitpos, span = max((end - start + 31u) / 32u, (uint32_t)MIN_SPAN_BITS);
+        const uint32_t my_hi = min(end, start + (lane + 1) * span);
+        uint32_t entry = min(end, start + lane * span);
+        bool valid = lane == 0 || entry < end;
+        Span sp;
+        // (every lane makes every call - a lane that has nothing to decode passes an empty range - so that the warp stays
+        // converged: lanes skipping a call ran ahead into the next shuffle and never rejoined the others)
+        spec_decode<false>(wbase, M.lit, M.dist, entry, valid ? my_hi : 0u, sp, nullptr);
+        for (;;) {
+            const uint32_t p_exit = __shfl_up_sync(full, sp.exit, 1);
+            const int p_status = __shfl_up_sync(full, sp.status, 1);
+            const bool p_valid = __shfl_up_sync(full, (int)valid, 1) != 0;
+            const bool now_valid = lane == 0 || (p_valid && p_status == SP_OK);
+            const bool redo = lane != 0 && now_valid && (!valid || entry != p_exit);
+            if (!__any_sync(full, redo || (valid && !now_valid))) break;
+            valid = now_valid;
+            if (redo) entry = p_exit;
+            Span again;
+            spec_decode<false>(wbase, M.lit, M.dist, entry, redo ? my_hi : 0u, again, nullptr);
+            if (redo) sp = again;
+        }
+        // exactly one valid lane saw the end-of-block code (it invalidates its successors); a bad code on a valid lane is real
+        const uint32_t endm = __ballot_sync(full, valid && sp.status == SP_END), badm = __ballot_sync(full, valid && sp.status == SP_BAD);
+        if (badm || !endm) {
+            bad = true;
+            break;
+        }
+        bitpos = __shfl_sync(full, sp.exit, __ffs(endm) - 1);
+        const uint32_t nb = valid ? sp.nbytes : 0u, nt = valid ? sp.ntok : 0u;
+        uint32_t ib = nb, it = nt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t vb = __shfl_up_sync(full, ib, d), vt = __shfl_up_sync(full, it, d);
+            if (lane >= (uint32_t)d) ib += vb, it += vt;
+        }
+        const uint32_t total_b = __shfl_sync(full, ib, 31);
+        if (total_b > blk.ulen - pos || bitpos > end) {  // (sums of <= 2^19 bits worth of tokens cannot wrap)
+            bad = true;
+            break;
+        }
+        // ---- emission + copy, in segments of lanes whose tokens fit the list (one segment unless the block has > TOK_CAP tokens) ----
+        bool fail = false;
+        for (uint32_t lo = 0; lo < 32;) {
+            const uint32_t t0 = lo ? __shfl_sync(full, it, lo - 1) : 0u, b0 = lo ? __shfl_sync(full, ib, lo - 1) : 0u;
+            const uint32_t hi = lo + __popc(__ballot_sync(full, lane >= lo && it - t0 <= TOK_CAP));  // (it is monotone: a prefix of the lanes)
+            {
+                Span again;
+                spec_decode<true>(wbase, M.lit, M.dist, entry, valid && lane >= lo && lane < hi ? my_hi : 0u, again, list + (it - nt - t0));
+            }
+            const uint32_t seg_tokens = __shfl_sync(full, it, hi - 1) - t0;
+            lo = hi;
+            __syncwarp();  // the token list is visible to the whole warp
+            uint32_t cur = pos + b0;  // output position of the batch inside the block
+            uint32_t tnext = lane < seg_tokens ? list[lane] : 0u;
+            for (uint32_t base = 0; base < seg_tokens;) {
+                const uint32_t t = tnext;
+                const bool have = base + lane < seg_tokens, is_lit = t >> 31;
+                const uint32_t n = have ? (is_lit ? 1u : (t & 511u)) : 0u, dist = (t >> 9) & 0xffffu;
+                uint32_t incl = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(full, incl, d);
+                    if (lane >= (uint32_t)d) incl += v;
+                }
+                const uint32_t ntake = __popc(__ballot_sync(full, have && incl <= SPAN));  // >= 1: a token is at most 258 bytes
+                const uint32_t total = __shfl_sync(full, incl, ntake - 1);
+                base += ntake;
+                tnext = base + lane < seg_tokens ? list[base + lane] : 0u;  // (in flight while this batch is assembled)
+                const bool mine = lane < ntake, is_match = mine && !is_lit;
+                const uint32_t o = incl - n;
+                const int s = (int)o - (int)dist;  // source position relative to the batch
+                if (is_match && (int)cur + s < 0) fail = true;
+                if (mine && is_lit) M.span[o] = (uint8_t)t;
+                // a source in front of the batch is complete in global memory (earlier batches are written out)
+                const bool far = is_match && !fail && s + (int)n <= 0;
+                if (far && n <= COOP_LEN) {  // one lane per match; all loads are issued before the first store waits for one
+                    const uint8_t *src = dst + cur + s;
+                    uint8_t v[COOP_LEN];
+#pragma unroll
+                    for (uint32_t k = 0; k < COOP_LEN; ++k)
+                        if (k < n) v[k] = src[k];
+#pragma unroll
+                    for (uint32_t k = 0; k < COOP_LEN; ++k)
+                        if (k < n) M.span[o + k] = v[k];
+                }
+                uint32_t far_long = __ballot_sync(full, far && n > COOP_LEN);
+                while (far_long) {  // whole warp per long match; nothing to wait for between them
+                    const int tl = __ffs(far_long) - 1;
+                    far_long &= far_long - 1;
+                    const uint32_t o_t = __shfl_sync(full, o, tl), n_t = __shfl_sync(full, n, tl);
+                    const uint8_t *src = dst + cur + __shfl_sync(full, s, tl);
+                    for (uint32_t i0 = 0; i0 < n_t; i0 += 32)  // (uniform trip count, predicated body)
+                        if (i0 + lane < n_t) M.span[o_t + i0 + lane] = src[i0 + lane];
+                }
+                uint32_t pending = __ballot_sync(full, is_match && !fail && !far);
+                __syncwarp();
+                while (pending) {  // matches that read this batch's output (or overlap themselves): in stream order, through shared memory
+                    const int tl = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    const uint32_t o_t = __shfl_sync(full, o, tl), n_t = __shfl_sync(full, n, tl), d_t = __shfl_sync(full, dist, tl);
+                    const int s_t = (int)o_t - (int)d_t;
+                    if (d_t >= n_t) {  // (uniform branches, uniform trip counts, predicated bodies)
+                        for (uint32_t i0 = 0; i0 < n_t; i0 += 32) {
+                            const int idx = s_t + (int)(i0 + lane);
+                            if (i0 + lane < n_t) M.span[o_t + i0 + lane] = idx >= 0 ? M.span[idx] : dst[(int)cur + idx];
+                        }
+                    } else {  // overlapping match: the last d_t bytes repeat
+                        for (uint32_t i0 = 0; i0 < n_t; i0 += 32) {
+                            const int idx = s_t + (int)((i0 + lane) % d_t);
+                            if (i0 + lane < n_t) M.span[o_t + i0 + lane] = idx >= 0 ? M.span[idx] : dst[(int)cur + idx];
+                        }
+                    }
+                    __syncwarp();
+                }
+                for (uint32_t i0 = 0; i0 < total; i0 += 32)
+                    if (i0 + lane < total) dst[cur + i0 + lane] = M.span[i0 + lane];
+                cur += total;
+                __syncwarp();  // the next batch reuses the span and may read what was just written
+            }
+        }
+        if (__any_sync(full, fail)) {
+            bad = true;
+            break;
+        }
+        pos += total_b;
+        if (final_block) break;
+        if (lane == 0) br.init_at(wbase, bitpos);  // back to the register reader for the next block header
+    }
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        atomicAnd(slot_bitmap + (slot >> 5), ~(1u << (slot & 31)));
+        if (bad || pos != blk.ulen) atomicOr(error, 1u);
+    }
+}
+
+
+// Kernel selection: the speculative kernel by default; SEEKSV_B200_INFLATE=serial selects the one-decoding-lane form above
+// (SEEKSV_B200_INFLATE_GROUP=16: its two-blocks-per-warp variant) - kept for comparison, same results (tests run both).
+static int inflate_mode()  // (read per launch, so that one process can compare the kernels)
+{
+    const char *e = getenv("SEEKSV_B200_INFLATE");
+    if (!e || strcmp(e, "serial") != 0) return 0;
+    const char *g = getenv("SEEKSV_B200_INFLATE_GROUP");
+    return g && atoi(g) == 16 ? 2 : 1;
+}
+
+constexpr int SPEC_MIN_CTAS = 6;  // 6 CTAs of 4 warps per SM: <= 85 registers per thread, 6 x 33 KB of shared memory
+static int spec_carveout()       // share of the L1 / shared-memory array given to shared memory (percent)
+{
+    const char *e = getenv("SEEKSV_B200_INFLATE_CARVEOUT");
+    return e ? atoi(e) : 100;
+}
+
+// the token-list slots of the speculative kernel: bitmap words (one per SM, bits >= slots-per-SM preset) + the lists
+static int spec_scratch(svb_ctx *ctx)
+{
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (ctx->inflate_scratch) return 0;
+    int ctas = 0;
+    CK(cudaFuncSetAttribute(inflate_bgzf_spec<SPEC_MIN_CTAS>, cudaFuncAttributePreferredSharedMemoryCarveout, spec_carveout()));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, inflate_bgzf_spec<SPEC_MIN_CTAS>, SPEC_WARPS * 32, 0));
+    const uint32_t per_sm = (uint32_t)std::min(32, std::max(1, ctas) * SPEC_WARPS), words = (uint32_t)ctx->sm_count;
+    const size_t head = ((size_t)words * 4 + 255) & ~(size_t)255, bytes = head + (size_t)words * per_sm * TOK_CAP * sizeof(uint32_t);
+    uint8_t *p = nullptr;
+    if (cudaMalloc((void **)&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate %llu bytes of inflate scratch", (unsigned long long)bytes);
+    }
+    std::vector<uint32_t> init(words, per_sm >= 32 ? 0u : ~0u << per_sm);
+    CK(cudaMemcpy(p, init.data(), (size_t)words * 4, cudaMemcpyHostToDevice));
+    ctx->inflate_scratch = p, ctx->inflate_slot_words = words, ctx->inflate_slots_per_sm = per_sm, ctx->inflate_scratch_head = (uint32_t)head;
+    return 0;
+}
+
+static int launch_inflate(svb_ctx *ctx, cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out,
+                          uint32_t *d_err)
+{
+    const int mode = inflate_mode();
+    if (mode == 0) {
+        CKR(spec_scratch(ctx));
+        const uint32_t grid = (n_blocks + SPEC_WARPS - 1) / SPEC_WARPS;
+        inflate_bgzf_spec<SPEC_MIN_CTAS><<<grid, SPEC_WARPS * 32, 0, s>>>(d_file, (const InflateBlock *)d_blocks, n_blocks, d_out, d_err,
+                                                                           (uint32_t *)ctx->inflate_scratch, ctx->inflate_slot_words,
+                                                                           ctx->inflate_slots_per_sm,
+                                                                           (uint32_t *)(ctx->inflate_scratch + ctx->inflate_scratch_head));
+        return 0;
+    }
     const uint32_t grid = (n_blocks + BLOCKS_PER_CTA - 1) / BLOCKS_PER_CTA;
-    if (group == 16) inflate_bgzf<16><<<grid, BLOCKS_PER_CTA * 16, 0, s>>>(d_file, (const InflateBlock *)d_blocks, n_blocks, d_out, d_err);
+    if (mode == 2) inflate_bgzf<16><<<grid, BLOCKS_PER_CTA * 16, 0, s>>>(d_file, (const InflateBlock *)d_blocks, n_blocks, d_out, d_err);
     else inflate_bgzf<32><<<grid, BLOCKS_PER_CTA * 32, 0, s>>>(d_file, (const InflateBlock *)d_blocks, n_blocks, d_out, d_err);
+    return 0;
 }
 
 // asynchronous launch over a range of blocks; *d_err is OR-ed with 1 when a block is corrupt
-int inflate_launch(cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err)
+int inflate_launch(svb_ctx *ctx, cudaStream_t s, const uint8_t *d_file, const void *d_blocks, uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err)
 {
     if (!n_blocks) return 0;
-    launch_inflate(s, d_file, d_blocks, n_blocks, d_out, d_err);
+    CKR(launch_inflate(ctx, s, d_file, d_blocks, n_blocks, d_out, d_err));
     return cudaGetLastError() == cudaSuccess ? 0 : SVB_ERR_CUDA;
 }
 
@@ -467,7 +1014,7 @@ int inflate_on_device(svb_ctx *ctx, const uint8_t *d_file, const void *d_blocks,
     CK(cudaMemsetAsync(err.p, 0, 4, s));
     if (n_blocks) {
         ProfScope ps(ctx, "inflate_bgzf", out_bytes);
-        launch_inflate(s, d_file, d_blocks, n_blocks, d_out, err.p);
+        CKR(launch_inflate(ctx, s, d_file, d_blocks, n_blocks, d_out, err.p));
     }
     uint32_t h = 0;
     CK(cudaMemcpyAsync(&h, err.p, 4, cudaMemcpyDeviceToHost, s));

@@ -245,11 +245,9 @@ def test_synthetic_cli_vs_reference_binary(genome, extra, tmp_path):
             assert outs[("b200", sample, what)] == v, (sample, what)
 
 
-def test_device_inflate_matches_zlib(ctx, tmp_path, monkeypatch):
-    """BGZF inflate on the device (one warp per block) == zlib, for dynamic / fixed / stored deflate blocks and
-    for the host-thread inflate path (SEEKSV_B200_HOST_INFLATE=1)."""
+def _deflate_cases():
     import random
-    import seeksv_b200
+    import zlib
     from oracle import bamio
     rng = random.Random(11)
     raw = bamio.read_bgzf(_bam("micro", "tumor"))
@@ -258,26 +256,77 @@ def test_device_inflate_matches_zlib(ctx, tmp_path, monkeypatch):
                                          ("fixed", 6, 4, 0xff00), ("tiny_blocks", 6, 0, 777), ("huffman_only", 6, 2, 0x8000),
                                          ("rle", 6, 3, 0xfff0)):
         cases[name] = bamio.bgzf_compress(raw, level, block, strategy)
-    # incompressible + highly repetitive payload after a valid BAM (long matches, dist < len copies, long codes)
+    # incompressible + highly repetitive payload after a valid BAM (long matches, dist < len copies, long codes, several deflate
+    # blocks per BGZF block, a single-code distance alphabet)
     noise = bytes(rng.randrange(256) for _ in range(70000)) + b"A" * 100000 + bytes(range(256)) * 300
     cases["mixed"] = bamio.bgzf_compress(raw + noise, 6)
+    # skewed symbol statistics: literal/length codes of up to 15 bits (second-level tables), periodic data that a decoder
+    # started at a wrong bit position does not resynchronise on (many speculation rounds)
+    skew = bytearray()
+    for k in range(60000):
+        r = rng.random()
+        skew.append(0 if r < 0.5 else 1 if r < 0.75 else 2 if r < 0.87 else rng.randrange(256))
+    cases["skewed"] = bamio.bgzf_compress(bytes(skew) + bytes([7, 7, 9]) * 40000 + bytes(rng.randrange(4) for _ in range(50000)), 9)
+    return raw, cases
+
+
+def test_device_inflate_matches_zlib(ctx, tmp_path, monkeypatch):
+    """BGZF inflate on the device == zlib, for dynamic / fixed / stored deflate blocks, with the speculative kernel (default),
+    the one-decoding-lane kernel (SEEKSV_B200_INFLATE=serial) and the host-thread inflate path (SEEKSV_B200_HOST_INFLATE=1)."""
+    import seeksv_b200
+    from seeksv_b200.lib import inflate_bgzf
+    raw, cases = _deflate_cases()
     for name, img in cases.items():
         want = __import__("gzip").decompress(img)
-        for host in ("0", "1"):
+        for host, kernel in (("0", ""), ("0", "serial"), ("1", "")):
             monkeypatch.setenv("SEEKSV_B200_HOST_INFLATE", host)
-            if name == "mixed":
+            monkeypatch.setenv("SEEKSV_B200_INFLATE", kernel)
+            if name in ("mixed", "skewed"):
                 # not a well-formed record chain: the first pass that walks it must fail cleanly; the inflate kernel alone
                 # must not
-                bad = seeksv_b200.Bam.from_bgzf(ctx, img)
-                with pytest.raises(seeksv_b200.SvbError):
-                    bad.getclip()
-                bad.close()
-                from seeksv_b200.lib import inflate_bgzf
-                assert inflate_bgzf(ctx, img) == want
+                if name == "mixed":
+                    bad = seeksv_b200.Bam.from_bgzf(ctx, img)
+                    with pytest.raises(seeksv_b200.SvbError):
+                        bad.getclip()
+                    bad.close()
+                assert inflate_bgzf(ctx, img) == want, (name, kernel)
                 continue
             bam = seeksv_b200.Bam.from_bgzf(ctx, img)
-            assert bam.copy_stream() == want, (name, host)
+            assert bam.copy_stream() == want, (name, host, kernel)
             bam.close()
+
+
+def test_device_inflate_refuses_corrupt_streams(ctx, monkeypatch):
+    """A damaged deflate payload must come back as SVB_ERR_FORMAT (or, when the damage happens to decode, as the right number of
+    bytes) - never as a fault: the kernel bounds every read by the block's payload and checks LEN against NLEN."""
+    import random
+    import struct
+    import seeksv_b200
+    from seeksv_b200.lib import inflate_bgzf
+    from oracle import bamio
+    raw, cases = _deflate_cases()
+    rng = random.Random(5)
+    for kernel in ("", "serial"):
+        monkeypatch.setenv("SEEKSV_B200_INFLATE", kernel)
+        for name in ("level1", "level0_stored", "fixed", "skewed"):
+            img = bytearray(cases[name])
+            bsize = struct.unpack_from("<H", img, 16)[0] + 1
+            for trial in range(6):
+                bad = bytearray(img)
+                if trial == 0:      # zeroed payload: endless empty stored blocks
+                    bad[18:bsize - 8] = bytes(bsize - 26)
+                elif trial == 1:    # all ones: reserved block type / invalid codes
+                    bad[18:bsize - 8] = b"\xff" * (bsize - 26)
+                else:               # a few random bytes damaged inside the first block's payload
+                    for _ in range(trial):
+                        bad[18 + rng.randrange(bsize - 26)] ^= 1 << rng.randrange(8)
+                try:
+                    got = inflate_bgzf(ctx, bytes(bad))
+                    assert len(got) == len(__import__("gzip").decompress(bytes(img)))
+                except seeksv_b200.SvbError:
+                    pass
+        # the context is still usable
+        assert inflate_bgzf(ctx, cases["level1"]) == raw
 
 
 def test_depth_accounting_closed_form_equals_literal_walk(tmp_path, monkeypatch):

@@ -8,7 +8,7 @@ bam = W + "/c2_chr21_46709983.bam"
 image = open(bam, "rb").read()
 ctx = S.Context(0)
 ctx.prof(True)
-for it in range(3):
+for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     ctx.prof_reset()
     t = time.perf_counter()
     out = S.lib.inflate_bgzf(ctx, image)
