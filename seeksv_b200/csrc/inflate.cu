@@ -481,7 +481,7 @@ struct SpecMem {
             uint8_t cl_fast[128];  // code-length alphabet: (len << 5) | symbol, 7-bit lookup
             uint16_t rank[288];    // rank of a symbol among the symbols of its code length
         };
-        uint8_t span[SPAN];        // copy phase: the output bytes of the current token batch
+        alignas(16) uint8_t span[SPAN + 16];  // copy phase: the output bytes of the current token batch (from index address & 3)
     };
     uint32_t cnt[16], first[16], cum[16];
 };
@@ -871,53 +871,78 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, MIN_CTAS)
                 base += ntake;
                 tnext = base + lane < seg_tokens ? list[base + lane] : 0u;  // (in flight while this batch is assembled)
                 const bool mine = lane < ntake, is_match = mine && !is_lit;
-                const uint32_t o = incl - n;
-                const int s = (int)o - (int)dist;  // source position relative to the batch
-                if (is_match && (int)cur + s < 0) fail = true;
+                // Span index j <-> global byte g[j], with g 4-byte aligned: the batch starts at index al = address & 3, so that
+                // whole words of the span are whole words of the output (word loads of far sources, word stores of the flush).
+                uint8_t *g = dst + cur;
+                const uint32_t al = (uint32_t)(uintptr_t)g & 3u;
+                g -= al;
+                const uint32_t o = al + incl - n;
+                const int s = (int)o - (int)dist;  // source, as a span index (negative or < al: in front of the batch)
+                if (is_match && (int)(cur - al) + s < 0) fail = true;
                 if (mine && is_lit) M.span[o] = (uint8_t)t;
                 // a source in front of the batch is complete in global memory (earlier batches are written out)
-                const bool far = is_match && !fail && s + (int)n <= 0;
-                if (far && n <= COOP_LEN) {  // one lane per match; all loads are issued before the first store waits for one
-                    const uint8_t *src = dst + cur + s;
-                    uint8_t v[COOP_LEN];
+                const bool far = is_match && !fail && s + (int)n <= (int)al;
+                if (far && n <= COOP_LEN) {
+                    // one lane per match: <= 5 aligned words cover the <= 16 source bytes (reading a few bytes around the source
+                    // is harmless: they lie in the output buffer or its padding); all loads are issued before the first use
+                    const uint32_t *wp = (const uint32_t *)((uintptr_t)(g + s) & ~(uintptr_t)3);
+                    const uint32_t sa = (uint32_t)(uintptr_t)(g + s) & 3u, need = sa + n;
+                    uint32_t w[5];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) w[k] = (uint32_t)k * 4 < need ? wp[k] : 0u;
+                    uint32_t v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = __funnelshift_r(w[k], w[k + 1], sa * 8);
 #pragma unroll
                     for (uint32_t k = 0; k < COOP_LEN; ++k)
-                        if (k < n) v[k] = src[k];
-#pragma unroll
-                    for (uint32_t k = 0; k < COOP_LEN; ++k)
-                        if (k < n) M.span[o + k] = v[k];
+                        if (k < n) M.span[o + k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));
                 }
                 uint32_t far_long = __ballot_sync(full, far && n > COOP_LEN);
                 while (far_long) {  // whole warp per long match; nothing to wait for between them
                     const int tl = __ffs(far_long) - 1;
                     far_long &= far_long - 1;
                     const uint32_t o_t = __shfl_sync(full, o, tl), n_t = __shfl_sync(full, n, tl);
-                    const uint8_t *src = dst + cur + __shfl_sync(full, s, tl);
-                    for (uint32_t i0 = 0; i0 < n_t; i0 += 32)  // (uniform trip count, predicated body)
-                        if (i0 + lane < n_t) M.span[o_t + i0 + lane] = src[i0 + lane];
+                    const uint8_t *src = g + __shfl_sync(full, s, tl) + lane;
+                    uint8_t *to = M.span + o_t + lane;
+#pragma unroll 1
+                    for (uint32_t i = lane; i < n_t + lane; i += 32, src += 32, to += 32)  // (uniform trip count, predicated body)
+                        if (i < n_t) *to = *src;
                 }
                 uint32_t pending = __ballot_sync(full, is_match && !fail && !far);
                 __syncwarp();
                 while (pending) {  // matches that read this batch's output (or overlap themselves): in stream order, through shared memory
                     const int tl = __ffs(pending) - 1;
                     pending &= pending - 1;
-                    const uint32_t o_t = __shfl_sync(full, o, tl), n_t = __shfl_sync(full, n, tl), d_t = __shfl_sync(full, dist, tl);
+                    const uint32_t on = __shfl_sync(full, o | n << 16, tl), d_t = __shfl_sync(full, dist, tl);
+                    const uint32_t o_t = on & 0xffffu, n_t = on >> 16;
                     const int s_t = (int)o_t - (int)d_t;
-                    if (d_t >= n_t) {  // (uniform branches, uniform trip counts, predicated bodies)
-                        for (uint32_t i0 = 0; i0 < n_t; i0 += 32) {
+                    if (s_t >= (int)al && n_t <= 32 && d_t >= n_t) {  // the usual case: source inside the span, one step (uniform branch)
+                        if (lane < n_t) M.span[o_t + lane] = M.span[s_t + lane];
+                    } else if (d_t >= n_t) {
+#pragma unroll 1
+                        for (uint32_t i0 = 0; i0 < n_t; i0 += 32) {  // (uniform trip count, predicated body)
                             const int idx = s_t + (int)(i0 + lane);
-                            if (i0 + lane < n_t) M.span[o_t + i0 + lane] = idx >= 0 ? M.span[idx] : dst[(int)cur + idx];
+                            if (i0 + lane < n_t) M.span[o_t + i0 + lane] = idx >= (int)al ? M.span[idx] : g[idx];
                         }
                     } else {  // overlapping match: the last d_t bytes repeat
+#pragma unroll 1
                         for (uint32_t i0 = 0; i0 < n_t; i0 += 32) {
                             const int idx = s_t + (int)((i0 + lane) % d_t);
-                            if (i0 + lane < n_t) M.span[o_t + i0 + lane] = idx >= 0 ? M.span[idx] : dst[(int)cur + idx];
+                            if (i0 + lane < n_t) M.span[o_t + i0 + lane] = idx >= (int)al ? M.span[idx] : g[idx];
                         }
                     }
                     __syncwarp();
                 }
-                for (uint32_t i0 = 0; i0 < total; i0 += 32)
-                    if (i0 + lane < total) dst[cur + i0 + lane] = M.span[i0 + lane];
+                {   // write the batch out: whole words, the <= 3 bytes at either end one by one
+                    const uint32_t e = al + total;
+#pragma unroll 1
+                    for (uint32_t m0 = 0; m0 * 4 < e; m0 += 32) {
+                        const uint32_t m = m0 + lane, b0 = m * 4, b1 = b0 + 4;
+                        if (b0 >= al && b1 <= e) ((uint32_t *)g)[m] = ((const uint32_t *)M.span)[m];
+                        else if (b0 < e && b1 > al)
+                            for (uint32_t j = max(b0, al); j < min(b1, e); ++j) g[j] = M.span[j];
+                    }
+                }
                 cur += total;
                 __syncwarp();  // the next batch reuses the span and may read what was just written
             }

@@ -16,6 +16,6 @@ for cfg in "SEEKSV_B200_INFLATE_CARVEOUT=100"; do
   env $cfg timeout 300 python tools/inflate_bench.py >> gpurun_out/r2_inflate_bench.log 2>&1
 done
 cat gpurun_out/r2_inflate_bench.log
-true
-true
-bash tools/gpu_ncu_inflate.sh r2_inflate_spec_v4
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -x -q -m gpu -k "inflate_refuses or inflate_matches" > gpurun_out/r2_inflate_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/r2_inflate_memcheck.log
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -x -q -m gpu -k "inflate_refuses or inflate_matches" > gpurun_out/r2_inflate_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/r2_inflate_memcheck.log
+bash tools/gpu_ncu_inflate.sh r2_inflate_spec_v5
