@@ -482,6 +482,7 @@ struct SpecMem {
             uint16_t rank[288];    // rank of a symbol among the symbols of its code length
         };
         alignas(16) uint8_t span[SPAN + 16];  // copy phase: the output bytes of the current token batch (from index address & 3)
+        uint32_t ring[8 * 32];               // decode passes: the lanes' input rings
     };
     uint32_t cnt[16], first[16], cum[16];
 };
@@ -586,12 +587,26 @@ struct Span {
 // One lane decodes tokens from bit `bp` until its position reaches `bound` (tested between tokens). EMIT: the tokens are appended
 // to tk[] (bit 31 literal, byte in bits 0-7; else length in bits 0-8, distance in bits 9-24); otherwise only counted. Bit
 // positions count from the word wbase.
+// Input words reach the lane through a private 8-word ring in shared memory filled by cp.async: a word is requested five
+// word-crossings (~11 tokens) before its first use and NO register waits for it in between. (Read-ahead in registers does not
+// work: rotating w3 -> w2 -> ... reads the register of a load in flight at the very next crossing, and the loop spent 15-20 % of
+// its time on that scoreboard; profiles/r2_inflate.md.) Layout ring[(word & 7) * 32 + lane]: conflict-free.
+__device__ __forceinline__ void ring_request(uint32_t *ring_lane, const uint32_t *wbase, uint32_t word)
+{
+    const uint32_t sm = (uint32_t)__cvta_generic_to_shared(ring_lane + (word & 7u) * 32u);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\tcp.async.commit_group;" ::"r"(sm), "l"(wbase + word) : "memory");
+}
 template <bool EMIT>
 __device__ __forceinline__ void spec_decode(const uint32_t *__restrict__ wbase, const uint32_t *lit, const uint32_t *dtab, uint32_t bp,
-                                            const uint32_t bound, Span &r, uint32_t *tk)
+                                            const uint32_t bound, Span &r, uint32_t *tk, uint32_t *ring_lane)
 {
     uint32_t wi = bp >> 5, sh = bp & 31u;
-    uint32_t w0 = __ldg(wbase + wi), w1 = __ldg(wbase + wi + 1), w2 = __ldg(wbase + wi + 2), w3 = __ldg(wbase + wi + 3);
+    uint32_t w0 = 0, w1 = 0, w2 = 0;  // the window: words wi, wi + 1, wi + 2
+    if (bp < bound) {
+        w0 = __ldg(wbase + wi), w1 = __ldg(wbase + wi + 1), w2 = __ldg(wbase + wi + 2);
+#pragma unroll
+        for (uint32_t k = 3; k < 8; ++k) ring_request(ring_lane, wbase, wi + k);  // five groups in flight
+    }
     uint32_t nb = 0, nt = 0;
     int status = SP_OK;
     // (no break / early exit: the loop has ONE way out, behind which the compiler reconverges the warp - with early exits the
@@ -632,15 +647,16 @@ __device__ __forceinline__ void spec_decode(const uint32_t *__restrict__ wbase, 
             }
         }
         bp += used, sh += used;
-        if (sh >= 32) {
-            sh -= 32, ++wi;
-            w0 = w1, w1 = w2, w2 = w3, w3 = __ldg(wbase + wi + 3);
-        }
-        if (sh >= 32) {
-            sh -= 32, ++wi;
-            w0 = w1, w1 = w2, w2 = w3, w3 = __ldg(wbase + wi + 3);
-        }
+#pragma unroll
+        for (int twice = 0; twice < 2; ++twice)  // a token has at most 48 bits: up to two word crossings
+            if (sh >= 32) {
+                sh -= 32, ++wi;
+                ring_request(ring_lane, wbase, wi + 7);  // into the slot of word wi - 1
+                asm volatile("cp.async.wait_group 5;" ::: "memory");  // the oldest request - word wi + 2 - has landed
+                w0 = w1, w1 = w2, w2 = ring_lane[((wi + 2) & 7u) * 32u];
+            }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");  // nothing of this call may land in the ring later
     r.exit = bp, r.nbytes = nb, r.ntok = nt, r.status = status;
 }
 
@@ -809,7 +825,7 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, MIN_CTAS)
         Span sp;
         // (every lane makes every call - a lane that has nothing to decode passes an empty range - so that the warp stays
         // converged: lanes skipping a call ran ahead into the next shuffle and never rejoined the others)
-        spec_decode<false>(wbase, M.lit, M.dist, entry, valid ? my_hi : 0u, sp, nullptr);
+        spec_decode<false>(wbase, M.lit, M.dist, entry, valid ? my_hi : 0u, sp, nullptr, M.ring + lane);
         for (;;) {
             const uint32_t p_exit = __shfl_up_sync(full, sp.exit, 1);
             const int p_status = __shfl_up_sync(full, sp.status, 1);
@@ -820,7 +836,7 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, MIN_CTAS)
             valid = now_valid;
             if (redo) entry = p_exit;
             Span again;
-            spec_decode<false>(wbase, M.lit, M.dist, entry, redo ? my_hi : 0u, again, nullptr);
+            spec_decode<false>(wbase, M.lit, M.dist, entry, redo ? my_hi : 0u, again, nullptr, M.ring + lane);
             if (redo) sp = again;
         }
         // exactly one valid lane saw the end-of-block code (it invalidates its successors); a bad code on a valid lane is real
@@ -849,7 +865,7 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, MIN_CTAS)
             const uint32_t hi = lo + __popc(__ballot_sync(full, lane >= lo && it - t0 <= TOK_CAP));  // (it is monotone: a prefix of the lanes)
             {
                 Span again;
-                spec_decode<true>(wbase, M.lit, M.dist, entry, valid && lane >= lo && lane < hi ? my_hi : 0u, again, list + (it - nt - t0));
+                spec_decode<true>(wbase, M.lit, M.dist, entry, valid && lane >= lo && lane < hi ? my_hi : 0u, again, list + (it - nt - t0), M.ring + lane);
             }
             const uint32_t seg_tokens = __shfl_sync(full, it, hi - 1) - t0;
             lo = hi;
@@ -882,20 +898,17 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, MIN_CTAS)
                 if (mine && is_lit) M.span[o] = (uint8_t)t;
                 // a source in front of the batch is complete in global memory (earlier batches are written out)
                 const bool far = is_match && !fail && s + (int)n <= (int)al;
-                if (far && n <= COOP_LEN) {
-                    // one lane per match: <= 5 aligned words cover the <= 16 source bytes (reading a few bytes around the source
-                    // is harmless: they lie in the output buffer or its padding); all loads are issued before the first use
+                // one lane per short match: <= 5 aligned words cover the <= 16 source bytes (reading a few bytes around the source is
+                // harmless: they lie in the output buffer or its padding). The loads are issued here and used after the long matches.
+                const bool far_short = far && n <= COOP_LEN;
+                const uint32_t sa = (uint32_t)(uintptr_t)(g + s) & 3u;
+                uint32_t w[5] = {0, 0, 0, 0, 0};
+                if (far_short) {
                     const uint32_t *wp = (const uint32_t *)((uintptr_t)(g + s) & ~(uintptr_t)3);
-                    const uint32_t sa = (uint32_t)(uintptr_t)(g + s) & 3u, need = sa + n;
-                    uint32_t w[5];
+                    const uint32_t need = sa + n;
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) w[k] = (uint32_t)k * 4 < need ? wp[k] : 0u;
-                    uint32_t v[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) v[k] = __funnelshift_r(w[k], w[k + 1], sa * 8);
-#pragma unroll
-                    for (uint32_t k = 0; k < COOP_LEN; ++k)
-                        if (k < n) M.span[o + k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));
+                    for (int k = 0; k < 5; ++k)
+                        if ((uint32_t)k * 4 < need) w[k] = wp[k];
                 }
                 uint32_t far_long = __ballot_sync(full, far && n > COOP_LEN);
                 while (far_long) {  // whole warp per long match; nothing to wait for between them
@@ -907,6 +920,14 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, MIN_CTAS)
 #pragma unroll 1
                     for (uint32_t i = lane; i < n_t + lane; i += 32, src += 32, to += 32)  // (uniform trip count, predicated body)
                         if (i < n_t) *to = *src;
+                }
+                if (far_short) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = __funnelshift_r(w[k], w[k + 1], sa * 8);
+#pragma unroll
+                    for (uint32_t k = 0; k < COOP_LEN; ++k)
+                        if (k < n) M.span[o + k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));
                 }
                 uint32_t pending = __ballot_sync(full, is_match && !fail && !far);
                 __syncwarp();

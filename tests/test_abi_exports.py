@@ -197,3 +197,20 @@ def test_getsv_reads_the_realigned_clips_as_bam_too(lib, d, s, tmp_path):
     assert r.returncode == 0, r.stderr
     assert read_text(out) == read_text(os.path.join(GOLDEN, d, s + ".n0D.sv"))
     assert r.stdout == read_text(os.path.join(GOLDEN, d, s + ".n0D.stdout"))
+
+
+def test_usage_texts_are_byte_identical_to_the_reference():
+    """the usage texts and exit codes are part of the CLI contract. tests/golden/usage/* holds what the reference
+    binary prints for `seeksv`, `seeksv getclip`, `seeksv getsv`, `seeksv somatic` (oracle/_ref/seeksv, checked live when it is built)."""
+    import subprocess
+    exe = os.path.join(ROOT, "seeksv_b200", "bin", "seeksv")
+    ref = os.path.join(ROOT, "oracle", "_ref", "seeksv")
+    gold = os.path.join(ROOT, "tests", "golden", "usage")
+    for name, argv in (("top", []), ("getclip", ["getclip"]), ("getsv", ["getsv"]), ("somatic", ["somatic"])):
+        r = subprocess.run([exe] + argv, capture_output=True)
+        assert r.stdout == open(os.path.join(gold, name + ".stdout"), "rb").read(), name
+        assert r.stderr == open(os.path.join(gold, name + ".stderr"), "rb").read(), name
+        assert r.returncode == int(open(os.path.join(gold, name + ".rc")).read()), name
+        if os.path.exists(ref):
+            q = subprocess.run([ref] + argv, capture_output=True)
+            assert (q.stdout, q.stderr, q.returncode) == (r.stdout, r.stderr, r.returncode), name

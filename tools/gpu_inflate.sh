@@ -17,5 +17,4 @@ for cfg in "SEEKSV_B200_INFLATE_CARVEOUT=100"; do
 done
 cat gpurun_out/r2_inflate_bench.log
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -x -q -m gpu -k "inflate_refuses or inflate_matches" > gpurun_out/r2_inflate_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/r2_inflate_memcheck.log
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -x -q -m gpu -k "inflate_refuses or inflate_matches" > gpurun_out/r2_inflate_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/r2_inflate_memcheck.log
-bash tools/gpu_ncu_inflate.sh r2_inflate_spec_v5
+bash tools/gpu_ncu_inflate.sh r2_inflate_spec_v7
