@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(256) guess_starts(const uint8_t *__restrict__ 
         if (lane == 0) guess[c] = first;
         return;
     }
-    uint64_t limit = min(n, start + ((uint64_t)8 << CHUNK_LOG2));
+    // search window: 8 chunks, but never less than the 128 KiB the 16 KiB chunks have always had - with the small chunks of a small
+    // stream (index_records) a record of a 40 kb read is longer than 8 chunks and no start was found inside it
+    uint64_t limit = min(n, start + max((uint64_t)8 << CHUNK_LOG2, (uint64_t)128 << 10));
     uint64_t found = BAD_OFFSET;
     for (uint64_t base = start; base < limit; base += 32) {
         uint64_t o = base + lane, nx = 0, nx2 = 0;
@@ -413,7 +415,9 @@ int repair_guesses(svb_ctx *ctx, svb_bam *bam)
         CK(cudaMemcpyAsync(&h, flag.p, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         if (!h) break;
-        if (round >= 256) return svb_fail(ctx, SVB_ERR_FORMAT, "corrupt BAM record chain (block_size < 32)");
+        // every round settles at least the first wrong chunk of every run, so n_chunks rounds always suffice for a sound chain; runs
+        // longer than a few chunks only occur behind records longer than guess_starts' window (> 128 KiB)
+        if ((uint64_t)round >= std::min<uint64_t>(n_chunks + 2, 4096)) return svb_fail(ctx, SVB_ERR_FORMAT, "corrupt BAM record chain (block_size < 32)");
         ProfScope ps(ctx, "repair_chain", 0);
         CK(cudaMemcpyAsync(snap.p, bam->d_exit, n_chunks * 8, cudaMemcpyDeviceToDevice, s));
         repair_chain<<<nblk(n_chunks, 128), 128, 0, s>>>(bam->d_data, bam->nbytes, n_chunks, bam->chunk_log2, bam->d_guess, bam->d_count,
