@@ -201,7 +201,7 @@ def ncu_traffic(kernel_scope):
             hdr, units = rows[0], rows[1]
             ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             for r in rows[2:]:
-                if kernel.replace(" ", "") in r[ki].replace(" ", ""):
+                if kernel.replace(" ", "").replace("(bool)", "") in r[ki].replace(" ", "").replace("(bool)", ""):
                     tot = float(r[ri]) * unit.get(units[ri], 1.0) + float(r[wi]) * unit.get(units[wi], 1.0)
                     return tot, "profiles/%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch on C2)" % os.path.basename(f)
         except Exception:
@@ -445,7 +445,8 @@ def partitioned_main(args, torch, dist, rank, world, local):
     if not args.value_only:
         devnull = os.open(os.devnull, os.O_WRONLY)
         saved, saved_out = os.dup(2), os.dup(1)
-        os.dup2(devnull, 2)
+        if not os.environ.get("SEEKSV_B200_TIMING"):      # (the commands' progress lines; the phase timings go to stderr too)
+            os.dup2(devnull, 2)
         sys.stdout.flush()
         os.dup2(devnull, 1)
         try:

@@ -264,6 +264,12 @@ void svb_free(void *p);
  * svb_read_gz returns the decompressed content of any gzip or plain text file in a malloc'ed buffer (svb_free);
  * files written by svb_write_gz are inflated member-parallel. n_threads <= 0: all host cores. */
 int svb_write_gz(const char *path, const void *data, uint64_t n, int n_threads);
+/* Multi-GPU getclip (python -m seeksv_b200.mgpu): one rank's clip / clip.fq texts as gzip files per (chromosome, side) block,
+ * <part_prefix>.<b>.clip.gz and <part_prefix>.<b>.fq.gz, b = 0, 1, ... in text order. The whole-file outputs are concatenations
+ * of the ranks' block files: per chromosome (file order) the '5' blocks of all ranks, then the '3' blocks - the per-chromosome
+ * flush of DisplaySClipReadsAndClipFq (clip_reads.h:300-345,423-438). *blocks: "chromosome<TAB>side\n" per block (svb_free). */
+int svb_write_range_blocks(const char *part_prefix, const void *clip, uint64_t n_clip, const void *fq, uint64_t n_fq, int n_threads,
+                           char **blocks, uint64_t *blocks_len);
 /* The same file image made on the device (gzip.cu): text in host memory -> malloc'ed gzip image (svb_free). */
 int svb_gzip_text(svb_ctx *ctx, const void *text, uint64_t n, char **gz, uint64_t *gz_len);
 int svb_read_gz(const char *path, char **data, uint64_t *n);
@@ -271,6 +277,18 @@ int svb_read_gz(const char *path, char **data, uint64_t *n);
  * svb_free). This is the conversion svb_bam_open / getsv apply to an input whose name does not end in ".bam"; it replaces
  * samopen(fn, "r") + sam_read1 of the linked libbam (bam_import.o; call sites clip_reads.h:375, getsv.h:445). */
 int svb_sam_to_stream(const char *sam_path, char **stream, uint64_t *nbytes, uint64_t *first_record);
+
+/* Sharded getsv (python -m seeksv_b200.mgpu getsv): the caller runs the three BAM passes of getsv on the shards of the BAM and
+ * combines them (NCCL); svb_main("getsv") keeps the host bookkeeping. With a provider registered, getsv opens the BAM for its
+ * header only and calls the provider once, after MergeJunction (getsv.cpp:1325-1482), with the junctions (for
+ * FindDiscordantReadPairs, getsv.cpp:990-1247; none when -n < 100000) and the merged depth windows (main_depth,
+ * bam2depth.cpp:17-142; none with -D) in the order in which it asks for their results. The provider fills stats = {records
+ * behind the insert-size statistics, mean, deviation} (CalculateInsertsizeDeviation, cluster.cpp:15-83), one count per junction
+ * and one depth per window position, and returns 0. NULL unregisters. */
+typedef int (*svb_shard_provider_fn)(const svb_junction *junctions, uint64_t n_junctions, const svb_window *windows, uint64_t n_windows,
+                                     int32_t min_mapq, int32_t pairs_used, int32_t times, int64_t *stats, int32_t *counts, int32_t *depth,
+                                     void *user);
+void svb_set_shard_provider(svb_shard_provider_fn fn, void *user);
 
 /* ---- whole commands (what the CLI calls; same arguments as the reference's Call* functions,
  *      seeksv.cpp:128-410). They print the reference's progress lines to stderr and return the

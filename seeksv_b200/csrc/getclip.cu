@@ -1042,6 +1042,13 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         cap.clip = want64(H_CLIP, stream_bytes / 40 + (1 << 20)), cap.fq = want64(H_FQ, stream_bytes / 96 + (1 << 20));
         cap.un1 = pair_mode ? want64(H_UN1, stream_bytes / 64 + (1 << 20)) : 1, cap.un2 = pair_mode ? want64(H_UN2, stream_bytes / 64 + (1 << 20)) : 1;
         cap.exp = export_mode ? want64(H_EXPORT, stream_bytes / 32 + (1 << 20)) : 1;
+        if (unmapped_only) {
+            // a stream of nothing but unmapped-branch records (the shards' exported mates): every record is queued and nearly all of
+            // its bytes come back as FASTQ text - the estimates above (and the hints of the shard's own pass) would overflow and cost
+            // two or three repeats of the whole call
+            cap.un = (uint32_t)std::min<uint64_t>(stream_bytes / 100 + 4096, 0xfffffff0u);
+            cap.un1 = cap.un2 = stream_bytes + (1 << 20);
+        }
     }
     ClipCtl h{};
     for (int attempt = 0;; ++attempt) {
@@ -1191,9 +1198,11 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         break;
     }
     if (!bam->counted) CKR(accept_counts(ctx, bam, h.c64[0], h.c64[1]));
-    ctx->hint[H_CLIPPED] = h.counters[0], ctx->hint[H_UNMAPPED] = h.counters[1], ctx->hint[H_SWITCH] = h.counters[2], ctx->hint[H_CAND] = h.counters[3];
-    ctx->hint[H_ARENA] = h.arena_bytes, ctx->hint[H_CLIP] = h.clip_bytes, ctx->hint[H_FQ] = h.fq_bytes;
-    ctx->hint[H_UN1] = h.un1_bytes, ctx->hint[H_UN2] = h.un2_bytes, ctx->hint[H_EXPORT] = h.export_bytes;
+    if (!unmapped_only) {  // (the mates' stream is another kind of input: its needs say nothing about the next shard)
+        ctx->hint[H_CLIPPED] = h.counters[0], ctx->hint[H_UNMAPPED] = h.counters[1], ctx->hint[H_SWITCH] = h.counters[2], ctx->hint[H_CAND] = h.counters[3];
+        ctx->hint[H_ARENA] = h.arena_bytes, ctx->hint[H_CLIP] = h.clip_bytes, ctx->hint[H_FQ] = h.fq_bytes;
+        ctx->hint[H_UN1] = h.un1_bytes, ctx->hint[H_UN2] = h.un2_bytes, ctx->hint[H_EXPORT] = h.export_bytes;
+    }
     res->n_candidates = h.counters[3], res->n_clusters = h.n_cl;
     res->text_len[0] = h.clip_bytes, res->text_len[1] = h.fq_bytes, res->text_len[2] = h.un1_bytes, res->text_len[3] = h.un2_bytes;
     res->export_len = h.export_bytes, res->n_parts = n_parts;

@@ -469,6 +469,14 @@ struct ShardResults {
 };
 ShardResults g_shard;
 
+// The same hand-over without the file and without a second join: a caller that drives the sharded passes itself registers a
+// provider (svb_set_shard_provider); getsv calls it ONCE, after the junction merge, with the junctions and depth windows in the
+// order in which it will ask for their results, and goes on with what the provider filled in.
+struct ShardProvider {
+    svb_shard_provider_fn fn = nullptr;
+    void *user = nullptr;
+} g_provider;
+
 int open_original(svb_ctx *ctx, const std::string &path, svb_bam **out)
 {
     if (g_shard.on) return svb_bam_open_refs(ctx, path.c_str(), nullptr, 0, 0, n_threads(), out);  // header only: no records are loaded
@@ -567,12 +575,16 @@ int cmd_getsv(int argc, char **argv)
             if (!g.open()) return 1;
             return open_original(g.ctx, original_bam, &bam) != 0 ? 2 : 0;
         });
+    // the two clip files are read side by side (the text inflates while the alignments are parsed); errors in the reference's order
+    std::string clip_err;
+    std::future<bool> clip_read = std::async(std::launch::async, [&]() { return read_text_maybe_gz(clipfile, clip_text, clip_err); });
     if (!load_alignments(clip_aln, alns, err)) {
+        clip_read.wait();
         std::cerr << "[main_samview] fail to open file for reading." << std::endl;
         return fail(err);
     }
     ph.mark("getsv: read clip alignments");
-    if (!read_text_maybe_gz(clipfile, clip_text, err)) return fail(err);
+    if (!clip_read.get()) return fail(clip_err);
     ph.mark("getsv: read clip.gz");
     JunctionMap jm;
     if (!seed_file.empty()) {  // ReadBreakpoint, seeksv.cpp:215-219
@@ -622,6 +634,40 @@ int cmd_getsv(int argc, char **argv)
         }
         return true;
     };
+    if (g_provider.fn) {  // sharded run: the ranks' passes are driven by the caller, this command keeps the bookkeeping
+        if (!need_bam()) return 1;  // (header only)
+        std::vector<svb_junction> pj;
+        if (pairs_used >= 100000) {
+            pj.resize(jm.size());
+            size_t k = 0;
+            for (auto &kv : jm) to_device_junction(kv.first, bam, pj[k++]);
+        }
+        std::vector<svb_window> pw;
+        uint64_t total = 0;
+        if (with_depth) {
+            PosDepth p2d;
+            RangeDepth r2d;
+            WindowMap b2e;
+            JunctionRanges jr;
+            collect_breaks(jm, flank_len, p2d, r2d, jr);
+            merge_ranges(r2d, b2e);
+            std::vector<Win> hw;
+            std::map<std::string, int32_t> tid_of;
+            std::vector<uint32_t> lens;
+            for (int32_t t = 0; t < svb_bam_n_ref(bam); ++t) {
+                tid_of.insert(std::make_pair(std::string(svb_bam_ref_name(bam, t)), t));
+                lens.push_back(svb_bam_ref_len(bam, t));
+            }
+            total = device_windows(b2e, tid_of, lens, pw, hw);
+        }
+        g_shard.counts.assign(pj.size(), 0), g_shard.depth.assign(total, 0);
+        int64_t st[3] = {0, 0, 0};
+        if (g_provider.fn(pj.data(), pj.size(), pw.data(), pw.size(), min_mapq, pairs_used, times, st, g_shard.counts.data(),
+                          g_shard.depth.data(), g_provider.user) != 0)
+            return fail("[seeksv_b200] the shard provider failed");
+        g_shard.n = (int32_t)std::min<int64_t>(st[0], INT32_MAX), g_shard.mean = (int32_t)st[1], g_shard.dev = (int32_t)st[2];
+        ph.mark("getsv: sharded passes (provider)");
+    }
     int mean = 0, dev = 0;
     if (pairs_used >= 100000) {
         if (!need_bam()) return 1;
@@ -773,6 +819,74 @@ int cmd_somatic(int argc, char **argv)
     return 0;
 }
 }  // namespace
+
+extern "C" void svb_set_shard_provider(svb_shard_provider_fn fn, void *user) { g_provider.fn = fn, g_provider.user = user; }
+
+// One rank's part of the multi-GPU getclip outputs. A shard's clip text (coordinate range or whole chromosomes of a sorted BAM) is
+// a sequence of (chromosome, side) blocks, and the whole-file text is a concatenation of the shards' blocks: per chromosome the
+// '5' blocks of all shards, then the '3' blocks (DisplaySClipReadsAndClipFq flushes per chromosome, clip_reads.h:300-345,423-438).
+// So every rank compresses ITS blocks into gzip members of their own files (<prefix>.<b>.clip.gz / .fq.gz) - gzip members
+// concatenate - and the merging rank only orders files; no text travels and nothing is compressed twice.
+// *blocks: one line "chromosome<TAB>side" per block, malloc'ed (svb_free).
+extern "C" int svb_write_range_blocks(const char *part_prefix, const void *clip, uint64_t n_clip, const void *fq, uint64_t n_fq, int n_threads,
+                                      char **blocks, uint64_t *blocks_len)
+{
+    if (!part_prefix || !blocks || !blocks_len || (!clip && n_clip) || (!fq && n_fq)) return SVB_ERR_ARG;
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    struct Block {
+        const char *chrom;
+        size_t chrom_len;
+        char side;
+        uint64_t c0, c1, lines;
+    };
+    std::vector<Block> bl;
+    const char *c = (const char *)clip, *ce = c + n_clip;
+    for (const char *p = c; p < ce;) {
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(ce - p));
+        if (!nl) return SVB_ERR_FORMAT;
+        const char *t1 = (const char *)memchr(p, '\t', (size_t)(nl - p));
+        const char *t2 = t1 ? (const char *)memchr(t1 + 1, '\t', (size_t)(nl - t1 - 1)) : nullptr;
+        if (!t2 || t2 + 1 >= nl) return SVB_ERR_FORMAT;
+        const size_t len = (size_t)(t1 - p);
+        const char side = t2[1];
+        if (bl.empty() || bl.back().side != side || bl.back().chrom_len != len || memcmp(bl.back().chrom, p, len) != 0)
+            bl.push_back(Block{p, len, side, (uint64_t)(p - c), 0, 0});
+        bl.back().c1 = (uint64_t)(nl + 1 - c), bl.back().lines += 1;
+        p = nl + 1;
+    }
+    // four FASTQ lines per clip line
+    std::vector<uint64_t> f_end(bl.size(), 0);
+    {
+        const char *f = (const char *)fq, *fe = f + n_fq, *q = f;
+        for (size_t b = 0; b < bl.size(); ++b) {
+            for (uint64_t k = 0; k < 4 * bl[b].lines; ++k) {
+                const char *nl = q < fe ? (const char *)memchr(q, '\n', (size_t)(fe - q)) : nullptr;
+                if (!nl) return SVB_ERR_FORMAT;
+                q = nl + 1;
+            }
+            f_end[b] = (uint64_t)(q - f);
+        }
+        if (q != fe) return SVB_ERR_FORMAT;
+    }
+    std::vector<GzJob> jobs;
+    std::string list;
+    for (size_t b = 0; b < bl.size(); ++b) {
+        const std::string base = std::string(part_prefix) + "." + std::to_string(b);
+        jobs.push_back(GzJob{base + ".clip.gz", c + bl[b].c0, bl[b].c1 - bl[b].c0});
+        const uint64_t f0 = b ? f_end[b - 1] : 0;
+        jobs.push_back(GzJob{base + ".fq.gz", (const char *)fq + f0, f_end[b] - f0});
+        list.append(bl[b].chrom, bl[b].chrom_len);
+        list += '\t', list += bl[b].side, list += '\n';
+    }
+    std::string err;
+    if (!jobs.empty() && !write_gz_many(jobs, n_threads, err)) return SVB_ERR_IO;
+    *blocks = (char *)malloc(list.size() + 1);
+    if (!*blocks) return SVB_ERR_IO;
+    memcpy(*blocks, list.data(), list.size());
+    (*blocks)[list.size()] = 0;
+    *blocks_len = list.size();
+    return 0;
+}
 
 extern "C" int svb_write_gz(const char *path, const void *data, uint64_t n, int n_threads)
 {
@@ -991,6 +1105,7 @@ extern "C" int svb_main(int argc, char **argv)
         std::cerr << "[seeksv_b200] cannot read SEEKSV_B200_SHARD_RESULTS" << std::endl;
         return 1;
     }
+    if (g_provider.fn && strcmp(argv[1], "getsv") == 0) g_shard.on = true;  // results arrive through the provider
     if (strcmp(argv[1], "run") == 0) return cmd_run(argc - 1, argv + 1);
     const char *cmds[4] = {"getclip", "getsv", "somatic", "cluster"};
     int i = 0;

@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 from typing import List, Optional, Sequence, Tuple
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -56,6 +57,7 @@ EXPORTS = [
     "svb_clusters_gz", "svb_gzip_text", "svb_bam_open_voffsets", "svb_bai_linear_offsets", "svb_bam_peek_record", "svb_voffset_distance",
     "svb_sam_to_stream", "svb_main", "svb_getsv_passes", "svb_clusters_text_len", "svb_clusters_export_device",
     "svb_clusters_export_parts", "svb_bam_set_own_offset", "svb_insert_partial", "svb_insert_sq", "svb_pairs_depth", "svb_plan_somatic", "svb_insert_partial_async",
+    "svb_write_range_blocks", "svb_set_shard_provider",
 ]
 
 
@@ -146,8 +148,65 @@ def load():
     L.svb_sam_to_stream.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.svb_free.argtypes = [vp]
     L.svb_free.restype = None
+    L.svb_write_range_blocks.argtypes = [C.c_char_p, vp, u64, vp, u64, C.c_int, C.POINTER(vp), C.POINTER(u64)]
+    L.svb_set_shard_provider.argtypes = [vp, vp]
+    L.svb_set_shard_provider.restype = None
     _lib = L
     return L
+
+
+# int provider(junctions, n_j, windows, n_w, min_mapq, pairs_used, times, int64 stats[3], int32 counts[n_j], int32 depth[positions], user)
+SHARD_PROVIDER = C.CFUNCTYPE(C.c_int, C.POINTER(Junction), C.c_uint64, C.POINTER(Window), C.c_uint64, C.c_int32, C.c_int32, C.c_int32,
+                             C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p)
+
+
+def set_shard_provider(fn):
+    """svb_set_shard_provider: `fn(juncs, wins, min_mapq, pairs_used, times) -> (n, mean, dev, counts, depth)` is called once by the
+    next `run_cli(["getsv", ...])` after its junction merge (sharded runs, seeksv_b200/mgpu.py); None unregisters. Returns the ctypes
+    callback, which the caller has to keep alive while it is registered."""
+    L = load()
+    if fn is None:
+        L.svb_set_shard_provider(None, None)
+        return None
+
+    def thunk(pj, nj, pw, nw, min_mapq, pairs_used, times, stats, counts, depth, _user):
+        try:
+            juncs = [(pj[i].up_tid, pj[i].up_pos, pj[i].up_strand.decode(), pj[i].down_tid, pj[i].down_pos, pj[i].down_strand.decode())
+                     for i in range(nj)]
+            wins = [(pw[i].tid, pw[i].begin, pw[i].end) for i in range(nw)]
+            n, mean, dev, c, d = fn(juncs, wins, min_mapq, pairs_used, times)
+            stats[0], stats[1], stats[2] = int(n), int(mean), int(dev)
+            if len(c) != nj or len(d) != sum(w[2] - w[1] + 1 for w in wins):
+                return 2
+            import numpy as np
+            c, d = np.ascontiguousarray(c, dtype=np.int32), np.ascontiguousarray(d, dtype=np.int32)
+            if nj:
+                C.memmove(counts, c.ctypes.data, 4 * nj)
+            if len(d):
+                C.memmove(depth, d.ctypes.data, 4 * len(d))
+            return 0
+        except Exception as e:      # noqa: BLE001 - an exception must not unwind through the C frames
+            sys.stderr.write("[seeksv_b200] shard provider: %r\n" % (e,))
+            return 1
+    cb = SHARD_PROVIDER(thunk)
+    L.svb_set_shard_provider(C.cast(cb, C.c_void_p), None)
+    return cb
+
+
+def write_range_blocks(part_prefix: str, clip: bytes, fq: bytes, threads: int = 0):
+    """svb_write_range_blocks: this rank's clip / clip.fq texts as gzip files per (chromosome, side) block; returns [(chromosome, side)]"""
+    L = load()
+    out, n = C.c_void_p(), C.c_uint64()
+    pc, pf = C.c_char_p(clip), C.c_char_p(fq)      # (pointers into the bytes objects: no copy)
+    rc = L.svb_write_range_blocks(part_prefix.encode(), C.cast(pc, C.c_void_p), len(clip), C.cast(pf, C.c_void_p), len(fq), threads,
+                                  C.byref(out), C.byref(n))
+    if rc != 0:
+        raise SvbError("svb_write_range_blocks = %d" % rc)
+    try:
+        text = C.string_at(out, n.value)
+    finally:
+        L.svb_free(out)
+    return [tuple(line.split(b"\t")) for line in text.split(b"\n")[:-1]]
 
 
 class Context:

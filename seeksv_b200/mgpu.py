@@ -20,6 +20,24 @@ import os
 import struct
 import sys
 import tempfile
+import time
+
+
+class _Phases:
+    """wall-clock phase marks of one command on this rank (SEEKSV_B200_TIMING=1 prints them to stderr)"""
+
+    def __init__(self, name, rank):
+        self.on, self.name, self.rank, self.t, self.rows = bool(os.environ.get("SEEKSV_B200_TIMING")), name, rank, time.perf_counter(), []
+
+    def mark(self, what):
+        if self.on:
+            now = time.perf_counter()
+            self.rows.append("%s %.1f" % (what, 1e3 * (now - self.t)))
+            self.t = now
+
+    def done(self):
+        if self.on:
+            os.write(2, ("[time] mgpu %s rank %d: %s ms\n" % (self.name, self.rank, ", ".join(self.rows))).encode())
 
 
 def _init_dist():
@@ -86,11 +104,39 @@ def _gather_bytes(parts, dist, device):
     return out
 
 
+def assemble_block_files(prefix, lists):
+    """lists[r] = the (chromosome, side) blocks rank r wrote with lib.write_range_blocks(prefix + ".part<r>", ...): concatenates the
+    block files into prefix.clip.gz / prefix.clip.fq.gz - per chromosome (order of first appearance over the ranks) the '5' blocks of
+    all ranks, then the '3' blocks - and removes them."""
+    from . import lib
+    order, groups = [], {}
+    for r, bl in enumerate(lists):
+        for b, (chrom, side) in enumerate(bl):
+            if chrom not in groups:
+                order.append(chrom)
+                groups[chrom] = {b"5": [], b"3": []}
+            groups[chrom][side].append("%s.part%d.%d" % (prefix, r, b))
+    files = [f for chrom in order for side in (b"5", b"3") for f in groups[chrom][side]]
+    for ext, pext in ((".clip.gz", ".clip.gz"), (".clip.fq.gz", ".fq.gz")):
+        if not files:
+            lib.write_gz(prefix + ext, b"")
+            continue
+        with open(prefix + ext, "wb") as out:
+            for f in files:
+                with open(f + pext, "rb") as src:
+                    n = os.fstat(src.fileno()).st_size
+                    off = 0
+                    while off < n:
+                        off += os.sendfile(out.fileno(), src.fileno(), off, n - off)
+                os.unlink(f + pext)
+
+
 def run_getclip(ctx, dist, device, a):
     from . import lib, sharding
     rank = dist.get_rank() if dist else 0
     world = dist.get_world_size() if dist else 1
     kw = dict(match_rate=a.match_rate, min_mapq=a.min_mapq, save_low_quality=a.save_low_quality)
+    ph = _Phases("getclip", rank)
     if a.by == "chromosome":
         worker = sharding.open_ref_shard(ctx, a.bam, rank, world, a.bai, **kw)
         lasts = sharding.all_gather_objects(worker.last_mapped_tid(), dist)
@@ -101,15 +147,23 @@ def run_getclip(ctx, dist, device, a):
         cl = None
         if worker.bam is not None:
             cl = worker.bam.getclip_handle(prev_tid=p.prev_tid, export_unmapped=True, key_range=(p.key_lo, p.key_hi), halo_bytes=p.halo_bytes, **kw)
-    mine = [cl.text(0), cl.text(1), cl.unmapped_records()] if cl is not None else [b"", b"", b""]
-    every = _gather_bytes(mine, dist, device)
+    ph.mark("open+getclip")
+    # Every rank compresses the (chromosome, side) blocks of ITS clip / clip.fq text into gzip files of their own; gzip members
+    # concatenate, so rank 0 only has to put the files in order (per chromosome the '5' blocks of all ranks, then the '3' blocks -
+    # clip_reads.h:300-345,423-438). No text crosses ranks and nothing is compressed twice. Only the unmapped-branch records travel
+    # (NCCL): mates are paired by name across the whole file.
+    part = "%s.part%d" % (a.prefix, rank)
+    threads = int(os.environ.get("SEEKSV_B200_THREADS", "0"))
+    blocks = lib.write_range_blocks(part, cl.text(0), cl.text(1), threads) if cl is not None else []
+    ph.mark("block files")
+    lists = sharding.all_gather_objects(blocks, dist)
+    every = _gather_bytes([cl.unmapped_records() if cl is not None else b""], dist, device)
+    ph.mark("gather")
     names, lens = (worker.bam.ref_names, worker.bam.ref_lens) if worker.bam is not None else ([], [])
     if rank == 0:
-        if a.by == "chromosome":
-            clip, fq = b"".join(e[0] for e in every), b"".join(e[1] for e in every)
-        else:
-            clip, fq = sharding.merge_range_texts_fast([(e[0], e[1]) for e in every])
-        records = b"".join(e[2] for e in every)
+        assemble_block_files(a.prefix, lists)
+        ph.mark("assemble")
+        records = b"".join(e[0] for e in every)
         u1 = u2 = b""
         if records:   # mates are paired by name across the whole file: the shards' unmapped-branch records, in file order, as one stream
             mini = lib.Bam.from_host(ctx, records, 0, len(names))
@@ -118,12 +172,16 @@ def run_getclip(ctx, dist, device, a):
             u1, u2 = cu.text(2), cu.text(3)
             cu.close()
             mini.close()
-        for ext, t in zip((".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz"), (clip, fq, u1, u2)):
-            lib.write_gz(a.prefix + ext, t)
+        ph.mark("pair")
+        lib.write_gz(a.prefix + ".unmapped_1.fq.gz", u1)
+        lib.write_gz(a.prefix + ".unmapped_2.fq.gz", u2)
+        ph.mark("write_gz")
         print("[GetSClipReads] finished!", file=sys.stderr)
     if cl is not None:
         cl.close()
     worker.close()
+    ph.mark("close")
+    ph.done()
 
 
 def shard_for_passes(ctx, dist, bam_path, bai, rank, world):
@@ -169,40 +227,74 @@ def _opt(argv, letter, default, cast=int):
 
 
 def run_getsv(ctx, dist, device, a):
-    """a.rest = the arguments of `seeksv getsv` (options and the five files)"""
+    """a.rest = the arguments of `seeksv getsv` (options and the five files). Rank 0 runs the command itself (one join of the clip
+    files, the junction bookkeeping, the output files) with a shard provider registered: when the command has merged its junctions
+    it hands them over, rank 0 broadcasts them, every rank runs the BAM passes on its own records and the results are added up
+    with NCCL collectives on device tensors. The ranks load their shards while rank 0 reads and joins the clip files."""
+    import threading
     from . import lib, sharding
     rank = dist.get_rank() if dist else 0
     world = dist.get_world_size() if dist else 1
     files = [x for i, x in enumerate(a.rest) if not x.startswith("-") and (i == 0 or a.rest[i - 1] not in ("-F", "-B", "-t", "-l", "-q", "-Q", "-w", "-n", "-a", "-b", "-d", "-e", "-m", "-i", "-R", "-f", "-T", "-L"))]
     if len(files) != 5 or "-F" in a.rest or "-B" in a.rest:
         raise SystemExit("mgpu getsv: five files, no -F / -B (use the single-process command for those)")
-    clip_aln, bam_path, clip_gz = files[0], files[1], files[2]
-    min_mapq, pairs_used, flank, flank_len = _opt(a.rest, "q", 20), _opt(a.rest, "n", 5000000), _opt(a.rest, "l", 50), _opt(a.rest, "L", 200)
-    with_depth = "-D" not in a.rest
-    worker = shard_for_passes(ctx, dist, bam_path, a.bai, rank, world)
-    names, lens = sharding.all_gather_objects((worker.bam.ref_names, worker.bam.ref_lens) if worker.bam is not None else None, dist)[0]
-    gw = sharding.GpuShardWorker(worker.bam, device) if worker.bam is not None else _NoRecords(device)
-    juncs, wins = lib.plan_getsv(clip_aln, clip_gz, names, lens, flank, flank_len)      # host, the same on every rank
-    if not with_depth:
-        wins = []
-    n = mean = dev = 0
-    if pairs_used >= 100000:
-        n, mean, dev = sharding.sharded_insert_stats(gw, dist, device, min_mapq, pairs_used)
-    else:
-        juncs = []
-    t = sharding.sharded_pairs_depth(gw, dist, min_mapq, mean, dev, 4, juncs, wins).cpu().numpy()
+    bam_path = files[1]
+    ph = _Phases("getsv", rank)
+    box = {}
+
+    def load_shard():
+        try:
+            # (dist = None: a context without a mapped-branch record is widened by this rank alone - the width of a shard's context
+            # changes nothing in the other ranks' plans - so that no collective runs on this helper thread)
+            box["worker"] = shard_for_passes(ctx, None, bam_path, a.bai, rank, world)
+        except Exception as e:      # noqa: BLE001
+            box["error"] = e
+
+    def passes(juncs, wins, min_mapq, pairs_used, times):
+        """on every rank, with the same arguments: (n, mean, dev, counts, depth)"""
+        loader.join()
+        if "error" in box:
+            raise box["error"]
+        worker = box["worker"]
+        gw = sharding.GpuShardWorker(worker.bam, device) if worker.bam is not None else _NoRecords(device)
+        n = mean = dev = 0
+        if pairs_used >= 100000:
+            n, mean, dev = sharding.sharded_insert_stats(gw, dist, device, min_mapq, pairs_used)
+        t = sharding.sharded_pairs_depth(gw, dist, min_mapq, mean, dev, times, juncs, wins).cpu().numpy()
+        return n, mean, dev, t[:len(juncs)], t[len(juncs):len(juncs) + sum(w[2] - w[1] + 1 for w in wins)]
+
+    loader = threading.Thread(target=load_shard)
+    loader.start()
     rc = 0
     if rank == 0:
-        with tempfile.NamedTemporaryFile(suffix=".svbr", delete=False) as tf:
-            res = tf.name
-        _write_results(res, n, mean, dev, t[:len(juncs)].tolist() if pairs_used >= 100000 else [], t[len(juncs):len(juncs) + sum(w[2] - w[1] + 1 for w in wins)])
-        os.environ["SEEKSV_B200_SHARD_RESULTS"] = res
+        def provider(juncs, wins, min_mapq, pairs_used, times):
+            ph.mark("join (command)")
+            box["called"] = True
+            if dist is not None:
+                dist.broadcast_object_list([juncs, wins, min_mapq, pairs_used, times], src=0)
+            out = passes(juncs, wins, min_mapq, pairs_used, times)
+            ph.mark("passes")
+            return out
+        keep = lib.set_shard_provider(provider)
         try:
             rc = lib.run_cli(["getsv"] + list(a.rest))
         finally:
-            del os.environ["SEEKSV_B200_SHARD_RESULTS"]
-            os.unlink(res)
-    worker.close()
+            lib.set_shard_provider(None)
+            del keep
+        ph.mark("output")
+        if dist is not None and not box.get("called"):      # the command stopped before its passes: release the other ranks
+            dist.broadcast_object_list([None] * 5, src=0)
+    else:
+        plan = [None] * 5
+        dist.broadcast_object_list(plan, src=0)
+        if plan[0] is not None:
+            passes(*plan)
+        ph.mark("passes")
+    loader.join()
+    if "worker" in box:
+        box["worker"].close()
+    ph.mark("close")
+    ph.done()
     return rc
 
 

@@ -29,6 +29,17 @@ CONFIGS = {
     "c3mini": ["--genome", ",".join("chr%s:%d" % (n, 300000 + 20000 * i) for i, n in enumerate(list(range(1, 23)) + ["X", "Y"])),
                "--cov", "30", "--nsv", "240", "--seed", "20261018"],
     "c5mini": ["--genome", "chr21:6000000", "--virus", "--cov", "30", "--nsv", "80", "--seed", "20261019"],
+    # the shapes of configs 5 and 3 at the C2 size (round 2):
+    #   c5: the C2 chromosome + HBV / HPV16 contigs at 6000x with 40 planted integrations (9.6 M records)
+    #   c3w8: 24 contigs of 1.95 Mb (same total as C2): every one of 8 coordinate-range shards crosses chromosome boundaries
+    "c5": ["--genome", "chr21:46709983", "--virus", "--cov", "30", "--nsv", "500", "--seed", "20261020"],
+    "c3w8": ["--genome", ",".join("chr%s:1946249" % n for n in list(range(1, 23)) + ["X", "Y"]), "--cov", "30", "--nsv", "500",
+             "--seed", "20261021"],
+}
+# config 4 at the C2 size: a 60x tumour and a 30x normal of the same donor (python tests/golden/make_c2_digests.py <workdir> c4)
+PAIRS = {
+    "c4": (["--genome", "chr21:46709983", "--cov", "60", "--nsv", "500", "--seed", "20261022", "--sample", "tumor"],
+           ["--genome", "chr21:46709983", "--cov", "30", "--nsv", "500", "--seed", "20261022", "--sample", "normal"]),
 }
 
 
@@ -40,7 +51,40 @@ def main():
     assert os.path.exists(SEEKSV), "oracle/build_ref.sh first"
     work = sys.argv[1] if len(sys.argv) > 1 else tempfile.mkdtemp(prefix="c2_")
     for name in (sys.argv[2:] or ["c2"]):
-        one(work, name, CONFIGS[name])
+        if name in PAIRS:
+            pair(work, name, *PAIRS[name])
+        else:
+            one(work, name, CONFIGS[name])
+
+
+def pair(work, name, tumor_args, normal_args):
+    """tumour: getclip -> minialign -> getsv; normal: getclip; somatic(normal.bam, normal.clip.gz, tumour.sv)"""
+    out = {"tumor_args": tumor_args, "normal_args": normal_args, "reference": "oracle/_ref/seeksv (v1.2.3 built from the unmodified sources)"}
+    pre = {}
+    for kind, args in (("tumor", tumor_args), ("normal", normal_args)):
+        pre[kind] = os.path.join(work, name + "." + kind)
+        if not os.path.exists(pre[kind] + ".bam"):
+            subprocess.run([os.path.join(BIN, "svsim"), "--out", pre[kind]] + args, check=True)
+        ref = pre[kind] + ".ref"
+        subprocess.run([SEEKSV, "getclip", "-o", ref, pre[kind] + ".bam"], check=True, stderr=subprocess.DEVNULL)
+        for ext in (".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz"):
+            with gzip.open(ref + ext, "rb") as f:
+                out[kind + ext] = digest(f.read())
+    ref = pre["tumor"] + ".ref"
+    with open(ref + ".clip.sam", "wb") as o:
+        subprocess.run([os.path.join(BIN, "minialign"), pre["tumor"] + ".fa", ref + ".clip.fq.gz"], check=True, stdout=o)
+    out["tumor.clip.sam"] = digest(open(ref + ".clip.sam", "rb").read())
+    r = subprocess.run([SEEKSV, "getsv", ref + ".clip.sam", pre["tumor"] + ".bam", ref + ".clip.gz", ref + ".sv", ref + ".unm"], check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+    out["tumor getsv"] = {"sv": digest(open(ref + ".sv", "rb").read()), "stdout": digest(r.stdout)}
+    subprocess.run([SEEKSV, "somatic", pre["normal"] + ".bam", pre["normal"] + ".ref.clip.gz", ref + ".sv", ref + ".somatic"], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out["somatic"] = digest(open(ref + ".somatic", "rb").read())
+    out["somatic rows"] = open(ref + ".somatic", "rb").read().count(b"\n")
+    with open(os.path.join(HERE, "c2", name + ".digests.json"), "w") as f:
+        json.dump(out, f, indent=1)
+        f.write("\n")
+    print(json.dumps(out, indent=1))
 
 
 def one(work, name, svsim_args):

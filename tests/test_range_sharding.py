@@ -12,7 +12,7 @@ import pytest
 
 from conftest import GOLDEN, read_text
 from oracle import bamio, getclip_oracle
-from seeksv_b200 import sharding
+from seeksv_b200 import lib, mgpu, sharding
 
 CASES = [("fuzz", "f11"), ("fuzz", "f12"), ("micro", "tumor"), ("example", "cancer"), ("example", "normal"), ("fuzz", "f106"), ("fuzz", "e3")]
 
@@ -78,7 +78,7 @@ class OracleRangeWorker:
 
 
 @pytest.mark.parametrize("d,s", CASES)
-def test_range_shards_reproduce_the_whole_file(d, s):
+def test_range_shards_reproduce_the_whole_file(d, s, tmp_path):
     path = os.path.join(GOLDEN, d, s + ".sort.bam")
     h, recs, voffs = records_with_voffsets(path)
     golden = [read_text(os.path.join(GOLDEN, d, s + e)) for e in (".clip.txt", ".clip.fq.txt", ".unmapped_1.fq.txt", ".unmapped_2.fq.txt")]
@@ -96,12 +96,27 @@ def test_range_shards_reproduce_the_whole_file(d, s):
         clip, fq = sharding.merge_range_texts([(p[0], p[1]) for p in parts])
         u1, u2 = workers[0].pair_unmapped(b"".join(p[4] for p in parts))
         assert (clip, fq, u1, u2) == tuple(golden), world
+        # the multi-GPU commands' way (seeksv_b200/mgpu.py): every rank writes its blocks as gzip files, rank 0 orders the files
+        prefix = str(tmp_path / ("w%d" % world))
+        lists = [lib.write_range_blocks("%s.part%d" % (prefix, r), p[0].encode("latin-1"), p[1].encode("latin-1"), 2) for r, p in enumerate(parts)]
+        mgpu.assemble_block_files(prefix, lists)
+        assert lib.read_gz(prefix + ".clip.gz").decode("latin-1") == golden[0], world
+        assert lib.read_gz(prefix + ".clip.fq.gz").decode("latin-1") == golden[1], world
+        assert not [f for f in os.listdir(str(tmp_path)) if ".part" in f]
     assert seen_multi
 
 
-def test_merge_orders_sides_per_chromosome():
+def test_merge_orders_sides_per_chromosome(tmp_path):
     a = ("c1\t5\t5\tx\nc1\t9\t3\tx\n", "@a\nA\n+\nI\n@b\nC\n+\nI\n")
     b = ("c1\t20\t5\ty\nc1\t30\t3\ty\nc2\t4\t5\tz\n", "@c\nG\n+\nI\n@d\nT\n+\nI\n@e\nN\n+\nI\n")
     clip, fq = sharding.merge_range_texts([a, b])
     assert clip == "c1\t5\t5\tx\nc1\t20\t5\ty\nc1\t9\t3\tx\nc1\t30\t3\ty\nc2\t4\t5\tz\n"
     assert fq == "@a\nA\n+\nI\n@c\nG\n+\nI\n@b\nC\n+\nI\n@d\nT\n+\nI\n@e\nN\n+\nI\n"
+    prefix = str(tmp_path / "m")
+    lists = [lib.write_range_blocks("%s.part%d" % (prefix, r), p[0].encode(), p[1].encode(), 1) for r, p in enumerate((a, b))]
+    assert lists == [[(b"c1", b"5"), (b"c1", b"3")], [(b"c1", b"5"), (b"c1", b"3"), (b"c2", b"5")]]
+    mgpu.assemble_block_files(prefix, lists)
+    assert lib.read_gz(prefix + ".clip.gz").decode() == clip and lib.read_gz(prefix + ".clip.fq.gz").decode() == fq
+    # no blocks at all: empty, valid gzip files
+    mgpu.assemble_block_files(prefix + "e", [[], []])
+    assert lib.read_gz(prefix + "e.clip.gz") == b"" and lib.read_gz(prefix + "e.clip.fq.gz") == b""
