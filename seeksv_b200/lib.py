@@ -588,8 +588,11 @@ class Bam:
 
 def _host_ptr(obj):
     """(void*, nbytes, keepalive) for bytes / bytearray / numpy arrays / torch CPU tensors"""
-    if isinstance(obj, (bytes, bytearray)):
-        buf = (C.c_char * len(obj)).from_buffer_copy(obj) if isinstance(obj, bytes) else (C.c_char * len(obj)).from_buffer(obj)
+    if isinstance(obj, bytes):       # a pointer into the bytes object itself: no copy (the callee only reads)
+        p = C.c_char_p(obj)
+        return C.cast(p, C.c_void_p), len(obj), (p, obj)
+    if isinstance(obj, bytearray):
+        buf = (C.c_char * len(obj)).from_buffer(obj)
         return C.cast(buf, C.c_void_p), len(obj), buf
     if hasattr(obj, "data_ptr"):     # torch tensor
         return C.c_void_p(obj.data_ptr()), obj.numel() * obj.element_size(), obj

@@ -161,21 +161,28 @@ def run_getclip(ctx, dist, device, a):
     ph.mark("gather")
     names, lens = (worker.bam.ref_names, worker.bam.ref_lens) if worker.bam is not None else ([], [])
     if rank == 0:
-        assemble_block_files(a.prefix, lists)
-        ph.mark("assemble")
+        import threading
+        assembler = threading.Thread(target=assemble_block_files, args=(a.prefix, lists))   # (sendfile: no GIL held) next to the pairing
+        assembler.start()
         records = b"".join(e[0] for e in every)
+        ph.mark("records")
         u1 = u2 = b""
         if records:   # mates are paired by name across the whole file: the shards' unmapped-branch records, in file order, as one stream
             mini = lib.Bam.from_host(ctx, records, 0, len(names))
             mini.set_refs(names, lens)
+            ph.mark("pair:upload")
             cu = mini.getclip_handle(unmapped_only=True, **kw)
+            ph.mark("pair:device")
             u1, u2 = cu.text(2), cu.text(3)
+            ph.mark("pair:texts")
             cu.close()
             mini.close()
-        ph.mark("pair")
+        ph.mark("pair:close")
         lib.write_gz(a.prefix + ".unmapped_1.fq.gz", u1)
         lib.write_gz(a.prefix + ".unmapped_2.fq.gz", u2)
         ph.mark("write_gz")
+        assembler.join()
+        ph.mark("assemble (rest)")
         print("[GetSClipReads] finished!", file=sys.stderr)
     if cl is not None:
         cl.close()
