@@ -285,6 +285,12 @@ class Clusters:
         self.ctx.check(self.ctx.L.svb_clusters_text(self.h, which, C.byref(d), C.byref(n)), "svb_clusters_text")
         return C.string_at(d, n.value) if n.value else b""
 
+    def gz(self, which: int) -> bytes:
+        """gzip file image of output `which` (gz_outputs)"""
+        d, n = C.c_char_p(), C.c_uint64()
+        self.ctx.check(self.ctx.L.svb_clusters_gz(self.h, which, C.byref(d), C.byref(n)), "svb_clusters_gz")
+        return C.string_at(d, n.value) if n.value else b""
+
     def export_device(self) -> Tuple[int, int]:
         """(device pointer, bytes) of the exported unmapped-branch records"""
         d, n = C.c_void_p(), C.c_uint64()
@@ -481,14 +487,16 @@ class Bam:
             self.ctx.L.svb_clusters_free(out)
 
     def getclip_handle(self, match_rate=0.9, min_mapq=1, save_low_quality=False, prev_tid=0, export_unmapped=False, key_range=None,
-                       halo_bytes=0, with_rows=False, unmapped_only=False, export_partitions=0) -> Clusters:
-        """svb_getclip, results left in HBM behind a Clusters handle"""
+                       halo_bytes=0, with_rows=False, unmapped_only=False, export_partitions=0, gz_outputs=False) -> Clusters:
+        """svb_getclip, results left in HBM behind a Clusters handle (gz_outputs: the four outputs are compressed on the device,
+        Clusters.gz gives the file images)"""
         p = GetclipParams(match_rate, min_mapq, 1 if save_low_quality else 0, prev_tid, 1 if export_unmapped else 0)
         if key_range is not None:
             (p.key_lo_tid, p.key_lo_pos), (p.key_hi_tid, p.key_hi_pos) = key_range
             p.key_filter = 1
         p.halo_bytes, p.with_rows = halo_bytes, 1 if with_rows else 0
         p.unmapped_only, p.export_partitions = 1 if unmapped_only else 0, export_partitions
+        p.gz_outputs = 1 if gz_outputs else 0
         out = C.c_void_p()
         self.ctx.check(self.ctx.L.svb_getclip(self.ctx.h, self.h, C.byref(p), C.byref(out)), "svb_getclip")
         return Clusters(self.ctx, out)

@@ -157,33 +157,52 @@ def run_getclip(ctx, dist, device, a):
     blocks = lib.write_range_blocks(part, cl.text(0), cl.text(1), threads) if cl is not None else []
     ph.mark("block files")
     lists = sharding.all_gather_objects(blocks, dist)
-    every = _gather_bytes([cl.unmapped_records() if cl is not None else b""], dist, device)
-    ph.mark("gather")
+    # the shards' unmapped-branch records go to rank 0 from HBM to HBM (NCCL point-to-point on the library's own export buffer) and
+    # are paired there as one stream, in file order; they never pass through host memory
+    import torch
+    dptr, n_exp = cl.export_device() if cl is not None else (0, 0)
+    sizes = [s[0] for s in sharding._all_gather_i64([n_exp], dist, device)]
+    if rank != 0 and n_exp:
+        dist.send(sharding._as_tensor(dptr, n_exp, device), 0)
     names, lens = (worker.bam.ref_names, worker.bam.ref_lens) if worker.bam is not None else ([], [])
     if rank == 0:
+        total = sum(sizes)
+        records = torch.empty(total + 256, dtype=torch.uint8, device=device)
+        records[total:].zero_()
+        off = 0
+        for src, k in enumerate(sizes):
+            if k and src == 0:
+                records[off:off + k].copy_(sharding._as_tensor(dptr, k, device))
+            elif k:
+                dist.recv(records[off:off + k], src)
+            off += k
+        torch.cuda.synchronize()
+        ph.mark("gather")
         import threading
         assembler = threading.Thread(target=assemble_block_files, args=(a.prefix, lists))   # (sendfile: no GIL held) next to the pairing
         assembler.start()
-        records = b"".join(e[0] for e in every)
-        ph.mark("records")
-        u1 = u2 = b""
-        if records:   # mates are paired by name across the whole file: the shards' unmapped-branch records, in file order, as one stream
-            mini = lib.Bam.from_host(ctx, records, 0, len(names))
+        u1 = u2 = None
+        if total:   # mates are paired by name across the whole file; the two FASTQ files are compressed on the device
+            mini = lib.Bam.from_device(ctx, records.data_ptr(), total, 0, len(names), keep=records)
             mini.set_refs(names, lens)
-            ph.mark("pair:upload")
-            cu = mini.getclip_handle(unmapped_only=True, **kw)
+            cu = mini.getclip_handle(unmapped_only=True, gz_outputs=True, **kw)
             ph.mark("pair:device")
-            u1, u2 = cu.text(2), cu.text(3)
-            ph.mark("pair:texts")
+            u1, u2 = cu.gz(2), cu.gz(3)
+            ph.mark("pair:gz")
             cu.close()
             mini.close()
-        ph.mark("pair:close")
-        lib.write_gz(a.prefix + ".unmapped_1.fq.gz", u1)
-        lib.write_gz(a.prefix + ".unmapped_2.fq.gz", u2)
-        ph.mark("write_gz")
+        for ext, image in ((".unmapped_1.fq.gz", u1), (".unmapped_2.fq.gz", u2)):
+            if image is None:
+                lib.write_gz(a.prefix + ext, b"")
+            else:
+                with open(a.prefix + ext, "wb") as f:
+                    f.write(image)
+        ph.mark("write")
         assembler.join()
         ph.mark("assemble (rest)")
         print("[GetSClipReads] finished!", file=sys.stderr)
+    else:
+        ph.mark("gather")
     if cl is not None:
         cl.close()
     worker.close()
@@ -283,11 +302,18 @@ def run_getsv(ctx, dist, device, a):
             ph.mark("passes")
             return out
         keep = lib.set_shard_provider(provider)
+        threads = os.environ.get("SEEKSV_B200_THREADS")
+        if dist is not None:    # the one join of the run: all host cores (the other ranks only load their shards meanwhile)
+            os.environ["SEEKSV_B200_THREADS"] = str(os.cpu_count() or 2)
         try:
             rc = lib.run_cli(["getsv"] + list(a.rest))
         finally:
             lib.set_shard_provider(None)
             del keep
+            if threads is not None:
+                os.environ["SEEKSV_B200_THREADS"] = threads
+            elif dist is not None:
+                del os.environ["SEEKSV_B200_THREADS"]
         ph.mark("output")
         if dist is not None and not box.get("called"):      # the command stopped before its passes: release the other ranks
             dist.broadcast_object_list([None] * 5, src=0)

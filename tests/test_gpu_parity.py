@@ -805,10 +805,112 @@ def test_getclip_reads_sam_text_input(d, s, tmp_path):
         assert _zcat(pre + ext) == read_text(os.path.join(GOLDEN, d, s + name)), ext
 
 
-@pytest.mark.parametrize("name", ["c3mini", "c5mini"])
+@pytest.fixture(scope="module")
+def c3w8_prefix(tmp_path_factory):
+    """BASELINE.json's config 3 shape at the C2 size: 24 contigs of 1.95 Mb (9.3 M records), generated once per module"""
+    import json
+    svsim = os.path.join(ROOT, "seeksv_b200", "bin", "svsim")
+    if not os.path.exists(svsim):
+        pytest.skip("needs the svsim tool (python -m seeksv_b200.build)")
+    with open(os.path.join(GOLDEN, "c2", "c3w8.digests.json")) as f:
+        want = json.load(f)
+    pre = str(tmp_path_factory.mktemp("c3w8") / "c3w8")
+    subprocess.run([svsim, "--out", pre] + want["svsim_args"], check=True, stderr=subprocess.DEVNULL)
+    return pre, want
+
+
+def test_config3_shape_at_c2_size_equals_the_reference_digests(c3w8_prefix, tmp_path):
+    """24 chromosomes, 9.3 M records, through the CLI: every output against the reference's digests (tests/golden/c2/c3w8.digests.json)"""
+    pre, want = c3w8_prefix
+    _check_digests(pre, want, tmp_path)
+
+
+def test_config3_eight_range_shards_cross_chromosome_boundaries(ctx, c3w8_prefix):
+    """The same BAM cut into 8 coordinate-range shards (what 8 ranks would load): every shard spans several of the 1.95 Mb
+    chromosomes, so halo, key ownership, the prev_tid hand-over and the per-chromosome merge are all exercised at every cut; the
+    shards run one after the other and the merged outputs must have the whole-file digests of the REFERENCE."""
+    import hashlib
+    from seeksv_b200 import sharding
+    pre, want = c3w8_prefix
+    path = pre + ".bam"
+    whole = __import__("seeksv_b200").Bam.open(ctx, path)
+    n_ref, lens, n_records = len(whole.ref_names), whole.ref_lens, whole.n_records
+    n_w, tot_w, mean_w, _ = whole.insert_stats(20, 5000000)
+    juncs = [(t, p, "+", t, p + 300, "-") for t in range(n_ref) for p in range(1000, lens[t] - 1000, 200000)]
+    want_counts = whole.discordant_support(juncs, 20, mean_w, 25, 4)
+    whole.close()
+    plans = sharding.plan_range_shards(path, None, n_ref, 8)
+    assert len([p for p in plans if not p.empty]) == 8
+    parts, own_records, stats, got = [], 0, [], []
+    for p in plans:      # one shard in HBM at a time
+        w = sharding.RangeShardWorker(ctx, path, p)
+        assert w.context_has_mapped_record()
+        texts = w.bam.getclip(prev_tid=p.prev_tid, export_unmapped=True, key_range=(p.key_lo, p.key_hi), halo_bytes=p.halo_bytes)
+        parts.append((texts[0], texts[1], w.bam.last_unmapped_records))
+        chroms = {line.split(b"\t", 1)[0] for line in texts[0].split(b"\n")[:-1]}
+        assert len(chroms) >= 2, "every shard is meant to cross a chromosome boundary"
+        v = w.own_view()
+        own_records += v.n_records
+        stats.append(v.insert_stats(20, 5000000))
+        got.append(v.discordant_support(juncs, 20, mean_w, 25, 4))
+        v.close()
+        w.close()
+    clip, fq = sharding.merge_range_texts_fast([(p[0], p[1]) for p in parts])
+
+    def dig(data):
+        return {"md5": hashlib.md5(data).hexdigest(), "bytes": len(data)}
+    assert dig(clip) == want[".clip.gz"] and dig(fq) == want[".clip.fq.gz"]
+    import seeksv_b200
+    mini = seeksv_b200.Bam.from_host(ctx, b"".join(p[2] for p in parts), 0, n_ref)
+    cu = mini.getclip_handle(unmapped_only=True)
+    assert dig(cu.text(2)) == want[".unmapped_1.fq.gz"] and dig(cu.text(3)) == want[".unmapped_2.fq.gz"]
+    cu.close()
+    mini.close()
+    assert own_records == n_records
+    assert sum(x[0] for x in stats) == n_w and sum(x[1] for x in stats) == tot_w
+    assert [sum(col) for col in zip(*got)] == list(want_counts)
+
+
+def test_config4_tumour_normal_pair_at_c2_size_equals_the_reference_digests(tmp_path):
+    """BASELINE.json's config 4 shape: a 60x tumour (18.4 M records) and a 30x normal of the same donor, C2-sized chromosome:
+    getclip on both, getsv on the tumour, somatic against the normal - every output against the digests of the reference's own run
+    (tests/golden/c2/c4.digests.json, tests/golden/make_c2_digests.py <dir> c4)."""
+    import hashlib
+    import json
+    svsim, mini = (os.path.join(ROOT, "seeksv_b200", "bin", t) for t in ("svsim", "minialign"))
+    if not (os.path.exists(svsim) and os.path.exists(mini)):
+        pytest.skip("needs the svsim / minialign tools (python -m seeksv_b200.build)")
+    with open(os.path.join(GOLDEN, "c2", "c4.digests.json")) as f:
+        want = json.load(f)
+
+    def dig(data):
+        return {"md5": hashlib.md5(data).hexdigest(), "bytes": len(data)}
+    pre = {}
+    for kind in ("tumor", "normal"):
+        pre[kind] = str(tmp_path / kind)
+        subprocess.run([svsim, "--out", pre[kind]] + want[kind + "_args"], check=True, stderr=subprocess.DEVNULL)
+        r = subprocess.run([_cli(), "getclip", "-o", pre[kind] + ".out", pre[kind] + ".bam"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        for ext in (".clip.gz", ".clip.fq.gz", ".unmapped_1.fq.gz", ".unmapped_2.fq.gz"):
+            with gzip.open(pre[kind] + ".out" + ext, "rb") as f:
+                assert dig(f.read()) == want[kind + ext], (kind, ext)
+    out = pre["tumor"] + ".out"
+    with open(out + ".clip.sam", "wb") as o:
+        subprocess.run([mini, pre["tumor"] + ".fa", out + ".clip.fq.gz"], check=True, stdout=o)
+    assert dig(open(out + ".clip.sam", "rb").read()) == want["tumor.clip.sam"]
+    r = subprocess.run([_cli(), "getsv", out + ".clip.sam", pre["tumor"] + ".bam", out + ".clip.gz", out + ".sv", out + ".unm"], capture_output=True)
+    assert r.returncode == 0, r.stderr
+    assert dig(open(out + ".sv", "rb").read()) == want["tumor getsv"]["sv"] and dig(r.stdout) == want["tumor getsv"]["stdout"]
+    r = subprocess.run([_cli(), "somatic", pre["normal"] + ".bam", pre["normal"] + ".out.clip.gz", out + ".sv", out + ".somatic"], capture_output=True)
+    assert r.returncode == 0, r.stderr
+    assert dig(open(out + ".somatic", "rb").read()) == want["somatic"]
+
+
+@pytest.mark.parametrize("name", ["c3mini", "c5mini", "c5"])
 def test_other_config_shapes_equal_the_reference_digests(name, tmp_path):
     """Stand-ins for the shapes of BASELINE.json's configs 3 and 5 (24 contigs chr1..chrY whose names sort chr1 < chr10 < ... < chr2;
-    a human contig plus HBV / HPV16 contigs at several thousand x), 2.5 M / 1.6 M records: digests of the reference's outputs
+    a human contig plus HBV / HPV16 contigs at several thousand x), 2.5 M / 1.6 M records, and config 5's shape at full size (c5:
+    the C2 chromosome + both virus contigs at 6000x with 40 planted integrations, 9.6 M records): digests of the reference's outputs
     (tests/golden/c2/<name>.digests.json) against the CLI's."""
     import json
     svsim = os.path.join(ROOT, "seeksv_b200", "bin", "svsim")
