@@ -293,6 +293,7 @@ def partitioned_main(args, torch, dist, rank, world, local):
     vec_all = torch.zeros(world * (world + 4), dtype=torch.int64, device=device)
     part = torch.zeros(4, dtype=torch.int64, device=device)
     sizes_host = torch.zeros(world, dtype=torch.int64).pin_memory()
+    cap_flag = torch.zeros(1, dtype=torch.int32, device=device)      # a pile-up at libbam's cap cut by a shard boundary (sharding.py)
     phases = {}
 
     def shard_step(keep=False):
@@ -339,7 +340,7 @@ def partitioned_main(args, torch, dist, rank, world, local):
         t3 = time.perf_counter()
         gw = sharding.GpuShardWorker(b, device)
         gw._arrays = prepared
-        t = sharding.sharded_pairs_depth(gw, dist, 20, mean, dev, 4, juncs, wins)
+        t = sharding.sharded_pairs_depth(gw, dist, 20, mean, dev, 4, juncs, wins, cap_flag=cap_flag)   # (flag checked after the timed loops)
         t4 = time.perf_counter()
         got = done.get()
         if isinstance(got, Exception):
@@ -420,6 +421,7 @@ def partitioned_main(args, torch, dist, rank, world, local):
     ms_prof, _, _ = timed(shard_step, args.steps)
     prof = ctx.prof_read()
     ctx.prof(False)
+    assert int(cap_flag.item()) == 0, "a pile-up of >= 8000 reads is cut by a shard boundary: the sharded depth is not the whole-file depth"
 
     # ---- end to end: the two commands on N GPUs through the multi-GPU entry points, BGZF file -> output files --------------------
     out_dir = os.path.join(WORK, "pout")

@@ -17,7 +17,7 @@
 // ---- device control block ------------------------------------------------------------------------------------------------------
 struct ClipCtl {
     uint32_t counters[4];  // [0] clipped records [1] unmapped-branch records [2] chromosome switches [3] candidates
-    uint32_t flags[4];     // [0] row slots overflowed [1] chain does not verify [2] spare [3] spare
+    uint32_t flags[4];     // [0] row slots overflowed [1] chain does not verify [2] a read reaches the next range shard's keys from outside its halo [3] spare
     uint64_t c64[2];       // records, end of the chain
     uint32_t n_seg, n_cl, un_skip, un_own;
     uint32_t abort_main, abort_side, tk_cluster, tk_text;  // tickets of the persistent warps of cluster_build / text_write
@@ -131,7 +131,7 @@ struct ClipParams {
 };
 
 struct Emit {
-    bool e5 = false, e3 = false;
+    bool e5 = false, e3 = false, halo_miss = false;
     int32_t pos5 = 0, pos3 = 0;
     uint32_t b5 = 0, l5 = 0, r5 = 0, b3 = 0, l3 = 0, r3 = 0;
 };
@@ -150,10 +150,11 @@ __device__ Emit eval_clip(const uint8_t *__restrict__ d, uint64_t o, const Core 
     bool s1 = op1 == OP_S, s2 = op2 == OP_S;
     if (!s1 && !s2) return E;
     // GenerateCigar's l (clip_reads.cpp:322): M, D, =, N - X is not counted (quirk Q5)
-    int32_t reflen = 0;
+    int32_t reflen = 0, eq_len = 0;
     for (uint32_t j = 0; j < k.n_cigar; ++j) {
         uint32_t w = ldu32(cig + 4 * j), op = w & 15;
         if (op == OP_M || op == OP_D || op == OP_EQ || op == OP_N) reflen += (int32_t)(w >> 4);
+        if (op == OP_EQ) eq_len += (int32_t)(w >> 4);
     }
     const uint8_t *aux = cig + 4 * k.n_cigar + (k.l_qseq + 1) / 2 + k.l_qseq;
     int32_t xc = aux_xc(aux, (uint32_t)max((int64_t)0, (int64_t)(p + 4 + k.block_size - aux)));
@@ -179,6 +180,13 @@ __device__ Emit eval_clip(const uint8_t *__restrict__ d, uint64_t o, const Core 
         E.b3 = len1, E.l3 = (uint32_t)mid, E.r3 = len2;  // clip_reads.cpp:154,185
     }
     E.pos5 = k.pos + 1, E.pos3 = k.pos + reflen;
+    // Range shards: a '3' key at or beyond this shard's upper bound belongs to the next shard, which sees this record only if it
+    // lies in its halo - and the halo comes from the .bai, whose alignment end (bam_calend: M, D, N) does not count the `=`
+    // operations that GenerateCigar's length does. A record that ends, by libbam's count, at or before the start of the window in
+    // front of the cut is not promised to the next shard: refuse loudly instead of dropping the cluster member (svb_getclip fails).
+    if (E.e3 && eq_len > 0 && (k.tid > P.hi_tid || (k.tid == P.hi_tid && E.pos3 >= P.hi_pos)) &&
+        k.pos + reflen - eq_len <= ((((P.hi_pos - 1) >> 14) - 1) << 14))
+        E.halo_miss = true;
     E.e5 = E.e5 && P.owns(k.tid, E.pos5);
     E.e3 = E.e3 && P.owns(k.tid, E.pos3);
     return E;
@@ -234,6 +242,7 @@ __global__ void __launch_bounds__(128)
             tid = k.tid;
             E = eval_clip(d, o, k, P);
         }
+        if (E.halo_miss) ctl->flags[2] = 1;
         const uint32_t mine = (uint32_t)E.e5 + (uint32_t)E.e3;
         if (mine) {
             // cluster_build reads this record's bases and qualities next: ask L2 for those lines now (the head and the aux block
@@ -1178,6 +1187,10 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
             CKR(repair_guesses(ctx, bam));
             continue;
         }
+        if (h.flags[2])
+            return svb_fail(ctx, SVB_ERR_FORMAT,
+                            "a soft-clipped read with `=` CIGAR operations reaches a breakpoint key of the next coordinate-range shard from "
+                            "outside that shard's halo (the .bai counts M, D, N only): shard by chromosome or run the single-process command");
         bool again = false;
         auto grow32 = [&](uint32_t &c, uint32_t need) {
             if (need > c) c = need + need / 16 + 64, again = true;

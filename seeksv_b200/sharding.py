@@ -346,12 +346,35 @@ def sharded_insert_stats(worker, dist, device, min_mapq: int, max_pairs: int):
     return n, mean, mean_dev(n, mean * n, sq)[1]
 
 
-def sharded_pairs_depth(worker, dist, min_mapq, mean, dev, times, junctions, windows):
+PILEUP_CAP = 8000  # libbam's pileup buffer refuses reads above this many at one position (quirk Q12)
+
+
+def cap_cut_by_shards(own, total, n_junctions: int):
+    """The libbam pileup cap is global per position. Every shard emulates it on its own records, so the summed depth equals the
+    whole-file depth unless a position that reaches the cap got reads from MORE THAN ONE shard (a > 8000x pile-up cut by a shard
+    boundary). Returns a 0/1 tensor (on the tensors' device): 1 = this rank contributed part, not all, of such a position."""
+    d_own, d_tot = own[n_junctions:], total[n_junctions:]
+    return ((d_tot >= PILEUP_CAP) & (d_own > 0) & (d_own < d_tot)).any().to(total.dtype).reshape(1)
+
+
+def sharded_pairs_depth(worker, dist, min_mapq, mean, dev, times, junctions, windows, cap_flag=None):
     """per-junction discordant-pair counts and per-position window depth, summed over the shards with ONE all_reduce of the
-    tensor the workers filled (device memory under NCCL)"""
+    tensor the workers filled (device memory under NCCL). A pile-up that reaches libbam's cap across a shard boundary cannot be
+    reproduced by adding shards up: it is detected and refused loudly - RuntimeError here, or, when the caller passes cap_flag (a
+    one-element tensor it checks itself, e.g. after a timed loop), OR-ed into that tensor without a synchronisation."""
     t = worker.pairs_depth(min_mapq, mean, dev, times, junctions, windows)
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        own = t.clone()
         dist.all_reduce(t)
+        flag = cap_cut_by_shards(own, t, len(junctions))
+        if cap_flag is not None:
+            cap_flag |= flag.to(cap_flag.dtype)
+        else:
+            dist.all_reduce(flag)
+            if int(flag.item()):
+                raise RuntimeError("a pile-up of %d or more reads is cut by a shard boundary: libbam's pileup cap (bam2depth.cpp:17-142 via "
+                                   "bam_plp) is global per position and is not reproduced by range shards - shard --by chromosome or run "
+                                   "the single-process command" % PILEUP_CAP)
     return t
 
 

@@ -461,6 +461,45 @@ def test_coordinate_range_shards_of_one_bam_reproduce_the_whole_file(ctx, d, s):
             w.close()
 
 
+def test_range_shards_refuse_a_read_that_reaches_the_next_shard_from_outside_its_halo(ctx, tmp_path):
+    """The documented limit of coordinate-range shards: the halo of a shard comes from the .bai, whose alignment
+    end counts M, D, N only, while getclip's '3' breakpoint position also counts `=`. A soft-clipped read with a 60 kb `=` operation
+    in front of a cut ends, for getclip, in the NEXT shard's key range, but that shard's halo does not hold the record. The shard
+    that has the record must fail loudly (no silent loss of a cluster member); the whole-file run is exact."""
+    import random
+    import seeksv_b200
+    from oracle import bamio, getclip_oracle
+    from seeksv_b200 import sharding
+    bamtool = os.path.join(ROOT, "oracle", "_ref", "bamtool")
+    if not os.path.exists(bamtool):
+        pytest.skip("needs oracle/_ref/bamtool (libbam's indexer)")
+    rng = random.Random(3)
+    h = bamio.Header(["c1"], [200000])
+    recs = []
+    for i, pos in enumerate(range(100, 150000, 40)):
+        recs.append(bamio.make_rec("r%d" % i, 0, 0, pos, 60, "100M", -1, -1, 0, "".join(rng.choice("ACGT") for _ in range(100)), "I" * 100))
+    seq = "".join(rng.choice("ACGT") for _ in range(10 + 60000 + 50))
+    recs.append(bamio.make_rec("long_eq", 0, 0, 20000, 60, "10M60000=50S", -1, -1, 0, seq, "I" * len(seq)))   # libbam's end 20010, getclip's key 80010
+    recs.sort(key=lambda r: (r.tid, r.pos))
+    path = str(tmp_path / "halo.bam")
+    bamio.write_bam(path, h, recs)
+    subprocess.run([bamtool, "index", path], check=True)
+    want = getclip_oracle.getclip(h, recs)
+    assert want[0].count("\n") == 1 and want[0].split("\t")[1] == "80010"
+    whole = seeksv_b200.Bam.open(ctx, path)
+    assert tuple(t.decode("latin-1") for t in whole.getclip()) == tuple(want)
+    whole.close()
+    plans = sharding.plan_range_shards(path, None, 1, 2)
+    assert plans[0].key_hi[1] < 80010 and (((plans[0].key_hi[1] - 1) >> 14) - 1) << 14 > 20010, "the cut has to lie between the two ends"
+    w0 = sharding.RangeShardWorker(ctx, path, plans[0])
+    with pytest.raises(seeksv_b200.SvbError, match="halo"):
+        w0.getclip()
+    w0.close()
+    w1 = sharding.RangeShardWorker(ctx, path, plans[1])      # the owner of the key does not see the record: nothing to cluster there
+    assert w1.getclip()[0] == ""
+    w1.close()
+
+
 def seeksv_b200_header(path):
     from oracle import bamio
     return bamio.read_bam(path)[0].names

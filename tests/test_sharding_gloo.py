@@ -233,6 +233,29 @@ def _stats_worker(rank, world, port, q):
             results.append(((n, mean, dev), want))
             t = sharding.sharded_pairs_depth(W(), dist, 20, mean, dev, 4, [], [])
             results.append((t.tolist()[:2], [sum(r + 1 for r in range(world)), sum(10 * (r + 1) for r in range(world))]))
+
+        # libbam's pileup cap is global per position: a >= 8000x position fed by TWO shards must be refused loudly, on every rank;
+        # the same depth from one shard alone is fine (that shard's own cap emulation is exact)
+        class C:
+            def __init__(self, vals):
+                self.vals = vals
+
+            def pairs_depth(self, *a):
+                return torch.tensor(self.vals, dtype=torch.int32)
+        juncs, wins = [(0, 1, "+", 0, 2, "-")], [(0, 1, 3)]        # one junction count in front of three depth positions
+        cut = {0: [3, 5000, 10, 0], 1: [2, 4000, 0, 7]}.get(rank, [0, 0, 0, 0])
+        try:
+            sharding.sharded_pairs_depth(C(cut), dist, 20, 0, 0, 4, juncs, wins)
+            raised = False
+        except RuntimeError as e:
+            raised = "pile-up" in str(e)
+        results.append(([raised], [True]))
+        flag = torch.zeros(1, dtype=torch.int32)
+        sharding.sharded_pairs_depth(C(cut), dist, 20, 0, 0, 4, juncs, wins, cap_flag=flag)        # the caller checks later (bench.py)
+        results.append(([int(flag.item())], [1 if rank < 2 else 0]))
+        whole = {0: [3, 9000, 10, 0], 1: [2, 0, 0, 7]}.get(rank, [0, 0, 0, 0])
+        t = sharding.sharded_pairs_depth(C(whole), dist, 20, 0, 0, 4, juncs, wins)
+        results.append((t.tolist(), [5, 9000, 10, 7]))
         q.put((rank, results))
     finally:
         dist.destroy_process_group()
