@@ -653,6 +653,168 @@ bool sam_to_bam_stream(const std::vector<uint8_t> &text, BamHeader &h, std::vect
 }
 
 // gzip file written by write_gz_many: every member announces its size in an 'SV' extra sub-field
+// Inflate of the members our own writers produce (svb_write_gz, gzip.cu): dynamic-Huffman blocks of LITERALS only. zlib decodes
+// such a stream one symbol per table lookup (~120 MB/s per thread: getsv spent 14-31 ms on the 30 MB clip text of C2); here a
+// 12-bit table returns up to two literals per lookup. Anything else in the stream (a stored or fixed block, a length symbol, a
+// damaged code) makes this return false and the caller falls back to zlib, which also reports the errors.
+namespace {
+struct LitBits {
+    const uint8_t *p, *end;
+    uint64_t buf = 0;
+    int cnt = 0;
+    inline void refill()
+    {
+        if (end - p >= 8) {
+            uint64_t w;
+            memcpy(&w, p, 8);
+            buf |= w << cnt;
+            const int adv = (63 - cnt) >> 3;
+            p += adv, cnt += adv * 8;
+        } else
+            while (cnt <= 56 && p < end) buf |= (uint64_t)*p++ << cnt, cnt += 8;
+    }
+    inline uint32_t take(int k)
+    {
+        const uint32_t v = (uint32_t)(buf & ((1ull << k) - 1));
+        buf >>= k, cnt -= k;
+        return v;
+    }
+};
+
+bool inflate_literal_stream(const uint8_t *in, size_t n, uint8_t *out, uint32_t ulen)
+{
+    static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    constexpr int TB = 12;
+    std::vector<uint32_t> tab(1u << TB), one(1u << TB);
+    LitBits b{in, in + n};
+    uint8_t *o = out, *const oe = out + ulen;
+    for (;;) {
+        b.refill();
+        if (b.cnt < 17) return false;
+        const uint32_t final_block = b.take(1), type = b.take(2);
+        if (type != 2) return false;
+        const int n_lit = (int)b.take(5) + 257, n_dist = (int)b.take(5) + 1, n_cl = (int)b.take(4) + 4;
+        if (n_lit > 286 || n_dist > 30) return false;
+        uint8_t cl[19] = {0}, lens[320] = {0};
+        for (int i = 0; i < n_cl; ++i) {
+            b.refill();
+            cl[order[i]] = (uint8_t)b.take(3);
+        }
+        // code-length alphabet: canonical codes, 7-bit lookup
+        uint8_t cl_sym[128], cl_len[128];
+        memset(cl_len, 0, sizeof cl_len);
+        {
+            int cnt[8] = {0};
+            for (int i = 0; i < 19; ++i) cnt[cl[i]]++;
+            cnt[0] = 0;
+            uint32_t next[8], code = 0;
+            for (int l = 1; l < 8; ++l) code = (code + cnt[l - 1]) << 1, next[l] = code;
+            for (int s = 0; s < 19; ++s)
+                if (cl[s]) {
+                    uint32_t c = next[cl[s]]++, r = 0;
+                    for (int k = 0; k < cl[s]; ++k) r |= ((c >> k) & 1u) << (cl[s] - 1 - k);
+                    for (uint32_t k = r; k < 128; k += 1u << cl[s]) cl_sym[k] = (uint8_t)s, cl_len[k] = cl[s];
+                }
+        }
+        for (int i = 0, total = n_lit + n_dist; i < total;) {
+            b.refill();
+            const uint32_t k = (uint32_t)(b.buf & 127);
+            if (!cl_len[k] || b.cnt < cl_len[k] + 7) return false;
+            b.take(cl_len[k]);
+            const int s = cl_sym[k];
+            if (s < 16) lens[i++] = (uint8_t)s;
+            else {
+                int rep, v = 0;
+                if (s == 16) {
+                    if (!i) return false;
+                    v = lens[i - 1], rep = 3 + (int)b.take(2);
+                } else if (s == 17) rep = 3 + (int)b.take(3);
+                else rep = 11 + (int)b.take(7);
+                if (i + rep > total) return false;
+                while (rep--) lens[i++] = (uint8_t)v;
+            }
+        }
+        if (!lens[256]) return false;
+        // literal/length alphabet: canonical codes -> single-symbol table, then pairs
+        int cnt[16] = {0};
+        for (int s = 0; s < n_lit; ++s) cnt[lens[s]]++;
+        cnt[0] = 0;
+        uint32_t next[16], first_code[16], code = 0;
+        int left = 1;
+        for (int l = 1; l <= 15; ++l) {
+            code = (code + cnt[l - 1]) << 1, next[l] = first_code[l] = code;
+            left = (left << 1) - cnt[l];
+            if (left < 0) return false;
+        }
+        uint16_t sorted[288], offs[16];
+        offs[1] = 0;
+        for (int l = 1; l < 15; ++l) offs[l + 1] = (uint16_t)(offs[l] + cnt[l]);
+        {
+            uint16_t at[16];
+            memcpy(at, offs, sizeof at);
+            for (int s = 0; s < n_lit; ++s)
+                if (lens[s]) sorted[at[lens[s]]++] = (uint16_t)s;
+        }
+        std::fill(one.begin(), one.end(), 0u);
+        for (int s = 0; s < 256 && s < n_lit; ++s) {  // (end of block and length symbols take the slow path)
+            const int l = lens[s];
+            if (!l) continue;
+            const uint32_t c = next[l]++;
+            if (l > TB) continue;
+            uint32_t r = 0;
+            for (int k = 0; k < l; ++k) r |= ((c >> k) & 1u) << (l - 1 - k);
+            const uint32_t e = (uint32_t)l | 1u << 4 | (uint32_t)s << 8;
+            for (uint32_t k = r; k < (1u << TB); k += 1u << l) one[k] = e;
+        }
+        for (uint32_t k = 0; k < (1u << TB); ++k) {
+            const uint32_t e = one[k];
+            uint32_t t = e;
+            if (e) {
+                const int l1 = (int)(e & 15);
+                const uint32_t e2 = one[k >> l1];  // the bits behind the first code, zero-extended: trusted only if the code fits
+                if (e2 && l1 + (int)(e2 & 15) <= TB) t = (uint32_t)(l1 + (e2 & 15)) | 2u << 4 | (e & 0xff00u) | ((e2 >> 8) & 0xffu) << 16;
+            }
+            tab[k] = t;
+        }
+        for (;;) {  // tokens of this block
+            b.refill();
+            if (oe - o >= 8 && b.cnt >= 48) {
+                for (int rep = 0; rep < 3; ++rep) {  // three lookups (<= 36 bits) per refill
+                    const uint32_t e = tab[b.buf & ((1u << TB) - 1)];
+                    if (!e) goto slow;
+                    o[0] = (uint8_t)(e >> 8), o[1] = (uint8_t)(e >> 16);
+                    o += (e >> 4) & 3;
+                    b.buf >>= e & 15, b.cnt -= (int)(e & 15);
+                }
+                continue;
+            }
+        slow: {
+            // one symbol, canonically (long codes, the end of the block, the last bytes of the member)
+            if (b.cnt < 1) return false;
+            uint32_t c = 0;
+            int l = 0, s = -1;
+            uint64_t w = b.buf;
+            for (l = 1; l <= 15; ++l) {
+                c = c << 1 | (uint32_t)(w & 1);
+                w >>= 1;
+                if (cnt[l] && c >= first_code[l] && c - first_code[l] < (uint32_t)cnt[l]) {
+                    s = sorted[offs[l] + (c - first_code[l])];
+                    break;
+                }
+            }
+            if (s < 0 || b.cnt < l) return false;
+            b.take(l);
+            if (s == 256) break;
+            if (s > 256 || o >= oe) return false;
+            *o++ = (uint8_t)s;
+        }
+        }
+        if (final_block) break;
+    }
+    return o == oe;
+}
+}  // namespace
+
 static bool read_indexed_gz(const uint8_t *f, uint64_t n, std::string &out)
 {
     struct Member {
@@ -675,10 +837,20 @@ static bool read_indexed_gz(const uint8_t *f, uint64_t n, std::string &out)
     out.resize(total);
     std::atomic<size_t> next(0);
     std::atomic<bool> bad(false);
+    const char *mode = getenv("SEEKSV_B200_GZ_READ");  // "zlib": every member through zlib (tests compare the two)
+    const bool fast = !(mode && strcmp(mode, "zlib") == 0);
     auto work = [&]() {
         for (;;) {
             size_t i = next.fetch_add(1);
             if (i >= ms.size()) return;
+            if (fast && ms[i].ulen && ms[i].size > 28) {  // our writers' literal-only members: the fast decoder, checked like zlib checks them
+                const uint8_t *m = f + ms[i].off, *t = m + ms[i].size - 8;
+                const uint32_t want_crc = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+                uint8_t *dst = (uint8_t *)&out[ms[i].uoff];
+                if (inflate_literal_stream(m + 20, (size_t)ms[i].size - 28, dst, ms[i].ulen) &&
+                    (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, ms[i].ulen) == want_crc)
+                    continue;
+            }
             z_stream zs;
             memset(&zs, 0, sizeof zs);
             if (inflateInit2(&zs, 15 + 16) != Z_OK) {

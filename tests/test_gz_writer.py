@@ -37,7 +37,9 @@ def test_writer_output_is_plain_gzip_and_reader_round_trips(tmp_path, monkeypatc
         raw = open(p, "rb").read()
         assert raw[:4] == b"\x1f\x8b\x08\x04" and raw[12:14] == b"SV", name
         assert gzip.decompress(raw) == data, name
-        assert L.read_gz(p) == data, name
+        for reader in ("", "zlib"):     # the two-literals-per-lookup decoder of our own members (falls back to zlib), and zlib alone
+            monkeypatch.setenv("SEEKSV_B200_GZ_READ", reader)
+            assert L.read_gz(p) == data, (name, reader)
 
 
 def test_reader_accepts_foreign_gzip_and_plain_text(tmp_path):
@@ -51,3 +53,23 @@ def test_reader_accepts_foreign_gzip_and_plain_text(tmp_path):
     assert L.read_gz(q) == data
     with pytest.raises(L.SvbError):
         L.read_gz(str(tmp_path / "missing.gz"))
+
+
+def test_fast_reader_rejects_damage_like_zlib_does(tmp_path, monkeypatch):
+    """a damaged member must not come back as text from either reader (the fast decoder checks CRC-32 and length, then zlib decides)"""
+    rnd = random.Random(9)
+    data = bytes(rnd.choices(b"ACGTN\t\n0123456789", k=400000))
+    p = str(tmp_path / "x.gz")
+    L.write_gz(p, data, threads=2)
+    raw = bytearray(open(p, "rb").read())
+    for reader in ("", "zlib"):
+        monkeypatch.setenv("SEEKSV_B200_GZ_READ", reader)
+        for trial in range(20):
+            bad = bytearray(raw)
+            bad[40 + rnd.randrange(len(raw) - 60)] ^= 1 << rnd.randrange(8)
+            q = str(tmp_path / "bad.gz")
+            open(q, "wb").write(bad)
+            try:
+                assert L.read_gz(q) != data or bytes(bad) == bytes(raw)
+            except L.SvbError:
+                pass
