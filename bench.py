@@ -502,7 +502,12 @@ def partitioned_main(args, torch, dist, rank, world, local):
                        "checked": "sharded clip / clip.fq / unmapped FASTQ / statistics / pair counts / depths == the whole-file run (untimed prologue)",
                        "l2_note": "each shard (%.2f GB) is far larger than the 126 MB L2; no flush needed" % (nbytes / 1e9)},
             "e2e": {"value": n_total / wall_e2e if wall_e2e == wall_e2e else None, "unit": "records/s", "ms_per_step": 1e3 * wall_e2e,
-                    "h2d_bytes_per_step": 2 * os.path.getsize(bam_path), "d2h_bytes_per_step": None,
+                    "h2d_bytes_per_step": 2 * os.path.getsize(bam_path),
+                    "d2h_bytes_per_step": (len(ref["clip"][0]) + len(ref["clip"][1]) + 4 * (nj + n_pos)
+                                           + int(sum(os.path.getsize(os.path.join(out_dir, f)) for f in os.listdir(out_dir) if f.startswith("x.unmapped")))
+                                           ) if wall_e2e == wall_e2e else None,
+                    "d2h_note": "all ranks together: the clip / clip.fq TEXT of every shard (device -> pinned host, compressed into gzip block files by "
+                                "that rank's host threads), the two unmapped FASTQ files compressed on rank 0's device, pair counts and depths",
                     "path": "seeksv_b200.mgpu getclip + getsv on N ranks: BGZF file (page cache) -> each rank loads its shard twice -> device passes -> "
                             "NCCL merges -> rank 0 writes the reference's files"},
             "gpu_launches": int(sum(v["launches"] for v in kern.values())),

@@ -976,10 +976,18 @@ extern "C" int svb_plan_getsv(const char *clip_aln, const char *clip_file, int32
     if (!clip_aln || !clip_file || !junctions || !n_j || !windows || !n_w || (n_ref && (!ref_names || !ref_lens))) return SVB_ERR_ARG;
     std::string err, clip_text;
     AlignmentSet alns;
-    if (!load_alignments(clip_aln, alns, err) || !read_text_maybe_gz(clip_file, clip_text, err)) return SVB_ERR_IO;
+    Phase ph;
+    if (!load_alignments(clip_aln, alns, err)) return SVB_ERR_IO;
+    ph.mark("plan: read clip alignments");
+    if (!read_text_maybe_gz(clip_file, clip_text, err)) return SVB_ERR_IO;
+    ph.mark("plan: read clip.gz");
     JunctionMap jm;
-    join_clips_with_alignments(parse_clip_text(clip_text, n_threads()), alns, jm);
+    std::vector<ClipLine> lines = parse_clip_text(clip_text, n_threads());
+    ph.mark("plan: tokenise");
+    join_clips_with_alignments(lines, alns, jm);
+    ph.mark("plan: join");
     merge_junctions(jm, reach);
+    ph.mark("plan: merge");
     std::map<std::string, int32_t> tid_of;
     std::vector<uint32_t> lens(ref_lens, ref_lens + n_ref);
     for (int32_t t = 0; t < n_ref; ++t) tid_of.insert(std::make_pair(std::string(ref_names[t]), t));
