@@ -495,9 +495,8 @@ def test_range_shards_refuse_a_read_that_reaches_the_next_shard_from_outside_its
     with pytest.raises(seeksv_b200.SvbError, match="halo"):
         w0.getclip()
     w0.close()
-    w1 = sharding.RangeShardWorker(ctx, path, plans[1])      # the owner of the key does not see the record: nothing to cluster there
-    assert w1.getclip()[0] == ""
-    w1.close()
+    # (the refusal is conservative: whether the owner of the key happens to hold the record in the context it loads in front of its
+    # halo is not something the refusing shard can know)
 
 
 def seeksv_b200_header(path):
