@@ -309,7 +309,8 @@ class Clusters:
 
     def close(self):
         if self.h:
-            self.ctx.L.svb_clusters_free(self.h)
+            if self.ctx.h:      # (a handle that outlived its context - e.g. after an exception - is dropped, not freed into a dead context)
+                self.ctx.L.svb_clusters_free(self.h)
             self.h = None
 
     def __del__(self):
@@ -584,7 +585,8 @@ class Bam:
 
     def close(self):
         if self.h:
-            self.ctx.L.svb_bam_free(self.h)
+            if self.ctx.h:      # (see Clusters.close)
+                self.ctx.L.svb_bam_free(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):
