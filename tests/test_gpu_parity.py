@@ -872,7 +872,8 @@ def test_config3_eight_range_shards_cross_chromosome_boundaries(ctx, c3w8_prefix
     pre, want = c3w8_prefix
     path = pre + ".bam"
     whole = __import__("seeksv_b200").Bam.open(ctx, path)
-    n_ref, lens, n_records = len(whole.ref_names), whole.ref_lens, whole.n_records
+    names, lens, n_records = whole.ref_names, whole.ref_lens, whole.n_records
+    n_ref = len(names)
     n_w, tot_w, mean_w, _ = whole.insert_stats(20, 5000000)
     juncs = [(t, p, "+", t, p + 300, "-") for t in range(n_ref) for p in range(1000, lens[t] - 1000, 200000)]
     want_counts = whole.discordant_support(juncs, 20, mean_w, 25, 4)
@@ -900,6 +901,7 @@ def test_config3_eight_range_shards_cross_chromosome_boundaries(ctx, c3w8_prefix
     assert dig(clip) == want[".clip.gz"] and dig(fq) == want[".clip.fq.gz"]
     import seeksv_b200
     mini = seeksv_b200.Bam.from_host(ctx, b"".join(p[2] for p in parts), 0, n_ref)
+    mini.set_refs(names, lens)
     cu = mini.getclip_handle(unmapped_only=True)
     assert dig(cu.text(2)) == want[".unmapped_1.fq.gz"] and dig(cu.text(3)) == want[".unmapped_2.fq.gz"]
     cu.close()
