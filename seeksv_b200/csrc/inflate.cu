@@ -911,23 +911,15 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, MIN_CTAS)
                         if ((uint32_t)k * 4 < need) w[k] = wp[k];
                 }
                 uint32_t far_long = __ballot_sync(full, far && n > COOP_LEN);
-                {   // whole warp per long match, 32 bytes per step; a step's bytes are stored after the NEXT step's loads are issued
-                    uint8_t held = 0, *held_to = nullptr;
-                    while (far_long) {
-                        const int tl = __ffs(far_long) - 1;
-                        far_long &= far_long - 1;
-                        const uint32_t o_t = __shfl_sync(full, o, tl), n_t = __shfl_sync(full, n, tl);
-                        const uint8_t *src = g + __shfl_sync(full, s, tl) + lane;
-                        uint8_t *to = M.span + o_t + lane;
+                while (far_long) {  // whole warp per long match; nothing to wait for between them
+                    const int tl = __ffs(far_long) - 1;
+                    far_long &= far_long - 1;
+                    const uint32_t o_t = __shfl_sync(full, o, tl), n_t = __shfl_sync(full, n, tl);
+                    const uint8_t *src = g + __shfl_sync(full, s, tl) + lane;
+                    uint8_t *to = M.span + o_t + lane;
 #pragma unroll 1
-                        for (uint32_t i = lane; i < n_t + lane; i += 32, src += 32, to += 32) {  // (uniform trip count, predicated body)
-                            uint8_t v = 0;
-                            if (i < n_t) v = *src;
-                            if (held_to) *held_to = held;
-                            held = v, held_to = i < n_t ? to : nullptr;
-                        }
-                    }
-                    if (held_to) *held_to = held;
+                    for (uint32_t i = lane; i < n_t + lane; i += 32, src += 32, to += 32)  // (uniform trip count, predicated body)
+                        if (i < n_t) *to = *src;
                 }
                 if (far_short) {
                     uint32_t v[4];
