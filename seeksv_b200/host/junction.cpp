@@ -146,18 +146,40 @@ static int hw_threads(int n) { return n > 0 ? n : (int)std::max(1u, std::thread:
 // isspace() of the "C" locale (what `fin >> token` skips) without the call per byte: 30 MB of clip text went through it
 static inline bool is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
+// atoi() of a token without a heap copy (the token is followed by a tab or a newline inside the text, never by a digit)
+static inline int token_int(std::string_view t)
+{
+    if (t.size() > 9) return atoi(std::string(t).c_str());  // (may overflow: leave it to the library)
+    size_t i = 0;
+    bool neg = false;
+    if (i < t.size() && (t[i] == '-' || t[i] == '+')) neg = t[i] == '-', ++i;
+    int v = 0;
+    for (; i < t.size() && t[i] >= '0' && t[i] <= '9'; ++i) v = v * 10 + (t[i] - '0');
+    return neg ? -v : v;
+}
+
 std::vector<ClipLine> parse_clip_text(const std::string &text, int n_threads)
 {
     // `fin >> chr >> pos >> orientation >> cigar >> ... >> support; getline(...)` (getsv.h:453-456): whitespace-separated
     // tokens, the rest of the line is dropped. Fields are views into `text`; line chunks are parsed in parallel.
+    // One pass per chunk finds every byte below 0x21 eight bytes at a time (all white space is below 0x21; sequence, quality and
+    // number characters are not): a tab closes a field, a newline closes the line, anything else - a blank, a carriage return, an
+    // empty field among the first nine - sends that line through the generic `>>` rule.
     const char *b = text.data(), *e = b + text.size();
     auto chunks = line_chunks(b, e, text.size() > (1u << 20) ? hw_threads(n_threads) : 1);
     std::vector<std::vector<ClipLine>> part(chunks.size());
     run_parallel(chunks.size(), hw_threads(n_threads), [&](size_t ci) {
-        const char *p = chunks[ci].first, *ce = chunks[ci].second;
-        while (p < ce) {
-            const char *nl = (const char *)memchr(p, '\n', ce - p);
-            if (!nl) nl = ce;
+        const char *const cb = chunks[ci].first, *const ce = chunks[ci].second;
+        std::vector<ClipLine> &out = part[ci];
+        out.reserve((size_t)(ce - cb) / 200 + 16);
+        auto emit = [&](const std::string_view *t) {
+            ClipLine c;
+            c.chr = t[0], c.pos = token_int(t[1]), c.side = t[2][0], c.cigar = t[3];
+            c.aligned_seq = t[4], c.aligned_qual = t[5], c.clipped_seq = t[6], c.clipped_qual = t[7];
+            c.support = token_int(t[8]);
+            out.push_back(c);
+        };
+        auto generic = [&](const char *p, const char *nl) {
             std::string_view t[9];
             int nt = 0;
             const char *q = p;
@@ -167,21 +189,56 @@ std::vector<ClipLine> parse_clip_text(const std::string &text, int n_threads)
                 while (q < nl && !is_space(*q)) ++q;
                 if (q > s0) t[nt++] = std::string_view(s0, (size_t)(q - s0));
             }
-            if (nt == 9) {
-                ClipLine c;
-                c.chr = t[0], c.pos = atoi(std::string(t[1]).c_str()), c.side = t[2][0], c.cigar = t[3];
-                c.aligned_seq = t[4], c.aligned_qual = t[5], c.clipped_seq = t[6], c.clipped_qual = t[7];
-                c.support = atoi(std::string(t[8]).c_str());
-                part[ci].push_back(c);
+            if (nt == 9) emit(t);
+        };
+        std::string_view t[9];
+        int nf = 0;
+        bool special = false;
+        const char *line = cb, *field = cb, *p = cb;
+        auto close_field = [&](const char *q) {
+            if (nf < 9) {
+                if (q == field) special = true;
+                t[nf] = std::string_view(field, (size_t)(q - field));
             }
-            p = nl < ce ? nl + 1 : ce;
+            ++nf, field = q + 1;
+        };
+        auto close_line = [&](const char *q) {
+            close_field(q);
+            if (special || nf < 9) generic(line, q);
+            else emit(t);
+            nf = 0, special = false, line = field = q + 1;
+        };
+        while (p < ce) {
+            const char *q = ce;
+            if (ce - p >= 8) {
+                uint64_t x;
+                memcpy(&x, p, 8);
+                const uint64_t m = (x - 0x2121212121212121ull) & ~x & 0x8080808080808080ull;  // (the LOWEST flag is exact)
+                if (!m) {
+                    p += 8;
+                    continue;
+                }
+                q = p + (__builtin_ctzll(m) >> 3);
+            } else {
+                for (q = p; q < ce && (unsigned char)*q >= 0x21; ++q) {}
+                if (q == ce) break;
+            }
+            const char c = *q;
+            if (c == '\t') close_field(q);
+            else if (c == '\n') close_line(q);
+            else special = true;
+            p = q + 1;
+        }
+        if (line < ce) {  // last line without a newline
+            close_field(ce);
+            if (special || nf < 9) generic(line, ce);
+            else emit(t);
         }
     });
-    std::vector<ClipLine> out;
-    size_t total = 0;
-    for (auto &v : part) total += v.size();
-    out.reserve(total);
-    for (auto &v : part) out.insert(out.end(), v.begin(), v.end());
+    std::vector<size_t> at(part.size() + 1, 0);
+    for (size_t i = 0; i < part.size(); ++i) at[i + 1] = at[i] + part[i].size();
+    std::vector<ClipLine> out(at.back());
+    run_parallel(part.size(), hw_threads(n_threads), [&](size_t ci) { std::copy(part[ci].begin(), part[ci].end(), out.begin() + (ptrdiff_t)at[ci]); });
     return out;
 }
 
@@ -476,7 +533,16 @@ void join_clips_with_alignments(const std::vector<ClipLine> &lines, const Alignm
     // keys are (sequence the alignment was filed under, (chromosome, position)); views into the clip text, no copies
     typedef std::pair<std::string_view, std::pair<std::string, int>> AlnKey;
     const std::vector<Alignment> &alns = set.recs;
-    std::map<AlnKey, AlignInfo> found;
+    // the reference's std::map<key, info> of one run - a handful of entries: kept as a sorted vector (insert keeps the FIRST entry of
+    // a key, iteration is in key order, exactly as the map's) so that a run costs no node allocations
+    struct Found : std::vector<std::pair<AlnKey, AlignInfo>> {
+        void insert(std::pair<AlnKey, AlignInfo> &&kv)
+        {
+            auto it = std::lower_bound(begin(), end(), kv.first, [](const std::pair<AlnKey, AlignInfo> &a, const AlnKey &b) { return a.first < b; });
+            if (it != end() && !(kv.first < it->first)) return;
+            std::vector<std::pair<AlnKey, AlignInfo>>::insert(it, std::move(kv));
+        }
+    } found;
     const ClipLine *head = nullptr;  // first line of the current run
     std::string_view current;
     size_t ai = 0;

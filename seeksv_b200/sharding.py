@@ -150,11 +150,27 @@ class RangePlan:
 KEY_MIN, KEY_MAX = (-(2 ** 31), -(2 ** 31)), (2 ** 31 - 1, 2 ** 31 - 1)
 
 
+_PLAN_CACHE = {}
+
+
 def plan_range_shards(bam_path: str, bai_path: Optional[str], n_ref: int, world: int, context_steps: int = 1) -> List[RangePlan]:
+    """the same plan on every rank, from the .bai alone (memoised per file state: the commands of one process plan once)"""
+    import os
+    bai_path = bai_path or bam_path + ".bai"
+    key = (os.path.abspath(bam_path), os.path.abspath(bai_path), os.path.getmtime(bam_path), os.path.getsize(bam_path),
+           os.path.getmtime(bai_path), n_ref, world, context_steps)
+    if key not in _PLAN_CACHE:
+        if len(_PLAN_CACHE) > 64:
+            _PLAN_CACHE.clear()
+        _PLAN_CACHE[key] = _plan_range_shards(bam_path, bai_path, n_ref, world, context_steps)
+    import copy
+    return copy.deepcopy(_PLAN_CACHE[key])
+
+
+def _plan_range_shards(bam_path: str, bai_path: str, n_ref: int, world: int, context_steps: int) -> List[RangePlan]:
     import bisect
     import os
     from . import lib
-    bai_path = bai_path or bam_path + ".bai"
     lin = [lib.bai_linear_offsets(bai_path, t) for t in range(n_ref)]
     vset = sorted({v for L in lin for v in L if v})
     size = os.path.getsize(bam_path)
