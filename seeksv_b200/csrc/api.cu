@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstring>
 #include <atomic>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <future>
 #include <thread>
 
@@ -315,62 +317,89 @@ extern "C" int svb_bam_from_host(svb_ctx *ctx, const void *h_stream, uint64_t nb
     return finish_bam(ctx, b, out);
 }
 
-// Fill a pinned slab from a file with parallel pread()s: the kernel copies straight out of the page cache, without the
-// page faults that touching a fresh mapping of the file costs (one per 4 KiB, ~200 k per GB - CPU time the ranks of a
-// multi-GPU run do not have). Returns false on a short read.
-static bool parallel_pread(uint8_t *dst, int fd, uint64_t file_off, uint64_t n, int n_threads)
-{
-    const uint64_t PART = 1ull << 20;
-    uint64_t parts = (n + PART - 1) / PART;
-    int nt = (int)std::min<uint64_t>((uint64_t)std::max(1, n_threads), parts);
-    std::atomic<uint64_t> next(0);
-    std::atomic<bool> ok(true);
-    auto work = [&]() {
+// The staging copies of one load (page cache -> pinned slab, 32 MiB at a time) on a pool of threads that lives as long as the load:
+// spawning 15 threads per slab cost a quarter to a third of the copy itself (23 slabs for the C2 file). A job is cut into 1 MiB
+// parts; the caller takes part in the work and returns when the slab is filled. pread first (no page faults on a fresh mapping),
+// memcpy from the mapping for any part pread cannot deliver.
+class StagePool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    uint64_t gen = 0;
+    bool stop = false;
+    uint8_t *dst = nullptr;
+    const uint8_t *src = nullptr;
+    int fd = -1;
+    uint64_t off = 0, n = 0, parts = 0;
+    std::atomic<uint64_t> next{0}, done{0};
+    std::atomic<int> active{0};  // workers inside work(): a new job is published only when none is left in the previous one
+    static constexpr uint64_t PART = 1ull << 20;
+    void work()
+    {
         for (;;) {
-            uint64_t i = next.fetch_add(1);
+            const uint64_t i = next.fetch_add(1);
             if (i >= parts) return;
-            uint64_t a = i * PART, b = std::min(n, a + PART);
-            while (a < b) {
-                ssize_t r = pread(fd, dst + a, b - a, (off_t)(file_off + a));
-                if (r <= 0) {
-                    ok = false;
-                    return;
-                }
-                a += (uint64_t)r;
+            uint64_t a = i * PART;
+            const uint64_t b = std::min(n, a + PART);
+            bool by_read = fd >= 0;
+            while (by_read && a < b) {
+                const ssize_t r = pread(fd, dst + a, b - a, (off_t)(off + a));
+                if (r <= 0) by_read = false;
+                else a += (uint64_t)r;
+            }
+            if (a < b) memcpy(dst + a, src + a, b - a);
+            if (done.fetch_add(1) + 1 == parts) {
+                std::lock_guard<std::mutex> lock(m);
+                cv_done.notify_all();
             }
         }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(work);
-    work();
-    for (auto &t : th) t.join();
-    return ok;
-}
-
-// Parallel memcpy into a pinned slab (the source is any pageable buffer)
-static void parallel_copy(uint8_t *dst, const uint8_t *src, uint64_t n, int n_threads)
-{
-    const uint64_t PART = 1ull << 20;
-    uint64_t parts = (n + PART - 1) / PART;
-    int nt = (int)std::min<uint64_t>((uint64_t)std::max(1, n_threads), parts);
-    if (nt <= 1) {
-        memcpy(dst, src, n);
-        return;
     }
-    std::atomic<uint64_t> next(0);
-    auto work = [&]() {
-        for (;;) {
-            uint64_t i = next.fetch_add(1);
-            if (i >= parts) return;
-            uint64_t a = i * PART, b = std::min(n, a + PART);
-            memcpy(dst + a, src + a, b - a);
+
+public:
+    explicit StagePool(int n_threads)
+    {
+        for (int t = 1; t < n_threads; ++t)
+            th.emplace_back([this]() {
+                uint64_t seen = 0;
+                for (;;) {
+                    {
+                        std::unique_lock<std::mutex> lock(m);
+                        cv_job.wait(lock, [&]() { return stop || gen != seen; });
+                        if (stop) return;
+                        seen = gen;
+                        active.fetch_add(1);
+                    }
+                    work();
+                    active.fetch_sub(1);
+                }
+            });
+    }
+    ~StagePool()
+    {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            stop = true;
         }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(work);
-    work();
-    for (auto &t : th) t.join();
-}
+        cv_job.notify_all();
+        for (auto &t : th) t.join();
+    }
+    // fills dst[0, n) from the file (fd at file_off) or, failing that, from src
+    void run(uint8_t *dst_, int fd_, uint64_t file_off, const uint8_t *src_, uint64_t n_)
+    {
+        if (!n_) return;
+        while (active.load() != 0) std::this_thread::yield();  // (stragglers of the previous job making their last, failing, grab)
+        {
+            std::lock_guard<std::mutex> lock(m);
+            dst = dst_, src = src_, fd = fd_, off = file_off, n = n_, parts = (n_ + PART - 1) / PART;
+            done.store(0), next.store(0);
+            ++gen;
+        }
+        cv_job.notify_all();
+        work();
+        std::unique_lock<std::mutex> lock(m);
+        cv_done.wait(lock, [&]() { return done.load() >= parts; });
+    }
+};
 
 static bool use_host_inflate()
 {
@@ -504,13 +533,14 @@ int load_bgzf_device_inflate(svb_ctx *ctx, svb_bam *b, const uint8_t *h_file, ui
     };
     size_t next_block = 0;
     int lane = 0, slab = 0;
+    StagePool stage(n_threads);
     for (uint64_t o = 0; o < file_bytes; o += Slabs::SLAB) {
         const uint64_t n = std::min(Slabs::SLAB, file_bytes - o);
         const bool last = o + n >= file_bytes;
         CK(cudaEventSynchronize(sl.done[slab]));
         {
             WallScope wc(ctx, "stage_copy(wall)", (double)n);
-            if (fd < 0 || !parallel_pread(sl.p[slab], fd, fd_base + o, n, n_threads)) parallel_copy(sl.p[slab], h_file + o, n, n_threads);
+            stage.run(sl.p[slab], fd, fd_base + o, h_file + o, n);
         }
         CK(cudaMemcpyAsync(d_file.p + o, sl.p[slab], n, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaEventRecord(sl.done[slab], ctx->copy_stream));
