@@ -43,7 +43,12 @@ int svb_ctx_create(int device, svb_ctx **out);
 void svb_ctx_destroy(svb_ctx *ctx);
 const char *svb_last_error(const svb_ctx *ctx); /* ctx may be NULL: error of the last failed create */
 /* The CUDA stream every launch of this ctx goes to (cudaStream_t), so that callers can bracket calls
- * with their own CUDA events. */
+ * with their own CUDA events. One stream per context IS the contract (SURVEY.md section 8b asks for "one
+ * stream argument"; it is an argument of the context instead of every call): the entry points are
+ * stream-ordered sequences that share the context's workspaces, pinned pools and control block, so two
+ * calls on one context may not overlap anyway. A caller that wants concurrency gives each concurrent
+ * activity its own context on the same device (bench.py's pairing thread, seeksv_b200/mgpu.py's loader
+ * thread do); contexts are cheap after the first. */
 void *svb_ctx_stream(svb_ctx *ctx);
 
 /* Per-kernel device time accounting (CUDA events on the ctx stream). Enable, run, then read back:
