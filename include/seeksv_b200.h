@@ -247,6 +247,41 @@ int svb_insert_partial_async(svb_ctx *ctx, svb_bam *bam, int32_t min_mapq, int64
 int svb_pairs_depth(svb_ctx *ctx, svb_bam *bam, const svb_pair_params *p, const svb_junction *junctions, uint64_t n_junctions,
                     const svb_window *windows, uint64_t n_windows, int32_t *counts, int32_t *depth_out);
 
+/* ---- clip_join: P.clip.gz lines x realigned clip alignments -> junction candidates ----
+ * Replaces the lock-step loop of InputSoftInfoStoreBreakpoint<T> (getsv.h:423-541) with GetAlignInfo (getsv.cpp:25-71) and the
+ * key rules of GetJunction (getsv.cpp:1705-1845) on the device. The caller tokenises the two files (the host layer does:
+ * host/junction.cpp parse_clip_text / parse_sam_alignments / parse_bam_alignments) and passes plain arrays:
+ *   lines  - one per clip.gz line, file order: its clipped sequence (bytes seqs[seq_off, seq_off + seq_len)), breakpoint
+ *            position, side character ('5' / '3') and the RANK of its chromosome name;
+ *   alns   - one per alignment, file order: its read name (bytes names[name_off, ...) - the realigner names a read by its
+ *            clipped sequence), FLAG, 0-based POS, MAPQ, CIGAR words cigars[cigar_off, cigar_off + n_cigar) and the rank of its
+ *            chromosome name: the name of its tid, "" for a tid outside the header, "Exogenous" when FLAG & 4 (GetAlignInfo).
+ * Ranks number the distinct names by std::string::compare order (the reference keys its maps on the names), below 2^30.
+ * Result: every (head line of a run of equal clipped sequences, member of the run's alignment set) pair that GetJunction
+ * stores, with the junction key it stores it under, stably sorted into Junction::operator< order (getsv.h:187-225) - candidates
+ * of one key keep the order in which the reference's loop meets them, which is all its order-dependent accumulation (quirk Q8)
+ * depends on. The accumulation itself and MergeJunction stay with the caller (host/junction.cpp). variant: 0 '+' side 5,
+ * 1 '+' side 3, 2 / 3 '-' side 5 (alignment first / line first), 4 / 5 '-' side 3 (line first / alignment first);
+ * uniq: 2 unique, 1 repeat (secondary or MAPQ 0). *cands is malloc'ed (svb_free). Sets of more than 4096 alignments for one
+ * run are refused (SVB_ERR_FORMAT): the caller's host join handles them. */
+typedef struct svb_join_line {
+    uint32_t seq_off, seq_len;
+    int32_t chr_rank, pos;
+    uint32_t side;
+} svb_join_line;
+typedef struct svb_join_aln {
+    uint32_t name_off, name_len, flag, cigar_off, n_cigar;
+    int32_t chr_rank, pos, mapq;
+} svb_join_aln;
+typedef struct svb_join_cand {
+    uint32_t line, aln; /* indices into lines (the run's head) and alns */
+    int32_t up_rank, up_pos, down_rank, down_pos;
+    uint8_t up_strand, down_strand, variant, uniq;
+} svb_join_cand;
+int svb_clip_join(svb_ctx *ctx, const svb_join_line *lines, uint64_t n_lines, const char *seqs, uint64_t seq_bytes,
+                  const svb_join_aln *alns, uint64_t n_alns, const char *names, uint64_t name_bytes, const uint32_t *cigars,
+                  uint64_t n_cigar_words, svb_join_cand **cands, uint64_t *n_cands);
+
 /* Host-side planning step of getsv, exposed so that callers which keep the BAM resident (bench.py, sharded
  * runs) can drive the device passes themselves: joins P.clip.gz with the realigned clip.bam/clip.sam
  * (InputSoftInfoStoreBreakpoint getsv.h:423-541 + GetJunction getsv.cpp:1705), merges junctions (MergeJunction

@@ -51,6 +51,7 @@ extern "C" int svb_ctx_create(int device, svb_ctx **out)
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->join_event, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->sw_event, cudaEventDisableTiming));
     CK(cudaHostAlloc((void **)&c->ctl_host, 4096, cudaHostAllocDefault));
     for (int i = 0; i < svb_ctx::N_AUX; ++i) CK(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
     {
@@ -85,6 +86,7 @@ extern "C" void svb_ctx_destroy(svb_ctx *ctx)
     if (ctx->inflate_scratch) cudaFree(ctx->inflate_scratch);
     if (ctx->ctl_host) cudaFreeHost(ctx->ctl_host);
     if (ctx->join_event) cudaEventDestroy(ctx->join_event);
+    if (ctx->sw_event) cudaEventDestroy(ctx->sw_event);
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (cudaStream_t a : ctx->aux)

@@ -84,6 +84,7 @@ struct svb_ctx {
     uint64_t hint[16] = {};
     bool walk_attr = false;                           // the walker's shared-memory opt-in is set on this device
     cudaEvent_t join_event = nullptr;                 // side stream -> main stream
+    cudaEvent_t sw_event = nullptr;                   // side stream -> main stream: getclip's sorted chromosome-switch list is there
     // inflate.cu: slot bitmap + per-resident-warp match lists of the speculative inflate kernel (allocated on first use)
     uint8_t *inflate_scratch = nullptr;
     uint32_t inflate_slot_words = 0, inflate_slots_per_sm = 0, inflate_scratch_head = 0;

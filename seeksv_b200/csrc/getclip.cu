@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(128)
 
 // the expensive part of GetSClipReads for the queued soft-clipped records: one thread each, one candidate append per warp
 __global__ void __launch_bounds__(128)
-    clip_eval(const uint8_t *__restrict__ d, ClipQueues q, ClipParams P, CandArrays c, uint32_t cand_cap, ClipCtl *ctl)
+    clip_eval(const uint8_t *__restrict__ d, ClipQueues q, ClipParams P, CandArrays c, uint32_t cand_cap, ClipCtl *ctl, uint32_t chunk_log2,
+              uint32_t *__restrict__ bucket_cnt, uint32_t *__restrict__ arrival)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n = min(q.counters[0], q.clipped_cap);
@@ -265,6 +266,10 @@ __global__ void __launch_bounds__(128)
         if (lane == 0) b0 = atomicAdd(&q.counters[3], total);
         b0 = __shfl_sync(0xffffffffu, b0, 0);
         uint32_t s = b0 + incl - mine;
+        // the candidates of a record join the bucket of the chunk the record starts in; `arrival` is their (arbitrary) place in it
+        const uint32_t a0 = mine ? atomicAdd(&bucket_cnt[o >> chunk_log2], mine) : 0u;
+        if (mine && s < cand_cap) arrival[s] = a0;
+        if (mine == 2 && s + 1 < cand_cap) arrival[s + 1] = a0 + 1;
         if (E.e5 && s < cand_cap) {
             c.off[s] = o, c.tid[s] = tid, c.pos[s] = E.pos5, c.begin[s] = E.b5, c.ll[s] = E.l5, c.rl[s] = E.r5, c.side[s] = 0;
         }
@@ -275,31 +280,65 @@ __global__ void __launch_bounds__(128)
     }
 }
 
-// first sort: (record offset, candidate index)
-__global__ void cand_sort_input(const uint32_t *__restrict__ n_ptr, uint32_t cap, const uint64_t *__restrict__ off, uint64_t *__restrict__ key,
-                                uint32_t *__restrict__ val, ClipCtl *ctl)
+// ---- candidates in BAM order without a sort ---------------------------------------------------------------------------------------
+// clip_eval appends candidates in arbitrary order; the clustering needs them in file order (InsertSeq is greedy, clip_reads.cpp:260-283),
+// then stably by (flush run, side, position). Round 2 first sorted (record offset, index) pairs with four radix passes (68 us for
+// 190 k candidates on C2: latency of the passes, not data). The record offset already says which 16 KiB chunk a candidate comes from
+// and a chunk holds a handful of them (at most ~900: a record is at least 36 bytes), so file order = chunk order (a prefix sum over
+// the per-chunk counts clip_eval left) + the order inside a chunk (every candidate counts the members of its bucket in front of it).
+struct BucketScanOp {
+    uint64_t n_chunks;
+    const uint32_t *cnt;
+    uint32_t *base;
+    __device__ uint64_t n() const { return n_chunks; }
+    __device__ void load(uint64_t c, uint64_t (&v)[1]) const { v[0] = cnt[c]; }
+    __device__ void store(uint64_t c, const uint64_t (&excl)[1], const uint64_t (&)[1]) const { base[c] = (uint32_t)excl[0]; }
+    __device__ void total(const uint64_t (&)[1]) const {}
+};
+
+// bucket members side by side (arbitrary order inside a bucket): grouped[base(chunk) + arrival] = candidate
+__global__ void cand_group(const uint32_t *__restrict__ n_ptr, uint32_t cap, uint32_t chunk_log2, const uint64_t *__restrict__ off,
+                           const uint32_t *__restrict__ bucket_base, const uint32_t *__restrict__ arrival, uint32_t *__restrict__ grouped, ClipCtl *ctl)
 {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && *n_ptr > cap) ctl->abort_main = 1;
-    const uint32_t n = min(*n_ptr, cap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) key[i] = off[i], val[i] = i;
+    if (*n_ptr > cap) {  // more candidates than slots: the call is repeated with the reported size, nothing below is used
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->abort_main = 1;
+        return;
+    }
+    const uint32_t n = *n_ptr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        grouped[bucket_base[off[i] >> chunk_log2] + arrival[i]] = i;
 }
 
-// second sort key = flush run (number of chromosome switches before the record) | side | position
+// sort key = flush run (number of chromosome switches before the record) | side | position, written at the candidate's place in
+// file order: the stable sort that follows keeps that order inside a breakpoint key
 static constexpr uint32_t SW_LINEAR = 1024;
 __global__ void __launch_bounds__(256)
-    make_keys(const uint32_t *__restrict__ counters, uint32_t cand_cap, uint32_t sw_cap, const uint32_t *__restrict__ order, CandArrays c,
+    make_keys(const uint32_t *__restrict__ counters, uint32_t cand_cap, uint32_t sw_cap, uint32_t chunk_log2, const uint32_t *__restrict__ grouped,
+              const uint32_t *__restrict__ bucket_base, const uint32_t *__restrict__ bucket_cnt, CandArrays c,
               const uint64_t *__restrict__ sw_sorted, uint64_t *__restrict__ key, uint32_t *__restrict__ val)
 {
     __shared__ uint64_t ssw[SW_LINEAR];
-    const uint32_t n = min(counters[3], cand_cap), n_sw = min(counters[2], sw_cap);
+    if (counters[3] > cand_cap) return;
+    const uint32_t n = counters[3], n_sw = min(counters[2], sw_cap);
     const bool linear = n_sw <= SW_LINEAR;  // few switches (a coordinate-sorted BAM has one per chromosome): count them directly
     if (linear) {
         for (uint32_t j = threadIdx.x; j < n_sw; j += blockDim.x) ssw[j] = sw_sorted[j];
         __syncthreads();
     }
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t s = order[i];
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const uint32_t s = grouped[p];
         const uint64_t r = c.off[s];
+        const uint32_t sd = c.side[s];
+        // place inside the bucket: members with a smaller record offset, and the '5' candidate of the same record (clip_eval's
+        // order for a read clipped on both sides)
+        const uint64_t ch = r >> chunk_log2;
+        const uint32_t b0 = bucket_base[ch], b1 = b0 + bucket_cnt[ch];
+        uint32_t before = 0;
+        for (uint32_t q = b0; q < b1; ++q) {
+            const uint32_t t = grouped[q];
+            const uint64_t rt = c.off[t];
+            before += (rt < r) || (rt == r && c.side[t] < sd);
+        }
         uint32_t run = 0;
         if (linear) {
             for (uint32_t j = 0; j < n_sw; ++j) run += ssw[j] < r;
@@ -312,8 +351,8 @@ __global__ void __launch_bounds__(256)
             }
             run = lo;
         }
-        key[i] = ((uint64_t)run << 33) | ((uint64_t)c.side[s] << 32) | (uint32_t)(c.pos[s] ^ 0x80000000);
-        val[i] = s;
+        key[b0 + before] = ((uint64_t)run << 33) | ((uint64_t)sd << 32) | (uint32_t)(c.pos[s] ^ 0x80000000);
+        val[b0 + before] = s;
     }
 }
 
@@ -955,8 +994,9 @@ struct ClipBuffers {
     uint64_t *clip_off, *fq_off, *off1, *off2;
     char *nblob;
     uint32_t *noff;
-    RadixScratch rs_off, rs_key, rs_sw, rs_un, rs_hash;
-    ScanScratch sc_chunk, sc_seg, sc_stats, sc_cl, sc_text, sc_un;
+    uint32_t *bucket_cnt, *bucket_base;  // candidates per 16 KiB chunk and their prefix (file order without a sort)
+    RadixScratch rs_key, rs_sw, rs_un, rs_hash;
+    ScanScratch sc_chunk, sc_bucket, sc_seg, sc_stats, sc_cl, sc_text, sc_un;
     size_t zero_end;  // [0, zero_end) is cleared before the first launch
 };
 
@@ -966,12 +1006,13 @@ void carve(Bump &b, ClipBuffers &B, const Caps &cap, uint64_t n_chunks, int off_
     // --- cleared region: control block, tickets, look-back states
     B.ctl = b.get<ClipCtl>(1);
     B.ticket = b.get<unsigned long long>(1);
-    B.rs_off = radix_scratch(b, cap.cand, off_passes);
     B.rs_key = radix_scratch(b, cap.cand, key_passes);
     B.rs_sw = radix_scratch(b, cap.sw, off_passes);
     B.rs_un = radix_scratch(b, cap.un, off_passes);
     B.rs_hash = radix_scratch(b, cap.un, 4);
     B.sc_chunk = scan_scratch(b, n_chunks, 1, 8);
+    B.sc_bucket = scan_scratch(b, n_chunks, 1, 8);
+    B.bucket_cnt = b.get<uint32_t>(n_chunks + 1);
     B.sc_seg = scan_scratch(b, cap.cand, 1, 8);
     B.sc_stats = scan_scratch(b, cap.cand, 1, 2);
     B.sc_cl = scan_scratch(b, cap.cand, 1, 4);
@@ -985,6 +1026,7 @@ void carve(Bump &b, ClipBuffers &B, const Caps &cap, uint64_t n_chunks, int off_
     B.q.counters = B.ctl ? B.ctl->counters : nullptr;
     B.q.first_mb = b.get<uint64_t>(n_chunks);
     B.q.last_mb_tid = b.get<int32_t>(n_chunks);
+    B.bucket_base = b.get<uint32_t>(n_chunks + 1);
     // --- candidates
     B.c.off = b.get<uint64_t>(cap.cand), B.c.tid = b.get<int32_t>(cap.cand), B.c.pos = b.get<int32_t>(cap.cand);
     B.c.begin = b.get<uint32_t>(cap.cand), B.c.ll = b.get<uint32_t>(cap.cand), B.c.rl = b.get<uint32_t>(cap.cand);
@@ -1094,8 +1136,15 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         launch_chunk_scan(ctx, s, bam, B.sc_chunk, &ctl->flags[1], ctl->c64);
         CK(cudaEventRecord(ctx->fork_event, s));
 
-        // ---- 2. side stream: unmapped-branch records - pair mates by name, emit the two FASTQ files (or export the records)
+        // ---- 2. side stream: the switch list, sorted (make_keys numbers the flush runs with it) - first, so that the main stream
+        //         never waits for the mates; then the unmapped-branch records - pair mates by name, emit the two FASTQ files (or
+        //         export the records)
         CK(cudaStreamWaitEvent(side, ctx->fork_event, 0));
+        {
+            RadixJob js{{B.q.switches, B.sw_sorted}, {nullptr, nullptr}, &ctl->counters[2], cap.sw, 0, off_passes, B.rs_sw};
+            radix_sort(ctx, side, js);
+        }
+        CK(cudaEventRecord(ctx->sw_event, side));
         {
             ProfScope ps(ctx, "unmapped_pair", 0, side);
             RadixJob ju{{B.q.unmapped, B.un_sorted}, {nullptr, nullptr}, &ctl->counters[1], cap.un, 0, off_passes, B.rs_un};
@@ -1125,29 +1174,26 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
             unmapped_write<<<grid_for(ctx, (uint64_t)cap.un * 32, 128, 8), 128, 0, side>>>(ctl, B.un_sorted, B.mate_of, bam->d_data, B.off1, B.off2,
                                                                                          res->d_text[2], res->d_text[3]);
         }
-        {   // the switch list, sorted (make_keys numbers the flush runs with it)
-            RadixJob js{{B.q.switches, B.sw_sorted}, {nullptr, nullptr}, &ctl->counters[2], cap.sw, 0, off_passes, B.rs_sw};
-            radix_sort(ctx, side, js);
-        }
         CK(cudaEventRecord(ctx->join_event, side));
 
-        if (unmapped_only) CK(cudaStreamWaitEvent(s, ctx->join_event, 0));
         // ---- 3. main stream: evaluate the queued soft-clipped records, order candidates: BAM order first (stable base), then (run, side, pos)
         if (!unmapped_only) {
         {
             ProfScope ps(ctx, "clip_eval", 0);
-            clip_eval<<<grid_for(ctx, cap.clipped, 128, 8), 128, 0, s>>>(bam->d_data, B.q, P, B.c, cap.cand, ctl);
+            clip_eval<<<grid_for(ctx, cap.clipped, 128, 8), 128, 0, s>>>(bam->d_data, B.q, P, B.c, cap.cand, ctl, bam->chunk_log2, B.bucket_cnt,
+                                                                        (uint32_t *)B.key[1]);
         }
         {
             // a both-side-clipped read yields two candidates with the same record offset but different sides, so
-            // (key, record) is unique and the two-pass stable sort is deterministic
+            // (key, record, side) is unique and the order is deterministic
             ProfScope ps(ctx, "sort_candidates", 0);
             const unsigned g = grid_for(ctx, cap.cand, 256, 4);
-            cand_sort_input<<<g, 256, 0, s>>>(&ctl->counters[3], cap.cand, B.c.off, B.key[0], B.val[0], ctl);
-            RadixJob j1{{B.key[0], B.key[1]}, {B.val[0], B.val[1]}, &ctl->counters[3], cap.cand, 0, off_passes, B.rs_off};
-            radix_sort(ctx, s, j1);
-            CK(cudaStreamWaitEvent(s, ctx->join_event, 0));  // (the sorted switch list comes from the side stream)
-            make_keys<<<g, 256, 0, s>>>(ctl->counters, cap.cand, cap.sw, B.val[1], B.c, B.sw_sorted, B.key[0], B.val[0]);
+            BucketScanOp opb{n_chunks, B.bucket_cnt, B.bucket_base};
+            launch_scan<1, 8>(ctx, s, opb, B.sc_bucket, n_chunks);
+            cand_group<<<g, 256, 0, s>>>(&ctl->counters[3], cap.cand, bam->chunk_log2, B.c.off, B.bucket_base, (const uint32_t *)B.key[1], B.val[1], ctl);
+            CK(cudaStreamWaitEvent(s, ctx->sw_event, 0));  // (the sorted switch list comes from the side stream)
+            make_keys<<<g, 256, 0, s>>>(ctl->counters, cap.cand, cap.sw, bam->chunk_log2, B.val[1], B.bucket_base, B.bucket_cnt, B.c, B.sw_sorted, B.key[0],
+                                        B.val[0]);
             RadixJob j2{{B.key[0], B.key[1]}, {B.val[0], B.val[1]}, &ctl->counters[3], cap.cand, 0, key_passes, B.rs_key};
             radix_sort(ctx, s, j2);
         }
@@ -1177,7 +1223,8 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
                                                                                      B.fq_off, res->d_text[0], res->d_text[1]);
         }
         }
-        // ---- the one read-back
+        // ---- the one read-back (after the side stream's work)
+        CK(cudaStreamWaitEvent(s, ctx->join_event, 0));
         CK(cudaMemcpyAsync(ctx->ctl_host, ctl, sizeof(ClipCtl), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());

@@ -448,18 +448,16 @@ JunctionKey make_key(const std::string &uc, int up, char us, const std::string &
     return k;
 }
 
-// GetJunction, getsv.cpp:1705-1845
-void add_junction(const ClipLine &line, AlignInfo &ai, JunctionMap &jm)
+// GetJunction, getsv.cpp:1705-1845: the entry one (line, alignment) pair stores - false: nothing is stored
+bool junction_entry(const ClipLine &line, AlignInfo &ai, JunctionKey &key, SeqInfo &up, SeqInfo &down)
 {
     int uniq;
     if (ai.type == 'u') uniq = 2;
     else if (ai.type == 'r') uniq = 1;
-    else return;  // 'n': nothing is stored (quirk Q7)
+    else return false;  // 'n': nothing is stored (quirk Q7)
     CigarVec cig = cigar_from_text(std::string(line.cigar));
     const std::string chr(line.chr), clipped_seq(line.clipped_seq), aligned_seq(line.aligned_seq);
     const int pos = line.pos, sup = line.support;
-    JunctionKey key;
-    SeqInfo up, down;
     auto rev = [](CigarVec v) {
         std::reverse(v.begin(), v.end());
         return v;
@@ -474,7 +472,7 @@ void add_junction(const ClipLine &line, AlignInfo &ai, JunctionMap &jm)
             up = make_seq(aligned_seq, cig, 0, 0, sup, 0);
             down = make_seq(clipped_seq, ai.cigar, ai.lclip, ai.rclip, 0, uniq);
         } else
-            return;
+            return false;
     } else if (ai.strand == '-') {
         if (line.side == '5') {
             if (std::make_pair(ai.chr, ai.pos) <= std::make_pair(chr, pos)) {
@@ -500,9 +498,15 @@ void add_junction(const ClipLine &line, AlignInfo &ai, JunctionMap &jm)
                 down = make_seq(reverse_complement(aligned_seq), rev(cig), 0, 0, sup, 0);
             }
         } else
-            return;
+            return false;
     } else
-        return;
+        return false;
+    return true;
+}
+
+// ... and how the map takes it: every entry of the key with the same clip-length signature accumulates (quirk Q8)
+void store_junction(const JunctionKey &key, const SeqInfo &up, const SeqInfo &down, JunctionMap &jm)
+{
     auto range = jm.equal_range(key);
     bool fresh = true;
     for (auto it = range.first; it != range.second; ++it) {
@@ -522,6 +526,13 @@ void add_junction(const ClipLine &line, AlignInfo &ai, JunctionMap &jm)
         o.up = up, o.down = down;
         jm.insert(std::make_pair(key, o));
     }
+}
+
+void add_junction(const ClipLine &line, AlignInfo &ai, JunctionMap &jm)
+{
+    JunctionKey key;
+    SeqInfo up, down;
+    if (junction_entry(line, ai, key, up, down)) store_junction(key, up, down, jm);
 }
 }  // namespace
 
@@ -582,6 +593,93 @@ void join_clips_with_alignments(const std::vector<ClipLine> &lines, const Alignm
         found.insert(std::make_pair(AlnKey(current, std::make_pair(info.chr, info.pos)), info));
     }
     cross();
+}
+
+// ---- device join (svb_clip_join, csrc/clipjoin.cu): what the host keeps ---------------------------------------------------------
+// The arrays the device join takes: clipped sequences and read names packed into two blobs, chromosome names replaced by their
+// rank in std::string::compare order (the reference keys its maps on the names; "" = tid outside the header, "Exogenous" = unmapped
+// alignment, GetAlignInfo getsv.cpp:25-71).
+bool pack_join_inputs(const std::vector<ClipLine> &lines, const AlignmentSet &set, JoinArrays &J)
+{
+    const std::vector<Alignment> &alns = set.recs;
+    // names -> ranks
+    std::map<std::string, int32_t> rank;
+    rank[""] = 0, rank["Exogenous"] = 0;
+    for (const std::string &n : set.ref_names) rank[n] = 0;
+    {
+        std::string_view last;
+        for (const ClipLine &l : lines)
+            if (l.chr != last) {
+                last = l.chr;
+                rank.emplace(std::string(l.chr), 0);
+            }
+    }
+    if (rank.size() >= (1u << 30)) return false;
+    J.rank_names.clear();
+    for (auto &kv : rank) kv.second = (int32_t)J.rank_names.size(), J.rank_names.push_back(kv.first);
+    std::vector<int32_t> tid_rank(set.ref_names.size());
+    for (size_t t = 0; t < set.ref_names.size(); ++t) tid_rank[t] = rank[set.ref_names[t]];
+    const int32_t r_none = rank[""], r_exo = rank["Exogenous"];
+    // lines
+    uint64_t seq_bytes = 0;
+    for (const ClipLine &l : lines) seq_bytes += l.clipped_seq.size();
+    uint64_t name_bytes = 0;
+    for (const Alignment &a : alns) name_bytes += a.qname.size();
+    if (seq_bytes >= (1ull << 32) || name_bytes >= (1ull << 32) || set.cigar_words.size() >= (1ull << 32)) return false;
+    J.lines.resize(lines.size()), J.seqs.resize(seq_bytes), J.alns.resize(alns.size()), J.names.resize(name_bytes);
+    {
+        uint64_t o = 0;
+        std::string_view last;
+        int32_t last_rank = 0;
+        for (size_t i = 0; i < lines.size(); ++i) {
+            const ClipLine &l = lines[i];
+            if (i == 0 || l.chr != last) last = l.chr, last_rank = rank[std::string(l.chr)];
+            J.lines[i] = svb_join_line{(uint32_t)o, (uint32_t)l.clipped_seq.size(), last_rank, l.pos, (uint32_t)(unsigned char)l.side};
+            memcpy(&J.seqs[o], l.clipped_seq.data(), l.clipped_seq.size());
+            o += l.clipped_seq.size();
+        }
+    }
+    {
+        uint64_t o = 0;
+        for (size_t j = 0; j < alns.size(); ++j) {
+            const Alignment &a = alns[j];
+            const int32_t r = (a.flag & 4) ? r_exo : (a.tid >= 0 && (size_t)a.tid < tid_rank.size()) ? tid_rank[a.tid] : r_none;
+            J.alns[j] = svb_join_aln{(uint32_t)o, (uint32_t)a.qname.size(), a.flag, a.cigar_begin, a.cigar_n, r, a.pos, a.mapq};
+            memcpy(&J.names[o], a.qname.data(), a.qname.size());
+            o += a.qname.size();
+        }
+    }
+    return true;
+}
+
+// The candidates of the device join, in its (stable Junction::operator<) order, enter the map exactly as GetJunction stores them:
+// the order-dependent accumulation only looks at entries of the candidate's own key, and candidates of one key arrive in the order
+// in which the reference's loop meets them. Every device key is checked against the host's own rule on the way.
+bool accumulate_join_candidates(const std::vector<ClipLine> &lines, const AlignmentSet &set, const JoinArrays &J, const svb_join_cand *cands,
+                                uint64_t n, JunctionMap &jm, std::string &err)
+{
+    for (uint64_t i = 0; i < n; ++i) {
+        const svb_join_cand &c = cands[i];
+        if (c.line >= lines.size() || c.aln >= set.recs.size()) {
+            err = "clip_join: candidate out of range";
+            return false;
+        }
+        AlignInfo ai = align_info(set, set.recs[c.aln]);
+        JunctionKey key;
+        SeqInfo up, down;
+        if (!junction_entry(lines[c.line], ai, key, up, down)) {
+            err = "clip_join: the device stored a pair the host rule drops";
+            return false;
+        }
+        if (c.up_rank < 0 || (size_t)c.up_rank >= J.rank_names.size() || c.down_rank < 0 || (size_t)c.down_rank >= J.rank_names.size() ||
+            J.rank_names[c.up_rank] != key.up_chr || J.rank_names[c.down_rank] != key.down_chr || c.up_pos != key.up_pos ||
+            c.down_pos != key.down_pos || (char)c.up_strand != key.up_strand || (char)c.down_strand != key.down_strand) {
+            err = "clip_join: device key differs from the host rule";
+            return false;
+        }
+        store_junction(key, up, down, jm);
+    }
+    return true;
 }
 
 // MergeJunction, getsv.cpp:1325-1482

@@ -13,6 +13,8 @@
 #include <utility>
 #include <vector>
 
+#include "../../include/seeksv_b200.h"
+
 namespace svb {
 
 typedef std::vector<std::pair<int, char>> CigarVec;
@@ -88,6 +90,16 @@ void find_junctions(const uint8_t *stream, uint64_t n, uint64_t first, const std
                     JunctionMap &jm);
 void join_clips_with_alignments(const std::vector<ClipLine> &lines, const AlignmentSet &alns, JunctionMap &jm);
 void merge_junctions(JunctionMap &jm, int search_length);
+// the device form of the join (svb_clip_join): inputs packed for it, and its candidates taken into the map
+struct JoinArrays {
+    std::vector<svb_join_line> lines;
+    std::vector<svb_join_aln> alns;
+    std::string seqs, names;
+    std::vector<std::string> rank_names;  // rank -> chromosome name
+};
+bool pack_join_inputs(const std::vector<ClipLine> &lines, const AlignmentSet &alns, JoinArrays &out);
+bool accumulate_join_candidates(const std::vector<ClipLine> &lines, const AlignmentSet &alns, const JoinArrays &arrays, const svb_join_cand *cands,
+                                uint64_t n, JunctionMap &jm, std::string &err);
 
 typedef std::map<std::pair<std::string, int>, int> PosDepth;        // pos2depth
 typedef std::map<ChrRange, unsigned long> RangeDepth;               // range2depth

@@ -196,6 +196,49 @@ def test_pileup_cap_matches_oracle(ctx, tmp_path):
     bam.close()
 
 
+@pytest.mark.parametrize("chunk_log2", [None, "14", "12"])
+def test_candidate_order_without_a_sort_matches_oracle(ctx, tmp_path, monkeypatch, chunk_log2):
+    """File order of the candidates comes from per-chunk buckets, not from a sort (getclip.cu: cand_group / make_keys): short
+    records (hundreds per 16 KiB chunk), most of them clipped on both sides, piled on a few breakpoint keys on two chromosomes,
+    so that the greedy clustering sees long runs of equal keys whose members share chunks - any slip in the order inside a
+    bucket, or between the '5' and the '3' candidate of one read, changes which read founds a cluster and which CIGAR it keeps.
+    A stream this small gets 1 KiB chunks by default; 16 KiB chunks (what a real BAM gets) hold ~300 of these records each."""
+    import random
+    if chunk_log2:
+        monkeypatch.setenv("SEEKSV_B200_CHUNK_LOG2", chunk_log2)
+    import seeksv_b200
+    from oracle import bamio, getclip_oracle
+    rng = random.Random(11)
+    h = bamio.Header(["c1", "c2"], [60000, 60000], "@SQ\tSN:c1\tLN:60000\n@SQ\tSN:c2\tLN:60000\n")
+    recs = []
+    for tid in (0, 1):
+        pos = 100
+        for _ in range(6000):
+            pos += rng.choice((0, 0, 0, 0, 1, 2, 40))
+            kind = rng.randrange(6)
+            left, right = rng.choice((3, 4, 5, 9)), rng.choice((3, 4, 6))
+            mid = rng.choice((8, 9, 10, 12))
+            if kind <= 2:
+                cig, n = "%dS%dM%dS" % (left, mid, right), left + mid + right
+            elif kind == 3:
+                cig, n = "%dS%dM" % (left, mid), left + mid
+            elif kind == 4:
+                cig, n = "%dM%dS" % (mid, right), mid + right
+            else:
+                cig, n = "%dM" % mid, mid
+            seq = "".join(rng.choice("ACGT") if rng.random() < 0.1 else "ACGT"[(pos + j) & 3] for j in range(n))
+            qual = "".join(chr(33 + rng.randrange(2, 40)) for _ in range(n))
+            recs.append(bamio.make_rec("q%d" % len(recs), rng.choice((0, 16, 0, 1024)), tid, pos, rng.choice((60, 60, 5)), cig, -1, -1, 0, seq, qual))
+    path = str(tmp_path / "order.bam")
+    bamio.write_bam(path, h, recs)
+    want = getclip_oracle.getclip(h, recs)
+    bam = seeksv_b200.Bam.open(ctx, path)
+    got = bam.getclip()
+    for g, w in zip(got, want):
+        assert g.decode("latin-1") == w
+    bam.close()
+
+
 def test_no_cpu_fallback():
     """the product never imports the oracle, and the library refuses to run without its CUDA device"""
     import seeksv_b200.lib as lib
