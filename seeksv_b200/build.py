@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libseeksv_b200.so")
 CLI = os.path.join(HERE, "bin", "seeksv")
 OBJ = os.path.join(HERE, "build")
-CU = ["csrc/walk.cu", "csrc/getclip.cu", "csrc/getsv.cu", "csrc/inflate.cu", "csrc/gzip.cu", "csrc/api.cu"]
+CU = ["csrc/walk.cu", "csrc/getclip.cu", "csrc/getsv.cu", "csrc/inflate.cu", "csrc/gzip.cu", "csrc/clipjoin.cu", "csrc/api.cu"]
 CPP = ["host/bamfile.cpp", "host/junction.cpp", "host/commands.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -80,6 +80,11 @@ def build_tools():
         src = os.path.join(tools, tool + ".cpp")
         if _stale(out, [src]):
             _run(["g++", "-O2", "-std=c++17", "-pthread", src, "-o", out, "-lz"])
+    # the device join's rules on the CPU, against the host mirror (tests; needs the host layer's sources)
+    out = os.path.join(os.path.dirname(CLI), "clipjoin_sim")
+    deps = [os.path.join(tools, "clipjoin_sim.cpp"), os.path.join(HERE, "host/junction.cpp"), os.path.join(HERE, "host/bamfile.cpp")]
+    if _stale(out, deps + _headers()):
+        _run(["g++", "-O2", "-std=c++17", "-pthread"] + deps + ["-o", out, "-lz"])
 
 
 if __name__ == "__main__":

@@ -55,8 +55,7 @@ __global__ void cj_walk(CjView v, const CjCtl *ctl, const uint32_t *__restrict__
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t k0, k1;
         chunk_bounds(n_runs, c, &k0, &k1);
-        // guess: the breaker of boundary k0 - 1 is the first alignment of block k0 - 1
-        const uint64_t e = c == 0 ? 0 : (k0 - 1 < n_blocks ? (uint64_t)block_start[k0 - 1] + 1 : v.n_alns);
+        const uint64_t e = c == 0 ? 0 : cj_guess_entry(v, run_head, block_start, n_blocks, k0);
         entry[c] = e;
         exit_[c] = cj_walk_chunk(v, run_head, k0, k1, e, breaker);
     }

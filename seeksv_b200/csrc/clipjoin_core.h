@@ -92,6 +92,28 @@ CJ_HD bool cj_named_like_run(const CjView &v, uint64_t j, uint64_t head_line)
     return cj_bytes_equal(v.names + a.name_off, a.name_len, v.seqs + l.seq_off, l.seq_len);
 }
 
+// Entry guess of the chunk that starts at boundary k0 (k0 >= 2): the first unconsumed alignment after the breaker of boundary
+// k0 - 1. In well-formed input that breaker is the first alignment of the block named like run k0 - 1, and block j belongs to run
+// j; a missing or extra read upstream shifts the block numbers, so the blocks around number k0 - 1 are searched for one that is
+// named like run k0 - 1 and whose predecessor is named like run k0 - 2 (two deep, as the BAM walker's guesses). A wrong guess costs
+// repair rounds, never correctness.
+static constexpr int64_t CJ_GUESS_WINDOW = 512;
+CJ_HD uint64_t cj_guess_entry(const CjView &v, const uint32_t *run_head, const uint32_t *block_start, uint64_t n_blocks, uint64_t k0)
+{
+    const uint64_t kb = k0 - 1;
+    if (n_blocks == 0) return v.n_alns;
+    const int64_t center = (int64_t)(kb < n_blocks ? kb : n_blocks - 1);
+    for (int64_t d = 0; d <= CJ_GUESS_WINDOW; ++d)
+        for (int sgn = 0; sgn < (d ? 2 : 1); ++sgn) {
+            const int64_t j = sgn ? center - d : center + d;
+            if (j < 0 || j >= (int64_t)n_blocks) continue;
+            if (!cj_named_like_run(v, block_start[j], run_head[kb])) continue;
+            if (j > 0 && kb > 0 && !cj_named_like_run(v, block_start[j - 1], run_head[kb - 1])) continue;
+            return (uint64_t)block_start[j] + 1;
+        }
+    return kb < n_blocks ? (uint64_t)block_start[kb] + 1 : v.n_alns;
+}
+
 // One chunk of run boundaries: boundaries k in [k0, k1) (k >= 1), entry = first alignment not yet consumed. breaker[k] = index
 // of b_k, or n_alns when the alignments ran out (then every later boundary gets n_alns too). Returns the exit (next
 // unconsumed alignment).

@@ -1208,6 +1208,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         }
         {
             ProfScope ps(ctx, "cluster_build", 0);
+            // (occupancy is not what bounds this kernel: 32- and 40-register builds with 12 / 16 CTAs per SM ran in the same 0.175 ms)
             cluster_build<<<grid_for(ctx, (uint64_t)cap.cand * 32, 128, 16), 128, 0, s>>>(bam->d_data, ctl, B.start, order, B.c, B.maxl, B.maxr, B.arena_off,
                                                                                         B.arena_seq, B.arena_qual, prm->match_rate, B.co);
         }

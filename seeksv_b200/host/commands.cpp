@@ -300,6 +300,61 @@ int cmd_getclip(int argc, char **argv)
 }
 
 // clip.bam (BGZF) or SAM text -> alignment list + reference names
+// The join of the clip lines with the clip alignments (InputSoftInfoStoreBreakpoint, getsv.h:423-541). `getsv` runs it on the GPU
+// (svb_clip_join) - on a context of its own, because the command's main context is busy loading the original BAM on a helper
+// thread at that moment (one context, one thread). The host keeps tokenising, the order-dependent accumulation and MergeJunction.
+// SEEKSV_B200_DEVICE_JOIN=0 selects the host mirror (join_clips_with_alignments); it also takes over when the device refuses the
+// input (a run of lines with thousands of alignments), and it is what svb_plan_getsv - documented as "no GPU work" - uses unless
+// SEEKSV_B200_DEVICE_JOIN=1 asks for the device there too.
+bool device_join_enabled(bool by_default)
+{
+    const char *e = getenv("SEEKSV_B200_DEVICE_JOIN");
+    return e ? atoi(e) != 0 : by_default;
+}
+bool join_clips(const std::vector<ClipLine> &lines, const AlignmentSet &set, JunctionMap &jm, std::string &err, bool device_by_default)
+{
+    if (!device_join_enabled(device_by_default)) {
+        join_clips_with_alignments(lines, set, jm);
+        return true;
+    }
+    static std::map<int, svb_ctx *> cached;  // (kept for the life of the process, like the command context)
+    static std::mutex mu;
+    svb_ctx *ctx = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        const int dev = device_index();
+        auto it = cached.find(dev);
+        if (it != cached.end()) ctx = it->second;
+        else {
+            if (svb_ctx_create(dev, &ctx) != 0) {
+                err = svb_last_error(nullptr);
+                return false;
+            }
+            cached[dev] = ctx;
+        }
+    }
+    JoinArrays J;
+    if (!pack_join_inputs(lines, set, J)) {
+        join_clips_with_alignments(lines, set, jm);
+        return true;
+    }
+    svb_join_cand *cands = nullptr;
+    uint64_t n = 0;
+    int rc = svb_clip_join(ctx, J.lines.data(), J.lines.size(), J.seqs.data(), J.seqs.size(), J.alns.data(), J.alns.size(), J.names.data(),
+                           J.names.size(), set.cigar_words.data(), set.cigar_words.size(), &cands, &n);
+    if (rc == SVB_ERR_FORMAT) {  // refused: a set too large for the per-run sort
+        join_clips_with_alignments(lines, set, jm);
+        return true;
+    }
+    if (rc != 0) {
+        err = svb_last_error(ctx);
+        return false;
+    }
+    const bool ok = accumulate_join_candidates(lines, set, J, cands, n, jm, err);
+    svb_free(cands);
+    return ok;
+}
+
 bool load_alignments(const std::string &path, AlignmentSet &set, std::string &err)
 {
     std::vector<uint8_t> file;
@@ -613,10 +668,16 @@ int cmd_getsv(int argc, char **argv)
         find_junctions(stream.data(), stream.size(), ch.first_record, ch.names, connect_min_mapq, jm);
         std::cerr << "'FindJunction' finished" << std::endl;
     }
-    join_clips_with_alignments(parse_clip_text(clip_text, n_threads()), alns, jm);
+    {
+        std::vector<ClipLine> lines = parse_clip_text(clip_text, n_threads());
+        ph.mark("getsv: tokenise clip lines");
+        // (`getsv -n 0 -D` has no BAM pass and runs without a GPU: the host mirror joins there)
+        if (!join_clips(lines, alns, jm, err, pairs_used >= 100000 || with_depth)) return fail("[seeksv_b200] " + err);
+    }
     std::cerr << "'InputSoftInfoStoreBreakpoint' finished" << std::endl;
+    ph.mark("getsv: join");
     merge_junctions(jm, flank);
-    ph.mark("getsv: join + merge junctions");
+    ph.mark("getsv: merge junctions");
 
     auto need_bam = [&]() -> bool {
         int rc = prefetch.wait();
@@ -984,7 +1045,7 @@ extern "C" int svb_plan_getsv(const char *clip_aln, const char *clip_file, int32
     JunctionMap jm;
     std::vector<ClipLine> lines = parse_clip_text(clip_text, n_threads());
     ph.mark("plan: tokenise");
-    join_clips_with_alignments(lines, alns, jm);
+    if (!join_clips(lines, alns, jm, err, false)) return SVB_ERR_CUDA;
     ph.mark("plan: join");
     merge_junctions(jm, reach);
     ph.mark("plan: merge");

@@ -57,7 +57,7 @@ EXPORTS = [
     "svb_clusters_gz", "svb_gzip_text", "svb_bam_open_voffsets", "svb_bai_linear_offsets", "svb_bam_peek_record", "svb_voffset_distance",
     "svb_sam_to_stream", "svb_main", "svb_getsv_passes", "svb_clusters_text_len", "svb_clusters_export_device",
     "svb_clusters_export_parts", "svb_bam_set_own_offset", "svb_insert_partial", "svb_insert_sq", "svb_pairs_depth", "svb_plan_somatic", "svb_insert_partial_async",
-    "svb_write_range_blocks", "svb_set_shard_provider",
+    "svb_write_range_blocks", "svb_set_shard_provider", "svb_clip_join",
 ]
 
 
@@ -151,6 +151,7 @@ def load():
     L.svb_write_range_blocks.argtypes = [C.c_char_p, vp, u64, vp, u64, C.c_int, C.POINTER(vp), C.POINTER(u64)]
     L.svb_set_shard_provider.argtypes = [vp, vp]
     L.svb_set_shard_provider.restype = None
+    L.svb_clip_join.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, u64, vp, u64, C.POINTER(vp), C.POINTER(u64)]
     _lib = L
     return L
 
@@ -632,6 +633,24 @@ def plan_getsv(clip_alignments: str, clip_file: str, ref_names: Sequence[str], r
         L.svb_free(pj)
         L.svb_free(pw)
     return juncs, wins
+
+
+JOIN_LINE_BYTES, JOIN_ALN_BYTES, JOIN_CAND_BYTES = 20, 32, 28     # sizeof svb_join_line / svb_join_aln / svb_join_cand
+
+
+def clip_join_raw(ctx: "Context", lines: bytes, seqs: bytes, alns: bytes, names: bytes, cigars: bytes) -> bytes:
+    """svb_clip_join on packed arrays (the structs of include/seeksv_b200.h as raw little-endian bytes): the junction candidates
+    of the device join, sorted, as raw svb_join_cand bytes."""
+    L = load()
+    out, n = C.c_void_p(), C.c_uint64()
+    assert len(lines) % JOIN_LINE_BYTES == 0 and len(alns) % JOIN_ALN_BYTES == 0 and len(cigars) % 4 == 0
+    rc = L.svb_clip_join(ctx.h, lines, len(lines) // JOIN_LINE_BYTES, seqs, len(seqs), alns, len(alns) // JOIN_ALN_BYTES, names, len(names),
+                         cigars, len(cigars) // 4, C.byref(out), C.byref(n))
+    ctx.check(rc, "svb_clip_join")
+    try:
+        return C.string_at(out, n.value * JOIN_CAND_BYTES)
+    finally:
+        L.svb_free(out)
 
 
 def plan_somatic(normal_clip: str, tumor_sv: str, ref_names: Sequence[str], match_rate=0.9, offset=30, min_len=10, mean_insert=0):

@@ -1,15 +1,18 @@
 // clipjoin_sim - the device join's rules (seeksv_b200/csrc/clipjoin_core.h) run in serial loops on the CPU and checked against the
 // host mirror of the reference's loop (host/junction.cpp: join_clips_with_alignments; InputSoftInfoStoreBreakpoint, getsv.h:423-541).
 //
-//   clipjoin_sim <clip.sam | clip.bam> <P.clip.gz> [--wrong-guesses]
+//   clipjoin_sim <clip.sam | clip.bam> <P.clip.gz> [--wrong-guesses | --dump DIR]
 //
 // Test infrastructure for the build container (no GPU there): the kernels of csrc/clipjoin.cu are index loops around the same
 // functions, with chained scans and radix sorts where this file uses std:: algorithms. Prints "OK <runs> <candidates> <entries>
 // <repair rounds>" when the two junction maps are identical (keys, sequences, CIGARs, clip lengths, support, uniqueness, order),
 // "DIFF ..." and exit code 1 otherwise. --wrong-guesses starts every chunk from a deliberately wrong entry (entry 0), so the
-// verify / repair rounds are exercised on well-formed input too.
+// verify / repair rounds are exercised on well-formed input too. --dump DIR writes the packed input arrays of svb_clip_join
+// (lines.bin, seqs.bin, alns.bin, names.bin, cigars.bin) and the sorted candidates (cands.bin) as raw structs: the GPU tests feed
+// the arrays to the C ABI and expect exactly these candidates back.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -48,6 +51,7 @@ int main(int argc, char **argv)
         return 2;
     }
     const bool wrong = argc > 3 && !strcmp(argv[3], "--wrong-guesses");
+    const std::string dump = argc > 4 && !strcmp(argv[3], "--dump") ? argv[4] : "";
     std::string err, text;
     AlignmentSet set;
     if (!load(argv[1], set, err) || !read_text_maybe_gz(argv[2], text, err)) {
@@ -83,7 +87,7 @@ int main(int argc, char **argv)
         for (uint64_t c = 0; c < n_chunks; ++c) {
             uint64_t k0, k1;
             bounds(c, k0, k1);
-            uint64_t e = c == 0 ? 0 : (k0 - 1 < block_start.size() ? (uint64_t)block_start[k0 - 1] + 1 : m);
+            uint64_t e = c == 0 ? 0 : cj_guess_entry(v, run_head.data(), block_start.data(), block_start.size(), k0);
             if (wrong && c > 0) e = 0;
             entry[c] = e;
             exit_[c] = cj_walk_chunk(v, run_head.data(), k0, k1, e, breaker.data());
@@ -126,6 +130,22 @@ int main(int argc, char **argv)
         // two stable sorts: positions, then chromosome ranks + strands
         std::stable_sort(cands.begin(), cands.end(), [](const svb_join_cand &a, const svb_join_cand &b) { return cj_key_low(a) < cj_key_low(b); });
         std::stable_sort(cands.begin(), cands.end(), [](const svb_join_cand &a, const svb_join_cand &b) { return cj_key_high(a) < cj_key_high(b); });
+    }
+    if (!dump.empty()) {
+        auto put = [&](const char *name, const void *p, size_t n) {
+            FILE *f = fopen((dump + "/" + name).c_str(), "wb");
+            if (!f || (n && fwrite(p, 1, n, f) != n)) {
+                fprintf(stderr, "cannot write %s/%s\n", dump.c_str(), name);
+                exit(2);
+            }
+            fclose(f);
+        };
+        put("lines.bin", J.lines.data(), J.lines.size() * sizeof(svb_join_line));
+        put("seqs.bin", J.seqs.data(), J.seqs.size());
+        put("alns.bin", J.alns.data(), J.alns.size() * sizeof(svb_join_aln));
+        put("names.bin", J.names.data(), J.names.size());
+        put("cigars.bin", set.cigar_words.data(), set.cigar_words.size() * 4);
+        put("cands.bin", cands.data(), cands.size() * sizeof(svb_join_cand));
     }
     if (!accumulate_join_candidates(lines, set, J, cands.data(), cands.size(), got, err)) {
         printf("DIFF %s\n", err.c_str());
