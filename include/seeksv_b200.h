@@ -313,6 +313,12 @@ int svb_write_range_blocks(const char *part_prefix, const void *clip, uint64_t n
 /* The same file image made on the device (gzip.cu): text in host memory -> malloc'ed gzip image (svb_free). */
 int svb_gzip_text(svb_ctx *ctx, const void *text, uint64_t n, char **gz, uint64_t *gz_len);
 int svb_read_gz(const char *path, char **data, uint64_t *n);
+/* The same for a file whose members hold at most 64 KiB of text each (what svb_clusters_gz / the getclip command write): the
+ * members are inflated on the GPU by the BGZF inflate kernel - `getsv` reads P.clip.gz this way while the host cores stage the
+ * BAM. *data points into pinned memory owned by the context and stays valid until the next call on this context (or
+ * svb_ctx_destroy); it is NUL-terminated behind *n bytes. SVB_ERR_FORMAT: not such a file - use svb_read_gz. The CRC32 fields of
+ * the members are not checked on this path (the deflate streams and the ISIZE fields are). */
+int svb_read_gz_device(svb_ctx *ctx, const char *path, const char **data, uint64_t *n);
 /* SAM text -> the uncompressed BAM byte stream svb_bam_from_host takes ("BAM\1" header + packed records; host only, malloc'ed,
  * svb_free). This is the conversion svb_bam_open / getsv apply to an input whose name does not end in ".bam"; it replaces
  * samopen(fn, "r") + sam_read1 of the linked libbam (bam_import.o; call sites clip_reads.h:375, getsv.h:445). */

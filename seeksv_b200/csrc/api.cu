@@ -214,6 +214,7 @@ void svb_ctx::pinned_put(char *p, uint64_t cap)
 }
 svb_ctx::~svb_ctx()
 {
+    if (read_buf) pinned_put(read_buf, read_cap), read_buf = nullptr;
     for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
     for (auto &b : pinned_free) cudaFreeHost(b.first);
 }
@@ -637,6 +638,56 @@ extern "C" int svb_inflate_bgzf(svb_ctx *ctx, const void *h_file, uint64_t file_
     CKR(inflate_on_device(ctx, d_file.p, d_blocks.p, (uint32_t)blocks.size(), d_out.p, (double)total));
     CK(cudaMemcpyAsync(h_out, d_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// A gzip text file written by this library's device gzip (gzip.cu: one member per 64 KiB of text, 'SV' size field) -> its text,
+// inflated by the BGZF inflate kernel. SVB_ERR_FORMAT: not such a file (the caller reads it with svb_read_gz / zlib instead).
+extern "C" int svb_read_gz_device(svb_ctx *ctx, const char *path, const char **data, uint64_t *n)
+{
+    if (!ctx || !path || !data || !n) return svb_fail(ctx, SVB_ERR_ARG, "svb_read_gz_device: null argument");
+    CK(cudaSetDevice(ctx->device));
+    *data = nullptr, *n = 0;
+    MappedFile mf;
+    std::string err;
+    if (!mf.open(path, err)) return svb_fail(ctx, SVB_ERR_IO, "%s", err.c_str());
+    const uint8_t *f = mf.data;
+    const uint64_t size = mf.size;
+    std::vector<BgzfBlock> blocks;
+    uint64_t o = 0, total = 0;
+    while (o < size) {
+        if (o + 28 > size || f[o] != 0x1f || f[o + 1] != 0x8b || f[o + 2] != 8 || f[o + 3] != 4 || f[o + 10] != 8 || f[o + 11] != 0 ||
+            f[o + 12] != 'S' || f[o + 13] != 'V' || f[o + 14] != 4 || f[o + 15] != 0)
+            return svb_fail(ctx, SVB_ERR_FORMAT, "%s: not a gzip file of this library's device writer", path);
+        const uint64_t sz = f[o + 16] | (f[o + 17] << 8) | (f[o + 18] << 16) | ((uint64_t)f[o + 19] << 24);
+        if (sz < 28 || o + sz > size) return svb_fail(ctx, SVB_ERR_FORMAT, "%s: member size beyond the file", path);
+        const uint8_t *t = f + o + sz - 4;
+        const uint32_t ulen = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+        if (ulen > 65536) return svb_fail(ctx, SVB_ERR_FORMAT, "%s: members of more than 64 KiB (a host-written file)", path);
+        if (ulen) blocks.push_back(BgzfBlock{o + 20, total, (uint32_t)(sz - 28), ulen});
+        total += ulen;
+        o += sz;
+    }
+    if (blocks.size() >= (1ull << 32)) return svb_fail(ctx, SVB_ERR_FORMAT, "%s: too many members", path);
+    if (ctx->read_buf) ctx->pinned_put(ctx->read_buf, ctx->read_cap), ctx->read_buf = nullptr, ctx->read_cap = 0;
+    ctx->read_buf = ctx->pinned_get(total + 1, &ctx->read_cap);
+    if (!ctx->read_buf) return svb_fail(ctx, SVB_ERR_CUDA, "cannot allocate %llu bytes of pinned memory", (unsigned long long)total);
+    if (total) {
+        cudaStream_t s = ctx->stream;
+        DevBuf<uint8_t> d_file, d_out;
+        DevBuf<BgzfBlock> d_blocks;
+        CK(d_file.alloc(size + SVB_INFLATE_PAD, s));
+        CK(d_out.alloc(total + 256, s));
+        CK(d_blocks.alloc(blocks.size(), s));
+        CK(cudaMemsetAsync(d_file.p + size, 0, SVB_INFLATE_PAD, s));
+        CK(cudaMemcpyAsync(d_file.p, f, size, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_blocks.p, blocks.data(), blocks.size() * sizeof(BgzfBlock), cudaMemcpyHostToDevice, s));
+        CKR(inflate_on_device(ctx, d_file.p, d_blocks.p, (uint32_t)blocks.size(), d_out.p, (double)total));
+        CK(cudaMemcpyAsync(ctx->read_buf, d_out.p, total, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    ctx->read_buf[total] = 0;
+    *data = ctx->read_buf, *n = total;
     return 0;
 }
 

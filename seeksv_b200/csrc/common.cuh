@@ -84,6 +84,8 @@ struct svb_ctx {
     uint64_t hint[16] = {};
     bool walk_attr = false;                           // the walker's shared-memory opt-in is set on this device
     cudaEvent_t join_event = nullptr;                 // side stream -> main stream
+    char *read_buf = nullptr;                         // svb_read_gz_device: the text it returned last (pinned pool)
+    uint64_t read_cap = 0;
     cudaEvent_t sw_event = nullptr;                   // side stream -> main stream: getclip's sorted chromosome-switch list is there
     // inflate.cu: slot bitmap + per-resident-warp match lists of the speculative inflate kernel (allocated on first use)
     uint8_t *inflate_scratch = nullptr;

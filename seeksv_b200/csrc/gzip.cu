@@ -3,8 +3,11 @@
 // Replaces the ogzstream writes of the reference (gzstream.C:53-114; call sites clip_reads.h:392-395,308-345) for the CLI path:
 // the text is produced on the device anyway, so compressing it there shrinks the device->host copy (~45 %) and takes the
 // deflate work off the host cores, which the ranks of a multi-GPU run share. Format = what host/bamfile.cpp:write_gz_many
-// writes: 1 MiB members, each a gzip header with an 'SV' extra sub-field (member size), dynamic-Huffman deflate blocks with
-// literals only (one per 64 KiB piece; RFC 1951 3.2.7), CRC32 and ISIZE. Any gzip reader concatenates the members.
+// writes, with smaller members: every 64 KiB piece of the text is a gzip member of its own - a gzip header with an 'SV' extra
+// sub-field (member size), ONE dynamic-Huffman deflate block with literals only (RFC 1951 3.2.7), CRC32 and ISIZE. Any gzip reader
+// concatenates the members; members of at most 64 KiB of text are also what the device inflate kernel (inflate.cu, made for BGZF
+// blocks) takes, so getsv reads P.clip.gz back through the GPU (svb_read_gz_device) instead of the host cores, which are busy
+// staging the BAM at that moment. (Until the third session of round 2 the members were 1 MiB = 16 blocks.)
 //
 //   gz_hist_crc   one CTA per piece: byte histogram (per-warp shared-memory counters) and the piece's raw CRC-32
 //   gz_codes      one warp per piece: length-limited Huffman code (<= 15 bits), canonical codes, the block header bits
@@ -15,7 +18,7 @@
 
 namespace {
 
-constexpr uint32_t PIECE = 64u << 10, MEMBER = 1u << 20, PPM = MEMBER / PIECE, GZ_THREADS = 256, SLICE = PIECE / GZ_THREADS;
+constexpr uint32_t PIECE = 64u << 10, MEMBER = PIECE, PPM = MEMBER / PIECE, GZ_THREADS = 256, SLICE = PIECE / GZ_THREADS;
 constexpr uint32_t HDR_WORDS = 48;  // dynamic block header: <= 17 + 57 + 258 * 5 bits = 1364 bits
 constexpr uint32_t GZ_HEAD = 20;    // 10 bytes header + XLEN + 'S' 'V' LEN + 4 bytes member size
 
@@ -292,13 +295,25 @@ __global__ void gz_layout(uint32_t n_pieces, uint32_t n_members, uint64_t n, con
         member_crc[m] = ~(raw ^ crc_shift(0xffffffffu, member_len));
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint64_t acc = 0;
-        member_off[0] = 0;
-        for (uint32_t m = 0; m < n_members; ++m) {
-            acc += member_off[m + 1];
-            member_off[m + 1] = acc;
-        }
+    // member sizes -> offsets: every thread adds up a contiguous share, the shares are scanned in shared memory
+    __shared__ uint64_t share[1024];
+    const uint32_t per = (n_members + blockDim.x - 1) / blockDim.x;
+    const uint32_t m0 = min(n_members, threadIdx.x * per), m1 = min(n_members, m0 + per);
+    uint64_t mine = 0;
+    for (uint32_t m = m0; m < m1; ++m) mine += member_off[m + 1];
+    share[threadIdx.x] = mine;
+    __syncthreads();
+    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+        const uint64_t v = threadIdx.x >= d ? share[threadIdx.x - d] : 0;
+        __syncthreads();
+        share[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint64_t acc = share[threadIdx.x] - mine;
+    if (threadIdx.x == 0) member_off[0] = 0;
+    for (uint32_t m = m0; m < m1; ++m) {
+        acc += member_off[m + 1];
+        member_off[m + 1] = acc;
     }
 }
 

@@ -306,6 +306,25 @@ int cmd_getclip(int argc, char **argv)
 // SEEKSV_B200_DEVICE_JOIN=0 selects the host mirror (join_clips_with_alignments); it also takes over when the device refuses the
 // input (a run of lines with thousands of alignments), and it is what svb_plan_getsv - documented as "no GPU work" - uses unless
 // SEEKSV_B200_DEVICE_JOIN=1 asks for the device there too.
+// getsv's second context: the clip files are read and joined on it while the command's own context loads the BAM on a helper
+// thread (one context, one thread at a time). Kept for the life of the process, like the command context.
+svb_ctx *side_context(std::string &err)
+{
+    static std::map<int, svb_ctx *> cached;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    const int dev = device_index();
+    auto it = cached.find(dev);
+    if (it != cached.end()) return it->second;
+    svb_ctx *ctx = nullptr;
+    if (svb_ctx_create(dev, &ctx) != 0) {
+        err = svb_last_error(nullptr);
+        return nullptr;
+    }
+    cached[dev] = ctx;
+    return ctx;
+}
+
 bool device_join_enabled(bool by_default)
 {
     const char *e = getenv("SEEKSV_B200_DEVICE_JOIN");
@@ -317,22 +336,8 @@ bool join_clips(const std::vector<ClipLine> &lines, const AlignmentSet &set, Jun
         join_clips_with_alignments(lines, set, jm);
         return true;
     }
-    static std::map<int, svb_ctx *> cached;  // (kept for the life of the process, like the command context)
-    static std::mutex mu;
-    svb_ctx *ctx = nullptr;
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        const int dev = device_index();
-        auto it = cached.find(dev);
-        if (it != cached.end()) ctx = it->second;
-        else {
-            if (svb_ctx_create(dev, &ctx) != 0) {
-                err = svb_last_error(nullptr);
-                return false;
-            }
-            cached[dev] = ctx;
-        }
-    }
+    svb_ctx *ctx = side_context(err);
+    if (!ctx) return false;
     JoinArrays J;
     if (!pack_join_inputs(lines, set, J)) {
         join_clips_with_alignments(lines, set, jm);
@@ -631,8 +636,25 @@ int cmd_getsv(int argc, char **argv)
             return open_original(g.ctx, original_bam, &bam) != 0 ? 2 : 0;
         });
     // the two clip files are read side by side (the text inflates while the alignments are parsed); errors in the reference's order
+    // P.clip.gz as our getclip writes it (gzip members of <= 64 KiB of text) is inflated on the GPU, on the side context: the host
+    // cores are busy staging the BAM just now. Anything else (a reference-made file, host-written members, plain text) goes
+    // through the host reader as before. SEEKSV_B200_GZ_READ=host|zlib keeps everything on the host.
     std::string clip_err;
-    std::future<bool> clip_read = std::async(std::launch::async, [&]() { return read_text_maybe_gz(clipfile, clip_text, clip_err); });
+    const char *clip_data = nullptr;
+    uint64_t clip_size = 0;
+    const bool gpu_command = pairs_used >= 100000 || with_depth;
+    std::future<bool> clip_read = std::async(std::launch::async, [&]() {
+        const char *mode = getenv("SEEKSV_B200_GZ_READ");
+        if (gpu_command && !mode) {
+            std::string e2;
+            svb_ctx *side = side_context(e2);
+            if (side && svb_read_gz_device(side, clipfile.c_str(), &clip_data, &clip_size) == 0) return true;
+            clip_data = nullptr, clip_size = 0;
+        }
+        if (!read_text_maybe_gz(clipfile, clip_text, clip_err)) return false;
+        clip_data = clip_text.data(), clip_size = clip_text.size();
+        return true;
+    });
     if (!load_alignments(clip_aln, alns, err)) {
         clip_read.wait();
         std::cerr << "[main_samview] fail to open file for reading." << std::endl;
@@ -669,10 +691,10 @@ int cmd_getsv(int argc, char **argv)
         std::cerr << "'FindJunction' finished" << std::endl;
     }
     {
-        std::vector<ClipLine> lines = parse_clip_text(clip_text, n_threads());
+        std::vector<ClipLine> lines = parse_clip_text(clip_data, (size_t)clip_size, n_threads());
         ph.mark("getsv: tokenise clip lines");
         // (`getsv -n 0 -D` has no BAM pass and runs without a GPU: the host mirror joins there)
-        if (!join_clips(lines, alns, jm, err, pairs_used >= 100000 || with_depth)) return fail("[seeksv_b200] " + err);
+        if (!join_clips(lines, alns, jm, err, gpu_command)) return fail("[seeksv_b200] " + err);
     }
     std::cerr << "'InputSoftInfoStoreBreakpoint' finished" << std::endl;
     ph.mark("getsv: join");

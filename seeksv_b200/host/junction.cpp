@@ -158,15 +158,17 @@ static inline int token_int(std::string_view t)
     return neg ? -v : v;
 }
 
-std::vector<ClipLine> parse_clip_text(const std::string &text, int n_threads)
+std::vector<ClipLine> parse_clip_text(const std::string &text, int n_threads) { return parse_clip_text(text.data(), text.size(), n_threads); }
+
+std::vector<ClipLine> parse_clip_text(const char *text_begin, size_t text_size, int n_threads)
 {
     // `fin >> chr >> pos >> orientation >> cigar >> ... >> support; getline(...)` (getsv.h:453-456): whitespace-separated
     // tokens, the rest of the line is dropped. Fields are views into `text`; line chunks are parsed in parallel.
     // One pass per chunk finds every byte below 0x21 eight bytes at a time (all white space is below 0x21; sequence, quality and
     // number characters are not): a tab closes a field, a newline closes the line, anything else - a blank, a carriage return, an
     // empty field among the first nine - sends that line through the generic `>>` rule.
-    const char *b = text.data(), *e = b + text.size();
-    auto chunks = line_chunks(b, e, text.size() > (1u << 20) ? hw_threads(n_threads) : 1);
+    const char *b = text_begin, *e = b + text_size;
+    auto chunks = line_chunks(b, e, text_size > (1u << 20) ? hw_threads(n_threads) : 1);
     std::vector<std::vector<ClipLine>> part(chunks.size());
     run_parallel(chunks.size(), hw_threads(n_threads), [&](size_t ci) {
         const char *const cb = chunks[ci].first, *const ce = chunks[ci].second;

@@ -71,6 +71,7 @@ struct FlankRanges {
 };
 
 std::vector<ClipLine> parse_clip_text(const std::string &text, int n_threads = 0);
+std::vector<ClipLine> parse_clip_text(const char *text, size_t size, int n_threads);  // (views point into `text`)
 // packed BAM records (after the header) -> alignment list; qname views point into `set.storage`
 bool parse_bam_alignments(AlignmentSet &set, uint64_t first_record);
 // SAM text (in set.storage) -> alignment list, parsed by n_threads threads

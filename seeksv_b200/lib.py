@@ -57,7 +57,7 @@ EXPORTS = [
     "svb_clusters_gz", "svb_gzip_text", "svb_bam_open_voffsets", "svb_bai_linear_offsets", "svb_bam_peek_record", "svb_voffset_distance",
     "svb_sam_to_stream", "svb_main", "svb_getsv_passes", "svb_clusters_text_len", "svb_clusters_export_device",
     "svb_clusters_export_parts", "svb_bam_set_own_offset", "svb_insert_partial", "svb_insert_sq", "svb_pairs_depth", "svb_plan_somatic", "svb_insert_partial_async",
-    "svb_write_range_blocks", "svb_set_shard_provider", "svb_clip_join",
+    "svb_write_range_blocks", "svb_set_shard_provider", "svb_clip_join", "svb_read_gz_device",
 ]
 
 
@@ -151,6 +151,7 @@ def load():
     L.svb_write_range_blocks.argtypes = [C.c_char_p, vp, u64, vp, u64, C.c_int, C.POINTER(vp), C.POINTER(u64)]
     L.svb_set_shard_provider.argtypes = [vp, vp]
     L.svb_set_shard_provider.restype = None
+    L.svb_read_gz_device.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(u64)]
     L.svb_clip_join.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, u64, vp, u64, C.POINTER(vp), C.POINTER(u64)]
     _lib = L
     return L
@@ -738,6 +739,14 @@ def sam_to_stream(path: str):
         return C.string_at(p, n.value), first.value
     finally:
         L.svb_free(p)
+
+
+def read_gz_device(ctx: "Context", path: str) -> bytes:
+    """svb_read_gz_device: a gzip file of the device writer (members of <= 64 KiB of text), inflated on the GPU"""
+    L = load()
+    p, n = C.c_void_p(), C.c_uint64()
+    ctx.check(L.svb_read_gz_device(ctx.h, path.encode(), C.byref(p), C.byref(n)), "svb_read_gz_device(%s)" % path)
+    return C.string_at(p, n.value)
 
 
 def read_gz(path: str) -> bytes:
