@@ -422,38 +422,86 @@ __global__ void __launch_bounds__(128)
 {
     if (ctl->abort_main) return;
     const uint32_t n_seg = ctl->n_seg, lane = threadIdx.x & 31;
-    // warps take four keys at a time from a ticket counter: a key with many reads (a real breakpoint) keeps its warp busy for a
+    const uint32_t n_members = start[n_seg];
+    // What a member needs before its bases can be fetched is a chain of dependent loads - order -> candidate fields -> record
+    // head: three round trips per member when the warp walks the members one by one, and that latency, not occupancy, is what
+    // bounded this kernel (0.175 ms at 32, 40 or 56 registers alike). The lanes fetch the chain for 32 consecutive members at
+    // once; the sequential greedy loop takes each member's values from the lane that holds them.
+    uint32_t m_base = 0xffffffffu, m_x = 0, m_begin = 0, m_ll = 0, m_rl = 0, m_side = 0, m_w = 0, m_w2 = 0;
+    int32_t m_lqseq = 0;
+    uint64_t m_rec = 0;
+    // warps take sixteen keys (~32 members: one fetch of member chains) at a time from a ticket counter: a key with many reads (a real breakpoint) keeps its warp busy for a
     // while, and a fixed assignment left the last warps running alone
     for (;;) {
         uint32_t s0 = 0;
-        if (lane == 0) s0 = atomicAdd(&ctl->tk_cluster, 4u);
+        if (lane == 0) s0 = atomicAdd(&ctl->tk_cluster, 16u);
         s0 = __shfl_sync(0xffffffffu, s0, 0);
         if (s0 >= n_seg) break;
-        const uint32_t s1 = min(s0 + 4u, n_seg);
+        const uint32_t s1 = min(s0 + 16u, n_seg);
+        // the keys' own fields, one key per lane
+        uint32_t g_a = 0, g_b = 0, g_maxl = 0, g_maxr = 0;
+        uint64_t g_off = 0;
+        if (s0 + lane < s1) {
+            const uint32_t sg = s0 + lane;
+            g_a = start[sg], g_b = start[sg + 1], g_maxl = maxl_[sg], g_maxr = maxr_[sg], g_off = arena_off[sg];
+        }
       for (uint32_t s = s0; s < s1; ++s) {
-        const uint32_t a = start[s], b = start[s + 1];
-        const uint32_t maxl = maxl_[s], stride = maxl + maxr_[s];
-        char *S = arena_seq + arena_off[s], *Q = arena_qual + arena_off[s];
+        const uint32_t a = __shfl_sync(0xffffffffu, g_a, s - s0), b = __shfl_sync(0xffffffffu, g_b, s - s0);
+        const uint32_t maxl = __shfl_sync(0xffffffffu, g_maxl, s - s0), stride = maxl + __shfl_sync(0xffffffffu, g_maxr, s - s0);
+        const uint64_t seg_off = __shfl_sync(0xffffffffu, g_off, s - s0);
+        char *S = arena_seq + seg_off, *Q = arena_qual + seg_off;
         uint32_t ncl = 0;
         for (uint32_t k = a; k < b; ++k) {
-            const uint32_t x = order[k];
-            const uint64_t rec = c.off[x];
-            const uint32_t begin = c.begin[x], ll = c.ll[x], rl = c.rl[x], side = c.side[x];
+            if (m_base == 0xffffffffu || k < m_base || k >= m_base + 32) {  // (warp-uniform) the next 32 members' chains
+                m_base = k;
+                const uint32_t kk = k + lane;
+                if (kk < n_members) {
+                    m_x = order[kk];
+                    m_rec = c.off[m_x], m_begin = c.begin[m_x], m_ll = c.ll[m_x], m_rl = c.rl[m_x], m_side = c.side[m_x];
+                    const uint8_t *hp = d + m_rec;
+                    m_w = ldu32(hp + 12), m_w2 = ldu32(hp + 16), m_lqseq = ldi32(hp + 20);
+                }
+            }
+            const int src = (int)(k - m_base);
+            const uint32_t x = __shfl_sync(0xffffffffu, m_x, src);
+            const uint64_t rec = __shfl_sync(0xffffffffu, m_rec, src);
+            const uint32_t begin = __shfl_sync(0xffffffffu, m_begin, src), ll = __shfl_sync(0xffffffffu, m_ll, src);
+            const uint32_t rl = __shfl_sync(0xffffffffu, m_rl, src), side = __shfl_sync(0xffffffffu, m_side, src);
+            const uint32_t w = __shfl_sync(0xffffffffu, m_w, src), w2 = __shfl_sync(0xffffffffu, m_w2, src);
+            const int32_t l_qseq = __shfl_sync(0xffffffffu, m_lqseq, src);
             const uint8_t *p = d + rec;
-            uint32_t w = ldu32(p + 12), w2 = ldu32(p + 16);
-            int32_t l_qseq = ldi32(p + 20);
+            (void)x;
             const uint8_t *seq = p + 36 + (w & 0xff) + 4 * (w2 & 0xffff);
             const uint8_t *qual = seq + (l_qseq + 1) / 2;
-            const bool noq = l_qseq > 0 && qual[0] == 0xff;
+            const uint8_t q_first = l_qseq > 0 ? qual[0] : 0;
             char *tS = S + (uint64_t)ncl * stride, *tQ = Q + (uint64_t)ncl * stride;  // tentative new cluster
-            // GetSeq (clip_reads.cpp:286-306): 4-bit codes -> "=ACMGRSVTWYHKDBN", quality + 33
-            for (uint32_t j = lane; j < ll + rl; j += 32) {
-                uint32_t idx = begin + j;
-                uint32_t nib = (seq[idx >> 1] >> ((~idx & 1) << 2)) & 15;
-                uint32_t col = maxl - ll + j;
-                tS[col] = "=ACMGRSVTWYHKDBN"[nib];
-                tQ[col] = noq ? '*' : (char)(qual[idx] + 33);
+            // GetSeq (clip_reads.cpp:286-306): 4-bit codes -> "=ACMGRSVTWYHKDBN", quality + 33. All loads of (up to) 256 bases are
+            // issued before the first store: with one load -> store per loop iteration every 32 bases waited for their own round trip
+            // to the record (ncu: 44 % of the kernel's stall samples sat on these two loads).
+            const uint32_t n_bases = ll + rl;
+            bool noq = false;
+            for (uint32_t j0 = 0; j0 < n_bases; j0 += 256) {
+                uint8_t sb[8], qb[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t j = j0 + u * 32 + lane;
+                    sb[u] = 0, qb[u] = 0;
+                    if (j < n_bases) sb[u] = seq[(begin + j) >> 1], qb[u] = qual[begin + j];
+                }
+                noq = l_qseq > 0 && q_first == 0xff;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t j = j0 + u * 32 + lane;
+                    if (j < n_bases) {
+                        const uint32_t idx = begin + j, nib = (sb[u] >> ((~idx & 1) << 2)) & 15, col = maxl - ll + j;
+                        // "=ACMGRSV" / "TWYHKDBN" packed into two registers (an indexed constant load serialises over distinct indices)
+                        const uint64_t tab = (nib & 8) ? 0x4E42444B48595754ull : 0x565352474D43413Dull;
+                        tS[col] = (char)(tab >> ((nib & 7) * 8));
+                        tQ[col] = noq ? '*' : (char)(qb[u] + 33);
+                    }
+                }
             }
+            noq = l_qseq > 0 && q_first == 0xff;
             __syncwarp();
             int found = -1;
             for (uint32_t cl = 0; cl < ncl; ++cl) {
@@ -618,11 +666,52 @@ struct TextScanOp {
     }
 };
 
-// one warp per cluster writes its clip.gz line and its FASTQ record
+// One thread per cluster: everything of its clip.gz line that is not a copy of bases or qualities - the head
+// "chr \t pos \t side \t cigar \t", the tabs between the four strings, the tail "\t support \n" - and the frame bytes of its FASTQ
+// record. In the warp-per-cluster writer below this was lane-0 code: two thirds of that kernel's instructions ran with one
+// active lane (ncu: 11.5 threads per instruction).
+__global__ void __launch_bounds__(128)
+    text_heads(const ClipCtl *__restrict__ ctl, const uint32_t *__restrict__ cl_seg, const uint32_t *__restrict__ cl_slot,
+               const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c, ClusterOut out,
+               const uint8_t *__restrict__ d, NameTable names, const uint64_t *__restrict__ clip_off, const uint64_t *__restrict__ fq_off,
+               char *__restrict__ clip, char *__restrict__ fq)
+{
+    if (ctl->abort_main) return;
+    const uint32_t n_cl = ctl->n_cl;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cl; i += gridDim.x * blockDim.x) {
+        const uint32_t s = cl_seg[i], a = start[s], k = a + cl_slot[i], x = order[a];
+        const uint32_t L = out.len_l[k], R = out.len_r[k], side = c.side[x];
+        const bool noq = out.noqual[k];
+        const uint32_t aN = side == 0 ? R : L, cN = side == 0 ? L : R, aQN = noq ? 1 : aN, cQN = noq ? 1 : cN;
+        char *q = clip + clip_off[i];
+        const int32_t tid = c.tid[x];
+        const char *nm = names.blob + names.off[tid];
+        const uint32_t nl = names.off[tid + 1] - names.off[tid];
+        for (uint32_t j = 0; j < nl; ++j) *q++ = nm[j];
+        *q++ = '\t';
+        q = put_dec_i(q, c.pos[x]);
+        *q++ = '\t';
+        *q++ = side == 0 ? '5' : '3';
+        *q++ = '\t';
+        q += cigar_text(d + out.cig_off[k], q);
+        *q++ = '\t';
+        q += aN, *q++ = '\t';
+        q += aQN, *q++ = '\t';
+        q += cN, *q++ = '\t';
+        q += cQN, *q++ = '\t';
+        q = put_dec(q, out.support[k]);
+        *q++ = '\n';
+        char *f = fq + fq_off[i];  // FASTQ record named by its own sequence (clip_reads.h:320,339)
+        f[0] = '@', f[1 + cN] = '\n', f[2 + 2 * cN] = '\n', f[3 + 2 * cN] = '+', f[4 + 2 * cN] = '\n', f[5 + 2 * cN + cQN] = '\n';
+    }
+}
+
+// one warp per cluster copies the four strings of its clip.gz line and of its FASTQ record into the places text_heads leaves free
+// (the two kernels write disjoint bytes and run side by side on two streams; the head's length follows from the line's size)
 __global__ void __launch_bounds__(128)
     text_write(ClipCtl *__restrict__ ctl, const uint32_t *__restrict__ cl_seg, const uint32_t *__restrict__ cl_slot,
                const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c, ClusterOut out,
-               const uint8_t *__restrict__ d, NameTable names, const uint32_t *__restrict__ maxl_, const uint32_t *__restrict__ maxr_, const uint64_t *__restrict__ arena_off,
+               const uint32_t *__restrict__ maxl_, const uint32_t *__restrict__ maxr_, const uint64_t *__restrict__ arena_off,
                const char *__restrict__ arena_seq, const char *__restrict__ arena_qual, const uint64_t *__restrict__ clip_off,
                const uint64_t *__restrict__ fq_off, char *__restrict__ clip, char *__restrict__ fq)
 {
@@ -634,63 +723,68 @@ __global__ void __launch_bounds__(128)
         i0 = __shfl_sync(0xffffffffu, i0, 0);
         if (i0 >= n_cl) break;
         const uint32_t i1 = min(i0 + 8u, n_cl);
-      for (uint32_t i = i0; i < i1; ++i) {
-        uint32_t s = cl_seg[i], a = start[s], slot = cl_slot[i], k = a + slot;
-        uint32_t x = order[a];
-        uint32_t maxl = maxl_[s], stride = maxl + maxr_[s];
-        const char *S = arena_seq + arena_off[s] + (uint64_t)slot * stride, *Q = arena_qual + arena_off[s] + (uint64_t)slot * stride;
-        uint32_t L = out.len_l[k], R = out.len_r[k];
-        bool noq = out.noqual[k];
-        uint32_t side = c.side[x];
-        // '5': aligned = right part, clipped = left part; '3': aligned = left, clipped = right (clip_reads.h:308-332)
-        const char *aS = side == 0 ? S + maxl : S + maxl - L, *aQ = side == 0 ? Q + maxl : Q + maxl - L;
-        const char *cS = side == 0 ? S + maxl - L : S + maxl, *cQ = side == 0 ? Q + maxl - L : Q + maxl;
-        uint32_t aN = side == 0 ? R : L, cN = side == 0 ? L : R;
-        uint32_t aQN = noq ? 1 : aN, cQN = noq ? 1 : cN;
-        char *o = clip + clip_off[i];
-        uint32_t head = 0;
-        if (lane == 0) {
-            int32_t tid = c.tid[x];
-            const char *nm = names.blob + names.off[tid];
-            uint32_t nl = names.off[tid + 1] - names.off[tid];
-            char *q = o;
-            for (uint32_t j = 0; j < nl; ++j) *q++ = nm[j];
-            *q++ = '\t';
-            q = put_dec_i(q, c.pos[x]);
-            *q++ = '\t';
-            *q++ = side == 0 ? '5' : '3';
-            *q++ = '\t';
-            q += cigar_text(d + out.cig_off[k], q);
-            *q++ = '\t';
-            head = (uint32_t)(q - o);
+        for (uint32_t i = i0; i < i1; ++i) {
+            const uint32_t s = cl_seg[i], a = start[s], slot = cl_slot[i], k = a + slot, x = order[a];
+            const uint32_t maxl = maxl_[s], stride = maxl + maxr_[s];
+            const char *S = arena_seq + arena_off[s] + (uint64_t)slot * stride, *Q = arena_qual + arena_off[s] + (uint64_t)slot * stride;
+            const uint32_t L = out.len_l[k], R = out.len_r[k], side = c.side[x];
+            const bool noq = out.noqual[k];
+            // '5': aligned = right part, clipped = left part; '3': aligned = left, clipped = right (clip_reads.h:308-332)
+            const char *aS = side == 0 ? S + maxl : S + maxl - L, *aQ = side == 0 ? Q + maxl : Q + maxl - L;
+            const char *cS = side == 0 ? S + maxl - L : S + maxl, *cQ = side == 0 ? Q + maxl - L : Q + maxl;
+            const uint32_t aN = side == 0 ? R : L, cN = side == 0 ? L : R;
+            const uint32_t aQN = noq ? 1 : aN;
+            const uint64_t line_begin = clip_off[i], line_end = i + 1 < n_cl ? clip_off[i + 1] : ctl->clip_bytes;
+            const uint32_t cQN = noq ? 1 : cN;
+            // line = head | aligned \t alignedQ \t clipped \t clippedQ \t support \n
+            const uint32_t head = (uint32_t)(line_end - line_begin) - (aN + aQN + cN + cQN + 5 + dec_len(out.support[k]));
+            char *qa = clip + line_begin + head, *qaq = qa + aN + 1, *qc = qaq + aQN + 1, *qcq = qc + cN + 1;
+            char *f = fq + fq_off[i];
+            // bases and qualities of a part are fetched together, up to 256 of each per lane-round, before anything is stored: one
+            // exposed round trip to the arena per part instead of one per 32 bytes and string (ncu: the copy loops held 30 % of the
+            // stall samples); the clipped part is stored three times (clip line, FASTQ name, FASTQ sequence) from one fetch
+            for (uint32_t j0 = 0; j0 < aN; j0 += 256) {
+                char s8[8], q8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t j = j0 + u * 32 + lane;
+                    s8[u] = 0, q8[u] = 0;
+                    if (j < aN) {
+                        s8[u] = aS[j];
+                        if (!noq) q8[u] = aQ[j];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t j = j0 + u * 32 + lane;
+                    if (j < aN) {
+                        qa[j] = s8[u];
+                        if (!noq) qaq[j] = q8[u];
+                    }
+                }
+            }
+            for (uint32_t j0 = 0; j0 < cN; j0 += 256) {
+                char s8[8], q8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t j = j0 + u * 32 + lane;
+                    s8[u] = 0, q8[u] = 0;
+                    if (j < cN) {
+                        s8[u] = cS[j];
+                        if (!noq) q8[u] = cQ[j];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t j = j0 + u * 32 + lane;
+                    if (j < cN) {
+                        qc[j] = s8[u], f[1 + j] = s8[u], f[2 + cN + j] = s8[u];
+                        if (!noq) qcq[j] = q8[u], f[5 + 2 * cN + j] = q8[u];
+                    }
+                }
+            }
+            if (noq && lane == 0) qaq[0] = '*', qcq[0] = '*', f[5 + 2 * cN] = '*';
         }
-        head = __shfl_sync(0xffffffffu, head, 0);
-        char *q = o + head;
-        for (uint32_t j = lane; j < aN; j += 32) q[j] = aS[j];
-        q += aN;
-        if (lane == 0) *q = '\t';
-        ++q;
-        for (uint32_t j = lane; j < aQN; j += 32) q[j] = noq ? '*' : aQ[j];
-        q += aQN;
-        if (lane == 0) *q = '\t';
-        ++q;
-        for (uint32_t j = lane; j < cN; j += 32) q[j] = cS[j];
-        q += cN;
-        if (lane == 0) *q = '\t';
-        ++q;
-        for (uint32_t j = lane; j < cQN; j += 32) q[j] = noq ? '*' : cQ[j];
-        q += cQN;
-        if (lane == 0) {
-            *q++ = '\t';
-            q = put_dec(q, out.support[k]);
-            *q++ = '\n';
-        }
-        // FASTQ record named by its own sequence (clip_reads.h:320,339)
-        char *f = fq + fq_off[i];
-        if (lane == 0) f[0] = '@', f[1 + cN] = '\n', f[2 + 2 * cN] = '\n', f[3 + 2 * cN] = '+', f[4 + 2 * cN] = '\n', f[5 + 2 * cN + cQN] = '\n';
-        for (uint32_t j = lane; j < cN; j += 32) f[1 + j] = cS[j], f[2 + cN + j] = cS[j];
-        for (uint32_t j = lane; j < cQN; j += 32) f[5 + 2 * cN + j] = noq ? '*' : cQ[j];
-      }
     }
 }
 
@@ -1219,9 +1313,15 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
             launch_scan<1, 4>(ctx, s, op3, B.sc_cl, cap.cand);
             TextScanOp op4{B.cl_seg, B.cl_slot, B.start, order, B.c, B.co, bam->d_data, nt, B.clip_off, B.fq_off, cap.clip, cap.fq, ctl};
             launch_scan<2, 2>(ctx, s, op4, B.sc_text, cap.cand);
-            text_write<<<grid_for(ctx, (uint64_t)cap.cand * 32, 128, 16), 128, 0, s>>>(ctl, B.cl_seg, B.cl_slot, B.start, order, B.c, B.co, bam->d_data, nt,
-                                                                                     B.maxl, B.maxr, B.arena_off, B.arena_seq, B.arena_qual, B.clip_off,
-                                                                                     B.fq_off, res->d_text[0], res->d_text[1]);
+            // the heads on the side stream (long idle by now), the strings here: disjoint bytes of the same two texts
+            CK(cudaEventRecord(ctx->fork_event, s));
+            CK(cudaStreamWaitEvent(side, ctx->fork_event, 0));
+            text_heads<<<grid_for(ctx, cap.cand, 128, 8), 128, 0, side>>>(ctl, B.cl_seg, B.cl_slot, B.start, order, B.c, B.co, bam->d_data, nt, B.clip_off,
+                                                                         B.fq_off, res->d_text[0], res->d_text[1]);
+            CK(cudaEventRecord(ctx->join_event, side));
+            text_write<<<grid_for(ctx, (uint64_t)cap.cand * 32, 128, 16), 128, 0, s>>>(ctl, B.cl_seg, B.cl_slot, B.start, order, B.c, B.co, B.maxl, B.maxr,
+                                                                                     B.arena_off, B.arena_seq, B.arena_qual, B.clip_off, B.fq_off,
+                                                                                     res->d_text[0], res->d_text[1]);
         }
         }
         // ---- the one read-back (after the side stream's work)
