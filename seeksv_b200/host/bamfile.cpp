@@ -1127,11 +1127,15 @@ static bool gz_member(const char *data, size_t n, std::vector<uint8_t> &out)
     return true;
 }
 
-// The reference writes through ogzstream (gzstream.C:53-61); here every file is cut into 1 MiB parts that are compressed as
-// independent gzip members by one thread pool over ALL files (zcat / gzread concatenate members transparently).
+// The reference writes through ogzstream (gzstream.C:53-61); here every file is cut into parts that are compressed as
+// independent gzip members by one thread pool over ALL files (zcat / gzread concatenate members transparently). The default
+// (Huffman-only) writer makes members of 64 KiB of text, like the device writer (csrc/gzip.cu): such a file can be inflated by the
+// GPU's BGZF inflate kernel (svb_read_gz_device: getsv reads P.clip.gz that way - in a multi-GPU run the file is rank 0's
+// concatenation of every rank's block files, a quarter of a second of host inflate at 8 x C2). With an explicit zlib level the
+// members stay at 1 MiB (LZ77 matches do not cross members).
 bool write_gz_many(const std::vector<GzJob> &jobs, int n_threads, std::string &err)
 {
-    const uint64_t PART = 1ull << 20;
+    const uint64_t PART = gz_level() < 0 ? (64ull << 10) : (1ull << 20);
     struct Part {
         size_t job;
         uint64_t a, b;

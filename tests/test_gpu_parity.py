@@ -628,19 +628,25 @@ def test_device_gzip_on_awkward_texts(ctx, tmp_path):
         assert L.read_gz_device(ctx, p) == data, len(data)
 
 
-def test_device_gz_reader_refuses_what_it_cannot_read(ctx, tmp_path):
-    """host-written members (1 MiB of text each), a foreign gzip file and plain text are SVB_ERR_FORMAT for svb_read_gz_device (getsv
-    then reads them on the host); a damaged member of the right form does not take the process down"""
+def test_device_gz_reader_refuses_what_it_cannot_read(ctx, tmp_path, monkeypatch):
+    """members of 1 MiB of text (the host writer with an explicit zlib level), a foreign gzip file and plain text are SVB_ERR_FORMAT for
+    svb_read_gz_device (getsv then reads them on the host); the host writer's default members (64 KiB of text, Huffman only) are read
+    on the device like the device writer's; a damaged member of the right form does not take the process down"""
     import seeksv_b200.lib as L
     text = b"chr1\t100\t5\t50M\tACGT\tIIII\tGG\tII\t1\n" * 40000
     host = str(tmp_path / "host.gz")
     L.write_gz(host, text)
+    assert L.read_gz_device(ctx, host) == text and L.read_gz(host) == text
+    monkeypatch.setenv("SEEKSV_B200_GZ_LEVEL", "6")
+    zl = str(tmp_path / "zlib.gz")
+    L.write_gz(zl, text)
+    monkeypatch.delenv("SEEKSV_B200_GZ_LEVEL")
     foreign = str(tmp_path / "foreign.gz")
     with gzip.open(foreign, "wb") as f:
         f.write(text)
     plain = str(tmp_path / "plain.txt")
     open(plain, "wb").write(text)
-    for p in (host, foreign, plain):
+    for p in (zl, foreign, plain):
         with pytest.raises(L.SvbError):
             L.read_gz_device(ctx, p)
         assert L.read_gz(p) == text
