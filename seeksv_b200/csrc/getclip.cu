@@ -394,7 +394,9 @@ struct SegStatsOp {
             mr = max(mr, c.rl[x]);
         }
         maxl[s] = ml, maxr[s] = mr;
-        v[0] = (uint64_t)(start[s + 1] - start[s]) * (ml + mr);
+        // (a key with ONE member needs no arena: nothing is compared or merged, the text is decoded straight from the record)
+        const uint32_t members = start[s + 1] - start[s];
+        v[0] = members > 1 ? (uint64_t)members * (ml + mr) : 0;
     }
     __device__ void store(uint64_t s, const uint64_t (&excl)[1], const uint64_t (&)[1]) const { arena_off[s] = excl[0]; }
     __device__ void total(const uint64_t (&t)[1]) const
@@ -410,6 +412,31 @@ struct ClusterOut {
     uint8_t *noqual;
     uint32_t *seg_ncl;
 };
+
+// 98 % of the breakpoint keys hold a single soft-clipped read (C2: 89.9 k of 91.5 k): InsertSeq (clip_reads.cpp:260-283) has
+// nothing to compare it with, so its cluster IS the read. One thread per such key fills the cluster's fields; its strings are
+// never staged - text_write decodes them from the record. (Until the third session of round 2 these keys went through the warp-
+// sequential kernel below like the others and were most of its 0.17 ms.)
+__global__ void __launch_bounds__(128)
+    cluster_singletons(const uint8_t *__restrict__ d, const ClipCtl *__restrict__ ctl, const uint32_t *__restrict__ start,
+                       const uint32_t *__restrict__ order, CandArrays c, ClusterOut out)
+{
+    if (ctl->abort_main) return;
+    const uint32_t n_seg = ctl->n_seg;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_seg; s += gridDim.x * blockDim.x) {
+        const uint32_t a = start[s];
+        if (start[s + 1] - a != 1) continue;
+        const uint32_t x = order[a];
+        const uint64_t rec = c.off[x];
+        const uint8_t *p = d + rec;
+        const uint32_t w = ldu32(p + 12), w2 = ldu32(p + 16);
+        const int32_t l_qseq = ldi32(p + 20);
+        const uint8_t *qual = p + 36 + (w & 0xff) + 4 * (w2 & 0xffff) + (l_qseq + 1) / 2;
+        out.len_l[a] = c.ll[x], out.len_r[a] = c.rl[x], out.cig_off[a] = rec, out.support[a] = 1;
+        out.noqual[a] = l_qseq > 0 && qual[0] == 0xff;
+        out.seg_ncl[s] = 1;
+    }
+}
 
 // One warp per breakpoint key: the reference's sequential greedy InsertSeq (clip_reads.cpp:260-283) in
 // BAM order, with lane-parallel string compares and consensus updates. Strings live in a per-segment
@@ -449,6 +476,7 @@ __global__ void __launch_bounds__(128)
         const uint32_t a = __shfl_sync(0xffffffffu, g_a, s - s0), b = __shfl_sync(0xffffffffu, g_b, s - s0);
         const uint32_t maxl = __shfl_sync(0xffffffffu, g_maxl, s - s0), stride = maxl + __shfl_sync(0xffffffffu, g_maxr, s - s0);
         const uint64_t seg_off = __shfl_sync(0xffffffffu, g_off, s - s0);
+        if (b - a == 1) continue;  // (cluster_singletons)
         char *S = arena_seq + seg_off, *Q = arena_qual + seg_off;
         uint32_t ncl = 0;
         for (uint32_t k = a; k < b; ++k) {
@@ -706,11 +734,21 @@ __global__ void __launch_bounds__(128)
     }
 }
 
-// one warp per cluster copies the four strings of its clip.gz line and of its FASTQ record into the places text_heads leaves free
-// (the two kernels write disjoint bytes and run side by side on two streams; the head's length follows from the line's size)
+// One warp per cluster writes the four strings of its clip.gz line and of its FASTQ record into the places text_heads leaves free
+// (the two kernels write disjoint bytes and run side by side on two streams; the head's length follows from the line's size).
+// Source of the strings: the cluster's arena slot, or - for a key with a single member - the record itself (4-bit bases ->
+// "=ACMGRSVTWYHKDBN", quality + 33; GetSeq, clip_reads.cpp:286-306). The lanes fetch the chains of dependent loads that lead to
+// the strings (cluster -> key -> candidate -> record head) for the eight clusters of a ticket side by side.
+__device__ __forceinline__ char base_char(uint32_t packed_byte, uint32_t idx)
+{
+    const uint32_t nib = (packed_byte >> ((~idx & 1) << 2)) & 15;
+    const uint64_t tab = (nib & 8) ? 0x4E42444B48595754ull : 0x565352474D43413Dull;  // "TWYHKDBN" : "=ACMGRSV"
+    return (char)(tab >> ((nib & 7) * 8));
+}
+
 __global__ void __launch_bounds__(128)
     text_write(ClipCtl *__restrict__ ctl, const uint32_t *__restrict__ cl_seg, const uint32_t *__restrict__ cl_slot,
-               const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c, ClusterOut out,
+               const uint32_t *__restrict__ start, const uint32_t *__restrict__ order, CandArrays c, ClusterOut out, const uint8_t *__restrict__ d,
                const uint32_t *__restrict__ maxl_, const uint32_t *__restrict__ maxr_, const uint64_t *__restrict__ arena_off,
                const char *__restrict__ arena_seq, const char *__restrict__ arena_qual, const uint64_t *__restrict__ clip_off,
                const uint64_t *__restrict__ fq_off, char *__restrict__ clip, char *__restrict__ fq)
@@ -722,64 +760,94 @@ __global__ void __launch_bounds__(128)
         if (lane == 0) i0 = atomicAdd(&ctl->tk_text, 8u);
         i0 = __shfl_sync(0xffffffffu, i0, 0);
         if (i0 >= n_cl) break;
-        const uint32_t i1 = min(i0 + 8u, n_cl);
-        for (uint32_t i = i0; i < i1; ++i) {
-            const uint32_t s = cl_seg[i], a = start[s], slot = cl_slot[i], k = a + slot, x = order[a];
-            const uint32_t maxl = maxl_[s], stride = maxl + maxr_[s];
-            const char *S = arena_seq + arena_off[s] + (uint64_t)slot * stride, *Q = arena_qual + arena_off[s] + (uint64_t)slot * stride;
-            const uint32_t L = out.len_l[k], R = out.len_r[k], side = c.side[x];
-            const bool noq = out.noqual[k];
-            // '5': aligned = right part, clipped = left part; '3': aligned = left, clipped = right (clip_reads.h:308-332)
-            const char *aS = side == 0 ? S + maxl : S + maxl - L, *aQ = side == 0 ? Q + maxl : Q + maxl - L;
-            const char *cS = side == 0 ? S + maxl - L : S + maxl, *cQ = side == 0 ? Q + maxl - L : Q + maxl;
-            const uint32_t aN = side == 0 ? R : L, cN = side == 0 ? L : R;
-            const uint32_t aQN = noq ? 1 : aN;
-            const uint64_t line_begin = clip_off[i], line_end = i + 1 < n_cl ? clip_off[i + 1] : ctl->clip_bytes;
-            const uint32_t cQN = noq ? 1 : cN;
+        const uint32_t cnt = min(8u, n_cl - i0);
+        // lane j < cnt: everything cluster i0 + j needs
+        uint32_t m_single = 0, m_L = 0, m_R = 0, m_side = 0, m_noq = 0, m_head = 0, m_aAt = 0, m_cAt = 0;
+        int32_t m_lqseq = 0;
+        uint64_t m_src = 0, m_line = 0, m_fq = 0;
+        if (lane < cnt) {
+            const uint32_t i = i0 + lane;
+            const uint32_t sg = cl_seg[i], a = start[sg], slot = cl_slot[i], k = a + slot, x = order[a];
+            m_single = start[sg + 1] - a == 1;
+            m_L = out.len_l[k], m_R = out.len_r[k], m_side = c.side[x], m_noq = out.noqual[k];
+            const uint32_t aN = m_side == 0 ? m_R : m_L, cN = m_side == 0 ? m_L : m_R;
+            const uint32_t aQN = m_noq ? 1 : aN, cQN = m_noq ? 1 : cN;
+            m_line = clip_off[i], m_fq = fq_off[i];
+            const uint64_t line_end = i + 1 < n_cl ? clip_off[i + 1] : ctl->clip_bytes;
             // line = head | aligned \t alignedQ \t clipped \t clippedQ \t support \n
-            const uint32_t head = (uint32_t)(line_end - line_begin) - (aN + aQN + cN + cQN + 5 + dec_len(out.support[k]));
+            m_head = (uint32_t)(line_end - m_line) - (aN + aQN + cN + cQN + 5 + dec_len(out.support[k]));
+            // '5': aligned = right part, clipped = left part; '3': aligned = left, clipped = right (clip_reads.h:308-332)
+            if (m_single) {  // bases [begin, begin + L) are the left part, [begin + L, begin + L + R) the right part
+                const uint64_t rec = out.cig_off[k];
+                const uint8_t *p = d + rec;
+                const uint32_t w = ldu32(p + 12), w2 = ldu32(p + 16);
+                m_lqseq = ldi32(p + 20);
+                m_src = rec + 36 + (w & 0xff) + 4 * (w2 & 0xffff);  // the packed bases; the qualities follow them
+                const uint32_t begin = c.begin[x];
+                m_aAt = m_side == 0 ? begin + m_L : begin, m_cAt = m_side == 0 ? begin : begin + m_L;
+            } else {  // slot = [left part right-aligned at column maxl | right part from column maxl]
+                const uint32_t maxl = maxl_[sg], stride = maxl + maxr_[sg];
+                m_src = arena_off[sg] + (uint64_t)slot * stride;
+                m_aAt = m_side == 0 ? maxl : maxl - m_L, m_cAt = m_side == 0 ? maxl - m_L : maxl;
+            }
+        }
+        for (uint32_t j = 0; j < cnt; ++j) {
+            const bool single = __shfl_sync(0xffffffffu, m_single, j) != 0, noq = __shfl_sync(0xffffffffu, m_noq, j) != 0;
+            const uint32_t L = __shfl_sync(0xffffffffu, m_L, j), R = __shfl_sync(0xffffffffu, m_R, j), side = __shfl_sync(0xffffffffu, m_side, j);
+            const uint32_t head = __shfl_sync(0xffffffffu, m_head, j), aAt = __shfl_sync(0xffffffffu, m_aAt, j), cAt = __shfl_sync(0xffffffffu, m_cAt, j);
+            const int32_t l_qseq = __shfl_sync(0xffffffffu, m_lqseq, j);
+            const uint64_t src = __shfl_sync(0xffffffffu, m_src, j), line_begin = __shfl_sync(0xffffffffu, m_line, j);
+            const uint64_t fq_begin = __shfl_sync(0xffffffffu, m_fq, j);
+            const uint32_t aN = side == 0 ? R : L, cN = side == 0 ? L : R, aQN = noq ? 1 : aN;
+            // bytes of the bases and of the qualities, indexed by base number (record) or by column (arena slot)
+            const uint8_t *sB = single ? d + src : (const uint8_t *)arena_seq + src;
+            const uint8_t *qB = single ? d + src + (l_qseq + 1) / 2 : (const uint8_t *)arena_qual + src;
             char *qa = clip + line_begin + head, *qaq = qa + aN + 1, *qc = qaq + aQN + 1, *qcq = qc + cN + 1;
-            char *f = fq + fq_off[i];
+            char *f = fq + fq_begin;
             // bases and qualities of a part are fetched together, up to 256 of each per lane-round, before anything is stored: one
-            // exposed round trip to the arena per part instead of one per 32 bytes and string (ncu: the copy loops held 30 % of the
-            // stall samples); the clipped part is stored three times (clip line, FASTQ name, FASTQ sequence) from one fetch
+            // exposed round trip per part instead of one per 32 bytes and string; the clipped part is stored three times (clip
+            // line, FASTQ name, FASTQ sequence) from one fetch
             for (uint32_t j0 = 0; j0 < aN; j0 += 256) {
-                char s8[8], q8[8];
+                uint8_t s8[8], q8[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const uint32_t j = j0 + u * 32 + lane;
+                    const uint32_t t = j0 + u * 32 + lane;
                     s8[u] = 0, q8[u] = 0;
-                    if (j < aN) {
-                        s8[u] = aS[j];
-                        if (!noq) q8[u] = aQ[j];
+                    if (t < aN) {
+                        s8[u] = single ? sB[(aAt + t) >> 1] : sB[aAt + t];
+                        if (!noq) q8[u] = qB[aAt + t];
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const uint32_t j = j0 + u * 32 + lane;
-                    if (j < aN) {
-                        qa[j] = s8[u];
-                        if (!noq) qaq[j] = q8[u];
+                    const uint32_t t = j0 + u * 32 + lane;
+                    if (t < aN) {
+                        qa[t] = single ? base_char(s8[u], aAt + t) : (char)s8[u];
+                        if (!noq) qaq[t] = single ? (char)(q8[u] + 33) : (char)q8[u];
                     }
                 }
             }
             for (uint32_t j0 = 0; j0 < cN; j0 += 256) {
-                char s8[8], q8[8];
+                uint8_t s8[8], q8[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const uint32_t j = j0 + u * 32 + lane;
+                    const uint32_t t = j0 + u * 32 + lane;
                     s8[u] = 0, q8[u] = 0;
-                    if (j < cN) {
-                        s8[u] = cS[j];
-                        if (!noq) q8[u] = cQ[j];
+                    if (t < cN) {
+                        s8[u] = single ? sB[(cAt + t) >> 1] : sB[cAt + t];
+                        if (!noq) q8[u] = qB[cAt + t];
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const uint32_t j = j0 + u * 32 + lane;
-                    if (j < cN) {
-                        qc[j] = s8[u], f[1 + j] = s8[u], f[2 + cN + j] = s8[u];
-                        if (!noq) qcq[j] = q8[u], f[5 + 2 * cN + j] = q8[u];
+                    const uint32_t t = j0 + u * 32 + lane;
+                    if (t < cN) {
+                        const char ch = single ? base_char(s8[u], cAt + t) : (char)s8[u];
+                        qc[t] = ch, f[1 + t] = ch, f[2 + cN + t] = ch;
+                        if (!noq) {
+                            const char qh = single ? (char)(q8[u] + 33) : (char)q8[u];
+                            qcq[t] = qh, f[5 + 2 * cN + t] = qh;
+                        }
                     }
                 }
             }
@@ -1303,6 +1371,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
         {
             ProfScope ps(ctx, "cluster_build", 0);
             // (occupancy is not what bounds this kernel: 32- and 40-register builds with 12 / 16 CTAs per SM ran in the same 0.175 ms)
+            cluster_singletons<<<grid_for(ctx, cap.cand, 128, 8), 128, 0, s>>>(bam->d_data, ctl, B.start, order, B.c, B.co);
             cluster_build<<<grid_for(ctx, (uint64_t)cap.cand * 32, 128, 16), 128, 0, s>>>(bam->d_data, ctl, B.start, order, B.c, B.maxl, B.maxr, B.arena_off,
                                                                                         B.arena_seq, B.arena_qual, prm->match_rate, B.co);
         }
@@ -1319,7 +1388,7 @@ extern "C" int svb_getclip(svb_ctx *ctx, svb_bam *bam, const svb_getclip_params 
             text_heads<<<grid_for(ctx, cap.cand, 128, 8), 128, 0, side>>>(ctl, B.cl_seg, B.cl_slot, B.start, order, B.c, B.co, bam->d_data, nt, B.clip_off,
                                                                          B.fq_off, res->d_text[0], res->d_text[1]);
             CK(cudaEventRecord(ctx->join_event, side));
-            text_write<<<grid_for(ctx, (uint64_t)cap.cand * 32, 128, 16), 128, 0, s>>>(ctl, B.cl_seg, B.cl_slot, B.start, order, B.c, B.co, B.maxl, B.maxr,
+            text_write<<<grid_for(ctx, (uint64_t)cap.cand * 32, 128, 16), 128, 0, s>>>(ctl, B.cl_seg, B.cl_slot, B.start, order, B.c, B.co, bam->d_data, B.maxl, B.maxr,
                                                                                      B.arena_off, B.arena_seq, B.arena_qual, B.clip_off, B.fq_off,
                                                                                      res->d_text[0], res->d_text[1]);
         }
