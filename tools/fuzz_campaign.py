@@ -8,6 +8,7 @@ getsv (plain, `-n 0 -D`, `-B`) -> somatic(self), and then
     checker on inputs beyond the committed fixtures;
   * the host layer of the product (`seeksv getsv -n 0 -D`, no BAM pass -> runs without a GPU) must reproduce the `-n 0 -D`
     outputs;
+  * the rules of the device join (tools/clipjoin_sim.cpp) must build the host mirror's junction map from the same two files;
   * with --gpu (on a B200 box with oracle/_ref present; bwa's SAM is then replaced by tools/minialign) the product CLI runs the
     whole pipeline too.
 Prints one line per seed and a summary; exit status 1 if anything differed. Test infrastructure, not product code.
@@ -33,6 +34,7 @@ SEEKSV = os.path.join(ROOT, "oracle", "_ref", "seeksv")
 BAMTOOL = os.path.join(ROOT, "oracle", "_ref", "bamtool")
 CLI = os.path.join(ROOT, "seeksv_b200", "bin", "seeksv")
 MINI = os.path.join(ROOT, "seeksv_b200", "bin", "minialign")
+JOIN_SIM = os.path.join(ROOT, "seeksv_b200", "bin", "clipjoin_sim")
 
 
 def text(p):
@@ -106,6 +108,14 @@ def one_seed(seed, records, work, bwa, gpu, n_opts=0, edge=False, connect_n=0):
                 bad.append("host -n0 -D .sv")
             if r.stdout != ref["out.n0D"]:
                 bad.append("host -n0 -D stdout")
+
+    # --- the rules of the device join (csrc/clipjoin_core.h, run serially by tools/clipjoin_sim.cpp) against the host mirror, on the
+    #     reference's own clip.gz and the aligner's SAM: also with every chunk's entry guess wrong (repair rounds)
+    if os.path.exists(JOIN_SIM):
+        for extra in ([], ["--wrong-guesses"]):
+            r = run([JOIN_SIM, sam, pre + ".clip.gz"] + extra)
+            if r.returncode != 0 or not r.stdout.startswith(("OK", "SKIP")):
+                bad.append("clip_join rules %s: %s" % (" ".join(extra), r.stdout.strip()[:80]))
 
     # --- the whole product pipeline (B200 only)
     if gpu:
