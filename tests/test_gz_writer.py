@@ -17,7 +17,7 @@ def _cases():
         "empty": b"",
         "one_byte": b"A",
         "one_symbol": b"I" * 300000,
-        "clip_text": text * 6,                                    # several 1 MiB members
+        "clip_text": text * 6,                                    # many members
         "incompressible": rnd.randbytes(2_200_000),
         "skewed": bytes(rnd.choices(range(256), weights=[2 ** (-i / 8) for i in range(256)], k=1_500_000)),
         "needs_length_limit": b"".join(bytes([i]) * (2 ** min(i, 21)) for i in range(23)),  # Fibonacci-like: codes > 15 bits
@@ -40,6 +40,33 @@ def test_writer_output_is_plain_gzip_and_reader_round_trips(tmp_path, monkeypatc
         for reader in ("", "zlib"):     # the two-literals-per-lookup decoder of our own members (falls back to zlib), and zlib alone
             monkeypatch.setenv("SEEKSV_B200_GZ_READ", reader)
             assert L.read_gz(p) == data, (name, reader)
+
+
+def _members(raw):
+    """(member size, ISIZE) of every member of a file of our writers, walked through the 'SV' size fields"""
+    out, o = [], 0
+    while o < len(raw):
+        assert raw[o:o + 4] == b"\x1f\x8b\x08\x04" and raw[o + 12:o + 16] == b"SV\x04\x00", o
+        size = int.from_bytes(raw[o + 16:o + 20], "little")
+        assert 28 <= size <= len(raw) - o
+        out.append((size, int.from_bytes(raw[o + size - 4:o + size], "little")))
+        o += size
+    return out
+
+
+def test_default_members_hold_at_most_64_kib_of_text(tmp_path, monkeypatch):
+    """what makes a file readable by the device inflate kernel (svb_read_gz_device; getsv reads P.clip.gz through it): the default
+    writer's members are 64 KiB of text each; with an explicit zlib level they stay at 1 MiB"""
+    data = _cases()["clip_text"]
+    monkeypatch.delenv("SEEKSV_B200_GZ_LEVEL", raising=False)
+    p = str(tmp_path / "d.gz")
+    L.write_gz(p, data, threads=2)
+    ms = _members(open(p, "rb").read())
+    assert sum(u for _, u in ms) == len(data) and all(u == 65536 for _, u in ms[:-1]) and 0 < ms[-1][1] <= 65536
+    monkeypatch.setenv("SEEKSV_B200_GZ_LEVEL", "1")
+    L.write_gz(p, data, threads=2)
+    ms = _members(open(p, "rb").read())
+    assert sum(u for _, u in ms) == len(data) and all(u == 1 << 20 for _, u in ms[:-1])
 
 
 def test_reader_accepts_foreign_gzip_and_plain_text(tmp_path):
