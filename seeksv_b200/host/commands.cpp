@@ -339,7 +339,7 @@ bool join_clips(const std::vector<ClipLine> &lines, const AlignmentSet &set, Jun
     svb_ctx *ctx = side_context(err);
     if (!ctx) return false;
     JoinArrays J;
-    if (!pack_join_inputs(lines, set, J)) {
+    if (!pack_join_inputs(lines, set, J, n_threads())) {
         join_clips_with_alignments(lines, set, jm);
         return true;
     }

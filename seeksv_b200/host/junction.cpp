@@ -601,56 +601,76 @@ void join_clips_with_alignments(const std::vector<ClipLine> &lines, const Alignm
 // The arrays the device join takes: clipped sequences and read names packed into two blobs, chromosome names replaced by their
 // rank in std::string::compare order (the reference keys its maps on the names; "" = tid outside the header, "Exogenous" = unmapped
 // alignment, GetAlignInfo getsv.cpp:25-71).
-bool pack_join_inputs(const std::vector<ClipLine> &lines, const AlignmentSet &set, JoinArrays &J)
+bool pack_join_inputs(const std::vector<ClipLine> &lines, const AlignmentSet &set, JoinArrays &J, int n_threads)
 {
     const std::vector<Alignment> &alns = set.recs;
+    // Both passes over the lines / alignments touch one short string per element somewhere in tens of megabytes of file text: a
+    // cache miss per element (10 ms single-threaded at C2 size - as long as the host join itself), so the elements are cut into
+    // shares: per-share chromosome names and byte counts first, then every share fills its part of the arrays.
+    const int nt = hw_threads(n_threads);
+    const size_t shares = (size_t)std::max(1, std::min(nt, 64));
+    auto share = [&](size_t n, size_t k) { return std::make_pair(n * k / shares, n * (k + 1) / shares); };
+    std::vector<uint64_t> seq_at(shares + 1, 0), name_at(shares + 1, 0);
+    std::vector<std::vector<std::string>> chr_seen(shares);
+    run_parallel(shares, nt, [&](size_t k) {
+        auto [l0, l1] = share(lines.size(), k);
+        uint64_t sb = 0;
+        std::string_view last;
+        for (size_t i = l0; i < l1; ++i) {
+            const ClipLine &l = lines[i];
+            sb += l.clipped_seq.size();
+            if (i == l0 || l.chr != last) {
+                last = l.chr;
+                if (std::find(chr_seen[k].begin(), chr_seen[k].end(), l.chr) == chr_seen[k].end()) chr_seen[k].push_back(std::string(l.chr));
+            }
+        }
+        seq_at[k + 1] = sb;
+        auto [a0, a1] = share(alns.size(), k);
+        uint64_t nb = 0;
+        for (size_t j = a0; j < a1; ++j) nb += alns[j].qname.size();
+        name_at[k + 1] = nb;
+    });
+    for (size_t k = 0; k < shares; ++k) seq_at[k + 1] += seq_at[k], name_at[k + 1] += name_at[k];
     // names -> ranks
     std::map<std::string, int32_t> rank;
     rank[""] = 0, rank["Exogenous"] = 0;
     for (const std::string &n : set.ref_names) rank[n] = 0;
-    {
-        std::string_view last;
-        for (const ClipLine &l : lines)
-            if (l.chr != last) {
-                last = l.chr;
-                rank.emplace(std::string(l.chr), 0);
-            }
-    }
+    for (const auto &seen : chr_seen)
+        for (const std::string &n : seen) rank.emplace(n, 0);
     if (rank.size() >= (1u << 30)) return false;
     J.rank_names.clear();
     for (auto &kv : rank) kv.second = (int32_t)J.rank_names.size(), J.rank_names.push_back(kv.first);
     std::vector<int32_t> tid_rank(set.ref_names.size());
     for (size_t t = 0; t < set.ref_names.size(); ++t) tid_rank[t] = rank[set.ref_names[t]];
     const int32_t r_none = rank[""], r_exo = rank["Exogenous"];
-    // lines
-    uint64_t seq_bytes = 0;
-    for (const ClipLine &l : lines) seq_bytes += l.clipped_seq.size();
-    uint64_t name_bytes = 0;
-    for (const Alignment &a : alns) name_bytes += a.qname.size();
+    const uint64_t seq_bytes = seq_at[shares], name_bytes = name_at[shares];
     if (seq_bytes >= (1ull << 32) || name_bytes >= (1ull << 32) || set.cigar_words.size() >= (1ull << 32)) return false;
     J.lines.resize(lines.size()), J.seqs.resize(seq_bytes), J.alns.resize(alns.size()), J.names.resize(name_bytes);
-    {
-        uint64_t o = 0;
-        std::string_view last;
-        int32_t last_rank = 0;
-        for (size_t i = 0; i < lines.size(); ++i) {
-            const ClipLine &l = lines[i];
-            if (i == 0 || l.chr != last) last = l.chr, last_rank = rank[std::string(l.chr)];
-            J.lines[i] = svb_join_line{(uint32_t)o, (uint32_t)l.clipped_seq.size(), last_rank, l.pos, (uint32_t)(unsigned char)l.side};
-            memcpy(&J.seqs[o], l.clipped_seq.data(), l.clipped_seq.size());
-            o += l.clipped_seq.size();
+    const std::map<std::string, int32_t> &ranks = rank;  // (read-only from here on: shared by the threads)
+    run_parallel(shares, nt, [&](size_t k) {
+        {
+            auto [l0, l1] = share(lines.size(), k);
+            uint64_t o = seq_at[k];
+            std::string_view last;
+            int32_t last_rank = 0;
+            for (size_t i = l0; i < l1; ++i) {
+                const ClipLine &l = lines[i];
+                if (i == l0 || l.chr != last) last = l.chr, last_rank = ranks.find(std::string(l.chr))->second;
+                J.lines[i] = svb_join_line{(uint32_t)o, (uint32_t)l.clipped_seq.size(), last_rank, l.pos, (uint32_t)(unsigned char)l.side};
+                memcpy(&J.seqs[o], l.clipped_seq.data(), l.clipped_seq.size());
+                o += l.clipped_seq.size();
+            }
         }
-    }
-    {
-        uint64_t o = 0;
-        for (size_t j = 0; j < alns.size(); ++j) {
+        auto [a0, a1] = share(alns.size(), k);
+        uint64_t o = name_at[k];
+        for (size_t j = a0; j < a1; ++j) {
             const Alignment &a = alns[j];
             const int32_t r = (a.flag & 4) ? r_exo : (a.tid >= 0 && (size_t)a.tid < tid_rank.size()) ? tid_rank[a.tid] : r_none;
             J.alns[j] = svb_join_aln{(uint32_t)o, (uint32_t)a.qname.size(), a.flag, a.cigar_begin, a.cigar_n, r, a.pos, a.mapq};
             memcpy(&J.names[o], a.qname.data(), a.qname.size());
             o += a.qname.size();
         }
-    }
+    });
     return true;
 }
 

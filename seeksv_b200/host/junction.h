@@ -98,7 +98,7 @@ struct JoinArrays {
     std::string seqs, names;
     std::vector<std::string> rank_names;  // rank -> chromosome name
 };
-bool pack_join_inputs(const std::vector<ClipLine> &lines, const AlignmentSet &alns, JoinArrays &out);
+bool pack_join_inputs(const std::vector<ClipLine> &lines, const AlignmentSet &alns, JoinArrays &out, int n_threads = 0);
 bool accumulate_join_candidates(const std::vector<ClipLine> &lines, const AlignmentSet &alns, const JoinArrays &arrays, const svb_join_cand *cands,
                                 uint64_t n, JunctionMap &jm, std::string &err);
 

@@ -11,6 +11,7 @@
 // (lines.bin, seqs.bin, alns.bin, names.bin, cigars.bin) and the sorted candidates (cands.bin) as raw structs: the GPU tests feed
 // the arrays to the C ABI and expect exactly these candidates back.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,12 +59,20 @@ int main(int argc, char **argv)
         fprintf(stderr, "%s\n", err.c_str());
         return 2;
     }
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const bool timing = getenv("CLIPJOIN_SIM_TIMING") != nullptr;
+    double t0 = now();
     std::vector<ClipLine> lines = parse_clip_text(text, 4);
+    double t1 = now();
     JunctionMap want, got;
     join_clips_with_alignments(lines, set, want);
+    double t2 = now();
 
     JoinArrays J;
-    if (!pack_join_inputs(lines, set, J)) {
+    const bool packed = pack_join_inputs(lines, set, J);
+    double t3 = now();
+    if (timing) fprintf(stderr, "tokenise %.1f ms, host join %.1f ms, pack %.1f ms\n", t1 - t0, t2 - t1, t3 - t2);
+    if (!packed) {
         fprintf(stderr, "inputs too large for the device join\n");
         return 2;
     }
@@ -147,7 +156,10 @@ int main(int argc, char **argv)
         put("cigars.bin", set.cigar_words.data(), set.cigar_words.size() * 4);
         put("cands.bin", cands.data(), cands.size() * sizeof(svb_join_cand));
     }
-    if (!accumulate_join_candidates(lines, set, J, cands.data(), cands.size(), got, err)) {
+    double t4 = now();
+    const bool accumulated = accumulate_join_candidates(lines, set, J, cands.data(), cands.size(), got, err);
+    if (timing) fprintf(stderr, "rules (serial) %.1f ms, accumulate %.1f ms\n", t4 - t3, now() - t4);
+    if (!accumulated) {
         printf("DIFF %s\n", err.c_str());
         return 1;
     }
