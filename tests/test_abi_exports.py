@@ -214,3 +214,17 @@ def test_usage_texts_are_byte_identical_to_the_reference():
         if os.path.exists(ref):
             q = subprocess.run([ref] + argv, capture_output=True)
             assert (q.stdout, q.stderr, q.returncode) == (r.stdout, r.stderr, r.returncode), name
+
+
+def test_join_struct_sizes_match_the_python_binding(tmp_path):
+    """svb_join_line / svb_join_aln / svb_join_cand travel as raw bytes through lib.clip_join_raw and tools/clipjoin_sim --dump:
+    the sizes the binding assumes are the C sizes (no padding)"""
+    import subprocess
+    from seeksv_b200 import lib as L
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "seeksv_b200.h"\nint main(void){printf("%zu %zu %zu\\n", sizeof(svb_join_line), '
+                   'sizeof(svb_join_aln), sizeof(svb_join_cand));return 0;}\n')
+    exe = str(tmp_path / "sz")
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(x) for x in out] == [L.JOIN_LINE_BYTES, L.JOIN_ALN_BYTES, L.JOIN_CAND_BYTES]
